@@ -1,0 +1,83 @@
+/* include/ue_gpu.h — C ABI of the B200 pandf1 / jac_calc drop-in.
+ *
+ * These entry points are what an ISO_C_BINDING shim compiled into the
+ * reference's `bbb` package binds.  They replace, one for
+ * one, the bodies of the two reference interface routines
+ *
+ *   Pandf1rhs_interface(neq,time,yl,yldot)              bbb/oderhs.m:12331-12345
+ *   jac_calc_interface(neq,t,yl,yldot00,ml,mu,wk,
+ *                      nnzmx,jac,ja,ia)                 bbb/oderhs.m:12297-12329
+ *
+ * and carry across the ambient module state those routines read (the named
+ * inputs listed in include/ue_params.h).
+ *
+ * Conventions (reference: Forthon builds with 8-byte default INTEGER and REAL):
+ *   - all integers are int64_t, all reals are double;
+ *   - arrays are caller-owned, Fortran-contiguous; index *content* (ja, ia,
+ *     igyl, ixm1, ...) is 1-based / Fortran-valued exactly as in the reference;
+ *   - every function returns 0 on success, <0 on error; the message is
+ *     available from ue_gpu_last_error() so the shim can `call xerrab(msg)`
+ *     (reference error path: com/error.f:1-13);
+ *   - there is NO CPU fallback: if no CUDA device is present ue_gpu_init fails.
+ */
+#ifndef UE_GPU_H
+#define UE_GPU_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- static inputs (once per allocate/ueinit; names in ue_params.h) -------- */
+int ue_gpu_set_int(const char* name, int64_t value);
+int ue_gpu_set_real(const char* name, double value);
+int ue_gpu_set_real_array(const char* name, const double* data, int64_t n);
+int ue_gpu_set_int_array(const char* name, const int64_t* data, int64_t n);
+/* Validate that every named input is present and the switch set is one the
+ * kernels implement, upload to the device, build the window tables. */
+int ue_gpu_init(void);
+
+/* ---- per-solve inputs (change every exmain / psetnk) ----------------------
+ * dtuse, ylodt (group Time_dep_nwt, bbb/bbb.v), suscal, sfscal (group Ynorm):
+ * length neq each.  Scalars nufak/dtreal/dtphi come through ue_gpu_set_real. */
+int ue_gpu_step_params(int64_t neq, const double* dtuse, const double* ylodt,
+                       const double* suscal, const double* sfscal);
+
+/* ---- Pandf1rhs_interface: pandf1(-1,-1,0,neq,time,yl,yldot) ---------------
+ * yl has neq+2 entries (yl(neq+1) = Jacobian-mode flag, yl(neq+2) = nufak);
+ * yldot receives neq entries. */
+int ue_gpu_pandf1(int64_t neq, double time, const double* yl, double* yldot);
+
+/* ---- jac_calc_interface ----------------------------------------------------
+ * Finite-difference Jacobian of pandf1 about yl (bbb/oderhs.m:8533-8760) in the
+ * reference's CSR layout: jac/ja (nnz, columns ascending within a row, 1-based)
+ * and ia (neq+1, 1-based, ia(neq+1)=nnz+1).  yldot00 = pandf1(yl) as computed
+ * by the caller (psetnk / sfsetnk), neq+2 long.  yl is left unchanged.
+ * Returns -2 with the reference's "More storage needed" message if nnz>nnzmx. */
+int ue_gpu_jac_calc(int64_t neq, double t, const double* yl, const double* yldot00,
+                    int64_t ml, int64_t mu, int64_t nnzmx,
+                    double* jac, int64_t* ja, int64_t* ia, int64_t* nnz_out);
+
+/* ---- device-resident variants (inputs/outputs already in HBM) -------------
+ * Same semantics; pointers are device pointers on the current device.  Used by
+ * bench.py for the kernel-only figure and by a host that keeps yl on the GPU. */
+int ue_gpu_pandf1_dev(int64_t neq, double time, const double* d_yl, double* d_yldot);
+int ue_gpu_jac_calc_dev(int64_t neq, double t, const double* d_yl, const double* d_yldot00,
+                        int64_t ml, int64_t mu, int64_t nnzmx,
+                        double* d_jac, int64_t* d_ja, int64_t* d_ia, int64_t* nnz_out);
+
+/* ---- column-range split (ppp MPISplitIndex / LocalJacBuilder analogue) ----
+ * Restrict the next jac_calc calls to perturbed unknowns iv in [ivmin,ivmax]
+ * (1-based, inclusive): the returned CSR holds only those columns.  (1,neq)
+ * restores the full Jacobian.  Reference: ppp/parallel.F90:176-381. */
+int ue_gpu_set_column_range(int64_t ivmin, int64_t ivmax);
+
+/* ---- diagnostics ----------------------------------------------------------- */
+int ue_gpu_kernel_launches(int64_t* n);      /* launches since init (for bench.py) */
+int ue_gpu_last_kernel_ms(double* jac_ms, double* res_ms); /* CUDA-event times of the last calls */
+const char* ue_gpu_last_error(void);
+int ue_gpu_finalize(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UE_GPU_H */

@@ -1,0 +1,104 @@
+// include/ue_param_store.hpp — name-keyed storage behind ue_*_set_* (C++ helper
+// shared by the product library and the test oracle; boundary plumbing only,
+// no physics).  The field list comes from ue_params.h.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "ue_params.h"
+
+struct UeParams {
+#define X(n) int64_t n;
+  UE_INT_SCALARS(X)
+#undef X
+#define X(n) double n;
+  UE_REAL_SCALARS(X)
+#undef X
+#define X(n) const double* n;
+  UE_REAL_PLANES(X)
+  UE_REAL_LINES(X)
+#undef X
+#define X(n) const int64_t* n;
+  UE_INT_PLANES(X)
+  UE_INT_LINES(X)
+#undef X
+};
+
+struct UeStore {
+  UeParams p;
+  std::map<std::string, int64_t*> iscal;
+  std::map<std::string, double*> rscal;
+  std::map<std::string, const double**> rarr;
+  std::map<std::string, const int64_t**> iarr;
+  std::map<std::string, bool> is_plane;
+  std::map<std::string, std::vector<double>> rdata;
+  std::map<std::string, std::vector<int64_t>> idata;
+  std::map<std::string, bool> seen;
+
+  UeStore() {
+    std::memset(&p, 0, sizeof(p));
+#define X(n) iscal[#n] = &p.n; seen[#n] = false;
+    UE_INT_SCALARS(X)
+#undef X
+#define X(n) rscal[#n] = &p.n; seen[#n] = false;
+    UE_REAL_SCALARS(X)
+#undef X
+#define X(n) rarr[#n] = &p.n; seen[#n] = false; is_plane[#n] = true;
+    UE_REAL_PLANES(X)
+#undef X
+#define X(n) rarr[#n] = &p.n; seen[#n] = false; is_plane[#n] = false;
+    UE_REAL_LINES(X)
+#undef X
+#define X(n) iarr[#n] = &p.n; seen[#n] = false; is_plane[#n] = true;
+    UE_INT_PLANES(X)
+#undef X
+#define X(n) iarr[#n] = &p.n; seen[#n] = false; is_plane[#n] = false;
+    UE_INT_LINES(X)
+#undef X
+  }
+  int set_int(const char* name, int64_t v) {
+    auto it = iscal.find(name);
+    if (it == iscal.end()) return -1;
+    *it->second = v; seen[name] = true; return 0;
+  }
+  int set_real(const char* name, double v) {
+    auto it = rscal.find(name);
+    if (it == rscal.end()) return -1;
+    *it->second = v; seen[name] = true; return 0;
+  }
+  int set_real_array(const char* name, const double* d, int64_t n) {
+    auto it = rarr.find(name);
+    if (it == rarr.end() || n < 0) return -1;
+    auto& v = rdata[name];
+    v.assign(d, d + n);
+    *it->second = v.data(); seen[name] = true; return 0;
+  }
+  int set_int_array(const char* name, const int64_t* d, int64_t n) {
+    auto it = iarr.find(name);
+    if (it == iarr.end() || n < 0) return -1;
+    auto& v = idata[name];
+    v.assign(d, d + n);
+    *it->second = v.data(); seen[name] = true; return 0;
+  }
+  // names never set; also checks plane sizes once nx, ny are known
+  std::string missing() const {
+    std::string s;
+    for (auto& kv : seen) if (!kv.second) { s += kv.first; s += ' '; }
+    return s;
+  }
+  std::string bad_sizes() const {
+    std::string s;
+    const int64_t ncell = (p.nx + 2) * (p.ny + 2);
+    for (auto& kv : rdata) if (is_plane.at(kv.first) && (int64_t)kv.second.size() != ncell) { s += kv.first; s += ' '; }
+    for (auto& kv : idata) if (is_plane.at(kv.first) && (int64_t)kv.second.size() != ncell) { s += kv.first; s += ' '; }
+    return s;
+  }
+  int64_t len(const char* name) const {
+    auto a = rdata.find(name); if (a != rdata.end()) return (int64_t)a->second.size();
+    auto b = idata.find(name); if (b != idata.end()) return (int64_t)b->second.size();
+    return -1;
+  }
+};
