@@ -1,0 +1,126 @@
+"""ctypes binding of the C ABI in include/ue_gpu.h.
+
+`UeLib(path, prefix)` binds one shared library that exports the ABI under a
+given symbol prefix.  The product library is `uedge_b200/csrc/libuegpu.so`
+(prefix ``ue_gpu_``); `load_gpu()` loads it and fails loudly if it is missing —
+there is no CPU fallback on the product path.  Tests bind the CPU oracle with
+the same class (prefix ``ue_ora_``) purely as a checker.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+GPU_LIB = os.path.join(_HERE, "csrc", "libuegpu.so")
+
+_i64 = C.c_int64
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int64)
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+class UeError(RuntimeError):
+    """Raised where the reference would call xerrab (com/error.f:1-13)."""
+
+
+class UeLib:
+    def __init__(self, path, prefix):
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                "%s not found — build it first (python -c 'import __graft_entry__ as g; g.build()')" % path
+            )
+        self.lib = C.CDLL(path)
+        self.prefix = prefix
+        self.neq = None
+        f = self._f
+        f("set_int", [C.c_char_p, _i64])
+        f("set_real", [C.c_char_p, C.c_double])
+        f("set_real_array", [C.c_char_p, _dp, _i64])
+        f("set_int_array", [C.c_char_p, _ip, _i64])
+        f("init", [])
+        f("step_params", [_i64, _dp, _dp, _dp, _dp])
+        f("pandf1", [_i64, C.c_double, _dp, _dp])
+        f("jac_calc", [_i64, C.c_double, _dp, _dp, _i64, _i64, _i64, _dp, _ip, _ip, _ip])
+        f("set_column_range", [_i64, _i64])
+        getattr(self.lib, prefix + "last_error").restype = C.c_char_p
+
+    def _f(self, name, argtypes):
+        fn = getattr(self.lib, self.prefix + name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+        return fn
+
+    def _call(self, name, *args):
+        rc = getattr(self.lib, self.prefix + name)(*args)
+        if rc != 0:
+            msg = getattr(self.lib, self.prefix + "last_error")().decode()
+            raise UeError("%s%s failed (%d): %s" % (self.prefix, name, rc, msg))
+
+    # ---- static inputs -------------------------------------------------------
+    def load_static(self, static):
+        for k, v in static["ints"].items():
+            self._call("set_int", k.encode(), int(v))
+        for k, v in static["reals"].items():
+            self._call("set_real", k.encode(), float(v))
+        for grp in ("planes", "lines"):
+            for k, v in static[grp].items():
+                a = np.ascontiguousarray(v, dtype=np.float64).reshape(-1)
+                self._call("set_real_array", k.encode(), _d(a), a.size)
+        for grp in ("iplanes", "ilines"):
+            for k, v in static[grp].items():
+                a = np.ascontiguousarray(v, dtype=np.int64).reshape(-1)
+                self._call("set_int_array", k.encode(), _i(a), a.size)
+        self.neq = int(static["ints"]["neq"])
+        self.nnzmx_default = None
+
+    def set_real(self, name, v):
+        self._call("set_real", name.encode(), float(v))
+
+    def set_int(self, name, v):
+        self._call("set_int", name.encode(), int(v))
+
+    def init(self):
+        self._call("init")
+
+    def step_params(self, dtuse, ylodt, suscal, sfscal):
+        a = [np.ascontiguousarray(x, dtype=np.float64) for x in (dtuse, ylodt, suscal, sfscal)]
+        self._call("step_params", self.neq, *[_d(x) for x in a])
+
+    # ---- hot path ---------------------------------------------------------------
+    def pandf1(self, yl, time=0.0):
+        """Pandf1rhs_interface: full residual pandf1(-1,-1,0,neq,time,yl,yldot)."""
+        yl = np.ascontiguousarray(yl, dtype=np.float64)
+        assert yl.size == self.neq + 2
+        yldot = np.zeros(self.neq)
+        self._call("pandf1", self.neq, float(time), _d(yl), _d(yldot))
+        return yldot
+
+    def jac_calc(self, yl, yldot00, ml, mu, nnzmx, t=0.0):
+        """jac_calc_interface: returns (jac, ja, ia) in the reference's 1-based CSR."""
+        yl = np.ascontiguousarray(yl, dtype=np.float64)
+        y0 = np.zeros(self.neq + 2)
+        y0[: self.neq] = np.asarray(yldot00, dtype=np.float64)[: self.neq]
+        jac = np.zeros(nnzmx)
+        ja = np.zeros(nnzmx, dtype=np.int64)
+        ia = np.zeros(self.neq + 1, dtype=np.int64)
+        nnz = C.c_int64(0)
+        self._call("jac_calc", self.neq, float(t), _d(yl), _d(y0), int(ml), int(mu), int(nnzmx), _d(jac), _i(ja), _i(ia),
+                   C.byref(nnz))
+        n = nnz.value
+        return jac[:n].copy(), ja[:n].copy(), ia
+
+    def set_column_range(self, ivmin, ivmax):
+        self._call("set_column_range", int(ivmin), int(ivmax))
+
+
+def load_gpu():
+    """The product library.  Raises if it has not been built: no fallback."""
+    return UeLib(GPU_LIB, "ue_gpu_")
