@@ -1,0 +1,151 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Tolerances are BASELINE.json's: residual 1e-12 relative (to the largest |yldot| of the same
+equation type: converged states have yldot -> 0), Jacobian entries 1e-8 relative, CSR pattern
+(ia/ja) bit-exact."""
+import numpy as np
+import pytest
+
+from tests.util import bind, make_case, oracle, psetnk_inputs
+from uedge_b200.capi import load_gpu
+
+pytestmark = pytest.mark.gpu
+
+RES_RTOL = 1e-12
+JAC_RTOL = 1e-8
+
+
+def _pair(name, perturb, istabon=0):
+    c, yl = make_case(name, istabon=istabon, perturb=perturb)
+    gpu = bind(load_gpu(), c)
+    ora = bind(oracle(), c)
+    return c, yl, gpu, ora
+
+
+def _res_err(fg, fo):
+    scale = np.abs(fo).reshape(-1, 5).max(axis=0)
+    return (np.abs(fg - fo).reshape(-1, 5) / scale).max()
+
+
+@pytest.mark.parametrize("name,perturb", [("d3dHsm", 1e-3), ("d3dHsm", 0.05), ("case2", 0.0), ("d3dHsm4x", 1e-3)])
+def test_residual_parity(built, name, perturb):
+    c, yl, gpu, ora = _pair(name, perturb)
+    fg, fo = gpu.pandf1(yl), ora.pandf1(yl)
+    assert np.isfinite(fg).all()
+    assert _res_err(fg, fo) < RES_RTOL
+
+
+def test_residual_converged_state_on_gpu(built):
+    """The reference's converged state must also be a root of the CUDA residual."""
+    c, yl, gpu, ora = _pair("d3dHsm", 0.0)
+    f = gpu.pandf1(yl).reshape(-1, 5)
+    assert np.abs(f).max() < 5e-6
+
+
+def test_residual_timestep_term(built):
+    """yl(neq+1)<0 and dtreal<1e15 adds -(yl-ylodt)/dtuse on interior rows (oderhs.m:7963-8037)."""
+    c, yl, gpu, ora = _pair("d3dHsm", 1e-3)
+    n = c.bbb.neq
+    rng = np.random.default_rng(3)
+    dt = 10.0 ** rng.uniform(-6, -3, n)
+    yo = yl[:n] * (1 + 1e-2 * rng.uniform(-1, 1, n))
+    for lib in (gpu, ora):
+        lib.set_real("dtreal", 1e-4)
+        lib.step_params(dt, yo, np.ones(n), np.ones(n))
+    fg, fo = gpu.pandf1(yl), ora.pandf1(yl)
+    assert _res_err(fg, fo) < RES_RTOL
+    for lib in (gpu, ora):
+        lib.set_real("dtreal", 1e20)
+
+
+def _jac_pair(c, yl, gpu, ora, dt=None):
+    b = c.bbb
+    y, su = psetnk_inputs(c, yl)
+    dtuse = np.full(b.neq, 1e20) if dt is None else dt
+    for lib in (gpu, ora):
+        lib.step_params(dtuse, y[: b.neq], su, np.ones(b.neq))
+    fg, fo = gpu.pandf1(y), ora.pandf1(y)
+    jg = gpu.jac_calc(y, fg, b.lbw, b.ubw, b.nnzmx)
+    jo = ora.jac_calc(y, fo, b.lbw, b.ubw, b.nnzmx)
+    return jg, jo
+
+
+def _check_jac(jg, jo):
+    (vg, jag, iag), (vo, jao, iao) = jg, jo
+    assert np.array_equal(iag, iao), "ia differs: nnz %d vs %d" % (len(vg), len(vo))
+    assert np.array_equal(jag, jao), "ja differs"
+    rows = np.repeat(np.arange(len(iao) - 1), np.diff(iao))
+    rowmax = np.zeros(len(iao) - 1)
+    np.maximum.at(rowmax, rows, np.abs(vo))
+    # entries are finite differences of O(1e-8) increments: compare relative to the entry, with a floor
+    # at the FD noise level of its row (1e-16 * |f| / dyl ~ 1e-8 of the row's largest entry)
+    err = np.abs(vg - vo) / np.maximum(np.abs(vo), 1e-2 * rowmax[rows])
+    assert err.max() < JAC_RTOL, "max rel err %g at %d" % (err.max(), err.argmax())
+
+
+@pytest.mark.parametrize("name,perturb", [("d3dHsm", 1e-3), ("d3dHsm", 0.05), ("case2", 0.0)])
+def test_jacobian_parity(built, name, perturb):
+    c, yl, gpu, ora = _pair(name, perturb)
+    _check_jac(*_jac_pair(c, yl, gpu, ora))
+
+
+def test_jacobian_parity_with_dt(built):
+    c, yl, gpu, ora = _pair("d3dHsm", 1e-2)
+    rng = np.random.default_rng(5)
+    _check_jac(*_jac_pair(c, yl, gpu, ora, dt=10.0 ** rng.uniform(-6, -2, c.bbb.neq)))
+
+
+def test_jacobian_parity_4x(built):
+    c, yl, gpu, ora = _pair("d3dHsm4x", 1e-3)
+    _check_jac(*_jac_pair(c, yl, gpu, ora))
+
+
+def test_jacobian_column_range_split(built):
+    """ppp-style column split: the union of per-range CSRs equals the full CSR."""
+    c, yl, gpu, ora = _pair("d3dHsm", 1e-3)
+    b = c.bbb
+    y, su = psetnk_inputs(c, yl)
+    gpu.step_params(np.full(b.neq, 1e20), y[: b.neq], su, np.ones(b.neq))
+    f = gpu.pandf1(y)
+    full = gpu.jac_calc(y, f, b.lbw, b.ubw, b.nnzmx)
+    parts = []
+    cuts = [1, 301, 577, b.neq + 1]
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        gpu.set_column_range(lo, hi - 1)
+        parts.append(gpu.jac_calc(y, f, b.lbw, b.ubw, b.nnzmx))
+    gpu.set_column_range(1, b.neq)
+    vals, cols, ia = full
+    for i in range(b.neq):
+        cc = np.concatenate([p[1][p[2][i] - 1 : p[2][i + 1] - 1] for p in parts])
+        vv = np.concatenate([p[0][p[2][i] - 1 : p[2][i + 1] - 1] for p in parts])
+        assert np.array_equal(cc, cols[ia[i] - 1 : ia[i + 1] - 1])
+        assert np.array_equal(vv, vals[ia[i] - 1 : ia[i + 1] - 1])
+
+
+def test_jacobian_is_deterministic(built):
+    c, yl, gpu, ora = _pair("d3dHsm", 1e-3)
+    b = c.bbb
+    y, su = psetnk_inputs(c, yl)
+    gpu.step_params(np.full(b.neq, 1e20), y[: b.neq], su, np.ones(b.neq))
+    f = gpu.pandf1(y)
+    a = gpu.jac_calc(y, f, b.lbw, b.ubw, b.nnzmx)
+    bb = gpu.jac_calc(y, f, b.lbw, b.ubw, b.nnzmx)
+    assert all(np.array_equal(p, q) for p, q in zip(a, bb))
+
+
+def test_negative_density_is_trapped(built):
+    c, yl, gpu, ora = _pair("d3dHsm", 0.0)
+    y = yl.copy()
+    y[5 * 40] = -1.0
+    with pytest.raises(Exception, match="ni is negative"):
+        gpu.pandf1(y)
+
+
+def test_nnzmx_overflow_message(built):
+    c, yl, gpu, ora = _pair("d3dHsm", 1e-3)
+    b = c.bbb
+    y, su = psetnk_inputs(c, yl)
+    gpu.step_params(np.full(b.neq, 1e20), y[: b.neq], su, np.ones(b.neq))
+    f = gpu.pandf1(y)
+    with pytest.raises(Exception, match="More storage needed"):
+        gpu.jac_calc(y, f, b.lbw, b.ubw, 1000)

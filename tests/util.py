@@ -1,0 +1,50 @@
+"""Shared helpers for the parity tests."""
+import os
+
+import numpy as np
+
+from uedge_b200.capi import UeLib
+from uedge_b200.cases import (d3dhsm_case, load_grid_npz, load_rate_tables_npz, load_state_npz, refine_grid,
+                              refine_state)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_LIB = os.path.join(ROOT, "oracle", "libue_oracle.so")
+
+
+def oracle():
+    """The CPU oracle bound through the same ctypes class as the product (checker only)."""
+    return UeLib(ORACLE_LIB, "ue_ora_")
+
+
+def make_case(name="d3dHsm", istabon=0, perturb=0.0, seed=1234):
+    g = load_grid_npz()
+    state = load_state_npz("case2_state.npz" if name == "case2" else "d3dHsm_state.npz")
+    if name == "d3dHsm4x":
+        g = refine_grid(g, 4, 4)
+        state = refine_state(state, 4, 4)
+    c = d3dhsm_case(g, istabon=10 if name == "case2" else istabon)
+    if c.com.istabon == 10:
+        c.set_rate_tables(load_rate_tables_npz())
+    c.setup()
+    yl = c.set_state(*state)
+    if perturb:
+        rng = np.random.default_rng(seed)
+        yl[: c.bbb.neq] *= 1.0 + perturb * rng.uniform(-1.0, 1.0, c.bbb.neq)
+    return c, yl
+
+
+def bind(lib, c):
+    lib.load_static(c.static_inputs())
+    lib.init()
+    return lib
+
+
+def psetnk_inputs(c, yl):
+    """(yl with Jacobian flag, suscal) as psetnk/sfsetnk prepare them (bbb/oderhs.m:9453-9468, 9848-9857)."""
+    y = yl.copy()
+    y[c.bbb.neq] = 1.0
+    return y, c.suscal(yl)
+
+
+def csr_to_dense_rows(jac, ja, ia):
+    return [(ja[ia[i] - 1 : ia[i + 1] - 1], jac[ia[i] - 1 : ia[i + 1] - 1]) for i in range(len(ia) - 1)]

@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Generate the committed fixtures under tests/golden/ from the reference tree.
+
+Run ONCE in the build container (where /root/reference exists); the GPU box has
+no reference tree, so tests read only the .npz files written here.
+
+  d3d_16x8_grid.npz   mesh of builder/test/facets/gridue (same mesh as the one stored in
+                      pyexamples/d3dHsmNew/d3dHsm.h5: com/rm, com/zm agree to 3e-14)
+  d3dHsm_state.npz    converged state of pyexamples/d3dHsmNew/d3dHsm.h5 (written by UEDGE 8.0.4.1)
+                      + the guard-cell rm/zm stored in that file (pins guardc)
+  case2_state.npz     restart state builder/test/Forthon_cases/Forthon_case2/h5d3d_ex.16x8
+  ehr2_tables.npz     DEGAS2 hydrogen tables of Forthon_case2/ehr2.dat (istabon=10), SI units
+  case2_golden.json   numbers printed in Forthon_case2/output_forthon_case2.rtf
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from uedge_b200.aphdata import read_ehr  # noqa: E402
+from uedge_b200.cases import state_from_h5  # noqa: E402
+from uedge_b200.gridue import FIELDS, read_gridue  # noqa: E402
+from uedge_b200.h5lite import read_h5  # noqa: E402
+
+REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+OUT = "tests/golden"
+os.makedirs(OUT, exist_ok=True)
+
+g = read_gridue(os.path.join(REF, "builder/test/facets/gridue"))
+np.savez_compressed(os.path.join(OUT, "d3d_16x8_grid.npz"), **{k: g[k] for k in FIELDS},
+                    dims=np.array([g["nxm"], g["nym"], g["ixpt1"], g["ixpt2"], g["iysptrx1"]]))
+
+h5 = os.path.join(REF, "pyexamples/d3dHsmNew/d3dHsm.h5")
+ni, up, te, ti, ng = state_from_h5(h5)
+d = read_h5(h5)
+np.savez_compressed(os.path.join(OUT, "d3dHsm_state.npz"), ni=ni, up=up, te=te, ti=ti, ng=ng,
+                    rm=d["com/rm"].transpose(2, 1, 0), zm=d["com/zm"].transpose(2, 1, 0))
+
+ni, up, te, ti, ng = state_from_h5(os.path.join(REF, "builder/test/Forthon_cases/Forthon_case2/h5d3d_ex.16x8"))
+np.savez_compressed(os.path.join(OUT, "case2_state.npz"), ni=ni, up=up, te=te, ti=ti, ng=ng)
+
+t = read_ehr(os.path.join(REF, "builder/test/Forthon_cases/Forthon_case2/ehr2.dat"))
+np.savez_compressed(os.path.join(OUT, "ehr2_tables.npz"), wsveh=t[0], wsveh0=t[1], welms1=t[2], welms2=t[3])
+
+json.dump({
+    "source": "builder/test/Forthon_cases/Forthon_case2/output_forthon_case2.rtf",
+    "fnrm": [0.7926655291535246, 0.3962737862594912, 0.3718767383113360e-01, 0.7156208214503779e-03,
+             0.8680565629223895e-07, 0.1176826431444834e-10],
+    "yyc": [-0.00965086, -0.00741261, -0.00258718, 0.0028399, 0.00850614, 0.01416487, 0.01984442, 0.02554944,
+            0.03127981, 0.03415233],
+}, open(os.path.join(OUT, "case2_golden.json"), "w"), indent=1)
+print("wrote fixtures to", OUT)

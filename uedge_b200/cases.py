@@ -15,11 +15,18 @@ from .h5lite import read_h5
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def d3dhsm_case(grid, istabon=0):
+def d3dhsm_case(grid, istabon=0, v8_0_defaults=True):
+    """v8_0_defaults: oldseec=1, isoldalbarea=1 — the defaults of UEDGE 8.0.x that wrote the
+    d3dHsm.h5 restart file (changed in 8.1: src/uedge/defaults.yaml)."""
     c = Case(grid)
     b, com = c.bbb, c.com
-    com.nxleg = np.array([[4, 4]]); com.nxcore = np.array([[4, 4]])
-    com.nysol = np.array([6]); com.nycore = np.array([2])
+    f = grid["nxm"] // 16
+    fy = grid["nym"] // 8
+    com.nxleg = np.array([[4 * f, 4 * f]]); com.nxcore = np.array([[4 * f, 4 * f]])
+    com.nysol = np.array([6 * fy]); com.nycore = np.array([2 * fy])
+    if v8_0_defaults:
+        b.oldseec = 1.0
+        b.isoldalbarea = 1.0
     b.methn = b.methu = b.methe = b.methi = b.methg = 33
     b.ncore[0] = 2.5e19
     b.tcoree = 100.0; b.tcorei = 100.0; b.tedge = 2.0
@@ -29,6 +36,71 @@ def d3dhsm_case(grid, istabon=0):
     b.flalfgx = np.full(10, 1.0e20); b.flalfgy = np.full(10, 1.0e20)
     com.istabon = istabon
     return c
+
+
+GOLDEN = os.path.join(os.path.dirname(_HERE), "tests", "golden")
+
+
+def load_grid_npz(path=None):
+    """Mesh fixture written by tools/make_golden.py (same content as a gridue file)."""
+    z = np.load(path or os.path.join(GOLDEN, "d3d_16x8_grid.npz"))
+    nxm, nym, ixpt1, ixpt2, iys = [int(v) for v in z["dims"]]
+    g = dict(nxm=nxm, nym=nym, ixpt1=ixpt1, ixpt2=ixpt2, iysptrx1=iys, runid="fixture")
+    for k in ("rm", "zm", "psi", "br", "bz", "bpol", "bphi", "b"):
+        g[k] = z[k]
+    return g
+
+
+def load_state_npz(name):
+    z = np.load(os.path.join(GOLDEN, name))
+    return z["ni"], z["up"], z["te"], z["ti"], z["ng"]
+
+
+def load_rate_tables_npz():
+    z = np.load(os.path.join(GOLDEN, "ehr2_tables.npz"))
+    return [z["wsveh"], z["wsveh0"], z["welms1"], z["welms2"]]
+
+
+def refine_grid(g, fx=4, fy=4):
+    """Synthetic refinement of a single-null mesh: every interior cell is split fx x fy by bilinear
+    subdivision of its four corners in (R,Z); field components are interpolated bilinearly at the new
+    corners/centres.  Stand-in for the reference's griddubl/grid-sequencing (bbb/griddubl.m), which
+    needs the flx/grd generators; used only for the "4x refined" scaling configuration (BASELINE.json)."""
+    nxm, nym = g["nxm"], g["nym"]
+    NX, NY = nxm * fx, nym * fy
+    out = dict(nxm=NX, nym=NY, ixpt1=g["ixpt1"] * fx, ixpt2=g["ixpt2"] * fx, iysptrx1=g["iysptrx1"] * fy, runid="synthetic %dx%d" % (fx, fy))
+    for k in ("rm", "zm", "psi", "br", "bz", "bpol", "bphi", "b"):
+        a = g[k]
+        o = np.zeros((5, NY + 2, NX + 2))
+        for iy in range(1, nym + 1):
+            for ix in range(1, nxm + 1):
+                c1, c2, c3, c4 = a[1, iy, ix], a[2, iy, ix], a[3, iy, ix], a[4, iy, ix]
+
+                def bil(s, t):
+                    return (1 - s) * (1 - t) * c1 + s * (1 - t) * c2 + (1 - s) * t * c3 + s * t * c4
+
+                for jy in range(fy):
+                    for jx in range(fx):
+                        s0, s1, t0, t1 = jx / fx, (jx + 1) / fx, jy / fy, (jy + 1) / fy
+                        X, Y = (ix - 1) * fx + jx + 1, (iy - 1) * fy + jy + 1
+                        o[1, Y, X], o[2, Y, X], o[3, Y, X], o[4, Y, X] = bil(s0, t0), bil(s1, t0), bil(s0, t1), bil(s1, t1)
+                        o[0, Y, X] = bil(0.5 * (s0 + s1), 0.5 * (t0 + t1))
+        out[k] = o
+    return out
+
+
+def refine_state(planes, fx=4, fy=4):
+    """Piecewise-constant prolongation of cell planes [iy, ix] (guards kept one cell wide)."""
+    res = []
+    for a in planes:
+        ny, nx = a.shape[0] - 2, a.shape[1] - 2
+        o = np.zeros((ny * fy + 2, nx * fx + 2))
+        o[1:-1, 1:-1] = np.repeat(np.repeat(a[1:-1, 1:-1], fy, axis=0), fx, axis=1)
+        o[0, 1:-1] = np.repeat(a[0, 1:-1], fx); o[-1, 1:-1] = np.repeat(a[-1, 1:-1], fx)
+        o[1:-1, 0] = np.repeat(a[1:-1, 0], fy); o[1:-1, -1] = np.repeat(a[1:-1, -1], fy)
+        o[0, 0], o[0, -1], o[-1, 0], o[-1, -1] = a[0, 0], a[0, -1], a[-1, 0], a[-1, -1]
+        res.append(o)
+    return res
 
 
 def state_from_h5(path):
