@@ -1,0 +1,226 @@
+#!/usr/bin/env python
+"""bench.py — Jacobian assembly (nnz/s) and residual evaluations (evals/s) of the pandf1/jac_calc hot path.
+
+Contract: python bench.py --gpus N --steps K --warmup W  prints ONE JSON line.
+A "step" is one full Jacobian assembly (ue_gpu_jac_calc) of the d3dHsm configuration plus the two
+residual evaluations psetnk does around it (bbb/oderhs.m:9453-9471).
+`--impl reference` times the CPU restatement of the reference algorithm (the reference itself is
+MPPL/Fortran and cannot be built in this image) on the box's host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def clocks_sampler(stop, out):
+    q = "clocks.sm,clocks.max.sm,clocks_throttle_reasons.active"
+    while not stop.is_set():
+        try:
+            r = subprocess.run(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-i", "0"],
+                               capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+            out.append((float(r[0]), float(r[1]), r[2].strip()))
+        except Exception:
+            pass
+        stop.wait(0.2)
+
+
+def reasons_of(mask_strs):
+    names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+    got = set()
+    for m in mask_strs:
+        try:
+            v = int(m, 16)
+        except Exception:
+            continue
+        for bit, n in names.items():
+            if v & bit:
+                got.add(n)
+    return sorted(got)
+
+
+def cpu_baseline(c, yl, budget_s=15.0):
+    """Oracle ("port") Jacobian on one host core: bounded sample, same algorithm/cost structure as
+    jac_calc (2*neq windowed pandf1)."""
+    from tests.util import bind, oracle, psetnk_inputs
+    b = c.bbb
+    ora = bind(oracle(), c)
+    y, su = psetnk_inputs(c, yl)
+    ora.step_params(np.full(b.neq, 1e20), y[: b.neq], su, np.ones(b.neq))
+    f0 = ora.pandf1(y)
+    t0 = time.perf_counter(); reps = 0; nnz = 0
+    while True:
+        jac, ja, ia = ora.jac_calc(y, f0, b.lbw, b.ubw, b.nnzmx)
+        nnz = len(jac); reps += 1
+        if time.perf_counter() - t0 > budget_s or reps >= 20:
+            break
+    dt = (time.perf_counter() - t0) / reps
+    t1 = time.perf_counter(); r2 = 0
+    while time.perf_counter() - t1 < 2.0:
+        ora.pandf1(y); r2 += 1
+    tres = (time.perf_counter() - t1) / r2
+    return dict(value=nnz / dt, unit="nnz/s", cores=1, kind="port",
+                sample="%d full serial Jacobians of %s (neq=%d, nnz=%d), %.3f s each; residual %.3f ms" % (reps, c.name, b.neq, nnz, dt, tres * 1e3),
+                resid_evals_per_s=1.0 / tres, jac_s=dt)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--config", default="d3dHsm")
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    from tests.util import make_case, psetnk_inputs
+    name = a.config
+    c, yl = make_case(name, perturb=1e-3)
+    c.name = name
+    b = c.bbb
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        cb = cpu_baseline(c, yl, budget_s=20.0)
+        line = dict(metric="jacobian_nnz_per_s", value=cb["value"], unit="nnz/s", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
+                    ms_per_step=cb["jac_s"] * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                    impl="reference", config=dict(workload="%s full Jacobian assembly, neq=%d" % (name, b.neq)),
+                    cpu_baseline=dict(value=cb["value"], unit="nnz/s", cores=cb["cores"], kind=cb["kind"], sample=cb["sample"]),
+                    e2e=dict(value=cb["value"], unit="nnz/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                    resid_evals_per_s=cb["resid_evals_per_s"])
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from uedge_b200.capi import load_gpu
+    gpu = load_gpu()
+    gpu.load_static(c.static_inputs()); gpu.init()
+    y, su = psetnk_inputs(c, yl)
+    gpu.step_params(np.full(b.neq, 1e20), y[: b.neq], su, np.ones(b.neq))
+    lib = gpu.lib
+    neq = b.neq
+    # multi-GPU: replicas-with-column-split (ppp MPI design): rank r assembles columns of its contiguous iv range
+    lo = 1 + (neq * rank) // world; hi = (neq * (rank + 1)) // world
+    if world > 1:
+        gpu.set_column_range(lo, hi)
+    f0 = gpu.pandf1(y)
+    # pinned host buffers for the end-to-end path
+    hy = torch.from_numpy(y.copy()).pin_memory(); hf = torch.zeros(neq + 2, dtype=torch.float64).pin_memory(); hf[:neq] = torch.from_numpy(f0)
+    nnzmx = int(b.nnzmx)
+    hjac = torch.zeros(nnzmx, dtype=torch.float64).pin_memory(); hja = torch.zeros(nnzmx, dtype=torch.int64).pin_memory()
+    hia = torch.zeros(neq + 1, dtype=torch.int64).pin_memory(); hyd = torch.zeros(neq, dtype=torch.float64).pin_memory()
+    P = lambda t: C.cast(t.data_ptr(), C.c_void_p)
+    nnz = C.c_int64(0)
+    lib.ue_gpu_jac_calc.argtypes = [C.c_int64, C.c_double] + [C.c_void_p] * 2 + [C.c_int64] * 3 + [C.c_void_p] * 3 + [C.POINTER(C.c_int64)]
+    lib.ue_gpu_pandf1.argtypes = [C.c_int64, C.c_double, C.c_void_p, C.c_void_p]
+    bufs = [C.c_void_p() for _ in range(6)]
+    lib.ue_gpu_device_buffers(*[C.byref(x) for x in bufs])
+    d_yl, d_yldot, d_y00, d_jac, d_ja, d_ia = bufs
+    lib.ue_gpu_jac_calc_dev.argtypes = [C.c_int64, C.c_double] + [C.c_void_p] * 2 + [C.c_int64] * 3 + [C.c_void_p] * 3 + [C.POINTER(C.c_int64)]
+    lib.ue_gpu_pandf1_dev.argtypes = [C.c_int64, C.c_double, C.c_void_p, C.c_void_p]
+    jms = C.c_double(0); rms = C.c_double(0)
+
+    def step_e2e():
+        assert lib.ue_gpu_pandf1(neq, 0.0, P(hy), P(hyd)) == 0
+        assert lib.ue_gpu_jac_calc(neq, 0.0, P(hy), P(hf), int(b.lbw), int(b.ubw), nnzmx, P(hjac), P(hja), P(hia), C.byref(nnz)) == 0
+        assert lib.ue_gpu_pandf1(neq, 0.0, P(hy), P(hyd)) == 0
+
+    def step_dev():
+        assert lib.ue_gpu_pandf1_dev(neq, 0.0, d_yl, d_yldot) == 0
+        assert lib.ue_gpu_jac_calc_dev(neq, 0.0, d_yl, d_y00, int(b.lbw), int(b.ubw), nnzmx, d_jac, d_ja, d_ia, C.byref(nnz)) == 0
+        lib.ue_gpu_last_kernel_ms(C.byref(jms), C.byref(rms))
+        assert lib.ue_gpu_pandf1_dev(neq, 0.0, d_yl, d_yldot) == 0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # > 126 MB L2
+
+    def timed(fn, steps):
+        tot = 0.0; jm = []; rm = []
+        for _ in range(steps):
+            flush.fill_(1.0)
+            barrier()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            tot += time.perf_counter() - t0
+            jm.append(jms.value); rm.append(rms.value)
+        return tot, jm, rm
+
+    step_e2e()  # fills the library's device buffers (d_yl, d_yldot00)
+    for _ in range(a.warmup):
+        step_dev(); step_e2e()
+    samples = []; stop = threading.Event()
+    th = threading.Thread(target=clocks_sampler, args=(stop, samples)); th.start()
+    l0 = C.c_int64(0); lib.ue_gpu_kernel_launches(C.byref(l0))
+    t_dev, jm, rm = timed(step_dev, a.steps)
+    l1 = C.c_int64(0); lib.ue_gpu_kernel_launches(C.byref(l1))
+    t_e2e, _, _ = timed(step_e2e, a.steps)
+    stop.set(); th.join()
+    nnz_local = nnz.value
+    if world > 1:
+        v = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64); dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = v.tolist()
+        n = torch.tensor([nnz_local], device="cuda", dtype=torch.int64); dist.all_reduce(n)
+        nnz_total = int(n.item())
+    else:
+        nnz_total = nnz_local
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms_dev = t_dev / a.steps * 1e3; ms_e2e = t_e2e / a.steps * 1e3
+    jac_ms = float(np.mean(jm)); res_ms = float(np.mean(rm))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6453.1))
+    G = 16 + 3  # static real planes + int planes the kernels read (include/ue_params.h)
+    ncell = (c.com.nx + 2) * (c.com.ny + 2)
+    alg_bytes = 8 * (2 * (neq + 2) + G * ncell) + 16 * nnz_total + 8 * (neq + 1)
+    achieved = alg_bytes / (jac_ms * 1e-3) / 1e9
+    sm = sorted(s[0] for s in samples) or [0.0]
+    line = dict(metric="jacobian_nnz_per_s", value=nnz_total / (ms_dev * 1e-3), unit="nnz/s", n_gpus=world, steps=a.steps, warmup=a.warmup,
+                ms_per_step=ms_dev, higher_is_better=True, scaling="strong" if world > 1 else "weak", vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload="%s: 1 residual + 1 full FD Jacobian (neq=%d, nnz=%d) + 1 residual per step" % (name, neq, nnz_total),
+                            l2="flushed between steps (192 MB fill)", parallelism="replicas, Jacobian columns split over %d ranks" % world),
+                e2e=dict(value=nnz_total / (ms_e2e * 1e-3), unit="nnz/s", h2d_bytes_per_step=8 * (3 * (neq + 2) + neq),
+                         d2h_bytes_per_step=16 * nnz_total + 8 * (neq + 1) + 2 * 8 * neq, ms_per_step=ms_e2e),
+                gpu_launches=int(l1.value - l0.value),
+                resid_evals_per_s=1e3 / res_ms if res_ms > 0 else None, jac_kernel_ms=jac_ms, resid_kernel_ms=res_ms,
+                roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+                              note="algorithmic bytes = 8*(2(neq+2)+G*Ncell)+16*nnz+8*(neq+1), G=%d; latency/FP64-issue bound at this size (see DESIGN.md)" % G),
+                clocks=dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max([s[1] for s in samples] or [0.0]), reasons=reasons_of([s[2] for s in samples])))
+    if not a.no_cpu and world == 1:
+        cb = cpu_baseline(c, yl)
+        line["cpu_baseline"] = dict(value=cb["value"], unit="nnz/s", cores=cb["cores"], kind=cb["kind"], sample=cb["sample"])
+        line["cpu_resid_evals_per_s"] = cb["resid_evals_per_s"]
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -71,6 +71,12 @@ int ue_gpu_jac_calc_dev(int64_t neq, double t, const double* d_yl, const double*
  * restores the full Jacobian.  Reference: ppp/parallel.F90:176-381. */
 int ue_gpu_set_column_range(int64_t ivmin, int64_t ivmax);
 
+/* Device buffers owned by the library (yl, yldot, yldot00: neq+2; jac/ja: fragment capacity; ia: neq+1),
+ * for callers that keep the state resident between calls. */
+int ue_gpu_device_buffers(double** yl, double** yldot, double** yldot00, double** jac, int64_t** ja, int64_t** ia);
+/* Copy one intermediate field plane (ids: enum Plane in uedge_b200/csrc/ue_device.cuh) to the host. */
+int ue_gpu_get_plane(int64_t plane, double* out);
+
 /* ---- diagnostics ----------------------------------------------------------- */
 int ue_gpu_kernel_launches(int64_t* n);      /* launches since init (for bench.py) */
 int ue_gpu_last_kernel_ms(double* jac_ms, double* res_ms); /* CUDA-event times of the last calls */

@@ -34,6 +34,7 @@
 #include <string>
 #include <vector>
 
+#include "ue_math.h"
 #include "ue_param_store.hpp"
 
 namespace {
@@ -117,9 +118,9 @@ inline double powi(double x, int64_t n) {  // integer power by repeated squaring
 // ---- hydrogen rates (aph/aphrates.m) --------------------------------------------
 void table_idx(double tev_j, double dens, int& je, int& jd, double& fje, double& fjd) {
   // aph/aphrates.m:1043-1056 (identical in rra/erl1/erl2)
-  double zloge = std::log(tev_j / P.ev);
+  double zloge = ue_log(tev_j / P.ev);
   double rle = std::max(rlemin, std::min(zloge, rlemax));
-  double zlogd = std::log10(dens);
+  double zlogd = ue_log10(dens);
   double rld = std::max(rldmin, std::min(zlogd, rldmax));
   je = (int)((rle - rlemin) / delekpt) + 1; je = std::min(je, mpe - 1);
   jd = (int)((rld - rldmin) / deldkpt) + 1; jd = std::min(jd, mpd - 1);
@@ -129,11 +130,11 @@ void table_idx(double tev_j, double dens, int& je, int& jd, double& fje, double&
 double table_val(const V& w, double tev_j, double dens) {
   int je, jd; double fje, fjd;
   table_idx(tev_j, dens, je, jd, fje, fjd);
-  auto W = [&](int a, int b) { return std::log(w[(a - 1) + mpe * (b - 1)]); };
+  auto W = [&](int a, int b) { return ue_log(w[(a - 1) + mpe * (b - 1)]); };
   double r11 = W(je, jd), r12 = W(je, jd + 1), r21 = W(je + 1, jd), r22 = W(je + 1, jd + 1);
   double r1 = r11 + fjd * (r12 - r11);
   double r2 = r21 + fjd * (r22 - r21);
-  return std::exp(r1 + fje * (r2 - r1));
+  return ue_exp(r1 + fje * (r2 - r1));
 }
 double rsa(double tej, double dens) {  // aph/aphrates.m:872-1131
   if (P.istabon == 0) { double a = tej / (10 * P.ev); return 3.0e-14 * a * a / (3.0 + a * a); }
@@ -145,7 +146,7 @@ double rra(double tej, double dens) {  // aph/aphrates.m:617-870
 }
 double rcx(double t0) {  // aph/aphrates.m:395-399 (analytic for istabon 0 and >3)
   double a = 3 * t0 / (10 * P.ev);
-  return 1.7e-14 * std::pow(a, 0.333);
+  return 1.7e-14 * ue_pow(a, 0.333);
 }
 double rqa0(double tej) {  // aph/aphrates.m:444-447
   double a = tej / (10 * P.ev);
@@ -250,15 +251,13 @@ int convsr_vo(int ixl, int iyl, const double* yl) {
 
 // ---- convsr_aux (convert.m:379-875), orthogonal stencils fx0=1, others 0 ----------
 inline double interp_log(const V& a, int ix, int iy, int k) {
-  // interpni/interppri/interpng/interppg (convert.m:453-482) with
-  // fxm=fxp=fxmy=fxpy=0, fx0=1 (geometry.m:849-870): the zero-weighted terms add 0.
-  return std::exp(0. * std::log(A(a, IXM1(ix, iy + k), iy + k)) + 1. * std::log(A(a, ix, iy + k)) +
-                  0. * std::log(A(a, IXP1(ix, iy + k), iy + k)) + 0. * std::log(A(a, IXM1(ix, iy + 1 - k), iy + 1 - k)) +
-                  0. * std::log(A(a, IXP1(ix, iy + 1 - k), iy + 1 - k)));
+  // interpni/interppri/interpng/interppg (convert.m:453-482) on an orthogonal mesh: fx0 = 1 and
+  // fxm = fxp = fxmy = fxpy = 0 (geometry.m:849-870), so the four zero-weighted log terms add an exact 0
+  // (all densities/pressures are positive and finite) and are not evaluated.
+  return ue_exp(1. * ue_log(A(a, ix, iy + k)));
 }
-inline double interp_lin(const V& a, int ix, int iy, int k) {  // interpte/interpti/interptg (convert.m:422-442)
-  return 0. * A(a, IXM1(ix, iy + k), iy + k) + 1. * A(a, ix, iy + k) + 0. * A(a, IXP1(ix, iy + k), iy + k) +
-         0. * A(a, IXM1(ix, iy + 1 - k), iy + 1 - k) + 0. * A(a, IXP1(ix, iy + 1 - k), iy + 1 - k);
+inline double interp_lin(const V& a, int ix, int iy, int k) {  // interpte/interpti/interptg (convert.m:422-442), same remark
+  return 1. * A(a, ix, iy + k);
 }
 // list of ix visited by "do ix = ixm1(is,jrow), min(nx,ie), inc" (convert.m:583-584 etc.)
 inline void xrange(int is, int ie, int jinc, int jstart, std::vector<int>& out) {
@@ -406,9 +405,9 @@ void neudifpg(const Win& w) {
       double qsh = csh * (A(pg, ix, iy) - A(pg, ix2, iy)) + qtgf * nconv;
       double qr = std::fabs(qsh / qfl);
       if (ix == P.ixlb || ix == P.ixrb) { qr = P.gcfacgx * qr; qtgf = P.gcfacgx * qtgf; }
-      A(conxg, ix, iy) = csh / std::pow(1 + std::pow(qr, P.flgamg), 1 / P.flgamg);
+      A(conxg, ix, iy) = csh / ue_pow(1 + ue_pow(qr, P.flgamg), 1 / P.flgamg);
       if (P.isdifxg_aug == 1) A(conxg, ix, iy) = csh * (1 + qr);
-      A(floxg, ix, iy) = (qtgf / tgf) / std::pow(1 + std::pow(qr, P.flgamg), 1 / P.flgamg);
+      A(floxg, ix, iy) = (qtgf / tgf) / ue_pow(1 + ue_pow(qr, P.flgamg), 1 / P.flgamg);
       A(floxg, ix, iy) = A(floxg, ix, iy) + P.cngflox * G(sx, ix, iy) * A(uu, ix, iy) / tgf;
     }
     A(conxg, nx + 1, iy) = 0;
@@ -434,9 +433,9 @@ void neudifpg(const Win& w) {
       double qr = std::fabs(qsh / qfl);
       if (iy == 0) { qr = P.gcfacgy * qr; qtgf = P.gcfacgy * qtgf; }
       if (iy == ny) { qr = P.gcfacgy * qr; qtgf = P.gcfacgy * qtgf; }
-      A(conyg, ix, iy) = csh / std::pow(1 + std::pow(qr, P.flgamg), 1 / P.flgamg);
+      A(conyg, ix, iy) = csh / ue_pow(1 + ue_pow(qr, P.flgamg), 1 / P.flgamg);
       if (P.isdifyg_aug == 1) A(conyg, ix, iy) = csh * (1 + qr);
-      A(floyg, ix, iy) = (qtgf / tgf) / std::pow(1 + std::pow(qr, P.flgamg), 1 / P.flgamg);
+      A(floyg, ix, iy) = (qtgf / tgf) / ue_pow(1 + ue_pow(qr, P.flgamg), 1 / P.flgamg);
       A(floyg, ix, iy) = A(floyg, ix, iy) + P.cngfloy * G(sy, ix, iy) * A(vy, ix, iy) / tgf;
     }
   fd2tra(w, floxg, floyg, conxg, conyg, pg, fngx, fngy, 0, (int)P.methg);  // oderhs.m:6340
@@ -602,7 +601,7 @@ int bouncon(const Win& w, const double* yl, double* yldot) {
         double bcel = (1 - P.newbcl * 0) * P.bcee + P.newbcl * 0 * (2. + kappal);
         double bcil = (1 - P.newbcl * 0) * P.bcei + P.newbcl * 0 * (2.5);
         double t0 = A(te, ixt, iy) / ev;
-        double f_cgpld = .5 * (1. - std::cos(pi * (t0 - P.temin) / (.3 - P.temin)));
+        double f_cgpld = .5 * (1. - ue_cos(pi * (t0 - P.temin) / (.3 - P.temin)));
         if (t0 < P.temin) f_cgpld = 0.;
         if (t0 > 0.3) f_cgpld = 1.;
         t0 = std::max(A(tg, ixt1, iy), P.tgmin * ev);
@@ -666,7 +665,7 @@ int bouncon(const Win& w, const double* yl, double* yldot) {
         double bcer = (1 - P.newbcr * 0) * P.bcee + P.newbcr * 0 * (2. + kappar);
         double bcir = (1 - P.newbcr * 0) * P.bcei + P.newbcr * 0 * (2.5);
         double t0 = A(te, ixt, iy) / ev;
-        double f_cgpld = .5 * (1. - std::cos(pi * (t0 - P.temin) / (.3 - P.temin)));
+        double f_cgpld = .5 * (1. - ue_cos(pi * (t0 - P.temin) / (.3 - P.temin)));
         if (t0 < P.temin) f_cgpld = 0.;
         if (t0 > 0.3) f_cgpld = 1.;
         t0 = std::max(A(tg, ixt1, iy), P.tgmin * ev);
@@ -725,8 +724,8 @@ int pandf(int xc, int yc, const double* yl, double* yldot) {
       double teev = 0.5 * (A(te, ix, iy) + A(te, ix1, iy)) / ev;
       double nexface = 0.5 * (A(ne, ix, iy) + A(ne, ix1, iy));
       if (P.islnlamcon == 1) A(loglambda, ix, iy) = P.lnlam;
-      else if (teev < 50.) A(loglambda, ix, iy) = 23.4 - 1.15 * std::log10(1.e-6 * nexface) + 3.45 * std::log10(teev);
-      else A(loglambda, ix, iy) = 25.3 - 1.15 * std::log10(1.e-6 * nexface) + 2.33167537087122e+00 * std::log10(teev);
+      else if (teev < 50.) A(loglambda, ix, iy) = 23.4 - 1.15 * ue_log10(1.e-6 * nexface) + 3.45 * ue_log10(teev);
+      else A(loglambda, ix, iy) = 25.3 - 1.15 * ue_log10(1.e-6 * nexface) + 2.33167537087122e+00 * ue_log10(teev);
     }
   // radial velocity: only the diffusive part survives (cfydd=cfrd=cfyef=cfybf=cfvycf=cfvycr=0) (oderhs.m:1174-1320)
   for (int iy = j1; iy <= j5; ++iy)
@@ -740,7 +739,7 @@ int pandf(int xc, int yc, const double* yl, double* yldot) {
     for (int ix = i1; ix <= i6; ++ix) {
       double difnimix = A(diffusivwrk, ix, iy);
       double vydd = A(vy, ix, iy) - 1. * difnimix * (2 * (1 - P.isvylog) * ((A(niy1, ix, iy) - A(niy0, ix, iy)) / G(dynog, ix, iy)) / (A(niy1, ix, iy) + A(niy0, ix, iy)) +
-                                                     P.isvylog * (std::log(A(niy1, ix, iy)) - std::log(A(niy0, ix, iy))) / G(dynog, ix, iy));
+                                                     P.isvylog * (ue_log(A(niy1, ix, iy)) - ue_log(A(niy0, ix, iy))) / G(dynog, ix, iy));
       A(vy, ix, iy) = vydd;
     }
   for (int ix = i1; ix <= i6; ++ix) A(vy, ix, ny + 1) = 0.0;  // oderhs.m:1466-1468
@@ -907,7 +906,7 @@ int pandf(int xc, int yc, const double* yl, double* yldot) {
       if (P.isgxvon == 0) csh = A(visx, ix, iy) * G(vol, ix, iy) * G(gx, ix, iy) * G(gx, ix, iy);
       else csh = A(visx, ix, iy) * G(vol, ix, iy) * G(gx, ix, iy) * 2 * G(gxf, ix, iy) * G(gxf, ix1, iy) / (G(gxf, ix, iy) + G(gxf, ix1, iy));
       double msh = std::fabs(csh * (A(upi, ix1, iy) - A(upi, ix, iy)));
-      A(visx, ix, iy) = A(visx, ix, iy) / std::pow(1 + std::pow(msh / (mfl + 1.e-20 * msh), P.flgamv), 1 / P.flgamv);
+      A(visx, ix, iy) = A(visx, ix, iy) / ue_pow(1 + ue_pow(msh / (mfl + 1.e-20 * msh), P.flgamv), 1 / P.flgamv);
       A(visy, ix, iy) = (P.fcdif * P.travis + 0.) * A(nm, ix, iy) + 4 * 0.;
     }
 
@@ -1121,7 +1120,7 @@ int pandf(int xc, int yc, const double* yl, double* yldot) {
       double lxtec = 0.5 * (A(te, ix, iy) + A(te, ix2, iy)) / (std::fabs(A(te, ix, iy) - A(te, ix2, iy)) * G(gxf, ix, iy) + 100. * cutlo);
       double qsh = csh * (A(te, ix, iy) - A(te, ix2, iy)) * (1. + lxtec / P.lxtemax);
       double qr = (1 - P.isflxlde) * std::fabs(qsh / qfl);
-      A(conxe, ix, iy) = (1 - P.isflxlde) * csh / ((1 + qr) * (1 + qr)) + P.isflxlde * csh / std::pow(1 + std::pow(std::fabs(qsh / qfl), P.flgam), 1 / P.flgam);
+      A(conxe, ix, iy) = (1 - P.isflxlde) * csh / ((1 + qr) * (1 + qr)) + P.isflxlde * csh / ue_pow(1 + ue_pow(std::fabs(qsh / qfl), P.flgam), 1 / P.flgam);
       A(floxe, ix, iy) = A(floxe, ix, iy) + (sgn(qr * qr, qsh) / ((1 + qr) * (1 + qr))) * P.flalfea[ix] * G(sx, ix, iy) *
                                                 (A(ne, ix, iy) * G(rr, ix, iy) * vt0 + A(ne, ix2, iy) * G(rr, ix2, iy) * vt1) / 2;
       if (P.isflxldi != 2) {
@@ -1134,7 +1133,7 @@ int pandf(int xc, int yc, const double* yl, double* yldot) {
         double lxtic = 0.5 * (A(ti, ix, iy) + A(ti, ix2, iy)) / (std::fabs(A(ti, ix, iy) - A(ti, ix2, iy)) * G(gxf, ix, iy) + 100. * cutlo);
         qsh = csh * (A(ti, ix, iy) - A(ti, ix2, iy)) * (1. + lxtic / P.lxtimax);
         qr = (1 - P.isflxldi) * std::fabs(qsh / qfl);
-        A(conxi, ix, iy) = (1 - P.isflxldi) * csh / ((1 + qr) * (1 + qr)) + P.isflxldi * csh / std::pow(1 + std::pow(std::fabs(qsh / qfl), P.flgam), 1 / P.flgam);
+        A(conxi, ix, iy) = (1 - P.isflxldi) * csh / ((1 + qr) * (1 + qr)) + P.isflxldi * csh / ue_pow(1 + ue_pow(std::fabs(qsh / qfl), P.flgam), 1 / P.flgam);
         A(floxi, ix, iy) = A(floxi, ix, iy) + (sgn(qr * qr, qsh) / ((1 + qr) * (1 + qr))) * P.flalfia[ix] * G(sx, ix, iy) *
                                                   (A(ne, ix, iy) * G(rr, ix, iy) * vt0 + A(ne, ix2, iy) * G(rr, ix2, iy) * vt1) / 2;
       } else A(conxi, ix, iy) = G(sx, ix, iy) * A(hcxi, ix, iy) * G(gxf, ix, iy);
@@ -1217,7 +1216,7 @@ int pandf(int xc, int yc, const double* yl, double* yldot) {
       int ix1 = IXM1(ix, iy), ix2 = IXM1(ix, iy + 1), ix3 = IXM1(ix, iy - 1);
       double thetacc = 0.5 * (0. + 0.);
       double dupdx = G(gx, ix, iy) * (A(upi, ix, iy) - A(upi, ix1, iy));
-      A(wvh, ix, iy) = P.cfvcsx * P.cfvisx * std::cos(thetacc) * A(visx, ix, iy) * (dupdx * dupdx);
+      A(wvh, ix, iy) = P.cfvcsx * P.cfvisx * ue_cos(thetacc) * A(visx, ix, iy) * (dupdx * dupdx);
       double dupdy;
       const int64_t isx = P.isxpty[ix + NXS * iy];
       if (isx == 0) dupdy = 0.5 * (A(upi, ix, iy) + A(upi, ix1, iy) - A(upi, ix, iy - 1) - A(upi, ix3, iy - 1)) * G(gyf, ix, iy - 1);
@@ -1232,7 +1231,7 @@ int pandf(int xc, int yc, const double* yl, double* yldot) {
         dupdy = 0.25 * ((A(upi, ix, iy + 1) + A(upi, ix2, iy + 1) - A(upi, ix, iy) - A(upi, ix1, iy)) * G(gyf, ix, iy) +
                         (A(upi, ix, iy) + A(upi, ix1, iy) - A(upi, ix, iy - 1) - A(upi, ix3, iy - 1)) * G(gyf, ix, iy - 1));
       A(wvh, ix, iy) = A(wvh, ix, iy) + P.cfvcsy * P.cfvisy * A(visy, ix, iy) * (dupdy * dupdy);
-      A(wvh, ix, iy) = A(wvh, ix, iy) - std::sin(thetacc) * P.cfvcsy * P.cfvisy * A(visy, ix, iy) * dupdx * dupdy;
+      A(wvh, ix, iy) = A(wvh, ix, iy) - ue_ksin(thetacc) * P.cfvcsy * P.cfvisy * A(visy, ix, iy) * dupdx * dupdy;
       A(resei, ix, iy) = A(resei, ix, iy) + A(wvh, ix, iy) * G(vol, ix, iy);
     }
   for (int iy = w.iys; iy <= w.iyf; ++iy)  // oderhs.m:4936-4947
@@ -1393,7 +1392,7 @@ int ue_ora_init(void) {
     dkpt.resize(mpd); ekpt.resize(mpe);
     dkpt[0] = 16.0; for (int j = 1; j < mpd; ++j) dkpt[j] = dkpt[j - 1] + 0.5;
     rldmin = dkpt[0]; rldmax = dkpt[mpd - 1]; deldkpt = (rldmax - rldmin) / double(mpd - 1);
-    ekpt[0] = -1.2 * std::log(10.0); for (int j = 1; j < mpe; ++j) ekpt[j] = ekpt[j - 1] + 0.1 * std::log(10.0);
+    ekpt[0] = -1.2 * ue_log(10.0); for (int j = 1; j < mpe; ++j) ekpt[j] = ekpt[j - 1] + 0.1 * ue_log(10.0);
     rlemin = ekpt[0]; rlemax = ekpt[mpe - 1]; delekpt = (rlemax - rlemin) / double(mpe - 1);
   }
   for (V* v : all_planes()) v->assign(NC, 0.0);

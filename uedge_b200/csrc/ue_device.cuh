@@ -29,6 +29,7 @@
 #pragma once
 #include <cstdint>
 
+#include "ue_math.h"
 #include "ue_param_store.hpp"
 
 #define UE_NV 5  // unknowns per cell: ni, up, te, ti, ng (convert.m:33-152 ordering)
@@ -135,27 +136,27 @@ __device__ __forceinline__ int in_rng(int v, int lo, int hi) { return v >= lo &&
 
 // ---- hydrogen rates (aph/aphrates.m) ----------------------------------------------------
 __device__ inline double d_table(const double* __restrict__ w, double tej, double dens) {
-  const double zloge = log(tej / D.ev);
+  const double zloge = ue_log(tej / D.ev);
   const double rle = fmax(DT.rlemin, fmin(zloge, DT.rlemax));
-  const double zlogd = log10(dens);
+  const double zlogd = ue_log10(dens);
   const double rld = fmax(DT.rldmin, fmin(zlogd, DT.rldmax));
   int je = (int)((rle - DT.rlemin) / DT.delekpt) + 1; je = min(je, DT.mpe - 1);
   int jd = (int)((rld - DT.rldmin) / DT.deldkpt) + 1; jd = min(jd, DT.mpd - 1);
   const double fje = (rle - DT.ekpt[je - 1]) / (DT.ekpt[je] - DT.ekpt[je - 1]);
   const double fjd = (rld - DT.dkpt[jd - 1]) / (DT.dkpt[jd] - DT.dkpt[jd - 1]);
   const int mpe = DT.mpe;
-  const double r11 = log(__ldg(&w[(je - 1) + mpe * (jd - 1)])), r12 = log(__ldg(&w[(je - 1) + mpe * jd]));
-  const double r21 = log(__ldg(&w[je + mpe * (jd - 1)])), r22 = log(__ldg(&w[je + mpe * jd]));
+  const double r11 = ue_log(__ldg(&w[(je - 1) + mpe * (jd - 1)])), r12 = ue_log(__ldg(&w[(je - 1) + mpe * jd]));
+  const double r21 = ue_log(__ldg(&w[je + mpe * (jd - 1)])), r22 = ue_log(__ldg(&w[je + mpe * jd]));
   const double r1 = r11 + fjd * (r12 - r11);
   const double r2 = r21 + fjd * (r22 - r21);
-  return exp(r1 + fje * (r2 - r1));
+  return ue_exp(r1 + fje * (r2 - r1));
 }
 __device__ inline double d_rsa(double tej, double dens) {
   if (D.istabon == 0) { const double a = tej / (10 * D.ev); return 3.0e-14 * a * a / (3.0 + a * a); }
   return d_table(D.wsveh, tej, dens);
 }
 __device__ inline double d_rra(double tej, double dens) { return (D.istabon == 0) ? 0. : d_table(D.wsveh0, tej, dens); }
-__device__ inline double d_rcx(double t0) { const double a = 3 * t0 / (10 * D.ev); return 1.7e-14 * pow(a, 0.333); }
+__device__ inline double d_rcx(double t0) { const double a = 3 * t0 / (10 * D.ev); return 1.7e-14 * ue_pow(a, 0.333); }
 __device__ inline double d_rqa0(double tej) { const double a = tej / (10 * D.ev); return D.erad * D.ev * 3.0e-14 * a * a / (3.0 + a * a); }
 __device__ inline double d_erl1(double tej, double dens) {
   if (D.istabon == 0) return (d_rqa0(tej) - 13.6 * D.ev * d_rsa(tej, dens)) * dens;
@@ -256,14 +257,11 @@ template <bool WIN> __device__ __forceinline__ void f_psor(const Acc<WIN>& a, in
 }
 // orthogonal-mesh y-face interpolants (convert.m:422-482 with fx0=1, other weights 0)
 template <bool WIN, typename F> __device__ __forceinline__ double f_ilog(const Acc<WIN>& a, F f, int ix, int iy, int k) {
-  const int NXS = a.NXS;
-  return exp(0. * log(f(a, IXM1(ix, iy + k), iy + k)) + 1. * log(f(a, ix, iy + k)) + 0. * log(f(a, IXP1(ix, iy + k), iy + k)) +
-             0. * log(f(a, IXM1(ix, iy + 1 - k), iy + 1 - k)) + 0. * log(f(a, IXP1(ix, iy + 1 - k), iy + 1 - k)));
+  // zero-weighted neighbour terms add an exact 0 for positive finite fields and are not evaluated
+  return ue_exp(1. * ue_log(f(a, ix, iy + k)));
 }
 template <bool WIN, typename F> __device__ __forceinline__ double f_ilin(const Acc<WIN>& a, F f, int ix, int iy, int k) {
-  const int NXS = a.NXS;
-  return 0. * f(a, IXM1(ix, iy + k), iy + k) + 1. * f(a, ix, iy + k) + 0. * f(a, IXP1(ix, iy + k), iy + k) +
-         0. * f(a, IXM1(ix, iy + 1 - k), iy + 1 - k) + 0. * f(a, IXP1(ix, iy + 1 - k), iy + 1 - k);
+  return 1. * f(a, ix, iy + k);
 }
 template <bool WIN> struct Fld {
   static __device__ __forceinline__ double ni(const Acc<WIN>& a, int ix, int iy) { return a.get(PL_NI, ix, iy); }
@@ -346,8 +344,8 @@ __device__ void phase1_cell(const Acc<WIN>& a, const Win& w, int ix, int iy) {
     const double teev = 0.5 * (te + te_e) / ev;
     const double nexface = 0.5 * (ne + ne_e);
     if (D.islnlamcon == 1) loglambda = D.lnlam;
-    else if (teev < 50.) loglambda = 23.4 - 1.15 * log10(1.e-6 * nexface) + 3.45 * log10(teev);
-    else loglambda = 25.3 - 1.15 * log10(1.e-6 * nexface) + 2.33167537087122e+00 * log10(teev);
+    else if (teev < 50.) loglambda = 23.4 - 1.15 * ue_log10(1.e-6 * nexface) + 3.45 * ue_log10(teev);
+    else loglambda = 25.3 - 1.15 * ue_log10(1.e-6 * nexface) + 2.33167537087122e+00 * ue_log10(teev);
   }
   // ---- radial velocity (oderhs.m:1174-1320, diffusive part) -------------------------------------
   double vy = a.get(PL_VY, ix, iy);
@@ -357,7 +355,7 @@ __device__ void phase1_cell(const Acc<WIN>& a, const Win& w, int ix, int iy) {
     const double gtey = (tey1 - tey0) / dynog;
     double vydd = D.vcony + 0. + 0. - (D.difpr + 0.) * (2 * gpry / (pr_n + pr_c) - 3.0 * gtey / (tey1 + tey0));
     const double difnimix = D.fcdif * D.difni + 0.;
-    vydd = vydd - 1. * difnimix * (2 * (1 - D.isvylog) * ((niy1 - niy0) / dynog) / (niy1 + niy0) + D.isvylog * (log(niy1) - log(niy0)) / dynog);
+    vydd = vydd - 1. * difnimix * (2 * (1 - D.isvylog) * ((niy1 - niy0) / dynog) / (niy1 + niy0) + D.isvylog * (ue_log(niy1) - ue_log(niy0)) / dynog);
     vy = vydd;
     a.set(PL_VY, ix, iy, vy);
   }
@@ -402,7 +400,7 @@ __device__ void phase1_cell(const Acc<WIN>& a, const Win& w, int ix, int iy) {
     if (D.isgxvon == 0) csh = visx * vol * gx * gx;
     else csh = visx * vol * gx * 2 * gxf * GG(gxf, ixw, iy) / (gxf + GG(gxf, ixw, iy));
     const double msh = fabs(csh * (a.get(PL_UP, ixw, iy) - a.get(PL_UP, ix, iy)));
-    visx = visx / pow(1 + pow(msh / (mfl + 1.e-20 * msh), D.flgamv), 1 / D.flgamv);
+    visx = visx / ue_pow(1 + ue_pow(msh / (mfl + 1.e-20 * msh), D.flgamv), 1 / D.flgamv);
     a.set(PL_VISX, ix, iy, visx);
   }
   // ---- neutral x-flux (neudifpg, oderhs.m:6126-6225 + fd2tra) ------------------------------------------------
@@ -428,9 +426,9 @@ __device__ void phase1_cell(const Acc<WIN>& a, const Win& w, int ix, int iy) {
     const double qsh = csh * (pg - pg_e) + qtgf * nconv;
     double qr = fabs(qsh / qfl);
     if (ix == ixlb || ix == ixrb) { qr = D.gcfacgx * qr; qtgf = D.gcfacgx * qtgf; }
-    double conxg = csh / pow(1 + pow(qr, D.flgamg), 1 / D.flgamg);
+    double conxg = csh / ue_pow(1 + ue_pow(qr, D.flgamg), 1 / D.flgamg);
     if (D.isdifxg_aug == 1) conxg = csh * (1 + qr);
-    double floxg = (qtgf / tgf) / pow(1 + pow(qr, D.flgamg), 1 / D.flgamg);
+    double floxg = (qtgf / tgf) / ue_pow(1 + ue_pow(qr, D.flgamg), 1 / D.flgamg);
     floxg = floxg + D.cngflox * sx * uu / tgf;
     if (methgx == 2) fngx = floxg * (pg_e + pg) / 2. - conxg * (pg_e - pg);
     else fngx = d_upwind(floxg, pg, pg_e) - conxg * (pg_e - pg);
@@ -472,9 +470,9 @@ __device__ void phase1_cell(const Acc<WIN>& a, const Win& w, int ix, int iy) {
     double qr = fabs(qsh / qfl);
     if (iy == 0) { qr = D.gcfacgy * qr; qtgf = D.gcfacgy * qtgf; }
     if (iy == ny) { qr = D.gcfacgy * qr; qtgf = D.gcfacgy * qtgf; }
-    double conyg = csh / pow(1 + pow(qr, D.flgamg), 1 / D.flgamg);
+    double conyg = csh / ue_pow(1 + ue_pow(qr, D.flgamg), 1 / D.flgamg);
     if (D.isdifyg_aug == 1) conyg = csh * (1 + qr);
-    double floyg = (qtgf / tgf) / pow(1 + pow(qr, D.flgamg), 1 / D.flgamg);
+    double floyg = (qtgf / tgf) / ue_pow(1 + ue_pow(qr, D.flgamg), 1 / D.flgamg);
     floyg = floyg + D.cngfloy * sy * vy / tgf;
     const double pg = f_pg(a, ix, iy), pg_n = f_pg(a, ix, iy + 1);
     if (methgy == 2) fngy = floyg * (pg_n + pg) / 2. - conyg * (pg_n - pg);
@@ -586,7 +584,7 @@ __device__ void phase1_cell(const Acc<WIN>& a, const Win& w, int ix, int iy) {
     const double lxtec = 0.5 * (te + te_e) / (fabs(te - te_e) * gxf + 100. * cutlo);
     double qsh = csh * (te - te_e) * (1. + lxtec / D.lxtemax);
     double qr = (1 - D.isflxlde) * fabs(qsh / qfl);
-    const double conxe = (1 - D.isflxlde) * csh / ((1 + qr) * (1 + qr)) + D.isflxlde * csh / pow(1 + pow(fabs(qsh / qfl), D.flgam), 1 / D.flgam);
+    const double conxe = (1 - D.isflxlde) * csh / ((1 + qr) * (1 + qr)) + D.isflxlde * csh / ue_pow(1 + ue_pow(fabs(qsh / qfl), D.flgam), 1 / D.flgam);
     const double rr = GG(rr, ix, iy), rr_e = GG(rr, ix1, iy);
     double floxe = 0. + (d_sgn(qr * qr, qsh) / ((1 + qr) * (1 + qr))) * D.flalfea[ix] * sx * (ne * rr * vt0 + ne_e * rr_e * vt1) / 2;
     double conxi, floxi = 0.;
@@ -600,7 +598,7 @@ __device__ void phase1_cell(const Acc<WIN>& a, const Win& w, int ix, int iy) {
       const double lxtic = 0.5 * (ti + ti_e) / (fabs(ti - ti_e) * gxf + 100. * cutlo);
       qsh = csh * (ti - ti_e) * (1. + lxtic / D.lxtimax);
       qr = (1 - D.isflxldi) * fabs(qsh / qfl);
-      conxi = (1 - D.isflxldi) * csh / ((1 + qr) * (1 + qr)) + D.isflxldi * csh / pow(1 + pow(fabs(qsh / qfl), D.flgam), 1 / D.flgam);
+      conxi = (1 - D.isflxldi) * csh / ((1 + qr) * (1 + qr)) + D.isflxldi * csh / ue_pow(1 + ue_pow(fabs(qsh / qfl), D.flgam), 1 / D.flgam);
       floxi = floxi + (d_sgn(qr * qr, qsh) / ((1 + qr) * (1 + qr))) * D.flalfia[ix] * sx * (ne * rr * vt0 + ne_e * rr_e * vt1) / 2;
     } else conxi = sx * hcxi * gxf;
     floxe = floxe + D.cfcvte * 1.25 * (ne + ne_e) * vex * sx - 0.;
@@ -752,8 +750,8 @@ __device__ void phase2_interior(const Acc<WIN>& a, const Win& w, int ix, int iy,
       const double teev = 0.5 * (a.get(PL_TE, jx, iy) + a.get(PL_TE, je, iy)) / ev;
       const double nexface = 0.5 * (f_ne(a, jx, iy) + f_ne(a, je, iy));
       if (D.islnlamcon == 1) return (double)D.lnlam;
-      if (teev < 50.) return 23.4 - 1.15 * log10(1.e-6 * nexface) + 3.45 * log10(teev);
-      return 25.3 - 1.15 * log10(1.e-6 * nexface) + 2.33167537087122e+00 * log10(teev);
+      if (teev < 50.) return 23.4 - 1.15 * ue_log10(1.e-6 * nexface) + 3.45 * ue_log10(teev);
+      return 25.3 - 1.15 * ue_log10(1.e-6 * nexface) + 2.33167537087122e+00 * ue_log10(teev);
     };
     const double w3 = 0.0 + ((D.zi * D.zi) / D.mi) * ni;
     const double aa = fmax(te, D.temin * ev);
@@ -773,7 +771,7 @@ __device__ void phase2_interior(const Acc<WIN>& a, const Win& w, int ix, int iy,
     const int ixn = IXM1(ix, iy + 1), ixs = IXM1(ix, iy - 1);
     const double thetacc = 0.5 * (0. + 0.);
     const double dupdx = gx * (up - up_w);
-    double wvh = D.cfvcsx * D.cfvisx * cos(thetacc) * a.get(PL_VISX, ix, iy) * (dupdx * dupdx);
+    double wvh = D.cfvcsx * D.cfvisx * ue_cos(thetacc) * a.get(PL_VISX, ix, iy) * (dupdx * dupdx);
     double dupdy;
     const int64_t isx = D.isxpty[ix + NXS * iy];
     const double up_n = a.get(PL_UP, ix, iy + 1), up_nw = a.get(PL_UP, ixn, iy + 1), up_s = a.get(PL_UP, ix, iy - 1), up_sw = a.get(PL_UP, ixs, iy - 1);
@@ -788,7 +786,7 @@ __device__ void phase2_interior(const Acc<WIN>& a, const Win& w, int ix, int iy,
       dupdy = 0.25 * ((up_n + up_nw - up - up_w) * GG(gyf, ix, iy) + (up + up_w - up_s - up_sw) * GG(gyf, ix, iy - 1));
     const double visy = f_visy(a, ix, iy);
     wvh = wvh + D.cfvcsy * D.cfvisy * visy * (dupdy * dupdy);
-    wvh = wvh - sin(thetacc) * D.cfvcsy * D.cfvisy * visy * dupdx * dupdy;
+    wvh = wvh - ue_ksin(thetacc) * D.cfvcsy * D.cfvisy * visy * dupdx * dupdy;
     resei = resei + wvh * vol;
   }
   resei = resei + a.get(PL_PWRIBKG, ix, iy) * vol;
@@ -954,7 +952,7 @@ __device__ int phase2_guard(const Acc<WIN>& a, const Win& w, int ix, int iy, dou
       const double bcel = (1 - D.newbcl * 0) * D.bcee + D.newbcl * 0 * (2. + kappal);
       const double bcil = (1 - D.newbcl * 0) * D.bcei + D.newbcl * 0 * (2.5);
       double t0 = te / ev;
-      double f_cgpld = .5 * (1. - cos(pi * (t0 - D.temin) / (.3 - D.temin)));
+      double f_cgpld = .5 * (1. - ue_cos(pi * (t0 - D.temin) / (.3 - D.temin)));
       if (t0 < D.temin) f_cgpld = 0.;
       if (t0 > 0.3) f_cgpld = 1.;
       t0 = fmax(f_tg(a, ixt1, iy), D.tgmin * ev);
@@ -1007,7 +1005,7 @@ __device__ int phase2_guard(const Acc<WIN>& a, const Win& w, int ix, int iy, dou
       const double bcer = (1 - D.newbcr * 0) * D.bcee + D.newbcr * 0 * (2. + kappar);
       const double bcir = (1 - D.newbcr * 0) * D.bcei + D.newbcr * 0 * (2.5);
       double t0 = te / ev;
-      double f_cgpld = .5 * (1. - cos(pi * (t0 - D.temin) / (.3 - D.temin)));
+      double f_cgpld = .5 * (1. - ue_cos(pi * (t0 - D.temin) / (.3 - D.temin)));
       if (t0 < D.temin) f_cgpld = 0.;
       if (t0 > 0.3) f_cgpld = 1.;
       t0 = fmax(f_tg(a, ixt1, iy), D.tgmin * ev);
