@@ -97,24 +97,48 @@ __host__ __device__ inline Win make_win(const UeParams& P, int xc, int yc) {
 
 #ifdef __CUDACC__
 // ---- field accessor ------------------------------------------------------------------------
+// Acc<false>: fields are the HBM planes.  Acc<true> (Jacobian): a perturbation of cell C0=(xc,yc) can
+// change phase-0 fields only at C0 and phase-1 fields only at C0, its west/east neighbours (row yc
+// connectivity) and its south neighbour, so only those four cells have private copies (in shared
+// memory); every other read falls through to the base planes.  `resco` (phase 2) is kept per
+// candidate row in a rectangle [rx0..rx0+rw) x [ry0..ry0+rh).
 template <bool WIN>
 struct Acc {
   double* base;   // [PL_COUNT][NC] planes in HBM (base state)
-  double* sm;     // WIN: [PL_COUNT][bw*bh] staged box in shared memory
   int NXS, NC;
-  int bx0, by0, bw, bh;  // WIN: box origin / extent
+  // WIN only
+  double* sm4;    // [4][PL_COUNT] private copies of C0, Cw, Ce, Cs
+  int xc, yc, xw, xe;
+  double* rres;   // [rw*rh] resco of candidate rows
+  const int* rmask;  // [rw*rh] rows-written mask of candidate cells (bit 0 <=> interior rows written)
+  int rx0, ry0, rw, rh;
+  __device__ __forceinline__ int slot(int ix, int iy) const {
+    if (iy == yc) { if (ix == xc) return 0; if (ix == xw) return 1; if (ix == xe) return 2; return -1; }
+    if (iy == yc - 1 && ix == xc) return 3;
+    return -1;
+  }
   __device__ __forceinline__ double get(int pl, int ix, int iy) const {
     if (WIN) {
-      const unsigned lx = (unsigned)(ix - bx0), ly = (unsigned)(iy - by0);
-      if (lx < (unsigned)bw && ly < (unsigned)bh) return sm[pl * (bw * bh) + ly * bw + lx];
+      if (pl == PL_RESCO) {
+        const unsigned lx = (unsigned)(ix - rx0), ly = (unsigned)(iy - ry0);
+        if (lx < (unsigned)rw && ly < (unsigned)rh && (rmask[ly * rw + lx] & 0x100)) return rres[ly * rw + lx];
+      } else {
+        const int k = slot(ix, iy);
+        if (k >= 0) return sm4[k * PL_COUNT + pl];
+      }
     }
     return base[(size_t)pl * NC + ix + NXS * iy];
   }
   __device__ __forceinline__ void set(int pl, int ix, int iy, double v) const {
     if (WIN) {
-      const unsigned lx = (unsigned)(ix - bx0), ly = (unsigned)(iy - by0);
-      if (lx < (unsigned)bw && ly < (unsigned)bh) sm[pl * (bw * bh) + ly * bw + lx] = v;
-      return;  // writes outside the box would only re-store base values
+      if (pl == PL_RESCO) {
+        const unsigned lx = (unsigned)(ix - rx0), ly = (unsigned)(iy - ry0);
+        if (lx < (unsigned)rw && ly < (unsigned)rh) rres[ly * rw + lx] = v;
+      } else {
+        const int k = slot(ix, iy);
+        if (k >= 0) sm4[k * PL_COUNT + pl] = v;
+      }
+      return;
     }
     base[(size_t)pl * NC + ix + NXS * iy] = v;
   }
@@ -285,45 +309,81 @@ __device__ inline bool in_xlist(int ix, int xc, int jinc, int jstart, int NXS) {
 }
 
 // ============================================================================================
-// phase 1 — everything that lives on one cell / its east and north faces
+// phase 1 — everything that lives on one cell / its east and north faces, split into ROLES that
+// are independent of each other inside a sub-phase so that different warps can take them:
+//   sub-phase 1a:  p1_xpart (x-gradients, thermal force, upe)   p1_ypart (y-face values, vy, vey)
+//                  p1_visx  (parallel viscosity)
+//   sub-phase 1b:  p1_fx (fngx,fnix)  p1_fy (fngy,fniy)  p1_exe (feex)  p1_exi (feix)  p1_ey (feey,feiy)
+// 1b reads only same-cell outputs of 1a.  A role that needs a quantity owned by another role of the
+// same sub-phase recomputes it with the same device function (bit-identical).
 // ============================================================================================
-template <bool WIN>
-__device__ void phase1_cell(const Acc<WIN>& a, const Win& w, int ix, int iy) {
+struct P1Rng { bool r16, r15, rfx, rfy; };
+__device__ __forceinline__ P1Rng p1_ranges(const Win& w, int ix, int iy) {
+  P1Rng r;
+  r.r16 = in_rng(ix, w.i1, w.i6) && in_rng(iy, w.j1, w.j6);  // [i1..i6]x[j1..j6]
+  r.r15 = in_rng(ix, w.i1, w.i6) && in_rng(iy, w.j1, w.j5);  // [i1..i6]x[j1..j5]
+  r.rfx = in_rng(ix, w.i1, w.i5) && in_rng(iy, w.j4, w.j8);  // x-face fluxes
+  r.rfy = in_rng(ix, w.i4, w.i8) && in_rng(iy, w.j1, w.j5);  // y-face fluxes
+  return r;
+}
+// Coulomb logarithm on the east face of (ix,iy) (oderhs.m:1138-1155)
+template <bool WIN> __device__ inline double f_loglambda(const Acc<WIN>& a, int ix, int iy) {
   const int NXS = a.NXS;
-  const int nx = (int)D.nx, ny = (int)D.ny;
+  const int ix1 = IXP1(ix, iy);
+  const double teev = 0.5 * (a.get(PL_TE, ix, iy) + a.get(PL_TE, ix1, iy)) / D.ev;
+  const double nexface = 0.5 * (f_ne(a, ix, iy) + f_ne(a, ix1, iy));
+  if (D.islnlamcon == 1) return D.lnlam;
+  if (teev < 50.) return 23.4 - 1.15 * ue_log10(1.e-6 * nexface) + 3.45 * ue_log10(teev);
+  return 25.3 - 1.15 * ue_log10(1.e-6 * nexface) + 2.33167537087122e+00 * ue_log10(teev);
+}
+
+// ---- 1a: x-part (convert.m:608-618, 736-749; oderhs.m:1516-1534, 1738-1762) ------------------------
+template <bool WIN>
+__device__ void p1_xpart(const Acc<WIN>& a, const Win& w, int ix, int iy) {
+  const int NXS = a.NXS;
+  const int nx = (int)D.nx;
   const double ev = D.ev, cutlo = D.cutlo;
-  const int ixlb = (int)D.ixlb, ixrb = (int)D.ixrb;
-  const int ix1 = IXP1(ix, iy);  // east neighbour
-  // ---- which auxiliary quantities convsr_aux refreshes at this cell -------------------
-  bool do_xg, do_yf;
-  if (!WIN) { do_xg = (ix <= nx); do_yf = (iy <= ny); }
-  else {
-    const int xc = w.xc, yc = w.yc;
-    do_xg = (iy == yc) && in_xlist(ix, xc, iy, iy, NXS);                                       // convert.m:608-618, 736-749
-    const int jlo = max(yc - 1, 0), jhi = min(yc, ny);
-    do_yf = (iy >= jlo && iy <= jhi) && (in_xlist(ix, xc, yc, yc, NXS) || ix == IXP1(xc, iy));  // convert.m:627-784
-  }
-  const double ni = a.get(PL_NI, ix, iy), te = a.get(PL_TE, ix, iy), ti = a.get(PL_TI, ix, iy), ng = a.get(PL_NG, ix, iy);
-  const double ne = f_ne(a, ix, iy);
-  const double ni_e = a.get(PL_NI, ix1, iy), te_e = a.get(PL_TE, ix1, iy), ti_e = a.get(PL_TI, ix1, iy), ng_e = a.get(PL_NG, ix1, iy);
-  const double ne_e = f_ne(a, ix1, iy);
-  const double gxf = GG(gxf, ix, iy), gx = GG(gx, ix, iy), gx_e = GG(gx, ix1, iy), sx = GG(sx, ix, iy), rrv = GG(rrv, ix, iy);
-  double gpix = a.get(PL_GPIX, ix, iy), gpex = a.get(PL_GPEX, ix, iy);
-  double gtex;
+  const int ix1 = IXP1(ix, iy);
+  bool do_xg;
+  if (!WIN) do_xg = (ix <= nx);
+  else do_xg = (iy == w.yc) && in_xlist(ix, w.xc, iy, iy, NXS);
+  const double gxf = GG(gxf, ix, iy), rrv = GG(rrv, ix, iy);
   if (do_xg) {
-    gpix = (f_pri(a, ix1, iy) - f_pri(a, ix, iy)) * gxf;
-    gpex = (f_pre(a, ix1, iy) - f_pre(a, ix, iy)) * gxf;
-    a.set(PL_GPIX, ix, iy, gpix); a.set(PL_GPEX, ix, iy, gpex);
+    a.set(PL_GPIX, ix, iy, (f_pri(a, ix1, iy) - f_pri(a, ix, iy)) * gxf);
+    a.set(PL_GPEX, ix, iy, (f_pre(a, ix1, iy) - f_pre(a, ix, iy)) * gxf);
   }
-  // gtex is a pure function of te (convert.m:741); never perturbed outside the refresh list
-  gtex = (te_e - te) * gxf;
-  const bool has_n = (iy <= ny);  // north face exists
-  double niy0 = 0, niy1 = 0, gpiy = 0, gpey = 0, tey0 = 0, tey1 = 0, tiy0 = 0, tiy1 = 0, dynog = 1;
-  if (has_n) {
-    dynog = GG(dynog, ix, iy);
-    niy0 = a.get(PL_NIY0, ix, iy); niy1 = a.get(PL_NIY1, ix, iy); gpiy = a.get(PL_GPIY, ix, iy); gpey = a.get(PL_GPEY, ix, iy);
-    tey0 = f_ilin(a, Fld<WIN>::te, ix, iy, 0); tey1 = f_ilin(a, Fld<WIN>::te, ix, iy, 1);
-    tiy0 = f_ilin(a, Fld<WIN>::ti, ix, iy, 0); tiy1 = f_ilin(a, Fld<WIN>::ti, ix, iy, 1);
+  const P1Rng r = p1_ranges(w, ix, iy);
+  if (r.r16) {
+    const double ni = a.get(PL_NI, ix, iy), ni_e = a.get(PL_NI, ix1, iy), te = a.get(PL_TE, ix, iy), te_e = a.get(PL_TE, ix1, iy);
+    const double ne = f_ne(a, ix, iy), ne_e = f_ne(a, ix1, iy);
+    const double gtex = (te_e - te) * gxf;  // convert.m:741
+    const double nbarx = 0.5 * (ne + ne_e);
+    const double ltmax = fmin(fabs(te / (rrv * gtex + cutlo)), GG(lcone, ix, iy));
+    const double lmfpe = 2e16 * ((te / ev) * (te / ev)) / ne;
+    const double flxlimf = D.flalftf * ltmax / (D.flalftf * ltmax + lmfpe);
+    a.set(PL_FRICE, ix, iy, -D.cthe * flxlimf * nbarx * rrv * gtex + 0.);
+    double upe = 0. + a.get(PL_UP, ix, iy) * D.zi * 0.5 * (ni + ni_e);
+    upe = (upe - 0.) / (0.5 * (ne + ne_e));
+    a.set(PL_UPE, ix, iy, upe);
+  }
+}
+
+// ---- 1a: y-part (convert.m:627-784; oderhs.m:1174-1320, 1466-1468, 1729-1792) -----------------------
+template <bool WIN>
+__device__ void p1_ypart(const Acc<WIN>& a, const Win& w, int ix, int iy) {
+  const int NXS = a.NXS;
+  const int ny = (int)D.ny;
+  const P1Rng r = p1_ranges(w, ix, iy);
+  if (iy <= ny) {
+    bool do_yf;
+    if (!WIN) do_yf = true;
+    else {
+      const int jlo = max(w.yc - 1, 0), jhi = min(w.yc, ny);
+      do_yf = (iy >= jlo && iy <= jhi) && (in_xlist(ix, w.xc, w.yc, w.yc, NXS) || ix == IXP1(w.xc, iy));
+    }
+    const double dynog = GG(dynog, ix, iy);
+    double niy0 = a.get(PL_NIY0, ix, iy), niy1 = a.get(PL_NIY1, ix, iy), gpiy = a.get(PL_GPIY, ix, iy), gpey = a.get(PL_GPEY, ix, iy);
+    const double tey0 = f_ilin(a, Fld<WIN>::te, ix, iy, 0), tey1 = f_ilin(a, Fld<WIN>::te, ix, iy, 1);
     if (do_yf) {
       niy0 = f_ilog(a, Fld<WIN>::ni, ix, iy, 0); niy1 = f_ilog(a, Fld<WIN>::ni, ix, iy, 1);
       const double priy0 = f_ilog(a, Fld<WIN>::pri, ix, iy, 0), priy1 = f_ilog(a, Fld<WIN>::pri, ix, iy, 1);
@@ -332,302 +392,351 @@ __device__ void phase1_cell(const Acc<WIN>& a, const Win& w, int ix, int iy) {
       gpey = (ney1 * tey1 - ney0 * tey0) / dynog;
       a.set(PL_NIY0, ix, iy, niy0); a.set(PL_NIY1, ix, iy, niy1); a.set(PL_GPIY, ix, iy, gpiy); a.set(PL_GPEY, ix, iy, gpey);
     }
+    double vy = a.get(PL_VY, ix, iy);
+    if (r.r15) {
+      const double gpry = (0. + gpiy) + gpey;
+      const double pr_n = f_pr(a, ix, iy + 1), pr_c = f_pr(a, ix, iy);
+      const double gtey = (tey1 - tey0) / dynog;
+      double vydd = D.vcony + 0. + 0. - (D.difpr + 0.) * (2 * gpry / (pr_n + pr_c) - 3.0 * gtey / (tey1 + tey0));
+      const double difnimix = D.fcdif * D.difni + 0.;
+      vydd = vydd - 1. * difnimix * (2 * (1 - D.isvylog) * ((niy1 - niy0) / dynog) / (niy1 + niy0) + D.isvylog * (ue_log(niy1) - ue_log(niy0)) / dynog);
+      vy = vydd;
+      a.set(PL_VY, ix, iy, vy);
+    }
+    double vey = a.get(PL_VEY, ix, iy);
+    if (r.r16) vey = 0.;
+    if (r.r15) {
+      const double ney0 = 0. + D.zi * niy0, ney1 = 0. + D.zi * niy1;
+      vey = 0. + vy * D.zi * 0.5 * (niy0 + niy1);
+      vey = (vey - 0.) / (0.5 * (ney0 + ney1));
+    }
+    if (r.r16) a.set(PL_VEY, ix, iy, vey);
+  } else {  // iy == ny+1
+    if (in_rng(ix, w.i1, w.i6)) a.set(PL_VY, ix, iy, 0.0);     // oderhs.m:1466-1468
+    if (r.r16) a.set(PL_VEY, ix, iy, 0.);                       // oderhs.m:1729-1733
+    if (in_rng(ix, w.i4, w.i8)) a.set(PL_FNIY, ix, iy, 0.0);   // oderhs.m:3315-3317
   }
-  const double ney0 = 0. + D.zi * niy0, ney1 = 0. + D.zi * niy1;
-  const bool r16 = in_rng(ix, w.i1, w.i6) && in_rng(iy, w.j1, w.j6);  // [i1..i6]x[j1..j6]
-  const bool r15 = in_rng(ix, w.i1, w.i6) && in_rng(iy, w.j1, w.j5);  // [i1..i6]x[j1..j5]
-  const bool rfx = in_rng(ix, w.i1, w.i5) && in_rng(iy, w.j4, w.j8);  // x-face fluxes
-  const bool rfy = in_rng(ix, w.i4, w.i8) && in_rng(iy, w.j1, w.j5);  // y-face fluxes
-  // ---- Coulomb logarithm (oderhs.m:1138-1155) -----------------------------------------------
-  double loglambda;
-  {
-    const double teev = 0.5 * (te + te_e) / ev;
-    const double nexface = 0.5 * (ne + ne_e);
-    if (D.islnlamcon == 1) loglambda = D.lnlam;
-    else if (teev < 50.) loglambda = 23.4 - 1.15 * ue_log10(1.e-6 * nexface) + 3.45 * ue_log10(teev);
-    else loglambda = 25.3 - 1.15 * ue_log10(1.e-6 * nexface) + 2.33167537087122e+00 * ue_log10(teev);
-  }
-  // ---- radial velocity (oderhs.m:1174-1320, diffusive part) -------------------------------------
-  double vy = a.get(PL_VY, ix, iy);
-  if (r15) {
-    const double gpry = (0. + gpiy) + gpey;
-    const double pr_n = f_pr(a, ix, iy + 1), pr_c = f_pr(a, ix, iy);
-    const double gtey = (tey1 - tey0) / dynog;
-    double vydd = D.vcony + 0. + 0. - (D.difpr + 0.) * (2 * gpry / (pr_n + pr_c) - 3.0 * gtey / (tey1 + tey0));
-    const double difnimix = D.fcdif * D.difni + 0.;
-    vydd = vydd - 1. * difnimix * (2 * (1 - D.isvylog) * ((niy1 - niy0) / dynog) / (niy1 + niy0) + D.isvylog * (ue_log(niy1) - ue_log(niy0)) / dynog);
-    vy = vydd;
-    a.set(PL_VY, ix, iy, vy);
-  }
-  if (iy == ny + 1 && in_rng(ix, w.i1, w.i6)) { vy = 0.0; a.set(PL_VY, ix, iy, vy); }  // oderhs.m:1466-1468
-  // ---- thermal force (oderhs.m:1516-1534) ----------------------------------------------------------
-  if (r16) {
-    const double nbarx = 0.5 * (ne + ne_e);
-    const double ltmax = fmin(fabs(te / (rrv * gtex + cutlo)), GG(lcone, ix, iy));
-    const double lmfpe = 2e16 * ((te / ev) * (te / ev)) / ne;
-    const double flxlimf = D.flalftf * ltmax / (D.flalftf * ltmax + lmfpe);
-    a.set(PL_FRICE, ix, iy, -D.cthe * flxlimf * nbarx * rrv * gtex + 0.);
-  }
-  // ---- electron velocities (oderhs.m:1738-1792); fqp = fqy = 0 -----------------------------------------
-  double upe = a.get(PL_UPE, ix, iy), vey = a.get(PL_VEY, ix, iy);
-  if (r16) {
-    upe = 0. + a.get(PL_UP, ix, iy) * D.zi * 0.5 * (ni + ni_e);
-    upe = (upe - 0.) / (0.5 * (ne + ne_e));
-    a.set(PL_UPE, ix, iy, upe);
-  }
-  if (r16) vey = 0.;  // oderhs.m:1729-1733
-  if (r15) {
-    vey = 0. + vy * D.zi * 0.5 * (niy0 + niy1);
-    vey = (vey - 0.) / (0.5 * (ney0 + ney1));
-  }
-  if (r16) a.set(PL_VEY, ix, iy, vey);
-  const double vex = upe * rrv + 0. - 0.;
+}
+
+// ---- 1a: parallel viscosity (oderhs.m:2718-2787) -------------------------------------------------------
+template <bool WIN>
+__device__ void p1_visx(const Acc<WIN>& a, const Win& w, int ix, int iy) {
+  const int NXS = a.NXS;
+  const double ev = D.ev;
+  const P1Rng r = p1_ranges(w, ix, iy);
+  if (!r.r16) return;
+  const double ni = a.get(PL_NI, ix, iy), ti = a.get(PL_TI, ix, iy);
+  const double gxf = GG(gxf, ix, iy), gx = GG(gx, ix, iy);
+  const double loglambda = f_loglambda(a, ix, iy);
+  const double tvw = (D.zi * D.zi) / sqrt((D.mi + D.mi) / (2 * D.mp));
+  const double wsum = 0.0 + tvw * ni;
+  const double ctaui = 2.1e13 / (loglambda * (D.zi * D.zi));
+  const double tv2 = ctaui / (ev * sqrt(ev));
+  const double aa = (D.convis == 0) ? fmax(ti, D.temin * ev) : D.afix * ev;
+  const double rr = GG(rr, ix, iy), vol = GG(vol, ix, iy);
+  const double visxtmp = tv2 * D.coef * rr * rr * aa * aa * sqrt(aa) * ni / wsum;
+  double visx = D.parvis * visxtmp + 0. * f_nm(a, ix, iy);
+  const int ixw = IXM1(ix, iy);
+  const double t0 = fmax(ti, D.temin * ev);
+  const double mfl = D.flalfv * f_nm(a, ix, iy) * rr * vol * gx * (t0 / D.mi);
+  double csh;
+  if (D.isgxvon == 0) csh = visx * vol * gx * gx;
+  else csh = visx * vol * gx * 2 * gxf * GG(gxf, ixw, iy) / (gxf + GG(gxf, ixw, iy));
+  const double msh = fabs(csh * (a.get(PL_UP, ixw, iy) - a.get(PL_UP, ix, iy)));
+  visx = visx / ue_pow(1 + ue_pow(msh / (mfl + 1.e-20 * msh), D.flgamv), 1 / D.flgamv);
+  a.set(PL_VISX, ix, iy, visx);
+}
+
+// ---- x-face particle fluxes (neudifpg oderhs.m:6126-6225 + fd2tra; oderhs.m:3197-3244) -----------------
+template <bool WIN> __device__ inline double f_fngx(const Acc<WIN>& a, int ix, int iy) {
+  const int NXS = a.NXS;
+  const double ev = D.ev;
+  const int ixlb = (int)D.ixlb, ixrb = (int)D.ixrb;
+  const int ix1 = IXP1(ix, iy);
+  const int methgx = (int)(D.methg % 10);
+  const double ng = a.get(PL_NG, ix, iy), ng_e = a.get(PL_NG, ix1, iy);
+  const double gxf = GG(gxf, ix, iy), gx = GG(gx, ix, iy), gx_e = GG(gx, ix1, iy), sx = GG(sx, ix, iy);
   const double uu = f_uu(a, ix, iy);
-  // ---- parallel viscosity (oderhs.m:2718-2787) -----------------------------------------------------------
-  if (r16) {
-    const double tvw = (D.zi * D.zi) / sqrt((D.mi + D.mi) / (2 * D.mp));
-    const double wsum = 0.0 + tvw * ni;
-    const double ctaui = 2.1e13 / (loglambda * (D.zi * D.zi));
-    const double tv2 = ctaui / (ev * sqrt(ev));
-    const double aa = (D.convis == 0) ? fmax(ti, D.temin * ev) : D.afix * ev;
-    const double rr = GG(rr, ix, iy), vol = GG(vol, ix, iy);
-    const double visxtmp = tv2 * D.coef * rr * rr * aa * aa * sqrt(aa) * ni / wsum;
-    double visx = D.parvis * visxtmp + 0. * f_nm(a, ix, iy);
-    const int ixw = IXM1(ix, iy);
-    const double t0 = fmax(ti, D.temin * ev);
-    const double mfl = D.flalfv * f_nm(a, ix, iy) * rr * vol * gx * (t0 / D.mi);
-    double csh;
-    if (D.isgxvon == 0) csh = visx * vol * gx * gx;
-    else csh = visx * vol * gx * 2 * gxf * GG(gxf, ixw, iy) / (gxf + GG(gxf, ixw, iy));
-    const double msh = fabs(csh * (a.get(PL_UP, ixw, iy) - a.get(PL_UP, ix, iy)));
-    visx = visx / ue_pow(1 + ue_pow(msh / (mfl + 1.e-20 * msh), D.flgamv), 1 / D.flgamv);
-    a.set(PL_VISX, ix, iy, visx);
+  const double tg = f_tg(a, ix, iy), tg_e = f_tg(a, ix1, iy);
+  const double ngxface = 0.5 * (ng + ng_e);
+  const double t0 = fmax(tg, D.temin * ev), t1 = fmax(tg_e, D.temin * ev);
+  const double vtn = sqrt(t0 / D.mg), vtnp = sqrt(t1 / D.mg);
+  const double nu1 = f_nuix(a, ix, iy) + vtn / D.lgmax, nu2 = f_nuix(a, ix1, iy) + vtnp / D.lgmax;
+  const double tgf = 0.5 * (tg + tg_e);
+  const double flalfgx_adj = D.flalfgxa[ix] * (1. + d_powi(D.cflbg * D.ngbackg / ngxface, D.inflbg));
+  const double qfl = flalfgx_adj * sx * (vtn + vtnp) * D.rt8opi * (ng * gx + ng_e * gx_e) / (8 * (gx + gx_e));
+  const double csh = (1 - D.isgasdc) * D.cdifg * sx * gxf * (1 / D.mg) * d_ave(1. / nu1, 1. / nu2) + D.isgasdc * sx * gxf * D.difcng / tgf +
+                     (D.rld2dxg * D.rld2dxg) * sx * (1 / gxf) * 0.5 * (a.get(PL_NUIZ, ix, iy) + a.get(PL_NUIZ, ix1, iy)) / tgf;
+  double qtgf = D.alftng * D.fgtdx[ix] * sx * d_ave(gx / nu1, gx_e / nu2) * (vtn * vtn - vtnp * vtnp);
+  const double vygtan = 0.;
+  qtgf = qtgf - vygtan * sx;
+  double nconv = 2.0 * (ng * ng_e) / (ng + ng_e);
+  if (methgx != 2) nconv = ng * 0.5 * (1 + d_sgn(1., qtgf)) + ng_e * 0.5 * (1 - d_sgn(1., qtgf));
+  const double pg = f_pg(a, ix, iy), pg_e = f_pg(a, ix1, iy);
+  const double qsh = csh * (pg - pg_e) + qtgf * nconv;
+  double qr = fabs(qsh / qfl);
+  if (ix == ixlb || ix == ixrb) { qr = D.gcfacgx * qr; qtgf = D.gcfacgx * qtgf; }
+  double conxg = csh / ue_pow(1 + ue_pow(qr, D.flgamg), 1 / D.flgamg);
+  if (D.isdifxg_aug == 1) conxg = csh * (1 + qr);
+  double floxg = (qtgf / tgf) / ue_pow(1 + ue_pow(qr, D.flgamg), 1 / D.flgamg);
+  floxg = floxg + D.cngflox * sx * uu / tgf;
+  if (methgx == 2) return floxg * (pg_e + pg) / 2. - conxg * (pg_e - pg);
+  return d_upwind(floxg, pg, pg_e) - conxg * (pg_e - pg);
+}
+template <bool WIN> __device__ inline double f_fnix(const Acc<WIN>& a, int ix, int iy) {
+  const int NXS = a.NXS;
+  const int ix1 = IXP1(ix, iy);
+  const double ni = a.get(PL_NI, ix, iy), ni_e = a.get(PL_NI, ix1, iy), sx = GG(sx, ix, iy);
+  const double uu = f_uu(a, ix, iy);
+  const int methnx = (int)(D.methn % 10);
+  double t2;
+  if (methnx == 2) t2 = (ni + ni_e) / 2;
+  else t2 = (uu >= 0.) ? ni : ni_e;
+  double fnix = D.cnfx * uu * sx * t2;
+  const double r1 = D.nlimix * ni / ni_e, r2 = D.nlimix * ni_e / ni;
+  fnix = fnix / sqrt(1 + r1 * r1 + r2 * r2);
+  return fnix;
+}
+template <bool WIN>
+__device__ void p1_fx(const Acc<WIN>& a, const Win& w, int ix, int iy) {
+  const P1Rng r = p1_ranges(w, ix, iy);
+  if (!r.rfx) return;
+  a.set(PL_FNGX, ix, iy, f_fngx(a, ix, iy));
+  a.set(PL_FNIX, ix, iy, f_fnix(a, ix, iy));
+}
+
+// ---- y-face particle fluxes (oderhs.m:6239-6328 + fd2tra; oderhs.m:3264-3312) -----------------------------
+template <bool WIN> __device__ inline double f_fngy(const Acc<WIN>& a, int ix, int iy) {
+  const int NXS = a.NXS;
+  const int ny = (int)D.ny;
+  const double ev = D.ev;
+  const int methgy = (int)(D.methg / 10);
+  const double dynog = GG(dynog, ix, iy);
+  const double vy = a.get(PL_VY, ix, iy);
+  const double ng = a.get(PL_NG, ix, iy), ng_n = a.get(PL_NG, ix, iy + 1);
+  const double ngy0 = f_ilog(a, Fld<WIN>::ng, ix, iy, 0), ngy1 = f_ilog(a, Fld<WIN>::ng, ix, iy, 1);
+  const double tg = f_tg(a, ix, iy), tg_n = f_tg(a, ix, iy + 1);
+  const double gy = GG(gy, ix, iy), gy_n = GG(gy, ix, iy + 1), sy = GG(sy, ix, iy);
+  const double ngyface = 0.5 * (ng + ng_n);
+  const double t0 = fmax(tg, D.tgmin * ev), t1 = fmax(tg_n, D.tgmin * ev);
+  const double vtn = sqrt(t0 / D.mg), vtnp = sqrt(t1 / D.mg);
+  const double nu1 = f_nuix(a, ix, iy) + vtn / D.lgmax, nu2 = f_nuix(a, ix, iy + 1) + vtnp / D.lgmax;
+  const double tgf = 0.5 * (tg + tg_n);
+  const double flalfgy_adj = D.flalfgya[iy] * (1. + d_powi(D.cflbg * D.ngbackg / ngyface, D.inflbg));
+  double qfl = flalfgy_adj * sy * (vtn + vtnp) * D.rt8opi * (ngy0 * gy + ngy1 * gy_n) / (8 * (gy + gy_n));
+  if (iy == 0) qfl = flalfgy_adj * sy * (vtn + vtnp) * D.rt8opi * (ngy0 + ngy1) / 8.;
+  const double csh = (1 - D.isgasdc) * (D.cdifg * sy / dynog) * (1 / D.mg) * d_ave(1. / nu1, 1. / nu2) + D.isgasdc * sy * D.difcng / (dynog * tgf) +
+                     (D.rld2dyg * D.rld2dyg) * sy * dynog * 0.5 * (a.get(PL_NUIZ, ix, iy) + a.get(PL_NUIZ, ix, iy + 1)) / tgf;
+  double qtgf = D.alftng * D.fgtdy[iy] * sy * d_ave(gy / nu1, gy_n / nu2) * (vtn * vtn - vtnp * vtnp);
+  double nconv = 2.0 * (ngy0 * ngy1) / (ngy0 + ngy1);
+  if (methgy != 2) nconv = ngy0 * 0.5 * (1 + d_sgn(1., qtgf)) + ngy1 * 0.5 * (1 - d_sgn(1., qtgf));
+  const double pgy0 = f_ilog(a, Fld<WIN>::pg, ix, iy, 0), pgy1 = f_ilog(a, Fld<WIN>::pg, ix, iy, 1);
+  const double qsh = csh * (pgy0 - pgy1) + qtgf * nconv;
+  double qr = fabs(qsh / qfl);
+  if (iy == 0) { qr = D.gcfacgy * qr; qtgf = D.gcfacgy * qtgf; }
+  if (iy == ny) { qr = D.gcfacgy * qr; qtgf = D.gcfacgy * qtgf; }
+  double conyg = csh / ue_pow(1 + ue_pow(qr, D.flgamg), 1 / D.flgamg);
+  if (D.isdifyg_aug == 1) conyg = csh * (1 + qr);
+  double floyg = (qtgf / tgf) / ue_pow(1 + ue_pow(qr, D.flgamg), 1 / D.flgamg);
+  floyg = floyg + D.cngfloy * sy * vy / tgf;
+  const double pg = f_pg(a, ix, iy), pg_n = f_pg(a, ix, iy + 1);
+  if (methgy == 2) return floyg * (pg_n + pg) / 2. - conyg * (pg_n - pg);
+  return d_upwind(floyg, pg, pg_n) - conyg * (pg_n - pg);
+}
+template <bool WIN> __device__ inline double f_fniy(const Acc<WIN>& a, int ix, int iy) {
+  const int NXS = a.NXS;
+  const double vy = a.get(PL_VY, ix, iy), sy = GG(sy, ix, iy);
+  const double niy0 = a.get(PL_NIY0, ix, iy), niy1 = a.get(PL_NIY1, ix, iy);
+  const double ni = a.get(PL_NI, ix, iy), ni_n = a.get(PL_NI, ix, iy + 1);
+  const int methny = (int)(D.methn / 10);
+  double t2;
+  if (methny == 2) t2 = (niy0 + niy1) / 2;
+  else t2 = (vy >= 0.) ? niy0 : niy1;
+  double fniy = D.cnfy * vy * sy * t2;
+  if (vy * (ni - ni_n) < 0.) {
+    const double r1 = D.nlimiy / ni_n, r2 = D.nlimiy / ni;
+    fniy = fniy / (1 + r1 * r1 + r2 * r2);
   }
-  // ---- neutral x-flux (neudifpg, oderhs.m:6126-6225 + fd2tra) ------------------------------------------------
-  double fngx = a.get(PL_FNGX, ix, iy), fnix = a.get(PL_FNIX, ix, iy);
-  if (rfx) {
-    const int methgx = (int)(D.methg % 10);
-    const double tg = f_tg(a, ix, iy), tg_e = f_tg(a, ix1, iy);
-    const double ngxface = 0.5 * (ng + ng_e);
-    const double t0 = fmax(tg, D.temin * ev), t1 = fmax(tg_e, D.temin * ev);
-    const double vtn = sqrt(t0 / D.mg), vtnp = sqrt(t1 / D.mg);
-    const double nu1 = f_nuix(a, ix, iy) + vtn / D.lgmax, nu2 = f_nuix(a, ix1, iy) + vtnp / D.lgmax;
-    const double tgf = 0.5 * (tg + tg_e);
-    const double flalfgx_adj = D.flalfgxa[ix] * (1. + d_powi(D.cflbg * D.ngbackg / ngxface, D.inflbg));
-    const double qfl = flalfgx_adj * sx * (vtn + vtnp) * D.rt8opi * (ng * gx + ng_e * gx_e) / (8 * (gx + gx_e));
-    const double csh = (1 - D.isgasdc) * D.cdifg * sx * gxf * (1 / D.mg) * d_ave(1. / nu1, 1. / nu2) + D.isgasdc * sx * gxf * D.difcng / tgf +
-                       (D.rld2dxg * D.rld2dxg) * sx * (1 / gxf) * 0.5 * (a.get(PL_NUIZ, ix, iy) + a.get(PL_NUIZ, ix1, iy)) / tgf;
-    double qtgf = D.alftng * D.fgtdx[ix] * sx * d_ave(gx / nu1, gx_e / nu2) * (vtn * vtn - vtnp * vtnp);
-    const double vygtan = 0.;
-    qtgf = qtgf - vygtan * sx;
-    double nconv = 2.0 * (ng * ng_e) / (ng + ng_e);
-    if (methgx != 2) nconv = ng * 0.5 * (1 + d_sgn(1., qtgf)) + ng_e * 0.5 * (1 - d_sgn(1., qtgf));
-    const double pg = f_pg(a, ix, iy), pg_e = f_pg(a, ix1, iy);
-    const double qsh = csh * (pg - pg_e) + qtgf * nconv;
-    double qr = fabs(qsh / qfl);
-    if (ix == ixlb || ix == ixrb) { qr = D.gcfacgx * qr; qtgf = D.gcfacgx * qtgf; }
-    double conxg = csh / ue_pow(1 + ue_pow(qr, D.flgamg), 1 / D.flgamg);
-    if (D.isdifxg_aug == 1) conxg = csh * (1 + qr);
-    double floxg = (qtgf / tgf) / ue_pow(1 + ue_pow(qr, D.flgamg), 1 / D.flgamg);
-    floxg = floxg + D.cngflox * sx * uu / tgf;
-    if (methgx == 2) fngx = floxg * (pg_e + pg) / 2. - conxg * (pg_e - pg);
-    else fngx = d_upwind(floxg, pg, pg_e) - conxg * (pg_e - pg);
-    a.set(PL_FNGX, ix, iy, fngx);
-    // ---- ion x-flux (oderhs.m:3197-3244) --------------------------------------------------------------------
-    const int methnx = (int)(D.methn % 10);
-    double t2;
-    if (methnx == 2) t2 = (ni + ni_e) / 2;
-    else t2 = (uu >= 0.) ? ni : ni_e;
-    fnix = D.cnfx * uu * sx * t2;
-    const double r1 = D.nlimix * ni / ni_e, r2 = D.nlimix * ni_e / ni;
-    fnix = fnix / sqrt(1 + r1 * r1 + r2 * r2);
-    a.set(PL_FNIX, ix, iy, fnix);
-  }
-  // ---- neutral / ion y-flux (oderhs.m:6239-6328, 3264-3312) ------------------------------------------------------
-  double fngy = a.get(PL_FNGY, ix, iy), fniy = a.get(PL_FNIY, ix, iy);
-  double ngy0 = 0, ngy1 = 0;
-  if (has_n && (rfy || r16)) { ngy0 = f_ilog(a, Fld<WIN>::ng, ix, iy, 0); ngy1 = f_ilog(a, Fld<WIN>::ng, ix, iy, 1); }
-  if (rfy) {
-    const int methgy = (int)(D.methg / 10);
-    const double ng_n = a.get(PL_NG, ix, iy + 1);
-    const double tg = f_tg(a, ix, iy), tg_n = f_tg(a, ix, iy + 1);
-    const double gy = GG(gy, ix, iy), gy_n = GG(gy, ix, iy + 1), sy = GG(sy, ix, iy);
-    const double ngyface = 0.5 * (ng + ng_n);
-    const double t0 = fmax(tg, D.tgmin * ev), t1 = fmax(tg_n, D.tgmin * ev);
-    const double vtn = sqrt(t0 / D.mg), vtnp = sqrt(t1 / D.mg);
-    const double nu1 = f_nuix(a, ix, iy) + vtn / D.lgmax, nu2 = f_nuix(a, ix, iy + 1) + vtnp / D.lgmax;
-    const double tgf = 0.5 * (tg + tg_n);
-    const double flalfgy_adj = D.flalfgya[iy] * (1. + d_powi(D.cflbg * D.ngbackg / ngyface, D.inflbg));
-    double qfl = flalfgy_adj * sy * (vtn + vtnp) * D.rt8opi * (ngy0 * gy + ngy1 * gy_n) / (8 * (gy + gy_n));
-    if (iy == 0) qfl = flalfgy_adj * sy * (vtn + vtnp) * D.rt8opi * (ngy0 + ngy1) / 8.;
-    const double csh = (1 - D.isgasdc) * (D.cdifg * sy / dynog) * (1 / D.mg) * d_ave(1. / nu1, 1. / nu2) + D.isgasdc * sy * D.difcng / (dynog * tgf) +
-                       (D.rld2dyg * D.rld2dyg) * sy * dynog * 0.5 * (a.get(PL_NUIZ, ix, iy) + a.get(PL_NUIZ, ix, iy + 1)) / tgf;
-    double qtgf = D.alftng * D.fgtdy[iy] * sy * d_ave(gy / nu1, gy_n / nu2) * (vtn * vtn - vtnp * vtnp);
-    double nconv = 2.0 * (ngy0 * ngy1) / (ngy0 + ngy1);
-    if (methgy != 2) nconv = ngy0 * 0.5 * (1 + d_sgn(1., qtgf)) + ngy1 * 0.5 * (1 - d_sgn(1., qtgf));
-    const double pgy0 = f_ilog(a, Fld<WIN>::pg, ix, iy, 0), pgy1 = f_ilog(a, Fld<WIN>::pg, ix, iy, 1);
-    const double qsh = csh * (pgy0 - pgy1) + qtgf * nconv;
-    double qr = fabs(qsh / qfl);
-    if (iy == 0) { qr = D.gcfacgy * qr; qtgf = D.gcfacgy * qtgf; }
-    if (iy == ny) { qr = D.gcfacgy * qr; qtgf = D.gcfacgy * qtgf; }
-    double conyg = csh / ue_pow(1 + ue_pow(qr, D.flgamg), 1 / D.flgamg);
-    if (D.isdifyg_aug == 1) conyg = csh * (1 + qr);
-    double floyg = (qtgf / tgf) / ue_pow(1 + ue_pow(qr, D.flgamg), 1 / D.flgamg);
-    floyg = floyg + D.cngfloy * sy * vy / tgf;
-    const double pg = f_pg(a, ix, iy), pg_n = f_pg(a, ix, iy + 1);
-    if (methgy == 2) fngy = floyg * (pg_n + pg) / 2. - conyg * (pg_n - pg);
-    else fngy = d_upwind(floyg, pg, pg_n) - conyg * (pg_n - pg);
-    a.set(PL_FNGY, ix, iy, fngy);
-    const int methny = (int)(D.methn / 10);
-    const double ni_n = a.get(PL_NI, ix, iy + 1);
-    double t2;
-    if (methny == 2) t2 = (niy0 + niy1) / 2;
-    else t2 = (vy >= 0.) ? niy0 : niy1;
-    fniy = D.cnfy * vy * sy * t2;
-    if (vy * (ni - ni_n) < 0.) {
-      const double r1 = D.nlimiy / ni_n, r2 = D.nlimiy / ni;
-      fniy = fniy / (1 + r1 * r1 + r2 * r2);
-    }
-    a.set(PL_FNIY, ix, iy, fniy);
-  }
-  if (iy == ny + 1 && in_rng(ix, w.i4, w.i8)) a.set(PL_FNIY, ix, iy, 0.0);  // oderhs.m:3315-3317
-  // ---- heat-conduction coefficients (oderhs.m:2801-3017) ----------------------------------------------------------
-  double hcxe = 0, hcxi = 0, hcye = 0, hcyi = 0;
-  if (r16) {
-    const int iyp1 = min(ny + 1, iy + 1);
-    double w1 = 0., w2 = 0.;
-    {
-      const double tv = D.zi * D.zi;
-      const double a2 = (D.zi * D.zi) * sqrt(2 * D.mi * D.mi / (D.mi + D.mi));
-      w1 = w1 + tv * (ni * gx + ni_e * gx_e) / (gx + gx_e);
-      w2 = w2 + a2 * (ni * gx + ni_e * gx_e) / (gx + gx_e);
-    }
-    const double ctaue = 3.5e11 * D.zi / loglambda;
-    const double ctaui = 2.1e13 / (loglambda * (D.zi * D.zi));
-    const double fxe = D.kxe * D.ce * ctaue / (D.me * ev * sqrt(ev));
-    const double fxi = D.kxi * D.ci * ctaui / (ev * sqrt(ev * D.mp));
-    double fxet = fxe, fxit = fxi;
-    if ((iy <= D.iysptrx) && ix > D.ixpt1 && ix <= D.ixpt2) {
-      fxet = fxe / (1. + (D.rkxecore - 1.) * d_powi(D.yyf[iy] / (D.yyf[0] + 4.e-50), D.inkxc));
-      fxit = D.kxicore * fxi;
-    }
-    double niavex = (ni * gx + ni_e * gx_e) / (gx + gx_e);
-    const double gy = GG(gy, ix, iy), gy_p = GG(gy, ix, iyp1);
-    const double niavey = (niy0 * gy + niy1 * gy_p) / (gy + gy_p);
-    hcxe = 0. + fxet * niavex / w1;
-    const double diffusivwrk = D.fcdif * D.difni + 0.;
-    double kyemix = D.fcdif * D.kye + 0.;
-    if (D.kyet > 1.e-20 && iy > D.iysptrx) kyemix = (1. - D.ckyet) * kyemix + D.ckyet * D.kyet * diffusivwrk;
-    hcye = 0. + (kyemix + 2.33 * (0. + 0.)) * D.zi * niavey;
-    double hcxij = fxit * niavex / w2;
-    double kyimix = D.fcdif * D.kyi + 0.;
-    if (D.kyit > 1.e-20 && iy > D.iysptrx) kyimix = (1. - D.ckyit) * kyimix + D.ckyit * D.kyit * diffusivwrk;
-    const double hcyij = 0. + (kyimix + (0. + 0.)) * niavey;
-    // ion parallel conduction with flux limit (oderhs.m:2906-2965)
-    double aa, tiave = 0.;
-    if (D.concap == 0) {
-      tiave = (ti * gx + ti_e * gx_e) / (gx + gx_e);
-      if (ix == ixlb) tiave = a.get(PL_TI, ixlb + 1, iy);
-      if (ix == ixrb) tiave = a.get(PL_TI, ixrb, iy);
-      aa = fmax(tiave, D.temin * ev);
-    } else aa = D.afix * ev;
-    hcxij = hcxij * rrv * rrv * aa * aa * sqrt(aa);
-    const double lmfpi = 1.e16 * ((tiave / ev) * (tiave / ev)) / ni;
+  return fniy;
+}
+template <bool WIN>
+__device__ void p1_fy(const Acc<WIN>& a, const Win& w, int ix, int iy) {
+  const P1Rng r = p1_ranges(w, ix, iy);
+  if (!r.rfy) return;
+  a.set(PL_FNGY, ix, iy, f_fngy(a, ix, iy));
+  a.set(PL_FNIY, ix, iy, f_fniy(a, ix, iy));
+}
+
+// ---- x-face electron energy flux (oderhs.m:2850-2874, 2968-3000, 3941-3965, 4024-4036 + fd2tra) --------------
+template <bool WIN>
+__device__ void p1_exe(const Acc<WIN>& a, const Win& w, int ix, int iy) {
+  const int NXS = a.NXS;
+  const double ev = D.ev, cutlo = D.cutlo;
+  const int ixlb = (int)D.ixlb, ixrb = (int)D.ixrb;
+  const P1Rng r = p1_ranges(w, ix, iy);
+  if (!r.rfx) return;
+  const int ix1 = IXP1(ix, iy);
+  const double ni = a.get(PL_NI, ix, iy), ni_e = a.get(PL_NI, ix1, iy), te = a.get(PL_TE, ix, iy), te_e = a.get(PL_TE, ix1, iy);
+  const double ne = f_ne(a, ix, iy), ne_e = f_ne(a, ix1, iy);
+  const double gxf = GG(gxf, ix, iy), gx = GG(gx, ix, iy), gx_e = GG(gx, ix1, iy), sx = GG(sx, ix, iy), rrv = GG(rrv, ix, iy);
+  const double loglambda = f_loglambda(a, ix, iy);
+  double w1 = 0.;
+  w1 = w1 + (D.zi * D.zi) * (ni * gx + ni_e * gx_e) / (gx + gx_e);
+  const double ctaue = 3.5e11 * D.zi / loglambda;
+  const double fxe = D.kxe * D.ce * ctaue / (D.me * ev * sqrt(ev));
+  double fxet = fxe;
+  if ((iy <= D.iysptrx) && ix > D.ixpt1 && ix <= D.ixpt2) fxet = fxe / (1. + (D.rkxecore - 1.) * d_powi(D.yyf[iy] / (D.yyf[0] + 4.e-50), D.inkxc));
+  const double niavex = (ni * gx + ni_e * gx_e) / (gx + gx_e);
+  double hcxe = 0. + fxet * niavex / w1;
+  double ae;
+  if (D.concap == 0) {
+    double teave = (te * gx + te_e * gx_e) / (gx + gx_e);
+    if (ix == ixlb) teave = a.get(PL_TE, ixlb + 1, iy);
+    if (ix == ixrb) teave = a.get(PL_TE, ixrb, iy);
+    ae = fmax(teave, D.temin * ev);
+  } else ae = D.afix * ev;
+  const double zeffave = (f_zeff(a, ix, iy) * gx + f_zeff(a, ix1, iy) * gx_e) / (gx + gx_e);
+  const double zcoef = 0.308 + 0.767 * zeffave - 0.075 * (zeffave * zeffave);
+  hcxe = hcxe * rrv * rrv * ae * ae * sqrt(ae) * zcoef;
+  const double lmfpe = 2e16 * ((te / ev) * (te / ev)) / ne;
+  const double neavex = (ne * gx + ne_e * gx_e) / (gx + gx_e);
+  const double dte = te - te_e;
+  const double ste = 0.5 * D.alfkxe * (te + te_e);
+  hcxe = hcxe * (cutlo + dte * dte) / (cutlo + dte * dte + ste * ste) + 0. * neavex;
+  hcxe = hcxe / ((1. + lmfpe / D.lmfplim) * (1 + hcxe * (gx * gx) * D.tdiflim / ne));
+  const double t0 = fmax(te, D.temin * ev), t1 = fmax(te_e, D.temin * ev);
+  const double vt0 = sqrt(t0 / D.me), vt1 = sqrt(t1 / D.me);
+  double wallfac = 1.;
+  if ((ix == ixlb || ix == ixrb) && (D.isplflxl == 0)) wallfac = D.flalfepl / D.flalfe;
+  const double qfl = wallfac * D.flalfe * sx * rrv * (ne * vt0 * t0 + ne_e * vt1 * t1) / 2;
+  const double csh = sx * hcxe * gxf;
+  const double lxtec = 0.5 * (te + te_e) / (fabs(te - te_e) * gxf + 100. * cutlo);
+  const double qsh = csh * (te - te_e) * (1. + lxtec / D.lxtemax);
+  const double qr = (1 - D.isflxlde) * fabs(qsh / qfl);
+  const double conxe = (1 - D.isflxlde) * csh / ((1 + qr) * (1 + qr)) + D.isflxlde * csh / ue_pow(1 + ue_pow(fabs(qsh / qfl), D.flgam), 1 / D.flgam);
+  const double rr = GG(rr, ix, iy), rr_e = GG(rr, ix1, iy);
+  double floxe = 0. + (d_sgn(qr * qr, qsh) / ((1 + qr) * (1 + qr))) * D.flalfea[ix] * sx * (ne * rr * vt0 + ne_e * rr_e * vt1) / 2;
+  const double vex = a.get(PL_UPE, ix, iy) * rrv + 0. - 0.;
+  floxe = floxe + D.cfcvte * 1.25 * (ne + ne_e) * vex * sx - 0.;
+  double feex;
+  if ((int)(D.methe % 10) == 2) feex = floxe * (te_e + te) / 2. - conxe * (te_e - te);
+  else feex = d_upwind(floxe, te, te_e) - conxe * (te_e - te);
+  a.set(PL_FEEX, ix, iy, feex);
+}
+
+// ---- x-face ion energy flux (oderhs.m:2875-2965, 3001-3009, 3967-3993, 4065-4071, 4234-4240 + fd2tra) ---------
+template <bool WIN>
+__device__ void p1_exi(const Acc<WIN>& a, const Win& w, int ix, int iy) {
+  const int NXS = a.NXS;
+  const double ev = D.ev, cutlo = D.cutlo;
+  const int ixlb = (int)D.ixlb, ixrb = (int)D.ixrb;
+  const P1Rng r = p1_ranges(w, ix, iy);
+  if (!r.rfx) return;
+  const int ix1 = IXP1(ix, iy);
+  const double ni = a.get(PL_NI, ix, iy), ni_e = a.get(PL_NI, ix1, iy), ti = a.get(PL_TI, ix, iy), ti_e = a.get(PL_TI, ix1, iy);
+  const double ng = a.get(PL_NG, ix, iy), ng_e = a.get(PL_NG, ix1, iy);
+  const double ne = f_ne(a, ix, iy), ne_e = f_ne(a, ix1, iy);
+  const double gxf = GG(gxf, ix, iy), gx = GG(gx, ix, iy), gx_e = GG(gx, ix1, iy), sx = GG(sx, ix, iy), rrv = GG(rrv, ix, iy);
+  const double loglambda = f_loglambda(a, ix, iy);
+  double w2 = 0.;
+  w2 = w2 + ((D.zi * D.zi) * sqrt(2 * D.mi * D.mi / (D.mi + D.mi))) * (ni * gx + ni_e * gx_e) / (gx + gx_e);
+  const double ctaui = 2.1e13 / (loglambda * (D.zi * D.zi));
+  const double fxi = D.kxi * D.ci * ctaui / (ev * sqrt(ev * D.mp));
+  double fxit = fxi;
+  if ((iy <= D.iysptrx) && ix > D.ixpt1 && ix <= D.ixpt2) fxit = D.kxicore * fxi;
+  double niavex = (ni * gx + ni_e * gx_e) / (gx + gx_e);
+  double hcxij = fxit * niavex / w2;
+  double aa, tiave = 0.;
+  if (D.concap == 0) {
+    tiave = (ti * gx + ti_e * gx_e) / (gx + gx_e);
+    if (ix == ixlb) tiave = a.get(PL_TI, ixlb + 1, iy);
+    if (ix == ixrb) tiave = a.get(PL_TI, ixrb, iy);
+    aa = fmax(tiave, D.temin * ev);
+  } else aa = D.afix * ev;
+  hcxij = hcxij * rrv * rrv * aa * aa * sqrt(aa);
+  const double lmfpi = 1.e16 * ((tiave / ev) * (tiave / ev)) / ni;
+  niavex = (ni * gx + ni_e * gx_e) / (gx + gx_e);
+  hcxij = hcxij / (1. + lmfpi / D.lmfplim);
+  const double dti = ti - ti_e;
+  const double sti = 0.5 * D.alfkxi * (ti + ti_e);
+  hcxij = hcxij * (cutlo + dti * dti) / (cutlo + dti * dti + sti * sti) + 0. * niavex;
+  if (D.isflxldi == 2) {
     niavex = (ni * gx + ni_e * gx_e) / (gx + gx_e);
-    hcxij = hcxij / (1. + lmfpi / D.lmfplim);
-    const double dti = ti - ti_e;
-    const double sti = 0.5 * D.alfkxi * (ti + ti_e);
-    hcxij = hcxij * (cutlo + dti * dti) / (cutlo + dti * dti + sti * sti) + 0. * niavex;
-    if (D.isflxldi == 2) {
-      niavex = (ni * gx + ni_e * gx_e) / (gx + gx_e);
-      double wallfac = 1.;
-      if ((ix == ixlb || ix == ixrb) && (D.isplflxl == 0)) wallfac = D.flalfipl / D.flalfi;
-      const double qflx = wallfac * D.flalfi * rrv * sqrt(aa / D.mi) * niavex * aa;
-      const double cshx = hcxij;
-      const double lxtic = 0.5 * (ti + ti_e) / (fabs(ti - ti_e) * gxf + 100. * cutlo);
-      const double qshx = cshx * (ti - ti_e) * gxf * (1. + lxtic / D.lxtimax);
-      hcxij = cshx / (1 + fabs(qshx / qflx));
-    }
-    hcxi = 0. + hcxij;
-    hcyi = 0. + hcyij;
-    // electron parallel conduction (oderhs.m:2968-3000)
-    double ae;
-    if (D.concap == 0) {
-      double teave = (te * gx + te_e * gx_e) / (gx + gx_e);
-      if (ix == ixlb) teave = a.get(PL_TE, ixlb + 1, iy);
-      if (ix == ixrb) teave = a.get(PL_TE, ixrb, iy);
-      ae = fmax(teave, D.temin * ev);
-    } else ae = D.afix * ev;
-    const double zeffave = (f_zeff(a, ix, iy) * gx + f_zeff(a, ix1, iy) * gx_e) / (gx + gx_e);
-    const double zcoef = 0.308 + 0.767 * zeffave - 0.075 * (zeffave * zeffave);
-    hcxe = hcxe * rrv * rrv * ae * ae * sqrt(ae) * zcoef;
-    const double lmfpe = 2e16 * ((te / ev) * (te / ev)) / ne;
-    const double neavex = (ne * gx + ne_e * gx_e) / (gx + gx_e);
-    const double dte = te - te_e;
-    const double ste = 0.5 * D.alfkxe * (te + te_e);
-    hcxe = hcxe * (cutlo + dte * dte) / (cutlo + dte * dte + ste * ste) + 0. * neavex;
-    hcxe = hcxe / ((1. + lmfpe / D.lmfplim) * (1 + hcxe * (gx * gx) * D.tdiflim / ne));
-    // neutral contribution (isupgon = 0), oderhs.m:3001-3014
-    const double nucx = a.get(PL_NUCX, ix, iy);
-    hcxi = hcxi + D.cftiexclg * D.cfneut * D.cfneutsor_ei * D.kxn * (ng * ti + ng_e * ti_e) / (D.mi * (nucx + a.get(PL_NUCX, ix1, iy)));
-    hcyi = hcyi + D.cftiexclg * D.cfneut * D.cfneutsor_ei * D.kyn * (ngy0 * tiy0 + ngy1 * tiy1) / (D.mi * (nucx + a.get(PL_NUCX, ix, iyp1)));
-  }
-  // ---- x-face energy fluxes (oderhs.m:3941-3996, 4024-4071, 4234-4240 + fd2tra) ------------------------------------
-  if (rfx) {
-    // NB: the reference reads hcxe/hcxi over [i1..i5]x[j4..j8] which is inside [i1..i6]x[j1..j6]
-    const double t0 = fmax(te, D.temin * ev), t1 = fmax(te_e, D.temin * ev);
-    double vt0 = sqrt(t0 / D.me), vt1 = sqrt(t1 / D.me);
     double wallfac = 1.;
-    if ((ix == ixlb || ix == ixrb) && (D.isplflxl == 0)) wallfac = D.flalfepl / D.flalfe;
-    double qfl = wallfac * D.flalfe * sx * rrv * (ne * vt0 * t0 + ne_e * vt1 * t1) / 2;
-    double csh = sx * hcxe * gxf;
-    const double lxtec = 0.5 * (te + te_e) / (fabs(te - te_e) * gxf + 100. * cutlo);
-    double qsh = csh * (te - te_e) * (1. + lxtec / D.lxtemax);
-    double qr = (1 - D.isflxlde) * fabs(qsh / qfl);
-    const double conxe = (1 - D.isflxlde) * csh / ((1 + qr) * (1 + qr)) + D.isflxlde * csh / ue_pow(1 + ue_pow(fabs(qsh / qfl), D.flgam), 1 / D.flgam);
+    if ((ix == ixlb || ix == ixrb) && (D.isplflxl == 0)) wallfac = D.flalfipl / D.flalfi;
+    const double qflx = wallfac * D.flalfi * rrv * sqrt(aa / D.mi) * niavex * aa;
+    const double cshx = hcxij;
+    const double lxtic = 0.5 * (ti + ti_e) / (fabs(ti - ti_e) * gxf + 100. * cutlo);
+    const double qshx = cshx * (ti - ti_e) * gxf * (1. + lxtic / D.lxtimax);
+    hcxij = cshx / (1 + fabs(qshx / qflx));
+  }
+  double hcxi = 0. + hcxij;
+  hcxi = hcxi + D.cftiexclg * D.cfneut * D.cfneutsor_ei * D.kxn * (ng * ti + ng_e * ti_e) / (D.mi * (a.get(PL_NUCX, ix, iy) + a.get(PL_NUCX, ix1, iy)));
+  double conxi, floxi = 0.;
+  if (D.isflxldi != 2) {
+    const double u0 = fmax(ti, D.temin * ev), u1 = fmax(ti_e, D.temin * ev);
+    const double vt0 = sqrt(u0 / D.mi), vt1 = sqrt(u1 / D.mi);
+    double wallfac = 1.;
+    if ((ix == ixlb || ix == ixrb) && (D.isplflxl == 0)) wallfac = D.flalfipl / D.flalfi;
+    const double qfl = wallfac * D.flalfia[ix] * sx * rrv * (ne * vt0 * u0 + ne_e * vt1 * u1) / 2;
+    const double csh = sx * hcxi * gxf;
+    const double lxtic = 0.5 * (ti + ti_e) / (fabs(ti - ti_e) * gxf + 100. * cutlo);
+    const double qsh = csh * (ti - ti_e) * (1. + lxtic / D.lxtimax);
+    const double qr = (1 - D.isflxldi) * fabs(qsh / qfl);
+    conxi = (1 - D.isflxldi) * csh / ((1 + qr) * (1 + qr)) + D.isflxldi * csh / ue_pow(1 + ue_pow(fabs(qsh / qfl), D.flgam), 1 / D.flgam);
     const double rr = GG(rr, ix, iy), rr_e = GG(rr, ix1, iy);
-    double floxe = 0. + (d_sgn(qr * qr, qsh) / ((1 + qr) * (1 + qr))) * D.flalfea[ix] * sx * (ne * rr * vt0 + ne_e * rr_e * vt1) / 2;
-    double conxi, floxi = 0.;
-    if (D.isflxldi != 2) {
-      const double u0 = fmax(ti, D.temin * ev), u1 = fmax(ti_e, D.temin * ev);
-      vt0 = sqrt(u0 / D.mi); vt1 = sqrt(u1 / D.mi);
-      wallfac = 1.;
-      if ((ix == ixlb || ix == ixrb) && (D.isplflxl == 0)) wallfac = D.flalfipl / D.flalfi;
-      qfl = wallfac * D.flalfia[ix] * sx * rrv * (ne * vt0 * u0 + ne_e * vt1 * u1) / 2;
-      csh = sx * hcxi * gxf;
-      const double lxtic = 0.5 * (ti + ti_e) / (fabs(ti - ti_e) * gxf + 100. * cutlo);
-      qsh = csh * (ti - ti_e) * (1. + lxtic / D.lxtimax);
-      qr = (1 - D.isflxldi) * fabs(qsh / qfl);
-      conxi = (1 - D.isflxldi) * csh / ((1 + qr) * (1 + qr)) + D.isflxldi * csh / ue_pow(1 + ue_pow(fabs(qsh / qfl), D.flgam), 1 / D.flgam);
-      floxi = floxi + (d_sgn(qr * qr, qsh) / ((1 + qr) * (1 + qr))) * D.flalfia[ix] * sx * (ne * rr * vt0 + ne_e * rr_e * vt1) / 2;
-    } else conxi = sx * hcxi * gxf;
-    floxe = floxe + D.cfcvte * 1.25 * (ne + ne_e) * vex * sx - 0.;
-    floxi = floxi + D.cfcvti * 2.5 * fnix;
-    floxi = floxi + D.cftiexclg * D.cfneut * D.cfneutsor_ei * D.cngtgx * D.cfcvti * 2.5 * fngx;
-    const int methex = (int)(D.methe % 10), methix = (int)(D.methi % 10);
-    double feex, feix;
-    if (methex == 2) feex = floxe * (te_e + te) / 2. - conxe * (te_e - te);
-    else feex = d_upwind(floxe, te, te_e) - conxe * (te_e - te);
-    if (methix == 2) feix = floxi * (ti_e + ti) / 2. - conxi * (ti_e - ti);
-    else feix = d_upwind(floxi, ti, ti_e) - conxi * (ti_e - ti);
-    a.set(PL_FEEX, ix, iy, feex); a.set(PL_FEIX, ix, iy, feix);
-  }
-  // ---- y-face energy fluxes (oderhs.m:4001-4006, 4078-4128, 4244-4249 + fd2tra) ------------------------------------
-  if (rfy) {
-    const double sy = GG(sy, ix, iy);
-    const double conye = sy * hcye / dynog, conyi = sy * hcyi / dynog;
-    double floye = 0. + (D.cfloye / 2.) * (ney0 + ney1) * vey * sy + (0. + 0.) * 0.5 * sy * (ney0 + ney1);
-    double floyi = 0. + D.cfloyi * fniy + (0. + 0.) * 0.5 * sy * (niy0 + niy1);
-    floyi = floyi + D.cftiexclg * D.cfneut * D.cfneutsor_ei * D.cngtgy * 2.5 * fngy;
-    const double te_n = a.get(PL_TE, ix, iy + 1), ti_n = a.get(PL_TI, ix, iy + 1);
-    const int methey = (int)(D.methe / 10), methiy = (int)(D.methi / 10);
-    double feey, feiy;
-    if (methey == 2) feey = floye * (te_n + te) / 2. - conye * (te_n - te);
-    else feey = d_upwind(floye, te, te_n) - conye * (te_n - te);
-    if (methiy == 2) feiy = floyi * (ti_n + ti) / 2. - conyi * (ti_n - ti);
-    else feiy = d_upwind(floyi, ti, ti_n) - conyi * (ti_n - ti);
-    a.set(PL_FEEY, ix, iy, feey); a.set(PL_FEIY, ix, iy, feiy);
-  }
+    floxi = floxi + (d_sgn(qr * qr, qsh) / ((1 + qr) * (1 + qr))) * D.flalfia[ix] * sx * (ne * rr * vt0 + ne_e * rr_e * vt1) / 2;
+  } else conxi = sx * hcxi * gxf;
+  floxi = floxi + D.cfcvti * 2.5 * f_fnix(a, ix, iy);
+  const double cg = D.cftiexclg * D.cfneut * D.cfneutsor_ei * D.cngtgx * D.cfcvti * 2.5;
+  floxi = floxi + ((cg != 0.) ? cg * f_fngx(a, ix, iy) : 0.);  // cg*fngx with cg == 0 adds an exact 0
+  double feix;
+  if ((int)(D.methi % 10) == 2) feix = floxi * (ti_e + ti) / 2. - conxi * (ti_e - ti);
+  else feix = d_upwind(floxi, ti, ti_e) - conxi * (ti_e - ti);
+  a.set(PL_FEIX, ix, iy, feix);
+}
+
+// ---- y-face energy fluxes (oderhs.m:2871-2899, 3010-3013, 4001-4006, 4078-4128, 4244-4249 + fd2tra) ------------
+template <bool WIN>
+__device__ void p1_ey(const Acc<WIN>& a, const Win& w, int ix, int iy) {
+  const int NXS = a.NXS;
+  const int ny = (int)D.ny;
+  const P1Rng r = p1_ranges(w, ix, iy);
+  if (!r.rfy) return;
+  const int iyp1 = min(ny + 1, iy + 1);
+  const double te = a.get(PL_TE, ix, iy), ti = a.get(PL_TI, ix, iy);
+  const double niy0 = a.get(PL_NIY0, ix, iy), niy1 = a.get(PL_NIY1, ix, iy);
+  const double ney0 = 0. + D.zi * niy0, ney1 = 0. + D.zi * niy1;
+  const double dynog = GG(dynog, ix, iy), sy = GG(sy, ix, iy);
+  const double gy = GG(gy, ix, iy), gy_p = GG(gy, ix, iyp1);
+  const double niavey = (niy0 * gy + niy1 * gy_p) / (gy + gy_p);
+  const double diffusivwrk = D.fcdif * D.difni + 0.;
+  double kyemix = D.fcdif * D.kye + 0.;
+  if (D.kyet > 1.e-20 && iy > D.iysptrx) kyemix = (1. - D.ckyet) * kyemix + D.ckyet * D.kyet * diffusivwrk;
+  const double hcye = 0. + (kyemix + 2.33 * (0. + 0.)) * D.zi * niavey;
+  double kyimix = D.fcdif * D.kyi + 0.;
+  if (D.kyit > 1.e-20 && iy > D.iysptrx) kyimix = (1. - D.ckyit) * kyimix + D.ckyit * D.kyit * diffusivwrk;
+  const double hcyij = 0. + (kyimix + (0. + 0.)) * niavey;
+  double hcyi = 0. + hcyij;
+  const double cn = D.cftiexclg * D.cfneut * D.cfneutsor_ei * D.kyn;
+  if (cn != 0.) {
+    const double ngy0 = f_ilog(a, Fld<WIN>::ng, ix, iy, 0), ngy1 = f_ilog(a, Fld<WIN>::ng, ix, iy, 1);
+    const double tiy0 = f_ilin(a, Fld<WIN>::ti, ix, iy, 0), tiy1 = f_ilin(a, Fld<WIN>::ti, ix, iy, 1);
+    hcyi = hcyi + cn * (ngy0 * tiy0 + ngy1 * tiy1) / (D.mi * (a.get(PL_NUCX, ix, iy) + a.get(PL_NUCX, ix, iyp1)));
+  } else hcyi = hcyi + 0.;
+  const double conye = sy * hcye / dynog, conyi = sy * hcyi / dynog;
+  const double vey = a.get(PL_VEY, ix, iy);
+  const double floye = 0. + (D.cfloye / 2.) * (ney0 + ney1) * vey * sy + (0. + 0.) * 0.5 * sy * (ney0 + ney1);
+  double floyi = 0. + D.cfloyi * f_fniy(a, ix, iy) + (0. + 0.) * 0.5 * sy * (niy0 + niy1);
+  const double cg = D.cftiexclg * D.cfneut * D.cfneutsor_ei * D.cngtgy * 2.5;
+  floyi = floyi + ((cg != 0.) ? cg * f_fngy(a, ix, iy) : 0.);
+  const double te_n = a.get(PL_TE, ix, iy + 1), ti_n = a.get(PL_TI, ix, iy + 1);
+  double feey, feiy;
+  if ((int)(D.methe / 10) == 2) feey = floye * (te_n + te) / 2. - conye * (te_n - te);
+  else feey = d_upwind(floye, te, te_n) - conye * (te_n - te);
+  if ((int)(D.methi / 10) == 2) feiy = floyi * (ti_n + ti) / 2. - conyi * (ti_n - ti);
+  else feiy = d_upwind(floyi, ti, ti_n) - conyi * (ti_n - ti);
+  a.set(PL_FEEY, ix, iy, feey); a.set(PL_FEIY, ix, iy, feiy);
 }
 
 // ---- momentum fluxes (oderhs.m:3483-3581), evaluated by the consumer cell -----------------------------------------------
@@ -667,137 +776,6 @@ template <bool WIN> __device__ inline double f_fmiy(const Acc<WIN>& a, int ix, i
   const double p0 = a.get(PL_UP, ix, iy), p1 = a.get(PL_UP, ix, iy + 1);
   if ((int)(D.methu / 10) == 2) return floy * (p1 + p0) / 2. - cony * (p1 - p0);
   return d_upwind(floy, p0, p1) - cony * (p1 - p0);
-}
-
-// ============================================================================================
-// phase 2a — interior cell: volume sources + flux divergences -> 5 rows (before rscalf)
-// ============================================================================================
-template <bool WIN>
-__device__ void phase2_interior(const Acc<WIN>& a, const Win& w, int ix, int iy, double out[UE_NV], const int64_t* __restrict__ iseqalg) {
-  const int NXS = a.NXS;
-  const int ny = (int)D.ny;
-  const double ev = D.ev;
-  const int ix1 = IXM1(ix, iy), ix2 = IXP1(ix, iy);
-  const double vol = GG(vol, ix, iy), gx = GG(gx, ix, iy), gxf = GG(gxf, ix, iy), gxf_w = GG(gxf, ix1, iy);
-  const double rrv = GG(rrv, ix, iy), rrv_w = GG(rrv, ix1, iy), sx = GG(sx, ix, iy);
-  const double ni = a.get(PL_NI, ix, iy), te = a.get(PL_TE, ix, iy), ti = a.get(PL_TI, ix, iy), ng = a.get(PL_NG, ix, iy);
-  const double up = a.get(PL_UP, ix, iy), up_w = a.get(PL_UP, ix1, iy);
-  const double ne = f_ne(a, ix, iy);
-  const double gpex = a.get(PL_GPEX, ix, iy), gpex_w = a.get(PL_GPEX, ix1, iy);
-  const double gpix = a.get(PL_GPIX, ix, iy), gpix_w = a.get(PL_GPIX, ix1, iy);
-  const double upe = a.get(PL_UPE, ix, iy), upe_w = a.get(PL_UPE, ix1, iy);
-  const double vey = a.get(PL_VEY, ix, iy);
-  // ---- seec, smoc, seic (oderhs.m:2471-2575) ----------------------------------------------------
-  double seec = 0., seic = 0., smoc = 0.;
-  {
-    const double gx_e = GG(gx, ix2, iy), gx_w = GG(gx, ix1, iy);
-    const double t1old = .5 * D.cvgp * (upe * rrv * d_ave(gx, gx_e) * gpex / gxf + upe_w * rrv_w * d_ave(gx, gx_w) * gpex_w / gxf_w);
-    const double t2old = 0.;
-    const int iyp1 = min(iy + 1, ny + 1), iym1 = max(iy - 1, 0);
-    const double vex = upe * rrv + 0. - 0., vex_w = upe_w * rrv_w + 0. - 0.;
-    const double t1new = .5 * D.cvgp * (vex * d_ave(gx, gx_e) * gpex / gxf + vex_w * d_ave(gx, gx_w) * gpex_w / gxf_w);
-    const double gy = GG(gy, ix, iy);
-    const double t2new = .5 * D.cvgp * (vey * d_ave(gy, GG(gy, ix, iyp1)) * a.get(PL_GPEY, ix, iy) / GG(gyf, ix, iy) +
-                                       vey * d_ave(gy, GG(gy, ix, iym1)) * a.get(PL_GPEY, ix, iym1) / GG(gyf, ix, iym1));
-    seec = seec + (t1old * vol - t2old) * D.oldseec + ((t1new + t2new) * vol) * (1 - D.oldseec);
-    smoc = ((-D.cpgx * gpex - 0.) * rrv + 0.) * sx / gxf;
-    double tv = gpix / gxf;
-    double t1 = gpix_w / gxf_w;
-    t1 = .5 * D.cvgp * (up * rrv * d_ave(gx_e, gx) * tv + up_w * rrv_w * d_ave(gx, gx_w) * t1);
-    seic = seic + D.cfvgpx * t1 * vol;
-    const double t0 = -D.cpiup * (gpix * rrv - 0.) * sx / gxf;
-    smoc = smoc + D.cpgx * t0;
-    tv = 0.25 * (a.get(PL_FRICE, ix, iy) + a.get(PL_FRICE, ix1, iy)) * (upe + upe_w - up - up_w);
-    const double nz2 = 0. + ni * (D.zi * D.zi);
-    seec = seec - (D.zi * D.zi) * ni * tv * vol / nz2;
-    const double t1y = .5 * D.cvgp * (a.get(PL_VY, ix, iy) * a.get(PL_GPIY, ix, iy) + a.get(PL_VY, ix, iy - 1) * a.get(PL_GPIY, ix, iy - 1) + 0. + 0.);
-    const double t2y = t1y;
-    seec = seec - D.fluxfacy * t1y * vol;
-    seic = seic + D.fluxfacy * D.cfvgpy * t2y * vol;
-  }
-  double psor, psorxr, psordis;
-  f_psor(a, ix, iy, psor, psorxr, psordis);
-  // ---- particle balance (oderhs.m:3407-3456) --------------------------------------------------------
-  double resco = 0. + 0. * ni + 0. + D.cfneut * D.cfneutsor_ni * D.cnsor * psor + D.cfneut * D.cfneutsor_ni * D.cnsor * psorxr +
-                 D.cfneut * D.cfneutsor_ni * D.cnsor * 0. - 0. + 0.;
-  resco = resco - ((a.get(PL_FNIX, ix, iy) - a.get(PL_FNIX, ix1, iy)) + D.fluxfacy * (a.get(PL_FNIY, ix, iy) - a.get(PL_FNIY, ix, iy - 1)));
-  a.set(PL_RESCO, ix, iy, resco);
-  // ---- neutral balance (oderhs.m:6587-6595) -----------------------------------------------------------
-  const double psorg = -psor, psorrg = -psorxr;
-  double resng = D.cngsor * (psorg + 0. + psorrg) + 0. + 0. * vol;
-  resng = resng - D.cfneutdiv * D.cfneutdiv_fng * ((a.get(PL_FNGX, ix, iy) - a.get(PL_FNGX, ix1, iy)) + D.fluxfacy * (a.get(PL_FNGY, ix, iy) - a.get(PL_FNGY, ix, iy - 1)));
-  // ---- momentum (oderhs.m:3746-3866) -------------------------------------------------------------------
-  const double ng_e = a.get(PL_NG, ix2, iy);
-  const double dp1 = D.cngmom * (1 / D.fac2sp) * (ng_e * f_tg(a, ix2, iy) - ng * f_tg(a, ix, iy));
-  double resmo = smoc + 0. * up - D.cfneut * D.cfneutsor_mi * sx * rrv * dp1 -
-                 D.cfneut * D.cfneutsor_mi * D.cmwall * 0.5 * (ng + ng_e) * D.mi * up * 0.5 * (a.get(PL_NUCX, ix, iy) + a.get(PL_NUCX, ix2, iy)) * GG(volv, ix, iy) +
-                 0. + D.cfmsor * (0. + 0.) + 0. + 0. + 0.;
-  resmo = resmo - (f_fmix(a, ix2, ix, iy) - f_fmix(a, ix, ix1, iy) + D.fluxfacy * (f_fmiy(a, ix, iy) - f_fmiy(a, ix, iy - 1)));
-  // ---- energy (oderhs.m:4300-4313, 4439-4478, 4519-4555, 4589-4640) ---------------------------------------
-  double resee = seec + 0. * te + 0. + 0. - 0.;
-  double resei = seic + 0. * ti + 0. + 0. - 0.;
-  resee = resee - (a.get(PL_FEEX, ix, iy) - a.get(PL_FEEX, ix1, iy) + D.fluxfacy * (a.get(PL_FEEY, ix, iy) - a.get(PL_FEEY, ix, iy - 1)));
-  resei = resei - (a.get(PL_FEIX, ix, iy) - a.get(PL_FEIX, ix1, iy) + D.fluxfacy * (a.get(PL_FEIY, ix, iy) - a.get(PL_FEIY, ix, iy - 1)));
-  const double psorrgc = -psorxr;
-  const double vsoree = -D.cfneut * D.cfneutsor_ee * D.cnsor * 13.6 * ev * D.fac2sp * psor + D.cfneut * D.cfneutsor_ee * D.cnsor * 13.6 * ev * D.fac2sp * psorrgc -
-                        D.cfneut * D.cfneutsor_ee * D.cnsor * a.get(PL_ERLIZ, ix, iy) - D.cfneut * D.cfneutsor_ee * D.cnsor * a.get(PL_ERLRC, ix, iy) -
-                        D.cfneut * D.cfneutsor_ee * D.cnsor * D.ediss * ev * (0.5 * psordis);
-  // equipartition (oderhs.m:3091-3101); loglambda of this cell's east and west faces
-  double eqp;
-  {
-    auto lnl = [&](int jx) {
-      const int je = IXP1(jx, iy);
-      const double teev = 0.5 * (a.get(PL_TE, jx, iy) + a.get(PL_TE, je, iy)) / ev;
-      const double nexface = 0.5 * (f_ne(a, jx, iy) + f_ne(a, je, iy));
-      if (D.islnlamcon == 1) return (double)D.lnlam;
-      if (teev < 50.) return 23.4 - 1.15 * ue_log10(1.e-6 * nexface) + 3.45 * ue_log10(teev);
-      return 25.3 - 1.15 * ue_log10(1.e-6 * nexface) + 2.33167537087122e+00 * ue_log10(teev);
-    };
-    const double w3 = 0.0 + ((D.zi * D.zi) / D.mi) * ni;
-    const double aa = fmax(te, D.temin * ev);
-    const double loglmcc = 0.5 * (lnl(ix) + lnl(ix1));
-    const double coef1 = D.feqp * 4.8e-15 * loglmcc * sqrt(ev) * ev * D.mp;
-    eqp = coef1 * w3 * ne / (aa * sqrt(aa));
-    const double d = aa - ti, s = D.alfeqp * (aa + ti);
-    eqp = eqp * (d * d) / (D.cutlo + d * d + s * s);
-  }
-  const double w0 = vol * eqp * (te - ti);
-  resee = resee - w0 + vsoree;
-  const double us = up + up_w;
-  resei = resei + w0 + D.cfneut * D.cfneutsor_ei * D.ctsor * 1.25e-1 * D.mi * (us * us) * D.fac2sp * psor + D.cfneut * D.cfneutsor_ei * D.ceisor * D.cnsor * D.eion * ev * psordis -
-          D.cfneut * D.cfneutsor_ei * D.ccoldsor * ng * a.get(PL_NUCX, ix, iy) * (1.5 * ti - 0.125 * D.mi * (us * us) - D.eion * ev) * vol;
-  // viscous heating (oderhs.m:4879-4930)
-  {
-    const int ixn = IXM1(ix, iy + 1), ixs = IXM1(ix, iy - 1);
-    const double thetacc = 0.5 * (0. + 0.);
-    const double dupdx = gx * (up - up_w);
-    double wvh = D.cfvcsx * D.cfvisx * ue_cos(thetacc) * a.get(PL_VISX, ix, iy) * (dupdx * dupdx);
-    double dupdy;
-    const int64_t isx = D.isxpty[ix + NXS * iy];
-    const double up_n = a.get(PL_UP, ix, iy + 1), up_nw = a.get(PL_UP, ixn, iy + 1), up_s = a.get(PL_UP, ix, iy - 1), up_sw = a.get(PL_UP, ixs, iy - 1);
-    if (isx == 0) dupdy = 0.5 * (up + up_w - up_s - up_sw) * GG(gyf, ix, iy - 1);
-    else if (isx == -1) dupdy = 0.5 * (up_n + up_nw - up - up_w) * GG(gyf, ix, iy);
-    else if (isx == 1 && D.isvhyha == 1) {
-      const double upxavep1 = 0.5 * (up_n + up_nw), upxave0 = 0.5 * (up + up_w), upxavem1 = 0.5 * (up_s + up_sw);
-      const double upf0 = 2. * upxavep1 * upxave0 * (upxavep1 + upxave0) / ((upxavep1 + upxave0) * (upxavep1 + upxave0) + D.upvhflr * D.upvhflr);
-      const double upfm1 = 2. * upxave0 * upxavem1 * (upxave0 + upxavem1) / ((upxave0 + upxavem1) * (upxave0 + upxavem1) + D.upvhflr * D.upvhflr);
-      dupdy = (upf0 - upfm1) * GG(gy, ix, iy);
-    } else
-      dupdy = 0.25 * ((up_n + up_nw - up - up_w) * GG(gyf, ix, iy) + (up + up_w - up_s - up_sw) * GG(gyf, ix, iy - 1));
-    const double visy = f_visy(a, ix, iy);
-    wvh = wvh + D.cfvcsy * D.cfvisy * visy * (dupdy * dupdy);
-    wvh = wvh - ue_ksin(thetacc) * D.cfvcsy * D.cfvisy * visy * dupdx * dupdy;
-    resei = resei + wvh * vol;
-  }
-  resei = resei + a.get(PL_PWRIBKG, ix, iy) * vol;
-  // ---- rows (oderhs.m:4953-4996) ---------------------------------------------------------------------------
-  const int64_t c = (int64_t)(ix + NXS * iy) * UE_NV;
-  out[0] = (1 - iseqalg[c + 0]) * resco / (vol * D.n0);
-  out[1] = (1 - iseqalg[c + 1]) * resmo / (GG(volv, ix, iy) * D.fnorm);
-  if (ix == D.ixrb) out[1] = resmo / (GG(volv, ix, iy) * D.fnorm);
-  out[2] = (1 - iseqalg[c + 2]) * resee / (vol * D.ennorm);
-  out[3] = (1 - iseqalg[c + 3]) * resei / (vol * D.ennorm);
-  out[4] = (1 - iseqalg[c + 4]) * resng / (vol * D.n0g);
 }
 
 // ============================================================================================
@@ -1061,6 +1039,171 @@ __device__ bool rightplate_up(const Acc<WIN>& a, const Win& w, int ix, int iy, d
   if (D.isupss == 1 && up2 + ueb > cs) val = D.nurlxu * (up2 - up1) / D.vpnorm;
   if (D.isupss == -1) val = D.nurlxu * (up2 - up1) / D.vpnorm;
   return true;
+}
+
+// ============================================================================================
+// phase 2a — interior cell rows (before rscalf), one ROLE per equation group so that four warps can
+// work on the same cell:  p2_n (ni, ng rows + resco)   p2_m (up row)   p2_e (te row)   p2_i (ti row)
+// ============================================================================================
+template <bool WIN> __device__ inline double f_eqp(const Acc<WIN>& a, int ix, int iy) {  // oderhs.m:3091-3101
+  const int NXS = a.NXS;
+  const double ev = D.ev;
+  const int ix1 = IXM1(ix, iy);
+  const double ni = a.get(PL_NI, ix, iy), te = a.get(PL_TE, ix, iy), ti = a.get(PL_TI, ix, iy);
+  const double w3 = 0.0 + ((D.zi * D.zi) / D.mi) * ni;
+  const double aa = fmax(te, D.temin * ev);
+  const double loglmcc = 0.5 * (f_loglambda(a, ix, iy) + f_loglambda(a, ix1, iy));
+  const double coef1 = D.feqp * 4.8e-15 * loglmcc * sqrt(ev) * ev * D.mp;
+  double eqp = coef1 * w3 * f_ne(a, ix, iy) / (aa * sqrt(aa));
+  const double d = aa - ti, s = D.alfeqp * (aa + ti);
+  eqp = eqp * (d * d) / (D.cutlo + d * d + s * s);
+  return eqp;
+}
+
+template <bool WIN>
+__device__ void p2_n(const Acc<WIN>& a, int ix, int iy, double out[UE_NV], const int64_t* __restrict__ iseqalg) {
+  const int NXS = a.NXS;
+  const int ix1 = IXM1(ix, iy);
+  const double vol = GG(vol, ix, iy);
+  const double ni = a.get(PL_NI, ix, iy);
+  double psor, psorxr, psordis;
+  f_psor(a, ix, iy, psor, psorxr, psordis);
+  // particle balance (oderhs.m:3407-3456)
+  double resco = 0. + 0. * ni + 0. + D.cfneut * D.cfneutsor_ni * D.cnsor * psor + D.cfneut * D.cfneutsor_ni * D.cnsor * psorxr +
+                 D.cfneut * D.cfneutsor_ni * D.cnsor * 0. - 0. + 0.;
+  resco = resco - ((a.get(PL_FNIX, ix, iy) - a.get(PL_FNIX, ix1, iy)) + D.fluxfacy * (a.get(PL_FNIY, ix, iy) - a.get(PL_FNIY, ix, iy - 1)));
+  a.set(PL_RESCO, ix, iy, resco);
+  // neutral balance (oderhs.m:6587-6595)
+  const double psorg = -psor, psorrg = -psorxr;
+  double resng = D.cngsor * (psorg + 0. + psorrg) + 0. + 0. * vol;
+  resng = resng - D.cfneutdiv * D.cfneutdiv_fng * ((a.get(PL_FNGX, ix, iy) - a.get(PL_FNGX, ix1, iy)) + D.fluxfacy * (a.get(PL_FNGY, ix, iy) - a.get(PL_FNGY, ix, iy - 1)));
+  const int64_t c = (int64_t)(ix + NXS * iy) * UE_NV;
+  out[0] = (1 - iseqalg[c + 0]) * resco / (vol * D.n0);
+  out[4] = (1 - iseqalg[c + 4]) * resng / (vol * D.n0g);
+}
+
+template <bool WIN>
+__device__ void p2_m(const Acc<WIN>& a, const Win& w, int ix, int iy, double out[UE_NV], const int64_t* __restrict__ iseqalg) {
+  const int NXS = a.NXS;
+  const int ix1 = IXM1(ix, iy), ix2 = IXP1(ix, iy);
+  const double gxf = GG(gxf, ix, iy), rrv = GG(rrv, ix, iy), sx = GG(sx, ix, iy);
+  const double ng = a.get(PL_NG, ix, iy), up = a.get(PL_UP, ix, iy);
+  // momentum source (oderhs.m:2496-2498, 2521-2525)
+  double smoc = ((-D.cpgx * a.get(PL_GPEX, ix, iy) - 0.) * rrv + 0.) * sx / gxf;
+  const double t0 = -D.cpiup * (a.get(PL_GPIX, ix, iy) * rrv - 0.) * sx / gxf;
+  smoc = smoc + D.cpgx * t0;
+  // oderhs.m:3746-3866
+  const double ng_e = a.get(PL_NG, ix2, iy);
+  const double dp1 = D.cngmom * (1 / D.fac2sp) * (ng_e * f_tg(a, ix2, iy) - ng * f_tg(a, ix, iy));
+  double resmo = smoc + 0. * up - D.cfneut * D.cfneutsor_mi * sx * rrv * dp1 -
+                 D.cfneut * D.cfneutsor_mi * D.cmwall * 0.5 * (ng + ng_e) * D.mi * up * 0.5 * (a.get(PL_NUCX, ix, iy) + a.get(PL_NUCX, ix2, iy)) * GG(volv, ix, iy) +
+                 0. + D.cfmsor * (0. + 0.) + 0. + 0. + 0.;
+  resmo = resmo - (f_fmix(a, ix2, ix, iy) - f_fmix(a, ix, ix1, iy) + D.fluxfacy * (f_fmiy(a, ix, iy) - f_fmiy(a, ix, iy - 1)));
+  const int64_t c = (int64_t)(ix + NXS * iy) * UE_NV;
+  out[1] = (1 - iseqalg[c + 1]) * resmo / (GG(volv, ix, iy) * D.fnorm);
+  if (ix == D.ixrb) out[1] = resmo / (GG(volv, ix, iy) * D.fnorm);
+  double v;
+  if (rightplate_up<WIN>(a, w, ix, iy, v)) out[1] = v;
+}
+
+template <bool WIN>
+__device__ void p2_e(const Acc<WIN>& a, int ix, int iy, double out[UE_NV], const int64_t* __restrict__ iseqalg) {
+  const int NXS = a.NXS;
+  const int ny = (int)D.ny;
+  const double ev = D.ev;
+  const int ix1 = IXM1(ix, iy), ix2 = IXP1(ix, iy);
+  const double vol = GG(vol, ix, iy), gx = GG(gx, ix, iy), gxf = GG(gxf, ix, iy), gxf_w = GG(gxf, ix1, iy);
+  const double rrv = GG(rrv, ix, iy), rrv_w = GG(rrv, ix1, iy);
+  const double ni = a.get(PL_NI, ix, iy), te = a.get(PL_TE, ix, iy), ti = a.get(PL_TI, ix, iy);
+  const double up = a.get(PL_UP, ix, iy), up_w = a.get(PL_UP, ix1, iy);
+  const double gpex = a.get(PL_GPEX, ix, iy), gpex_w = a.get(PL_GPEX, ix1, iy);
+  const double upe = a.get(PL_UPE, ix, iy), upe_w = a.get(PL_UPE, ix1, iy);
+  const double vey = a.get(PL_VEY, ix, iy);
+  double seec = 0.;
+  {  // oderhs.m:2471-2495, 2534-2538, 2557-2572
+    const double gx_e = GG(gx, ix2, iy), gx_w = GG(gx, ix1, iy);
+    const double t1old = .5 * D.cvgp * (upe * rrv * d_ave(gx, gx_e) * gpex / gxf + upe_w * rrv_w * d_ave(gx, gx_w) * gpex_w / gxf_w);
+    const double t2old = 0.;
+    const int iyp1 = min(iy + 1, ny + 1), iym1 = max(iy - 1, 0);
+    const double vex = upe * rrv + 0. - 0., vex_w = upe_w * rrv_w + 0. - 0.;
+    const double t1new = .5 * D.cvgp * (vex * d_ave(gx, gx_e) * gpex / gxf + vex_w * d_ave(gx, gx_w) * gpex_w / gxf_w);
+    const double gy = GG(gy, ix, iy);
+    const double t2new = .5 * D.cvgp * (vey * d_ave(gy, GG(gy, ix, iyp1)) * a.get(PL_GPEY, ix, iy) / GG(gyf, ix, iy) +
+                                       vey * d_ave(gy, GG(gy, ix, iym1)) * a.get(PL_GPEY, ix, iym1) / GG(gyf, ix, iym1));
+    seec = seec + (t1old * vol - t2old) * D.oldseec + ((t1new + t2new) * vol) * (1 - D.oldseec);
+    const double tv = 0.25 * (a.get(PL_FRICE, ix, iy) + a.get(PL_FRICE, ix1, iy)) * (upe + upe_w - up - up_w);
+    const double nz2 = 0. + ni * (D.zi * D.zi);
+    seec = seec - (D.zi * D.zi) * ni * tv * vol / nz2;
+    const double t1y = .5 * D.cvgp * (a.get(PL_VY, ix, iy) * a.get(PL_GPIY, ix, iy) + a.get(PL_VY, ix, iy - 1) * a.get(PL_GPIY, ix, iy - 1) + 0. + 0.);
+    seec = seec - D.fluxfacy * t1y * vol;
+  }
+  double psor, psorxr, psordis;
+  f_psor(a, ix, iy, psor, psorxr, psordis);
+  double resee = seec + 0. * te + 0. + 0. - 0.;
+  resee = resee - (a.get(PL_FEEX, ix, iy) - a.get(PL_FEEX, ix1, iy) + D.fluxfacy * (a.get(PL_FEEY, ix, iy) - a.get(PL_FEEY, ix, iy - 1)));
+  const double psorrgc = -psorxr;
+  const double vsoree = -D.cfneut * D.cfneutsor_ee * D.cnsor * 13.6 * ev * D.fac2sp * psor + D.cfneut * D.cfneutsor_ee * D.cnsor * 13.6 * ev * D.fac2sp * psorrgc -
+                        D.cfneut * D.cfneutsor_ee * D.cnsor * a.get(PL_ERLIZ, ix, iy) - D.cfneut * D.cfneutsor_ee * D.cnsor * a.get(PL_ERLRC, ix, iy) -
+                        D.cfneut * D.cfneutsor_ee * D.cnsor * D.ediss * ev * (0.5 * psordis);
+  const double w0 = vol * f_eqp(a, ix, iy) * (te - ti);
+  resee = resee - w0 + vsoree;
+  const int64_t c = (int64_t)(ix + NXS * iy) * UE_NV;
+  out[2] = (1 - iseqalg[c + 2]) * resee / (vol * D.ennorm);
+}
+
+template <bool WIN>
+__device__ void p2_i(const Acc<WIN>& a, int ix, int iy, double out[UE_NV], const int64_t* __restrict__ iseqalg) {
+  const int NXS = a.NXS;
+  const double ev = D.ev;
+  const int ix1 = IXM1(ix, iy), ix2 = IXP1(ix, iy);
+  const double vol = GG(vol, ix, iy), gx = GG(gx, ix, iy), gxf = GG(gxf, ix, iy), gxf_w = GG(gxf, ix1, iy);
+  const double rrv = GG(rrv, ix, iy), rrv_w = GG(rrv, ix1, iy);
+  const double te = a.get(PL_TE, ix, iy), ti = a.get(PL_TI, ix, iy), ng = a.get(PL_NG, ix, iy);
+  const double up = a.get(PL_UP, ix, iy), up_w = a.get(PL_UP, ix1, iy);
+  double seic = 0.;
+  {  // oderhs.m:2514-2520, 2557-2574
+    const double gx_e = GG(gx, ix2, iy), gx_w = GG(gx, ix1, iy);
+    const double tv = a.get(PL_GPIX, ix, iy) / gxf;
+    double t1 = a.get(PL_GPIX, ix1, iy) / gxf_w;
+    t1 = .5 * D.cvgp * (up * rrv * d_ave(gx_e, gx) * tv + up_w * rrv_w * d_ave(gx, gx_w) * t1);
+    seic = seic + D.cfvgpx * t1 * vol;
+    const double t1y = .5 * D.cvgp * (a.get(PL_VY, ix, iy) * a.get(PL_GPIY, ix, iy) + a.get(PL_VY, ix, iy - 1) * a.get(PL_GPIY, ix, iy - 1) + 0. + 0.);
+    const double t2y = t1y;
+    seic = seic + D.fluxfacy * D.cfvgpy * t2y * vol;
+  }
+  double psor, psorxr, psordis;
+  f_psor(a, ix, iy, psor, psorxr, psordis);
+  double resei = seic + 0. * ti + 0. + 0. - 0.;
+  resei = resei - (a.get(PL_FEIX, ix, iy) - a.get(PL_FEIX, ix1, iy) + D.fluxfacy * (a.get(PL_FEIY, ix, iy) - a.get(PL_FEIY, ix, iy - 1)));
+  const double w0 = vol * f_eqp(a, ix, iy) * (te - ti);
+  const double us = up + up_w;
+  resei = resei + w0 + D.cfneut * D.cfneutsor_ei * D.ctsor * 1.25e-1 * D.mi * (us * us) * D.fac2sp * psor + D.cfneut * D.cfneutsor_ei * D.ceisor * D.cnsor * D.eion * ev * psordis -
+          D.cfneut * D.cfneutsor_ei * D.ccoldsor * ng * a.get(PL_NUCX, ix, iy) * (1.5 * ti - 0.125 * D.mi * (us * us) - D.eion * ev) * vol;
+  {  // viscous heating (oderhs.m:4879-4930)
+    const int ixn = IXM1(ix, iy + 1), ixs = IXM1(ix, iy - 1);
+    const double thetacc = 0.5 * (0. + 0.);
+    const double dupdx = gx * (up - up_w);
+    double wvh = D.cfvcsx * D.cfvisx * ue_cos(thetacc) * a.get(PL_VISX, ix, iy) * (dupdx * dupdx);
+    double dupdy;
+    const int64_t isx = D.isxpty[ix + NXS * iy];
+    const double up_n = a.get(PL_UP, ix, iy + 1), up_nw = a.get(PL_UP, ixn, iy + 1), up_s = a.get(PL_UP, ix, iy - 1), up_sw = a.get(PL_UP, ixs, iy - 1);
+    if (isx == 0) dupdy = 0.5 * (up + up_w - up_s - up_sw) * GG(gyf, ix, iy - 1);
+    else if (isx == -1) dupdy = 0.5 * (up_n + up_nw - up - up_w) * GG(gyf, ix, iy);
+    else if (isx == 1 && D.isvhyha == 1) {
+      const double upxavep1 = 0.5 * (up_n + up_nw), upxave0 = 0.5 * (up + up_w), upxavem1 = 0.5 * (up_s + up_sw);
+      const double upf0 = 2. * upxavep1 * upxave0 * (upxavep1 + upxave0) / ((upxavep1 + upxave0) * (upxavep1 + upxave0) + D.upvhflr * D.upvhflr);
+      const double upfm1 = 2. * upxave0 * upxavem1 * (upxave0 + upxavem1) / ((upxave0 + upxavem1) * (upxave0 + upxavem1) + D.upvhflr * D.upvhflr);
+      dupdy = (upf0 - upfm1) * GG(gy, ix, iy);
+    } else
+      dupdy = 0.25 * ((up_n + up_nw - up - up_w) * GG(gyf, ix, iy) + (up + up_w - up_s - up_sw) * GG(gyf, ix, iy - 1));
+    const double visy = f_visy(a, ix, iy);
+    wvh = wvh + D.cfvcsy * D.cfvisy * visy * (dupdy * dupdy);
+    wvh = wvh - ue_ksin(thetacc) * D.cfvcsy * D.cfvisy * visy * dupdx * dupdy;
+    resei = resei + wvh * vol;
+  }
+  resei = resei + a.get(PL_PWRIBKG, ix, iy) * vol;
+  const int64_t c = (int64_t)(ix + NXS * iy) * UE_NV;
+  out[3] = (1 - iseqalg[c + 3]) * resei / (vol * D.ennorm);
 }
 
 // ============================================================================================

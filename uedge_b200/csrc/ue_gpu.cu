@@ -52,7 +52,6 @@ int *d_rowcnt = nullptr, *d_rowfill = nullptr;
 int64_t *d_ia = nullptr, *d_ja = nullptr;
 double* d_jac = nullptr;
 int64_t g_cap_total = 0, g_nnzcap = 0;
-int g_box_narrow = 0, g_box_wide = 0, g_ext_narrow = 0, g_ext_wide = 0;
 size_t g_smem_narrow = 0, g_smem_wide = 0;
 
 #define CK(call)                                                                                   \
@@ -80,37 +79,55 @@ int dev_copy(const T* h, size_t n, const T** out) {
 __global__ void k_phase0(double* base, const double* __restrict__ yl, int NXS, int NC, int* err) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= NC) return;
-  Acc<false> a{base, nullptr, NXS, NC, 0, 0, 0, 0};
+  Acc<false> a; a.base = base; a.NXS = NXS; a.NC = NC;
   phase0_cell<false>(a, yl + (size_t)c * UE_NV, c % NXS, c / NXS, err);
 }
-__global__ void k_phase1(double* base, int NXS, int NC) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= NC) return;
-  Acc<false> a{base, nullptr, NXS, NC, 0, 0, 0, 0};
+// phase 1: 32 cells per block, one ROLE per warp (lane = cell); 1b reads only same-cell outputs of 1a
+__global__ void __launch_bounds__(160) k_phase1(double* base, int NXS, int NC) {
+  const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  Acc<false> a; a.base = base; a.NXS = NXS; a.NC = NC;
   const Win w = make_win(D, -1, -1);
-  phase1_cell<false>(a, w, c % NXS, c / NXS);
+  const int ix = c % NXS, iy = c / NXS;
+  if (c < NC) {
+    if (role == 0) p1_xpart<false>(a, w, ix, iy);
+    else if (role == 1) p1_ypart<false>(a, w, ix, iy);
+    else if (role == 2) p1_visx<false>(a, w, ix, iy);
+  }
+  __syncthreads();
+  if (c < NC) {
+    if (role == 0) p1_fx<false>(a, w, ix, iy);
+    else if (role == 1) p1_fy<false>(a, w, ix, iy);
+    else if (role == 2) p1_exe<false>(a, w, ix, iy);
+    else if (role == 3) p1_exi<false>(a, w, ix, iy);
+    else p1_ey<false>(a, w, ix, iy);
+  }
 }
-__global__ void k_phase2(double* base, double* __restrict__ tmp, int NXS, int NC) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// phase 2: 32 cells per block, four role-warps (equation groups); guard cells go to role 0
+__global__ void __launch_bounds__(128) k_phase2(double* base, double* __restrict__ tmp, int NXS, int NC) {
+  const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   if (c >= NC) return;
-  Acc<false> a{base, nullptr, NXS, NC, 0, 0, 0, 0};
+  Acc<false> a; a.base = base; a.NXS = NXS; a.NC = NC;
   const Win w = make_win(D, -1, -1);
   const int ix = c % NXS, iy = c / NXS;
   double r[UE_NV] = {0., 0., 0., 0., 0.};
+  double* o = tmp + (size_t)c * UE_NV;
   if (ix >= 1 && ix <= D.nx && iy >= 1 && iy <= D.ny) {
-    phase2_interior<false>(a, w, ix, iy, r, D.iseqalg);
-    double v;
-    if (rightplate_up<false>(a, w, ix, iy, v)) r[1] = v;
-  } else {
+    if (role == 0) { p2_n<false>(a, ix, iy, r, D.iseqalg); o[0] = r[0]; o[4] = r[4]; }
+    else if (role == 1) { p2_m<false>(a, w, ix, iy, r, D.iseqalg); o[1] = r[1]; }
+    else if (role == 2) { p2_e<false>(a, ix, iy, r, D.iseqalg); o[2] = r[2]; }
+    else { p2_i<false>(a, ix, iy, r, D.iseqalg); o[3] = r[3]; }
+  } else if (role == 0) {
     phase2_guard<false>(a, w, ix, iy, r);
+    for (int k = 0; k < UE_NV; ++k) o[k] = r[k];
   }
-  for (int k = 0; k < UE_NV; ++k) tmp[(size_t)c * UE_NV + k] = r[k];
 }
 __global__ void k_phase3(double* base, const double* __restrict__ tmp, double* __restrict__ yldot, const double* __restrict__ yl,
                          const double* __restrict__ dtuse, const double* __restrict__ ylodt, int64_t neq, int NXS, int NC) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= NC) return;
-  Acc<false> a{base, nullptr, NXS, NC, 0, 0, 0, 0};
+  Acc<false> a; a.base = base; a.NXS = NXS; a.NC = NC;
   const int ix = c % NXS, iy = c / NXS;
   double r[UE_NV];
   for (int k = 0; k < UE_NV; ++k) r[k] = tmp[(size_t)c * UE_NV + k];
@@ -119,132 +136,202 @@ __global__ void k_phase3(double* base, const double* __restrict__ tmp, double* _
 }
 
 // ------------------------------------------------------------------------------------------------
-// batched Jacobian kernel: one block per perturbed unknown
+// batched Jacobian kernel.  A block takes NP perturbed unknowns; 8 warps.  Only the four cells whose
+// phase-1 fields can change are recomputed (lane = (perturbation, cell), warp = role), then the candidate
+// rows of a small rectangle around the perturbed cell (regular windows: 5 x 3 cells; windows touching an
+// X-point cut or the integrated core-flux rows: all ix x 3 rows).
 // ------------------------------------------------------------------------------------------------
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_jac(const int* __restrict__ ivlist, double* base, const double* __restrict__ yl,
-                                               const double* __restrict__ yldot00, const double* __restrict__ suscal,
-                                               const double* __restrict__ sfscal, const double* __restrict__ dtuse,
-                                               const double* __restrict__ ylodt, int64_t neq, int64_t ml, int64_t mu, int NXS, int NC,
-                                               const int64_t* __restrict__ coloff, int* __restrict__ colcnt, int* __restrict__ colrow,
-                                               double* __restrict__ colval, int* __restrict__ rowcnt, int* err) {
+struct PInfo {
+  Win w;
+  int64_t iv;
+  int xc, yc, xw, xe, rx0, ry0, rw, rh;
+  double yold, dyl;
+};
+__host__ __device__ inline void cand_rect(const UeParams& P, const Win& w, int xc, int yc, bool wide, int& rx0, int& ry0, int& rw, int& rh) {
+  const int nx = (int)P.nx, ny = (int)P.ny;
+  ry0 = yc - 1 < 0 ? 0 : yc - 1;
+  const int ry1 = yc + 1 > ny + 1 ? ny + 1 : yc + 1;
+  rh = ry1 - ry0 + 1;
+  if (wide) { rx0 = 0; rw = nx + 2; }
+  else { rx0 = xc - 2 < 0 ? 0 : xc - 2; const int rx1 = xc + 2 > nx + 1 ? nx + 1 : xc + 2; rw = rx1 - rx0 + 1; }
+}
+__host__ __device__ inline bool is_wide(const UeParams& P, const Win& w, int yc) { return w.xccuts || (P.iflcore == 1 && yc <= 1); }
+
+template <int NP>
+__global__ void __launch_bounds__(256) k_jac(const int* __restrict__ ivlist, int nlist, int ncand_max, double* base, const double* __restrict__ yl,
+                                             const double* __restrict__ yldot00, const double* __restrict__ suscal, const double* __restrict__ sfscal,
+                                             const double* __restrict__ dtuse, const double* __restrict__ ylodt, int64_t neq, int64_t ml, int64_t mu, int NXS,
+                                             int NC, const int64_t* __restrict__ coloff, int* __restrict__ colcnt, int* __restrict__ colrow,
+                                             double* __restrict__ colval, int* __restrict__ rowcnt, int* err) {
   extern __shared__ double smem[];
-  __shared__ int s_scan[BLOCK];
-  const int tid = threadIdx.x;
-  const int64_t iv = ivlist[blockIdx.x];  // 1-based unknown
-  const int xc = (int)D.igyl[iv - 1], yc = (int)D.igyl[neq + iv - 1];
-  const Win w = make_win(D, xc, yc);
-  const int nxx = (int)D.nx, nyy = (int)D.ny;
-  Acc<true> a;
-  a.base = base; a.NXS = NXS; a.NC = NC;
-  a.bx0 = w.i1; a.by0 = w.j1; a.bw = w.i6 - w.i1 + 1; a.bh = w.j6 - w.j1 + 1;
-  const int bsz = a.bw * a.bh;
-  a.sm = smem;
-  // extended box of candidate rows
-  const int ex0 = max(0, w.i2 - 1), ex1 = min(nxx + 1, w.i5 + 1), ey0 = max(0, w.j2 - 1), ey1 = min(nyy + 1, w.j5 + 1);
-  const int ew = ex1 - ex0 + 1, eh = ey1 - ey0 + 1, ecells = ew * eh;
-  double* rows = smem + (size_t)PL_COUNT * bsz;          // [ecells][UE_NV]
-  int* rmask = (int*)(rows + (size_t)ecells * UE_NV);     // [ecells]
-  // ---- stage the window box of every field from the base planes -------------------------------
-  for (int q = tid; q < PL_COUNT * bsz; q += BLOCK) {
-    const int pl = q / bsz, l = q - pl * bsz;
-    const int lx = l % a.bw, ly = l / a.bw;
-    smem[q] = base[(size_t)pl * NC + (a.bx0 + lx) + NXS * (a.by0 + ly)];
-  }
-  // ---- perturbation (oderhs.m:8676-8678) -------------------------------------------------------
-  const double yold = yl[iv - 1];
-  const double dyl = D.delpert * (fabs(yold) + D.dylconst / suscal[iv - 1]);
-  __syncthreads();
-  if (tid == 0) {
-    double ycell[UE_NV];
-    const int64_t c = (int64_t)(xc + NXS * yc) * UE_NV;
-    for (int k = 0; k < UE_NV; ++k) ycell[k] = yl[c + k];
-    ycell[(iv - 1) - c] = yold + dyl;
-    phase0_cell<true>(a, ycell, xc, yc, err);
+  __shared__ PInfo pinfo[NP];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* sm4 = smem;                                           // [NP][4][PL_COUNT]
+  double* rows = sm4 + (size_t)NP * 4 * PL_COUNT;               // [NP][ncand_max][UE_NV]
+  double* rres = rows + (size_t)NP * ncand_max * UE_NV;         // [NP][ncand_max]
+  int* rmask = (int*)(rres + (size_t)NP * ncand_max);           // [NP][ncand_max]
+  const int p0 = blockIdx.x * NP;
+  const int np = min(NP, nlist - p0);
+  if (tid < np) {
+    PInfo& q = pinfo[tid];
+    q.iv = ivlist[p0 + tid];
+    q.xc = (int)D.igyl[q.iv - 1]; q.yc = (int)D.igyl[neq + q.iv - 1];
+    q.w = make_win(D, q.xc, q.yc);
+    q.xw = IXM1(q.xc, q.yc); q.xe = IXP1(q.xc, q.yc);
+    cand_rect(D, q.w, q.xc, q.yc, is_wide(D, q.w, q.yc), q.rx0, q.ry0, q.rw, q.rh);
+    q.yold = yl[q.iv - 1];
+    q.dyl = D.delpert * (fabs(q.yold) + D.dylconst / suscal[q.iv - 1]);  // oderhs.m:8676-8678
   }
   __syncthreads();
-  // ---- phase 1 over the box ----------------------------------------------------------------------
-  for (int l = tid; l < bsz; l += BLOCK) phase1_cell<true>(a, w, a.bx0 + l % a.bw, a.by0 + l / a.bw);
-  __syncthreads();
-  // ---- phase 2 over the extended box ---------------------------------------------------------------
-  for (int l = tid; l < ecells; l += BLOCK) {
-    const int ix = ex0 + l % ew, iy = ey0 + l / ew;
-    double r[UE_NV] = {0., 0., 0., 0., 0.};
-    int m = 0;
-    if (ix >= 1 && ix <= nxx && iy >= 1 && iy <= nyy) {
-      if (in_rng(ix, w.i2, w.i5) && in_rng(iy, w.j2, w.j5)) {
-        phase2_interior<true>(a, w, ix, iy, r, D.iseqalg);
-        m = 0x1f;
-        double v;
-        if (rightplate_up<true>(a, w, ix, iy, v)) r[1] = v;
-      }
-    } else {
-      m = phase2_guard<true>(a, w, ix, iy, r);
-    }
-    for (int k = 0; k < UE_NV; ++k) rows[(size_t)l * UE_NV + k] = r[k];
-    rmask[l] = m;
-  }
-  __syncthreads();
-  // ---- phase 3 (rscalf + dt term) on interior cells of the window --------------------------------------
-  // the perturbed yl differs from yl only in entry iv; rscalf / the dt term read yl of their own cell only
-  for (int l = tid; l < ecells; l += BLOCK) {
-    const int ix = ex0 + l % ew, iy = ey0 + l / ew;
-    if (ix >= 1 && ix <= nxx && iy >= 1 && iy <= nyy && in_rng(ix, w.i2, w.i5) && in_rng(iy, w.j2, w.j5)) {
-      double r[UE_NV], ycell[UE_NV];
-      const int64_t c = (int64_t)(ix + NXS * iy) * UE_NV;
-      for (int k = 0; k < UE_NV; ++k) { r[k] = rows[(size_t)l * UE_NV + k]; ycell[k] = yl[c + k]; }
-      if (ix == xc && iy == yc) ycell[(iv - 1) - c] = yold + dyl;
-      phase3_interior<true>(a, ix, iy, r, ycell, yl[neq], D.iseqalg, dtuse, ylodt);
-      for (int k = 0; k < UE_NV; ++k) rows[(size_t)l * UE_NV + k] = r[k];
-    }
-  }
-  __syncthreads();
-  // ---- difference, clip, ordered compaction into this column's CSC fragment (oderhs.m:8685-8719) -------------
-  const int64_t ii1 = max(iv - mu, (int64_t)1), ii2 = min(iv + ml, neq);
-  const int ncand = ecells * UE_NV;
-  const int chunk = (ncand + BLOCK - 1) / BLOCK;
-  const int q0 = tid * chunk, q1 = min(ncand, q0 + chunk);
-  const double sf = sfscal[iv - 1];
-  auto eval = [&](int q, double& val, int64_t& ii) -> bool {
-    const int l = q / UE_NV, k = q - l * UE_NV;
-    const int ix = ex0 + l % ew, iy = ey0 + l / ew;
-    ii = ((int64_t)(ix + NXS * iy)) * UE_NV + k + 1;
-    if (ii < ii1 || ii > ii2) return false;
-    const bool written = (rmask[l] >> k) & 1;
-    if (!written && ii != iv) return false;
-    const double y00 = yldot00[ii - 1];
-    const double wk = written ? rows[q] : y00;
-    double jacelem = (wk - y00) / dyl;
-    if (ii == iv) {
-      if (D.iseqalg[iv - 1] * (1 - D.isbcwdt) == 0) jacelem = jacelem - 1 / dtuse[iv - 1];
-      if (D.nufak > 0 && yl[neq] == 1) jacelem = jacelem - D.nufak;
-    }
-    val = jacelem;
-    return fabs(jacelem * sf) > D.jaccliplim;
+  auto make_acc = [&](int p) {
+    const PInfo& q = pinfo[p];
+    Acc<true> a;
+    a.base = base; a.NXS = NXS; a.NC = NC;
+    a.sm4 = sm4 + (size_t)p * 4 * PL_COUNT;
+    a.xc = q.xc; a.yc = q.yc; a.xw = q.xw; a.xe = q.xe;
+    a.rres = rres + (size_t)p * ncand_max; a.rmask = rmask + (size_t)p * ncand_max;
+    a.rx0 = q.rx0; a.ry0 = q.ry0; a.rw = q.rw; a.rh = q.rh;
+    return a;
   };
-  int cnt = 0;
-  for (int q = q0; q < q1; ++q) { double v; int64_t ii; if (eval(q, v, ii)) ++cnt; }
-  s_scan[tid] = cnt;
-  __syncthreads();
-  // exclusive scan (BLOCK <= 512; simple Hillis-Steele)
-  for (int off = 1; off < BLOCK; off <<= 1) {
-    int v = (tid >= off) ? s_scan[tid - off] : 0;
-    __syncthreads();
-    s_scan[tid] += v;
-    __syncthreads();
+  auto slot_cell = [&](const PInfo& q, int k, int& ix, int& iy) -> bool {  // false: slot duplicates another or does not exist
+    iy = q.yc; ix = q.xc;
+    if (k == 1) { ix = q.xw; return q.xw != q.xc; }
+    if (k == 2) { ix = q.xe; return q.xe != q.xc && q.xe != q.xw; }
+    if (k == 3) { iy = q.yc - 1; return q.yc >= 1; }
+    return true;
+  };
+  // ---- stage the four private cells from the base planes; clear the candidate masks ------------------
+  for (int i = tid; i < np * 4 * PL_COUNT; i += 256) {
+    const int p = i / (4 * PL_COUNT), k = (i / PL_COUNT) & 3, pl = i % PL_COUNT;
+    int ix, iy;
+    slot_cell(pinfo[p], k, ix, iy);
+    if (iy < 0) iy = 0;
+    sm4[i] = base[(size_t)pl * NC + ix + NXS * iy];
   }
-  int pos = s_scan[tid] - cnt;
-  const int64_t o = coloff[iv - 1];
-  for (int q = q0; q < q1; ++q) {
-    double v; int64_t ii;
-    if (eval(q, v, ii)) {
-      colrow[o + pos] = (int)ii;
-      colval[o + pos] = v;
-      atomicAdd(&rowcnt[ii - 1], 1);
-      ++pos;
+  for (int i = tid; i < np * ncand_max; i += 256) rmask[(i / ncand_max) * ncand_max + i % ncand_max] = 0;
+  __syncthreads();
+  // ---- phase 0 on the perturbed cell --------------------------------------------------------------------
+  if (tid < np) {
+    const PInfo& q = pinfo[tid];
+    const Acc<true> a = make_acc(tid);
+    double ycell[UE_NV];
+    const int64_t c = (int64_t)(q.xc + NXS * q.yc) * UE_NV;
+    for (int k = 0; k < UE_NV; ++k) ycell[k] = yl[c + k];
+    ycell[(q.iv - 1) - c] = q.yold + q.dyl;
+    phase0_cell<true>(a, ycell, q.xc, q.yc, err);
+  }
+  __syncthreads();
+  // ---- phase 1a / 1b: warp = role, lane = (perturbation, slot) ----------------------------------------------
+  for (int it = lane; it < np * 4; it += 32) {
+    const int p = it >> 2, k = it & 3;
+    int ix, iy;
+    if (!slot_cell(pinfo[p], k, ix, iy)) continue;
+    const Acc<true> a = make_acc(p);
+    if (warp == 0) p1_xpart<true>(a, pinfo[p].w, ix, iy);
+    else if (warp == 1) p1_ypart<true>(a, pinfo[p].w, ix, iy);
+    else if (warp == 2) p1_visx<true>(a, pinfo[p].w, ix, iy);
+  }
+  __syncthreads();
+  for (int it = lane; it < np * 4; it += 32) {
+    const int p = it >> 2, k = it & 3;
+    int ix, iy;
+    if (!slot_cell(pinfo[p], k, ix, iy)) continue;
+    const Acc<true> a = make_acc(p);
+    if (warp == 0) p1_fx<true>(a, pinfo[p].w, ix, iy);
+    else if (warp == 1) p1_fy<true>(a, pinfo[p].w, ix, iy);
+    else if (warp == 2) p1_exe<true>(a, pinfo[p].w, ix, iy);
+    else if (warp == 3) p1_exi<true>(a, pinfo[p].w, ix, iy);
+    else if (warp == 4) p1_ey<true>(a, pinfo[p].w, ix, iy);
+  }
+  __syncthreads();
+  // ---- phase 2 over the candidate rows: role = warp & 3, two warps per role split the items ------------------
+  {
+    const int role = warp & 3, half = warp >> 2;
+    const int nitems = np * ncand_max;
+    for (int it = lane + 32 * half; it < nitems; it += 64) {
+      const int p = it / ncand_max, l = it - p * ncand_max;
+      const PInfo& q = pinfo[p];
+      if (l >= q.rw * q.rh) continue;
+      const int ix = q.rx0 + l % q.rw, iy = q.ry0 + l / q.rw;
+      const Acc<true> a = make_acc(p);
+      double r[UE_NV] = {0., 0., 0., 0., 0.};
+      double* o = rows + ((size_t)p * ncand_max + l) * UE_NV;
+      int* mk = rmask + (size_t)p * ncand_max + l;
+      if (ix >= 1 && ix <= D.nx && iy >= 1 && iy <= D.ny) {
+        if (in_rng(ix, q.w.i2, q.w.i5) && in_rng(iy, q.w.j2, q.w.j5)) {
+          if (role == 0) { p2_n<true>(a, ix, iy, r, D.iseqalg); o[0] = r[0]; o[4] = r[4]; atomicOr(mk, 0x111); }
+          else if (role == 1) { p2_m<true>(a, q.w, ix, iy, r, D.iseqalg); o[1] = r[1]; atomicOr(mk, 0x2); }
+          else if (role == 2) { p2_e<true>(a, ix, iy, r, D.iseqalg); o[2] = r[2]; atomicOr(mk, 0x4); }
+          else { p2_i<true>(a, ix, iy, r, D.iseqalg); o[3] = r[3]; atomicOr(mk, 0x8); }
+        }
+      } else if (role == 0) {
+        const int m = phase2_guard<true>(a, q.w, ix, iy, r);
+        for (int k = 0; k < UE_NV; ++k) o[k] = r[k];
+        atomicOr(mk, m);
+      }
     }
   }
-  if (tid == BLOCK - 1) colcnt[iv - 1] = s_scan[tid];
+  __syncthreads();
+  // ---- phase 3 (rscalf + dt term) on the interior candidate rows ----------------------------------------------
+  for (int it = tid; it < np * ncand_max; it += 256) {
+    const int p = it / ncand_max, l = it - p * ncand_max;
+    const PInfo& q = pinfo[p];
+    if (l >= q.rw * q.rh) continue;
+    const int ix = q.rx0 + l % q.rw, iy = q.ry0 + l / q.rw;
+    if (ix >= 1 && ix <= D.nx && iy >= 1 && iy <= D.ny && in_rng(ix, q.w.i2, q.w.i5) && in_rng(iy, q.w.j2, q.w.j5)) {
+      const Acc<true> a = make_acc(p);
+      double r[UE_NV], ycell[UE_NV];
+      double* o = rows + ((size_t)p * ncand_max + l) * UE_NV;
+      const int64_t c = (int64_t)(ix + NXS * iy) * UE_NV;
+      for (int k = 0; k < UE_NV; ++k) { r[k] = o[k]; ycell[k] = yl[c + k]; }
+      if (ix == q.xc && iy == q.yc) ycell[(q.iv - 1) - c] = q.yold + q.dyl;
+      phase3_interior<true>(a, ix, iy, r, ycell, yl[neq], D.iseqalg, dtuse, ylodt);
+      for (int k = 0; k < UE_NV; ++k) o[k] = r[k];
+    }
+  }
+  __syncthreads();
+  // ---- difference, clip, ordered compaction into the column's CSC fragment (oderhs.m:8685-8719) ----------------
+  for (int p = warp; p < np; p += 8) {
+    const PInfo& q = pinfo[p];
+    const int64_t iv = q.iv;
+    const int64_t ii1 = max(iv - mu, (int64_t)1), ii2 = min(iv + ml, neq);
+    const double sf = sfscal[iv - 1];
+    const int ncand = q.rw * q.rh * UE_NV;
+    const int64_t o = coloff[iv - 1];
+    int nout = 0;
+    for (int q0 = 0; q0 < ncand; q0 += 32) {
+      const int qq = q0 + lane;
+      bool keep = false; double val = 0.; int64_t ii = 0;
+      if (qq < ncand) {
+        const int l = qq / UE_NV, k = qq - l * UE_NV;
+        const int ix = q.rx0 + l % q.rw, iy = q.ry0 + l / q.rw;
+        ii = ((int64_t)(ix + NXS * iy)) * UE_NV + k + 1;
+        if (ii >= ii1 && ii <= ii2) {
+          const bool written = (rmask[(size_t)p * ncand_max + l] >> k) & 1;
+          if (written || ii == iv) {
+            const double y00 = yldot00[ii - 1];
+            const double wk = written ? rows[((size_t)p * ncand_max + l) * UE_NV + k] : y00;
+            double jacelem = (wk - y00) / q.dyl;
+            if (ii == iv) {
+              if (D.iseqalg[iv - 1] * (1 - D.isbcwdt) == 0) jacelem = jacelem - 1 / dtuse[iv - 1];
+              if (D.nufak > 0 && yl[neq] == 1) jacelem = jacelem - D.nufak;
+            }
+            val = jacelem;
+            keep = fabs(jacelem * sf) > D.jaccliplim;
+          }
+        }
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const int pos = nout + __popc(bal & ((1u << lane) - 1));
+        colrow[o + pos] = (int)ii;
+        colval[o + pos] = val;
+        atomicAdd(&rowcnt[ii - 1], 1);
+      }
+      nout += __popc(bal);
+    }
+    if (lane == 0) colcnt[iv - 1] = nout;
+  }
 }
 
 // ---- CSC fragments -> CSR ---------------------------------------------------------------------------------------
@@ -346,30 +433,31 @@ void free_all() {
   g_ready = false;
 }
 
-// classify unknowns by window width and lay out the per-column fragment buffers
+// classify unknowns (regular / wide candidate rectangle) and lay out the per-column fragment buffers
+int g_ncand_narrow = 0, g_ncand_wide = 0;
+constexpr int NP_NARROW = 8, NP_WIDE = 2;
 int build_lists() {
   const UeParams& P = S.p;
   h_list_narrow.clear(); h_list_wide.clear();
   h_coloff.assign(neq, 0);
   int64_t off = 0;
-  g_box_narrow = g_box_wide = g_ext_narrow = g_ext_wide = 0;
+  g_ncand_narrow = g_ncand_wide = 1;
   for (int64_t iv = 1; iv <= neq; ++iv) {
     const int xc = (int)P.igyl[iv - 1], yc = (int)P.igyl[neq + iv - 1];
     const Win w = make_win(P, xc, yc);
-    const int bsz = (w.i6 - w.i1 + 1) * (w.j6 - w.j1 + 1);
-    const int ex0 = std::max(0, w.i2 - 1), ex1 = std::min(nx + 1, w.i5 + 1), ey0 = std::max(0, w.j2 - 1), ey1 = std::min(ny + 1, w.j5 + 1);
-    const int ecells = (ex1 - ex0 + 1) * (ey1 - ey0 + 1);
-    const bool wide = (w.i6 - w.i1 + 1) > 8;
+    const bool wide = is_wide(P, w, yc);
+    int rx0, ry0, rw, rh;
+    cand_rect(P, w, xc, yc, wide, rx0, ry0, rw, rh);
     h_coloff[iv - 1] = off;
-    off += (int64_t)ecells * UE_NV;
+    off += (int64_t)rw * rh * UE_NV;
     if (iv < g_ivmin || iv > g_ivmax) continue;
-    if (wide) { h_list_wide.push_back((int)iv); g_box_wide = std::max(g_box_wide, bsz); g_ext_wide = std::max(g_ext_wide, ecells); }
-    else { h_list_narrow.push_back((int)iv); g_box_narrow = std::max(g_box_narrow, bsz); g_ext_narrow = std::max(g_ext_narrow, ecells); }
+    if (wide) { h_list_wide.push_back((int)iv); g_ncand_wide = std::max(g_ncand_wide, rw * rh); }
+    else { h_list_narrow.push_back((int)iv); g_ncand_narrow = std::max(g_ncand_narrow, rw * rh); }
   }
   g_cap_total = off;
-  auto smem_of = [](int bsz, int ecells) { return (size_t)PL_COUNT * bsz * 8 + (size_t)ecells * UE_NV * 8 + (size_t)ecells * 4 + 16; };
-  g_smem_narrow = smem_of(g_box_narrow, g_ext_narrow);
-  g_smem_wide = smem_of(g_box_wide, g_ext_wide);
+  auto smem_of = [](int np, int ncand) { return (size_t)np * 4 * PL_COUNT * 8 + (size_t)np * ncand * UE_NV * 8 + (size_t)np * ncand * 8 + (size_t)np * ncand * 4 + 16; };
+  g_smem_narrow = smem_of(NP_NARROW, g_ncand_narrow);
+  g_smem_wide = smem_of(NP_WIDE, g_ncand_wide);
   return 0;
 }
 
@@ -384,11 +472,11 @@ int upload_lists() {
 }
 
 int run_residual_dev(const double* dyl, double* dyldot, bool need_rows) {
-  const int B = 128, G = (NC + B - 1) / B;
+  const int B = 128, G = (NC + B - 1) / B, G32 = (NC + 31) / 32;
   CK(cudaMemsetAsync(d_err, 0, sizeof(int), g_stream));
   k_phase0<<<G, B, 0, g_stream>>>(d_base, dyl, NXS, NC, d_err);
-  k_phase1<<<G, B, 0, g_stream>>>(d_base, NXS, NC);
-  k_phase2<<<G, B, 0, g_stream>>>(d_base, d_tmp, NXS, NC);
+  k_phase1<<<G32, 160, 0, g_stream>>>(d_base, NXS, NC);
+  k_phase2<<<G32, 128, 0, g_stream>>>(d_base, d_tmp, NXS, NC);
   g_launches += 3;
   if (need_rows) { k_phase3<<<G, B, 0, g_stream>>>(d_base, d_tmp, dyldot, dyl, d_dtuse, d_ylodt, neq, NXS, NC); g_launches += 1; }
   CK(cudaGetLastError());
@@ -411,13 +499,15 @@ int run_jac_dev(const double* dyl, const double* dy00, int64_t ml, int64_t mu, i
   CK(cudaMemsetAsync(d_rowfill, 0, neq * sizeof(int), g_stream));
   CK(cudaMemsetAsync(d_colcnt, 0, neq * sizeof(int), g_stream));
   if (!h_list_narrow.empty()) {
-    k_jac<64><<<(unsigned)h_list_narrow.size(), 64, g_smem_narrow, g_stream>>>(d_list_narrow, d_base, dyl, dy00, d_suscal, d_sfscal, d_dtuse, d_ylodt, neq, ml, mu,
-                                                                              NXS, NC, d_coloff, d_colcnt, d_colrow, d_colval, d_rowcnt, d_err);
+    const int n = (int)h_list_narrow.size();
+    k_jac<NP_NARROW><<<(n + NP_NARROW - 1) / NP_NARROW, 256, g_smem_narrow, g_stream>>>(d_list_narrow, n, g_ncand_narrow, d_base, dyl, dy00, d_suscal, d_sfscal, d_dtuse,
+                                                                                      d_ylodt, neq, ml, mu, NXS, NC, d_coloff, d_colcnt, d_colrow, d_colval, d_rowcnt, d_err);
     g_launches += 1;
   }
   if (!h_list_wide.empty()) {
-    k_jac<256><<<(unsigned)h_list_wide.size(), 256, g_smem_wide, g_stream>>>(d_list_wide, d_base, dyl, dy00, d_suscal, d_sfscal, d_dtuse, d_ylodt, neq, ml, mu,
-                                                                            NXS, NC, d_coloff, d_colcnt, d_colrow, d_colval, d_rowcnt, d_err);
+    const int n = (int)h_list_wide.size();
+    k_jac<NP_WIDE><<<(n + NP_WIDE - 1) / NP_WIDE, 256, g_smem_wide, g_stream>>>(d_list_wide, n, g_ncand_wide, d_base, dyl, dy00, d_suscal, d_sfscal, d_dtuse, d_ylodt,
+                                                                                neq, ml, mu, NXS, NC, d_coloff, d_colcnt, d_colrow, d_colval, d_rowcnt, d_err);
     g_launches += 1;
   }
   CK(cudaGetLastError());
@@ -534,8 +624,8 @@ int ue_gpu_init(void) {
   int dev = 0; cudaGetDevice(&dev);
   int maxsm = 0; cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   if ((int64_t)g_smem_wide > maxsm || (int64_t)g_smem_narrow > maxsm) { g_err = "window box does not fit shared memory (mesh too wide for this build)"; return -6; }
-  CK(cudaFuncSetAttribute(k_jac<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(g_smem_narrow, 1024)));
-  CK(cudaFuncSetAttribute(k_jac<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(g_smem_wide, 1024)));
+  CK(cudaFuncSetAttribute(k_jac<NP_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(g_smem_narrow, 1024)));
+  CK(cudaFuncSetAttribute(k_jac<NP_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(g_smem_wide, 1024)));
   g_launches = 0;
   g_ready = true;
   return 0;
