@@ -157,20 +157,26 @@ __host__ __device__ inline void cand_rect(const UeParams& P, const Win& w, int x
 }
 __host__ __device__ inline bool is_wide(const UeParams& P, const Win& w, int yc) { return w.xccuts || (P.iflcore == 1 && yc <= 1); }
 
-template <int NP>
-__global__ void __launch_bounds__(256) k_jac(const int* __restrict__ ivlist, int nlist, int ncand_max, double* base, const double* __restrict__ yl,
+// One launch covers both classes: blocks [0, nb_a) take NP_A unknowns each from list A (regular windows),
+// the remaining blocks take NP_B unknowns each from list B (wide windows).
+constexpr int NP_MAX = 8;
+__global__ void __launch_bounds__(256) k_jac(const int* __restrict__ list_a, int n_a, int np_a, int ncand_a, int nb_a, const int* __restrict__ list_b, int n_b,
+                                             int np_b, int ncand_b, double* base, const double* __restrict__ yl,
                                              const double* __restrict__ yldot00, const double* __restrict__ suscal, const double* __restrict__ sfscal,
                                              const double* __restrict__ dtuse, const double* __restrict__ ylodt, int64_t neq, int64_t ml, int64_t mu, int NXS,
                                              int NC, const int64_t* __restrict__ coloff, int* __restrict__ colcnt, int* __restrict__ colrow,
                                              double* __restrict__ colval, int* __restrict__ rowcnt, int* err) {
   extern __shared__ double smem[];
-  __shared__ PInfo pinfo[NP];
+  __shared__ PInfo pinfo[NP_MAX];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool cls_a = (int)blockIdx.x < nb_a;
+  const int* __restrict__ ivlist = cls_a ? list_a : list_b;
+  const int nlist = cls_a ? n_a : n_b, NP = cls_a ? np_a : np_b, ncand_max = cls_a ? ncand_a : ncand_b;
   double* sm4 = smem;                                           // [NP][4][PL_COUNT]
   double* rows = sm4 + (size_t)NP * 4 * PL_COUNT;               // [NP][ncand_max][UE_NV]
   double* rres = rows + (size_t)NP * ncand_max * UE_NV;         // [NP][ncand_max]
   int* rmask = (int*)(rres + (size_t)NP * ncand_max);           // [NP][ncand_max]
-  const int p0 = blockIdx.x * NP;
+  const int p0 = (cls_a ? (int)blockIdx.x : (int)blockIdx.x - nb_a) * NP;
   const int np = min(NP, nlist - p0);
   if (tid < np) {
     PInfo& q = pinfo[tid];
@@ -336,26 +342,24 @@ __global__ void __launch_bounds__(256) k_jac(const int* __restrict__ ivlist, int
 
 // ---- CSC fragments -> CSR ---------------------------------------------------------------------------------------
 __global__ void k_scan(const int* __restrict__ rowcnt, int64_t* __restrict__ ia, int64_t n) {
-  // single block; ia is 1-based: ia[0] = 1, ia[i+1] = ia[i] + rowcnt[i]
+  // single block of 1024 threads; ia is 1-based: ia[0] = 1, ia[i+1] = ia[i] + rowcnt[i].
+  // Each thread owns a contiguous chunk: serial sum, block scan of the 1024 partials, serial write-out.
   __shared__ int64_t s[1024];
-  __shared__ int64_t carry;
-  if (threadIdx.x == 0) { carry = 1; ia[0] = 1; }
+  const int t = threadIdx.x;
+  const int64_t chunk = (n + 1023) / 1024, b0 = t * chunk, b1 = min(n, b0 + chunk);
+  int64_t sum = 0;
+  for (int64_t i = b0; i < b1; ++i) sum += rowcnt[i];
+  s[t] = sum;
   __syncthreads();
-  for (int64_t b = 0; b < n; b += 1024) {
-    const int64_t i = b + threadIdx.x;
-    s[threadIdx.x] = (i < n) ? rowcnt[i] : 0;
+  for (int off = 1; off < 1024; off <<= 1) {
+    const int64_t v = (t >= off) ? s[t - off] : 0;
     __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-      int64_t v = (threadIdx.x >= off) ? s[threadIdx.x - off] : 0;
-      __syncthreads();
-      s[threadIdx.x] += v;
-      __syncthreads();
-    }
-    if (i < n) ia[i + 1] = carry + s[threadIdx.x];
-    __syncthreads();
-    if (threadIdx.x == 1023) carry += s[1023];
+    s[t] += v;
     __syncthreads();
   }
+  int64_t run = 1 + s[t] - sum;
+  if (t == 0) ia[0] = 1;
+  for (int64_t i = b0; i < b1; ++i) { run += rowcnt[i]; ia[i + 1] = run; }
 }
 __global__ void k_fill(int64_t neq, int64_t ivmin, int64_t ivmax, const int64_t* __restrict__ coloff, const int* __restrict__ colcnt,
                        const int* __restrict__ colrow, const double* __restrict__ colval, const int64_t* __restrict__ ia, int* __restrict__ rowfill,
@@ -371,18 +375,38 @@ __global__ void k_fill(int64_t neq, int64_t ivmin, int64_t ivmax, const int64_t*
     jac[p] = colval[o + e];
   }
 }
+// one warp per row: rank sort of the row's entries by column (rows hold a few tens of entries)
 __global__ void k_sortrows(int64_t neq, const int64_t* __restrict__ ia, double* __restrict__ jac, int64_t* __restrict__ ja) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int CAP = 96;
+  __shared__ int64_t scol[4][CAP];
+  __shared__ double sval[4][CAP];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * 4 + wib;
   if (r >= neq) return;
   const int64_t b = ia[r] - 1, e = ia[r + 1] - 1;
-  for (int64_t i = b + 1; i < e; ++i) {  // insertion sort by column: rows hold a few tens of entries
-    const int64_t cj = ja[i]; const double cv = jac[i];
-    int64_t j = i - 1;
-    while (j >= b && ja[j] > cj) { ja[j + 1] = ja[j]; jac[j + 1] = jac[j]; --j; }
-    ja[j + 1] = cj; jac[j + 1] = cv;
+  const int n = (int)(e - b);
+  if (n <= 1) return;
+  if (n <= CAP) {
+    for (int i = lane; i < n; i += 32) { scol[wib][i] = ja[b + i]; sval[wib][i] = jac[b + i]; }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+      const int64_t c = scol[wib][i];
+      int rank = 0;
+      for (int j = 0; j < n; ++j) rank += (scol[wib][j] < c);
+      ja[b + rank] = c; jac[b + rank] = sval[wib][i];
+    }
+  } else if (lane == 0) {  // dense row: serial insertion sort
+    for (int64_t i = b + 1; i < e; ++i) {
+      const int64_t cj = ja[i]; const double cv = jac[i];
+      int64_t j = i - 1;
+      while (j >= b && ja[j] > cj) { ja[j + 1] = ja[j]; jac[j + 1] = jac[j]; --j; }
+      ja[j + 1] = cj; jac[j + 1] = cv;
+    }
   }
 }
 
+}  // namespace (kernels)
+namespace {
 // ------------------------------------------------------------------------------------------------
 int check_switches() {
   const UeParams& P = S.p;
@@ -435,7 +459,7 @@ void free_all() {
 
 // classify unknowns (regular / wide candidate rectangle) and lay out the per-column fragment buffers
 int g_ncand_narrow = 0, g_ncand_wide = 0;
-constexpr int NP_NARROW = 8, NP_WIDE = 2;
+int g_np_a = 8, g_np_b = 2;  // unknowns per block (regular / wide); chosen in build_lists from the problem size
 int build_lists() {
   const UeParams& P = S.p;
   h_list_narrow.clear(); h_list_wide.clear();
@@ -456,8 +480,20 @@ int build_lists() {
   }
   g_cap_total = off;
   auto smem_of = [](int np, int ncand) { return (size_t)np * 4 * PL_COUNT * 8 + (size_t)np * ncand * UE_NV * 8 + (size_t)np * ncand * 8 + (size_t)np * ncand * 4 + 16; };
-  g_smem_narrow = smem_of(NP_NARROW, g_ncand_narrow);
-  g_smem_wide = smem_of(NP_WIDE, g_ncand_wide);
+  // Blocks are latency-bound and two fit an SM (128 registers x 256 threads): pick the smallest batch per
+  // block that still runs in ONE wave (so that phase 2 needs the fewest passes); large problems are
+  // throughput-bound and take the fullest batches.
+  int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int64_t na = (int64_t)h_list_narrow.size(), nb = (int64_t)h_list_wide.size();
+  const int cand[4][2] = {{4, 1}, {4, 2}, {8, 2}, {8, 4}};
+  g_np_a = 8; g_np_b = 4;
+  for (auto& c : cand) {
+    const int64_t blocks = (na + c[0] - 1) / c[0] + (nb + c[1] - 1) / c[1];
+    if (blocks <= 2 * (int64_t)sms) { g_np_a = c[0]; g_np_b = c[1]; break; }
+  }
+  if (nb > 0 && g_ncand_wide > 256 && g_np_b > 2) g_np_b = 2;  // very wide rows: keep shared memory per block moderate
+  g_smem_narrow = smem_of(g_np_a, g_ncand_narrow);
+  g_smem_wide = smem_of(g_np_b, g_ncand_wide);
   return 0;
 }
 
@@ -498,17 +534,15 @@ int run_jac_dev(const double* dyl, const double* dy00, int64_t ml, int64_t mu, i
   CK(cudaMemsetAsync(d_rowcnt, 0, neq * sizeof(int), g_stream));
   CK(cudaMemsetAsync(d_rowfill, 0, neq * sizeof(int), g_stream));
   CK(cudaMemsetAsync(d_colcnt, 0, neq * sizeof(int), g_stream));
-  if (!h_list_narrow.empty()) {
-    const int n = (int)h_list_narrow.size();
-    k_jac<NP_NARROW><<<(n + NP_NARROW - 1) / NP_NARROW, 256, g_smem_narrow, g_stream>>>(d_list_narrow, n, g_ncand_narrow, d_base, dyl, dy00, d_suscal, d_sfscal, d_dtuse,
-                                                                                      d_ylodt, neq, ml, mu, NXS, NC, d_coloff, d_colcnt, d_colrow, d_colval, d_rowcnt, d_err);
-    g_launches += 1;
-  }
-  if (!h_list_wide.empty()) {
-    const int n = (int)h_list_wide.size();
-    k_jac<NP_WIDE><<<(n + NP_WIDE - 1) / NP_WIDE, 256, g_smem_wide, g_stream>>>(d_list_wide, n, g_ncand_wide, d_base, dyl, dy00, d_suscal, d_sfscal, d_dtuse, d_ylodt,
-                                                                                neq, ml, mu, NXS, NC, d_coloff, d_colcnt, d_colrow, d_colval, d_rowcnt, d_err);
-    g_launches += 1;
+  {
+    const int na = (int)h_list_narrow.size(), nb = (int)h_list_wide.size();
+    const int nba = (na + g_np_a - 1) / g_np_a, nbb = (nb + g_np_b - 1) / g_np_b;
+    if (nba + nbb > 0) {
+      k_jac<<<nba + nbb, 256, std::max(g_smem_narrow, g_smem_wide), g_stream>>>(d_list_narrow, na, g_np_a, g_ncand_narrow, nba, d_list_wide, nb, g_np_b, g_ncand_wide, d_base,
+                                                                            dyl, dy00, d_suscal, d_sfscal, d_dtuse, d_ylodt, neq, ml, mu, NXS, NC, d_coloff, d_colcnt,
+                                                                            d_colrow, d_colval, d_rowcnt, d_err);
+      g_launches += 1;
+    }
   }
   CK(cudaGetLastError());
   k_scan<<<1, 1024, 0, g_stream>>>(d_rowcnt, dia, neq);
@@ -525,7 +559,7 @@ int run_jac_dev(const double* dyl, const double* dy00, int64_t ml, int64_t mu, i
   const int64_t ncol = g_ivmax - g_ivmin + 1;
   if (ncol > 0) {
     k_fill<<<(unsigned)ncol, 64, 0, g_stream>>>(neq, g_ivmin, g_ivmax, d_coloff, d_colcnt, d_colrow, d_colval, dia, d_rowfill, djac, dja);
-    k_sortrows<<<(unsigned)((neq + 127) / 128), 128, 0, g_stream>>>(neq, dia, djac, dja);
+    k_sortrows<<<(unsigned)((neq + 3) / 4), 128, 0, g_stream>>>(neq, dia, djac, dja);
     g_launches += 2;
   }
   CK(cudaGetLastError());
@@ -624,8 +658,7 @@ int ue_gpu_init(void) {
   int dev = 0; cudaGetDevice(&dev);
   int maxsm = 0; cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   if ((int64_t)g_smem_wide > maxsm || (int64_t)g_smem_narrow > maxsm) { g_err = "window box does not fit shared memory (mesh too wide for this build)"; return -6; }
-  CK(cudaFuncSetAttribute(k_jac<NP_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(g_smem_narrow, 1024)));
-  CK(cudaFuncSetAttribute(k_jac<NP_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(g_smem_wide, 1024)));
+  CK(cudaFuncSetAttribute(k_jac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(std::max(g_smem_narrow, g_smem_wide), 1024)));
   g_launches = 0;
   g_ready = true;
   return 0;
@@ -705,7 +738,8 @@ int ue_gpu_set_column_range(int64_t ivmin, int64_t ivmax) {
   g_ivmin = ivmin; g_ivmax = ivmax;
   const size_t s1 = g_smem_narrow, s2 = g_smem_wide;
   build_lists();
-  g_smem_narrow = std::max(g_smem_narrow, s1); g_smem_wide = std::max(g_smem_wide, s2);
+  (void)s1; (void)s2;
+  CK(cudaFuncSetAttribute(k_jac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(std::max(g_smem_narrow, g_smem_wide), 1024)));
   return upload_lists();
 }
 
