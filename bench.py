@@ -2,8 +2,9 @@
 """bench.py — Jacobian assembly (nnz/s) and residual evaluations (evals/s) of the pandf1/jac_calc hot path.
 
 Contract: python bench.py --gpus N --steps K --warmup W  prints ONE JSON line.
-A "step" is one full Jacobian assembly (ue_gpu_jac_calc) of the d3dHsm configuration plus the two
-residual evaluations psetnk does around it (bbb/oderhs.m:9453-9471).
+A "step" is what sfsetnk/psetnk do to get a Jacobian (bbb/oderhs.m:9851-9857, 9466-9468): one residual
+evaluation rhsnk(yl) followed by one full finite-difference Jacobian assembly jac_calc(yl, yldot00), on the
+d3dHsm configuration.  Both arms (CUDA and CPU) time the same step; residual evaluations/s are reported too.
 `--impl reference` times the CPU restatement of the reference algorithm (the reference itself is
 MPPL/Fortran and cannot be built in this image) on the box's host cores.
 """
@@ -48,29 +49,45 @@ def reasons_of(mask_strs):
     return sorted(got)
 
 
-def cpu_baseline(c, yl, budget_s=15.0):
-    """Oracle ("port") Jacobian on one host core: bounded sample, same algorithm/cost structure as
-    jac_calc (2*neq windowed pandf1)."""
-    from tests.util import bind, oracle, psetnk_inputs
+def cpu_baseline(c, name, perturb, budget_s=12.0, nproc=None):
+    """CPU arm: the oracle's jac_calc (same algorithm and cost structure as the reference: 2*neq windowed
+    pandf1 calls) split over ALL host cores by contiguous column ranges, one process per core holding the
+    full state — the reference's MPI row-split design (ppp/mpi_parallel.F90).  Also times one core alone.
+    Must run before CUDA is initialised (fork)."""
+    from tests.cpu_pool import OraclePool
     b = c.bbb
-    ora = bind(oracle(), c)
-    y, su = psetnk_inputs(c, yl)
-    ora.step_params(np.full(b.neq, 1e20), y[: b.neq], su, np.ones(b.neq))
-    f0 = ora.pandf1(y)
-    t0 = time.perf_counter(); reps = 0; nnz = 0
+    nproc = nproc or os.cpu_count()
+    pool = OraclePool(name, perturb, nproc=nproc)
+    pool.jacobian(b.neq)  # warm-up
+    t0 = time.perf_counter(); reps = 0
     while True:
-        jac, ja, ia = ora.jac_calc(y, f0, b.lbw, b.ubw, b.nnzmx)
-        nnz = len(jac); reps += 1
-        if time.perf_counter() - t0 > budget_s or reps >= 20:
+        jac, ja, ia = pool.jacobian(b.neq)
+        reps += 1
+        if time.perf_counter() - t0 > budget_s or reps >= 30:
             break
     dt = (time.perf_counter() - t0) / reps
-    t1 = time.perf_counter(); r2 = 0
-    while time.perf_counter() - t1 < 2.0:
-        ora.pandf1(y); r2 += 1
-    tres = (time.perf_counter() - t1) / r2
-    return dict(value=nnz / dt, unit="nnz/s", cores=1, kind="port",
-                sample="%d full serial Jacobians of %s (neq=%d, nnz=%d), %.3f s each; residual %.3f ms" % (reps, c.name, b.neq, nnz, dt, tres * 1e3),
-                resid_evals_per_s=1.0 / tres, jac_s=dt)
+    pool.close()
+    nnz = len(jac)
+    p1 = OraclePool(name, perturb, nproc=1)
+    p1.jacobian(b.neq)
+    t1 = time.perf_counter(); r1 = 0
+    while True:
+        p1.jacobian(b.neq); r1 += 1
+        if time.perf_counter() - t1 > budget_s / 2 or r1 >= 10:
+            break
+    dt1 = (time.perf_counter() - t1) / r1
+    p1.close()
+    from tests.util import bind, oracle, make_case
+    ora = bind(oracle(), c)
+    yl = make_case(name, perturb=perturb)[1]
+    t2 = time.perf_counter(); r2 = 0
+    while time.perf_counter() - t2 < 1.5:
+        ora.pandf1(yl); r2 += 1
+    tres = (time.perf_counter() - t2) / r2
+    return dict(value=nnz / dt, unit="nnz/s", cores=nproc, kind="port",
+                sample="%d full Jacobians of %s (neq=%d, nnz=%d) split over %d processes: %.2f ms each; 1 process: %.2f ms; serial residual %.3f ms"
+                       % (reps, name, b.neq, nnz, nproc, dt * 1e3, dt1 * 1e3, tres * 1e3),
+                resid_evals_per_s=1.0 / tres, jac_s=dt, serial_value=nnz / dt1)
 
 
 def main():
@@ -92,15 +109,19 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        cb = cpu_baseline(c, yl, budget_s=20.0)
+        cb = cpu_baseline(c, name, 1e-3, budget_s=20.0)
         line = dict(metric="jacobian_nnz_per_s", value=cb["value"], unit="nnz/s", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
                     ms_per_step=cb["jac_s"] * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
                     impl="reference", config=dict(workload="%s full Jacobian assembly, neq=%d" % (name, b.neq)),
                     cpu_baseline=dict(value=cb["value"], unit="nnz/s", cores=cb["cores"], kind=cb["kind"], sample=cb["sample"]),
                     e2e=dict(value=cb["value"], unit="nnz/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                    resid_evals_per_s=cb["resid_evals_per_s"])
+                    resid_evals_per_s=cb["resid_evals_per_s"], serial_nnz_per_s=cb["serial_value"])
         print(json.dumps(line))
         return
+
+    cb = None
+    if not a.no_cpu and world == 1:
+        cb = cpu_baseline(c, name, 1e-3)  # before CUDA init (the pool forks)
 
     import torch
     import torch.distributed as dist
@@ -137,15 +158,17 @@ def main():
     jms = C.c_double(0); rms = C.c_double(0)
 
     def step_e2e():
-        assert lib.ue_gpu_pandf1(neq, 0.0, P(hy), P(hyd)) == 0
+        assert lib.ue_gpu_pandf1(neq, 0.0, P(hy), P(hf)) == 0          # yldot00 = rhsnk(yl)
         assert lib.ue_gpu_jac_calc(neq, 0.0, P(hy), P(hf), int(b.lbw), int(b.ubw), nnzmx, P(hjac), P(hja), P(hia), C.byref(nnz)) == 0
-        assert lib.ue_gpu_pandf1(neq, 0.0, P(hy), P(hyd)) == 0
 
     def step_dev():
-        assert lib.ue_gpu_pandf1_dev(neq, 0.0, d_yl, d_yldot) == 0
+        assert lib.ue_gpu_pandf1_dev(neq, 0.0, d_yl, d_y00) == 0
+        lib.ue_gpu_assume_base_current(1)
         assert lib.ue_gpu_jac_calc_dev(neq, 0.0, d_yl, d_y00, int(b.lbw), int(b.ubw), nnzmx, d_jac, d_ja, d_ia, C.byref(nnz)) == 0
         lib.ue_gpu_last_kernel_ms(C.byref(jms), C.byref(rms))
-        assert lib.ue_gpu_pandf1_dev(neq, 0.0, d_yl, d_yldot) == 0
+
+    def resid_e2e():
+        assert lib.ue_gpu_pandf1(neq, 0.0, P(hy), P(hyd)) == 0
 
     def barrier():
         torch.cuda.synchronize()
@@ -176,6 +199,7 @@ def main():
     t_dev, jm, rm = timed(step_dev, a.steps)
     l1 = C.c_int64(0); lib.ue_gpu_kernel_launches(C.byref(l1))
     t_e2e, _, _ = timed(step_e2e, a.steps)
+    t_res_e2e, _, _ = timed(resid_e2e, a.steps)
     stop.set(); th.join()
     nnz_local = nnz.value
     if world > 1:
@@ -204,19 +228,20 @@ def main():
     sm = sorted(s[0] for s in samples) or [0.0]
     line = dict(metric="jacobian_nnz_per_s", value=nnz_total / (ms_dev * 1e-3), unit="nnz/s", n_gpus=world, steps=a.steps, warmup=a.warmup,
                 ms_per_step=ms_dev, higher_is_better=True, scaling="strong" if world > 1 else "weak", vs_baseline=None, dtype="f64", data="synthetic",
-                config=dict(workload="%s: 1 residual + 1 full FD Jacobian (neq=%d, nnz=%d) + 1 residual per step" % (name, neq, nnz_total),
+                config=dict(workload="%s: rhsnk + jac_calc (1 residual + 1 full FD Jacobian, neq=%d, nnz=%d) per step" % (name, neq, nnz_total),
                             l2="flushed between steps (192 MB fill)", parallelism="replicas, Jacobian columns split over %d ranks" % world),
-                e2e=dict(value=nnz_total / (ms_e2e * 1e-3), unit="nnz/s", h2d_bytes_per_step=8 * (3 * (neq + 2) + neq),
-                         d2h_bytes_per_step=16 * nnz_total + 8 * (neq + 1) + 2 * 8 * neq, ms_per_step=ms_e2e),
+                e2e=dict(value=nnz_total / (ms_e2e * 1e-3), unit="nnz/s", h2d_bytes_per_step=8 * (2 * (neq + 2) + neq),
+                         d2h_bytes_per_step=16 * nnz_total + 8 * (neq + 1) + 8 * neq, ms_per_step=ms_e2e,
+                         resid_evals_per_s=a.steps / t_res_e2e),
                 gpu_launches=int(l1.value - l0.value),
                 resid_evals_per_s=1e3 / res_ms if res_ms > 0 else None, jac_kernel_ms=jac_ms, resid_kernel_ms=res_ms,
                 roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
                               note="algorithmic bytes = 8*(2(neq+2)+G*Ncell)+16*nnz+8*(neq+1), G=%d; latency/FP64-issue bound at this size (see DESIGN.md)" % G),
                 clocks=dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max([s[1] for s in samples] or [0.0]), reasons=reasons_of([s[2] for s in samples])))
-    if not a.no_cpu and world == 1:
-        cb = cpu_baseline(c, yl)
+    if cb is not None:
         line["cpu_baseline"] = dict(value=cb["value"], unit="nnz/s", cores=cb["cores"], kind=cb["kind"], sample=cb["sample"])
         line["cpu_resid_evals_per_s"] = cb["resid_evals_per_s"]
+        line["cpu_serial_nnz_per_s"] = cb["serial_value"]
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -65,6 +65,11 @@ int ue_gpu_jac_calc_dev(int64_t neq, double t, const double* d_yl, const double*
                         int64_t ml, int64_t mu, int64_t nnzmx,
                         double* d_jac, int64_t* d_ja, int64_t* d_ia, int64_t* nnz_out);
 
+/* Device-pointer callers only: assert (flag=1) that d_yl is unchanged since the last ue_gpu_pandf1_dev, so the
+ * next ue_gpu_jac_calc_dev reuses the base fields instead of re-evaluating phases 0-2.  The host-pointer entry
+ * points detect this themselves (psetnk/sfsetnk call rhsnk(yl) right before jac_calc, oderhs.m:9466, 9851). */
+int ue_gpu_assume_base_current(int64_t flag);
+
 /* ---- column-range split (ppp MPISplitIndex / LocalJacBuilder analogue) ----
  * Restrict the next jac_calc calls to perturbed unknowns iv in [ivmin,ivmax]
  * (1-based, inclusive): the returned CSR holds only those columns.  (1,neq)

@@ -21,11 +21,14 @@ def _init(name, perturb):
 
 
 def _jac_range(rng):
+    import time
     c, ora = _W["c"], _W["ora"]
     b = c.bbb
+    t0 = time.perf_counter()
     ora.pandf1(_W["y"])  # base state (OMPJacBuilder does the same before the split, omp_parallel.F90:319)
     ora.set_column_range(*rng)
-    return ora.jac_calc(_W["y"], _W["f0"], b.lbw, b.ubw, b.nnzmx)
+    out = ora.jac_calc(_W["y"], _W["f0"], b.lbw, b.ubw, b.nnzmx)
+    return out, time.perf_counter() - t0
 
 
 def _resid(_):
@@ -38,9 +41,22 @@ class OraclePool:
         ctx = mp.get_context("fork")
         self.pool = ctx.Pool(self.nproc, initializer=_init, initargs=(name, perturb))
 
+        self.weights = None
+
     def jacobian(self, neq):
+        """One parallel assembly.  Ranges are re-balanced with the per-worker times of the previous call,
+        as the reference does (ppp/omp_parallel.F90:199-229, 395-444)."""
         from uedge_b200.split import merge_csr, split_index
-        parts = self.pool.map(_jac_range, split_index(neq, self.nproc), chunksize=1)
+        ranges = split_index(neq, self.nproc, self.weights)
+        res = self.pool.map(_jac_range, ranges, chunksize=1)
+        parts = [r[0] for r in res]
+        times = np.array([r[1] for r in res])
+        n = np.array([hi - lo + 1 for lo, hi in ranges], dtype=float)
+        speed = n / np.maximum(times, 1e-9)  # unknowns per second in each range
+        w = (1.0 / self.nproc) if self.weights is None else np.asarray(self.weights)
+        # new range sizes ~ proportional to the measured speed, damped
+        neww = speed / speed.sum()
+        self.weights = 0.5 * (np.full(self.nproc, 1.0 / self.nproc) if self.weights is None else w) + 0.5 * neww
         return merge_csr(parts, neq)
 
     def close(self):

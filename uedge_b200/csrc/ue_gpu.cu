@@ -32,6 +32,8 @@ bool g_ready = false;
 int nx, ny, NXS, NC;
 int64_t neq = 0;
 int64_t g_launches = 0;
+std::vector<double> g_base_yl;   // yl (first neq entries) for which the base planes in d_base are current
+bool g_base_valid = false, g_jac_trust_base = false, g_base_dev_valid = false;
 float g_jac_ms = 0.f, g_res_ms = 0.f;
 cudaStream_t g_stream = nullptr;
 cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
@@ -528,8 +530,10 @@ int check_errflag() {
   return 0;
 }
 
-int run_jac_dev(const double* dyl, const double* dy00, int64_t ml, int64_t mu, int64_t nnzmx, double* djac, int64_t* dja, int64_t* dia, int64_t* nnz_out) {
-  int rc = run_residual_dev(dyl, nullptr, false);  // base planes at yl
+int run_jac_dev(const double* dyl, const double* dy00, int64_t ml, int64_t mu, int64_t nnzmx, double* djac, int64_t* dja, int64_t* dia, int64_t* nnz_out,
+                bool base_current) {
+  int rc = 0;
+  if (!base_current) rc = run_residual_dev(dyl, nullptr, false);  // base planes at yl
   if (rc) return rc;
   CK(cudaMemsetAsync(d_rowcnt, 0, neq * sizeof(int), g_stream));
   CK(cudaMemsetAsync(d_rowfill, 0, neq * sizeof(int), g_stream));
@@ -571,8 +575,9 @@ int run_jac_dev(const double* dyl, const double* dy00, int64_t ml, int64_t mu, i
 // ====================================================================================================
 extern "C" {
 
-int ue_gpu_set_int(const char* n, int64_t v) { if (S.set_int(n, v)) { g_err = std::string("unknown int input ") + n; return -1; } return 0; }
+int ue_gpu_set_int(const char* n, int64_t v) { g_base_valid = g_base_dev_valid = false; if (S.set_int(n, v)) { g_err = std::string("unknown int input ") + n; return -1; } return 0; }
 int ue_gpu_set_real(const char* n, double v) {
+  g_base_valid = g_base_dev_valid = false;
   if (S.set_real(n, v)) { g_err = std::string("unknown real input ") + n; return -1; }
   if (g_ready) {  // scalars such as nufak, dtreal may change between solves: patch the device copy in place
     const size_t off = (size_t)((char*)S.rscal[n] - (char*)&S.p);
@@ -679,6 +684,7 @@ int ue_gpu_pandf1_dev(int64_t n, double time, const double* dyl, double* dyldot)
   (void)time;
   if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
   if (n != neq) { g_err = "pandf1: neq mismatch"; return -1; }
+  g_base_valid = false; g_base_dev_valid = false;
   CK(cudaEventRecord(g_ev0, g_stream));
   int rc = run_residual_dev(dyl, dyldot, true);
   if (rc) return rc;
@@ -686,6 +692,7 @@ int ue_gpu_pandf1_dev(int64_t n, double time, const double* dyl, double* dyldot)
   rc = check_errflag();
   if (rc) return rc;
   cudaEventElapsedTime(&g_res_ms, g_ev0, g_ev1);
+  g_base_dev_valid = true;
   return 0;
 }
 
@@ -693,10 +700,13 @@ int ue_gpu_pandf1(int64_t n, double time, const double* yl, double* yldot) {
   if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
   if (n != neq) { g_err = "pandf1: neq mismatch"; return -1; }
   CK(cudaMemcpyAsync(d_yl, yl, (neq + 2) * 8, cudaMemcpyHostToDevice, g_stream));
+  g_base_valid = false;
   int rc = ue_gpu_pandf1_dev(n, time, d_yl, d_yldot);
   if (rc) return rc;
   CK(cudaMemcpyAsync(yldot, d_yldot, neq * 8, cudaMemcpyDeviceToHost, g_stream));
   CK(cudaStreamSynchronize(g_stream));
+  g_base_yl.assign(yl, yl + neq);  // the base planes now describe this yl (they do not depend on yl(neq+1..2))
+  g_base_valid = true;
   return 0;
 }
 
@@ -706,7 +716,10 @@ int ue_gpu_jac_calc_dev(int64_t n, double t, const double* dyl, const double* dy
   if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
   if (n != neq) { g_err = "jac_calc: neq mismatch"; return -1; }
   CK(cudaEventRecord(g_ev0, g_stream));
-  int rc = run_jac_dev(dyl, dy00, ml, mu, std::min(nnzmx, g_nnzcap), djac, dja, dia, nnz_out);
+  const bool cur = g_base_valid && g_jac_trust_base;
+  g_jac_trust_base = false;
+  int rc = run_jac_dev(dyl, dy00, ml, mu, std::min(nnzmx, g_nnzcap), djac, dja, dia, nnz_out, cur);
+  g_base_valid = false;  // device-pointer callers may change d_yl behind our back
   if (rc) return rc;
   CK(cudaEventRecord(g_ev1, g_stream));
   rc = check_errflag();
@@ -721,6 +734,9 @@ int ue_gpu_jac_calc(int64_t n, double t, const double* yl, const double* yldot00
   if (n != neq) { g_err = "jac_calc: neq mismatch"; return -1; }
   CK(cudaMemcpyAsync(d_yl, yl, (neq + 2) * 8, cudaMemcpyHostToDevice, g_stream));
   CK(cudaMemcpyAsync(d_yldot00, yldot00, neq * 8, cudaMemcpyHostToDevice, g_stream));
+  // psetnk / sfsetnk evaluate rhsnk(yl) immediately before jac_calc (oderhs.m:9466-9468, 9851-9856): if yl is
+  // bit-identical to that call's, the base planes are already on the device and phases 0-2 are skipped
+  g_jac_trust_base = g_base_valid && (int64_t)g_base_yl.size() == neq && std::memcmp(g_base_yl.data(), yl, neq * 8) == 0;
   int64_t nnz = 0;
   int rc = ue_gpu_jac_calc_dev(n, t, d_yl, d_yldot00, ml, mu, nnzmx, d_jac, d_ja, d_ia, &nnz);
   *nnz_out = nnz;
@@ -743,6 +759,9 @@ int ue_gpu_set_column_range(int64_t ivmin, int64_t ivmax) {
   return upload_lists();
 }
 
+// Device-pointer callers: assert that d_yl has not changed since the last ue_gpu_pandf1_dev call, so the next
+// ue_gpu_jac_calc_dev may reuse the base planes (the host-pointer entry points check this themselves).
+int ue_gpu_assume_base_current(int64_t flag) { g_jac_trust_base = (flag != 0); if (flag) g_base_valid = g_base_dev_valid; return 0; }
 int ue_gpu_kernel_launches(int64_t* n) { *n = g_launches; return 0; }
 int ue_gpu_last_kernel_ms(double* jac_ms, double* res_ms) { *jac_ms = g_jac_ms; *res_ms = g_res_ms; return 0; }
 // device buffers owned by the library (for callers that keep state resident, e.g. bench.py)
