@@ -98,11 +98,14 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--config", default="d3dHsm")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--mode", default="replicas", choices=["replicas", "columns"],
+                    help="N>1: 'replicas' = every GPU assembles the full Jacobian of its own state (ensemble, weak scaling); "
+                         "'columns' = one Jacobian, columns split over the ranks (ppp MPI design, strong scaling)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     from tests.util import make_case, psetnk_inputs
     name = a.config
-    c, yl = make_case(name, perturb=1e-3)
+    c, yl = make_case(name, perturb=1e-3, seed=1234 + rank)   # replicas: every rank has its own state
     c.name = name
     b = c.bbb
 
@@ -138,7 +141,7 @@ def main():
     neq = b.neq
     # multi-GPU: replicas-with-column-split (ppp MPI design): rank r assembles columns of its contiguous iv range
     lo = 1 + (neq * rank) // world; hi = (neq * (rank + 1)) // world
-    if world > 1:
+    if world > 1 and a.mode == "columns":
         gpu.set_column_range(lo, hi)
     f0 = gpu.pandf1(y)
     # pinned host buffers for the end-to-end path
@@ -227,9 +230,10 @@ def main():
     achieved = alg_bytes / (jac_ms * 1e-3) / 1e9
     sm = sorted(s[0] for s in samples) or [0.0]
     line = dict(metric="jacobian_nnz_per_s", value=nnz_total / (ms_dev * 1e-3), unit="nnz/s", n_gpus=world, steps=a.steps, warmup=a.warmup,
-                ms_per_step=ms_dev, higher_is_better=True, scaling="strong" if world > 1 else "weak", vs_baseline=None, dtype="f64", data="synthetic",
+                ms_per_step=ms_dev, higher_is_better=True, scaling="strong" if (world > 1 and a.mode == "columns") else "weak", vs_baseline=None, dtype="f64", data="synthetic",
                 config=dict(workload="%s: rhsnk + jac_calc (1 residual + 1 full FD Jacobian, neq=%d, nnz=%d) per step" % (name, neq, nnz_total),
-                            l2="flushed between steps (192 MB fill)", parallelism="replicas, Jacobian columns split over %d ranks" % world),
+                            l2="flushed between steps (192 MB fill)", parallelism=("%d independent replicas (one state per GPU), no collective" % world) if a.mode == "replicas" or world == 1
+                            else "one Jacobian, columns split over %d ranks (replicated state)" % world),
                 e2e=dict(value=nnz_total / (ms_e2e * 1e-3), unit="nnz/s", h2d_bytes_per_step=8 * (2 * (neq + 2) + neq),
                          d2h_bytes_per_step=16 * nnz_total + 8 * (neq + 1) + 8 * neq, ms_per_step=ms_e2e,
                          resid_evals_per_s=a.steps / t_res_e2e),

@@ -21,7 +21,11 @@
 #include <string.h>
 
 #ifdef __CUDACC__
+#ifdef UE_MATH_NOINLINE
+#define UE_HD __host__ __device__ __noinline__
+#else
 #define UE_HD __host__ __device__ __forceinline__
+#endif
 #else
 #define UE_HD static inline
 #endif

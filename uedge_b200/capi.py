@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-GPU_LIB = os.path.join(_HERE, "csrc", "libuegpu.so")
+GPU_LIB = os.environ.get("UE_GPU_LIB", os.path.join(_HERE, "csrc", "libuegpu.so"))
 
 _i64 = C.c_int64
 _dp = C.POINTER(C.c_double)

@@ -17,6 +17,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -42,6 +43,7 @@ std::vector<void*> g_static_allocs;
 double *d_base = nullptr, *d_yl = nullptr, *d_yldot00 = nullptr, *d_tmp = nullptr, *d_yldot = nullptr;
 double *d_dtuse = nullptr, *d_ylodt = nullptr, *d_suscal = nullptr, *d_sfscal = nullptr;
 int* d_err = nullptr;
+int* h_err = nullptr;  // pinned
 // Jacobian work space
 int64_t g_ivmin = 1, g_ivmax = 0;
 std::vector<int> h_list_narrow, h_list_wide;
@@ -365,7 +367,7 @@ __global__ void k_scan(const int* __restrict__ rowcnt, int64_t* __restrict__ ia,
 }
 __global__ void k_fill(int64_t neq, int64_t ivmin, int64_t ivmax, const int64_t* __restrict__ coloff, const int* __restrict__ colcnt,
                        const int* __restrict__ colrow, const double* __restrict__ colval, const int64_t* __restrict__ ia, int* __restrict__ rowfill,
-                       double* __restrict__ jac, int64_t* __restrict__ ja) {
+                       double* __restrict__ jac, int64_t* __restrict__ ja, int64_t nnzmx) {
   const int64_t iv = ivmin + blockIdx.x;
   if (iv > ivmax) return;
   const int64_t o = coloff[iv - 1];
@@ -373,12 +375,11 @@ __global__ void k_fill(int64_t neq, int64_t ivmin, int64_t ivmax, const int64_t*
   for (int e = threadIdx.x; e < n; e += blockDim.x) {
     const int row = colrow[o + e];
     const int64_t p = ia[row - 1] - 1 + atomicAdd(&rowfill[row - 1], 1);
-    ja[p] = iv;
-    jac[p] = colval[o + e];
+    if (p < nnzmx) { ja[p] = iv; jac[p] = colval[o + e]; }   // overflow is reported by the host after the sequence
   }
 }
 // one warp per row: rank sort of the row's entries by column (rows hold a few tens of entries)
-__global__ void k_sortrows(int64_t neq, const int64_t* __restrict__ ia, double* __restrict__ jac, int64_t* __restrict__ ja) {
+__global__ void k_sortrows(int64_t neq, const int64_t* __restrict__ ia, double* __restrict__ jac, int64_t* __restrict__ ja, int64_t nnzmx) {
   constexpr int CAP = 96;
   __shared__ int64_t scol[4][CAP];
   __shared__ double sval[4][CAP];
@@ -387,7 +388,7 @@ __global__ void k_sortrows(int64_t neq, const int64_t* __restrict__ ia, double* 
   if (r >= neq) return;
   const int64_t b = ia[r] - 1, e = ia[r + 1] - 1;
   const int n = (int)(e - b);
-  if (n <= 1) return;
+  if (n <= 1 || e > nnzmx) return;
   if (n <= CAP) {
     for (int i = lane; i < n; i += 32) { scol[wib][i] = ja[b + i]; sval[wib][i] = jac[b + i]; }
     __syncwarp();
@@ -447,11 +448,13 @@ int check_switches() {
   return 0;
 }
 
+void drop_graphs();
 void free_all() {
+  drop_graphs();
   for (void* p : g_static_allocs) cudaFree(p);
   g_static_allocs.clear();
   void* ptrs[] = {d_base, d_yl, d_yldot00, d_tmp, d_yldot, d_dtuse, d_ylodt, d_suscal, d_sfscal, d_err, d_list_narrow, d_list_wide, d_coloff,
-                  d_colcnt, d_colrow, d_colval, d_rowcnt, d_rowfill, d_ia, d_ja, d_jac};
+                  d_colcnt, d_colrow, d_colval, d_ia, d_ja, d_jac};
   for (void* p : ptrs) if (p) cudaFree(p);
   d_base = d_yl = d_yldot00 = d_tmp = d_yldot = d_dtuse = d_ylodt = d_suscal = d_sfscal = nullptr;
   d_err = nullptr; d_list_narrow = d_list_wide = nullptr; d_coloff = nullptr; d_colcnt = d_colrow = nullptr; d_colval = nullptr;
@@ -509,16 +512,65 @@ int upload_lists() {
   return 0;
 }
 
-int run_residual_dev(const double* dyl, double* dyldot, bool need_rows) {
+// ---- launch sequences; replayed as CUDA graphs (the sequences are launch-latency bound) -----------------
+struct GKey {
+  int kind; const void *p0, *p1, *p2, *p3, *p4; int64_t a, b, c; int flag;
+  bool operator<(const GKey& o) const { return std::memcmp(this, &o, sizeof(GKey)) < 0; }
+};
+std::map<GKey, cudaGraphExec_t> g_graphs;
+void drop_graphs() { for (auto& kv : g_graphs) cudaGraphExecDestroy(kv.second); g_graphs.clear(); }
+
+int enqueue_residual(const double* dyl, double* dyldot, bool need_rows) {
   const int B = 128, G = (NC + B - 1) / B, G32 = (NC + 31) / 32;
   CK(cudaMemsetAsync(d_err, 0, sizeof(int), g_stream));
   k_phase0<<<G, B, 0, g_stream>>>(d_base, dyl, NXS, NC, d_err);
   k_phase1<<<G32, 160, 0, g_stream>>>(d_base, NXS, NC);
   k_phase2<<<G32, 128, 0, g_stream>>>(d_base, d_tmp, NXS, NC);
-  g_launches += 3;
-  if (need_rows) { k_phase3<<<G, B, 0, g_stream>>>(d_base, d_tmp, dyldot, dyl, d_dtuse, d_ylodt, neq, NXS, NC); g_launches += 1; }
-  CK(cudaGetLastError());
+  if (need_rows) k_phase3<<<G, B, 0, g_stream>>>(d_base, d_tmp, dyldot, dyl, d_dtuse, d_ylodt, neq, NXS, NC);
   return 0;
+}
+int enqueue_jac(const double* dyl, const double* dy00, int64_t ml, int64_t mu, int64_t nnzmx, double* djac, int64_t* dja, int64_t* dia, bool base_current) {
+  if (!base_current) { int rc = enqueue_residual(dyl, nullptr, false); if (rc) return rc; }
+  CK(cudaMemsetAsync(d_colcnt, 0, 3 * neq * sizeof(int), g_stream));
+  const int na = (int)h_list_narrow.size(), nb = (int)h_list_wide.size();
+  const int nba = (na + g_np_a - 1) / g_np_a, nbb = (nb + g_np_b - 1) / g_np_b;
+  if (nba + nbb > 0)
+    k_jac<<<nba + nbb, 256, std::max(g_smem_narrow, g_smem_wide), g_stream>>>(d_list_narrow, na, g_np_a, g_ncand_narrow, nba, d_list_wide, nb, g_np_b, g_ncand_wide, d_base, dyl,
+                                                                          dy00, d_suscal, d_sfscal, d_dtuse, d_ylodt, neq, ml, mu, NXS, NC, d_coloff, d_colcnt, d_colrow,
+                                                                          d_colval, d_rowcnt, d_err);
+  k_scan<<<1, 1024, 0, g_stream>>>(d_rowcnt, dia, neq);
+  const int64_t ncol = g_ivmax - g_ivmin + 1;
+  if (ncol > 0) {
+    k_fill<<<(unsigned)ncol, 64, 0, g_stream>>>(neq, g_ivmin, g_ivmax, d_coloff, d_colcnt, d_colrow, d_colval, dia, d_rowfill, djac, dja, nnzmx);
+    k_sortrows<<<(unsigned)((neq + 3) / 4), 128, 0, g_stream>>>(neq, dia, djac, dja, nnzmx);
+  }
+  return 0;
+}
+template <typename F>
+int replay(const GKey& key, F enqueue) {
+  auto it = g_graphs.find(key);
+  if (it == g_graphs.end()) {
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue();
+    cudaError_t e = cudaStreamEndCapture(g_stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) { g_err = std::string("CUDA graph capture failed: ") + cudaGetErrorString(e); return -10; }
+    cudaGraphExec_t ex = nullptr;
+    CK(cudaGraphInstantiate(&ex, graph, 0));
+    cudaGraphDestroy(graph);
+    if (g_graphs.size() > 64) drop_graphs();
+    it = g_graphs.emplace(key, ex).first;
+  }
+  CK(cudaGraphLaunch(it->second, g_stream));
+  return 0;
+}
+
+int run_residual_dev(const double* dyl, double* dyldot, bool need_rows) {
+  GKey k; std::memset(&k, 0, sizeof k);
+  k.kind = 1; k.p0 = dyl; k.p1 = dyldot; k.flag = need_rows;
+  g_launches += need_rows ? 4 : 3;
+  return replay(k, [&]() { return enqueue_residual(dyl, dyldot, need_rows); });
 }
 
 int check_errflag() {
@@ -532,25 +584,11 @@ int check_errflag() {
 
 int run_jac_dev(const double* dyl, const double* dy00, int64_t ml, int64_t mu, int64_t nnzmx, double* djac, int64_t* dja, int64_t* dia, int64_t* nnz_out,
                 bool base_current) {
-  int rc = 0;
-  if (!base_current) rc = run_residual_dev(dyl, nullptr, false);  // base planes at yl
+  GKey k; std::memset(&k, 0, sizeof k);
+  k.kind = 2; k.p0 = dyl; k.p1 = dy00; k.p2 = djac; k.p3 = dja; k.p4 = dia; k.a = ml; k.b = mu; k.c = nnzmx; k.flag = base_current;
+  g_launches += (base_current ? 0 : 3) + 4;
+  int rc = replay(k, [&]() { return enqueue_jac(dyl, dy00, ml, mu, nnzmx, djac, dja, dia, base_current); });
   if (rc) return rc;
-  CK(cudaMemsetAsync(d_rowcnt, 0, neq * sizeof(int), g_stream));
-  CK(cudaMemsetAsync(d_rowfill, 0, neq * sizeof(int), g_stream));
-  CK(cudaMemsetAsync(d_colcnt, 0, neq * sizeof(int), g_stream));
-  {
-    const int na = (int)h_list_narrow.size(), nb = (int)h_list_wide.size();
-    const int nba = (na + g_np_a - 1) / g_np_a, nbb = (nb + g_np_b - 1) / g_np_b;
-    if (nba + nbb > 0) {
-      k_jac<<<nba + nbb, 256, std::max(g_smem_narrow, g_smem_wide), g_stream>>>(d_list_narrow, na, g_np_a, g_ncand_narrow, nba, d_list_wide, nb, g_np_b, g_ncand_wide, d_base,
-                                                                            dyl, dy00, d_suscal, d_sfscal, d_dtuse, d_ylodt, neq, ml, mu, NXS, NC, d_coloff, d_colcnt,
-                                                                            d_colrow, d_colval, d_rowcnt, d_err);
-      g_launches += 1;
-    }
-  }
-  CK(cudaGetLastError());
-  k_scan<<<1, 1024, 0, g_stream>>>(d_rowcnt, dia, neq);
-  g_launches += 1;
   int64_t last = 0;
   CK(cudaMemcpyAsync(&last, dia + neq, sizeof(int64_t), cudaMemcpyDeviceToHost, g_stream));
   CK(cudaStreamSynchronize(g_stream));
@@ -560,13 +598,6 @@ int run_jac_dev(const double* dyl, const double* dy00, int64_t ml, int64_t mu, i
     g_err = "*** jac_calc -- More storage needed for Jacobian. Storage exceeded. Increase lenpfac.";
     return -2;
   }
-  const int64_t ncol = g_ivmax - g_ivmin + 1;
-  if (ncol > 0) {
-    k_fill<<<(unsigned)ncol, 64, 0, g_stream>>>(neq, g_ivmin, g_ivmax, d_coloff, d_colcnt, d_colrow, d_colval, dia, d_rowfill, djac, dja);
-    k_sortrows<<<(unsigned)((neq + 3) / 4), 128, 0, g_stream>>>(neq, dia, djac, dja);
-    g_launches += 2;
-  }
-  CK(cudaGetLastError());
   return 0;
 }
 
@@ -639,6 +670,7 @@ int ue_gpu_init(void) {
   CK(cudaMalloc(&d_suscal, neq * sizeof(double)));
   CK(cudaMalloc(&d_sfscal, neq * sizeof(double)));
   CK(cudaMalloc(&d_err, sizeof(int)));
+  if (!h_err) CK(cudaMallocHost(&h_err, sizeof(int)));
   {
     std::vector<double> big(neq, 1e20), one(neq, 1.0), zero(neq, 0.0);
     CK(cudaMemcpy(d_dtuse, big.data(), neq * 8, cudaMemcpyHostToDevice));
@@ -651,11 +683,11 @@ int ue_gpu_init(void) {
   if ((rc = upload_lists())) return rc;
   CK(cudaMalloc(&d_coloff, neq * sizeof(int64_t)));
   CK(cudaMemcpy(d_coloff, h_coloff.data(), neq * sizeof(int64_t), cudaMemcpyHostToDevice));
-  CK(cudaMalloc(&d_colcnt, neq * sizeof(int)));
+  CK(cudaMalloc(&d_colcnt, 3 * neq * sizeof(int)));  // colcnt | rowcnt | rowfill contiguous: one memset per Jacobian
   CK(cudaMalloc(&d_colrow, g_cap_total * sizeof(int)));
   CK(cudaMalloc(&d_colval, g_cap_total * sizeof(double)));
-  CK(cudaMalloc(&d_rowcnt, neq * sizeof(int)));
-  CK(cudaMalloc(&d_rowfill, neq * sizeof(int)));
+  d_rowcnt = d_colcnt + neq;
+  d_rowfill = d_colcnt + 2 * neq;
   g_nnzcap = g_cap_total;
   CK(cudaMalloc(&d_ia, (neq + 1) * sizeof(int64_t)));
   CK(cudaMalloc(&d_ja, g_nnzcap * sizeof(int64_t)));
@@ -697,16 +729,23 @@ int ue_gpu_pandf1_dev(int64_t n, double time, const double* dyl, double* dyldot)
 }
 
 int ue_gpu_pandf1(int64_t n, double time, const double* yl, double* yldot) {
+  (void)time;
   if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
   if (n != neq) { g_err = "pandf1: neq mismatch"; return -1; }
+  g_base_valid = false; g_base_dev_valid = false;
   CK(cudaMemcpyAsync(d_yl, yl, (neq + 2) * 8, cudaMemcpyHostToDevice, g_stream));
-  g_base_valid = false;
-  int rc = ue_gpu_pandf1_dev(n, time, d_yl, d_yldot);
+  CK(cudaEventRecord(g_ev0, g_stream));
+  int rc = run_residual_dev(d_yl, d_yldot, true);
   if (rc) return rc;
+  CK(cudaEventRecord(g_ev1, g_stream));
   CK(cudaMemcpyAsync(yldot, d_yldot, neq * 8, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
+  CK(cudaMemcpyAsync(h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));  // the only synchronisation of the call
+  if (*h_err & 1) { g_err = "***  ni is negative - calculation stopped"; return -3; }
+  if (*h_err & 2) { g_err = "***  ng is negative - calculation stopped"; return -3; }
+  cudaEventElapsedTime(&g_res_ms, g_ev0, g_ev1);
   g_base_yl.assign(yl, yl + neq);  // the base planes now describe this yl (they do not depend on yl(neq+1..2))
-  g_base_valid = true;
+  g_base_valid = true; g_base_dev_valid = true;
   return 0;
 }
 
@@ -754,6 +793,7 @@ int ue_gpu_set_column_range(int64_t ivmin, int64_t ivmax) {
   g_ivmin = ivmin; g_ivmax = ivmax;
   const size_t s1 = g_smem_narrow, s2 = g_smem_wide;
   build_lists();
+  drop_graphs();
   (void)s1; (void)s2;
   CK(cudaFuncSetAttribute(k_jac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(std::max(g_smem_narrow, g_smem_wide), 1024)));
   return upload_lists();
