@@ -112,6 +112,43 @@ def test_jacobian_parity_4x(built):
     _check_jac(*_jac_pair(c, yl, gpu, ora))
 
 
+# switch-set variants: every branch the kernels claim to support, residual AND Jacobian bit-identical to the oracle
+VARIANTS = {
+    "central_differencing": {"bbb.methn": 22, "bbb.methu": 22, "bbb.methe": 22, "bbb.methi": 22, "bbb.methg": 22},
+    "mixed_schemes": {"bbb.methn": 23, "bbb.methu": 32, "bbb.methe": 23, "bbb.methi": 32, "bbb.methg": 23},
+    "core_power_flux_bc": {"bbb.iflcore": 1, "bbb.pcoree": 4.0e5, "bbb.pcorei": 4.0e5},
+    "core_particle_flux_bc": {"bbb.isnicore": 0, "bbb.curcore": 10.0},
+    "wall_flux_bcs": {"bbb.istewc": 0, "bbb.istiwc": 0, "bbb.istepfc": 1, "bbb.istipfc": 1, "bbb.isupcore": 1},
+    "supersonic_plates": {"bbb.isupss": 1},
+    "extrap_plates": {"bbb.isupss": -1},
+    "albedo_like_recycling": {"bbb.recycp": -0.5},
+    "flux_limits": {"bbb.isflxlde": 1, "bbb.flgam": 2.0, "bbb.isflxldi": 1, "bbb.flalfv": 0.5, "bbb.flalfgx": np.full(10, 1.0), "bbb.flalfgy": np.full(10, 1.0)},
+    "ion_flux_limit_off": {"bbb.isflxldi": 0, "bbb.isplflxl": 1},
+    "viscosity_options": {"bbb.isgxvon": 1, "bbb.ishavisy": 0, "bbb.isvhyha": 1},
+    "log_radial_velocity": {"bbb.isvylog": 1, "bbb.difpr": 0.3},
+    "cx_model_2_recomb": {"bbb.icnucx": 2, "bbb.isrecmon": 1, "com.istabon": 10},
+    "const_rates": {"bbb.icnuiz": 1, "bbb.icnucx": 1, "bbb.islnlamcon": 1},
+    "turbulent_kye": {"bbb.kyet": 0.5, "bbb.kyit": 0.5},
+    "v81_defaults": {"bbb.oldseec": 0.0, "bbb.isoldalbarea": 0.0},
+    "neutral_options": {"bbb.cngmom": 1.0, "bbb.cmwall": 0.5, "bbb.cngtgx": 1.0, "bbb.cngtgy": 1.0, "bbb.kxn": 1.0, "bbb.kyn": 1.0,
+                        "bbb.isgasdc": 1, "bbb.cngflox": 1.0, "bbb.alftng": 0.5, "bbb.isdifxg_aug": 1, "bbb.isdifyg_aug": 1},
+    "wide_jacobian_box": {"bbb.xlinc": 3, "bbb.xrinc": 2, "bbb.yinc": 3},
+    "no_core_all": {"bbb.isjaccorall": 0},
+}
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+def test_switch_variants(built, variant):
+    c, yl = make_case("d3dHsm", perturb=2e-3, overrides=VARIANTS[variant])
+    gpu = bind(load_gpu(), c)
+    ora = bind(oracle(), c)
+    fg, fo = gpu.pandf1(yl), ora.pandf1(yl)
+    assert np.isfinite(fo).all()
+    assert np.array_equal(fg, fo), "%s: %d residual entries differ" % (variant, (fg != fo).sum())
+    jg, jo, noise = _jac_pair(c, yl, gpu, ora)
+    _check_jac(jg, jo, noise)
+
+
 def test_jacobian_column_range_split(built):
     """ppp-style column split: the union of per-range CSRs equals the full CSR."""
     c, yl, gpu, ora = _pair("d3dHsm", 1e-3)

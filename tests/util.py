@@ -16,13 +16,23 @@ def oracle():
     return UeLib(ORACLE_LIB, "ue_ora_")
 
 
-def make_case(name="d3dHsm", istabon=0, perturb=0.0, seed=1234):
+def make_case(name="d3dHsm", istabon=0, perturb=0.0, seed=1234, overrides=None):
     g = load_grid_npz()
     state = load_state_npz("case2_state.npz" if name == "case2" else "d3dHsm_state.npz")
     if name == "d3dHsm4x":
         g = refine_grid(g, 4, 4)
         state = refine_state(state, 4, 4)
     c = d3dhsm_case(g, istabon=10 if name == "case2" else istabon)
+    if overrides:
+        for k, v in overrides.items():
+            pkg, nm = k.split(".")
+            ns = getattr(c, pkg)
+            cur = getattr(ns, nm) if nm in ns else None
+            if isinstance(cur, np.ndarray) and not isinstance(v, np.ndarray):
+                cur = cur.copy()
+                cur.flat[0] = v   # species-indexed inputs: species 1
+                v = cur
+            setattr(ns, nm, v)
     if c.com.istabon == 10:
         c.set_rate_tables(load_rate_tables_npz())
     c.setup()
