@@ -225,6 +225,11 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6453.1))
     G = 16 + 3  # static real planes + int planes the kernels read (include/ue_params.h)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["dram_bytes_per_launch"].get(name)
+    except Exception:
+        pass
     ncell = (c.com.nx + 2) * (c.com.ny + 2)
     alg_bytes = 8 * (2 * (neq + 2) + G * ncell) + 16 * nnz_total + 8 * (neq + 1)
     achieved = alg_bytes / (jac_ms * 1e-3) / 1e9
@@ -239,8 +244,9 @@ def main():
                          resid_evals_per_s=a.steps / t_res_e2e),
                 gpu_launches=int(l1.value - l0.value),
                 resid_evals_per_s=1e3 / res_ms if res_ms > 0 else None, jac_kernel_ms=jac_ms, resid_kernel_ms=res_ms,
-                roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
-                              note="algorithmic bytes = 8*(2(neq+2)+G*Ncell)+16*nnz+8*(neq+1), G=%d; latency/FP64-issue bound at this size (see DESIGN.md)" % G),
+                roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
+                              kernel="k_jac (+ scan/fill/sort, CUDA events around the Jacobian sequence)", peak_source="MEASURED_PEAKS.json hbm_gbs",
+                              note="algorithmic bytes = 8*(2(neq+2)+G*Ncell)+16*nnz+8*(neq+1), G=%d; the kernel is latency/instruction-issue bound at this size, not HBM bound (DESIGN.md 3.4)" % G),
                 clocks=dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max([s[1] for s in samples] or [0.0]), reasons=reasons_of([s[2] for s in samples])))
     if cb is not None:
         line["cpu_baseline"] = dict(value=cb["value"], unit="nnz/s", cores=cb["cores"], kind=cb["kind"], sample=cb["sample"])

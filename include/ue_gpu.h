@@ -57,6 +57,12 @@ int ue_gpu_jac_calc(int64_t neq, double t, const double* yl, const double* yldot
                     int64_t ml, int64_t mu, int64_t nnzmx,
                     double* jac, int64_t* ja, int64_t* ia, int64_t* nnz_out);
 
+/* ---- sfsetnk (bbb/oderhs.m:9815-9884) with the Jacobian kept on the device --------------------------
+ * f0 = pandf1(yl | yl(neq+1)=1); J = jac_calc(yl,f0); J <- J diag(1/su) (amudia); sf(i) = 1/max_k|J_ik| (rnrms,
+ * normtype 0); ydt_max0 = max(cutlo, max_i |f0_i sf_i|).  Returns -7 with the reference's "Jacobian row = 0"
+ * message if a row vanishes.  Uses dtuse/sfscal of the last ue_gpu_step_params. */
+int ue_gpu_sfsetnk(int64_t neq, const double* yl, const double* su, int64_t ml, int64_t mu, double* sf, double* ydt_max0);
+
 /* ---- device-resident variants (inputs/outputs already in HBM) -------------
  * Same semantics; pointers are device pointers on the current device.  Used by
  * bench.py for the kernel-only figure and by a host that keeps yl on the GPU. */

@@ -8,7 +8,7 @@ import re
 import numpy as np
 import pytest
 
-from tests.util import ROOT, bind, make_case, oracle, psetnk_inputs
+from tests.util import ROOT, bind, make_case, newton_solve, oracle, psetnk_inputs
 from uedge_b200.cases import GOLDEN, load_grid_npz
 
 
@@ -65,6 +65,18 @@ def test_oracle_windowed_equals_full_difference(built):
             ref = col[i] - (1e-20 if (i == iv and c.iseqalg[iv] == 0) else 0.0)
             if len(hit):
                 assert abs(val - ref) <= 1e-6 * max(abs(ref), abs(val)) + 1e-3 * np.abs(col).max() * 1e-6
+
+
+def test_newton_recovers_reference_steady_state(built):
+    """End to end: Newton with the oracle's residual + FD Jacobian, started 1e-3 away, must return to the
+    reference's converged state d3dHsm.h5 within 1e-8 in the su-normalised variables (north-star criterion)."""
+    c, yref = make_case("d3dHsm")
+    _, y0 = make_case("d3dHsm", perturb=1e-3, seed=7)
+    ora = bind(oracle(), c)
+    y, hist = newton_solve(ora, c, y0)
+    assert hist[-1] < 1e-6 and hist[0] > 1.0
+    n = c.bbb.neq
+    assert np.abs((y[:n] - yref[:n]) * c.suscal(yref)).max() < 1e-8
 
 
 def test_case2_fnrm_documented_mismatch(built):

@@ -117,6 +117,20 @@ class UeLib:
         n = nnz.value
         return jac[:n].copy(), ja[:n].copy(), ia
 
+    def sfsetnk(self, yl, su, ml, mu):
+        """Row scale factors sf and ydt_max0 as sfsetnk computes them (bbb/oderhs.m:9815-9884); product library only."""
+        fn = getattr(self.lib, self.prefix + "sfsetnk")
+        fn.argtypes = [_i64, _dp, _dp, _i64, _i64, _dp, _dp]
+        fn.restype = C.c_int
+        yl = np.ascontiguousarray(yl, dtype=np.float64)
+        su = np.ascontiguousarray(su, dtype=np.float64)
+        sf = np.zeros(self.neq)
+        ym = C.c_double(0.0)
+        rc = fn(self.neq, _d(yl), _d(su), int(ml), int(mu), _d(sf), C.byref(ym))
+        if rc != 0:
+            raise UeError("sfsetnk failed (%d): %s" % (rc, getattr(self.lib, self.prefix + "last_error")().decode()))
+        return sf, ym.value
+
     def set_column_range(self, ivmin, ivmax):
         self._call("set_column_range", int(ivmin), int(ivmax))
 

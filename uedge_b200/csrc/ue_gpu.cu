@@ -164,7 +164,7 @@ __host__ __device__ inline bool is_wide(const UeParams& P, const Win& w, int yc)
 // One launch covers both classes: blocks [0, nb_a) take NP_A unknowns each from list A (regular windows),
 // the remaining blocks take NP_B unknowns each from list B (wide windows).
 constexpr int NP_MAX = 8;
-__global__ void __launch_bounds__(256) k_jac(const int* __restrict__ list_a, int n_a, int np_a, int ncand_a, int nb_a, const int* __restrict__ list_b, int n_b,
+__global__ void __launch_bounds__(256, 3) k_jac(const int* __restrict__ list_a, int n_a, int np_a, int ncand_a, int nb_a, const int* __restrict__ list_b, int n_b,
                                              int np_b, int ncand_b, double* base, const double* __restrict__ yl,
                                              const double* __restrict__ yldot00, const double* __restrict__ suscal, const double* __restrict__ sfscal,
                                              const double* __restrict__ dtuse, const double* __restrict__ ylodt, int64_t neq, int64_t ml, int64_t mu, int NXS,
@@ -405,6 +405,28 @@ __global__ void k_sortrows(int64_t neq, const int64_t* __restrict__ ia, double* 
       while (j >= b && ja[j] > cj) { ja[j + 1] = ja[j]; jac[j + 1] = jac[j]; --j; }
       ja[j + 1] = cj; jac[j + 1] = cv;
     }
+  }
+}
+
+// sfsetnk scaling chain (oderhs.m:9862-9881): column scaling by 1/su (amudia, svr/svrut4.m:1104-1130), row max-norm
+// (rnrms with normtype=0, svr/svrut4.m:1002-1052), sf = 1/norm, and ydt_max0 = max|yldot0*sf|.  One warp per row.
+__global__ void k_rownorm(int64_t neq, const int64_t* __restrict__ ia, const int64_t* __restrict__ ja, const double* __restrict__ jac,
+                          const double* __restrict__ su, const double* __restrict__ yldot0, double* __restrict__ sf, unsigned long long* ydtmax_bits, int* zero_row) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= neq) return;
+  double m = 0.0;
+  for (int64_t k = ia[r] - 1 + lane; k < ia[r + 1] - 1; k += 32) {
+    const double t = 1. / su[ja[k] - 1];
+    m = fmax(m, fabs(jac[k] * t));
+  }
+  for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if (lane == 0) {
+    if (fabs(m) < 1e20 * D.cutlo) { atomicMin(zero_row, (int)(r + 1)); sf[r] = 0.; return; }
+    const double s = 1. / m;
+    sf[r] = s;
+    const double v = fabs(yldot0[r] * s);
+    atomicMax(ydtmax_bits, (unsigned long long)__double_as_longlong(v));  // v >= 0: bit pattern is monotone
   }
 }
 
@@ -802,6 +824,41 @@ int ue_gpu_set_column_range(int64_t ivmin, int64_t ivmax) {
 // Device-pointer callers: assert that d_yl has not changed since the last ue_gpu_pandf1_dev call, so the next
 // ue_gpu_jac_calc_dev may reuse the base planes (the host-pointer entry points check this themselves).
 int ue_gpu_assume_base_current(int64_t flag) { g_jac_trust_base = (flag != 0); if (flag) g_base_valid = g_base_dev_valid; return 0; }
+// sfsetnk (bbb/oderhs.m:9815-9884) with the Jacobian kept on the device: f0 = pandf1(yl | flag=1), J = jac_calc,
+// J <- J*diag(1/su), sf(i) = 1/max_k|J_ik|, ydt_max0 = max_i|f0_i sf_i|.  Only sf (neq doubles) returns to the host.
+int ue_gpu_sfsetnk(int64_t n, const double* yl, const double* su, int64_t ml, int64_t mu, double* sf, double* ydt_max0) {
+  if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
+  if (n != neq) { g_err = "sfsetnk: neq mismatch"; return -1; }
+  std::vector<double> y(yl, yl + neq + 2);
+  y[neq] = 1.;  // oderhs.m:9848
+  CK(cudaMemcpyAsync(d_yl, y.data(), (neq + 2) * 8, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(d_suscal, su, neq * 8, cudaMemcpyHostToDevice, g_stream));
+  g_base_valid = false; g_base_dev_valid = false;
+  int rc = run_residual_dev(d_yl, d_yldot00, true);
+  if (rc) return rc;
+  int64_t nnz = 0;
+  rc = run_jac_dev(d_yl, d_yldot00, ml, mu, g_nnzcap, d_jac, d_ja, d_ia, &nnz, true);
+  if (rc) return rc;
+  static unsigned long long* d_bits = nullptr; static int* d_zero = nullptr;
+  if (!d_bits) { CK(cudaMalloc(&d_bits, 8)); CK(cudaMalloc(&d_zero, 4)); }
+  const unsigned long long cut = (unsigned long long)0;  // ydt_max0 starts at cutlo (oderhs.m:9871); applied on the host
+  const int big = 0x7fffffff;
+  CK(cudaMemcpyAsync(d_bits, &cut, 8, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(d_zero, &big, 4, cudaMemcpyHostToDevice, g_stream));
+  k_rownorm<<<(unsigned)((neq + 3) / 4), 128, 0, g_stream>>>(neq, d_ia, d_ja, d_jac, d_suscal, d_yldot00, d_tmp, d_bits, d_zero);
+  g_launches += 1;
+  unsigned long long bits = 0; int zero = 0;
+  CK(cudaMemcpyAsync(sf, d_tmp, neq * 8, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaMemcpyAsync(&bits, d_bits, 8, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaMemcpyAsync(&zero, d_zero, 4, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  rc = check_errflag();
+  if (rc) return rc;
+  if (zero != big) { char b[96]; snprintf(b, sizeof b, "*** Error: Jacobian row = 0 for eqn iv = %d", zero); g_err = b; return -7; }
+  double v; std::memcpy(&v, &bits, 8);
+  *ydt_max0 = std::max(v, S.p.cutlo);
+  return 0;
+}
 int ue_gpu_kernel_launches(int64_t* n) { *n = g_launches; return 0; }
 int ue_gpu_last_kernel_ms(double* jac_ms, double* res_ms) { *jac_ms = g_jac_ms; *res_ms = g_res_ms; return 0; }
 // device buffers owned by the library (for callers that keep state resident, e.g. bench.py)
