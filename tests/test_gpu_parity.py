@@ -227,3 +227,42 @@ def test_nnzmx_overflow_message(built):
     f = gpu.pandf1(y)
     with pytest.raises(Exception, match="More storage needed"):
         gpu.jac_calc(y, f, b.lbw, b.ubw, 1000)
+
+
+def test_solver_style_buffer_reuse(built):
+    """NKSOL calls rhsnk with the same work arrays every time: from the second call on the host entry point replays
+    one graph holding upload, kernels and download.  Results must not depend on which path ran."""
+    c, yl, gpu, ora = _pair("d3dHsm", 1e-3)
+    n = c.bbb.neq
+    rng = np.random.default_rng(5)
+    ybuf, fbuf = yl.copy(), np.zeros(n)
+    for it in range(5):
+        ybuf[:n] = yl[:n] * (1 + 1e-3 * rng.uniform(-1, 1, n))
+        gpu.pandf1(ybuf, out=fbuf)
+        assert np.array_equal(fbuf, ora.pandf1(ybuf)), "call %d" % it
+    ybuf[5 * 40] = -1.0
+    with pytest.raises(Exception, match="ni is negative"):
+        gpu.pandf1(ybuf, out=fbuf)
+
+
+def test_jacobian_with_foreign_yldot00(built):
+    """yldot00 that is not the vector the preceding residual call returned must be uploaded and used as given."""
+    c, yl, gpu, ora = _pair("d3dHsm", 1e-3)
+    b = c.bbb
+    y, su = psetnk_inputs(c, yl)
+    for lib in (gpu, ora):
+        lib.step_params(np.full(b.neq, 1e20), y[: b.neq], su, np.ones(b.neq))
+    f = gpu.pandf1(y)
+    assert np.array_equal(f, ora.pandf1(y))
+    f2 = f.copy()
+    f2[7::11] *= 1 + 1e-9
+    jg = gpu.jac_calc(y, f2, b.lbw, b.ubw, b.nnzmx)
+    jo = ora.jac_calc(y, f2, b.lbw, b.ubw, b.nnzmx)
+    assert all(np.array_equal(p, q) for p, q in zip(jg, jo))
+    # and a different yl than the preceding residual call: nothing may be reused
+    y3 = y.copy()
+    y3[: b.neq] *= 1 + 1e-4
+    f3 = ora.pandf1(y3)
+    jg = gpu.jac_calc(y3, f3, b.lbw, b.ubw, b.nnzmx)
+    jo = ora.jac_calc(y3, f3, b.lbw, b.ubw, b.nnzmx)
+    assert all(np.array_equal(p, q) for p, q in zip(jg, jo))

@@ -95,11 +95,12 @@ class UeLib:
         self._call("step_params", self.neq, *[_d(x) for x in a])
 
     # ---- hot path ---------------------------------------------------------------
-    def pandf1(self, yl, time=0.0):
-        """Pandf1rhs_interface: full residual pandf1(-1,-1,0,neq,time,yl,yldot)."""
+    def pandf1(self, yl, time=0.0, out=None):
+        """Pandf1rhs_interface: full residual pandf1(-1,-1,0,neq,time,yl,yldot).  `out` reuses a caller buffer."""
         yl = np.ascontiguousarray(yl, dtype=np.float64)
         assert yl.size == self.neq + 2
-        yldot = np.zeros(self.neq)
+        yldot = np.zeros(self.neq) if out is None else out
+        assert yldot.dtype == np.float64 and yldot.size >= self.neq and yldot.flags.c_contiguous
         self._call("pandf1", self.neq, float(time), _d(yl), _d(yldot))
         return yldot
 

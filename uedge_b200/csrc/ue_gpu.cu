@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -33,6 +34,9 @@ bool g_ready = false;
 int nx, ny, NXS, NC;
 int64_t neq = 0;
 int64_t g_launches = 0;
+bool g_host_graphs = true;
+std::set<std::pair<const void*, const void*>> g_seen_host;
+std::vector<double> g_last_yldot;  // host copy of the last residual returned (d_yldot still holds it)
 std::vector<double> g_base_yl;   // yl (first neq entries) for which the base planes in d_base are current
 bool g_base_valid = false, g_jac_trust_base = false, g_base_dev_valid = false;
 float g_jac_ms = 0.f, g_res_ms = 0.f;
@@ -755,18 +759,38 @@ int ue_gpu_pandf1(int64_t n, double time, const double* yl, double* yldot) {
   if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
   if (n != neq) { g_err = "pandf1: neq mismatch"; return -1; }
   g_base_valid = false; g_base_dev_valid = false;
-  CK(cudaMemcpyAsync(d_yl, yl, (neq + 2) * 8, cudaMemcpyHostToDevice, g_stream));
-  CK(cudaEventRecord(g_ev0, g_stream));
-  int rc = run_residual_dev(d_yl, d_yldot, true);
-  if (rc) return rc;
-  CK(cudaEventRecord(g_ev1, g_stream));
-  CK(cudaMemcpyAsync(yldot, d_yldot, neq * 8, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaMemcpyAsync(h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+  // H2D(yl) -> phases 0-3 -> D2H(yldot), D2H(err) as ONE graph launch and ONE synchronisation
+  GKey k; std::memset(&k, 0, sizeof k);
+  k.kind = 3; k.p0 = yl; k.p1 = yldot;
+  g_launches += 4;
+  int rc = 0;
+  // Solvers call with the same work arrays every time (NKSOL's savf/u); a pointer pair seen for the first time takes
+  // the plain path so that callers with fresh buffers per call do not pay a capture each time.
+  bool use_graph = g_host_graphs && (g_graphs.count(k) || !g_seen_host.insert({yl, yldot}).second);
+  if (g_seen_host.size() > 256) g_seen_host.clear();
+  if (use_graph) {
+    rc = replay(k, [&]() {
+      CK(cudaMemcpyAsync(d_yl, yl, (neq + 2) * 8, cudaMemcpyHostToDevice, g_stream));
+      int r = enqueue_residual(d_yl, d_yldot, true);
+      if (r) return r;
+      CK(cudaMemcpyAsync(yldot, d_yldot, neq * 8, cudaMemcpyDeviceToHost, g_stream));
+      CK(cudaMemcpyAsync(h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+      return 0;
+    });
+    if (rc == -10) { g_host_graphs = false; use_graph = false; cudaGetLastError(); }  // not capturable: plain path from now on
+  }
+  if (!use_graph) {
+    CK(cudaMemcpyAsync(d_yl, yl, (neq + 2) * 8, cudaMemcpyHostToDevice, g_stream));
+    rc = run_residual_dev(d_yl, d_yldot, true);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(yldot, d_yldot, neq * 8, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaMemcpyAsync(h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+  } else if (rc) return rc;
   CK(cudaStreamSynchronize(g_stream));  // the only synchronisation of the call
   if (*h_err & 1) { g_err = "***  ni is negative - calculation stopped"; return -3; }
   if (*h_err & 2) { g_err = "***  ng is negative - calculation stopped"; return -3; }
-  cudaEventElapsedTime(&g_res_ms, g_ev0, g_ev1);
-  g_base_yl.assign(yl, yl + neq);  // the base planes now describe this yl (they do not depend on yl(neq+1..2))
+  g_base_yl.assign(yl, yl + neq + 2);  // the base planes (and d_yl) now describe this yl
+  g_last_yldot.assign(yldot, yldot + neq);
   g_base_valid = true; g_base_dev_valid = true;
   return 0;
 }
@@ -791,20 +815,35 @@ int ue_gpu_jac_calc_dev(int64_t n, double t, const double* dyl, const double* dy
 
 int ue_gpu_jac_calc(int64_t n, double t, const double* yl, const double* yldot00, int64_t ml, int64_t mu, int64_t nnzmx, double* jac, int64_t* ja,
                     int64_t* ia, int64_t* nnz_out) {
+  (void)t;
   if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
   if (n != neq) { g_err = "jac_calc: neq mismatch"; return -1; }
-  CK(cudaMemcpyAsync(d_yl, yl, (neq + 2) * 8, cudaMemcpyHostToDevice, g_stream));
-  CK(cudaMemcpyAsync(d_yldot00, yldot00, neq * 8, cudaMemcpyHostToDevice, g_stream));
   // psetnk / sfsetnk evaluate rhsnk(yl) immediately before jac_calc (oderhs.m:9466-9468, 9851-9856): if yl is
-  // bit-identical to that call's, the base planes are already on the device and phases 0-2 are skipped
-  g_jac_trust_base = g_base_valid && (int64_t)g_base_yl.size() == neq && std::memcmp(g_base_yl.data(), yl, neq * 8) == 0;
-  int64_t nnz = 0;
-  int rc = ue_gpu_jac_calc_dev(n, t, d_yl, d_yldot00, ml, mu, nnzmx, d_jac, d_ja, d_ia, &nnz);
-  *nnz_out = nnz;
+  // bit-identical to that call's, the base fields (and yl itself) are already on the device and phases 0-2 and the
+  // upload are skipped; likewise yldot00 if it is the vector that call returned.
+  const bool same_y = g_base_valid && (int64_t)g_base_yl.size() == neq + 2 && std::memcmp(g_base_yl.data(), yl, neq * 8) == 0;
+  const bool same_flags = same_y && std::memcmp(g_base_yl.data() + neq, yl + neq, 16) == 0;
+  const bool same_f = same_y && (int64_t)g_last_yldot.size() == neq && std::memcmp(g_last_yldot.data(), yldot00, neq * 8) == 0;
+  if (!same_flags) CK(cudaMemcpyAsync(d_yl, yl, (neq + 2) * 8, cudaMemcpyHostToDevice, g_stream));
+  const double* dy00 = d_yldot;
+  if (!same_f) { CK(cudaMemcpyAsync(d_yldot00, yldot00, neq * 8, cudaMemcpyHostToDevice, g_stream)); dy00 = d_yldot00; }
+  GKey k; std::memset(&k, 0, sizeof k);
+  const int64_t lim = std::min(nnzmx, g_nnzcap);
+  k.kind = 2; k.p0 = d_yl; k.p1 = dy00; k.p2 = d_jac; k.p3 = d_ja; k.p4 = d_ia; k.a = ml; k.b = mu; k.c = lim; k.flag = same_y;
+  g_launches += (same_y ? 0 : 3) + 4;
+  int rc = replay(k, [&]() { return enqueue_jac(d_yl, dy00, ml, mu, lim, d_jac, d_ja, d_ia, same_y); });
   if (rc) return rc;
+  CK(cudaMemcpyAsync(ia, d_ia, (neq + 1) * 8, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaMemcpyAsync(h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  if (!same_y) { g_base_valid = false; g_base_dev_valid = false; }  // base fields now belong to this yl, but we keep no host copy
+  if (*h_err & 1) { g_err = "***  ni is negative - calculation stopped"; return -3; }
+  if (*h_err & 2) { g_err = "***  ng is negative - calculation stopped"; return -3; }
+  const int64_t nnz = ia[neq] - 1;
+  *nnz_out = nnz;
+  if (nnz > nnzmx) { g_err = "*** jac_calc -- More storage needed for Jacobian. Storage exceeded. Increase lenpfac."; return -2; }
   CK(cudaMemcpyAsync(jac, d_jac, nnz * 8, cudaMemcpyDeviceToHost, g_stream));
   CK(cudaMemcpyAsync(ja, d_ja, nnz * 8, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaMemcpyAsync(ia, d_ia, (neq + 1) * 8, cudaMemcpyDeviceToHost, g_stream));
   CK(cudaStreamSynchronize(g_stream));
   return 0;
 }
