@@ -240,29 +240,67 @@ def test_solver_style_buffer_reuse(built):
         ybuf[:n] = yl[:n] * (1 + 1e-3 * rng.uniform(-1, 1, n))
         gpu.pandf1(ybuf, out=fbuf)
         assert np.array_equal(fbuf, ora.pandf1(ybuf)), "call %d" % it
+    # psetnk's second rhsnk: same unknowns, Jacobian flag off and the time-step term on (only the last phase reruns)
+    dt = 10.0 ** rng.uniform(-6, -3, n)
+    for lib in (gpu, ora):
+        lib.set_real("dtreal", 1e-4)
+        lib.step_params(dt, yl[:n], np.ones(n), np.ones(n))
+    ybuf[n] = 1.0
+    gpu.pandf1(ybuf, out=fbuf)
+    assert np.array_equal(fbuf, ora.pandf1(ybuf))
+    ybuf[n] = -1.0
+    f_on = gpu.pandf1(ybuf, out=fbuf).copy()
+    assert np.array_equal(f_on, ora.pandf1(ybuf))
+    ybuf[n] = 1.0
+    assert not np.array_equal(gpu.pandf1(ybuf), f_on)
+    for lib in (gpu, ora):
+        lib.set_real("dtreal", 1e20)
     ybuf[5 * 40] = -1.0
     with pytest.raises(Exception, match="ni is negative"):
         gpu.pandf1(ybuf, out=fbuf)
 
 
-def test_jacobian_with_foreign_yldot00(built):
-    """yldot00 that is not the vector the preceding residual call returned must be uploaded and used as given."""
+def test_jacobian_without_preceding_residual(built):
+    """jac_calc for a yl other than the last residual call's: everything is uploaded, the residual is re-evaluated on
+    the device and yldot00 is verified against it; the result is the same Jacobian."""
     c, yl, gpu, ora = _pair("d3dHsm", 1e-3)
     b = c.bbb
     y, su = psetnk_inputs(c, yl)
     for lib in (gpu, ora):
         lib.step_params(np.full(b.neq, 1e20), y[: b.neq], su, np.ones(b.neq))
-    f = gpu.pandf1(y)
-    assert np.array_equal(f, ora.pandf1(y))
-    f2 = f.copy()
-    f2[7::11] *= 1 + 1e-9
-    jg = gpu.jac_calc(y, f2, b.lbw, b.ubw, b.nnzmx)
-    jo = ora.jac_calc(y, f2, b.lbw, b.ubw, b.nnzmx)
-    assert all(np.array_equal(p, q) for p, q in zip(jg, jo))
-    # and a different yl than the preceding residual call: nothing may be reused
+    gpu.pandf1(y)
     y3 = y.copy()
     y3[: b.neq] *= 1 + 1e-4
     f3 = ora.pandf1(y3)
     jg = gpu.jac_calc(y3, f3, b.lbw, b.ubw, b.nnzmx)
     jo = ora.jac_calc(y3, f3, b.lbw, b.ubw, b.nnzmx)
     assert all(np.array_equal(p, q) for p, q in zip(jg, jo))
+    # the base fields now describe y3: a second call takes the short path and must agree
+    jg2 = gpu.jac_calc(y3, f3, b.lbw, b.ubw, b.nnzmx)
+    assert all(np.array_equal(p, q) for p, q in zip(jg2, jo))
+
+
+def test_foreign_yldot00_is_refused(built):
+    """The dependency-pruned windows equal the reference's full windows only if yldot00 is pandf1(yl) bit for bit
+    (rows outside the dependency set then difference to exactly zero).  Any other yldot00 fails loudly."""
+    c, yl, gpu, ora = _pair("d3dHsm", 1e-3)
+    b = c.bbb
+    y, su = psetnk_inputs(c, yl)
+    gpu.step_params(np.full(b.neq, 1e20), y[: b.neq], su, np.ones(b.neq))
+    f = gpu.pandf1(y)
+    f2 = f.copy()
+    f2[7::11] *= 1 + 1e-9
+    with pytest.raises(Exception, match="yldot00 is not pandf1"):
+        gpu.jac_calc(y, f2, b.lbw, b.ubw, b.nnzmx)
+    # changing the time-step vector between the two calls makes the cached residual stale: also verified
+    gpu.pandf1(y)
+    dt = np.full(b.neq, 1e-4)
+    gpu.set_real("dtreal", 1e-4)
+    gpu.step_params(dt, y[: b.neq] * 1.01, su, np.ones(b.neq))
+    yneg = y.copy()
+    yneg[b.neq] = -1.0
+    fdt = gpu.pandf1(yneg)
+    assert not np.array_equal(fdt, f)
+    with pytest.raises(Exception, match="yldot00 is not pandf1"):
+        gpu.jac_calc(yneg, f, b.lbw, b.ubw, b.nnzmx)
+    gpu.set_real("dtreal", 1e20)

@@ -107,27 +107,40 @@ struct Acc {
   double* base;   // [PL_COUNT][NC] planes in HBM (base state)
   int NXS, NC;
   // WIN only
-  double* sm4;    // [4][PL_COUNT] private copies of C0, Cw, Ce, Cs
+  double* priv;   // private copies of C0, Cw, Ce, Cs: plane pl of slot k at priv[pl * ps + k * ks]
+  int ps, ks;
   int xc, yc, xw, xe;
   double* rres;   // [rw*rh] resco of candidate rows
   const int* rmask;  // [rw*rh] rows-written mask of candidate cells (bit 0 <=> interior rows written)
   int rx0, ry0, rw, rh;
+  // slot() and get() are written with selects, not branches: a read then is ONE generic load whose address was
+  // chosen arithmetically, so the compiler can keep many reads of a role function in flight (with branches every
+  // read became its own control-flow region and the loads serialised at L2 latency).
   __device__ __forceinline__ int slot(int ix, int iy) const {
-    if (iy == yc) { if (ix == xc) return 0; if (ix == xw) return 1; if (ix == xe) return 2; return -1; }
-    if (iy == yc - 1 && ix == xc) return 3;
-    return -1;
+    const bool r0 = iy == yc;
+    int k = -1;
+    k = (r0 && ix == xe) ? 2 : k;
+    k = (r0 && ix == xw) ? 1 : k;
+    k = (r0 && ix == xc) ? 0 : k;
+    k = (iy == yc - 1 && ix == xc) ? 3 : k;
+    return k;
   }
   __device__ __forceinline__ double get(int pl, int ix, int iy) const {
+    const double* g = base + ((size_t)pl * NC + ix + NXS * iy);
     if (WIN) {
       if (pl == PL_RESCO) {
         const unsigned lx = (unsigned)(ix - rx0), ly = (unsigned)(iy - ry0);
-        if (lx < (unsigned)rw && ly < (unsigned)rh && (rmask[ly * rw + lx] & 0x100)) return rres[ly * rw + lx];
-      } else {
-        const int k = slot(ix, iy);
-        if (k >= 0) return sm4[k * PL_COUNT + pl];
+        const bool in = lx < (unsigned)rw && ly < (unsigned)rh;
+        const int idx = in ? (int)(ly * rw + lx) : 0;
+        const bool use = in && (rmask[idx] & 0x100);
+        const double* p = use ? rres + idx : g;
+        return *p;
       }
+      const int k = slot(ix, iy);
+      const double* p = k >= 0 ? priv + ((size_t)pl * ps + k * ks) : g;
+      return *p;
     }
-    return base[(size_t)pl * NC + ix + NXS * iy];
+    return *g;
   }
   __device__ __forceinline__ void set(int pl, int ix, int iy, double v) const {
     if (WIN) {
@@ -136,7 +149,7 @@ struct Acc {
         if (lx < (unsigned)rw && ly < (unsigned)rh) rres[ly * rw + lx] = v;
       } else {
         const int k = slot(ix, iy);
-        if (k >= 0) sm4[k * PL_COUNT + pl] = v;
+        if (k >= 0) priv[(size_t)pl * ps + k * ks] = v;
       }
       return;
     }

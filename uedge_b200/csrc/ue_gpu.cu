@@ -35,6 +35,7 @@ int nx, ny, NXS, NC;
 int64_t neq = 0;
 int64_t g_launches = 0;
 bool g_host_graphs = true;
+std::vector<double> g_step_host[4];  // last dtuse, ylodt, suscal, sfscal uploaded
 std::set<std::pair<const void*, const void*>> g_seen_host;
 std::vector<double> g_last_yldot;  // host copy of the last residual returned (d_yldot still holds it)
 std::vector<double> g_base_yl;   // yl (first neq entries) for which the base planes in d_base are current
@@ -53,6 +54,12 @@ int64_t g_ivmin = 1, g_ivmax = 0;
 std::vector<int> h_list_narrow, h_list_wide;
 std::vector<int64_t> h_coloff;  // per column offset into the fragment buffers (1-based iv -> h_coloff[iv-1])
 int *d_list_narrow = nullptr, *d_list_wide = nullptr;
+std::vector<unsigned char> h_uinfo;  // UInfo records of the column range, regular windows first
+void* d_uinfo = nullptr;
+double *d_priv = nullptr, *d_jrows = nullptr, *d_rres = nullptr;
+int* d_rmask = nullptr;
+int g_nitems = 0;
+bool g_jac_batched = true;
 int64_t* d_coloff = nullptr;
 int *d_colcnt = nullptr, *d_colrow = nullptr;
 double* d_colval = nullptr;
@@ -168,6 +175,15 @@ __host__ __device__ inline bool is_wide(const UeParams& P, const Win& w, int yc)
 // One launch covers both classes: blocks [0, nb_a) take NP_A unknowns each from list A (regular windows),
 // the remaining blocks take NP_B unknowns each from list B (wide windows).
 constexpr int NP_MAX = 8;
+#ifdef UE_JAC_PROFILE
+__device__ long long g_prof[2048 * 8];
+__device__ long long g_profw[2048 * 16];
+#define PROF(i) do { if (threadIdx.x == 0 && blockIdx.x < 2048) g_prof[blockIdx.x * 8 + (i)] = clock64(); } while (0)
+#define PROFW(j) do { if ((threadIdx.x & 31) == 0 && blockIdx.x < 2048) g_profw[blockIdx.x * 16 + (j) * 8 + (threadIdx.x >> 5)] = clock64(); } while (0)
+#else
+#define PROF(i) do { } while (0)
+#define PROFW(j) do { } while (0)
+#endif
 __global__ void __launch_bounds__(256, 3) k_jac(const int* __restrict__ list_a, int n_a, int np_a, int ncand_a, int nb_a, const int* __restrict__ list_b, int n_b,
                                              int np_b, int ncand_b, double* base, const double* __restrict__ yl,
                                              const double* __restrict__ yldot00, const double* __restrict__ suscal, const double* __restrict__ sfscal,
@@ -176,6 +192,7 @@ __global__ void __launch_bounds__(256, 3) k_jac(const int* __restrict__ list_a, 
                                              double* __restrict__ colval, int* __restrict__ rowcnt, int* err) {
   extern __shared__ double smem[];
   __shared__ PInfo pinfo[NP_MAX];
+  PROF(0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool cls_a = (int)blockIdx.x < nb_a;
   const int* __restrict__ ivlist = cls_a ? list_a : list_b;
@@ -201,7 +218,7 @@ __global__ void __launch_bounds__(256, 3) k_jac(const int* __restrict__ list_a, 
     const PInfo& q = pinfo[p];
     Acc<true> a;
     a.base = base; a.NXS = NXS; a.NC = NC;
-    a.sm4 = sm4 + (size_t)p * 4 * PL_COUNT;
+    a.priv = sm4 + (size_t)p * 4 * PL_COUNT; a.ps = 1; a.ks = PL_COUNT;
     a.xc = q.xc; a.yc = q.yc; a.xw = q.xw; a.xe = q.xe;
     a.rres = rres + (size_t)p * ncand_max; a.rmask = rmask + (size_t)p * ncand_max;
     a.rx0 = q.rx0; a.ry0 = q.ry0; a.rw = q.rw; a.rh = q.rh;
@@ -224,6 +241,7 @@ __global__ void __launch_bounds__(256, 3) k_jac(const int* __restrict__ list_a, 
   }
   for (int i = tid; i < np * ncand_max; i += 256) rmask[(i / ncand_max) * ncand_max + i % ncand_max] = 0;
   __syncthreads();
+  PROF(1);
   // ---- phase 0 on the perturbed cell --------------------------------------------------------------------
   if (tid < np) {
     const PInfo& q = pinfo[tid];
@@ -235,6 +253,7 @@ __global__ void __launch_bounds__(256, 3) k_jac(const int* __restrict__ list_a, 
     phase0_cell<true>(a, ycell, q.xc, q.yc, err);
   }
   __syncthreads();
+  PROF(2);
   // ---- phase 1a / 1b: warp = role, lane = (perturbation, slot) ----------------------------------------------
   for (int it = lane; it < np * 4; it += 32) {
     const int p = it >> 2, k = it & 3;
@@ -246,6 +265,7 @@ __global__ void __launch_bounds__(256, 3) k_jac(const int* __restrict__ list_a, 
     else if (warp == 2) p1_visx<true>(a, pinfo[p].w, ix, iy);
   }
   __syncthreads();
+  PROF(3);
   for (int it = lane; it < np * 4; it += 32) {
     const int p = it >> 2, k = it & 3;
     int ix, iy;
@@ -257,7 +277,9 @@ __global__ void __launch_bounds__(256, 3) k_jac(const int* __restrict__ list_a, 
     else if (warp == 3) p1_exi<true>(a, pinfo[p].w, ix, iy);
     else if (warp == 4) p1_ey<true>(a, pinfo[p].w, ix, iy);
   }
+  PROFW(0);
   __syncthreads();
+  PROF(4);
   // ---- phase 2 over the candidate rows: role = warp & 3, two warps per role split the items ------------------
   {
     const int role = warp & 3, half = warp >> 2;
@@ -285,7 +307,9 @@ __global__ void __launch_bounds__(256, 3) k_jac(const int* __restrict__ list_a, 
       }
     }
   }
+  PROFW(1);
   __syncthreads();
+  PROF(5);
   // ---- phase 3 (rscalf + dt term) on the interior candidate rows ----------------------------------------------
   for (int it = tid; it < np * ncand_max; it += 256) {
     const int p = it / ncand_max, l = it - p * ncand_max;
@@ -304,6 +328,7 @@ __global__ void __launch_bounds__(256, 3) k_jac(const int* __restrict__ list_a, 
     }
   }
   __syncthreads();
+  PROF(6);
   // ---- difference, clip, ordered compaction into the column's CSC fragment (oderhs.m:8685-8719) ----------------
   for (int p = warp; p < np; p += 8) {
     const PInfo& q = pinfo[p];
@@ -346,6 +371,207 @@ __global__ void __launch_bounds__(256, 3) k_jac(const int* __restrict__ list_a, 
     }
     if (lane == 0) colcnt[iv - 1] = nout;
   }
+  PROF(7);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batched Jacobian, role-per-block form.  Every perturbed unknown of the column range is processed at once:
+// each phase is one launch whose blocks all run the SAME role function (blockIdx.y = role) over 128 items, so the
+// instruction stream of a role is fetched once per SM and shared by all its warps (k_jac's blocks interleave eight
+// different streams and stall on instruction fetch).  The private cells and candidate rows live in global memory
+// (L2-resident: ~1.6 KB per unknown), plane-major so that a warp's accesses coalesce.
+//   item (u, k)  : unknown u, private slot k (C0, Cw, Ce, Cs)      -> phases 0, 1a, 1b
+//   item (u, l)  : unknown u, candidate cell l of its rectangle     -> phases 2, 3, compaction
+// ------------------------------------------------------------------------------------------------
+struct UInfo {
+  Win w;
+  int iv, xc, yc, xw, xe, rx0, ry0, rw, rh;
+  int off;  // first candidate item of this unknown
+};
+struct JArgs {
+  const UInfo* ui;
+  int NU, na, ncn, ncw, nitems;  // unknowns, of which na regular (ncn candidates each); the rest wide (ncw each)
+  double *priv, *rows, *rres;
+  int* rmask;
+  double* base;
+  const double *yl, *yldot00, *suscal, *sfscal, *dtuse, *ylodt;
+  int64_t neq, ml, mu;
+  int NXS, NC;
+  const int64_t* coloff;
+  int *colcnt, *colrow;
+  double* colval;
+  int *rowcnt, *err;
+};
+__device__ __forceinline__ Acc<true> jb_acc(const JArgs& A, const UInfo& q, int u) {
+  Acc<true> a;
+  a.base = A.base; a.NXS = A.NXS; a.NC = A.NC;
+  a.priv = A.priv + (size_t)u * 4; a.ps = A.NU * 4; a.ks = 1;
+  a.xc = q.xc; a.yc = q.yc; a.xw = q.xw; a.xe = q.xe;
+  a.rres = A.rres + q.off; a.rmask = A.rmask + q.off;
+  a.rx0 = q.rx0; a.ry0 = q.ry0; a.rw = q.rw; a.rh = q.rh;
+  return a;
+}
+__device__ __forceinline__ bool jb_slot_cell(const UInfo& q, int k, int& ix, int& iy) {  // false: slot duplicates another or does not exist
+  iy = q.yc; ix = q.xc;
+  if (k == 1) { ix = q.xw; return q.xw != q.xc; }
+  if (k == 2) { ix = q.xe; return q.xe != q.xc && q.xe != q.xw; }
+  if (k == 3) { iy = q.yc - 1; return q.yc >= 1; }
+  return true;
+}
+__device__ __forceinline__ double jb_dyl(const JArgs& A, const UInfo& q, double& yold) {  // oderhs.m:8676-8678
+  yold = A.yl[q.iv - 1];
+  return D.delpert * (fabs(yold) + D.dylconst / A.suscal[q.iv - 1]);
+}
+__device__ __forceinline__ bool jb_item(const JArgs& A, int it, int& u, int& l) {
+  if (it >= A.nitems) return false;
+  const int nn = A.na * A.ncn;
+  if (it < nn) { u = it / A.ncn; l = it - u * A.ncn; }
+  else { const int r = it - nn; const int j = r / A.ncw; u = A.na + j; l = r - j * A.ncw; }
+  return true;
+}
+// stage the private cells of 32 unknowns from the base planes, then phase 0 on their perturbed cells
+__global__ void __launch_bounds__(128) k_jb_stage0(JArgs A) {
+  const int u0 = blockIdx.x * 32, tid = threadIdx.x;
+  const int NU4 = A.NU * 4;
+  const int j = tid, u = u0 + (j >> 2), k = j & 3;
+  if (u < A.NU) {
+    const UInfo& q = A.ui[u];
+    int ix, iy;
+    jb_slot_cell(q, k, ix, iy);
+    if (iy < 0) iy = 0;
+    const int cell = ix + A.NXS * iy;
+#pragma unroll 4
+    for (int pl = 0; pl < PL_COUNT; ++pl) A.priv[(size_t)pl * NU4 + u * 4 + k] = A.base[(size_t)pl * A.NC + cell];
+  }
+  __syncthreads();
+  const int up = u0 + tid;
+  if (tid < 32 && up < A.NU) {
+    const UInfo& q = A.ui[up];
+    const Acc<true> a = jb_acc(A, q, up);
+    double ycell[UE_NV], yold;
+    const double dyl = jb_dyl(A, q, yold);
+    const int64_t c = (int64_t)(q.xc + A.NXS * q.yc) * UE_NV;
+    for (int k2 = 0; k2 < UE_NV; ++k2) ycell[k2] = A.yl[c + k2];
+    ycell[(q.iv - 1) - c] = yold + dyl;
+    phase0_cell<true>(a, ycell, q.xc, q.yc, A.err);
+  }
+}
+__global__ void __launch_bounds__(128) k_jb_p1a(JArgs A) {
+  const int it = blockIdx.x * 128 + threadIdx.x, u = it >> 2, k = it & 3;
+  if (u >= A.NU) return;
+  const UInfo& q = A.ui[u];
+  int ix, iy;
+  if (!jb_slot_cell(q, k, ix, iy)) return;
+  const Acc<true> a = jb_acc(A, q, u);
+  const int role = blockIdx.y;
+  if (role == 0) p1_xpart<true>(a, q.w, ix, iy);
+  else if (role == 1) p1_ypart<true>(a, q.w, ix, iy);
+  else p1_visx<true>(a, q.w, ix, iy);
+}
+__global__ void __launch_bounds__(128) k_jb_p1b(JArgs A) {
+  const int it = blockIdx.x * 128 + threadIdx.x, u = it >> 2, k = it & 3;
+  if (u >= A.NU) return;
+  const UInfo& q = A.ui[u];
+  int ix, iy;
+  if (!jb_slot_cell(q, k, ix, iy)) return;
+  const Acc<true> a = jb_acc(A, q, u);
+  const int role = blockIdx.y;
+  if (role == 0) p1_fx<true>(a, q.w, ix, iy);
+  else if (role == 1) p1_fy<true>(a, q.w, ix, iy);
+  else if (role == 2) p1_exe<true>(a, q.w, ix, iy);
+  else if (role == 3) p1_exi<true>(a, q.w, ix, iy);
+  else p1_ey<true>(a, q.w, ix, iy);
+}
+// phase 2 on the candidate rows; role = equation group, guard rows go to role 0.  rows[k][item], rmask[item]
+__global__ void __launch_bounds__(128) k_jb_p2(JArgs A) {
+  int u, l;
+  if (!jb_item(A, blockIdx.x * 128 + threadIdx.x, u, l)) return;
+  const UInfo& q = A.ui[u];
+  if (l >= q.rw * q.rh) return;
+  const int ix = q.rx0 + l % q.rw, iy = q.ry0 + l / q.rw;
+  const Acc<true> a = jb_acc(A, q, u);
+  const int role = blockIdx.y;
+  double r[UE_NV] = {0., 0., 0., 0., 0.};
+  double* o = A.rows + q.off + l;
+  const size_t NI = A.nitems;
+  int* mk = A.rmask + q.off + l;
+  if (ix >= 1 && ix <= D.nx && iy >= 1 && iy <= D.ny) {
+    if (in_rng(ix, q.w.i2, q.w.i5) && in_rng(iy, q.w.j2, q.w.j5)) {
+      if (role == 0) { p2_n<true>(a, ix, iy, r, D.iseqalg); o[0] = r[0]; o[4 * NI] = r[4]; atomicOr(mk, 0x111); }
+      else if (role == 1) { p2_m<true>(a, q.w, ix, iy, r, D.iseqalg); o[1 * NI] = r[1]; atomicOr(mk, 0x2); }
+      else if (role == 2) { p2_e<true>(a, ix, iy, r, D.iseqalg); o[2 * NI] = r[2]; atomicOr(mk, 0x4); }
+      else { p2_i<true>(a, ix, iy, r, D.iseqalg); o[3 * NI] = r[3]; atomicOr(mk, 0x8); }
+    }
+  } else if (role == 0) {
+    const int m = phase2_guard<true>(a, q.w, ix, iy, r);
+    for (int k = 0; k < UE_NV; ++k) o[k * NI] = r[k];
+    atomicOr(mk, m);
+  }
+}
+// phase 3 on the interior candidate rows, then difference / clip / ordered compaction into the column's CSC
+// fragment (oderhs.m:8685-8719): one warp per unknown
+__global__ void __launch_bounds__(128) k_jb_p3c(JArgs A) {
+  const int lane = threadIdx.x & 31, u = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (u >= A.NU) return;
+  const UInfo& q = A.ui[u];
+  const Acc<true> a = jb_acc(A, q, u);
+  const size_t NI = A.nitems;
+  const int NXS = A.NXS;
+  const int64_t neq = A.neq;
+  double yold;
+  const double dyl = jb_dyl(A, q, yold);
+  const int ncell = q.rw * q.rh;
+  for (int l = lane; l < ncell; l += 32) {
+    const int ix = q.rx0 + l % q.rw, iy = q.ry0 + l / q.rw;
+    if (ix >= 1 && ix <= D.nx && iy >= 1 && iy <= D.ny && in_rng(ix, q.w.i2, q.w.i5) && in_rng(iy, q.w.j2, q.w.j5)) {
+      double r[UE_NV], ycell[UE_NV];
+      double* o = A.rows + q.off + l;
+      const int64_t c = (int64_t)(ix + NXS * iy) * UE_NV;
+      for (int k = 0; k < UE_NV; ++k) { r[k] = o[k * NI]; ycell[k] = A.yl[c + k]; }
+      if (ix == q.xc && iy == q.yc) ycell[(q.iv - 1) - c] = yold + dyl;
+      phase3_interior<true>(a, ix, iy, r, ycell, A.yl[neq], D.iseqalg, A.dtuse, A.ylodt);
+      for (int k = 0; k < UE_NV; ++k) o[k * NI] = r[k];
+    }
+  }
+  __syncwarp();
+  const int64_t iv = q.iv;
+  const int64_t ii1 = max(iv - A.mu, (int64_t)1), ii2 = min(iv + A.ml, neq);
+  const double sf = A.sfscal[iv - 1];
+  const int ncand = ncell * UE_NV;
+  const int64_t o = A.coloff[iv - 1];
+  int nout = 0;
+  for (int q0 = 0; q0 < ncand; q0 += 32) {
+    const int qq = q0 + lane;
+    bool keep = false; double val = 0.; int64_t ii = 0;
+    if (qq < ncand) {
+      const int l = qq / UE_NV, k = qq - l * UE_NV;
+      const int ix = q.rx0 + l % q.rw, iy = q.ry0 + l / q.rw;
+      ii = ((int64_t)(ix + NXS * iy)) * UE_NV + k + 1;
+      if (ii >= ii1 && ii <= ii2) {
+        const bool written = (A.rmask[q.off + l] >> k) & 1;
+        if (written || ii == iv) {
+          const double y00 = A.yldot00[ii - 1];
+          const double wk = written ? A.rows[(size_t)k * NI + q.off + l] : y00;
+          double jacelem = (wk - y00) / dyl;
+          if (ii == iv) {
+            if (D.iseqalg[iv - 1] * (1 - D.isbcwdt) == 0) jacelem = jacelem - 1 / A.dtuse[iv - 1];
+            if (D.nufak > 0 && A.yl[neq] == 1) jacelem = jacelem - D.nufak;
+          }
+          val = jacelem;
+          keep = fabs(jacelem * sf) > D.jaccliplim;
+        }
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const int pos = nout + __popc(bal & ((1u << lane) - 1));
+      A.colrow[o + pos] = (int)ii;
+      A.colval[o + pos] = val;
+      atomicAdd(&A.rowcnt[ii - 1], 1);
+    }
+    nout += __popc(bal);
+  }
+  if (lane == 0) A.colcnt[iv - 1] = nout;
 }
 
 // ---- CSC fragments -> CSR ---------------------------------------------------------------------------------------
@@ -414,6 +640,12 @@ __global__ void k_sortrows(int64_t neq, const int64_t* __restrict__ ia, double* 
 
 // sfsetnk scaling chain (oderhs.m:9862-9881): column scaling by 1/su (amudia, svr/svrut4.m:1104-1130), row max-norm
 // (rnrms with normtype=0, svr/svrut4.m:1002-1052), sf = 1/norm, and ydt_max0 = max|yldot0*sf|.  One warp per row.
+// yldot00 must be the residual of yl bit for bit (see ue_gpu_jac_calc)
+__global__ void k_samebits(const double* __restrict__ a, const double* __restrict__ b, int64_t n, int* __restrict__ err) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && __double_as_longlong(a[i]) != __double_as_longlong(b[i])) atomicOr(err, 4);
+}
+
 __global__ void k_rownorm(int64_t neq, const int64_t* __restrict__ ia, const int64_t* __restrict__ ja, const double* __restrict__ jac,
                           const double* __restrict__ su, const double* __restrict__ yldot0, double* __restrict__ sf, unsigned long long* ydtmax_bits, int* zero_row) {
   const int lane = threadIdx.x & 31;
@@ -477,11 +709,16 @@ int check_switches() {
 void drop_graphs();
 void free_all() {
   drop_graphs();
+  g_seen_host.clear(); g_last_yldot.clear(); g_base_yl.clear();
+  for (auto& h : g_step_host) h.clear();
+  g_base_valid = g_base_dev_valid = false;
   for (void* p : g_static_allocs) cudaFree(p);
   g_static_allocs.clear();
   void* ptrs[] = {d_base, d_yl, d_yldot00, d_tmp, d_yldot, d_dtuse, d_ylodt, d_suscal, d_sfscal, d_err, d_list_narrow, d_list_wide, d_coloff,
                   d_colcnt, d_colrow, d_colval, d_ia, d_ja, d_jac};
   for (void* p : ptrs) if (p) cudaFree(p);
+  for (void* p : {(void*)d_uinfo, (void*)d_priv, (void*)d_jrows, (void*)d_rres, (void*)d_rmask}) if (p) cudaFree(p);
+  d_uinfo = nullptr; d_priv = d_jrows = d_rres = nullptr; d_rmask = nullptr;
   d_base = d_yl = d_yldot00 = d_tmp = d_yldot = d_dtuse = d_ylodt = d_suscal = d_sfscal = nullptr;
   d_err = nullptr; d_list_narrow = d_list_wide = nullptr; d_coloff = nullptr; d_colcnt = d_colrow = nullptr; d_colval = nullptr;
   d_rowcnt = d_rowfill = nullptr; d_ia = d_ja = nullptr; d_jac = nullptr;
@@ -535,6 +772,28 @@ int upload_lists() {
   CK(cudaMalloc(&d_list_wide, std::max<size_t>(1, h_list_wide.size()) * sizeof(int)));
   if (!h_list_narrow.empty()) CK(cudaMemcpy(d_list_narrow, h_list_narrow.data(), h_list_narrow.size() * sizeof(int), cudaMemcpyHostToDevice));
   if (!h_list_wide.empty()) CK(cudaMemcpy(d_list_wide, h_list_wide.data(), h_list_wide.size() * sizeof(int), cudaMemcpyHostToDevice));
+  // role-per-block form: static per-unknown records and the private-cell / candidate-row work space
+  const UeParams& P = S.p;
+  const size_t na = h_list_narrow.size(), nb = h_list_wide.size(), NU = na + nb;
+  std::vector<UInfo> ui(NU);
+  for (size_t u = 0; u < NU; ++u) {
+    UInfo& q = ui[u];
+    q.iv = u < na ? h_list_narrow[u] : h_list_wide[u - na];
+    q.xc = (int)P.igyl[q.iv - 1]; q.yc = (int)P.igyl[neq + q.iv - 1];
+    q.w = make_win(P, q.xc, q.yc);
+    q.xw = (int)P.ixm1[q.xc + NXS * q.yc]; q.xe = (int)P.ixp1[q.xc + NXS * q.yc];
+    cand_rect(P, q.w, q.xc, q.yc, is_wide(P, q.w, q.yc), q.rx0, q.ry0, q.rw, q.rh);
+    q.off = u < na ? (int)(u * g_ncand_narrow) : (int)(na * g_ncand_narrow + (u - na) * g_ncand_wide);
+  }
+  g_nitems = (int)(na * g_ncand_narrow + nb * g_ncand_wide);
+  for (void* p : {(void*)d_uinfo, (void*)d_priv, (void*)d_jrows, (void*)d_rres, (void*)d_rmask}) if (p) cudaFree(p);
+  d_uinfo = nullptr; d_priv = d_jrows = d_rres = nullptr; d_rmask = nullptr;
+  CK(cudaMalloc(&d_uinfo, std::max<size_t>(1, NU) * sizeof(UInfo)));
+  if (NU) CK(cudaMemcpy(d_uinfo, ui.data(), NU * sizeof(UInfo), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&d_priv, std::max<size_t>(1, NU) * 4 * PL_COUNT * sizeof(double)));
+  CK(cudaMalloc(&d_jrows, std::max<size_t>(1, (size_t)g_nitems) * UE_NV * sizeof(double)));
+  CK(cudaMalloc(&d_rres, std::max<size_t>(1, (size_t)g_nitems) * sizeof(double)));
+  CK(cudaMalloc(&d_rmask, std::max<size_t>(1, (size_t)g_nitems) * sizeof(int)));
   return 0;
 }
 
@@ -559,11 +818,30 @@ int enqueue_jac(const double* dyl, const double* dy00, int64_t ml, int64_t mu, i
   if (!base_current) { int rc = enqueue_residual(dyl, nullptr, false); if (rc) return rc; }
   CK(cudaMemsetAsync(d_colcnt, 0, 3 * neq * sizeof(int), g_stream));
   const int na = (int)h_list_narrow.size(), nb = (int)h_list_wide.size();
+  if (g_jac_batched) {
+    const int NU = na + nb;
+    if (NU > 0) {
+      JArgs A;
+      A.ui = (const UInfo*)d_uinfo; A.NU = NU; A.na = na; A.ncn = g_ncand_narrow; A.ncw = g_ncand_wide; A.nitems = g_nitems;
+      A.priv = d_priv; A.rows = d_jrows; A.rres = d_rres; A.rmask = d_rmask; A.base = d_base;
+      A.yl = dyl; A.yldot00 = dy00; A.suscal = d_suscal; A.sfscal = d_sfscal; A.dtuse = d_dtuse; A.ylodt = d_ylodt;
+      A.neq = neq; A.ml = ml; A.mu = mu; A.NXS = NXS; A.NC = NC;
+      A.coloff = d_coloff; A.colcnt = d_colcnt; A.colrow = d_colrow; A.colval = d_colval; A.rowcnt = d_rowcnt; A.err = d_err;
+      CK(cudaMemsetAsync(d_rmask, 0, (size_t)g_nitems * sizeof(int), g_stream));
+      const unsigned gs = (unsigned)((NU * 4 + 127) / 128), gi = (unsigned)((g_nitems + 127) / 128);
+      k_jb_stage0<<<(unsigned)((NU + 31) / 32), 128, 0, g_stream>>>(A);
+      k_jb_p1a<<<dim3(gs, 3), 128, 0, g_stream>>>(A);
+      k_jb_p1b<<<dim3(gs, 5), 128, 0, g_stream>>>(A);
+      k_jb_p2<<<dim3(gi, 4), 128, 0, g_stream>>>(A);
+      k_jb_p3c<<<(unsigned)((NU + 3) / 4), 128, 0, g_stream>>>(A);
+    }
+  } else {
   const int nba = (na + g_np_a - 1) / g_np_a, nbb = (nb + g_np_b - 1) / g_np_b;
   if (nba + nbb > 0)
     k_jac<<<nba + nbb, 256, std::max(g_smem_narrow, g_smem_wide), g_stream>>>(d_list_narrow, na, g_np_a, g_ncand_narrow, nba, d_list_wide, nb, g_np_b, g_ncand_wide, d_base, dyl,
                                                                           dy00, d_suscal, d_sfscal, d_dtuse, d_ylodt, neq, ml, mu, NXS, NC, d_coloff, d_colcnt, d_colrow,
                                                                           d_colval, d_rowcnt, d_err);
+  }
   k_scan<<<1, 1024, 0, g_stream>>>(d_rowcnt, dia, neq);
   const int64_t ncol = g_ivmax - g_ivmin + 1;
   if (ncol > 0) {
@@ -612,7 +890,7 @@ int run_jac_dev(const double* dyl, const double* dy00, int64_t ml, int64_t mu, i
                 bool base_current) {
   GKey k; std::memset(&k, 0, sizeof k);
   k.kind = 2; k.p0 = dyl; k.p1 = dy00; k.p2 = djac; k.p3 = dja; k.p4 = dia; k.a = ml; k.b = mu; k.c = nnzmx; k.flag = base_current;
-  g_launches += (base_current ? 0 : 3) + 4;
+  g_launches += (base_current ? 0 : 3) + (g_jac_batched ? 8 : 4);
   int rc = replay(k, [&]() { return enqueue_jac(dyl, dy00, ml, mu, nnzmx, djac, dja, dia, base_current); });
   if (rc) return rc;
   int64_t last = 0;
@@ -634,6 +912,10 @@ extern "C" {
 
 int ue_gpu_set_int(const char* n, int64_t v) { g_base_valid = g_base_dev_valid = false; if (S.set_int(n, v)) { g_err = std::string("unknown int input ") + n; return -1; } return 0; }
 int ue_gpu_set_real(const char* n, double v) {
+  if (g_ready) {  // the shim re-sends nufak before every Jacobian: an unchanged value keeps the cached base fields
+    auto it = S.rscal.find(n);
+    if (it != S.rscal.end() && std::memcmp(it->second, &v, 8) == 0) return 0;
+  }
   g_base_valid = g_base_dev_valid = false;
   if (S.set_real(n, v)) { g_err = std::string("unknown real input ") + n; return -1; }
   if (g_ready) {  // scalars such as nufak, dtreal may change between solves: patch the device copy in place
@@ -722,6 +1004,7 @@ int ue_gpu_init(void) {
   int maxsm = 0; cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   if ((int64_t)g_smem_wide > maxsm || (int64_t)g_smem_narrow > maxsm) { g_err = "window box does not fit shared memory (mesh too wide for this build)"; return -6; }
   CK(cudaFuncSetAttribute(k_jac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(std::max(g_smem_narrow, g_smem_wide), 1024)));
+  { const char* e = getenv("UE_JAC_BLOCKED"); g_jac_batched = !(e && e[0] == '1'); }  // developer A/B switch
   g_launches = 0;
   g_ready = true;
   return 0;
@@ -730,11 +1013,20 @@ int ue_gpu_init(void) {
 int ue_gpu_step_params(int64_t n, const double* dt, const double* yo, const double* su, const double* sf) {
   if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
   if (n != neq) { g_err = "step_params: neq mismatch"; return -1; }
-  CK(cudaMemcpyAsync(d_dtuse, dt, n * 8, cudaMemcpyHostToDevice, g_stream));
-  CK(cudaMemcpyAsync(d_ylodt, yo, n * 8, cudaMemcpyHostToDevice, g_stream));
-  CK(cudaMemcpyAsync(d_suscal, su, n * 8, cudaMemcpyHostToDevice, g_stream));
-  CK(cudaMemcpyAsync(d_sfscal, sf, n * 8, cudaMemcpyHostToDevice, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
+  // The interface routines call this before every residual/Jacobian; the vectors change only
+  // between nonlinear solves, so unchanged ones are recognised on the host and not uploaded again.
+  const double* src[4] = {dt, yo, su, sf};
+  double* dst[4] = {d_dtuse, d_ylodt, d_suscal, d_sfscal};
+  bool any = false;
+  for (int i = 0; i < 4; i++) {
+    std::vector<double>& h = g_step_host[i];
+    if ((int64_t)h.size() == n && std::memcmp(h.data(), src[i], n * 8) == 0) continue;
+    h.assign(src[i], src[i] + n);
+    CK(cudaMemcpyAsync(dst[i], h.data(), n * 8, cudaMemcpyHostToDevice, g_stream));
+    any = true;
+    if (i < 2) g_last_yldot.clear();  // dtuse / ylodt enter the residual rows: the cached yldot is stale
+  }
+  if (any) CK(cudaStreamSynchronize(g_stream));
   return 0;
 }
 
@@ -758,6 +1050,20 @@ int ue_gpu_pandf1(int64_t n, double time, const double* yl, double* yldot) {
   (void)time;
   if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
   if (n != neq) { g_err = "pandf1: neq mismatch"; return -1; }
+  if (g_base_valid && (int64_t)g_base_yl.size() == neq + 2 && std::memcmp(g_base_yl.data(), yl, neq * 8) == 0) {
+    // Same unknowns as the previous call, only yl(neq+1)/yl(neq+2) may differ (psetnk re-evaluates f0 with the Jacobian
+    // flag off right after jac_calc, oderhs.m:9470-9471).  Fluxes and guard rows do not read the flags: only the row
+    // scaling / time-step phase is redone.
+    CK(cudaMemcpyAsync(d_yl + neq, yl + neq, 16, cudaMemcpyHostToDevice, g_stream));
+    const int B = 128, G = (NC + B - 1) / B;
+    k_phase3<<<G, B, 0, g_stream>>>(d_base, d_tmp, d_yldot, d_yl, d_dtuse, d_ylodt, neq, NXS, NC);
+    g_launches += 1;
+    CK(cudaMemcpyAsync(yldot, d_yldot, neq * 8, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    g_base_yl[neq] = yl[neq]; g_base_yl[neq + 1] = yl[neq + 1];
+    g_last_yldot.assign(yldot, yldot + neq);
+    return 0;
+  }
   g_base_valid = false; g_base_dev_valid = false;
   // H2D(yl) -> phases 0-3 -> D2H(yldot), D2H(err) as ONE graph launch and ONE synchronisation
   GKey k; std::memset(&k, 0, sizeof k);
@@ -824,21 +1130,41 @@ int ue_gpu_jac_calc(int64_t n, double t, const double* yl, const double* yldot00
   const bool same_y = g_base_valid && (int64_t)g_base_yl.size() == neq + 2 && std::memcmp(g_base_yl.data(), yl, neq * 8) == 0;
   const bool same_flags = same_y && std::memcmp(g_base_yl.data() + neq, yl + neq, 16) == 0;
   const bool same_f = same_y && (int64_t)g_last_yldot.size() == neq && std::memcmp(g_last_yldot.data(), yldot00, neq * 8) == 0;
+  if (!same_y) { g_base_valid = false; g_base_dev_valid = false; }
   if (!same_flags) CK(cudaMemcpyAsync(d_yl, yl, (neq + 2) * 8, cudaMemcpyHostToDevice, g_stream));
   const double* dy00 = d_yldot;
-  if (!same_f) { CK(cudaMemcpyAsync(d_yldot00, yldot00, neq * 8, cudaMemcpyHostToDevice, g_stream)); dy00 = d_yldot00; }
+  bool base_current = same_y;
+  if (!same_f) {
+    // yldot00 did not come from the immediately preceding ue_gpu_pandf1(yl).  The dependency-pruned windows are only
+    // equivalent to the reference's full windows if yldot00 IS pandf1(yl) bit for bit, so evaluate it and compare;
+    // anything else is refused rather than answered with a different sparsity pattern.
+    CK(cudaMemcpyAsync(d_yldot00, yldot00, neq * 8, cudaMemcpyHostToDevice, g_stream));
+    if (!same_y) {
+      int r = run_residual_dev(d_yl, d_yldot, true);
+      if (r) return r;
+    } else {
+      const int B = 128, G = (NC + B - 1) / B;
+      k_phase3<<<G, B, 0, g_stream>>>(d_base, d_tmp, d_yldot, d_yl, d_dtuse, d_ylodt, neq, NXS, NC);
+      g_launches += 1;
+    }
+    k_samebits<<<(unsigned)((neq + 255) / 256), 256, 0, g_stream>>>(d_yldot, d_yldot00, neq, d_err);
+    g_launches += 1;
+    g_last_yldot.clear();
+    base_current = true;
+  }
   GKey k; std::memset(&k, 0, sizeof k);
   const int64_t lim = std::min(nnzmx, g_nnzcap);
-  k.kind = 2; k.p0 = d_yl; k.p1 = dy00; k.p2 = d_jac; k.p3 = d_ja; k.p4 = d_ia; k.a = ml; k.b = mu; k.c = lim; k.flag = same_y;
-  g_launches += (same_y ? 0 : 3) + 4;
-  int rc = replay(k, [&]() { return enqueue_jac(d_yl, dy00, ml, mu, lim, d_jac, d_ja, d_ia, same_y); });
+  k.kind = 2; k.p0 = d_yl; k.p1 = dy00; k.p2 = d_jac; k.p3 = d_ja; k.p4 = d_ia; k.a = ml; k.b = mu; k.c = lim; k.flag = base_current;
+  g_launches += (base_current ? 0 : 3) + (g_jac_batched ? 8 : 4);
+  int rc = replay(k, [&]() { return enqueue_jac(d_yl, dy00, ml, mu, lim, d_jac, d_ja, d_ia, base_current); });
   if (rc) return rc;
   CK(cudaMemcpyAsync(ia, d_ia, (neq + 1) * 8, cudaMemcpyDeviceToHost, g_stream));
   CK(cudaMemcpyAsync(h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
   CK(cudaStreamSynchronize(g_stream));
-  if (!same_y) { g_base_valid = false; g_base_dev_valid = false; }  // base fields now belong to this yl, but we keep no host copy
   if (*h_err & 1) { g_err = "***  ni is negative - calculation stopped"; return -3; }
   if (*h_err & 2) { g_err = "***  ng is negative - calculation stopped"; return -3; }
+  if (*h_err & 4) { g_err = "jac_calc: yldot00 is not pandf1(yl) as evaluated by this library (call order rhsnk -> jac_calc, oderhs.m:9466-9468)"; return -4; }
+  if (!same_y) { g_base_yl.assign(yl, yl + neq + 2); g_base_valid = true; g_base_dev_valid = true; }  // base fields describe this yl now
   const int64_t nnz = ia[neq] - 1;
   *nnz_out = nnz;
   if (nnz > nnzmx) { g_err = "*** jac_calc -- More storage needed for Jacobian. Storage exceeded. Increase lenpfac."; return -2; }
@@ -914,3 +1240,12 @@ int ue_gpu_get_plane(int64_t pl, double* out) {
 }
 int ue_gpu_finalize(void) { free_all(); return 0; }
 }
+
+#ifdef UE_JAC_PROFILE
+extern "C" int ue_gpu_debug_phase_clocks(long long* out, int nblocks) {
+  return cudaMemcpyFromSymbol(out, g_prof, sizeof(long long) * 8 * nblocks) == cudaSuccess ? 0 : -1;
+}
+extern "C" int ue_gpu_debug_warp_clocks(long long* out, int nblocks) {
+  return cudaMemcpyFromSymbol(out, g_profw, sizeof(long long) * 16 * nblocks) == cudaSuccess ? 0 : -1;
+}
+#endif
