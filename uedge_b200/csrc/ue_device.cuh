@@ -99,9 +99,8 @@ __host__ __device__ inline Win make_win(const UeParams& P, int xc, int yc) {
 // ---- field accessor ------------------------------------------------------------------------
 // Acc<false>: fields are the HBM planes.  Acc<true> (Jacobian): a perturbation of cell C0=(xc,yc) can
 // change phase-0 fields only at C0 and phase-1 fields only at C0, its west/east neighbours (row yc
-// connectivity) and its south neighbour, so only those four cells have private copies (in shared
-// memory); every other read falls through to the base planes.  `resco` (phase 2) is kept per
-// candidate row in a rectangle [rx0..rx0+rw) x [ry0..ry0+rh).
+// connectivity) and its south neighbour, so only those four cells have private copies; every other
+// read falls through to the base planes.  `resco` (phase 2) is kept per candidate row of the unknown.
 template <bool WIN>
 struct Acc {
   double* base;   // [PL_COUNT][NC] planes in HBM (base state)
@@ -110,9 +109,10 @@ struct Acc {
   double* priv;   // private copies of C0, Cw, Ce, Cs: plane pl of slot k at priv[pl * ps + k * ks]
   int ps, ks;
   int xc, yc, xw, xe;
-  double* rres;   // [rw*rh] resco of candidate rows
-  const int* rmask;  // [rw*rh] rows-written mask of candidate cells (bit 0 <=> interior rows written)
-  int rx0, ry0, rw, rh;
+  double* rres;      // resco of this unknown's candidate rows (one per candidate cell)
+  const int* rmask;  // rows-written mask of the candidate cells (bit 8 <=> resco written)
+  int rself, reast;  // candidate index of the row being evaluated / of its east neighbour IXP1 (-1: not a candidate);
+                     // PL_RESCO is only written for the own row (p2_n) and read for the east neighbour (phase 3)
   // slot() and get() are written with selects, not branches: a read then is ONE generic load whose address was
   // chosen arithmetically, so the compiler can keep many reads of a role function in flight (with branches every
   // read became its own control-flow region and the loads serialised at L2 latency).
@@ -129,10 +129,8 @@ struct Acc {
     const double* g = base + ((size_t)pl * NC + ix + NXS * iy);
     if (WIN) {
       if (pl == PL_RESCO) {
-        const unsigned lx = (unsigned)(ix - rx0), ly = (unsigned)(iy - ry0);
-        const bool in = lx < (unsigned)rw && ly < (unsigned)rh;
-        const int idx = in ? (int)(ly * rw + lx) : 0;
-        const bool use = in && (rmask[idx] & 0x100);
+        const int idx = reast >= 0 ? reast : 0;
+        const bool use = reast >= 0 && (rmask[idx] & 0x100);
         const double* p = use ? rres + idx : g;
         return *p;
       }
@@ -145,8 +143,7 @@ struct Acc {
   __device__ __forceinline__ void set(int pl, int ix, int iy, double v) const {
     if (WIN) {
       if (pl == PL_RESCO) {
-        const unsigned lx = (unsigned)(ix - rx0), ly = (unsigned)(iy - ry0);
-        if (lx < (unsigned)rw && ly < (unsigned)rh) rres[ly * rw + lx] = v;
+        if (rself >= 0) rres[rself] = v;
       } else {
         const int k = slot(ix, iy);
         if (k >= 0) priv[(size_t)pl * ps + k * ks] = v;

@@ -6,9 +6,9 @@
 //
 // Kernels (all FP64, -fmad=false; see ue_device.cuh for the physics):
 //   k_phase0/1/2/3      full residual, one thread per cell, SoA planes in HBM
-//   k_jac<BLOCK>        batched Jacobian: one thread block per perturbed unknown, all
-//                       unknowns ("every colour") in flight in one launch; window box staged in
-//                       shared memory; ordered in-block compaction of the column
+//   k_jb_stage0/p1a/p1b/p2/p3c   batched Jacobian: all perturbed unknowns ("every colour") in flight, one launch
+//                       per phase, blockIdx.y = role function; private cells + candidate rows in L2-resident
+//                       global memory; ordered warp compaction of each column
 //   k_scan / k_fill / k_sortrows   CSC fragments -> reference CSR (csrcsc, svr/svrut4.m:1536-1608)
 #include <cuda_runtime.h>
 
@@ -51,15 +51,15 @@ int* d_err = nullptr;
 int* h_err = nullptr;  // pinned
 // Jacobian work space
 int64_t g_ivmin = 1, g_ivmax = 0;
-std::vector<int> h_list_narrow, h_list_wide;
+std::vector<int> h_list;  // unknowns (iv) of the column range
 std::vector<int64_t> h_coloff;  // per column offset into the fragment buffers (1-based iv -> h_coloff[iv-1])
-int *d_list_narrow = nullptr, *d_list_wide = nullptr;
+std::vector<int> h_cellcand_off, h_cand_cell, h_cand_east;  // per-cell candidate lists (CSR-like)
+int *d_cand_cell = nullptr, *d_cand_east = nullptr, *d_item_u = nullptr;
 std::vector<unsigned char> h_uinfo;  // UInfo records of the column range, regular windows first
 void* d_uinfo = nullptr;
 double *d_priv = nullptr, *d_jrows = nullptr, *d_rres = nullptr;
 int* d_rmask = nullptr;
 int g_nitems = 0;
-bool g_jac_batched = true;
 int64_t* d_coloff = nullptr;
 int *d_colcnt = nullptr, *d_colrow = nullptr;
 double* d_colval = nullptr;
@@ -67,7 +67,6 @@ int *d_rowcnt = nullptr, *d_rowfill = nullptr;
 int64_t *d_ia = nullptr, *d_ja = nullptr;
 double* d_jac = nullptr;
 int64_t g_cap_total = 0, g_nnzcap = 0;
-size_t g_smem_narrow = 0, g_smem_wide = 0;
 
 #define CK(call)                                                                                   \
   do {                                                                                             \
@@ -151,246 +150,28 @@ __global__ void k_phase3(double* base, const double* __restrict__ tmp, double* _
 }
 
 // ------------------------------------------------------------------------------------------------
-// batched Jacobian kernel.  A block takes NP perturbed unknowns; 8 warps.  Only the four cells whose
-// phase-1 fields can change are recomputed (lane = (perturbation, cell), warp = role), then the candidate
-// rows of a small rectangle around the perturbed cell (regular windows: 5 x 3 cells; windows touching an
-// X-point cut or the integrated core-flux rows: all ix x 3 rows).
-// ------------------------------------------------------------------------------------------------
-struct PInfo {
-  Win w;
-  int64_t iv;
-  int xc, yc, xw, xe, rx0, ry0, rw, rh;
-  double yold, dyl;
-};
-__host__ __device__ inline void cand_rect(const UeParams& P, const Win& w, int xc, int yc, bool wide, int& rx0, int& ry0, int& rw, int& rh) {
-  const int nx = (int)P.nx, ny = (int)P.ny;
-  ry0 = yc - 1 < 0 ? 0 : yc - 1;
-  const int ry1 = yc + 1 > ny + 1 ? ny + 1 : yc + 1;
-  rh = ry1 - ry0 + 1;
-  if (wide) { rx0 = 0; rw = nx + 2; }
-  else { rx0 = xc - 2 < 0 ? 0 : xc - 2; const int rx1 = xc + 2 > nx + 1 ? nx + 1 : xc + 2; rw = rx1 - rx0 + 1; }
-}
-__host__ __device__ inline bool is_wide(const UeParams& P, const Win& w, int yc) { return w.xccuts || (P.iflcore == 1 && yc <= 1); }
-
-// One launch covers both classes: blocks [0, nb_a) take NP_A unknowns each from list A (regular windows),
-// the remaining blocks take NP_B unknowns each from list B (wide windows).
-constexpr int NP_MAX = 8;
-#ifdef UE_JAC_PROFILE
-__device__ long long g_prof[2048 * 8];
-__device__ long long g_profw[2048 * 16];
-#define PROF(i) do { if (threadIdx.x == 0 && blockIdx.x < 2048) g_prof[blockIdx.x * 8 + (i)] = clock64(); } while (0)
-#define PROFW(j) do { if ((threadIdx.x & 31) == 0 && blockIdx.x < 2048) g_profw[blockIdx.x * 16 + (j) * 8 + (threadIdx.x >> 5)] = clock64(); } while (0)
-#else
-#define PROF(i) do { } while (0)
-#define PROFW(j) do { } while (0)
-#endif
-__global__ void __launch_bounds__(256, 3) k_jac(const int* __restrict__ list_a, int n_a, int np_a, int ncand_a, int nb_a, const int* __restrict__ list_b, int n_b,
-                                             int np_b, int ncand_b, double* base, const double* __restrict__ yl,
-                                             const double* __restrict__ yldot00, const double* __restrict__ suscal, const double* __restrict__ sfscal,
-                                             const double* __restrict__ dtuse, const double* __restrict__ ylodt, int64_t neq, int64_t ml, int64_t mu, int NXS,
-                                             int NC, const int64_t* __restrict__ coloff, int* __restrict__ colcnt, int* __restrict__ colrow,
-                                             double* __restrict__ colval, int* __restrict__ rowcnt, int* err) {
-  extern __shared__ double smem[];
-  __shared__ PInfo pinfo[NP_MAX];
-  PROF(0);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool cls_a = (int)blockIdx.x < nb_a;
-  const int* __restrict__ ivlist = cls_a ? list_a : list_b;
-  const int nlist = cls_a ? n_a : n_b, NP = cls_a ? np_a : np_b, ncand_max = cls_a ? ncand_a : ncand_b;
-  double* sm4 = smem;                                           // [NP][4][PL_COUNT]
-  double* rows = sm4 + (size_t)NP * 4 * PL_COUNT;               // [NP][ncand_max][UE_NV]
-  double* rres = rows + (size_t)NP * ncand_max * UE_NV;         // [NP][ncand_max]
-  int* rmask = (int*)(rres + (size_t)NP * ncand_max);           // [NP][ncand_max]
-  const int p0 = (cls_a ? (int)blockIdx.x : (int)blockIdx.x - nb_a) * NP;
-  const int np = min(NP, nlist - p0);
-  if (tid < np) {
-    PInfo& q = pinfo[tid];
-    q.iv = ivlist[p0 + tid];
-    q.xc = (int)D.igyl[q.iv - 1]; q.yc = (int)D.igyl[neq + q.iv - 1];
-    q.w = make_win(D, q.xc, q.yc);
-    q.xw = IXM1(q.xc, q.yc); q.xe = IXP1(q.xc, q.yc);
-    cand_rect(D, q.w, q.xc, q.yc, is_wide(D, q.w, q.yc), q.rx0, q.ry0, q.rw, q.rh);
-    q.yold = yl[q.iv - 1];
-    q.dyl = D.delpert * (fabs(q.yold) + D.dylconst / suscal[q.iv - 1]);  // oderhs.m:8676-8678
-  }
-  __syncthreads();
-  auto make_acc = [&](int p) {
-    const PInfo& q = pinfo[p];
-    Acc<true> a;
-    a.base = base; a.NXS = NXS; a.NC = NC;
-    a.priv = sm4 + (size_t)p * 4 * PL_COUNT; a.ps = 1; a.ks = PL_COUNT;
-    a.xc = q.xc; a.yc = q.yc; a.xw = q.xw; a.xe = q.xe;
-    a.rres = rres + (size_t)p * ncand_max; a.rmask = rmask + (size_t)p * ncand_max;
-    a.rx0 = q.rx0; a.ry0 = q.ry0; a.rw = q.rw; a.rh = q.rh;
-    return a;
-  };
-  auto slot_cell = [&](const PInfo& q, int k, int& ix, int& iy) -> bool {  // false: slot duplicates another or does not exist
-    iy = q.yc; ix = q.xc;
-    if (k == 1) { ix = q.xw; return q.xw != q.xc; }
-    if (k == 2) { ix = q.xe; return q.xe != q.xc && q.xe != q.xw; }
-    if (k == 3) { iy = q.yc - 1; return q.yc >= 1; }
-    return true;
-  };
-  // ---- stage the four private cells from the base planes; clear the candidate masks ------------------
-  for (int i = tid; i < np * 4 * PL_COUNT; i += 256) {
-    const int p = i / (4 * PL_COUNT), k = (i / PL_COUNT) & 3, pl = i % PL_COUNT;
-    int ix, iy;
-    slot_cell(pinfo[p], k, ix, iy);
-    if (iy < 0) iy = 0;
-    sm4[i] = base[(size_t)pl * NC + ix + NXS * iy];
-  }
-  for (int i = tid; i < np * ncand_max; i += 256) rmask[(i / ncand_max) * ncand_max + i % ncand_max] = 0;
-  __syncthreads();
-  PROF(1);
-  // ---- phase 0 on the perturbed cell --------------------------------------------------------------------
-  if (tid < np) {
-    const PInfo& q = pinfo[tid];
-    const Acc<true> a = make_acc(tid);
-    double ycell[UE_NV];
-    const int64_t c = (int64_t)(q.xc + NXS * q.yc) * UE_NV;
-    for (int k = 0; k < UE_NV; ++k) ycell[k] = yl[c + k];
-    ycell[(q.iv - 1) - c] = q.yold + q.dyl;
-    phase0_cell<true>(a, ycell, q.xc, q.yc, err);
-  }
-  __syncthreads();
-  PROF(2);
-  // ---- phase 1a / 1b: warp = role, lane = (perturbation, slot) ----------------------------------------------
-  for (int it = lane; it < np * 4; it += 32) {
-    const int p = it >> 2, k = it & 3;
-    int ix, iy;
-    if (!slot_cell(pinfo[p], k, ix, iy)) continue;
-    const Acc<true> a = make_acc(p);
-    if (warp == 0) p1_xpart<true>(a, pinfo[p].w, ix, iy);
-    else if (warp == 1) p1_ypart<true>(a, pinfo[p].w, ix, iy);
-    else if (warp == 2) p1_visx<true>(a, pinfo[p].w, ix, iy);
-  }
-  __syncthreads();
-  PROF(3);
-  for (int it = lane; it < np * 4; it += 32) {
-    const int p = it >> 2, k = it & 3;
-    int ix, iy;
-    if (!slot_cell(pinfo[p], k, ix, iy)) continue;
-    const Acc<true> a = make_acc(p);
-    if (warp == 0) p1_fx<true>(a, pinfo[p].w, ix, iy);
-    else if (warp == 1) p1_fy<true>(a, pinfo[p].w, ix, iy);
-    else if (warp == 2) p1_exe<true>(a, pinfo[p].w, ix, iy);
-    else if (warp == 3) p1_exi<true>(a, pinfo[p].w, ix, iy);
-    else if (warp == 4) p1_ey<true>(a, pinfo[p].w, ix, iy);
-  }
-  PROFW(0);
-  __syncthreads();
-  PROF(4);
-  // ---- phase 2 over the candidate rows: role = warp & 3, two warps per role split the items ------------------
-  {
-    const int role = warp & 3, half = warp >> 2;
-    const int nitems = np * ncand_max;
-    for (int it = lane + 32 * half; it < nitems; it += 64) {
-      const int p = it / ncand_max, l = it - p * ncand_max;
-      const PInfo& q = pinfo[p];
-      if (l >= q.rw * q.rh) continue;
-      const int ix = q.rx0 + l % q.rw, iy = q.ry0 + l / q.rw;
-      const Acc<true> a = make_acc(p);
-      double r[UE_NV] = {0., 0., 0., 0., 0.};
-      double* o = rows + ((size_t)p * ncand_max + l) * UE_NV;
-      int* mk = rmask + (size_t)p * ncand_max + l;
-      if (ix >= 1 && ix <= D.nx && iy >= 1 && iy <= D.ny) {
-        if (in_rng(ix, q.w.i2, q.w.i5) && in_rng(iy, q.w.j2, q.w.j5)) {
-          if (role == 0) { p2_n<true>(a, ix, iy, r, D.iseqalg); o[0] = r[0]; o[4] = r[4]; atomicOr(mk, 0x111); }
-          else if (role == 1) { p2_m<true>(a, q.w, ix, iy, r, D.iseqalg); o[1] = r[1]; atomicOr(mk, 0x2); }
-          else if (role == 2) { p2_e<true>(a, ix, iy, r, D.iseqalg); o[2] = r[2]; atomicOr(mk, 0x4); }
-          else { p2_i<true>(a, ix, iy, r, D.iseqalg); o[3] = r[3]; atomicOr(mk, 0x8); }
-        }
-      } else if (role == 0) {
-        const int m = phase2_guard<true>(a, q.w, ix, iy, r);
-        for (int k = 0; k < UE_NV; ++k) o[k] = r[k];
-        atomicOr(mk, m);
-      }
-    }
-  }
-  PROFW(1);
-  __syncthreads();
-  PROF(5);
-  // ---- phase 3 (rscalf + dt term) on the interior candidate rows ----------------------------------------------
-  for (int it = tid; it < np * ncand_max; it += 256) {
-    const int p = it / ncand_max, l = it - p * ncand_max;
-    const PInfo& q = pinfo[p];
-    if (l >= q.rw * q.rh) continue;
-    const int ix = q.rx0 + l % q.rw, iy = q.ry0 + l / q.rw;
-    if (ix >= 1 && ix <= D.nx && iy >= 1 && iy <= D.ny && in_rng(ix, q.w.i2, q.w.i5) && in_rng(iy, q.w.j2, q.w.j5)) {
-      const Acc<true> a = make_acc(p);
-      double r[UE_NV], ycell[UE_NV];
-      double* o = rows + ((size_t)p * ncand_max + l) * UE_NV;
-      const int64_t c = (int64_t)(ix + NXS * iy) * UE_NV;
-      for (int k = 0; k < UE_NV; ++k) { r[k] = o[k]; ycell[k] = yl[c + k]; }
-      if (ix == q.xc && iy == q.yc) ycell[(q.iv - 1) - c] = q.yold + q.dyl;
-      phase3_interior<true>(a, ix, iy, r, ycell, yl[neq], D.iseqalg, dtuse, ylodt);
-      for (int k = 0; k < UE_NV; ++k) o[k] = r[k];
-    }
-  }
-  __syncthreads();
-  PROF(6);
-  // ---- difference, clip, ordered compaction into the column's CSC fragment (oderhs.m:8685-8719) ----------------
-  for (int p = warp; p < np; p += 8) {
-    const PInfo& q = pinfo[p];
-    const int64_t iv = q.iv;
-    const int64_t ii1 = max(iv - mu, (int64_t)1), ii2 = min(iv + ml, neq);
-    const double sf = sfscal[iv - 1];
-    const int ncand = q.rw * q.rh * UE_NV;
-    const int64_t o = coloff[iv - 1];
-    int nout = 0;
-    for (int q0 = 0; q0 < ncand; q0 += 32) {
-      const int qq = q0 + lane;
-      bool keep = false; double val = 0.; int64_t ii = 0;
-      if (qq < ncand) {
-        const int l = qq / UE_NV, k = qq - l * UE_NV;
-        const int ix = q.rx0 + l % q.rw, iy = q.ry0 + l / q.rw;
-        ii = ((int64_t)(ix + NXS * iy)) * UE_NV + k + 1;
-        if (ii >= ii1 && ii <= ii2) {
-          const bool written = (rmask[(size_t)p * ncand_max + l] >> k) & 1;
-          if (written || ii == iv) {
-            const double y00 = yldot00[ii - 1];
-            const double wk = written ? rows[((size_t)p * ncand_max + l) * UE_NV + k] : y00;
-            double jacelem = (wk - y00) / q.dyl;
-            if (ii == iv) {
-              if (D.iseqalg[iv - 1] * (1 - D.isbcwdt) == 0) jacelem = jacelem - 1 / dtuse[iv - 1];
-              if (D.nufak > 0 && yl[neq] == 1) jacelem = jacelem - D.nufak;
-            }
-            val = jacelem;
-            keep = fabs(jacelem * sf) > D.jaccliplim;
-          }
-        }
-      }
-      const unsigned bal = __ballot_sync(0xffffffffu, keep);
-      if (keep) {
-        const int pos = nout + __popc(bal & ((1u << lane) - 1));
-        colrow[o + pos] = (int)ii;
-        colval[o + pos] = val;
-        atomicAdd(&rowcnt[ii - 1], 1);
-      }
-      nout += __popc(bal);
-    }
-    if (lane == 0) colcnt[iv - 1] = nout;
-  }
-  PROF(7);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Batched Jacobian, role-per-block form.  Every perturbed unknown of the column range is processed at once:
-// each phase is one launch whose blocks all run the SAME role function (blockIdx.y = role) over 128 items, so the
-// instruction stream of a role is fetched once per SM and shared by all its warps (k_jac's blocks interleave eight
-// different streams and stall on instruction fetch).  The private cells and candidate rows live in global memory
-// (L2-resident: ~1.6 KB per unknown), plane-major so that a warp's accesses coalesce.
-//   item (u, k)  : unknown u, private slot k (C0, Cw, Ce, Cs)      -> phases 0, 1a, 1b
-//   item (u, l)  : unknown u, candidate cell l of its rectangle     -> phases 2, 3, compaction
+// Batched Jacobian (jac_calc, oderhs.m:8533-8760).  Every perturbed unknown of the column range is processed at
+// once.  A perturbation of cell C0 = (xc,yc) changes phase-0 fields only at C0 and phase-1 fields only at C0, its
+// west/east neighbours and its south neighbour: those four cells get private copies; the residual rows that can
+// change are a short CANDIDATE LIST of cells around them (host-built from the index maps, so X-point cuts need no
+// special windows).  Each phase is one launch whose blocks all run the SAME role function (blockIdx.y = role) over
+// 128 items: the instruction stream of a role is fetched once per SM and shared by all its warps.  Private cells
+// and candidate rows live in global memory (L2-resident, ~1.6 KB per unknown), plane-major so accesses coalesce.
+//   item (u, k)  : unknown u, private slot k (C0, Cw, Ce, Cs)    -> phases 0, 1a, 1b
+//   item (u, l)  : unknown u, candidate cell l of its list        -> phases 2, 3, compaction
+// Rows outside the list cannot change and difference to exactly zero in the reference (jaccliplim = 0 drops them).
 // ------------------------------------------------------------------------------------------------
 struct UInfo {
   Win w;
-  int iv, xc, yc, xw, xe, rx0, ry0, rw, rh;
-  int off;  // first candidate item of this unknown
+  int iv, xc, yc, xw, xe;
+  int off;   // first candidate item of this unknown (rows / rres / rmask)
+  int n;     // number of candidate cells
+  int coff;  // first entry of its cell's candidate list in cand_cell / cand_east
 };
 struct JArgs {
   const UInfo* ui;
-  int NU, na, ncn, ncw, nitems;  // unknowns, of which na regular (ncn candidates each); the rest wide (ncw each)
+  const int *cand_cell, *cand_east, *item_u;
+  int NU, nitems;
   double *priv, *rows, *rres;
   int* rmask;
   double* base;
@@ -408,7 +189,7 @@ __device__ __forceinline__ Acc<true> jb_acc(const JArgs& A, const UInfo& q, int 
   a.priv = A.priv + (size_t)u * 4; a.ps = A.NU * 4; a.ks = 1;
   a.xc = q.xc; a.yc = q.yc; a.xw = q.xw; a.xe = q.xe;
   a.rres = A.rres + q.off; a.rmask = A.rmask + q.off;
-  a.rx0 = q.rx0; a.ry0 = q.ry0; a.rw = q.rw; a.rh = q.rh;
+  a.rself = -1; a.reast = -1;
   return a;
 }
 __device__ __forceinline__ bool jb_slot_cell(const UInfo& q, int k, int& ix, int& iy) {  // false: slot duplicates another or does not exist
@@ -422,18 +203,11 @@ __device__ __forceinline__ double jb_dyl(const JArgs& A, const UInfo& q, double&
   yold = A.yl[q.iv - 1];
   return D.delpert * (fabs(yold) + D.dylconst / A.suscal[q.iv - 1]);
 }
-__device__ __forceinline__ bool jb_item(const JArgs& A, int it, int& u, int& l) {
-  if (it >= A.nitems) return false;
-  const int nn = A.na * A.ncn;
-  if (it < nn) { u = it / A.ncn; l = it - u * A.ncn; }
-  else { const int r = it - nn; const int j = r / A.ncw; u = A.na + j; l = r - j * A.ncw; }
-  return true;
-}
 // stage the private cells of 32 unknowns from the base planes, then phase 0 on their perturbed cells
 __global__ void __launch_bounds__(128) k_jb_stage0(JArgs A) {
   const int u0 = blockIdx.x * 32, tid = threadIdx.x;
   const int NU4 = A.NU * 4;
-  const int j = tid, u = u0 + (j >> 2), k = j & 3;
+  const int u = u0 + (tid >> 2), k = tid & 3;
   if (u < A.NU) {
     const UInfo& q = A.ui[u];
     int ix, iy;
@@ -484,17 +258,20 @@ __global__ void __launch_bounds__(128) k_jb_p1b(JArgs A) {
 }
 // phase 2 on the candidate rows; role = equation group, guard rows go to role 0.  rows[k][item], rmask[item]
 __global__ void __launch_bounds__(128) k_jb_p2(JArgs A) {
-  int u, l;
-  if (!jb_item(A, blockIdx.x * 128 + threadIdx.x, u, l)) return;
+  const int it = blockIdx.x * 128 + threadIdx.x;
+  if (it >= A.nitems) return;
+  const int u = A.item_u[it];
   const UInfo& q = A.ui[u];
-  if (l >= q.rw * q.rh) return;
-  const int ix = q.rx0 + l % q.rw, iy = q.ry0 + l / q.rw;
-  const Acc<true> a = jb_acc(A, q, u);
+  const int l = it - q.off;
+  const int cell = A.cand_cell[q.coff + l];
+  const int ix = cell % A.NXS, iy = cell / A.NXS;
+  Acc<true> a = jb_acc(A, q, u);
+  a.rself = l;
   const int role = blockIdx.y;
   double r[UE_NV] = {0., 0., 0., 0., 0.};
-  double* o = A.rows + q.off + l;
+  double* o = A.rows + it;
   const size_t NI = A.nitems;
-  int* mk = A.rmask + q.off + l;
+  int* mk = A.rmask + it;
   if (ix >= 1 && ix <= D.nx && iy >= 1 && iy <= D.ny) {
     if (in_rng(ix, q.w.i2, q.w.i5) && in_rng(iy, q.w.j2, q.w.j5)) {
       if (role == 0) { p2_n<true>(a, ix, iy, r, D.iseqalg); o[0] = r[0]; o[4 * NI] = r[4]; atomicOr(mk, 0x111); }
@@ -514,21 +291,22 @@ __global__ void __launch_bounds__(128) k_jb_p3c(JArgs A) {
   const int lane = threadIdx.x & 31, u = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (u >= A.NU) return;
   const UInfo& q = A.ui[u];
-  const Acc<true> a = jb_acc(A, q, u);
+  Acc<true> a = jb_acc(A, q, u);
   const size_t NI = A.nitems;
   const int NXS = A.NXS;
   const int64_t neq = A.neq;
   double yold;
   const double dyl = jb_dyl(A, q, yold);
-  const int ncell = q.rw * q.rh;
-  for (int l = lane; l < ncell; l += 32) {
-    const int ix = q.rx0 + l % q.rw, iy = q.ry0 + l / q.rw;
+  for (int l = lane; l < q.n; l += 32) {
+    const int cell = A.cand_cell[q.coff + l];
+    const int ix = cell % NXS, iy = cell / NXS;
     if (ix >= 1 && ix <= D.nx && iy >= 1 && iy <= D.ny && in_rng(ix, q.w.i2, q.w.i5) && in_rng(iy, q.w.j2, q.w.j5)) {
       double r[UE_NV], ycell[UE_NV];
       double* o = A.rows + q.off + l;
-      const int64_t c = (int64_t)(ix + NXS * iy) * UE_NV;
+      const int64_t c = (int64_t)cell * UE_NV;
       for (int k = 0; k < UE_NV; ++k) { r[k] = o[k * NI]; ycell[k] = A.yl[c + k]; }
       if (ix == q.xc && iy == q.yc) ycell[(q.iv - 1) - c] = yold + dyl;
+      a.reast = A.cand_east[q.coff + l];
       phase3_interior<true>(a, ix, iy, r, ycell, A.yl[neq], D.iseqalg, A.dtuse, A.ylodt);
       for (int k = 0; k < UE_NV; ++k) o[k * NI] = r[k];
     }
@@ -537,7 +315,7 @@ __global__ void __launch_bounds__(128) k_jb_p3c(JArgs A) {
   const int64_t iv = q.iv;
   const int64_t ii1 = max(iv - A.mu, (int64_t)1), ii2 = min(iv + A.ml, neq);
   const double sf = A.sfscal[iv - 1];
-  const int ncand = ncell * UE_NV;
+  const int ncand = q.n * UE_NV;
   const int64_t o = A.coloff[iv - 1];
   int nout = 0;
   for (int q0 = 0; q0 < ncand; q0 += 32) {
@@ -545,8 +323,7 @@ __global__ void __launch_bounds__(128) k_jb_p3c(JArgs A) {
     bool keep = false; double val = 0.; int64_t ii = 0;
     if (qq < ncand) {
       const int l = qq / UE_NV, k = qq - l * UE_NV;
-      const int ix = q.rx0 + l % q.rw, iy = q.ry0 + l / q.rw;
-      ii = ((int64_t)(ix + NXS * iy)) * UE_NV + k + 1;
+      ii = (int64_t)A.cand_cell[q.coff + l] * UE_NV + k + 1;
       if (ii >= ii1 && ii <= ii2) {
         const bool written = (A.rmask[q.off + l] >> k) & 1;
         if (written || ii == iv) {
@@ -714,82 +491,109 @@ void free_all() {
   g_base_valid = g_base_dev_valid = false;
   for (void* p : g_static_allocs) cudaFree(p);
   g_static_allocs.clear();
-  void* ptrs[] = {d_base, d_yl, d_yldot00, d_tmp, d_yldot, d_dtuse, d_ylodt, d_suscal, d_sfscal, d_err, d_list_narrow, d_list_wide, d_coloff,
+  void* ptrs[] = {d_base, d_yl, d_yldot00, d_tmp, d_yldot, d_dtuse, d_ylodt, d_suscal, d_sfscal, d_err, d_cand_cell, d_cand_east, d_item_u, d_coloff,
                   d_colcnt, d_colrow, d_colval, d_ia, d_ja, d_jac};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (void* p : {(void*)d_uinfo, (void*)d_priv, (void*)d_jrows, (void*)d_rres, (void*)d_rmask}) if (p) cudaFree(p);
   d_uinfo = nullptr; d_priv = d_jrows = d_rres = nullptr; d_rmask = nullptr;
   d_base = d_yl = d_yldot00 = d_tmp = d_yldot = d_dtuse = d_ylodt = d_suscal = d_sfscal = nullptr;
-  d_err = nullptr; d_list_narrow = d_list_wide = nullptr; d_coloff = nullptr; d_colcnt = d_colrow = nullptr; d_colval = nullptr;
+  d_err = nullptr; d_cand_cell = d_cand_east = d_item_u = nullptr; d_coloff = nullptr; d_colcnt = d_colrow = nullptr; d_colval = nullptr;
   d_rowcnt = d_rowfill = nullptr; d_ia = d_ja = nullptr; d_jac = nullptr;
   g_ready = false;
 }
 
-// classify unknowns (regular / wide candidate rectangle) and lay out the per-column fragment buffers
-int g_ncand_narrow = 0, g_ncand_wide = 0;
-int g_np_a = 8, g_np_b = 2;  // unknowns per block (regular / wide); chosen in build_lists from the problem size
+// Candidate rows of a perturbation at cell (xc,yc): a superset of the cells whose residual rows can change.
+// The four private cells are C0, Cw = ixm1(C0), Ce = ixp1(C0) (row yc connectivity) and Cs = (xc,yc-1).  A row
+// (ix,iy') can read them only if iy' is within one row of yc and ix is within one poloidal step of {xw,xc,xe},
+// where "one step" is taken through the index maps of the rows involved (and plain ix+-1), so that cells across an
+// X-point cut are found where the maps connect them.  On a regular part of the mesh this is the 5 x 3 rectangle
+// around (xc,yc).  With the integrated core-power condition (iflcore=1, boundary.m:485-523) the row that carries
+// the poloidal sum, (min(ixpt2,nx), 0), also depends on every cell of rows 0 and 1.
+void cell_candidates(const UeParams& P, int xc, int yc, std::vector<int>& out) {
+  const int nxs = (int)P.nx + 2, nys = (int)P.ny + 2;
+  auto M1 = [&](int ix, int iy) { return (int)P.ixm1[ix + nxs * iy]; };
+  auto P1 = [&](int ix, int iy) { return (int)P.ixp1[ix + nxs * iy]; };
+  const int seeds[3] = {M1(xc, yc), xc, P1(xc, yc)};
+  out.clear();
+  for (int iy = std::max(0, yc - 1); iy <= std::min(nys - 1, yc + 1); ++iy) {
+    std::vector<char> in(nxs, 0);
+    for (int sd : seeds) {
+      in[sd] = 1;
+      if (sd - 1 >= 0) in[sd - 1] = 1;
+      if (sd + 1 < nxs) in[sd + 1] = 1;
+      for (int r = std::max(0, std::min(iy, yc) - 1); r <= std::min(nys - 1, std::max(iy, yc) + 1); ++r) {
+        in[M1(sd, r)] = 1; in[P1(sd, r)] = 1;
+        for (int ix = 0; ix < nxs; ++ix) if (M1(ix, r) == sd || P1(ix, r) == sd) in[ix] = 1;
+      }
+    }
+    for (int ix = 0; ix < nxs; ++ix) if (in[ix]) out.push_back(ix + nxs * iy);
+  }
+  if (P.iflcore == 1 && yc <= 1) {
+    const int cell = std::min((int)P.ixpt2, (int)P.nx);  // row 0
+    if (std::find(out.begin(), out.end(), cell) == out.end()) out.push_back(cell);
+  }
+  std::sort(out.begin(), out.end());
+}
+
 int build_lists() {
   const UeParams& P = S.p;
-  h_list_narrow.clear(); h_list_wide.clear();
+  // per-cell candidate lists and, for each entry, the list position of its east neighbour (rscalf reads the
+  // density row of ixp1, oderhs.m:8140-8160)
+  h_cellcand_off.assign(NC + 1, 0); h_cand_cell.clear(); h_cand_east.clear();
+  std::vector<int> cand;
+  for (int c = 0; c < NC; ++c) {
+    cell_candidates(P, c % NXS, c / NXS, cand);
+    h_cellcand_off[c] = (int)h_cand_cell.size();
+    for (int cc : cand) {
+      const int e = (int)P.ixp1[cc];  // same row
+      const int ecell = e + NXS * (cc / NXS);
+      const auto it = std::lower_bound(cand.begin(), cand.end(), ecell);
+      h_cand_cell.push_back(cc);
+      h_cand_east.push_back(it != cand.end() && *it == ecell ? (int)(it - cand.begin()) : -1);
+    }
+  }
+  h_cellcand_off[NC] = (int)h_cand_cell.size();
+  // unknowns of the column range and the capacity of every column's CSC fragment
+  h_list.clear();
   h_coloff.assign(neq, 0);
   int64_t off = 0;
-  g_ncand_narrow = g_ncand_wide = 1;
   for (int64_t iv = 1; iv <= neq; ++iv) {
-    const int xc = (int)P.igyl[iv - 1], yc = (int)P.igyl[neq + iv - 1];
-    const Win w = make_win(P, xc, yc);
-    const bool wide = is_wide(P, w, yc);
-    int rx0, ry0, rw, rh;
-    cand_rect(P, w, xc, yc, wide, rx0, ry0, rw, rh);
+    const int c = (int)P.igyl[iv - 1] + NXS * (int)P.igyl[neq + iv - 1];
     h_coloff[iv - 1] = off;
-    off += (int64_t)rw * rh * UE_NV;
-    if (iv < g_ivmin || iv > g_ivmax) continue;
-    if (wide) { h_list_wide.push_back((int)iv); g_ncand_wide = std::max(g_ncand_wide, rw * rh); }
-    else { h_list_narrow.push_back((int)iv); g_ncand_narrow = std::max(g_ncand_narrow, rw * rh); }
+    off += (int64_t)(h_cellcand_off[c + 1] - h_cellcand_off[c]) * UE_NV;
+    if (iv >= g_ivmin && iv <= g_ivmax) h_list.push_back((int)iv);
   }
   g_cap_total = off;
-  auto smem_of = [](int np, int ncand) { return (size_t)np * 4 * PL_COUNT * 8 + (size_t)np * ncand * UE_NV * 8 + (size_t)np * ncand * 8 + (size_t)np * ncand * 4 + 16; };
-  // Blocks are latency-bound and two fit an SM (128 registers x 256 threads): pick the smallest batch per
-  // block that still runs in ONE wave (so that phase 2 needs the fewest passes); large problems are
-  // throughput-bound and take the fullest batches.
-  int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-  const int64_t na = (int64_t)h_list_narrow.size(), nb = (int64_t)h_list_wide.size();
-  const int cand[4][2] = {{4, 1}, {4, 2}, {8, 2}, {8, 4}};
-  g_np_a = 8; g_np_b = 4;
-  for (auto& c : cand) {
-    const int64_t blocks = (na + c[0] - 1) / c[0] + (nb + c[1] - 1) / c[1];
-    if (blocks <= 2 * (int64_t)sms) { g_np_a = c[0]; g_np_b = c[1]; break; }
-  }
-  if (nb > 0 && g_ncand_wide > 256 && g_np_b > 2) g_np_b = 2;  // very wide rows: keep shared memory per block moderate
-  g_smem_narrow = smem_of(g_np_a, g_ncand_narrow);
-  g_smem_wide = smem_of(g_np_b, g_ncand_wide);
   return 0;
 }
 
 int upload_lists() {
-  if (d_list_narrow) { cudaFree(d_list_narrow); d_list_narrow = nullptr; }
-  if (d_list_wide) { cudaFree(d_list_wide); d_list_wide = nullptr; }
-  CK(cudaMalloc(&d_list_narrow, std::max<size_t>(1, h_list_narrow.size()) * sizeof(int)));
-  CK(cudaMalloc(&d_list_wide, std::max<size_t>(1, h_list_wide.size()) * sizeof(int)));
-  if (!h_list_narrow.empty()) CK(cudaMemcpy(d_list_narrow, h_list_narrow.data(), h_list_narrow.size() * sizeof(int), cudaMemcpyHostToDevice));
-  if (!h_list_wide.empty()) CK(cudaMemcpy(d_list_wide, h_list_wide.data(), h_list_wide.size() * sizeof(int), cudaMemcpyHostToDevice));
-  // role-per-block form: static per-unknown records and the private-cell / candidate-row work space
   const UeParams& P = S.p;
-  const size_t na = h_list_narrow.size(), nb = h_list_wide.size(), NU = na + nb;
+  const size_t NU = h_list.size();
   std::vector<UInfo> ui(NU);
+  std::vector<int> item_u;
   for (size_t u = 0; u < NU; ++u) {
     UInfo& q = ui[u];
-    q.iv = u < na ? h_list_narrow[u] : h_list_wide[u - na];
+    q.iv = h_list[u];
     q.xc = (int)P.igyl[q.iv - 1]; q.yc = (int)P.igyl[neq + q.iv - 1];
     q.w = make_win(P, q.xc, q.yc);
-    q.xw = (int)P.ixm1[q.xc + NXS * q.yc]; q.xe = (int)P.ixp1[q.xc + NXS * q.yc];
-    cand_rect(P, q.w, q.xc, q.yc, is_wide(P, q.w, q.yc), q.rx0, q.ry0, q.rw, q.rh);
-    q.off = u < na ? (int)(u * g_ncand_narrow) : (int)(na * g_ncand_narrow + (u - na) * g_ncand_wide);
+    const int c = q.xc + NXS * q.yc;
+    q.xw = (int)P.ixm1[c]; q.xe = (int)P.ixp1[c];
+    q.coff = h_cellcand_off[c]; q.n = h_cellcand_off[c + 1] - h_cellcand_off[c];
+    q.off = (int)item_u.size();
+    item_u.insert(item_u.end(), q.n, (int)u);
   }
-  g_nitems = (int)(na * g_ncand_narrow + nb * g_ncand_wide);
-  for (void* p : {(void*)d_uinfo, (void*)d_priv, (void*)d_jrows, (void*)d_rres, (void*)d_rmask}) if (p) cudaFree(p);
-  d_uinfo = nullptr; d_priv = d_jrows = d_rres = nullptr; d_rmask = nullptr;
+  g_nitems = (int)item_u.size();
+  for (void* p : {(void*)d_uinfo, (void*)d_priv, (void*)d_jrows, (void*)d_rres, (void*)d_rmask, (void*)d_cand_cell, (void*)d_cand_east, (void*)d_item_u}) if (p) cudaFree(p);
+  d_uinfo = nullptr; d_priv = d_jrows = d_rres = nullptr; d_rmask = nullptr; d_cand_cell = d_cand_east = d_item_u = nullptr;
   CK(cudaMalloc(&d_uinfo, std::max<size_t>(1, NU) * sizeof(UInfo)));
   if (NU) CK(cudaMemcpy(d_uinfo, ui.data(), NU * sizeof(UInfo), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&d_cand_cell, std::max<size_t>(1, h_cand_cell.size()) * sizeof(int)));
+  CK(cudaMalloc(&d_cand_east, std::max<size_t>(1, h_cand_east.size()) * sizeof(int)));
+  CK(cudaMemcpy(d_cand_cell, h_cand_cell.data(), h_cand_cell.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_cand_east, h_cand_east.data(), h_cand_east.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&d_item_u, std::max<size_t>(1, item_u.size()) * sizeof(int)));
+  if (!item_u.empty()) CK(cudaMemcpy(d_item_u, item_u.data(), item_u.size() * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&d_priv, std::max<size_t>(1, NU) * 4 * PL_COUNT * sizeof(double)));
   CK(cudaMalloc(&d_jrows, std::max<size_t>(1, (size_t)g_nitems) * UE_NV * sizeof(double)));
   CK(cudaMalloc(&d_rres, std::max<size_t>(1, (size_t)g_nitems) * sizeof(double)));
@@ -817,30 +621,22 @@ int enqueue_residual(const double* dyl, double* dyldot, bool need_rows) {
 int enqueue_jac(const double* dyl, const double* dy00, int64_t ml, int64_t mu, int64_t nnzmx, double* djac, int64_t* dja, int64_t* dia, bool base_current) {
   if (!base_current) { int rc = enqueue_residual(dyl, nullptr, false); if (rc) return rc; }
   CK(cudaMemsetAsync(d_colcnt, 0, 3 * neq * sizeof(int), g_stream));
-  const int na = (int)h_list_narrow.size(), nb = (int)h_list_wide.size();
-  if (g_jac_batched) {
-    const int NU = na + nb;
-    if (NU > 0) {
-      JArgs A;
-      A.ui = (const UInfo*)d_uinfo; A.NU = NU; A.na = na; A.ncn = g_ncand_narrow; A.ncw = g_ncand_wide; A.nitems = g_nitems;
-      A.priv = d_priv; A.rows = d_jrows; A.rres = d_rres; A.rmask = d_rmask; A.base = d_base;
-      A.yl = dyl; A.yldot00 = dy00; A.suscal = d_suscal; A.sfscal = d_sfscal; A.dtuse = d_dtuse; A.ylodt = d_ylodt;
-      A.neq = neq; A.ml = ml; A.mu = mu; A.NXS = NXS; A.NC = NC;
-      A.coloff = d_coloff; A.colcnt = d_colcnt; A.colrow = d_colrow; A.colval = d_colval; A.rowcnt = d_rowcnt; A.err = d_err;
-      CK(cudaMemsetAsync(d_rmask, 0, (size_t)g_nitems * sizeof(int), g_stream));
-      const unsigned gs = (unsigned)((NU * 4 + 127) / 128), gi = (unsigned)((g_nitems + 127) / 128);
-      k_jb_stage0<<<(unsigned)((NU + 31) / 32), 128, 0, g_stream>>>(A);
-      k_jb_p1a<<<dim3(gs, 3), 128, 0, g_stream>>>(A);
-      k_jb_p1b<<<dim3(gs, 5), 128, 0, g_stream>>>(A);
-      k_jb_p2<<<dim3(gi, 4), 128, 0, g_stream>>>(A);
-      k_jb_p3c<<<(unsigned)((NU + 3) / 4), 128, 0, g_stream>>>(A);
-    }
-  } else {
-  const int nba = (na + g_np_a - 1) / g_np_a, nbb = (nb + g_np_b - 1) / g_np_b;
-  if (nba + nbb > 0)
-    k_jac<<<nba + nbb, 256, std::max(g_smem_narrow, g_smem_wide), g_stream>>>(d_list_narrow, na, g_np_a, g_ncand_narrow, nba, d_list_wide, nb, g_np_b, g_ncand_wide, d_base, dyl,
-                                                                          dy00, d_suscal, d_sfscal, d_dtuse, d_ylodt, neq, ml, mu, NXS, NC, d_coloff, d_colcnt, d_colrow,
-                                                                          d_colval, d_rowcnt, d_err);
+  const int NU = (int)h_list.size();
+  if (NU > 0) {
+    JArgs A;
+    A.ui = (const UInfo*)d_uinfo; A.cand_cell = d_cand_cell; A.cand_east = d_cand_east; A.item_u = d_item_u;
+    A.NU = NU; A.nitems = g_nitems;
+    A.priv = d_priv; A.rows = d_jrows; A.rres = d_rres; A.rmask = d_rmask; A.base = d_base;
+    A.yl = dyl; A.yldot00 = dy00; A.suscal = d_suscal; A.sfscal = d_sfscal; A.dtuse = d_dtuse; A.ylodt = d_ylodt;
+    A.neq = neq; A.ml = ml; A.mu = mu; A.NXS = NXS; A.NC = NC;
+    A.coloff = d_coloff; A.colcnt = d_colcnt; A.colrow = d_colrow; A.colval = d_colval; A.rowcnt = d_rowcnt; A.err = d_err;
+    CK(cudaMemsetAsync(d_rmask, 0, (size_t)g_nitems * sizeof(int), g_stream));
+    const unsigned gs = (unsigned)((NU * 4 + 127) / 128), gi = (unsigned)((g_nitems + 127) / 128);
+    k_jb_stage0<<<(unsigned)((NU + 31) / 32), 128, 0, g_stream>>>(A);
+    k_jb_p1a<<<dim3(gs, 3), 128, 0, g_stream>>>(A);
+    k_jb_p1b<<<dim3(gs, 5), 128, 0, g_stream>>>(A);
+    k_jb_p2<<<dim3(gi, 4), 128, 0, g_stream>>>(A);
+    k_jb_p3c<<<(unsigned)((NU + 3) / 4), 128, 0, g_stream>>>(A);
   }
   k_scan<<<1, 1024, 0, g_stream>>>(d_rowcnt, dia, neq);
   const int64_t ncol = g_ivmax - g_ivmin + 1;
@@ -890,7 +686,7 @@ int run_jac_dev(const double* dyl, const double* dy00, int64_t ml, int64_t mu, i
                 bool base_current) {
   GKey k; std::memset(&k, 0, sizeof k);
   k.kind = 2; k.p0 = dyl; k.p1 = dy00; k.p2 = djac; k.p3 = dja; k.p4 = dia; k.a = ml; k.b = mu; k.c = nnzmx; k.flag = base_current;
-  g_launches += (base_current ? 0 : 3) + (g_jac_batched ? 8 : 4);
+  g_launches += (base_current ? 0 : 3) + 8;
   int rc = replay(k, [&]() { return enqueue_jac(dyl, dy00, ml, mu, nnzmx, djac, dja, dia, base_current); });
   if (rc) return rc;
   int64_t last = 0;
@@ -1000,11 +796,6 @@ int ue_gpu_init(void) {
   CK(cudaMalloc(&d_ia, (neq + 1) * sizeof(int64_t)));
   CK(cudaMalloc(&d_ja, g_nnzcap * sizeof(int64_t)));
   CK(cudaMalloc(&d_jac, g_nnzcap * sizeof(double)));
-  int dev = 0; cudaGetDevice(&dev);
-  int maxsm = 0; cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  if ((int64_t)g_smem_wide > maxsm || (int64_t)g_smem_narrow > maxsm) { g_err = "window box does not fit shared memory (mesh too wide for this build)"; return -6; }
-  CK(cudaFuncSetAttribute(k_jac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(std::max(g_smem_narrow, g_smem_wide), 1024)));
-  { const char* e = getenv("UE_JAC_BLOCKED"); g_jac_batched = !(e && e[0] == '1'); }  // developer A/B switch
   g_launches = 0;
   g_ready = true;
   return 0;
@@ -1155,7 +946,7 @@ int ue_gpu_jac_calc(int64_t n, double t, const double* yl, const double* yldot00
   GKey k; std::memset(&k, 0, sizeof k);
   const int64_t lim = std::min(nnzmx, g_nnzcap);
   k.kind = 2; k.p0 = d_yl; k.p1 = dy00; k.p2 = d_jac; k.p3 = d_ja; k.p4 = d_ia; k.a = ml; k.b = mu; k.c = lim; k.flag = base_current;
-  g_launches += (base_current ? 0 : 3) + (g_jac_batched ? 8 : 4);
+  g_launches += (base_current ? 0 : 3) + 8;
   int rc = replay(k, [&]() { return enqueue_jac(d_yl, dy00, ml, mu, lim, d_jac, d_ja, d_ia, base_current); });
   if (rc) return rc;
   CK(cudaMemcpyAsync(ia, d_ia, (neq + 1) * 8, cudaMemcpyDeviceToHost, g_stream));
@@ -1178,11 +969,8 @@ int ue_gpu_set_column_range(int64_t ivmin, int64_t ivmax) {
   if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
   if (ivmin < 1 || ivmax > neq) { g_err = "column range outside 1..neq"; return -1; }
   g_ivmin = ivmin; g_ivmax = ivmax;
-  const size_t s1 = g_smem_narrow, s2 = g_smem_wide;
   build_lists();
   drop_graphs();
-  (void)s1; (void)s2;
-  CK(cudaFuncSetAttribute(k_jac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(std::max(g_smem_narrow, g_smem_wide), 1024)));
   return upload_lists();
 }
 
@@ -1240,12 +1028,3 @@ int ue_gpu_get_plane(int64_t pl, double* out) {
 }
 int ue_gpu_finalize(void) { free_all(); return 0; }
 }
-
-#ifdef UE_JAC_PROFILE
-extern "C" int ue_gpu_debug_phase_clocks(long long* out, int nblocks) {
-  return cudaMemcpyFromSymbol(out, g_prof, sizeof(long long) * 8 * nblocks) == cudaSuccess ? 0 : -1;
-}
-extern "C" int ue_gpu_debug_warp_clocks(long long* out, int nblocks) {
-  return cudaMemcpyFromSymbol(out, g_profw, sizeof(long long) * 16 * nblocks) == cudaSuccess ? 0 : -1;
-}
-#endif
