@@ -156,7 +156,7 @@ __global__ void k_phase3(double* base, const double* __restrict__ tmp, double* _
 // change are a short CANDIDATE LIST of cells around them (host-built from the index maps, so X-point cuts need no
 // special windows).  Each phase is one launch whose blocks all run the SAME role function (blockIdx.y = role) over
 // 128 items: the instruction stream of a role is fetched once per SM and shared by all its warps.  Private cells
-// and candidate rows live in global memory (L2-resident, ~1.6 KB per unknown), plane-major so accesses coalesce.
+// and candidate rows live in global memory (L2-resident, ~1.6 KB per unknown).
 //   item (u, k)  : unknown u, private slot k (C0, Cw, Ce, Cs)    -> phases 0, 1a, 1b
 //   item (u, l)  : unknown u, candidate cell l of its list        -> phases 2, 3, compaction
 // Rows outside the list cannot change and difference to exactly zero in the reference (jaccliplim = 0 drops them).
@@ -171,7 +171,7 @@ struct UInfo {
 struct JArgs {
   const UInfo* ui;
   const int *cand_cell, *cand_east, *item_u;
-  int NU, nitems;
+  int NU, nitems, role0;
   double *priv, *rows, *rres;
   int* rmask;
   double* base;
@@ -186,7 +186,7 @@ struct JArgs {
 __device__ __forceinline__ Acc<true> jb_acc(const JArgs& A, const UInfo& q, int u) {
   Acc<true> a;
   a.base = A.base; a.NXS = A.NXS; a.NC = A.NC;
-  a.priv = A.priv + (size_t)u * 4; a.ps = A.NU * 4; a.ks = 1;
+  a.priv = A.priv + (size_t)u * 4 * PL_COUNT; a.ps = 1; a.ks = PL_COUNT;
   a.xc = q.xc; a.yc = q.yc; a.xw = q.xw; a.xe = q.xe;
   a.rres = A.rres + q.off; a.rmask = A.rmask + q.off;
   a.rself = -1; a.reast = -1;
@@ -206,7 +206,6 @@ __device__ __forceinline__ double jb_dyl(const JArgs& A, const UInfo& q, double&
 // stage the private cells of 32 unknowns from the base planes, then phase 0 on their perturbed cells
 __global__ void __launch_bounds__(128) k_jb_stage0(JArgs A) {
   const int u0 = blockIdx.x * 32, tid = threadIdx.x;
-  const int NU4 = A.NU * 4;
   const int u = u0 + (tid >> 2), k = tid & 3;
   if (u < A.NU) {
     const UInfo& q = A.ui[u];
@@ -214,8 +213,12 @@ __global__ void __launch_bounds__(128) k_jb_stage0(JArgs A) {
     jb_slot_cell(q, k, ix, iy);
     if (iy < 0) iy = 0;
     const int cell = ix + A.NXS * iy;
-#pragma unroll 4
-    for (int pl = 0; pl < PL_COUNT; ++pl) A.priv[(size_t)pl * NU4 + u * 4 + k] = A.base[(size_t)pl * A.NC + cell];
+    double v[PL_COUNT];
+#pragma unroll
+    for (int pl = 0; pl < PL_COUNT; ++pl) v[pl] = A.base[(size_t)pl * A.NC + cell];  // all loads in flight together
+    double* dst = A.priv + ((size_t)u * 4 + k) * PL_COUNT;
+#pragma unroll
+    for (int pl = 0; pl < PL_COUNT; ++pl) dst[pl] = v[pl];
   }
   __syncthreads();
   const int up = u0 + tid;
@@ -237,7 +240,7 @@ __global__ void __launch_bounds__(128) k_jb_p1a(JArgs A) {
   int ix, iy;
   if (!jb_slot_cell(q, k, ix, iy)) return;
   const Acc<true> a = jb_acc(A, q, u);
-  const int role = blockIdx.y;
+  const int role = blockIdx.y + A.role0;
   if (role == 0) p1_xpart<true>(a, q.w, ix, iy);
   else if (role == 1) p1_ypart<true>(a, q.w, ix, iy);
   else p1_visx<true>(a, q.w, ix, iy);
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(128) k_jb_p1b(JArgs A) {
   int ix, iy;
   if (!jb_slot_cell(q, k, ix, iy)) return;
   const Acc<true> a = jb_acc(A, q, u);
-  const int role = blockIdx.y;
+  const int role = blockIdx.y + A.role0;
   if (role == 0) p1_fx<true>(a, q.w, ix, iy);
   else if (role == 1) p1_fy<true>(a, q.w, ix, iy);
   else if (role == 2) p1_exe<true>(a, q.w, ix, iy);
@@ -267,7 +270,7 @@ __global__ void __launch_bounds__(128) k_jb_p2(JArgs A) {
   const int ix = cell % A.NXS, iy = cell / A.NXS;
   Acc<true> a = jb_acc(A, q, u);
   a.rself = l;
-  const int role = blockIdx.y;
+  const int role = blockIdx.y + A.role0;
   double r[UE_NV] = {0., 0., 0., 0., 0.};
   double* o = A.rows + it;
   const size_t NI = A.nitems;
@@ -633,9 +636,17 @@ int enqueue_jac(const double* dyl, const double* dy00, int64_t ml, int64_t mu, i
     CK(cudaMemsetAsync(d_rmask, 0, (size_t)g_nitems * sizeof(int), g_stream));
     const unsigned gs = (unsigned)((NU * 4 + 127) / 128), gi = (unsigned)((g_nitems + 127) / 128);
     k_jb_stage0<<<(unsigned)((NU + 31) / 32), 128, 0, g_stream>>>(A);
-    k_jb_p1a<<<dim3(gs, 3), 128, 0, g_stream>>>(A);
-    k_jb_p1b<<<dim3(gs, 5), 128, 0, g_stream>>>(A);
-    k_jb_p2<<<dim3(gi, 4), 128, 0, g_stream>>>(A);
+    A.role0 = 0;
+    if (getenv("UE_DEBUG_SPLIT_ROLES")) {  // developer aid: one launch per role so that a launch list shows each role's duration
+      for (int r = 0; r < 3; ++r) { A.role0 = r; k_jb_p1a<<<dim3(gs, 1), 128, 0, g_stream>>>(A); }
+      for (int r = 0; r < 5; ++r) { A.role0 = r; k_jb_p1b<<<dim3(gs, 1), 128, 0, g_stream>>>(A); }
+      for (int r = 0; r < 4; ++r) { A.role0 = r; k_jb_p2<<<dim3(gi, 1), 128, 0, g_stream>>>(A); }
+      A.role0 = 0;
+    } else {
+      k_jb_p1a<<<dim3(gs, 3), 128, 0, g_stream>>>(A);
+      k_jb_p1b<<<dim3(gs, 5), 128, 0, g_stream>>>(A);
+      k_jb_p2<<<dim3(gi, 4), 128, 0, g_stream>>>(A);
+    }
     k_jb_p3c<<<(unsigned)((NU + 3) / 4), 128, 0, g_stream>>>(A);
   }
   k_scan<<<1, 1024, 0, g_stream>>>(d_rowcnt, dia, neq);
