@@ -9,3 +9,5 @@ for l in sys.stdin:
         d=json.loads(l); print('$c', {k:round(d[k],4) for k in ('ms_per_step','jac_kernel_ms','resid_kernel_ms')}, {k:round(d['e2e'][k],4) for k in ('ms_per_step','resid_evals_per_s')}, d['gpu_launches'])
 "
 done
+python tools/host_overhead.py d3dHsm
+python tools/host_overhead.py d3dHsm4x

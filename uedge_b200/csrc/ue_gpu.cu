@@ -48,7 +48,9 @@ std::vector<void*> g_static_allocs;
 double *d_base = nullptr, *d_yl = nullptr, *d_yldot00 = nullptr, *d_tmp = nullptr, *d_yldot = nullptr;
 double *d_dtuse = nullptr, *d_ylodt = nullptr, *d_suscal = nullptr, *d_sfscal = nullptr;
 int* d_err = nullptr;
-int* h_err = nullptr;  // pinned
+volatile long long* h_flags = nullptr;  // pinned + mapped: [0] error bits of the last sequence, [1] ia(neq+1) of the last Jacobian
+long long* d_hflags = nullptr;          // device alias of h_flags
+int64_t g_nnz_guess = 0;
 // Jacobian work space
 int64_t g_ivmin = 1, g_ivmax = 0;
 std::vector<int> h_list;  // unknowns (iv) of the column range
@@ -138,8 +140,10 @@ __global__ void __launch_bounds__(128) k_phase2(double* base, double* __restrict
   }
 }
 __global__ void k_phase3(double* base, const double* __restrict__ tmp, double* __restrict__ yldot, const double* __restrict__ yl,
-                         const double* __restrict__ dtuse, const double* __restrict__ ylodt, int64_t neq, int NXS, int NC) {
+                         const double* __restrict__ dtuse, const double* __restrict__ ylodt, int64_t neq, int NXS, int NC, const int* __restrict__ err,
+                         long long* hflags) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0) hflags[0] = *err;  // error bits of phases 0-2 go straight to mapped host memory: no copy node, no extra sync
   if (c >= NC) return;
   Acc<false> a; a.base = base; a.NXS = NXS; a.NC = NC;
   const int ix = c % NXS, iy = c / NXS;
@@ -321,41 +325,49 @@ __global__ void __launch_bounds__(128) k_jb_p3c(JArgs A) {
   const int ncand = q.n * UE_NV;
   const int64_t o = A.coloff[iv - 1];
   int nout = 0;
-  for (int q0 = 0; q0 < ncand; q0 += 32) {
-    const int qq = q0 + lane;
-    bool keep = false; double val = 0.; int64_t ii = 0;
-    if (qq < ncand) {
-      const int l = qq / UE_NV, k = qq - l * UE_NV;
-      ii = (int64_t)A.cand_cell[q.coff + l] * UE_NV + k + 1;
-      if (ii >= ii1 && ii <= ii2) {
-        const bool written = (A.rmask[q.off + l] >> k) & 1;
-        if (written || ii == iv) {
-          const double y00 = A.yldot00[ii - 1];
-          const double wk = written ? A.rows[(size_t)k * NI + q.off + l] : y00;
-          double jacelem = (wk - y00) / dyl;
-          if (ii == iv) {
-            if (D.iseqalg[iv - 1] * (1 - D.isbcwdt) == 0) jacelem = jacelem - 1 / A.dtuse[iv - 1];
-            if (D.nufak > 0 && A.yl[neq] == 1) jacelem = jacelem - D.nufak;
+  constexpr int CH = 4;  // candidates per lane and pass: their loads are issued together, the ordered ballots follow
+  for (int q0 = 0; q0 < ncand; q0 += 32 * CH) {
+    bool keep[CH]; double val[CH]; int64_t ii[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int qq = q0 + 32 * c + lane;
+      keep[c] = false; val[c] = 0.; ii[c] = 0;
+      if (qq < ncand) {
+        const int l = qq / UE_NV, k = qq - l * UE_NV;
+        ii[c] = (int64_t)A.cand_cell[q.coff + l] * UE_NV + k + 1;
+        if (ii[c] >= ii1 && ii[c] <= ii2) {
+          const bool written = (A.rmask[q.off + l] >> k) & 1;
+          if (written || ii[c] == iv) {
+            const double y00 = A.yldot00[ii[c] - 1];
+            const double wk = written ? A.rows[(size_t)k * NI + q.off + l] : y00;
+            double jacelem = (wk - y00) / dyl;
+            if (ii[c] == iv) {
+              if (D.iseqalg[iv - 1] * (1 - D.isbcwdt) == 0) jacelem = jacelem - 1 / A.dtuse[iv - 1];
+              if (D.nufak > 0 && A.yl[neq] == 1) jacelem = jacelem - D.nufak;
+            }
+            val[c] = jacelem;
+            keep[c] = fabs(jacelem * sf) > D.jaccliplim;
           }
-          val = jacelem;
-          keep = fabs(jacelem * sf) > D.jaccliplim;
         }
       }
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    if (keep) {
-      const int pos = nout + __popc(bal & ((1u << lane) - 1));
-      A.colrow[o + pos] = (int)ii;
-      A.colval[o + pos] = val;
-      atomicAdd(&A.rowcnt[ii - 1], 1);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const unsigned bal = __ballot_sync(0xffffffffu, keep[c]);
+      if (keep[c]) {
+        const int pos = nout + __popc(bal & ((1u << lane) - 1));
+        A.colrow[o + pos] = (int)ii[c];
+        A.colval[o + pos] = val[c];
+        atomicAdd(&A.rowcnt[ii[c] - 1], 1);
+      }
+      nout += __popc(bal);
     }
-    nout += __popc(bal);
   }
   if (lane == 0) A.colcnt[iv - 1] = nout;
 }
 
 // ---- CSC fragments -> CSR ---------------------------------------------------------------------------------------
-__global__ void k_scan(const int* __restrict__ rowcnt, int64_t* __restrict__ ia, int64_t n) {
+__global__ void k_scan(const int* __restrict__ rowcnt, int64_t* __restrict__ ia, int64_t n, const int* __restrict__ err, long long* hflags) {
   // single block of 1024 threads; ia is 1-based: ia[0] = 1, ia[i+1] = ia[i] + rowcnt[i].
   // Each thread owns a contiguous chunk: serial sum, block scan of the 1024 partials, serial write-out.
   __shared__ int64_t s[1024];
@@ -374,6 +386,7 @@ __global__ void k_scan(const int* __restrict__ rowcnt, int64_t* __restrict__ ia,
   int64_t run = 1 + s[t] - sum;
   if (t == 0) ia[0] = 1;
   for (int64_t i = b0; i < b1; ++i) { run += rowcnt[i]; ia[i + 1] = run; }
+  if (t == 1023) { hflags[1] = 1 + s[1023]; hflags[0] = *err; }  // nnz + 1 and the error bits, to mapped host memory
 }
 __global__ void k_fill(int64_t neq, int64_t ivmin, int64_t ivmax, const int64_t* __restrict__ coloff, const int* __restrict__ colcnt,
                        const int* __restrict__ colrow, const double* __restrict__ colval, const int64_t* __restrict__ ia, int* __restrict__ rowfill,
@@ -618,7 +631,7 @@ int enqueue_residual(const double* dyl, double* dyldot, bool need_rows) {
   k_phase0<<<G, B, 0, g_stream>>>(d_base, dyl, NXS, NC, d_err);
   k_phase1<<<G32, 160, 0, g_stream>>>(d_base, NXS, NC);
   k_phase2<<<G32, 128, 0, g_stream>>>(d_base, d_tmp, NXS, NC);
-  if (need_rows) k_phase3<<<G, B, 0, g_stream>>>(d_base, d_tmp, dyldot, dyl, d_dtuse, d_ylodt, neq, NXS, NC);
+  if (need_rows) k_phase3<<<G, B, 0, g_stream>>>(d_base, d_tmp, dyldot, dyl, d_dtuse, d_ylodt, neq, NXS, NC, d_err, d_hflags);
   return 0;
 }
 int enqueue_jac(const double* dyl, const double* dy00, int64_t ml, int64_t mu, int64_t nnzmx, double* djac, int64_t* dja, int64_t* dia, bool base_current) {
@@ -649,7 +662,7 @@ int enqueue_jac(const double* dyl, const double* dy00, int64_t ml, int64_t mu, i
     }
     k_jb_p3c<<<(unsigned)((NU + 3) / 4), 128, 0, g_stream>>>(A);
   }
-  k_scan<<<1, 1024, 0, g_stream>>>(d_rowcnt, dia, neq);
+  k_scan<<<1, 1024, 0, g_stream>>>(d_rowcnt, dia, neq, d_err, d_hflags);
   const int64_t ncol = g_ivmax - g_ivmin + 1;
   if (ncol > 0) {
     k_fill<<<(unsigned)ncol, 64, 0, g_stream>>>(neq, g_ivmin, g_ivmax, d_coloff, d_colcnt, d_colrow, d_colval, dia, d_rowfill, djac, dja, nnzmx);
@@ -684,13 +697,16 @@ int run_residual_dev(const double* dyl, double* dyldot, bool need_rows) {
   return replay(k, [&]() { return enqueue_residual(dyl, dyldot, need_rows); });
 }
 
-int check_errflag() {
-  int h = 0;
-  CK(cudaMemcpyAsync(&h, d_err, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
+int err_of_flags() {  // after a synchronisation: error bits the last sequence posted to mapped host memory
+  const long long h = h_flags[0];
   if (h & 1) { g_err = "***  ni is negative - calculation stopped"; return -3; }
   if (h & 2) { g_err = "***  ng is negative - calculation stopped"; return -3; }
+  if (h & 4) { g_err = "jac_calc: yldot00 is not pandf1(yl) as evaluated by this library (call order rhsnk -> jac_calc, oderhs.m:9466-9468)"; return -4; }
   return 0;
+}
+int check_errflag() {
+  CK(cudaStreamSynchronize(g_stream));
+  return err_of_flags();
 }
 
 int run_jac_dev(const double* dyl, const double* dy00, int64_t ml, int64_t mu, int64_t nnzmx, double* djac, int64_t* dja, int64_t* dia, int64_t* nnz_out,
@@ -700,10 +716,8 @@ int run_jac_dev(const double* dyl, const double* dy00, int64_t ml, int64_t mu, i
   g_launches += (base_current ? 0 : 3) + 8;
   int rc = replay(k, [&]() { return enqueue_jac(dyl, dy00, ml, mu, nnzmx, djac, dja, dia, base_current); });
   if (rc) return rc;
-  int64_t last = 0;
-  CK(cudaMemcpyAsync(&last, dia + neq, sizeof(int64_t), cudaMemcpyDeviceToHost, g_stream));
   CK(cudaStreamSynchronize(g_stream));
-  const int64_t nnz = last - 1;
+  const int64_t nnz = (int64_t)h_flags[1] - 1;  // k_scan posts ia(neq+1) to mapped host memory
   *nnz_out = nnz;
   if (nnz > nnzmx) {
     g_err = "*** jac_calc -- More storage needed for Jacobian. Storage exceeded. Increase lenpfac.";
@@ -785,7 +799,11 @@ int ue_gpu_init(void) {
   CK(cudaMalloc(&d_suscal, neq * sizeof(double)));
   CK(cudaMalloc(&d_sfscal, neq * sizeof(double)));
   CK(cudaMalloc(&d_err, sizeof(int)));
-  if (!h_err) CK(cudaMallocHost(&h_err, sizeof(int)));
+  if (!h_flags) {
+    CK(cudaHostAlloc((void**)&h_flags, 4 * sizeof(long long), cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void**)&d_hflags, (void*)h_flags, 0));
+  }
+  h_flags[0] = h_flags[1] = 0; g_nnz_guess = 0;
   {
     std::vector<double> big(neq, 1e20), one(neq, 1.0), zero(neq, 0.0);
     CK(cudaMemcpy(d_dtuse, big.data(), neq * 8, cudaMemcpyHostToDevice));
@@ -858,7 +876,7 @@ int ue_gpu_pandf1(int64_t n, double time, const double* yl, double* yldot) {
     // scaling / time-step phase is redone.
     CK(cudaMemcpyAsync(d_yl + neq, yl + neq, 16, cudaMemcpyHostToDevice, g_stream));
     const int B = 128, G = (NC + B - 1) / B;
-    k_phase3<<<G, B, 0, g_stream>>>(d_base, d_tmp, d_yldot, d_yl, d_dtuse, d_ylodt, neq, NXS, NC);
+    k_phase3<<<G, B, 0, g_stream>>>(d_base, d_tmp, d_yldot, d_yl, d_dtuse, d_ylodt, neq, NXS, NC, d_err, d_hflags);
     g_launches += 1;
     CK(cudaMemcpyAsync(yldot, d_yldot, neq * 8, cudaMemcpyDeviceToHost, g_stream));
     CK(cudaStreamSynchronize(g_stream));
@@ -882,7 +900,6 @@ int ue_gpu_pandf1(int64_t n, double time, const double* yl, double* yldot) {
       int r = enqueue_residual(d_yl, d_yldot, true);
       if (r) return r;
       CK(cudaMemcpyAsync(yldot, d_yldot, neq * 8, cudaMemcpyDeviceToHost, g_stream));
-      CK(cudaMemcpyAsync(h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
       return 0;
     });
     if (rc == -10) { g_host_graphs = false; use_graph = false; cudaGetLastError(); }  // not capturable: plain path from now on
@@ -892,11 +909,9 @@ int ue_gpu_pandf1(int64_t n, double time, const double* yl, double* yldot) {
     rc = run_residual_dev(d_yl, d_yldot, true);
     if (rc) return rc;
     CK(cudaMemcpyAsync(yldot, d_yldot, neq * 8, cudaMemcpyDeviceToHost, g_stream));
-    CK(cudaMemcpyAsync(h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
   } else if (rc) return rc;
   CK(cudaStreamSynchronize(g_stream));  // the only synchronisation of the call
-  if (*h_err & 1) { g_err = "***  ni is negative - calculation stopped"; return -3; }
-  if (*h_err & 2) { g_err = "***  ng is negative - calculation stopped"; return -3; }
+  if ((rc = err_of_flags())) return rc;
   g_base_yl.assign(yl, yl + neq + 2);  // the base planes (and d_yl) now describe this yl
   g_last_yldot.assign(yldot, yldot + neq);
   g_base_valid = true; g_base_dev_valid = true;
@@ -946,7 +961,7 @@ int ue_gpu_jac_calc(int64_t n, double t, const double* yl, const double* yldot00
       if (r) return r;
     } else {
       const int B = 128, G = (NC + B - 1) / B;
-      k_phase3<<<G, B, 0, g_stream>>>(d_base, d_tmp, d_yldot, d_yl, d_dtuse, d_ylodt, neq, NXS, NC);
+      k_phase3<<<G, B, 0, g_stream>>>(d_base, d_tmp, d_yldot, d_yl, d_dtuse, d_ylodt, neq, NXS, NC, d_err, d_hflags);
       g_launches += 1;
     }
     k_samebits<<<(unsigned)((neq + 255) / 256), 256, 0, g_stream>>>(d_yldot, d_yldot00, neq, d_err);
@@ -960,26 +975,33 @@ int ue_gpu_jac_calc(int64_t n, double t, const double* yl, const double* yldot00
   g_launches += (base_current ? 0 : 3) + 8;
   int rc = replay(k, [&]() { return enqueue_jac(d_yl, dy00, ml, mu, lim, d_jac, d_ja, d_ia, base_current); });
   if (rc) return rc;
+  // ia always; jac/ja speculatively with the previous call's nnz (the pattern rarely changes between Newton steps), so
+  // that the usual call needs ONE synchronisation; a larger nnz fetches the remainder afterwards.
+  const int64_t guess = std::min(g_nnz_guess, std::min(nnzmx, lim));
   CK(cudaMemcpyAsync(ia, d_ia, (neq + 1) * 8, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaMemcpyAsync(h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+  if (guess > 0) {
+    CK(cudaMemcpyAsync(jac, d_jac, guess * 8, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaMemcpyAsync(ja, d_ja, guess * 8, cudaMemcpyDeviceToHost, g_stream));
+  }
   CK(cudaStreamSynchronize(g_stream));
-  if (*h_err & 1) { g_err = "***  ni is negative - calculation stopped"; return -3; }
-  if (*h_err & 2) { g_err = "***  ng is negative - calculation stopped"; return -3; }
-  if (*h_err & 4) { g_err = "jac_calc: yldot00 is not pandf1(yl) as evaluated by this library (call order rhsnk -> jac_calc, oderhs.m:9466-9468)"; return -4; }
+  if ((rc = err_of_flags())) return rc;
   if (!same_y) { g_base_yl.assign(yl, yl + neq + 2); g_base_valid = true; g_base_dev_valid = true; }  // base fields describe this yl now
-  const int64_t nnz = ia[neq] - 1;
+  const int64_t nnz = (int64_t)h_flags[1] - 1;
   *nnz_out = nnz;
   if (nnz > nnzmx) { g_err = "*** jac_calc -- More storage needed for Jacobian. Storage exceeded. Increase lenpfac."; return -2; }
-  CK(cudaMemcpyAsync(jac, d_jac, nnz * 8, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaMemcpyAsync(ja, d_ja, nnz * 8, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
+  g_nnz_guess = nnz;
+  if (nnz > guess) {
+    CK(cudaMemcpyAsync(jac + guess, d_jac + guess, (nnz - guess) * 8, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaMemcpyAsync(ja + guess, d_ja + guess, (nnz - guess) * 8, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+  }
   return 0;
 }
 
 int ue_gpu_set_column_range(int64_t ivmin, int64_t ivmax) {
   if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
   if (ivmin < 1 || ivmax > neq) { g_err = "column range outside 1..neq"; return -1; }
-  g_ivmin = ivmin; g_ivmax = ivmax;
+  g_ivmin = ivmin; g_ivmax = ivmax; g_nnz_guess = 0;
   build_lists();
   drop_graphs();
   return upload_lists();
