@@ -224,6 +224,14 @@ def main():
     t_e2e, _, _ = timed(step_e2e, a.steps)
     t_res_e2e, _, _ = timed(resid_e2e, a.steps)
     stop.set(); th.join()
+
+    def warm(fn, steps):  # same step without the L2 flush (what a Newton loop sees); reported next to the flushed figure
+        barrier(); t0 = time.perf_counter()
+        for it in range(steps):
+            hy.copy_(ystates[it & 1]); fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / steps * 1e3
+    warm_dev, warm_e2e, warm_res = warm(step_dev, 4 * a.steps), warm(step_e2e, 4 * a.steps), warm(resid_e2e, 4 * a.steps)
     nnz_local = nnz.value
     if world > 1:
         v = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64); dist.all_reduce(v, op=dist.ReduceOp.MAX)
@@ -245,9 +253,10 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6453.1))
     G = 16 + 3  # static real planes + int planes the kernels read (include/ue_params.h)
-    traffic = None
+    traffic = None; fp64_pct = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["dram_bytes_per_launch"].get(name)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        traffic = tj["dram_bytes_per_launch"].get(name); fp64_pct = tj["fp64_pipe_pct"].get(name)
     except Exception:
         pass
     ncell = (c.com.nx + 2) * (c.com.ny + 2)
@@ -262,12 +271,13 @@ def main():
                             else "one Jacobian, columns split over %d ranks (replicated state)" % world),
                 e2e=dict(value=nnz_total / (ms_e2e * 1e-3), unit="nnz/s", h2d_bytes_per_step=8 * (2 * (neq + 2) + neq),
                          d2h_bytes_per_step=16 * nnz_total + 8 * (neq + 1) + 8 * neq, ms_per_step=ms_e2e,
-                         resid_evals_per_s=a.steps / t_res_e2e),
+                         resid_evals_per_s=a.steps / t_res_e2e, warm_ms_per_step=warm_e2e, warm_resid_evals_per_s=1e3 / warm_res),
+                warm_ms_per_step=warm_dev,
                 gpu_launches=int(l1.value - l0.value),
                 resid_evals_per_s=1e3 / res_ms if res_ms > 0 else None, jac_kernel_ms=jac_ms, resid_kernel_ms=res_ms,
                 roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
-                              kernel="k_jac (+ scan/fill/sort, CUDA events around the Jacobian sequence)", peak_source="MEASURED_PEAKS.json hbm_gbs",
-                              note="algorithmic bytes = 8*(2(neq+2)+G*Ncell)+16*nnz+8*(neq+1), G=%d; the kernel is latency/instruction-issue bound at this size, not HBM bound (DESIGN.md 3.4)" % G),
+                              kernel="Jacobian sequence k_jb_stage0/p1a/p1b/p2/p3c + scan/fill/sort (dominant: k_jb_p2), CUDA events on the library stream", fp64_pipe_pct_of_dominant_kernel=fp64_pct, peak_source="MEASURED_PEAKS.json hbm_gbs",
+                              note="algorithmic bytes = 8*(2(neq+2)+G*Ncell)+16*nnz+8*(neq+1), G=%d; latency bound (d3dHsm) / FP64-issue bound (4x), not HBM bound: DESIGN.md 3.4; traffic is ncu's cold-cache replay figure" % G),
                 clocks=dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max([s[1] for s in samples] or [0.0]), reasons=reasons_of([s[2] for s in samples])))
     if cb is not None:
         line["cpu_baseline"] = dict(value=cb["value"], unit="nnz/s", cores=cb["cores"], kind=cb["kind"], sample=cb["sample"])
