@@ -79,6 +79,15 @@ int64_t g_cap_total = 0, g_nnzcap = 0;
     }                                                                                              \
   } while (0)
 
+// Launch on the library stream.  (Programmatic dependent launch was measured and rejected: with griddepcontrol
+// prologues and programmatic graph edges the d3dHsm step went from 0.174 to 0.194 ms.)
+template <typename... KArgs, typename... Args>
+cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = g_stream;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 template <typename T>
 int dev_copy(const T* h, size_t n, const T** out) {
   T* p = nullptr;
@@ -140,10 +149,10 @@ __global__ void __launch_bounds__(128) k_phase2(double* base, double* __restrict
   }
 }
 __global__ void k_phase3(double* base, const double* __restrict__ tmp, double* __restrict__ yldot, const double* __restrict__ yl,
-                         const double* __restrict__ dtuse, const double* __restrict__ ylodt, int64_t neq, int NXS, int NC, const int* __restrict__ err,
+                         const double* __restrict__ dtuse, const double* __restrict__ ylodt, int64_t neq, int NXS, int NC, int* err,
                          long long* hflags) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0) hflags[0] = *err;  // error bits of phases 0-2 go straight to mapped host memory: no copy node, no extra sync
+  if (c == 0) { hflags[0] = *err; *err = 0; }  // error bits of phases 0-2 go straight to mapped host memory (no copy node) and are cleared for the next sequence
   if (c >= NC) return;
   Acc<false> a; a.base = base; a.NXS = NXS; a.NC = NC;
   const int ix = c % NXS, iy = c / NXS;
@@ -210,6 +219,11 @@ __device__ __forceinline__ double jb_dyl(const JArgs& A, const UInfo& q, double&
 // stage the private cells of 32 unknowns from the base planes, then phase 0 on their perturbed cells
 __global__ void __launch_bounds__(128) k_jb_stage0(JArgs A) {
   const int u0 = blockIdx.x * 32, tid = threadIdx.x;
+  {  // clear this Jacobian's counters (colcnt | rowcnt | rowfill are contiguous) and the candidate-row masks
+    const int nthr = gridDim.x * 128, t0 = blockIdx.x * 128 + tid;
+    for (int64_t i = t0; i < 3 * A.neq; i += nthr) A.colcnt[i] = 0;
+    for (int i = t0; i < A.nitems; i += nthr) A.rmask[i] = 0;
+  }
   const int u = u0 + (tid >> 2), k = tid & 3;
   if (u < A.NU) {
     const UInfo& q = A.ui[u];
@@ -367,7 +381,7 @@ __global__ void __launch_bounds__(128) k_jb_p3c(JArgs A) {
 }
 
 // ---- CSC fragments -> CSR ---------------------------------------------------------------------------------------
-__global__ void k_scan(const int* __restrict__ rowcnt, int64_t* __restrict__ ia, int64_t n, const int* __restrict__ err, long long* hflags) {
+__global__ void k_scan(const int* __restrict__ rowcnt, int64_t* __restrict__ ia, int64_t n, int* err, long long* hflags) {
   // single block of 1024 threads; ia is 1-based: ia[0] = 1, ia[i+1] = ia[i] + rowcnt[i].
   // Each thread owns a contiguous chunk: serial sum, block scan of the 1024 partials, serial write-out.
   __shared__ int64_t s[1024];
@@ -386,7 +400,7 @@ __global__ void k_scan(const int* __restrict__ rowcnt, int64_t* __restrict__ ia,
   int64_t run = 1 + s[t] - sum;
   if (t == 0) ia[0] = 1;
   for (int64_t i = b0; i < b1; ++i) { run += rowcnt[i]; ia[i + 1] = run; }
-  if (t == 1023) { hflags[1] = 1 + s[1023]; hflags[0] = *err; }  // nnz + 1 and the error bits, to mapped host memory
+  if (t == 1023) { hflags[1] = 1 + s[1023]; hflags[0] = *err; *err = 0; }  // nnz + 1 and the error bits, to mapped host memory
 }
 __global__ void k_fill(int64_t neq, int64_t ivmin, int64_t ivmax, const int64_t* __restrict__ coloff, const int* __restrict__ colcnt,
                        const int* __restrict__ colrow, const double* __restrict__ colval, const int64_t* __restrict__ ia, int* __restrict__ rowfill,
@@ -627,17 +641,16 @@ void drop_graphs() { for (auto& kv : g_graphs) cudaGraphExecDestroy(kv.second); 
 
 int enqueue_residual(const double* dyl, double* dyldot, bool need_rows) {
   const int B = 128, G = (NC + B - 1) / B, G32 = (NC + 31) / 32;
-  CK(cudaMemsetAsync(d_err, 0, sizeof(int), g_stream));
-  k_phase0<<<G, B, 0, g_stream>>>(d_base, dyl, NXS, NC, d_err);
-  k_phase1<<<G32, 160, 0, g_stream>>>(d_base, NXS, NC);
-  k_phase2<<<G32, 128, 0, g_stream>>>(d_base, d_tmp, NXS, NC);
-  if (need_rows) k_phase3<<<G, B, 0, g_stream>>>(d_base, d_tmp, dyldot, dyl, d_dtuse, d_ylodt, neq, NXS, NC, d_err, d_hflags);
+  CK(launch(k_phase0, dim3(G), dim3(B), d_base, dyl, NXS, NC, d_err));
+  CK(launch(k_phase1, dim3(G32), dim3(160), d_base, NXS, NC));
+  CK(launch(k_phase2, dim3(G32), dim3(128), d_base, d_tmp, NXS, NC));
+  if (need_rows) CK(launch(k_phase3, dim3(G), dim3(B), d_base, d_tmp, dyldot, dyl, d_dtuse, d_ylodt, neq, NXS, NC, d_err, d_hflags));
   return 0;
 }
 int enqueue_jac(const double* dyl, const double* dy00, int64_t ml, int64_t mu, int64_t nnzmx, double* djac, int64_t* dja, int64_t* dia, bool base_current) {
   if (!base_current) { int rc = enqueue_residual(dyl, nullptr, false); if (rc) return rc; }
-  CK(cudaMemsetAsync(d_colcnt, 0, 3 * neq * sizeof(int), g_stream));
   const int NU = (int)h_list.size();
+  if (NU == 0) CK(cudaMemsetAsync(d_colcnt, 0, 3 * neq * sizeof(int), g_stream));  // otherwise k_jb_stage0 clears the counters
   if (NU > 0) {
     JArgs A;
     A.ui = (const UInfo*)d_uinfo; A.cand_cell = d_cand_cell; A.cand_east = d_cand_east; A.item_u = d_item_u;
@@ -646,27 +659,26 @@ int enqueue_jac(const double* dyl, const double* dy00, int64_t ml, int64_t mu, i
     A.yl = dyl; A.yldot00 = dy00; A.suscal = d_suscal; A.sfscal = d_sfscal; A.dtuse = d_dtuse; A.ylodt = d_ylodt;
     A.neq = neq; A.ml = ml; A.mu = mu; A.NXS = NXS; A.NC = NC;
     A.coloff = d_coloff; A.colcnt = d_colcnt; A.colrow = d_colrow; A.colval = d_colval; A.rowcnt = d_rowcnt; A.err = d_err;
-    CK(cudaMemsetAsync(d_rmask, 0, (size_t)g_nitems * sizeof(int), g_stream));
     const unsigned gs = (unsigned)((NU * 4 + 127) / 128), gi = (unsigned)((g_nitems + 127) / 128);
-    k_jb_stage0<<<(unsigned)((NU + 31) / 32), 128, 0, g_stream>>>(A);
+    CK(launch(k_jb_stage0, dim3((unsigned)((NU + 31) / 32)), dim3(128), A));
     A.role0 = 0;
     if (getenv("UE_DEBUG_SPLIT_ROLES")) {  // developer aid: one launch per role so that a launch list shows each role's duration
-      for (int r = 0; r < 3; ++r) { A.role0 = r; k_jb_p1a<<<dim3(gs, 1), 128, 0, g_stream>>>(A); }
-      for (int r = 0; r < 5; ++r) { A.role0 = r; k_jb_p1b<<<dim3(gs, 1), 128, 0, g_stream>>>(A); }
-      for (int r = 0; r < 4; ++r) { A.role0 = r; k_jb_p2<<<dim3(gi, 1), 128, 0, g_stream>>>(A); }
+      for (int r = 0; r < 3; ++r) { A.role0 = r; CK(launch(k_jb_p1a, dim3(dim3(gs, 1)), dim3(128), A)); }
+      for (int r = 0; r < 5; ++r) { A.role0 = r; CK(launch(k_jb_p1b, dim3(dim3(gs, 1)), dim3(128), A)); }
+      for (int r = 0; r < 4; ++r) { A.role0 = r; CK(launch(k_jb_p2, dim3(dim3(gi, 1)), dim3(128), A)); }
       A.role0 = 0;
     } else {
-      k_jb_p1a<<<dim3(gs, 3), 128, 0, g_stream>>>(A);
-      k_jb_p1b<<<dim3(gs, 5), 128, 0, g_stream>>>(A);
-      k_jb_p2<<<dim3(gi, 4), 128, 0, g_stream>>>(A);
+      CK(launch(k_jb_p1a, dim3(dim3(gs, 3)), dim3(128), A));
+      CK(launch(k_jb_p1b, dim3(dim3(gs, 5)), dim3(128), A));
+      CK(launch(k_jb_p2, dim3(dim3(gi, 4)), dim3(128), A));
     }
-    k_jb_p3c<<<(unsigned)((NU + 3) / 4), 128, 0, g_stream>>>(A);
+    CK(launch(k_jb_p3c, dim3((unsigned)((NU + 3) / 4)), dim3(128), A));
   }
-  k_scan<<<1, 1024, 0, g_stream>>>(d_rowcnt, dia, neq, d_err, d_hflags);
+  CK(launch(k_scan, dim3(1), dim3(1024), d_rowcnt, dia, neq, d_err, d_hflags));
   const int64_t ncol = g_ivmax - g_ivmin + 1;
   if (ncol > 0) {
-    k_fill<<<(unsigned)ncol, 64, 0, g_stream>>>(neq, g_ivmin, g_ivmax, d_coloff, d_colcnt, d_colrow, d_colval, dia, d_rowfill, djac, dja, nnzmx);
-    k_sortrows<<<(unsigned)((neq + 3) / 4), 128, 0, g_stream>>>(neq, dia, djac, dja, nnzmx);
+    CK(launch(k_fill, dim3((unsigned)ncol), dim3(64), neq, g_ivmin, g_ivmax, d_coloff, d_colcnt, d_colrow, d_colval, dia, d_rowfill, djac, dja, nnzmx));
+    CK(launch(k_sortrows, dim3((unsigned)((neq + 3) / 4)), dim3(128), neq, dia, djac, dja, nnzmx));
   }
   return 0;
 }
@@ -674,15 +686,21 @@ template <typename F>
 int replay(const GKey& key, F enqueue) {
   auto it = g_graphs.find(key);
   if (it == g_graphs.end()) {
-    cudaGraph_t graph = nullptr;
-    CK(cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeThreadLocal));
-    int rc = enqueue();
-    cudaError_t e = cudaStreamEndCapture(g_stream, &graph);
-    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-    if (e != cudaSuccess) { g_err = std::string("CUDA graph capture failed: ") + cudaGetErrorString(e); return -10; }
     cudaGraphExec_t ex = nullptr;
-    CK(cudaGraphInstantiate(&ex, graph, 0));
-    cudaGraphDestroy(graph);
+    for (int attempt = 0; attempt < 1 && !ex; ++attempt) {
+      cudaGraph_t graph = nullptr;
+      CK(cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeThreadLocal));
+      int rc = enqueue();
+      cudaError_t e = cudaStreamEndCapture(g_stream, &graph);
+      if (e == cudaSuccess && rc == 0) e = cudaGraphInstantiate(&ex, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      if (e == cudaSuccess && rc == 0) break;
+      ex = nullptr;
+      cudaGetLastError();
+      if (rc) return rc;
+      g_err = std::string("CUDA graph capture failed: ") + cudaGetErrorString(e);
+      return -10;
+    }
     if (g_graphs.size() > 64) drop_graphs();
     it = g_graphs.emplace(key, ex).first;
   }
@@ -799,6 +817,7 @@ int ue_gpu_init(void) {
   CK(cudaMalloc(&d_suscal, neq * sizeof(double)));
   CK(cudaMalloc(&d_sfscal, neq * sizeof(double)));
   CK(cudaMalloc(&d_err, sizeof(int)));
+  CK(cudaMemset(d_err, 0, sizeof(int)));  // afterwards the kernel that posts the error bits clears them
   if (!h_flags) {
     CK(cudaHostAlloc((void**)&h_flags, 4 * sizeof(long long), cudaHostAllocMapped));
     CK(cudaHostGetDevicePointer((void**)&d_hflags, (void*)h_flags, 0));
@@ -876,7 +895,7 @@ int ue_gpu_pandf1(int64_t n, double time, const double* yl, double* yldot) {
     // scaling / time-step phase is redone.
     CK(cudaMemcpyAsync(d_yl + neq, yl + neq, 16, cudaMemcpyHostToDevice, g_stream));
     const int B = 128, G = (NC + B - 1) / B;
-    k_phase3<<<G, B, 0, g_stream>>>(d_base, d_tmp, d_yldot, d_yl, d_dtuse, d_ylodt, neq, NXS, NC, d_err, d_hflags);
+    CK(launch(k_phase3, dim3(G), dim3(B), d_base, d_tmp, d_yldot, d_yl, d_dtuse, d_ylodt, neq, NXS, NC, d_err, d_hflags));
     g_launches += 1;
     CK(cudaMemcpyAsync(yldot, d_yldot, neq * 8, cudaMemcpyDeviceToHost, g_stream));
     CK(cudaStreamSynchronize(g_stream));
@@ -961,10 +980,10 @@ int ue_gpu_jac_calc(int64_t n, double t, const double* yl, const double* yldot00
       if (r) return r;
     } else {
       const int B = 128, G = (NC + B - 1) / B;
-      k_phase3<<<G, B, 0, g_stream>>>(d_base, d_tmp, d_yldot, d_yl, d_dtuse, d_ylodt, neq, NXS, NC, d_err, d_hflags);
+      CK(launch(k_phase3, dim3(G), dim3(B), d_base, d_tmp, d_yldot, d_yl, d_dtuse, d_ylodt, neq, NXS, NC, d_err, d_hflags));
       g_launches += 1;
     }
-    k_samebits<<<(unsigned)((neq + 255) / 256), 256, 0, g_stream>>>(d_yldot, d_yldot00, neq, d_err);
+    CK(launch(k_samebits, dim3((unsigned)((neq + 255) / 256)), dim3(256), d_yldot, d_yldot00, neq, d_err));
     g_launches += 1;
     g_last_yldot.clear();
     base_current = true;
@@ -1031,7 +1050,7 @@ int ue_gpu_sfsetnk(int64_t n, const double* yl, const double* su, int64_t ml, in
   const int big = 0x7fffffff;
   CK(cudaMemcpyAsync(d_bits, &cut, 8, cudaMemcpyHostToDevice, g_stream));
   CK(cudaMemcpyAsync(d_zero, &big, 4, cudaMemcpyHostToDevice, g_stream));
-  k_rownorm<<<(unsigned)((neq + 3) / 4), 128, 0, g_stream>>>(neq, d_ia, d_ja, d_jac, d_suscal, d_yldot00, d_tmp, d_bits, d_zero);
+  CK(launch(k_rownorm, dim3((unsigned)((neq + 3) / 4)), dim3(128), neq, d_ia, d_ja, d_jac, d_suscal, d_yldot00, d_tmp, d_bits, d_zero));
   g_launches += 1;
   unsigned long long bits = 0; int zero = 0;
   CK(cudaMemcpyAsync(sf, d_tmp, neq * 8, cudaMemcpyDeviceToHost, g_stream));
