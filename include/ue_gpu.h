@@ -63,6 +63,14 @@ int ue_gpu_jac_calc(int64_t neq, double t, const double* yl, const double* yldot
  * message if a row vanishes.  Uses dtuse/sfscal of the last ue_gpu_step_params. */
 int ue_gpu_sfsetnk(int64_t neq, const double* yl, const double* su, int64_t ml, int64_t mu, double* sf, double* ydt_max0);
 
+/* ---- psetnk's scaling chain (bbb/oderhs.m:9473-9485) on the Jacobian the last ue_gpu_jac_calc left on the device ----
+ * J <- J diag(1/su) (amudia, svr/svrut4.m:1104-1148); J <- diag(sf) J (diamua, :1054-1102); if isrnorm==1 the rows are
+ * normalised with normtype 0/1/2 = max/1/2-norm (jac_norm_rows -> roscal -> rnrms, oderhs.m:8959-8992, svrut4.m:954-1052)
+ * and the factors returned in fnormnw.  The pattern (ja, ia) is the one ue_gpu_jac_calc returned; only the nnz values
+ * come back, ready for jac_lu_decomp.  su, sf, fnormnw: neq doubles; jac: nnz doubles. */
+int ue_gpu_jac_scale(int64_t neq, const double* su, const double* sf, int64_t isrnorm, int64_t normtype,
+                     int64_t nnz, double* jac, double* fnormnw);
+
 /* ---- device-resident variants (inputs/outputs already in HBM) -------------
  * Same semantics; pointers are device pointers on the current device.  Used by
  * bench.py for the kernel-only figure and by a host that keeps yl on the GPU. */

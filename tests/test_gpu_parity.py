@@ -178,6 +178,37 @@ def test_sfsetnk_on_device(built):
     assert ymax_g == max(np.abs(f0 * sf_o).max(), 1e-300)
 
 
+@pytest.mark.parametrize("normtype", [0, 1, 2])
+def test_psetnk_scaling_chain_on_device(built, normtype):
+    """amudia -> diamua -> roscal on the device-resident Jacobian (oderhs.m:9473-9485, svr/svrut4.m:954-1148) against
+    the same chain in plain IEEE arithmetic on the oracle's CSR: bit-identical values and row factors."""
+    c, yl, gpu, ora = _pair("d3dHsm", 1e-3)
+    b = c.bbb
+    y, su = psetnk_inputs(c, yl)
+    rng = np.random.default_rng(11)
+    sf = 10.0 ** rng.uniform(-3, 3, b.neq)
+    for lib in (gpu, ora):
+        lib.step_params(np.full(b.neq, 1e20), y[: b.neq], su, sf)
+    f0 = gpu.pandf1(y)
+    jg, jag, iag = gpu.jac_calc(y, f0, b.lbw, b.ubw, b.nnzmx)
+    jo, jao, iao = ora.jac_calc(y, ora.pandf1(y), b.lbw, b.ubw, b.nnzmx)
+    assert np.array_equal(jg, jo) and np.array_equal(jag, jao)
+    scaled, fac = gpu.jac_scale(su, sf, len(jg), isrnorm=1, normtype=normtype)
+    rows = np.repeat(np.arange(b.neq), np.diff(iao))
+    a = (jo * (1.0 / su)[jao - 1]) * sf[rows]
+    nrm = np.zeros(b.neq)
+    for i in range(b.neq):  # serial sums in storage order, as rnrms does
+        s = 0.0
+        for v in a[iao[i] - 1 : iao[i + 1] - 1]:
+            s = max(s, abs(v)) if normtype == 0 else (s + abs(v) if normtype == 1 else s + v * v)
+        nrm[i] = np.sqrt(s) if normtype == 2 else s
+    d = 1.0 / nrm
+    assert np.array_equal(fac, d)
+    assert np.array_equal(scaled, a * d[rows])
+    with pytest.raises(Exception, match="nnz is not that of the last"):
+        gpu.jac_scale(su, sf, len(jg) - 1)
+
+
 def test_jacobian_column_range_split(built):
     """ppp-style column split: the union of per-range CSRs equals the full CSR."""
     c, yl, gpu, ora = _pair("d3dHsm", 1e-3)

@@ -118,6 +118,17 @@ class UeLib:
         n = nnz.value
         return jac[:n].copy(), ja[:n].copy(), ia
 
+    def jac_scale(self, su, sf, nnz, isrnorm=1, normtype=0):
+        """psetnk's scaling chain on the device-resident Jacobian of the last jac_calc (bbb/oderhs.m:9473-9485); product library only."""
+        fn = getattr(self.lib, self.prefix + "jac_scale")
+        fn.argtypes = [_i64, _dp, _dp, _i64, _i64, _i64, _dp, _dp]
+        fn.restype = C.c_int
+        su = np.ascontiguousarray(su, dtype=np.float64); sf = np.ascontiguousarray(sf, dtype=np.float64)
+        jac = np.zeros(nnz); fac = np.zeros(self.neq)
+        if fn(self.neq, _d(su), _d(sf), int(isrnorm), int(normtype), int(nnz), _d(jac), _d(fac)) != 0:
+            raise UeError("jac_scale failed: %s" % getattr(self.lib, self.prefix + "last_error")().decode())
+        return jac, fac
+
     def sfsetnk(self, yl, su, ml, mu):
         """Row scale factors sf and ydt_max0 as sfsetnk computes them (bbb/oderhs.m:9815-9884); product library only."""
         fn = getattr(self.lib, self.prefix + "sfsetnk")

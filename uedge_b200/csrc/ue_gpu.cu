@@ -447,6 +447,30 @@ __global__ void k_sortrows(int64_t neq, const int64_t* __restrict__ ia, double* 
 
 // sfsetnk scaling chain (oderhs.m:9862-9881): column scaling by 1/su (amudia, svr/svrut4.m:1104-1130), row max-norm
 // (rnrms with normtype=0, svr/svrut4.m:1002-1052), sf = 1/norm, and ydt_max0 = max|yldot0*sf|.  One warp per row.
+// psetnk scaling chain, one thread per row (rows are <= ~80 entries; the 1- and 2-norms are serial sums in the reference's
+// order so that the factors are bit-identical): amudia, diamua, roscal (svr/svrut4.m:954-1148)
+__global__ void k_rowscale(int64_t neq, const int64_t* __restrict__ ia, const int64_t* __restrict__ ja, double* __restrict__ jac,
+                           const double* __restrict__ su, const double* __restrict__ sf, int isrnorm, int normtype, double* __restrict__ fac) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= neq) return;
+  const int64_t k1 = ia[i] - 1, k2 = ia[i + 1] - 1;
+  const double sfi = sf[i];
+  double scal = 0.;
+  for (int64_t k = k1; k < k2; ++k) {
+    double a = jac[k] * (1. / su[ja[k] - 1]);
+    a = a * sfi;
+    jac[k] = a;
+    if (normtype == 0) scal = fmax(scal, fabs(a));
+    else if (normtype == 1) scal = scal + fabs(a);
+    else scal = scal + a * a;
+  }
+  if (!isrnorm) { fac[i] = 1.; return; }
+  if (normtype == 2) scal = sqrt(scal);
+  const double d = 1.0 / scal;
+  fac[i] = d;
+  for (int64_t k = k1; k < k2; ++k) jac[k] = jac[k] * d;
+}
+
 // yldot00 must be the residual of yl bit for bit (see ue_gpu_jac_calc)
 __global__ void k_samebits(const double* __restrict__ a, const double* __restrict__ b, int64_t n, int* __restrict__ err) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1062,6 +1086,22 @@ int ue_gpu_sfsetnk(int64_t n, const double* yl, const double* su, int64_t ml, in
   if (zero != big) { char b[96]; snprintf(b, sizeof b, "*** Error: Jacobian row = 0 for eqn iv = %d", zero); g_err = b; return -7; }
   double v; std::memcpy(&v, &bits, 8);
   *ydt_max0 = std::max(v, S.p.cutlo);
+  return 0;
+}
+int ue_gpu_jac_scale(int64_t n, const double* su, const double* sf, int64_t isrnorm, int64_t normtype, int64_t nnz, double* jac, double* fnormnw) {
+  if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
+  if (n != neq) { g_err = "jac_scale: neq mismatch"; return -1; }
+  if (nnz != (int64_t)h_flags[1] - 1) { g_err = "jac_scale: nnz is not that of the last ue_gpu_jac_calc"; return -1; }
+  if (normtype < 0 || normtype > 2) { g_err = "jac_scale: normtype must be 0, 1 or 2"; return -1; }
+  static double* d_sc = nullptr; static int64_t cap = 0;  // su | sf | factors
+  if (cap < 3 * neq) { if (d_sc) cudaFree(d_sc); CK(cudaMalloc(&d_sc, 3 * neq * 8)); cap = 3 * neq; }
+  CK(cudaMemcpyAsync(d_sc, su, neq * 8, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(d_sc + neq, sf, neq * 8, cudaMemcpyHostToDevice, g_stream));
+  CK(launch(k_rowscale, dim3((unsigned)((neq + 127) / 128)), dim3(128), neq, (const int64_t*)d_ia, (const int64_t*)d_ja, d_jac, (const double*)d_sc, (const double*)(d_sc + neq), (int)isrnorm, (int)normtype, d_sc + 2 * neq));
+  g_launches += 1;
+  CK(cudaMemcpyAsync(jac, d_jac, nnz * 8, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaMemcpyAsync(fnormnw, d_sc + 2 * neq, neq * 8, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
   return 0;
 }
 int ue_gpu_kernel_launches(int64_t* n) { *n = g_launches; return 0; }
