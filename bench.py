@@ -105,7 +105,7 @@ def main():
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     from tests.util import make_case, psetnk_inputs
     name = a.config
-    c, yl = make_case(name, perturb=1e-3, seed=1234 + rank)   # replicas: every rank has its own state
+    c, yl = make_case(name, perturb=1e-3, seed=1234 + (rank if a.mode == "replicas" else 0))   # replicas: every rank has its own state; columns: one shared state
     c.name = name
     b = c.bbb
 

@@ -209,21 +209,23 @@ def test_psetnk_scaling_chain_on_device(built, normtype):
         gpu.jac_scale(su, sf, len(jg) - 1)
 
 
-def test_jacobian_column_range_split(built):
+@pytest.mark.parametrize("name,cuts", [("d3dHsm", [1, 301, 577, 901]), ("d3dHsm4x", [1, 5611, 11221])])
+def test_jacobian_column_range_split(built, name, cuts):
     """ppp-style column split: the union of per-range CSRs equals the full CSR."""
-    c, yl, gpu, ora = _pair("d3dHsm", 1e-3)
+    c, yl, gpu, ora = _pair(name, 1e-3)
     b = c.bbb
     y, su = psetnk_inputs(c, yl)
     gpu.step_params(np.full(b.neq, 1e20), y[: b.neq], su, np.ones(b.neq))
     f = gpu.pandf1(y)
     full = gpu.jac_calc(y, f, b.lbw, b.ubw, b.nnzmx)
     parts = []
-    cuts = [1, 301, 577, b.neq + 1]
+    assert cuts[-1] == b.neq + 1
     for lo, hi in zip(cuts[:-1], cuts[1:]):
         gpu.set_column_range(lo, hi - 1)
         parts.append(gpu.jac_calc(y, f, b.lbw, b.ubw, b.nnzmx))
     gpu.set_column_range(1, b.neq)
     vals, cols, ia = full
+    assert sum(len(p[0]) for p in parts) == len(vals)
     for i in range(b.neq):
         cc = np.concatenate([p[1][p[2][i] - 1 : p[2][i + 1] - 1] for p in parts])
         vv = np.concatenate([p[0][p[2][i] - 1 : p[2][i + 1] - 1] for p in parts])

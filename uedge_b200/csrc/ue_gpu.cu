@@ -967,7 +967,7 @@ int ue_gpu_jac_calc_dev(int64_t n, double t, const double* dyl, const double* dy
   if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
   if (n != neq) { g_err = "jac_calc: neq mismatch"; return -1; }
   CK(cudaEventRecord(g_ev0, g_stream));
-  const bool cur = g_base_valid && g_jac_trust_base;
+  const bool cur = g_base_dev_valid && g_jac_trust_base;  // the host-pointer bookkeeping (g_base_valid, g_base_yl) is not involved
   g_jac_trust_base = false;
   int rc = run_jac_dev(dyl, dy00, ml, mu, std::min(nnzmx, g_nnzcap), djac, dja, dia, nnz_out, cur);
   g_base_valid = false;  // device-pointer callers may change d_yl behind our back
@@ -1052,7 +1052,7 @@ int ue_gpu_set_column_range(int64_t ivmin, int64_t ivmax) {
 
 // Device-pointer callers: assert that d_yl has not changed since the last ue_gpu_pandf1_dev call, so the next
 // ue_gpu_jac_calc_dev may reuse the base planes (the host-pointer entry points check this themselves).
-int ue_gpu_assume_base_current(int64_t flag) { g_jac_trust_base = (flag != 0); if (flag) g_base_valid = g_base_dev_valid; return 0; }
+int ue_gpu_assume_base_current(int64_t flag) { g_jac_trust_base = (flag != 0); return 0; }
 // sfsetnk (bbb/oderhs.m:9815-9884) with the Jacobian kept on the device: f0 = pandf1(yl | flag=1), J = jac_calc,
 // J <- J*diag(1/su), sf(i) = 1/max_k|J_ik|, ydt_max0 = max_i|f0_i sf_i|.  Only sf (neq doubles) returns to the host.
 int ue_gpu_sfsetnk(int64_t n, const double* yl, const double* su, int64_t ml, int64_t mu, double* sf, double* ydt_max0) {
