@@ -177,11 +177,25 @@ def main():
         assert lib.ue_gpu_set_real(b"nufak", nufak) == 0
         assert lib.ue_gpu_jac_calc(neq, 0.0, P(hy), P(hf), int(b.lbw), int(b.ubw), nnzmx, P(hjac), P(hja), P(hia), C.byref(nnz)) == 0
 
-    def step_dev():
+    lib.ue_gpu_rhs_jac_dev.argtypes = [C.c_int64, C.c_void_p, C.c_void_p] + [C.c_int64] * 3 + [C.c_void_p] * 3 + [C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+    evms = C.c_double(0); ev_samples = []
+
+    def step_dev():  # inputs resident in HBM; residual + Jacobian as one stream sequence, timed by CUDA events on the library's stream
+        assert lib.ue_gpu_rhs_jac_dev(neq, d_yl, d_y00, int(b.lbw), int(b.ubw), nnzmx, d_jac, d_ja, d_ia, C.byref(nnz), C.byref(evms)) == 0
+        ev_samples.append(evms.value)
+
+    def kernels_dev():  # the two sequences separately, for the per-sequence CUDA-event times
         assert lib.ue_gpu_pandf1_dev(neq, 0.0, d_yl, d_y00) == 0
         lib.ue_gpu_assume_base_current(1)
         assert lib.ue_gpu_jac_calc_dev(neq, 0.0, d_yl, d_y00, int(b.lbw), int(b.ubw), nnzmx, d_jac, d_ja, d_ia, C.byref(nnz)) == 0
         lib.ue_gpu_last_kernel_ms(C.byref(jms), C.byref(rms))
+
+    lib.ue_gpu_rhs_jac.argtypes = [C.c_int64, C.c_void_p, C.c_void_p] + [C.c_int64] * 3 + [C.c_void_p] * 3 + [C.POINTER(C.c_int64)]
+
+    def step_e2e_fused():  # optional integration: the pair as one C-ABI call
+        shim_params()
+        assert lib.ue_gpu_set_real(b"nufak", nufak) == 0
+        assert lib.ue_gpu_rhs_jac(neq, P(hy), P(hf), int(b.lbw), int(b.ubw), nnzmx, P(hjac), P(hja), P(hia), C.byref(nnz)) == 0
 
     def resid_e2e():
         shim_params()
@@ -219,10 +233,14 @@ def main():
     samples = []; stop = threading.Event()
     th = threading.Thread(target=clocks_sampler, args=(stop, samples)); th.start()
     l0 = C.c_int64(0); lib.ue_gpu_kernel_launches(C.byref(l0))
-    t_dev, jm, rm = timed(step_dev, a.steps)
+    del ev_samples[:]
+    t_dev_host, _, _ = timed(step_dev, a.steps)
+    t_dev = sum(ev_samples) * 1e-3  # CUDA events: seconds for a.steps steps
     l1 = C.c_int64(0); lib.ue_gpu_kernel_launches(C.byref(l1))
+    _, jm, rm = timed(kernels_dev, a.steps)
     t_e2e, _, _ = timed(step_e2e, a.steps)
     t_res_e2e, _, _ = timed(resid_e2e, a.steps)
+    t_fused, _, _ = timed(step_e2e_fused, a.steps)
     stop.set(); th.join()
 
     def warm(fn, steps):  # same step without the L2 flush (what a Newton loop sees); reported next to the flushed figure
@@ -234,8 +252,8 @@ def main():
     warm_dev, warm_e2e, warm_res = warm(step_dev, 4 * a.steps), warm(step_e2e, 4 * a.steps), warm(resid_e2e, 4 * a.steps)
     nnz_local = nnz.value
     if world > 1:
-        v = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64); dist.all_reduce(v, op=dist.ReduceOp.MAX)
-        t_dev, t_e2e = v.tolist()
+        v = torch.tensor([t_dev, t_e2e, t_dev_host], device="cuda", dtype=torch.float64); dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e, t_dev_host = v.tolist()
         n = torch.tensor([nnz_local], device="cuda", dtype=torch.int64); dist.all_reduce(n)
         nnz_total = int(n.item())
     else:
@@ -267,12 +285,12 @@ def main():
                 ms_per_step=ms_dev, higher_is_better=True, scaling="strong" if (world > 1 and a.mode == "columns") else "weak", vs_baseline=None, dtype="f64", data="synthetic",
                 config=dict(workload="%s: rhsnk + jac_calc (1 residual + 1 full FD Jacobian, neq=%d, nnz=%d) per step" % (name, neq, nnz_total),
                             l2="flushed between steps (192 MB fill)",
-                            timer="host clock around the synchronize()d step (>= device time); jac_kernel_ms/resid_kernel_ms are CUDA events on the library's stream", parallelism=("%d independent replicas (one state per GPU), no collective" % world) if a.mode == "replicas" or world == 1
+                            timer="value/ms_per_step: CUDA events on the library's stream around the residual+Jacobian sequence (ue_gpu_rhs_jac_dev); e2e: host clock around the two C-ABI calls; host_clock_ms_per_step: host clock around the device-resident step", parallelism=("%d independent replicas (one state per GPU), no collective" % world) if a.mode == "replicas" or world == 1
                             else "one Jacobian, columns split over %d ranks (replicated state)" % world),
                 e2e=dict(value=nnz_total / (ms_e2e * 1e-3), unit="nnz/s", h2d_bytes_per_step=8 * (2 * (neq + 2) + neq),
                          d2h_bytes_per_step=16 * nnz_total + 8 * (neq + 1) + 8 * neq, ms_per_step=ms_e2e,
-                         resid_evals_per_s=a.steps / t_res_e2e, warm_ms_per_step=warm_e2e, warm_resid_evals_per_s=1e3 / warm_res),
-                warm_ms_per_step=warm_dev,
+                         resid_evals_per_s=a.steps / t_res_e2e, warm_ms_per_step=warm_e2e, warm_resid_evals_per_s=1e3 / warm_res, fused_call_ms_per_step=t_fused / a.steps * 1e3),
+                warm_ms_per_step=warm_dev, host_clock_ms_per_step=t_dev_host / a.steps * 1e3,
                 gpu_launches=int(l1.value - l0.value),
                 resid_evals_per_s=1e3 / res_ms if res_ms > 0 else None, jac_kernel_ms=jac_ms, resid_kernel_ms=res_ms,
                 roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,

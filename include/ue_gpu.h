@@ -63,6 +63,12 @@ int ue_gpu_jac_calc(int64_t neq, double t, const double* yl, const double* yldot
  * message if a row vanishes.  Uses dtuse/sfscal of the last ue_gpu_step_params. */
 int ue_gpu_sfsetnk(int64_t neq, const double* yl, const double* su, int64_t ml, int64_t mu, double* sf, double* ydt_max0);
 
+/* ---- rhsnk(yl) + jac_calc(yl, yldot00) in one call ------------------------------------------------------------------
+ * The pair psetnk and sfsetnk issue back to back (bbb/oderhs.m:9466-9468, 9851-9857): yldot00 (neq) = pandf1(yl) and the
+ * Jacobian at yl, with one upload of yl and one synchronisation.  Same outputs and errors as the two separate calls. */
+int ue_gpu_rhs_jac(int64_t neq, const double* yl, double* yldot00, int64_t ml, int64_t mu, int64_t nnzmx,
+                   double* jac, int64_t* ja, int64_t* ia, int64_t* nnz_out);
+
 /* ---- psetnk's scaling chain (bbb/oderhs.m:9473-9485) on the Jacobian the last ue_gpu_jac_calc left on the device ----
  * J <- J diag(1/su) (amudia, svr/svrut4.m:1104-1148); J <- diag(sf) J (diamua, :1054-1102); if isrnorm==1 the rows are
  * normalised with normtype 0/1/2 = max/1/2-norm (jac_norm_rows -> roscal -> rnrms, oderhs.m:8959-8992, svrut4.m:954-1052)
@@ -75,6 +81,10 @@ int ue_gpu_jac_scale(int64_t neq, const double* su, const double* sf, int64_t is
  * Same semantics; pointers are device pointers on the current device.  Used by
  * bench.py for the kernel-only figure and by a host that keeps yl on the GPU. */
 int ue_gpu_pandf1_dev(int64_t neq, double time, const double* d_yl, double* d_yldot);
+/* rhsnk(yl) followed by jac_calc(yl, yldot00) - the pair psetnk/sfsetnk issue (oderhs.m:9466-9468, 9851-9857) - as one
+ * stream sequence without a host round trip in between; *ms = CUDA-event time of the sequence on the library stream. */
+int ue_gpu_rhs_jac_dev(int64_t neq, const double* d_yl, double* d_yldot00, int64_t ml, int64_t mu, int64_t nnzmx,
+                       double* d_jac, int64_t* d_ja, int64_t* d_ia, int64_t* nnz_out, double* ms);
 int ue_gpu_jac_calc_dev(int64_t neq, double t, const double* d_yl, const double* d_yldot00,
                         int64_t ml, int64_t mu, int64_t nnzmx,
                         double* d_jac, int64_t* d_ja, int64_t* d_ia, int64_t* nnz_out);

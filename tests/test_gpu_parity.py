@@ -178,6 +178,22 @@ def test_sfsetnk_on_device(built):
     assert ymax_g == max(np.abs(f0 * sf_o).max(), 1e-300)
 
 
+def test_fused_rhs_jac_equals_the_two_calls(built):
+    c, yl, gpu, ora = _pair("d3dHsm", 1e-3)
+    b = c.bbb
+    y, su = psetnk_inputs(c, yl)
+    gpu.step_params(np.full(b.neq, 1e20), y[: b.neq], su, np.ones(b.neq))
+    for k in range(3):
+        yk = y.copy(); yk[: b.neq] *= 1 + 1e-5 * k
+        f1 = gpu.pandf1(yk)
+        j1 = gpu.jac_calc(yk, f1, b.lbw, b.ubw, b.nnzmx)
+        f2, j2 = gpu.rhs_jac(yk, b.lbw, b.ubw, b.nnzmx)
+        assert np.array_equal(f1, f2) and all(np.array_equal(p, q) for p, q in zip(j1, j2))
+    yk[5 * 40] = -1.0
+    with pytest.raises(Exception, match="ni is negative"):
+        gpu.rhs_jac(yk, b.lbw, b.ubw, b.nnzmx)
+
+
 @pytest.mark.parametrize("normtype", [0, 1, 2])
 def test_psetnk_scaling_chain_on_device(built, normtype):
     """amudia -> diamua -> roscal on the device-resident Jacobian (oderhs.m:9473-9485, svr/svrut4.m:954-1148) against

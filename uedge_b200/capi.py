@@ -118,6 +118,19 @@ class UeLib:
         n = nnz.value
         return jac[:n].copy(), ja[:n].copy(), ia
 
+    def rhs_jac(self, yl, ml, mu, nnzmx):
+        """rhsnk(yl) + jac_calc(yl, yldot00) in one call (what psetnk/sfsetnk issue back to back); product library only."""
+        fn = getattr(self.lib, self.prefix + "rhs_jac")
+        fn.argtypes = [_i64, _dp, _dp, _i64, _i64, _i64, _dp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        fn.restype = C.c_int
+        yl = np.ascontiguousarray(yl, dtype=np.float64)
+        f = np.zeros(self.neq); jac = np.zeros(nnzmx); ja = np.zeros(nnzmx, dtype=np.int64); ia = np.zeros(self.neq + 1, dtype=np.int64)
+        nnz = C.c_int64(0)
+        if fn(self.neq, _d(yl), _d(f), int(ml), int(mu), int(nnzmx), _d(jac), _i(ja), _i(ia), C.byref(nnz)) != 0:
+            raise UeError("rhs_jac failed: %s" % getattr(self.lib, self.prefix + "last_error")().decode())
+        n = nnz.value
+        return f, (jac[:n].copy(), ja[:n].copy(), ia)
+
     def jac_scale(self, su, sf, nnz, isrnorm=1, normtype=0):
         """psetnk's scaling chain on the device-resident Jacobian of the last jac_calc (bbb/oderhs.m:9473-9485); product library only."""
         fn = getattr(self.lib, self.prefix + "jac_scale")

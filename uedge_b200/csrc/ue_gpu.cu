@@ -56,7 +56,8 @@ int64_t g_ivmin = 1, g_ivmax = 0;
 std::vector<int> h_list;  // unknowns (iv) of the column range
 std::vector<int64_t> h_coloff;  // per column offset into the fragment buffers (1-based iv -> h_coloff[iv-1])
 std::vector<int> h_cellcand_off, h_cand_cell, h_cand_east;  // per-cell candidate lists (CSR-like)
-int *d_cand_cell = nullptr, *d_cand_east = nullptr, *d_item_u = nullptr;
+int *d_cand_cell = nullptr, *d_cand_east = nullptr, *d_item_u = nullptr, *d_guard_items = nullptr;
+int g_nguard = 0;
 std::vector<unsigned char> h_uinfo;  // UInfo records of the column range, regular windows first
 void* d_uinfo = nullptr;
 double *d_priv = nullptr, *d_jrows = nullptr, *d_rres = nullptr;
@@ -128,8 +129,8 @@ __global__ void __launch_bounds__(160) k_phase1(double* base, int NXS, int NC) {
     else p1_ey<false>(a, w, ix, iy);
   }
 }
-// phase 2: 32 cells per block, four role-warps (equation groups); guard cells go to role 0
-__global__ void __launch_bounds__(128) k_phase2(double* base, double* __restrict__ tmp, int NXS, int NC) {
+// phase 2: 32 cells per block, five role-warps: four equation groups on interior cells, the guard-cell rows (bouncon)
+__global__ void __launch_bounds__(160) k_phase2(double* base, double* __restrict__ tmp, int NXS, int NC) {
   const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   if (c >= NC) return;
@@ -142,8 +143,8 @@ __global__ void __launch_bounds__(128) k_phase2(double* base, double* __restrict
     if (role == 0) { p2_n<false>(a, ix, iy, r, D.iseqalg); o[0] = r[0]; o[4] = r[4]; }
     else if (role == 1) { p2_m<false>(a, w, ix, iy, r, D.iseqalg); o[1] = r[1]; }
     else if (role == 2) { p2_e<false>(a, ix, iy, r, D.iseqalg); o[2] = r[2]; }
-    else { p2_i<false>(a, ix, iy, r, D.iseqalg); o[3] = r[3]; }
-  } else if (role == 0) {
+    else if (role == 3) { p2_i<false>(a, ix, iy, r, D.iseqalg); o[3] = r[3]; }
+  } else if (role == 4) {
     phase2_guard<false>(a, w, ix, iy, r);
     for (int k = 0; k < UE_NV; ++k) o[k] = r[k];
   }
@@ -152,7 +153,7 @@ __global__ void k_phase3(double* base, const double* __restrict__ tmp, double* _
                          const double* __restrict__ dtuse, const double* __restrict__ ylodt, int64_t neq, int NXS, int NC, int* err,
                          long long* hflags) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0) { hflags[0] = *err; *err = 0; }  // error bits of phases 0-2 go straight to mapped host memory (no copy node) and are cleared for the next sequence
+  if (c == 0) { hflags[0] = err[0]; err[0] = 0; }  // error bits of the residual sequence (err[0]) go straight to mapped host memory (no copy node) and are cleared
   if (c >= NC) return;
   Acc<false> a; a.base = base; a.NXS = NXS; a.NC = NC;
   const int ix = c % NXS, iy = c / NXS;
@@ -183,8 +184,8 @@ struct UInfo {
 };
 struct JArgs {
   const UInfo* ui;
-  const int *cand_cell, *cand_east, *item_u;
-  int NU, nitems, role0;
+  const int *cand_cell, *cand_east, *item_u, *guard_items;  // guard_items: candidate items whose cell is a guard cell
+  int NU, nitems, nguard, role0;
   double *priv, *rows, *rres;
   int* rmask;
   double* base;
@@ -277,9 +278,15 @@ __global__ void __launch_bounds__(128) k_jb_p1b(JArgs A) {
   else if (role == 3) p1_exi<true>(a, q.w, ix, iy);
   else p1_ey<true>(a, q.w, ix, iy);
 }
-// phase 2 on the candidate rows; role = equation group, guard rows go to role 0.  rows[k][item], rmask[item]
+// phase 2 on the candidate rows; roles 0-3 = equation groups on interior rows, role 4 = guard rows.  rows[k][item], rmask[item]
 __global__ void __launch_bounds__(128) k_jb_p2(JArgs A) {
-  const int it = blockIdx.x * 128 + threadIdx.x;
+  const int ry = blockIdx.y + A.role0;
+  const int role = ry == 0 ? 4 : ry - 1;  // the guard role (long, divergent rows) is dispatched first, the equation groups follow
+  int it = blockIdx.x * 128 + threadIdx.x;
+  if (role == 4) {  // the guard role walks the (short) list of guard items only
+    if (it >= A.nguard) return;
+    it = A.guard_items[it];
+  }
   if (it >= A.nitems) return;
   const int u = A.item_u[it];
   const UInfo& q = A.ui[u];
@@ -288,7 +295,6 @@ __global__ void __launch_bounds__(128) k_jb_p2(JArgs A) {
   const int ix = cell % A.NXS, iy = cell / A.NXS;
   Acc<true> a = jb_acc(A, q, u);
   a.rself = l;
-  const int role = blockIdx.y + A.role0;
   double r[UE_NV] = {0., 0., 0., 0., 0.};
   double* o = A.rows + it;
   const size_t NI = A.nitems;
@@ -298,9 +304,9 @@ __global__ void __launch_bounds__(128) k_jb_p2(JArgs A) {
       if (role == 0) { p2_n<true>(a, ix, iy, r, D.iseqalg); o[0] = r[0]; o[4 * NI] = r[4]; atomicOr(mk, 0x111); }
       else if (role == 1) { p2_m<true>(a, q.w, ix, iy, r, D.iseqalg); o[1 * NI] = r[1]; atomicOr(mk, 0x2); }
       else if (role == 2) { p2_e<true>(a, ix, iy, r, D.iseqalg); o[2 * NI] = r[2]; atomicOr(mk, 0x4); }
-      else { p2_i<true>(a, ix, iy, r, D.iseqalg); o[3 * NI] = r[3]; atomicOr(mk, 0x8); }
+      else if (role == 3) { p2_i<true>(a, ix, iy, r, D.iseqalg); o[3 * NI] = r[3]; atomicOr(mk, 0x8); }
     }
-  } else if (role == 0) {
+  } else if (role == 4) {
     const int m = phase2_guard<true>(a, q.w, ix, iy, r);
     for (int k = 0; k < UE_NV; ++k) o[k * NI] = r[k];
     atomicOr(mk, m);
@@ -400,7 +406,7 @@ __global__ void k_scan(const int* __restrict__ rowcnt, int64_t* __restrict__ ia,
   int64_t run = 1 + s[t] - sum;
   if (t == 0) ia[0] = 1;
   for (int64_t i = b0; i < b1; ++i) { run += rowcnt[i]; ia[i + 1] = run; }
-  if (t == 1023) { hflags[1] = 1 + s[1023]; hflags[0] = *err; *err = 0; }  // nnz + 1 and the error bits, to mapped host memory
+  if (t == 1023) { hflags[1] = 1 + s[1023]; hflags[2] = err[0] | err[1]; err[0] = err[1] = 0; }  // nnz + 1 and the error bits (err[1]: Jacobian sequence) to mapped host memory
 }
 __global__ void k_fill(int64_t neq, int64_t ivmin, int64_t ivmax, const int64_t* __restrict__ coloff, const int* __restrict__ colcnt,
                        const int* __restrict__ colrow, const double* __restrict__ colval, const int64_t* __restrict__ ia, int* __restrict__ rowfill,
@@ -545,13 +551,13 @@ void free_all() {
   g_base_valid = g_base_dev_valid = false;
   for (void* p : g_static_allocs) cudaFree(p);
   g_static_allocs.clear();
-  void* ptrs[] = {d_base, d_yl, d_yldot00, d_tmp, d_yldot, d_dtuse, d_ylodt, d_suscal, d_sfscal, d_err, d_cand_cell, d_cand_east, d_item_u, d_coloff,
+  void* ptrs[] = {d_base, d_yl, d_yldot00, d_tmp, d_yldot, d_dtuse, d_ylodt, d_suscal, d_sfscal, d_err, d_cand_cell, d_cand_east, d_item_u, d_guard_items, d_coloff,
                   d_colcnt, d_colrow, d_colval, d_ia, d_ja, d_jac};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (void* p : {(void*)d_uinfo, (void*)d_priv, (void*)d_jrows, (void*)d_rres, (void*)d_rmask}) if (p) cudaFree(p);
   d_uinfo = nullptr; d_priv = d_jrows = d_rres = nullptr; d_rmask = nullptr;
   d_base = d_yl = d_yldot00 = d_tmp = d_yldot = d_dtuse = d_ylodt = d_suscal = d_sfscal = nullptr;
-  d_err = nullptr; d_cand_cell = d_cand_east = d_item_u = nullptr; d_coloff = nullptr; d_colcnt = d_colrow = nullptr; d_colval = nullptr;
+  d_err = nullptr; d_cand_cell = d_cand_east = d_item_u = d_guard_items = nullptr; d_coloff = nullptr; d_colcnt = d_colrow = nullptr; d_colval = nullptr;
   d_rowcnt = d_rowfill = nullptr; d_ia = d_ja = nullptr; d_jac = nullptr;
   g_ready = false;
 }
@@ -625,7 +631,7 @@ int upload_lists() {
   const UeParams& P = S.p;
   const size_t NU = h_list.size();
   std::vector<UInfo> ui(NU);
-  std::vector<int> item_u;
+  std::vector<int> item_u, guard_items;
   for (size_t u = 0; u < NU; ++u) {
     UInfo& q = ui[u];
     q.iv = h_list[u];
@@ -636,10 +642,15 @@ int upload_lists() {
     q.coff = h_cellcand_off[c]; q.n = h_cellcand_off[c + 1] - h_cellcand_off[c];
     q.off = (int)item_u.size();
     item_u.insert(item_u.end(), q.n, (int)u);
+    for (int l = 0; l < q.n; ++l) {
+      const int cell = h_cand_cell[q.coff + l], ix = cell % NXS, iy = cell / NXS;
+      if (!(ix >= 1 && ix <= nx && iy >= 1 && iy <= ny)) guard_items.push_back(q.off + l);
+    }
   }
+  g_nguard = (int)guard_items.size();
   g_nitems = (int)item_u.size();
-  for (void* p : {(void*)d_uinfo, (void*)d_priv, (void*)d_jrows, (void*)d_rres, (void*)d_rmask, (void*)d_cand_cell, (void*)d_cand_east, (void*)d_item_u}) if (p) cudaFree(p);
-  d_uinfo = nullptr; d_priv = d_jrows = d_rres = nullptr; d_rmask = nullptr; d_cand_cell = d_cand_east = d_item_u = nullptr;
+  for (void* p : {(void*)d_uinfo, (void*)d_priv, (void*)d_jrows, (void*)d_rres, (void*)d_rmask, (void*)d_cand_cell, (void*)d_cand_east, (void*)d_item_u, (void*)d_guard_items}) if (p) cudaFree(p);
+  d_uinfo = nullptr; d_priv = d_jrows = d_rres = nullptr; d_rmask = nullptr; d_cand_cell = d_cand_east = d_item_u = d_guard_items = nullptr;
   CK(cudaMalloc(&d_uinfo, std::max<size_t>(1, NU) * sizeof(UInfo)));
   if (NU) CK(cudaMemcpy(d_uinfo, ui.data(), NU * sizeof(UInfo), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&d_cand_cell, std::max<size_t>(1, h_cand_cell.size()) * sizeof(int)));
@@ -648,6 +659,8 @@ int upload_lists() {
   CK(cudaMemcpy(d_cand_east, h_cand_east.data(), h_cand_east.size() * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&d_item_u, std::max<size_t>(1, item_u.size()) * sizeof(int)));
   if (!item_u.empty()) CK(cudaMemcpy(d_item_u, item_u.data(), item_u.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&d_guard_items, std::max<size_t>(1, guard_items.size()) * sizeof(int)));
+  if (!guard_items.empty()) CK(cudaMemcpy(d_guard_items, guard_items.data(), guard_items.size() * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&d_priv, std::max<size_t>(1, NU) * 4 * PL_COUNT * sizeof(double)));
   CK(cudaMalloc(&d_jrows, std::max<size_t>(1, (size_t)g_nitems) * UE_NV * sizeof(double)));
   CK(cudaMalloc(&d_rres, std::max<size_t>(1, (size_t)g_nitems) * sizeof(double)));
@@ -667,7 +680,7 @@ int enqueue_residual(const double* dyl, double* dyldot, bool need_rows) {
   const int B = 128, G = (NC + B - 1) / B, G32 = (NC + 31) / 32;
   CK(launch(k_phase0, dim3(G), dim3(B), d_base, dyl, NXS, NC, d_err));
   CK(launch(k_phase1, dim3(G32), dim3(160), d_base, NXS, NC));
-  CK(launch(k_phase2, dim3(G32), dim3(128), d_base, d_tmp, NXS, NC));
+  CK(launch(k_phase2, dim3(G32), dim3(160), d_base, d_tmp, NXS, NC));
   if (need_rows) CK(launch(k_phase3, dim3(G), dim3(B), d_base, d_tmp, dyldot, dyl, d_dtuse, d_ylodt, neq, NXS, NC, d_err, d_hflags));
   return 0;
 }
@@ -677,24 +690,24 @@ int enqueue_jac(const double* dyl, const double* dy00, int64_t ml, int64_t mu, i
   if (NU == 0) CK(cudaMemsetAsync(d_colcnt, 0, 3 * neq * sizeof(int), g_stream));  // otherwise k_jb_stage0 clears the counters
   if (NU > 0) {
     JArgs A;
-    A.ui = (const UInfo*)d_uinfo; A.cand_cell = d_cand_cell; A.cand_east = d_cand_east; A.item_u = d_item_u;
+    A.ui = (const UInfo*)d_uinfo; A.cand_cell = d_cand_cell; A.cand_east = d_cand_east; A.item_u = d_item_u; A.guard_items = d_guard_items; A.nguard = g_nguard;
     A.NU = NU; A.nitems = g_nitems;
     A.priv = d_priv; A.rows = d_jrows; A.rres = d_rres; A.rmask = d_rmask; A.base = d_base;
     A.yl = dyl; A.yldot00 = dy00; A.suscal = d_suscal; A.sfscal = d_sfscal; A.dtuse = d_dtuse; A.ylodt = d_ylodt;
     A.neq = neq; A.ml = ml; A.mu = mu; A.NXS = NXS; A.NC = NC;
-    A.coloff = d_coloff; A.colcnt = d_colcnt; A.colrow = d_colrow; A.colval = d_colval; A.rowcnt = d_rowcnt; A.err = d_err;
+    A.coloff = d_coloff; A.colcnt = d_colcnt; A.colrow = d_colrow; A.colval = d_colval; A.rowcnt = d_rowcnt; A.err = d_err + 1;
     const unsigned gs = (unsigned)((NU * 4 + 127) / 128), gi = (unsigned)((g_nitems + 127) / 128);
     CK(launch(k_jb_stage0, dim3((unsigned)((NU + 31) / 32)), dim3(128), A));
     A.role0 = 0;
     if (getenv("UE_DEBUG_SPLIT_ROLES")) {  // developer aid: one launch per role so that a launch list shows each role's duration
       for (int r = 0; r < 3; ++r) { A.role0 = r; CK(launch(k_jb_p1a, dim3(dim3(gs, 1)), dim3(128), A)); }
       for (int r = 0; r < 5; ++r) { A.role0 = r; CK(launch(k_jb_p1b, dim3(dim3(gs, 1)), dim3(128), A)); }
-      for (int r = 0; r < 4; ++r) { A.role0 = r; CK(launch(k_jb_p2, dim3(dim3(gi, 1)), dim3(128), A)); }
+      for (int r = 0; r < 5; ++r) { A.role0 = r; CK(launch(k_jb_p2, dim3(dim3(gi, 1)), dim3(128), A)); }
       A.role0 = 0;
     } else {
       CK(launch(k_jb_p1a, dim3(dim3(gs, 3)), dim3(128), A));
       CK(launch(k_jb_p1b, dim3(dim3(gs, 5)), dim3(128), A));
-      CK(launch(k_jb_p2, dim3(dim3(gi, 4)), dim3(128), A));
+      CK(launch(k_jb_p2, dim3(dim3(gi, 5)), dim3(128), A));
     }
     CK(launch(k_jb_p3c, dim3((unsigned)((NU + 3) / 4)), dim3(128), A));
   }
@@ -740,7 +753,8 @@ int run_residual_dev(const double* dyl, double* dyldot, bool need_rows) {
 }
 
 int err_of_flags() {  // after a synchronisation: error bits the last sequence posted to mapped host memory
-  const long long h = h_flags[0];
+  const long long h = h_flags[0] | h_flags[2];
+  h_flags[0] = h_flags[2] = 0;
   if (h & 1) { g_err = "***  ni is negative - calculation stopped"; return -3; }
   if (h & 2) { g_err = "***  ng is negative - calculation stopped"; return -3; }
   if (h & 4) { g_err = "jac_calc: yldot00 is not pandf1(yl) as evaluated by this library (call order rhsnk -> jac_calc, oderhs.m:9466-9468)"; return -4; }
@@ -840,13 +854,13 @@ int ue_gpu_init(void) {
   CK(cudaMalloc(&d_ylodt, neq * sizeof(double)));
   CK(cudaMalloc(&d_suscal, neq * sizeof(double)));
   CK(cudaMalloc(&d_sfscal, neq * sizeof(double)));
-  CK(cudaMalloc(&d_err, sizeof(int)));
-  CK(cudaMemset(d_err, 0, sizeof(int)));  // afterwards the kernel that posts the error bits clears them
+  CK(cudaMalloc(&d_err, 2 * sizeof(int)));  // [0] residual sequence, [1] Jacobian sequence
+  CK(cudaMemset(d_err, 0, 2 * sizeof(int)));  // afterwards the kernel that posts the error bits clears them
   if (!h_flags) {
     CK(cudaHostAlloc((void**)&h_flags, 4 * sizeof(long long), cudaHostAllocMapped));
     CK(cudaHostGetDevicePointer((void**)&d_hflags, (void*)h_flags, 0));
   }
-  h_flags[0] = h_flags[1] = 0; g_nnz_guess = 0;
+  h_flags[0] = h_flags[1] = h_flags[2] = 0; g_nnz_guess = 0;
   {
     std::vector<double> big(neq, 1e20), one(neq, 1.0), zero(neq, 0.0);
     CK(cudaMemcpy(d_dtuse, big.data(), neq * 8, cudaMemcpyHostToDevice));
@@ -979,6 +993,69 @@ int ue_gpu_jac_calc_dev(int64_t n, double t, const double* dyl, const double* dy
   return 0;
 }
 
+int ue_gpu_rhs_jac_dev(int64_t n, const double* dyl, double* dyldot00, int64_t ml, int64_t mu, int64_t nnzmx, double* djac, int64_t* dja, int64_t* dia,
+                       int64_t* nnz_out, double* ms) {
+  if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
+  if (n != neq) { g_err = "rhs_jac: neq mismatch"; return -1; }
+  g_base_valid = false; g_base_dev_valid = false;
+  const int64_t lim = std::min(nnzmx, g_nnzcap);
+  CK(cudaEventRecord(g_ev0, g_stream));
+  int rc = run_residual_dev(dyl, dyldot00, true);
+  if (rc) return rc;
+  GKey k; std::memset(&k, 0, sizeof k);
+  k.kind = 2; k.p0 = dyl; k.p1 = dyldot00; k.p2 = djac; k.p3 = dja; k.p4 = dia; k.a = ml; k.b = mu; k.c = lim; k.flag = 1;
+  g_launches += 8;
+  rc = replay(k, [&]() { return enqueue_jac(dyl, dyldot00, ml, mu, lim, djac, dja, dia, true); });
+  if (rc) return rc;
+  CK(cudaEventRecord(g_ev1, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  if ((rc = err_of_flags())) return rc;
+  g_base_dev_valid = true;
+  float f = 0.f; cudaEventElapsedTime(&f, g_ev0, g_ev1); *ms = f;
+  const int64_t nnz = (int64_t)h_flags[1] - 1;
+  *nnz_out = nnz;
+  if (nnz > nnzmx) { g_err = "*** jac_calc -- More storage needed for Jacobian. Storage exceeded. Increase lenpfac."; return -2; }
+  return 0;
+}
+
+// Host-pointer form of the pair: upload yl once, residual + Jacobian as one stream sequence, one synchronisation.
+int ue_gpu_rhs_jac(int64_t n, const double* yl, double* yldot00, int64_t ml, int64_t mu, int64_t nnzmx, double* jac, int64_t* ja, int64_t* ia,
+                   int64_t* nnz_out) {
+  if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
+  if (n != neq) { g_err = "rhs_jac: neq mismatch"; return -1; }
+  g_base_valid = false; g_base_dev_valid = false;
+  const int64_t lim = std::min(nnzmx, g_nnzcap);
+  CK(cudaMemcpyAsync(d_yl, yl, (neq + 2) * 8, cudaMemcpyHostToDevice, g_stream));
+  int rc = run_residual_dev(d_yl, d_yldot, true);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(yldot00, d_yldot, neq * 8, cudaMemcpyDeviceToHost, g_stream));
+  GKey k; std::memset(&k, 0, sizeof k);
+  k.kind = 2; k.p0 = d_yl; k.p1 = d_yldot; k.p2 = d_jac; k.p3 = d_ja; k.p4 = d_ia; k.a = ml; k.b = mu; k.c = lim; k.flag = 1;
+  g_launches += 8;
+  rc = replay(k, [&]() { return enqueue_jac(d_yl, d_yldot, ml, mu, lim, d_jac, d_ja, d_ia, true); });
+  if (rc) return rc;
+  const int64_t guess = std::min(g_nnz_guess, std::min(nnzmx, lim));
+  CK(cudaMemcpyAsync(ia, d_ia, (neq + 1) * 8, cudaMemcpyDeviceToHost, g_stream));
+  if (guess > 0) {
+    CK(cudaMemcpyAsync(jac, d_jac, guess * 8, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaMemcpyAsync(ja, d_ja, guess * 8, cudaMemcpyDeviceToHost, g_stream));
+  }
+  CK(cudaStreamSynchronize(g_stream));
+  if ((rc = err_of_flags())) return rc;
+  g_base_yl.assign(yl, yl + neq + 2); g_last_yldot.assign(yldot00, yldot00 + neq);
+  g_base_valid = true; g_base_dev_valid = true;
+  const int64_t nnz = (int64_t)h_flags[1] - 1;
+  *nnz_out = nnz;
+  if (nnz > nnzmx) { g_err = "*** jac_calc -- More storage needed for Jacobian. Storage exceeded. Increase lenpfac."; return -2; }
+  g_nnz_guess = nnz;
+  if (nnz > guess) {
+    CK(cudaMemcpyAsync(jac + guess, d_jac + guess, (nnz - guess) * 8, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaMemcpyAsync(ja + guess, d_ja + guess, (nnz - guess) * 8, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+  }
+  return 0;
+}
+
 int ue_gpu_jac_calc(int64_t n, double t, const double* yl, const double* yldot00, int64_t ml, int64_t mu, int64_t nnzmx, double* jac, int64_t* ja,
                     int64_t* ia, int64_t* nnz_out) {
   (void)t;
@@ -1007,7 +1084,7 @@ int ue_gpu_jac_calc(int64_t n, double t, const double* yl, const double* yldot00
       CK(launch(k_phase3, dim3(G), dim3(B), d_base, d_tmp, d_yldot, d_yl, d_dtuse, d_ylodt, neq, NXS, NC, d_err, d_hflags));
       g_launches += 1;
     }
-    CK(launch(k_samebits, dim3((unsigned)((neq + 255) / 256)), dim3(256), d_yldot, d_yldot00, neq, d_err));
+    CK(launch(k_samebits, dim3((unsigned)((neq + 255) / 256)), dim3(256), d_yldot, d_yldot00, neq, d_err + 1));
     g_launches += 1;
     g_last_yldot.clear();
     base_current = true;
