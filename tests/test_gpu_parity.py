@@ -149,6 +149,32 @@ def test_switch_variants(built, variant):
     _check_jac(jg, jo, noise)
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_switch_combinations(built, seed):
+    """Random combinations of 3-5 of the single-switch variants above (later ones win on a shared key), on a random state
+    and with the time-step term and nufak on: the switches must also be right TOGETHER, bit for bit."""
+    rng = np.random.default_rng(1000 + seed)
+    names = list(rng.choice(sorted(VARIANTS), size=int(rng.integers(3, 6)), replace=False))
+    ov = {}
+    for nme in names:
+        ov.update(VARIANTS[nme])
+    c, yl = make_case("d3dHsm", perturb=float(rng.choice([1e-3, 5e-3, 2e-2])), seed=int(rng.integers(1 << 30)), overrides=ov)
+    gpu = bind(load_gpu(), c)
+    ora = bind(oracle(), c)
+    n = c.bbb.neq
+    for lib in (gpu, ora):
+        lib.set_real("nufak", 1.0e3)
+    fg, fo = gpu.pandf1(yl), ora.pandf1(yl)
+    assert np.isfinite(fo).all(), names
+    assert np.array_equal(fg, fo), "%s: %d residual entries differ" % (names, (fg != fo).sum())
+    dt = 10.0 ** rng.uniform(-6, -2, n)
+    jg, jo, noise = _jac_pair(c, yl, gpu, ora, dt=dt)
+    assert np.array_equal(jg[2], jo[2]) and np.array_equal(jg[1], jo[1]), names
+    assert np.array_equal(jg[0], jo[0]), names
+    for lib in (gpu, ora):
+        lib.set_real("nufak", 0.0)
+
+
 def test_newton_on_gpu_recovers_reference_steady_state(built):
     """Newton driven entirely by the CUDA residual and Jacobian returns to the reference's converged state."""
     c, yref = make_case("d3dHsm")
