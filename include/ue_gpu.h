@@ -77,6 +77,14 @@ int ue_gpu_rhs_jac(int64_t neq, const double* yl, double* yldot00, int64_t ml, i
 int ue_gpu_jac_scale(int64_t neq, const double* su, const double* sf, int64_t isrnorm, int64_t normtype,
                      int64_t nnz, double* jac, double* fnormnw);
 
+/* ---- optional: page-lock caller arrays -------------------------------------------------------------------------------
+ * If yl / yldot (NKSOL's work arrays) and jac / ja / ia (group Jacobian, bbb.v:2861-2873) are page-locked - by these
+ * calls or by the caller's own cudaHostAlloc / cudaHostRegister - the kernels read yl and write yldot, jac, ja, ia in
+ * place over the bus and the entry points above issue no copies.  Pageable arrays work unchanged (staged copies).
+ * Unpin before the array is freed. */
+int ue_gpu_pin_host_array(void* p, int64_t bytes);
+int ue_gpu_unpin_host_array(void* p);
+
 /* ---- device-resident variants (inputs/outputs already in HBM) -------------
  * Same semantics; pointers are device pointers on the current device.  Used by
  * bench.py for the kernel-only figure and by a host that keeps yl on the GPU. */

@@ -204,6 +204,54 @@ def test_sfsetnk_on_device(built):
     assert ymax_g == max(np.abs(f0 * sf_o).max(), 1e-300)
 
 
+def test_page_locked_caller_arrays(built):
+    """With page-locked caller arrays the kernels read yl and write yldot / jac / ja / ia directly (no copy nodes);
+    the results are those of the copy path, for fresh pointers (un-captured) and repeated ones (graph replay)."""
+    import torch
+    c, yl, gpu, ora = _pair("d3dHsm", 1e-3)
+    b = c.bbb; n = b.neq
+    y, su = psetnk_inputs(c, yl)
+    for lib in (gpu, ora):
+        lib.step_params(np.full(n, 1e20), y[:n], su, np.ones(n))
+    pin = lambda k, dt=torch.float64: torch.zeros(k, dtype=dt).pin_memory()
+    hy, hf, hjac, hja, hia = pin(n + 2), pin(n + 2), pin(b.nnzmx), pin(b.nnzmx, torch.int64), pin(n + 1, torch.int64)
+    for it in range(4):
+        yk = y.copy(); yk[:n] *= 1 + 1e-6 * it
+        hy.numpy()[:] = yk
+        f = gpu.pandf1(hy.numpy(), out=hf.numpy())
+        fo = ora.pandf1(yk)
+        assert np.array_equal(f[:n], fo), "call %d" % it
+        jg = gpu.jac_calc(hy.numpy(), hf.numpy(), b.lbw, b.ubw, b.nnzmx, out=(hjac.numpy(), hja.numpy(), hia.numpy()))
+        jo = ora.jac_calc(yk, fo, b.lbw, b.ubw, b.nnzmx)
+        assert all(np.array_equal(p, q) for p, q in zip(jg, jo)), "call %d" % it
+    hy.numpy()[5 * 40] = -1.0
+    with pytest.raises(Exception, match="ni is negative"):
+        gpu.pandf1(hy.numpy(), out=hf.numpy())
+
+
+def test_pin_host_array(built):
+    """ue_gpu_pin_host_array on ordinary (pageable) arrays switches the same call to the direct path; same results."""
+    import ctypes as C
+    c, yl, gpu, ora = _pair("d3dHsm", 1e-3)
+    n = c.bbb.neq
+    ybuf, fbuf = yl.copy(), np.zeros(n)
+    f_copy = gpu.pandf1(ybuf, out=fbuf).copy()
+    lib = gpu.lib
+    lib.ue_gpu_pin_host_array.argtypes = [C.c_void_p, C.c_int64]; lib.ue_gpu_unpin_host_array.argtypes = [C.c_void_p]
+    assert lib.ue_gpu_pin_host_array(ybuf.ctypes.data, ybuf.nbytes) == 0
+    assert lib.ue_gpu_pin_host_array(fbuf.ctypes.data, fbuf.nbytes) == 0
+    assert lib.ue_gpu_pin_host_array(fbuf.ctypes.data, fbuf.nbytes) == 0  # idempotent
+    for it in range(3):
+        ybuf[:n] = yl[:n] * (1 + 1e-6 * it)
+        fbuf[:] = 0.0
+        gpu.pandf1(ybuf, out=fbuf)
+        assert np.array_equal(fbuf, ora.pandf1(ybuf))
+    assert lib.ue_gpu_unpin_host_array(ybuf.ctypes.data) == 0
+    assert lib.ue_gpu_unpin_host_array(fbuf.ctypes.data) == 0
+    ybuf[:n] = yl[:n]
+    assert np.array_equal(gpu.pandf1(ybuf, out=fbuf), f_copy)
+
+
 def test_fused_rhs_jac_equals_the_two_calls(built):
     c, yl, gpu, ora = _pair("d3dHsm", 1e-3)
     b = c.bbb

@@ -104,19 +104,23 @@ class UeLib:
         self._call("pandf1", self.neq, float(time), _d(yl), _d(yldot))
         return yldot
 
-    def jac_calc(self, yl, yldot00, ml, mu, nnzmx, t=0.0):
-        """jac_calc_interface: returns (jac, ja, ia) in the reference's 1-based CSR."""
+    def jac_calc(self, yl, yldot00, ml, mu, nnzmx, t=0.0, out=None):
+        """jac_calc_interface: returns (jac, ja, ia) in the reference's 1-based CSR.  `out` = (jac, ja, ia) caller buffers
+        (e.g. page-locked ones); yldot00 is then passed as given if it is a float64 array of at least neq entries."""
         yl = np.ascontiguousarray(yl, dtype=np.float64)
-        y0 = np.zeros(self.neq + 2)
-        y0[: self.neq] = np.asarray(yldot00, dtype=np.float64)[: self.neq]
-        jac = np.zeros(nnzmx)
-        ja = np.zeros(nnzmx, dtype=np.int64)
-        ia = np.zeros(self.neq + 1, dtype=np.int64)
+        if out is None:
+            y0 = np.zeros(self.neq + 2)
+            y0[: self.neq] = np.asarray(yldot00, dtype=np.float64)[: self.neq]
+            jac = np.zeros(nnzmx); ja = np.zeros(nnzmx, dtype=np.int64); ia = np.zeros(self.neq + 1, dtype=np.int64)
+        else:
+            jac, ja, ia = out
+            y0 = yldot00
+            assert y0.dtype == np.float64 and y0.size >= self.neq and jac.size >= nnzmx and ja.size >= nnzmx and ia.size >= self.neq + 1
         nnz = C.c_int64(0)
         self._call("jac_calc", self.neq, float(t), _d(yl), _d(y0), int(ml), int(mu), int(nnzmx), _d(jac), _i(ja), _i(ia),
                    C.byref(nnz))
         n = nnz.value
-        return jac[:n].copy(), ja[:n].copy(), ia
+        return jac[:n].copy(), ja[:n].copy(), ia.copy() if out is not None else ia
 
     def rhs_jac(self, yl, ml, mu, nnzmx):
         """rhsnk(yl) + jac_calc(yl, yldot00) in one call (what psetnk/sfsetnk issue back to back); product library only."""

@@ -102,11 +102,19 @@ int dev_copy(const T* h, size_t n, const T** out) {
 // ------------------------------------------------------------------------------------------------
 // full-residual kernels
 // ------------------------------------------------------------------------------------------------
-__global__ void k_phase0(double* base, const double* __restrict__ yl, int NXS, int NC, int* err) {
+// yl may be the caller's pinned host array (zero-copy read over the bus): then yl_keep receives the device copy that
+// the later phases and the Jacobian read (yl_keep == nullptr: yl already is that copy).
+__global__ void k_phase0(double* base, const double* __restrict__ yl, double* __restrict__ yl_keep, int64_t neq, int NXS, int NC, int* err) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= NC) return;
   Acc<false> a; a.base = base; a.NXS = NXS; a.NC = NC;
-  phase0_cell<false>(a, yl + (size_t)c * UE_NV, c % NXS, c / NXS, err);
+  double ycell[UE_NV];
+  for (int k = 0; k < UE_NV; ++k) ycell[k] = yl[(size_t)c * UE_NV + k];
+  if (yl_keep) {
+    for (int k = 0; k < UE_NV; ++k) yl_keep[(size_t)c * UE_NV + k] = ycell[k];
+    if (c == 0) { yl_keep[neq] = yl[neq]; yl_keep[neq + 1] = yl[neq + 1]; }
+  }
+  phase0_cell<false>(a, ycell, c % NXS, c / NXS, err);
 }
 // phase 1: 32 cells per block, one ROLE per warp (lane = cell); 1b reads only same-cell outputs of 1a
 __global__ void __launch_bounds__(160) k_phase1(double* base, int NXS, int NC) {
@@ -151,7 +159,7 @@ __global__ void __launch_bounds__(160) k_phase2(double* base, double* __restrict
 }
 __global__ void k_phase3(double* base, const double* __restrict__ tmp, double* __restrict__ yldot, const double* __restrict__ yl,
                          const double* __restrict__ dtuse, const double* __restrict__ ylodt, int64_t neq, int NXS, int NC, int* err,
-                         long long* hflags) {
+                         long long* hflags, double* __restrict__ yldot_host /* caller's pinned host array or nullptr */) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0) { hflags[0] = err[0]; err[0] = 0; }  // error bits of the residual sequence (err[0]) go straight to mapped host memory (no copy node) and are cleared
   if (c >= NC) return;
@@ -161,6 +169,7 @@ __global__ void k_phase3(double* base, const double* __restrict__ tmp, double* _
   for (int k = 0; k < UE_NV; ++k) r[k] = tmp[(size_t)c * UE_NV + k];
   if (ix >= 1 && ix <= D.nx && iy >= 1 && iy <= D.ny) phase3_interior<false>(a, ix, iy, r, yl + (size_t)c * UE_NV, yl[neq], D.iseqalg, dtuse, ylodt);
   for (int k = 0; k < UE_NV; ++k) yldot[(size_t)c * UE_NV + k] = r[k];
+  if (yldot_host) for (int k = 0; k < UE_NV; ++k) yldot_host[(size_t)c * UE_NV + k] = r[k];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -387,7 +396,7 @@ __global__ void __launch_bounds__(128) k_jb_p3c(JArgs A) {
 }
 
 // ---- CSC fragments -> CSR ---------------------------------------------------------------------------------------
-__global__ void k_scan(const int* __restrict__ rowcnt, int64_t* __restrict__ ia, int64_t n, int* err, long long* hflags) {
+__global__ void k_scan(const int* __restrict__ rowcnt, int64_t* __restrict__ ia, int64_t n, int* err, long long* hflags, int64_t* __restrict__ ia_host) {
   // single block of 1024 threads; ia is 1-based: ia[0] = 1, ia[i+1] = ia[i] + rowcnt[i].
   // Each thread owns a contiguous chunk: serial sum, block scan of the 1024 partials, serial write-out.
   __shared__ int64_t s[1024];
@@ -404,8 +413,8 @@ __global__ void k_scan(const int* __restrict__ rowcnt, int64_t* __restrict__ ia,
     __syncthreads();
   }
   int64_t run = 1 + s[t] - sum;
-  if (t == 0) ia[0] = 1;
-  for (int64_t i = b0; i < b1; ++i) { run += rowcnt[i]; ia[i + 1] = run; }
+  if (t == 0) { ia[0] = 1; if (ia_host) ia_host[0] = 1; }
+  for (int64_t i = b0; i < b1; ++i) { run += rowcnt[i]; ia[i + 1] = run; if (ia_host) ia_host[i + 1] = run; }
   if (t == 1023) { hflags[1] = 1 + s[1023]; hflags[2] = err[0] | err[1]; err[0] = err[1] = 0; }  // nnz + 1 and the error bits (err[1]: Jacobian sequence) to mapped host memory
 }
 __global__ void k_fill(int64_t neq, int64_t ivmin, int64_t ivmax, const int64_t* __restrict__ coloff, const int* __restrict__ colcnt,
@@ -421,8 +430,10 @@ __global__ void k_fill(int64_t neq, int64_t ivmin, int64_t ivmax, const int64_t*
     if (p < nnzmx) { ja[p] = iv; jac[p] = colval[o + e]; }   // overflow is reported by the host after the sequence
   }
 }
-// one warp per row: rank sort of the row's entries by column (rows hold a few tens of entries)
-__global__ void k_sortrows(int64_t neq, const int64_t* __restrict__ ia, double* __restrict__ jac, int64_t* __restrict__ ja, int64_t nnzmx) {
+// one warp per row: rank sort of the row's entries by column (rows hold a few tens of entries).  jac_host/ja_host: the
+// caller's page-locked arrays (or nullptr): the sorted row is also written there, so no copy follows the sequence.
+__global__ void k_sortrows(int64_t neq, const int64_t* __restrict__ ia, double* __restrict__ jac, int64_t* __restrict__ ja, int64_t nnzmx,
+                           double* __restrict__ jac_host, int64_t* __restrict__ ja_host) {
   constexpr int CAP = 96;
   __shared__ int64_t scol[4][CAP];
   __shared__ double sval[4][CAP];
@@ -431,8 +442,10 @@ __global__ void k_sortrows(int64_t neq, const int64_t* __restrict__ ia, double* 
   if (r >= neq) return;
   const int64_t b = ia[r] - 1, e = ia[r + 1] - 1;
   const int n = (int)(e - b);
-  if (n <= 1 || e > nnzmx) return;
-  if (n <= CAP) {
+  if (n <= 0 || e > nnzmx) return;
+  if (n == 1) {
+    if (jac_host && lane == 0) { ja_host[b] = ja[b]; jac_host[b] = jac[b]; }
+  } else if (n <= CAP) {
     for (int i = lane; i < n; i += 32) { scol[wib][i] = ja[b + i]; sval[wib][i] = jac[b + i]; }
     __syncwarp();
     for (int i = lane; i < n; i += 32) {
@@ -441,12 +454,22 @@ __global__ void k_sortrows(int64_t neq, const int64_t* __restrict__ ia, double* 
       for (int j = 0; j < n; ++j) rank += (scol[wib][j] < c);
       ja[b + rank] = c; jac[b + rank] = sval[wib][i];
     }
-  } else if (lane == 0) {  // dense row: serial insertion sort
-    for (int64_t i = b + 1; i < e; ++i) {
-      const int64_t cj = ja[i]; const double cv = jac[i];
-      int64_t j = i - 1;
-      while (j >= b && ja[j] > cj) { ja[j + 1] = ja[j]; jac[j + 1] = jac[j]; --j; }
-      ja[j + 1] = cj; jac[j + 1] = cv;
+    if (jac_host) {  // second pass in storage order: contiguous writes over the bus
+      __syncwarp();
+      for (int i = lane; i < n; i += 32) { ja_host[b + i] = ja[b + i]; jac_host[b + i] = jac[b + i]; }
+    }
+  } else {
+    if (lane == 0) {  // dense row: serial insertion sort
+      for (int64_t i = b + 1; i < e; ++i) {
+        const int64_t cj = ja[i]; const double cv = jac[i];
+        int64_t j = i - 1;
+        while (j >= b && ja[j] > cj) { ja[j + 1] = ja[j]; jac[j + 1] = jac[j]; --j; }
+        ja[j + 1] = cj; jac[j + 1] = cv;
+      }
+    }
+    if (jac_host) {
+      __syncwarp();
+      for (int64_t i = b + lane; i < e; i += 32) { ja_host[i] = ja[i]; jac_host[i] = jac[i]; }
     }
   }
 }
@@ -676,15 +699,19 @@ struct GKey {
 std::map<GKey, cudaGraphExec_t> g_graphs;
 void drop_graphs() { for (auto& kv : g_graphs) cudaGraphExecDestroy(kv.second); g_graphs.clear(); }
 
-int enqueue_residual(const double* dyl, double* dyldot, bool need_rows) {
+// yl_src: where phase 0 reads yl (dyl itself, or the caller's device-visible host array, then copied to dyl);
+// yldot_host: optional device-visible host destination written by phase 3 next to dyldot
+int enqueue_residual(const double* dyl, double* dyldot, bool need_rows, const double* yl_src = nullptr, double* yldot_host = nullptr) {
   const int B = 128, G = (NC + B - 1) / B, G32 = (NC + 31) / 32;
-  CK(launch(k_phase0, dim3(G), dim3(B), d_base, dyl, NXS, NC, d_err));
+  if (yl_src && yl_src != dyl) CK(launch(k_phase0, dim3(G), dim3(B), d_base, yl_src, const_cast<double*>(dyl), neq, NXS, NC, d_err));
+  else CK(launch(k_phase0, dim3(G), dim3(B), d_base, dyl, (double*)nullptr, neq, NXS, NC, d_err));
   CK(launch(k_phase1, dim3(G32), dim3(160), d_base, NXS, NC));
   CK(launch(k_phase2, dim3(G32), dim3(160), d_base, d_tmp, NXS, NC));
-  if (need_rows) CK(launch(k_phase3, dim3(G), dim3(B), d_base, d_tmp, dyldot, dyl, d_dtuse, d_ylodt, neq, NXS, NC, d_err, d_hflags));
+  if (need_rows) CK(launch(k_phase3, dim3(G), dim3(B), d_base, d_tmp, dyldot, dyl, d_dtuse, d_ylodt, neq, NXS, NC, d_err, d_hflags, yldot_host));
   return 0;
 }
-int enqueue_jac(const double* dyl, const double* dy00, int64_t ml, int64_t mu, int64_t nnzmx, double* djac, int64_t* dja, int64_t* dia, bool base_current) {
+int enqueue_jac(const double* dyl, const double* dy00, int64_t ml, int64_t mu, int64_t nnzmx, double* djac, int64_t* dja, int64_t* dia, bool base_current,
+                double* jac_host = nullptr, int64_t* ja_host = nullptr, int64_t* ia_host = nullptr) {
   if (!base_current) { int rc = enqueue_residual(dyl, nullptr, false); if (rc) return rc; }
   const int NU = (int)h_list.size();
   if (NU == 0) CK(cudaMemsetAsync(d_colcnt, 0, 3 * neq * sizeof(int), g_stream));  // otherwise k_jb_stage0 clears the counters
@@ -711,11 +738,11 @@ int enqueue_jac(const double* dyl, const double* dy00, int64_t ml, int64_t mu, i
     }
     CK(launch(k_jb_p3c, dim3((unsigned)((NU + 3) / 4)), dim3(128), A));
   }
-  CK(launch(k_scan, dim3(1), dim3(1024), d_rowcnt, dia, neq, d_err, d_hflags));
+  CK(launch(k_scan, dim3(1), dim3(1024), d_rowcnt, dia, neq, d_err, d_hflags, ia_host));
   const int64_t ncol = g_ivmax - g_ivmin + 1;
   if (ncol > 0) {
     CK(launch(k_fill, dim3((unsigned)ncol), dim3(64), neq, g_ivmin, g_ivmax, d_coloff, d_colcnt, d_colrow, d_colval, dia, d_rowfill, djac, dja, nnzmx));
-    CK(launch(k_sortrows, dim3((unsigned)((neq + 3) / 4)), dim3(128), neq, dia, djac, dja, nnzmx));
+    CK(launch(k_sortrows, dim3((unsigned)((neq + 3) / 4)), dim3(128), neq, dia, djac, dja, nnzmx, jac_host, ja_host));
   }
   return 0;
 }
@@ -759,6 +786,15 @@ int err_of_flags() {  // after a synchronisation: error bits the last sequence p
   if (h & 2) { g_err = "***  ng is negative - calculation stopped"; return -3; }
   if (h & 4) { g_err = "jac_calc: yldot00 is not pandf1(yl) as evaluated by this library (call order rhsnk -> jac_calc, oderhs.m:9466-9468)"; return -4; }
   return 0;
+}
+// Device-visible alias of a caller's host array if it is page-locked (cudaHostAlloc / cudaHostRegister): kernels can then
+// read or write it directly and the copy nodes disappear from the sequence.  Pageable memory returns nullptr.
+template <typename T>
+T* device_alias(const T* host) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, (const void*)host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+  return (T*)at.devicePointer;
 }
 int check_errflag() {
   CK(cudaStreamSynchronize(g_stream));
@@ -933,7 +969,7 @@ int ue_gpu_pandf1(int64_t n, double time, const double* yl, double* yldot) {
     // scaling / time-step phase is redone.
     CK(cudaMemcpyAsync(d_yl + neq, yl + neq, 16, cudaMemcpyHostToDevice, g_stream));
     const int B = 128, G = (NC + B - 1) / B;
-    CK(launch(k_phase3, dim3(G), dim3(B), d_base, d_tmp, d_yldot, d_yl, d_dtuse, d_ylodt, neq, NXS, NC, d_err, d_hflags));
+    CK(launch(k_phase3, dim3(G), dim3(B), d_base, d_tmp, d_yldot, d_yl, d_dtuse, d_ylodt, neq, NXS, NC, d_err, d_hflags, (double*)nullptr));
     g_launches += 1;
     CK(cudaMemcpyAsync(yldot, d_yldot, neq * 8, cudaMemcpyDeviceToHost, g_stream));
     CK(cudaStreamSynchronize(g_stream));
@@ -951,22 +987,23 @@ int ue_gpu_pandf1(int64_t n, double time, const double* yl, double* yldot) {
   // the plain path so that callers with fresh buffers per call do not pay a capture each time.
   bool use_graph = g_host_graphs && (g_graphs.count(k) || !g_seen_host.insert({yl, yldot}).second);
   if (g_seen_host.size() > 256) g_seen_host.clear();
+  // page-locked caller arrays: phase 0 reads yl and phase 3 writes yldot directly (no copy nodes)
+  const double* yl_dev = device_alias(yl);
+  double* yldot_dev = device_alias(yldot);
+  auto body = [&]() {
+    if (!yl_dev) CK(cudaMemcpyAsync(d_yl, yl, (neq + 2) * 8, cudaMemcpyHostToDevice, g_stream));
+    int r = enqueue_residual(d_yl, d_yldot, true, yl_dev, yldot_dev);
+    if (r) return r;
+    if (!yldot_dev) CK(cudaMemcpyAsync(yldot, d_yldot, neq * 8, cudaMemcpyDeviceToHost, g_stream));
+    return 0;
+  };
   if (use_graph) {
-    rc = replay(k, [&]() {
-      CK(cudaMemcpyAsync(d_yl, yl, (neq + 2) * 8, cudaMemcpyHostToDevice, g_stream));
-      int r = enqueue_residual(d_yl, d_yldot, true);
-      if (r) return r;
-      CK(cudaMemcpyAsync(yldot, d_yldot, neq * 8, cudaMemcpyDeviceToHost, g_stream));
-      return 0;
-    });
+    k.flag = (yl_dev ? 1 : 0) | (yldot_dev ? 2 : 0);
+    rc = replay(k, body);
     if (rc == -10) { g_host_graphs = false; use_graph = false; cudaGetLastError(); }  // not capturable: plain path from now on
   }
-  if (!use_graph) {
-    CK(cudaMemcpyAsync(d_yl, yl, (neq + 2) * 8, cudaMemcpyHostToDevice, g_stream));
-    rc = run_residual_dev(d_yl, d_yldot, true);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(yldot, d_yldot, neq * 8, cudaMemcpyDeviceToHost, g_stream));
-  } else if (rc) return rc;
+  if (!use_graph) rc = body();
+  if (rc) return rc;
   CK(cudaStreamSynchronize(g_stream));  // the only synchronisation of the call
   if ((rc = err_of_flags())) return rc;
   g_base_yl.assign(yl, yl + neq + 2);  // the base planes (and d_yl) now describe this yl
@@ -1018,6 +1055,35 @@ int ue_gpu_rhs_jac_dev(int64_t n, const double* dyl, double* dyldot00, int64_t m
   return 0;
 }
 
+// Tail of the host-pointer Jacobian calls: fetch ia / jac / ja unless the kernels wrote them to the caller's arrays
+// directly, one synchronisation in the usual case, error bits and nnz from mapped host memory.
+static int finish_host_jac(bool direct, const double* yl, bool same_y, int64_t nnzmx, int64_t lim, double* jac, int64_t* ja, int64_t* ia, int64_t* nnz_out) {
+  // copies: ia always; jac/ja speculatively with the previous call's nnz (the pattern rarely changes between Newton
+  // steps); a larger nnz fetches the remainder afterwards
+  const int64_t guess = direct ? 0 : std::min(g_nnz_guess, std::min(nnzmx, lim));
+  if (!direct) {
+    CK(cudaMemcpyAsync(ia, d_ia, (neq + 1) * 8, cudaMemcpyDeviceToHost, g_stream));
+    if (guess > 0) {
+      CK(cudaMemcpyAsync(jac, d_jac, guess * 8, cudaMemcpyDeviceToHost, g_stream));
+      CK(cudaMemcpyAsync(ja, d_ja, guess * 8, cudaMemcpyDeviceToHost, g_stream));
+    }
+  }
+  CK(cudaStreamSynchronize(g_stream));
+  int rc = err_of_flags();
+  if (rc) return rc;
+  if (!same_y) { g_base_yl.assign(yl, yl + neq + 2); g_base_valid = true; g_base_dev_valid = true; }  // base fields describe this yl now
+  const int64_t nnz = (int64_t)h_flags[1] - 1;
+  *nnz_out = nnz;
+  if (nnz > nnzmx) { g_err = "*** jac_calc -- More storage needed for Jacobian. Storage exceeded. Increase lenpfac."; return -2; }
+  g_nnz_guess = nnz;
+  if (!direct && nnz > guess) {
+    CK(cudaMemcpyAsync(jac + guess, d_jac + guess, (nnz - guess) * 8, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaMemcpyAsync(ja + guess, d_ja + guess, (nnz - guess) * 8, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+  }
+  return 0;
+}
+
 // Host-pointer form of the pair: upload yl once, residual + Jacobian as one stream sequence, one synchronisation.
 int ue_gpu_rhs_jac(int64_t n, const double* yl, double* yldot00, int64_t ml, int64_t mu, int64_t nnzmx, double* jac, int64_t* ja, int64_t* ia,
                    int64_t* nnz_out) {
@@ -1025,34 +1091,29 @@ int ue_gpu_rhs_jac(int64_t n, const double* yl, double* yldot00, int64_t ml, int
   if (n != neq) { g_err = "rhs_jac: neq mismatch"; return -1; }
   g_base_valid = false; g_base_dev_valid = false;
   const int64_t lim = std::min(nnzmx, g_nnzcap);
-  CK(cudaMemcpyAsync(d_yl, yl, (neq + 2) * 8, cudaMemcpyHostToDevice, g_stream));
-  int rc = run_residual_dev(d_yl, d_yldot, true);
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(yldot00, d_yldot, neq * 8, cudaMemcpyDeviceToHost, g_stream));
+  const double* yl_dev = device_alias(yl);
+  double* f_dev = device_alias(yldot00);
+  double* jac_dev = device_alias(jac); int64_t* ja_dev = device_alias(ja); int64_t* ia_dev = device_alias(ia);
+  const bool direct = jac_dev && ja_dev && ia_dev;
   GKey k; std::memset(&k, 0, sizeof k);
-  k.kind = 2; k.p0 = d_yl; k.p1 = d_yldot; k.p2 = d_jac; k.p3 = d_ja; k.p4 = d_ia; k.a = ml; k.b = mu; k.c = lim; k.flag = 1;
-  g_launches += 8;
-  rc = replay(k, [&]() { return enqueue_jac(d_yl, d_yldot, ml, mu, lim, d_jac, d_ja, d_ia, true); });
+  k.kind = 5; k.p0 = yl; k.p1 = yldot00; k.p2 = jac; k.p3 = ja; k.p4 = ia; k.a = ml; k.b = mu; k.c = lim;
+  k.flag = (yl_dev ? 1 : 0) | (f_dev ? 2 : 0) | (direct ? 4 : 0);
+  g_launches += 12;
+  auto body = [&]() {
+    if (!yl_dev) CK(cudaMemcpyAsync(d_yl, yl, (neq + 2) * 8, cudaMemcpyHostToDevice, g_stream));
+    int r = enqueue_residual(d_yl, d_yldot, true, yl_dev, f_dev);
+    if (r) return r;
+    if (!f_dev) CK(cudaMemcpyAsync(yldot00, d_yldot, neq * 8, cudaMemcpyDeviceToHost, g_stream));
+    return direct ? enqueue_jac(d_yl, d_yldot, ml, mu, lim, d_jac, d_ja, d_ia, true, jac_dev, ja_dev, ia_dev)
+                  : enqueue_jac(d_yl, d_yldot, ml, mu, lim, d_jac, d_ja, d_ia, true);
+  };
+  // same policy as ue_gpu_pandf1: a pointer set seen for the first time runs un-captured
+  const bool use_graph = g_host_graphs && (g_graphs.count(k) || !g_seen_host.insert({yl, jac}).second);
+  int rc = use_graph ? replay(k, body) : body();
   if (rc) return rc;
-  const int64_t guess = std::min(g_nnz_guess, std::min(nnzmx, lim));
-  CK(cudaMemcpyAsync(ia, d_ia, (neq + 1) * 8, cudaMemcpyDeviceToHost, g_stream));
-  if (guess > 0) {
-    CK(cudaMemcpyAsync(jac, d_jac, guess * 8, cudaMemcpyDeviceToHost, g_stream));
-    CK(cudaMemcpyAsync(ja, d_ja, guess * 8, cudaMemcpyDeviceToHost, g_stream));
-  }
-  CK(cudaStreamSynchronize(g_stream));
-  if ((rc = err_of_flags())) return rc;
-  g_base_yl.assign(yl, yl + neq + 2); g_last_yldot.assign(yldot00, yldot00 + neq);
-  g_base_valid = true; g_base_dev_valid = true;
-  const int64_t nnz = (int64_t)h_flags[1] - 1;
-  *nnz_out = nnz;
-  if (nnz > nnzmx) { g_err = "*** jac_calc -- More storage needed for Jacobian. Storage exceeded. Increase lenpfac."; return -2; }
-  g_nnz_guess = nnz;
-  if (nnz > guess) {
-    CK(cudaMemcpyAsync(jac + guess, d_jac + guess, (nnz - guess) * 8, cudaMemcpyDeviceToHost, g_stream));
-    CK(cudaMemcpyAsync(ja + guess, d_ja + guess, (nnz - guess) * 8, cudaMemcpyDeviceToHost, g_stream));
-    CK(cudaStreamSynchronize(g_stream));
-  }
+  rc = finish_host_jac(direct, yl, false, nnzmx, lim, jac, ja, ia, nnz_out);
+  if (rc) return rc;
+  g_last_yldot.assign(yldot00, yldot00 + neq);
   return 0;
 }
 
@@ -1081,7 +1142,7 @@ int ue_gpu_jac_calc(int64_t n, double t, const double* yl, const double* yldot00
       if (r) return r;
     } else {
       const int B = 128, G = (NC + B - 1) / B;
-      CK(launch(k_phase3, dim3(G), dim3(B), d_base, d_tmp, d_yldot, d_yl, d_dtuse, d_ylodt, neq, NXS, NC, d_err, d_hflags));
+      CK(launch(k_phase3, dim3(G), dim3(B), d_base, d_tmp, d_yldot, d_yl, d_dtuse, d_ylodt, neq, NXS, NC, d_err, d_hflags, (double*)nullptr));
       g_launches += 1;
     }
     CK(launch(k_samebits, dim3((unsigned)((neq + 255) / 256)), dim3(256), d_yldot, d_yldot00, neq, d_err + 1));
@@ -1091,31 +1152,18 @@ int ue_gpu_jac_calc(int64_t n, double t, const double* yl, const double* yldot00
   }
   GKey k; std::memset(&k, 0, sizeof k);
   const int64_t lim = std::min(nnzmx, g_nnzcap);
-  k.kind = 2; k.p0 = d_yl; k.p1 = dy00; k.p2 = d_jac; k.p3 = d_ja; k.p4 = d_ia; k.a = ml; k.b = mu; k.c = lim; k.flag = base_current;
+  // page-locked caller arrays: k_scan / k_sortrows write ia, jac, ja there directly and no copy follows
+  double* jac_dev = device_alias(jac); int64_t* ja_dev = device_alias(ja); int64_t* ia_dev = device_alias(ia);
+  const bool direct = jac_dev && ja_dev && ia_dev;
+  k.kind = direct ? 4 : 2; k.p0 = d_yl; k.p1 = dy00; k.p2 = direct ? (void*)jac_dev : (void*)d_jac; k.p3 = direct ? (void*)ja_dev : (void*)d_ja;
+  k.p4 = direct ? (void*)ia_dev : (void*)d_ia; k.a = ml; k.b = mu; k.c = lim; k.flag = base_current;
   g_launches += (base_current ? 0 : 3) + 8;
-  int rc = replay(k, [&]() { return enqueue_jac(d_yl, dy00, ml, mu, lim, d_jac, d_ja, d_ia, base_current); });
+  int rc = replay(k, [&]() {
+    return direct ? enqueue_jac(d_yl, dy00, ml, mu, lim, d_jac, d_ja, d_ia, base_current, jac_dev, ja_dev, ia_dev)
+                  : enqueue_jac(d_yl, dy00, ml, mu, lim, d_jac, d_ja, d_ia, base_current);
+  });
   if (rc) return rc;
-  // ia always; jac/ja speculatively with the previous call's nnz (the pattern rarely changes between Newton steps), so
-  // that the usual call needs ONE synchronisation; a larger nnz fetches the remainder afterwards.
-  const int64_t guess = std::min(g_nnz_guess, std::min(nnzmx, lim));
-  CK(cudaMemcpyAsync(ia, d_ia, (neq + 1) * 8, cudaMemcpyDeviceToHost, g_stream));
-  if (guess > 0) {
-    CK(cudaMemcpyAsync(jac, d_jac, guess * 8, cudaMemcpyDeviceToHost, g_stream));
-    CK(cudaMemcpyAsync(ja, d_ja, guess * 8, cudaMemcpyDeviceToHost, g_stream));
-  }
-  CK(cudaStreamSynchronize(g_stream));
-  if ((rc = err_of_flags())) return rc;
-  if (!same_y) { g_base_yl.assign(yl, yl + neq + 2); g_base_valid = true; g_base_dev_valid = true; }  // base fields describe this yl now
-  const int64_t nnz = (int64_t)h_flags[1] - 1;
-  *nnz_out = nnz;
-  if (nnz > nnzmx) { g_err = "*** jac_calc -- More storage needed for Jacobian. Storage exceeded. Increase lenpfac."; return -2; }
-  g_nnz_guess = nnz;
-  if (nnz > guess) {
-    CK(cudaMemcpyAsync(jac + guess, d_jac + guess, (nnz - guess) * 8, cudaMemcpyDeviceToHost, g_stream));
-    CK(cudaMemcpyAsync(ja + guess, d_ja + guess, (nnz - guess) * 8, cudaMemcpyDeviceToHost, g_stream));
-    CK(cudaStreamSynchronize(g_stream));
-  }
-  return 0;
+  return finish_host_jac(direct, yl, same_y, nnzmx, lim, jac, ja, ia, nnz_out);
 }
 
 int ue_gpu_set_column_range(int64_t ivmin, int64_t ivmax) {
@@ -1179,6 +1227,21 @@ int ue_gpu_jac_scale(int64_t n, const double* su, const double* sf, int64_t isrn
   CK(cudaMemcpyAsync(jac, d_jac, nnz * 8, cudaMemcpyDeviceToHost, g_stream));
   CK(cudaMemcpyAsync(fnormnw, d_sc + 2 * neq, neq * 8, cudaMemcpyDeviceToHost, g_stream));
   CK(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+// Page-lock a caller array (the solver's work arrays, the Jacobian storage) so that the kernels can read / write it
+// directly.  Optional: without it the entry points use staged copies.
+int ue_gpu_pin_host_array(void* p, int64_t bytes) {
+  cudaError_t e = cudaHostRegister(p, (size_t)bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return 0; }
+  if (e != cudaSuccess) { g_err = std::string("cudaHostRegister: ") + cudaGetErrorString(e); cudaGetLastError(); return -10; }
+  return 0;
+}
+int ue_gpu_unpin_host_array(void* p) {
+  drop_graphs();  // captured sequences may hold the device alias of this array
+  g_seen_host.clear();
+  cudaError_t e = cudaHostUnregister(p);
+  if (e != cudaSuccess) { g_err = std::string("cudaHostUnregister: ") + cudaGetErrorString(e); cudaGetLastError(); return -10; }
   return 0;
 }
 int ue_gpu_kernel_launches(int64_t* n) { *n = g_launches; return 0; }
