@@ -77,6 +77,11 @@ int ue_gpu_rhs_jac(int64_t neq, const double* yl, double* yldot00, int64_t ml, i
 int ue_gpu_jac_scale(int64_t neq, const double* su, const double* sf, int64_t isrnorm, int64_t normtype,
                      int64_t nnz, double* jac, double* fnormnw);
 
+/* ---- parity probe: include/ue_math.h evaluated on the device -----------------------------------------------------------
+ * op 0 exp, 1 log, 2 log10, 3 pow(x,y), 4 cos, 5 sqrt; host arrays of n doubles.  The CPU checker evaluates the same
+ * header; the two must agree bit for bit (that is what makes the value-dependent Jacobian pattern reproducible). */
+int ue_gpu_math_probe(int64_t op, int64_t n, const double* x, const double* y, double* out);
+
 /* ---- optional: page-lock caller arrays -------------------------------------------------------------------------------
  * If yl / yldot (NKSOL's work arrays) and jac / ja / ia (group Jacobian, bbb.v:2861-2873) are page-locked - by these
  * calls or by the caller's own cudaHostAlloc / cudaHostRegister - the kernels read yl and write yldot, jac, ja, ia in

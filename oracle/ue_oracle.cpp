@@ -1476,4 +1476,20 @@ int ue_ora_get_plane(const char* name, double* out) {
   g_err = "no such plane"; return -1;
 }
 const char* ue_ora_plane_names(void) { return plane_names; }
+// include/ue_math.h evaluated on the host: op 0 exp, 1 log, 2 log10, 3 pow(x,y), 4 cos, 5 sqrt (tests compare with libm
+// and, bit for bit, with the same header evaluated on the device)
+int ue_ora_math_probe(int64_t op, int64_t n, const double* x, const double* y, double* out) {
+  for (int64_t i = 0; i < n; ++i) {
+    switch (op) {
+      case 0: out[i] = ue_exp(x[i]); break;
+      case 1: out[i] = ue_log(x[i]); break;
+      case 2: out[i] = ue_log10(x[i]); break;
+      case 3: out[i] = ue_pow(x[i], y[i]); break;
+      case 4: out[i] = ue_cos(x[i]); break;
+      case 5: out[i] = ue_sqrt(x[i]); break;
+      default: return -1;
+    }
+  }
+  return 0;
+}
 }

@@ -204,6 +204,22 @@ def test_sfsetnk_on_device(built):
     assert ymax_g == max(np.abs(f0 * sf_o).max(), 1e-300)
 
 
+def test_portable_math_bit_identical_on_device(built):
+    """include/ue_math.h gives the same bits on the B200 and on the host over wide argument ranges."""
+    import ctypes as C
+    from tests.test_oracle_golden import _math_inputs
+    glib, olib = load_gpu().lib, oracle().lib
+    sig = [C.c_int64, C.c_int64] + [C.POINTER(C.c_double)] * 3
+    glib.ue_gpu_math_probe.argtypes = sig; olib.ue_ora_math_probe.argtypes = sig
+    P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    for op, (x, y) in _math_inputs().items():
+        yy = np.zeros_like(x) if y is None else y
+        og, oo = np.zeros_like(x), np.zeros_like(x)
+        assert glib.ue_gpu_math_probe(op, x.size, P(x), P(yy), P(og)) == 0
+        assert olib.ue_ora_math_probe(op, x.size, P(x), P(yy), P(oo)) == 0
+        assert np.array_equal(og, oo), (op, int((og != oo).sum()))
+
+
 def test_page_locked_caller_arrays(built):
     """With page-locked caller arrays the kernels read yl and write yldot / jac / ja / ia directly (no copy nodes);
     the results are those of the copy path, for fresh pointers (un-captured) and repeated ones (graph replay)."""

@@ -98,6 +98,65 @@ def test_case2_fnrm_documented_mismatch(built):
     assert abs(fnrm0 - 3.6156245) < 1e-5
 
 
+def _math_inputs():
+    rng = np.random.default_rng(42)
+    n = 20000
+    return {
+        0: (rng.uniform(-700, 700, n), None),                      # exp
+        1: (10.0 ** rng.uniform(-300, 300, n), None),              # log
+        2: (10.0 ** rng.uniform(-30, 30, n), None),                # log10
+        3: (10.0 ** rng.uniform(-20, 25, n), rng.choice([0.333, 1.5, 2.5, -0.5, 0.25, 3.0, -1.5, 0.71], n)),  # pow
+        4: (rng.uniform(-np.pi, np.pi, n), None),                  # cos
+        5: (10.0 ** rng.uniform(-300, 300, n), None),              # sqrt
+    }
+
+
+def test_portable_math_accuracy(built):
+    """include/ue_math.h (shared by the checker and the kernels) against libm: a few ulp at most."""
+    import ctypes as C
+    lib = oracle().lib
+    fn = lib.ue_ora_math_probe
+    fn.argtypes = [C.c_int64, C.c_int64] + [C.POINTER(C.c_double)] * 3
+    ref = {0: np.exp, 1: np.log, 2: np.log10, 4: np.cos, 5: np.sqrt}
+    P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    for op, (x, y) in _math_inputs().items():
+        yy = np.zeros_like(x) if y is None else y
+        out = np.zeros_like(x)
+        assert fn(op, x.size, P(x), P(yy), P(out)) == 0
+        want = np.power(x, yy) if op == 3 else ref[op](x)
+        ulp = np.abs(out - want) / np.spacing(np.abs(want))
+        if op == 4:  # cos: plain-double reduction by pi/2, i.e. an ABSOLUTE error of 2 ulp(1) (its only use is cos(0), oderhs.m:4879)
+            assert (np.abs(out - want) <= 4.5e-16).all(), (op, np.abs(out - want).max())
+            continue
+        # pow = exp(y log x): error grows with |y ln x| (documented in the header); the others stay within 2 ulp
+        bound = 2.0 if op != 3 else 2.0 + 2.0 * np.abs(yy * np.log(x))
+        assert (ulp <= bound).all(), (op, ulp.max())
+
+
+def test_case2_converges_near_the_2007_golden_profiles(built):
+    """Forthon_case2 (istabon=10 tables, restart h5d3d_ex.16x8, ncore raised to 2.5e19): Newton on the oracle converges and
+    the outer-midplane profiles land within a few per cent of output_forthon_case2.rtf (2007).  Defaults and boundary
+    models changed since then (the same reason fnrm0 is not reproducible), so this is a physics sanity pin of the table
+    path, not a digit-for-digit one."""
+    import ctypes as C
+    gold = json.load(open(os.path.join(GOLDEN, "case2_golden.json")))
+    c, yl = make_case("case2")
+    ora = bind(oracle(), c)
+    y, hist = newton_solve(ora, c, yl, iters=40)
+    assert hist[-1] < 1e-6
+    ora.pandf1(y)
+    lib = ora.lib
+    def plane(nm):
+        out = np.zeros((c.com.ny + 2) * (c.com.nx + 2))
+        assert lib.ue_ora_get_plane(nm.encode(), out.ctypes.data_as(C.POINTER(C.c_double))) == 0
+        return out.reshape(c.com.ny + 2, c.com.nx + 2)[:, c.com.ixmp]
+    ev = 1.6022e-19
+    ni, te, ti = plane("ni"), plane("te") / ev, plane("ti") / ev
+    assert np.abs(ni / np.array(gold["midplane_ni"]) - 1).max() < 0.03
+    assert np.abs(te / np.array(gold["midplane_te"]) - 1).max() < 0.06
+    assert np.abs(ti / np.array(gold["midplane_ti"]) - 1).max() < 0.03
+
+
 def test_unsupported_switch_is_refused(built):
     c, yl = make_case("d3dHsm")
     s = c.static_inputs()

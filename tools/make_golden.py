@@ -50,5 +50,14 @@ json.dump({
              0.8680565629223895e-07, 0.1176826431444834e-10],
     "yyc": [-0.00965086, -0.00741261, -0.00258718, 0.0028399, 0.00850614, 0.01416487, 0.01984442, 0.02554944,
             0.03127981, 0.03415233],
+    # converged outer-midplane profiles printed at the end of the same file (ni [m^-3], up [m/s], te, ti [eV])
+    "midplane_ni": [2.50000000e+19, 2.33721451e+19, 2.00349826e+19, 1.65067380e+19, 1.34076191e+19, 1.09788036e+19,
+                    9.18858968e+18, 8.00094888e+18, 7.40016731e+18, 7.40016731e+18],
+    "midplane_up": [0.0, -32.62027825, 730.93989383, 3915.89582457, 6102.24137545, 7199.82503778, 7672.80715756,
+                    7789.14414326, 7734.00426862, 7734.00426862],
+    "midplane_te": [100.0, 97.49739971, 85.78344749, 59.91034579, 43.35906036, 33.5923757, 26.3980251, 19.09156522,
+                    8.93259829, 2.0],
+    "midplane_ti": [100.0, 95.59396205, 86.51726616, 76.10545898, 65.54926912, 54.82427298, 43.07235412, 29.09750451,
+                    11.89098495, 2.0],
 }, open(os.path.join(OUT, "case2_golden.json"), "w"), indent=1)
 print("wrote fixtures to", OUT)

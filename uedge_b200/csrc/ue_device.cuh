@@ -17,9 +17,8 @@
 //
 // The same device functions serve two drivers through the accessor template:
 //   Acc<false>  full residual: fields live in HBM planes (SoA, ix fastest), one thread per cell;
-//   Acc<true>   Jacobian: one thread block per perturbed unknown; the window box
-//               [i1..i6]x[j1..j6] of every field is staged in shared memory, reads outside the
-//               box fall through to the base planes, phases are separated by __syncthreads().
+//   Acc<true>   Jacobian: private copies of the four cells a perturbation can change, every other read
+//               falls through to the base planes; one launch per phase over all unknowns (ue_gpu.cu).
 // Index windows, recompute ranges and the frozen-term gates are the reference's
 // (oderhs.m:868-1019) so that the value-dependent sparsity pattern is reproduced.
 //

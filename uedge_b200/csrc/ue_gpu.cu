@@ -500,6 +500,22 @@ __global__ void k_rowscale(int64_t neq, const int64_t* __restrict__ ia, const in
   for (int64_t k = k1; k < k2; ++k) jac[k] = jac[k] * d;
 }
 
+// include/ue_math.h on the device (parity probe: must equal the host evaluation bit for bit)
+__global__ void k_math_probe(int op, int64_t n, const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double r = 0.;
+  switch (op) {
+    case 0: r = ue_exp(x[i]); break;
+    case 1: r = ue_log(x[i]); break;
+    case 2: r = ue_log10(x[i]); break;
+    case 3: r = ue_pow(x[i], y[i]); break;
+    case 4: r = ue_cos(x[i]); break;
+    default: r = ue_sqrt(x[i]); break;
+  }
+  out[i] = r;
+}
+
 // yldot00 must be the residual of yl bit for bit (see ue_gpu_jac_calc)
 __global__ void k_samebits(const double* __restrict__ a, const double* __restrict__ b, int64_t n, int* __restrict__ err) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1242,6 +1258,18 @@ int ue_gpu_unpin_host_array(void* p) {
   g_seen_host.clear();
   cudaError_t e = cudaHostUnregister(p);
   if (e != cudaSuccess) { g_err = std::string("cudaHostUnregister: ") + cudaGetErrorString(e); cudaGetLastError(); return -10; }
+  return 0;
+}
+int ue_gpu_math_probe(int64_t op, int64_t n, const double* x, const double* y, double* out) {
+  if (op < 0 || op > 5 || n <= 0) { g_err = "math_probe: bad arguments"; return -1; }
+  double* d = nullptr;
+  CK(cudaMalloc(&d, 3 * n * 8));
+  CK(cudaMemcpy(d, x, n * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d + n, y, n * 8, cudaMemcpyHostToDevice));
+  k_math_probe<<<(unsigned)((n + 255) / 256), 256>>>((int)op, n, d, d + n, d + 2 * n);
+  cudaError_t e = cudaMemcpy(out, d + 2 * n, n * 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) { g_err = std::string("math_probe: ") + cudaGetErrorString(e); return -10; }
   return 0;
 }
 int ue_gpu_kernel_launches(int64_t* n) { *n = g_launches; return 0; }
