@@ -1,5 +1,7 @@
 """Shared helpers for the parity tests."""
 import os
+import re
+
 
 import numpy as np
 
@@ -19,9 +21,11 @@ def oracle():
 def make_case(name="d3dHsm", istabon=0, perturb=0.0, seed=1234, overrides=None):
     g = load_grid_npz()
     state = load_state_npz("case2_state.npz" if name == "case2" else "d3dHsm_state.npz")
-    if name == "d3dHsm4x":
-        g = refine_grid(g, 4, 4)
-        state = refine_state(state, 4, 4)
+    m = re.fullmatch(r"d3dHsm(\d+)x", name)
+    if m:  # synthetic refinement (BASELINE configs[4] is the 4x one)
+        f = int(m.group(1))
+        g = refine_grid(g, f, f)
+        state = refine_state(state, f, f)
     c = d3dhsm_case(g, istabon=10 if name == "case2" else istabon)
     if overrides:
         for k, v in overrides.items():

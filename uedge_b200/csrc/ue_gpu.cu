@@ -273,7 +273,10 @@ __global__ void __launch_bounds__(128) k_jb_p1a(JArgs A) {
   else if (role == 1) p1_ypart<true>(a, q.w, ix, iy);
   else p1_visx<true>(a, q.w, ix, iy);
 }
-__global__ void __launch_bounds__(128) k_jb_p1b(JArgs A) {
+// MINB: resident blocks per SM the register allocation must allow.  Small grids run one latency-bound pass (all the
+// registers the compiler wants); large grids are throughput-bound and gain from the higher occupancy despite a few spills.
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_jb_p1b(JArgs A) {
   const int it = blockIdx.x * 128 + threadIdx.x, u = it >> 2, k = it & 3;
   if (u >= A.NU) return;
   const UInfo& q = A.ui[u];
@@ -288,7 +291,8 @@ __global__ void __launch_bounds__(128) k_jb_p1b(JArgs A) {
   else p1_ey<true>(a, q.w, ix, iy);
 }
 // phase 2 on the candidate rows; roles 0-3 = equation groups on interior rows, role 4 = guard rows.  rows[k][item], rmask[item]
-__global__ void __launch_bounds__(128) k_jb_p2(JArgs A) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_jb_p2(JArgs A) {
   const int ry = blockIdx.y + A.role0;
   const int role = ry == 0 ? 4 : ry - 1;  // the guard role (long, divergent rows) is dispatched first, the equation groups follow
   int it = blockIdx.x * 128 + threadIdx.x;
@@ -744,13 +748,14 @@ int enqueue_jac(const double* dyl, const double* dy00, int64_t ml, int64_t mu, i
     A.role0 = 0;
     if (getenv("UE_DEBUG_SPLIT_ROLES")) {  // developer aid: one launch per role so that a launch list shows each role's duration
       for (int r = 0; r < 3; ++r) { A.role0 = r; CK(launch(k_jb_p1a, dim3(dim3(gs, 1)), dim3(128), A)); }
-      for (int r = 0; r < 5; ++r) { A.role0 = r; CK(launch(k_jb_p1b, dim3(dim3(gs, 1)), dim3(128), A)); }
-      for (int r = 0; r < 5; ++r) { A.role0 = r; CK(launch(k_jb_p2, dim3(dim3(gi, 1)), dim3(128), A)); }
+      for (int r = 0; r < 5; ++r) { A.role0 = r; CK(launch(k_jb_p1b<1>, dim3(dim3(gs, 1)), dim3(128), A)); }
+      for (int r = 0; r < 5; ++r) { A.role0 = r; CK(launch(k_jb_p2<1>, dim3(dim3(gi, 1)), dim3(128), A)); }
       A.role0 = 0;
     } else {
       CK(launch(k_jb_p1a, dim3(dim3(gs, 3)), dim3(128), A));
-      CK(launch(k_jb_p1b, dim3(dim3(gs, 5)), dim3(128), A));
-      CK(launch(k_jb_p2, dim3(dim3(gi, 5)), dim3(128), A));
+      const bool big = NU >= 4096;  // more than ~2 waves of blocks per role: throughput-bound
+      if (big) { CK(launch(k_jb_p1b<6>, dim3(dim3(gs, 5)), dim3(128), A)); CK(launch(k_jb_p2<6>, dim3(dim3(gi, 5)), dim3(128), A)); }
+      else { CK(launch(k_jb_p1b<1>, dim3(dim3(gs, 5)), dim3(128), A)); CK(launch(k_jb_p2<1>, dim3(dim3(gi, 5)), dim3(128), A)); }
     }
     CK(launch(k_jb_p3c, dim3((unsigned)((NU + 3) / 4)), dim3(128), A));
   }
