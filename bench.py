@@ -170,12 +170,16 @@ def main():
     def shim_params():
         assert lib.ue_gpu_step_params(neq, NP(sp_dt), NP(sp_yo), NP(sp_su), NP(sp_sf)) == 0
 
+    jac_call_s = []
+
     def step_e2e():
         shim_params()
         assert lib.ue_gpu_pandf1(neq, 0.0, P(hy), P(hf)) == 0          # yldot00 = rhsnk(yl)
+        tj = time.perf_counter()
         shim_params()
         assert lib.ue_gpu_set_real(b"nufak", nufak) == 0
         assert lib.ue_gpu_jac_calc(neq, 0.0, P(hy), P(hf), int(b.lbw), int(b.ubw), nnzmx, P(hjac), P(hja), P(hia), C.byref(nnz)) == 0
+        jac_call_s.append(time.perf_counter() - tj)
 
     lib.ue_gpu_rhs_jac_dev.argtypes = [C.c_int64, C.c_void_p, C.c_void_p] + [C.c_int64] * 3 + [C.c_void_p] * 3 + [C.POINTER(C.c_int64), C.POINTER(C.c_double)]
     evms = C.c_double(0); ev_samples = []
@@ -238,7 +242,9 @@ def main():
     t_dev = sum(ev_samples) * 1e-3  # CUDA events: seconds for a.steps steps
     l1 = C.c_int64(0); lib.ue_gpu_kernel_launches(C.byref(l1))
     _, jm, rm = timed(kernels_dev, a.steps)
+    del jac_call_s[:]
     t_e2e, _, _ = timed(step_e2e, a.steps)
+    jac_call_ms = 1e3 * sum(jac_call_s) / max(1, len(jac_call_s))
     t_res_e2e, _, _ = timed(resid_e2e, a.steps)
     t_fused, _, _ = timed(step_e2e_fused, a.steps)
     stop.set(); th.join()
@@ -289,7 +295,8 @@ def main():
                             else "one Jacobian, columns split over %d ranks (replicated state)" % world),
                 e2e=dict(value=nnz_total / (ms_e2e * 1e-3), unit="nnz/s", h2d_bytes_per_step=8 * (2 * (neq + 2) + neq),
                          d2h_bytes_per_step=16 * nnz_total + 8 * (neq + 1) + 8 * neq, ms_per_step=ms_e2e,
-                         resid_evals_per_s=a.steps / t_res_e2e, warm_ms_per_step=warm_e2e, warm_resid_evals_per_s=1e3 / warm_res, fused_call_ms_per_step=t_fused / a.steps * 1e3),
+                         resid_evals_per_s=a.steps / t_res_e2e, warm_ms_per_step=warm_e2e, warm_resid_evals_per_s=1e3 / warm_res, fused_call_ms_per_step=t_fused / a.steps * 1e3,
+                         jac_calc_call_ms=jac_call_ms, jac_calc_call_nnz_per_s=nnz_total / world / (jac_call_ms * 1e-3) * world),
                 warm_ms_per_step=warm_dev, host_clock_ms_per_step=t_dev_host / a.steps * 1e3,
                 gpu_launches=int(l1.value - l0.value),
                 resid_evals_per_s=1e3 / res_ms if res_ms > 0 else None, jac_kernel_ms=jac_ms, resid_kernel_ms=res_ms,

@@ -443,3 +443,41 @@ def test_foreign_yldot00_is_refused(built):
     with pytest.raises(Exception, match="yldot00 is not pandf1"):
         gpu.jac_calc(yneg, f, b.lbw, b.ubw, b.nnzmx)
     gpu.set_real("dtreal", 1e20)
+
+
+def test_large_grid_properties(built):
+    """8x-refined grid (neq = 42 900, too large for the scalar oracle in a test): size-independent properties.
+    (1) the column-split union equals the full Jacobian; (2) two evaluations are bit-identical; (3) J v equals the
+    directional finite difference of the CUDA residual, (f(y + eps v) - f(y)) / eps, for random v."""
+    import scipy.sparse as sp
+    c, yl = make_case("d3dHsm8x", perturb=1e-3)
+    gpu = bind(load_gpu(), c)
+    b = c.bbb; n = b.neq
+    y, su = psetnk_inputs(c, yl)
+    y[n + 1] = 0.0
+    gpu.set_real("nufak", 0.0)
+    gpu.step_params(np.full(n, 1e20), y[:n], su, np.ones(n))
+    f = gpu.pandf1(y)
+    full = gpu.jac_calc(y, f, b.lbw, b.ubw, b.nnzmx)
+    again = gpu.jac_calc(y, f, b.lbw, b.ubw, b.nnzmx)
+    assert all(np.array_equal(p, q) for p, q in zip(full, again))
+    parts = []
+    cuts = [1, n // 3, (2 * n) // 3 + 7, n + 1]
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        gpu.set_column_range(lo, hi - 1)
+        parts.append(gpu.jac_calc(y, f, b.lbw, b.ubw, b.nnzmx))
+    gpu.set_column_range(1, n)
+    assert sum(len(p[0]) for p in parts) == len(full[0])
+    mats = [sp.csr_matrix((p[0], p[1] - 1, p[2] - 1), shape=(n, n)) for p in parts]
+    J = sp.csr_matrix((full[0], full[1] - 1, full[2] - 1), shape=(n, n))
+    assert abs(sum(mats) - J).max() == 0.0
+    # directional derivative; the -1/dtuse diagonal term (dtuse = 1e20) is far below the noise
+    rng = np.random.default_rng(3)
+    for _ in range(3):
+        v = rng.uniform(-1, 1, n) / su            # a perturbation of relative size O(1) in every unknown
+        eps = 1e-7
+        y2 = y.copy(); y2[:n] += eps * v
+        fd = (gpu.pandf1(y2) - f) / eps
+        jv = J @ v
+        scale = np.abs(J) @ np.abs(v) + 1e-300      # row-wise size of the terms
+        assert (np.abs(fd - jv) / scale).max() < 2e-4
