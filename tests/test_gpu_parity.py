@@ -44,9 +44,12 @@ def test_residual_converged_state_on_gpu(built):
     assert np.abs(f).max() < 5e-6
 
 
-def test_residual_timestep_term(built):
-    """yl(neq+1)<0 and dtreal<1e15 adds -(yl-ylodt)/dtuse on interior rows (oderhs.m:7963-8037)."""
-    c, yl, gpu, ora = _pair("d3dHsm", 1e-3)
+@pytest.mark.parametrize("isbcwdt", [0, 1])
+def test_residual_timestep_term(built, isbcwdt):
+    """yl(neq+1)<0 and dtreal<1e15 adds -(yl-ylodt)/dtuse on interior rows, and on the guard rows too when isbcwdt=1
+    (oderhs.m:7963-8037; pyexamples/d3dHsmNew starts with isbcwdt=1)."""
+    c, yl = make_case("d3dHsm", perturb=1e-3, overrides={"bbb.isbcwdt": isbcwdt})
+    gpu, ora = bind(load_gpu(), c), bind(oracle(), c)
     n = c.bbb.neq
     rng = np.random.default_rng(3)
     dt = 10.0 ** rng.uniform(-6, -3, n)
@@ -54,8 +57,14 @@ def test_residual_timestep_term(built):
     for lib in (gpu, ora):
         lib.set_real("dtreal", 1e-4)
         lib.step_params(dt, yo, np.ones(n), np.ones(n))
-    fg, fo = gpu.pandf1(yl), ora.pandf1(yl)
-    assert _res_err(fg, fo) < RES_RTOL
+    y = yl.copy(); y[n] = -1.0
+    fg, fo = gpu.pandf1(y), ora.pandf1(y)
+    assert np.array_equal(fg, fo)
+    y[n] = 1.0
+    assert not np.array_equal(gpu.pandf1(y), fg)  # without the flag the term is absent
+    # Jacobian with the term's diagonal contribution (-1/dtuse on every row when isbcwdt=1)
+    jg, jo, noise = _jac_pair(c, yl, gpu, ora, dt=dt)
+    assert all(np.array_equal(p, q) for p, q in zip(jg, jo))
     for lib in (gpu, ora):
         lib.set_real("dtreal", 1e20)
 

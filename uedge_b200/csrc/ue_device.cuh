@@ -1215,6 +1215,20 @@ __device__ void p2_i(const Acc<WIN>& a, int ix, int iy, double out[UE_NV], const
   out[3] = (1 - iseqalg[c + 3]) * resei / (vol * D.ennorm);
 }
 
+// time-step term of the nksol equations (oderhs.m:7963-8037): rows of interior cells, and of the guard cells too when
+// isbcwdt = 1; only for calls from nksol (yl(neq+1) < 0), never for the Jacobian evaluations
+__device__ __forceinline__ void phase3_dt(int ix, int iy, double r[UE_NV], const double* ycell, double ylflag, int64_t c,
+                                          const double* __restrict__ dtuse, const double* __restrict__ ylodt) {
+  (void)iy;
+  if (D.dtreal < 1.e15 && ylflag < 0) {
+    for (int k = 0; k < UE_NV; ++k) {
+      if (k == 1 && ix == D.nx + 2 * D.isbcwdt) continue;  // oderhs.m:7991: the algebraic up row at ix = nx unless isbcwdt = 1
+      r[k] = (1. - 0.) * r[k];
+      r[k] = r[k] - (ycell[k] - ylodt[c + k]) / dtuse[c + k];
+    }
+  }
+}
+
 // ============================================================================================
 // phase 3 — rscalf (oderhs.m:8096-8210) and the time-step term (oderhs.m:7963-8037) on an interior cell
 // ============================================================================================
@@ -1242,12 +1256,6 @@ __device__ void phase3_interior(const Acc<WIN>& a, int ix, int iy, double r[UE_N
     if (iseqalg[c + 2] == 0) r[2] = (r[2] * D.nnorm - ycell[2] * nbedot) / f_ne(a, ix, iy);
     if (iseqalg[c + 3] == 0) r[3] = (r[3] * D.nnorm - ycell[3] * (nbidot + D.cngtgx * nbg2dot)) / ((0. + ni) + D.cngtgx * a.get(PL_NG, ix, iy));
   }
-  if (D.dtreal < 1.e15 && ylflag < 0 && D.isbcwdt == 0) {
-    for (int k = 0; k < UE_NV; ++k) {
-      if (k == 1 && ix == D.nx) continue;  // oderhs.m:7991
-      r[k] = (1. - 0.) * r[k];
-      r[k] = r[k] - (ycell[k] - ylodt[c + k]) / dtuse[c + k];
-    }
-  }
+  phase3_dt(ix, iy, r, ycell, ylflag, c, dtuse, ylodt);
 }
 #endif  // __CUDACC__

@@ -168,6 +168,7 @@ __global__ void k_phase3(double* base, const double* __restrict__ tmp, double* _
   double r[UE_NV];
   for (int k = 0; k < UE_NV; ++k) r[k] = tmp[(size_t)c * UE_NV + k];
   if (ix >= 1 && ix <= D.nx && iy >= 1 && iy <= D.ny) phase3_interior<false>(a, ix, iy, r, yl + (size_t)c * UE_NV, yl[neq], D.iseqalg, dtuse, ylodt);
+  else if (D.isbcwdt == 1) phase3_dt(ix, iy, r, yl + (size_t)c * UE_NV, yl[neq], (int64_t)c * UE_NV, dtuse, ylodt);  // guard rows carry the term too
   for (int k = 0; k < UE_NV; ++k) yldot[(size_t)c * UE_NV + k] = r[k];
   if (yldot_host) for (int k = 0; k < UE_NV; ++k) yldot_host[(size_t)c * UE_NV + k] = r[k];
 }
