@@ -58,6 +58,8 @@ std::vector<int64_t> h_coloff;  // per column offset into the fragment buffers (
 std::vector<int> h_cellcand_off, h_cand_cell, h_cand_east;  // per-cell candidate lists (CSR-like)
 int *d_cand_cell = nullptr, *d_cand_east = nullptr, *d_item_u = nullptr, *d_guard_items = nullptr;
 int g_nguard = 0;
+int* d_guard_cells = nullptr;  // all guard cells, sorted by kind and padded per kind to whole warps (-1)
+int g_nguard_cells = 0;
 std::vector<unsigned char> h_uinfo;  // UInfo records of the column range, regular windows first
 void* d_uinfo = nullptr;
 double *d_priv = nullptr, *d_jrows = nullptr, *d_rres = nullptr;
@@ -137,24 +139,34 @@ __global__ void __launch_bounds__(160) k_phase1(double* base, int NXS, int NC) {
     else p1_ey<false>(a, w, ix, iy);
   }
 }
-// phase 2: 32 cells per block, five role-warps: four equation groups on interior cells, the guard-cell rows (bouncon)
-__global__ void __launch_bounds__(160) k_phase2(double* base, double* __restrict__ tmp, int NXS, int NC) {
+// phase 2: 32 cells per block, four role-warps (equation groups on interior cells) plus a guard-row warp (bouncon).
+// The guard warp does not take the block's own cells: it takes 32 entries of a list of all guard cells sorted by kind
+// (bottom, top, corner, left plate, right plate) and padded per kind to whole warps, so that a warp runs ONE kind's
+// code instead of all of them one after the other.
+__global__ void __launch_bounds__(160) k_phase2(double* base, double* __restrict__ tmp, int NXS, int NC, const int* __restrict__ guard_cells, int nguard) {
   const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + lane;
-  if (c >= NC) return;
   Acc<false> a; a.base = base; a.NXS = NXS; a.NC = NC;
   const Win w = make_win(D, -1, -1);
-  const int ix = c % NXS, iy = c / NXS;
   double r[UE_NV] = {0., 0., 0., 0., 0.};
+  if (role == 4) {
+    const int g = blockIdx.x * 32 + lane;
+    if (g >= nguard) return;
+    const int c = guard_cells[g];
+    if (c < 0) return;
+    phase2_guard<false>(a, w, c % NXS, c / NXS, r);
+    double* o = tmp + (size_t)c * UE_NV;
+    for (int k = 0; k < UE_NV; ++k) o[k] = r[k];
+    return;
+  }
+  const int c = blockIdx.x * 32 + lane;
+  if (c >= NC) return;
+  const int ix = c % NXS, iy = c / NXS;
   double* o = tmp + (size_t)c * UE_NV;
   if (ix >= 1 && ix <= D.nx && iy >= 1 && iy <= D.ny) {
     if (role == 0) { p2_n<false>(a, ix, iy, r, D.iseqalg); o[0] = r[0]; o[4] = r[4]; }
     else if (role == 1) { p2_m<false>(a, w, ix, iy, r, D.iseqalg); o[1] = r[1]; }
     else if (role == 2) { p2_e<false>(a, ix, iy, r, D.iseqalg); o[2] = r[2]; }
-    else if (role == 3) { p2_i<false>(a, ix, iy, r, D.iseqalg); o[3] = r[3]; }
-  } else if (role == 4) {
-    phase2_guard<false>(a, w, ix, iy, r);
-    for (int k = 0; k < UE_NV; ++k) o[k] = r[k];
+    else { p2_i<false>(a, ix, iy, r, D.iseqalg); o[3] = r[3]; }
   }
 }
 __global__ void k_phase3(double* base, const double* __restrict__ tmp, double* __restrict__ yldot, const double* __restrict__ yl,
@@ -300,6 +312,7 @@ __global__ void __launch_bounds__(128, MINB) k_jb_p2(JArgs A) {
   if (role == 4) {  // the guard role walks the (short) list of guard items only
     if (it >= A.nguard) return;
     it = A.guard_items[it];
+    if (it < 0) return;  // padding between the kinds
   }
   if (it >= A.nitems) return;
   const int u = A.item_u[it];
@@ -595,13 +608,13 @@ void free_all() {
   g_base_valid = g_base_dev_valid = false;
   for (void* p : g_static_allocs) cudaFree(p);
   g_static_allocs.clear();
-  void* ptrs[] = {d_base, d_yl, d_yldot00, d_tmp, d_yldot, d_dtuse, d_ylodt, d_suscal, d_sfscal, d_err, d_cand_cell, d_cand_east, d_item_u, d_guard_items, d_coloff,
+  void* ptrs[] = {d_base, d_yl, d_yldot00, d_tmp, d_yldot, d_dtuse, d_ylodt, d_suscal, d_sfscal, d_err, d_cand_cell, d_cand_east, d_item_u, d_guard_items, d_guard_cells, d_coloff,
                   d_colcnt, d_colrow, d_colval, d_ia, d_ja, d_jac};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (void* p : {(void*)d_uinfo, (void*)d_priv, (void*)d_jrows, (void*)d_rres, (void*)d_rmask}) if (p) cudaFree(p);
   d_uinfo = nullptr; d_priv = d_jrows = d_rres = nullptr; d_rmask = nullptr;
   d_base = d_yl = d_yldot00 = d_tmp = d_yldot = d_dtuse = d_ylodt = d_suscal = d_sfscal = nullptr;
-  d_err = nullptr; d_cand_cell = d_cand_east = d_item_u = d_guard_items = nullptr; d_coloff = nullptr; d_colcnt = d_colrow = nullptr; d_colval = nullptr;
+  d_err = nullptr; d_cand_cell = d_cand_east = d_item_u = d_guard_items = d_guard_cells = nullptr; d_coloff = nullptr; d_colcnt = d_colrow = nullptr; d_colval = nullptr;
   d_rowcnt = d_rowfill = nullptr; d_ia = d_ja = nullptr; d_jac = nullptr;
   g_ready = false;
 }
@@ -637,6 +650,22 @@ void cell_candidates(const UeParams& P, int xc, int yc, std::vector<int>& out) {
     if (std::find(out.begin(), out.end(), cell) == out.end()) out.push_back(cell);
   }
   std::sort(out.begin(), out.end());
+}
+
+// kind of a guard cell = which part of bouncon sets its rows; lists are sorted by kind and padded to whole warps
+int guard_kind(int ix, int iy) {
+  const bool yb = (iy == 0 || iy == ny + 1), xb = (ix == 0 || ix == nx + 1);
+  if (yb) return xb ? 2 : (iy == 0 ? 0 : 1);
+  return ix == 0 ? 3 : 4;
+}
+template <typename KeyOf>
+std::vector<int> sort_pad_by_kind(const std::vector<int>& items, KeyOf cell_of) {
+  std::vector<int> out;
+  for (int kind = 0; kind < 5; ++kind) {
+    for (int it : items) { const int c = cell_of(it); if (guard_kind(c % NXS, c / NXS) == kind) out.push_back(it); }
+    while (out.size() % 32) out.push_back(-1);
+  }
+  return out;
 }
 
 int build_lists() {
@@ -691,6 +720,7 @@ int upload_lists() {
       if (!(ix >= 1 && ix <= nx && iy >= 1 && iy <= ny)) guard_items.push_back(q.off + l);
     }
   }
+  guard_items = sort_pad_by_kind(guard_items, [&](int it) { const UInfo& q = ui[item_u[it]]; return h_cand_cell[q.coff + (it - q.off)]; });
   g_nguard = (int)guard_items.size();
   g_nitems = (int)item_u.size();
   for (void* p : {(void*)d_uinfo, (void*)d_priv, (void*)d_jrows, (void*)d_rres, (void*)d_rmask, (void*)d_cand_cell, (void*)d_cand_east, (void*)d_item_u, (void*)d_guard_items}) if (p) cudaFree(p);
@@ -727,7 +757,7 @@ int enqueue_residual(const double* dyl, double* dyldot, bool need_rows, const do
   if (yl_src && yl_src != dyl) CK(launch(k_phase0, dim3(G), dim3(B), d_base, yl_src, const_cast<double*>(dyl), neq, NXS, NC, d_err));
   else CK(launch(k_phase0, dim3(G), dim3(B), d_base, dyl, (double*)nullptr, neq, NXS, NC, d_err));
   CK(launch(k_phase1, dim3(G32), dim3(160), d_base, NXS, NC));
-  CK(launch(k_phase2, dim3(G32), dim3(160), d_base, d_tmp, NXS, NC));
+  CK(launch(k_phase2, dim3(std::max(G32, (g_nguard_cells + 31) / 32)), dim3(160), d_base, d_tmp, NXS, NC, (const int*)d_guard_cells, g_nguard_cells));
   if (need_rows) CK(launch(k_phase3, dim3(G), dim3(B), d_base, d_tmp, dyldot, dyl, d_dtuse, d_ylodt, neq, NXS, NC, d_err, d_hflags, yldot_host));
   return 0;
 }
@@ -929,6 +959,14 @@ int ue_gpu_init(void) {
   g_ivmin = 1; g_ivmax = neq;
   build_lists();
   if ((rc = upload_lists())) return rc;
+  {  // guard cells of the full residual, sorted by kind
+    std::vector<int> cells;
+    for (int c = 0; c < NC; ++c) { const int ix = c % NXS, iy = c / NXS; if (!(ix >= 1 && ix <= nx && iy >= 1 && iy <= ny)) cells.push_back(c); }
+    const std::vector<int> gc = sort_pad_by_kind(cells, [](int c) { return c; });
+    g_nguard_cells = (int)gc.size();
+    CK(cudaMalloc(&d_guard_cells, std::max<size_t>(1, gc.size()) * sizeof(int)));
+    CK(cudaMemcpy(d_guard_cells, gc.data(), gc.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
   CK(cudaMalloc(&d_coloff, neq * sizeof(int64_t)));
   CK(cudaMemcpy(d_coloff, h_coloff.data(), neq * sizeof(int64_t), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&d_colcnt, 3 * neq * sizeof(int)));  // colcnt | rowcnt | rowfill contiguous: one memset per Jacobian
