@@ -37,6 +37,7 @@ struct UeStore {
   std::map<std::string, std::vector<double>> rdata;
   std::map<std::string, std::vector<int64_t>> idata;
   std::map<std::string, bool> seen;
+  std::map<std::string, double> zero_only;  // UE_ZERO_REALS / UE_ZERO_INTS: checked, never used
 
   UeStore() {
     std::memset(&p, 0, sizeof(p));
@@ -58,13 +59,21 @@ struct UeStore {
 #define X(n) iarr[#n] = &p.n; seen[#n] = false; is_plane[#n] = false;
     UE_INT_LINES(X)
 #undef X
+#define X(n) zero_only[#n] = 0.; seen[#n] = false;
+    UE_ZERO_REALS(X)
+    UE_ZERO_INTS(X)
+#undef X
   }
   int set_int(const char* name, int64_t v) {
+    auto z = zero_only.find(name);
+    if (z != zero_only.end()) { z->second = (double)v; seen[name] = true; return 0; }
     auto it = iscal.find(name);
     if (it == iscal.end()) return -1;
     *it->second = v; seen[name] = true; return 0;
   }
   int set_real(const char* name, double v) {
+    auto z = zero_only.find(name);
+    if (z != zero_only.end()) { z->second = v; seen[name] = true; return 0; }
     auto it = rscal.find(name);
     if (it == rscal.end()) return -1;
     *it->second = v; seen[name] = true; return 0;
@@ -88,6 +97,11 @@ struct UeStore {
     std::string s;
     for (auto& kv : seen) if (!kv.second) { s += kv.first; s += ' '; }
     return s;
+  }
+  // first input of the must-be-zero lists that is not zero (empty: none)
+  std::string nonzero_frozen() const {
+    for (auto& kv : zero_only) if (kv.second != 0.) return kv.first;
+    return std::string();
   }
   std::string bad_sizes() const {
     std::string s;

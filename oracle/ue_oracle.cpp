@@ -1335,6 +1335,7 @@ void csrcsc(int64_t n, const double* a, const int64_t* ja, const int64_t* ia, do
 }
 
 int check_switches() {
+  { const std::string z = S.nonzero_frozen(); if (!z.empty()) { g_err = "input " + z + " must be 0: the term it switches on is outside the built hot path"; return -5; } }
   struct { const char* n; int64_t v, want; } eq[] = {
       {"nisp", P.nisp, 1}, {"nusp", P.nusp, 1}, {"ngsp", P.ngsp, 1}, {"numvar", P.numvar, 5}, {"isnonog", P.isnonog, 0}, {"isphion", P.isphion, 0},
       {"isphiofft", P.isphiofft, 0}, {"isimpon", P.isimpon, 0}, {"isupgon", P.isupgon, 0}, {"isngon", P.isngon, 1}, {"istgon", P.istgon, 0},

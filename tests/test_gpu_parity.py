@@ -359,6 +359,15 @@ def test_jacobian_is_deterministic(built):
     assert all(np.array_equal(p, q) for p, q in zip(a, bb))
 
 
+def test_coefficient_outside_the_built_path_is_refused_on_gpu(built):
+    c, yl = make_case("d3dHsm", overrides={"bbb.cfyef": 1.0})
+    gpu = load_gpu()
+    with pytest.raises(Exception, match="cfyef must be 0"):  # at ue_gpu_init, or at once if the library is already initialised
+        gpu.load_static(c.static_inputs())
+        gpu.init()
+    bind(gpu, make_case("d3dHsm")[0])  # and a clean set of inputs is accepted again
+
+
 def test_negative_density_is_trapped(built):
     c, yl, gpu, ora = _pair("d3dHsm", 0.0)
     y = yl.copy()

@@ -167,6 +167,17 @@ def test_unsupported_switch_is_refused(built):
         ora.init()
 
 
+@pytest.mark.parametrize("name", ["cfybf", "cfydd", "facbee", "iszeffcon", "nlimgx"])
+def test_coefficient_outside_the_built_path_is_refused(built, name):
+    """Coefficients that switch on terms the built path does not evaluate (drifts, Bohm-like diffusion, ...) cross the
+    ABI only to be checked: a non-zero value is refused by name instead of being ignored."""
+    c, yl = make_case("d3dHsm", overrides={"bbb." + name: 1})
+    ora = oracle()
+    ora.load_static(c.static_inputs())
+    with pytest.raises(Exception, match=name + " must be 0"):
+        ora.init()
+
+
 def test_refined_grid_setup():
     c, yl = make_case("d3dHsm4x")
     assert c.com.nx == 64 and c.com.ny == 32 and c.bbb.neq == 5 * 66 * 34

@@ -70,6 +70,10 @@ class UeLib:
             self._call("set_int", k.encode(), int(v))
         for k, v in static["reals"].items():
             self._call("set_real", k.encode(), float(v))
+        for k, v in static.get("zero_ints", {}).items():
+            self._call("set_int", k.encode(), int(v))
+        for k, v in static.get("zero_reals", {}).items():
+            self._call("set_real", k.encode(), float(v))
         for grp in ("planes", "lines"):
             for k, v in static[grp].items():
                 a = np.ascontiguousarray(v, dtype=np.float64).reshape(-1)

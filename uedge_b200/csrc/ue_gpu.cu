@@ -565,6 +565,7 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 int check_switches() {
   const UeParams& P = S.p;
+  { const std::string z = S.nonzero_frozen(); if (!z.empty()) { g_err = "input " + z + " must be 0: the term it switches on is outside the built hot path"; return -5; } }
   struct { const char* n; int64_t v, want; } eq[] = {
       {"nisp", P.nisp, 1}, {"nusp", P.nusp, 1}, {"ngsp", P.ngsp, 1}, {"numvar", P.numvar, UE_NV}, {"isnonog", P.isnonog, 0}, {"isphion", P.isphion, 0},
       {"isphiofft", P.isphiofft, 0}, {"isimpon", P.isimpon, 0}, {"isupgon", P.isupgon, 0}, {"isngon", P.isngon, 1}, {"istgon", P.istgon, 0},
@@ -877,6 +878,11 @@ extern "C" {
 
 int ue_gpu_set_int(const char* n, int64_t v) { g_base_valid = g_base_dev_valid = false; if (S.set_int(n, v)) { g_err = std::string("unknown int input ") + n; return -1; } return 0; }
 int ue_gpu_set_real(const char* n, double v) {
+  if (S.zero_only.count(n)) {  // checked at ue_gpu_init; after it, a non-zero value is refused at once
+    S.set_real(n, v);
+    if (g_ready && v != 0.) { g_err = std::string("input ") + n + " must be 0: the term it switches on is outside the built hot path"; return -5; }
+    return 0;
+  }
   if (g_ready) {  // the shim re-sends nufak before every Jacobian: an unchanged value keeps the cached base fields
     auto it = S.rscal.find(n);
     if (it != S.rscal.end() && std::memcmp(it->second, &v, 8) == 0) return 0;
