@@ -77,6 +77,12 @@ int ue_gpu_rhs_jac(int64_t neq, const double* yl, double* yldot00, int64_t ml, i
 int ue_gpu_jac_scale(int64_t neq, const double* su, const double* sf, int64_t isrnorm, int64_t normtype,
                      int64_t nnz, double* jac, double* fnormnw);
 
+/* ---- guard for array inputs the built path does not read --------------------------------------------------------------
+ * Volume sources (volpsor, volmsor, pwrsore, pwrsori, voljcsor: bbb/oderhs.m:3407-3456, 4300-4330), user profiles
+ * (dif_use, kye_use, kyi_use, tray_use, ...) and wall sources are assumed to vanish.  The shim calls this once per array
+ * after ueinit; a non-zero element returns -5 with a message naming the array (-> xerrab) instead of being ignored. */
+int ue_gpu_assert_zero(const char* name, const double* a, int64_t n);
+
 /* ---- parity probe: include/ue_math.h evaluated on the device -----------------------------------------------------------
  * op 0 exp, 1 log, 2 log10, 3 pow(x,y), 4 cos, 5 sqrt; host arrays of n doubles.  The CPU checker evaluates the same
  * header; the two must agree bit for bit (that is what makes the value-dependent Jacobian pattern reproducible). */

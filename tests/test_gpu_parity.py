@@ -368,6 +368,18 @@ def test_coefficient_outside_the_built_path_is_refused_on_gpu(built):
     bind(gpu, make_case("d3dHsm")[0])  # and a clean set of inputs is accepted again
 
 
+def test_assert_zero_guard(built):
+    import ctypes as C
+    lib = load_gpu().lib
+    lib.ue_gpu_assert_zero.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.c_int64]
+    lib.ue_gpu_last_error.restype = C.c_char_p
+    a = np.zeros(100)
+    assert lib.ue_gpu_assert_zero(b"volpsor", a.ctypes.data_as(C.POINTER(C.c_double)), a.size) == 0
+    a[37] = 1e-30
+    assert lib.ue_gpu_assert_zero(b"volpsor", a.ctypes.data_as(C.POINTER(C.c_double)), a.size) == -5
+    assert b"volpsor must be identically 0" in lib.ue_gpu_last_error()
+
+
 def test_negative_density_is_trapped(built):
     c, yl, gpu, ora = _pair("d3dHsm", 0.0)
     y = yl.copy()

@@ -1310,6 +1310,13 @@ int ue_gpu_unpin_host_array(void* p) {
   if (e != cudaSuccess) { g_err = std::string("cudaHostUnregister: ") + cudaGetErrorString(e); cudaGetLastError(); return -10; }
   return 0;
 }
+// Arrays whose terms the built hot path does not evaluate (volume sources volpsor/volmsor/pwrsore/pwrsori, user
+// profiles *_use, ...): the shim passes them here once after ueinit; any non-zero element is refused by name.
+int ue_gpu_assert_zero(const char* name, const double* a, int64_t n) {
+  for (int64_t i = 0; i < n; ++i)
+    if (a[i] != 0.) { g_err = std::string("array ") + name + " must be identically 0: the term it feeds is outside the built hot path"; return -5; }
+  return 0;
+}
 int ue_gpu_math_probe(int64_t op, int64_t n, const double* x, const double* y, double* out) {
   if (op < 0 || op > 5 || n <= 0) { g_err = "math_probe: bad arguments"; return -1; }
   double* d = nullptr;
