@@ -48,7 +48,7 @@ std::vector<void*> g_static_allocs;
 double *d_base = nullptr, *d_yl = nullptr, *d_yldot00 = nullptr, *d_tmp = nullptr, *d_yldot = nullptr;
 double *d_dtuse = nullptr, *d_ylodt = nullptr, *d_suscal = nullptr, *d_sfscal = nullptr;
 int* d_err = nullptr;
-volatile long long* h_flags = nullptr;  // pinned + mapped: [0] error bits of the last sequence, [1] ia(neq+1) of the last Jacobian
+volatile long long* h_flags = nullptr;  // pinned + mapped: [0] error bits of the residual sequence, [1] ia(neq+1) of the last Jacobian, [2] error bits of the Jacobian sequence
 long long* d_hflags = nullptr;          // device alias of h_flags
 int64_t g_nnz_guess = 0;
 // Jacobian work space
@@ -60,7 +60,6 @@ int *d_cand_cell = nullptr, *d_cand_east = nullptr, *d_item_u = nullptr, *d_guar
 int g_nguard = 0;
 int* d_guard_cells = nullptr;  // all guard cells, sorted by kind and padded per kind to whole warps (-1)
 int g_nguard_cells = 0;
-std::vector<unsigned char> h_uinfo;  // UInfo records of the column range, regular windows first
 void* d_uinfo = nullptr;
 double *d_priv = nullptr, *d_jrows = nullptr, *d_rres = nullptr;
 int* d_rmask = nullptr;
