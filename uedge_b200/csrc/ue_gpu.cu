@@ -273,6 +273,61 @@ __global__ void __launch_bounds__(128) k_jb_stage0(JArgs A) {
     phase0_cell<true>(a, ycell, q.xc, q.yc, A.err);
   }
 }
+// Small grids: phases 0, 1a and 1b of 32 unknowns in ONE block (all dependencies are per unknown, so block-level
+// barriers suffice): 5 role groups of P01_ITEMS (unknown, slot) items.  Saves two launches and their cold
+// instruction/constant/L1 misses; the private cells stay in this SM's L1 from staging to the last phase-1 role
+// (d3dHsm: Jacobian sequence 70 -> 63 us warm; no change with L2 flushed).  Large grids keep one launch per phase.
+constexpr int P01_ITEMS = 64;  // (unknown, slot) items per block of k_jb_p01: 16 unknowns (8 and 32 per block measured slower)
+__global__ void __launch_bounds__(5 * P01_ITEMS, 1) k_jb_p01(JArgs A) {
+  const int u0 = blockIdx.x * (P01_ITEMS / 4), tid = threadIdx.x;
+  {  // clear this Jacobian's counters (colcnt | rowcnt | rowfill are contiguous) and the candidate-row masks
+    const int nthr = gridDim.x * 5 * P01_ITEMS, t0 = blockIdx.x * 5 * P01_ITEMS + tid;
+    for (int64_t i = t0; i < 3 * A.neq; i += nthr) A.colcnt[i] = 0;
+    for (int i = t0; i < A.nitems; i += nthr) A.rmask[i] = 0;
+  }
+  const int grp = tid / P01_ITEMS, j = tid % P01_ITEMS;          // role group, item within the block
+  const int u = u0 + (j >> 2), k = j & 3;
+  const bool live = u < A.NU;
+  int ix = 0, iy = 0;
+  bool slot_ok = false;
+  if (live) slot_ok = jb_slot_cell(A.ui[u], k, ix, iy);
+  if (live) {  // staging: the five groups split the planes
+    const int cy = iy < 0 ? 0 : iy;
+    const int cell = ix + A.NXS * cy;
+    double* dst = A.priv + ((size_t)u * 4 + k) * PL_COUNT;
+    for (int pl = grp; pl < PL_COUNT; pl += 5) dst[pl] = A.base[(size_t)pl * A.NC + cell];
+  }
+  __syncthreads();
+  if (tid < P01_ITEMS / 4 && u0 + tid < A.NU) {
+    const int up = u0 + tid;
+    const UInfo& q = A.ui[up];
+    const Acc<true> a = jb_acc(A, q, up);
+    double ycell[UE_NV], yold;
+    const double dyl = jb_dyl(A, q, yold);
+    const int64_t c = (int64_t)(q.xc + A.NXS * q.yc) * UE_NV;
+    for (int k2 = 0; k2 < UE_NV; ++k2) ycell[k2] = A.yl[c + k2];
+    ycell[(q.iv - 1) - c] = yold + dyl;
+    phase0_cell<true>(a, ycell, q.xc, q.yc, A.err);
+  }
+  __syncthreads();
+  if (live && slot_ok) {
+    const UInfo& q = A.ui[u];
+    const Acc<true> a = jb_acc(A, q, u);
+    if (grp == 0) p1_xpart<true>(a, q.w, ix, iy);
+    else if (grp == 1) p1_ypart<true>(a, q.w, ix, iy);
+    else if (grp == 2) p1_visx<true>(a, q.w, ix, iy);
+  }
+  __syncthreads();
+  if (live && slot_ok) {
+    const UInfo& q = A.ui[u];
+    const Acc<true> a = jb_acc(A, q, u);
+    if (grp == 0) p1_fx<true>(a, q.w, ix, iy);
+    else if (grp == 1) p1_fy<true>(a, q.w, ix, iy);
+    else if (grp == 2) p1_exe<true>(a, q.w, ix, iy);
+    else if (grp == 3) p1_exi<true>(a, q.w, ix, iy);
+    else p1_ey<true>(a, q.w, ix, iy);
+  }
+}
 __global__ void __launch_bounds__(128) k_jb_p1a(JArgs A) {
   const int it = blockIdx.x * 128 + threadIdx.x, u = it >> 2, k = it & 3;
   if (u >= A.NU) return;
@@ -761,6 +816,7 @@ int enqueue_residual(const double* dyl, double* dyldot, bool need_rows, const do
   if (need_rows) CK(launch(k_phase3, dim3(G), dim3(B), d_base, d_tmp, dyldot, dyl, d_dtuse, d_ylodt, neq, NXS, NC, d_err, d_hflags, yldot_host));
   return 0;
 }
+int jac_launches() { return (int)h_list.size() >= 4096 ? 8 : 6; }  // kernels of one Jacobian sequence (large / small grids)
 int enqueue_jac(const double* dyl, const double* dy00, int64_t ml, int64_t mu, int64_t nnzmx, double* djac, int64_t* dja, int64_t* dia, bool base_current,
                 double* jac_host = nullptr, int64_t* ja_host = nullptr, int64_t* ia_host = nullptr) {
   if (!base_current) { int rc = enqueue_residual(dyl, nullptr, false); if (rc) return rc; }
@@ -775,18 +831,22 @@ int enqueue_jac(const double* dyl, const double* dy00, int64_t ml, int64_t mu, i
     A.neq = neq; A.ml = ml; A.mu = mu; A.NXS = NXS; A.NC = NC;
     A.coloff = d_coloff; A.colcnt = d_colcnt; A.colrow = d_colrow; A.colval = d_colval; A.rowcnt = d_rowcnt; A.err = d_err + 1;
     const unsigned gs = (unsigned)((NU * 4 + 127) / 128), gi = (unsigned)((g_nitems + 127) / 128);
-    CK(launch(k_jb_stage0, dim3((unsigned)((NU + 31) / 32)), dim3(128), A));
+    const bool big = NU >= 4096;  // more than ~2 waves of blocks per role: throughput-bound
     A.role0 = 0;
     if (getenv("UE_DEBUG_SPLIT_ROLES")) {  // developer aid: one launch per role so that a launch list shows each role's duration
+      CK(launch(k_jb_stage0, dim3((unsigned)((NU + 31) / 32)), dim3(128), A));
       for (int r = 0; r < 3; ++r) { A.role0 = r; CK(launch(k_jb_p1a, dim3(dim3(gs, 1)), dim3(128), A)); }
       for (int r = 0; r < 5; ++r) { A.role0 = r; CK(launch(k_jb_p1b<1>, dim3(dim3(gs, 1)), dim3(128), A)); }
       for (int r = 0; r < 5; ++r) { A.role0 = r; CK(launch(k_jb_p2<1>, dim3(dim3(gi, 1)), dim3(128), A)); }
       A.role0 = 0;
-    } else {
+    } else if (big) {
+      CK(launch(k_jb_stage0, dim3((unsigned)((NU + 31) / 32)), dim3(128), A));
       CK(launch(k_jb_p1a, dim3(dim3(gs, 3)), dim3(128), A));
-      const bool big = NU >= 4096;  // more than ~2 waves of blocks per role: throughput-bound
-      if (big) { CK(launch(k_jb_p1b<6>, dim3(dim3(gs, 5)), dim3(128), A)); CK(launch(k_jb_p2<6>, dim3(dim3(gi, 5)), dim3(128), A)); }
-      else { CK(launch(k_jb_p1b<1>, dim3(dim3(gs, 5)), dim3(128), A)); CK(launch(k_jb_p2<1>, dim3(dim3(gi, 5)), dim3(128), A)); }
+      CK(launch(k_jb_p1b<6>, dim3(dim3(gs, 5)), dim3(128), A));
+      CK(launch(k_jb_p2<6>, dim3(dim3(gi, 5)), dim3(128), A));
+    } else {
+      CK(launch(k_jb_p01, dim3((unsigned)((NU * 4 + P01_ITEMS - 1) / P01_ITEMS)), dim3(5 * P01_ITEMS), A));
+      CK(launch(k_jb_p2<1>, dim3(dim3(gi, 5)), dim3(128), A));
     }
     CK(launch(k_jb_p3c, dim3((unsigned)((NU + 3) / 4)), dim3(128), A));
   }
@@ -857,7 +917,7 @@ int run_jac_dev(const double* dyl, const double* dy00, int64_t ml, int64_t mu, i
                 bool base_current) {
   GKey k; std::memset(&k, 0, sizeof k);
   k.kind = 2; k.p0 = dyl; k.p1 = dy00; k.p2 = djac; k.p3 = dja; k.p4 = dia; k.a = ml; k.b = mu; k.c = nnzmx; k.flag = base_current;
-  g_launches += (base_current ? 0 : 3) + 8;
+  g_launches += (base_current ? 0 : 3) + jac_launches();
   int rc = replay(k, [&]() { return enqueue_jac(dyl, dy00, ml, mu, nnzmx, djac, dja, dia, base_current); });
   if (rc) return rc;
   CK(cudaStreamSynchronize(g_stream));
@@ -1106,7 +1166,7 @@ int ue_gpu_rhs_jac_dev(int64_t n, const double* dyl, double* dyldot00, int64_t m
   if (rc) return rc;
   GKey k; std::memset(&k, 0, sizeof k);
   k.kind = 2; k.p0 = dyl; k.p1 = dyldot00; k.p2 = djac; k.p3 = dja; k.p4 = dia; k.a = ml; k.b = mu; k.c = lim; k.flag = 1;
-  g_launches += 8;
+  g_launches += jac_launches();
   rc = replay(k, [&]() { return enqueue_jac(dyl, dyldot00, ml, mu, lim, djac, dja, dia, true); });
   if (rc) return rc;
   CK(cudaEventRecord(g_ev1, g_stream));
@@ -1163,7 +1223,7 @@ int ue_gpu_rhs_jac(int64_t n, const double* yl, double* yldot00, int64_t ml, int
   GKey k; std::memset(&k, 0, sizeof k);
   k.kind = 5; k.p0 = yl; k.p1 = yldot00; k.p2 = jac; k.p3 = ja; k.p4 = ia; k.a = ml; k.b = mu; k.c = lim;
   k.flag = (yl_dev ? 1 : 0) | (f_dev ? 2 : 0) | (direct ? 4 : 0);
-  g_launches += 12;
+  g_launches += 4 + jac_launches();
   auto body = [&]() {
     if (!yl_dev) CK(cudaMemcpyAsync(d_yl, yl, (neq + 2) * 8, cudaMemcpyHostToDevice, g_stream));
     int r = enqueue_residual(d_yl, d_yldot, true, yl_dev, f_dev);
@@ -1222,7 +1282,7 @@ int ue_gpu_jac_calc(int64_t n, double t, const double* yl, const double* yldot00
   const bool direct = jac_dev && ja_dev && ia_dev;
   k.kind = direct ? 4 : 2; k.p0 = d_yl; k.p1 = dy00; k.p2 = direct ? (void*)jac_dev : (void*)d_jac; k.p3 = direct ? (void*)ja_dev : (void*)d_ja;
   k.p4 = direct ? (void*)ia_dev : (void*)d_ia; k.a = ml; k.b = mu; k.c = lim; k.flag = base_current;
-  g_launches += (base_current ? 0 : 3) + 8;
+  g_launches += (base_current ? 0 : 3) + jac_launches();
   int rc = replay(k, [&]() {
     return direct ? enqueue_jac(d_yl, dy00, ml, mu, lim, d_jac, d_ja, d_ia, base_current, jac_dev, ja_dev, ia_dev)
                   : enqueue_jac(d_yl, dy00, ml, mu, lim, d_jac, d_ja, d_ia, base_current);
