@@ -184,6 +184,77 @@ def test_switch_combinations(built, seed):
         lib.set_real("nufak", 0.0)
 
 
+_FUZZ_SKIP = {"ev", "qe", "me", "mp", "pi", "cutlo", "rt8opi", "difni2", "difpr2", "difax", "dif4order", "kye4order", "kyi4order", "l_parloss",
+              "dtreal", "nufak", "delpert", "dylconst", "jaccliplim", "istgcon", "isoldalbarea", "sygytotc", "zi", "lgmax", "cne_sgvi",
+              "lmfplim", "lxtimax", "lxtemax", "flalfipl", "flalfepl", "flalftf", "cfnus_i", "cfnus_e", "temp0", "n0", "n0g", "nnorm",
+              "ennorm", "fnorm", "vpnorm", "tbmin", "recycm", "engbsr", "ebind", "cfnetap", "fracvgpgp", "fnnuiz"}
+_FUZZ_ZERO_OK = ["vcony", "sigvi_floor", "fnuizx", "alfkxi", "alfkxe", "alfeqp", "nlimix", "nlimiy", "cmneut", "upcore", "tdiflim", "cngmom",
+                 "cmwall", "cngtgx", "cngtgy", "kxn", "kyn", "alftng", "ccoldsor", "kyet", "kyit"]
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_coefficient_fuzz(built, seed):
+    """Every real coefficient that crosses the ABI is an ordinary multiplier on both sides: scale ~60 of the non-zero ones
+    by random factors and give a few zero-default ones small values; residual and Jacobian stay bit-identical.  Catches
+    a term that one side evaluates and the other skips or hard-codes."""
+    rng = np.random.default_rng(7000 + seed)
+    c, yl = make_case("d3dHsm", perturb=2e-3, seed=50 + seed)
+    s = c.static_inputs()
+    names = [k for k, v in s["reals"].items() if k not in _FUZZ_SKIP and v != 0.0 and abs(v) < 1e15]
+    for k in rng.choice(names, size=min(60, len(names)), replace=False):
+        s["reals"][k] = float(s["reals"][k]) * float(rng.uniform(0.8, 1.25))
+    for k in rng.choice(_FUZZ_ZERO_OK, size=6, replace=False):
+        if s["reals"][k] == 0.0:
+            s["reals"][k] = float(rng.uniform(0.05, 0.3))
+    gpu, ora = load_gpu(), oracle()
+    for lib in (gpu, ora):
+        lib.load_static(s)
+        lib.init()
+    n = c.bbb.neq
+    fg, fo = gpu.pandf1(yl), ora.pandf1(yl)
+    assert np.isfinite(fo).all()
+    assert np.array_equal(fg, fo), "%d residual entries differ" % (fg != fo).sum()
+    y, su = psetnk_inputs(c, yl)
+    for lib in (gpu, ora):
+        lib.step_params(np.full(n, 1e20), y[:n], su, np.ones(n))
+    f1, f2 = gpu.pandf1(y), ora.pandf1(y)
+    jg = gpu.jac_calc(y, f1, c.bbb.lbw, c.bbb.ubw, c.bbb.nnzmx)
+    jo = ora.jac_calc(y, f2, c.bbb.lbw, c.bbb.ubw, c.bbb.nnzmx)
+    assert all(np.array_equal(p, q) for p, q in zip(jg, jo))
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_array_input_fuzz(built, seed):
+    """Random per-element factors (+-10 %) on every geometry plane and on the 1-D coefficient arrays: physically
+    inconsistent, but both sides must consume exactly the same numbers in the same way, and the dependency pruning of
+    the Jacobian must not rely on any symmetry of the mesh."""
+    rng = np.random.default_rng(9000 + seed)
+    c, yl = make_case("d3dHsm", perturb=2e-3, seed=80 + seed)
+    s = c.static_inputs()
+    for k in s["planes"]:
+        a = np.array(s["planes"][k], dtype=np.float64)
+        s["planes"][k] = a * rng.uniform(0.9, 1.1, a.shape)
+    for k in ("fgtdx", "fgtdy", "flalfea", "flalfia", "flalfva", "flalfgxa", "flalfgxya", "flalfgya", "tewalli", "tiwalli", "tewallo", "tiwallo",
+              "alblb", "albrb", "albedoi", "albedoo"):
+        a = np.array(s["lines"][k], dtype=np.float64)
+        s["lines"][k] = np.minimum(a * rng.uniform(0.9, 1.1, a.shape), np.where(a <= 1.0, 1.0, np.inf))
+    gpu, ora = load_gpu(), oracle()
+    for lib in (gpu, ora):
+        lib.load_static(s)
+        lib.init()
+    n = c.bbb.neq
+    fg, fo = gpu.pandf1(yl), ora.pandf1(yl)
+    assert np.isfinite(fo).all()
+    assert np.array_equal(fg, fo), "%d residual entries differ" % (fg != fo).sum()
+    y, su = psetnk_inputs(c, yl)
+    for lib in (gpu, ora):
+        lib.step_params(np.full(n, 1e20), y[:n], su, np.ones(n))
+    f1, f2 = gpu.pandf1(y), ora.pandf1(y)
+    jg = gpu.jac_calc(y, f1, c.bbb.lbw, c.bbb.ubw, c.bbb.nnzmx)
+    jo = ora.jac_calc(y, f2, c.bbb.lbw, c.bbb.ubw, c.bbb.nnzmx)
+    assert all(np.array_equal(p, q) for p, q in zip(jg, jo))
+
+
 def test_newton_on_gpu_recovers_reference_steady_state(built):
     """Newton driven entirely by the CUDA residual and Jacobian returns to the reference's converged state."""
     c, yref = make_case("d3dHsm")

@@ -167,6 +167,15 @@ def test_unsupported_switch_is_refused(built):
         ora.init()
 
 
+def test_history_dependent_rate_blending_is_refused(built):
+    """fnnuiz < 1 makes the reference's Jacobian depend on the order of the perturbations (oderhs.m:1950-1961)."""
+    c, yl = make_case("d3dHsm", overrides={"bbb.fnnuiz": 0.9})
+    ora = oracle()
+    ora.load_static(c.static_inputs())
+    with pytest.raises(Exception, match="fnnuiz must be 1"):
+        ora.init()
+
+
 @pytest.mark.parametrize("name", ["cfybf", "cfydd", "facbee", "iszeffcon", "nlimgx"])
 def test_coefficient_outside_the_built_path_is_refused(built, name):
     """Coefficients that switch on terms the built path does not evaluate (drifts, Bohm-like diffusion, ...) cross the

@@ -637,6 +637,9 @@ int check_switches() {
   if (P.isupcore != 0 && P.isupcore != 1) { g_err = "isupcore must be 0 or 1"; return -5; }
   if (P.iflcore != 0 && P.iflcore != 1) { g_err = "iflcore must be 0 or 1"; return -5; }
   if (P.istabon != 0 && P.istabon != 10) { g_err = "istabon must be 0 or 10"; return -5; }
+  // fnnuiz < 1 blends the new ionisation rate with the value left by the PREVIOUS pandf call (oderhs.m:1950-1961): the
+  // reference's Jacobian then depends on the order in which the unknowns were perturbed; not reproducible in parallel
+  if (P.fnnuiz != 1.) { g_err = "fnnuiz must be 1 (history-dependent rate blending is outside the built hot path)"; return -5; }
   if (P.difpr2 != 0 || P.difni2 != 0 || P.difax != 0 || P.dif4order != 0 || P.kye4order != 0 || P.kyi4order != 0) { g_err = "difpr2/difni2/difax/4th-order terms not built"; return -5; }
   if (P.l_parloss <= 1e9) { g_err = "l_parloss<=1e9 (nuvl) not built"; return -5; }
   if (P.yinc >= 6 || P.xrinc >= 20) { g_err = "yinc>=6 / xrinc>=20 windows not built"; return -5; }
