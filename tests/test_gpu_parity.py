@@ -255,6 +255,54 @@ def test_array_input_fuzz(built, seed):
     assert all(np.array_equal(p, q) for p, q in zip(jg, jo))
 
 
+_INT_CHOICES = {
+    "methn": [22, 23, 32, 33], "methu": [22, 23, 32, 33], "methe": [22, 23, 32, 33], "methi": [22, 23, 32, 33], "methg": [22, 23, 32, 33],
+    "isjaccorall": [0, 1], "isbcwdt": [0, 1], "icnuiz": [0, 1, 2], "icnucx": [0, 1, 2], "isrecmon": [0, 1], "ingb": [1, 2, 3], "inflbg": [2, 4],
+    "isgasdc": [0, 1], "isdifxg_aug": [0, 1], "isdifyg_aug": [0, 1], "isvylog": [0, 1], "isgxvon": [0, 1], "convis": [0, 1], "concap": [0, 1],
+    "isflxlde": [0, 1], "isflxldi": [0, 1, 2], "isplflxl": [0, 1], "inkxc": [1, 2, 3], "ishavisy": [0, 1], "isvhyha": [0, 1],
+    "islnlamcon": [0, 1], "iteb": [1, 2], "ifxnsgi": [0, 1], "isnicore": [0, 1], "isupcore": [0, 1], "iflcore": [0, 1], "ifluxni": [0, 1],
+    "isupss": [-1, 0, 1], "isextrnp": [0, 1], "isbohmcalc": [0, 1], "newbcl": [0, 1], "newbcr": [0, 1], "xlinc": [2, 3], "xrinc": [1, 2],
+    "yinc": [2, 3],
+}
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_integer_switch_fuzz(built, seed):
+    """Random values (from each switch's valid set) for a dozen integer switches at a time."""
+    rng = np.random.default_rng(11000 + seed)
+    c, yl = make_case("d3dHsm", perturb=2e-3, seed=120 + seed)
+    s = c.static_inputs()
+    picked = {}
+    for k in rng.choice(sorted(_INT_CHOICES), size=12, replace=False):
+        picked[str(k)] = int(rng.choice(_INT_CHOICES[str(k)]))
+        s["ints"][str(k)] = picked[str(k)]
+    if s["ints"]["iflcore"] == 1:
+        s["reals"]["pcoree"] = s["reals"]["pcorei"] = 4.0e5
+    gpu, ora = load_gpu(), oracle()
+    try:
+        for lib in (gpu, ora):
+            lib.load_static(s)
+            lib.init()
+    except Exception as e:  # a combination both sides refuse is fine; they must refuse alike
+        with pytest.raises(Exception):
+            ora.load_static(s); ora.init()
+        with pytest.raises(Exception):
+            gpu.load_static(s); gpu.init()
+        return
+    n = c.bbb.neq
+    fg, fo = gpu.pandf1(yl), ora.pandf1(yl)
+    if not np.isfinite(fo).all():
+        pytest.skip("non-physical combination: %s" % picked)
+    assert np.array_equal(fg, fo), "%s: %d residual entries differ" % (picked, (fg != fo).sum())
+    y, su = psetnk_inputs(c, yl)
+    for lib in (gpu, ora):
+        lib.step_params(np.full(n, 1e20), y[:n], su, np.ones(n))
+    f1, f2 = gpu.pandf1(y), ora.pandf1(y)
+    jg = gpu.jac_calc(y, f1, c.bbb.lbw, c.bbb.ubw, c.bbb.nnzmx)
+    jo = ora.jac_calc(y, f2, c.bbb.lbw, c.bbb.ubw, c.bbb.nnzmx)
+    assert all(np.array_equal(p, q) for p, q in zip(jg, jo)), picked
+
+
 def test_newton_on_gpu_recovers_reference_steady_state(built):
     """Newton driven entirely by the CUDA residual and Jacobian returns to the reference's converged state."""
     c, yref = make_case("d3dHsm")
