@@ -303,6 +303,29 @@ def test_integer_switch_fuzz(built, seed):
     assert all(np.array_equal(p, q) for p, q in zip(jg, jo)), picked
 
 
+@pytest.mark.parametrize("name,seed", [("d3dHsm", 0), ("d3dHsm", 1), ("d3dHsm", 2), ("d3dHsm", 3), ("case2", 4), ("d3dHsm2x", 5)])
+def test_rough_states(built, name, seed):
+    """States far from any equilibrium: densities and temperatures scaled cell by cell by factors in [0.3, 3], gas by
+    [0.1, 10], velocities by [-2, 2] (flow reversals).  Exercises the upwind switches, flux limiters and floors on both
+    sides of every branch; residual and Jacobian stay bit-identical."""
+    rng = np.random.default_rng(13000 + seed)
+    c, yl = make_case(name)
+    gpu, ora = bind(load_gpu(), c), bind(oracle(), c)
+    n = c.bbb.neq
+    y = yl.copy()
+    Y = y[:n].reshape(-1, 5)
+    Y[:, 0] *= np.exp(rng.uniform(np.log(0.3), np.log(3.0), len(Y)))
+    Y[:, 1] *= rng.uniform(-2.0, 2.0, len(Y))
+    Y[:, 2] *= np.exp(rng.uniform(np.log(0.3), np.log(3.0), len(Y)))
+    Y[:, 3] *= np.exp(rng.uniform(np.log(0.3), np.log(3.0), len(Y)))
+    Y[:, 4] *= np.exp(rng.uniform(np.log(0.1), np.log(10.0), len(Y)))
+    fg, fo = gpu.pandf1(y), ora.pandf1(y)
+    assert np.isfinite(fo).all()
+    assert np.array_equal(fg, fo), "%d residual entries differ" % (fg != fo).sum()
+    jg, jo, noise = _jac_pair(c, y, gpu, ora)
+    assert all(np.array_equal(p, q) for p, q in zip(jg, jo))
+
+
 def test_newton_on_gpu_recovers_reference_steady_state(built):
     """Newton driven entirely by the CUDA residual and Jacobian returns to the reference's converged state."""
     c, yref = make_case("d3dHsm")
