@@ -49,6 +49,7 @@ UeParams& P = S.p;
 std::string g_err;
 int nx, ny, NXS, NC;
 int64_t neq;
+bool HASG = true;  // isngon = 1: the atom density is an unknown; isngon = 0: frozen field `ngfix`, numvar = 4
 
 typedef std::vector<double> V;
 
@@ -141,12 +142,58 @@ double table_val(const V& w, double tev_j, double dens) {
   double r2 = r21 + fjd * (r22 - r21);
   return ue_exp(r1 + fje * (r2 - r1));
 }
+// istabon = 7 (the package default, com/com.v:322): R.B. Campbell's polynomial fits in x = log10(ne), y = log10(Te[eV])
+double sionf(double temp, double den) {  // aph/aphrates.m:1133-1176
+  auto ain = [](double x) { return -49.05905 + 2.51313783 * x - 0.049159714 * x * x; };
+  auto bin = [](double x) { return 41.1855162 - 2.3298672 * x + 4.24769144e-2 * x * x; };
+  auto cin = [](double x) { return -32.798921 + 1.72102919 * x - 0.038692357 * x * x; };
+  auto din = [](double x) { return 27.370466 - 1.6824361 * x + 0.0462317894 * x * x; };
+  auto ein = [](double x) { return -7.9990454 + 0.127573157 * x - 6.3586911e-3 * x * x; };
+  auto gin = [](double x) { return -4.5832951 + 0.776264783 * x - 1.8866089e-2 * x * x; };
+  auto hin = [](double x) { return 3.08056833 - 0.39114789 * x + 9.86833304e-3 * x * x; };
+  auto riin = [](double x) { return -0.4648639 + 0.0551428018 * x - 1.404213e-3 * x * x; };
+  double x = std::min(22.e0, ue_log10(den)), y = ue_log10(temp);
+  return ue_pow(10., ain(x) + bin(x) * y + cin(x) * y * y + din(x) * y * y * y + ein(x) * y * y * y * y + gin(x) * y * y * y * y * y +
+                         hin(x) * y * y * y * y * y * y + riin(x) * y * y * y * y * y * y * y);
+}
+double srecf(double temp, double den) {  // aph/aphrates.m:1180-1226
+  auto ar = [](double x) { return -0.4575652 - 2.144012 * x + 6.7072142e-2 * x * x - 1.391667e-4 * x * x * x; };
+  auto br = [](double x) { return -121.8401 + 18.001822 * x - 0.8679488 * x * x + 1.33165e-2 * x * x * x; };
+  auto cr = [](double x) { return 80.897256 - 13.29602 * x + 0.71881414 * x * x - 0.0126549 * x * x * x; };
+  auto dr = [](double x) { return 56.406823 - 7.301996 * x + 0.29339793 * x * x - 3.50898e-3 * x * x * x; };
+  auto er = [](double x) { return -55.73559 + 7.9634283 * x - 0.370274 * x * x + 5.567961e-3 * x * x * x; };
+  auto gr = [](double x) { return 10.866692 - 1.584193 * x + 0.07563791 * x * x - 1.177562e-3 * x * x * x; };
+  double x = std::min(22.e0, ue_log10(den)), y = ue_log10(temp);
+  return ue_pow(10., ar(x) + br(x) * y + cr(x) * y * y + dr(x) * y * y * y + er(x) * y * y * y * y + gr(x) * y * y * y * y * y);
+}
+double svradp(double temp, double den) {  // aph/aphrates.m:1230-1300
+  auto ai = [](double x) { return -275.845 + 37.010817 * x - 1.788045 * x * x + 0.029078333 * x * x * x; };
+  auto bi = [](double x) { return 2200.9478 - 326.1153 * x + 16.148655 * x * x - 0.2660702 * x * x * x; };
+  auto ci = [](double x) { return -2.935221e3 + 4.3757698e2 * x - 21.73964 * x * x + 0.358962 * x * x * x; };
+  auto di = [](double x) { return 1604.1466 - 239.6959 * x + 11.923707 * x * x - 0.1970501 * x * x * x; };
+  auto ei = [](double x) { return -390.8635 + 58.474495 * x - 2.910997 * x * x + 0.048133829 * x * x * x; };
+  auto gi = [](double x) { return 35.012574 - 5.24202 * x + 0.26109962 * x * x - 4.319238e-3 * x * x * x; };
+  auto ae = [](double x) { return 2860.4173 - 610.2452 * x + 48.275821 * x * x - 1.687994 * x * x * x + 0.02201375 * x * x * x * x; };
+  auto be = [](double x) { return 10612.067 - 2046.397 * x + 147.73914 * x * x - 4.729973 * x * x * x + 0.056671796 * x * x * x * x; };
+  auto ce = [](double x) { return -4.231708e4 + 8494.6102 * x - 639.0226 * x * x + 21.350311 * x * x * x - 0.2673466 * x * x * x * x; };
+  auto de = [](double x) { return -8.385144e3 + 1887.6244 * x - 157.8502 * x * x + 5.820501 * x * x * x - 0.07992837 * x * x * x * x; };
+  auto ee = [](double x) { return 3.938282e4 - 8.131339e3 * x + 628.8119 * x * x - 21.58636 * x * x * x + 0.27756029 * x * x * x * x; };
+  auto ge = [](double x) { return -1.038281e4 + 2.1349333e3 * x - 164.4201 * x * x + 5.6210487 * x * x * x - 0.07197622 * x * x * x * x; };
+  auto sionfl = [&](double x, double y) { return ue_pow(10., ai(x) + bi(x) * y + ci(x) * y * y + di(x) * y * y * y + ei(x) * y * y * y * y + gi(x) * y * y * y * y * y); };
+  auto etai = [&](double x, double y) {
+    return (ue_pow(10., ae(x) + be(x) * y + ce(x) * y * y + de(x) * y * y * y + ee(x) * y * y * y * y + ge(x) * y * y * y * y * y)) / sionfl(x, y);
+  };
+  double x = std::min(22.e0, ue_log10(den)), y = ue_log10(temp);
+  return std::max(0.e0, (13.6e0 + etai(x, std::min(2.e0, y)))) * 1.602e-19 * sionfl(x, y);  // etai frozen above 100 eV
+}
 double rsa(double tej, double dens) {  // aph/aphrates.m:872-1131
   if (P.istabon == 0) { double a = tej / (10 * P.ev); return 3.0e-14 * a * a / (3.0 + a * a); }
+  if (P.istabon == 7) return sionf(tej / P.ev, dens);  // :1033-1036
   return table_val(wsveh, tej, dens);
 }
 double rra(double tej, double dens) {  // aph/aphrates.m:617-870
   if (P.istabon == 0) return 0.;
+  if (P.istabon == 7) return srecf(tej / P.ev, dens);  // :775-778
   return table_val(wsveh0, tej, dens);
 }
 double rcx(double t0) {  // aph/aphrates.m:395-399 (analytic for istabon 0 and >3)
@@ -159,10 +206,11 @@ double rqa0(double tej) {  // aph/aphrates.m:444-447
 }
 double erl1(double tej, double dens) {  // aph/aphrates.m:2-147
   if (P.istabon == 0) return (rqa0(tej) - 13.6 * P.ev * rsa(tej, dens)) * dens;
+  if (P.istabon == 7) return (svradp(tej / P.ev, dens) - 13.6 * P.ev * rsa(tej, dens)) * dens;  // rqa: :601-606
   return table_val(welms1, tej, dens);
 }
 double erl2(double tej, double dens) {  // aph/aphrates.m:149-294
-  if (P.istabon == 0) return (13.6 * P.ev + 1.5 * tej) * dens * rra(tej, dens);
+  if (P.istabon == 0 || P.istabon == 7) return (13.6 * P.ev + 1.5 * tej) * dens * rra(tej, dens);
   return table_val(welms2, tej, dens);
 }
 
@@ -237,8 +285,10 @@ int convsr_vo(int ixl, int iyl, const double* yl) {
       double ntemp = P.nnorm;  // isflxvar == 0
       A(te, ix, iy) = yl[IDXTE(ix, iy)] * P.ennorm / (1.5 * ntemp);
       A(te, ix, iy) = std::max(A(te, ix, iy), P.temin * P.ev);
-      A(ng, ix, iy) = yl[IDXG(ix, iy)] * P.n0g;
-      if (A(ng, ix, iy) < 0) inegng = 1;
+      if (HASG) {  // convert.m:285
+        A(ng, ix, iy) = yl[IDXG(ix, iy)] * P.n0g;
+        if (A(ng, ix, iy) < 0) inegng = 1;
+      }
       A(ti, ix, iy) = yl[IDXTI(ix, iy)] * P.ennorm / (1.5 * ntemp);
       A(ti, ix, iy) = std::max(A(ti, ix, iy), P.temin * P.ev);
     }
@@ -472,7 +522,7 @@ int bouncon(const Win& w, const double* yl, double* yldot) {
       }
     }
     // corners, boundary.m:290-303
-    yldot[IDXN(ixlb, 0)] = P.nurlxn * (ave(A(ni, ixlb, 1), A(ni, ixlb + 1, 0)) - A(ni, ixlb, 0)) / P.n0;
+    if (P.isfixlb != 2) yldot[IDXN(ixlb, 0)] = P.nurlxn * (ave(A(ni, ixlb, 1), A(ni, ixlb + 1, 0)) - A(ni, ixlb, 0)) / P.n0;
     yldot[IDXN(ixrb + 1, 0)] = P.nurlxn * (ave(A(ni, ixrb + 1, 1), A(ni, ixrb, 0)) - A(ni, ixrb + 1, 0)) / P.n0;
     for (int ix = w.i4; ix <= w.i8; ++ix) {  // parallel velocity, boundary.m:308-383
       int64_t iv2 = IDXU(ix, 0);
@@ -510,7 +560,7 @@ int bouncon(const Win& w, const double* yl, double* yldot) {
         else yldot[iv2] = P.nurlxi * (P.tiwalli[ix] * ev - A(ti, ix, 0)) / (P.temp0 * ev);
       }
     }
-    for (int ix = w.i4; ix <= w.i8; ++ix) {  // neutral density, boundary.m:632-767
+    for (int ix = w.i4; ix <= w.i8 && HASG; ++ix) {  // neutral density, boundary.m:632-767
       int64_t iv = IDXG(ix, 0);
       double t0 = std::max(P.cdifg * A(tg, ix, 0), P.tgmin * ev);
       double vyn = 0.25 * std::sqrt(8 * t0 / (pi * P.mg));
@@ -528,14 +578,14 @@ int bouncon(const Win& w, const double* yl, double* yldot) {
       yldot[IDXU(ixlb, 0)] = -P.nurlxu * (A(up, ixlb, 0) - 0.5 * (A(up, ixlb, 1) + A(up, ixlb + 1, 0))) / P.vpnorm;
       yldot[IDXTE(ixlb, 0)] = P.nurlxe * (0.5 * (A(te, ixlb + 1, 0) + A(te, ixlb, 1)) - A(te, ixlb, 0)) / (P.temp0 * ev);
       yldot[IDXTI(ixlb, 0)] = P.nurlxi * (0.5 * (A(ti, ixlb + 1, 0) + A(ti, ixlb, 1)) - A(ti, ixlb, 0)) / (P.temp0 * ev);
-      yldot[IDXG(ixlb, 0)] = P.nurlxg * (A(ng, ixlb + 1, 0) - A(ng, ixlb, 0)) / P.n0g;
+      if (HASG) yldot[IDXG(ixlb, 0)] = P.nurlxg * (A(ng, ixlb + 1, 0) - A(ng, ixlb, 0)) / P.n0g;
     }
     if (w.xcnearrb || w.openbox) {  // boundary.m:939-983
       yldot[IDXU(ixrb, 0)] = -P.nurlxu * (A(up, ixrb, 0) - 0.5 * (A(up, ixrb - 1, 0) + A(up, ixrb, 1))) / P.vpnorm;
       yldot[IDXU(ixrb + 1, 0)] = -P.nurlxu * (A(up, ixrb + 1, 0) - A(up, ixrb, 0)) / P.vpnorm;
       yldot[IDXTE(ixrb + 1, 0)] = P.nurlxe * (0.5 * (A(te, ixrb + 1, 1) + A(te, ixrb, 0)) - A(te, ixrb + 1, 0)) / (P.temp0 * ev);
       yldot[IDXTI(ixrb + 1, 0)] = P.nurlxi * (0.5 * (A(ti, ixrb + 1, 1) + A(ti, ixrb, 0)) - A(ti, ixrb + 1, 0)) / (P.temp0 * ev);
-      yldot[IDXG(ixrb + 1, 0)] = P.nurlxg * (A(ng, ixrb, 0) - A(ng, ixrb + 1, 0)) / P.n0g;
+      if (HASG) yldot[IDXG(ixrb + 1, 0)] = P.nurlxg * (A(ng, ixrb, 0) - A(ng, ixrb + 1, 0)) / P.n0g;
     }
   }
   // ===== iy = ny+1 boundary (boundary.m:1125-1653) =====
@@ -559,7 +609,7 @@ int bouncon(const Win& w, const double* yl, double* yldot) {
       if (P.istiwcix[ix] == 0) yldot[iv2] = P.nurlxi * (A(feiy, ix, ny) / (P.n0 * P.vpnorm * G(sy, ix, ny))) / (P.temp0 * ev);
       else yldot[iv2] = P.nurlxi * (P.tiwallo[ix] * ev - A(ti, ix, ny + 1)) / (P.temp0 * ev);
     }
-    for (int ix = w.i4; ix <= w.i8; ++ix) {  // boundary.m:1366-1462
+    for (int ix = w.i4; ix <= w.i8 && HASG; ++ix) {  // boundary.m:1366-1462
       int64_t iv = IDXG(ix, ny + 1);
       double t0 = std::max(P.cdifg * A(tg, ix, ny + 1), P.tgmin * ev);
       double vyn = 0.25 * std::sqrt(8 * t0 / (pi * P.mg));
@@ -572,18 +622,30 @@ int bouncon(const Win& w, const double* yl, double* yldot) {
       yldot[IDXU(ixlb, ny + 1)] = -P.nurlxu * (A(up, ixlb, ny + 1) - 0.5 * (A(up, ixlb, ny) + A(up, ixlb + 1, ny + 1))) / P.vpnorm;
       yldot[IDXTE(ixlb, ny + 1)] = P.nurlxe * (0.5 * (A(te, ixlb + 1, ny + 1) + A(te, ixlb, ny)) - A(te, ixlb, ny + 1)) / (P.temp0 * ev);
       yldot[IDXTI(ixlb, ny + 1)] = P.nurlxi * (0.5 * (A(ti, ixlb + 1, ny + 1) + A(ti, ixlb, ny)) - A(ti, ixlb, ny + 1)) / (P.temp0 * ev);
-      yldot[IDXG(ixlb, ny + 1)] = P.nurlxg * (A(ng, ixlb + 1, ny + 1) - A(ng, ixlb, ny + 1)) / P.n0g;
+      if (HASG) yldot[IDXG(ixlb, ny + 1)] = P.nurlxg * (A(ng, ixlb + 1, ny + 1) - A(ng, ixlb, ny + 1)) / P.n0g;
     }
     if (w.xcnearrb || w.openbox) {  // boundary.m:1585-1630
       yldot[IDXU(ixrb, ny + 1)] = -P.nurlxu * (A(up, ixrb, ny + 1) - 0.5 * (A(up, ixrb - 1, ny + 1) + A(up, ixrb, ny))) / P.vpnorm;
       yldot[IDXU(ixrb + 1, ny + 1)] = -P.nurlxu * (A(up, ixrb + 1, ny + 1) - A(up, ixrb, ny + 1)) / P.vpnorm;
       yldot[IDXTE(ixrb + 1, ny + 1)] = P.nurlxe * (0.5 * (A(te, ixrb, ny + 1) + A(te, ixrb + 1, ny)) - A(te, ixrb + 1, ny + 1)) / (P.temp0 * ev);
       yldot[IDXTI(ixrb + 1, ny + 1)] = P.nurlxi * (0.5 * (A(ti, ixrb, ny + 1) + A(ti, ixrb + 1, ny)) - A(ti, ixrb + 1, ny + 1)) / (P.temp0 * ev);
-      yldot[IDXG(ixrb + 1, ny + 1)] = P.nurlxg * (A(ng, ixrb, ny + 1) - A(ng, ixrb + 1, ny + 1)) / P.n0g;
+      if (HASG) yldot[IDXG(ixrb + 1, ny + 1)] = P.nurlxg * (A(ng, ixrb, ny + 1) - A(ng, ixrb + 1, ny + 1)) / P.n0g;
     }
   }
-  // ===== left plate, ix = ixlb (boundary.m:1655-2318), isfixlb = 0 =====
-  if (w.xcnearlb || w.openbox) {
+  // ===== ix = 0 as a symmetry plane, isfixlb = 2 (boundary.m:1666-1770; rlimiter beyond the mesh) =====
+  if (w.i3 <= 0 && P.isfixlb == 2)
+    for (int iy = w.j2; iy <= w.j5; ++iy) {
+      yldot[IDXN(0, iy)] = P.nurlxn * (1 / P.n0) * (A(ni, 1, iy) - A(ni, 0, iy));
+      yldot[IDXU(0, iy)] = P.nurlxu * (0. - A(up, 0, iy)) / P.vpnorm;
+      yldot[IDXTE(0, iy)] = P.nurlxe * A(ne, 0, iy) * (A(te, 1, iy) - A(te, 0, iy)) / P.ennorm;
+      yldot[IDXTI(0, iy)] = P.nurlxi * A(ne, 0, iy) * (A(ti, 1, iy) - A(ti, 0, iy)) / P.ennorm;
+      if (HASG) yldot[IDXG(0, iy)] = P.nurlxg * (A(ng, 1, iy) - A(ng, 0, iy)) / P.n0g;
+    }
+  // velocity forced to zero on the cut of a half-space problem (boundary.m:1772-1785)
+  if (P.isfixlb == 2 && w.i2 <= P.ixpt2 && w.i5 >= P.ixpt2 && w.j2 <= P.iysptrx2)
+    for (int iy = 0; iy <= P.iysptrx2; ++iy) yldot[IDXU((int)P.ixpt2, iy)] = P.nurlxu * (0. - A(up, (int)P.ixpt2, iy)) / P.vpnorm;
+  // ===== left plate, ix = ixlb (boundary.m:1787-2318), isfixlb = 0 =====
+  if ((w.xcnearlb || w.openbox) && P.isfixlb == 0) {
     const int ixt = ixlb;
     if (w.i3 <= ixlb + P.isextrnp)  // boundary.m:1796-1845 (isextrnp = 0)
       for (int iy = w.j2; iy <= w.j5; ++iy) {
@@ -626,7 +688,7 @@ int bouncon(const Win& w, const double* yl, double* yldot) {
                                                P.cftiexclg * (-P.cmneut * A(fnix, ixt, iy) * P.recycp * P.cmntgpl * (A(ti, ixt, iy) - P.eidisspl * ev))) /
                                   (P.vpnorm * P.ennorm * G(sx, ixt, iy));
         }
-        {  // neutral density, boundary.m:2075-2115
+        if (HASG) {  // neutral density, boundary.m:2075-2115
           int64_t iv = IDXG(ixt, iy);
           double recy = P.recylb[iy];
           if (recy > 0.) {
@@ -690,7 +752,7 @@ int bouncon(const Win& w, const double* yl, double* yldot) {
                                               P.cftiexclg * (-P.cmneut * A(fnix, ixt1, iy) * P.recycp * P.cmntgpl * (A(ti, ixt, iy) - P.eidisspl * ev))) /
                                   (P.vpnorm * P.ennorm * G(sx, ixt1, iy));
         }
-        {  // boundary.m:2759-2799
+        if (HASG) {  // boundary.m:2759-2799
           int64_t ivg = IDXG(ixt, iy);
           double recy = P.recyrb[iy];
           if (recy > 0.) {
@@ -854,6 +916,16 @@ int pandf(int xc, int yc, const double* yl, double* yldot) {
     }
 
   neudifpg(w);  // oderhs.m:2428
+
+  // half-space problem: no flux and no gradients through the cut (oderhs.m:2447-2466)
+  if (P.isfixlb == 2) {
+    const int ix = (int)P.ixpt2;
+    if (ix >= i2 && ix <= i5 + 1 && P.iysptrx1 > 0)
+      for (int iy = 0; iy <= P.iysptrx1; ++iy) {
+        A(gpex, ix, iy) = 0.; A(frice, ix, iy) = 0.; A(ex, ix, iy) = 0.; A(upe, ix, iy) = 0.;
+        A(gpix, ix, iy) = 0.; A(frici, ix, iy) = 0.; A(uu, ix, iy) = 0.; A(upi, ix, iy) = 0.;
+      }
+  }
 
   // electron / ion pressure-work and momentum sources (oderhs.m:2471-2579)
   for (int iy = j2; iy <= j5; ++iy)
@@ -1253,7 +1325,7 @@ int pandf(int xc, int yc, const double* yl, double* yldot) {
       if (ix == ixrb) yldot[iv] = A(resmo, ix, iy) / (G(volv, ix, iy) * P.fnorm);
       iv = IDXTE(ix, iy); yldot[iv] = (1 - P.iseqalg[iv]) * A(resee, ix, iy) / (G(vol, ix, iy) * P.ennorm);
       iv = IDXTI(ix, iy); yldot[iv] = (1 - P.iseqalg[iv]) * A(resei, ix, iy) / (G(vol, ix, iy) * P.ennorm);
-      iv = IDXG(ix, iy); yldot[iv] = (1 - P.iseqalg[iv]) * A(resng, ix, iy) / (G(vol, ix, iy) * P.n0g);
+      if (HASG) { iv = IDXG(ix, iy); yldot[iv] = (1 - P.iseqalg[iv]) * A(resng, ix, iy) / (G(vol, ix, iy) * P.n0g); }
     }
   rc = bouncon(w, yl, yldot);  // oderhs.m:5009
   if (rc) return rc;
@@ -1274,7 +1346,7 @@ void rscalf(const Win& w, const double* yl, double* yldot) {
       int64_t iv = IDXN(ix, iy);
       nbidot = nbidot + yldot[iv] * P.n0;
       nbedot = nbedot + P.zi * yldot[iv] * P.n0;
-      double nbg2dot = yldot[IDXG(ix, iy)] * P.n0g;
+      double nbg2dot = HASG ? yldot[IDXG(ix, iy)] * P.n0g : 0.;  // oderhs.m:8118
       int ix1 = IXP1(ix, iy);
       int64_t iv2 = IDXU(ix, iy);
       if (P.iseqalg[iv2] == 0) {
@@ -1309,7 +1381,7 @@ int pandf1(int xc, int yc, const double* yl, double* yldot) {
         if (ix != nx + 2 * P.isbcwdt) { iv = IDXU(ix, iy); yldot[iv] = (1. - 0.) * yldot[iv]; yldot[iv] = yldot[iv] - (yl[iv] - ylodt[iv]) / dtuse[iv]; }
         iv = IDXTE(ix, iy); yldot[iv] = (1. - 0.) * yldot[iv]; yldot[iv] = yldot[iv] - (yl[iv] - ylodt[iv]) / dtuse[iv];
         iv = IDXTI(ix, iy); yldot[iv] = (1. - 0.) * yldot[iv]; yldot[iv] = yldot[iv] - (yl[iv] - ylodt[iv]) / dtuse[iv];
-        iv = IDXG(ix, iy); yldot[iv] = (1. - 0.) * yldot[iv]; yldot[iv] = yldot[iv] - (yl[iv] - ylodt[iv]) / dtuse[iv];
+        if (HASG) { iv = IDXG(ix, iy); yldot[iv] = (1. - 0.) * yldot[iv]; yldot[iv] = yldot[iv] - (yl[iv] - ylodt[iv]) / dtuse[iv]; }
       }
   }
   return 0;
@@ -1337,22 +1409,24 @@ void csrcsc(int64_t n, const double* a, const int64_t* ja, const int64_t* ia, do
 int check_switches() {
   { const std::string z = S.nonzero_frozen(); if (!z.empty()) { g_err = "input " + z + " must be 0: the term it switches on is outside the built hot path"; return -5; } }
   struct { const char* n; int64_t v, want; } eq[] = {
-      {"nisp", P.nisp, 1}, {"nusp", P.nusp, 1}, {"ngsp", P.ngsp, 1}, {"numvar", P.numvar, 5}, {"isnonog", P.isnonog, 0}, {"isphion", P.isphion, 0},
-      {"isphiofft", P.isphiofft, 0}, {"isimpon", P.isimpon, 0}, {"isupgon", P.isupgon, 0}, {"isngon", P.isngon, 1}, {"istgon", P.istgon, 0},
+      {"nisp", P.nisp, 1}, {"nusp", P.nusp, 1}, {"ngsp", P.ngsp, 1}, {"numvar", P.numvar, 4 + (P.isngon == 1)}, {"isnonog", P.isnonog, 0}, {"isphion", P.isphion, 0},
+      {"isphiofft", P.isphiofft, 0}, {"isimpon", P.isimpon, 0}, {"isupgon", P.isupgon, 0}, {"istgon", P.istgon, 0},
       {"ineudif", P.ineudif, 2}, {"isflxvar", P.isflxvar, 0}, {"ismcnon", P.ismcnon, 0}, {"ifixsrc", P.ifixsrc, 0}, {"ifixpsor", P.ifixpsor, 0},
       {"ishymol", P.ishymol, 0}, {"ishosor", P.ishosor, 0}, {"isupdrag", P.isupdrag, 0}, {"isofric", P.isofric, 0}, {"jhswitch", P.jhswitch, 0},
       {"isfeexpl0", P.isfeexpl0, 0}, {"isfeixpl0", P.isfeixpl0, 0}, {"is1D_gbx", P.is1D_gbx, 0}, {"isnglf", P.isnglf, 0}, {"isudsym", P.isudsym, 0},
-      {"islimon", P.islimon, 0}, {"isdifbetap", P.isdifbetap, 0}, {"isugfm1side", P.isugfm1side, 0}, {"nxomit", P.nxomit, 0}, {"isfixlb", P.isfixlb, 0},
+      {"islimon", P.islimon, 0}, {"isdifbetap", P.isdifbetap, 0}, {"isugfm1side", P.isugfm1side, 0}, {"nxomit", P.nxomit, 0},
       {"isfixrb", P.isfixrb, 0}, {"isextrnp", P.isextrnp, 0}, {"isextrnpf", P.isextrnpf, 0}, {"isextrtpf", P.isextrtpf, 0}, {"isextrngc", P.isextrngc, 0},
       {"isextrnw", P.isextrnw, 0}, {"isextrtw", P.isextrtw, 0}, {"isnfmiy", P.isnfmiy, 0}, {"isybdrywd", P.isybdrywd, 0}, {"isnewpot", P.isnewpot, 0},
       {"isbohmms", P.isbohmms, 0}, {"isgpye", P.isgpye, 0}, {"isngcore", P.isngcore, 0}, {"ibctepl", P.ibctepl, 1}, {"ibctipl", P.ibctipl, 1},
       {"ibctepr", P.ibctepr, 1}, {"ibctipr", P.ibctipr, 1}, {"iskaplex", P.iskaplex, 0}};
   for (auto& e : eq) if (e.v != e.want) { g_err = std::string("switch outside the built hot path: ") + e.n; return -5; }
+  if (P.isngon != 0 && P.isngon != 1) { g_err = "isngon must be 0 or 1"; return -5; }
+  if (P.isfixlb != 0 && P.isfixlb != 2) { g_err = "isfixlb must be 0 or 2"; return -5; }
   if (P.isbohmcalc != 0 && P.isbohmcalc != 1) { g_err = "isbohmcalc must be 0/1 with facb*=0"; return -5; }
   if (P.isnicore != 0 && P.isnicore != 1) { g_err = "isnicore must be 0 or 1"; return -5; }
   if (P.isupcore != 0 && P.isupcore != 1) { g_err = "isupcore must be 0 or 1"; return -5; }
   if (P.iflcore != 0 && P.iflcore != 1) { g_err = "iflcore must be 0 or 1"; return -5; }
-  if (P.istabon != 0 && P.istabon != 10) { g_err = "istabon must be 0 or 10"; return -5; }
+  if (P.istabon != 0 && P.istabon != 7 && P.istabon != 10) { g_err = "istabon must be 0, 7 or 10"; return -5; }
   // fnnuiz < 1 blends the new ionisation rate with the value left by the PREVIOUS pandf call (oderhs.m:1950-1961): the
   // reference's Jacobian then depends on the order in which the unknowns were perturbed; not reproducible in parallel
   if (P.fnnuiz != 1.) { g_err = "fnnuiz must be 1 (history-dependent rate blending is outside the built hot path)"; return -5; }
@@ -1405,6 +1479,8 @@ int ue_ora_init(void) {
     rlemin = ekpt[0]; rlemax = ekpt[mpe - 1]; delekpt = (rlemax - rlemin) / double(mpe - 1);
   }
   for (V* v : all_planes()) v->assign(NC, 0.0);
+  HASG = P.isngon == 1;
+  if (!HASG) ng.assign(P.ngfix, P.ngfix + NC);  // never advanced: the field ueinit left (odesetup.m:1399-1406)
   fniycbo.assign(NXS, 0.); feeycbo.assign(NXS, 0.); feiycbo.assign(NXS, 0.);
   dtuse.assign(neq, 1e20); ylodt.assign(neq, 0.); suscal.assign(neq, 1.); sfscal.assign(neq, 1.);
   g_ivmin = 1; g_ivmax = neq;

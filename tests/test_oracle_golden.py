@@ -206,3 +206,44 @@ def test_product_library_exports_abi():
     dll = ctypes.CDLL(lib)
     for n in names:
         assert hasattr(dll, n), n
+
+
+def test_case1_transient_lands_near_the_2007_output(built):
+    """builder/test/Forthon_cases/Forthon_case1: slab mesh (idealgrd), symmetry plane at ix=0 (isfixlb=2), four unknowns
+    per cell (isngon=0), Campbell rate fits (istabon=7, the package default).  The deck integrates the restart=0 profiles
+    of ueinit with vodpk to t = runtim*trange = 4e-4 s (rtol 1e-4) and its 2007 output prints ni, up, te, ti at that time
+    (tests/golden/case1_state.npz).  Integrating the oracle's residual over the same interval lands within a few per cent
+    of those arrays -- a sanity pin of the slab geometry and the isfixlb=2 / isngon=0 / istabon=7 branches, not a
+    digit-for-digit one (a 0.4 ms snapshot of a fast transient computed by a 2007 build)."""
+    from scipy.integrate import solve_ivp
+    from uedge_b200.cases import forthon_case1
+    z = np.load(os.path.join(GOLDEN, "case1_state.npz"))
+    c = forthon_case1()
+    c.setup()
+    b, com = c.bbb, c.com
+    nx, ny = com.nx, com.ny
+    assert (nx, ny, b.numvar, b.neq) == (6, 10, 4, 384)  # README-FORTHON-tests: (6+2)*(10+2) mesh, 384 variables
+    assert (com.ixpt1, com.ixpt2, com.iysptrx) == (-1, 4, 0)
+    # restart=0 profiles for a half-space problem (bbb/odesetup.m:1356-1457)
+    IY, IX = np.meshgrid(np.arange(ny + 2), np.arange(nx + 2), indexing="ij")
+    px = (nx + 3 - IX) / float(nx + 3)
+    py = (ny + 3 - IY) / float(ny + 3)
+    ttbeg = b.tinit * b.ev
+    te, ti, ni = ttbeg * px * py, b.tscal * ttbeg * px * py, b.nibeg[0] * py
+    up = np.sqrt(te[0, 0] / b.mi[0]) * px * py
+    up[:, nx + 1] = up[:, nx]
+    yl = c.set_state(ni, up, te, ti, c.initial_ng())
+    o = bind(oracle(), c)
+    neq = b.neq
+    o.step_params(np.full(neq, 1e20), yl[:neq], c.suscal(yl), np.ones(neq))
+    sol = solve_ivp(lambda t, y: o.pandf1(np.r_[y, 1.0, 0.0]), [0, b.runtim * 4.0e3], yl[:neq].copy(), method="BDF", rtol=1e-7, atol=1e-10)
+    assert sol.status == 0
+    y = sol.y[:, -1].reshape(ny + 2, nx + 2, 4)
+    got = dict(ni=y[:, :, 0] * b.n0[0], up=y[:, :, 1] * b.fnorm[0] / (b.mi[0] * b.n0[0]),
+               te=y[:, :, 2] * b.ennorm / (1.5 * b.nnorm), ti=y[:, :, 3] * b.ennorm / (1.5 * b.nnorm))
+    for k, tol in (("ni", 0.03), ("up", 0.07), ("te", 0.01), ("ti", 0.005)):
+        assert np.abs(got[k] - z[k]).max() <= tol * np.abs(z[k]).max(), k
+    # boundary rows are reproduced to the printed digits: core density/temperatures, symmetry plane, wall temperature
+    assert np.allclose(got["ni"][0, 1:5], 2.0e19, rtol=1e-7) and np.allclose(got["te"][0, 1:5], 100 * b.ev, rtol=1e-7)
+    assert np.allclose(got["te"][1:-1, 0], got["te"][1:-1, 1], rtol=1e-6) and np.abs(got["up"][1:-1, 0]).max() < 1e-3
+    assert np.allclose(z["te"][1:-1, 0], z["te"][1:-1, 1], rtol=1e-8) and np.allclose(z["te"][-1, 1:-1], 2 * b.ev, rtol=1e-4)

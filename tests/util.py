@@ -6,8 +6,8 @@ import re
 import numpy as np
 
 from uedge_b200.capi import UeLib
-from uedge_b200.cases import (d3dhsm_case, load_grid_npz, load_rate_tables_npz, load_state_npz, refine_grid,
-                              refine_state)
+from uedge_b200.cases import (box2_case, d3dhsm_case, forthon_case1, initial_profiles, load_grid_npz,
+                              load_rate_tables_npz, load_state_npz, refine_grid, refine_state)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_LIB = os.path.join(ROOT, "oracle", "libue_oracle.so")
@@ -18,7 +18,38 @@ def oracle():
     return UeLib(ORACLE_LIB, "ue_ora_")
 
 
+def apply_overrides(c, overrides):
+    for k, v in (overrides or {}).items():
+        pkg, nm = k.split(".")
+        ns = getattr(c, pkg)
+        cur = getattr(ns, nm) if nm in ns else None
+        if isinstance(cur, np.ndarray) and not isinstance(v, np.ndarray):
+            cur = cur.copy()
+            cur.flat[0] = v   # species-indexed inputs: species 1
+            v = cur
+        setattr(ns, nm, v)
+
+
+def make_slab_case(name, perturb=0.0, seed=1234, overrides=None):
+    """`case1`: Forthon_case1 at the steady state its reference output prints (ng: the frozen initial profile);
+    `box2d`: pyexamples/box2 with diffusive atoms at ueinit-like smooth profiles."""
+    c = forthon_case1() if name == "case1" else box2_case()
+    apply_overrides(c, overrides)
+    c.setup()
+    if name == "case1":
+        z = np.load(os.path.join(ROOT, "tests", "golden", "case1_state.npz"))
+        yl = c.set_state(z["ni"], z["up"], z["te"], z["ti"], c.initial_ng())
+    else:
+        yl = c.set_state(*initial_profiles(c))
+    if perturb:
+        rng = np.random.default_rng(seed)
+        yl[: c.bbb.neq] *= 1.0 + perturb * rng.uniform(-1.0, 1.0, c.bbb.neq)
+    return c, yl
+
+
 def make_case(name="d3dHsm", istabon=0, perturb=0.0, seed=1234, overrides=None):
+    if name in ("case1", "box2d"):
+        return make_slab_case(name, perturb, seed, overrides)
     g = load_grid_npz()
     state = load_state_npz("case2_state.npz" if name == "case2" else "d3dHsm_state.npz")
     m = re.fullmatch(r"d3dHsm(\d+)x", name)

@@ -61,3 +61,24 @@ json.dump({
                     11.89098495, 2.0],
 }, open(os.path.join(OUT, "case2_golden.json"), "w"), indent=1)
 print("wrote fixtures to", OUT)
+
+
+def rtf_arrays(path):
+    """Arrays printed by the 2007 Forthon test decks (`print bbb.ni` ... inside an RTF capture):
+    name -> nested-list text -> ndarray in the printed index order [ix, iy(, ifld)]."""
+    import ast
+    import re
+    txt = open(path).read().replace("\\\n", "\n")
+    out = {}
+    for m in re.finditer(r"^(\w+) = \n(.*?)(?=^\*{5,}|^>>>)", txt, flags=re.S | re.M):
+        body = re.sub(r",\s*\]", "]", m.group(2))
+        body = re.sub(r"\]\s*\[", "], [", body)
+        out[m.group(1)] = np.array(ast.literal_eval(body.strip()))
+    return out
+
+
+# Forthon_case1: slab, 4 unknowns per cell (isngon=0), evolved to steady state by vodpk; final ni, up, te, ti
+a = rtf_arrays(os.path.join(REF, "builder/test/Forthon_cases/Forthon_case1/output_forthon_case1.rtf"))
+np.savez_compressed(os.path.join(OUT, "case1_state.npz"),
+                    ni=a["ni"][:, :, 0].T.copy(), up=a["up"][:, :, 0].T.copy(), te=a["te"].T.copy(), ti=a["ti"].T.copy())
+print("case1:", {k: v.shape for k, v in a.items()})

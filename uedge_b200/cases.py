@@ -11,6 +11,7 @@ import numpy as np
 from .case import Case
 from .gridue import read_gridue
 from .h5lite import read_h5
+from .slabgrid import idealgrd
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -36,6 +37,72 @@ def d3dhsm_case(grid, istabon=0, v8_0_defaults=True):
     b.flalfgx = np.full(10, 1.0e20); b.flalfgy = np.full(10, 1.0e20)
     com.istabon = istabon
     return c
+
+
+def forthon_case1():
+    """builder/test/Forthon_cases/Forthon_case1/rd_forthon_case1.py: slab (mhdgeo=-1) 6x10, symmetry plane at ix=0
+    (isfixlb=2), no core region (nycore=0), four unknowns per cell (ni, up, te, ti; isngon=0: frozen atom density)."""
+    g = idealgrd(nxleg2=2, nxcore2=4, nycore=0, nysol=10, zax=1.0, zaxpt=0.75, alfyt=-1.0e-5)
+    c = Case(g)
+    b, com = c.bbb, c.com
+    com.nxleg = np.array([[0, 2]]); com.nxcore = np.array([[0, 4]])
+    com.nysol = np.array([10]); com.nycore = np.array([0])
+    b.isngon = np.zeros_like(b.isngon)
+    b.isfixlb = np.array([2, 0])
+    b.ncore[0] = 2.0e19; b.tcoree = 100.0; b.tcorei = 100.0
+    b.recycp[0] = 0.9
+    b.n0g = np.full_like(np.asarray(b.n0g, dtype=float), 1.0e16)
+    b.difni[0] = 1.0; b.kye = 1.0
+    b.flalfe = 0.21; b.flalfi = 0.21
+    b.flalfgx = np.full(10, 1.0e10); b.flalfgy = np.full(10, 1.0e10)
+    return c
+
+
+def box2_case(isupgon=0):
+    """pyexamples/box2/box2_in.py:12-140: slab 6x6 with a core region (nycore=2), symmetry plane at ix=0, core power
+    boundary condition.  isupgon=0 gives the diffusive-atom variant of the deck (isngon=1); the deck's own inertial
+    atoms (isupgon=1, nhsp=2) are not built yet."""
+    if isupgon != 0:
+        raise NotImplementedError("box2 with inertial neutrals (isupgon=1)")
+    g = idealgrd(nxleg2=3, nxcore2=3, nycore=2, nysol=4, radx=4.0e-2, rad0=0.0, radm=-1.0e-2, za0=0.0, zax=3.0, zaxpt=2.25,
+                 alfyt=-2.0, alfxt=2.76, btfix=2.0, bpolfix=0.2)
+    c = Case(g)
+    b, com = c.bbb, c.com
+    com.nxleg = np.array([[0, 3]]); com.nxcore = np.array([[0, 3]])
+    com.nysol = np.array([4]); com.nycore = np.array([2])
+    b.isfixlb = np.array([2, 0])
+    b.isnicore[0] = 1; b.ncore[0] = 1.1e19; b.iflcore = 1
+    b.tcoree = 25.0; b.tcorei = 25.0; b.pcoree = 2.5e4; b.pcorei = 2.5e4
+    b.recycp[0] = 0.98; b.albdsi[0] = 0.99; b.albdso[0] = 0.99
+    b.istepfc = 0; b.istipfc = 0; b.istewc = 0; b.istiwc = 0
+    b.bcee = 4.0; b.bcei = 2.5; b.bcen = 0.0
+    b.isupss[0] = 0; b.isupcore[0] = 0
+    b.difni[0] = 0.5; b.kye = 0.7; b.kyi = 0.7; b.travis[0] = 1.0; b.parvis[0] = 1.0
+    b.flalfe = 0.2; b.flalfi = 0.2; b.flalfv = 0.5
+    b.flalfgx = np.full(10, 1.0); b.flalfgy = np.full(10, 1.0); b.flalfgxy = np.full(10, 1.0)
+    b.methn = b.methu = b.methe = b.methi = b.methg = 33
+    b.cngfx[0] = 1.0; b.cngfy[0] = 1.0; b.cngflox[0] = 1.0; b.cngfloy[0] = 0.0
+    b.cngmom[0] = 1.0; b.eion = 5.0; b.ediss = 10.0; b.isrecmon = 1
+    b.cfupcx = 1.0; b.cfticx = 1.0
+    com.istabon = 0
+    return c
+
+
+def initial_profiles(c):
+    """restart=0 profiles of ueinit (bbb/odesetup.m:1335-1470) for a half-space (isfixlb>0) slab: flat density,
+    linearly shaped temperatures and parallel velocity.  Used as a smooth, deterministic test/bench state."""
+    b, com = c.bbb, c.com
+    nx, ny = com.nx, com.ny
+    IY, IX = np.meshgrid(np.arange(ny + 2), np.arange(nx + 2), indexing="ij")
+    px = (nx + 3 - IX) / float(nx + 3)
+    py = (ny + 3 - IY) / float(ny + 3)
+    ttbeg = float(b.tinit) * b.ev if "tinit" in b else 40.0 * b.ev
+    te = ttbeg * px * py
+    ti = float(b.tscal) * ttbeg * px * py
+    ni = float(b.nibeg[0]) * (1.0 + 0.0 * px) * (0.5 + 0.5 * py)
+    cs = np.sqrt((te + ti) / (b.minu[0] * b.mp))
+    up = 0.3 * cs * (1.0 - px)
+    return ni, up, te, ti, c.initial_ng()
 
 
 GOLDEN = os.path.join(os.path.dirname(_HERE), "tests", "golden")
