@@ -83,7 +83,7 @@ def _jac_pair(c, yl, gpu, ora, dt=None):
     rng = np.random.default_rng(99)
     y2 = y.copy()
     y2[: b.neq] *= 1 + 0.05 * rng.uniform(-1, 1, b.neq)
-    fscale = np.abs(ora.pandf1(y2)).reshape(-1, 5).max(axis=0)
+    fscale = np.abs(ora.pandf1(y2)).reshape(-1, b.numvar).max(axis=0)
     ora.pandf1(y)
     dyl = 1e-8 * (np.abs(y[: b.neq]) + 1.0 / su)
     return jg, jo, (fscale, dyl)
@@ -95,7 +95,7 @@ def _check_jac(jg, jo, noise):
     assert np.array_equal(iag, iao), "ia differs: nnz %d vs %d" % (len(vg), len(vo))
     assert np.array_equal(jag, jao), "ja differs"
     rows = np.repeat(np.arange(len(iao) - 1), np.diff(iao))
-    floor = 64 * 2.2e-16 * fscale[rows % 5] / dyl[jao - 1]
+    floor = 64 * 2.2e-16 * fscale[rows % len(fscale)] / dyl[jao - 1]
     err = np.abs(vg - vo)
     bad = err > JAC_RTOL * np.abs(vo) + floor
     assert not bad.any(), "%d entries off; worst rel %g" % (bad.sum(), (err / np.abs(vo))[bad].max())

@@ -1,0 +1,91 @@
+"""GPU parity tests for the slab family (BASELINE configs[0] lineage): analytic slab mesh (mhdgeo=-1, idealgrd), ix=0 as a
+symmetry plane (isfixlb=2), four unknowns per cell (isngon=0: frozen atom density) and the package-default rate fits
+(istabon=7).  `case1` is builder/test/Forthon_cases/Forthon_case1 at the state its reference output prints.
+Everything is compared bit for bit with the CPU oracle, as in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from tests.test_gpu_parity import _check_jac, _jac_pair
+from tests.util import bind, make_case, oracle
+from uedge_b200.capi import UeError, load_gpu
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(name, perturb, overrides=None, seed=1234):
+    c, yl = make_case(name, perturb=perturb, overrides=overrides, seed=seed)
+    return c, yl, bind(load_gpu(), c), bind(oracle(), c)
+
+
+@pytest.mark.parametrize("perturb", [0.0, 1e-3, 0.05])
+def test_case1_residual_parity(built, perturb):
+    c, yl, gpu, ora = _pair("case1", perturb)
+    assert c.bbb.numvar == 4 and c.bbb.neq == 384
+    fg, fo = gpu.pandf1(yl), ora.pandf1(yl)
+    assert np.isfinite(fg).all() and fg.size == 384
+    assert np.array_equal(fg, fo), "%d of %d entries differ" % ((fg != fo).sum(), fg.size)
+
+
+@pytest.mark.parametrize("perturb", [0.0, 1e-2])
+def test_case1_jacobian_parity(built, perturb):
+    c, yl, gpu, ora = _pair("case1", perturb)
+    jg, jo, noise = _jac_pair(c, yl, gpu, ora)
+    assert len(jo[0]) > 3000
+    _check_jac(jg, jo, noise)
+
+
+def test_case1_jacobian_with_timestep_term(built):
+    c, yl, gpu, ora = _pair("case1", 1e-3, overrides={"bbb.isbcwdt": 1})
+    n = c.bbb.neq
+    rng = np.random.default_rng(11)
+    dt = 10.0 ** rng.uniform(-6, -3, n)
+    yo = yl[:n] * (1 + 1e-2 * rng.uniform(-1, 1, n))
+    for lib in (gpu, ora):
+        lib.set_real("dtreal", 1e-4)
+        lib.step_params(dt, yo, np.ones(n), np.ones(n))
+    y = yl.copy(); y[n] = -1.0
+    assert np.array_equal(gpu.pandf1(y), ora.pandf1(y))
+    jg, jo, noise = _jac_pair(c, yl, gpu, ora, dt=dt)
+    assert all(np.array_equal(p, q) for p, q in zip(jg, jo))
+    for lib in (gpu, ora):
+        lib.set_real("dtreal", 1e20)
+
+
+@pytest.mark.parametrize("ov", [
+    {"com.istabon": 7},                        # Campbell fits on the tokamak mesh
+    {"bbb.isngon": 0},                         # frozen atoms (numvar = 4) on the tokamak mesh, X-point cuts included
+    {"bbb.isngon": 0, "com.istabon": 7, "bbb.isbcwdt": 1},
+])
+def test_d3dhsm_variants_of_the_new_switches(built, ov):
+    c, yl, gpu, ora = _pair("d3dHsm", 1e-3, overrides=ov)
+    assert c.bbb.numvar == (4 if ov.get("bbb.isngon", 1) == 0 else 5)
+    fg, fo = gpu.pandf1(yl), ora.pandf1(yl)
+    assert np.array_equal(fg, fo)
+    _check_jac(*_jac_pair(c, yl, gpu, ora))
+
+
+def test_case1_column_split_and_one_call_form(built):
+    """ppp column split (ue_gpu_set_column_range) and ue_gpu_rhs_jac with four unknowns per cell."""
+    c, yl, gpu, ora = _pair("case1", 1e-3)
+    b = c.bbb
+    jg, jo, noise = _jac_pair(c, yl, gpu, ora)
+    y = yl.copy(); y[b.neq] = 1.0
+    f, (jac, ja, ia) = gpu.rhs_jac(y, b.lbw, b.ubw, b.nnzmx)
+    assert np.array_equal(jac, jo[0]) and np.array_equal(ja, jo[1]) and np.array_equal(ia, jo[2])
+    half = b.neq // 2
+    parts = []
+    for lo, hi in ((1, half), (half + 1, b.neq)):
+        gpu.set_column_range(lo, hi)
+        fg = gpu.pandf1(y)
+        parts.append(gpu.jac_calc(y, fg, b.lbw, b.ubw, b.nnzmx))
+    gpu.set_column_range(1, b.neq)
+    from uedge_b200.split import merge_csr
+    jac2, ja2, ia2 = merge_csr(parts, b.neq)
+    assert np.array_equal(jac2, jo[0]) and np.array_equal(ja2, jo[1]) and np.array_equal(ia2, jo[2])
+
+
+def test_half_space_with_core_region_is_refused(built):
+    """isfixlb=2 with iysptrx1 > 0 (pyexamples/box2) also zeroes fluxes on the cut at ixpt2: not built, refused by name."""
+    c, yl = make_case("box2d")
+    with pytest.raises(UeError, match="isfixlb=2 with a core region"):
+        bind(load_gpu(), c)

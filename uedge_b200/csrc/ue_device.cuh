@@ -31,7 +31,10 @@
 #include "ue_math.h"
 #include "ue_param_store.hpp"
 
-#define UE_NV 5  // unknowns per cell: ni, up, te, ti, ng (convert.m:33-152 ordering)
+#define UE_NV 5  // row slots per cell inside the kernels: ni, up, te, ti, ng (convert.m:33-152 ordering)
+// Unknowns per cell in the CALLER's vectors (yl, yldot, iseqalg, dtuse, ...): 5, or 4 when isngon = 0 (no ng unknown: the
+// atom density is then the frozen input plane `ngfix` and row slot 4 is computed but never stored).
+#define NVX ((int)D.numvar)
 
 enum Plane : int {
   // phase-0 outputs
@@ -184,24 +187,75 @@ __device__ inline double d_table(const double* __restrict__ w, double tej, doubl
   const double r2 = r21 + fjd * (r22 - r21);
   return ue_exp(r1 + fje * (r2 - r1));
 }
+// istabon = 7 (the package default): R.B. Campbell's polynomial fits in x = log10(ne), y = log10(Te[eV]) (aph/aphrates.m:1133-1300)
+__device__ inline double d_sionf(double temp, double den) {
+  const double x = fmin(22.e0, ue_log10(den)), y = ue_log10(temp);
+  const double ain = -49.05905 + 2.51313783 * x - 0.049159714 * x * x;
+  const double bin = 41.1855162 - 2.3298672 * x + 4.24769144e-2 * x * x;
+  const double cin = -32.798921 + 1.72102919 * x - 0.038692357 * x * x;
+  const double din = 27.370466 - 1.6824361 * x + 0.0462317894 * x * x;
+  const double ein = -7.9990454 + 0.127573157 * x - 6.3586911e-3 * x * x;
+  const double gin = -4.5832951 + 0.776264783 * x - 1.8866089e-2 * x * x;
+  const double hin = 3.08056833 - 0.39114789 * x + 9.86833304e-3 * x * x;
+  const double riin = -0.4648639 + 0.0551428018 * x - 1.404213e-3 * x * x;
+  return ue_pow(10., ain + bin * y + cin * y * y + din * y * y * y + ein * y * y * y * y + gin * y * y * y * y * y + hin * y * y * y * y * y * y +
+                         riin * y * y * y * y * y * y * y);
+}
+__device__ inline double d_srecf(double temp, double den) {
+  const double x = fmin(22.e0, ue_log10(den)), y = ue_log10(temp);
+  const double ar = -0.4575652 - 2.144012 * x + 6.7072142e-2 * x * x - 1.391667e-4 * x * x * x;
+  const double br = -121.8401 + 18.001822 * x - 0.8679488 * x * x + 1.33165e-2 * x * x * x;
+  const double cr = 80.897256 - 13.29602 * x + 0.71881414 * x * x - 0.0126549 * x * x * x;
+  const double dr = 56.406823 - 7.301996 * x + 0.29339793 * x * x - 3.50898e-3 * x * x * x;
+  const double er = -55.73559 + 7.9634283 * x - 0.370274 * x * x + 5.567961e-3 * x * x * x;
+  const double gr = 10.866692 - 1.584193 * x + 0.07563791 * x * x - 1.177562e-3 * x * x * x;
+  return ue_pow(10., ar + br * y + cr * y * y + dr * y * y * y + er * y * y * y * y + gr * y * y * y * y * y);
+}
+__device__ inline double d_svradp_sionfl(double x, double y) {
+  const double ai = -275.845 + 37.010817 * x - 1.788045 * x * x + 0.029078333 * x * x * x;
+  const double bi = 2200.9478 - 326.1153 * x + 16.148655 * x * x - 0.2660702 * x * x * x;
+  const double ci = -2.935221e3 + 4.3757698e2 * x - 21.73964 * x * x + 0.358962 * x * x * x;
+  const double di = 1604.1466 - 239.6959 * x + 11.923707 * x * x - 0.1970501 * x * x * x;
+  const double ei = -390.8635 + 58.474495 * x - 2.910997 * x * x + 0.048133829 * x * x * x;
+  const double gi = 35.012574 - 5.24202 * x + 0.26109962 * x * x - 4.319238e-3 * x * x * x;
+  return ue_pow(10., ai + bi * y + ci * y * y + di * y * y * y + ei * y * y * y * y + gi * y * y * y * y * y);
+}
+__device__ inline double d_svradp(double temp, double den) {
+  const double x = fmin(22.e0, ue_log10(den)), y = ue_log10(temp);
+  const double ym = fmin(2.e0, y);  // etai frozen above 100 eV
+  const double ae = 2860.4173 - 610.2452 * x + 48.275821 * x * x - 1.687994 * x * x * x + 0.02201375 * x * x * x * x;
+  const double be = 10612.067 - 2046.397 * x + 147.73914 * x * x - 4.729973 * x * x * x + 0.056671796 * x * x * x * x;
+  const double ce = -4.231708e4 + 8494.6102 * x - 639.0226 * x * x + 21.350311 * x * x * x - 0.2673466 * x * x * x * x;
+  const double de = -8.385144e3 + 1887.6244 * x - 157.8502 * x * x + 5.820501 * x * x * x - 0.07992837 * x * x * x * x;
+  const double ee = 3.938282e4 - 8.131339e3 * x + 628.8119 * x * x - 21.58636 * x * x * x + 0.27756029 * x * x * x * x;
+  const double ge = -1.038281e4 + 2.1349333e3 * x - 164.4201 * x * x + 5.6210487 * x * x * x - 0.07197622 * x * x * x * x;
+  const double etai = (ue_pow(10., ae + be * ym + ce * ym * ym + de * ym * ym * ym + ee * ym * ym * ym * ym + ge * ym * ym * ym * ym * ym)) / d_svradp_sionfl(x, ym);
+  return fmax(0.e0, (13.6e0 + etai)) * 1.602e-19 * d_svradp_sionfl(x, y);
+}
 __device__ inline double d_rsa(double tej, double dens) {
   if (D.istabon == 0) { const double a = tej / (10 * D.ev); return 3.0e-14 * a * a / (3.0 + a * a); }
+  if (D.istabon == 7) return d_sionf(tej / D.ev, dens);
   return d_table(D.wsveh, tej, dens);
 }
-__device__ inline double d_rra(double tej, double dens) { return (D.istabon == 0) ? 0. : d_table(D.wsveh0, tej, dens); }
+__device__ inline double d_rra(double tej, double dens) {
+  if (D.istabon == 0) return 0.;
+  if (D.istabon == 7) return d_srecf(tej / D.ev, dens);
+  return d_table(D.wsveh0, tej, dens);
+}
 __device__ inline double d_rcx(double t0) { const double a = 3 * t0 / (10 * D.ev); return 1.7e-14 * ue_pow(a, 0.333); }
 __device__ inline double d_rqa0(double tej) { const double a = tej / (10 * D.ev); return D.erad * D.ev * 3.0e-14 * a * a / (3.0 + a * a); }
 __device__ inline double d_erl1(double tej, double dens) {
   if (D.istabon == 0) return (d_rqa0(tej) - 13.6 * D.ev * d_rsa(tej, dens)) * dens;
+  if (D.istabon == 7) return (d_svradp(tej / D.ev, dens) - 13.6 * D.ev * d_rsa(tej, dens)) * dens;  // aph/aphrates.m:28-31, 601-606
   return d_table(D.welms1, tej, dens);
 }
 __device__ inline double d_erl2(double tej, double dens) {
-  if (D.istabon == 0) return (13.6 * D.ev + 1.5 * tej) * dens * d_rra(tej, dens);
+  if (D.istabon == 0 || D.istabon == 7) return (13.6 * D.ev + 1.5 * tej) * dens * d_rra(tej, dens);
   return d_table(D.welms2, tej, dens);
 }
 
 // unknown index (0-based) of variable k in cell (ix,iy)
-__device__ __forceinline__ int64_t d_iv(int ix, int iy, int k, int NXS) { return ((int64_t)(ix + NXS * iy)) * UE_NV + k; }
+__device__ __forceinline__ int64_t d_iv(int ix, int iy, int k, int NXS) { return ((int64_t)(ix + NXS * iy)) * NVX + k; }
 
 // ============================================================================================
 // phase 0 — convsr_vo + pointwise part of convsr_aux + volumetric rates at one cell
@@ -214,7 +268,7 @@ __device__ void phase0_cell(const Acc<WIN>& a, const double* ycell /* the cell's
   const double up = ycell[1] * D.fnorm / (D.mi * D.n0);    // convert.m:352-356
   double te = ycell[2] * D.ennorm / (1.5 * D.nnorm);       // convert.m:281-282
   te = fmax(te, D.temin * ev);
-  const double ng = ycell[4] * D.n0g;                      // convert.m:287
+  const double ng = D.isngon == 1 ? ycell[4] * D.n0g : D.ngfix[ix + NXS * iy];  // convert.m:285-287; isngon = 0: never advanced
   double ti = ycell[3] * D.ennorm / (1.5 * D.nnorm);       // convert.m:310-311
   ti = fmax(ti, D.temin * ev);
   if (ni < 0) atomicOr(errflag, 1);                         // convert.m:318-322
@@ -885,7 +939,9 @@ __device__ int phase2_guard(const Acc<WIN>& a, const Win& w, int ix, int iy, dou
     }
     // corner cells and the special rows next to them (boundary.m:290-303, 897-983, 1209-1226, 1543-1630)
     if (ix == ixlb) {
-      out[0] = D.nurlxn * (d_ave(a.get(PL_NI, ixlb, iyc), a.get(PL_NI, ixlb + 1, iy)) - a.get(PL_NI, ixlb, iy)) / D.n0; mask |= 1;
+      if (!(bottom && D.isfixlb == 2)) {  // boundary.m:291: the bottom-left corner keeps the iy=0 condition on a symmetry plane
+        out[0] = D.nurlxn * (d_ave(a.get(PL_NI, ixlb, iyc), a.get(PL_NI, ixlb + 1, iy)) - a.get(PL_NI, ixlb, iy)) / D.n0; mask |= 1;
+      }
       if (gl) {
         out[1] = -D.nurlxu * (a.get(PL_UP, ixlb, iy) - 0.5 * (a.get(PL_UP, ixlb, iyc) + a.get(PL_UP, ixlb + 1, iy))) / D.vpnorm;
         if (bottom) {
@@ -922,6 +978,17 @@ __device__ int phase2_guard(const Acc<WIN>& a, const Win& w, int ix, int iy, dou
   }
   // ---- plates --------------------------------------------------------------------------------------------
   if (!in_rng(iy, w.j2, w.j5)) return 0;
+  if (ix == 0 && D.isfixlb == 2) {  // ix = 0 is a symmetry plane (boundary.m:1666-1770; rlimiter lies beyond the mesh)
+    if (w.i3 <= 0) {
+      out[0] = D.nurlxn * (1 / D.n0) * (a.get(PL_NI, 1, iy) - a.get(PL_NI, 0, iy));
+      out[1] = D.nurlxu * (0. - a.get(PL_UP, 0, iy)) / D.vpnorm;
+      out[2] = D.nurlxe * f_ne(a, 0, iy) * (a.get(PL_TE, 1, iy) - a.get(PL_TE, 0, iy)) / D.ennorm;
+      out[3] = D.nurlxi * f_ne(a, 0, iy) * (a.get(PL_TI, 1, iy) - a.get(PL_TI, 0, iy)) / D.ennorm;
+      out[4] = D.nurlxg * (a.get(PL_NG, 1, iy) - a.get(PL_NG, 0, iy)) / D.n0g;
+      mask = 0x1f;
+    }
+    return mask;
+  }
   if (ix == ixlb && gl) {  // boundary.m:1793-2259
     const int ixt = ixlb, ixt1 = IXP1(ixt, iy);
     if (w.i3 <= ixlb + D.isextrnp) { out[0] = D.nurlxn * (a.get(PL_NI, ixt1, iy) - a.get(PL_NI, ixt, iy)) / D.n0; mask |= 1; }
@@ -1086,9 +1153,9 @@ __device__ void p2_n(const Acc<WIN>& a, int ix, int iy, double out[UE_NV], const
   const double psorg = -psor, psorrg = -psorxr;
   double resng = D.cngsor * (psorg + 0. + psorrg) + 0. + 0. * vol;
   resng = resng - D.cfneutdiv * D.cfneutdiv_fng * ((a.get(PL_FNGX, ix, iy) - a.get(PL_FNGX, ix1, iy)) + D.fluxfacy * (a.get(PL_FNGY, ix, iy) - a.get(PL_FNGY, ix, iy - 1)));
-  const int64_t c = (int64_t)(ix + NXS * iy) * UE_NV;
+  const int64_t c = (int64_t)(ix + NXS * iy) * NVX;
   out[0] = (1 - iseqalg[c + 0]) * resco / (vol * D.n0);
-  out[4] = (1 - iseqalg[c + 4]) * resng / (vol * D.n0g);
+  out[4] = D.isngon == 1 ? (1 - iseqalg[c + 4]) * resng / (vol * D.n0g) : 0.;
 }
 
 template <bool WIN>
@@ -1108,7 +1175,7 @@ __device__ void p2_m(const Acc<WIN>& a, const Win& w, int ix, int iy, double out
                  D.cfneut * D.cfneutsor_mi * D.cmwall * 0.5 * (ng + ng_e) * D.mi * up * 0.5 * (a.get(PL_NUCX, ix, iy) + a.get(PL_NUCX, ix2, iy)) * GG(volv, ix, iy) +
                  0. + D.cfmsor * (0. + 0.) + 0. + 0. + 0.;
   resmo = resmo - (f_fmix(a, ix2, ix, iy) - f_fmix(a, ix, ix1, iy) + D.fluxfacy * (f_fmiy(a, ix, iy) - f_fmiy(a, ix, iy - 1)));
-  const int64_t c = (int64_t)(ix + NXS * iy) * UE_NV;
+  const int64_t c = (int64_t)(ix + NXS * iy) * NVX;
   out[1] = (1 - iseqalg[c + 1]) * resmo / (GG(volv, ix, iy) * D.fnorm);
   if (ix == D.ixrb) out[1] = resmo / (GG(volv, ix, iy) * D.fnorm);
   double v;
@@ -1156,7 +1223,7 @@ __device__ void p2_e(const Acc<WIN>& a, int ix, int iy, double out[UE_NV], const
                         D.cfneut * D.cfneutsor_ee * D.cnsor * D.ediss * ev * (0.5 * psordis);
   const double w0 = vol * f_eqp(a, ix, iy) * (te - ti);
   resee = resee - w0 + vsoree;
-  const int64_t c = (int64_t)(ix + NXS * iy) * UE_NV;
+  const int64_t c = (int64_t)(ix + NXS * iy) * NVX;
   out[2] = (1 - iseqalg[c + 2]) * resee / (vol * D.ennorm);
 }
 
@@ -1211,7 +1278,7 @@ __device__ void p2_i(const Acc<WIN>& a, int ix, int iy, double out[UE_NV], const
     resei = resei + wvh * vol;
   }
   resei = resei + a.get(PL_PWRIBKG, ix, iy) * vol;
-  const int64_t c = (int64_t)(ix + NXS * iy) * UE_NV;
+  const int64_t c = (int64_t)(ix + NXS * iy) * NVX;
   out[3] = (1 - iseqalg[c + 3]) * resei / (vol * D.ennorm);
 }
 
@@ -1221,7 +1288,9 @@ __device__ __forceinline__ void phase3_dt(int ix, int iy, double r[UE_NV], const
                                           const double* __restrict__ dtuse, const double* __restrict__ ylodt) {
   (void)iy;
   if (D.dtreal < 1.e15 && ylflag < 0) {
+#pragma unroll
     for (int k = 0; k < UE_NV; ++k) {
+      if (k >= NVX) continue;
       if (k == 1 && ix == D.nx + 2 * D.isbcwdt) continue;  // oderhs.m:7991: the algebraic up row at ix = nx unless isbcwdt = 1
       r[k] = (1. - 0.) * r[k];
       r[k] = r[k] - (ycell[k] - ylodt[c + k]) / dtuse[c + k];
@@ -1236,16 +1305,16 @@ template <bool WIN>
 __device__ void phase3_interior(const Acc<WIN>& a, int ix, int iy, double r[UE_NV], const double* ycell /* this cell's entries of yl */, double ylflag /* yl(neq+1) */,
                                 const int64_t* __restrict__ iseqalg, const double* __restrict__ dtuse, const double* __restrict__ ylodt) {
   const int NXS = a.NXS;
-  const int64_t c = (int64_t)(ix + NXS * iy) * UE_NV;
+  const int64_t c = (int64_t)(ix + NXS * iy) * NVX;
   if (D.isflxvar != 1 && D.isrscalf == 1) {
     const double ni = a.get(PL_NI, ix, iy);
     double nbedot = 0., nbidot = 0.;
     nbidot = nbidot + r[0] * D.n0;
     nbedot = nbedot + D.zi * r[0] * D.n0;
-    const double nbg2dot = r[4] * D.n0g;
+    const double nbg2dot = D.isngon == 1 ? r[4] * D.n0g : 0.;  // oderhs.m:8118
     const int ix1 = IXP1(ix, iy);
     if (iseqalg[c + 1] == 0) {
-      const int64_t c1 = (int64_t)(ix1 + NXS * iy) * UE_NV;
+      const int64_t c1 = (int64_t)(ix1 + NXS * iy) * NVX;
       const double yldot_np1 = a.get(PL_RESCO, ix1, iy) / (GG(vol, ix1, iy) * D.n0);
       double nbvdot, nbv;
       if (iseqalg[c + 0] == 1) { nbvdot = yldot_np1 * D.n0; nbv = a.get(PL_NI, ix1, iy); }      // isnupdot1sd = 0

@@ -109,10 +109,13 @@ __global__ void k_phase0(double* base, const double* __restrict__ yl, double* __
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= NC) return;
   Acc<false> a; a.base = base; a.NXS = NXS; a.NC = NC;
-  double ycell[UE_NV];
-  for (int k = 0; k < UE_NV; ++k) ycell[k] = yl[(size_t)c * UE_NV + k];
+  const int nv = NVX;
+  double ycell[UE_NV] = {0., 0., 0., 0., 0.};
+#pragma unroll
+  for (int k = 0; k < UE_NV; ++k) if (k < nv) ycell[k] = yl[(size_t)c * nv + k];
   if (yl_keep) {
-    for (int k = 0; k < UE_NV; ++k) yl_keep[(size_t)c * UE_NV + k] = ycell[k];
+#pragma unroll
+    for (int k = 0; k < UE_NV; ++k) if (k < nv) yl_keep[(size_t)c * nv + k] = ycell[k];
     if (c == 0) { yl_keep[neq] = yl[neq]; yl_keep[neq + 1] = yl[neq + 1]; }
   }
   phase0_cell<false>(a, ycell, c % NXS, c / NXS, err);
@@ -176,12 +179,17 @@ __global__ void k_phase3(double* base, const double* __restrict__ tmp, double* _
   if (c >= NC) return;
   Acc<false> a; a.base = base; a.NXS = NXS; a.NC = NC;
   const int ix = c % NXS, iy = c / NXS;
+  const int nv = NVX;  // unknowns per cell in the caller's vectors (4 when isngon = 0); tmp keeps UE_NV row slots
   double r[UE_NV];
   for (int k = 0; k < UE_NV; ++k) r[k] = tmp[(size_t)c * UE_NV + k];
-  if (ix >= 1 && ix <= D.nx && iy >= 1 && iy <= D.ny) phase3_interior<false>(a, ix, iy, r, yl + (size_t)c * UE_NV, yl[neq], D.iseqalg, dtuse, ylodt);
-  else if (D.isbcwdt == 1) phase3_dt(ix, iy, r, yl + (size_t)c * UE_NV, yl[neq], (int64_t)c * UE_NV, dtuse, ylodt);  // guard rows carry the term too
-  for (int k = 0; k < UE_NV; ++k) yldot[(size_t)c * UE_NV + k] = r[k];
-  if (yldot_host) for (int k = 0; k < UE_NV; ++k) yldot_host[(size_t)c * UE_NV + k] = r[k];
+  if (ix >= 1 && ix <= D.nx && iy >= 1 && iy <= D.ny) phase3_interior<false>(a, ix, iy, r, yl + (size_t)c * nv, yl[neq], D.iseqalg, dtuse, ylodt);
+  else if (D.isbcwdt == 1) phase3_dt(ix, iy, r, yl + (size_t)c * nv, yl[neq], (int64_t)c * nv, dtuse, ylodt);  // guard rows carry the term too
+#pragma unroll
+  for (int k = 0; k < UE_NV; ++k) if (k < nv) yldot[(size_t)c * nv + k] = r[k];
+  if (yldot_host) {
+#pragma unroll
+    for (int k = 0; k < UE_NV; ++k) if (k < nv) yldot_host[(size_t)c * nv + k] = r[k];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -265,10 +273,11 @@ __global__ void __launch_bounds__(128) k_jb_stage0(JArgs A) {
   if (tid < 32 && up < A.NU) {
     const UInfo& q = A.ui[up];
     const Acc<true> a = jb_acc(A, q, up);
-    double ycell[UE_NV], yold;
+    double ycell[UE_NV] = {0., 0., 0., 0., 0.}, yold;
     const double dyl = jb_dyl(A, q, yold);
-    const int64_t c = (int64_t)(q.xc + A.NXS * q.yc) * UE_NV;
-    for (int k2 = 0; k2 < UE_NV; ++k2) ycell[k2] = A.yl[c + k2];
+    const int64_t c = (int64_t)(q.xc + A.NXS * q.yc) * NVX;
+#pragma unroll
+    for (int k2 = 0; k2 < UE_NV; ++k2) if (k2 < NVX) ycell[k2] = A.yl[c + k2];
     ycell[(q.iv - 1) - c] = yold + dyl;
     phase0_cell<true>(a, ycell, q.xc, q.yc, A.err);
   }
@@ -302,10 +311,11 @@ __global__ void __launch_bounds__(5 * P01_ITEMS, 1) k_jb_p01(JArgs A) {
     const int up = u0 + tid;
     const UInfo& q = A.ui[up];
     const Acc<true> a = jb_acc(A, q, up);
-    double ycell[UE_NV], yold;
+    double ycell[UE_NV] = {0., 0., 0., 0., 0.}, yold;
     const double dyl = jb_dyl(A, q, yold);
-    const int64_t c = (int64_t)(q.xc + A.NXS * q.yc) * UE_NV;
-    for (int k2 = 0; k2 < UE_NV; ++k2) ycell[k2] = A.yl[c + k2];
+    const int64_t c = (int64_t)(q.xc + A.NXS * q.yc) * NVX;
+#pragma unroll
+    for (int k2 = 0; k2 < UE_NV; ++k2) if (k2 < NVX) ycell[k2] = A.yl[c + k2];
     ycell[(q.iv - 1) - c] = yold + dyl;
     phase0_cell<true>(a, ycell, q.xc, q.yc, A.err);
   }
@@ -409,10 +419,12 @@ __global__ void __launch_bounds__(128) k_jb_p3c(JArgs A) {
     const int cell = A.cand_cell[q.coff + l];
     const int ix = cell % NXS, iy = cell / NXS;
     if (ix >= 1 && ix <= D.nx && iy >= 1 && iy <= D.ny && in_rng(ix, q.w.i2, q.w.i5) && in_rng(iy, q.w.j2, q.w.j5)) {
-      double r[UE_NV], ycell[UE_NV];
+      double r[UE_NV], ycell[UE_NV] = {0., 0., 0., 0., 0.};
       double* o = A.rows + q.off + l;
-      const int64_t c = (int64_t)cell * UE_NV;
-      for (int k = 0; k < UE_NV; ++k) { r[k] = o[k * NI]; ycell[k] = A.yl[c + k]; }
+      const int64_t c = (int64_t)cell * NVX;
+      for (int k = 0; k < UE_NV; ++k) r[k] = o[k * NI];
+#pragma unroll
+      for (int k = 0; k < UE_NV; ++k) if (k < NVX) ycell[k] = A.yl[c + k];
       if (ix == q.xc && iy == q.yc) ycell[(q.iv - 1) - c] = yold + dyl;
       a.reast = A.cand_east[q.coff + l];
       phase3_interior<true>(a, ix, iy, r, ycell, A.yl[neq], D.iseqalg, A.dtuse, A.ylodt);
@@ -423,7 +435,8 @@ __global__ void __launch_bounds__(128) k_jb_p3c(JArgs A) {
   const int64_t iv = q.iv;
   const int64_t ii1 = max(iv - A.mu, (int64_t)1), ii2 = min(iv + A.ml, neq);
   const double sf = A.sfscal[iv - 1];
-  const int ncand = q.n * UE_NV;
+  const int nv = NVX;
+  const int ncand = q.n * nv;
   const int64_t o = A.coloff[iv - 1];
   int nout = 0;
   constexpr int CH = 4;  // candidates per lane and pass: their loads are issued together, the ordered ballots follow
@@ -434,8 +447,8 @@ __global__ void __launch_bounds__(128) k_jb_p3c(JArgs A) {
       const int qq = q0 + 32 * c + lane;
       keep[c] = false; val[c] = 0.; ii[c] = 0;
       if (qq < ncand) {
-        const int l = qq / UE_NV, k = qq - l * UE_NV;
-        ii[c] = (int64_t)A.cand_cell[q.coff + l] * UE_NV + k + 1;
+        const int l = qq / nv, k = qq - l * nv;
+        ii[c] = (int64_t)A.cand_cell[q.coff + l] * nv + k + 1;
         if (ii[c] >= ii1 && ii[c] <= ii2) {
           const bool written = (A.rmask[q.off + l] >> k) & 1;
           if (written || ii[c] == iv) {
@@ -621,12 +634,12 @@ int check_switches() {
   const UeParams& P = S.p;
   { const std::string z = S.nonzero_frozen(); if (!z.empty()) { g_err = "input " + z + " must be 0: the term it switches on is outside the built hot path"; return -5; } }
   struct { const char* n; int64_t v, want; } eq[] = {
-      {"nisp", P.nisp, 1}, {"nusp", P.nusp, 1}, {"ngsp", P.ngsp, 1}, {"numvar", P.numvar, UE_NV}, {"isnonog", P.isnonog, 0}, {"isphion", P.isphion, 0},
-      {"isphiofft", P.isphiofft, 0}, {"isimpon", P.isimpon, 0}, {"isupgon", P.isupgon, 0}, {"isngon", P.isngon, 1}, {"istgon", P.istgon, 0},
+      {"nisp", P.nisp, 1}, {"nusp", P.nusp, 1}, {"ngsp", P.ngsp, 1}, {"numvar", P.numvar, 4 + (P.isngon == 1)}, {"isnonog", P.isnonog, 0}, {"isphion", P.isphion, 0},
+      {"isphiofft", P.isphiofft, 0}, {"isimpon", P.isimpon, 0}, {"isupgon", P.isupgon, 0}, {"istgon", P.istgon, 0},
       {"ineudif", P.ineudif, 2}, {"isflxvar", P.isflxvar, 0}, {"ismcnon", P.ismcnon, 0}, {"ifixsrc", P.ifixsrc, 0}, {"ifixpsor", P.ifixpsor, 0},
       {"ishymol", P.ishymol, 0}, {"ishosor", P.ishosor, 0}, {"isupdrag", P.isupdrag, 0}, {"isofric", P.isofric, 0}, {"jhswitch", P.jhswitch, 0},
       {"isfeexpl0", P.isfeexpl0, 0}, {"isfeixpl0", P.isfeixpl0, 0}, {"is1D_gbx", P.is1D_gbx, 0}, {"isnglf", P.isnglf, 0}, {"isudsym", P.isudsym, 0},
-      {"islimon", P.islimon, 0}, {"isdifbetap", P.isdifbetap, 0}, {"isugfm1side", P.isugfm1side, 0}, {"nxomit", P.nxomit, 0}, {"isfixlb", P.isfixlb, 0},
+      {"islimon", P.islimon, 0}, {"isdifbetap", P.isdifbetap, 0}, {"isugfm1side", P.isugfm1side, 0}, {"nxomit", P.nxomit, 0},
       {"isfixrb", P.isfixrb, 0}, {"isextrnp", P.isextrnp, 0}, {"isextrnpf", P.isextrnpf, 0}, {"isextrtpf", P.isextrtpf, 0}, {"isextrngc", P.isextrngc, 0},
       {"isextrnw", P.isextrnw, 0}, {"isextrtw", P.isextrtw, 0}, {"isnfmiy", P.isnfmiy, 0}, {"isybdrywd", P.isybdrywd, 0}, {"isnewpot", P.isnewpot, 0},
       {"isbohmms", P.isbohmms, 0}, {"isgpye", P.isgpye, 0}, {"isngcore", P.isngcore, 0}, {"ibctepl", P.ibctepl, 1}, {"ibctipl", P.ibctipl, 1},
@@ -636,7 +649,12 @@ int check_switches() {
   if (P.isnicore != 0 && P.isnicore != 1) { g_err = "isnicore must be 0 or 1"; return -5; }
   if (P.isupcore != 0 && P.isupcore != 1) { g_err = "isupcore must be 0 or 1"; return -5; }
   if (P.iflcore != 0 && P.iflcore != 1) { g_err = "iflcore must be 0 or 1"; return -5; }
-  if (P.istabon != 0 && P.istabon != 10) { g_err = "istabon must be 0 or 10"; return -5; }
+  if (P.istabon != 0 && P.istabon != 7 && P.istabon != 10) { g_err = "istabon must be 0, 7 or 10"; return -5; }
+  if (P.isngon != 0 && P.isngon != 1) { g_err = "isngon must be 0 or 1"; return -5; }
+  if (P.isfixlb != 0 && P.isfixlb != 2) { g_err = "isfixlb must be 0 or 2"; return -5; }
+  // a half-space problem WITH a core region also forces fluxes and velocities to zero on the cut at ixpt2
+  // (oderhs.m:2447-2466, boundary.m:1772-1785): not built yet
+  if (P.isfixlb == 2 && P.iysptrx1 > 0) { g_err = "isfixlb=2 with a core region (iysptrx1 > 0) is outside the built hot path"; return -5; }
   // fnnuiz < 1 blends the new ionisation rate with the value left by the PREVIOUS pandf call (oderhs.m:1950-1961): the
   // reference's Jacobian then depends on the order in which the unknowns were perturbed; not reproducible in parallel
   if (P.fnnuiz != 1.) { g_err = "fnnuiz must be 1 (history-dependent rate blending is outside the built hot path)"; return -5; }
@@ -971,7 +989,7 @@ int ue_gpu_init(void) {
   nx = (int)P.nx; ny = (int)P.ny; NXS = nx + 2; NC = NXS * (ny + 2); neq = P.neq;
   std::string b = S.bad_sizes();
   if (!b.empty()) { g_err = "bad plane sizes: " + b; return -1; }
-  if (neq != (int64_t)NC * UE_NV) { g_err = "neq != numvar*(nx+2)*(ny+2)"; return -1; }
+  if (neq != (int64_t)NC * S.p.numvar) { g_err = "neq != numvar*(nx+2)*(ny+2)"; return -1; }
   if (S.len("igyl") != 2 * neq || S.len("iseqalg") != neq) { g_err = "igyl/iseqalg length"; return -1; }
   int rc = check_switches();
   if (rc) return rc;
@@ -1004,7 +1022,7 @@ int ue_gpu_init(void) {
   CK(cudaMemset(d_base, 0, (size_t)PL_COUNT * NC * sizeof(double)));
   CK(cudaMalloc(&d_yl, (neq + 2) * sizeof(double)));
   CK(cudaMalloc(&d_yldot00, (neq + 2) * sizeof(double)));
-  CK(cudaMalloc(&d_tmp, neq * sizeof(double)));
+  CK(cudaMalloc(&d_tmp, (size_t)NC * UE_NV * sizeof(double)));  // UE_NV row slots per cell (numvar may be 4)
   CK(cudaMalloc(&d_yldot, neq * sizeof(double)));
   CK(cudaMalloc(&d_dtuse, neq * sizeof(double)));
   CK(cudaMalloc(&d_ylodt, neq * sizeof(double)));
