@@ -516,9 +516,13 @@ int bouncon(const Win& w, const double* yl, double* yldot) {
         if (P.isnicore == 1) yldot[iv1] = P.nurlxn * (P.ncore - A(ni, ix, 0)) / P.n0;
         else  // isnicore == 0, boundary.m:211-215 (fniycbo = 0: drift coefficients zero)
           yldot[iv1] = -P.nurlxn * (P.qe * (A(fniy, ix, 0) - fniycbo[ix]) / G(sy, ix, 0) - P.curcore * G(gyf, ix, 0) / P.sygytotc) / (P.qe * P.vpnorm * P.n0);
-      } else {  // isnwconiix == 0, boundary.m:259-265
+      } else if (P.isnwconiix[ix] == 0) {  // boundary.m:259-265
         yldot[iv1] = P.nurlxn * ((1 - P.ifluxni) * (A(niy1, ix, 0) - A(niy0, ix, 0)) -
                                  P.ifluxni * (A(fniy, ix, 0) / (G(sy, ix, 0) * P.vpnorm) - 0.001 * A(ni, ix, 1) * A(vy, ix, 0) / P.vpnorm)) / P.n0;
+      } else if (P.isnwconiix[ix] == 1) {  // fixed wall density, boundary.m:267-270
+        yldot[iv1] = P.nurlxn * (P.nwalli[ix] - A(ni, ix, 0)) / P.n0;
+      } else if (P.isnwconiix[ix] == 3) {  // specified gradient length, boundary.m:278-282
+        yldot[iv1] = -P.nurlxn * (A(niy0, ix, 0) - A(niy1, ix, 0) * (2 * G(gyf, ix, 0) * P.lynipf[ix] - 1) / (2 * G(gyf, ix, 0) * P.lynipf[ix] + 1) - P.nwimin) / P.n0;
       }
     }
     // corners, boundary.m:290-303
@@ -554,10 +558,21 @@ int bouncon(const Win& w, const double* yl, double* yldot) {
           }
         }
       } else {
+        // boundary.m:550-565, 597-612: 0 zero flux, 1 fixed, 2 extrapolation, 3 specified gradient length
         if (P.istepfcix[ix] == 0) yldot[iv1] = -P.nurlxe * (A(feey, ix, 0) / (P.n0 * P.vpnorm * G(sy, ix, 0))) / (P.temp0 * ev);
-        else yldot[iv1] = P.nurlxe * (P.tewalli[ix] * ev - A(te, ix, 0)) / (P.temp0 * ev);  // == 1
+        else if (P.istepfcix[ix] == 1) yldot[iv1] = P.nurlxe * (P.tewalli[ix] * ev - A(te, ix, 0)) / (P.temp0 * ev);
+        else if (P.istepfcix[ix] == 2) {
+          double tbound = A(te, ix, 1) - G(gyf, ix, 1) * (A(te, ix, 2) - A(te, ix, 1)) / G(gyf, ix, 0);
+          tbound = std::max(tbound, P.tbmin * ev);
+          yldot[iv1] = P.nurlxe * (tbound - A(te, ix, 0)) / (P.temp0 * ev);
+        } else yldot[iv1] = P.nurlxe * ((A(te, ix, 1) - A(te, ix, 0)) - 0.5 * (A(te, ix, 1) + A(te, ix, 0)) / (G(gyf, ix, 0) * P.lytepf[ix])) / (P.temp0 * ev);
         if (P.istipfcix[ix] == 0) yldot[iv2] = -P.nurlxi * (A(feiy, ix, 0) / (P.n0 * P.vpnorm * G(sy, ix, 0))) / (P.temp0 * ev);
-        else yldot[iv2] = P.nurlxi * (P.tiwalli[ix] * ev - A(ti, ix, 0)) / (P.temp0 * ev);
+        else if (P.istipfcix[ix] == 1) yldot[iv2] = P.nurlxi * (P.tiwalli[ix] * ev - A(ti, ix, 0)) / (P.temp0 * ev);
+        else if (P.istipfcix[ix] == 2) {
+          double tbound = A(ti, ix, 1) - G(gyf, ix, 1) * (A(ti, ix, 2) - A(ti, ix, 1)) / G(gyf, ix, 0);
+          tbound = std::max(tbound, P.tbmin * ev);
+          yldot[iv2] = P.nurlxi * (tbound - A(ti, ix, 0)) / (P.temp0 * ev);
+        } else yldot[iv2] = P.nurlxi * ((A(ti, ix, 1) - A(ti, ix, 0)) - 0.5 * (A(ti, ix, 1) + A(ti, ix, 0)) / (G(gyf, ix, 0) * P.lytipf[ix])) / (P.temp0 * ev);
       }
     }
     for (int ix = w.i4; ix <= w.i8 && HASG; ++ix) {  // neutral density, boundary.m:632-767
@@ -572,6 +587,18 @@ int bouncon(const Win& w, const double* yl, double* yldot) {
         double fng_chem = 0., sputflxpf = 0.;
         double fng_alb = (1 - P.albedoi[ix]) * nharmave * vyn * G(sy, ix, 0);
         yldot[iv] = -P.nurlxg * (A(fngy, ix, 0) + fng_alb - fng_chem + sputflxpf) / (vyn * G(sy, ix, 0) * P.n0g);
+        if (P.matwalli[ix] > 0) {  // recycling wall, boundary.m:733-760
+          if (P.recycwit[ix] > 0.) {
+            double fniy_recy = P.fac2sp * A(fniy, ix, 0);
+            if (P.isrefluxclip == 1) fniy_recy = std::min(fniy_recy, 0.);
+            yldot[iv] = -P.nurlxg * (A(fngy, ix, 0) + fniy_recy * P.recycwit[ix] - P.fngyi_use[ix] - P.fngysi[ix] + fng_alb - fng_chem + sputflxpf) /
+                        (vyn * P.n0g * G(sy, ix, 0));
+          } else if (P.recycwit[ix] < -1) yldot[iv] = P.nurlxg * (P.ngbackg - A(ng, ix, 0)) / P.n0g;
+          else {
+            nharmave = 2. * (A(ng, ix, 0) * A(ng, ix, 1)) / (A(ng, ix, 0) + A(ng, ix, 1));
+            yldot[iv] = -P.nurlxg * (A(fngy, ix, 0) + (1 + P.recycwit[ix]) * nharmave * vyn * G(sy, ix, 0)) / (vyn * P.n0g * G(sy, ix, 0));
+          }
+        }
       }
     }
     if (w.xcnearlb || w.openbox) {  // boundary.m:897-938
@@ -590,10 +617,14 @@ int bouncon(const Win& w, const double* yl, double* yldot) {
   }
   // ===== iy = ny+1 boundary (boundary.m:1125-1653) =====
   if (w.j7 >= (ny + 1)) {  // isextrnw = isextrtw = 0
-    for (int ix = w.i4; ix <= w.i8; ++ix) {  // boundary.m:1133-1207, isnwconoix == 0
+    for (int ix = w.i4; ix <= w.i8; ++ix) {  // boundary.m:1133-1207
       int64_t iv1 = IDXN(ix, ny + 1);
-      yldot[iv1] = P.nurlxn * ((1 - P.ifluxni) * (A(niy0, ix, ny) - A(niy1, ix, ny)) +
-                               P.ifluxni * (A(fniy, ix, ny) / (G(sy, ix, ny) * P.vpnorm) - 0.001 * A(ni, ix, ny) * A(vy, ix, ny) / P.vpnorm)) / P.n0;
+      if (P.isnwconoix[ix] == 0)
+        yldot[iv1] = P.nurlxn * ((1 - P.ifluxni) * (A(niy0, ix, ny) - A(niy1, ix, ny)) +
+                                 P.ifluxni * (A(fniy, ix, ny) / (G(sy, ix, ny) * P.vpnorm) - 0.001 * A(ni, ix, ny) * A(vy, ix, ny) / P.vpnorm)) / P.n0;
+      else if (P.isnwconoix[ix] == 1) yldot[iv1] = P.nurlxn * (P.nwallo[ix] - A(ni, ix, ny + 1)) / P.n0;
+      else  // == 3, specified gradient length
+        yldot[iv1] = -P.nurlxn * (A(niy1, ix, ny) - A(niy0, ix, ny) * (2 * G(gyf, ix, ny) * P.lyniwc[ix] - 1) / (2 * G(gyf, ix, ny) * P.lyniwc[ix] + 1) - P.nwomin) / P.n0;
     }
     yldot[IDXN(ixlb, ny + 1)] = P.nurlxn * (ave(A(ni, ixlb, ny), A(ni, ixlb + 1, ny + 1)) - A(ni, ixlb, ny + 1)) / P.n0;       // :1209-1217
     yldot[IDXN(ixrb + 1, ny + 1)] = P.nurlxn * (ave(A(ni, ixrb + 1, ny), A(ni, ixrb, ny + 1)) - A(ni, ixrb + 1, ny + 1)) / P.n0;  // :1218-1226
@@ -605,9 +636,19 @@ int bouncon(const Win& w, const double* yl, double* yldot) {
     for (int ix = w.i4; ix <= w.i8; ++ix) {  // boundary.m:1311-1362
       int64_t iv1 = IDXTE(ix, ny + 1), iv2 = IDXTI(ix, ny + 1);
       if (P.istewcix[ix] == 0) yldot[iv1] = P.nurlxe * (A(feey, ix, ny) / (P.n0 * P.vpnorm * G(sy, ix, ny))) / (P.temp0 * ev);
-      else yldot[iv1] = P.nurlxe * (P.tewallo[ix] * ev - A(te, ix, ny + 1)) / (P.temp0 * ev);
+      else if (P.istewcix[ix] == 1) yldot[iv1] = P.nurlxe * (P.tewallo[ix] * ev - A(te, ix, ny + 1)) / (P.temp0 * ev);
+      else if (P.istewcix[ix] == 2) {
+        double tbound = A(te, ix, ny) + G(gyf, ix, ny - 1) * (A(te, ix, ny) - A(te, ix, ny - 1)) / G(gyf, ix, ny);
+        tbound = std::max(tbound, P.tbmin * ev);
+        yldot[iv1] = P.nurlxe * (tbound - A(te, ix, ny + 1)) / (P.temp0 * ev);
+      } else yldot[iv1] = P.nurlxe * ((A(te, ix, ny) - A(te, ix, ny + 1)) - 0.5 * (A(te, ix, ny) + A(te, ix, ny + 1)) / (G(gyf, ix, ny) * P.lytewc[ix])) / (P.temp0 * ev);
       if (P.istiwcix[ix] == 0) yldot[iv2] = P.nurlxi * (A(feiy, ix, ny) / (P.n0 * P.vpnorm * G(sy, ix, ny))) / (P.temp0 * ev);
-      else yldot[iv2] = P.nurlxi * (P.tiwallo[ix] * ev - A(ti, ix, ny + 1)) / (P.temp0 * ev);
+      else if (P.istiwcix[ix] == 1) yldot[iv2] = P.nurlxi * (P.tiwallo[ix] * ev - A(ti, ix, ny + 1)) / (P.temp0 * ev);
+      else if (P.istiwcix[ix] == 2) {
+        double tbound = A(ti, ix, ny) + G(gyf, ix, ny - 1) * (A(ti, ix, ny) - A(ti, ix, ny - 1)) / G(gyf, ix, ny);
+        tbound = std::max(tbound, P.tbmin * ev);
+        yldot[iv2] = P.nurlxi * (tbound - A(ti, ix, ny + 1)) / (P.temp0 * ev);
+      } else yldot[iv2] = P.nurlxi * ((A(ti, ix, ny) - A(ti, ix, ny + 1)) - 0.5 * (A(ti, ix, ny) + A(ti, ix, ny + 1)) / (G(gyf, ix, ny) * P.lytiwc[ix])) / (P.temp0 * ev);
     }
     for (int ix = w.i4; ix <= w.i8 && HASG; ++ix) {  // boundary.m:1366-1462
       int64_t iv = IDXG(ix, ny + 1);
@@ -617,6 +658,18 @@ int bouncon(const Win& w, const double* yl, double* yldot) {
       double nharmave = 2. * (A(ng, ix, ny) * A(ng, ix, ny + 1)) / (A(ng, ix, ny) + A(ng, ix, ny + 1));
       double fng_alb = (1 - P.albedoo[ix]) * nharmave * vyn * G(sy, ix, ny);
       yldot[iv] = P.nurlxg * (A(fngy, ix, ny) - fng_alb + fng_chem + sputflxw) / (vyn * G(sy, ix, ny) * P.n0g);
+      if (P.matwallo[ix] > 0) {  // recycling wall, boundary.m:1424-1452
+        if (P.recycwot[ix] > 0.) {
+          double fniy_recy = P.fac2sp * A(fniy, ix, ny);
+          if (P.isrefluxclip == 1) fniy_recy = std::max(fniy_recy, 0.);
+          yldot[iv] = P.nurlxg * (A(fngy, ix, ny) + fniy_recy * P.recycwot[ix] + P.fngyso[ix] + P.fngyo_use[ix] - fng_alb + fng_chem + sputflxw) /
+                      (vyn * P.n0g * G(sy, ix, ny));
+        } else if (P.recycwot[ix] < -1) yldot[iv] = P.nurlxg * (P.ngbackg - A(ng, ix, ny + 1)) / P.n0g;
+        else {
+          nharmave = 2. * (A(ng, ix, ny) * A(ng, ix, ny + 1)) / (A(ng, ix, ny) + A(ng, ix, ny + 1));
+          yldot[iv] = P.nurlxg * (A(fngy, ix, ny) - (1 + P.recycwot[ix]) * nharmave * vyn * G(sy, ix, ny)) / (vyn * P.n0g * G(sy, ix, ny));
+        }
+      }
     }
     if (w.xcnearlb || w.openbox) {  // boundary.m:1543-1583
       yldot[IDXU(ixlb, ny + 1)] = -P.nurlxu * (A(up, ixlb, ny + 1) - 0.5 * (A(up, ixlb, ny) + A(up, ixlb + 1, ny + 1))) / P.vpnorm;
@@ -1438,10 +1491,9 @@ int check_switches() {
     if ((mx != 2 && mx != 3) || (my != 2 && my != 3)) { g_err = "meth* must use schemes 2 (central) or 3 (upwind)"; return -5; }
   }
   for (int ix = 0; ix < NXS; ++ix) {
-    if (P.matwalli[ix] != 0 || P.matwallo[ix] != 0) { g_err = "matwalli/matwallo>0 not built"; return -5; }
     if (P.fngysi[ix] != 0 || P.fngyso[ix] != 0 || P.fngyi_use[ix] != 0 || P.fngyo_use[ix] != 0) { g_err = "wall gas sources not built"; return -5; }
-    if (P.isnwconiix[ix] != 0 || P.isnwconoix[ix] != 0) { g_err = "isnwconi/o != 0 not built"; return -5; }
-    if (P.istepfcix[ix] > 1 || P.istipfcix[ix] > 1 || P.istewcix[ix] > 1 || P.istiwcix[ix] > 1) { g_err = "istepfc/istewc > 1 not built"; return -5; }
+    for (int64_t v : {P.isnwconiix[ix], P.isnwconoix[ix]}) if (v != 0 && v != 1 && v != 3) { g_err = "isnwconi/o must be 0, 1 or 3"; return -5; }
+    for (int64_t v : {P.istepfcix[ix], P.istipfcix[ix], P.istewcix[ix], P.istiwcix[ix]}) if (v < 0 || v > 3) { g_err = "istepfc/istipfc/istewc/istiwc must be 0..3"; return -5; }
   }
   return 0;
 }

@@ -84,8 +84,69 @@ def test_case1_column_split_and_one_call_form(built):
     assert np.array_equal(jac2, jo[0]) and np.array_equal(ja2, jo[1]) and np.array_equal(ia2, jo[2])
 
 
-def test_half_space_with_core_region_is_refused(built):
-    """isfixlb=2 with iysptrx1 > 0 (pyexamples/box2) also zeroes fluxes on the cut at ixpt2: not built, refused by name."""
+@pytest.mark.parametrize("perturb,seed", [(0.0, 1), (1e-2, 2), (0.2, 3)])
+def test_box2_diffusive_variant_parity(built, perturb, seed):
+    """pyexamples/box2 (slab 6x6 with a core region, iysptrx=2, core power condition iflcore=1, symmetry plane) with the
+    deck's physics except the neutral model: diffusive atoms (isupgon=0, isngon=1) instead of inertial ones.  Exercises
+    the half-space cut at ixpt2: fluxes/gradients forced to zero (oderhs.m:2447-2466) and up -> 0 rows
+    (boundary.m:1772-1785)."""
+    c, yl, gpu, ora = _pair("box2d", perturb, seed=seed)
+    assert (c.com.nx, c.com.ny, c.com.ixpt1, c.com.ixpt2, c.com.iysptrx) == (6, 6, -1, 3, 2) and c.bbb.neq == 320
+    fg, fo = gpu.pandf1(yl), ora.pandf1(yl)
+    assert np.isfinite(fo).all() and np.array_equal(fg, fo), "%d of %d entries differ" % ((fg != fo).sum(), fg.size)
+    jg, jo, noise = _jac_pair(c, yl, gpu, ora)
+    assert len(jo[0]) > 3000
+    _check_jac(jg, jo, noise)
+
+
+@pytest.mark.parametrize("ov", [
+    {"bbb.isupcore": 1, "bbb.iflcore": 0},
+    {"bbb.isngon": 0, "com.istabon": 7},
+    {"bbb.methn": 22, "bbb.methu": 22, "bbb.methe": 22, "bbb.methi": 22, "bbb.methg": 22, "bbb.isbcwdt": 1},
+    {"bbb.xlinc": 3, "bbb.xrinc": 2, "bbb.yinc": 3},
+])
+def test_box2_switch_variants(built, ov):
+    c, yl, gpu, ora = _pair("box2d", 0.05, overrides=ov, seed=7)
+    fg, fo = gpu.pandf1(yl), ora.pandf1(yl)
+    assert np.array_equal(fg, fo)
+    _check_jac(*_jac_pair(c, yl, gpu, ora))
+
+
+def test_box2_rough_state(built):
+    """Flow reversals and steep cell-to-cell jumps around the cut."""
     c, yl = make_case("box2d")
-    with pytest.raises(UeError, match="isfixlb=2 with a core region"):
-        bind(load_gpu(), c)
+    n, nv = c.bbb.neq, c.bbb.numvar
+    rng = np.random.default_rng(5)
+    y = yl[:n].reshape(-1, nv).copy()
+    y[:, [0, 2, 3, 4]] *= 3.0 ** rng.uniform(-1, 1, (y.shape[0], 4))
+    y[:, 1] = (np.abs(y[:, 1]) + 0.05) * rng.choice([-1.0, 1.0], y.shape[0]) * rng.uniform(0.2, 2.0, y.shape[0])
+    yl[:n] = y.reshape(-1)
+    gpu, ora = bind(load_gpu(), c), bind(oracle(), c)
+    fg, fo = gpu.pandf1(yl), ora.pandf1(yl)
+    assert np.array_equal(fg, fo)
+    _check_jac(*_jac_pair(c, yl, gpu, ora))
+
+
+WALL_BC_SETS = [
+    # the wall conditions of pyexamples/input_example/input.py:30-48 and builder/test/level_2/rdd3d_cfdupg.8x4
+    {"bbb.istepfc": 3, "bbb.lyte": np.array([0.03, 0.03]), "bbb.matwso": 1, "bbb.recycw": 0.9, "bbb.isnwcono": 1, "bbb.isnwconi": 1,
+     "bbb.nwallo": 1.0e18, "bbb.nwalli": 1.0e18},
+    # extrapolated wall temperatures (second interior row enters the guard rows), gradient-length wall densities
+    {"bbb.istepfc": 2, "bbb.istipfc": 2, "bbb.istewc": 2, "bbb.istiwc": 2, "bbb.isnwcono": 3, "bbb.isnwconi": 3, "bbb.lyni": np.array([0.05, 0.02])},
+    {"bbb.istipfc": 3, "bbb.istiwc": 3, "bbb.istewc": 3, "bbb.lyte": np.array([0.02, 0.04]), "bbb.lyti": np.array([0.05, 0.03]),
+     "bbb.matwso": 1, "bbb.matwsi": 1, "bbb.recycw": -0.5, "bbb.isrefluxclip": 0},
+    {"bbb.matwso": 1, "bbb.matwsi": 1, "bbb.recycw": -2.0, "bbb.albdso": 0.9, "bbb.albdsi": 0.8},
+]
+
+
+@pytest.mark.parametrize("name", ["d3dHsm", "box2d"])
+@pytest.mark.parametrize("k", range(len(WALL_BC_SETS)))
+def test_wall_boundary_condition_variants(built, name, k):
+    c, yl, gpu, ora = _pair(name, 0.02, overrides=WALL_BC_SETS[k], seed=20 + k)
+    fg, fo = gpu.pandf1(yl), ora.pandf1(yl)
+    assert np.isfinite(fo).all() and np.array_equal(fg, fo), "%d of %d entries differ" % ((fg != fo).sum(), fg.size)
+    # the variant must actually change guard rows
+    c0, yl0 = make_case(name, perturb=0.02, seed=20 + k)
+    assert not np.array_equal(bind(oracle(), c0).pandf1(yl0), fo)
+    bind(ora, c)
+    _check_jac(*_jac_pair(c, yl, gpu, ora))

@@ -329,6 +329,17 @@ template <bool WIN> __device__ __forceinline__ double f_uu(const Acc<WIN>& a, in
   const int NXS = a.NXS;
   return GG(rrv, ix, iy) * a.get(PL_UP, ix, iy) + 0. - 0. - 0.;
 }
+// Half-space problem with a core region (isfixlb = 2, iysptrx1 > 0): after the velocities, the electron drift velocity and
+// the neutral fluxes are formed, the reference sets gpex, frice, ex, upe, gpix, frici, uu, upi to zero on the cut face
+// ix = ixpt2, iy <= iysptrx1 (oderhs.m:2447-2466); every later reader sees zeros there.  (Every windowed evaluation that
+// recomputes those fields there is an "xccuts" window spanning all ix, so it re-applies the zeroing: the fields are
+// zero in every state a reader can see.)  gpix, gpex, frice have only later readers and are stored as zeros; upe, uu
+// and upi (= up) also have earlier readers (vex, the neutral convection, upe itself), so their later readers go through
+// the *_cut accessors below.
+__device__ __forceinline__ bool d_cut(int ix, int iy) { return D.isfixlb == 2 && D.iysptrx1 > 0 && ix == (int)D.ixpt2 && iy <= (int)D.iysptrx1; }
+template <bool WIN> __device__ __forceinline__ double f_uu_cut(const Acc<WIN>& a, int ix, int iy) { return d_cut(ix, iy) ? 0. : f_uu(a, ix, iy); }
+template <bool WIN> __device__ __forceinline__ double f_upi_cut(const Acc<WIN>& a, int ix, int iy) { return d_cut(ix, iy) ? 0. : a.get(PL_UP, ix, iy); }
+template <bool WIN> __device__ __forceinline__ double f_upe_cut(const Acc<WIN>& a, int ix, int iy) { return d_cut(ix, iy) ? 0. : a.get(PL_UPE, ix, iy); }
 template <bool WIN> __device__ __forceinline__ double f_visy(const Acc<WIN>& a, int ix, int iy) {  // oderhs.m:2784
   return (D.fcdif * D.travis + 0.) * f_nm(a, ix, iy) + 4 * 0.;
 }
@@ -412,8 +423,8 @@ __device__ void p1_xpart(const Acc<WIN>& a, const Win& w, int ix, int iy) {
   else do_xg = (iy == w.yc) && in_xlist(ix, w.xc, iy, iy, NXS);
   const double gxf = GG(gxf, ix, iy), rrv = GG(rrv, ix, iy);
   if (do_xg) {
-    a.set(PL_GPIX, ix, iy, (f_pri(a, ix1, iy) - f_pri(a, ix, iy)) * gxf);
-    a.set(PL_GPEX, ix, iy, (f_pre(a, ix1, iy) - f_pre(a, ix, iy)) * gxf);
+    a.set(PL_GPIX, ix, iy, d_cut(ix, iy) ? 0. : (f_pri(a, ix1, iy) - f_pri(a, ix, iy)) * gxf);
+    a.set(PL_GPEX, ix, iy, d_cut(ix, iy) ? 0. : (f_pre(a, ix1, iy) - f_pre(a, ix, iy)) * gxf);
   }
   const P1Rng r = p1_ranges(w, ix, iy);
   if (r.r16) {
@@ -424,7 +435,7 @@ __device__ void p1_xpart(const Acc<WIN>& a, const Win& w, int ix, int iy) {
     const double ltmax = fmin(fabs(te / (rrv * gtex + cutlo)), GG(lcone, ix, iy));
     const double lmfpe = 2e16 * ((te / ev) * (te / ev)) / ne;
     const double flxlimf = D.flalftf * ltmax / (D.flalftf * ltmax + lmfpe);
-    a.set(PL_FRICE, ix, iy, -D.cthe * flxlimf * nbarx * rrv * gtex + 0.);
+    a.set(PL_FRICE, ix, iy, d_cut(ix, iy) ? 0. : -D.cthe * flxlimf * nbarx * rrv * gtex + 0.);
     double upe = 0. + a.get(PL_UP, ix, iy) * D.zi * 0.5 * (ni + ni_e);
     upe = (upe - 0.) / (0.5 * (ne + ne_e));
     a.set(PL_UPE, ix, iy, upe);
@@ -505,7 +516,7 @@ __device__ void p1_visx(const Acc<WIN>& a, const Win& w, int ix, int iy) {
   double csh;
   if (D.isgxvon == 0) csh = visx * vol * gx * gx;
   else csh = visx * vol * gx * 2 * gxf * GG(gxf, ixw, iy) / (gxf + GG(gxf, ixw, iy));
-  const double msh = fabs(csh * (a.get(PL_UP, ixw, iy) - a.get(PL_UP, ix, iy)));
+  const double msh = fabs(csh * (f_upi_cut(a, ixw, iy) - f_upi_cut(a, ix, iy)));
   visx = visx / ue_pow(1 + ue_pow(msh / (mfl + 1.e-20 * msh), D.flgamv), 1 / D.flgamv);
   a.set(PL_VISX, ix, iy, visx);
 }
@@ -550,7 +561,7 @@ template <bool WIN> __device__ inline double f_fnix(const Acc<WIN>& a, int ix, i
   const int NXS = a.NXS;
   const int ix1 = IXP1(ix, iy);
   const double ni = a.get(PL_NI, ix, iy), ni_e = a.get(PL_NI, ix1, iy), sx = GG(sx, ix, iy);
-  const double uu = f_uu(a, ix, iy);
+  const double uu = f_uu_cut(a, ix, iy);
   const int methnx = (int)(D.methn % 10);
   double t2;
   if (methnx == 2) t2 = (ni + ni_e) / 2;
@@ -807,7 +818,7 @@ template <bool WIN> __device__ inline double f_fmix(const Acc<WIN>& a, int ixc, 
   // fmix at cell centre ixc = ixp1(ixw): upwind(flox(ixc), up(ixw), up(ixc)) - conx(ixc)*(up(ixc)-up(ixw))   (fd2tra pos=1)
   const int NXS = a.NXS;
   const int ixm = IXM1(ixc, iy);
-  const double uuv = 0.5 * (f_uu(a, ixm, iy) + f_uu(a, ixc, iy));
+  const double uuv = 0.5 * (f_uu_cut(a, ixm, iy) + f_uu_cut(a, ixc, iy));
   const double vol = GG(vol, ixc, iy), gx = GG(gx, ixc, iy);
   const double flox = D.cmfx * f_nm(a, ixc, iy) * uuv * vol * gx;
   double conx;
@@ -841,6 +852,11 @@ template <bool WIN> __device__ inline double f_fmiy(const Acc<WIN>& a, int ix, i
   return d_upwind(floy, p0, p1) - cony * (p1 - p0);
 }
 
+// half-space problem: the velocity rows on the cut ix = ixpt2, iy <= iysptrx2 are overwritten by up -> 0 whenever the
+// row window reaches the cut (boundary.m:1772-1785)
+__device__ __forceinline__ bool cut_up_gate(const Win& w) {
+  return D.isfixlb == 2 && w.i2 <= (int)D.ixpt2 && w.i5 >= (int)D.ixpt2 && w.j2 <= (int)D.iysptrx2;
+}
 // ============================================================================================
 // phase 2b — guard-cell rows (bouncon, boundary.m:102-2800).  Returns a 5-bit mask of rows written.
 // `ix,iy` is a guard cell; the right-plate momentum row that lives in interior column nx is
@@ -869,9 +885,14 @@ __device__ int phase2_guard(const Acc<WIN>& a, const Win& w, int ix, int iy, dou
         if (core) {
           if (D.isnicore == 1) out[0] = D.nurlxn * (D.ncore - ni) / D.n0;
           else out[0] = -D.nurlxn * (D.qe * (a.get(PL_FNIY, ix, 0) - 0.) / sy - D.curcore * GG(gyf, ix, 0) / D.sygytotc) / (D.qe * D.vpnorm * D.n0);
-        } else {
+        } else if (D.isnwconiix[ix] == 0) {
           out[0] = D.nurlxn * ((1 - D.ifluxni) * (a.get(PL_NIY1, ix, 0) - a.get(PL_NIY0, ix, 0)) -
                                D.ifluxni * (a.get(PL_FNIY, ix, 0) / (sy * D.vpnorm) - 0.001 * a.get(PL_NI, ix, 1) * a.get(PL_VY, ix, 0) / D.vpnorm)) / D.n0;
+        } else if (D.isnwconiix[ix] == 1) {  // fixed wall density (boundary.m:267-270)
+          out[0] = D.nurlxn * (D.nwalli[ix] - ni) / D.n0;
+        } else {  // == 3: specified gradient length (boundary.m:278-282)
+          const double gyf0 = GG(gyf, ix, 0);
+          out[0] = -D.nurlxn * (a.get(PL_NIY0, ix, 0) - a.get(PL_NIY1, ix, 0) * (2 * gyf0 * D.lynipf[ix] - 1) / (2 * gyf0 * D.lynipf[ix] + 1) - D.nwimin) / D.n0;
         }
         // parallel velocity (boundary.m:313-380)
         if (core) {
@@ -898,10 +919,30 @@ __device__ int phase2_guard(const Acc<WIN>& a, const Win& w, int ix, int iy, dou
             }
           }
         } else {
-          if (D.istepfcix[ix] == 0) out[2] = -D.nurlxe * (a.get(PL_FEEY, ix, 0) / (D.n0 * D.vpnorm * sy)) / (D.temp0 * ev);
-          else out[2] = D.nurlxe * (D.tewalli[ix] * ev - te) / (D.temp0 * ev);
-          if (D.istipfcix[ix] == 0) out[3] = -D.nurlxi * (a.get(PL_FEIY, ix, 0) / (D.n0 * D.vpnorm * sy)) / (D.temp0 * ev);
-          else out[3] = D.nurlxi * (D.tiwalli[ix] * ev - ti) / (D.temp0 * ev);
+          // boundary.m:550-565, 597-612: 0 zero flux, 1 fixed, 2 extrapolation from rows 1 and 2, 3 specified gradient length
+          const int64_t me = D.istepfcix[ix], mi = D.istipfcix[ix];
+          if (me == 0) out[2] = -D.nurlxe * (a.get(PL_FEEY, ix, 0) / (D.n0 * D.vpnorm * sy)) / (D.temp0 * ev);
+          else if (me == 1) out[2] = D.nurlxe * (D.tewalli[ix] * ev - te) / (D.temp0 * ev);
+          else if (me == 2) {
+            const double t1 = a.get(PL_TE, ix, 1);
+            double tbound = t1 - GG(gyf, ix, 1) * (a.get(PL_TE, ix, 2) - t1) / GG(gyf, ix, 0);
+            tbound = fmax(tbound, D.tbmin * ev);
+            out[2] = D.nurlxe * (tbound - te) / (D.temp0 * ev);
+          } else {
+            const double t1 = a.get(PL_TE, ix, 1);
+            out[2] = D.nurlxe * ((t1 - te) - 0.5 * (t1 + te) / (GG(gyf, ix, 0) * D.lytepf[ix])) / (D.temp0 * ev);
+          }
+          if (mi == 0) out[3] = -D.nurlxi * (a.get(PL_FEIY, ix, 0) / (D.n0 * D.vpnorm * sy)) / (D.temp0 * ev);
+          else if (mi == 1) out[3] = D.nurlxi * (D.tiwalli[ix] * ev - ti) / (D.temp0 * ev);
+          else if (mi == 2) {
+            const double t1 = a.get(PL_TI, ix, 1);
+            double tbound = t1 - GG(gyf, ix, 1) * (a.get(PL_TI, ix, 2) - t1) / GG(gyf, ix, 0);
+            tbound = fmax(tbound, D.tbmin * ev);
+            out[3] = D.nurlxi * (tbound - ti) / (D.temp0 * ev);
+          } else {
+            const double t1 = a.get(PL_TI, ix, 1);
+            out[3] = D.nurlxi * ((t1 - ti) - 0.5 * (t1 + ti) / (GG(gyf, ix, 0) * D.lytipf[ix])) / (D.temp0 * ev);
+          }
         }
         // neutral density (boundary.m:632-767)
         {
@@ -916,17 +957,54 @@ __device__ int phase2_guard(const Acc<WIN>& a, const Win& w, int ix, int iy, dou
             const double fng_chem = 0., sputflxpf = 0.;
             const double fng_alb = (1 - D.albedoi[ix]) * nharmave * vyn * sy;
             out[4] = -D.nurlxg * (a.get(PL_FNGY, ix, 0) + fng_alb - fng_chem + sputflxpf) / (vyn * sy * D.n0g);
+            if (D.matwalli[ix] > 0) {  // recycling wall (boundary.m:733-760)
+              const double rw = D.recycwit[ix];
+              if (rw > 0.) {
+                double fniy_recy = D.fac2sp * a.get(PL_FNIY, ix, 0);
+                if (D.isrefluxclip == 1) fniy_recy = fmin(fniy_recy, 0.);
+                out[4] = -D.nurlxg * (a.get(PL_FNGY, ix, 0) + fniy_recy * rw - D.fngyi_use[ix] - D.fngysi[ix] + fng_alb - fng_chem + sputflxpf) / (vyn * D.n0g * sy);
+              } else if (rw < -1) out[4] = D.nurlxg * (D.ngbackg - ng) / D.n0g;
+              else {
+                const double nh2 = 2. * (ng * ng1) / (ng + ng1);
+                out[4] = -D.nurlxg * (a.get(PL_FNGY, ix, 0) + (1 + rw) * nh2 * vyn * sy) / (vyn * D.n0g * sy);
+              }
+            }
           }
         }
       } else {  // outer wall (boundary.m:1133-1462)
-        out[0] = D.nurlxn * ((1 - D.ifluxni) * (a.get(PL_NIY0, ix, ny) - a.get(PL_NIY1, ix, ny)) +
-                             D.ifluxni * (a.get(PL_FNIY, ix, ny) / (sy * D.vpnorm) - 0.001 * a.get(PL_NI, ix, ny) * a.get(PL_VY, ix, ny) / D.vpnorm)) / D.n0;
+        if (D.isnwconoix[ix] == 0)
+          out[0] = D.nurlxn * ((1 - D.ifluxni) * (a.get(PL_NIY0, ix, ny) - a.get(PL_NIY1, ix, ny)) +
+                               D.ifluxni * (a.get(PL_FNIY, ix, ny) / (sy * D.vpnorm) - 0.001 * a.get(PL_NI, ix, ny) * a.get(PL_VY, ix, ny) / D.vpnorm)) / D.n0;
+        else if (D.isnwconoix[ix] == 1) out[0] = D.nurlxn * (D.nwallo[ix] - ni) / D.n0;
+        else {
+          const double gyfn = GG(gyf, ix, ny);
+          out[0] = -D.nurlxn * (a.get(PL_NIY1, ix, ny) - a.get(PL_NIY0, ix, ny) * (2 * gyfn * D.lyniwc[ix] - 1) / (2 * gyfn * D.lyniwc[ix] + 1) - D.nwomin) / D.n0;
+        }
         if (D.isupwoix[ix] == 2) out[1] = D.nurlxu * f_nm(a, ix, ny) / D.fnorm * (a.get(PL_UP, ix, ny) - up);
         else out[1] = D.nurlxu * f_nm(a, ix, ny) / D.fnorm * (0. - up);
-        if (D.istewcix[ix] == 0) out[2] = D.nurlxe * (a.get(PL_FEEY, ix, ny) / (D.n0 * D.vpnorm * sy)) / (D.temp0 * ev);
-        else out[2] = D.nurlxe * (D.tewallo[ix] * ev - te) / (D.temp0 * ev);
-        if (D.istiwcix[ix] == 0) out[3] = D.nurlxi * (a.get(PL_FEIY, ix, ny) / (D.n0 * D.vpnorm * sy)) / (D.temp0 * ev);
-        else out[3] = D.nurlxi * (D.tiwallo[ix] * ev - ti) / (D.temp0 * ev);
+        const int64_t me = D.istewcix[ix], mi = D.istiwcix[ix];  // boundary.m:1314-1357
+        if (me == 0) out[2] = D.nurlxe * (a.get(PL_FEEY, ix, ny) / (D.n0 * D.vpnorm * sy)) / (D.temp0 * ev);
+        else if (me == 1) out[2] = D.nurlxe * (D.tewallo[ix] * ev - te) / (D.temp0 * ev);
+        else if (me == 2) {
+          const double t1 = a.get(PL_TE, ix, ny);
+          double tbound = t1 + GG(gyf, ix, ny - 1) * (t1 - a.get(PL_TE, ix, ny - 1)) / GG(gyf, ix, ny);
+          tbound = fmax(tbound, D.tbmin * ev);
+          out[2] = D.nurlxe * (tbound - te) / (D.temp0 * ev);
+        } else {
+          const double t1 = a.get(PL_TE, ix, ny);
+          out[2] = D.nurlxe * ((t1 - te) - 0.5 * (t1 + te) / (GG(gyf, ix, ny) * D.lytewc[ix])) / (D.temp0 * ev);
+        }
+        if (mi == 0) out[3] = D.nurlxi * (a.get(PL_FEIY, ix, ny) / (D.n0 * D.vpnorm * sy)) / (D.temp0 * ev);
+        else if (mi == 1) out[3] = D.nurlxi * (D.tiwallo[ix] * ev - ti) / (D.temp0 * ev);
+        else if (mi == 2) {
+          const double t1 = a.get(PL_TI, ix, ny);
+          double tbound = t1 + GG(gyf, ix, ny - 1) * (t1 - a.get(PL_TI, ix, ny - 1)) / GG(gyf, ix, ny);
+          tbound = fmax(tbound, D.tbmin * ev);
+          out[3] = D.nurlxi * (tbound - ti) / (D.temp0 * ev);
+        } else {
+          const double t1 = a.get(PL_TI, ix, ny);
+          out[3] = D.nurlxi * ((t1 - ti) - 0.5 * (t1 + ti) / (GG(gyf, ix, ny) * D.lytiwc[ix])) / (D.temp0 * ev);
+        }
         const double t0 = fmax(D.cdifg * f_tg(a, ix, ny + 1), D.tgmin * ev);
         const double vyn = 0.25 * sqrt(8 * t0 / (pi * D.mg));
         const double fng_chem = 0., sputflxw = 0.;
@@ -934,9 +1012,22 @@ __device__ int phase2_guard(const Acc<WIN>& a, const Win& w, int ix, int iy, dou
         const double nharmave = 2. * (ngc * ng) / (ngc + ng);
         const double fng_alb = (1 - D.albedoo[ix]) * nharmave * vyn * sy;
         out[4] = D.nurlxg * (a.get(PL_FNGY, ix, ny) - fng_alb + fng_chem + sputflxw) / (vyn * sy * D.n0g);
+        if (D.matwallo[ix] > 0) {  // recycling wall (boundary.m:1424-1452)
+          const double rw = D.recycwot[ix];
+          if (rw > 0.) {
+            double fniy_recy = D.fac2sp * a.get(PL_FNIY, ix, ny);
+            if (D.isrefluxclip == 1) fniy_recy = fmax(fniy_recy, 0.);
+            out[4] = D.nurlxg * (a.get(PL_FNGY, ix, ny) + fniy_recy * rw + D.fngyso[ix] + D.fngyo_use[ix] - fng_alb + fng_chem + sputflxw) / (vyn * D.n0g * sy);
+          } else if (rw < -1) out[4] = D.nurlxg * (D.ngbackg - ng) / D.n0g;
+          else {
+            const double nh2 = 2. * (ngc * ng) / (ngc + ng);
+            out[4] = D.nurlxg * (a.get(PL_FNGY, ix, ny) - (1 + rw) * nh2 * vyn * sy) / (vyn * D.n0g * sy);
+          }
+        }
       }
       mask = 0x1f;
     }
+    if (bottom && ix == (int)D.ixpt2 && cut_up_gate(w)) { out[1] = D.nurlxu * (0. - a.get(PL_UP, ix, 0)) / D.vpnorm; mask |= 2; }  // boundary.m:1772-1785 (iy = 0)
     // corner cells and the special rows next to them (boundary.m:290-303, 897-983, 1209-1226, 1543-1630)
     if (ix == ixlb) {
       if (!(bottom && D.isfixlb == 2)) {  // boundary.m:291: the bottom-left corner keeps the iy=0 condition on a symmetry plane
@@ -1180,6 +1271,7 @@ __device__ void p2_m(const Acc<WIN>& a, const Win& w, int ix, int iy, double out
   if (ix == D.ixrb) out[1] = resmo / (GG(volv, ix, iy) * D.fnorm);
   double v;
   if (rightplate_up<WIN>(a, w, ix, iy, v)) out[1] = v;
+  if (cut_up_gate(w) && ix == (int)D.ixpt2 && iy <= (int)D.iysptrx2) out[1] = D.nurlxu * (0. - up) / D.vpnorm;  // boundary.m:1772-1785
 }
 
 template <bool WIN>
@@ -1193,7 +1285,9 @@ __device__ void p2_e(const Acc<WIN>& a, int ix, int iy, double out[UE_NV], const
   const double ni = a.get(PL_NI, ix, iy), te = a.get(PL_TE, ix, iy), ti = a.get(PL_TI, ix, iy);
   const double up = a.get(PL_UP, ix, iy), up_w = a.get(PL_UP, ix1, iy);
   const double gpex = a.get(PL_GPEX, ix, iy), gpex_w = a.get(PL_GPEX, ix1, iy);
-  const double upe = a.get(PL_UPE, ix, iy), upe_w = a.get(PL_UPE, ix1, iy);
+  const double upe_raw = a.get(PL_UPE, ix, iy), upe_raw_w = a.get(PL_UPE, ix1, iy);  // vex was formed before the cut zeroing
+  const double upe = f_upe_cut(a, ix, iy), upe_w = f_upe_cut(a, ix1, iy);
+  const double upi = f_upi_cut(a, ix, iy), upi_w = f_upi_cut(a, ix1, iy);
   const double vey = a.get(PL_VEY, ix, iy);
   double seec = 0.;
   {  // oderhs.m:2471-2495, 2534-2538, 2557-2572
@@ -1201,13 +1295,13 @@ __device__ void p2_e(const Acc<WIN>& a, int ix, int iy, double out[UE_NV], const
     const double t1old = .5 * D.cvgp * (upe * rrv * d_ave(gx, gx_e) * gpex / gxf + upe_w * rrv_w * d_ave(gx, gx_w) * gpex_w / gxf_w);
     const double t2old = 0.;
     const int iyp1 = min(iy + 1, ny + 1), iym1 = max(iy - 1, 0);
-    const double vex = upe * rrv + 0. - 0., vex_w = upe_w * rrv_w + 0. - 0.;
+    const double vex = upe_raw * rrv + 0. - 0., vex_w = upe_raw_w * rrv_w + 0. - 0.;
     const double t1new = .5 * D.cvgp * (vex * d_ave(gx, gx_e) * gpex / gxf + vex_w * d_ave(gx, gx_w) * gpex_w / gxf_w);
     const double gy = GG(gy, ix, iy);
     const double t2new = .5 * D.cvgp * (vey * d_ave(gy, GG(gy, ix, iyp1)) * a.get(PL_GPEY, ix, iy) / GG(gyf, ix, iy) +
                                        vey * d_ave(gy, GG(gy, ix, iym1)) * a.get(PL_GPEY, ix, iym1) / GG(gyf, ix, iym1));
     seec = seec + (t1old * vol - t2old) * D.oldseec + ((t1new + t2new) * vol) * (1 - D.oldseec);
-    const double tv = 0.25 * (a.get(PL_FRICE, ix, iy) + a.get(PL_FRICE, ix1, iy)) * (upe + upe_w - up - up_w);
+    const double tv = 0.25 * (a.get(PL_FRICE, ix, iy) + a.get(PL_FRICE, ix1, iy)) * (upe + upe_w - upi - upi_w);
     const double nz2 = 0. + ni * (D.zi * D.zi);
     seec = seec - (D.zi * D.zi) * ni * tv * vol / nz2;
     const double t1y = .5 * D.cvgp * (a.get(PL_VY, ix, iy) * a.get(PL_GPIY, ix, iy) + a.get(PL_VY, ix, iy - 1) * a.get(PL_GPIY, ix, iy - 1) + 0. + 0.);
@@ -1252,26 +1346,27 @@ __device__ void p2_i(const Acc<WIN>& a, int ix, int iy, double out[UE_NV], const
   double resei = seic + 0. * ti + 0. + 0. - 0.;
   resei = resei - (a.get(PL_FEIX, ix, iy) - a.get(PL_FEIX, ix1, iy) + D.fluxfacy * (a.get(PL_FEIY, ix, iy) - a.get(PL_FEIY, ix, iy - 1)));
   const double w0 = vol * f_eqp(a, ix, iy) * (te - ti);
-  const double us = up + up_w;
+  const double upi = f_upi_cut(a, ix, iy), upi_w = f_upi_cut(a, ix1, iy);
+  const double us = upi + upi_w;
   resei = resei + w0 + D.cfneut * D.cfneutsor_ei * D.ctsor * 1.25e-1 * D.mi * (us * us) * D.fac2sp * psor + D.cfneut * D.cfneutsor_ei * D.ceisor * D.cnsor * D.eion * ev * psordis -
           D.cfneut * D.cfneutsor_ei * D.ccoldsor * ng * a.get(PL_NUCX, ix, iy) * (1.5 * ti - 0.125 * D.mi * (us * us) - D.eion * ev) * vol;
   {  // viscous heating (oderhs.m:4879-4930)
     const int ixn = IXM1(ix, iy + 1), ixs = IXM1(ix, iy - 1);
     const double thetacc = 0.5 * (0. + 0.);
-    const double dupdx = gx * (up - up_w);
+    const double dupdx = gx * (upi - upi_w);
     double wvh = D.cfvcsx * D.cfvisx * ue_cos(thetacc) * a.get(PL_VISX, ix, iy) * (dupdx * dupdx);
     double dupdy;
     const int64_t isx = D.isxpty[ix + NXS * iy];
-    const double up_n = a.get(PL_UP, ix, iy + 1), up_nw = a.get(PL_UP, ixn, iy + 1), up_s = a.get(PL_UP, ix, iy - 1), up_sw = a.get(PL_UP, ixs, iy - 1);
-    if (isx == 0) dupdy = 0.5 * (up + up_w - up_s - up_sw) * GG(gyf, ix, iy - 1);
-    else if (isx == -1) dupdy = 0.5 * (up_n + up_nw - up - up_w) * GG(gyf, ix, iy);
+    const double up_n = f_upi_cut(a, ix, iy + 1), up_nw = f_upi_cut(a, ixn, iy + 1), up_s = f_upi_cut(a, ix, iy - 1), up_sw = f_upi_cut(a, ixs, iy - 1);
+    if (isx == 0) dupdy = 0.5 * (upi + upi_w - up_s - up_sw) * GG(gyf, ix, iy - 1);
+    else if (isx == -1) dupdy = 0.5 * (up_n + up_nw - upi - upi_w) * GG(gyf, ix, iy);
     else if (isx == 1 && D.isvhyha == 1) {
-      const double upxavep1 = 0.5 * (up_n + up_nw), upxave0 = 0.5 * (up + up_w), upxavem1 = 0.5 * (up_s + up_sw);
+      const double upxavep1 = 0.5 * (up_n + up_nw), upxave0 = 0.5 * (upi + upi_w), upxavem1 = 0.5 * (up_s + up_sw);
       const double upf0 = 2. * upxavep1 * upxave0 * (upxavep1 + upxave0) / ((upxavep1 + upxave0) * (upxavep1 + upxave0) + D.upvhflr * D.upvhflr);
       const double upfm1 = 2. * upxave0 * upxavem1 * (upxave0 + upxavem1) / ((upxave0 + upxavem1) * (upxave0 + upxavem1) + D.upvhflr * D.upvhflr);
       dupdy = (upf0 - upfm1) * GG(gy, ix, iy);
     } else
-      dupdy = 0.25 * ((up_n + up_nw - up - up_w) * GG(gyf, ix, iy) + (up + up_w - up_s - up_sw) * GG(gyf, ix, iy - 1));
+      dupdy = 0.25 * ((up_n + up_nw - upi - upi_w) * GG(gyf, ix, iy) + (upi + upi_w - up_s - up_sw) * GG(gyf, ix, iy - 1));
     const double visy = f_visy(a, ix, iy);
     wvh = wvh + D.cfvcsy * D.cfvisy * visy * (dupdy * dupdy);
     wvh = wvh - ue_ksin(thetacc) * D.cfvcsy * D.cfvisy * visy * dupdx * dupdy;

@@ -652,9 +652,7 @@ int check_switches() {
   if (P.istabon != 0 && P.istabon != 7 && P.istabon != 10) { g_err = "istabon must be 0, 7 or 10"; return -5; }
   if (P.isngon != 0 && P.isngon != 1) { g_err = "isngon must be 0 or 1"; return -5; }
   if (P.isfixlb != 0 && P.isfixlb != 2) { g_err = "isfixlb must be 0 or 2"; return -5; }
-  // a half-space problem WITH a core region also forces fluxes and velocities to zero on the cut at ixpt2
-  // (oderhs.m:2447-2466, boundary.m:1772-1785): not built yet
-  if (P.isfixlb == 2 && P.iysptrx1 > 0) { g_err = "isfixlb=2 with a core region (iysptrx1 > 0) is outside the built hot path"; return -5; }
+  if (P.isfixlb == 2 && (P.ixpt2 < 1 || P.ixpt2 > P.nx)) { g_err = "isfixlb=2 needs the cut ixpt2 inside the mesh"; return -5; }
   // fnnuiz < 1 blends the new ionisation rate with the value left by the PREVIOUS pandf call (oderhs.m:1950-1961): the
   // reference's Jacobian then depends on the order in which the unknowns were perturbed; not reproducible in parallel
   if (P.fnnuiz != 1.) { g_err = "fnnuiz must be 1 (history-dependent rate blending is outside the built hot path)"; return -5; }
@@ -666,10 +664,9 @@ int check_switches() {
     if ((mx != 2 && mx != 3) || (my != 2 && my != 3)) { g_err = "meth* must use schemes 2 (central) or 3 (upwind)"; return -5; }
   }
   for (int ix = 0; ix < NXS; ++ix) {
-    if (P.matwalli[ix] != 0 || P.matwallo[ix] != 0) { g_err = "matwalli/matwallo>0 not built"; return -5; }
     if (P.fngysi[ix] != 0 || P.fngyso[ix] != 0 || P.fngyi_use[ix] != 0 || P.fngyo_use[ix] != 0) { g_err = "wall gas sources not built"; return -5; }
-    if (P.isnwconiix[ix] != 0 || P.isnwconoix[ix] != 0) { g_err = "isnwconi/o != 0 not built"; return -5; }
-    if (P.istepfcix[ix] > 1 || P.istipfcix[ix] > 1 || P.istewcix[ix] > 1 || P.istiwcix[ix] > 1) { g_err = "istepfc/istewc > 1 not built"; return -5; }
+    for (int64_t v : {P.isnwconiix[ix], P.isnwconoix[ix]}) if (v != 0 && v != 1 && v != 3) { g_err = "isnwconi/o must be 0, 1 or 3"; return -5; }
+    for (int64_t v : {P.istepfcix[ix], P.istipfcix[ix], P.istewcix[ix], P.istiwcix[ix]}) if (v < 0 || v > 3) { g_err = "istepfc/istipfc/istewc/istiwc must be 0..3"; return -5; }
   }
   for (int iy = 0; iy < ny + 2; ++iy)
     if (P.recylb[iy] < -1. || P.recyrb[iy] < -1.) { g_err = "recylb/recyrb < -1 not built"; return -5; }
@@ -721,6 +718,10 @@ void cell_candidates(const UeParams& P, int xc, int yc, std::vector<int>& out) {
     }
     for (int ix = 0; ix < nxs; ++ix) if (in[ix]) out.push_back(ix + nxs * iy);
   }
+  // extrapolation boundary conditions (istepfc/istipfc/istewc/istiwc = 2) read the second interior row
+  // (boundary.m:555-559, 1320-1324): a perturbation there changes the guard row two rows away
+  if (yc == 2 && (P.istepfcix[xc] == 2 || P.istipfcix[xc] == 2)) out.push_back(xc);
+  if (yc == nys - 3 && (P.istewcix[xc] == 2 || P.istiwcix[xc] == 2)) out.push_back(xc + nxs * (nys - 1));
   if (P.iflcore == 1 && yc <= 1) {
     const int cell = std::min((int)P.ixpt2, (int)P.nx);  // row 0
     if (std::find(out.begin(), out.end(), cell) == out.end()) out.push_back(cell);
