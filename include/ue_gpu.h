@@ -42,6 +42,11 @@ int ue_gpu_init(void);
 int ue_gpu_step_params(int64_t neq, const double* dtuse, const double* ylodt,
                        const double* suscal, const double* sfscal);
 
+/* ---- set_dt(neq,yl,f0) of the nksol driver (bbb/oderhs.m:9886-10147, called from bbb/odesolve.m:299): f0 = rhsnk(yl),
+ * then dtuse(iv) from ylodt (last ue_gpu_step_params), deldt, dtreal and model_dt (0..3).  dtuse stays on the device
+ * for the calls that follow and is also returned (neq doubles) for the Fortran module array. */
+int ue_gpu_set_dt(int64_t neq, const double* yl, double* f0, double* dtuse);
+
 /* ---- Pandf1rhs_interface: pandf1(-1,-1,0,neq,time,yl,yldot) ---------------
  * yl has neq+2 entries (yl(neq+1) = Jacobian-mode flag, yl(neq+2) = nufak);
  * yldot receives neq entries. */

@@ -2,11 +2,12 @@
 //
 // CPU restatement (plain scalar C++, double precision, no FMA contraction) of the
 // reference's residual pandf1 and finite-difference Jacobian jac_calc for the
-// switch set of the d3dHsm family: single hydrogen ion species + diffusive
-// atoms (nisp=nusp=ngsp=1, isupgon=0, isngon=1, istgon=0), orthogonal mesh
-// (isnonog=0), no potential equation (isphion=0), no impurities (isimpon=0),
-// ineudif=2 (neudifpg), all cross-field drift coefficients zero.  Any other
-// switch value is refused by ue_ora_init.
+// switch set of the d3dHsm and slab families: single hydrogen ion species +
+// diffusive atoms (nisp=nusp=ngsp=1, isupgon=0, istgon=0; isngon=1, or 0 = frozen
+// atom density and four unknowns per cell), orthogonal mesh (isnonog=0), ix=0 a plate or a
+// symmetry plane (isfixlb 0/2), no potential equation (isphion=0), no impurities
+// (isimpon=0), ineudif=2 (neudifpg), rates istabon 0/7/10, all cross-field drift
+// coefficients zero.  Any other switch value is refused by ue_ora_init.
 //
 // It keeps the reference's *stateful, windowed* semantics: all intermediate
 // fields are persistent arrays (the Fortran module state); a call with xc,yc>=0
@@ -19,6 +20,8 @@
 //    the UEDGE version that wrote it) max|yldot| <= 2.2e-6 against 1e5 a per-mille away, all five equations and all
 //    boundary rows; geometry (guardc/nphygeo) equals the stored mesh; Newton on this residual + Jacobian returns to that
 //    state within 4e-9 (normalised).
+//  * SANITY ONLY: Forthon_case1 (slab, isfixlb=2, isngon=0, istabon=7).  Integrating this residual from the restart=0 profiles
+//    to t = 4e-4 s lands within 0.3-5 % of the ni/up/te/ti arrays its 2007 output prints at that time.
 //  * SANITY ONLY: Forthon_case2 (istabon=10 tables).  The converged midplane profiles land within 2-4 % of
 //    output_forthon_case2.rtf (2007); its printed initial fnrm = 0.79266 is NOT reproduced (3.6156 here): defaults and
 //    boundary models changed since 2007.
@@ -70,7 +73,7 @@ V floxe, floxi, floye, floyi, conxe, conxi, conye, conyi, feex, feey, feix, feiy
 V erliz, erlrc, eeli, vsoreec, vsoree, wvh, pwribkg;
 V fniycbo, feeycbo, feiycbo;
 // per-solve inputs
-V dtuse, ylodt, suscal, sfscal;
+V dtuse, ylodt, suscal, sfscal, dtoptv;
 // rate tables (istabon=10)
 int mpe = 0, mpd = 0;
 V wsveh, wsveh0, welms1, welms2, ekpt, dkpt;
@@ -1534,7 +1537,7 @@ int ue_ora_init(void) {
   HASG = P.isngon == 1;
   if (!HASG) ng.assign(P.ngfix, P.ngfix + NC);  // never advanced: the field ueinit left (odesetup.m:1399-1406)
   fniycbo.assign(NXS, 0.); feeycbo.assign(NXS, 0.); feiycbo.assign(NXS, 0.);
-  dtuse.assign(neq, 1e20); ylodt.assign(neq, 0.); suscal.assign(neq, 1.); sfscal.assign(neq, 1.);
+  dtuse.assign(neq, 1e20); ylodt.assign(neq, 0.); suscal.assign(neq, 1.); sfscal.assign(neq, 1.); dtoptv.assign(neq, 0.);
   g_ivmin = 1; g_ivmax = neq;
   return 0;
 }
@@ -1551,6 +1554,47 @@ int ue_ora_pandf1_win(int64_t xc, int64_t yc, int64_t n, const double* yl, doubl
   return pandf1((int)xc, (int)yc, yl, yldot);
 }
 int ue_ora_pandf1(int64_t n, double time, const double* yl, double* yldot) { (void)time; return ue_ora_pandf1_win(-1, -1, n, yl, yldot); }
+
+// set_dt (oderhs.m:9886-10147): the per-unknown pseudo time step of the nksol equations, model_dt 0..3.
+// f0 = rhsnk(yl) first (oderhs.m:9914); ylodt is the vector of the last step_params call.  dtoptv persists between
+// calls (a velocity row whose |f0| <= cutlo keeps its previous value, oderhs.m:9950-9951).
+int ue_ora_set_dt(int64_t n, const double* yl, double* f0, double* dtuse_out) {
+  if (n != neq) { g_err = "set_dt: neq mismatch"; return -1; }
+  if (P.model_dt < 0 || P.model_dt > 3) { g_err = "model_dt must be 0..3"; return -5; }
+  int rc = pandf1(-1, -1, yl, f0);
+  if (rc) return rc;
+  auto model = [&](double dtopt) {
+    if (P.model_dt == 0) return P.dtreal;
+    if (P.model_dt == 1) return P.dtreal * dtopt / (P.dtreal + dtopt);
+    if (P.model_dt == 2) return dtopt;
+    return std::sqrt(P.dtreal * dtopt);
+  };
+  for (int iy = 0; iy <= ny + 1; ++iy) {
+    const int iym1 = std::max(0, iy - 1), iyp1 = std::min(ny + 1, iy + 1);
+    for (int ix = 0; ix <= nx + 1; ++ix) {
+      auto plain = [&](int64_t iv) {
+        dtoptv[iv] = P.deldt * std::fabs(ylodt[iv] / (f0[iv] + P.cutlo));
+        dtuse[iv] = model(dtoptv[iv]);
+      };
+      plain(IDXN(ix, iy));
+      if (ix != nx + 2 * P.isbcwdt) {
+        const int ixm1u = std::max(0, IXM1(ix, iy)), ixp1u = std::min(nx + 1, IXP1(ix, iy));
+        const int64_t iv = IDXU(ix, iy);
+        const double up_5ca = (std::fabs(ylodt[iv]) + std::fabs(ylodt[IDXU(ixm1u, iy)]) + std::fabs(ylodt[IDXU(ixp1u, iy)]) + std::fabs(ylodt[IDXU(ix, iyp1)]) +
+                               std::fabs(ylodt[IDXU(ix, iym1)])) / 5;
+        if (std::fabs(f0[iv]) > P.cutlo) dtoptv[iv] = P.deldt * std::fabs(up_5ca / (f0[iv]));
+        dtuse[iv] = model(dtoptv[iv]);
+      }
+      plain(IDXTE(ix, iy));
+      plain(IDXTI(ix, iy));
+      if (HASG) plain(IDXG(ix, iy));
+    }
+  }
+  if (P.isbcwdt == 0)
+    for (int64_t iv = 0; iv < neq; ++iv) if (P.iseqalg[iv] == 1) dtuse[iv] = 1.e20;
+  std::copy(dtuse.begin(), dtuse.end(), dtuse_out);
+  return 0;
+}
 
 int ue_ora_set_column_range(int64_t ivmin, int64_t ivmax) { g_ivmin = ivmin; g_ivmax = ivmax; return 0; }
 

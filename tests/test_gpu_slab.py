@@ -150,3 +150,35 @@ def test_wall_boundary_condition_variants(built, name, k):
     assert not np.array_equal(bind(oracle(), c0).pandf1(yl0), fo)
     bind(ora, c)
     _check_jac(*_jac_pair(c, yl, gpu, ora))
+
+
+@pytest.mark.parametrize("name,model_dt,isbcwdt", [("d3dHsm", 0, 0), ("d3dHsm", 1, 1), ("d3dHsm", 2, 0), ("d3dHsm", 3, 1), ("case1", 1, 0), ("box2d", 3, 1)])
+def test_set_dt_on_device(built, name, model_dt, isbcwdt):
+    """set_dt of the nksol driver (bbb/oderhs.m:9886-10147): f0 = rhsnk(yl) and the per-unknown pseudo time step, left on the
+    device for the residual / Jacobian calls that follow."""
+    c, yl, gpu, ora = _pair(name, 1e-2, overrides={"bbb.model_dt": model_dt, "bbb.isbcwdt": isbcwdt, "bbb.dtreal": 1e-5})
+    n = c.bbb.neq
+    rng = np.random.default_rng(31)
+    yo = yl[:n] * (1 + 1e-2 * rng.uniform(-1, 1, n)) + 1e-3  # no exact zeros: a zero ylodt entry gives dtuse = 0
+    for lib in (gpu, ora):
+        lib.step_params(np.full(n, 1e20), yo, np.ones(n), np.ones(n))
+    y = yl.copy(); y[n] = -1.0
+    (fg, dg), (fo, do) = gpu.set_dt(y), ora.set_dt(y)
+    assert np.array_equal(fg, fo) and np.array_equal(dg, do)
+    assert np.isfinite(do).all() and (do > 0).all()
+    if model_dt == 0:
+        assert set(np.unique(do)) <= {1e-5, 1e20}
+    else:
+        assert len(np.unique(do)) > n // 4
+    # the residual and the Jacobian that follow use the dtuse the call left behind (no step_params in between)
+    assert np.array_equal(gpu.pandf1(y), ora.pandf1(y))
+    y[n] = 1.0
+    fg, fo = gpu.pandf1(y), ora.pandf1(y)
+    b = c.bbb
+    jg, jo = gpu.jac_calc(y, fg, b.lbw, b.ubw, b.nnzmx), ora.jac_calc(y, fo, b.lbw, b.ubw, b.nnzmx)
+    assert all(np.array_equal(p, q) for p, q in zip(jg, jo))
+    # and a step_params call with the returned vector is recognised as unchanged / gives the same rows
+    for lib in (gpu, ora):
+        lib.step_params(do, yo, np.ones(n), np.ones(n))
+    y[n] = -1.0
+    assert np.array_equal(gpu.pandf1(y), ora.pandf1(y))

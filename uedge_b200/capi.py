@@ -99,6 +99,17 @@ class UeLib:
         self._call("step_params", self.neq, *[_d(x) for x in a])
 
     # ---- hot path ---------------------------------------------------------------
+    def set_dt(self, yl):
+        """set_dt of the nksol driver: (f0, dtuse)."""
+        fn = getattr(self.lib, self.prefix + "set_dt")
+        fn.argtypes = [_i64, _dp, _dp, _dp]
+        fn.restype = C.c_int
+        yl = np.ascontiguousarray(yl, dtype=np.float64)
+        f0 = np.zeros(self.neq); dt = np.zeros(self.neq)
+        if fn(self.neq, _d(yl), _d(f0), _d(dt)) != 0:
+            raise UeError("set_dt failed: %s" % getattr(self.lib, self.prefix + "last_error")().decode())
+        return f0, dt
+
     def pandf1(self, yl, time=0.0, out=None):
         """Pandf1rhs_interface: full residual pandf1(-1,-1,0,neq,time,yl,yldot).  `out` reuses a caller buffer."""
         yl = np.ascontiguousarray(yl, dtype=np.float64)

@@ -46,7 +46,7 @@ cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 
 std::vector<void*> g_static_allocs;
 double *d_base = nullptr, *d_yl = nullptr, *d_yldot00 = nullptr, *d_tmp = nullptr, *d_yldot = nullptr;
-double *d_dtuse = nullptr, *d_ylodt = nullptr, *d_suscal = nullptr, *d_sfscal = nullptr;
+double *d_dtuse = nullptr, *d_ylodt = nullptr, *d_suscal = nullptr, *d_sfscal = nullptr, *d_dtoptv = nullptr;
 int* d_err = nullptr;
 volatile long long* h_flags = nullptr;  // pinned + mapped: [0] error bits of the residual sequence, [1] ia(neq+1) of the last Jacobian, [2] error bits of the Jacobian sequence
 long long* d_hflags = nullptr;          // device alias of h_flags
@@ -602,6 +602,41 @@ __global__ void k_math_probe(int op, int64_t n, const double* __restrict__ x, co
 }
 
 // yldot00 must be the residual of yl bit for bit (see ue_gpu_jac_calc)
+// set_dt (oderhs.m:9886-10147), model_dt 0..3: one thread per cell; f0 is the residual just evaluated.  dtoptv persists
+// between calls (a velocity row with |f0| <= cutlo keeps its previous value).
+__device__ __forceinline__ double d_dtmodel(double dtopt) {
+  if (D.model_dt == 0) return D.dtreal;
+  if (D.model_dt == 1) return D.dtreal * dtopt / (D.dtreal + dtopt);
+  if (D.model_dt == 2) return dtopt;
+  return sqrt(D.dtreal * dtopt);
+}
+__global__ void k_set_dt(const double* __restrict__ f0, const double* __restrict__ ylodt, double* __restrict__ dtoptv, double* __restrict__ dtuse,
+                         double* __restrict__ dtuse_host, int NXS, int NC) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= NC) return;
+  const int nv = NVX, nx = (int)D.nx, ny = (int)D.ny;
+  const int ix = c % NXS, iy = c / NXS;
+  const int iym1 = max(0, iy - 1), iyp1 = min(ny + 1, iy + 1);
+#pragma unroll
+  for (int k = 0; k < UE_NV; ++k) {
+    if (k >= nv) continue;
+    const int64_t iv = (int64_t)c * nv + k;
+    bool wr = true;
+    if (k == 1) {
+      wr = (ix != nx + 2 * D.isbcwdt);
+      if (wr) {
+        const int ixm1u = max(0, IXM1(ix, iy)), ixp1u = min(nx + 1, IXP1(ix, iy));
+        const double up_5ca = (fabs(ylodt[iv]) + fabs(ylodt[d_iv(ixm1u, iy, 1, NXS)]) + fabs(ylodt[d_iv(ixp1u, iy, 1, NXS)]) + fabs(ylodt[d_iv(ix, iyp1, 1, NXS)]) +
+                               fabs(ylodt[d_iv(ix, iym1, 1, NXS)])) / 5;
+        if (fabs(f0[iv]) > D.cutlo) dtoptv[iv] = D.deldt * fabs(up_5ca / (f0[iv]));
+      }
+    } else dtoptv[iv] = D.deldt * fabs(ylodt[iv] / (f0[iv] + D.cutlo));
+    double dt = wr ? d_dtmodel(dtoptv[iv]) : dtuse[iv];
+    if (D.isbcwdt == 0 && D.iseqalg[iv] == 1) dt = 1.e20;
+    dtuse[iv] = dt;
+    dtuse_host[iv] = dt;
+  }
+}
 __global__ void k_samebits(const double* __restrict__ a, const double* __restrict__ b, int64_t n, int* __restrict__ err) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && __double_as_longlong(a[i]) != __double_as_longlong(b[i])) atomicOr(err, 4);
@@ -684,6 +719,7 @@ void free_all() {
   void* ptrs[] = {d_base, d_yl, d_yldot00, d_tmp, d_yldot, d_dtuse, d_ylodt, d_suscal, d_sfscal, d_err, d_cand_cell, d_cand_east, d_item_u, d_guard_items, d_guard_cells, d_coloff,
                   d_colcnt, d_colrow, d_colval, d_ia, d_ja, d_jac};
   for (void* p : ptrs) if (p) cudaFree(p);
+  if (d_dtoptv) { cudaFree(d_dtoptv); d_dtoptv = nullptr; }
   for (void* p : {(void*)d_uinfo, (void*)d_priv, (void*)d_jrows, (void*)d_rres, (void*)d_rmask}) if (p) cudaFree(p);
   d_uinfo = nullptr; d_priv = d_jrows = d_rres = nullptr; d_rmask = nullptr;
   d_base = d_yl = d_yldot00 = d_tmp = d_yldot = d_dtuse = d_ylodt = d_suscal = d_sfscal = nullptr;
@@ -1027,6 +1063,8 @@ int ue_gpu_init(void) {
   CK(cudaMalloc(&d_yldot, neq * sizeof(double)));
   CK(cudaMalloc(&d_dtuse, neq * sizeof(double)));
   CK(cudaMalloc(&d_ylodt, neq * sizeof(double)));
+  CK(cudaMalloc(&d_dtoptv, neq * sizeof(double)));
+  CK(cudaMemset(d_dtoptv, 0, neq * sizeof(double)));
   CK(cudaMalloc(&d_suscal, neq * sizeof(double)));
   CK(cudaMalloc(&d_sfscal, neq * sizeof(double)));
   CK(cudaMalloc(&d_err, 2 * sizeof(int)));  // [0] residual sequence, [1] Jacobian sequence
@@ -1311,6 +1349,29 @@ int ue_gpu_jac_calc(int64_t n, double t, const double* yl, const double* yldot00
   });
   if (rc) return rc;
   return finish_host_jac(direct, yl, same_y, nnzmx, lim, jac, ja, ia, nnz_out);
+}
+
+// set_dt(neq, yl, f0) of the nksol driver (bbb/odesolve.m:299, bbb/oderhs.m:9886-10147): f0 = rhsnk(yl), then the
+// per-unknown time step dtuse from ylodt (last ue_gpu_step_params), deldt, dtreal and model_dt (0..3).  dtuse stays on
+// the device for the residual and Jacobian calls that follow and is returned to the caller's array as well.
+int ue_gpu_set_dt(int64_t n, const double* yl, double* f0, double* dtuse) {
+  if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
+  if (n != neq) { g_err = "set_dt: neq mismatch"; return -1; }
+  if (S.p.model_dt < 0 || S.p.model_dt > 3) { g_err = "model_dt must be 0..3"; return -5; }
+  int rc = ue_gpu_pandf1(n, 0., yl, f0);  // leaves the residual in d_yldot
+  if (rc) return rc;
+  static double* h_dt = nullptr; static int64_t h_cap = 0;  // pinned staging for the returned vector
+  if (h_cap < neq) { if (h_dt) cudaFreeHost(h_dt); CK(cudaHostAlloc((void**)&h_dt, neq * 8, cudaHostAllocMapped)); h_cap = neq; }
+  double* h_dt_dev = nullptr;
+  CK(cudaHostGetDevicePointer((void**)&h_dt_dev, h_dt, 0));
+  const int B = 128, G = (NC + B - 1) / B;
+  CK(launch(k_set_dt, dim3(G), dim3(B), (const double*)d_yldot, (const double*)d_ylodt, d_dtoptv, d_dtuse, h_dt_dev, NXS, NC));
+  g_launches += 1;
+  CK(cudaStreamSynchronize(g_stream));
+  std::memcpy(dtuse, h_dt, neq * 8);
+  g_step_host[0].assign(dtuse, dtuse + neq);  // what the device now holds: an identical vector in step_params is not re-sent
+  g_last_yldot.clear();                       // dtuse enters the residual rows
+  return 0;
 }
 
 int ue_gpu_set_column_range(int64_t ivmin, int64_t ivmax) {
