@@ -44,6 +44,8 @@ enum Plane : int {
   PL_FNIX, PL_FNIY, PL_FNGX, PL_FNGY, PL_FEEX, PL_FEEY, PL_FEIX, PL_FEIY,
   // phase-2 output needed by rscalf
   PL_RESCO,
+  // feex on the cut face of a half-space problem as a WINDOWED evaluation computes it (vex = 0 there, see f_upe_pre)
+  PL_FEEXC,
   PL_COUNT
 };
 
@@ -340,6 +342,27 @@ __device__ __forceinline__ bool d_cut(int ix, int iy) { return D.isfixlb == 2 &&
 template <bool WIN> __device__ __forceinline__ double f_uu_cut(const Acc<WIN>& a, int ix, int iy) { return d_cut(ix, iy) ? 0. : f_uu(a, ix, iy); }
 template <bool WIN> __device__ __forceinline__ double f_upi_cut(const Acc<WIN>& a, int ix, int iy) { return d_cut(ix, iy) ? 0. : a.get(PL_UP, ix, iy); }
 template <bool WIN> __device__ __forceinline__ double f_upe_cut(const Acc<WIN>& a, int ix, int iy) { return d_cut(ix, iy) ? 0. : a.get(PL_UPE, ix, iy); }
+// upe BEFORE the zeroing, i.e. the value vex = upe*rrv is formed from (oderhs.m:1744-1792).  The reference's arrays are
+// persistent: upi on the cut was zeroed by the previous evaluation, and a Jacobian-mode evaluation refreshes upi only at
+// (xc,yc) and (ixm1(xc,yc),yc) (oderhs.m:1577-1643) while it recomputes upe -- from that upi -- over its whole window.
+// So a windowed evaluation forms vex on the cut from upi = 0 unless the cut cell is one of those two cells, whereas the
+// full evaluation (yldot00) used upi = up.  With up != 0 on the cut the electron-energy rows next to it therefore differ
+// from yldot00 in EVERY window that recomputes them, and the reference's Jacobian carries those finite-difference
+// artefacts as entries; they are reproduced here (f_upe_pre, PL_FEEXC, and the extra candidate rows in ue_lists.hpp).
+template <bool WIN> __device__ __forceinline__ double f_upe_pre(const Acc<WIN>& a, int ix, int iy) {
+  if (WIN && d_cut(ix, iy)) {
+    const int NXS = a.NXS;
+    const bool refreshed = iy == a.yc && (ix == a.xc || (a.xc > 0 && IXM1(a.xc, a.yc) == ix));
+    if (!refreshed) return 0.;
+  }
+  return a.get(PL_UPE, ix, iy);
+}
+// feex(ix,iy) for a row evaluation: on the cut face a windowed evaluation sees the vex = 0 variant unless it recomputed the
+// face itself (private cell)
+template <bool WIN> __device__ __forceinline__ double f_feex(const Acc<WIN>& a, int ix, int iy) {
+  if (WIN && d_cut(ix, iy) && a.slot(ix, iy) < 0) return a.get(PL_FEEXC, ix, iy);
+  return a.get(PL_FEEX, ix, iy);
+}
 template <bool WIN> __device__ __forceinline__ double f_visy(const Acc<WIN>& a, int ix, int iy) {  // oderhs.m:2784
   return (D.fcdif * D.travis + 0.) * f_nm(a, ix, iy) + 4 * 0.;
 }
@@ -690,12 +713,21 @@ __device__ void p1_exe(const Acc<WIN>& a, const Win& w, int ix, int iy) {
   const double conxe = (1 - D.isflxlde) * csh / ((1 + qr) * (1 + qr)) + D.isflxlde * csh / ue_pow(1 + ue_pow(fabs(qsh / qfl), D.flgam), 1 / D.flgam);
   const double rr = GG(rr, ix, iy), rr_e = GG(rr, ix1, iy);
   double floxe = 0. + (d_sgn(qr * qr, qsh) / ((1 + qr) * (1 + qr))) * D.flalfea[ix] * sx * (ne * rr * vt0 + ne_e * rr_e * vt1) / 2;
-  const double vex = a.get(PL_UPE, ix, iy) * rrv + 0. - 0.;
+  const double floxe0 = floxe;
+  const double vex = f_upe_pre(a, ix, iy) * rrv + 0. - 0.;
   floxe = floxe + D.cfcvte * 1.25 * (ne + ne_e) * vex * sx - 0.;
   double feex;
   if ((int)(D.methe % 10) == 2) feex = floxe * (te_e + te) / 2. - conxe * (te_e - te);
   else feex = d_upwind(floxe, te, te_e) - conxe * (te_e - te);
   a.set(PL_FEEX, ix, iy, feex);
+  if (!WIN && d_cut(ix, iy)) {  // the variant a windowed evaluation computes on the cut face: vex = 0
+    const double vex0 = 0. * rrv + 0. - 0.;
+    const double fl = floxe0 + D.cfcvte * 1.25 * (ne + ne_e) * vex0 * sx - 0.;
+    double f0;
+    if ((int)(D.methe % 10) == 2) f0 = fl * (te_e + te) / 2. - conxe * (te_e - te);
+    else f0 = d_upwind(fl, te, te_e) - conxe * (te_e - te);
+    a.set(PL_FEEXC, ix, iy, f0);
+  }
 }
 
 // ---- x-face ion energy flux (oderhs.m:2875-2965, 3001-3009, 3967-3993, 4065-4071, 4234-4240 + fd2tra) ---------
@@ -1285,7 +1317,7 @@ __device__ void p2_e(const Acc<WIN>& a, int ix, int iy, double out[UE_NV], const
   const double ni = a.get(PL_NI, ix, iy), te = a.get(PL_TE, ix, iy), ti = a.get(PL_TI, ix, iy);
   const double up = a.get(PL_UP, ix, iy), up_w = a.get(PL_UP, ix1, iy);
   const double gpex = a.get(PL_GPEX, ix, iy), gpex_w = a.get(PL_GPEX, ix1, iy);
-  const double upe_raw = a.get(PL_UPE, ix, iy), upe_raw_w = a.get(PL_UPE, ix1, iy);  // vex was formed before the cut zeroing
+  const double upe_raw = f_upe_pre(a, ix, iy), upe_raw_w = f_upe_pre(a, ix1, iy);  // vex was formed before the cut zeroing
   const double upe = f_upe_cut(a, ix, iy), upe_w = f_upe_cut(a, ix1, iy);
   const double upi = f_upi_cut(a, ix, iy), upi_w = f_upi_cut(a, ix1, iy);
   const double vey = a.get(PL_VEY, ix, iy);
@@ -1310,7 +1342,7 @@ __device__ void p2_e(const Acc<WIN>& a, int ix, int iy, double out[UE_NV], const
   double psor, psorxr, psordis;
   f_psor(a, ix, iy, psor, psorxr, psordis);
   double resee = seec + 0. * te + 0. + 0. - 0.;
-  resee = resee - (a.get(PL_FEEX, ix, iy) - a.get(PL_FEEX, ix1, iy) + D.fluxfacy * (a.get(PL_FEEY, ix, iy) - a.get(PL_FEEY, ix, iy - 1)));
+  resee = resee - (f_feex(a, ix, iy) - f_feex(a, ix1, iy) + D.fluxfacy * (a.get(PL_FEEY, ix, iy) - a.get(PL_FEEY, ix, iy - 1)));
   const double psorrgc = -psorxr;
   const double vsoree = -D.cfneut * D.cfneutsor_ee * D.cnsor * 13.6 * ev * D.fac2sp * psor + D.cfneut * D.cfneutsor_ee * D.cnsor * 13.6 * ev * D.fac2sp * psorrgc -
                         D.cfneut * D.cfneutsor_ee * D.cnsor * a.get(PL_ERLIZ, ix, iy) - D.cfneut * D.cfneutsor_ee * D.cnsor * a.get(PL_ERLRC, ix, iy) -

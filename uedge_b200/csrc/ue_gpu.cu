@@ -24,6 +24,7 @@
 
 #include "ue_device.cuh"
 #include "ue_gpu.h"
+#include "ue_lists.hpp"
 
 
 namespace {
@@ -726,43 +727,6 @@ void free_all() {
   d_err = nullptr; d_cand_cell = d_cand_east = d_item_u = d_guard_items = d_guard_cells = nullptr; d_coloff = nullptr; d_colcnt = d_colrow = nullptr; d_colval = nullptr;
   d_rowcnt = d_rowfill = nullptr; d_ia = d_ja = nullptr; d_jac = nullptr;
   g_ready = false;
-}
-
-// Candidate rows of a perturbation at cell (xc,yc): a superset of the cells whose residual rows can change.
-// The four private cells are C0, Cw = ixm1(C0), Ce = ixp1(C0) (row yc connectivity) and Cs = (xc,yc-1).  A row
-// (ix,iy') can read them only if iy' is within one row of yc and ix is within one poloidal step of {xw,xc,xe},
-// where "one step" is taken through the index maps of the rows involved (and plain ix+-1), so that cells across an
-// X-point cut are found where the maps connect them.  On a regular part of the mesh this is the 5 x 3 rectangle
-// around (xc,yc).  With the integrated core-power condition (iflcore=1, boundary.m:485-523) the row that carries
-// the poloidal sum, (min(ixpt2,nx), 0), also depends on every cell of rows 0 and 1.
-void cell_candidates(const UeParams& P, int xc, int yc, std::vector<int>& out) {
-  const int nxs = (int)P.nx + 2, nys = (int)P.ny + 2;
-  auto M1 = [&](int ix, int iy) { return (int)P.ixm1[ix + nxs * iy]; };
-  auto P1 = [&](int ix, int iy) { return (int)P.ixp1[ix + nxs * iy]; };
-  const int seeds[3] = {M1(xc, yc), xc, P1(xc, yc)};
-  out.clear();
-  for (int iy = std::max(0, yc - 1); iy <= std::min(nys - 1, yc + 1); ++iy) {
-    std::vector<char> in(nxs, 0);
-    for (int sd : seeds) {
-      in[sd] = 1;
-      if (sd - 1 >= 0) in[sd - 1] = 1;
-      if (sd + 1 < nxs) in[sd + 1] = 1;
-      for (int r = std::max(0, std::min(iy, yc) - 1); r <= std::min(nys - 1, std::max(iy, yc) + 1); ++r) {
-        in[M1(sd, r)] = 1; in[P1(sd, r)] = 1;
-        for (int ix = 0; ix < nxs; ++ix) if (M1(ix, r) == sd || P1(ix, r) == sd) in[ix] = 1;
-      }
-    }
-    for (int ix = 0; ix < nxs; ++ix) if (in[ix]) out.push_back(ix + nxs * iy);
-  }
-  // extrapolation boundary conditions (istepfc/istipfc/istewc/istiwc = 2) read the second interior row
-  // (boundary.m:555-559, 1320-1324): a perturbation there changes the guard row two rows away
-  if (yc == 2 && (P.istepfcix[xc] == 2 || P.istipfcix[xc] == 2)) out.push_back(xc);
-  if (yc == nys - 3 && (P.istewcix[xc] == 2 || P.istiwcix[xc] == 2)) out.push_back(xc + nxs * (nys - 1));
-  if (P.iflcore == 1 && yc <= 1) {
-    const int cell = std::min((int)P.ixpt2, (int)P.nx);  // row 0
-    if (std::find(out.begin(), out.end(), cell) == out.end()) out.push_back(cell);
-  }
-  std::sort(out.begin(), out.end());
 }
 
 // kind of a guard cell = which part of bouncon sets its rows; lists are sorted by kind and padded to whole warps
