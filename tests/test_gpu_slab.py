@@ -182,3 +182,11 @@ def test_set_dt_on_device(built, name, model_dt, isbcwdt):
         lib.step_params(do, yo, np.ones(n), np.ones(n))
     y[n] = -1.0
     assert np.array_equal(gpu.pandf1(y), ora.pandf1(y))
+
+
+@pytest.mark.parametrize("name", ["case1", "box2d"])
+@pytest.mark.parametrize("seed", range(6))
+def test_slab_fuzz(built, name, seed):
+    """Coefficient / array-input / integer-switch fuzz on the slab family (same inputs as the CPU logic check)."""
+    from tests.test_hostcheck import run_fuzzed
+    run_fuzzed(load_gpu(), name, seed)

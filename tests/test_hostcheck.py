@@ -77,3 +77,62 @@ def test_kernel_logic_set_dt(hk):
         (fo, do), (fh, dh) = ora.set_dt(y), hk.set_dt(y)
         assert np.array_equal(fo, fh) and np.array_equal(do, dh)
         assert np.array_equal(ora.pandf1(y), hk.pandf1(y))
+
+
+def fuzzed_slab_inputs(name, seed):
+    """The coefficient / array-input / integer-switch fuzz of tests/test_gpu_parity.py applied to a slab-family case:
+    scaled real coefficients, +-10 % noise on every geometry plane and 1-D array, a dozen random integer switches."""
+    from tests.test_gpu_parity import _FUZZ_SKIP, _FUZZ_ZERO_OK, _INT_CHOICES
+    rng = np.random.default_rng(13000 + seed)
+    c, yl = make_case(name, perturb=5e-3, seed=200 + seed)
+    s = c.static_inputs()
+    names = [k for k, v in s["reals"].items() if k not in _FUZZ_SKIP | {"deldt", "nwimin", "nwomin"} and v != 0.0 and abs(v) < 1e15]
+    for k in rng.choice(names, size=min(60, len(names)), replace=False):
+        s["reals"][k] = float(s["reals"][k]) * float(rng.uniform(0.8, 1.25))
+    for k in rng.choice(_FUZZ_ZERO_OK, size=6, replace=False):
+        if s["reals"][k] == 0.0:
+            s["reals"][k] = float(rng.uniform(0.05, 0.3))
+    for k in s["planes"]:
+        a = np.array(s["planes"][k], dtype=np.float64)
+        s["planes"][k] = a * rng.uniform(0.9, 1.1, a.shape)
+    for k in ("fgtdx", "fgtdy", "flalfea", "flalfia", "flalfva", "flalfgxa", "flalfgxya", "flalfgya", "tewalli", "tiwalli", "tewallo", "tiwallo",
+              "alblb", "albrb", "albedoi", "albedoo"):
+        a = np.array(s["lines"][k], dtype=np.float64)
+        s["lines"][k] = np.minimum(a * rng.uniform(0.9, 1.1, a.shape), np.where(a <= 1.0, 1.0, np.inf))
+    picked = {}
+    for k in rng.choice(sorted(_INT_CHOICES), size=12, replace=False):
+        picked[str(k)] = int(rng.choice(_INT_CHOICES[str(k)]))
+        s["ints"][str(k)] = picked[str(k)]
+    if s["ints"]["iflcore"] == 1:
+        s["reals"]["pcoree"] = s["reals"]["pcorei"] = 2.5e4
+    return c, yl, s, picked, 10.0 ** rng.uniform(-6, -2, c.bbb.neq)
+
+
+def run_fuzzed(lib, name, seed):
+    """Residual and Jacobian of `lib` against the oracle on fuzzed_slab_inputs (bit for bit)."""
+    c, yl, s, picked, dt = fuzzed_slab_inputs(name, seed)
+    ora = oracle()
+    ora.load_static(s)
+    try:
+        ora.init()
+    except Exception:
+        pytest.skip("combination refused: %s" % picked)
+    lib.load_static(s); lib.init()
+    n = c.bbb.neq
+    fo, fh = ora.pandf1(yl), lib.pandf1(yl)
+    if not np.isfinite(fo).all():
+        pytest.skip("non-physical combination: %s" % picked)
+    assert np.array_equal(fo, fh), "%s: %d residual entries differ" % (picked, (fo != fh).sum())
+    y, su = psetnk_inputs(c, yl)
+    for l in (ora, lib):
+        l.step_params(dt, y[:n], su, np.ones(n))
+    f1, f2 = ora.pandf1(y), lib.pandf1(y)
+    jo = ora.jac_calc(y, f1, c.bbb.lbw, c.bbb.ubw, c.bbb.nnzmx)
+    jh = lib.jac_calc(y, f2, c.bbb.lbw, c.bbb.ubw, c.bbb.nnzmx)
+    assert all(np.array_equal(p, q) for p, q in zip(jo, jh)), picked
+
+
+@pytest.mark.parametrize("name", ["case1", "box2d"])
+@pytest.mark.parametrize("seed", range(6))
+def test_kernel_logic_fuzz_slab(hk, name, seed):
+    run_fuzzed(hk, name, seed)
