@@ -524,6 +524,10 @@ int bouncon(const Win& w, const double* yl, double* yldot) {
                                  P.ifluxni * (A(fniy, ix, 0) / (G(sy, ix, 0) * P.vpnorm) - 0.001 * A(ni, ix, 1) * A(vy, ix, 0) / P.vpnorm)) / P.n0;
       } else if (P.isnwconiix[ix] == 1) {  // fixed wall density, boundary.m:267-270
         yldot[iv1] = P.nurlxn * (P.nwalli[ix] - A(ni, ix, 0)) / P.n0;
+      } else if (P.isnwconiix[ix] == 2) {  // extrapolation, boundary.m:271-277
+        double nbound = A(ni, ix, 1) - G(gyf, ix, 1) * (A(ni, ix, 2) - A(ni, ix, 1)) / G(gyf, ix, 0);
+        nbound = 1.2 * nbound / (1 + 0.5 * ue_exp(-2 * (nbound / A(ni, ix, 1) - 1))) + 0.2 * A(ni, ix, 1);
+        yldot[iv1] = P.nurlxn * (nbound - A(ni, ix, 0)) / P.n0;
       } else if (P.isnwconiix[ix] == 3) {  // specified gradient length, boundary.m:278-282
         yldot[iv1] = -P.nurlxn * (A(niy0, ix, 0) - A(niy1, ix, 0) * (2 * G(gyf, ix, 0) * P.lynipf[ix] - 1) / (2 * G(gyf, ix, 0) * P.lynipf[ix] + 1) - P.nwimin) / P.n0;
       }
@@ -535,7 +539,11 @@ int bouncon(const Win& w, const double* yl, double* yldot) {
       int64_t iv2 = IDXU(ix, 0);
       if (P.isixcore[ix] == 1) {
         if (P.isupcore == 0) yldot[iv2] = P.nurlxu * (P.upcore - A(up, ix, 0)) / P.vpnorm;
-        else yldot[iv2] = P.nurlxu * (A(up, ix, 1) - A(up, ix, 0)) / P.vpnorm;  // isupcore == 1
+        else if (P.isupcore == 1) yldot[iv2] = P.nurlxu * (A(up, ix, 1) - A(up, ix, 0)) / P.vpnorm;
+        else if (P.isupcore == 2)  // d2(up)/dy2 = 0, boundary.m:323-326
+          yldot[iv2] = P.nurlxu * ((A(up, ix, 1) - A(up, ix, 0)) * G(gy, ix, 1) - (A(up, ix, 2) - A(up, ix, 1)) * G(gy, ix, 2)) / (G(gy, ix, 1) * P.vpnorm);
+        else  // == 3: no radial momentum flux, boundary.m:327-329
+          yldot[iv2] = -P.nurlxu * A(fmiy, ix, 0) / (P.vpnorm * G(sy, ix, 0) * P.fnorm);
       } else if (P.isupwiix[ix] == 2) {
         yldot[iv2] = P.nurlxu * A(nm, ix, 0) / P.fnorm * (A(up, ix, 1) - A(up, ix, 0));
       } else {
@@ -559,6 +567,9 @@ int bouncon(const Win& w, const double* yl, double* yldot) {
             yldot[iv1] = -P.nurlxe * (feeytotc - P.pcoree) / (P.vpnorm * P.ennorm);
             yldot[iv2] = -P.nurlxi * (feiytotc - P.pcorei) / (P.vpnorm * P.ennorm);
           }
+        } else if (P.iflcore == -1) {  // zero radial temperature gradient, boundary.m:546-548, 594-596
+          yldot[iv1] = -P.nurlxe * (A(te, ix, 0) - A(te, ix, 1)) * P.n0 / P.ennorm;
+          yldot[iv2] = -P.nurlxi * (A(ti, ix, 0) - A(ti, ix, 1)) * P.n0 / P.ennorm;
         }
       } else {
         // boundary.m:550-565, 597-612: 0 zero flux, 1 fixed, 2 extrapolation, 3 specified gradient length
@@ -583,9 +594,19 @@ int bouncon(const Win& w, const double* yl, double* yldot) {
       double t0 = std::max(P.cdifg * A(tg, ix, 0), P.tgmin * ev);
       double vyn = 0.25 * std::sqrt(8 * t0 / (pi * P.mg));
       double nharmave = 2. * (A(ng, ix, 0) * A(ng, ix, 1)) / (A(ng, ix, 0) + A(ng, ix, 1));
-      if (P.isixcore[ix] == 1) {  // isngcore == 0
-        double fng_alb = (1 - P.albedoc) * nharmave * vyn * G(sy, ix, 0);
-        yldot[iv] = -P.nurlxg * (A(fngy, ix, 0) + fng_alb) / (vyn * G(sy, ix, 0) * P.n0g);
+      if (P.isixcore[ix] == 1) {  // boundary.m:651-681
+        if (P.isngcore == 0) {
+          double fng_alb = (1 - P.albedoc) * nharmave * vyn * G(sy, ix, 0);
+          yldot[iv] = -P.nurlxg * (A(fngy, ix, 0) + fng_alb) / (vyn * G(sy, ix, 0) * P.n0g);
+        } else if (P.isngcore == 1) yldot[iv] = P.nurlxg * (P.ngcore - A(ng, ix, 0)) / P.n0g;
+        else if (P.isngcore == 2) {
+          double lengg = std::sqrt(A(tg, ix, 0) / (P.mg * (A(nuix, ix, 0) * A(nuiz, ix, 0))));
+          yldot[iv] = P.nurlxn * ((A(ng, ix, 1) - A(ng, ix, 0)) - 0.5 * (A(ng, ix, 1) + A(ng, ix, 0)) / (G(gyf, ix, 0) * lengg)) / P.n0g;
+        } else if (P.isngcore == 3) {
+          double nbound = A(ng, ix, 1) - G(gyf, ix, 1) * (A(ng, ix, 2) - A(ng, ix, 1)) / G(gyf, ix, 0);
+          nbound = 1.2 * nbound / (1 + 0.5 * ue_exp(-2 * (nbound / A(ng, ix, 1) - 1))) + 0.2 * A(ng, ix, 1);
+          yldot[iv] = P.nurlxn * (nbound - A(ng, ix, 0)) / P.n0g;
+        } else yldot[iv] = P.nurlxn * (A(ng, ix, 1) - A(ng, ix, 0)) / P.n0g;  // == 4
       } else {  // chemsputi = 0, no ion sputtering, matwalli = 0, fngysi = fngyi_use = 0
         double fng_chem = 0., sputflxpf = 0.;
         double fng_alb = (1 - P.albedoi[ix]) * nharmave * vyn * G(sy, ix, 0);
@@ -626,6 +647,11 @@ int bouncon(const Win& w, const double* yl, double* yldot) {
         yldot[iv1] = P.nurlxn * ((1 - P.ifluxni) * (A(niy0, ix, ny) - A(niy1, ix, ny)) +
                                  P.ifluxni * (A(fniy, ix, ny) / (G(sy, ix, ny) * P.vpnorm) - 0.001 * A(ni, ix, ny) * A(vy, ix, ny) / P.vpnorm)) / P.n0;
       else if (P.isnwconoix[ix] == 1) yldot[iv1] = P.nurlxn * (P.nwallo[ix] - A(ni, ix, ny + 1)) / P.n0;
+      else if (P.isnwconoix[ix] == 2) {  // extrapolation, boundary.m:1192-1198
+        double nbound = A(ni, ix, ny) + G(gyf, ix, ny - 1) * (A(ni, ix, ny) - A(ni, ix, ny - 1)) / G(gyf, ix, ny);
+        nbound = 1.2 * nbound / (1 + 0.5 * ue_exp(-2 * (nbound / A(ni, ix, ny) - 1))) + 0.2 * A(ni, ix, ny);
+        yldot[iv1] = P.nurlxn * (nbound - A(ni, ix, ny + 1)) / P.n0;
+      }
       else  // == 3, specified gradient length
         yldot[iv1] = -P.nurlxn * (A(niy1, ix, ny) - A(niy0, ix, ny) * (2 * G(gyf, ix, ny) * P.lyniwc[ix] - 1) / (2 * G(gyf, ix, ny) * P.lyniwc[ix] + 1) - P.nwomin) / P.n0;
     }
@@ -1473,15 +1499,16 @@ int check_switches() {
       {"islimon", P.islimon, 0}, {"isdifbetap", P.isdifbetap, 0}, {"isugfm1side", P.isugfm1side, 0}, {"nxomit", P.nxomit, 0},
       {"isfixrb", P.isfixrb, 0}, {"isextrnp", P.isextrnp, 0}, {"isextrnpf", P.isextrnpf, 0}, {"isextrtpf", P.isextrtpf, 0}, {"isextrngc", P.isextrngc, 0},
       {"isextrnw", P.isextrnw, 0}, {"isextrtw", P.isextrtw, 0}, {"isnfmiy", P.isnfmiy, 0}, {"isybdrywd", P.isybdrywd, 0}, {"isnewpot", P.isnewpot, 0},
-      {"isbohmms", P.isbohmms, 0}, {"isgpye", P.isgpye, 0}, {"isngcore", P.isngcore, 0}, {"ibctepl", P.ibctepl, 1}, {"ibctipl", P.ibctipl, 1},
+      {"isbohmms", P.isbohmms, 0}, {"isgpye", P.isgpye, 0}, {"ibctepl", P.ibctepl, 1}, {"ibctipl", P.ibctipl, 1},
       {"ibctepr", P.ibctepr, 1}, {"ibctipr", P.ibctipr, 1}, {"iskaplex", P.iskaplex, 0}};
   for (auto& e : eq) if (e.v != e.want) { g_err = std::string("switch outside the built hot path: ") + e.n; return -5; }
   if (P.isngon != 0 && P.isngon != 1) { g_err = "isngon must be 0 or 1"; return -5; }
   if (P.isfixlb != 0 && P.isfixlb != 2) { g_err = "isfixlb must be 0 or 2"; return -5; }
   if (P.isbohmcalc != 0 && P.isbohmcalc != 1) { g_err = "isbohmcalc must be 0/1 with facb*=0"; return -5; }
   if (P.isnicore != 0 && P.isnicore != 1) { g_err = "isnicore must be 0 or 1"; return -5; }
-  if (P.isupcore != 0 && P.isupcore != 1) { g_err = "isupcore must be 0 or 1"; return -5; }
-  if (P.iflcore != 0 && P.iflcore != 1) { g_err = "iflcore must be 0 or 1"; return -5; }
+  if (P.isupcore < 0 || P.isupcore > 3) { g_err = "isupcore must be 0..3"; return -5; }
+  if (P.iflcore < -1 || P.iflcore > 1) { g_err = "iflcore must be -1, 0 or 1"; return -5; }
+  if (P.isngcore < 0 || P.isngcore > 4) { g_err = "isngcore must be 0..4"; return -5; }
   if (P.istabon != 0 && P.istabon != 7 && P.istabon != 10) { g_err = "istabon must be 0, 7 or 10"; return -5; }
   // fnnuiz < 1 blends the new ionisation rate with the value left by the PREVIOUS pandf call (oderhs.m:1950-1961): the
   // reference's Jacobian then depends on the order in which the unknowns were perturbed; not reproducible in parallel
@@ -1495,7 +1522,7 @@ int check_switches() {
   }
   for (int ix = 0; ix < NXS; ++ix) {
     if (P.fngysi[ix] != 0 || P.fngyso[ix] != 0 || P.fngyi_use[ix] != 0 || P.fngyo_use[ix] != 0) { g_err = "wall gas sources not built"; return -5; }
-    for (int64_t v : {P.isnwconiix[ix], P.isnwconoix[ix]}) if (v != 0 && v != 1 && v != 3) { g_err = "isnwconi/o must be 0, 1 or 3"; return -5; }
+    for (int64_t v : {P.isnwconiix[ix], P.isnwconoix[ix]}) if (v < 0 || v > 3) { g_err = "isnwconi/o must be 0..3"; return -5; }
     for (int64_t v : {P.istepfcix[ix], P.istipfcix[ix], P.istewcix[ix], P.istiwcix[ix]}) if (v < 0 || v > 3) { g_err = "istepfc/istipfc/istewc/istiwc must be 0..3"; return -5; }
   }
   return 0;

@@ -136,6 +136,11 @@ WALL_BC_SETS = [
     {"bbb.istipfc": 3, "bbb.istiwc": 3, "bbb.istewc": 3, "bbb.lyte": np.array([0.02, 0.04]), "bbb.lyti": np.array([0.05, 0.03]),
      "bbb.matwso": 1, "bbb.matwsi": 1, "bbb.recycw": -0.5, "bbb.isrefluxclip": 0},
     {"bbb.matwso": 1, "bbb.matwsi": 1, "bbb.recycw": -2.0, "bbb.albdso": 0.9, "bbb.albdsi": 0.8},
+    # core-boundary variants: second-derivative velocity, extrapolated atoms; extrapolated wall densities
+    {"bbb.isupcore": 2, "bbb.isngcore": 3, "bbb.isnwcono": 2, "bbb.isnwconi": 2},
+    {"bbb.isupcore": 3, "bbb.isngcore": 2, "bbb.iflcore": -1},
+    {"bbb.isngcore": 1, "bbb.ngcore": 2.0e15, "bbb.isupcore": 1},
+    {"bbb.isngcore": 4, "bbb.iflcore": 0},
 ]
 
 

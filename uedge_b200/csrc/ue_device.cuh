@@ -922,6 +922,11 @@ __device__ int phase2_guard(const Acc<WIN>& a, const Win& w, int ix, int iy, dou
                                D.ifluxni * (a.get(PL_FNIY, ix, 0) / (sy * D.vpnorm) - 0.001 * a.get(PL_NI, ix, 1) * a.get(PL_VY, ix, 0) / D.vpnorm)) / D.n0;
         } else if (D.isnwconiix[ix] == 1) {  // fixed wall density (boundary.m:267-270)
           out[0] = D.nurlxn * (D.nwalli[ix] - ni) / D.n0;
+        } else if (D.isnwconiix[ix] == 2) {  // extrapolation (boundary.m:271-277)
+          const double n1 = a.get(PL_NI, ix, 1);
+          double nbound = n1 - GG(gyf, ix, 1) * (a.get(PL_NI, ix, 2) - n1) / GG(gyf, ix, 0);
+          nbound = 1.2 * nbound / (1 + 0.5 * ue_exp(-2 * (nbound / n1 - 1))) + 0.2 * n1;
+          out[0] = D.nurlxn * (nbound - ni) / D.n0;
         } else {  // == 3: specified gradient length (boundary.m:278-282)
           const double gyf0 = GG(gyf, ix, 0);
           out[0] = -D.nurlxn * (a.get(PL_NIY0, ix, 0) - a.get(PL_NIY1, ix, 0) * (2 * gyf0 * D.lynipf[ix] - 1) / (2 * gyf0 * D.lynipf[ix] + 1) - D.nwimin) / D.n0;
@@ -929,7 +934,11 @@ __device__ int phase2_guard(const Acc<WIN>& a, const Win& w, int ix, int iy, dou
         // parallel velocity (boundary.m:313-380)
         if (core) {
           if (D.isupcore == 0) out[1] = D.nurlxu * (D.upcore - up) / D.vpnorm;
-          else out[1] = D.nurlxu * (a.get(PL_UP, ix, 1) - up) / D.vpnorm;
+          else if (D.isupcore == 1) out[1] = D.nurlxu * (a.get(PL_UP, ix, 1) - up) / D.vpnorm;
+          else if (D.isupcore == 2) {  // d2(up)/dy2 = 0 (boundary.m:323-326)
+            const double u1 = a.get(PL_UP, ix, 1);
+            out[1] = D.nurlxu * ((u1 - up) * GG(gy, ix, 1) - (a.get(PL_UP, ix, 2) - u1) * GG(gy, ix, 2)) / (GG(gy, ix, 1) * D.vpnorm);
+          } else out[1] = -D.nurlxu * f_fmiy(a, ix, 0) / (D.vpnorm * sy * D.fnorm);  // == 3: no radial momentum flux (boundary.m:327-329)
         } else if (D.isupwiix[ix] == 2) out[1] = D.nurlxu * f_nm(a, ix, 0) / D.fnorm * (a.get(PL_UP, ix, 1) - up);
         else out[1] = D.nurlxu * f_nm(a, ix, 0) / D.fnorm * (0. - up);
         // temperatures (boundary.m:524-628)
@@ -949,6 +958,9 @@ __device__ int phase2_guard(const Acc<WIN>& a, const Win& w, int ix, int iy, dou
               out[2] = -D.nurlxe * (feeytotc - D.pcoree) / (D.vpnorm * D.ennorm);
               out[3] = -D.nurlxi * (feiytotc - D.pcorei) / (D.vpnorm * D.ennorm);
             }
+          } else if (D.iflcore == -1) {  // zero radial temperature gradient (boundary.m:546-548, 594-596)
+            out[2] = -D.nurlxe * (te - a.get(PL_TE, ix, 1)) * D.n0 / D.ennorm;
+            out[3] = -D.nurlxi * (ti - a.get(PL_TI, ix, 1)) * D.n0 / D.ennorm;
           }
         } else {
           // boundary.m:550-565, 597-612: 0 zero flux, 1 fixed, 2 extrapolation from rows 1 and 2, 3 specified gradient length
@@ -982,9 +994,19 @@ __device__ int phase2_guard(const Acc<WIN>& a, const Win& w, int ix, int iy, dou
           const double vyn = 0.25 * sqrt(8 * t0 / (pi * D.mg));
           const double ng1 = a.get(PL_NG, ix, 1);
           const double nharmave = 2. * (ng * ng1) / (ng + ng1);
-          if (core) {
-            const double fng_alb = (1 - D.albedoc) * nharmave * vyn * sy;
-            out[4] = -D.nurlxg * (a.get(PL_FNGY, ix, 0) + fng_alb) / (vyn * sy * D.n0g);
+          if (core) {  // boundary.m:651-681
+            if (D.isngcore == 0) {
+              const double fng_alb = (1 - D.albedoc) * nharmave * vyn * sy;
+              out[4] = -D.nurlxg * (a.get(PL_FNGY, ix, 0) + fng_alb) / (vyn * sy * D.n0g);
+            } else if (D.isngcore == 1) out[4] = D.nurlxg * (D.ngcore - ng) / D.n0g;
+            else if (D.isngcore == 2) {
+              const double lengg = sqrt(f_tg(a, ix, 0) / (D.mg * (f_nuix(a, ix, 0) * a.get(PL_NUIZ, ix, 0))));
+              out[4] = D.nurlxn * ((ng1 - ng) - 0.5 * (ng1 + ng) / (GG(gyf, ix, 0) * lengg)) / D.n0g;
+            } else if (D.isngcore == 3) {
+              double nbound = ng1 - GG(gyf, ix, 1) * (a.get(PL_NG, ix, 2) - ng1) / GG(gyf, ix, 0);
+              nbound = 1.2 * nbound / (1 + 0.5 * ue_exp(-2 * (nbound / ng1 - 1))) + 0.2 * ng1;
+              out[4] = D.nurlxn * (nbound - ng) / D.n0g;
+            } else out[4] = D.nurlxn * (ng1 - ng) / D.n0g;
           } else {
             const double fng_chem = 0., sputflxpf = 0.;
             const double fng_alb = (1 - D.albedoi[ix]) * nharmave * vyn * sy;
@@ -1008,6 +1030,12 @@ __device__ int phase2_guard(const Acc<WIN>& a, const Win& w, int ix, int iy, dou
           out[0] = D.nurlxn * ((1 - D.ifluxni) * (a.get(PL_NIY0, ix, ny) - a.get(PL_NIY1, ix, ny)) +
                                D.ifluxni * (a.get(PL_FNIY, ix, ny) / (sy * D.vpnorm) - 0.001 * a.get(PL_NI, ix, ny) * a.get(PL_VY, ix, ny) / D.vpnorm)) / D.n0;
         else if (D.isnwconoix[ix] == 1) out[0] = D.nurlxn * (D.nwallo[ix] - ni) / D.n0;
+        else if (D.isnwconoix[ix] == 2) {  // extrapolation (boundary.m:1192-1198)
+          const double n1 = a.get(PL_NI, ix, ny);
+          double nbound = n1 + GG(gyf, ix, ny - 1) * (n1 - a.get(PL_NI, ix, ny - 1)) / GG(gyf, ix, ny);
+          nbound = 1.2 * nbound / (1 + 0.5 * ue_exp(-2 * (nbound / n1 - 1))) + 0.2 * n1;
+          out[0] = D.nurlxn * (nbound - ni) / D.n0;
+        }
         else {
           const double gyfn = GG(gyf, ix, ny);
           out[0] = -D.nurlxn * (a.get(PL_NIY1, ix, ny) - a.get(PL_NIY0, ix, ny) * (2 * gyfn * D.lyniwc[ix] - 1) / (2 * gyfn * D.lyniwc[ix] + 1) - D.nwomin) / D.n0;

@@ -678,13 +678,14 @@ int check_switches() {
       {"islimon", P.islimon, 0}, {"isdifbetap", P.isdifbetap, 0}, {"isugfm1side", P.isugfm1side, 0}, {"nxomit", P.nxomit, 0},
       {"isfixrb", P.isfixrb, 0}, {"isextrnp", P.isextrnp, 0}, {"isextrnpf", P.isextrnpf, 0}, {"isextrtpf", P.isextrtpf, 0}, {"isextrngc", P.isextrngc, 0},
       {"isextrnw", P.isextrnw, 0}, {"isextrtw", P.isextrtw, 0}, {"isnfmiy", P.isnfmiy, 0}, {"isybdrywd", P.isybdrywd, 0}, {"isnewpot", P.isnewpot, 0},
-      {"isbohmms", P.isbohmms, 0}, {"isgpye", P.isgpye, 0}, {"isngcore", P.isngcore, 0}, {"ibctepl", P.ibctepl, 1}, {"ibctipl", P.ibctipl, 1},
+      {"isbohmms", P.isbohmms, 0}, {"isgpye", P.isgpye, 0}, {"ibctepl", P.ibctepl, 1}, {"ibctipl", P.ibctipl, 1},
       {"ibctepr", P.ibctepr, 1}, {"ibctipr", P.ibctipr, 1}, {"iskaplex", P.iskaplex, 0}, {"isnupdot1sd", P.isnupdot1sd, 0}};
   for (auto& e : eq) if (e.v != e.want) { g_err = std::string("switch outside the built hot path: ") + e.n; return -5; }
   if (P.isbohmcalc != 0 && P.isbohmcalc != 1) { g_err = "isbohmcalc must be 0/1 with facb*=0"; return -5; }
   if (P.isnicore != 0 && P.isnicore != 1) { g_err = "isnicore must be 0 or 1"; return -5; }
-  if (P.isupcore != 0 && P.isupcore != 1) { g_err = "isupcore must be 0 or 1"; return -5; }
-  if (P.iflcore != 0 && P.iflcore != 1) { g_err = "iflcore must be 0 or 1"; return -5; }
+  if (P.isupcore < 0 || P.isupcore > 3) { g_err = "isupcore must be 0..3"; return -5; }
+  if (P.iflcore < -1 || P.iflcore > 1) { g_err = "iflcore must be -1, 0 or 1"; return -5; }
+  if (P.isngcore < 0 || P.isngcore > 4) { g_err = "isngcore must be 0..4"; return -5; }
   if (P.istabon != 0 && P.istabon != 7 && P.istabon != 10) { g_err = "istabon must be 0, 7 or 10"; return -5; }
   if (P.isngon != 0 && P.isngon != 1) { g_err = "isngon must be 0 or 1"; return -5; }
   if (P.isfixlb != 0 && P.isfixlb != 2) { g_err = "isfixlb must be 0 or 2"; return -5; }
@@ -701,7 +702,7 @@ int check_switches() {
   }
   for (int ix = 0; ix < NXS; ++ix) {
     if (P.fngysi[ix] != 0 || P.fngyso[ix] != 0 || P.fngyi_use[ix] != 0 || P.fngyo_use[ix] != 0) { g_err = "wall gas sources not built"; return -5; }
-    for (int64_t v : {P.isnwconiix[ix], P.isnwconoix[ix]}) if (v != 0 && v != 1 && v != 3) { g_err = "isnwconi/o must be 0, 1 or 3"; return -5; }
+    for (int64_t v : {P.isnwconiix[ix], P.isnwconoix[ix]}) if (v < 0 || v > 3) { g_err = "isnwconi/o must be 0..3"; return -5; }
     for (int64_t v : {P.istepfcix[ix], P.istipfcix[ix], P.istewcix[ix], P.istiwcix[ix]}) if (v < 0 || v > 3) { g_err = "istepfc/istipfc/istewc/istiwc must be 0..3"; return -5; }
   }
   for (int iy = 0; iy < ny + 2; ++iy)

@@ -34,8 +34,14 @@ inline void cell_candidates(const UeParams& P, int xc, int yc, std::vector<int>&
   }
   // extrapolation boundary conditions (istepfc/istipfc/istewc/istiwc = 2) read the second interior row
   // (boundary.m:555-559, 1320-1324): a perturbation there changes the guard row two rows away
-  if (yc == 2 && (P.istepfcix[xc] == 2 || P.istipfcix[xc] == 2)) out.push_back(xc);
-  if (yc == nys - 3 && (P.istewcix[xc] == 2 || P.istiwcix[xc] == 2)) out.push_back(xc + nxs * (nys - 1));
+  // (likewise isnwconi/o = 2, and on the core boundary isupcore = 2 and isngcore = 3)
+  {
+    const bool core = P.isixcore[xc] == 1;
+    const bool lo = core ? (P.isupcore == 2 || P.isngcore == 3) : (P.istepfcix[xc] == 2 || P.istipfcix[xc] == 2 || P.isnwconiix[xc] == 2);
+    const bool hi = P.istewcix[xc] == 2 || P.istiwcix[xc] == 2 || P.isnwconoix[xc] == 2;
+    if (yc == 2 && lo) out.push_back(xc);
+    if (yc == nys - 3 && hi) out.push_back(xc + nxs * (nys - 1));
+  }
   // half-space problem with a core region: a window that recomputes the electron-energy rows on both sides of the cut
   // face forms vex there from the zeroed upi (see f_upe_pre in ue_device.cuh), so those rows differ from yldot00 in
   // every such window: the cells (ixpt2, iy) and (ixpt2+1, iy), iy <= iysptrx1, inside the row window are candidates
