@@ -136,3 +136,54 @@ def run_fuzzed(lib, name, seed):
 @pytest.mark.parametrize("seed", range(6))
 def test_kernel_logic_fuzz_slab(hk, name, seed):
     run_fuzzed(hk, name, seed)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_kernel_logic_switch_combinations(hk, seed):
+    """Random combinations of the single-switch variants of test_gpu_parity.py with the wall / core boundary-condition sets of
+    test_gpu_slab.py, on the tokamak mesh and on the box, with the time-step term and nufak on."""
+    from tests.test_gpu_parity import VARIANTS
+    from tests.test_gpu_slab import WALL_BC_SETS
+    rng = np.random.default_rng(17000 + seed)
+    ov = {}
+    for nme in rng.choice(sorted(VARIANTS), size=int(rng.integers(2, 5)), replace=False):
+        ov.update(VARIANTS[str(nme)])
+    ov.update(WALL_BC_SETS[int(rng.integers(len(WALL_BC_SETS)))])
+    name = ["d3dHsm", "box2d"][seed % 2]
+    if name == "box2d":
+        ov.pop("com.istabon", None)  # no rate tables loaded for the box
+        if ov.get("bbb.iflcore") == 1:
+            ov["bbb.pcoree"] = ov["bbb.pcorei"] = 2.5e4
+    c, yl = make_case(name, perturb=float(rng.choice([1e-3, 2e-2])), seed=int(rng.integers(1 << 30)), overrides=ov)
+    ora = bind(oracle(), c)
+    bind(hk, c)
+    n = c.bbb.neq
+    for lib in (ora, hk):
+        lib.set_real("nufak", 1.0e3)
+    fo, fh = ora.pandf1(yl), hk.pandf1(yl)
+    if not np.isfinite(fo).all():
+        pytest.skip("non-physical combination")
+    assert np.array_equal(fo, fh), "%s: %d residual entries differ" % (ov, (fo != fh).sum())
+    y, su = psetnk_inputs(c, yl)
+    dt = 10.0 ** rng.uniform(-6, -2, n)
+    for lib in (ora, hk):
+        lib.step_params(dt, y[:n], su, np.ones(n))
+    f1, f2 = ora.pandf1(y), hk.pandf1(y)
+    jo = ora.jac_calc(y, f1, c.bbb.lbw, c.bbb.ubw, c.bbb.nnzmx)
+    jh = hk.jac_calc(y, f2, c.bbb.lbw, c.bbb.ubw, c.bbb.nnzmx)
+    assert all(np.array_equal(p, q) for p, q in zip(jo, jh)), ov
+    for lib in (ora, hk):
+        lib.set_real("nufak", 0.0)
+
+
+def test_kernel_logic_all_single_switch_variants(hk):
+    from tests.test_gpu_parity import VARIANTS
+    for variant in sorted(VARIANTS):
+        c, yl = make_case("d3dHsm", perturb=2e-3, overrides=VARIANTS[variant])
+        _check(c, yl, hk)
+
+
+@pytest.mark.parametrize("name", ["case2", "d3dHsm2x"])
+def test_kernel_logic_other_grids(hk, name):
+    c, yl = make_case(name, perturb=1e-3)
+    _check(c, yl, hk)
