@@ -18,6 +18,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __constant__ static
 #define __restrict__
 #define __CUDACC__ 1
@@ -103,6 +104,14 @@ int ue_hk_init(void) {
   D = P;  // host pointers: the shim's "constant memory"
   std::memset(&DT, 0, sizeof DT);
   DT.mpe = (int)P.mpe; DT.mpd = (int)P.mpd;
+  DT.iscut = (P.isfixlb == 2 && P.iysptrx1 > 0) ? 1 : 0;
+  {
+    bool rare = P.isupcore >= 2 || P.iflcore == -1 || P.isngcore != 0;
+    for (int ix = 0; ix < (int)P.nx + 2; ++ix)
+      rare = rare || P.isnwconiix[ix] != 0 || P.isnwconoix[ix] != 0 || P.istepfcix[ix] >= 2 || P.istipfcix[ix] >= 2 || P.istewcix[ix] >= 2 || P.istiwcix[ix] >= 2 ||
+             P.matwalli[ix] > 0 || P.matwallo[ix] > 0;
+    DT.rarebc = rare ? 1 : 0;
+  }
   if (P.istabon == 10) {  // as ue_gpu_init
     DT.dkpt[0] = 16.0; for (int j = 1; j < DT.mpd; ++j) DT.dkpt[j] = DT.dkpt[j - 1] + 0.5;
     DT.rldmin = DT.dkpt[0]; DT.rldmax = DT.dkpt[DT.mpd - 1]; DT.deldkpt = (DT.rldmax - DT.rldmin) / double(DT.mpd - 1);

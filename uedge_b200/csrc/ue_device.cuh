@@ -53,6 +53,8 @@ struct DevTables {  // istabon=10 abscissae (aph/aphread.m:700-735)
   double ekpt[64], dkpt[16];
   double rlemin, rlemax, rldmin, rldmax, delekpt, deldkpt;
   int mpe, mpd;
+  int rarebc;  // derived at init: some column selects one of the boundary-condition options of guard_rare
+  int iscut;  // derived at init: isfixlb == 2 && iysptrx1 > 0 (half-space problem with a core region: see d_cut)
 };
 
 __constant__ UeParams D;      // scalars + device pointers to static planes/lines
@@ -190,7 +192,7 @@ __device__ inline double d_table(const double* __restrict__ w, double tej, doubl
   return ue_exp(r1 + fje * (r2 - r1));
 }
 // istabon = 7 (the package default): R.B. Campbell's polynomial fits in x = log10(ne), y = log10(Te[eV]) (aph/aphrates.m:1133-1300)
-__device__ inline double d_sionf(double temp, double den) {
+__device__ __noinline__ double d_sionf(double temp, double den) {
   const double x = fmin(22.e0, ue_log10(den)), y = ue_log10(temp);
   const double ain = -49.05905 + 2.51313783 * x - 0.049159714 * x * x;
   const double bin = 41.1855162 - 2.3298672 * x + 4.24769144e-2 * x * x;
@@ -203,7 +205,7 @@ __device__ inline double d_sionf(double temp, double den) {
   return ue_pow(10., ain + bin * y + cin * y * y + din * y * y * y + ein * y * y * y * y + gin * y * y * y * y * y + hin * y * y * y * y * y * y +
                          riin * y * y * y * y * y * y * y);
 }
-__device__ inline double d_srecf(double temp, double den) {
+__device__ __noinline__ double d_srecf(double temp, double den) {
   const double x = fmin(22.e0, ue_log10(den)), y = ue_log10(temp);
   const double ar = -0.4575652 - 2.144012 * x + 6.7072142e-2 * x * x - 1.391667e-4 * x * x * x;
   const double br = -121.8401 + 18.001822 * x - 0.8679488 * x * x + 1.33165e-2 * x * x * x;
@@ -213,7 +215,7 @@ __device__ inline double d_srecf(double temp, double den) {
   const double gr = 10.866692 - 1.584193 * x + 0.07563791 * x * x - 1.177562e-3 * x * x * x;
   return ue_pow(10., ar + br * y + cr * y * y + dr * y * y * y + er * y * y * y * y + gr * y * y * y * y * y);
 }
-__device__ inline double d_svradp_sionfl(double x, double y) {
+__device__ __noinline__ double d_svradp_sionfl(double x, double y) {
   const double ai = -275.845 + 37.010817 * x - 1.788045 * x * x + 0.029078333 * x * x * x;
   const double bi = 2200.9478 - 326.1153 * x + 16.148655 * x * x - 0.2660702 * x * x * x;
   const double ci = -2.935221e3 + 4.3757698e2 * x - 21.73964 * x * x + 0.358962 * x * x * x;
@@ -222,7 +224,7 @@ __device__ inline double d_svradp_sionfl(double x, double y) {
   const double gi = 35.012574 - 5.24202 * x + 0.26109962 * x * x - 4.319238e-3 * x * x * x;
   return ue_pow(10., ai + bi * y + ci * y * y + di * y * y * y + ei * y * y * y * y + gi * y * y * y * y * y);
 }
-__device__ inline double d_svradp(double temp, double den) {
+__device__ __noinline__ double d_svradp(double temp, double den) {
   const double x = fmin(22.e0, ue_log10(den)), y = ue_log10(temp);
   const double ym = fmin(2.e0, y);  // etai frozen above 100 eV
   const double ae = 2860.4173 - 610.2452 * x + 48.275821 * x * x - 1.687994 * x * x * x + 0.02201375 * x * x * x * x;
@@ -338,7 +340,7 @@ template <bool WIN> __device__ __forceinline__ double f_uu(const Acc<WIN>& a, in
 // zero in every state a reader can see.)  gpix, gpex, frice have only later readers and are stored as zeros; upe, uu
 // and upi (= up) also have earlier readers (vex, the neutral convection, upe itself), so their later readers go through
 // the *_cut accessors below.
-__device__ __forceinline__ bool d_cut(int ix, int iy) { return D.isfixlb == 2 && D.iysptrx1 > 0 && ix == (int)D.ixpt2 && iy <= (int)D.iysptrx1; }
+__device__ __forceinline__ bool d_cut(int ix, int iy) { return DT.iscut && ix == (int)D.ixpt2 && iy <= (int)D.iysptrx1; }
 template <bool WIN> __device__ __forceinline__ double f_uu_cut(const Acc<WIN>& a, int ix, int iy) { return d_cut(ix, iy) ? 0. : f_uu(a, ix, iy); }
 template <bool WIN> __device__ __forceinline__ double f_upi_cut(const Acc<WIN>& a, int ix, int iy) { return d_cut(ix, iy) ? 0. : a.get(PL_UP, ix, iy); }
 template <bool WIN> __device__ __forceinline__ double f_upe_cut(const Acc<WIN>& a, int ix, int iy) { return d_cut(ix, iy) ? 0. : a.get(PL_UPE, ix, iy); }
@@ -889,6 +891,143 @@ template <bool WIN> __device__ inline double f_fmiy(const Acc<WIN>& a, int ix, i
 __device__ __forceinline__ bool cut_up_gate(const Win& w) {
   return D.isfixlb == 2 && w.i2 <= (int)D.ixpt2 && w.i5 >= (int)D.ixpt2 && w.j2 <= (int)D.iysptrx2;
 }
+// The less common wall and core boundary-condition options (wall densities isnwconi/o 1-3, wall temperatures
+// istepfc/istipfc/istewc/istiwc 2-3, recycling walls matwalli/matwallo > 0, core options isupcore 2-3, iflcore -1,
+// isngcore 1-4), kept out of line so that the common path of phase2_guard stays short: DT.rarebc (derived at init)
+// says whether any of them is selected anywhere.  Overwrites the rows the common path has set for (ix, iy = 0 | ny+1).
+template <bool WIN>
+__device__ __noinline__ void guard_rare(const Acc<WIN>& a, int ix, int iy, double out[UE_NV]) {
+  const int NXS = a.NXS;
+  const int ny = (int)D.ny;
+  const double ev = D.ev, pi = D.pi;
+  const double ni = a.get(PL_NI, ix, iy), up = a.get(PL_UP, ix, iy), te = a.get(PL_TE, ix, iy), ti = a.get(PL_TI, ix, iy), ng = a.get(PL_NG, ix, iy);
+  if (iy == 0) {
+    const bool core = (D.isixcore[ix] == 1);
+    const double sy = GG(sy, ix, 0);
+    if (!core) {
+      const int64_t mn = D.isnwconiix[ix];
+      if (mn == 1) out[0] = D.nurlxn * (D.nwalli[ix] - ni) / D.n0;  // fixed wall density (boundary.m:267-270)
+      else if (mn == 2) {  // extrapolation (boundary.m:271-277)
+        const double n1 = a.get(PL_NI, ix, 1);
+        double nbound = n1 - GG(gyf, ix, 1) * (a.get(PL_NI, ix, 2) - n1) / GG(gyf, ix, 0);
+        nbound = 1.2 * nbound / (1 + 0.5 * ue_exp(-2 * (nbound / n1 - 1))) + 0.2 * n1;
+        out[0] = D.nurlxn * (nbound - ni) / D.n0;
+      } else if (mn == 3) {  // specified gradient length (boundary.m:278-282)
+        const double gyf0 = GG(gyf, ix, 0);
+        out[0] = -D.nurlxn * (a.get(PL_NIY0, ix, 0) - a.get(PL_NIY1, ix, 0) * (2 * gyf0 * D.lynipf[ix] - 1) / (2 * gyf0 * D.lynipf[ix] + 1) - D.nwimin) / D.n0;
+      }
+      // boundary.m:550-565, 597-612: 2 extrapolation from rows 1 and 2, 3 specified gradient length
+      const int64_t me = D.istepfcix[ix], mi = D.istipfcix[ix];
+      if (me == 2) {
+        const double t1 = a.get(PL_TE, ix, 1);
+        double tbound = t1 - GG(gyf, ix, 1) * (a.get(PL_TE, ix, 2) - t1) / GG(gyf, ix, 0);
+        tbound = fmax(tbound, D.tbmin * ev);
+        out[2] = D.nurlxe * (tbound - te) / (D.temp0 * ev);
+      } else if (me == 3) {
+        const double t1 = a.get(PL_TE, ix, 1);
+        out[2] = D.nurlxe * ((t1 - te) - 0.5 * (t1 + te) / (GG(gyf, ix, 0) * D.lytepf[ix])) / (D.temp0 * ev);
+      }
+      if (mi == 2) {
+        const double t1 = a.get(PL_TI, ix, 1);
+        double tbound = t1 - GG(gyf, ix, 1) * (a.get(PL_TI, ix, 2) - t1) / GG(gyf, ix, 0);
+        tbound = fmax(tbound, D.tbmin * ev);
+        out[3] = D.nurlxi * (tbound - ti) / (D.temp0 * ev);
+      } else if (mi == 3) {
+        const double t1 = a.get(PL_TI, ix, 1);
+        out[3] = D.nurlxi * ((t1 - ti) - 0.5 * (t1 + ti) / (GG(gyf, ix, 0) * D.lytipf[ix])) / (D.temp0 * ev);
+      }
+    } else {
+      if (D.isupcore == 2) {  // d2(up)/dy2 = 0 (boundary.m:323-326)
+        const double u1 = a.get(PL_UP, ix, 1);
+        out[1] = D.nurlxu * ((u1 - up) * GG(gy, ix, 1) - (a.get(PL_UP, ix, 2) - u1) * GG(gy, ix, 2)) / (GG(gy, ix, 1) * D.vpnorm);
+      } else if (D.isupcore == 3) out[1] = -D.nurlxu * f_fmiy(a, ix, 0) / (D.vpnorm * sy * D.fnorm);  // no radial momentum flux (boundary.m:327-329)
+      if (D.iflcore == -1) {  // zero radial temperature gradient (boundary.m:546-548, 594-596)
+        out[2] = -D.nurlxe * (te - a.get(PL_TE, ix, 1)) * D.n0 / D.ennorm;
+        out[3] = -D.nurlxi * (ti - a.get(PL_TI, ix, 1)) * D.n0 / D.ennorm;
+      }
+    }
+    // neutral density (boundary.m:651-681, 733-760)
+    const double t0 = fmax(D.cdifg * f_tg(a, ix, 0), D.tgmin * ev);
+    const double vyn = 0.25 * sqrt(8 * t0 / (pi * D.mg));
+    const double ng1 = a.get(PL_NG, ix, 1);
+    const double nharmave = 2. * (ng * ng1) / (ng + ng1);
+    if (core) {
+      if (D.isngcore == 1) out[4] = D.nurlxg * (D.ngcore - ng) / D.n0g;
+      else if (D.isngcore == 2) {
+        const double lengg = sqrt(f_tg(a, ix, 0) / (D.mg * (f_nuix(a, ix, 0) * a.get(PL_NUIZ, ix, 0))));
+        out[4] = D.nurlxn * ((ng1 - ng) - 0.5 * (ng1 + ng) / (GG(gyf, ix, 0) * lengg)) / D.n0g;
+      } else if (D.isngcore == 3) {
+        double nbound = ng1 - GG(gyf, ix, 1) * (a.get(PL_NG, ix, 2) - ng1) / GG(gyf, ix, 0);
+        nbound = 1.2 * nbound / (1 + 0.5 * ue_exp(-2 * (nbound / ng1 - 1))) + 0.2 * ng1;
+        out[4] = D.nurlxn * (nbound - ng) / D.n0g;
+      } else if (D.isngcore == 4) out[4] = D.nurlxn * (ng1 - ng) / D.n0g;
+    } else if (D.matwalli[ix] > 0) {  // recycling wall
+      const double fng_chem = 0., sputflxpf = 0.;
+      const double fng_alb = (1 - D.albedoi[ix]) * nharmave * vyn * sy;
+      const double rw = D.recycwit[ix];
+      if (rw > 0.) {
+        double fniy_recy = D.fac2sp * a.get(PL_FNIY, ix, 0);
+        if (D.isrefluxclip == 1) fniy_recy = fmin(fniy_recy, 0.);
+        out[4] = -D.nurlxg * (a.get(PL_FNGY, ix, 0) + fniy_recy * rw - D.fngyi_use[ix] - D.fngysi[ix] + fng_alb - fng_chem + sputflxpf) / (vyn * D.n0g * sy);
+      } else if (rw < -1) out[4] = D.nurlxg * (D.ngbackg - ng) / D.n0g;
+      else {
+        const double nh2 = 2. * (ng * ng1) / (ng + ng1);
+        out[4] = -D.nurlxg * (a.get(PL_FNGY, ix, 0) + (1 + rw) * nh2 * vyn * sy) / (vyn * D.n0g * sy);
+      }
+    }
+  } else {  // outer wall (boundary.m:1188-1204, 1314-1357, 1424-1452)
+    const double sy = GG(sy, ix, ny);
+    const int64_t mn = D.isnwconoix[ix];
+    if (mn == 1) out[0] = D.nurlxn * (D.nwallo[ix] - ni) / D.n0;
+    else if (mn == 2) {
+      const double n1 = a.get(PL_NI, ix, ny);
+      double nbound = n1 + GG(gyf, ix, ny - 1) * (n1 - a.get(PL_NI, ix, ny - 1)) / GG(gyf, ix, ny);
+      nbound = 1.2 * nbound / (1 + 0.5 * ue_exp(-2 * (nbound / n1 - 1))) + 0.2 * n1;
+      out[0] = D.nurlxn * (nbound - ni) / D.n0;
+    } else if (mn == 3) {
+      const double gyfn = GG(gyf, ix, ny);
+      out[0] = -D.nurlxn * (a.get(PL_NIY1, ix, ny) - a.get(PL_NIY0, ix, ny) * (2 * gyfn * D.lyniwc[ix] - 1) / (2 * gyfn * D.lyniwc[ix] + 1) - D.nwomin) / D.n0;
+    }
+    const int64_t me = D.istewcix[ix], mi = D.istiwcix[ix];
+    if (me == 2) {
+      const double t1 = a.get(PL_TE, ix, ny);
+      double tbound = t1 + GG(gyf, ix, ny - 1) * (t1 - a.get(PL_TE, ix, ny - 1)) / GG(gyf, ix, ny);
+      tbound = fmax(tbound, D.tbmin * ev);
+      out[2] = D.nurlxe * (tbound - te) / (D.temp0 * ev);
+    } else if (me == 3) {
+      const double t1 = a.get(PL_TE, ix, ny);
+      out[2] = D.nurlxe * ((t1 - te) - 0.5 * (t1 + te) / (GG(gyf, ix, ny) * D.lytewc[ix])) / (D.temp0 * ev);
+    }
+    if (mi == 2) {
+      const double t1 = a.get(PL_TI, ix, ny);
+      double tbound = t1 + GG(gyf, ix, ny - 1) * (t1 - a.get(PL_TI, ix, ny - 1)) / GG(gyf, ix, ny);
+      tbound = fmax(tbound, D.tbmin * ev);
+      out[3] = D.nurlxi * (tbound - ti) / (D.temp0 * ev);
+    } else if (mi == 3) {
+      const double t1 = a.get(PL_TI, ix, ny);
+      out[3] = D.nurlxi * ((t1 - ti) - 0.5 * (t1 + ti) / (GG(gyf, ix, ny) * D.lytiwc[ix])) / (D.temp0 * ev);
+    }
+    if (D.matwallo[ix] > 0) {
+      const double t0 = fmax(D.cdifg * f_tg(a, ix, ny + 1), D.tgmin * ev);
+      const double vyn = 0.25 * sqrt(8 * t0 / (pi * D.mg));
+      const double fng_chem = 0., sputflxw = 0.;
+      const double ngc = a.get(PL_NG, ix, ny);
+      const double nharmave = 2. * (ngc * ng) / (ngc + ng);
+      const double fng_alb = (1 - D.albedoo[ix]) * nharmave * vyn * sy;
+      const double rw = D.recycwot[ix];
+      if (rw > 0.) {
+        double fniy_recy = D.fac2sp * a.get(PL_FNIY, ix, ny);
+        if (D.isrefluxclip == 1) fniy_recy = fmax(fniy_recy, 0.);
+        out[4] = D.nurlxg * (a.get(PL_FNGY, ix, ny) + fniy_recy * rw + D.fngyso[ix] + D.fngyo_use[ix] - fng_alb + fng_chem + sputflxw) / (vyn * D.n0g * sy);
+      } else if (rw < -1) out[4] = D.nurlxg * (D.ngbackg - ng) / D.n0g;
+      else {
+        const double nh2 = 2. * (ngc * ng) / (ngc + ng);
+        out[4] = D.nurlxg * (a.get(PL_FNGY, ix, ny) - (1 + rw) * nh2 * vyn * sy) / (vyn * D.n0g * sy);
+      }
+    }
+  }
+}
+
 // ============================================================================================
 // phase 2b — guard-cell rows (bouncon, boundary.m:102-2800).  Returns a 5-bit mask of rows written.
 // `ix,iy` is a guard cell; the right-plate momentum row that lives in interior column nx is
@@ -917,28 +1056,14 @@ __device__ int phase2_guard(const Acc<WIN>& a, const Win& w, int ix, int iy, dou
         if (core) {
           if (D.isnicore == 1) out[0] = D.nurlxn * (D.ncore - ni) / D.n0;
           else out[0] = -D.nurlxn * (D.qe * (a.get(PL_FNIY, ix, 0) - 0.) / sy - D.curcore * GG(gyf, ix, 0) / D.sygytotc) / (D.qe * D.vpnorm * D.n0);
-        } else if (D.isnwconiix[ix] == 0) {
+        } else {  // isnwconi = 0; the other options: guard_rare
           out[0] = D.nurlxn * ((1 - D.ifluxni) * (a.get(PL_NIY1, ix, 0) - a.get(PL_NIY0, ix, 0)) -
                                D.ifluxni * (a.get(PL_FNIY, ix, 0) / (sy * D.vpnorm) - 0.001 * a.get(PL_NI, ix, 1) * a.get(PL_VY, ix, 0) / D.vpnorm)) / D.n0;
-        } else if (D.isnwconiix[ix] == 1) {  // fixed wall density (boundary.m:267-270)
-          out[0] = D.nurlxn * (D.nwalli[ix] - ni) / D.n0;
-        } else if (D.isnwconiix[ix] == 2) {  // extrapolation (boundary.m:271-277)
-          const double n1 = a.get(PL_NI, ix, 1);
-          double nbound = n1 - GG(gyf, ix, 1) * (a.get(PL_NI, ix, 2) - n1) / GG(gyf, ix, 0);
-          nbound = 1.2 * nbound / (1 + 0.5 * ue_exp(-2 * (nbound / n1 - 1))) + 0.2 * n1;
-          out[0] = D.nurlxn * (nbound - ni) / D.n0;
-        } else {  // == 3: specified gradient length (boundary.m:278-282)
-          const double gyf0 = GG(gyf, ix, 0);
-          out[0] = -D.nurlxn * (a.get(PL_NIY0, ix, 0) - a.get(PL_NIY1, ix, 0) * (2 * gyf0 * D.lynipf[ix] - 1) / (2 * gyf0 * D.lynipf[ix] + 1) - D.nwimin) / D.n0;
         }
         // parallel velocity (boundary.m:313-380)
         if (core) {
           if (D.isupcore == 0) out[1] = D.nurlxu * (D.upcore - up) / D.vpnorm;
-          else if (D.isupcore == 1) out[1] = D.nurlxu * (a.get(PL_UP, ix, 1) - up) / D.vpnorm;
-          else if (D.isupcore == 2) {  // d2(up)/dy2 = 0 (boundary.m:323-326)
-            const double u1 = a.get(PL_UP, ix, 1);
-            out[1] = D.nurlxu * ((u1 - up) * GG(gy, ix, 1) - (a.get(PL_UP, ix, 2) - u1) * GG(gy, ix, 2)) / (GG(gy, ix, 1) * D.vpnorm);
-          } else out[1] = -D.nurlxu * f_fmiy(a, ix, 0) / (D.vpnorm * sy * D.fnorm);  // == 3: no radial momentum flux (boundary.m:327-329)
+          else out[1] = D.nurlxu * (a.get(PL_UP, ix, 1) - up) / D.vpnorm;  // isupcore = 1; 2, 3: guard_rare
         } else if (D.isupwiix[ix] == 2) out[1] = D.nurlxu * f_nm(a, ix, 0) / D.fnorm * (a.get(PL_UP, ix, 1) - up);
         else out[1] = D.nurlxu * f_nm(a, ix, 0) / D.fnorm * (0. - up);
         // temperatures (boundary.m:524-628)
@@ -958,35 +1083,12 @@ __device__ int phase2_guard(const Acc<WIN>& a, const Win& w, int ix, int iy, dou
               out[2] = -D.nurlxe * (feeytotc - D.pcoree) / (D.vpnorm * D.ennorm);
               out[3] = -D.nurlxi * (feiytotc - D.pcorei) / (D.vpnorm * D.ennorm);
             }
-          } else if (D.iflcore == -1) {  // zero radial temperature gradient (boundary.m:546-548, 594-596)
-            out[2] = -D.nurlxe * (te - a.get(PL_TE, ix, 1)) * D.n0 / D.ennorm;
-            out[3] = -D.nurlxi * (ti - a.get(PL_TI, ix, 1)) * D.n0 / D.ennorm;
-          }
-        } else {
-          // boundary.m:550-565, 597-612: 0 zero flux, 1 fixed, 2 extrapolation from rows 1 and 2, 3 specified gradient length
-          const int64_t me = D.istepfcix[ix], mi = D.istipfcix[ix];
-          if (me == 0) out[2] = -D.nurlxe * (a.get(PL_FEEY, ix, 0) / (D.n0 * D.vpnorm * sy)) / (D.temp0 * ev);
-          else if (me == 1) out[2] = D.nurlxe * (D.tewalli[ix] * ev - te) / (D.temp0 * ev);
-          else if (me == 2) {
-            const double t1 = a.get(PL_TE, ix, 1);
-            double tbound = t1 - GG(gyf, ix, 1) * (a.get(PL_TE, ix, 2) - t1) / GG(gyf, ix, 0);
-            tbound = fmax(tbound, D.tbmin * ev);
-            out[2] = D.nurlxe * (tbound - te) / (D.temp0 * ev);
-          } else {
-            const double t1 = a.get(PL_TE, ix, 1);
-            out[2] = D.nurlxe * ((t1 - te) - 0.5 * (t1 + te) / (GG(gyf, ix, 0) * D.lytepf[ix])) / (D.temp0 * ev);
-          }
-          if (mi == 0) out[3] = -D.nurlxi * (a.get(PL_FEIY, ix, 0) / (D.n0 * D.vpnorm * sy)) / (D.temp0 * ev);
-          else if (mi == 1) out[3] = D.nurlxi * (D.tiwalli[ix] * ev - ti) / (D.temp0 * ev);
-          else if (mi == 2) {
-            const double t1 = a.get(PL_TI, ix, 1);
-            double tbound = t1 - GG(gyf, ix, 1) * (a.get(PL_TI, ix, 2) - t1) / GG(gyf, ix, 0);
-            tbound = fmax(tbound, D.tbmin * ev);
-            out[3] = D.nurlxi * (tbound - ti) / (D.temp0 * ev);
-          } else {
-            const double t1 = a.get(PL_TI, ix, 1);
-            out[3] = D.nurlxi * ((t1 - ti) - 0.5 * (t1 + ti) / (GG(gyf, ix, 0) * D.lytipf[ix])) / (D.temp0 * ev);
-          }
+          }  // iflcore = -1: guard_rare
+        } else {  // boundary.m:550-565, 597-612: 0 zero flux, 1 fixed; 2 extrapolation, 3 gradient length: guard_rare
+          if (D.istepfcix[ix] == 0) out[2] = -D.nurlxe * (a.get(PL_FEEY, ix, 0) / (D.n0 * D.vpnorm * sy)) / (D.temp0 * ev);
+          else out[2] = D.nurlxe * (D.tewalli[ix] * ev - te) / (D.temp0 * ev);
+          if (D.istipfcix[ix] == 0) out[3] = -D.nurlxi * (a.get(PL_FEIY, ix, 0) / (D.n0 * D.vpnorm * sy)) / (D.temp0 * ev);
+          else out[3] = D.nurlxi * (D.tiwalli[ix] * ev - ti) / (D.temp0 * ev);
         }
         // neutral density (boundary.m:632-767)
         {
@@ -994,77 +1096,24 @@ __device__ int phase2_guard(const Acc<WIN>& a, const Win& w, int ix, int iy, dou
           const double vyn = 0.25 * sqrt(8 * t0 / (pi * D.mg));
           const double ng1 = a.get(PL_NG, ix, 1);
           const double nharmave = 2. * (ng * ng1) / (ng + ng1);
-          if (core) {  // boundary.m:651-681
-            if (D.isngcore == 0) {
-              const double fng_alb = (1 - D.albedoc) * nharmave * vyn * sy;
-              out[4] = -D.nurlxg * (a.get(PL_FNGY, ix, 0) + fng_alb) / (vyn * sy * D.n0g);
-            } else if (D.isngcore == 1) out[4] = D.nurlxg * (D.ngcore - ng) / D.n0g;
-            else if (D.isngcore == 2) {
-              const double lengg = sqrt(f_tg(a, ix, 0) / (D.mg * (f_nuix(a, ix, 0) * a.get(PL_NUIZ, ix, 0))));
-              out[4] = D.nurlxn * ((ng1 - ng) - 0.5 * (ng1 + ng) / (GG(gyf, ix, 0) * lengg)) / D.n0g;
-            } else if (D.isngcore == 3) {
-              double nbound = ng1 - GG(gyf, ix, 1) * (a.get(PL_NG, ix, 2) - ng1) / GG(gyf, ix, 0);
-              nbound = 1.2 * nbound / (1 + 0.5 * ue_exp(-2 * (nbound / ng1 - 1))) + 0.2 * ng1;
-              out[4] = D.nurlxn * (nbound - ng) / D.n0g;
-            } else out[4] = D.nurlxn * (ng1 - ng) / D.n0g;
-          } else {
+          if (core) {  // isngcore = 0 (boundary.m:651-657); 1..4: guard_rare
+            const double fng_alb = (1 - D.albedoc) * nharmave * vyn * sy;
+            out[4] = -D.nurlxg * (a.get(PL_FNGY, ix, 0) + fng_alb) / (vyn * sy * D.n0g);
+          } else {  // recycling walls (matwalli > 0): guard_rare
             const double fng_chem = 0., sputflxpf = 0.;
             const double fng_alb = (1 - D.albedoi[ix]) * nharmave * vyn * sy;
             out[4] = -D.nurlxg * (a.get(PL_FNGY, ix, 0) + fng_alb - fng_chem + sputflxpf) / (vyn * sy * D.n0g);
-            if (D.matwalli[ix] > 0) {  // recycling wall (boundary.m:733-760)
-              const double rw = D.recycwit[ix];
-              if (rw > 0.) {
-                double fniy_recy = D.fac2sp * a.get(PL_FNIY, ix, 0);
-                if (D.isrefluxclip == 1) fniy_recy = fmin(fniy_recy, 0.);
-                out[4] = -D.nurlxg * (a.get(PL_FNGY, ix, 0) + fniy_recy * rw - D.fngyi_use[ix] - D.fngysi[ix] + fng_alb - fng_chem + sputflxpf) / (vyn * D.n0g * sy);
-              } else if (rw < -1) out[4] = D.nurlxg * (D.ngbackg - ng) / D.n0g;
-              else {
-                const double nh2 = 2. * (ng * ng1) / (ng + ng1);
-                out[4] = -D.nurlxg * (a.get(PL_FNGY, ix, 0) + (1 + rw) * nh2 * vyn * sy) / (vyn * D.n0g * sy);
-              }
-            }
           }
         }
       } else {  // outer wall (boundary.m:1133-1462)
-        if (D.isnwconoix[ix] == 0)
-          out[0] = D.nurlxn * ((1 - D.ifluxni) * (a.get(PL_NIY0, ix, ny) - a.get(PL_NIY1, ix, ny)) +
-                               D.ifluxni * (a.get(PL_FNIY, ix, ny) / (sy * D.vpnorm) - 0.001 * a.get(PL_NI, ix, ny) * a.get(PL_VY, ix, ny) / D.vpnorm)) / D.n0;
-        else if (D.isnwconoix[ix] == 1) out[0] = D.nurlxn * (D.nwallo[ix] - ni) / D.n0;
-        else if (D.isnwconoix[ix] == 2) {  // extrapolation (boundary.m:1192-1198)
-          const double n1 = a.get(PL_NI, ix, ny);
-          double nbound = n1 + GG(gyf, ix, ny - 1) * (n1 - a.get(PL_NI, ix, ny - 1)) / GG(gyf, ix, ny);
-          nbound = 1.2 * nbound / (1 + 0.5 * ue_exp(-2 * (nbound / n1 - 1))) + 0.2 * n1;
-          out[0] = D.nurlxn * (nbound - ni) / D.n0;
-        }
-        else {
-          const double gyfn = GG(gyf, ix, ny);
-          out[0] = -D.nurlxn * (a.get(PL_NIY1, ix, ny) - a.get(PL_NIY0, ix, ny) * (2 * gyfn * D.lyniwc[ix] - 1) / (2 * gyfn * D.lyniwc[ix] + 1) - D.nwomin) / D.n0;
-        }
+        out[0] = D.nurlxn * ((1 - D.ifluxni) * (a.get(PL_NIY0, ix, ny) - a.get(PL_NIY1, ix, ny)) +
+                             D.ifluxni * (a.get(PL_FNIY, ix, ny) / (sy * D.vpnorm) - 0.001 * a.get(PL_NI, ix, ny) * a.get(PL_VY, ix, ny) / D.vpnorm)) / D.n0;  // isnwcono = 0
         if (D.isupwoix[ix] == 2) out[1] = D.nurlxu * f_nm(a, ix, ny) / D.fnorm * (a.get(PL_UP, ix, ny) - up);
         else out[1] = D.nurlxu * f_nm(a, ix, ny) / D.fnorm * (0. - up);
-        const int64_t me = D.istewcix[ix], mi = D.istiwcix[ix];  // boundary.m:1314-1357
-        if (me == 0) out[2] = D.nurlxe * (a.get(PL_FEEY, ix, ny) / (D.n0 * D.vpnorm * sy)) / (D.temp0 * ev);
-        else if (me == 1) out[2] = D.nurlxe * (D.tewallo[ix] * ev - te) / (D.temp0 * ev);
-        else if (me == 2) {
-          const double t1 = a.get(PL_TE, ix, ny);
-          double tbound = t1 + GG(gyf, ix, ny - 1) * (t1 - a.get(PL_TE, ix, ny - 1)) / GG(gyf, ix, ny);
-          tbound = fmax(tbound, D.tbmin * ev);
-          out[2] = D.nurlxe * (tbound - te) / (D.temp0 * ev);
-        } else {
-          const double t1 = a.get(PL_TE, ix, ny);
-          out[2] = D.nurlxe * ((t1 - te) - 0.5 * (t1 + te) / (GG(gyf, ix, ny) * D.lytewc[ix])) / (D.temp0 * ev);
-        }
-        if (mi == 0) out[3] = D.nurlxi * (a.get(PL_FEIY, ix, ny) / (D.n0 * D.vpnorm * sy)) / (D.temp0 * ev);
-        else if (mi == 1) out[3] = D.nurlxi * (D.tiwallo[ix] * ev - ti) / (D.temp0 * ev);
-        else if (mi == 2) {
-          const double t1 = a.get(PL_TI, ix, ny);
-          double tbound = t1 + GG(gyf, ix, ny - 1) * (t1 - a.get(PL_TI, ix, ny - 1)) / GG(gyf, ix, ny);
-          tbound = fmax(tbound, D.tbmin * ev);
-          out[3] = D.nurlxi * (tbound - ti) / (D.temp0 * ev);
-        } else {
-          const double t1 = a.get(PL_TI, ix, ny);
-          out[3] = D.nurlxi * ((t1 - ti) - 0.5 * (t1 + ti) / (GG(gyf, ix, ny) * D.lytiwc[ix])) / (D.temp0 * ev);
-        }
+        if (D.istewcix[ix] == 0) out[2] = D.nurlxe * (a.get(PL_FEEY, ix, ny) / (D.n0 * D.vpnorm * sy)) / (D.temp0 * ev);
+        else out[2] = D.nurlxe * (D.tewallo[ix] * ev - te) / (D.temp0 * ev);
+        if (D.istiwcix[ix] == 0) out[3] = D.nurlxi * (a.get(PL_FEIY, ix, ny) / (D.n0 * D.vpnorm * sy)) / (D.temp0 * ev);
+        else out[3] = D.nurlxi * (D.tiwallo[ix] * ev - ti) / (D.temp0 * ev);
         const double t0 = fmax(D.cdifg * f_tg(a, ix, ny + 1), D.tgmin * ev);
         const double vyn = 0.25 * sqrt(8 * t0 / (pi * D.mg));
         const double fng_chem = 0., sputflxw = 0.;
@@ -1072,19 +1121,8 @@ __device__ int phase2_guard(const Acc<WIN>& a, const Win& w, int ix, int iy, dou
         const double nharmave = 2. * (ngc * ng) / (ngc + ng);
         const double fng_alb = (1 - D.albedoo[ix]) * nharmave * vyn * sy;
         out[4] = D.nurlxg * (a.get(PL_FNGY, ix, ny) - fng_alb + fng_chem + sputflxw) / (vyn * sy * D.n0g);
-        if (D.matwallo[ix] > 0) {  // recycling wall (boundary.m:1424-1452)
-          const double rw = D.recycwot[ix];
-          if (rw > 0.) {
-            double fniy_recy = D.fac2sp * a.get(PL_FNIY, ix, ny);
-            if (D.isrefluxclip == 1) fniy_recy = fmax(fniy_recy, 0.);
-            out[4] = D.nurlxg * (a.get(PL_FNGY, ix, ny) + fniy_recy * rw + D.fngyso[ix] + D.fngyo_use[ix] - fng_alb + fng_chem + sputflxw) / (vyn * D.n0g * sy);
-          } else if (rw < -1) out[4] = D.nurlxg * (D.ngbackg - ng) / D.n0g;
-          else {
-            const double nh2 = 2. * (ngc * ng) / (ngc + ng);
-            out[4] = D.nurlxg * (a.get(PL_FNGY, ix, ny) - (1 + rw) * nh2 * vyn * sy) / (vyn * D.n0g * sy);
-          }
-        }
       }
+      if (DT.rarebc) guard_rare<WIN>(a, ix, iy, out);  // the less common wall / core options overwrite the rows above
       mask = 0x1f;
     }
     if (bottom && ix == (int)D.ixpt2 && cut_up_gate(w)) { out[1] = D.nurlxu * (0. - a.get(PL_UP, ix, 0)) / D.vpnorm; mask |= 2; }  // boundary.m:1772-1785 (iy = 0)

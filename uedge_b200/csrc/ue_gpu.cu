@@ -518,8 +518,12 @@ __global__ void k_fill(int64_t neq, int64_t ivmin, int64_t ivmax, const int64_t*
 }
 // one warp per row: rank sort of the row's entries by column (rows hold a few tens of entries).  jac_host/ja_host: the
 // caller's page-locked arrays (or nullptr): the sorted row is also written there, so no copy follows the sequence.
+// Rows longer than CAP (a dense row: the integrated core-power row, or the electron-energy rows on a half-space cut, which
+// couple to every column of their window) are rank-sorted through a global scratch area (the CSC fragment buffers, free
+// again once k_fill has run) instead of shared memory.
 __global__ void k_sortrows(int64_t neq, const int64_t* __restrict__ ia, double* __restrict__ jac, int64_t* __restrict__ ja, int64_t nnzmx,
-                           double* __restrict__ jac_host, int64_t* __restrict__ ja_host) {
+                           double* __restrict__ jac_host, int64_t* __restrict__ ja_host, int* __restrict__ scr_col, double* __restrict__ scr_val,
+                           int64_t scr_cap) {
   constexpr int CAP = 96;
   __shared__ int64_t scol[4][CAP];
   __shared__ double sval[4][CAP];
@@ -544,8 +548,21 @@ __global__ void k_sortrows(int64_t neq, const int64_t* __restrict__ ia, double* 
       __syncwarp();
       for (int i = lane; i < n; i += 32) { ja_host[b + i] = ja[b + i]; jac_host[b + i] = jac[b + i]; }
     }
+  } else if (e <= scr_cap) {
+    for (int64_t i = b + lane; i < e; i += 32) { scr_col[i] = (int)ja[i]; scr_val[i] = jac[i]; }
+    __syncwarp();
+    for (int64_t i = b + lane; i < e; i += 32) {
+      const int c = scr_col[i];
+      int rank = 0;
+      for (int64_t j = b; j < e; ++j) rank += (scr_col[j] < c);
+      ja[b + rank] = c; jac[b + rank] = scr_val[i];
+    }
+    if (jac_host) {
+      __syncwarp();
+      for (int64_t i = b + lane; i < e; i += 32) { ja_host[i] = ja[i]; jac_host[i] = jac[i]; }
+    }
   } else {
-    if (lane == 0) {  // dense row: serial insertion sort
+    if (lane == 0) {  // no scratch space: serial insertion sort
       for (int64_t i = b + 1; i < e; ++i) {
         const int64_t cj = ja[i]; const double cv = jac[i];
         int64_t j = i - 1;
@@ -877,7 +894,7 @@ int enqueue_jac(const double* dyl, const double* dy00, int64_t ml, int64_t mu, i
   const int64_t ncol = g_ivmax - g_ivmin + 1;
   if (ncol > 0) {
     CK(launch(k_fill, dim3((unsigned)ncol), dim3(64), neq, g_ivmin, g_ivmax, d_coloff, d_colcnt, d_colrow, d_colval, dia, d_rowfill, djac, dja, nnzmx));
-    CK(launch(k_sortrows, dim3((unsigned)((neq + 3) / 4)), dim3(128), neq, dia, djac, dja, nnzmx, jac_host, ja_host));
+    CK(launch(k_sortrows, dim3((unsigned)((neq + 3) / 4)), dim3(128), neq, dia, djac, dja, nnzmx, jac_host, ja_host, d_colrow, d_colval, g_cap_total));
   }
   return 0;
 }
@@ -1011,6 +1028,14 @@ int ue_gpu_init(void) {
   DevTables t;
   std::memset(&t, 0, sizeof t);
   t.mpe = (int)P.mpe; t.mpd = (int)P.mpd;
+  t.iscut = (P.isfixlb == 2 && P.iysptrx1 > 0) ? 1 : 0;
+  {
+    bool rare = P.isupcore >= 2 || P.iflcore == -1 || P.isngcore != 0;
+    for (int ix = 0; ix < (int)P.nx + 2; ++ix)
+      rare = rare || P.isnwconiix[ix] != 0 || P.isnwconoix[ix] != 0 || P.istepfcix[ix] >= 2 || P.istipfcix[ix] >= 2 || P.istewcix[ix] >= 2 || P.istiwcix[ix] >= 2 ||
+             P.matwalli[ix] > 0 || P.matwallo[ix] > 0;
+    t.rarebc = rare ? 1 : 0;
+  }
   if (P.istabon == 10) {
     if (t.mpe < 2 || t.mpe > 64 || t.mpd < 2 || t.mpd > 16 || S.len("wsveh") != (int64_t)t.mpe * t.mpd) { g_err = "istabon=10 needs wsveh/wsveh0/welms1/welms2 (mpe<=64, mpd<=16)"; return -1; }
     t.dkpt[0] = 16.0; for (int j = 1; j < t.mpd; ++j) t.dkpt[j] = t.dkpt[j - 1] + 0.5;
