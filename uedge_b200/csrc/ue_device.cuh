@@ -1325,18 +1325,26 @@ template <bool WIN> __device__ inline double f_eqp(const Acc<WIN>& a, int ix, in
   return eqp;
 }
 
+// particle balance of an interior cell (oderhs.m:3407-3456); also evaluated for the east neighbour by the fused
+// phase-2/3 kernel of the full residual (rscalf reads resco(ixp1), oderhs.m:8140-8160)
+template <bool WIN>
+__device__ __forceinline__ double f_resco(const Acc<WIN>& a, int ix, int iy, double psor, double psorxr) {
+  const int NXS = a.NXS;
+  const int ix1 = IXM1(ix, iy);
+  const double ni = a.get(PL_NI, ix, iy);
+  double resco = 0. + 0. * ni + 0. + D.cfneut * D.cfneutsor_ni * D.cnsor * psor + D.cfneut * D.cfneutsor_ni * D.cnsor * psorxr +
+                 D.cfneut * D.cfneutsor_ni * D.cnsor * 0. - 0. + 0.;
+  resco = resco - ((a.get(PL_FNIX, ix, iy) - a.get(PL_FNIX, ix1, iy)) + D.fluxfacy * (a.get(PL_FNIY, ix, iy) - a.get(PL_FNIY, ix, iy - 1)));
+  return resco;
+}
 template <bool WIN>
 __device__ void p2_n(const Acc<WIN>& a, int ix, int iy, double out[UE_NV], const int64_t* __restrict__ iseqalg) {
   const int NXS = a.NXS;
   const int ix1 = IXM1(ix, iy);
   const double vol = GG(vol, ix, iy);
-  const double ni = a.get(PL_NI, ix, iy);
   double psor, psorxr, psordis;
   f_psor(a, ix, iy, psor, psorxr, psordis);
-  // particle balance (oderhs.m:3407-3456)
-  double resco = 0. + 0. * ni + 0. + D.cfneut * D.cfneutsor_ni * D.cnsor * psor + D.cfneut * D.cfneutsor_ni * D.cnsor * psorxr +
-                 D.cfneut * D.cfneutsor_ni * D.cnsor * 0. - 0. + 0.;
-  resco = resco - ((a.get(PL_FNIX, ix, iy) - a.get(PL_FNIX, ix1, iy)) + D.fluxfacy * (a.get(PL_FNIY, ix, iy) - a.get(PL_FNIY, ix, iy - 1)));
+  const double resco = f_resco(a, ix, iy, psor, psorxr);
   a.set(PL_RESCO, ix, iy, resco);
   // neutral balance (oderhs.m:6587-6595)
   const double psorg = -psor, psorrg = -psorxr;
@@ -1496,7 +1504,8 @@ __device__ __forceinline__ void phase3_dt(int ix, int iy, double r[UE_NV], const
 // ============================================================================================
 template <bool WIN>
 __device__ void phase3_interior(const Acc<WIN>& a, int ix, int iy, double r[UE_NV], const double* ycell /* this cell's entries of yl */, double ylflag /* yl(neq+1) */,
-                                const int64_t* __restrict__ iseqalg, const double* __restrict__ dtuse, const double* __restrict__ ylodt) {
+                                const int64_t* __restrict__ iseqalg, const double* __restrict__ dtuse, const double* __restrict__ ylodt,
+                                bool recompute_resco_east = false /* fused phase-2/3 kernel: the plane entry of the east cell may not be written yet */) {
   const int NXS = a.NXS;
   const int64_t c = (int64_t)(ix + NXS * iy) * NVX;
   if (D.isflxvar != 1 && D.isrscalf == 1) {
@@ -1508,7 +1517,13 @@ __device__ void phase3_interior(const Acc<WIN>& a, int ix, int iy, double r[UE_N
     const int ix1 = IXP1(ix, iy);
     if (iseqalg[c + 1] == 0) {
       const int64_t c1 = (int64_t)(ix1 + NXS * iy) * NVX;
-      const double yldot_np1 = a.get(PL_RESCO, ix1, iy) / (GG(vol, ix1, iy) * D.n0);
+      double resco_e;
+      if (recompute_resco_east) {
+        double psor, psorxr, psordis;
+        f_psor(a, ix1, iy, psor, psorxr, psordis);
+        resco_e = f_resco(a, ix1, iy, psor, psorxr);
+      } else resco_e = a.get(PL_RESCO, ix1, iy);
+      const double yldot_np1 = resco_e / (GG(vol, ix1, iy) * D.n0);
       double nbvdot, nbv;
       if (iseqalg[c + 0] == 1) { nbvdot = yldot_np1 * D.n0; nbv = a.get(PL_NI, ix1, iy); }      // isnupdot1sd = 0
       else if (iseqalg[c1 + 0] == 1) { nbvdot = r[0] * D.n0; nbv = ni; }

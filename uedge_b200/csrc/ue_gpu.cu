@@ -36,6 +36,7 @@ int nx, ny, NXS, NC;
 int64_t neq = 0;
 int64_t g_launches = 0;
 bool g_host_graphs = true;
+bool g_fuse23 = true;  // phases 2 and 3 of the full residual in one launch (UE_GPU_NO_FUSE23=1: two launches, for comparison)
 std::vector<double> g_step_host[4];  // last dtuse, ylodt, suscal, sfscal uploaded
 std::set<std::pair<const void*, const void*>> g_seen_host;
 std::vector<double> g_last_yldot;  // host copy of the last residual returned (d_yldot still holds it)
@@ -170,6 +171,53 @@ __global__ void __launch_bounds__(160) k_phase2(double* base, double* __restrict
     else if (role == 1) { p2_m<false>(a, w, ix, iy, r, D.iseqalg); o[1] = r[1]; }
     else if (role == 2) { p2_e<false>(a, ix, iy, r, D.iseqalg); o[2] = r[2]; }
     else { p2_i<false>(a, ix, iy, r, D.iseqalg); o[3] = r[3]; }
+  }
+}
+// Phases 2 and 3 of the full residual in one launch.  As k_phase2, plus: the four equation-group warps leave their rows
+// in shared memory, and after a barrier among them the first warp applies rscalf and the time-step term to its 32 cells
+// (phase3_interior; the particle balance of the east neighbour, which another block may own, is recomputed with the
+// same device function) and writes yldot; the guard warp finishes its own rows.  Saves one launch per residual.
+__global__ void __launch_bounds__(160) k_phase23(double* base, double* __restrict__ tmp, double* __restrict__ yldot, const double* __restrict__ yl,
+                                                 const double* __restrict__ dtuse, const double* __restrict__ ylodt, int64_t neq, int NXS, int NC,
+                                                 const int* __restrict__ guard_cells, int nguard, int* err, long long* hflags, double* __restrict__ yldot_host) {
+  __shared__ double srow[UE_NV][32];
+  const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+  Acc<false> a; a.base = base; a.NXS = NXS; a.NC = NC;
+  const Win w = make_win(D, -1, -1);
+  const int nv = NVX;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { hflags[0] = err[0]; err[0] = 0; }  // error bits of phases 0-1, as k_phase3
+  double r[UE_NV] = {0., 0., 0., 0., 0.};
+  if (role == 4) {
+    const int g = blockIdx.x * 32 + lane;
+    if (g >= nguard) return;
+    const int c = guard_cells[g];
+    if (c < 0) return;
+    const int ix = c % NXS, iy = c / NXS;
+    phase2_guard<false>(a, w, ix, iy, r);
+    double* o = tmp + (size_t)c * UE_NV;
+    for (int k = 0; k < UE_NV; ++k) o[k] = r[k];
+    if (D.isbcwdt == 1) phase3_dt(ix, iy, r, yl + (size_t)c * nv, yl[neq], (int64_t)c * nv, dtuse, ylodt);
+#pragma unroll
+    for (int k = 0; k < UE_NV; ++k) if (k < nv) { yldot[(size_t)c * nv + k] = r[k]; if (yldot_host) yldot_host[(size_t)c * nv + k] = r[k]; }
+    return;
+  }
+  const int c = blockIdx.x * 32 + lane;
+  const int ix = c % NXS, iy = c / NXS;
+  const bool interior = c < NC && ix >= 1 && ix <= D.nx && iy >= 1 && iy <= D.ny;
+  if (interior) {
+    double* o = tmp + (size_t)c * UE_NV;
+    if (role == 0) { p2_n<false>(a, ix, iy, r, D.iseqalg); o[0] = r[0]; o[4] = r[4]; srow[0][lane] = r[0]; srow[4][lane] = r[4]; }
+    else if (role == 1) { p2_m<false>(a, w, ix, iy, r, D.iseqalg); o[1] = r[1]; srow[1][lane] = r[1]; }
+    else if (role == 2) { p2_e<false>(a, ix, iy, r, D.iseqalg); o[2] = r[2]; srow[2][lane] = r[2]; }
+    else { p2_i<false>(a, ix, iy, r, D.iseqalg); o[3] = r[3]; srow[3][lane] = r[3]; }
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");  // the four equation-group warps only (the guard warp may have left)
+  if (role == 0 && interior) {
+#pragma unroll
+    for (int k = 0; k < UE_NV; ++k) r[k] = srow[k][lane];
+    phase3_interior<false>(a, ix, iy, r, yl + (size_t)c * nv, yl[neq], D.iseqalg, dtuse, ylodt, true);
+#pragma unroll
+    for (int k = 0; k < UE_NV; ++k) if (k < nv) { yldot[(size_t)c * nv + k] = r[k]; if (yldot_host) yldot_host[(size_t)c * nv + k] = r[k]; }
   }
 }
 __global__ void k_phase3(double* base, const double* __restrict__ tmp, double* __restrict__ yldot, const double* __restrict__ yl,
@@ -406,6 +454,7 @@ __global__ void __launch_bounds__(128, MINB) k_jb_p2(JArgs A) {
 }
 // phase 3 on the interior candidate rows, then difference / clip / ordered compaction into the column's CSC
 // fragment (oderhs.m:8685-8719): one warp per unknown
+// (Building the row pointer in the last block of this kernel instead of a separate k_scan launch was measured: no gain.)
 __global__ void __launch_bounds__(128) k_jb_p3c(JArgs A) {
   const int lane = threadIdx.x & 31, u = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (u >= A.NU) return;
@@ -852,10 +901,16 @@ int enqueue_residual(const double* dyl, double* dyldot, bool need_rows, const do
   if (yl_src && yl_src != dyl) CK(launch(k_phase0, dim3(G), dim3(B), d_base, yl_src, const_cast<double*>(dyl), neq, NXS, NC, d_err));
   else CK(launch(k_phase0, dim3(G), dim3(B), d_base, dyl, (double*)nullptr, neq, NXS, NC, d_err));
   CK(launch(k_phase1, dim3(G32), dim3(160), d_base, NXS, NC));
-  CK(launch(k_phase2, dim3(std::max(G32, (g_nguard_cells + 31) / 32)), dim3(160), d_base, d_tmp, NXS, NC, (const int*)d_guard_cells, g_nguard_cells));
-  if (need_rows) CK(launch(k_phase3, dim3(G), dim3(B), d_base, d_tmp, dyldot, dyl, d_dtuse, d_ylodt, neq, NXS, NC, d_err, d_hflags, yldot_host));
+  if (need_rows && g_fuse23)
+    CK(launch(k_phase23, dim3(std::max(G32, (g_nguard_cells + 31) / 32)), dim3(160), d_base, d_tmp, dyldot, dyl, (const double*)d_dtuse, (const double*)d_ylodt, neq, NXS, NC,
+              (const int*)d_guard_cells, g_nguard_cells, d_err, d_hflags, yldot_host));
+  else {
+    CK(launch(k_phase2, dim3(std::max(G32, (g_nguard_cells + 31) / 32)), dim3(160), d_base, d_tmp, NXS, NC, (const int*)d_guard_cells, g_nguard_cells));
+    if (need_rows) CK(launch(k_phase3, dim3(G), dim3(B), d_base, d_tmp, dyldot, dyl, d_dtuse, d_ylodt, neq, NXS, NC, d_err, d_hflags, yldot_host));
+  }
   return 0;
 }
+int res_launches() { return g_fuse23 ? 3 : 4; }  // kernels of one residual sequence with rows
 int jac_launches() { return (int)h_list.size() >= 4096 ? 8 : 6; }  // kernels of one Jacobian sequence (large / small grids)
 int enqueue_jac(const double* dyl, const double* dy00, int64_t ml, int64_t mu, int64_t nnzmx, double* djac, int64_t* dja, int64_t* dia, bool base_current,
                 double* jac_host = nullptr, int64_t* ja_host = nullptr, int64_t* ia_host = nullptr) {
@@ -927,7 +982,7 @@ int replay(const GKey& key, F enqueue) {
 int run_residual_dev(const double* dyl, double* dyldot, bool need_rows) {
   GKey k; std::memset(&k, 0, sizeof k);
   k.kind = 1; k.p0 = dyl; k.p1 = dyldot; k.flag = need_rows;
-  g_launches += need_rows ? 4 : 3;
+  g_launches += need_rows ? res_launches() : 3;
   return replay(k, [&]() { return enqueue_residual(dyl, dyldot, need_rows); });
 }
 
@@ -999,6 +1054,7 @@ int ue_gpu_set_int_array(const char* n, const int64_t* d, int64_t k) { if (S.set
 const char* ue_gpu_last_error(void) { return g_err.c_str(); }
 
 int ue_gpu_init(void) {
+  g_fuse23 = getenv("UE_GPU_NO_FUSE23") == nullptr;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_err = "no CUDA device: the B200 path has no CPU fallback"; return -9; }
   if (g_ready) free_all();
@@ -1156,7 +1212,7 @@ int ue_gpu_pandf1(int64_t n, double time, const double* yl, double* yldot) {
   // H2D(yl) -> phases 0-3 -> D2H(yldot), D2H(err) as ONE graph launch and ONE synchronisation
   GKey k; std::memset(&k, 0, sizeof k);
   k.kind = 3; k.p0 = yl; k.p1 = yldot;
-  g_launches += 4;
+  g_launches += res_launches();
   int rc = 0;
   // Solvers call with the same work arrays every time (NKSOL's savf/u); a pointer pair seen for the first time takes
   // the plain path so that callers with fresh buffers per call do not pay a capture each time.
@@ -1273,7 +1329,7 @@ int ue_gpu_rhs_jac(int64_t n, const double* yl, double* yldot00, int64_t ml, int
   GKey k; std::memset(&k, 0, sizeof k);
   k.kind = 5; k.p0 = yl; k.p1 = yldot00; k.p2 = jac; k.p3 = ja; k.p4 = ia; k.a = ml; k.b = mu; k.c = lim;
   k.flag = (yl_dev ? 1 : 0) | (f_dev ? 2 : 0) | (direct ? 4 : 0);
-  g_launches += 4 + jac_launches();
+  g_launches += res_launches() + jac_launches();
   auto body = [&]() {
     if (!yl_dev) CK(cudaMemcpyAsync(d_yl, yl, (neq + 2) * 8, cudaMemcpyHostToDevice, g_stream));
     int r = enqueue_residual(d_yl, d_yldot, true, yl_dev, f_dev);
