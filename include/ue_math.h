@@ -23,8 +23,16 @@
 
 #ifdef __CUDACC__
 #define UE_HD __host__ __device__ __forceinline__
+/* The long functions (log, exp, pow, cos) are NOT inlined on the device: the kernels are single cold passes whose time is
+ * dominated by instruction fetch, and a physics kernel calls them at dozens of sites. */
+#ifdef UE_MATH_FORCEINLINE
+#define UE_HD_BIG UE_HD
+#else
+#define UE_HD_BIG __host__ __device__ __noinline__
+#endif
 #else
 #define UE_HD static inline
+#define UE_HD_BIG static inline
 #endif
 
 UE_HD int64_t ue_d2bits(double x) {
@@ -45,7 +53,7 @@ UE_HD double ue_two_pow(int k) { /* 2^k, -1022 <= k <= 1023 */
   return ue_bits2d((int64_t)(k + 1023) << 52);
 }
 
-UE_HD double ue_log(double x) {
+UE_HD_BIG double ue_log(double x) {
   const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
   const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
                Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
@@ -76,7 +84,7 @@ UE_HD double ue_log(double x) {
 
 UE_HD double ue_log10(double x) { return ue_log(x) * 4.34294481903251816668e-01; }
 
-UE_HD double ue_exp(double x) {
+UE_HD_BIG double ue_exp(double x) {
   const double ln2HI = 6.93147180369123816490e-01, ln2LO = 1.90821492927058770002e-10, invln2 = 1.44269504088896338700e+00;
   const double P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03, P3 = 6.61375632143793436117e-05,
                P4 = -1.65339022054652515390e-06, P5 = 4.13813679705723846039e-08;
@@ -105,7 +113,7 @@ UE_HD double ue_sqrt(double x) {
 }
 
 /* x**y for x >= 0 (Fortran real power).  Exponents 0, 1, 2, 0.5 are exact shortcuts. */
-UE_HD double ue_pow(double x, double y) {
+UE_HD_BIG double ue_pow(double x, double y) {
   if (y == 0.0) return 1.0;
   if (y == 1.0) return x;
   if (y == 2.0) return x * x;
@@ -128,7 +136,7 @@ UE_HD double ue_kcos(double x) { /* |x| <= pi/4 */
   const double r = z * (C1 + z * (C2 + z * (C3 + z * (C4 + z * (C5 + z * C6)))));
   return 1.0 - (0.5 * z - z * r);
 }
-UE_HD double ue_cos(double x) { /* intended for |x| <= pi; larger |x| is folded by 2*pi steps */
+UE_HD_BIG double ue_cos(double x) { /* intended for |x| <= pi; larger |x| is folded by 2*pi steps */
   const double pi = 3.14159265358979311600e+00, pio2 = 1.57079632679489655800e+00, pio4 = 7.85398163397448278999e-01;
   if (x < 0.0) x = -x;
   if (x != x || x > 1.0e15) return 0.0 / 0.0;
