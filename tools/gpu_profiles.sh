@@ -8,10 +8,11 @@ python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/ref_d3dHsm.js
 for c in d3dHsm d3dHsm4x case1 box2d; do
   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$c.csv python bench.py --steps 2 --warmup 1 --no-cpu --config $c > gpurun_out/bench_under_ncu_$c.log 2>&1
 done
+# two iterations of tools/one_jac.py are enough for one complete residual + Jacobian sequence (9 / 11 kernels each)
 for c in d3dHsm d3dHsm4x box2d; do
-  ncu --set full --clock-control none -c 27 -o /tmp/full_$c -f python tools/one_jac.py $c 3 > /dev/null 2>&1
+  ncu --set full --clock-control none -c 22 -o /tmp/full_$c -f python tools/one_jac.py $c 2 > /dev/null 2>&1
   python tools/ncu_summary.py /tmp/full_$c.ncu-rep gpurun_out/ncu_full_$c.json
-  ncu --set full --clock-control none --cache-control none -c 27 -o /tmp/warm_$c -f python tools/one_jac.py $c 3 > /dev/null 2>&1
+  ncu --set full --clock-control none --cache-control none -c 22 -o /tmp/warm_$c -f python tools/one_jac.py $c 2 > /dev/null 2>&1
   python tools/ncu_summary.py /tmp/warm_$c.ncu-rep gpurun_out/ncu_warm_$c.json
 done
 ls -la gpurun_out
