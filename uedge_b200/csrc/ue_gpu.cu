@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(128) k_jb_p3c(JArgs A) {
       const int qq = q0 + 32 * c + lane;
       keep[c] = false; val[c] = 0.; ii[c] = 0;
       if (qq < ncand) {
-        const int l = qq / nv, k = qq - l * nv;
+        const int l = nv == 5 ? qq / 5 : (nv == 4 ? qq >> 2 : qq / nv), k = qq - l * nv;  // constant divisors for the two layouts
         ii[c] = (int64_t)A.cand_cell[q.coff + l] * nv + k + 1;
         if (ii[c] >= ii1 && ii[c] <= ii2) {
           const bool written = (A.rmask[q.off + l] >> k) & 1;
