@@ -28,7 +28,7 @@ extern "C" {
 #endif
 
 /* ---- static inputs (once per allocate/ueinit; names in ue_params.h) -------- */
-int ue_gpu_set_int(const char* name, int64_t value);
+int ue_gpu_set_int(const char* name, int64_t value);   /* after ue_gpu_init a CHANGED switch requires a new ue_gpu_init (model_dt excepted) */
 int ue_gpu_set_real(const char* name, double value);
 int ue_gpu_set_real_array(const char* name, const double* data, int64_t n);
 int ue_gpu_set_int_array(const char* name, const int64_t* data, int64_t n);

@@ -195,3 +195,21 @@ def test_slab_fuzz(built, name, seed):
     """Coefficient / array-input / integer-switch fuzz on the slab family (same inputs as the CPU logic check)."""
     from tests.test_hostcheck import run_fuzzed
     run_fuzzed(load_gpu(), name, seed)
+
+
+def test_switch_change_after_init_needs_reinit(built):
+    """Lists, derived flags and refusals are built from the switches at ue_gpu_init: a changed integer switch afterwards
+    disables the entry points until the caller re-initialises; model_dt (read by ue_gpu_set_dt only) is patched in place."""
+    c, yl = make_case("d3dHsm", perturb=1e-3)
+    gpu = bind(load_gpu(), c)
+    f = gpu.pandf1(yl)
+    gpu.set_int("isupcore", int(c.bbb.isupcore[0]))   # unchanged: nothing happens
+    assert np.array_equal(gpu.pandf1(yl), f)
+    gpu.set_int("model_dt", 2)                         # allowed at run time
+    assert np.array_equal(gpu.pandf1(yl), f)
+    gpu.set_int("model_dt", int(c.bbb.model_dt))
+    gpu.set_int("isupcore", 1 - int(c.bbb.isupcore[0]))
+    with pytest.raises(UeError, match="ue_gpu_init not called"):
+        gpu.pandf1(yl)
+    bind(gpu, c)                                       # re-initialise with the original switch set
+    assert np.array_equal(gpu.pandf1(yl), f)

@@ -32,6 +32,7 @@ namespace {
 UeStore S;
 std::string g_err;
 bool g_ready = false;
+bool g_alloc = false;  // device state of a previous ue_gpu_init exists (freed by the next one)
 int nx, ny, NXS, NC;
 int64_t neq = 0;
 int64_t g_launches = 0;
@@ -794,6 +795,7 @@ void free_all() {
   d_err = nullptr; d_cand_cell = d_cand_east = d_item_u = d_guard_items = d_guard_cells = nullptr; d_coloff = nullptr; d_colcnt = d_colrow = nullptr; d_colval = nullptr;
   d_rowcnt = d_rowfill = nullptr; d_ia = d_ja = nullptr; d_jac = nullptr;
   g_ready = false;
+  g_alloc = false;
 }
 
 // kind of a guard cell = which part of bouncon sets its rows; lists are sorted by kind and padded to whole warps
@@ -1030,7 +1032,28 @@ int run_jac_dev(const double* dyl, const double* dy00, int64_t ml, int64_t mu, i
 // ====================================================================================================
 extern "C" {
 
-int ue_gpu_set_int(const char* n, int64_t v) { g_base_valid = g_base_dev_valid = false; if (S.set_int(n, v)) { g_err = std::string("unknown int input ") + n; return -1; } return 0; }
+int ue_gpu_set_int(const char* n, int64_t v) {
+  // Before ue_gpu_init: stored.  After it: the device lists, derived flags and refusals were built from the switches, so a
+  // changed switch needs a new ue_gpu_init -- except model_dt (read by ue_gpu_set_dt only), which is patched in place.
+  if (g_ready) {
+    if (S.zero_only.count(n)) {  // as ue_gpu_set_real: checked at init, a non-zero value afterwards is refused at once
+      if (v != 0) { g_err = std::string("input ") + n + " must be 0: the term it switches on is outside the built hot path"; return -5; }
+      return 0;
+    }
+    auto it = S.iscal.find(n);
+    if (it != S.iscal.end() && *it->second == v) return 0;  // unchanged
+    if (it != S.iscal.end() && std::string(n) == "model_dt") {
+      *it->second = v;
+      const size_t off = (size_t)((char*)it->second - (char*)&S.p);
+      CK(cudaMemcpyToSymbol(D, &v, sizeof(int64_t), off));
+      return 0;
+    }
+    g_ready = false;  // entry points now fail with "ue_gpu_init not called" until the caller re-initialises
+  }
+  g_base_valid = g_base_dev_valid = false;
+  if (S.set_int(n, v)) { g_err = std::string("unknown int input ") + n; return -1; }
+  return 0;
+}
 int ue_gpu_set_real(const char* n, double v) {
   if (S.zero_only.count(n)) {  // checked at ue_gpu_init; after it, a non-zero value is refused at once
     S.set_real(n, v);
@@ -1057,7 +1080,7 @@ int ue_gpu_init(void) {
   g_fuse23 = getenv("UE_GPU_NO_FUSE23") == nullptr;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_err = "no CUDA device: the B200 path has no CPU fallback"; return -9; }
-  if (g_ready) free_all();
+  if (g_alloc) free_all();  // (g_ready may already be false: a switch was changed after the previous init)
   std::string m = S.missing();
   if (!m.empty()) { g_err = "missing inputs: " + m; return -1; }
   const UeParams& P = S.p;
@@ -1151,6 +1174,7 @@ int ue_gpu_init(void) {
   CK(cudaMalloc(&d_jac, g_nnzcap * sizeof(double)));
   g_launches = 0;
   g_ready = true;
+  g_alloc = true;
   return 0;
 }
 
