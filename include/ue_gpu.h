@@ -30,7 +30,7 @@ extern "C" {
 /* ---- static inputs (once per allocate/ueinit; names in ue_params.h) -------- */
 int ue_gpu_set_int(const char* name, int64_t value);   /* after ue_gpu_init a CHANGED switch requires a new ue_gpu_init (model_dt excepted) */
 int ue_gpu_set_real(const char* name, double value);
-int ue_gpu_set_real_array(const char* name, const double* data, int64_t n);
+int ue_gpu_set_real_array(const char* name, const double* data, int64_t n);   /* arrays are uploaded by ue_gpu_init: call it again after changing one */
 int ue_gpu_set_int_array(const char* name, const int64_t* data, int64_t n);
 /* Validate that every named input is present and the switch set is one the
  * kernels implement, upload to the device, build the window tables. */

@@ -1072,8 +1072,9 @@ int ue_gpu_set_real(const char* n, double v) {
   }
   return 0;
 }
-int ue_gpu_set_real_array(const char* n, const double* d, int64_t k) { if (S.set_real_array(n, d, k)) { g_err = std::string("unknown real array ") + n; return -1; } return 0; }
-int ue_gpu_set_int_array(const char* n, const int64_t* d, int64_t k) { if (S.set_int_array(n, d, k)) { g_err = std::string("unknown int array ") + n; return -1; } return 0; }
+// arrays are uploaded by ue_gpu_init: sending one afterwards disables the entry points until the next ue_gpu_init
+int ue_gpu_set_real_array(const char* n, const double* d, int64_t k) { g_ready = false; if (S.set_real_array(n, d, k)) { g_err = std::string("unknown real array ") + n; return -1; } return 0; }
+int ue_gpu_set_int_array(const char* n, const int64_t* d, int64_t k) { g_ready = false; if (S.set_int_array(n, d, k)) { g_err = std::string("unknown int array ") + n; return -1; } return 0; }
 const char* ue_gpu_last_error(void) { return g_err.c_str(); }
 
 int ue_gpu_init(void) {
