@@ -17,16 +17,20 @@ def test_split_index_covers_all():
         assert all(r[i][1] + 1 == r[i + 1][0] for i in range(k - 1))
 
 
-def test_pool_jacobian_equals_serial(built):
+import pytest
+
+
+@pytest.mark.parametrize("name", ["d3dHsm", "case1", "box2d"])
+def test_pool_jacobian_equals_serial(built, name):
     from tests.cpu_pool import OraclePool
-    c, yl = make_case("d3dHsm", perturb=1e-3)
+    c, yl = make_case(name, perturb=1e-3)
     b = c.bbb
     ora = bind(oracle(), c)
     y, su = psetnk_inputs(c, yl)
     ora.step_params(np.full(b.neq, 1e20), y[: b.neq], su, np.ones(b.neq))
     f0 = ora.pandf1(y)
     ref = ora.jac_calc(y, f0, b.lbw, b.ubw, b.nnzmx)
-    pool = OraclePool("d3dHsm", 1e-3, nproc=3)
+    pool = OraclePool(name, 1e-3, nproc=3)
     got = pool.jacobian(b.neq)
     pool.close()
     assert all(np.array_equal(p, q) for p, q in zip(ref, got))
