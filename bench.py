@@ -4,9 +4,16 @@
 Contract: python bench.py --gpus N --steps K --warmup W  prints ONE JSON line.
 A "step" is what sfsetnk/psetnk do to get a Jacobian (bbb/oderhs.m:9851-9857, 9466-9468): one residual
 evaluation rhsnk(yl) followed by one full finite-difference Jacobian assembly jac_calc(yl, yldot00), on the
-d3dHsm configuration.  Both arms (CUDA and CPU) time the same step; residual evaluations/s are reported too.
-`--impl reference` times the CPU restatement of the reference algorithm (the reference itself is
-MPPL/Fortran and cannot be built in this image) on the box's host cores.
+d3dHsm configuration (BASELINE.json configs[1]).  Both arms (CUDA and CPU) time the same step on the same state.
+
+N > 1 (torchrun, one rank per GPU): ONE Jacobian is assembled by the N GPUs — the reference's MPI design
+(ppp/mpi_parallel.F90): every rank holds the full state, assembles a contiguous range of columns, the CSC
+fragments are all-gathered over NCCL on the device and every rank ends with the full CSR (`scaling: "strong"`).
+The same measurement is repeated on the 4x- and 8x-refined grids (`grids`), and N independent replicas
+(one state per GPU, no collective) are kept as a secondary record (`replicas`).
+
+`--impl reference` times the CPU restatement of the reference algorithm (the reference itself is MPPL/Fortran and
+cannot be built in this image) with all host threads, in-process (the ppp OpenMP design).
 """
 import argparse
 import ctypes as C
@@ -23,11 +30,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
-def clocks_sampler(stop, out):
+def clocks_sampler(stop, out, dev):
     q = "clocks.sm,clocks.max.sm,clocks_throttle_reasons.active"
     while not stop.is_set():
         try:
-            r = subprocess.run(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-i", "0"],
+            r = subprocess.run(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-i", str(dev)],
                                capture_output=True, text=True, timeout=5).stdout.strip().split(",")
             out.append((float(r[0]), float(r[1]), r[2].strip()))
         except Exception:
@@ -49,45 +56,227 @@ def reasons_of(mask_strs):
     return sorted(got)
 
 
-def cpu_baseline(c, name, perturb, budget_s=12.0, nproc=None):
-    """CPU arm: the oracle's jac_calc (same algorithm and cost structure as the reference: 2*neq windowed
-    pandf1 calls) split over ALL host cores by contiguous column ranges, one process per core holding the
-    full state — the reference's MPI row-split design (ppp/mpi_parallel.F90).  Also times one core alone.
-    Must run before CUDA is initialised (fork)."""
-    from tests.cpu_pool import OraclePool
+def bench_state(name, seed=1234):
+    """Case + the two alternating states every arm uses (a Newton iteration never repeats a state)."""
+    from uedge_b200.cases import make_case, psetnk_inputs
+    c, yl = make_case(name, perturb=1e-3, seed=seed)
+    c.name = name
+    y, su = psetnk_inputs(c, yl)
+    neq = c.bbb.neq
+    y2 = y.copy()
+    y2[:neq] *= 1 + 1e-6 * np.random.default_rng(7).uniform(-1, 1, neq)
+    return c, [y, y2], su
+
+
+def cpu_baseline(c, ystates, su, budget_s=12.0, nthreads=None):
+    """CPU arm: the oracle's jac_calc (same algorithm and cost structure as the reference: 2*neq windowed pandf1
+    calls) on ALL host cores, in-process threads over contiguous column ranges with private state copies and a C++
+    merge — the reference's OpenMP design (ppp/omp_parallel.F90).  Built -O3 -march=native on this host."""
+    from oracle.cpu_arm import time_cpu_arm
     b = c.bbb
-    nproc = nproc or os.cpu_count()
-    pool = OraclePool(name, perturb, nproc=nproc)
-    pool.jacobian(b.neq)  # warm-up
-    t0 = time.perf_counter(); reps = 0
-    while True:
-        jac, ja, ia = pool.jacobian(b.neq)
-        reps += 1
-        if time.perf_counter() - t0 > budget_s or reps >= 30:
-            break
-    dt = (time.perf_counter() - t0) / reps
-    pool.close()
-    nnz = len(jac)
-    p1 = OraclePool(name, perturb, nproc=1)
-    p1.jacobian(b.neq)
-    t1 = time.perf_counter(); r1 = 0
-    while True:
-        p1.jacobian(b.neq); r1 += 1
-        if time.perf_counter() - t1 > budget_s / 2 or r1 >= 10:
-            break
-    dt1 = (time.perf_counter() - t1) / r1
-    p1.close()
-    from tests.util import bind, oracle, make_case
-    ora = bind(oracle(), c)
-    yl = make_case(name, perturb=perturb)[1]
-    t2 = time.perf_counter(); r2 = 0
-    while time.perf_counter() - t2 < 1.5:
-        ora.pandf1(yl); r2 += 1
-    tres = (time.perf_counter() - t2) / r2
-    return dict(value=nnz / dt, unit="nnz/s", cores=nproc, kind="port",
-                sample="%d full Jacobians of %s (neq=%d, nnz=%d) split over %d processes: %.2f ms each; 1 process: %.2f ms; serial residual %.3f ms"
-                       % (reps, name, b.neq, nnz, nproc, dt * 1e3, dt1 * 1e3, tres * 1e3),
-                resid_evals_per_s=1.0 / tres, jac_s=dt, serial_value=nnz / dt1)
+    r = time_cpu_arm(c, ystates[0], su, budget_s=budget_s, nthreads=nthreads, native=True)
+    sample = ("%d steps (residual + full Jacobian) of %s (neq=%d, nnz=%d), state 0 of the bench pair; %s; %d in-process threads "
+              "(contiguous column ranges, private state copies, C++ merge): Jacobian %.2f ms, 1 thread %.2f ms, parallel efficiency %.0f%%; "
+              "serial residual %.3f ms" % (r["reps"], c.name, b.neq, r["nnz"], r["flags"], r["threads"], r["jac_s"] * 1e3, r["serial_jac_s"] * 1e3,
+                                           100 * r["par_eff"], r["resid_s"] * 1e3))
+    return dict(value=r["nnz"] / r["step_s"], unit="nnz/s", cores=r["threads"], kind="port", sample=sample,
+                resid_evals_per_s=1.0 / r["resid_s"], step_s=r["step_s"], jac_s=r["jac_s"], serial_value=r["nnz"] / (r["serial_jac_s"] + r["resid_s"]),
+                par_eff=r["par_eff"], nnz=r["nnz"])
+
+
+class Gpu:
+    """The product library bound to one case on this rank's GPU (through the C ABI only)."""
+
+    def __init__(self, c, ystates, su, world, rank, dist, torch, split=True):
+        from uedge_b200.capi import load_gpu
+        self.c, self.world, self.rank, self.dist, self.torch = c, world, rank, dist, torch
+        self.gpu = load_gpu()
+        self.gpu.load_static(c.static_inputs()); self.gpu.init()
+        b = c.bbb
+        self.b = b
+        self.neq = neq = int(b.neq); self.nnzmx = int(b.nnzmx)
+        lib = self.lib = self.gpu.lib
+        self.split = split and world > 1
+        if self.split:
+            lib.ue_gpu_comm_unique_id.argtypes = [C.c_char_p]
+            lib.ue_gpu_comm_init.argtypes = [C.c_int64, C.c_int64, C.c_char_p]
+            idbuf = C.create_string_buffer(128)
+            if rank == 0:
+                assert lib.ue_gpu_comm_unique_id(idbuf) == 0, self.err()
+            t = torch.frombuffer(bytearray(idbuf.raw), dtype=torch.uint8).cuda()
+            dist.broadcast(t, 0)
+            idb = bytes(t.cpu().numpy().tobytes())
+            assert lib.ue_gpu_comm_init(world, rank, idb) == 0, self.err()
+        self.su = np.ascontiguousarray(su)
+        self.gpu.step_params(np.full(neq, 1e20), ystates[0][:neq], su, np.ones(neq))
+        self.sp = [np.full(neq, 1e20), ystates[0][:neq].copy(), self.su, np.ones(neq)]
+        self.ystates = [torch.from_numpy(v.copy()) for v in ystates]
+        self.nufak = float(b.nufak)
+        # host buffers: page-locked set and pageable set
+        self.pin = self._bufs(True)
+        self.pag = self._bufs(False)
+        P = C.c_void_p
+        lib.ue_gpu_jac_calc.argtypes = [C.c_int64, C.c_double] + [P] * 2 + [C.c_int64] * 3 + [P] * 3 + [C.POINTER(C.c_int64)]
+        lib.ue_gpu_pandf1.argtypes = [C.c_int64, C.c_double, P, P]
+        lib.ue_gpu_rhs_jac.argtypes = [C.c_int64, P, P] + [C.c_int64] * 3 + [P] * 3 + [C.POINTER(C.c_int64)]
+        lib.ue_gpu_rhs_jac_dev.argtypes = [C.c_int64, P, P] + [C.c_int64] * 3 + [P] * 3 + [C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+        lib.ue_gpu_jac_calc_dev.argtypes = [C.c_int64, C.c_double] + [P] * 2 + [C.c_int64] * 3 + [P] * 3 + [C.POINTER(C.c_int64)]
+        lib.ue_gpu_pandf1_dev.argtypes = [C.c_int64, C.c_double, P, P]
+        lib.ue_gpu_step_params.argtypes = [C.c_int64] + [P] * 4
+        lib.ue_gpu_set_real.argtypes = [C.c_char_p, C.c_double]
+        lib.ue_gpu_comm_info.argtypes = [C.POINTER(C.c_int64)] * 5
+        bufs = [C.c_void_p() for _ in range(6)]
+        lib.ue_gpu_device_buffers(*[C.byref(x) for x in bufs])
+        self.d_yl, self.d_yldot, self.d_y00, self.d_jac, self.d_ja, self.d_ia = bufs
+        self.nnz = C.c_int64(0); self.evms = C.c_double(0); self.jms = C.c_double(0); self.rms = C.c_double(0)
+        self.ev_samples = []; self.jm = []; self.rm = []
+        self.flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # > 126 MB L2
+
+    def err(self):
+        self.lib.ue_gpu_last_error.restype = C.c_char_p
+        return self.lib.ue_gpu_last_error().decode()
+
+    def _bufs(self, pinned):
+        torch = self.torch
+        mk = (lambda n, dt: torch.zeros(n, dtype=dt).pin_memory()) if pinned else (lambda n, dt: torch.zeros(n, dtype=dt))
+        return dict(y=mk(self.neq + 2, torch.float64), f=mk(self.neq + 2, torch.float64), jac=mk(self.nnzmx, torch.float64),
+                    ja=mk(self.nnzmx, torch.int64), ia=mk(self.neq + 1, torch.int64), yd=mk(self.neq, torch.float64))
+
+    def shim_params(self):
+        """what the Fortran shim does per call: step_params (+ nufak) before the residual and the Jacobian"""
+        NP = lambda x: x.ctypes.data_as(C.c_void_p)
+        assert self.lib.ue_gpu_step_params(self.neq, *[NP(x) for x in self.sp]) == 0, self.err()
+
+    # ---- the steps ------------------------------------------------------------------------------------------------
+    def step_dev(self):  # inputs resident in HBM; residual + Jacobian as one stream sequence, CUDA events on the library's stream
+        b = self.b
+        assert self.lib.ue_gpu_rhs_jac_dev(self.neq, self.d_yl, self.d_y00, int(b.lbw), int(b.ubw), self.nnzmx, self.d_jac, self.d_ja, self.d_ia,
+                                           C.byref(self.nnz), C.byref(self.evms)) == 0, self.err()
+        self.ev_samples.append(self.evms.value)
+
+    def kernels_dev(self):  # the two sequences separately, for the per-sequence CUDA-event times
+        b = self.b
+        assert self.lib.ue_gpu_pandf1_dev(self.neq, 0.0, self.d_yl, self.d_y00) == 0, self.err()
+        self.lib.ue_gpu_assume_base_current(1)
+        assert self.lib.ue_gpu_jac_calc_dev(self.neq, 0.0, self.d_yl, self.d_y00, int(b.lbw), int(b.ubw), self.nnzmx, self.d_jac, self.d_ja, self.d_ia,
+                                            C.byref(self.nnz)) == 0, self.err()
+        self.lib.ue_gpu_last_kernel_ms(C.byref(self.jms), C.byref(self.rms))
+        self.jm.append(self.jms.value); self.rm.append(self.rms.value)
+
+    def step_e2e(self, h):  # the two C-ABI calls of psetnk with HOST buffers h (pinned or pageable)
+        b = self.b
+        P = lambda t: C.cast(t.data_ptr(), C.c_void_p)
+        self.shim_params()
+        assert self.lib.ue_gpu_pandf1(self.neq, 0.0, P(h["y"]), P(h["f"])) == 0, self.err()
+        self.shim_params()
+        assert self.lib.ue_gpu_set_real(b"nufak", self.nufak) == 0
+        assert self.lib.ue_gpu_jac_calc(self.neq, 0.0, P(h["y"]), P(h["f"]), int(b.lbw), int(b.ubw), self.nnzmx, P(h["jac"]), P(h["ja"]), P(h["ia"]),
+                                        C.byref(self.nnz)) == 0, self.err()
+
+    def step_e2e_fused(self, h):  # optional integration (INTEGRATION.md 4b): the pair as one C-ABI call
+        b = self.b
+        P = lambda t: C.cast(t.data_ptr(), C.c_void_p)
+        self.shim_params()
+        assert self.lib.ue_gpu_set_real(b"nufak", self.nufak) == 0
+        assert self.lib.ue_gpu_rhs_jac(self.neq, P(h["y"]), P(h["f"]), int(b.lbw), int(b.ubw), self.nnzmx, P(h["jac"]), P(h["ja"]), P(h["ia"]), C.byref(self.nnz)) == 0, self.err()
+
+    def resid_e2e(self, h):
+        P = lambda t: C.cast(t.data_ptr(), C.c_void_p)
+        self.shim_params()
+        assert self.lib.ue_gpu_pandf1(self.neq, 0.0, P(h["y"]), P(h["yd"])) == 0, self.err()
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps, h=None, flush=True):
+        """K steps, each bracketed by barrier + synchronize; returns the summed host-clock seconds."""
+        tot = 0.0
+        hy = (h or self.pin)["y"]
+        for it in range(steps):
+            hy.copy_(self.ystates[it & 1])
+            if fn in (self.step_dev, self.kernels_dev):  # device-resident: the state is put in HBM before the timed region
+                self.torch.cuda.synchronize()
+                self._put_state(it & 1)
+            if flush:
+                self.flush.fill_(1.0)
+            self.barrier()
+            t0 = time.perf_counter()
+            fn() if h is None else fn(h)
+            self.torch.cuda.synchronize()
+            tot += time.perf_counter() - t0
+        return tot
+
+    def _put_state(self, k):
+        t = self.torch
+        if not hasattr(self, "_dyl_t"):
+            # torch view of the library's device yl buffer, through the CUDA array interface
+            class _W:
+                pass
+            w = _W()
+            w.__cuda_array_interface__ = dict(shape=(self.neq + 2,), typestr="<f8", data=(self.d_yl.value, False), version=2)
+            self._dyl_t = t.as_tensor(w, device="cuda")
+            self._ydev = [v.cuda() for v in self.ystates]
+        self._dyl_t.copy_(self._ydev[k])
+
+    def comm_info(self):
+        v = [C.c_int64(0) for _ in range(5)]
+        self.lib.ue_gpu_comm_info(*[C.byref(x) for x in v])
+        return [x.value for x in v]
+
+    def close(self):
+        self.lib.ue_gpu_finalize()
+
+
+def maxr(g, vals):
+    """max over ranks of a list of floats"""
+    if g.world == 1:
+        return list(vals)
+    v = g.torch.tensor(list(vals), device="cuda", dtype=g.torch.float64)
+    g.dist.all_reduce(v, op=g.dist.ReduceOp.MAX)
+    return v.tolist()
+
+
+def measure(name, steps, warmup, world, rank, dist, torch, split=True, full=True, seed=1234):
+    """One configuration on this rank.  Returns a dict of max-over-ranks figures (identical on every rank)."""
+    c, ystates, su = bench_state(name, seed)
+    g = Gpu(c, ystates, su, world, rank, dist, torch, split=split)
+    neq = g.neq
+    g.step_e2e(g.pin)  # fills the library's device buffers
+    for _ in range(max(3, warmup)):
+        g._put_state(0); g.step_dev(); g.step_e2e(g.pin)
+    l0 = C.c_int64(0); g.lib.ue_gpu_kernel_launches(C.byref(l0))
+    del g.ev_samples[:]
+    t_dev_host = g.timed(g.step_dev, steps)
+    t_dev = sum(g.ev_samples) * 1e-3  # CUDA events on the library's stream: seconds for `steps` steps
+    l1 = C.c_int64(0); g.lib.ue_gpu_kernel_launches(C.byref(l1))
+    nnz_dev = g.nnz.value  # state (steps-1)&1
+    comm = g.comm_info()
+    del g.jm[:], g.rm[:]
+    g.timed(g.kernels_dev, steps)
+    t_e2e = g.timed(g.step_e2e, steps, g.pin)
+    out = dict(name=name, neq=neq, nnz=nnz_dev, launches=int(l1.value - l0.value))
+    t_dev, t_e2e, t_dev_host, jm, rm = maxr(g, [t_dev, t_e2e, t_dev_host, float(np.mean(g.jm)), float(np.mean(g.rm))])
+    out.update(ms_dev=t_dev / steps * 1e3, ms_e2e=t_e2e / steps * 1e3, ms_dev_host=t_dev_host / steps * 1e3, jac_ms=jm, res_ms=rm,
+               comm_bytes=comm[4], col_range=(comm[2], comm[3]))
+    if full:
+        t_pag = g.timed(g.step_e2e, steps, g.pag)
+        t_res = g.timed(g.resid_e2e, steps, g.pin)
+        t_res_pag = g.timed(g.resid_e2e, steps, g.pag)
+        t_fused = g.timed(g.step_e2e_fused, steps, g.pin)
+        t_fused_pag = g.timed(g.step_e2e_fused, steps, g.pag)
+
+        def warm(fn, n, h=None):  # same step without the L2 flush (what a Newton loop sees); reported next to the flushed figure
+            return g.timed(fn, n, h, flush=False) / n * 1e3
+        w_dev, w_e2e, w_res = warm(g.step_dev, 2 * steps), warm(g.step_e2e, 2 * steps, g.pin), warm(g.resid_e2e, 2 * steps, g.pin)
+        t_pag, t_res, t_res_pag, t_fused, t_fused_pag, w_dev, w_e2e, w_res = maxr(g, [t_pag, t_res, t_res_pag, t_fused, t_fused_pag, w_dev, w_e2e, w_res])
+        out.update(ms_e2e_pageable=t_pag / steps * 1e3, ms_res_e2e=t_res / steps * 1e3, ms_res_e2e_pageable=t_res_pag / steps * 1e3,
+                   ms_fused=t_fused / steps * 1e3, ms_fused_pageable=t_fused_pag / steps * 1e3, warm_ms_dev=w_dev, warm_ms_e2e=w_e2e, warm_ms_res=w_res)
+    out["ncell"] = (c.com.nx + 2) * (c.com.ny + 2)
+    g.close()
+    return out
 
 
 def main():
@@ -98,33 +287,34 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--config", default="d3dHsm")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--mode", default="replicas", choices=["replicas", "columns"],
-                    help="N>1: 'replicas' = every GPU assembles the full Jacobian of its own state (ensemble, weak scaling); "
-                         "'columns' = one Jacobian, columns split over the ranks (ppp MPI design, strong scaling)")
+    ap.add_argument("--no-grids", action="store_true", help="skip the refined-grid sub-records")
+    ap.add_argument("--mode", default="columns", choices=["columns", "replicas"],
+                    help="N>1: 'columns' (default) = ONE Jacobian, columns split over the ranks, NCCL all-gather of the fragments (strong scaling); "
+                         "'replicas' = every GPU assembles the full Jacobian of its own state (ensemble, weak scaling)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    from tests.util import make_case, psetnk_inputs
     name = a.config
-    c, yl = make_case(name, perturb=1e-3, seed=1234 + (rank if a.mode == "replicas" else 0))   # replicas: every rank has its own state; columns: one shared state
-    c.name = name
-    b = c.bbb
 
     if a.impl == "reference":
         if rank != 0:
             return
-        cb = cpu_baseline(c, name, 1e-3, budget_s=20.0)
+        c, ystates, su = bench_state(name)
+        b = c.bbb
+        cb = cpu_baseline(c, ystates, su, budget_s=20.0)
         line = dict(metric="jacobian_nnz_per_s", value=cb["value"], unit="nnz/s", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
-                    ms_per_step=cb["jac_s"] * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-                    impl="reference", config=dict(workload="%s full Jacobian assembly, neq=%d" % (name, b.neq)),
+                    ms_per_step=cb["step_s"] * 1e3, higher_is_better=True, scaling="strong" if a.gpus > 1 else "weak", vs_baseline=None, dtype="f64", data="synthetic",
+                    impl="reference",
+                    config=dict(workload="%s: rhsnk + jac_calc (1 residual + 1 full FD Jacobian, neq=%d, nnz=%d) per step" % (name, b.neq, cb["nnz"])),
                     cpu_baseline=dict(value=cb["value"], unit="nnz/s", cores=cb["cores"], kind=cb["kind"], sample=cb["sample"]),
                     e2e=dict(value=cb["value"], unit="nnz/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                    resid_evals_per_s=cb["resid_evals_per_s"], serial_nnz_per_s=cb["serial_value"])
+                    resid_evals_per_s=cb["resid_evals_per_s"], serial_nnz_per_s=cb["serial_value"], parallel_efficiency=cb["par_eff"])
         print(json.dumps(line))
         return
 
     cb = None
-    if not a.no_cpu and world == 1:
-        cb = cpu_baseline(c, name, 1e-3)  # before CUDA init (the pool forks)
+    if not a.no_cpu and rank == 0 and world == 1:
+        c0, ys0, su0 = bench_state(name)
+        cb = cpu_baseline(c0, ys0, su0)
 
     import torch
     import torch.distributed as dist
@@ -132,144 +322,34 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from uedge_b200.capi import load_gpu
-    gpu = load_gpu()
-    gpu.load_static(c.static_inputs()); gpu.init()
-    y, su = psetnk_inputs(c, yl)
-    gpu.step_params(np.full(b.neq, 1e20), y[: b.neq], su, np.ones(b.neq))
-    lib = gpu.lib
-    neq = b.neq
-    # multi-GPU: replicas-with-column-split (ppp MPI design): rank r assembles columns of its contiguous iv range
-    lo = 1 + (neq * rank) // world; hi = (neq * (rank + 1)) // world
-    if world > 1 and a.mode == "columns":
-        gpu.set_column_range(lo, hi)
-    f0 = gpu.pandf1(y)
-    # pinned host buffers for the end-to-end path
-    hy = torch.from_numpy(y.copy()).pin_memory(); hf = torch.zeros(neq + 2, dtype=torch.float64).pin_memory(); hf[:neq] = torch.from_numpy(f0)
-    nnzmx = int(b.nnzmx)
-    hjac = torch.zeros(nnzmx, dtype=torch.float64).pin_memory(); hja = torch.zeros(nnzmx, dtype=torch.int64).pin_memory()
-    hia = torch.zeros(neq + 1, dtype=torch.int64).pin_memory(); hyd = torch.zeros(neq, dtype=torch.float64).pin_memory()
-    P = lambda t: C.cast(t.data_ptr(), C.c_void_p)
-    nnz = C.c_int64(0)
-    lib.ue_gpu_jac_calc.argtypes = [C.c_int64, C.c_double] + [C.c_void_p] * 2 + [C.c_int64] * 3 + [C.c_void_p] * 3 + [C.POINTER(C.c_int64)]
-    lib.ue_gpu_pandf1.argtypes = [C.c_int64, C.c_double, C.c_void_p, C.c_void_p]
-    bufs = [C.c_void_p() for _ in range(6)]
-    lib.ue_gpu_device_buffers(*[C.byref(x) for x in bufs])
-    d_yl, d_yldot, d_y00, d_jac, d_ja, d_ia = bufs
-    lib.ue_gpu_jac_calc_dev.argtypes = [C.c_int64, C.c_double] + [C.c_void_p] * 2 + [C.c_int64] * 3 + [C.c_void_p] * 3 + [C.POINTER(C.c_int64)]
-    lib.ue_gpu_pandf1_dev.argtypes = [C.c_int64, C.c_double, C.c_void_p, C.c_void_p]
-    jms = C.c_double(0); rms = C.c_double(0)
-
-    # what the Fortran shim does per call: step_params (+ nufak) before the residual and the Jacobian
-    sp_dt = np.full(neq, 1e20); sp_yo = y[:neq].copy(); sp_su = np.ascontiguousarray(su); sp_sf = np.ones(neq)
-    NP = lambda x: x.ctypes.data_as(C.c_void_p)
-    lib.ue_gpu_step_params.argtypes = [C.c_int64] + [C.c_void_p] * 4
-    lib.ue_gpu_set_real.argtypes = [C.c_char_p, C.c_double]
-    nufak = float(c.bbb.nufak)
-
-    def shim_params():
-        assert lib.ue_gpu_step_params(neq, NP(sp_dt), NP(sp_yo), NP(sp_su), NP(sp_sf)) == 0
-
-    jac_call_s = []
-
-    def step_e2e():
-        shim_params()
-        assert lib.ue_gpu_pandf1(neq, 0.0, P(hy), P(hf)) == 0          # yldot00 = rhsnk(yl)
-        tj = time.perf_counter()
-        shim_params()
-        assert lib.ue_gpu_set_real(b"nufak", nufak) == 0
-        assert lib.ue_gpu_jac_calc(neq, 0.0, P(hy), P(hf), int(b.lbw), int(b.ubw), nnzmx, P(hjac), P(hja), P(hia), C.byref(nnz)) == 0
-        jac_call_s.append(time.perf_counter() - tj)
-
-    lib.ue_gpu_rhs_jac_dev.argtypes = [C.c_int64, C.c_void_p, C.c_void_p] + [C.c_int64] * 3 + [C.c_void_p] * 3 + [C.POINTER(C.c_int64), C.POINTER(C.c_double)]
-    evms = C.c_double(0); ev_samples = []
-
-    def step_dev():  # inputs resident in HBM; residual + Jacobian as one stream sequence, timed by CUDA events on the library's stream
-        assert lib.ue_gpu_rhs_jac_dev(neq, d_yl, d_y00, int(b.lbw), int(b.ubw), nnzmx, d_jac, d_ja, d_ia, C.byref(nnz), C.byref(evms)) == 0
-        ev_samples.append(evms.value)
-
-    def kernels_dev():  # the two sequences separately, for the per-sequence CUDA-event times
-        assert lib.ue_gpu_pandf1_dev(neq, 0.0, d_yl, d_y00) == 0
-        lib.ue_gpu_assume_base_current(1)
-        assert lib.ue_gpu_jac_calc_dev(neq, 0.0, d_yl, d_y00, int(b.lbw), int(b.ubw), nnzmx, d_jac, d_ja, d_ia, C.byref(nnz)) == 0
-        lib.ue_gpu_last_kernel_ms(C.byref(jms), C.byref(rms))
-
-    lib.ue_gpu_rhs_jac.argtypes = [C.c_int64, C.c_void_p, C.c_void_p] + [C.c_int64] * 3 + [C.c_void_p] * 3 + [C.POINTER(C.c_int64)]
-
-    def step_e2e_fused():  # optional integration: the pair as one C-ABI call
-        shim_params()
-        assert lib.ue_gpu_set_real(b"nufak", nufak) == 0
-        assert lib.ue_gpu_rhs_jac(neq, P(hy), P(hf), int(b.lbw), int(b.ubw), nnzmx, P(hjac), P(hja), P(hia), C.byref(nnz)) == 0
-
-    def resid_e2e():
-        shim_params()
-        assert lib.ue_gpu_pandf1(neq, 0.0, P(hy), P(hyd)) == 0
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # > 126 MB L2
-
-    # a Newton iteration never repeats a state: alternate two states so that nothing is reused across steps
-    ystates = [y.copy(), y.copy()]
-    ystates[1][:neq] *= 1 + 1e-6 * np.random.default_rng(7).uniform(-1, 1, neq)
-    ystates = [torch.from_numpy(v) for v in ystates]
-
-    def timed(fn, steps):
-        tot = 0.0; jm = []; rm = []
-        for it in range(steps):
-            hy.copy_(ystates[it & 1])
-            flush.fill_(1.0)
-            barrier()
-            t0 = time.perf_counter()
-            fn()
-            torch.cuda.synchronize()
-            tot += time.perf_counter() - t0
-            jm.append(jms.value); rm.append(rms.value)
-        return tot, jm, rm
-
-    step_e2e()  # fills the library's device buffers (d_yl, d_yldot00)
-    for _ in range(a.warmup):
-        step_dev(); step_e2e()
+    split = a.mode == "columns"
     samples = []; stop = threading.Event()
-    th = threading.Thread(target=clocks_sampler, args=(stop, samples)); th.start()
-    l0 = C.c_int64(0); lib.ue_gpu_kernel_launches(C.byref(l0))
-    del ev_samples[:]
-    t_dev_host, _, _ = timed(step_dev, a.steps)
-    t_dev = sum(ev_samples) * 1e-3  # CUDA events: seconds for a.steps steps
-    l1 = C.c_int64(0); lib.ue_gpu_kernel_launches(C.byref(l1))
-    _, jm, rm = timed(kernels_dev, a.steps)
-    del jac_call_s[:]
-    t_e2e, _, _ = timed(step_e2e, a.steps)
-    jac_call_ms = 1e3 * sum(jac_call_s) / max(1, len(jac_call_s))
-    t_res_e2e, _, _ = timed(resid_e2e, a.steps)
-    t_fused, _, _ = timed(step_e2e_fused, a.steps)
+    th = threading.Thread(target=clocks_sampler, args=(stop, samples, local)); th.start()
+    seed = 1234 + (rank if not split else 0)
+    m = measure(name, a.steps, a.warmup, world, rank, dist, torch, split=split, full=True, seed=seed)
     stop.set(); th.join()
-
-    def warm(fn, steps):  # same step without the L2 flush (what a Newton loop sees); reported next to the flushed figure
-        barrier(); t0 = time.perf_counter()
-        for it in range(steps):
-            hy.copy_(ystates[it & 1]); fn()
-        torch.cuda.synchronize()
-        return (time.perf_counter() - t0) / steps * 1e3
-    warm_dev, warm_e2e, warm_res = warm(step_dev, 4 * a.steps), warm(step_e2e, 4 * a.steps), warm(resid_e2e, 4 * a.steps)
-    nnz_local = nnz.value
-    if world > 1:
-        v = torch.tensor([t_dev, t_e2e, t_dev_host], device="cuda", dtype=torch.float64); dist.all_reduce(v, op=dist.ReduceOp.MAX)
-        t_dev, t_e2e, t_dev_host = v.tolist()
-        n = torch.tensor([nnz_local], device="cuda", dtype=torch.int64); dist.all_reduce(n)
+    grids = {}
+    if not a.no_grids:
+        for gname in ("d3dHsm4x", "d3dHsm8x"):
+            r = measure(gname, min(a.steps, 10), 3, world, rank, dist, torch, split=split, full=False)
+            grids[gname] = dict(neq=r["neq"], nnz=r["nnz"], ms_per_step=r["ms_dev"], value=r["nnz"] / (r["ms_dev"] * 1e-3), unit="nnz/s",
+                                e2e_ms_per_step=r["ms_e2e"], e2e_value=r["nnz"] / (r["ms_e2e"] * 1e-3), jac_kernel_ms=r["jac_ms"], resid_kernel_ms=r["res_ms"],
+                                nccl_bytes_per_step_this_rank=r["comm_bytes"], gpu_launches=r["launches"])
+    replicas = None
+    if world > 1 and split:
+        r = measure(name, min(a.steps, 10), 3, world, rank, dist, torch, split=False, full=False, seed=1234 + rank)
+        n = torch.tensor([r["nnz"]], device="cuda", dtype=torch.int64); dist.all_reduce(n)
+        replicas = dict(parallelism="%d independent replicas (one state per GPU), no collective" % world, nnz_total=int(n.item()),
+                        ms_per_step=r["ms_dev"], value=int(n.item()) / (r["ms_dev"] * 1e-3), unit="nnz/s", scaling="weak")
+    nnz_total = m["nnz"]
+    if world > 1 and not split:
+        n = torch.tensor([m["nnz"]], device="cuda", dtype=torch.int64); dist.all_reduce(n)
         nnz_total = int(n.item())
-    else:
-        nnz_total = nnz_local
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    ms_dev = t_dev / a.steps * 1e3; ms_e2e = t_e2e / a.steps * 1e3
-    jac_ms = float(np.mean(jm)); res_ms = float(np.mean(rm))
+    neq = m["neq"]
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -277,37 +357,59 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6453.1))
     G = 16 + 3  # static real planes + int planes the kernels read (include/ue_params.h)
-    traffic = None; fp64_pct = None
+    prof = {}
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        traffic = tj["dram_bytes_per_launch"].get(name); fp64_pct = tj["fp64_pipe_pct"].get(name)
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
         pass
-    ncell = (c.com.nx + 2) * (c.com.ny + 2)
-    alg_bytes = 8 * (2 * (neq + 2) + G * ncell) + 16 * nnz_total + 8 * (neq + 1)
-    achieved = alg_bytes / (jac_ms * 1e-3) / 1e9
+    traffic = prof.get("dram_bytes_per_launch", {}).get(name); fp64_pct = prof.get("fp64_pipe_pct", {}).get(name)
+    flops = prof.get("fp64_flops_per_jacobian", {}).get(name)
+    alg_bytes = 8 * (2 * (neq + 2) + G * m["ncell"]) + 16 * m["nnz"] + 8 * (neq + 1)
+    achieved = alg_bytes / (m["jac_ms"] * 1e-3) / 1e9
     sm = sorted(s[0] for s in samples) or [0.0]
-    line = dict(metric="jacobian_nnz_per_s", value=nnz_total / (ms_dev * 1e-3), unit="nnz/s", n_gpus=world, steps=a.steps, warmup=a.warmup,
-                ms_per_step=ms_dev, higher_is_better=True, scaling="strong" if (world > 1 and a.mode == "columns") else "weak", vs_baseline=None, dtype="f64", data="synthetic",
-                config=dict(workload="%s: rhsnk + jac_calc (1 residual + 1 full FD Jacobian, neq=%d, nnz=%d) per step" % (name, neq, nnz_total),
+    if world == 1:
+        par = "1 GPU"
+    elif split:
+        par = ("one Jacobian, columns split over %d ranks (replicated state, ppp MPI design); CSC fragments all-gathered over NCCL on the device, "
+               "every rank returns the full CSR" % world)
+    else:
+        par = "%d independent replicas (one state per GPU), no collective" % world
+    fp64_peak = 1965e6 * 148 * 64 * 2 / 1e12  # 64 FP64 FMA lanes per SM per clock at the max SM clock: 37 TFLOP/s
+    line = dict(metric="jacobian_nnz_per_s", value=nnz_total / (m["ms_dev"] * 1e-3), unit="nnz/s", n_gpus=world, steps=a.steps, warmup=a.warmup,
+                ms_per_step=m["ms_dev"], higher_is_better=True, scaling="strong" if (world > 1 and split) else "weak", vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload="%s: rhsnk + jac_calc (1 residual + 1 full FD Jacobian, neq=%d, nnz=%d) per step" % (name, neq, m["nnz"]),
                             l2="flushed between steps (192 MB fill)",
-                            timer="value/ms_per_step: CUDA events on the library's stream around the residual+Jacobian sequence (ue_gpu_rhs_jac_dev); e2e: host clock around the two C-ABI calls; host_clock_ms_per_step: host clock around the device-resident step", parallelism=("%d independent replicas (one state per GPU), no collective" % world) if a.mode == "replicas" or world == 1
-                            else "one Jacobian, columns split over %d ranks (replicated state)" % world),
-                e2e=dict(value=nnz_total / (ms_e2e * 1e-3), unit="nnz/s", h2d_bytes_per_step=8 * (2 * (neq + 2) + neq),
-                         d2h_bytes_per_step=16 * nnz_total + 8 * (neq + 1) + 8 * neq, ms_per_step=ms_e2e,
-                         resid_evals_per_s=a.steps / t_res_e2e, warm_ms_per_step=warm_e2e, warm_resid_evals_per_s=1e3 / warm_res, fused_call_ms_per_step=t_fused / a.steps * 1e3,
-                         jac_calc_call_ms=jac_call_ms, jac_calc_call_nnz_per_s=nnz_total / world / (jac_call_ms * 1e-3) * world),
-                warm_ms_per_step=warm_dev, host_clock_ms_per_step=t_dev_host / a.steps * 1e3,
-                gpu_launches=int(l1.value - l0.value),
-                resid_evals_per_s=1e3 / res_ms if res_ms > 0 else None, jac_kernel_ms=jac_ms, resid_kernel_ms=res_ms,
-                roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
-                              kernel="Jacobian sequence k_jb_stage0/p1a/p1b/p2/p3c + scan/fill/sort (dominant: k_jb_p2), CUDA events on the library stream", fp64_pipe_pct_of_dominant_kernel=fp64_pct, peak_source="MEASURED_PEAKS.json hbm_gbs",
-                              note="algorithmic bytes = 8*(2(neq+2)+G*Ncell)+16*nnz+8*(neq+1), G=%d; latency bound (d3dHsm) / FP64-issue bound (4x), not HBM bound: DESIGN.md 3.4; traffic is ncu's cold-cache replay figure" % G),
+                            timer="value/ms_per_step: CUDA events on the library's stream around the residual+Jacobian sequence incl. the NCCL gather "
+                                  "(ue_gpu_rhs_jac_dev), max over ranks; e2e: host clock around the two C-ABI calls with host buffers, max over ranks",
+                            parallelism=par),
+                e2e=dict(value=nnz_total / (m["ms_e2e"] * 1e-3), unit="nnz/s", h2d_bytes_per_step=8 * (2 * (neq + 2) + neq),
+                         d2h_bytes_per_step=16 * m["nnz"] + 8 * (neq + 1) + 8 * neq, ms_per_step=m["ms_e2e"], buffers="page-locked host arrays (ue_gpu_pin_host_array / cudaHostAlloc)",
+                         pageable_ms_per_step=m["ms_e2e_pageable"], pageable_value=nnz_total / (m["ms_e2e_pageable"] * 1e-3),
+                         resid_evals_per_s=1e3 / m["ms_res_e2e"], pageable_resid_evals_per_s=1e3 / m["ms_res_e2e_pageable"],
+                         warm_ms_per_step=m["warm_ms_e2e"], warm_resid_evals_per_s=1e3 / m["warm_ms_res"],
+                         fused_call_ms_per_step=m["ms_fused"], fused_call_pageable_ms_per_step=m["ms_fused_pageable"]),
+                warm_ms_per_step=m["warm_ms_dev"], host_clock_ms_per_step=m["ms_dev_host"],
+                gpu_launches=m["launches"],
+                resid_evals_per_s=1e3 / m["res_ms"] if m["res_ms"] > 0 else None, jac_kernel_ms=m["jac_ms"], resid_kernel_ms=m["res_ms"],
+                nccl_bytes_per_step_this_rank=m["comm_bytes"],
+                roofline=dict(bound="latency (dependent FP64 chain per launch; neither HBM nor the FP64 pipe is near its roof: DESIGN.md 3.4)", achieved=achieved, peak=peak, unit="GB/s",
+                              frac=achieved / peak, traffic=traffic,
+                              kernel="Jacobian sequence (k_jb_p01|stage0/p1a/p1b, k_jb_p2, k_jb_p3c, CSR assembly), CUDA events on the library stream",
+                              fp64_pipe_pct_of_dominant_kernel=fp64_pct, peak_source="MEASURED_PEAKS.json hbm_gbs",
+                              fp64=dict(flops_per_jacobian=flops, achieved_tflops=(flops / (m["jac_ms"] * 1e-3) / 1e12) if flops else None, peak_tflops=fp64_peak,
+                                        frac=(flops / (m["jac_ms"] * 1e-3) / 1e12 / fp64_peak) if flops else None,
+                                        how="flops counted by the oracle built with a counting double type over the cell evaluations the kernels perform (tools/count_flops.py)"),
+                              note="algorithmic bytes = 8*(2(neq+2)+G*Ncell)+16*nnz+8*(neq+1), G=%d; traffic is ncu's cold-cache replay figure" % G),
                 clocks=dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max([s[1] for s in samples] or [0.0]), reasons=reasons_of([s[2] for s in samples])))
+    if grids:
+        line["grids"] = grids
+    if replicas:
+        line["replicas"] = replicas
     if cb is not None:
         line["cpu_baseline"] = dict(value=cb["value"], unit="nnz/s", cores=cb["cores"], kind=cb["kind"], sample=cb["sample"])
         line["cpu_resid_evals_per_s"] = cb["resid_evals_per_s"]
         line["cpu_serial_nnz_per_s"] = cb["serial_value"]
+        line["cpu_parallel_efficiency"] = cb["par_eff"]
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -124,6 +124,22 @@ int ue_gpu_assume_base_current(int64_t flag);
  * restores the full Jacobian.  Reference: ppp/parallel.F90:176-381. */
 int ue_gpu_set_column_range(int64_t ivmin, int64_t ivmax);
 
+/* ---- multi-GPU: ONE Jacobian assembled by several GPUs (ppp jac_calc_mpi: MPIJacBuilder + MPICollectBroadCastJacobian,
+ * ppp/mpi_parallel.F90:2-447) ------------------------------------------------------------------------------------------
+ * One host process per GPU (the reference's MPI ranks), every rank holding the full state.  After ue_gpu_comm_init every
+ * ue_gpu_jac_calc / ue_gpu_rhs_jac / *_dev call assembles only this rank's contiguous range of columns (MPISplitIndex;
+ * ranges balanced by the columns' candidate-list sizes), all-gathers the CSC fragments over NCCL on the library's stream
+ * (NVLink / NVSwitch) and transposes the full matrix on every rank: each rank returns the FULL CSR, as after the
+ * reference's MPI_BCAST.  All ranks must make the same calls in the same order.
+ *   ue_gpu_comm_unique_id : rank 0 obtains the 128-byte NCCL id; the host distributes it (MPI_Bcast in the Fortran host).
+ *   ue_gpu_comm_init      : collective; call after ue_gpu_init.  nranks = 1 is allowed (no communication).
+ *   ue_gpu_comm_info      : this rank's column range and the NCCL bytes it moved in the last Jacobian.
+ *   ue_gpu_comm_finalize  : back to single-GPU operation. */
+int ue_gpu_comm_unique_id(char* id128);
+int ue_gpu_comm_init(int64_t nranks, int64_t rank, const char* id128);
+int ue_gpu_comm_info(int64_t* nranks, int64_t* rank, int64_t* ivmin, int64_t* ivmax, int64_t* bytes_last_jac);
+int ue_gpu_comm_finalize(void);
+
 /* Device buffers owned by the library (yl, yldot, yldot00: neq+2; jac/ja: fragment capacity; ia: neq+1),
  * for callers that keep the state resident between calls. */
 int ue_gpu_device_buffers(double** yl, double** yldot, double** yldot00, double** jac, int64_t** ja, int64_t** ia);

@@ -39,7 +39,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ue_math.h"
@@ -49,52 +51,16 @@ namespace {
 
 UeStore S;
 UeParams& P = S.p;
-std::string g_err;
 int nx, ny, NXS, NC;
 int64_t neq;
 bool HASG = true;  // isngon = 1: the atom density is an unknown; isngon = 0: frozen field `ngfix`, numvar = 4
 
 typedef std::vector<double> V;
 
-// ---- persistent "module" state ------------------------------------------------
-// Compla / Gradients / Comflo / Conduc / Rhsides / Locflux groups of bbb/bbb.v,
-// restricted to what this switch set touches.
-V ne, nit, nm, nz2, ni, te, ti, ng, tg, up, pri, pre, pr, zeff, pg;
-V gprx, gpry, gpix, gpiy, gpex, gtex, gtix, gpey, gtey, gtiy;
-V niy0, niy1, nity0, nity1, ney0, ney1, priy0, priy1, tey0, tey1, tiy0, tiy1;
-V ngy0, ngy1, tgy0, tgy1, pgy0, pgy1;
-V loglambda, diffusivwrk, vy, frice, frici, ex, upi, uup, uu, upe, vex, vey;
-V nuiz, nurc, nucx, nuix, psorbgg, psorgc, psorc, psordis, psorxrc, psorrgc, psorg, psor, psorxr, psorrg;
-V snic, sniv, psori, smoc, smov, seec, seev, seic, seiv;
-V conxg, conyg, floxg, floyg, fngx, fngy, resng;
-V visx, visy, hcxe, hcxi, hcye, hcyi, hcxij, hcyij, eqp, w0, w1, w2, w3;
-V fnix, fniy, resco, flox, floy, conx, cony, fmix, fmiy, resmo;
-V floxe, floxi, floye, floyi, conxe, conxi, conye, conyi, feex, feey, feix, feiy, resee, resei;
-V erliz, erlrc, eeli, vsoreec, vsoree, wvh, pwribkg;
-V fniycbo, feeycbo, feiycbo;
-// per-solve inputs
-V dtuse, ylodt, suscal, sfscal, dtoptv;
 // rate tables (istabon=10)
 int mpe = 0, mpd = 0;
 V wsveh, wsveh0, welms1, welms2, ekpt, dkpt;
 double rlemin, rlemax, rldmin, rldmax, delekpt, deldkpt;
-// column range (ppp LocalJacBuilder analogue)
-int64_t g_ivmin = 1, g_ivmax = 0;
-
-std::vector<V*> all_planes() {
-  return {&ne, &nit, &nm, &nz2, &ni, &te, &ti, &ng, &tg, &up, &pri, &pre, &pr, &zeff, &pg,
-          &gprx, &gpry, &gpix, &gpiy, &gpex, &gtex, &gtix, &gpey, &gtey, &gtiy,
-          &niy0, &niy1, &nity0, &nity1, &ney0, &ney1, &priy0, &priy1, &tey0, &tey1, &tiy0, &tiy1,
-          &ngy0, &ngy1, &tgy0, &tgy1, &pgy0, &pgy1,
-          &loglambda, &diffusivwrk, &vy, &frice, &frici, &ex, &upi, &uup, &uu, &upe, &vex, &vey,
-          &nuiz, &nurc, &nucx, &nuix, &psorbgg, &psorgc, &psorc, &psordis, &psorxrc, &psorrgc, &psorg, &psor,
-          &psorxr, &psorrg, &snic, &sniv, &psori, &smoc, &smov, &seec, &seev, &seic, &seiv,
-          &conxg, &conyg, &floxg, &floyg, &fngx, &fngy, &resng,
-          &visx, &visy, &hcxe, &hcxi, &hcye, &hcyi, &hcxij, &hcyij, &eqp, &w0, &w1, &w2, &w3,
-          &fnix, &fniy, &resco, &flox, &floy, &conx, &cony, &fmix, &fmiy, &resmo,
-          &floxe, &floxi, &floye, &floyi, &conxe, &conxi, &conye, &conyi, &feex, &feey, &feix, &feiy, &resee, &resei,
-          &erliz, &erlrc, &eeli, &vsoreec, &vsoree, &wvh, &pwribkg};
-}
 const char* plane_names =
     "ne nit nm nz2 ni te ti ng tg up pri pre pr zeff pg gprx gpry gpix gpiy gpex gtex gtix gpey gtey gtiy "
     "niy0 niy1 nity0 nity1 ney0 ney1 priy0 priy1 tey0 tey1 tiy0 tiy1 ngy0 ngy1 tgy0 tgy1 pgy0 pgy1 "
@@ -265,6 +231,63 @@ Win make_win(int xc, int yc) {
   return w;
 }
 
+// ---- csrcsc (svr/svrut4.m:1536-1608): CSC -> CSR transpose, 1-based -----------------
+void csrcsc(int64_t n, const double* a, const int64_t* ja, const int64_t* ia, double* ao, int64_t* jao, int64_t* iao) {
+  for (int64_t i = 0; i <= n; ++i) iao[i] = 0;
+  for (int64_t i = 1; i <= n; ++i)
+    for (int64_t k = ia[i - 1]; k <= ia[i] - 1; ++k) { int64_t j = ja[k - 1] + 1; iao[j - 1] = iao[j - 1] + 1; }
+  iao[0] = 1;
+  for (int64_t i = 1; i <= n; ++i) iao[i] = iao[i - 1] + iao[i];
+  for (int64_t i = 1; i <= n; ++i)
+    for (int64_t k = ia[i - 1]; k <= ia[i] - 1; ++k) {
+      int64_t j = ja[k - 1];
+      int64_t next = iao[j - 1];
+      ao[next - 1] = a[k - 1];
+      jao[next - 1] = i;
+      iao[j - 1] = next + 1;
+    }
+  for (int64_t i = n; i >= 1; --i) iao[i] = iao[i - 1];
+  iao[0] = 1;
+}
+
+// ---- all mutable state + the routines that touch it: one instance per worker thread ----------
+struct Ora {
+// ---- persistent "module" state ------------------------------------------------
+// Compla / Gradients / Comflo / Conduc / Rhsides / Locflux groups of bbb/bbb.v,
+// restricted to what this switch set touches.
+V ne, nit, nm, nz2, ni, te, ti, ng, tg, up, pri, pre, pr, zeff, pg;
+V gprx, gpry, gpix, gpiy, gpex, gtex, gtix, gpey, gtey, gtiy;
+V niy0, niy1, nity0, nity1, ney0, ney1, priy0, priy1, tey0, tey1, tiy0, tiy1;
+V ngy0, ngy1, tgy0, tgy1, pgy0, pgy1;
+V loglambda, diffusivwrk, vy, frice, frici, ex, upi, uup, uu, upe, vex, vey;
+V nuiz, nurc, nucx, nuix, psorbgg, psorgc, psorc, psordis, psorxrc, psorrgc, psorg, psor, psorxr, psorrg;
+V snic, sniv, psori, smoc, smov, seec, seev, seic, seiv;
+V conxg, conyg, floxg, floyg, fngx, fngy, resng;
+V visx, visy, hcxe, hcxi, hcye, hcyi, hcxij, hcyij, eqp, w0, w1, w2, w3;
+V fnix, fniy, resco, flox, floy, conx, cony, fmix, fmiy, resmo;
+V floxe, floxi, floye, floyi, conxe, conxi, conye, conyi, feex, feey, feix, feiy, resee, resei;
+V erliz, erlrc, eeli, vsoreec, vsoree, wvh, pwribkg;
+V fniycbo, feeycbo, feiycbo;
+// per-solve inputs
+V dtuse, ylodt, suscal, sfscal, dtoptv;
+// column range (ppp LocalJacBuilder analogue)
+int64_t ivmin = 1, ivmax = 0;
+std::string err;
+
+std::vector<V*> all_planes() {
+  return {&ne, &nit, &nm, &nz2, &ni, &te, &ti, &ng, &tg, &up, &pri, &pre, &pr, &zeff, &pg,
+          &gprx, &gpry, &gpix, &gpiy, &gpex, &gtex, &gtix, &gpey, &gtey, &gtiy,
+          &niy0, &niy1, &nity0, &nity1, &ney0, &ney1, &priy0, &priy1, &tey0, &tey1, &tiy0, &tiy1,
+          &ngy0, &ngy1, &tgy0, &tgy1, &pgy0, &pgy1,
+          &loglambda, &diffusivwrk, &vy, &frice, &frici, &ex, &upi, &uup, &uu, &upe, &vex, &vey,
+          &nuiz, &nurc, &nucx, &nuix, &psorbgg, &psorgc, &psorc, &psordis, &psorxrc, &psorrgc, &psorg, &psor,
+          &psorxr, &psorrg, &snic, &sniv, &psori, &smoc, &smov, &seec, &seev, &seic, &seiv,
+          &conxg, &conyg, &floxg, &floyg, &fngx, &fngy, &resng,
+          &visx, &visy, &hcxe, &hcxi, &hcye, &hcyi, &hcxij, &hcyij, &eqp, &w0, &w1, &w2, &w3,
+          &fnix, &fniy, &resco, &flox, &floy, &conx, &cony, &fmix, &fmiy, &resmo,
+          &floxe, &floxi, &floye, &floyi, &conxe, &conxi, &conye, &conyi, &feex, &feey, &feix, &feiy, &resee, &resei,
+          &erliz, &erlrc, &eeli, &vsoreec, &vsoree, &wvh, &pwribkg};
+}
 // ---- convsr_vo (convert.m:158-375) -----------------------------------------------
 int convsr_vo(int ixl, int iyl, const double* yl) {
   int is, ie, js, je;
@@ -295,8 +318,8 @@ int convsr_vo(int ixl, int iyl, const double* yl) {
       A(ti, ix, iy) = yl[IDXTI(ix, iy)] * P.ennorm / (1.5 * ntemp);
       A(ti, ix, iy) = std::max(A(ti, ix, iy), P.temin * P.ev);
     }
-  if (inegni) { g_err = "***  ni is negative - calculation stopped"; return -3; }  // convert.m:318-322
-  if (inegng) { g_err = "***  ng is negative - calculation stopped"; return -3; }  // convert.m:323-327
+  if (inegni) { err = "***  ni is negative - calculation stopped"; return -3; }  // convert.m:318-322
+  if (inegng) { err = "***  ng is negative - calculation stopped"; return -3; }  // convert.m:323-327
   for (int iy = js; iy <= je; ++iy)
     for (int ix = is; ix <= ie; ++ix) {
       int ix2 = std::max(0, IXM1(ix, iy));
@@ -784,7 +807,7 @@ int bouncon(const Win& w, const double* yl, double* yldot) {
             double t0g = std::max(A(tg, ixt, iy), P.tgmin * ev);
             double vxg = 0.25 * std::sqrt(8 * t0g / (pi * P.mg));
             yldot[iv] = -P.nurlxg * (A(fngx, ixt, iy) + (1 + recy) * A(ng, ixt, iy) * vxg * G(sx, ixt, iy)) / (vxg * G(sx, ixt, iy) * P.n0g);
-          } else { g_err = "oracle: recylb < -1 not built"; return -4; }
+          } else { err = "oracle: recylb < -1 not built"; return -4; }
         }
       }
   }
@@ -848,7 +871,7 @@ int bouncon(const Win& w, const double* yl, double* yldot) {
             double t0g = std::max(A(tg, ixt, iy), P.tgmin * ev);
             double vxg = 0.25 * std::sqrt(8 * t0g / (pi * P.mg));
             yldot[ivg] = P.nurlxg * (A(fngx, ixt1, iy) - (1 + recy) * A(ng, ixt, iy) * vxg * G(sx, ixt1, iy)) / (vxg * G(sx, ixt1, iy) * P.n0g);
-          } else { g_err = "oracle: recyrb < -1 not built"; return -4; }
+          } else { err = "oracle: recyrb < -1 not built"; return -4; }
         }
       }
   }
@@ -1469,27 +1492,8 @@ int pandf1(int xc, int yc, const double* yl, double* yldot) {
   return 0;
 }
 
-// ---- csrcsc (svr/svrut4.m:1536-1608): CSC -> CSR transpose, 1-based -----------------
-void csrcsc(int64_t n, const double* a, const int64_t* ja, const int64_t* ia, double* ao, int64_t* jao, int64_t* iao) {
-  for (int64_t i = 0; i <= n; ++i) iao[i] = 0;
-  for (int64_t i = 1; i <= n; ++i)
-    for (int64_t k = ia[i - 1]; k <= ia[i] - 1; ++k) { int64_t j = ja[k - 1] + 1; iao[j - 1] = iao[j - 1] + 1; }
-  iao[0] = 1;
-  for (int64_t i = 1; i <= n; ++i) iao[i] = iao[i - 1] + iao[i];
-  for (int64_t i = 1; i <= n; ++i)
-    for (int64_t k = ia[i - 1]; k <= ia[i] - 1; ++k) {
-      int64_t j = ja[k - 1];
-      int64_t next = iao[j - 1];
-      ao[next - 1] = a[k - 1];
-      jao[next - 1] = i;
-      iao[j - 1] = next + 1;
-    }
-  for (int64_t i = n; i >= 1; --i) iao[i] = iao[i - 1];
-  iao[0] = 1;
-}
-
 int check_switches() {
-  { const std::string z = S.nonzero_frozen(); if (!z.empty()) { g_err = "input " + z + " must be 0: the term it switches on is outside the built hot path"; return -5; } }
+  { const std::string z = S.nonzero_frozen(); if (!z.empty()) { err = "input " + z + " must be 0: the term it switches on is outside the built hot path"; return -5; } }
   struct { const char* n; int64_t v, want; } eq[] = {
       {"nisp", P.nisp, 1}, {"nusp", P.nusp, 1}, {"ngsp", P.ngsp, 1}, {"numvar", P.numvar, 4 + (P.isngon == 1)}, {"isnonog", P.isnonog, 0}, {"isphion", P.isphion, 0},
       {"isphiofft", P.isphiofft, 0}, {"isimpon", P.isimpon, 0}, {"isupgon", P.isupgon, 0}, {"istgon", P.istgon, 0},
@@ -1501,93 +1505,39 @@ int check_switches() {
       {"isextrnw", P.isextrnw, 0}, {"isextrtw", P.isextrtw, 0}, {"isnfmiy", P.isnfmiy, 0}, {"isybdrywd", P.isybdrywd, 0}, {"isnewpot", P.isnewpot, 0},
       {"isbohmms", P.isbohmms, 0}, {"isgpye", P.isgpye, 0}, {"ibctepl", P.ibctepl, 1}, {"ibctipl", P.ibctipl, 1},
       {"ibctepr", P.ibctepr, 1}, {"ibctipr", P.ibctipr, 1}, {"iskaplex", P.iskaplex, 0}};
-  for (auto& e : eq) if (e.v != e.want) { g_err = std::string("switch outside the built hot path: ") + e.n; return -5; }
-  if (P.isngon != 0 && P.isngon != 1) { g_err = "isngon must be 0 or 1"; return -5; }
-  if (P.isfixlb != 0 && P.isfixlb != 2) { g_err = "isfixlb must be 0 or 2"; return -5; }
-  if (P.isbohmcalc != 0 && P.isbohmcalc != 1) { g_err = "isbohmcalc must be 0/1 with facb*=0"; return -5; }
-  if (P.isnicore != 0 && P.isnicore != 1) { g_err = "isnicore must be 0 or 1"; return -5; }
-  if (P.isupcore < 0 || P.isupcore > 3) { g_err = "isupcore must be 0..3"; return -5; }
-  if (P.iflcore < -1 || P.iflcore > 1) { g_err = "iflcore must be -1, 0 or 1"; return -5; }
-  if (P.isngcore < 0 || P.isngcore > 4) { g_err = "isngcore must be 0..4"; return -5; }
-  if (P.istabon != 0 && P.istabon != 7 && P.istabon != 10) { g_err = "istabon must be 0, 7 or 10"; return -5; }
+  for (auto& e : eq) if (e.v != e.want) { err = std::string("switch outside the built hot path: ") + e.n; return -5; }
+  if (P.isngon != 0 && P.isngon != 1) { err = "isngon must be 0 or 1"; return -5; }
+  if (P.isfixlb != 0 && P.isfixlb != 2) { err = "isfixlb must be 0 or 2"; return -5; }
+  if (P.isbohmcalc != 0 && P.isbohmcalc != 1) { err = "isbohmcalc must be 0/1 with facb*=0"; return -5; }
+  if (P.isnicore != 0 && P.isnicore != 1) { err = "isnicore must be 0 or 1"; return -5; }
+  if (P.isupcore < 0 || P.isupcore > 3) { err = "isupcore must be 0..3"; return -5; }
+  if (P.iflcore < -1 || P.iflcore > 1) { err = "iflcore must be -1, 0 or 1"; return -5; }
+  if (P.isngcore < 0 || P.isngcore > 4) { err = "isngcore must be 0..4"; return -5; }
+  if (P.istabon != 0 && P.istabon != 7 && P.istabon != 10) { err = "istabon must be 0, 7 or 10"; return -5; }
   // fnnuiz < 1 blends the new ionisation rate with the value left by the PREVIOUS pandf call (oderhs.m:1950-1961): the
   // reference's Jacobian then depends on the order in which the unknowns were perturbed; not reproducible in parallel
-  if (P.fnnuiz != 1.) { g_err = "fnnuiz must be 1 (history-dependent rate blending is outside the built hot path)"; return -5; }
-  if (P.difpr2 != 0 || P.difni2 != 0 || P.difax != 0 || P.dif4order != 0 || P.kye4order != 0 || P.kyi4order != 0) { g_err = "difpr2/difni2/difax/4th-order terms not built"; return -5; }
-  if (P.l_parloss <= 1e9) { g_err = "l_parloss<=1e9 (nuvl) not built"; return -5; }
-  if (P.cfjhf != 0 && false) { g_err = ""; return -5; }
+  if (P.fnnuiz != 1.) { err = "fnnuiz must be 1 (history-dependent rate blending is outside the built hot path)"; return -5; }
+  if (P.difpr2 != 0 || P.difni2 != 0 || P.difax != 0 || P.dif4order != 0 || P.kye4order != 0 || P.kyi4order != 0) { err = "difpr2/difni2/difax/4th-order terms not built"; return -5; }
+  if (P.l_parloss <= 1e9) { err = "l_parloss<=1e9 (nuvl) not built"; return -5; }
+  if (P.cfjhf != 0 && false) { err = ""; return -5; }
   for (int m : {(int)P.methn, (int)P.methu, (int)P.methe, (int)P.methi, (int)P.methg}) {
     int mx = m % 10, my = m / 10;
-    if ((mx != 2 && mx != 3) || (my != 2 && my != 3)) { g_err = "meth* must use schemes 2 (central) or 3 (upwind)"; return -5; }
+    if ((mx != 2 && mx != 3) || (my != 2 && my != 3)) { err = "meth* must use schemes 2 (central) or 3 (upwind)"; return -5; }
   }
   for (int ix = 0; ix < NXS; ++ix) {
-    if (P.fngysi[ix] != 0 || P.fngyso[ix] != 0 || P.fngyi_use[ix] != 0 || P.fngyo_use[ix] != 0) { g_err = "wall gas sources not built"; return -5; }
-    for (int64_t v : {P.isnwconiix[ix], P.isnwconoix[ix]}) if (v < 0 || v > 3) { g_err = "isnwconi/o must be 0..3"; return -5; }
-    for (int64_t v : {P.istepfcix[ix], P.istipfcix[ix], P.istewcix[ix], P.istiwcix[ix]}) if (v < 0 || v > 3) { g_err = "istepfc/istipfc/istewc/istiwc must be 0..3"; return -5; }
+    if (P.fngysi[ix] != 0 || P.fngyso[ix] != 0 || P.fngyi_use[ix] != 0 || P.fngyo_use[ix] != 0) { err = "wall gas sources not built"; return -5; }
+    for (int64_t v : {P.isnwconiix[ix], P.isnwconoix[ix]}) if (v < 0 || v > 3) { err = "isnwconi/o must be 0..3"; return -5; }
+    for (int64_t v : {P.istepfcix[ix], P.istipfcix[ix], P.istewcix[ix], P.istiwcix[ix]}) if (v < 0 || v > 3) { err = "istepfc/istipfc/istewc/istiwc must be 0..3"; return -5; }
   }
   return 0;
 }
-
-}  // namespace
-
-// =====================================================================================
-extern "C" {
-int ue_ora_set_int(const char* n, int64_t v) { return S.set_int(n, v); }
-int ue_ora_set_real(const char* n, double v) { return S.set_real(n, v); }
-int ue_ora_set_real_array(const char* n, const double* d, int64_t k) { return S.set_real_array(n, d, k); }
-int ue_ora_set_int_array(const char* n, const int64_t* d, int64_t k) { return S.set_int_array(n, d, k); }
-const char* ue_ora_last_error(void) { return g_err.c_str(); }
-
-int ue_ora_init(void) {
-  std::string m = S.missing();
-  if (!m.empty()) { g_err = "missing inputs: " + m; return -1; }
-  nx = (int)P.nx; ny = (int)P.ny; NXS = nx + 2; NC = NXS * (ny + 2); neq = P.neq;
-  std::string b = S.bad_sizes();
-  if (!b.empty()) { g_err = "bad plane sizes: " + b; return -1; }
-  if (neq != (int64_t)NC * P.numvar) { g_err = "neq != numvar*(nx+2)*(ny+2)"; return -1; }
-  int rc = check_switches();
-  if (rc) return rc;
-  // rate tables for istabon=10 (aph/aphread.m readehr1 + setauxvar :700-735)
-  mpe = (int)P.mpe; mpd = (int)P.mpd;
-  if (P.istabon == 10) {
-    if (mpe < 2 || mpd < 2 || S.len("wsveh") != (int64_t)mpe * mpd) { g_err = "istabon=10 needs wsveh/wsveh0/welms1/welms2 tables"; return -1; }
-    int64_t nt = (int64_t)mpe * mpd;
-    wsveh.assign(P.wsveh, P.wsveh + nt); wsveh0.assign(P.wsveh0, P.wsveh0 + nt);
-    welms1.assign(P.welms1, P.welms1 + nt); welms2.assign(P.welms2, P.welms2 + nt);
-    dkpt.resize(mpd); ekpt.resize(mpe);
-    dkpt[0] = 16.0; for (int j = 1; j < mpd; ++j) dkpt[j] = dkpt[j - 1] + 0.5;
-    rldmin = dkpt[0]; rldmax = dkpt[mpd - 1]; deldkpt = (rldmax - rldmin) / double(mpd - 1);
-    ekpt[0] = -1.2 * ue_log(10.0); for (int j = 1; j < mpe; ++j) ekpt[j] = ekpt[j - 1] + 0.1 * ue_log(10.0);
-    rlemin = ekpt[0]; rlemax = ekpt[mpe - 1]; delekpt = (rlemax - rlemin) / double(mpe - 1);
-  }
-  for (V* v : all_planes()) v->assign(NC, 0.0);
-  HASG = P.isngon == 1;
-  if (!HASG) ng.assign(P.ngfix, P.ngfix + NC);  // never advanced: the field ueinit left (odesetup.m:1399-1406)
-  fniycbo.assign(NXS, 0.); feeycbo.assign(NXS, 0.); feiycbo.assign(NXS, 0.);
-  dtuse.assign(neq, 1e20); ylodt.assign(neq, 0.); suscal.assign(neq, 1.); sfscal.assign(neq, 1.); dtoptv.assign(neq, 0.);
-  g_ivmin = 1; g_ivmax = neq;
-  return 0;
-}
-
-int ue_ora_step_params(int64_t n, const double* dt, const double* yo, const double* su, const double* sf) {
-  if (n != neq) { g_err = "step_params: neq mismatch"; return -1; }
-  dtuse.assign(dt, dt + n); ylodt.assign(yo, yo + n); suscal.assign(su, su + n); sfscal.assign(sf, sf + n);
-  return 0;
-}
-
-// general entry: pandf1(xc,yc,ieq,neq,time,yl,yldot); xc=yc=-1 is the full residual
-int ue_ora_pandf1_win(int64_t xc, int64_t yc, int64_t n, const double* yl, double* yldot) {
-  if (n != neq) { g_err = "pandf1: neq mismatch"; return -1; }
-  return pandf1((int)xc, (int)yc, yl, yldot);
-}
-int ue_ora_pandf1(int64_t n, double time, const double* yl, double* yldot) { (void)time; return ue_ora_pandf1_win(-1, -1, n, yl, yldot); }
 
 // set_dt (oderhs.m:9886-10147): the per-unknown pseudo time step of the nksol equations, model_dt 0..3.
 // f0 = rhsnk(yl) first (oderhs.m:9914); ylodt is the vector of the last step_params call.  dtoptv persists between
 // calls (a velocity row whose |f0| <= cutlo keeps its previous value, oderhs.m:9950-9951).
-int ue_ora_set_dt(int64_t n, const double* yl, double* f0, double* dtuse_out) {
-  if (n != neq) { g_err = "set_dt: neq mismatch"; return -1; }
-  if (P.model_dt < 0 || P.model_dt > 3) { g_err = "model_dt must be 0..3"; return -5; }
+int set_dt(int64_t n, const double* yl, double* f0, double* dtuse_out) {
+  if (n != neq) { err = "set_dt: neq mismatch"; return -1; }
+  if (P.model_dt < 0 || P.model_dt > 3) { err = "model_dt must be 0..3"; return -5; }
   int rc = pandf1(-1, -1, yl, f0);
   if (rc) return rc;
   auto model = [&](double dtopt) {
@@ -1623,21 +1573,17 @@ int ue_ora_set_dt(int64_t n, const double* yl, double* f0, double* dtuse_out) {
   return 0;
 }
 
-int ue_ora_set_column_range(int64_t ivmin, int64_t ivmax) { g_ivmin = ivmin; g_ivmax = ivmax; return 0; }
-
-// jac_calc (oderhs.m:8533-8760).  The caller must have evaluated pandf1(-1,-1) at yl
-// (psetnk/sfsetnk do, oderhs.m:9466, 9851) so that the module state is the base state.
-int ue_ora_jac_calc(int64_t n, double t, const double* yl_in, const double* yldot00, int64_t ml, int64_t mu, int64_t nnzmx,
-                    double* jac, int64_t* ja, int64_t* ia, int64_t* nnz_out) {
-  (void)t;
-  if (n != neq) { g_err = "jac_calc: neq mismatch"; return -1; }
-  std::vector<double> yl(yl_in, yl_in + neq + 2), wk(neq), rcsc;
-  std::vector<int64_t> icsc, jcsc(neq + 1);
-  rcsc.reserve(nnzmx); icsc.reserve(nnzmx);
+// jac_calc (oderhs.m:8533-8760), columns ivmin..ivmax only (ppp LocalJacBuilder, ppp/parallel.F90:176-381): the CSC
+// fragment rcsc/icsc with jcsc[iv-1] = 1-based start of column iv inside the fragment (nnz_frag+1 beyond the range).
+// The caller must have evaluated pandf1(-1,-1) at yl (psetnk/sfsetnk do, oderhs.m:9466, 9851): the module state is the base state.
+int jac_csc(const double* yl_in, const double* yldot00, int64_t ml, int64_t mu, int64_t nnzmx, std::vector<double>& rcsc,
+            std::vector<int64_t>& icsc, std::vector<int64_t>& jcsc) {
+  std::vector<double> yl(yl_in, yl_in + neq + 2), wk(neq);
+  rcsc.clear(); icsc.clear(); jcsc.assign(neq + 1, 0);
   int64_t nnz = 1;
   for (int64_t iv = 1; iv <= neq; ++iv) {
     jcsc[iv - 1] = nnz;
-    if (iv < g_ivmin || iv > g_ivmax) continue;
+    if (iv < ivmin || iv > ivmax) continue;
     int64_t ii1 = std::max(iv - mu, (int64_t)1), ii2 = std::min(iv + ml, neq);
     for (int64_t ii = ii1; ii <= ii2; ++ii) wk[ii - 1] = yldot00[ii - 1];
     int xc = (int)P.igyl[iv - 1], yc = (int)P.igyl[neq + iv - 1];
@@ -1656,7 +1602,7 @@ int ue_ora_jac_calc(int64_t n, double t, const double* yl_in, const double* yldo
         if (nnz > nnzmx) {
           char buf[256];
           snprintf(buf, sizeof buf, "*** jac_calc -- More storage needed for Jacobian. Storage exceeded at (i,j) = (%lld,%lld). Increase lenpfac.", (long long)ii, (long long)iv);
-          g_err = buf; return -2;
+          err = buf; return -2;
         }
         rcsc.push_back(jacelem); icsc.push_back(ii); nnz = nnz + 1;
       }
@@ -1666,14 +1612,138 @@ int ue_ora_jac_calc(int64_t n, double t, const double* yl_in, const double* yldo
     if (rc) return rc;
   }
   jcsc[neq] = nnz;
+  return 0;
+}
+};
+Ora g_o;
+std::vector<double> g_thread_w;  // column-range weights of the threaded Jacobian (previous call's timings)
+
+}  // namespace
+
+// =====================================================================================
+extern "C" {
+int ue_ora_set_int(const char* n, int64_t v) { return S.set_int(n, v); }
+int ue_ora_set_real(const char* n, double v) { return S.set_real(n, v); }
+int ue_ora_set_real_array(const char* n, const double* d, int64_t k) { return S.set_real_array(n, d, k); }
+int ue_ora_set_int_array(const char* n, const int64_t* d, int64_t k) { return S.set_int_array(n, d, k); }
+const char* ue_ora_last_error(void) { return g_o.err.c_str(); }
+
+int ue_ora_init(void) {
+  std::string& g_err = g_o.err;
+  std::string m = S.missing();
+  if (!m.empty()) { g_err = "missing inputs: " + m; return -1; }
+  nx = (int)P.nx; ny = (int)P.ny; NXS = nx + 2; NC = NXS * (ny + 2); neq = P.neq;
+  std::string b = S.bad_sizes();
+  if (!b.empty()) { g_err = "bad plane sizes: " + b; return -1; }
+  if (neq != (int64_t)NC * P.numvar) { g_err = "neq != numvar*(nx+2)*(ny+2)"; return -1; }
+  int rc = g_o.check_switches();
+  if (rc) return rc;
+  // rate tables for istabon=10 (aph/aphread.m readehr1 + setauxvar :700-735)
+  mpe = (int)P.mpe; mpd = (int)P.mpd;
+  if (P.istabon == 10) {
+    if (mpe < 2 || mpd < 2 || S.len("wsveh") != (int64_t)mpe * mpd) { g_err = "istabon=10 needs wsveh/wsveh0/welms1/welms2 tables"; return -1; }
+    int64_t nt = (int64_t)mpe * mpd;
+    wsveh.assign(P.wsveh, P.wsveh + nt); wsveh0.assign(P.wsveh0, P.wsveh0 + nt);
+    welms1.assign(P.welms1, P.welms1 + nt); welms2.assign(P.welms2, P.welms2 + nt);
+    dkpt.resize(mpd); ekpt.resize(mpe);
+    dkpt[0] = 16.0; for (int j = 1; j < mpd; ++j) dkpt[j] = dkpt[j - 1] + 0.5;
+    rldmin = dkpt[0]; rldmax = dkpt[mpd - 1]; deldkpt = (rldmax - rldmin) / double(mpd - 1);
+    ekpt[0] = -1.2 * ue_log(10.0); for (int j = 1; j < mpe; ++j) ekpt[j] = ekpt[j - 1] + 0.1 * ue_log(10.0);
+    rlemin = ekpt[0]; rlemax = ekpt[mpe - 1]; delekpt = (rlemax - rlemin) / double(mpe - 1);
+  }
+  for (V* v : g_o.all_planes()) v->assign(NC, 0.0);
+  HASG = P.isngon == 1;
+  if (!HASG) g_o.ng.assign(P.ngfix, P.ngfix + NC);  // never advanced: the field ueinit left (odesetup.m:1399-1406)
+  g_o.fniycbo.assign(NXS, 0.); g_o.feeycbo.assign(NXS, 0.); g_o.feiycbo.assign(NXS, 0.);
+  g_o.dtuse.assign(neq, 1e20); g_o.ylodt.assign(neq, 0.); g_o.suscal.assign(neq, 1.); g_o.sfscal.assign(neq, 1.); g_o.dtoptv.assign(neq, 0.);
+  g_o.ivmin = 1; g_o.ivmax = neq;
+  g_thread_w.clear();
+  return 0;
+}
+
+int ue_ora_step_params(int64_t n, const double* dt, const double* yo, const double* su, const double* sf) {
+  if (n != neq) { g_o.err = "step_params: neq mismatch"; return -1; }
+  g_o.dtuse.assign(dt, dt + n); g_o.ylodt.assign(yo, yo + n); g_o.suscal.assign(su, su + n); g_o.sfscal.assign(sf, sf + n);
+  return 0;
+}
+
+// general entry: pandf1(xc,yc,ieq,neq,time,yl,yldot); xc=yc=-1 is the full residual
+int ue_ora_pandf1_win(int64_t xc, int64_t yc, int64_t n, const double* yl, double* yldot) {
+  if (n != neq) { g_o.err = "pandf1: neq mismatch"; return -1; }
+  return g_o.pandf1((int)xc, (int)yc, yl, yldot);
+}
+int ue_ora_pandf1(int64_t n, double time, const double* yl, double* yldot) { (void)time; return ue_ora_pandf1_win(-1, -1, n, yl, yldot); }
+
+int ue_ora_set_dt(int64_t n, const double* yl, double* f0, double* dtuse_out) { return g_o.set_dt(n, yl, f0, dtuse_out); }
+
+int ue_ora_set_column_range(int64_t ivmin, int64_t ivmax) { g_o.ivmin = ivmin; g_o.ivmax = ivmax; return 0; }
+
+// serial jac_calc (oderhs.m:8533-8760): CSC by columns, then csrcsc
+int ue_ora_jac_calc(int64_t n, double t, const double* yl_in, const double* yldot00, int64_t ml, int64_t mu, int64_t nnzmx,
+                    double* jac, int64_t* ja, int64_t* ia, int64_t* nnz_out) {
+  (void)t;
+  if (n != neq) { g_o.err = "jac_calc: neq mismatch"; return -1; }
+  std::vector<double> rcsc; std::vector<int64_t> icsc, jcsc;
+  int rc = g_o.jac_csc(yl_in, yldot00, ml, mu, nnzmx, rcsc, icsc, jcsc);
+  if (rc) return rc;
+  csrcsc(neq, rcsc.data(), icsc.data(), jcsc.data(), jac, ja, ia);
+  *nnz_out = jcsc[neq] - 1;
+  return 0;
+}
+
+// Threaded jac_calc: the reference's OpenMP design (ppp/omp_parallel.F90:65-117 jac_calc_omp/OMPJacBuilder, 395-444
+// OMPSplitIndex, 119-164 OMPCollectJacobian).  Every worker thread takes a private copy of the whole module state (the
+// reference copies all threadprivate module arrays, omp_parallel.F90:319-332), assembles the CSC fragment of a contiguous
+// range of columns, and the fragments are concatenated in thread order (= column order) before one csrcsc.  The ranges are
+// re-weighted with the per-thread times of the previous call (omp_parallel.F90:199-229).  The full residual at yl must
+// have been evaluated by the caller (base state), as for the serial form.
+int ue_ora_jac_calc_threads(int64_t nthreads, int64_t n, const double* yl_in, const double* yldot00, int64_t ml, int64_t mu, int64_t nnzmx,
+                            double* jac, int64_t* ja, int64_t* ia, int64_t* nnz_out, double* thread_ms /* nthreads, may be NULL */) {
+  if (n != neq) { g_o.err = "jac_calc: neq mismatch"; return -1; }
+  const int T = (int)std::max<int64_t>(1, std::min<int64_t>(nthreads, neq));
+  if ((int)g_thread_w.size() != T) g_thread_w.assign(T, 1.0 / T);
+  // OMPSplitIndex: contiguous ranges with sizes proportional to the weights
+  std::vector<int64_t> lo(T), hi(T);
+  { double acc = 0.; int64_t prev = 0;
+    for (int t = 0; t < T; ++t) { acc += g_thread_w[t]; int64_t e = (t == T - 1) ? neq : std::min<int64_t>(neq, (int64_t)std::llround(acc * neq)); e = std::max(e, prev); lo[t] = prev + 1; hi[t] = e; prev = e; } }
+  std::vector<std::vector<double>> rc_(T); std::vector<std::vector<int64_t>> ic_(T), jc_(T);
+  std::vector<int> rcs(T, 0); std::vector<std::string> errs(T); std::vector<double> ms(T, 0.);
+  std::vector<std::thread> th;
+  for (int t = 0; t < T; ++t)
+    th.emplace_back([&, t]() {
+      auto t0 = std::chrono::steady_clock::now();
+      Ora w = g_o;  // private copy of the module state
+      w.ivmin = lo[t]; w.ivmax = hi[t];
+      rcs[t] = (lo[t] <= hi[t]) ? w.jac_csc(yl_in, yldot00, ml, mu, nnzmx, rc_[t], ic_[t], jc_[t]) : 0;
+      if (lo[t] > hi[t]) jc_[t].assign(neq + 1, 1);
+      errs[t] = w.err;
+      ms[t] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    });
+  for (auto& x : th) x.join();
+  for (int t = 0; t < T; ++t) if (rcs[t]) { g_o.err = errs[t]; return rcs[t]; }
+  // OMPCollectJacobian: concatenate in thread order
+  std::vector<double> rcsc; std::vector<int64_t> icsc, jcsc(neq + 1);
+  int64_t nnz = 1;
+  for (int t = 0; t < T; ++t) {
+    for (int64_t iv = lo[t]; iv <= hi[t]; ++iv) jcsc[iv - 1] = nnz + (jc_[t][iv - 1] - 1);
+    nnz += (int64_t)rc_[t].size();
+    rcsc.insert(rcsc.end(), rc_[t].begin(), rc_[t].end()); icsc.insert(icsc.end(), ic_[t].begin(), ic_[t].end());
+  }
+  jcsc[neq] = nnz;
+  if (nnz - 1 > nnzmx) { g_o.err = "*** jac_calc -- More storage needed for Jacobian. Increase lenpfac."; return -2; }
   csrcsc(neq, rcsc.data(), icsc.data(), jcsc.data(), jac, ja, ia);
   *nnz_out = nnz - 1;
+  // new weights ~ columns per unit time of each thread, damped by half
+  { double tot = 0.; std::vector<double> sp(T);
+    for (int t = 0; t < T; ++t) { sp[t] = (double)std::max<int64_t>(1, hi[t] - lo[t] + 1) / std::max(ms[t], 1e-6); tot += sp[t]; }
+    for (int t = 0; t < T; ++t) g_thread_w[t] = 0.5 * g_thread_w[t] + 0.5 * sp[t] / tot; }
+  if (thread_ms) for (int t = 0; t < T; ++t) thread_ms[t] = ms[t];
   return 0;
 }
 
 // debugging / parity helper: copy a named intermediate plane out
 int ue_ora_get_plane(const char* name, double* out) {
-  std::vector<V*> pl = all_planes();
+  std::vector<V*> pl = g_o.all_planes();
   std::string names(plane_names);
   size_t pos = 0; size_t k = 0;
   while (pos < names.size()) {
@@ -1681,7 +1751,7 @@ int ue_ora_get_plane(const char* name, double* out) {
     if (names.compare(pos, e - pos, name) == 0 && (e - pos) == strlen(name)) { std::copy(pl[k]->begin(), pl[k]->end(), out); return 0; }
     pos = e + 1; ++k;
   }
-  g_err = "no such plane"; return -1;
+  g_o.err = "no such plane"; return -1;
 }
 const char* ue_ora_plane_names(void) { return plane_names; }
 // include/ue_math.h evaluated on the host: op 0 exp, 1 log, 2 log10, 3 pow(x,y), 4 cos, 5 sqrt (tests compare with libm

@@ -3,10 +3,12 @@
 Tolerances are BASELINE.json's: residual 1e-12 relative (to the largest |yldot| of the same
 equation type: converged states have yldot -> 0), Jacobian entries 1e-8 relative, CSR pattern
 (ia/ja) bit-exact."""
+import os
+
 import numpy as np
 import pytest
 
-from tests.util import bind, make_case, newton_solve, oracle, psetnk_inputs
+from tests.util import ROOT, bind, make_case, newton_solve, oracle, psetnk_inputs
 from uedge_b200.capi import load_gpu
 
 pytestmark = pytest.mark.gpu
@@ -653,3 +655,19 @@ def test_large_grid_properties(built):
         jv = J @ v
         scale = np.abs(J) @ np.abs(v) + 1e-300      # row-wise size of the terms
         assert (np.abs(fd - jv) / scale).max() < 2e-4
+
+
+@pytest.mark.gpu
+def test_nccl_split_jacobian(built):
+    """ONE Jacobian assembled by 2 GPUs (ue_gpu_comm_init: column ranges + NCCL all-gather of the CSC fragments on the
+    device): every rank returns the single-GPU CSR bit for bit (values, ja, ia), also against the CPU oracle.  Needs 2 GPUs."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, UE_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29541", os.path.join(ROOT, "tests", "nccl_worker.py"), "d3dHsm", "d3dHsm4x", "case1"],
+                         env=env, capture_output=True, text=True, timeout=900)
+    assert "NCCL_SPLIT_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]

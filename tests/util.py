@@ -6,8 +6,9 @@ import re
 import numpy as np
 
 from uedge_b200.capi import UeLib
-from uedge_b200.cases import (box2_case, d3dhsm_case, forthon_case1, initial_profiles, load_grid_npz,
-                              load_rate_tables_npz, load_state_npz, refine_grid, refine_state)
+from uedge_b200.cases import (apply_overrides, box2_case, d3dhsm_case, forthon_case1, initial_profiles, load_grid_npz,  # noqa: F401
+                              load_rate_tables_npz, load_state_npz, make_case, make_slab_case, psetnk_inputs, refine_grid,
+                              refine_state)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_LIB = os.path.join(ROOT, "oracle", "libue_oracle.so")
@@ -18,77 +19,10 @@ def oracle():
     return UeLib(ORACLE_LIB, "ue_ora_")
 
 
-def apply_overrides(c, overrides):
-    for k, v in (overrides or {}).items():
-        pkg, nm = k.split(".")
-        ns = getattr(c, pkg)
-        cur = getattr(ns, nm) if nm in ns else None
-        if isinstance(cur, np.ndarray) and not isinstance(v, np.ndarray):
-            cur = cur.copy()
-            cur.flat[0] = v   # species-indexed inputs: species 1
-            v = cur
-        setattr(ns, nm, v)
-
-
-def make_slab_case(name, perturb=0.0, seed=1234, overrides=None):
-    """`case1`: Forthon_case1 at the steady state its reference output prints (ng: the frozen initial profile);
-    `box2d`: pyexamples/box2 with diffusive atoms at ueinit-like smooth profiles."""
-    c = forthon_case1() if name == "case1" else box2_case()
-    apply_overrides(c, overrides)
-    c.setup()
-    if name == "case1":
-        z = np.load(os.path.join(ROOT, "tests", "golden", "case1_state.npz"))
-        yl = c.set_state(z["ni"], z["up"], z["te"], z["ti"], c.initial_ng())
-    else:
-        yl = c.set_state(*initial_profiles(c))
-    if perturb:
-        rng = np.random.default_rng(seed)
-        yl[: c.bbb.neq] *= 1.0 + perturb * rng.uniform(-1.0, 1.0, c.bbb.neq)
-    return c, yl
-
-
-def make_case(name="d3dHsm", istabon=0, perturb=0.0, seed=1234, overrides=None):
-    if name in ("case1", "box2d"):
-        return make_slab_case(name, perturb, seed, overrides)
-    g = load_grid_npz()
-    state = load_state_npz("case2_state.npz" if name == "case2" else "d3dHsm_state.npz")
-    m = re.fullmatch(r"d3dHsm(\d+)x", name)
-    if m:  # synthetic refinement (BASELINE configs[4] is the 4x one)
-        f = int(m.group(1))
-        g = refine_grid(g, f, f)
-        state = refine_state(state, f, f)
-    c = d3dhsm_case(g, istabon=10 if name == "case2" else istabon)
-    if overrides:
-        for k, v in overrides.items():
-            pkg, nm = k.split(".")
-            ns = getattr(c, pkg)
-            cur = getattr(ns, nm) if nm in ns else None
-            if isinstance(cur, np.ndarray) and not isinstance(v, np.ndarray):
-                cur = cur.copy()
-                cur.flat[0] = v   # species-indexed inputs: species 1
-                v = cur
-            setattr(ns, nm, v)
-    if c.com.istabon == 10:
-        c.set_rate_tables(load_rate_tables_npz())
-    c.setup()
-    yl = c.set_state(*state)
-    if perturb:
-        rng = np.random.default_rng(seed)
-        yl[: c.bbb.neq] *= 1.0 + perturb * rng.uniform(-1.0, 1.0, c.bbb.neq)
-    return c, yl
-
-
 def bind(lib, c):
     lib.load_static(c.static_inputs())
     lib.init()
     return lib
-
-
-def psetnk_inputs(c, yl):
-    """(yl with Jacobian flag, suscal) as psetnk/sfsetnk prepare them (bbb/oderhs.m:9453-9468, 9848-9857)."""
-    y = yl.copy()
-    y[c.bbb.neq] = 1.0
-    return y, c.suscal(yl)
 
 
 def csr_to_dense_rows(jac, ja, ia):

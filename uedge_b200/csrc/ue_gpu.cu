@@ -11,6 +11,8 @@
 //                       global memory; ordered warp compaction of each column
 //   k_scan / k_fill / k_sortrows   CSC fragments -> reference CSR (csrcsc, svr/svrut4.m:1536-1608)
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
@@ -74,6 +76,23 @@ int *d_rowcnt = nullptr, *d_rowfill = nullptr;
 int64_t *d_ia = nullptr, *d_ja = nullptr;
 double* d_jac = nullptr;
 int64_t g_cap_total = 0, g_nnzcap = 0;
+// ---- multi-GPU: one Jacobian, columns split over the ranks, CSC fragments all-gathered over NCCL (ue_gpu_comm_init) ----
+// NCCL is bound at run time (dlopen of the copy already in the process, else libnccl.so.2): a single-GPU host needs no NCCL.
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+} NC_;
+ncclComm_t g_comm = nullptr;
+int g_nranks = 1, g_rank = 0;
+std::vector<int64_t> g_rank_lo, g_rank_hi;  // 1-based inclusive column range of every rank
+int64_t g_comm_bytes = 0;                   // bytes this rank sent + received through NCCL in the last Jacobian
 
 #define CK(call)                                                                                   \
   do {                                                                                             \
@@ -912,6 +931,32 @@ int enqueue_residual(const double* dyl, double* dyldot, bool need_rows, const do
   }
   return 0;
 }
+// MPICollectBroadCastJacobian (ppp/mpi_parallel.F90:262-364) on the device: the reference gathers the per-rank CSC fragments
+// on rank 0 and broadcasts the concatenation; here every rank broadcasts its own fragment range in place (the fragment
+// layout coloff is the same on all ranks), the per-row counts are all-reduced, and every rank transposes the full CSC.
+#define NCK(call)                                                                                              \
+  do {                                                                                                         \
+    ncclResult_t r_ = (call);                                                                                  \
+    if (r_ != ncclSuccess) { g_err = std::string("NCCL error: ") + NC_.GetErrorString(r_) + " at " #call; return -11; } \
+  } while (0)
+int comm_gather_columns() {
+  g_comm_bytes = 0;
+  NCK(NC_.GroupStart());
+  for (int r = 0; r < g_nranks; ++r) {
+    const int64_t lo = g_rank_lo[r], hi = g_rank_hi[r];
+    if (hi < lo) continue;
+    const int64_t off = h_coloff[lo - 1], end = hi < neq ? h_coloff[hi] : g_cap_total, cnt = end - off;
+    NCK(NC_.Broadcast(d_colval + off, d_colval + off, (size_t)cnt, ncclFloat64, r, g_comm, g_stream));
+    NCK(NC_.Broadcast(d_colrow + off, d_colrow + off, (size_t)cnt, ncclInt32, r, g_comm, g_stream));
+    NCK(NC_.Broadcast(d_colcnt + (lo - 1), d_colcnt + (lo - 1), (size_t)(hi - lo + 1), ncclInt32, r, g_comm, g_stream));
+    const int64_t b = cnt * 12 + (hi - lo + 1) * 4;
+    g_comm_bytes += (r == g_rank) ? b * (g_nranks - 1) : b;
+  }
+  NCK(NC_.AllReduce(d_rowcnt, d_rowcnt, (size_t)neq, ncclInt32, ncclSum, g_comm, g_stream));
+  g_comm_bytes += 2 * neq * 4;
+  NCK(NC_.GroupEnd());
+  return 0;
+}
 int res_launches() { return g_fuse23 ? 3 : 4; }  // kernels of one residual sequence with rows
 int jac_launches() { return (int)h_list.size() >= 4096 ? 8 : 6; }  // kernels of one Jacobian sequence (large / small grids)
 int enqueue_jac(const double* dyl, const double* dy00, int64_t ml, int64_t mu, int64_t nnzmx, double* djac, int64_t* dja, int64_t* dia, bool base_current,
@@ -947,16 +992,23 @@ int enqueue_jac(const double* dyl, const double* dy00, int64_t ml, int64_t mu, i
     }
     CK(launch(k_jb_p3c, dim3((unsigned)((NU + 3) / 4)), dim3(128), A));
   }
+  int64_t f_lo = g_ivmin, f_hi = g_ivmax;
+  if (g_nranks > 1) {  // every rank receives every other rank's column fragments; the CSR is then built from all columns
+    int rc = comm_gather_columns();
+    if (rc) return rc;
+    f_lo = 1; f_hi = neq;
+  }
   CK(launch(k_scan, dim3(1), dim3(1024), d_rowcnt, dia, neq, d_err, d_hflags, ia_host));
-  const int64_t ncol = g_ivmax - g_ivmin + 1;
+  const int64_t ncol = f_hi - f_lo + 1;
   if (ncol > 0) {
-    CK(launch(k_fill, dim3((unsigned)ncol), dim3(64), neq, g_ivmin, g_ivmax, d_coloff, d_colcnt, d_colrow, d_colval, dia, d_rowfill, djac, dja, nnzmx));
+    CK(launch(k_fill, dim3((unsigned)ncol), dim3(64), neq, f_lo, f_hi, d_coloff, d_colcnt, d_colrow, d_colval, dia, d_rowfill, djac, dja, nnzmx));
     CK(launch(k_sortrows, dim3((unsigned)((neq + 3) / 4)), dim3(128), neq, dia, djac, dja, nnzmx, jac_host, ja_host, d_colrow, d_colval, g_cap_total));
   }
   return 0;
 }
 template <typename F>
 int replay(const GKey& key, F enqueue) {
+  if (g_nranks > 1) return enqueue();  // the sequence contains NCCL calls: launched directly, not captured
   auto it = g_graphs.find(key);
   if (it == g_graphs.end()) {
     cudaGraphExec_t ex = nullptr;
@@ -1448,6 +1500,7 @@ int ue_gpu_set_dt(int64_t n, const double* yl, double* f0, double* dtuse) {
 int ue_gpu_set_column_range(int64_t ivmin, int64_t ivmax) {
   if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
   if (ivmin < 1 || ivmax > neq) { g_err = "column range outside 1..neq"; return -1; }
+  if (g_nranks > 1) { g_err = "set_column_range: the ranges are owned by ue_gpu_comm_init while a communicator is active"; return -1; }
   g_ivmin = ivmin; g_ivmax = ivmax; g_nnz_guess = 0;
   build_lists();
   drop_graphs();
@@ -1556,5 +1609,73 @@ int ue_gpu_get_plane(int64_t pl, double* out) {
   CK(cudaMemcpy(out, d_base + (size_t)pl * NC, NC * 8, cudaMemcpyDeviceToHost));
   return 0;
 }
-int ue_gpu_finalize(void) { free_all(); return 0; }
+// ---- multi-GPU ---------------------------------------------------------------------------------------------------------
+static int nccl_bind() {
+  if (NC_.h) return 0;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // the copy the host process already loaded (e.g. torch's)
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { g_err = std::string("cannot load libnccl.so.2: ") + dlerror(); return -11; }
+#define B(f) *(void**)(&NC_.f) = dlsym(h, "nccl" #f); if (!NC_.f) { g_err = "libnccl.so.2 lacks nccl" #f; return -11; }
+  B(GetUniqueId) B(CommInitRank) B(CommDestroy) B(GroupStart) B(GroupEnd) B(Broadcast) B(AllReduce) B(GetErrorString)
+#undef B
+  NC_.h = h;
+  return 0;
+}
+int ue_gpu_comm_unique_id(char* id128) {
+  int rc = nccl_bind();
+  if (rc) return rc;
+  ncclUniqueId id;
+  NCK(NC_.GetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  std::memcpy(id128, &id, 128);
+  return 0;
+}
+int ue_gpu_comm_init(int64_t nranks, int64_t rank, const char* id128) {
+  if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
+  if (nranks < 1 || rank < 0 || rank >= nranks) { g_err = "comm_init: bad rank / nranks"; return -1; }
+  int rc = nccl_bind();
+  if (rc) return rc;
+  if (g_comm) { NC_.CommDestroy(g_comm); g_comm = nullptr; g_nranks = 1; g_rank = 0; }
+  ncclUniqueId id;
+  std::memcpy(&id, id128, 128);
+  NCK(NC_.CommInitRank(&g_comm, (int)nranks, id, (int)rank));
+  // MPISplitIndex (ppp/mpi_parallel.F90:366-447): contiguous column ranges; the weight of a column is the size of its
+  // candidate list (the work of its evaluation), known from the index maps, so no timing feedback is needed
+  g_rank_lo.assign(nranks, 1); g_rank_hi.assign(nranks, 0);
+  int64_t prev = 0;
+  for (int r = 0; r < (int)nranks; ++r) {
+    int64_t e = neq;
+    if (r < (int)nranks - 1) {
+      const int64_t target = (int64_t)((double)g_cap_total * (r + 1) / (double)nranks);
+      e = (int64_t)(std::upper_bound(h_coloff.begin(), h_coloff.end(), target) - h_coloff.begin()) - 1;  // last column starting at or before the target
+      e = std::max(prev, std::min(e, neq));
+    }
+    g_rank_lo[r] = prev + 1; g_rank_hi[r] = e; prev = e;
+  }
+  g_ivmin = g_rank_lo[rank]; g_ivmax = g_rank_hi[rank]; g_nnz_guess = 0;
+  build_lists();
+  drop_graphs();
+  rc = upload_lists();
+  if (rc) return rc;
+  g_nranks = (int)nranks; g_rank = (int)rank;
+  if (g_nranks > 1) {  // first collective outside any timed region: NCCL sets up its channels and buffers here
+    CK(cudaMemsetAsync(d_colcnt, 0, 3 * neq * sizeof(int), g_stream));
+    rc = comm_gather_columns();
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(g_stream));
+  }
+  return 0;
+}
+int ue_gpu_comm_info(int64_t* nranks, int64_t* rank, int64_t* ivmin, int64_t* ivmax, int64_t* bytes_last_jac) {
+  *nranks = g_nranks; *rank = g_rank; *ivmin = g_ivmin; *ivmax = g_ivmax; *bytes_last_jac = g_nranks > 1 ? g_comm_bytes : 0;
+  return 0;
+}
+int ue_gpu_comm_finalize(void) {
+  if (g_comm) { cudaStreamSynchronize(g_stream); NC_.CommDestroy(g_comm); g_comm = nullptr; }
+  const bool was = g_nranks > 1;
+  g_nranks = 1; g_rank = 0;
+  if (was && g_ready) { g_ivmin = 1; g_ivmax = neq; build_lists(); drop_graphs(); return upload_lists(); }
+  return 0;
+}
+int ue_gpu_finalize(void) { ue_gpu_comm_finalize(); free_all(); return 0; }
 }
