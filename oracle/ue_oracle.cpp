@@ -40,6 +40,9 @@
 #include <cstdio>
 #include <cstring>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -1616,6 +1619,28 @@ int jac_csc(const double* yl_in, const double* yldot00, int64_t ml, int64_t mu, 
 }
 };
 Ora g_o;
+// persistent worker threads (an OpenMP runtime keeps its team alive between parallel regions; so does this)
+struct Pool {
+  std::vector<std::thread> th;
+  std::mutex m; std::condition_variable cv, done;
+  std::function<void(int)> job; int njob = 0, gen = 0, pending = 0; bool stop = false;
+  void worker(int id) {
+    int seen = 0;
+    for (;;) {
+      std::function<void(int)> f;
+      { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return stop || gen != seen; }); if (stop) return; seen = gen; if (id >= njob) continue; f = job; }
+      f(id);
+      { std::lock_guard<std::mutex> l(m); if (--pending == 0) done.notify_one(); }
+    }
+  }
+  void run(int n, std::function<void(int)> f) {
+    while ((int)th.size() < n) { int id = (int)th.size(); th.emplace_back([this, id] { worker(id); }); }
+    { std::lock_guard<std::mutex> l(m); job = f; njob = n; pending = n; ++gen; }
+    cv.notify_all();
+    std::unique_lock<std::mutex> l(m); done.wait(l, [&] { return pending == 0; });
+  }
+  ~Pool() { { std::lock_guard<std::mutex> l(m); stop = true; } cv.notify_all(); for (auto& t : th) t.join(); }
+} g_pool;
 std::vector<double> g_thread_w;  // column-range weights of the threaded Jacobian (previous call's timings)
 
 }  // namespace
@@ -1708,18 +1733,15 @@ int ue_ora_jac_calc_threads(int64_t nthreads, int64_t n, const double* yl_in, co
     for (int t = 0; t < T; ++t) { acc += g_thread_w[t]; int64_t e = (t == T - 1) ? neq : std::min<int64_t>(neq, (int64_t)std::llround(acc * neq)); e = std::max(e, prev); lo[t] = prev + 1; hi[t] = e; prev = e; } }
   std::vector<std::vector<double>> rc_(T); std::vector<std::vector<int64_t>> ic_(T), jc_(T);
   std::vector<int> rcs(T, 0); std::vector<std::string> errs(T); std::vector<double> ms(T, 0.);
-  std::vector<std::thread> th;
-  for (int t = 0; t < T; ++t)
-    th.emplace_back([&, t]() {
-      auto t0 = std::chrono::steady_clock::now();
-      Ora w = g_o;  // private copy of the module state
-      w.ivmin = lo[t]; w.ivmax = hi[t];
-      rcs[t] = (lo[t] <= hi[t]) ? w.jac_csc(yl_in, yldot00, ml, mu, nnzmx, rc_[t], ic_[t], jc_[t]) : 0;
-      if (lo[t] > hi[t]) jc_[t].assign(neq + 1, 1);
-      errs[t] = w.err;
-      ms[t] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    });
-  for (auto& x : th) x.join();
+  g_pool.run(T, [&](int t) {
+    auto t0 = std::chrono::steady_clock::now();
+    Ora w = g_o;  // private copy of the module state
+    w.ivmin = lo[t]; w.ivmax = hi[t];
+    rcs[t] = (lo[t] <= hi[t]) ? w.jac_csc(yl_in, yldot00, ml, mu, nnzmx, rc_[t], ic_[t], jc_[t]) : 0;
+    if (lo[t] > hi[t]) jc_[t].assign(neq + 1, 1);
+    errs[t] = w.err;
+    ms[t] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  });
   for (int t = 0; t < T; ++t) if (rcs[t]) { g_o.err = errs[t]; return rcs[t]; }
   // OMPCollectJacobian: concatenate in thread order
   std::vector<double> rcsc; std::vector<int64_t> icsc, jcsc(neq + 1);
