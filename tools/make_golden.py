@@ -82,3 +82,17 @@ a = rtf_arrays(os.path.join(REF, "builder/test/Forthon_cases/Forthon_case1/outpu
 np.savez_compressed(os.path.join(OUT, "case1_state.npz"),
                     ni=a["ni"][:, :, 0].T.copy(), up=a["up"][:, :, 0].T.copy(), te=a["te"].T.copy(), ti=a["ti"].T.copy())
 print("case1:", {k: v.shape for k, v in a.items()})
+
+
+# pyexamples/input_example: 8x4 non-orthogonal single-null mesh, inertial atoms, potential; converged state and the
+# reference's own stored pandf1 output + intermediate planes for eleven equation subsets (solution.h5: pytests/<subset>)
+g = read_gridue(os.path.join(REF, "pyexamples/input_example/gridue"))
+np.savez_compressed(os.path.join(OUT, "inputex_8x4_grid.npz"), **{k: g[k] for k in FIELDS},
+                    dims=np.array([g["nxm"], g["nym"], g["ixpt1"], g["ixpt2"], g["iysptrx1"]]))
+d = read_h5(os.path.join(REF, "pyexamples/input_example/solution.h5"))
+out = {}
+for k, v in d.items():
+    if k.startswith("bbb/") or k.startswith("pytests/"):
+        out[k.replace("/", "__")] = np.asarray(v)
+np.savez_compressed(os.path.join(OUT, "inputex_solution.npz"), **out)
+print("input_example:", len(out), "arrays")

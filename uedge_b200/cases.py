@@ -17,10 +17,10 @@ from .slabgrid import idealgrd
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def d3dhsm_case(grid, istabon=0, v8_0_defaults=True):
+def d3dhsm_case(grid, istabon=0, v8_0_defaults=True, cls=Case):
     """v8_0_defaults: oldseec=1, isoldalbarea=1 — the defaults of UEDGE 8.0.x that wrote the
     d3dHsm.h5 restart file (changed in 8.1: src/uedge/defaults.yaml)."""
-    c = Case(grid)
+    c = cls(grid)
     b, com = c.bbb, c.com
     f = grid["nxm"] // 16
     fy = grid["nym"] // 8
@@ -40,11 +40,11 @@ def d3dhsm_case(grid, istabon=0, v8_0_defaults=True):
     return c
 
 
-def forthon_case1():
+def forthon_case1(cls=Case):
     """builder/test/Forthon_cases/Forthon_case1/rd_forthon_case1.py: slab (mhdgeo=-1) 6x10, symmetry plane at ix=0
     (isfixlb=2), no core region (nycore=0), four unknowns per cell (ni, up, te, ti; isngon=0: frozen atom density)."""
     g = idealgrd(nxleg2=2, nxcore2=4, nycore=0, nysol=10, zax=1.0, zaxpt=0.75, alfyt=-1.0e-5)
-    c = Case(g)
+    c = cls(g)
     b, com = c.bbb, c.com
     com.nxleg = np.array([[0, 2]]); com.nxcore = np.array([[0, 4]])
     com.nysol = np.array([10]); com.nycore = np.array([0])
