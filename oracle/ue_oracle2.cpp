@@ -75,7 +75,7 @@ double ev, qe, me, mp, pi_, cutlo, rt8opi, temin, tgmin, nnorm, ennorm, temp0, v
     cfnidhg2, cftgeqp, flalftxy, flalfgnx, flalfgny, nlimgx, nlimgy, cfloxiplt, cfloygwall, cfjve, rsigpl, rsigplcore, bcen, bceew, bciew, cfqym, cfqydt,
     cfjpy, cfjp2, cfqybf, cfq2bf, cfqybbo, cfqydbo, cfydd_, cfjp2_, cfqyn, cfqyao, cfqya, cfqyae, cfjpy_, fqpsatlb_unused, lnlam_unused, phiwi0, phiwo0,
     kappamx, kappa0, cfsigm, fqsatlb_u, fupe_cur, dtphi_, cfhcxgc_u, lyphi0, lyphi1, isparmultdt_u, tewallmin_u, cfwjdotelim, cfeexdbo, cfeixdbo, cfkincor;
-V mi, zi, n0, fnorm, n0g_, mg_, ngbackg_, vcony, difpr, difni, difni2, difpr2, difax, travis, parvis, nlimix, nlimiy, dif4order, cpiup, cfvgpx, cfvgpy,
+V cngfx_, cngfy_, mi, zi, n0, fnorm, n0g_, mg_, ngbackg_, vcony, difpr, difni, difni2, difpr2, difax, travis, parvis, nlimix, nlimiy, dif4order, cpiup, cfvgpx, cfvgpy,
     cfvcsx, cfvcsy, cfvisxy, cngmom, cmwall, cngtgx, cngtgy, cdifg, lgmax, lgtmax, rld2dxg, rld2dyg, cngflox, cngfloy, rtg2ti, tgas, istgcon, keligig,
     ncore, ngcore, upcore, curcore, albedoc, csfaclb, csfacrb, recycp, nwimin, nwomin;
 // geometry planes / lines
@@ -567,6 +567,69 @@ struct O2 {
       }
   }
 
+  // ---- neudif (oderhs.m:5584-6057), ineudif = 1: the older diffusive-neutral model (ng and tg differenced separately);
+  //      orthogonal meshes only here (the 2007 Forthon cases ran with it); stretcx = 1
+  void neudif(const Win& w) {
+    const int methgx = methg % 10, methgy = methg / 10;
+    const double mg = mg_[0];
+    for (int iy = w.j4; iy <= w.j8; ++iy) {
+      for (int ix = w.i1; ix <= w.i5; ++ix) {
+        const int ix2 = IXP1(ix, iy);
+        double t0 = std::max(A(tg, ix, iy), temin * ev), t1 = std::max(A(tg, ix2, iy), temin * ev);
+        double vtn = std::sqrt(t0 / mg), vtnp = std::sqrt(t1 / mg);
+        double nu1 = A(nuix, ix, iy) + vtn / lgmax[0], nu2 = A(nuix, ix2, iy) + vtnp / lgmax[0];
+        double qfl = flalfgxa[ix] * A(sx, ix, iy) * (vtn + vtnp) * rt8opi * (A(ng, ix, iy) * A(gx, ix, iy) + A(ng, ix2, iy) * A(gx, ix2, iy)) / (8 * (A(gx, ix, iy) + A(gx, ix2, iy)));
+        double csh = (1 - isgasdc) * cdifg[0] * A(sx, ix, iy) * A(gxf, ix, iy) * ave(1. * (vtn * vtn) / nu1, 1. * (vtnp * vtnp) / nu2) + isgasdc * A(sx, ix, iy) * A(gxf, ix, iy) * difcng +
+                     (rld2dxg[0] * rld2dxg[0]) * A(sx, ix, iy) * (1 / A(gxf, ix, iy)) * 0.5 * (A(nuiz, ix, iy) + A(nuiz, ix2, iy));
+        double qtgf = cngfx_[0] * fgtdx[ix] * A(sx, ix, iy) * ave(1. * A(gx, ix, iy) / nu1, 1. * A(gx, ix2, iy) / nu2) * (vtn * vtn - vtnp * vtnp);
+        A(vygtan, ix, iy) = 0.;
+        qtgf = qtgf - A(vygtan, ix, iy) * A(sx, ix, iy);
+        double nconv = 2.0 * (A(ng, ix, iy) * A(ng, ix2, iy)) / (A(ng, ix, iy) + A(ng, ix2, iy));
+        if (methgx != 2) nconv = A(ng, ix, iy) * 0.5 * (1 + sgn(1., qtgf)) + A(ng, ix2, iy) * 0.5 * (1 - sgn(1., qtgf));
+        double qsh = csh * (A(ng, ix, iy) - A(ng, ix2, iy)) + qtgf * nconv;
+        double qr = std::fabs(qsh / qfl);
+        if (ix == ixlb || ix == ixrb) { qr = gcfacgx * qr; qtgf = gcfacgx * qtgf; }
+        A(conxg, ix, iy) = csh / ue_pow(1 + ue_pow(qr, flgamg), 1 / flgamg);
+        if (isdifxg_aug == 1) A(conxg, ix, iy) = csh * (1 + qr);
+        A(floxg, ix, iy) = qtgf / ue_pow(1 + ue_pow(qr, flgamg), 1 / flgamg);
+        A(floxg, ix, iy) = A(floxg, ix, iy) + cngflox[0] * A(sx, ix, iy) * A(uu[0], ix, iy);
+      }
+      A(conxg, nx + 1, iy) = 0;
+    }
+    for (int iy = w.j1; iy <= w.j5; ++iy)
+      for (int ix = w.i4; ix <= w.i8; ++ix) {
+        double t0 = std::max(A(tg, ix, iy), temin * ev), t1 = std::max(A(tg, ix, iy + 1), temin * ev);
+        double vtn = std::sqrt(t0 / mg), vtnp = std::sqrt(t1 / mg);
+        double nu1 = A(nuix, ix, iy) + vtn / lgmax[0], nu2 = A(nuix, ix, iy + 1) + vtnp / lgmax[0];
+        double qfl = flalfgya[iy] * A(sy, ix, iy) * (vtn + vtnp) * rt8opi * (A(ngy0, ix, iy) * A(gy, ix, iy) + A(ngy1, ix, iy) * A(gy, ix, iy + 1)) / (8 * (A(gy, ix, iy) + A(gy, ix, iy + 1)));
+        double csh = (1 - isgasdc) * cdifg[0] * A(sy, ix, iy) / (A(dynog, ix, iy)) * ave((vtn * vtn) / nu1, (vtnp * vtnp) / nu2) + isgasdc * A(sy, ix, iy) * A(gyf, ix, iy) * difcng +
+                     (rld2dyg[0] * rld2dyg[0]) * A(sy, ix, iy) * (1 / A(gyf, ix, iy)) * 0.5 * (A(nuiz, ix, iy) + A(nuiz, ix, iy + 1));
+        double qtgf = cngfy_[0] * fgtdy[iy] * A(sy, ix, iy) * ave(A(gy, ix, iy) / nu1, A(gy, ix, iy + 1) / nu2) * (vtn * vtn - vtnp * vtnp);
+        double nconv = 2.0 * (A(ngy0, ix, iy) * A(ngy1, ix, iy)) / (A(ngy0, ix, iy) + A(ngy1, ix, iy));
+        if (methgy != 2) nconv = A(ngy0, ix, iy) * 0.5 * (1 + sgn(1., qtgf)) + A(ngy1, ix, iy) * 0.5 * (1 - sgn(1., qtgf));
+        double qsh = csh * (A(ngy0, ix, iy) - A(ngy1, ix, iy)) + qtgf * nconv;
+        double qr = std::fabs(qsh / qfl);
+        if (iy == 0) { qr = gcfacgy * qr; qtgf = gcfacgy * qtgf; }
+        if (iy == ny) { qr = gcfacgy * qr; qtgf = gcfacgy * qtgf; }
+        A(conyg, ix, iy) = csh / ue_pow(1 + ue_pow(qr, flgamg), 1 / flgamg);
+        if (isdifyg_aug == 1) A(conyg, ix, iy) = csh * (1 + qr);
+        A(floyg, ix, iy) = qtgf / ue_pow(1 + ue_pow(qr, flgamg), 1 / flgamg);
+        A(floyg, ix, iy) = A(floyg, ix, iy) + cngfloy[0] * A(sy, ix, iy) * A(vy[0], ix, iy);
+      }
+    fd2tra(w, floxg, floyg, conxg, conyg, ng, fngx, fngy, 0, methg);
+    for (int iy = w.j1; iy <= w.j5; ++iy)
+      for (int ix = w.i1; ix <= w.i5; ++ix) {
+        const int ix1 = IXP1(ix, iy);
+        A(uug, ix, iy) = A(fngx, ix, iy) / (0.5 * (A(ng, ix, iy) + A(ng, ix1, iy)) * A(sx, ix, iy));
+        A(vyg, ix, iy) = A(fngy, ix, iy) / (0.5 * (A(ng, ix, iy) + A(ng, ix, iy + 1)) * A(sy, ix, iy));
+      }
+    for (int iy = w.j2; iy <= w.j5; ++iy)
+      for (int ix = w.i2; ix <= w.i5; ++ix) {
+        const int ix1 = IXM1(ix, iy);
+        A(resng, ix, iy) = cngsor * (A(psorg, ix, iy) + 0. + A(psorrg, ix, iy)) + 0. - A(fngx, ix, iy) + A(fngx, ix1, iy) - fluxfacy * (A(fngy, ix, iy) - A(fngy, ix, iy - 1)) + 0. * A(vol, ix, iy);
+      }
+  }
+
   // ---- neudifpg (oderhs.m:6058-6648), gas species 1 -------------------------------------------------------------------
   void neudifpg(const Win& w) {
     const int methgx = methg % 10, methgy = methg / 10;
@@ -872,7 +935,7 @@ struct O2 {
         if (isupgon == 1) { A(psor[1], ix, iy) = -A(psor[0], ix, iy); A(psorxr[1], ix, iy) = -A(psorxr[0], ix, iy); }
       }
 
-    neudifpg(w);  // oderhs.m:2428
+    if (ineudif == 1) neudif(w); else neudifpg(w);  // oderhs.m:2423-2435
 
     // half-space problem: no flux and no gradients through the cut (oderhs.m:2447-2466)
     if (isfixlb == 2) {
@@ -2420,7 +2483,9 @@ int init_all() {
   fnorm = VEC("fnorm", nusp); difutm_ = VEC("difutm", ns);
   n0g_ = VEC("n0g", 1); mg_ = VEC("mg", 1); ngbackg_ = VEC("ngbackg", 1); cngtgx = VEC("cngtgx", 1); cngtgy = VEC("cngtgy", 1); cdifg = VEC("cdifg", 1); lgmax = VEC("lgmax", 1); lgtmax = VEC("lgtmax", 2);
   rld2dxg = VEC("rld2dxg", 1); rld2dyg = VEC("rld2dyg", 1); cngflox = VEC("cngflox", 1); cngfloy = VEC("cngfloy", 1); rtg2ti = VEC("rtg2ti", 1); tgas = VEC("tgas", 1); istgcon = VEC("istgcon", 1);
-  keligig = VEC("keligig", 1); ngcore = VEC("ngcore", 1); albedoc = VEC("albedoc", 1); recycp = VEC("recycp", 1);
+  keligig = VEC("keligig", 1); cngfx_ = VEC("cngfx", 1); cngfy_ = VEC("cngfy", 1);
+  if (ineudif != 1 && ineudif != 2) { g_err = "oracle2: ineudif must be 1 or 2"; return -5; }
+  if (ineudif == 1 && (isnonog != 0 || isupgon != 0)) { g_err = "oracle2: ineudif=1 is restated for orthogonal meshes and diffusive atoms only"; return -5; } ngcore = VEC("ngcore", 1); albedoc = VEC("albedoc", 1); recycp = VEC("recycp", 1);
   const size_t nc = NC, nxs = NXS, nys = ny + 2;
 #define GP(n) n = ARR(#n, nc);
   GP(vol) GP(gx) GP(gy) GP(gxf) GP(gyf) GP(gxc) GP(gyc) GP(sx) GP(sxnp) GP(sy) GP(rr) GP(rrv) GP(volv) GP(syv) GP(dxnog) GP(dynog) GP(btot) GP(rbfbt) GP(rbfbt2) GP(lcone) GP(lconi) GP(angfx) GP(ngfix)
@@ -2457,7 +2522,7 @@ int init_all() {
                                                    {"cfvisxneoq", 0}, {"cfvyavis", 0}, {"cfanomvisxg", 0}, {"cfanomvisyg", 0}, {"isnewpot", 0}, {"jhswitch", 0}, {"isnfmiy", 0}, {"isybdrywd", 0}, {"isfeexpl0", 0},
                                                    {"isfeixpl0", 0}, {"cfeexdbo", 0}, {"cfeixdbo", 0}, {"cfniybbo", 0}, {"cfniydbo", 0}, {"cfeeybbo", 0}, {"cfeeydbo", 0}, {"isextrnp", 0}, {"isextrnpf", 0},
                                                    {"isextrtpf", 0}, {"isextrngc", 0}, {"isextrnw", 0}, {"isextrtw", 0}, {"isbohmms", 0}, {"ibctepl", 1}, {"ibctipl", 1}, {"ibctepr", 1}, {"ibctipr", 1}, {"isfixrb", 0},
-                                                   {"is1D_gbx", 0}, {"isnglf", 0}, {"iszeffcon", 0}, {"isup1up2", 0}, {"isflxvar", 0}, {"ineudif", 2}, {"istgon", 0}, {"isphilbc", 0}, {"isphirbc", 0}, {"ikapmod", 0},
+                                                   {"is1D_gbx", 0}, {"isnglf", 0}, {"iszeffcon", 0}, {"isup1up2", 0}, {"isflxvar", 0}, {"istgon", 0}, {"isphilbc", 0}, {"isphirbc", 0}, {"ikapmod", 0},
                                                    {"isfqpave", 0}, {"isphicore0", 0}, {"iskaprex", 0}};
   for (auto& m : must) { const V* v = find(m.n); if (!v) { g_err = std::string("oracle2: missing input ") + m.n; return -1; } if ((*v)[0] != m.want) { g_err = std::string("oracle2: switch outside this restatement: ") + m.n; return -5; } }
   if (fnnuiz != 1.) { g_err = "oracle2: fnnuiz must be 1"; return -5; }
