@@ -8,7 +8,9 @@ d3dHsm configuration (BASELINE.json configs[1]).  Both arms (CUDA and CPU) time 
 
 N > 1 (torchrun, one rank per GPU): ONE Jacobian is assembled by the N GPUs — the reference's MPI design
 (ppp/mpi_parallel.F90): every rank holds the full state, assembles a contiguous range of columns, the CSC
-fragments are all-gathered over NCCL on the device and every rank ends with the full CSR (`scaling: "strong"`).
+column results go straight into every GPU's copy of the structural slot arrays (peer stores over NVLink fused into the
+assembly kernel, `--transport p2p`; or two ncclAllReduce calls, `--transport nccl`) and every rank ends with the full CSR
+(`scaling: "strong"`).
 The same measurement is repeated on the 4x- and 8x-refined grids (`grids`), and N independent replicas
 (one state per GPU, no collective) are kept as a secondary record (`replicas`).
 
@@ -87,7 +89,7 @@ def cpu_baseline(c, ystates, su, budget_s=12.0, nthreads=None):
 class Gpu:
     """The product library bound to one case on this rank's GPU (through the C ABI only)."""
 
-    def __init__(self, c, ystates, su, world, rank, dist, torch, split=True):
+    def __init__(self, c, ystates, su, world, rank, dist, torch, split=True, transport="p2p"):
         from uedge_b200.capi import load_gpu
         self.c, self.world, self.rank, self.dist, self.torch = c, world, rank, dist, torch
         self.gpu = load_gpu()
@@ -98,15 +100,8 @@ class Gpu:
         lib = self.lib = self.gpu.lib
         self.split = split and world > 1
         if self.split:
-            lib.ue_gpu_comm_unique_id.argtypes = [C.c_char_p]
-            lib.ue_gpu_comm_init.argtypes = [C.c_int64, C.c_int64, C.c_char_p]
-            idbuf = C.create_string_buffer(128)
-            if rank == 0:
-                assert lib.ue_gpu_comm_unique_id(idbuf) == 0, self.err()
-            t = torch.frombuffer(bytearray(idbuf.raw), dtype=torch.uint8).cuda()
-            dist.broadcast(t, 0)
-            idb = bytes(t.cpu().numpy().tobytes())
-            assert lib.ue_gpu_comm_init(world, rank, idb) == 0, self.err()
+            from uedge_b200.capi import split_init
+            split_init(lib, world, rank, dist, torch, transport)
         self.su = np.ascontiguousarray(su)
         self.gpu.step_params(np.full(neq, 1e20), ystates[0][:neq], su, np.ones(neq))
         self.sp = [np.full(neq, 1e20), ystates[0][:neq].copy(), self.su, np.ones(neq)]
@@ -239,10 +234,10 @@ def maxr(g, vals):
     return v.tolist()
 
 
-def measure(name, steps, warmup, world, rank, dist, torch, split=True, full=True, seed=1234):
+def measure(name, steps, warmup, world, rank, dist, torch, split=True, full=True, seed=1234, transport="p2p"):
     """One configuration on this rank.  Returns a dict of max-over-ranks figures (identical on every rank)."""
     c, ystates, su = bench_state(name, seed)
-    g = Gpu(c, ystates, su, world, rank, dist, torch, split=split)
+    g = Gpu(c, ystates, su, world, rank, dist, torch, split=split, transport=transport)
     neq = g.neq
     g.step_e2e(g.pin)  # fills the library's device buffers
     for _ in range(max(3, warmup)):
@@ -291,6 +286,9 @@ def main():
     ap.add_argument("--mode", default="columns", choices=["columns", "replicas"],
                     help="N>1: 'columns' (default) = ONE Jacobian, columns split over the ranks, NCCL all-gather of the fragments (strong scaling); "
                          "'replicas' = every GPU assembles the full Jacobian of its own state (ensemble, weak scaling)")
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1, columns: 'p2p' = the assembly kernel stores each column into every GPU's slot arrays over NVLink (CUDA IPC peer "
+                         "memory) + device-side flag barrier; 'nccl' = two ncclAllReduce calls over the slot arrays (the baseline)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     name = a.config
@@ -326,15 +324,15 @@ def main():
     samples = []; stop = threading.Event()
     th = threading.Thread(target=clocks_sampler, args=(stop, samples, local)); th.start()
     seed = 1234 + (rank if not split else 0)
-    m = measure(name, a.steps, a.warmup, world, rank, dist, torch, split=split, full=True, seed=seed)
+    m = measure(name, a.steps, a.warmup, world, rank, dist, torch, split=split, full=True, seed=seed, transport=a.transport)
     stop.set(); th.join()
     grids = {}
     if not a.no_grids:
         for gname in ("d3dHsm4x", "d3dHsm8x"):
-            r = measure(gname, min(a.steps, 10), 3, world, rank, dist, torch, split=split, full=False)
+            r = measure(gname, min(a.steps, 10), 3, world, rank, dist, torch, split=split, full=False, transport=a.transport)
             grids[gname] = dict(neq=r["neq"], nnz=r["nnz"], ms_per_step=r["ms_dev"], value=r["nnz"] / (r["ms_dev"] * 1e-3), unit="nnz/s",
                                 e2e_ms_per_step=r["ms_e2e"], e2e_value=r["nnz"] / (r["ms_e2e"] * 1e-3), jac_kernel_ms=r["jac_ms"], resid_kernel_ms=r["res_ms"],
-                                nccl_bytes_per_step_this_rank=r["comm_bytes"], gpu_launches=r["launches"])
+                                peer_bytes_per_step_this_rank=r["comm_bytes"], gpu_launches=r["launches"])
     replicas = None
     if world > 1 and split:
         r = measure(name, min(a.steps, 10), 3, world, rank, dist, torch, split=False, full=False, seed=1234 + rank)
@@ -370,8 +368,9 @@ def main():
     if world == 1:
         par = "1 GPU"
     elif split:
-        par = ("one Jacobian, columns split over %d ranks (replicated state, ppp MPI design); CSC fragments all-gathered over NCCL on the device, "
-               "every rank returns the full CSR" % world)
+        how = ("the assembly kernel stores every column result into all GPUs' slot arrays over NVLink (CUDA IPC peer memory), device-side flag barrier, no collective call"
+               if a.transport == "p2p" else "slot arrays combined by two ncclAllReduce calls on the library stream")
+        par = "one Jacobian, columns split over %d ranks (replicated state, ppp MPI design); %s; every rank returns the full CSR" % (world, how)
     else:
         par = "%d independent replicas (one state per GPU), no collective" % world
     fp64_peak = 1965e6 * 148 * 64 * 2 / 1e12  # 64 FP64 FMA lanes per SM per clock at the max SM clock: 37 TFLOP/s
@@ -379,7 +378,7 @@ def main():
                 ms_per_step=m["ms_dev"], higher_is_better=True, scaling="strong" if (world > 1 and split) else "weak", vs_baseline=None, dtype="f64", data="synthetic",
                 config=dict(workload="%s: rhsnk + jac_calc (1 residual + 1 full FD Jacobian, neq=%d, nnz=%d) per step" % (name, neq, m["nnz"]),
                             l2="flushed between steps (192 MB fill)",
-                            timer="value/ms_per_step: CUDA events on the library's stream around the residual+Jacobian sequence incl. the NCCL gather "
+                            timer="value/ms_per_step: CUDA events on the library's stream around the residual+Jacobian sequence incl. the peer exchange "
                                   "(ue_gpu_rhs_jac_dev), max over ranks; e2e: host clock around the two C-ABI calls with host buffers, max over ranks",
                             parallelism=par),
                 e2e=dict(value=nnz_total / (m["ms_e2e"] * 1e-3), unit="nnz/s", h2d_bytes_per_step=8 * (2 * (neq + 2) + neq),
@@ -391,7 +390,7 @@ def main():
                 warm_ms_per_step=m["warm_ms_dev"], host_clock_ms_per_step=m["ms_dev_host"],
                 gpu_launches=m["launches"],
                 resid_evals_per_s=1e3 / m["res_ms"] if m["res_ms"] > 0 else None, jac_kernel_ms=m["jac_ms"], resid_kernel_ms=m["res_ms"],
-                nccl_bytes_per_step_this_rank=m["comm_bytes"],
+                peer_bytes_per_step_this_rank=m["comm_bytes"],
                 roofline=dict(bound="latency (dependent FP64 chain per launch; neither HBM nor the FP64 pipe is near its roof: DESIGN.md 3.4)", achieved=achieved, peak=peak, unit="GB/s",
                               frac=achieved / peak, traffic=traffic,
                               kernel="Jacobian sequence (k_jb_p01|stage0/p1a/p1b, k_jb_p2, k_jb_p3c, CSR assembly), CUDA events on the library stream",

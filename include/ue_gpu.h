@@ -134,7 +134,14 @@ int ue_gpu_set_column_range(int64_t ivmin, int64_t ivmax);
  *   ue_gpu_comm_unique_id : rank 0 obtains the 128-byte NCCL id; the host distributes it (MPI_Bcast in the Fortran host).
  *   ue_gpu_comm_init      : collective; call after ue_gpu_init.  nranks = 1 is allowed (no communication).
  *   ue_gpu_comm_info      : this rank's column range and the NCCL bytes it moved in the last Jacobian.
- *   ue_gpu_comm_finalize  : back to single-GPU operation. */
+ *   ue_gpu_comm_finalize  : back to single-GPU operation.
+ *   ue_gpu_comm_p2p_handle / ue_gpu_comm_init_p2p : the same split WITHOUT a collective call.  Every rank exports its slot
+ *                           arrays (64-byte CUDA IPC handle), the host gathers the handles (MPI_Allgather), every rank maps
+ *                           the others' arrays; the assembly kernel then stores each column result into all GPUs over
+ *                           NVLink and a device-side flag barrier replaces the all-reduce.  Ranks of ONE node (<= 8);
+ *                           synchronise the ranks on the host between ue_gpu_comm_init_p2p and the first Jacobian. */
+int ue_gpu_comm_p2p_handle(char* handle64);
+int ue_gpu_comm_init_p2p(int64_t nranks, int64_t rank, const char* handles /* nranks x 64 bytes, rank order */);
 int ue_gpu_comm_unique_id(char* id128);
 int ue_gpu_comm_init(int64_t nranks, int64_t rank, const char* id128);
 int ue_gpu_comm_info(int64_t* nranks, int64_t* rank, int64_t* ivmin, int64_t* ivmax, int64_t* bytes_last_jac);

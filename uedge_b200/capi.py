@@ -182,3 +182,35 @@ class UeLib:
 def load_gpu():
     """The product library.  Raises if it has not been built: no fallback."""
     return UeLib(GPU_LIB, "ue_gpu_")
+
+
+def split_init(lib, world, rank, dist, torch, transport="p2p"):
+    """Bind this rank's library instance to a WORLD-rank column split of the Jacobian (include/ue_gpu.h, multi-GPU block).
+    `dist` (torch.distributed) plays the part of the Fortran host's MPI: it only carries the 128-byte NCCL id or the
+    64-byte CUDA IPC handles between the processes and the host barrier; the data path is the library's own."""
+    import ctypes as C
+    if transport == "nccl":
+        lib.ue_gpu_comm_unique_id.argtypes = [C.c_char_p]
+        lib.ue_gpu_comm_init.argtypes = [C.c_int64, C.c_int64, C.c_char_p]
+        idbuf = C.create_string_buffer(128)
+        if rank == 0 and lib.ue_gpu_comm_unique_id(idbuf) != 0:
+            raise RuntimeError(lib.ue_gpu_last_error().decode())
+        t = torch.frombuffer(bytearray(idbuf.raw), dtype=torch.uint8).cuda()
+        dist.broadcast(t, 0)
+        rc = lib.ue_gpu_comm_init(world, rank, bytes(t.cpu().numpy().tobytes()))
+    elif transport == "p2p":
+        lib.ue_gpu_comm_p2p_handle.argtypes = [C.c_char_p]
+        lib.ue_gpu_comm_init_p2p.argtypes = [C.c_int64, C.c_int64, C.c_char_p]
+        hbuf = C.create_string_buffer(64)
+        if lib.ue_gpu_comm_p2p_handle(hbuf) != 0:
+            raise RuntimeError(lib.ue_gpu_last_error().decode())
+        mine = torch.frombuffer(bytearray(hbuf.raw), dtype=torch.uint8).cuda()
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        rc = lib.ue_gpu_comm_init_p2p(world, rank, b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
+    else:
+        raise ValueError("transport: nccl or p2p")
+    if rc != 0:
+        raise RuntimeError(lib.ue_gpu_last_error().decode())
+    torch.cuda.synchronize()
+    dist.barrier()

@@ -9,7 +9,7 @@
 //   k_jb_stage0/p1a/p1b/p2/p3c   batched Jacobian: all perturbed unknowns ("every colour") in flight, one launch
 //                       per phase, blockIdx.y = role function; private cells + candidate rows in L2-resident
 //                       global memory; ordered warp compaction of each column
-//   k_scan / k_fill / k_sortrows   CSC fragments -> reference CSR (csrcsc, svr/svrut4.m:1536-1608)
+//   k_csr                          structural CSR superset -> reference CSR in one pass (csrcsc, svr/svrut4.m:1536-1608)
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
@@ -70,9 +70,15 @@ double *d_priv = nullptr, *d_jrows = nullptr, *d_rres = nullptr;
 int* d_rmask = nullptr;
 int g_nitems = 0;
 int64_t* d_coloff = nullptr;
-int *d_colcnt = nullptr, *d_colrow = nullptr;
-double* d_colval = nullptr;
-int *d_rowcnt = nullptr, *d_rowfill = nullptr;
+// Structural CSR superset (built once from the candidate lists): every (row, column) pair a perturbation can reach, sorted by
+// row then column.  k_jb_p3c writes each candidate's value and keep flag straight into its slot; one count + one write pass
+// compact the kept slots into the reference's CSR (columns ascending): no atomics, no sort.
+int2* d_meta = nullptr;  // per slot: (fragment index | row-start flag, column)
+int* d_srow = nullptr;
+unsigned long long* d_tilest = nullptr;  // per-tile scan state of k_csr + 4 counters behind it
+double* d_frag = nullptr;                // column fragments: coloff[iv-1] + candidate index; NaN = entry not kept
+int64_t g_nslots = 0;
+constexpr int CSR_TILE = 2048;  // slots per block of the compaction kernel
 int64_t *d_ia = nullptr, *d_ja = nullptr;
 double* d_jac = nullptr;
 int64_t g_cap_total = 0, g_nnzcap = 0;
@@ -93,6 +99,16 @@ ncclComm_t g_comm = nullptr;
 int g_nranks = 1, g_rank = 0;
 std::vector<int64_t> g_rank_lo, g_rank_hi;  // 1-based inclusive column range of every rank
 int64_t g_comm_bytes = 0;                   // bytes this rank sent + received through NCCL in the last Jacobian
+// P2P transport (ue_gpu_comm_init_p2p): the fragment arrays of every rank are mapped into every other rank (CUDA IPC over
+// NVLink); k_jb_p3c stores its column results into all of them, a flag barrier replaces the collective
+bool g_p2p = false;
+unsigned long long g_epoch = 0;             // Jacobians assembled since the communicator was set up
+double* g_peer_frag[8] = {nullptr};
+void* g_peer_base[8] = {nullptr};
+unsigned long long* g_p2p_flags = nullptr;  // this rank's block: [0] epoch counter, [1..] = epoch posted by rank r-1; peers' blocks at g_peer_flags
+unsigned long long* g_peer_flags[8] = {nullptr};
+void* g_xchg = nullptr;                     // one allocation: 2 x fragment array + flag block, exported to the peers
+size_t g_xchg_bytes = 0;
 
 #define CK(call)                                                                                   \
   do {                                                                                             \
@@ -291,9 +307,10 @@ struct JArgs {
   int64_t neq, ml, mu;
   int NXS, NC;
   const int64_t* coloff;
-  int *colcnt, *colrow;
-  double* colval;
-  int *rowcnt, *err;
+  double* frag;           // column fragments (this GPU): coloff[iv-1] + candidate index; NaN = not kept
+  int npeer;              // > 0: also stored into the peers' fragment arrays over NVLink (ue_gpu_comm_init_p2p)
+  double* frag_peer[7];
+  int* err;
 };
 __device__ __forceinline__ Acc<true> jb_acc(const JArgs& A, const UInfo& q, int u) {
   Acc<true> a;
@@ -318,9 +335,8 @@ __device__ __forceinline__ double jb_dyl(const JArgs& A, const UInfo& q, double&
 // stage the private cells of 32 unknowns from the base planes, then phase 0 on their perturbed cells
 __global__ void __launch_bounds__(128) k_jb_stage0(JArgs A) {
   const int u0 = blockIdx.x * 32, tid = threadIdx.x;
-  {  // clear this Jacobian's counters (colcnt | rowcnt | rowfill are contiguous) and the candidate-row masks
+  {  // clear the candidate-row masks of this Jacobian
     const int nthr = gridDim.x * 128, t0 = blockIdx.x * 128 + tid;
-    for (int64_t i = t0; i < 3 * A.neq; i += nthr) A.colcnt[i] = 0;
     for (int i = t0; i < A.nitems; i += nthr) A.rmask[i] = 0;
   }
   const int u = u0 + (tid >> 2), k = tid & 3;
@@ -358,9 +374,8 @@ __global__ void __launch_bounds__(128) k_jb_stage0(JArgs A) {
 constexpr int P01_ITEMS = 64;  // (unknown, slot) items per block of k_jb_p01: 16 unknowns (8 and 32 per block measured slower)
 __global__ void __launch_bounds__(5 * P01_ITEMS, 1) k_jb_p01(JArgs A) {
   const int u0 = blockIdx.x * (P01_ITEMS / 4), tid = threadIdx.x;
-  {  // clear this Jacobian's counters (colcnt | rowcnt | rowfill are contiguous) and the candidate-row masks
+  {  // clear the candidate-row masks of this Jacobian
     const int nthr = gridDim.x * 5 * P01_ITEMS, t0 = blockIdx.x * 5 * P01_ITEMS + tid;
-    for (int64_t i = t0; i < 3 * A.neq; i += nthr) A.colcnt[i] = 0;
     for (int i = t0; i < A.nitems; i += nthr) A.rmask[i] = 0;
   }
   const int grp = tid / P01_ITEMS, j = tid % P01_ITEMS;          // role group, item within the block
@@ -474,7 +489,6 @@ __global__ void __launch_bounds__(128, MINB) k_jb_p2(JArgs A) {
 }
 // phase 3 on the interior candidate rows, then difference / clip / ordered compaction into the column's CSC
 // fragment (oderhs.m:8685-8719): one warp per unknown
-// (Building the row pointer in the last block of this kernel instead of a separate k_scan launch was measured: no gain.)
 __global__ void __launch_bounds__(128) k_jb_p3c(JArgs A) {
   const int lane = threadIdx.x & 31, u = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (u >= A.NU) return;
@@ -508,141 +522,126 @@ __global__ void __launch_bounds__(128) k_jb_p3c(JArgs A) {
   const int nv = NVX;
   const int ncand = q.n * nv;
   const int64_t o = A.coloff[iv - 1];
-  int nout = 0;
-  constexpr int CH = 4;  // candidates per lane and pass: their loads are issued together, the ordered ballots follow
-  for (int q0 = 0; q0 < ncand; q0 += 32 * CH) {
-    bool keep[CH]; double val[CH]; int64_t ii[CH];
-#pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const int qq = q0 + 32 * c + lane;
-      keep[c] = false; val[c] = 0.; ii[c] = 0;
-      if (qq < ncand) {
-        const int l = nv == 5 ? qq / 5 : (nv == 4 ? qq >> 2 : qq / nv), k = qq - l * nv;  // constant divisors for the two layouts
-        ii[c] = (int64_t)A.cand_cell[q.coff + l] * nv + k + 1;
-        if (ii[c] >= ii1 && ii[c] <= ii2) {
-          const bool written = (A.rmask[q.off + l] >> k) & 1;
-          if (written || ii[c] == iv) {
-            const double y00 = A.yldot00[ii[c] - 1];
-            const double wk = written ? A.rows[(size_t)k * NI + q.off + l] : y00;
-            double jacelem = (wk - y00) / dyl;
-            if (ii[c] == iv) {
-              if (D.iseqalg[iv - 1] * (1 - D.isbcwdt) == 0) jacelem = jacelem - 1 / A.dtuse[iv - 1];
-              if (D.nufak > 0 && A.yl[neq] == 1) jacelem = jacelem - D.nufak;
-            }
-            val[c] = jacelem;
-            keep[c] = fabs(jacelem * sf) > D.jaccliplim;
-          }
+  // difference, diagonal terms, clip (oderhs.m:8685-8706); every structural entry of this column is written: the value if it is
+  // kept, NaN if not (a NaN element fails the clip test in the reference as well, so the encoding loses nothing)
+  for (int qq = lane; qq < ncand; qq += 32) {
+    const int l = nv == 5 ? qq / 5 : (nv == 4 ? qq >> 2 : qq / nv), k = qq - l * nv;  // constant divisors for the two layouts
+    const int64_t ii = (int64_t)A.cand_cell[q.coff + l] * nv + k + 1;
+    bool keep = false; double val = 0.;
+    if (ii >= ii1 && ii <= ii2) {
+      const bool written = (A.rmask[q.off + l] >> k) & 1;
+      if (written || ii == iv) {
+        const double y00 = A.yldot00[ii - 1];
+        const double wk = written ? A.rows[(size_t)k * NI + q.off + l] : y00;
+        double jacelem = (wk - y00) / dyl;
+        if (ii == iv) {
+          if (D.iseqalg[iv - 1] * (1 - D.isbcwdt) == 0) jacelem = jacelem - 1 / A.dtuse[iv - 1];
+          if (D.nufak > 0 && A.yl[neq] == 1) jacelem = jacelem - D.nufak;
         }
+        val = jacelem;
+        keep = fabs(jacelem * sf) > D.jaccliplim;
       }
     }
-#pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const unsigned bal = __ballot_sync(0xffffffffu, keep[c]);
-      if (keep[c]) {
-        const int pos = nout + __popc(bal & ((1u << lane) - 1));
-        A.colrow[o + pos] = (int)ii[c];
-        A.colval[o + pos] = val[c];
-        atomicAdd(&A.rowcnt[ii[c] - 1], 1);
-      }
-      nout += __popc(bal);
-    }
+    const double out = keep ? val : __longlong_as_double(0x7ff8000000000000LL);
+    A.frag[o + qq] = out;
+    for (int p = 0; p < A.npeer; ++p) A.frag_peer[p][o + qq] = out;  // consecutive lanes, consecutive addresses: whole NVLink packets
   }
-  if (lane == 0) A.colcnt[iv - 1] = nout;
 }
 
-// ---- CSC fragments -> CSR ---------------------------------------------------------------------------------------
-__global__ void k_scan(const int* __restrict__ rowcnt, int64_t* __restrict__ ia, int64_t n, int* err, long long* hflags, int64_t* __restrict__ ia_host) {
-  // single block of 1024 threads; ia is 1-based: ia[0] = 1, ia[i+1] = ia[i] + rowcnt[i].
-  // Each thread owns a contiguous chunk: serial sum, block scan of the 1024 partials, serial write-out.
-  __shared__ int64_t s[1024];
-  const int t = threadIdx.x;
-  const int64_t chunk = (n + 1023) / 1024, b0 = t * chunk, b1 = min(n, b0 + chunk);
-  int64_t sum = 0;
-  for (int64_t i = b0; i < b1; ++i) sum += rowcnt[i];
-  s[t] = sum;
+// Cross-GPU barrier of the P2P transport.  Stream order guarantees that this rank's k_jb_p3c (and with it all its stores
+// into the peers' fragment arrays) has completed; lane r posts the new epoch into rank r's flag block and then waits until rank r
+// has posted the same epoch here.  A stalled peer is reported after ~2 s instead of hanging the GPU.
+__global__ void k_xbarrier(unsigned long long* mine, int nranks, int rank, int* err) {
+  __shared__ unsigned long long ep;
+  if (threadIdx.x == 0) { ep = mine[0] + 1; mine[0] = ep; }
+  __syncwarp();
+  const int r = threadIdx.x;
+  if (r < nranks && r != rank) {
+    __threadfence_system();
+    unsigned long long* theirs = ((unsigned long long**)(mine + 16))[r];  // peer flag blocks: pointer table at mine[16..]
+    *((volatile unsigned long long*)(theirs + 1 + rank)) = ep;
+    __threadfence_system();
+    volatile unsigned long long* in = mine + 1 + r;
+    const long long t0 = clock64();
+    while (*in < ep) { if (clock64() - t0 > 4000000000LL) { atomicOr(err, 8); break; } }
+  }
+  __threadfence_system();
+}
+
+// ---- structural superset -> reference CSR (csrcsc, svr/svrut4.m:1536-1608: rows in order, columns ascending) -----------
+// The index maps fix a superset of the pattern: slot s = (row srow[s], column scol[s]) in row-major, column-ascending order,
+// its value at frag[src[s]].  ONE pass: blocks take tiles of 2048 slots in ticket order, count their kept slots, obtain the number
+// of kept slots before the tile by summing the earlier tiles' published counts (state word = epoch | count; earlier
+// tickets are always running or finished, so the wait is bounded), stage the kept entries in
+// shared memory and write jac / ja in whole lines.  jac_host, ja_host, ia_host: the caller's page-locked arrays (or
+// nullptr), written as well so that no copy follows.  The last block resets the ticket and advances the epoch.
+__global__ void __launch_bounds__(256) k_csr(const double* __restrict__ frag, const int2* __restrict__ meta, const int* __restrict__ srow, int64_t nslots,
+                                             unsigned long long* st, int ntiles, int64_t neq, int64_t nnzmx, double* __restrict__ jac, int64_t* __restrict__ ja,
+                                             int64_t* __restrict__ ia, double* __restrict__ jac_host, int64_t* __restrict__ ja_host, int64_t* __restrict__ ia_host,
+                                             int* err, long long* hflags) {
+  __shared__ double sv[CSR_TILE];
+  __shared__ int sc[CSR_TILE];
+  __shared__ int swarp[8];
+  __shared__ int stile, stot;
+  __shared__ long long sbase;
+  __shared__ unsigned long long sepoch;
+  volatile unsigned long long* ctr = st + ntiles;  // [0] ticket, [1] finished blocks, [2] epoch of the previous launch
+  const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+  if (tid == 0) { stile = (int)atomicAdd((unsigned long long*)&ctr[0], 1ULL); sepoch = ctr[2] + 1; }
   __syncthreads();
-  for (int off = 1; off < 1024; off <<= 1) {
-    const int64_t v = (t >= off) ? s[t - off] : 0;
-    __syncthreads();
-    s[t] += v;
-    __syncthreads();
+  const int tile = stile;
+  const unsigned long long epoch = sepoch & 0x3fffffffULL;
+  const int64_t s0 = (int64_t)tile * CSR_TILE + (int64_t)tid * 8;
+  // meta[s] = (index of the slot's value in the fragment array | row-start flag in bit 31, column)
+  int2 m[8]; double v[8]; int c = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = (s0 + j < nslots) ? meta[s0 + j] : make_int2(-1, 0);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { v[j] = (s0 + j < nslots) ? frag[m[j].x & 0x7fffffff] : __longlong_as_double(0x7ff8000000000000LL); c += (v[j] == v[j]); }
+  int incl = c;  // inclusive scan over the warp, then over the 8 warps
+  for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += t; }
+  if (lane == 31) swarp[wib] = incl;
+  __syncthreads();
+  int wbase = 0, total = 0;
+  for (int i = 0; i < 8; ++i) { if (i < wib) wbase += swarp[i]; total += swarp[i]; }
+  if (wib == 0) {  // publish this tile's count, then sum the counts of all earlier tiles (32 at a time)
+    if (lane == 0) atomicExch(&st[tile], (epoch << 34) | (unsigned long long)total);
+    long long run = 0;
+    for (int i = lane; i < tile; i += 32) {
+      unsigned long long w;
+      do { w = ((volatile unsigned long long*)st)[i]; } while ((w >> 34) != epoch);
+      run += (long long)(w & 0xffffffffULL);
+    }
+    for (int off = 16; off; off >>= 1) run += __shfl_down_sync(0xffffffffu, run, off);
+    if (lane == 0) { sbase = run; stot = total; }
   }
-  int64_t run = 1 + s[t] - sum;
-  if (t == 0) { ia[0] = 1; if (ia_host) ia_host[0] = 1; }
-  for (int64_t i = b0; i < b1; ++i) { run += rowcnt[i]; ia[i + 1] = run; if (ia_host) ia_host[i + 1] = run; }
-  if (t == 1023) { hflags[1] = 1 + s[1023]; hflags[2] = err[0] | err[1]; err[0] = err[1] = 0; }  // nnz + 1 and the error bits (err[1]: Jacobian sequence) to mapped host memory
-}
-__global__ void k_fill(int64_t neq, int64_t ivmin, int64_t ivmax, const int64_t* __restrict__ coloff, const int* __restrict__ colcnt,
-                       const int* __restrict__ colrow, const double* __restrict__ colval, const int64_t* __restrict__ ia, int* __restrict__ rowfill,
-                       double* __restrict__ jac, int64_t* __restrict__ ja, int64_t nnzmx) {
-  const int64_t iv = ivmin + blockIdx.x;
-  if (iv > ivmax) return;
-  const int64_t o = coloff[iv - 1];
-  const int n = colcnt[iv - 1];
-  for (int e = threadIdx.x; e < n; e += blockDim.x) {
-    const int row = colrow[o + e];
-    const int64_t p = ia[row - 1] - 1 + atomicAdd(&rowfill[row - 1], 1);
-    if (p < nnzmx) { ja[p] = iv; jac[p] = colval[o + e]; }   // overflow is reported by the host after the sequence
-  }
-}
-// one warp per row: rank sort of the row's entries by column (rows hold a few tens of entries).  jac_host/ja_host: the
-// caller's page-locked arrays (or nullptr): the sorted row is also written there, so no copy follows the sequence.
-// Rows longer than CAP (a dense row: the integrated core-power row, or the electron-energy rows on a half-space cut, which
-// couple to every column of their window) are rank-sorted through a global scratch area (the CSC fragment buffers, free
-// again once k_fill has run) instead of shared memory.
-__global__ void k_sortrows(int64_t neq, const int64_t* __restrict__ ia, double* __restrict__ jac, int64_t* __restrict__ ja, int64_t nnzmx,
-                           double* __restrict__ jac_host, int64_t* __restrict__ ja_host, int* __restrict__ scr_col, double* __restrict__ scr_val,
-                           int64_t scr_cap) {
-  constexpr int CAP = 96;
-  __shared__ int64_t scol[4][CAP];
-  __shared__ double sval[4][CAP];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int64_t r = (int64_t)blockIdx.x * 4 + wib;
-  if (r >= neq) return;
-  const int64_t b = ia[r] - 1, e = ia[r + 1] - 1;
-  const int n = (int)(e - b);
-  if (n <= 0 || e > nnzmx) return;
-  if (n == 1) {
-    if (jac_host && lane == 0) { ja_host[b] = ja[b]; jac_host[b] = jac[b]; }
-  } else if (n <= CAP) {
-    for (int i = lane; i < n; i += 32) { scol[wib][i] = ja[b + i]; sval[wib][i] = jac[b + i]; }
-    __syncwarp();
-    for (int i = lane; i < n; i += 32) {
-      const int64_t c = scol[wib][i];
-      int rank = 0;
-      for (int j = 0; j < n; ++j) rank += (scol[wib][j] < c);
-      ja[b + rank] = c; jac[b + rank] = sval[wib][i];
-    }
-    if (jac_host) {  // second pass in storage order: contiguous writes over the bus
-      __syncwarp();
-      for (int i = lane; i < n; i += 32) { ja_host[b + i] = ja[b + i]; jac_host[b + i] = jac[b + i]; }
-    }
-  } else if (e <= scr_cap) {
-    for (int64_t i = b + lane; i < e; i += 32) { scr_col[i] = (int)ja[i]; scr_val[i] = jac[i]; }
-    __syncwarp();
-    for (int64_t i = b + lane; i < e; i += 32) {
-      const int c = scr_col[i];
-      int rank = 0;
-      for (int64_t j = b; j < e; ++j) rank += (scr_col[j] < c);
-      ja[b + rank] = c; jac[b + rank] = scr_val[i];
-    }
-    if (jac_host) {
-      __syncwarp();
-      for (int64_t i = b + lane; i < e; i += 32) { ja_host[i] = ja[i]; jac_host[i] = jac[i]; }
-    }
-  } else {
-    if (lane == 0) {  // no scratch space: serial insertion sort
-      for (int64_t i = b + 1; i < e; ++i) {
-        const int64_t cj = ja[i]; const double cv = jac[i];
-        int64_t j = i - 1;
-        while (j >= b && ja[j] > cj) { ja[j + 1] = ja[j]; jac[j + 1] = jac[j]; --j; }
-        ja[j + 1] = cj; jac[j + 1] = cv;
+  int lp = wbase + incl - c;  // kept slots of this tile before this thread's first slot
+  __syncthreads();
+  const long long base = sbase;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int64_t s = s0 + j;
+    if (s < nslots) {
+      if (m[j].x < 0) { const int r = srow[s]; ia[r - 1] = base + lp + 1; if (ia_host) ia_host[r - 1] = base + lp + 1; }
+      if (v[j] == v[j]) { sv[lp] = v[j]; sc[lp] = m[j].y; ++lp; }
+      if (s == nslots - 1) {
+        ia[neq] = base + lp + 1; if (ia_host) ia_host[neq] = base + lp + 1;
+        hflags[1] = base + lp + 1; hflags[2] = err[0] | err[1]; err[0] = err[1] = 0;  // nnz + 1 and the error bits to mapped host memory
       }
     }
-    if (jac_host) {
-      __syncwarp();
-      for (int64_t i = b + lane; i < e; i += 32) { ja_host[i] = ja[i]; jac_host[i] = jac[i]; }
+  }
+  __syncthreads();
+  for (int i = tid; i < stot; i += 256) {
+    const long long pos = base + i;
+    if (pos < nnzmx) {  // overflow is reported by the host after the sequence
+      const double x = sv[i]; const int64_t cidx = sc[i];
+      jac[pos] = x; ja[pos] = cidx;
+      if (jac_host) { jac_host[pos] = x; ja_host[pos] = cidx; }
     }
+  }
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd((unsigned long long*)&ctr[1], 1ULL) == (unsigned long long)(ntiles - 1)) { ctr[0] = 0; ctr[1] = 0; ctr[2] = sepoch; __threadfence(); }
   }
 }
 
@@ -799,20 +798,21 @@ int check_switches() {
 void drop_graphs();
 void free_all() {
   drop_graphs();
+  if (g_xchg) { cudaFree(g_xchg); g_xchg = nullptr; d_frag = nullptr; g_p2p_flags = nullptr; }
   g_seen_host.clear(); g_last_yldot.clear(); g_base_yl.clear();
   for (auto& h : g_step_host) h.clear();
   g_base_valid = g_base_dev_valid = false;
   for (void* p : g_static_allocs) cudaFree(p);
   g_static_allocs.clear();
   void* ptrs[] = {d_base, d_yl, d_yldot00, d_tmp, d_yldot, d_dtuse, d_ylodt, d_suscal, d_sfscal, d_err, d_cand_cell, d_cand_east, d_item_u, d_guard_items, d_guard_cells, d_coloff,
-                  d_colcnt, d_colrow, d_colval, d_ia, d_ja, d_jac};
+                  d_meta, d_srow, d_tilest, d_frag, d_ia, d_ja, d_jac};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (d_dtoptv) { cudaFree(d_dtoptv); d_dtoptv = nullptr; }
   for (void* p : {(void*)d_uinfo, (void*)d_priv, (void*)d_jrows, (void*)d_rres, (void*)d_rmask}) if (p) cudaFree(p);
   d_uinfo = nullptr; d_priv = d_jrows = d_rres = nullptr; d_rmask = nullptr;
   d_base = d_yl = d_yldot00 = d_tmp = d_yldot = d_dtuse = d_ylodt = d_suscal = d_sfscal = nullptr;
-  d_err = nullptr; d_cand_cell = d_cand_east = d_item_u = d_guard_items = d_guard_cells = nullptr; d_coloff = nullptr; d_colcnt = d_colrow = nullptr; d_colval = nullptr;
-  d_rowcnt = d_rowfill = nullptr; d_ia = d_ja = nullptr; d_jac = nullptr;
+  d_err = nullptr; d_cand_cell = d_cand_east = d_item_u = d_guard_items = d_guard_cells = nullptr; d_coloff = nullptr; d_meta = nullptr; d_srow = nullptr; d_tilest = nullptr; d_frag = nullptr;
+  d_ia = d_ja = nullptr; d_jac = nullptr;
   g_ready = false;
   g_alloc = false;
 }
@@ -865,6 +865,46 @@ int build_lists() {
   return 0;
 }
 
+// structural CSR superset: slot of every (column iv, candidate) pair in row-major, column-ascending order
+int build_superset() {
+  const UeParams& P = S.p;
+  const int nv = (int)P.numvar;
+  std::vector<unsigned long long> key; std::vector<int> where;
+  key.reserve((size_t)g_cap_total); where.reserve((size_t)g_cap_total);
+  for (int64_t iv = 1; iv <= neq; ++iv) {
+    const int c = (int)P.igyl[iv - 1] + NXS * (int)P.igyl[neq + iv - 1];
+    const int n = h_cellcand_off[c + 1] - h_cellcand_off[c];
+    for (int l = 0; l < n; ++l)
+      for (int k = 0; k < nv; ++k) {
+        const unsigned long long ii = (unsigned long long)h_cand_cell[h_cellcand_off[c] + l] * nv + k + 1;
+        key.push_back((ii << 32) | (unsigned long long)iv);
+        where.push_back((int)(h_coloff[iv - 1] + (int64_t)l * nv + k));
+      }
+  }
+  const size_t n = key.size();
+  std::vector<int> ord(n);
+  for (size_t i = 0; i < n; ++i) ord[i] = (int)i;
+  std::sort(ord.begin(), ord.end(), [&](int a, int b) { return key[a] < key[b]; });
+  std::vector<int2> meta(n); std::vector<int> srow(n);
+  for (size_t r = 0; r < n; ++r) {
+    srow[r] = (int)(key[ord[r]] >> 32);
+    meta[r].x = where[ord[r]] | ((r == 0 || srow[r - 1] != srow[r]) ? (int)0x80000000 : 0);
+    meta[r].y = (int)(key[ord[r]] & 0xffffffffu);
+  }
+  if (g_cap_total >= 0x7fffffff) { g_err = "grid too large for 31-bit fragment indices"; return -1; }
+  g_nslots = (int64_t)n;
+  const size_t nt = (n + CSR_TILE - 1) / CSR_TILE;
+  CK(cudaMalloc(&d_meta, n * sizeof(int2)));
+  CK(cudaMalloc(&d_srow, n * sizeof(int)));
+  CK(cudaMalloc(&d_tilest, (nt + 4) * sizeof(unsigned long long)));
+  CK(cudaMalloc(&d_frag, std::max<size_t>(1, (size_t)g_cap_total) * sizeof(double)));
+  CK(cudaMemcpy(d_meta, meta.data(), n * sizeof(int2), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_srow, srow.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemset(d_tilest, 0, (nt + 4) * sizeof(unsigned long long)));
+  CK(cudaMemset(d_frag, 0xff, std::max<size_t>(1, (size_t)g_cap_total) * sizeof(double)));  // all ones = NaN = not kept
+  return 0;
+}
+
 int upload_lists() {
   const UeParams& P = S.p;
   const size_t NU = h_list.size();
@@ -909,7 +949,7 @@ int upload_lists() {
 
 // ---- launch sequences; replayed as CUDA graphs (the sequences are launch-latency bound) -----------------
 struct GKey {
-  int kind; const void *p0, *p1, *p2, *p3, *p4; int64_t a, b, c; int flag;
+  int kind; const void *p0, *p1, *p2, *p3, *p4; int64_t a, b, c; int flag; int par;
   bool operator<(const GKey& o) const { return std::memcmp(this, &o, sizeof(GKey)) < 0; }
 };
 std::map<GKey, cudaGraphExec_t> g_graphs;
@@ -940,30 +980,26 @@ int enqueue_residual(const double* dyl, double* dyldot, bool need_rows, const do
     if (r_ != ncclSuccess) { g_err = std::string("NCCL error: ") + NC_.GetErrorString(r_) + " at " #call; return -11; } \
   } while (0)
 int comm_gather_columns() {
-  g_comm_bytes = 0;
+  // the fragment layout (coloff) is the same on all ranks: every rank broadcasts its own range of columns in place
   NCK(NC_.GroupStart());
+  int64_t mine = 0, total = 0;
   for (int r = 0; r < g_nranks; ++r) {
-    const int64_t lo = g_rank_lo[r], hi = g_rank_hi[r];
-    if (hi < lo) continue;
-    const int64_t off = h_coloff[lo - 1], end = hi < neq ? h_coloff[hi] : g_cap_total, cnt = end - off;
-    NCK(NC_.Broadcast(d_colval + off, d_colval + off, (size_t)cnt, ncclFloat64, r, g_comm, g_stream));
-    NCK(NC_.Broadcast(d_colrow + off, d_colrow + off, (size_t)cnt, ncclInt32, r, g_comm, g_stream));
-    NCK(NC_.Broadcast(d_colcnt + (lo - 1), d_colcnt + (lo - 1), (size_t)(hi - lo + 1), ncclInt32, r, g_comm, g_stream));
-    const int64_t b = cnt * 12 + (hi - lo + 1) * 4;
-    g_comm_bytes += (r == g_rank) ? b * (g_nranks - 1) : b;
+    if (g_rank_hi[r] < g_rank_lo[r]) continue;
+    const int64_t b0 = h_coloff[g_rank_lo[r] - 1], b1 = g_rank_hi[r] < neq ? h_coloff[g_rank_hi[r]] : g_cap_total;
+    NCK(NC_.Broadcast(d_frag + b0, d_frag + b0, (size_t)(b1 - b0), ncclFloat64, r, g_comm, g_stream));
+    total += (b1 - b0) * 8;
+    if (r == g_rank) mine = (b1 - b0) * 8;
   }
-  NCK(NC_.AllReduce(d_rowcnt, d_rowcnt, (size_t)neq, ncclInt32, ncclSum, g_comm, g_stream));
-  g_comm_bytes += 2 * neq * 4;
   NCK(NC_.GroupEnd());
+  g_comm_bytes = mine * (g_nranks - 1) + (total - mine);  // sent to every peer + received from every peer
   return 0;
 }
 int res_launches() { return g_fuse23 ? 3 : 4; }  // kernels of one residual sequence with rows
-int jac_launches() { return (int)h_list.size() >= 4096 ? 8 : 6; }  // kernels of one Jacobian sequence (large / small grids)
+int jac_launches() { return ((int)h_list.size() >= 4096 ? 6 : 4) + (g_p2p ? 1 : 0); }  // kernels of one Jacobian sequence (large / small grids)
 int enqueue_jac(const double* dyl, const double* dy00, int64_t ml, int64_t mu, int64_t nnzmx, double* djac, int64_t* dja, int64_t* dia, bool base_current,
                 double* jac_host = nullptr, int64_t* ja_host = nullptr, int64_t* ia_host = nullptr) {
   if (!base_current) { int rc = enqueue_residual(dyl, nullptr, false); if (rc) return rc; }
   const int NU = (int)h_list.size();
-  if (NU == 0) CK(cudaMemsetAsync(d_colcnt, 0, 3 * neq * sizeof(int), g_stream));  // otherwise k_jb_stage0 clears the counters
   if (NU > 0) {
     JArgs A;
     A.ui = (const UInfo*)d_uinfo; A.cand_cell = d_cand_cell; A.cand_east = d_cand_east; A.item_u = d_item_u; A.guard_items = d_guard_items; A.nguard = g_nguard;
@@ -971,7 +1007,11 @@ int enqueue_jac(const double* dyl, const double* dy00, int64_t ml, int64_t mu, i
     A.priv = d_priv; A.rows = d_jrows; A.rres = d_rres; A.rmask = d_rmask; A.base = d_base;
     A.yl = dyl; A.yldot00 = dy00; A.suscal = d_suscal; A.sfscal = d_sfscal; A.dtuse = d_dtuse; A.ylodt = d_ylodt;
     A.neq = neq; A.ml = ml; A.mu = mu; A.NXS = NXS; A.NC = NC;
-    A.coloff = d_coloff; A.colcnt = d_colcnt; A.colrow = d_colrow; A.colval = d_colval; A.rowcnt = d_rowcnt; A.err = d_err + 1;
+    A.coloff = d_coloff; A.err = d_err + 1;
+    const int par = g_p2p ? (int)(g_epoch & 1) : 0;  // P2P: two sets of fragment arrays, alternating with the Jacobian count
+    A.frag = d_frag + (size_t)par * g_cap_total;
+    A.npeer = 0;
+    if (g_p2p) for (int r = 0; r < g_nranks; ++r) if (r != g_rank) A.frag_peer[A.npeer++] = g_peer_frag[r] + (size_t)par * g_cap_total;
     const unsigned gs = (unsigned)((NU * 4 + 127) / 128), gi = (unsigned)((g_nitems + 127) / 128);
     const bool big = NU >= 4096;  // more than ~2 waves of blocks per role: throughput-bound
     A.role0 = 0;
@@ -992,35 +1032,38 @@ int enqueue_jac(const double* dyl, const double* dy00, int64_t ml, int64_t mu, i
     }
     CK(launch(k_jb_p3c, dim3((unsigned)((NU + 3) / 4)), dim3(128), A));
   }
-  int64_t f_lo = g_ivmin, f_hi = g_ivmax;
-  if (g_nranks > 1) {  // every rank receives every other rank's column fragments; the CSR is then built from all columns
-    int rc = comm_gather_columns();
-    if (rc) return rc;
-    f_lo = 1; f_hi = neq;
+  const int par = g_p2p ? (int)(g_epoch & 1) : 0;
+  if (g_nranks > 1) {  // every rank receives every other rank's slots; the CSR is then built from all columns on every rank
+    if (g_p2p) {  // the slots were stored into the peers' arrays by k_jb_p3c: signal, then wait for every peer's signal
+      CK(launch(k_xbarrier, dim3(1), dim3(32), g_p2p_flags, g_nranks, g_rank, d_err + 1));
+      ++g_epoch;
+    } else {
+      int rc = comm_gather_columns();
+      if (rc) return rc;
+    }
   }
-  CK(launch(k_scan, dim3(1), dim3(1024), d_rowcnt, dia, neq, d_err, d_hflags, ia_host));
-  const int64_t ncol = f_hi - f_lo + 1;
-  if (ncol > 0) {
-    CK(launch(k_fill, dim3((unsigned)ncol), dim3(64), neq, f_lo, f_hi, d_coloff, d_colcnt, d_colrow, d_colval, dia, d_rowfill, djac, dja, nnzmx));
-    CK(launch(k_sortrows, dim3((unsigned)((neq + 3) / 4)), dim3(128), neq, dia, djac, dja, nnzmx, jac_host, ja_host, d_colrow, d_colval, g_cap_total));
-  }
+  const unsigned nt = (unsigned)((g_nslots + CSR_TILE - 1) / CSR_TILE);
+  CK(launch(k_csr, dim3(nt), dim3(256), (const double*)(d_frag + (size_t)par * g_cap_total), (const int2*)d_meta, (const int*)d_srow, g_nslots, d_tilest, (int)nt, neq,
+            nnzmx, djac, dja, dia, jac_host, ja_host, ia_host, d_err, d_hflags));
   return 0;
 }
 template <typename F>
-int replay(const GKey& key, F enqueue) {
-  if (g_nranks > 1) return enqueue();  // the sequence contains NCCL calls: launched directly, not captured
+int replay(const GKey& key0, F enqueue) {
+  if (g_nranks > 1 && !g_p2p) return enqueue();  // the sequence contains NCCL calls: launched directly, not captured
+  GKey key = key0;
+  const bool hasjac = key.kind == 2 || key.kind == 4 || key.kind == 5;
+  key.par = (g_p2p && hasjac) ? (int)(g_epoch & 1) + 1 : 0;  // P2P: the fragment arrays alternate with the Jacobian count
   auto it = g_graphs.find(key);
+  bool fresh = false;
   if (it == g_graphs.end()) {
     cudaGraphExec_t ex = nullptr;
-    for (int attempt = 0; attempt < 1 && !ex; ++attempt) {
-      cudaGraph_t graph = nullptr;
-      CK(cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeThreadLocal));
-      int rc = enqueue();
-      cudaError_t e = cudaStreamEndCapture(g_stream, &graph);
-      if (e == cudaSuccess && rc == 0) e = cudaGraphInstantiate(&ex, graph, 0);
-      if (graph) cudaGraphDestroy(graph);
-      if (e == cudaSuccess && rc == 0) break;
-      ex = nullptr;
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue();  // (a captured Jacobian sequence advances g_epoch once: it is launched once right below)
+    cudaError_t e = cudaStreamEndCapture(g_stream, &graph);
+    if (e == cudaSuccess && rc == 0) e = cudaGraphInstantiate(&ex, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (!(e == cudaSuccess && rc == 0)) {
       cudaGetLastError();
       if (rc) return rc;
       g_err = std::string("CUDA graph capture failed: ") + cudaGetErrorString(e);
@@ -1028,8 +1071,10 @@ int replay(const GKey& key, F enqueue) {
     }
     if (g_graphs.size() > 64) drop_graphs();
     it = g_graphs.emplace(key, ex).first;
+    fresh = true;
   }
   CK(cudaGraphLaunch(it->second, g_stream));
+  if (!fresh && g_p2p && hasjac) ++g_epoch;
   return 0;
 }
 
@@ -1045,6 +1090,7 @@ int err_of_flags() {  // after a synchronisation: error bits the last sequence p
   h_flags[0] = h_flags[2] = 0;
   if (h & 1) { g_err = "***  ni is negative - calculation stopped"; return -3; }
   if (h & 2) { g_err = "***  ng is negative - calculation stopped"; return -3; }
+  if (h & 8) { g_err = "multi-GPU Jacobian: a peer GPU did not reach the exchange barrier within 2 s"; return -11; }
   if (h & 4) { g_err = "jac_calc: yldot00 is not pandf1(yl) as evaluated by this library (call order rhsnk -> jac_calc, oderhs.m:9466-9468)"; return -4; }
   return 0;
 }
@@ -1070,7 +1116,7 @@ int run_jac_dev(const double* dyl, const double* dy00, int64_t ml, int64_t mu, i
   int rc = replay(k, [&]() { return enqueue_jac(dyl, dy00, ml, mu, nnzmx, djac, dja, dia, base_current); });
   if (rc) return rc;
   CK(cudaStreamSynchronize(g_stream));
-  const int64_t nnz = (int64_t)h_flags[1] - 1;  // k_scan posts ia(neq+1) to mapped host memory
+  const int64_t nnz = (int64_t)h_flags[1] - 1;  // k_csr posts ia(neq+1) to mapped host memory
   *nnz_out = nnz;
   if (nnz > nnzmx) {
     g_err = "*** jac_calc -- More storage needed for Jacobian. Storage exceeded. Increase lenpfac.";
@@ -1216,11 +1262,7 @@ int ue_gpu_init(void) {
   }
   CK(cudaMalloc(&d_coloff, neq * sizeof(int64_t)));
   CK(cudaMemcpy(d_coloff, h_coloff.data(), neq * sizeof(int64_t), cudaMemcpyHostToDevice));
-  CK(cudaMalloc(&d_colcnt, 3 * neq * sizeof(int)));  // colcnt | rowcnt | rowfill contiguous: one memset per Jacobian
-  CK(cudaMalloc(&d_colrow, g_cap_total * sizeof(int)));
-  CK(cudaMalloc(&d_colval, g_cap_total * sizeof(double)));
-  d_rowcnt = d_colcnt + neq;
-  d_rowfill = d_colcnt + 2 * neq;
+  if ((rc = build_superset())) return rc;
   g_nnzcap = g_cap_total;
   CK(cudaMalloc(&d_ia, (neq + 1) * sizeof(int64_t)));
   CK(cudaMalloc(&d_ja, g_nnzcap * sizeof(int64_t)));
@@ -1460,7 +1502,7 @@ int ue_gpu_jac_calc(int64_t n, double t, const double* yl, const double* yldot00
   }
   GKey k; std::memset(&k, 0, sizeof k);
   const int64_t lim = std::min(nnzmx, g_nnzcap);
-  // page-locked caller arrays: k_scan / k_sortrows write ia, jac, ja there directly and no copy follows
+  // page-locked caller arrays: k_csr stores ia, jac, ja there directly and no copy follows
   double* jac_dev = device_alias(jac); int64_t* ja_dev = device_alias(ja); int64_t* ia_dev = device_alias(ia);
   const bool direct = jac_dev && ja_dev && ia_dev;
   k.kind = direct ? 4 : 2; k.p0 = d_yl; k.p1 = dy00; k.p2 = direct ? (void*)jac_dev : (void*)d_jac; k.p3 = direct ? (void*)ja_dev : (void*)d_ja;
@@ -1504,6 +1546,7 @@ int ue_gpu_set_column_range(int64_t ivmin, int64_t ivmax) {
   g_ivmin = ivmin; g_ivmax = ivmax; g_nnz_guess = 0;
   build_lists();
   drop_graphs();
+  CK(cudaMemset(d_frag, 0xff, (size_t)g_cap_total * sizeof(double)));  // entries of columns outside the range are never written: NaN = not kept
   return upload_lists();
 }
 
@@ -1630,15 +1673,7 @@ int ue_gpu_comm_unique_id(char* id128) {
   std::memcpy(id128, &id, 128);
   return 0;
 }
-int ue_gpu_comm_init(int64_t nranks, int64_t rank, const char* id128) {
-  if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
-  if (nranks < 1 || rank < 0 || rank >= nranks) { g_err = "comm_init: bad rank / nranks"; return -1; }
-  int rc = nccl_bind();
-  if (rc) return rc;
-  if (g_comm) { NC_.CommDestroy(g_comm); g_comm = nullptr; g_nranks = 1; g_rank = 0; }
-  ncclUniqueId id;
-  std::memcpy(&id, id128, 128);
-  NCK(NC_.CommInitRank(&g_comm, (int)nranks, id, (int)rank));
+static int comm_set_ranges(int64_t nranks, int64_t rank) {
   // MPISplitIndex (ppp/mpi_parallel.F90:366-447): contiguous column ranges; the weight of a column is the size of its
   // candidate list (the work of its evaluation), known from the index maps, so no timing feedback is needed
   g_rank_lo.assign(nranks, 1); g_rank_hi.assign(nranks, 0);
@@ -1655,23 +1690,83 @@ int ue_gpu_comm_init(int64_t nranks, int64_t rank, const char* id128) {
   g_ivmin = g_rank_lo[rank]; g_ivmax = g_rank_hi[rank]; g_nnz_guess = 0;
   build_lists();
   drop_graphs();
-  rc = upload_lists();
+  return upload_lists();
+}
+static void comm_release() {
+  if (g_comm) { cudaStreamSynchronize(g_stream); NC_.CommDestroy(g_comm); g_comm = nullptr; }
+  if (g_p2p) {
+    cudaStreamSynchronize(g_stream);
+    for (int r = 0; r < 8; ++r) { if (g_peer_base[r]) cudaIpcCloseMemHandle(g_peer_base[r]); g_peer_base[r] = nullptr; g_peer_frag[r] = nullptr; g_peer_flags[r] = nullptr; }
+    g_p2p = false;
+  }
+}
+int ue_gpu_comm_init(int64_t nranks, int64_t rank, const char* id128) {
+  if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
+  if (nranks < 1 || rank < 0 || rank >= nranks) { g_err = "comm_init: bad rank / nranks"; return -1; }
+  int rc = nccl_bind();
+  if (rc) return rc;
+  comm_release(); g_nranks = 1; g_rank = 0;
+  ncclUniqueId id;
+  std::memcpy(&id, id128, 128);
+  NCK(NC_.CommInitRank(&g_comm, (int)nranks, id, (int)rank));
+  rc = comm_set_ranges(nranks, rank);
   if (rc) return rc;
   g_nranks = (int)nranks; g_rank = (int)rank;
   if (g_nranks > 1) {  // first collective outside any timed region: NCCL sets up its channels and buffers here
-    CK(cudaMemsetAsync(d_colcnt, 0, 3 * neq * sizeof(int), g_stream));
     rc = comm_gather_columns();
     if (rc) return rc;
     CK(cudaStreamSynchronize(g_stream));
   }
   return 0;
 }
+// ---- P2P transport: the fragment arrays of all ranks mapped into each other (CUDA IPC, NVLink peer access) ---------------------
+static size_t xchg_flags_off() { return (((size_t)g_cap_total * 2 * 8) + 255) / 256 * 256; }
+int ue_gpu_comm_p2p_handle(char* handle64) {
+  if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
+  comm_release(); g_nranks = 1; g_rank = 0;
+  if (!g_xchg) {  // move the fragment array into one exportable allocation: 2 x fragments | flag block
+    g_xchg_bytes = xchg_flags_off() + 512;
+    CK(cudaMalloc(&g_xchg, g_xchg_bytes));
+    cudaFree(d_frag);
+    d_frag = (double*)g_xchg;
+    drop_graphs();
+  }
+  CK(cudaMemset(g_xchg, 0xff, xchg_flags_off()));
+  CK(cudaMemset((char*)g_xchg + xchg_flags_off(), 0, 512));
+  g_p2p_flags = (unsigned long long*)((char*)g_xchg + xchg_flags_off());
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, g_xchg));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+  std::memcpy(handle64, &h, 64);
+  return 0;
+}
+int ue_gpu_comm_init_p2p(int64_t nranks, int64_t rank, const char* handles) {
+  if (!g_ready || !g_xchg) { g_err = "comm_init_p2p: call ue_gpu_comm_p2p_handle on every rank first"; return -1; }
+  if (nranks < 1 || nranks > 8 || rank < 0 || rank >= nranks) { g_err = "comm_init_p2p: 1..8 ranks of one node"; return -1; }
+  unsigned long long table[8] = {0};
+  for (int r = 0; r < (int)nranks; ++r) {
+    if (r == (int)rank) { table[r] = (unsigned long long)g_p2p_flags; continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handles + 64 * r, 64);
+    void* base = nullptr;
+    CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    g_peer_base[r] = base;
+    g_peer_frag[r] = (double*)base;
+    g_peer_flags[r] = (unsigned long long*)((char*)base + xchg_flags_off());
+    table[r] = (unsigned long long)g_peer_flags[r];
+  }
+  CK(cudaMemcpy(g_p2p_flags + 16, table, sizeof table, cudaMemcpyHostToDevice));
+  int rc = comm_set_ranges(nranks, rank);
+  if (rc) return rc;
+  g_nranks = (int)nranks; g_rank = (int)rank; g_p2p = nranks > 1; g_epoch = 0; g_comm_bytes = 0;
+  return 0;  // the caller synchronises the ranks (MPI_Barrier / dist.barrier) before the first Jacobian
+}
 int ue_gpu_comm_info(int64_t* nranks, int64_t* rank, int64_t* ivmin, int64_t* ivmax, int64_t* bytes_last_jac) {
-  *nranks = g_nranks; *rank = g_rank; *ivmin = g_ivmin; *ivmax = g_ivmax; *bytes_last_jac = g_nranks > 1 ? g_comm_bytes : 0;
+  *nranks = g_nranks; *rank = g_rank; *ivmin = g_ivmin; *ivmax = g_ivmax; *bytes_last_jac = g_nranks > 1 ? (g_p2p ? (int64_t)9 * (g_nranks - 1) * ((g_ivmax < neq ? h_coloff[g_ivmax] : g_cap_total) - h_coloff[g_ivmin - 1]) / UE_NV * (int64_t)S.p.numvar : g_comm_bytes) : 0;
   return 0;
 }
 int ue_gpu_comm_finalize(void) {
-  if (g_comm) { cudaStreamSynchronize(g_stream); NC_.CommDestroy(g_comm); g_comm = nullptr; }
+  comm_release();
   const bool was = g_nranks > 1;
   g_nranks = 1; g_rank = 0;
   if (was && g_ready) { g_ivmin = 1; g_ivmax = neq; build_lists(); drop_graphs(); return upload_lists(); }
