@@ -28,7 +28,7 @@
 #ifdef UE_MATH_FORCEINLINE
 #define UE_HD_BIG UE_HD
 #else
-#define UE_HD_BIG __host__ __device__ __noinline__
+#define UE_HD_BIG static __host__ __device__ __noinline__
 #endif
 #else
 #define UE_HD static inline

@@ -1,0 +1,76 @@
+"""CPU logic check of the product's GENERAL path (uedge_b200/csrc/ue_gen_phys.h + ue_gen.cu) without a GPU: the same sources built
+for the host (tests/hostcheck, -DUE_GEN_HOST) must reproduce the general oracle BIT FOR BIT - residual, Jacobian values, ia/ja -
+both with the loop nests in the reference's order and REVERSED.  On the GPU the iterations of one nest run concurrently on the
+threads of a warp or block; identical results in both orders show that no iteration reads what another one of the same nest
+writes.  Every Jacobian column is evaluated on a private copy of the base planes (as each warp does), not in place as the
+reference and the oracle do - so the test also shows that the reference's perturb / restore sequence leaves no trace."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.test_oracle2_golden import twin
+from tests.util import psetnk_inputs
+from uedge_b200.cases import box2_case
+from uedge_b200.cases2 import SUBSETS, Lib2, Oracle2, box2_initial_state, inputex_case
+
+HK = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostcheck")
+
+
+def host(rev):
+    subprocess.run(["make", "-C", HK, "libuegen_host_rev.so" if rev else "libuegen_host.so"], check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    return Lib2(os.path.join(HK, "libuegen_host_rev.so" if rev else "libuegen_host.so"), "ue_genh_")
+
+
+def same(o, h, c, yl, step=None):
+    b = c.bbb
+    if step is not None:
+        for lib in (o, h):
+            lib.step_params(*step)
+    for lib in (o, h):
+        lib.pandf1(yl)
+    fo, fh = o.pandf1(yl), h.pandf1(yl)
+    assert np.array_equal(fo, fh)
+    for nm in ("fnix1", "fniy1", "feex", "feiy", "fmix1", "visx1", "hcxe", "resee", "resei"):  # (before the oracle's in-place Jacobian loop)
+        assert np.array_equal(o.plane(nm), h.plane(nm)), nm
+    jo, jh = o.jac_calc(yl, fo, b.lbw, b.ubw, b.nnzmx), h.jac_calc(yl, fh, b.lbw, b.ubw, b.nnzmx)
+    assert len(jo[0]) > b.neq
+    assert np.array_equal(jo[2], jh[2]) and np.array_equal(jo[1], jh[1]) and np.array_equal(jo[0], jh[0])
+
+
+@pytest.mark.parametrize("rev", [0, 1])
+@pytest.mark.parametrize("subset", SUBSETS)
+def test_input_example_subsets(built, subset, rev):
+    c, yl, _ = inputex_case(subset)
+    same(Oracle2().bind(c), host(rev).bind(c), c, yl)
+
+
+@pytest.mark.parametrize("rev", [0, 1])
+def test_box2_as_its_deck_runs_it(built, rev):
+    c = box2_case(isupgon=1)  # inertial atoms (box2_in.py:114-131)
+    yl = box2_initial_state(c)
+    assert c.bbb.numvar == 6 and c.bbb.neq == 384
+    same(Oracle2().bind(c), host(rev).bind(c), c, yl)
+
+
+@pytest.mark.parametrize("name", ["d3dHsm", "case2", "case1"])
+def test_d3dhsm_family_through_the_general_path(built, name):
+    """the d3dHsm family (one ion species, diffusive atoms, orthogonal mesh; DEGAS2 tables for case2) with psetnk's scalings and a
+    finite time step: here oracle2 is itself bit-identical to the kernels' oracle (tests/test_oracle2_golden.py)."""
+    c1, c2, yl = twin(name)
+    b = c2.bbb
+    y, su = psetnk_inputs(c1, yl)
+    step = (np.full(b.neq, 1e-4), 0.999 * y[: b.neq], su, np.ones(b.neq))
+    same(Oracle2().bind(c2), host(1).bind(c2), c2, y, step)
+
+
+def test_errors_are_reported(built):
+    c, yl, _ = inputex_case("default")
+    h = host(0).bind(c)
+    bad = yl.copy(); bad[0] = -1.0  # negative density
+    with pytest.raises(RuntimeError, match="ni is negative"):
+        h.pandf1(bad)
+    c.bbb.isimpon = 2
+    with pytest.raises(RuntimeError, match="isimpon"):
+        host(0).bind(c)

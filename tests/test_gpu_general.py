@@ -1,0 +1,89 @@
+"""GPU parity of the GENERAL path (libuegpu.so, entry points ue_gen_* of include/ue_gen.h) through the C ABI:
+  * against the reference's OWN stored vectors (pyexamples/input_example/solution.h5: pandf1 output and ~45 field planes for ten
+    subsets of equations on an 8x4 non-orthogonal mesh with inertial atoms and the potential equation);
+  * BIT FOR BIT against the general oracle: residual, Jacobian values, ia/ja - input_example subsets, pyexamples/box2 exactly as
+    its deck runs it (inertial atoms), and the d3dHsm family with psetnk's scalings and a finite time step."""
+import numpy as np
+import pytest
+
+from tests.refplanes import check_against_reference
+from tests.test_oracle2_golden import twin
+from tests.util import psetnk_inputs
+from uedge_b200.cases import box2_case
+from uedge_b200.cases2 import SUBSETS, Oracle2, box2_initial_state, inputex_case, load_gen
+
+pytestmark = pytest.mark.gpu
+
+
+def same(o, g, c, yl, step=None):
+    b = c.bbb
+    if step is not None:
+        for lib in (o, g):
+            lib.step_params(*step)
+    for lib in (o, g):
+        lib.pandf1(yl)
+    fo, fg = o.pandf1(yl), g.pandf1(yl)
+    assert np.array_equal(fo, fg)
+    for nm in ("fnix1", "fniy1", "feex", "feiy", "fmix1", "visx1", "hcxe", "resee", "resei", "fngx", "fngy", "fqx", "fqy"):
+        assert np.array_equal(o.plane(nm), g.plane(nm)), nm
+    jo, jg = o.jac_calc(yl, fo, b.lbw, b.ubw, b.nnzmx), g.jac_calc(yl, fg, b.lbw, b.ubw, b.nnzmx)
+    assert len(jo[0]) > b.neq
+    assert np.array_equal(jo[2], jg[2]) and np.array_equal(jo[1], jg[1]) and np.array_equal(jo[0], jg[0])
+    return jo, jg
+
+
+@pytest.mark.parametrize("subset", SUBSETS)
+def test_cuda_reproduces_the_reference_stored_vectors(built, subset):
+    c, yl, gold = inputex_case(subset)
+    check_against_reference(load_gen().bind(c), c, gold, subset, yl)
+
+
+@pytest.mark.parametrize("subset", SUBSETS)
+def test_input_example_bit_identical_to_oracle(built, subset):
+    c, yl, _ = inputex_case(subset)
+    same(Oracle2().bind(c), load_gen().bind(c), c, yl)
+
+
+def test_box2_as_its_deck_runs_it(built):
+    c = box2_case(isupgon=1)  # inertial atoms (box2_in.py:114-131)
+    yl = box2_initial_state(c)
+    same(Oracle2().bind(c), load_gen().bind(c), c, yl)
+
+
+@pytest.mark.parametrize("name", ["d3dHsm", "case2", "case1"])
+def test_d3dhsm_family_through_the_general_path(built, name):
+    c1, c2, yl = twin(name)
+    b = c2.bbb
+    y, su = psetnk_inputs(c1, yl)
+    step = (np.full(b.neq, 1e-4), 0.999 * y[: b.neq], su, np.ones(b.neq))
+    same(Oracle2().bind(c2), load_gen().bind(c2), c2, y, step)
+
+
+def test_perturbed_states_and_column_range(built):
+    c, yl, _ = inputex_case("default")
+    b = c.bbb
+    o, g = Oracle2().bind(c), load_gen().bind(c)
+    rng = np.random.default_rng(7)
+    for rep in range(3):
+        y = yl.copy(); y[: b.neq] *= 1.0 + 1e-3 * rng.standard_normal(b.neq)
+        jo, jg = same(o, g, c, y)
+    # columns 101..250 only (ppp column split): the CSR of that range
+    C = __import__("ctypes")
+    for lib in (o, g):
+        lib._f("set_column_range")(C.c_int64(101), C.c_int64(250))
+    fo = o.pandf1(y)
+    po, pg = o.jac_calc(y, fo, b.lbw, b.ubw, b.nnzmx), g.jac_calc(y, fo, b.lbw, b.ubw, b.nnzmx)
+    assert all(np.array_equal(p, q) for p, q in zip(po, pg)) and 0 < len(po[0]) < len(jo[0])
+    assert po[1].min() >= 101 and po[1].max() <= 250
+
+
+def test_errors_are_reported(built):
+    c, yl, _ = inputex_case("default")
+    g = load_gen().bind(c)
+    bad = yl.copy(); bad[0] = -1.0
+    with pytest.raises(RuntimeError, match="ni is negative"):
+        g.pandf1(bad)
+    g.pandf1(yl)  # and the library keeps working afterwards
+    c.bbb.isimpon = 2
+    with pytest.raises(RuntimeError, match="isimpon"):
+        load_gen().bind(c)

@@ -59,15 +59,17 @@ def forthon_case1(cls=Case):
     return c
 
 
-def box2_case(isupgon=0):
+def box2_case(isupgon=0, cls=Case):
     """pyexamples/box2/box2_in.py:12-140: slab 6x6 with a core region (nycore=2), symmetry plane at ix=0, core power
-    boundary condition.  isupgon=0 gives the diffusive-atom variant of the deck (isngon=1); the deck's own inertial
-    atoms (isupgon=1, nhsp=2) are not built yet."""
+    boundary condition.  isupgon=0 gives the diffusive-atom variant of the deck (isngon=1, the d3dHsm-family kernels);
+    isupgon=1 is the deck as it runs (inertial atoms as ion species 2, nhsp=2, box2_in.py:114-131): a Case2 for the general
+    path (include/ue_gen.h)."""
     if isupgon != 0:
-        raise NotImplementedError("box2 with inertial neutrals (isupgon=1)")
+        from .cases2 import box2_inertial_case
+        return box2_inertial_case()
     g = idealgrd(nxleg2=3, nxcore2=3, nycore=2, nysol=4, radx=4.0e-2, rad0=0.0, radm=-1.0e-2, za0=0.0, zax=3.0, zaxpt=2.25,
                  alfyt=-2.0, alfxt=2.76, btfix=2.0, bpolfix=0.2)
-    c = Case(g)
+    c = cls(g)
     b, com = c.bbb, c.com
     com.nxleg = np.array([[0, 3]]); com.nxcore = np.array([[0, 3]])
     com.nysol = np.array([4]); com.nycore = np.array([2])

@@ -45,53 +45,117 @@ def inputex_case(subset="default"):
     return c, yl, gold
 
 
-class Oracle2:
-    """ctypes binding of oracle/libue_oracle2.so (checker only)."""
+def box2_inertial_case():
+    """pyexamples/box2 exactly as its deck runs it (box2_in.py:12-140): the slab of box2_case with INERTIAL atoms -
+    isupgon(1)=1, isngon=0, nhsp=2, ziin=(1,0), cngmom=cmwall=cngtgx=cngtgy=kxn=kyn=0 (box2_in.py:114-131)."""
+    from .cases import box2_case
+    c = box2_case(0, cls=Case2)
+    b, com = c.bbb, c.com
+    b.isupgon = np.zeros_like(b.isupgon); b.isupgon[0] = 1
+    b.isngon = np.zeros_like(b.isngon)
+    com.ngsp = 1; com.nhsp = 2
+    b.ziin[0] = 1; b.ziin[1] = 0
+    b.cngmom = np.zeros_like(np.asarray(b.cngmom, dtype=float)); b.cmwall = np.zeros_like(np.asarray(b.cmwall, dtype=float))
+    b.cngtgx = np.zeros_like(np.asarray(b.cngtgx, dtype=float)); b.cngtgy = np.zeros_like(np.asarray(b.cngtgy, dtype=float))
+    b.kxn = 0.0; b.kyn = 0.0
+    b.isnion = np.asarray(b.isnion).copy(); b.isupon = np.asarray(b.isupon).copy()
+    b.isnion[:2] = 1; b.isupon[:2] = 1
+    c.setup()
+    return c
 
-    def __init__(self, path=None):
-        here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-        self.lib = C.CDLL(path or os.path.join(here, "oracle", "libue_oracle2.so"))
-        self.lib.ue_or2_last_error.restype = C.c_char_p
-        self.lib.ue_or2_set.argtypes = [C.c_char_p, C.c_void_p, C.c_int64]
+
+def box2_initial_state(c):
+    """restart=0 profiles of ueinit for a half-space slab (bbb/odesetup.m:1355-1452): densities nibeg(ifld)*proffacy, both
+    parallel velocities sqrt(te(0,0)/mi(1))*proffacx*proffacy with up(nx+1)=up(nx), te = ttbeg*proffacx*proffacy, ti = tscal*te."""
+    b, com = c.bbb, c.com
+    nx, ny = com.nx, com.ny
+    IY, IX = np.meshgrid(np.arange(ny + 2), np.arange(nx + 2), indexing="ij")
+    px = (nx + 3 - IX) / float(nx + 3)
+    py = (ny + 3 - IY) / float(ny + 3)
+    ttbeg = float(b.tinit) * b.ev if "tinit" in b else 40.0 * b.ev
+    te = ttbeg * px * py
+    ti = float(b.tscal) * ttbeg * px * py
+    ni = [float(b.nibeg[f]) * py for f in range(2)]
+    up = np.sqrt(te[0, 0] / b.mi[0]) * px * py
+    up[:, nx + 1] = up[:, nx]
+    return c.set_state2(ni, [up, up.copy()], te, ti, tg=np.full_like(te, float(b.tscal) * ttbeg))
+
+
+class Lib2:
+    """ctypes binding of one library that exports the generic-setter API <prefix>clear/set/init/step_params/pandf1/jac_calc/
+    get_plane/last_error: the product's general path (libuegpu.so, prefix ue_gen_, include/ue_gen.h), its host build for the
+    CPU logic check (tests/hostcheck, ue_genh_) or the oracle (oracle/libue_oracle2.so, ue_or2_)."""
+
+    def __init__(self, path, prefix):
+        self.lib = C.CDLL(path)
+        self.prefix = prefix
+        self._f("last_error").restype = C.c_char_p
+        self._f("set").argtypes = [C.c_char_p, C.c_void_p, C.c_int64]
+
+    def _f(self, name):
+        return getattr(self.lib, self.prefix + name)
 
     def _ck(self, rc, what):
         if rc != 0:
-            raise RuntimeError("%s failed (%d): %s" % (what, rc, self.lib.ue_or2_last_error().decode()))
+            raise RuntimeError("%s failed (%d): %s" % (what, rc, self._f("last_error")().decode()))
 
     def bind(self, c):
         self.c = c
-        self.lib.ue_or2_clear()
+        self._f("clear")()
         self.keep = c.inputs2()
         for k, v in self.keep.items():
-            self.lib.ue_or2_set(k.encode(), v.ctypes.data_as(C.c_void_p), v.size)
-        self._ck(self.lib.ue_or2_init(), "init")
+            self._f("set")(k.encode(), v.ctypes.data_as(C.c_void_p), v.size)
+        self._ck(self._f("init")(), "init")
         self.neq = int(c.bbb.neq); self.NC = (c.com.nx + 2) * (c.com.ny + 2)
         return self
 
     def step_params(self, dtuse, ylodt, su, sf):
         a = [np.ascontiguousarray(x, dtype=np.float64) for x in (dtuse, ylodt, su, sf)]
-        self.lib.ue_or2_step_params.argtypes = [C.c_int64] + [C.c_void_p] * 4
-        self._ck(self.lib.ue_or2_step_params(self.neq, *[x.ctypes.data_as(C.c_void_p) for x in a]), "step_params")
+        self._f("step_params").argtypes = [C.c_int64] + [C.c_void_p] * 4
+        self._ck(self._f("step_params")(self.neq, *[x.ctypes.data_as(C.c_void_p) for x in a]), "step_params")
 
     def pandf1(self, yl, xc=-1, yc=-1, out=None):
         yl = np.ascontiguousarray(yl, dtype=np.float64)
         yd = np.zeros(self.neq) if out is None else out
-        self.lib.ue_or2_pandf1_win.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
-        self._ck(self.lib.ue_or2_pandf1_win(xc, yc, self.neq, yl.ctypes.data_as(C.c_void_p), yd.ctypes.data_as(C.c_void_p)), "pandf1")
+        if xc < 0 and yc < 0:
+            self._f("pandf1").argtypes = [C.c_int64, C.c_double, C.c_void_p, C.c_void_p]
+            self._ck(self._f("pandf1")(self.neq, 0.0, yl.ctypes.data_as(C.c_void_p), yd.ctypes.data_as(C.c_void_p)), "pandf1")
+        else:  # (windowed evaluation: oracle only)
+            self._f("pandf1_win").argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+            self._ck(self._f("pandf1_win")(xc, yc, self.neq, yl.ctypes.data_as(C.c_void_p), yd.ctypes.data_as(C.c_void_p)), "pandf1")
         return yd
 
     def jac_calc(self, yl, f0, ml, mu, nnzmx):
         yl = np.ascontiguousarray(yl, dtype=np.float64)
         y0 = np.zeros(self.neq + 2); y0[: self.neq] = f0[: self.neq]
         jac = np.zeros(nnzmx); ja = np.zeros(nnzmx, dtype=np.int64); ia = np.zeros(self.neq + 1, dtype=np.int64); nnz = C.c_int64(0)
-        self.lib.ue_or2_jac_calc.argtypes = [C.c_int64, C.c_double] + [C.c_void_p] * 2 + [C.c_int64] * 3 + [C.c_void_p] * 3 + [C.POINTER(C.c_int64)]
+        self._f("jac_calc").argtypes = [C.c_int64, C.c_double] + [C.c_void_p] * 2 + [C.c_int64] * 3 + [C.c_void_p] * 3 + [C.POINTER(C.c_int64)]
         P = lambda a: a.ctypes.data_as(C.c_void_p)
-        self._ck(self.lib.ue_or2_jac_calc(self.neq, 0.0, P(yl), P(y0), int(ml), int(mu), int(nnzmx), P(jac), P(ja), P(ia), C.byref(nnz)), "jac_calc")
+        self._ck(self._f("jac_calc")(self.neq, 0.0, P(yl), P(y0), int(ml), int(mu), int(nnzmx), P(jac), P(ja), P(ia), C.byref(nnz)), "jac_calc")
         n = nnz.value
         return jac[:n].copy(), ja[:n].copy(), ia
 
     def plane(self, name):
         out = np.zeros(self.NC)
-        self.lib.ue_or2_get_plane.argtypes = [C.c_char_p, C.c_void_p]
-        self._ck(self.lib.ue_or2_get_plane(name.encode(), out.ctypes.data_as(C.c_void_p)), "get_plane " + name)
+        self._f("get_plane").argtypes = [C.c_char_p, C.c_void_p]
+        self._ck(self._f("get_plane")(name.encode(), out.ctypes.data_as(C.c_void_p)), "get_plane " + name)
         return out.reshape(self.c.com.ny + 2, self.c.com.nx + 2)
+
+
+_HERE = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class Oracle2(Lib2):
+    """oracle/libue_oracle2.so (checker only)."""
+
+    def __init__(self, path=None):
+        super().__init__(path or os.path.join(_HERE, "oracle", "libue_oracle2.so"), "ue_or2_")
+
+
+def load_gen():
+    """The product's general path: libuegpu.so, entry points ue_gen_* (include/ue_gen.h).  Fails loudly if the library is missing;
+    ue_gen_init fails without a CUDA device (there is no CPU fallback)."""
+    path = os.path.join(_HERE, "uedge_b200", "csrc", "libuegpu.so")
+    if not os.path.exists(path):
+        raise RuntimeError("libuegpu.so is not built: run __graft_entry__.build()")
+    return Lib2(path, "ue_gen_")

@@ -1,0 +1,573 @@
+// uedge_b200/csrc/ue_gen.cu — runtime of the GENERAL path (ue_gen_phys.h): C ABI ue_gen_* of include/ue_gen.h.
+//
+//   ue_gen_pandf1   : Pandf1rhs_interface (bbb/oderhs.m:8217-8254): one thread block evaluates the full domain in place
+//                     on the base set of field planes (the reference's module state).
+//   ue_gen_jac_calc : jac_calc_interface (bbb/oderhs.m:8533-8760): ONE WARP PER UNKNOWN.  Each warp owns a private copy
+//                     of the field planes (HBM: NPL x NC doubles per unknown, 180 GB make the copies affordable), perturbs
+//                     its unknown, runs the reference's windowed pandf1 (ranges i1..i8 x j1..j8 around the unknown's cell)
+//                     cooperatively, differences the band against yldot00 and appends the kept elements, rows ascending,
+//                     to its column fragment.  k_gen_count / k_gen_scan / k_gen_fill / k_gen_sortrows then transpose the
+//                     fragments into the reference CSR (csrcsc, svr/svrut4.m:1536-1608: rows in order, columns ascending).
+// The same file builds as plain C++ (-DUE_GEN_HOST, tests/hostcheck): contexts are then single threads and the loop nests
+// run in the reference's order, or reversed with -DUE_GEN_REVERSE.  The host build exists for tests only; the product is
+// the CUDA build and it fails loudly without a device.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "ue_gen_phys.h"
+#include "ue_gen.h"
+
+#if !defined(UE_GEN_HOST)
+#include <cuda_runtime.h>
+#endif
+
+namespace {
+
+typedef std::vector<double> V;
+std::map<std::string, V> IN;  // every named input (host copy)
+std::string g_err;
+std::string g_missing;
+bool g_ready = false;
+
+const char* kMessages[] = {"", "***  ni is negative - calculation stopped", "***  ng is negative - calculation stopped", "isnicore must be 0 or 1",
+                           "recylb < -1 not built", "recyrb < -1 not built"};
+
+// ---- memory: device (product) or host (hostcheck) ----------------------------------------------------------------------
+#if defined(UE_GEN_HOST)
+#define UE_PREFIX(x) ue_genh_##x
+double* mem_alloc(size_t n) { return (double*)std::calloc(std::max<size_t>(n, 1), sizeof(double)); }
+void mem_free(void* p) { std::free(p); }
+bool mem_put(void* d, const void* h, size_t bytes) { std::memcpy(d, h, bytes); return true; }
+bool mem_get(void* h, const void* d, size_t bytes) { std::memcpy(h, d, bytes); return true; }
+#else
+#define UE_PREFIX(x) ue_gen_##x
+bool ck(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  g_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + what;
+  return false;
+}
+double* mem_alloc(size_t n) {
+  void* p = nullptr;
+  if (!ck(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(double)), "cudaMalloc")) return nullptr;
+  cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(double));
+  return (double*)p;
+}
+void mem_free(void* p) { cudaFree(p); }
+bool mem_put(void* d, const void* h, size_t bytes) { return ck(cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice), "cudaMemcpy H2D"); }
+bool mem_get(void* h, const void* d, size_t bytes) { return ck(cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost), "cudaMemcpy D2H"); }
+#endif
+
+std::vector<void*> g_allocs;  // everything init allocated
+std::map<std::string, double*> g_dev;  // uploaded inputs by name
+Gen G;                  // constants + pointers as the evaluation contexts see them (device pointers in the CUDA build)
+Gen* d_G = nullptr;     // the same object in context-visible memory
+double* d_base = nullptr;   // base set of field planes (NPL x NC)
+double* d_priv = nullptr;   // private sets, one per unknown of a chunk
+size_t g_priv_cols = 0;
+double *d_yl = nullptr, *d_yldot = nullptr, *d_y00 = nullptr, *d_ylp = nullptr, *d_wk = nullptr;
+double* d_step = nullptr;   // dtuse | ylodt | suscal | sfscal
+int *d_cnt = nullptr, *d_frow = nullptr, *d_err = nullptr;
+double* d_fval = nullptr;
+int64_t *d_ia = nullptr, *d_ja = nullptr;
+double* d_jac = nullptr;
+int64_t g_nnzmx = 0;
+int NPL = 0;
+int COLCAP = 512;
+V g_last_yl;  // the state the base planes were last evaluated at
+int64_t g_ivmin = 1, g_ivmax = 0;
+
+const V* find(const char* n) { auto it = IN.find(n); return it == IN.end() ? nullptr : &it->second; }
+double SC(const char* n, int k = 0) {
+  const V* v = find(n);
+  if (!v || (int)v->size() <= k) { g_missing += std::string(n) + " "; return 0.; }
+  return (*v)[k];
+}
+// context-visible copy of a named input array (uploaded once)
+const double* ARR(const char* n, size_t need) {
+  const V* v = find(n);
+  if (!v || v->size() < need) { g_missing += std::string(n) + "[" + std::to_string(need) + "] "; return nullptr; }
+  auto it = g_dev.find(n);
+  if (it != g_dev.end()) return it->second;
+  double* d = mem_alloc(v->size());
+  if (!d) return nullptr;
+  g_allocs.push_back(d);
+  mem_put(d, v->data(), v->size() * sizeof(double));
+  g_dev[n] = d;
+  return d;
+}
+void VEC(const char* n, size_t need, double* dst) {
+  const V* v = find(n);
+  if (!v || v->size() < need) { g_missing += std::string(n) + "[" + std::to_string(need) + "] "; return; }
+  for (size_t i = 0; i < need; ++i) dst[i] = (*v)[i];
+}
+
+void free_all() {
+  for (void* p : g_allocs) mem_free(p);
+  g_allocs.clear(); g_dev.clear();
+  d_G = nullptr; d_base = d_priv = d_yl = d_yldot = d_y00 = d_ylp = d_wk = d_step = d_fval = d_jac = nullptr;
+  d_cnt = d_frow = d_err = nullptr; d_ia = d_ja = nullptr;
+  g_priv_cols = 0; g_nnzmx = 0; g_ready = false; g_last_yl.clear();
+}
+template <typename T> T* alloc_as(size_t n) {
+  double* p = mem_alloc((n * sizeof(T) + sizeof(double) - 1) / sizeof(double));
+  if (p) g_allocs.push_back(p);
+  return (T*)p;
+}
+
+// ---- the two evaluation bodies (shared by the kernels and the host build) ----------------------------------------------
+// full-domain residual in place on the context's planes
+HD int eval_full(Gen& g, const double* yl, double* yldot) { return g.pandf1(-1, -1, yl, yldot); }
+
+// one Jacobian column (oderhs.m:8600-8720).  g: private context (planes = private copy of the base set).
+// ylp: private copy of yl (neq+2); wk: private residual (neq); frow/fval: the column's fragment, capacity cap.
+HD int eval_column(Gen& g, const double* base, int npl, int64_t iv, const double* yl, double* ylp, double* wk, const double* yldot00, int64_t ml, int64_t mu,
+                   int cap, int* frow, double* fval, int* cnt) {
+  const int64_t neq = g.neq;
+  const int tid = g.TID();
+  const size_t nslab = (size_t)npl * g.NC;
+  double* priv = g.ne;  // first plane of the slab
+  g.sync();
+  for (size_t k = tid; k < nslab; k += g.nth) priv[k] = base[k];
+  for (int64_t k = tid; k < neq + 2; k += g.nth) ylp[k] = yl[k];
+  for (int64_t k = tid; k < neq; k += g.nth) wk[k] = yldot00[k];
+  g.sync();
+  const int xc = (int)g.igyld[iv - 1], yc = (int)g.igyld[neq + iv - 1];
+  const double yold = yl[iv - 1];
+  const double dyl = g.delpert * (fabs(yold) + g.dylconst / g.suscal[iv - 1]);
+  if (tid == 0) ylp[iv - 1] = yold + dyl;
+  g.sync();
+  const int rc = g.pandf1(xc, yc, ylp, wk);
+  g.sync();
+  if (rc) { if (tid == 0) *cnt = 0; return rc; }
+  const int64_t ii1 = mx(iv - mu, (int64_t)1), ii2 = mn(iv + ml, neq);
+  const bool isphi = g.IDXPHI(xc, yc) == iv - 1;
+  // difference, diagonal terms, clip; NaN marks an element that is not kept (a NaN element fails the clip test as well)
+  for (int64_t ii = ii1 + tid; ii <= ii2; ii += g.nth) {
+    double jacelem = (wk[ii - 1] - yldot00[ii - 1]) / dyl;
+    if (iv == ii) {
+      if (g.ALG(iv - 1) * (1 - g.isbcwdt) == 0) jacelem = jacelem - 1 / g.dtuse[iv - 1];
+      if (isphi) jacelem = jacelem - 1 / g.dtphi;  // oderhs.m:8694-8700
+    }
+    if (g.nufak > 0) if (iv == ii && yl[neq] == 1) jacelem = jacelem - g.nufak;
+    wk[ii - 1] = (fabs(jacelem * g.sfscal[iv - 1]) > g.jaccliplim) ? jacelem : (double)NAN;
+  }
+  g.sync();
+  if (tid == 0) {  // ordered append (rows ascending)
+    int n = 0;
+    for (int64_t ii = ii1; ii <= ii2; ++ii) {
+      const double v = wk[ii - 1];
+      if (v == v) { if (n < cap) { frow[n] = (int)ii; fval[n] = v; } ++n; }
+    }
+    *cnt = n;
+  }
+  return 0;
+}
+
+#if !defined(UE_GEN_HOST)
+// ---- kernels ---------------------------------------------------------------------------------------------------------
+extern __shared__ unsigned char g_smem[];
+__device__ void load_ctx(Gen* dst, const Gen* src, int tid, int nth) {  // word-wise copy of the constant part into shared memory
+  const int nw = (int)(sizeof(Gen) / sizeof(int));
+  for (int k = tid; k < nw; k += nth) ((int*)dst)[k] = ((const int*)src)[k];
+}
+__global__ void k_gen_full(const Gen* gsrc, double* base, const double* yl, double* yldot, int* err) {
+  Gen* g = (Gen*)g_smem;
+  load_ctx(g, gsrc, threadIdx.x, blockDim.x);
+  __syncthreads();
+  if (threadIdx.x == 0) { g->nth = blockDim.x; g->errc = 0; g->assign_planes(base); }
+  __syncthreads();
+  const int rc = eval_full(*g, yl, yldot);
+  if (rc && threadIdx.x == 0) { err[0] = rc; err[1] = g->errc; }
+}
+// one warp per unknown of the chunk [iv0, iv0 + ncol): every warp has its own context (shared memory) and its own planes
+__global__ void k_gen_cols(const Gen* gsrc, const double* base, double* priv, int npl, int64_t iv0, int ncol, const double* yl, double* ylp, double* wk,
+                           const double* yldot00, int64_t ml, int64_t mu, int cap, int* frow, double* fval, int* cnt, int* err) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Gen* g = (Gen*)g_smem + warp;
+  load_ctx(g, gsrc, lane, 32);
+  __syncwarp();
+  const int c = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (c >= ncol) return;
+  const size_t nslab = (size_t)npl * g->NC;
+  if (lane == 0) { g->nth = 32; g->errc = 0; g->assign_planes(priv + (size_t)c * nslab); }
+  __syncwarp();
+  const int64_t iv = iv0 + c;
+  const int64_t neq = g->neq;
+  const int rc = eval_column(*g, base, npl, iv, yl, ylp + (size_t)c * (neq + 2), wk + (size_t)c * neq, yldot00, ml, mu, cap, frow + (size_t)(iv - 1) * cap,
+                             fval + (size_t)(iv - 1) * cap, cnt + (iv - 1));
+  __syncwarp();
+  if (rc && lane == 0) { err[0] = rc; err[1] = g->errc; }
+  if (lane == 0 && cnt[iv - 1] > cap) err[2] = cnt[iv - 1];
+}
+// CSC fragments -> CSR: entries per row, exclusive scan, ordered fill (one thread per ROW walks the columns that can reach it)
+__global__ void k_gen_count(int64_t neq, int cap, const int* cnt, const int* frow, int* rowcnt) {
+  const int64_t iv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (iv >= neq) return;
+  const int n = min(cnt[iv], cap);
+  for (int k = 0; k < n; ++k) atomicAdd(&rowcnt[frow[iv * cap + k] - 1], 1);
+}
+__global__ void k_gen_scan(int64_t neq, const int* rowcnt, int64_t* ia, int* cursor) {  // one block
+  __shared__ long long carry;
+  __shared__ long long part[1024];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t b0 = 0; b0 < neq; b0 += blockDim.x) {
+    const int64_t i = b0 + threadIdx.x;
+    const long long v = i < neq ? rowcnt[i] : 0;
+    part[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < (int)blockDim.x; off <<= 1) {
+      const long long t = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+      __syncthreads();
+      part[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < neq) { ia[i] = carry + part[threadIdx.x] - v + 1; cursor[i] = 0; }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry += part[threadIdx.x];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) ia[neq] = carry + 1;
+}
+// scatter by row (cursor atomics), then every row is put in ascending column order by one thread (rows hold <= ~100 entries)
+__global__ void k_gen_fill(int64_t neq, int cap, const int* cnt, const int* frow, const double* fval, const int64_t* ia, int* cursor, int64_t nnzmx, double* jac, int64_t* ja) {
+  const int64_t iv = blockIdx.x + 1;
+  const int n = min(cnt[iv - 1], cap);
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    const int r = frow[(iv - 1) * cap + k];
+    const int64_t pos = ia[r - 1] - 1 + atomicAdd(&cursor[r - 1], 1);
+    if (pos < nnzmx) { jac[pos] = fval[(iv - 1) * cap + k]; ja[pos] = iv; }
+  }
+}
+__global__ void k_gen_sortrows(int64_t neq, const int64_t* ia, int64_t nnzmx, double* jac, int64_t* ja) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= neq) return;
+  const int64_t a = ia[r] - 1, b = min(ia[r + 1] - 1, nnzmx);
+  for (int64_t i = a + 1; i < b; ++i) {
+    const int64_t cj = ja[i]; const double cv = jac[i];
+    int64_t j = i - 1;
+    while (j >= a && ja[j] > cj) { ja[j + 1] = ja[j]; jac[j + 1] = jac[j]; --j; }
+    ja[j + 1] = cj; jac[j + 1] = cv;
+  }
+}
+#endif
+
+int report(int rc, int errc) {
+  if (errc > 0 && errc < (int)(sizeof(kMessages) / sizeof(kMessages[0]))) g_err = kMessages[errc];
+  else g_err = "pandf1 failed";
+  return rc;
+}
+
+int init_all() {
+  g_missing.clear();
+  free_all();
+  Gen& g = G;
+  std::memset((void*)&g, 0, sizeof(Gen));
+  auto I = [&](const char* n, int k = 0) { return (int)std::llround(SC(n, k)); };
+  g.nx = I("nx"); g.ny = I("ny"); g.NXS = g.nx + 2; g.NC = g.NXS * (g.ny + 2);
+  g.nisp = I("nisp"); g.nusp = I("nusp"); g.ngsp = I("ngsp"); g.nhsp = I("nhsp"); g.neq = (int64_t)std::llround(SC("neq"));
+  if (!g_missing.empty()) { g_err = "missing inputs: " + g_missing; return -1; }
+  if (g.nisp < 1 || g.nisp > 2 || g.nusp > g.nisp || g.ngsp != 1) { g_err = "nisp must be 1 or 2 (hydrogen ions + inertial atoms), ngsp 1"; return -5; }
+  g.nfsp = g.nisp;
+  g.ixpt1 = I("ixpt1"); g.ixpt2 = I("ixpt2"); g.iysptrx1 = I("iysptrx1"); g.iysptrx2 = I("iysptrx2"); g.iysptrx = I("iysptrx"); g.ixlb = I("ixlb"); g.ixrb = I("ixrb"); g.ixmp = I("ixmp");
+  g.xlinc = I("xlinc"); g.xrinc = I("xrinc"); g.yinc = I("yinc"); g.isjaccorall = I("isjaccorall");
+  g.methn = I("methn"); g.methu = I("methu"); g.methe = I("methe"); g.methi = I("methi"); g.methg = I("methg");
+#define GI(n) g.n = I(#n);
+  GI(isnonog) GI(isphion) GI(isphiofft) GI(ineudif) GI(isflxvar) GI(isrscalf) GI(isbcwdt) GI(icnuiz) GI(icnucx) GI(isrecmon) GI(ingb) GI(inflbg) GI(isgasdc) GI(isdifxg_aug) GI(isdifyg_aug)
+  GI(isvylog) GI(isgxvon) GI(convis) GI(concap) GI(isflxlde) GI(isflxldi) GI(isplflxl) GI(inkxc) GI(isgpye) GI(ishavisy) GI(isvhyha) GI(islnlamcon) GI(isnupdot1sd) GI(iteb) GI(istabon)
+  GI(ifxnsgi) GI(iflcore) GI(ifluxni) GI(isrefluxclip) GI(ibctepl) GI(ibctipl) GI(ibctepr) GI(ibctipr) GI(isbohmms) GI(isextrnp) GI(isextrnpf) GI(isextrtpf) GI(isextrngc) GI(isextrnw)
+  GI(isextrtw) GI(isnfmiy) GI(isybdrywd) GI(isnewpot) GI(jhswitch) GI(isfeexpl0) GI(isfeixpl0) GI(isintlog) GI(iskaplex) GI(isexunif) GI(isfdiax) GI(isugfm1side) GI(isvisxn_old) GI(isteon) GI(istion)
+#undef GI
+  g.isupgon = I("isupgon", 0); g.isngon = I("isngon", 0); g.istgon = I("istgon", 0); g.isfixlb = I("isfixlb", 0); g.isfixrb = I("isfixrb", 0); g.newbcl = I("newbcl", 0); g.newbcr = I("newbcr", 0);
+  g.isngcore1 = I("isngcore", 0);
+  for (int f = 0; f < 2; ++f) { g.isnicore[f] = I("isnicore", f); g.isupcore[f] = I("isupcore", f); g.isupss[f] = I("isupss", f); g.isnion[f] = I("isnion", f); g.isupon[f] = I("isupon", f); }
+  g.ev = SC("ev"); g.qe = SC("qe"); g.me = SC("me"); g.mp = SC("mp"); g.pi_ = SC("pi"); g.cutlo = SC("cutlo"); g.rt8opi = SC("rt8opi");
+#define GR(n) g.n = SC(#n);
+  GR(temin) GR(tgmin) GR(nnorm) GR(ennorm) GR(temp0) GR(vpnorm) GR(lnlam) GR(cfnus_i) GR(cfnus_e) GR(fcdif) GR(cthe) GR(flalftf) GR(cfnetap) GR(chioniz) GR(sigvi_floor) GR(cne_sgvi) GR(cnuiz)
+  GR(cfrecom) GR(cfdiss) GR(cnucx) GR(sigcx) GR(rnn2cx) GR(fnuizx) GR(fnucxx) GR(fnnuiz) GR(cvgp) GR(oldseec) GR(cpgx) GR(fracvgpgp) GR(fluxfacy) GR(coef) GR(afix) GR(flalfv) GR(flgamv) GR(kxe) GR(kxi)
+  GR(ce) GR(ci) GR(rkxecore) GR(kxicore) GR(kye) GR(kyi) GR(kyet) GR(kyit) GR(ckyet) GR(ckyit) GR(lmfplim) GR(alfkxi) GR(alfkxe) GR(flalfi) GR(flalfe) GR(flalfipl) GR(flalfepl) GR(lxtimax) GR(lxtemax)
+  GR(tdiflim) GR(cftiexclg) GR(cfneut) GR(cfneutsor_ei) GR(cfneutsor_ee) GR(cfneutsor_ni) GR(cfneutsor_mi) GR(cfneutdiv) GR(cfneutdiv_fng) GR(cfneutdiv_fmg) GR(kxn) GR(kyn) GR(feqp) GR(alfeqp) GR(cnfx) GR(cnfy)
+  GR(cnsor) GR(cmfx) GR(cmfy) GR(cfaccony) GR(fac2sp) GR(cfmsor) GR(flgam) GR(cfcvte) GR(cfcvti) GR(cfjhf) GR(cfloye) GR(cfloyi) GR(kye4order) GR(kyi4order) GR(bcee) GR(bcei) GR(chradi) GR(chradr)
+  GR(ebind) GR(ediss) GR(eion) GR(ctsor) GR(ceisor) GR(ccoldsor) GR(cfvisx) GR(cfvisy) GR(upvhflr) GR(tibg) GR(pwribkg_c) GR(cflbg) GR(difcng) GR(alftng) GR(gcfacgx) GR(gcfacgy) GR(flgamg) GR(cngsor)
+  GR(nurlxn) GR(nurlxu) GR(nurlxe) GR(nurlxi) GR(nurlxg) GR(nurlxp) GR(tcoree) GR(tcorei) GR(pcoree) GR(pcorei) GR(sygytotc) GR(csfacti) GR(cfueb) GR(cgpld) GR(cmneut) GR(eedisspl) GR(eidisspl) GR(cmntgpl)
+  GR(ckinfl) GR(isoldalbarea) GR(tbmin) GR(nufak) GR(dtreal) GR(dtphi) GR(dylconst) GR(jaccliplim) GR(kelhihg) GR(kelhghg) GR(lgvmax) GR(flgamvg) GR(cfvisxn) GR(cfvisyn) GR(flgamtg) GR(cfupcx) GR(cfticx)
+  GR(cfnidh) GR(cfnidh2) GR(cfnidhdis) GR(cfnidhgy) GR(cfnidhg2) GR(cftgeqp) GR(flalftxy) GR(flalfgnx) GR(flalfgny) GR(nlimgx) GR(nlimgy) GR(cfloxiplt) GR(cfloygwall) GR(cfjve) GR(rsigpl) GR(rsigplcore)
+  GR(bcen) GR(cfqym) GR(cfqydt) GR(cfqyao) GR(cfsigm)
+#undef GR
+  g.erad = SC("erad"); g.delpert = SC("del");
+  g.sigma1_ = SC("sigma1"); g.frfqpn_ = SC("frfqpn"); g.cffqpsat_ = SC("cffqpsat"); g.exjbdry_ = SC("exjbdry"); g.rnewpot_ = SC("rnewpot"); g.cfqyae_ = SC("cfqyae"); g.cfqyai_ = SC("cfqyai");
+  g.cfgpijr_ = SC("cfgpijr"); g.sigbar0_ = SC("sigbar0"); g.r0slab_ = SC("r0slab"); g.dx0_ = SC("dx0"); g.nfqya0core_ = I("nfqya0core"); g.nfqya0pf_ = I("nfqya0pf"); g.nfqya0ow_ = I("nfqya0ow");
+  g.kappamx_ = SC("kappamx"); g.cfkincor_ = SC("cfkincor"); g.gamsec_ = SC("gamsec"); g.cgengpl_ = SC("cgengpl"); g.cgmompl_ = SC("cgmompl"); g.nglfix_ = SC("nglfix"); g.ngrfix_ = SC("ngrfix");
+  g.eedisspr_ = SC("eedisspr"); g.eidisspr_ = SC("eidisspr"); g.cmntgpr_ = SC("cmntgpr"); g.phintewi_ = SC("phintewi"); g.phintewo_ = SC("phintewo");
+  const size_t ns = g.nisp;
+#define GV(n) VEC(#n, ns, g.n);
+  GV(mi) GV(zi) GV(n0) GV(vcony) GV(difpr) GV(difni) GV(difni2) GV(difpr2) GV(difax) GV(travis) GV(parvis) GV(nlimix) GV(nlimiy) GV(dif4order) GV(cpiup) GV(cfvgpx) GV(cfvgpy) GV(cfvcsx) GV(cfvcsy) GV(cfvisxy)
+  GV(cngmom) GV(cmwall) GV(ncore) GV(upcore) GV(curcore) GV(csfaclb) GV(csfacrb) GV(nwimin) GV(nwomin)
+#undef GV
+  VEC("fnorm", g.nusp, g.fnorm); VEC("difutm", ns, g.difutm_);
+  VEC("n0g", 1, g.n0g_); VEC("mg", 1, g.mg_); VEC("ngbackg", 1, g.ngbackg_); VEC("cngtgx", 1, g.cngtgx); VEC("cngtgy", 1, g.cngtgy); VEC("cdifg", 1, g.cdifg); VEC("lgmax", 1, g.lgmax); VEC("lgtmax", 2, g.lgtmax);
+  VEC("rld2dxg", 1, g.rld2dxg); VEC("rld2dyg", 1, g.rld2dyg); VEC("cngflox", 1, g.cngflox); VEC("cngfloy", 1, g.cngfloy); VEC("rtg2ti", 1, g.rtg2ti); VEC("tgas", 1, g.tgas); VEC("istgcon", 1, g.istgcon);
+  VEC("keligig", 1, g.keligig); VEC("cngfx", 1, g.cngfx_); VEC("cngfy", 1, g.cngfy_); VEC("ngcore", 1, g.ngcore); VEC("albedoc", 1, g.albedoc); VEC("recycp", 1, g.recycp);
+  if (g.ineudif != 1 && g.ineudif != 2) { g_err = "ineudif must be 1 or 2"; return -5; }
+  if (g.ineudif == 1 && (g.isnonog != 0 || g.isupgon != 0)) { g_err = "ineudif=1 is built for orthogonal meshes and diffusive atoms only"; return -5; }
+  const size_t nc = g.NC, nxs = g.NXS, nys = g.ny + 2;
+#define GP(n) g.n = ARR(#n, nc);
+  GP(vol) GP(gx) GP(gy) GP(gxf) GP(gyf) GP(gxc) GP(gyc) GP(sx) GP(sxnp) GP(sy) GP(rr) GP(rrv) GP(volv) GP(syv) GP(dxnog) GP(dynog) GP(btot) GP(rbfbt) GP(rbfbt2) GP(lcone) GP(lconi) GP(angfx) GP(ngfix)
+#undef GP
+  g.b_c = ARR("b_c", nc); g.rm_c = ARR("rm_c", nc);
+  g.ixm1d = ARR("ixm1", nc); g.ixp1d = ARR("ixp1", nc); g.isxptyd = ARR("isxpty", nc); g.isxptxd = ARR("isxptx", nc);
+  for (int k = 0; k < 2; ++k) {
+    auto S2 = [&](const char* n) { const double* p = ARR(n, 2 * nc); return p ? p + (size_t)k * nc : nullptr; };
+    g.fxm[k] = S2("fxm"); g.fx0[k] = S2("fx0"); g.fxp[k] = S2("fxp"); g.fxmy[k] = S2("fxmy"); g.fxpy[k] = S2("fxpy"); g.fym[k] = S2("fym"); g.fy0[k] = S2("fy0"); g.fyp[k] = S2("fyp");
+    g.fymx[k] = S2("fymx"); g.fypx[k] = S2("fypx"); g.fymv[k] = S2("fymv"); g.fy0v[k] = S2("fy0v"); g.fypv[k] = S2("fypv"); g.fymxv[k] = S2("fymxv"); g.fypxv[k] = S2("fypxv");
+  }
+#define GLX(n) g.n = ARR(#n, nxs);
+#define GLY(n) g.n = ARR(#n, nys);
+  GLX(fgtdx) GLY(fgtdy) GLX(flalfea) GLX(flalfia) GLX(flalfva) GLX(flalfgxa) GLX(flalfgxya) GLY(flalfgya) GLX(flalfvgxa) GLY(flalfvgya) GLX(flalfvgxya) GLX(flalftgxa) GLY(flalftgya) GLY(yyf)
+  GLX(nwalli) GLX(nwallo) GLX(lytepf) GLX(lytewc) GLX(lytipf) GLX(lytiwc) GLX(lynipf) GLX(lyniwc) GLX(tewalli) GLX(tiwalli) GLX(tewallo) GLX(tiwallo) GLY(recylb) GLY(recyrb) GLY(alblb) GLY(albrb)
+  GLX(recycwot) GLX(recycwit) GLX(fngysi) GLX(fngyso) GLX(fngyi_use) GLX(fngyo_use) GLY(fngxslb) GLY(fngxsrb) GLY(fngxlb_use) GLY(fngxrb_use) GLX(albedoi) GLX(albedoo)
+  GLX(istepfcix) GLX(istipfcix) GLX(istewcix) GLX(istiwcix) GLX(matwalli) GLX(matwallo) GLX(isixcore)
+  GLY(recycmlb) GLY(recycmrb) GLX(lyphiix1) GLX(lyphiix2) GLX(iphibcwoix) GLX(iphibcwiix) GLY(phi0l) GLY(phi0r) GLY(bctype)
+#undef GLX
+#undef GLY
+  g.lyup_ = ARR("lyup", 2);
+  g.isnwconiix = ARR("isnwconiix", 2 * nxs); g.isnwconoix = ARR("isnwconoix", 2 * nxs); g.isupwiix = ARR("isupwiix", 2 * nxs); g.isupwoix = ARR("isupwoix", 2 * nxs);
+  g.iseqalgd = ARR("iseqalg", (size_t)g.neq); g.igyld = ARR("igyl", (size_t)(2 * g.neq));
+  for (int f = 0; f < 2; ++f) {
+    const double *pn = ARR("idxn", 2 * nc), *pu = ARR("idxu", 2 * nc);
+    g.idxn_[f] = pn ? pn + (size_t)f * nc : nullptr; g.idxu_[f] = pu ? pu + (size_t)f * nc : nullptr;
+  }
+  g.idxte_ = ARR("idxte", nc); g.idxti_ = ARR("idxti", nc); g.idxg_ = ARR("idxg", nc); g.idxphi_ = ARR("idxphi", nc);
+  if (!g_missing.empty()) { g_err = "missing inputs: " + g_missing; return -1; }
+  if (!g_err.empty()) return -10;
+  g.iigsp = -1;
+  if (g.isupgon == 1) { if (g.nisp != 2 || g.zi[1] != 0.) { g_err = "isupgon=1 needs nisp=2 with zi(2)=0"; return -5; } g.iigsp = 1; }
+  // switches outside what is built
+  struct { const char* n; double want; } must[] = {{"isimpon", 0}, {"ismcnon", 0}, {"ishymol", 0}, {"ifixsrc", 0}, {"ifixpsor", 0}, {"isupdrag", 0}, {"isofric", 0}, {"ishosor", 0}, {"islimon", 0}, {"isudsym", 0},
+                                                   {"nxomit", 0}, {"isbohmcalc", 1}, {"isdifbetap", 0}, {"cfyef", 0}, {"cf2ef", 0}, {"cfybf", 0}, {"cf2bf", 0}, {"cfydd", 0}, {"cf2dd", 0}, {"cfrd", 0}, {"cfbgt", 0},
+                                                   {"cfvycf", 0}, {"cfvycr", 0}, {"cftef", 0}, {"cftdd", 0}, {"cfqybf", 0}, {"cfq2bf", 0}, {"cfjp2", 0}, {"cfjpy", 0}, {"cfqyn", 0}, {"cfeta1", 0}, {"cfrtaue", 0},
+                                                   {"cfcl_e", 0}, {"cfcl_i", 0}, {"facbni", 0}, {"facbup", 0}, {"facbee", 0}, {"facbei", 0}, {"rtauxfac", 0}, {"ispsorave", 0}, {"iseesorave", 0}, {"cfvisxneov", 0},
+                                                   {"cfvisxneoq", 0}, {"cfvyavis", 0}, {"cfanomvisxg", 0}, {"cfanomvisyg", 0}, {"isnewpot", 0}, {"jhswitch", 0}, {"isnfmiy", 0}, {"isybdrywd", 0}, {"isfeexpl0", 0},
+                                                   {"isfeixpl0", 0}, {"cfeexdbo", 0}, {"cfeixdbo", 0}, {"cfniybbo", 0}, {"cfniydbo", 0}, {"cfeeybbo", 0}, {"cfeeydbo", 0}, {"isextrnp", 0}, {"isextrnpf", 0},
+                                                   {"isextrtpf", 0}, {"isextrngc", 0}, {"isextrnw", 0}, {"isextrtw", 0}, {"isbohmms", 0}, {"ibctepl", 1}, {"ibctipl", 1}, {"ibctepr", 1}, {"ibctipr", 1}, {"isfixrb", 0},
+                                                   {"is1D_gbx", 0}, {"isnglf", 0}, {"iszeffcon", 0}, {"isup1up2", 0}, {"isflxvar", 0}, {"istgon", 0}, {"isphilbc", 0}, {"isphirbc", 0}, {"ikapmod", 0},
+                                                   {"isfqpave", 0}, {"isphicore0", 0}, {"iskaprex", 0}};
+  for (auto& m : must) {
+    const V* v = find(m.n);
+    if (!v) { g_err = std::string("missing input ") + m.n; return -1; }
+    if ((*v)[0] != m.want) { g_err = std::string("switch outside the built set: ") + m.n; return -5; }
+  }
+  if (g.fnnuiz != 1.) { g_err = "fnnuiz must be 1"; return -5; }
+  if (SC("l_parloss") <= 1e9) { g_err = "l_parloss<=1e9 (nuvl) not built"; return -5; }
+  if (g.isfixlb != 0 && g.isfixlb != 2) { g_err = "isfixlb must be 0 or 2"; return -5; }
+  if (g.istabon != 0 && g.istabon != 7 && g.istabon != 10) { g_err = "istabon must be 0, 7 or 10"; return -5; }
+  g.mpe = I("mpe"); g.mpd = I("mpd");
+  if (g.istabon == 10) {
+    const size_t nt = (size_t)g.mpe * g.mpd;
+    g.wsveh = ARR("wsveh", nt); g.wsveh0 = ARR("wsveh0", nt); g.welms1 = ARR("welms1", nt); g.welms2 = ARR("welms2", nt);
+    V dk(g.mpd), ek(g.mpe);
+    dk[0] = 16.0; for (int j = 1; j < g.mpd; ++j) dk[j] = dk[j - 1] + 0.5;
+    g.rldmin = dk[0]; g.rldmax = dk[g.mpd - 1]; g.deldkpt = (g.rldmax - g.rldmin) / double(g.mpd - 1);
+    ek[0] = -1.2 * ue_log(10.0); for (int j = 1; j < g.mpe; ++j) ek[j] = ek[j - 1] + 0.1 * ue_log(10.0);
+    g.rlemin = ek[0]; g.rlemax = ek[g.mpe - 1]; g.delekpt = (g.rlemax - g.rlemin) / double(g.mpe - 1);
+    IN["__dkpt"] = dk; IN["__ekpt"] = ek;
+    g.dkpt = ARR("__dkpt", g.mpd); g.ekpt = ARR("__ekpt", g.mpe);
+  }
+  if (!g_missing.empty()) { g_err = "missing inputs: " + g_missing; return -1; }
+  // ---- field planes: base set, initial contents (fields of equations that are off keep what the host left in them)
+  NPL = Gen::nplanes();
+  const size_t nslab = (size_t)NPL * nc;
+  V slab(nslab, 0.0);
+  g.assign_planes(slab.data());
+  auto init_plane = [&](const char* n, double* dst) { const V* v = find(n); if (v && v->size() >= nc) std::copy(v->begin(), v->begin() + nc, dst); };
+  init_plane("ni1_init", g.ni[0]); init_plane("ni2_init", g.ni[1]); init_plane("up1_init", g.up[0]); init_plane("up2_init", g.up[1]);
+  init_plane("te_init", g.te); init_plane("ti_init", g.ti); init_plane("ng_init", g.ng); init_plane("tg_init", g.tg); init_plane("phi_init", g.phi);
+  if (g.isngon != 1 && g.isupgon != 1) { const V* v = find("ngfix"); std::copy(v->begin(), v->begin() + nc, g.ng); }
+  for (int f = 0; f < g.nisp; ++f) for (size_t c = 0; c < nc; ++c) g.nm[f][c] = g.ni[f][c] * g.mi[f];
+  d_base = mem_alloc(nslab); if (!d_base) return -10; g_allocs.push_back(d_base);
+  if (!mem_put(d_base, slab.data(), nslab * sizeof(double))) return -10;
+  g.assign_planes(d_base);
+  const size_t neq = (size_t)g.neq;
+  d_step = mem_alloc(4 * neq); if (!d_step) return -10; g_allocs.push_back(d_step);
+  {
+    V st(4 * neq, 1.0);
+    for (size_t i = 0; i < neq; ++i) { st[i] = 1e20; st[neq + i] = 0.; }
+    mem_put(d_step, st.data(), st.size() * sizeof(double));
+  }
+  g.dtuse = d_step; g.ylodt = d_step + neq; g.suscal = d_step + 2 * neq; g.sfscal = d_step + 3 * neq;
+  d_yl = mem_alloc(neq + 2); d_yldot = mem_alloc(neq); d_y00 = mem_alloc(neq);
+  if (!d_yl || !d_yldot || !d_y00) return -10;
+  g_allocs.push_back(d_yl); g_allocs.push_back(d_yldot); g_allocs.push_back(d_y00);
+  d_err = alloc_as<int>(4);
+  d_G = alloc_as<Gen>(1);
+  if (!d_err || !d_G) return -10;
+  g.nth = 1; g.errc = 0;
+  if (!mem_put(d_G, &g, sizeof(Gen))) return -10;
+  if (const char* e = getenv("UE_GEN_COLCAP")) COLCAP = std::max(16, atoi(e));
+  g_ivmin = 1; g_ivmax = g.neq;
+  g_ready = true;
+  return 0;
+}
+
+int run_full(const double* yl_host, double* yldot_host) {
+  const size_t neq = (size_t)G.neq;
+  if (!mem_put(d_yl, yl_host, (neq + 2) * sizeof(double))) return -10;
+#if defined(UE_GEN_HOST)
+  Gen me = G; me.nth = 1; me.errc = 0;
+  const int rc = eval_full(me, d_yl, d_yldot);
+  if (rc) return report(rc, me.errc);
+#else
+  int zero[4] = {0, 0, 0, 0};
+  if (!mem_put(d_err, zero, sizeof zero)) return -10;
+  k_gen_full<<<1, 256, sizeof(Gen)>>>(d_G, d_base, d_yl, d_yldot, d_err);
+  if (!ck(cudaGetLastError(), "k_gen_full launch") || !ck(cudaDeviceSynchronize(), "k_gen_full")) return -10;
+  int e[4];
+  if (!mem_get(e, d_err, sizeof e)) return -10;
+  if (e[0]) return report(e[0], e[1]);
+#endif
+  if (yldot_host && !mem_get(yldot_host, d_yldot, neq * sizeof(double))) return -10;
+  g_last_yl.assign(yl_host, yl_host + neq + 2);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+int UE_PREFIX(clear)(void) { IN.clear(); return 0; }
+int UE_PREFIX(set)(const char* n, const double* d, int64_t k) {
+  if (!n || (!d && k > 0) || k < 0) { g_err = "set: null name / data"; return -1; }
+  IN[n].assign(d, d + k);
+  return 0;
+}
+const char* UE_PREFIX(last_error)(void) { return g_err.c_str(); }
+int UE_PREFIX(init)(void) {
+  g_err.clear();
+#if !defined(UE_GEN_HOST)
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_err = "no CUDA device: the general path has no CPU fallback"; return -10; }
+#endif
+  const int rc = init_all();
+  if (rc) free_all();
+  return rc;
+}
+int UE_PREFIX(finalize)(void) { free_all(); return 0; }
+int UE_PREFIX(step_params)(int64_t n, const double* dt, const double* yo, const double* su, const double* sf) {
+  if (!g_ready) { g_err = "init not called"; return -1; }
+  if (n != G.neq || !dt || !yo || !su || !sf) { g_err = "step_params: neq mismatch or null pointer"; return -1; }
+  const size_t neq = (size_t)n;
+  return (mem_put(d_step, dt, neq * 8) && mem_put(d_step + neq, yo, neq * 8) && mem_put(d_step + 2 * neq, su, neq * 8) && mem_put(d_step + 3 * neq, sf, neq * 8)) ? 0 : -10;
+}
+int UE_PREFIX(pandf1)(int64_t n, double time, const double* yl, double* yldot) {
+  (void)time;
+  if (!g_ready) { g_err = "init not called"; return -1; }
+  if (n != G.neq || !yl || !yldot) { g_err = "pandf1: neq mismatch or null pointer"; return -1; }
+  return run_full(yl, yldot);
+}
+int UE_PREFIX(set_column_range)(int64_t ivmin, int64_t ivmax) {
+  if (!g_ready) { g_err = "init not called"; return -1; }
+  g_ivmin = std::max<int64_t>(1, ivmin); g_ivmax = std::min<int64_t>(G.neq, ivmax);
+  return 0;
+}
+int UE_PREFIX(jac_calc)(int64_t n, double t, const double* yl, const double* yldot00, int64_t ml, int64_t mu, int64_t nnzmx, double* jac, int64_t* ja, int64_t* ia, int64_t* nnz_out) {
+  (void)t;
+  if (!g_ready) { g_err = "init not called"; return -1; }
+  if (n != G.neq || !yl || !yldot00 || !jac || !ja || !ia || !nnz_out) { g_err = "jac_calc: neq mismatch or null pointer"; return -1; }
+  const size_t neq = (size_t)n;
+  // the base planes must be those of yl (the reference calls jac_calc right after the residual at the same state)
+  if (g_last_yl.size() != neq + 2 || std::memcmp(g_last_yl.data(), yl, (neq + 2) * sizeof(double)) != 0) {
+    const int rc = run_full(yl, nullptr);
+    if (rc) return rc;
+  }
+  if (!mem_put(d_yl, yl, (neq + 2) * 8) || !mem_put(d_y00, yldot00, neq * 8)) return -10;
+  const int cap = COLCAP;
+  const size_t nslab = (size_t)NPL * G.NC;
+  const int64_t ncols_all = std::max<int64_t>(0, g_ivmax - g_ivmin + 1);
+  // private plane sets: as many unknowns at once as fit in 16 GB
+  size_t chunk = (size_t)std::max<int64_t>(1, std::min<int64_t>(ncols_all, (int64_t)((16ull << 30) / (nslab * 8))));
+  if (g_priv_cols < chunk) {
+    d_priv = mem_alloc(chunk * nslab); d_ylp = mem_alloc(chunk * (neq + 2)); d_wk = mem_alloc(chunk * neq);
+    if (!d_priv || !d_ylp || !d_wk) return -10;
+    g_allocs.push_back(d_priv); g_allocs.push_back(d_ylp); g_allocs.push_back(d_wk);
+    g_priv_cols = chunk;
+  }
+  if (!d_cnt) {
+    d_cnt = alloc_as<int>(2 * neq + 2); d_frow = alloc_as<int>(neq * cap); d_fval = mem_alloc(neq * cap);
+    d_ia = alloc_as<int64_t>(neq + 1);
+    if (!d_cnt || !d_frow || !d_fval || !d_ia) return -10;
+    g_allocs.push_back(d_fval);
+  }
+  if (g_nnzmx < nnzmx) {
+    d_jac = mem_alloc((size_t)nnzmx); d_ja = alloc_as<int64_t>((size_t)nnzmx);
+    if (!d_jac || !d_ja) return -10;
+    g_allocs.push_back(d_jac);
+    g_nnzmx = nnzmx;
+  }
+#if defined(UE_GEN_HOST)
+  std::memset(d_cnt, 0, (2 * neq + 2) * sizeof(int));
+  for (int64_t iv = g_ivmin; iv <= g_ivmax; ++iv) {
+    Gen me = G; me.nth = 1; me.errc = 0;
+    me.assign_planes(d_priv);
+    const int rc = eval_column(me, d_base, NPL, iv, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow + (size_t)(iv - 1) * cap, d_fval + (size_t)(iv - 1) * cap, d_cnt + (iv - 1));
+    if (rc) return report(rc, me.errc);
+    if (d_cnt[iv - 1] > cap) { g_err = "column fragment capacity exceeded: set UE_GEN_COLCAP"; return -2; }
+  }
+  // csrcsc (svr/svrut4.m:1536-1608) on the fragments
+  std::vector<int64_t> iao(neq + 1, 0);
+  for (size_t c = 0; c < neq; ++c) for (int k = 0; k < d_cnt[c]; ++k) iao[d_frow[c * cap + k]]++;
+  iao[0] = 1;
+  for (size_t i = 1; i <= neq; ++i) iao[i] += iao[i - 1];
+  const int64_t nnz = iao[neq] - 1;
+  if (nnz > nnzmx) { g_err = "*** jac_calc -- More storage needed for Jacobian. Increase lenpfac."; return -2; }
+  std::vector<int64_t> next(iao.begin(), iao.end() - 1);
+  for (size_t c = 0; c < neq; ++c)
+    for (int k = 0; k < d_cnt[c]; ++k) { const int r = d_frow[c * cap + k]; const int64_t p = next[r - 1]++; jac[p - 1] = d_fval[c * cap + k]; ja[p - 1] = (int64_t)c + 1; }
+  std::copy(iao.begin(), iao.end(), ia);
+  *nnz_out = nnz;
+  return 0;
+#else
+  int zero[4] = {0, 0, 0, 0};
+  if (!mem_put(d_err, zero, sizeof zero)) return -10;
+  if (!ck(cudaMemset(d_cnt, 0, (2 * neq + 2) * sizeof(int)), "memset")) return -10;
+  const int WPB = 4;
+  for (int64_t iv0 = g_ivmin; iv0 <= g_ivmax; iv0 += (int64_t)chunk) {
+    const int ncol = (int)std::min<int64_t>((int64_t)chunk, g_ivmax - iv0 + 1);
+    k_gen_cols<<<(ncol + WPB - 1) / WPB, 32 * WPB, WPB * sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, iv0, ncol, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err);
+    if (!ck(cudaGetLastError(), "k_gen_cols launch")) return -10;
+  }
+  int* rowcnt = d_cnt + neq;
+  k_gen_count<<<(unsigned)((neq + 127) / 128), 128>>>((int64_t)neq, cap, d_cnt, d_frow, rowcnt);
+  k_gen_scan<<<1, 1024>>>((int64_t)neq, rowcnt, d_ia, rowcnt);
+  k_gen_fill<<<(unsigned)neq, 64>>>((int64_t)neq, cap, d_cnt, d_frow, d_fval, d_ia, rowcnt, nnzmx, d_jac, d_ja);
+  k_gen_sortrows<<<(unsigned)((neq + 127) / 128), 128>>>((int64_t)neq, d_ia, nnzmx, d_jac, d_ja);
+  if (!ck(cudaGetLastError(), "CSR kernels launch") || !ck(cudaDeviceSynchronize(), "Jacobian kernels")) return -10;
+  int e[4];
+  if (!mem_get(e, d_err, sizeof e)) return -10;
+  if (e[0]) return report(e[0], e[1]);
+  if (e[2]) { g_err = "column fragment capacity exceeded (" + std::to_string(e[2]) + " entries): set UE_GEN_COLCAP"; return -2; }
+  if (!mem_get(ia, d_ia, (neq + 1) * sizeof(int64_t))) return -10;
+  const int64_t nnz = ia[neq] - 1;
+  if (nnz > nnzmx) { g_err = "*** jac_calc -- More storage needed for Jacobian. Increase lenpfac."; return -2; }
+  if (!mem_get(jac, d_jac, (size_t)nnz * 8) || !mem_get(ja, d_ja, (size_t)nnz * 8)) return -10;
+  *nnz_out = nnz;
+  return 0;
+#endif
+}
+// copy a named intermediate plane of the base set out ("fnix1", "fnix2", "feex", ...)
+int UE_PREFIX(get_plane)(const char* name, double* out) {
+  if (!g_ready || !name || !out) { g_err = "get_plane: not initialised / null pointer"; return -1; }
+  const size_t nc = (size_t)G.NC;
+  size_t k = 0; long found = -1;
+#define P1(x) if (found < 0 && std::strcmp(name, #x) == 0) found = (long)k; k += 1;
+#define P2(x) if (found < 0 && std::strcmp(name, #x "1") == 0) found = (long)k; if (found < 0 && std::strcmp(name, #x "2") == 0) found = (long)k + 1; k += 2;
+  UE_GEN_PLANES(P1, P2)
+#undef P1
+#undef P2
+  if (found < 0) { g_err = std::string("no such plane: ") + name; return -1; }
+  return mem_get(out, d_base + (size_t)found * nc, nc * sizeof(double)) ? 0 : -10;
+}
+}
