@@ -86,6 +86,40 @@ def cpu_baseline(c, ystates, su, budget_s=12.0, nthreads=None):
                 par_eff=r["par_eff"], nnz=r["nnz"])
 
 
+def general_records(steps=10):
+    """The GENERAL path (ue_gen_*, include/ue_gen.h) on the two reference decks it exists for: pyexamples/input_example (8x4
+    non-orthogonal mesh, inertial atoms, potential equation, numvar 7) and pyexamples/box2 as its deck runs it (inertial atoms).
+    Host clock around the C-ABI calls with pageable host buffers (this entry point has no device-buffer variant yet); the CPU
+    figure is the general oracle on one host thread, same step."""
+    from uedge_b200.cases import box2_case
+    from uedge_b200.cases2 import Oracle2, box2_initial_state, inputex_case, load_gen
+    out = {}
+    c1, y1, _ = inputex_case("default")
+    c2 = box2_case(isupgon=1)
+    for name, c, yl in (("input_example", c1, y1), ("box2_inertial_atoms", c2, box2_initial_state(c2))):
+        b = c.bbb
+        g, o = load_gen().bind(c), Oracle2().bind(c)
+        f = g.pandf1(yl); fo = o.pandf1(yl)
+        jg = g.jac_calc(yl, f, b.lbw, b.ubw, b.nnzmx); jo = o.jac_calc(yl, fo, b.lbw, b.ubw, b.nnzmx)
+        same = bool(np.array_equal(f, fo) and all(np.array_equal(p, q) for p, q in zip(jg, jo)))
+        y2 = yl.copy(); y2[: b.neq] *= 1.0 + 1e-9  # alternate two states so that every call evaluates
+        t = time.perf_counter()
+        for i in range(steps):
+            yy = y2 if i & 1 else yl
+            f = g.pandf1(yy); j = g.jac_calc(yy, f, b.lbw, b.ubw, b.nnzmx)
+        tg = (time.perf_counter() - t) / steps
+        t = time.perf_counter()
+        for i in range(steps):
+            g.pandf1(y2 if i & 1 else yl)
+        tr = (time.perf_counter() - t) / steps
+        t = time.perf_counter(); fo = o.pandf1(y2); tro = time.perf_counter() - t
+        t = time.perf_counter(); o.jac_calc(y2, fo, b.lbw, b.ubw, b.nnzmx); tjo = time.perf_counter() - t
+        out[name] = dict(neq=int(b.neq), numvar=int(b.numvar), nnz=len(j[0]), bit_identical_to_oracle=same, e2e_ms_per_step=tg * 1e3, e2e_value=len(j[0]) / tg, unit="nnz/s",
+                         resid_e2e_ms=tr * 1e3, cpu_1thread_ms_per_step=(tro + tjo) * 1e3, cpu_1thread_value=len(j[0]) / (tro + tjo), kernels="k_gen_full, k_gen_cols (one warp per unknown), k_gen_count/scan/fill/sortrows")
+        g._f("finalize")()
+    return out
+
+
 class Gpu:
     """The product library bound to one case on this rank's GPU (through the C ABI only)."""
 
@@ -333,6 +367,7 @@ def main():
             grids[gname] = dict(neq=r["neq"], nnz=r["nnz"], ms_per_step=r["ms_dev"], value=r["nnz"] / (r["ms_dev"] * 1e-3), unit="nnz/s",
                                 e2e_ms_per_step=r["ms_e2e"], e2e_value=r["nnz"] / (r["ms_e2e"] * 1e-3), jac_kernel_ms=r["jac_ms"], resid_kernel_ms=r["res_ms"],
                                 peer_bytes_per_step_this_rank=r["comm_bytes"], gpu_launches=r["launches"])
+    general = general_records() if (rank == 0 and world == 1 and not a.no_grids) else None
     replicas = None
     if world > 1 and split:
         r = measure(name, min(a.steps, 10), 3, world, rank, dist, torch, split=False, full=False, seed=1234 + rank)
@@ -402,6 +437,8 @@ def main():
                 clocks=dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max([s[1] for s in samples] or [0.0]), reasons=reasons_of([s[2] for s in samples])))
     if grids:
         line["grids"] = grids
+    if general:
+        line["general_path"] = general
     if replicas:
         line["replicas"] = replicas
     if cb is not None:

@@ -79,15 +79,17 @@ struct UeStore {
     *it->second = v; seen[name] = true; return 0;
   }
   int set_real_array(const char* name, const double* d, int64_t n) {
+    if (!name || n < 0 || (!d && n > 0)) return -1;  // (a NULL array with n > 0 is refused, not dereferenced)
     auto it = rarr.find(name);
-    if (it == rarr.end() || n < 0) return -1;
+    if (it == rarr.end()) return -1;
     auto& v = rdata[name];
     v.assign(d, d + n);
     *it->second = v.data(); seen[name] = true; return 0;
   }
   int set_int_array(const char* name, const int64_t* d, int64_t n) {
+    if (!name || n < 0 || (!d && n > 0)) return -1;
     auto it = iarr.find(name);
-    if (it == iarr.end() || n < 0) return -1;
+    if (it == iarr.end()) return -1;
     auto& v = idata[name];
     v.assign(d, d + n);
     *it->second = v.data(); seen[name] = true; return 0;
@@ -103,11 +105,27 @@ struct UeStore {
     for (auto& kv : zero_only) if (kv.second != 0.) return kv.first;
     return std::string();
   }
+  // expected length of a 1-D LINE by name: x-lines nx+2, y-lines ny+2, unknown-indexed neq / 2*neq, rate tables mpe*mpd
+  // (only read when istabon = 10).  -1: no fixed length.
+  int64_t line_length(const std::string& n) const {
+    static const char* ylines[] = {"fgtdy", "flalfgya", "yyf", "recylb", "recyrb", "alblb", "albrb", "fngxslb", "fngxsrb", "fngxlb_use", "fngxrb_use"};
+    static const char* tables[] = {"wsveh", "wsveh0", "welms1", "welms2"};
+    for (const char* y : ylines) if (n == y) return p.ny + 2;
+    for (const char* t : tables) if (n == t) return p.istabon == 10 ? (int64_t)p.mpe * p.mpd : -1;
+    if (n == "iseqalg") return p.neq;
+    if (n == "igyl") return 2 * p.neq;
+    return p.nx + 2;
+  }
+  // arrays whose length does not fit the mesh: planes must hold (nx+2)(ny+2) values, lines their length class
   std::string bad_sizes() const {
     std::string s;
     const int64_t ncell = (p.nx + 2) * (p.ny + 2);
-    for (auto& kv : rdata) if (is_plane.at(kv.first) && (int64_t)kv.second.size() != ncell) { s += kv.first; s += ' '; }
-    for (auto& kv : idata) if (is_plane.at(kv.first) && (int64_t)kv.second.size() != ncell) { s += kv.first; s += ' '; }
+    auto check = [&](const std::string& name, int64_t have) {
+      const int64_t want = is_plane.at(name) ? ncell : line_length(name);
+      if (want >= 0 && have != want) { s += name; s += '['; s += std::to_string(have); s += " != "; s += std::to_string(want); s += "] "; }
+    };
+    for (auto& kv : rdata) check(kv.first, (int64_t)kv.second.size());
+    for (auto& kv : idata) check(kv.first, (int64_t)kv.second.size());
     return s;
   }
   int64_t len(const char* name) const {

@@ -1659,7 +1659,7 @@ int ue_ora_init(void) {
   if (!m.empty()) { g_err = "missing inputs: " + m; return -1; }
   nx = (int)P.nx; ny = (int)P.ny; NXS = nx + 2; NC = NXS * (ny + 2); neq = P.neq;
   std::string b = S.bad_sizes();
-  if (!b.empty()) { g_err = "bad plane sizes: " + b; return -1; }
+  if (!b.empty()) { g_err = "bad array sizes (have != expected): " + b; return -1; }
   if (neq != (int64_t)NC * P.numvar) { g_err = "neq != numvar*(nx+2)*(ny+2)"; return -1; }
   int rc = g_o.check_switches();
   if (rc) return rc;

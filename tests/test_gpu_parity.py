@@ -71,6 +71,40 @@ def test_residual_timestep_term(built, isbcwdt):
         lib.set_real("dtreal", 1e20)
 
 
+@pytest.mark.gpu
+def test_time_step_inputs_changed_between_jacobian_and_residual(built):
+    """The host shim sends dtuse / ylodt / dtreal before EVERY residual: set_dt rewrites dtuse and dtreal may
+    change (icntnunk=1) between a Jacobian and the next rhsnk.  A Jacobian at one set of values, then residuals at two others -
+    every result must be the oracle's for the values in force at that call (cached graphs and unchanged-vector tests included)."""
+    c, yl = make_case("d3dHsm", perturb=1e-3, overrides={"bbb.isbcwdt": 1})
+    gpu, ora = bind(load_gpu(), c), bind(oracle(), c)
+    b = c.bbb
+    n = b.neq
+    y, su = psetnk_inputs(c, yl)
+    y[n] = -1.0
+    rng = np.random.default_rng(11)
+    dt1 = 10.0 ** rng.uniform(-6, -3, n)
+    for lib in (gpu, ora):
+        lib.set_real("dtreal", 1e-4)
+        lib.step_params(dt1, y[:n], su, np.ones(n))
+    fg, fo = gpu.pandf1(y), ora.pandf1(y)
+    jg, jo = gpu.jac_calc(y, fg, b.lbw, b.ubw, b.nnzmx), ora.jac_calc(y, fo, b.lbw, b.ubw, b.nnzmx)
+    assert np.array_equal(fg, fo) and all(np.array_equal(p, q) for p, q in zip(jg, jo))
+    seen = [fg]
+    for k, dtreal in enumerate((1e-5, 1e-4, 1e20)):  # new dtuse and ylodt (set_dt, next exmain) and a new dtreal each time
+        dt2 = dt1 * (0.5 + k)
+        yo = y[:n] * (1.0 - 1e-3 * (k + 1))
+        for lib in (gpu, ora):
+            lib.step_params(dt2, yo, su, np.ones(n))
+            lib.set_real("dtreal", dtreal)
+        fg, fo = gpu.pandf1(y), ora.pandf1(y)
+        assert np.array_equal(fg, fo)
+        assert all(not np.array_equal(fg, f) for f in seen)
+        seen.append(fg)
+    for lib in (gpu, ora):
+        lib.set_real("dtreal", 1e20)
+
+
 def _jac_pair(c, yl, gpu, ora, dt=None):
     b = c.bbb
     y, su = psetnk_inputs(c, yl)

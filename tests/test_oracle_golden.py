@@ -222,6 +222,24 @@ def test_coefficient_outside_the_built_path_is_refused(built, name):
         ora.init()
 
 
+@pytest.mark.parametrize("name,grp", [("recylb", "lines"), ("fngysi", "lines"), ("isixcore", "ilines"), ("matwallo", "ilines"), ("igyl", "ilines"), ("vol", "planes")])
+def test_short_arrays_are_refused_not_indexed(built, name, grp):
+    """1-D LINES have a length class (nx+2, ny+2, neq, 2*neq) just as planes have (nx+2)(ny+2): an array of any other length is
+    refused by name at init (shared store include/ue_param_store.hpp: the same check guards ue_gpu_init), before anything
+    indexes it; a NULL pointer with n > 0 is refused by the setter."""
+    import ctypes as C
+    c, yl = make_case("d3dHsm")
+    s = c.static_inputs()
+    s[grp][name] = np.asarray(s[grp][name]).reshape(-1)[:-1]
+    ora = oracle()
+    ora.load_static(s)
+    with pytest.raises(Exception, match="bad array sizes.*" + name):
+        ora.init()
+    f = ora.lib.ue_ora_set_real_array
+    f.argtypes = [C.c_char_p, C.c_void_p, C.c_int64]
+    assert f(b"vol", None, 180) != 0
+
+
 def test_refined_grid_setup():
     c, yl = make_case("d3dHsm4x")
     assert c.com.nx == 64 and c.com.ny == 32 and c.bbb.neq == 5 * 66 * 34

@@ -24,6 +24,12 @@ for r in rows[2:]:
         if k.startswith("dram_r") or k.startswith("dram_w"): d[k + "_bytes"] = tobytes(r[c], units[c])
         elif k == "duration_us": d[k] = float(r[c].replace(",", "")) * {"ns": 1e-3, "us": 1, "ms": 1e3}.get(units[c], 1)  # ncu picks the unit
         else: d[k] = float(r[c].replace(",", ""))
+    # FP64 operations the kernel executed (thread-level SASS counts: add + mul + 2 x fma), from the per-cycle rates of --set full
+    cyc = col("smsp__cycles_elapsed.avg")
+    ops = [col("smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed" % o) for o in ("dadd", "dmul", "dfma")]
+    if cyc is not None and all(o is not None for o in ops) and r[cyc] != "":
+        f = [float(r[o].replace(",", "") or 0) for o in ops]
+        d["fp64_flop"] = (f[0] + f[1] + 2 * f[2]) * float(r[cyc].replace(",", ""))
     d["top_stalls"] = [[n, round(float(r[i] or 0), 2)] for i, n in sorted(stall, key=lambda x: -float(r[x[0]] or 0))[:4]]
     res.append(d)
 json.dump(res, open(out, "w"), indent=1)

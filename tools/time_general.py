@@ -1,0 +1,37 @@
+"""Developer tool: wall-clock of the general path (ue_gen_*) against the general oracle on the same host, per case."""
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, ".")
+from tests.test_oracle2_golden import twin  # noqa: E402
+from tests.util import psetnk_inputs  # noqa: E402
+from uedge_b200.cases import box2_case  # noqa: E402
+from uedge_b200.cases2 import Oracle2, box2_initial_state, inputex_case, load_gen  # noqa: E402
+
+
+def cases():
+    c, yl, _ = inputex_case("default"); yield "input_example", c, yl
+    c = box2_case(isupgon=1); yield "box2 (inertial atoms)", c, box2_initial_state(c)
+    c1, c2, yl = twin("d3dHsm"); y, su = psetnk_inputs(c1, yl); yield "d3dHsm via general path", c2, y
+
+
+for name, c, yl in (cases() if __name__ == "__main__" else ()):
+    b = c.bbb
+    g, o = load_gen().bind(c), Oracle2().bind(c)
+    f = g.pandf1(yl); o.pandf1(yl)
+    g.jac_calc(yl, f, b.lbw, b.ubw, b.nnzmx)
+    n = 10
+    t = time.perf_counter()
+    for _ in range(n):
+        g.pandf1(yl)
+    tr = (time.perf_counter() - t) / n
+    t = time.perf_counter()
+    for _ in range(n):
+        j = g.jac_calc(yl, f, b.lbw, b.ubw, b.nnzmx)
+    tj = (time.perf_counter() - t) / n
+    t = time.perf_counter(); o.pandf1(yl); tro = time.perf_counter() - t
+    t = time.perf_counter(); o.jac_calc(yl, f, b.lbw, b.ubw, b.nnzmx); tjo = time.perf_counter() - t
+    print("%-26s neq %5d nnz %6d | GPU residual %.3f ms, Jacobian %.3f ms | oracle (1 thread) residual %.3f ms, Jacobian %.2f ms | x%.1f" %
+          (name, b.neq, len(j[0]), tr * 1e3, tj * 1e3, tro * 1e3, tjo * 1e3, tjo / tj), flush=True)

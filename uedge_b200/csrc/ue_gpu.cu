@@ -1185,7 +1185,7 @@ int ue_gpu_init(void) {
   const UeParams& P = S.p;
   nx = (int)P.nx; ny = (int)P.ny; NXS = nx + 2; NC = NXS * (ny + 2); neq = P.neq;
   std::string b = S.bad_sizes();
-  if (!b.empty()) { g_err = "bad plane sizes: " + b; return -1; }
+  if (!b.empty()) { g_err = "bad array sizes (have != expected): " + b; return -1; }
   if (neq != (int64_t)NC * S.p.numvar) { g_err = "neq != numvar*(nx+2)*(ny+2)"; return -1; }
   if (S.len("igyl") != 2 * neq || S.len("iseqalg") != neq) { g_err = "igyl/iseqalg length"; return -1; }
   int rc = check_switches();
