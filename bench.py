@@ -392,7 +392,7 @@ def main():
     G = 16 + 3  # static real planes + int planes the kernels read (include/ue_params.h)
     prof = {}
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
     except Exception:
         pass
     traffic = prof.get("dram_bytes_per_launch", {}).get(name); fp64_pct = prof.get("fp64_pipe_pct", {}).get(name)
@@ -403,8 +403,8 @@ def main():
     if world == 1:
         par = "1 GPU"
     elif split:
-        how = ("the assembly kernel stores every column result into all GPUs' slot arrays over NVLink (CUDA IPC peer memory), device-side flag barrier, no collective call"
-               if a.transport == "p2p" else "slot arrays combined by two ncclAllReduce calls on the library stream")
+        how = ("the assembly kernel stores every column fragment into all GPUs' fragment arrays over NVLink (CUDA IPC peer memory), device-side flag barrier, no collective call"
+               if a.transport == "p2p" else "column fragments exchanged by grouped in-place ncclBroadcast calls on the library stream")
         par = "one Jacobian, columns split over %d ranks (replicated state, ppp MPI design); %s; every rank returns the full CSR" % (world, how)
     else:
         par = "%d independent replicas (one state per GPU), no collective" % world
@@ -426,13 +426,14 @@ def main():
                 gpu_launches=m["launches"],
                 resid_evals_per_s=1e3 / m["res_ms"] if m["res_ms"] > 0 else None, jac_kernel_ms=m["jac_ms"], resid_kernel_ms=m["res_ms"],
                 peer_bytes_per_step_this_rank=m["comm_bytes"],
-                roofline=dict(bound="latency (dependent FP64 chain per launch; neither HBM nor the FP64 pipe is near its roof: DESIGN.md 3.4)", achieved=achieved, peak=peak, unit="GB/s",
+                roofline=dict(bound="hbm", limiter="latency: 4-6 dependent launches of 10-25 us, each a long FP64 dependency chain per thread (ncu: issue slots <25% busy, FP64 pipe <13%, "
+                                                  "DRAM <1% of peak; top stalls long_scoreboard / barrier / wait - profiles/r02_ncu_*); neither HBM nor the FP64 pipe is near its roof", achieved=achieved, peak=peak, unit="GB/s",
                               frac=achieved / peak, traffic=traffic,
                               kernel="Jacobian sequence (k_jb_p01|stage0/p1a/p1b, k_jb_p2, k_jb_p3c, CSR assembly), CUDA events on the library stream",
                               fp64_pipe_pct_of_dominant_kernel=fp64_pct, peak_source="MEASURED_PEAKS.json hbm_gbs",
                               fp64=dict(flops_per_jacobian=flops, achieved_tflops=(flops / (m["jac_ms"] * 1e-3) / 1e12) if flops else None, peak_tflops=fp64_peak,
                                         frac=(flops / (m["jac_ms"] * 1e-3) / 1e12 / fp64_peak) if flops else None,
-                                        how="flops counted by the oracle built with a counting double type over the cell evaluations the kernels perform (tools/count_flops.py)"),
+                                        how="FP64 operations the Jacobian kernels executed, from ncu's thread-level SASS counters (dadd + dmul + 2*dfma; profiles/r02_ncu_warm_*.json, tools/ncu_summary.py)"),
                               note="algorithmic bytes = 8*(2(neq+2)+G*Ncell)+16*nnz+8*(neq+1), G=%d; traffic is ncu's cold-cache replay figure" % G),
                 clocks=dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max([s[1] for s in samples] or [0.0]), reasons=reasons_of([s[2] for s in samples])))
     if grids:

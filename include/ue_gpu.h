@@ -47,6 +47,18 @@ int ue_gpu_step_params(int64_t neq, const double* dtuse, const double* ylodt,
  * for the calls that follow and is also returned (neq doubles) for the Fortran module array. */
 int ue_gpu_set_dt(int64_t neq, const double* yl, double* f0, double* dtuse);
 
+/* ---- Timing group of the reference (com/com.v:500-519): seconds spent in ue_gpu_pandf1 (ttotfe) and ue_gpu_jac_calc (ttotjf)
+ * since the last reset, host clock around the calls; ttjstor is 0 (storing is fused into the assembly kernels).  The shim adds
+ * them to the module variables after each call or once per exmain. */
+int ue_gpu_timing(double* ttotfe, double* ttotjf, double* ttjstor, int64_t reset);
+
+/* ---- vnormnk(n, v, s) = sqrt(sum((v(i)*s(i))**2)) of NKSOL (svr/nksol.m:1404-1419: fnrm, unrm, pnrm).  The sum has a fixed
+ * shape (1024 strided partial sums + binary tree): deterministic, within a few ulp of the reference's serial sum.
+ * ue_gpu_fnrm: the same norm of the residual the last ue_gpu_pandf1 left on the device, with the resident sfscal
+ * (nksol.m:1009 fnrm = vnormnk(n, savf, sf)) - nothing crosses the bus but the result. */
+int ue_gpu_vnormnk(int64_t neq, const double* v, const double* s, double* out);
+int ue_gpu_fnrm(double* out);
+
 /* ---- Pandf1rhs_interface: pandf1(-1,-1,0,neq,time,yl,yldot) ---------------
  * yl has neq+2 entries (yl(neq+1) = Jacobian-mode flag, yl(neq+2) = nufak);
  * yldot receives neq entries. */

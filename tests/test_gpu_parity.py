@@ -72,6 +72,36 @@ def test_residual_timestep_term(built, isbcwdt):
 
 
 @pytest.mark.gpu
+def test_vnormnk(built):
+    """vnormnk(n, v, s) = sqrt(sum((v*s)**2)) (svr/nksol.m:1404-1419) against the serial sum, to 1e-14 relative (the device sum
+    has a fixed tree shape); ue_gpu_fnrm = the same norm of the resident residual with the resident sfscal."""
+    import ctypes as C
+    c, yl = make_case("d3dHsm", perturb=1e-3)
+    gpu = bind(load_gpu(), c)
+    n = c.bbb.neq
+    rng = np.random.default_rng(5)
+    v = rng.standard_normal(n) * 10.0 ** rng.uniform(-8, 8, n); s = 10.0 ** rng.uniform(-3, 3, n)
+    ref = 0.0
+    for i in range(n):
+        ref = ref + (v[i] * s[i]) ** 2
+    ref = np.sqrt(ref)
+    out = C.c_double(0)
+    lib = gpu.lib
+    lib.ue_gpu_vnormnk.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+    assert lib.ue_gpu_vnormnk(n, v.ctypes.data, s.ctypes.data, C.byref(out)) == 0
+    assert abs(out.value - ref) <= 1e-14 * ref
+    a = out.value
+    assert lib.ue_gpu_vnormnk(n, v.ctypes.data, s.ctypes.data, C.byref(out)) == 0 and out.value == a  # deterministic
+    y, su = psetnk_inputs(c, yl)
+    sf = 10.0 ** rng.uniform(-2, 2, n)
+    gpu.step_params(np.full(n, 1e20), y[:n], su, sf)
+    f = gpu.pandf1(y)
+    lib.ue_gpu_fnrm.argtypes = [C.POINTER(C.c_double)]
+    assert lib.ue_gpu_fnrm(C.byref(out)) == 0
+    assert abs(out.value - np.sqrt(np.sum((f * sf) ** 2))) <= 1e-13 * out.value
+
+
+@pytest.mark.gpu
 def test_time_step_inputs_changed_between_jacobian_and_residual(built):
     """The host shim sends dtuse / ylodt / dtreal before EVERY residual: set_dt rewrites dtuse and dtreal may
     change (icntnunk=1) between a Jacobian and the next rhsnk.  A Jacobian at one set of values, then residuals at two others -
@@ -80,16 +110,18 @@ def test_time_step_inputs_changed_between_jacobian_and_residual(built):
     gpu, ora = bind(load_gpu(), c), bind(oracle(), c)
     b = c.bbb
     n = b.neq
-    y, su = psetnk_inputs(c, yl)
-    y[n] = -1.0
+    yj, su = psetnk_inputs(c, yl)  # yl(neq+1) = 1: psetnk's calls (rhsnk + jac_calc)
+    y = yj.copy(); y[n] = -1.0      # yl(neq+1) < 0: nksol's own residual calls (oderhs.m:7961-7964)
     rng = np.random.default_rng(11)
     dt1 = 10.0 ** rng.uniform(-6, -3, n)
     for lib in (gpu, ora):
         lib.set_real("dtreal", 1e-4)
-        lib.step_params(dt1, y[:n], su, np.ones(n))
-    fg, fo = gpu.pandf1(y), ora.pandf1(y)
-    jg, jo = gpu.jac_calc(y, fg, b.lbw, b.ubw, b.nnzmx), ora.jac_calc(y, fo, b.lbw, b.ubw, b.nnzmx)
+        lib.step_params(dt1, 0.9995 * y[:n], su, np.ones(n))
+    fg, fo = gpu.pandf1(yj), ora.pandf1(yj)
+    jg, jo = gpu.jac_calc(yj, fg, b.lbw, b.ubw, b.nnzmx), ora.jac_calc(yj, fo, b.lbw, b.ubw, b.nnzmx)
     assert np.array_equal(fg, fo) and all(np.array_equal(p, q) for p, q in zip(jg, jo))
+    fg, fo = gpu.pandf1(y), ora.pandf1(y)
+    assert np.array_equal(fg, fo)
     seen = [fg]
     for k, dtreal in enumerate((1e-5, 1e-4, 1e20)):  # new dtuse and ylodt (set_dt, next exmain) and a new dtreal each time
         dt2 = dt1 * (0.5 + k)

@@ -247,15 +247,15 @@ def test_refined_grid_setup():
 
 
 def test_product_library_exports_abi():
-    """Every function declared in include/ue_gpu.h is exported by libuegpu.so (no compute call)."""
+    """Every function declared in include/ue_gpu.h and include/ue_gen.h is exported by libuegpu.so (no compute call)."""
     lib = os.path.join(ROOT, "uedge_b200", "csrc", "libuegpu.so")
     if not os.path.exists(lib):
         import __graft_entry__ as ge
 
         ge.build()
-    hdr = open(os.path.join(ROOT, "include", "ue_gpu.h")).read()
-    names = set(re.findall(r"\b(ue_gpu_[a-z0-9_]+)\s*\(", hdr))
-    assert len(names) >= 14
+    hdr = open(os.path.join(ROOT, "include", "ue_gpu.h")).read() + open(os.path.join(ROOT, "include", "ue_gen.h")).read()
+    names = set(re.findall(r"\b(ue_g(?:pu|en)_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 40 and "ue_gen_jac_calc" in names and "ue_gpu_comm_init_p2p" in names
     dll = ctypes.CDLL(lib)
     for n in names:
         assert hasattr(dll, n), n

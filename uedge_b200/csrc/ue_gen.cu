@@ -73,11 +73,12 @@ double *d_yl = nullptr, *d_yldot = nullptr, *d_y00 = nullptr, *d_ylp = nullptr, 
 double* d_step = nullptr;   // dtuse | ylodt | suscal | sfscal
 int *d_cnt = nullptr, *d_frow = nullptr, *d_err = nullptr;
 double* d_fval = nullptr;
-int64_t *d_ia = nullptr, *d_ja = nullptr;
-double* d_jac = nullptr;
+int64_t *d_ia = nullptr, *d_ja = nullptr, *d_ja2 = nullptr;
+double *d_jac = nullptr, *d_jac2 = nullptr;
 int64_t g_nnzmx = 0;
 int NPL = 0;
 int COLCAP = 512;
+int g_tpu = 32;  // threads per unknown in the Jacobian kernel: 32 (a warp) or 64 (a two-warp block)
 V g_last_yl;  // the state the base planes were last evaluated at
 int64_t g_ivmin = 1, g_ivmax = 0;
 
@@ -110,7 +111,7 @@ void free_all() {
   for (void* p : g_allocs) mem_free(p);
   g_allocs.clear(); g_dev.clear();
   d_G = nullptr; d_base = d_priv = d_yl = d_yldot = d_y00 = d_ylp = d_wk = d_step = d_fval = d_jac = nullptr;
-  d_cnt = d_frow = d_err = nullptr; d_ia = d_ja = nullptr;
+  d_cnt = d_frow = d_err = nullptr; d_ia = d_ja = d_ja2 = nullptr; d_jac2 = nullptr;
   g_priv_cols = 0; g_nnzmx = 0; g_ready = false; g_last_yl.clear();
 }
 template <typename T> T* alloc_as(size_t n) {
@@ -186,21 +187,22 @@ __global__ void k_gen_full(const Gen* gsrc, double* base, const double* yl, doub
 }
 // one warp per unknown of the chunk [iv0, iv0 + ncol): every warp has its own context (shared memory) and its own planes
 __global__ void k_gen_cols(const Gen* gsrc, const double* base, double* priv, int npl, int64_t iv0, int ncol, const double* yl, double* ylp, double* wk,
-                           const double* yldot00, int64_t ml, int64_t mu, int cap, int* frow, double* fval, int* cnt, int* err) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  Gen* g = (Gen*)g_smem + warp;
-  load_ctx(g, gsrc, lane, 32);
-  __syncwarp();
-  const int c = blockIdx.x * (blockDim.x >> 5) + warp;
+                           const double* yldot00, int64_t ml, int64_t mu, int cap, int* frow, double* fval, int* cnt, int* err, int tpu) {
+  // a unit = the threads that evaluate one unknown: a warp (4 units per block) or, with tpu > 32, the whole block
+  const int unit = tpu > 32 ? 0 : (int)(threadIdx.x >> 5), lane = tpu > 32 ? (int)threadIdx.x : (int)(threadIdx.x & 31);
+  Gen* g = (Gen*)g_smem + unit;
+  load_ctx(g, gsrc, lane, tpu);
+  if (tpu > 32) __syncthreads(); else __syncwarp();
+  const int c = tpu > 32 ? (int)blockIdx.x : (int)(blockIdx.x * (blockDim.x >> 5) + unit);
   if (c >= ncol) return;
   const size_t nslab = (size_t)npl * g->NC;
-  if (lane == 0) { g->nth = 32; g->errc = 0; g->assign_planes(priv + (size_t)c * nslab); }
-  __syncwarp();
+  if (lane == 0) { g->nth = tpu; g->errc = 0; g->assign_planes(priv + (size_t)c * nslab); }
+  if (tpu > 32) __syncthreads(); else __syncwarp();
   const int64_t iv = iv0 + c;
   const int64_t neq = g->neq;
   const int rc = eval_column(*g, base, npl, iv, yl, ylp + (size_t)c * (neq + 2), wk + (size_t)c * neq, yldot00, ml, mu, cap, frow + (size_t)(iv - 1) * cap,
                              fval + (size_t)(iv - 1) * cap, cnt + (iv - 1));
-  __syncwarp();
+  if (tpu > 32) __syncthreads(); else __syncwarp();
   if (rc && lane == 0) { err[0] = rc; err[1] = g->errc; }
   if (lane == 0 && cnt[iv - 1] > cap) err[2] = cnt[iv - 1];
 }
@@ -244,15 +246,17 @@ __global__ void k_gen_fill(int64_t neq, int cap, const int* cnt, const int* frow
     if (pos < nnzmx) { jac[pos] = fval[(iv - 1) * cap + k]; ja[pos] = iv; }
   }
 }
-__global__ void k_gen_sortrows(int64_t neq, const int64_t* ia, int64_t nnzmx, double* jac, int64_t* ja) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per row: rank of every entry among the row's column numbers (they are distinct), written to the second buffer
+__global__ void k_gen_sortrows(int64_t neq, const int64_t* ia, int64_t nnzmx, const double* jac_in, const int64_t* ja_in, double* jac, int64_t* ja) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (r >= neq) return;
   const int64_t a = ia[r] - 1, b = min(ia[r + 1] - 1, nnzmx);
-  for (int64_t i = a + 1; i < b; ++i) {
-    const int64_t cj = ja[i]; const double cv = jac[i];
-    int64_t j = i - 1;
-    while (j >= a && ja[j] > cj) { ja[j + 1] = ja[j]; jac[j + 1] = jac[j]; --j; }
-    ja[j + 1] = cj; jac[j + 1] = cv;
+  for (int64_t i = a + lane; i < b; i += 32) {
+    const int64_t cj = ja_in[i];
+    int rank = 0;
+    for (int64_t j = a; j < b; ++j) rank += (ja_in[j] < cj);
+    ja[a + rank] = cj; jac[a + rank] = jac_in[i];
   }
 }
 #endif
@@ -409,6 +413,7 @@ int init_all() {
   g.nth = 1; g.errc = 0;
   if (!mem_put(d_G, &g, sizeof(Gen))) return -10;
   if (const char* e = getenv("UE_GEN_COLCAP")) COLCAP = std::max(16, atoi(e));
+  if (const char* e = getenv("UE_GEN_TPU")) g_tpu = atoi(e) > 32 ? 64 : 32;
   g_ivmin = 1; g_ivmax = g.neq;
   g_ready = true;
   return 0;
@@ -424,7 +429,8 @@ int run_full(const double* yl_host, double* yldot_host) {
 #else
   int zero[4] = {0, 0, 0, 0};
   if (!mem_put(d_err, zero, sizeof zero)) return -10;
-  k_gen_full<<<1, 256, sizeof(Gen)>>>(d_G, d_base, d_yl, d_yldot, d_err);
+  const int nthr = std::min(256, std::max(64, ((G.NC + 31) / 32) * 32));  // one cell per thread up to 256 threads
+  k_gen_full<<<1, nthr, sizeof(Gen)>>>(d_G, d_base, d_yl, d_yldot, d_err);
   if (!ck(cudaGetLastError(), "k_gen_full launch") || !ck(cudaDeviceSynchronize(), "k_gen_full")) return -10;
   int e[4];
   if (!mem_get(e, d_err, sizeof e)) return -10;
@@ -503,8 +509,9 @@ int UE_PREFIX(jac_calc)(int64_t n, double t, const double* yl, const double* yld
   }
   if (g_nnzmx < nnzmx) {
     d_jac = mem_alloc((size_t)nnzmx); d_ja = alloc_as<int64_t>((size_t)nnzmx);
-    if (!d_jac || !d_ja) return -10;
-    g_allocs.push_back(d_jac);
+    d_jac2 = mem_alloc((size_t)nnzmx); d_ja2 = alloc_as<int64_t>((size_t)nnzmx);
+    if (!d_jac || !d_ja || !d_jac2 || !d_ja2) return -10;
+    g_allocs.push_back(d_jac); g_allocs.push_back(d_jac2);
     g_nnzmx = nnzmx;
   }
 #if defined(UE_GEN_HOST)
@@ -536,14 +543,17 @@ int UE_PREFIX(jac_calc)(int64_t n, double t, const double* yl, const double* yld
   const int WPB = 4;
   for (int64_t iv0 = g_ivmin; iv0 <= g_ivmax; iv0 += (int64_t)chunk) {
     const int ncol = (int)std::min<int64_t>((int64_t)chunk, g_ivmax - iv0 + 1);
-    k_gen_cols<<<(ncol + WPB - 1) / WPB, 32 * WPB, WPB * sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, iv0, ncol, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err);
+    if (g_tpu > 32)
+      k_gen_cols<<<ncol, g_tpu, sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, iv0, ncol, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, g_tpu);
+    else
+      k_gen_cols<<<(ncol + WPB - 1) / WPB, 32 * WPB, WPB * sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, iv0, ncol, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, 32);
     if (!ck(cudaGetLastError(), "k_gen_cols launch")) return -10;
   }
   int* rowcnt = d_cnt + neq;
   k_gen_count<<<(unsigned)((neq + 127) / 128), 128>>>((int64_t)neq, cap, d_cnt, d_frow, rowcnt);
   k_gen_scan<<<1, 1024>>>((int64_t)neq, rowcnt, d_ia, rowcnt);
-  k_gen_fill<<<(unsigned)neq, 64>>>((int64_t)neq, cap, d_cnt, d_frow, d_fval, d_ia, rowcnt, nnzmx, d_jac, d_ja);
-  k_gen_sortrows<<<(unsigned)((neq + 127) / 128), 128>>>((int64_t)neq, d_ia, nnzmx, d_jac, d_ja);
+  k_gen_fill<<<(unsigned)neq, 64>>>((int64_t)neq, cap, d_cnt, d_frow, d_fval, d_ia, rowcnt, nnzmx, d_jac2, d_ja2);
+  k_gen_sortrows<<<(unsigned)((neq + 3) / 4), 128>>>((int64_t)neq, d_ia, nnzmx, d_jac2, d_ja2, d_jac, d_ja);
   if (!ck(cudaGetLastError(), "CSR kernels launch") || !ck(cudaDeviceSynchronize(), "Jacobian kernels")) return -10;
   int e[4];
   if (!mem_get(e, d_err, sizeof e)) return -10;

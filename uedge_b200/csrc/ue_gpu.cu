@@ -15,6 +15,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -1139,7 +1140,8 @@ int ue_gpu_set_int(const char* n, int64_t v) {
       return 0;
     }
     auto it = S.iscal.find(n);
-    if (it != S.iscal.end() && *it->second == v) return 0;  // unchanged
+    if (it == S.iscal.end()) { g_err = std::string("unknown int input ") + n; return -1; }  // (a typo must not disable the library)
+    if (*it->second == v) return 0;  // unchanged
     if (it != S.iscal.end() && std::string(n) == "model_dt") {
       *it->second = v;
       const size_t off = (size_t)((char*)it->second - (char*)&S.p);
@@ -1162,12 +1164,16 @@ int ue_gpu_set_real(const char* n, double v) {
     auto it = S.rscal.find(n);
     if (it != S.rscal.end() && std::memcmp(it->second, &v, 8) == 0) return 0;
   }
-  g_base_valid = g_base_dev_valid = false;
-  if (S.set_real(n, v)) { g_err = std::string("unknown real input ") + n; return -1; }
+  auto it = S.rscal.find(n);
+  if (it == S.rscal.end()) { g_err = std::string("unknown real input ") + n; return -1; }
+  const double old = *it->second;
+  S.set_real(n, v);
   if (g_ready) {  // scalars such as nufak, dtreal may change between solves: patch the device copy in place
-    const size_t off = (size_t)((char*)S.rscal[n] - (char*)&S.p);
+    if (int rc = check_switches()) { *it->second = old; return rc; }  // the refusals of ue_gpu_init hold afterwards too (fnnuiz, difpr2, l_parloss, ...)
+    const size_t off = (size_t)((char*)it->second - (char*)&S.p);
     CK(cudaMemcpyToSymbol(D, &v, sizeof(double), off));
   }
+  g_base_valid = g_base_dev_valid = false;
   return 0;
 }
 // arrays are uploaded by ue_gpu_init: sending one afterwards disables the entry points until the next ue_gpu_init
@@ -1309,7 +1315,24 @@ int ue_gpu_pandf1_dev(int64_t n, double time, const double* dyl, double* dyldot)
   return 0;
 }
 
+// Timing accumulators of the reference (com/com.v:500-519): ttotfe = time in residual evaluations, ttotjf = time in Jacobian
+// assemblies.  Host clock around the entry points (what the caller waits for).  ttjstor (time "storing" Jacobian elements) has no
+// separate phase here - the store is fused into the assembly kernels - and is reported as 0.
+double g_ttotfe = 0., g_ttotjf = 0.;
+struct Stopwatch {
+  double* acc; std::chrono::steady_clock::time_point t0;
+  explicit Stopwatch(double* a) : acc(a), t0(std::chrono::steady_clock::now()) {}
+  ~Stopwatch() { *acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+int ue_gpu_timing(double* ttotfe, double* ttotjf, double* ttjstor, int64_t reset) {
+  if (ttotfe) *ttotfe = g_ttotfe;
+  if (ttotjf) *ttotjf = g_ttotjf;
+  if (ttjstor) *ttjstor = 0.;
+  if (reset) g_ttotfe = g_ttotjf = 0.;
+  return 0;
+}
 int ue_gpu_pandf1(int64_t n, double time, const double* yl, double* yldot) {
+  Stopwatch sw_(&g_ttotfe);
   (void)time;
   if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
   if (n != neq) { g_err = "pandf1: neq mismatch"; return -1; }
@@ -1470,6 +1493,7 @@ int ue_gpu_rhs_jac(int64_t n, const double* yl, double* yldot00, int64_t ml, int
 int ue_gpu_jac_calc(int64_t n, double t, const double* yl, const double* yldot00, int64_t ml, int64_t mu, int64_t nnzmx, double* jac, int64_t* ja,
                     int64_t* ia, int64_t* nnz_out) {
   (void)t;
+  Stopwatch sw_(&g_ttotjf);
   if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
   if (n != neq) { g_err = "jac_calc: neq mismatch"; return -1; }
   // psetnk / sfsetnk evaluate rhsnk(yl) immediately before jac_calc (oderhs.m:9466-9468, 9851-9856): if yl is
@@ -1557,11 +1581,13 @@ int ue_gpu_assume_base_current(int64_t flag) { g_jac_trust_base = (flag != 0); r
 // J <- J*diag(1/su), sf(i) = 1/max_k|J_ik|, ydt_max0 = max_i|f0_i sf_i|.  Only sf (neq doubles) returns to the host.
 int ue_gpu_sfsetnk(int64_t n, const double* yl, const double* su, int64_t ml, int64_t mu, double* sf, double* ydt_max0) {
   if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
-  if (n != neq) { g_err = "sfsetnk: neq mismatch"; return -1; }
+  if (n != neq || !yl || !su || !sf || !ydt_max0) { g_err = "sfsetnk: neq mismatch or null pointer"; return -1; }
+  if (g_nranks == 1 && (g_ivmin != 1 || g_ivmax != neq)) { g_err = "sfsetnk needs the full Jacobian: reset ue_gpu_set_column_range(1, neq) first"; return -1; }
   std::vector<double> y(yl, yl + neq + 2);
   y[neq] = 1.;  // oderhs.m:9848
   CK(cudaMemcpyAsync(d_yl, y.data(), (neq + 2) * 8, cudaMemcpyHostToDevice, g_stream));
   CK(cudaMemcpyAsync(d_suscal, su, neq * 8, cudaMemcpyHostToDevice, g_stream));
+  g_step_host[2].assign(su, su + neq);  // the resident suscal is now `su`: a later ue_gpu_step_params compares against this
   g_base_valid = false; g_base_dev_valid = false;
   int rc = run_residual_dev(d_yl, d_yldot00, true);
   if (rc) return rc;
@@ -1587,6 +1613,43 @@ int ue_gpu_sfsetnk(int64_t n, const double* yl, const double* su, int64_t ml, in
   double v; std::memcpy(&v, &bits, 8);
   *ydt_max0 = std::max(v, S.p.cutlo);
   return 0;
+}
+// vnormnk(n, v, s) = sqrt(sum((v(i)*s(i))**2)) (svr/nksol.m:1404-1419): NKSOL's scaled norm (fnrm, unrm, pnrm).
+// Fixed summation shape (1024 strided partial sums, then a binary tree), so the result does not depend on the launch.
+__global__ void __launch_bounds__(1024) k_vnorm(int64_t n, const double* __restrict__ v, const double* __restrict__ s, double* __restrict__ out) {
+  __shared__ double part[1024];
+  double acc = 0.;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) { const double t = v[i] * s[i]; acc = acc + t * t; }
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = 512; off; off >>= 1) { if ((int)threadIdx.x < off) part[threadIdx.x] = part[threadIdx.x] + part[threadIdx.x + off]; __syncthreads(); }
+  if (threadIdx.x == 0) out[0] = part[0];
+}
+static int vnorm_dev(const double* dv, const double* ds, double* out) {
+  static double* d_sum = nullptr;
+  if (!d_sum) CK(cudaMalloc(&d_sum, 8));
+  CK(launch(k_vnorm, dim3(1), dim3(1024), neq, dv, ds, d_sum));
+  g_launches += 1;
+  double sum = 0.;
+  CK(cudaMemcpyAsync(&sum, d_sum, 8, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  *out = std::sqrt(sum);
+  return 0;
+}
+int ue_gpu_vnormnk(int64_t n, const double* v, const double* s, double* out) {
+  if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
+  if (n != neq || !v || !s || !out) { g_err = "vnormnk: neq mismatch or null pointer"; return -1; }
+  static double* d_vs = nullptr; static int64_t cap = 0;
+  if (cap < 2 * neq) { if (d_vs) cudaFree(d_vs); CK(cudaMalloc(&d_vs, 2 * neq * 8)); cap = 2 * neq; }
+  CK(cudaMemcpyAsync(d_vs, v, neq * 8, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(d_vs + neq, s, neq * 8, cudaMemcpyHostToDevice, g_stream));
+  return vnorm_dev(d_vs, d_vs + neq, out);
+}
+int ue_gpu_fnrm(double* out) {  // fnrm = vnormnk(neq, savf, sf) of the residual the last ue_gpu_pandf1 left on the device
+  if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
+  if (!out) { g_err = "fnrm: null pointer"; return -1; }
+  if (g_last_yldot.empty()) { g_err = "fnrm: no residual has been evaluated yet"; return -1; }
+  return vnorm_dev(d_yldot, d_sfscal, out);
 }
 int ue_gpu_jac_scale(int64_t n, const double* su, const double* sf, int64_t isrnorm, int64_t normtype, int64_t nnz, double* jac, double* fnormnw) {
   if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
