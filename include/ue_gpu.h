@@ -159,6 +159,11 @@ int ue_gpu_comm_init(int64_t nranks, int64_t rank, const char* id128);
 int ue_gpu_comm_info(int64_t* nranks, int64_t* rank, int64_t* ivmin, int64_t* ivmax, int64_t* bytes_last_jac);
 int ue_gpu_comm_finalize(void);
 
+/* CSC copy of the last Jacobian - the arrays rcsc / icsc / jcsc that jac_calc leaves in group Jacobian_csc (bbb/oderhs.m:8620-8752,
+ * read by jacmap and the ppp debug dumps): values, 1-based row numbers (ascending within a column), column pointers (neq+1).
+ * Not part of the hot path: built on the host from the column fragments on request. */
+int ue_gpu_get_csc(int64_t nnzmx, double* rcsc, int64_t* icsc, int64_t* jcsc, int64_t* nnz);
+
 /* Device buffers owned by the library (yl, yldot, yldot00: neq+2; jac/ja: fragment capacity; ia: neq+1),
  * for callers that keep the state resident between calls. */
 int ue_gpu_device_buffers(double** yl, double** yldot, double** yldot00, double** jac, int64_t** ja, int64_t** ia);

@@ -72,6 +72,36 @@ def test_residual_timestep_term(built, isbcwdt):
 
 
 @pytest.mark.gpu
+def test_csc_copy_and_timing_accumulators(built):
+    """rcsc/icsc/jcsc (oderhs.m:8620-8752) = the transpose of the CSR the call returned; ttotfe/ttotjf accumulate the time spent in
+    the two entry points (com/com.v:500-519)."""
+    import ctypes as C
+    c, yl = make_case("d3dHsm", perturb=1e-3)
+    gpu = bind(load_gpu(), c)
+    b = c.bbb
+    n = b.neq
+    y, su = psetnk_inputs(c, yl)
+    gpu.step_params(np.full(n, 1e20), y[:n], su, np.ones(n))
+    lib = gpu.lib
+    lib.ue_gpu_timing.argtypes = [C.POINTER(C.c_double)] * 3 + [C.c_int64]
+    t = [C.c_double(0) for _ in range(3)]
+    lib.ue_gpu_timing(*[C.byref(x) for x in t], 1)
+    f = gpu.pandf1(y)
+    jac, ja, ia = gpu.jac_calc(y, f, b.lbw, b.ubw, b.nnzmx)
+    lib.ue_gpu_timing(*[C.byref(x) for x in t], 0)
+    assert 0 < t[0].value < 1.0 and 0 < t[1].value < 1.0 and t[2].value == 0.0
+    nnz = len(jac)
+    rcsc = np.zeros(nnz); icsc = np.zeros(nnz, dtype=np.int64); jcsc = np.zeros(n + 1, dtype=np.int64); got = C.c_int64(0)
+    lib.ue_gpu_get_csc.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
+    assert lib.ue_gpu_get_csc(nnz, rcsc.ctypes.data, icsc.ctypes.data, jcsc.ctypes.data, C.byref(got)) == 0, lib.ue_gpu_last_error()
+    assert got.value == nnz
+    rows = np.repeat(np.arange(1, n + 1), np.diff(ia))          # CSR -> (row, col, val), sorted by (col, row)
+    order = np.lexsort((rows, ja))
+    assert np.array_equal(icsc, rows[order]) and np.array_equal(rcsc, jac[order])
+    assert np.array_equal(np.diff(jcsc), np.bincount(ja, minlength=n + 1)[1:]) and jcsc[0] == 1 and jcsc[n] == nnz + 1
+
+
+@pytest.mark.gpu
 def test_vnormnk(built):
     """vnormnk(n, v, s) = sqrt(sum((v*s)**2)) (svr/nksol.m:1404-1419) against the serial sum, to 1e-14 relative (the device sum
     has a fixed tree shape); ue_gpu_fnrm = the same norm of the resident residual with the resident sfscal."""

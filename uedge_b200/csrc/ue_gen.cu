@@ -276,6 +276,7 @@ int init_all() {
   g.nx = I("nx"); g.ny = I("ny"); g.NXS = g.nx + 2; g.NC = g.NXS * (g.ny + 2);
   g.nisp = I("nisp"); g.nusp = I("nusp"); g.ngsp = I("ngsp"); g.nhsp = I("nhsp"); g.neq = (int64_t)std::llround(SC("neq"));
   if (!g_missing.empty()) { g_err = "missing inputs: " + g_missing; return -1; }
+  if (g.NC >= (1 << 20)) { g_err = "mesh too large for the cooperative loop index arithmetic (2^20 cells)"; return -5; }
   if (g.nisp < 1 || g.nisp > 2 || g.nusp > g.nisp || g.ngsp != 1) { g_err = "nisp must be 1 or 2 (hydrogen ions + inertial atoms), ngsp 1"; return -5; }
   g.nfsp = g.nisp;
   g.ixpt1 = I("ixpt1"); g.ixpt2 = I("ixpt2"); g.iysptrx1 = I("iysptrx1"); g.iysptrx2 = I("iysptrx2"); g.iysptrx = I("iysptrx"); g.ixlb = I("ixlb"); g.ixrb = I("ixrb"); g.ixmp = I("ixmp");

@@ -35,9 +35,15 @@
 #define UE_K_(k, n) (k)
 #endif
 // cooperative loop over iy = j0..j1 (outer), ix = i0..i1 (inner): starts with a barrier of the context
+#if defined(__CUDA_ARCH__)
+// row of iteration q in a nest w wide: exact for q < 2^22 (a float division instead of the ~40-instruction integer one)
+#define UE_ROW_(q, w) __float2int_rz(__fdividef((float)(q) + 0.5f, (float)(w)))
+#else
+#define UE_ROW_(q, w) ((q) / (w))
+#endif
 #define FOR2(iy, j0, j1, ix, i0, i1)                                                                                               \
-  for (int _w = (i1) - (i0) + 1, _h = (j1) - (j0) + 1, _n = (sync(), (_w > 0 && _h > 0) ? _w * _h : 0), _k = TID(), _q = 0, ix = 0, iy = 0; \
-       _k < _n && ((_q = UE_K_(_k, _n)), (iy = (j0) + _q / _w), (ix = (i0) + _q % _w), true); _k += nth)
+  for (int _w = (i1) - (i0) + 1, _h = (j1) - (j0) + 1, _n = (sync(), (_w > 0 && _h > 0) ? _w * _h : 0), _k = TID(), _q = 0, _r = 0, ix = 0, iy = 0; \
+       _k < _n && ((_q = UE_K_(_k, _n)), (_r = UE_ROW_(_q, _w)), (iy = (j0) + _r), (ix = (i0) + _q - _r * _w), true); _k += nth)
 #define FOR1(v, a, b) \
   for (int _n = (sync(), (b) - (a) + 1), _k = TID(), v = 0; _k < _n && ((v = (a) + UE_K_(_k, _n)), true); _k += nth)
 #define FORXS(ix, xr) \

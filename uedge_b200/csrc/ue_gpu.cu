@@ -1709,6 +1709,37 @@ int ue_gpu_device_buffers(double** yl, double** yldot, double** yldot00, double*
   *yl = d_yl; *yldot = d_yldot; *yldot00 = d_yldot00; *jac = d_jac; *ja = d_ja; *ia = d_ia;
   return 0;
 }
+// CSC copy of the last Jacobian: rcsc / icsc / jcsc of jac_calc (oderhs.m:8620-8752; read by jacmap and the ppp debug dumps).
+// Built on the host from the column fragments the assembly kernel left on the device (NaN = element not kept); rows ascending.
+int ue_gpu_get_csc(int64_t nnzmx, double* rcsc, int64_t* icsc, int64_t* jcsc, int64_t* nnz_out) {
+  if (!g_ready) { g_err = "ue_gpu_init not called"; return -1; }
+  if (!rcsc || !icsc || !jcsc || !nnz_out) { g_err = "get_csc: null pointer"; return -1; }
+  if (h_flags[1] <= 0) { g_err = "get_csc: no Jacobian has been assembled yet"; return -1; }
+  const int par = g_p2p ? (int)((g_epoch + 1) & 1) : 0;  // the set the last Jacobian wrote
+  std::vector<double> frag((size_t)g_cap_total);
+  CK(cudaStreamSynchronize(g_stream));
+  CK(cudaMemcpy(frag.data(), d_frag + (size_t)par * g_cap_total, (size_t)g_cap_total * 8, cudaMemcpyDeviceToHost));
+  const int nv = (int)S.p.numvar;
+  int64_t nnz = 0;
+  std::vector<std::pair<int64_t, double>> col;
+  for (int64_t iv = 1; iv <= neq; ++iv) {
+    jcsc[iv - 1] = nnz + 1;
+    const int c = (int)S.p.igyl[iv - 1] + NXS * (int)S.p.igyl[neq + iv - 1];
+    const int n = h_cellcand_off[c + 1] - h_cellcand_off[c];
+    col.clear();
+    for (int l = 0; l < n; ++l)
+      for (int k = 0; k < nv; ++k) {
+        const double v = frag[(size_t)h_coloff[iv - 1] + (size_t)l * nv + k];
+        if (v == v) col.push_back({(int64_t)h_cand_cell[h_cellcand_off[c] + l] * nv + k + 1, v});
+      }
+    std::sort(col.begin(), col.end());
+    for (auto& e : col) { if (nnz < nnzmx) { icsc[nnz] = e.first; rcsc[nnz] = e.second; } ++nnz; }
+  }
+  jcsc[neq] = nnz + 1;
+  *nnz_out = nnz;
+  if (nnz > nnzmx) { g_err = "get_csc: nnzmx too small"; return -2; }
+  return 0;
+}
 // copy one intermediate base plane to the host (parity debugging; plane ids in ue_device.cuh)
 int ue_gpu_get_plane(int64_t pl, double* out) {
   if (!g_ready || pl < 0 || pl >= PL_COUNT) { g_err = "bad plane"; return -1; }
