@@ -78,9 +78,11 @@ def cpu_baseline(c, ystates, su, budget_s=12.0, nthreads=None):
     b = c.bbb
     r = time_cpu_arm(c, ystates[0], su, budget_s=budget_s, nthreads=nthreads, native=True)
     sample = ("%d steps (residual + full Jacobian) of %s (neq=%d, nnz=%d), state 0 of the bench pair; %s; %d in-process threads "
-              "(contiguous column ranges, private state copies, C++ merge): Jacobian %.2f ms, 1 thread %.2f ms, parallel efficiency %.0f%%; "
-              "serial residual %.3f ms" % (r["reps"], c.name, b.neq, r["nnz"], r["flags"], r["threads"], r["jac_s"] * 1e3, r["serial_jac_s"] * 1e3,
-                                           100 * r["par_eff"], r["resid_s"] * 1e3))
+              "(contiguous column ranges re-weighted by measured thread times, private state copies, C++ merge): Jacobian %.2f ms, 1 thread %.2f ms, "
+              "parallel efficiency %.0f%%; on %d threads %s ms = %s%% (the host reports %s physical cores for %d logical CPUs); serial residual %.3f ms"
+              % (r["reps"], c.name, b.neq, r["nnz"], r["flags"], r["threads"], r["jac_s"] * 1e3, r["serial_jac_s"] * 1e3, 100 * r["par_eff"], r["half_threads"],
+                 ("%.2f" % (r["half_jac_s"] * 1e3)) if r["half_jac_s"] else "-", ("%.0f" % (100 * r["half_par_eff"])) if r["half_par_eff"] else "-",
+                 r["physical_cores"], os.cpu_count(), r["resid_s"] * 1e3))
     return dict(value=r["nnz"] / r["step_s"], unit="nnz/s", cores=r["threads"], kind="port", sample=sample,
                 resid_evals_per_s=1.0 / r["resid_s"], step_s=r["step_s"], jac_s=r["jac_s"], serial_value=r["nnz"] / (r["serial_jac_s"] + r["resid_s"]),
                 par_eff=r["par_eff"], nnz=r["nnz"])

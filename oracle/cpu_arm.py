@@ -96,5 +96,22 @@ def time_cpu_arm(c, y, su, budget_s=12.0, nthreads=None, native=True):
     while time.perf_counter() - t2 < 1.0:
         o.residual(); r2 += 1
     tres = (time.perf_counter() - t2) / r2
+    # the same Jacobian on half the threads: on hosts whose "CPUs" are SMT siblings the second half adds little for FP64 code
+    half = max(1, nthreads // 2); tjh = None
+    if half < nthreads:
+        for _ in range(3):
+            o.step(half)
+        t3 = time.perf_counter(); r3 = 0; tjh = 0.0
+        while True:
+            dth, _, _ = o.step(half); tjh += dth; r3 += 1
+            if time.perf_counter() - t3 > budget_s / 6 or r3 >= 50:
+                break
+        tjh /= r3
+    try:
+        import psutil
+        phys = psutil.cpu_count(logical=False)
+    except Exception:
+        phys = None
     return dict(nnz=nnz, jac_s=tj, step_s=tstep, serial_jac_s=tj1, resid_s=tres, reps=reps, threads=nthreads, flags=o.flags,
-                par_eff=tj1 / (tj * nthreads), thread_ms=[float(x) for x in ms])
+                par_eff=tj1 / (tj * nthreads), thread_ms=[float(x) for x in ms], half_threads=half, half_jac_s=tjh,
+                half_par_eff=(tj1 / (tjh * half)) if tjh else None, physical_cores=phys)

@@ -1726,6 +1726,7 @@ int ue_ora_jac_calc_threads(int64_t nthreads, int64_t n, const double* yl_in, co
                             double* jac, int64_t* ja, int64_t* ia, int64_t* nnz_out, double* thread_ms /* nthreads, may be NULL */) {
   if (n != neq) { g_o.err = "jac_calc: neq mismatch"; return -1; }
   const int T = (int)std::max<int64_t>(1, std::min<int64_t>(nthreads, neq));
+  const auto tA = std::chrono::steady_clock::now();
   if ((int)g_thread_w.size() != T) g_thread_w.assign(T, 1.0 / T);
   // OMPSplitIndex: contiguous ranges with sizes proportional to the weights
   std::vector<int64_t> lo(T), hi(T);
@@ -1742,6 +1743,7 @@ int ue_ora_jac_calc_threads(int64_t nthreads, int64_t n, const double* yl_in, co
     errs[t] = w.err;
     ms[t] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   });
+  const auto tB = std::chrono::steady_clock::now();
   for (int t = 0; t < T; ++t) if (rcs[t]) { g_o.err = errs[t]; return rcs[t]; }
   // OMPCollectJacobian: concatenate in thread order
   std::vector<double> rcsc; std::vector<int64_t> icsc, jcsc(neq + 1);
@@ -1760,6 +1762,11 @@ int ue_ora_jac_calc_threads(int64_t nthreads, int64_t n, const double* yl_in, co
     for (int t = 0; t < T; ++t) { sp[t] = (double)std::max<int64_t>(1, hi[t] - lo[t] + 1) / std::max(ms[t], 1e-6); tot += sp[t]; }
     for (int t = 0; t < T; ++t) g_thread_w[t] = 0.5 * g_thread_w[t] + 0.5 * sp[t] / tot; }
   if (thread_ms) for (int t = 0; t < T; ++t) thread_ms[t] = ms[t];
+  if (getenv("UE_ORA_TIMING")) {
+    const auto tC = std::chrono::steady_clock::now();
+    fprintf(stderr, "threads %d: parallel section %.3f ms (slowest thread %.3f), merge + csrcsc %.3f ms\n", T, std::chrono::duration<double, std::milli>(tB - tA).count(),
+            *std::max_element(ms.begin(), ms.end()), std::chrono::duration<double, std::milli>(tC - tB).count());
+  }
   return 0;
 }
 
