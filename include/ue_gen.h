@@ -35,6 +35,8 @@ int ue_gen_jac_calc(int64_t neq, double t, const double* yl, const double* yldot
                     int64_t* ia, int64_t* nnz);
 /* one intermediate field plane of the last full evaluation by name ("fnix1", "feex", "resphi", ...): (ny+2) x (nx+2) doubles */
 int ue_gen_get_plane(const char* name, double* out);
+/* CUDA-event times (ms) of the kernels of the last ue_gen_pandf1 / ue_gen_jac_calc: residual, Jacobian columns, CSR transpose */
+int ue_gen_last_kernel_ms(double* resid_ms, double* cols_ms, double* csr_ms);
 const char* ue_gen_last_error(void);
 #ifdef __cplusplus
 }

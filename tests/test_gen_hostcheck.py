@@ -13,7 +13,7 @@ import pytest
 from tests.test_oracle2_golden import twin
 from tests.util import psetnk_inputs
 from uedge_b200.cases import box2_case
-from uedge_b200.cases2 import SUBSETS, Lib2, Oracle2, box2_initial_state, inputex_case
+from uedge_b200.cases2 import SUBSETS, Lib2, Oracle2, box2_initial_state, d3d_full_physics_case, inputex_case
 
 HK = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostcheck")
 
@@ -52,6 +52,24 @@ def test_box2_as_its_deck_runs_it(built, rev):
     yl = box2_initial_state(c)
     assert c.bbb.numvar == 6 and c.bbb.neq == 384
     same(Oracle2().bind(c), host(rev).bind(c), c, yl)
+
+
+def test_full_physics_on_the_d3d_mesh(built):
+    """everything switched on (non-orthogonal, inertial atoms, methg=66, potential) on the 16x8 DIII-D mesh, loop nests reversed"""
+    c, yl = d3d_full_physics_case()
+    same(Oracle2().bind(c), host(1).bind(c), c, yl)
+
+
+def test_band_copy_of_the_private_planes_is_sufficient(built, monkeypatch):
+    """Every Jacobian column works on a private copy of the field planes; only a band of rows around the perturbed cell (plus the
+    X-point rows and the line arrays) is copied from the base set.  With UE_GEN_POISON the host build fills everything else with NaN
+    first: on a refined mesh (32x16, 18 rows; band 11 rows) the Jacobian stays bit-identical to the oracle, so nothing outside the
+    band is read by what the band produces."""
+    from uedge_b200.cases import load_grid_npz, refine_grid
+    monkeypatch.setenv("UE_GEN_POISON", "1")
+    c, yl = d3d_full_physics_case(refine_grid(load_grid_npz(), 2, 2))
+    assert c.com.ny + 2 == 18
+    same(Oracle2().bind(c), host(0).bind(c), c, yl)
 
 
 @pytest.mark.parametrize("name", ["d3dHsm", "case2", "case1"])

@@ -10,7 +10,7 @@ from tests.refplanes import check_against_reference
 from tests.test_oracle2_golden import twin
 from tests.util import psetnk_inputs
 from uedge_b200.cases import box2_case
-from uedge_b200.cases2 import SUBSETS, Oracle2, box2_initial_state, inputex_case, load_gen
+from uedge_b200.cases2 import SUBSETS, Oracle2, box2_initial_state, d3d_full_physics_case, inputex_case, load_gen
 
 pytestmark = pytest.mark.gpu
 
@@ -48,6 +48,18 @@ def test_box2_as_its_deck_runs_it(built):
     c = box2_case(isupgon=1)  # inertial atoms (box2_in.py:114-131)
     yl = box2_initial_state(c)
     same(Oracle2().bind(c), load_gen().bind(c), c, yl)
+
+
+def test_full_physics_on_the_d3d_mesh(built):
+    """non-orthogonal stencils + inertial atoms + methg=66 + potential on the 16x8 DIII-D mesh of the headline case (1 260 unknowns,
+    X-point cuts with the 5-point stencils): bit-identical to the oracle, also with psetnk's scalings and a finite time step."""
+    c, yl = d3d_full_physics_case()
+    b = c.bbb
+    same(Oracle2().bind(c), load_gen().bind(c), c, yl)
+    su = c.suscal(yl)
+    step = (np.full(b.neq, 1e-5), 0.9995 * yl[: b.neq], su, 1.0 / np.maximum(np.abs(yl[: b.neq]), 1e-3))
+    y = yl.copy(); y[b.neq] = 1.0
+    same(Oracle2().bind(c), load_gen().bind(c), c, y, step)
 
 
 @pytest.mark.parametrize("name", ["d3dHsm", "case2", "case1"])

@@ -81,6 +81,33 @@ def box2_initial_state(c):
     return c.set_state2(ni, [up, up.copy()], te, ti, tg=np.full_like(te, float(b.tscal) * ttbeg))
 
 
+def d3d_full_physics_case(grid=None):
+    """The DIII-D single-null 16x8 mesh of d3dHsm (or a refinement) with everything the general path has switched on: non-orthogonal
+    stencils, inertial atoms (nhsp=2), log-interpolated gas flux (methg=66) and the potential equation, 7 unknowns per cell - the
+    input_example switch set on the headline mesh.  State: the d3dHsm restart with ni(,,2) := ng, the atoms moving with 30 % of the
+    ion velocity and phi = 3 Te/e.  No reference vector exists for this combination: oracle <-> CUDA parity and timing only."""
+    from .cases import d3dhsm_case, load_grid_npz, load_state_npz, refine_state
+    g = grid or load_grid_npz()
+    c = d3dhsm_case(g, cls=Case2)
+    b, com = c.bbb, c.com
+    b.oldseec = 0.0; b.isoldalbarea = 0.0
+    com.isnonog = 1
+    b.methg = 66
+    b.isupwo[1] = 0; b.ineudif = 2; com.ngsp = 1; com.nhsp = 2; b.ziin[1] = 0
+    b.isngon = np.zeros_like(b.isngon); b.isupgon = np.zeros_like(b.isupgon); b.isupgon[0] = 1
+    b.isnion = np.asarray(b.isnion).copy(); b.isupon = np.asarray(b.isupon).copy(); b.isnion[:2] = 1; b.isupon[:2] = 1
+    b.flalfgx = np.full(10, 1.0); b.flalfgy = np.full(10, 1.0); b.flalfvgx = 1.0; b.flalfvgy = 1.0; b.flalftgx = 1.0; b.flalftgy = 1.0
+    b.travis[1] = 0.0; b.difni[1] = 1.0
+    b.isphion = 1; b.isphiofft = 0
+    c.setup()
+    ni, up, te, ti, ng = load_state_npz("d3dHsm_state.npz")
+    fx, fy = g["nxm"] // 16, g["nym"] // 8
+    if fx > 1 or fy > 1:
+        ni, up, te, ti, ng = refine_state((ni, up, te, ti, ng), fx, fy)
+    yl = c.set_state2([ni, ng], [up, 0.3 * up], te, ti, ng=ng, phi=3.0 * te / b.ev, tg=ti)
+    return c, yl
+
+
 class Lib2:
     """ctypes binding of one library that exports the generic-setter API <prefix>clear/set/init/step_params/pandf1/jac_calc/
     get_plane/last_error: the product's general path (libuegpu.so, prefix ue_gen_, include/ue_gen.h), its host build for the

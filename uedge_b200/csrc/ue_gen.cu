@@ -78,6 +78,9 @@ double *d_jac = nullptr, *d_jac2 = nullptr;
 int64_t g_nnzmx = 0;
 int NPL = 0;
 int COLCAP = 512;
+float g_full_ms = 0.f, g_cols_ms = 0.f, g_csr_ms = 0.f;  // CUDA-event times of the last residual / column / CSR kernels
+#define UE_GEN_BAND_DEFAULT 5
+int g_band = UE_GEN_BAND_DEFAULT;  // rows of the private copy on each side of the perturbed cell (env UE_GEN_BAND; large = all rows)
 int g_tpu = 32;  // threads per unknown in the Jacobian kernel: 32 (a warp) or 64 (a two-warp block)
 V g_last_yl;  // the state the base planes were last evaluated at
 int64_t g_ivmin = 1, g_ivmax = 0;
@@ -120,6 +123,11 @@ template <typename T> T* alloc_as(size_t n) {
   return (T*)p;
 }
 
+// rows copied on each side of the perturbed cell's row, and the number of line arrays at the end of UE_GEN_PLANES
+#define UE_GEN_NLINE 12
+#if defined(UE_GEN_HOST)
+bool g_poison = false;  // test aid: fill the private planes with NaN before the band copy
+#endif
 // ---- the two evaluation bodies (shared by the kernels and the host build) ----------------------------------------------
 // full-domain residual in place on the context's planes
 HD int eval_full(Gen& g, const double* yl, double* yldot) { return g.pandf1(-1, -1, yl, yldot); }
@@ -127,17 +135,51 @@ HD int eval_full(Gen& g, const double* yl, double* yldot) { return g.pandf1(-1, 
 // one Jacobian column (oderhs.m:8600-8720).  g: private context (planes = private copy of the base set).
 // ylp: private copy of yl (neq+2); wk: private residual (neq); frow/fval: the column's fragment, capacity cap.
 HD int eval_column(Gen& g, const double* base, int npl, int64_t iv, const double* yl, double* ylp, double* wk, const double* yldot00, int64_t ml, int64_t mu,
-                   int cap, int* frow, double* fval, int* cnt) {
+                   int cap, int* frow, double* fval, int* cnt, int band) {
   const int64_t neq = g.neq;
   const int tid = g.TID();
-  const size_t nslab = (size_t)npl * g.NC;
   double* priv = g.ne;  // first plane of the slab
+  const int xc = (int)g.igyld[iv - 1], yc = (int)g.igyld[neq + iv - 1];
   g.sync();
-  for (size_t k = tid; k < nslab; k += g.nth) priv[k] = base[k];
+  // Private copy of the base planes: only the band of rows the windowed evaluation can touch (ranges j1p-1 .. j6p+2 of
+  // oderhs.m:868-964 around yc, all ix so that the X-point cuts stay connected), the two rows of the X-point vertex average
+  // (convert.m:831-868, evaluated by every window) and the line arrays in full.  Rows outside the band keep whatever an earlier
+  // unknown left there: nothing in the band's result reads them (tests/test_gen_hostcheck.py poisons them with NaN to show it).
+  {
+    const int NXS = g.NXS, NC = g.NC, nrow = g.ny + 2;
+    const int r0 = mx(0, yc - band), r1 = mn(nrow - 1, yc + band);
+    const int nfield = npl - UE_GEN_NLINE;
+#if defined(UE_GEN_HOST)
+    if (g_poison) for (size_t k = 0; k < (size_t)npl * NC; ++k) priv[k] = (double)NAN;
+#endif
+    const int w = (r1 - r0 + 1) * NXS;
+    {  // one flat loop over (plane, element of the band): independent loads, so that several are in flight per thread
+      const int tot = nfield * w;
+      const size_t o0 = (size_t)r0 * NXS;
+#pragma unroll 4
+      for (int k = tid; k < tot; k += g.nth) {
+        const int p = tot < (1 << 22) ? UE_ROW_(k, w) : k / w;  // (the float quotient is exact below 2^22)
+        const size_t o = (size_t)p * NC + o0 + (size_t)(k - p * w);
+        priv[o] = base[o];
+      }
+    }
+    if (g.iysptrx1 >= 0 && (g.iysptrx1 < r0 || g.iysptrx1 + 1 > r1)) {  // X-point rows jsx, jsx+1 when they lie outside the band
+      const int x0 = mx(0, g.iysptrx1), x1 = mn(nrow - 1, g.iysptrx1 + 1);
+      const int wx = (x1 - x0 + 1) * NXS;
+      for (int p = 0; p < nfield; ++p) {
+        const size_t o = (size_t)p * NC + (size_t)x0 * NXS;
+        for (int k = tid; k < wx; k += g.nth) priv[o + k] = base[o + k];
+      }
+    }
+    const int nl = mx(NXS, nrow);
+    for (int p = nfield; p < npl; ++p) {
+      const size_t o = (size_t)p * NC;
+      for (int k = tid; k < nl; k += g.nth) priv[o + k] = base[o + k];
+    }
+  }
   for (int64_t k = tid; k < neq + 2; k += g.nth) ylp[k] = yl[k];
   for (int64_t k = tid; k < neq; k += g.nth) wk[k] = yldot00[k];
   g.sync();
-  const int xc = (int)g.igyld[iv - 1], yc = (int)g.igyld[neq + iv - 1];
   const double yold = yl[iv - 1];
   const double dyl = g.delpert * (fabs(yold) + g.dylconst / g.suscal[iv - 1]);
   if (tid == 0) ylp[iv - 1] = yold + dyl;
@@ -186,8 +228,9 @@ __global__ void k_gen_full(const Gen* gsrc, double* base, const double* yl, doub
   if (rc && threadIdx.x == 0) { err[0] = rc; err[1] = g->errc; }
 }
 // one warp per unknown of the chunk [iv0, iv0 + ncol): every warp has its own context (shared memory) and its own planes
-__global__ void k_gen_cols(const Gen* gsrc, const double* base, double* priv, int npl, int64_t iv0, int ncol, const double* yl, double* ylp, double* wk,
-                           const double* yldot00, int64_t ml, int64_t mu, int cap, int* frow, double* fval, int* cnt, int* err, int tpu) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_gen_cols(const Gen* gsrc, const double* base, double* priv, int npl, int64_t iv0, int ncol, const double* yl, double* ylp, double* wk,
+                           const double* yldot00, int64_t ml, int64_t mu, int cap, int* frow, double* fval, int* cnt, int* err, int tpu, int band) {
   // a unit = the threads that evaluate one unknown: a warp (4 units per block) or, with tpu > 32, the whole block
   const int unit = tpu > 32 ? 0 : (int)(threadIdx.x >> 5), lane = tpu > 32 ? (int)threadIdx.x : (int)(threadIdx.x & 31);
   Gen* g = (Gen*)g_smem + unit;
@@ -201,7 +244,7 @@ __global__ void k_gen_cols(const Gen* gsrc, const double* base, double* priv, in
   const int64_t iv = iv0 + c;
   const int64_t neq = g->neq;
   const int rc = eval_column(*g, base, npl, iv, yl, ylp + (size_t)c * (neq + 2), wk + (size_t)c * neq, yldot00, ml, mu, cap, frow + (size_t)(iv - 1) * cap,
-                             fval + (size_t)(iv - 1) * cap, cnt + (iv - 1));
+                             fval + (size_t)(iv - 1) * cap, cnt + (iv - 1), band);
   if (tpu > 32) __syncthreads(); else __syncwarp();
   if (rc && lane == 0) { err[0] = rc; err[1] = g->errc; }
   if (lane == 0 && cnt[iv - 1] > cap) err[2] = cnt[iv - 1];
@@ -415,6 +458,10 @@ int init_all() {
   if (!mem_put(d_G, &g, sizeof(Gen))) return -10;
   if (const char* e = getenv("UE_GEN_COLCAP")) COLCAP = std::max(16, atoi(e));
   if (const char* e = getenv("UE_GEN_TPU")) g_tpu = atoi(e) > 32 ? 64 : 32;
+  if (const char* e = getenv("UE_GEN_BAND")) g_band = std::max(UE_GEN_BAND_DEFAULT, atoi(e));
+#if defined(UE_GEN_HOST)
+  g_poison = getenv("UE_GEN_POISON") != nullptr;
+#endif
   g_ivmin = 1; g_ivmax = g.neq;
   g_ready = true;
   return 0;
@@ -431,8 +478,13 @@ int run_full(const double* yl_host, double* yldot_host) {
   int zero[4] = {0, 0, 0, 0};
   if (!mem_put(d_err, zero, sizeof zero)) return -10;
   const int nthr = std::min(256, std::max(64, ((G.NC + 31) / 32) * 32));  // one cell per thread up to 256 threads
+  static cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (!e0) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
+  cudaEventRecord(e0);
   k_gen_full<<<1, nthr, sizeof(Gen)>>>(d_G, d_base, d_yl, d_yldot, d_err);
+  cudaEventRecord(e1);
   if (!ck(cudaGetLastError(), "k_gen_full launch") || !ck(cudaDeviceSynchronize(), "k_gen_full")) return -10;
+  cudaEventElapsedTime(&g_full_ms, e0, e1);
   int e[4];
   if (!mem_get(e, d_err, sizeof e)) return -10;
   if (e[0]) return report(e[0], e[1]);
@@ -494,8 +546,15 @@ int UE_PREFIX(jac_calc)(int64_t n, double t, const double* yl, const double* yld
   const int cap = COLCAP;
   const size_t nslab = (size_t)NPL * G.NC;
   const int64_t ncols_all = std::max<int64_t>(0, g_ivmax - g_ivmin + 1);
-  // private plane sets: as many unknowns at once as fit in 16 GB
-  size_t chunk = (size_t)std::max<int64_t>(1, std::min<int64_t>(ncols_all, (int64_t)((16ull << 30) / (nslab * 8))));
+  // private plane sets: as many unknowns at once as fit in half of the free device memory (host build: 1 GB)
+  size_t chunk = g_priv_cols;  // the allocation of the first Jacobian is kept (larger column ranges run in more chunks)
+  if (chunk == 0) {
+    size_t budget = 1ull << 30;
+#if !defined(UE_GEN_HOST)
+    { size_t fr = 0, tot = 0; if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) budget = fr / 2; }
+#endif
+    chunk = (size_t)std::max<int64_t>(1, std::min<int64_t>(ncols_all, (int64_t)(budget / (nslab * 8))));
+  }
   if (g_priv_cols < chunk) {
     d_priv = mem_alloc(chunk * nslab); d_ylp = mem_alloc(chunk * (neq + 2)); d_wk = mem_alloc(chunk * neq);
     if (!d_priv || !d_ylp || !d_wk) return -10;
@@ -520,7 +579,7 @@ int UE_PREFIX(jac_calc)(int64_t n, double t, const double* yl, const double* yld
   for (int64_t iv = g_ivmin; iv <= g_ivmax; ++iv) {
     Gen me = G; me.nth = 1; me.errc = 0;
     me.assign_planes(d_priv);
-    const int rc = eval_column(me, d_base, NPL, iv, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow + (size_t)(iv - 1) * cap, d_fval + (size_t)(iv - 1) * cap, d_cnt + (iv - 1));
+    const int rc = eval_column(me, d_base, NPL, iv, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow + (size_t)(iv - 1) * cap, d_fval + (size_t)(iv - 1) * cap, d_cnt + (iv - 1), g_band);
     if (rc) return report(rc, me.errc);
     if (d_cnt[iv - 1] > cap) { g_err = "column fragment capacity exceeded: set UE_GEN_COLCAP"; return -2; }
   }
@@ -542,20 +601,30 @@ int UE_PREFIX(jac_calc)(int64_t n, double t, const double* yl, const double* yld
   if (!mem_put(d_err, zero, sizeof zero)) return -10;
   if (!ck(cudaMemset(d_cnt, 0, (2 * neq + 2) * sizeof(int)), "memset")) return -10;
   const int WPB = 4;
+  static cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+  if (!e0) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); }
+  cudaEventRecord(e0);
   for (int64_t iv0 = g_ivmin; iv0 <= g_ivmax; iv0 += (int64_t)chunk) {
     const int ncol = (int)std::min<int64_t>((int64_t)chunk, g_ivmax - iv0 + 1);
+    // few unknowns: every warp is alone on its scheduler, registers are free (158, no spills); many unknowns: 4 blocks per SM
+    // (128 registers, a few spills) so that more chains overlap
     if (g_tpu > 32)
-      k_gen_cols<<<ncol, g_tpu, sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, iv0, ncol, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, g_tpu);
+      k_gen_cols<1><<<ncol, g_tpu, sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, iv0, ncol, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, g_tpu, g_band);
+    else if (ncol <= 4096)
+      k_gen_cols<1><<<(ncol + WPB - 1) / WPB, 32 * WPB, WPB * sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, iv0, ncol, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, 32, g_band);
     else
-      k_gen_cols<<<(ncol + WPB - 1) / WPB, 32 * WPB, WPB * sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, iv0, ncol, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, 32);
+      k_gen_cols<4><<<(ncol + WPB - 1) / WPB, 32 * WPB, WPB * sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, iv0, ncol, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, 32, g_band);
     if (!ck(cudaGetLastError(), "k_gen_cols launch")) return -10;
   }
+  cudaEventRecord(e1);
   int* rowcnt = d_cnt + neq;
   k_gen_count<<<(unsigned)((neq + 127) / 128), 128>>>((int64_t)neq, cap, d_cnt, d_frow, rowcnt);
   k_gen_scan<<<1, 1024>>>((int64_t)neq, rowcnt, d_ia, rowcnt);
   k_gen_fill<<<(unsigned)neq, 64>>>((int64_t)neq, cap, d_cnt, d_frow, d_fval, d_ia, rowcnt, nnzmx, d_jac2, d_ja2);
   k_gen_sortrows<<<(unsigned)((neq + 3) / 4), 128>>>((int64_t)neq, d_ia, nnzmx, d_jac2, d_ja2, d_jac, d_ja);
+  cudaEventRecord(e2);
   if (!ck(cudaGetLastError(), "CSR kernels launch") || !ck(cudaDeviceSynchronize(), "Jacobian kernels")) return -10;
+  cudaEventElapsedTime(&g_cols_ms, e0, e1); cudaEventElapsedTime(&g_csr_ms, e1, e2);
   int e[4];
   if (!mem_get(e, d_err, sizeof e)) return -10;
   if (e[0]) return report(e[0], e[1]);
@@ -567,6 +636,13 @@ int UE_PREFIX(jac_calc)(int64_t n, double t, const double* yl, const double* yld
   *nnz_out = nnz;
   return 0;
 #endif
+}
+// CUDA-event times (ms) of the kernels of the last calls: full-domain residual, Jacobian columns, CSR transpose (0 in the host build)
+int UE_PREFIX(last_kernel_ms)(double* resid_ms, double* cols_ms, double* csr_ms) {
+  if (resid_ms) *resid_ms = g_full_ms;
+  if (cols_ms) *cols_ms = g_cols_ms;
+  if (csr_ms) *csr_ms = g_csr_ms;
+  return 0;
 }
 // copy a named intermediate plane of the base set out ("fnix1", "fnix2", "feex", ...)
 int UE_PREFIX(get_plane)(const char* name, double* out) {
