@@ -10,7 +10,7 @@ from tests.refplanes import check_against_reference
 from tests.test_oracle2_golden import twin
 from tests.util import psetnk_inputs
 from uedge_b200.cases import box2_case
-from uedge_b200.cases2 import SUBSETS, Oracle2, box2_initial_state, d3d_full_physics_case, inputex_case, load_gen
+from uedge_b200.cases2 import SUBSETS, Oracle2, box2_initial_state, d3d_full_physics_case, inputex_case, load_gen, switch_variant
 
 pytestmark = pytest.mark.gpu
 
@@ -48,6 +48,22 @@ def test_box2_as_its_deck_runs_it(built):
     c = box2_case(isupgon=1)  # inertial atoms (box2_in.py:114-131)
     yl = box2_initial_state(c)
     same(Oracle2().bind(c), load_gen().bind(c), c, yl)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_switch_combinations(built, seed):
+    """random combinations of differencing schemes (0-8 in x and y), flux-limit / viscosity / conductivity options, rate models,
+    boundary options and 4th-order terms on the input_example case: bit-identical to the oracle (non-finite values included)."""
+    mods, desc = switch_variant(seed)
+    c, yl, _ = inputex_case("default", mods=mods)
+    b = c.bbb
+    o, g = Oracle2().bind(c), load_gen().bind(c)
+    for lib in (o, g):
+        lib.pandf1(yl)
+    fo, fg = o.pandf1(yl), g.pandf1(yl)
+    assert np.array_equal(fo, fg, equal_nan=True), desc
+    jo, jg = o.jac_calc(yl, fo, b.lbw, b.ubw, b.nnzmx), g.jac_calc(yl, fg, b.lbw, b.ubw, b.nnzmx)
+    assert all(np.array_equal(p, q, equal_nan=True) for p, q in zip(jo, jg)), desc
 
 
 def test_full_physics_on_the_d3d_mesh(built):

@@ -10,7 +10,7 @@ from .cases import GOLDEN, load_grid_npz
 SUBSETS = ("default", "ni", "ni-0", "ni-1", "up", "up-0", "up-1", "te", "ti", "phi")
 
 
-def inputex_case(subset="default"):
+def inputex_case(subset="default", mods=None):
     """pyexamples/input_example/input.py:19-110 on its 8x4 mesh; `subset` = which equations are on, as the groups
     pytests/<subset> of its solution.h5 record them (isnion/isupon/isteon/istion/isphion)."""
     g = load_grid_npz(os.path.join(GOLDEN, "inputex_8x4_grid.npz"))
@@ -36,6 +36,8 @@ def inputex_case(subset="default"):
     p = "pytests__%s__" % subset
     b.isnion = z[p + "isnion"].astype(np.int64).copy(); b.isupon = z[p + "isupon"].astype(np.int64).copy()
     b.isteon = int(z[p + "isteon"]); b.istion = int(z[p + "istion"]); b.isphion = int(z[p + "isphion"]); b.isphiofft = 0
+    if mods is not None:
+        mods(b, com)
     c.setup()
     T = lambda a: np.ascontiguousarray(a.T)
     nis, ups = z["bbb__nis"], z["bbb__ups"]
@@ -106,6 +108,45 @@ def d3d_full_physics_case(grid=None):
         ni, up, te, ti, ng = refine_state((ni, up, te, ti, ng), fx, fy)
     yl = c.set_state2([ni, ng], [up, 0.3 * up], te, ti, ng=ng, phi=3.0 * te / b.ev, tg=ti)
     return c, yl
+
+
+def switch_variant(seed):
+    """A random combination of the switches and coefficients the general path implements beyond the input_example deck (differencing
+    schemes 0-8, flux limits, viscosity and conductivity options, rate models, boundary options, 4th-order terms): returns a function
+    (b, com) -> None for inputex_case(mods=...), and a description."""
+    rng = np.random.default_rng(seed)
+    pick = lambda *a: a[int(rng.integers(len(a)))]
+    ch = {}
+    if rng.random() < 0.8:
+        m = pick(0, 1, 2, 3, 4, 5, 6, 7) + 10 * pick(0, 1, 2, 3, 4, 5, 6, 7)
+        ch["methn"] = pick(22, 33, 66, 23, 36, 62, 77); ch["methu"] = m; ch["methe"] = pick(m, 33, 22, 45, 54); ch["methi"] = pick(m, 33, 44, 55)
+        ch["methg"] = pick(66, 33, 22, 77, 63, 26)
+    for k, vals in (("isgxvon", (0, 1)), ("ishavisy", (1, 0)), ("isvhyha", (0, 1)), ("isvylog", (0, 1)), ("isintlog", (0, 1)), ("isflxlde", (0, 1)), ("isflxldi", (2, 0, 1)),
+                    ("convis", (0, 1)), ("concap", (0, 1)), ("isgpye", (0, 1)), ("isnupdot1sd", (0, 1)), ("islnlamcon", (0, 1)), ("icnuiz", (0, 1)), ("icnucx", (0, 1, 2)),
+                    ("isrecmon", (0, 1)), ("isplflxl", (0, 1)), ("isgasdc", (0, 1)), ("isdifxg_aug", (0, 1)), ("isdifyg_aug", (0, 1)), ("ifluxni", (1, 0)),
+                    ("isrefluxclip", (1, 0)), ("iflcore", (0, 1, -1)), ("isexunif", (0, 1)), ("isugfm1side", (0, 1)), ("oldseec", (0.0, 1.0)), ("isoldalbarea", (0.0, 1.0)),
+                    ("kye4order", (0.0, 1e-3)), ("kyi4order", (0.0, 2e-3)), ("isbcwdt", (0, 1)), ("inkxc", (0, 1, 2)), ("ingb", (2, 0, 1)), ("inflbg", (4, 2))):
+        if rng.random() < 0.35:
+            ch[k] = pick(*vals)
+    idx = {}
+    for k, i, vals in (("isupss", 0, (0, 1, -1)), ("isnicore", 0, (1, 0)), ("isupcore", 0, (0, 1, 2, 3)), ("isupcore", 1, (0, 1)), ("dif4order", 0, (0.0, 1e-3)),
+                       ("newbcl", 0, (0, 1)), ("newbcr", 0, (0, 1)), ("difpr", 0, (0.0, 0.3)), ("difni2", 0, (0.0, 0.2)), ("difpr2", 0, (0.0, 0.1)), ("difax", 0, (0.0, 0.5)),
+                       ("nlimix", 0, (0.0, 0.1)), ("nlimiy", 0, (0.0, 1e17)), ("vcony", 0, (0.0, 2.0)), ("cfvisxy", 0, (1.0, 0.0)), ("cfvisxy", 1, (1.0, 0.5))):
+        if rng.random() < 0.3:
+            idx[(k, i)] = pick(*vals)
+    istab = pick(0, 0, 7) if rng.random() < 0.4 else None
+
+    def mods(b, com):
+        for k, v in ch.items():
+            setattr(b, k, v)
+        for (k, i), v in idx.items():
+            a = np.asarray(getattr(b, k)).copy()
+            a[i] = v
+            setattr(b, k, a)
+        if istab is not None:
+            com.istabon = istab
+
+    return mods, dict(ch, **{"%s[%d]" % k: v for k, v in idx.items()}, istabon=istab)
 
 
 class Lib2:
