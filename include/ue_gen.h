@@ -35,6 +35,14 @@ int ue_gen_jac_calc(int64_t neq, double t, const double* yl, const double* yldot
                     int64_t* ia, int64_t* nnz);
 /* one intermediate field plane of the last full evaluation by name ("fnix1", "feex", "resphi", ...): (ny+2) x (nx+2) doubles */
 int ue_gen_get_plane(const char* name, double* out);
+/* ONE Jacobian over the GPUs of a node (ppp jac_calc_mpi, ppp/mpi_parallel.F90:2-447): one process per GPU, every rank with the full
+ * state.  Collective, after ue_gen_init on every rank; id128 is the NCCL id rank 0 obtained from ue_gpu_comm_unique_id and the host
+ * distributed (MPI_Bcast).  Afterwards ue_gen_jac_calc evaluates only this rank's share of the columns, exchanges the column fragments
+ * with the other ranks on the device (grouped in-place ncclBroadcast) and returns the FULL CSR on every rank.  ue_gen_last_comm_ms:
+ * CUDA-event time of that exchange in the last call. */
+int ue_gen_comm_init(int64_t nranks, int64_t rank, const char* id128);
+int ue_gen_comm_finalize(void);
+int ue_gen_last_comm_ms(double* comm_ms);
 /* CUDA-event times (ms) of the kernels of the last ue_gen_pandf1 / ue_gen_jac_calc: residual, Jacobian columns, CSR transpose */
 int ue_gen_last_kernel_ms(double* resid_ms, double* cols_ms, double* csr_ms);
 const char* ue_gen_last_error(void);

@@ -214,3 +214,19 @@ def split_init(lib, world, rank, dist, torch, transport="p2p"):
         raise RuntimeError(lib.ue_gpu_last_error().decode())
     torch.cuda.synchronize()
     dist.barrier()
+
+
+def split_init_gen(lib, world, rank, dist, torch):
+    """The same for the general path (ue_gen_comm_init, include/ue_gen.h): NCCL id from rank 0, then the collective init."""
+    import ctypes as C
+    lib.ue_gpu_comm_unique_id.argtypes = [C.c_char_p]
+    lib.ue_gen_comm_init.argtypes = [C.c_int64, C.c_int64, C.c_char_p]
+    idbuf = C.create_string_buffer(128)
+    if rank == 0 and lib.ue_gpu_comm_unique_id(idbuf) != 0:
+        raise RuntimeError(lib.ue_gpu_last_error().decode())
+    t = torch.frombuffer(bytearray(idbuf.raw), dtype=torch.uint8).cuda()
+    dist.broadcast(t, 0)
+    if lib.ue_gen_comm_init(world, rank, bytes(t.cpu().numpy().tobytes())) != 0:
+        raise RuntimeError(lib.ue_gen_last_error().decode())
+    torch.cuda.synchronize()
+    dist.barrier()

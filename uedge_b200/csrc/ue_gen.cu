@@ -24,6 +24,8 @@
 
 #if !defined(UE_GEN_HOST)
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 #endif
 
 namespace {
@@ -78,12 +80,24 @@ double *d_jac = nullptr, *d_jac2 = nullptr;
 int64_t g_nnzmx = 0;
 int NPL = 0;
 int COLCAP = 512;
+float g_comm_ms = 0.f;
 float g_full_ms = 0.f, g_cols_ms = 0.f, g_csr_ms = 0.f;  // CUDA-event times of the last residual / column / CSR kernels
 #define UE_GEN_BAND_DEFAULT 5
 int g_band = UE_GEN_BAND_DEFAULT;  // rows of the private copy on each side of the perturbed cell (env UE_GEN_BAND; large = all rows)
 int g_tpu = 32;  // threads per unknown in the Jacobian kernel: 32 (a warp) or 64 (a two-warp block)
 V g_last_yl;  // the state the base planes were last evaluated at
 int64_t g_ivmin = 1, g_ivmax = 0;
+
+#if !defined(UE_GEN_HOST)
+// multi-GPU state (ue_gen_comm_init)
+ncclComm_t gc_comm = nullptr;
+int gc_nranks = 1, gc_rank = 0;
+std::vector<int> gc_list_all, gc_list_off;   // unknowns (1-based) by rank, and the offsets of the rank segments (nranks + 1)
+int *d_list_all = nullptr, *d_list_off = nullptr, *d_pk_cnt = nullptr, *d_pk_row = nullptr;
+int64_t* d_pk_off = nullptr;
+long long* d_pk_tot = nullptr;
+double* d_pk_val = nullptr;
+#endif
 
 const V* find(const char* n) { auto it = IN.find(n); return it == IN.end() ? nullptr : &it->second; }
 double SC(const char* n, int k = 0) {
@@ -116,6 +130,10 @@ void free_all() {
   d_G = nullptr; d_base = d_priv = d_yl = d_yldot = d_y00 = d_ylp = d_wk = d_step = d_fval = d_jac = nullptr;
   d_cnt = d_frow = d_err = nullptr; d_ia = d_ja = d_ja2 = nullptr; d_jac2 = nullptr;
   g_priv_cols = 0; g_nnzmx = 0; g_ready = false; g_last_yl.clear();
+#if !defined(UE_GEN_HOST)
+  gc_nranks = 1; gc_rank = 0;  // (the lists belonged to the case that was just freed; the communicator itself lives until comm_finalize)
+  d_list_all = d_list_off = d_pk_cnt = d_pk_row = nullptr; d_pk_off = nullptr; d_pk_tot = nullptr; d_pk_val = nullptr;
+#endif
 }
 template <typename T> T* alloc_as(size_t n) {
   double* p = mem_alloc((n * sizeof(T) + sizeof(double) - 1) / sizeof(double));
@@ -229,7 +247,7 @@ __global__ void k_gen_full(const Gen* gsrc, double* base, const double* yl, doub
 }
 // one warp per unknown of the chunk [iv0, iv0 + ncol): every warp has its own context (shared memory) and its own planes
 template <int MINB>
-__global__ void __launch_bounds__(128, MINB) k_gen_cols(const Gen* gsrc, const double* base, double* priv, int npl, int64_t iv0, int ncol, const double* yl, double* ylp, double* wk,
+__global__ void __launch_bounds__(128, MINB) k_gen_cols(const Gen* gsrc, const double* base, double* priv, int npl, int64_t iv0, const int* ivlist, int ncol, const double* yl, double* ylp, double* wk,
                            const double* yldot00, int64_t ml, int64_t mu, int cap, int* frow, double* fval, int* cnt, int* err, int tpu, int band) {
   // a unit = the threads that evaluate one unknown: a warp (4 units per block) or, with tpu > 32, the whole block
   const int unit = tpu > 32 ? 0 : (int)(threadIdx.x >> 5), lane = tpu > 32 ? (int)threadIdx.x : (int)(threadIdx.x & 31);
@@ -241,7 +259,7 @@ __global__ void __launch_bounds__(128, MINB) k_gen_cols(const Gen* gsrc, const d
   const size_t nslab = (size_t)npl * g->NC;
   if (lane == 0) { g->nth = tpu; g->errc = 0; g->assign_planes(priv + (size_t)c * nslab); }
   if (tpu > 32) __syncthreads(); else __syncwarp();
-  const int64_t iv = iv0 + c;
+  const int64_t iv = ivlist ? (int64_t)ivlist[c] : iv0 + c;  // (multi-GPU: this rank's unknowns are a list of mesh rows)
   const int64_t neq = g->neq;
   const int rc = eval_column(*g, base, npl, iv, yl, ylp + (size_t)c * (neq + 2), wk + (size_t)c * neq, yldot00, ml, mu, cap, frow + (size_t)(iv - 1) * cap,
                              fval + (size_t)(iv - 1) * cap, cnt + (iv - 1), band);
@@ -301,6 +319,132 @@ __global__ void k_gen_sortrows(int64_t neq, const int64_t* ia, int64_t nnzmx, co
     for (int64_t j = a; j < b; ++j) rank += (ja_in[j] < cj);
     ja[a + rank] = cj; jac[a + rank] = jac_in[i];
   }
+}
+#endif
+
+#if !defined(UE_GEN_HOST)
+// ---- packing of the column fragments for the exchange (multi-GPU) ---------------------------------------------------------
+// segment = the unknowns of one rank in list order.  k_gen_segscan: block s scans the counts of segment s (exclusive) and leaves
+// the segment total; own = 1: the counts are first gathered from cnt[iv-1] (this rank's fresh results) into pk_cnt.
+__global__ void k_gen_segscan(const int* list_all, const int* list_off, int seg0, const int* cnt, int* pk_cnt, int64_t* pk_off, long long* tot, int own) {
+  const int s = seg0 + blockIdx.x;
+  const int a = list_off[s], b = list_off[s + 1];
+  __shared__ long long carry;
+  __shared__ long long part[1024];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int b0 = a; b0 < b; b0 += blockDim.x) {
+    const int j = b0 + threadIdx.x;
+    long long v = 0;
+    if (j < b) { if (own) pk_cnt[j] = cnt[list_all[j] - 1]; v = pk_cnt[j]; }
+    part[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < (int)blockDim.x; off <<= 1) {
+      const long long t = (int)threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+      __syncthreads();
+      part[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (j < b) pk_off[j] = carry + part[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry += part[threadIdx.x];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) tot[s] = carry;
+}
+// dir = 0: strided fragments of this rank's columns -> its packed segment; dir = 1: packed segments of all ranks -> strided fragments
+__global__ void k_gen_packcopy(const int* list_all, const int* list_off, int nseg, int j0, int j1, int cap, int* cnt, int* frow, double* fval, const int* pk_cnt,
+                               const int64_t* pk_off, int* pk_row, double* pk_val, int dir, int skip_seg) {
+  const int j = j0 + blockIdx.x;
+  if (j >= j1) return;
+  int s = 0;
+  while (s + 1 < nseg && list_off[s + 1] <= j) ++s;
+  if (dir == 1 && s == skip_seg) return;  // (own columns are already in place)
+  const int64_t iv = list_all[j];
+  const int n = min(pk_cnt[j], cap);
+  const size_t p = (size_t)list_off[s] * cap + (size_t)pk_off[j], q = (size_t)(iv - 1) * cap;
+  if (dir == 0) { for (int k = threadIdx.x; k < n; k += blockDim.x) { pk_row[p + k] = frow[q + k]; pk_val[p + k] = fval[q + k]; } }
+  else {
+    for (int k = threadIdx.x; k < n; k += blockDim.x) { frow[q + k] = pk_row[p + k]; fval[q + k] = pk_val[p + k]; }
+    if (threadIdx.x == 0) cnt[iv - 1] = pk_cnt[j];
+  }
+}
+// ---- multi-GPU: the columns of ONE Jacobian split over the ranks (ppp jac_calc_mpi, ppp/mpi_parallel.F90:2-447).  The column
+// kernel is throughput-bound once the mesh is large (one warp and one private plane set per unknown), so the split scales; the
+// fragments (count, rows, values per column) are exchanged in place with grouped ncclBroadcast calls and every rank builds the CSR.
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+} NCG;
+int nccl_bind() {
+  if (NCG.h) return 0;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // the copy the host process already loaded (e.g. torch's)
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { g_err = std::string("cannot load libnccl.so.2: ") + dlerror(); return -11; }
+#define B(f) *(void**)(&NCG.f) = dlsym(h, "nccl" #f); if (!NCG.f) { g_err = "libnccl.so.2 lacks nccl" #f; return -11; }
+  B(CommInitRank) B(CommDestroy) B(GroupStart) B(GroupEnd) B(Broadcast) B(AllGather) B(GetErrorString)
+#undef B
+  NCG.h = h;
+  return 0;
+}
+#define NCK(call)                                                                                                 \
+  do {                                                                                                            \
+    ncclResult_t r_ = (call);                                                                                     \
+    if (r_ != ncclSuccess) { g_err = std::string("NCCL error: ") + NCG.GetErrorString(r_) + " at " #call; return -11; } \
+  } while (0)
+// Ownership: mesh ROWS are dealt out cyclically (row iy belongs to rank iy mod nranks).  The windows of the rows near the X-point
+// span all ix (xccuts) and cost several times more than the others; a contiguous split would leave them all on the first ranks.
+int build_rank_lists(int nranks) {
+  const V* ig = find("igyl");
+  const size_t neq = (size_t)G.neq;
+  gc_list_all.clear(); gc_list_off.assign(nranks + 1, 0);
+  for (int r = 0; r < nranks; ++r) {
+    gc_list_off[r] = (int)gc_list_all.size();
+    for (size_t iv = 1; iv <= neq; ++iv) if (((int)(*ig)[neq + iv - 1]) % nranks == r) gc_list_all.push_back((int)iv);
+  }
+  gc_list_off[nranks] = (int)gc_list_all.size();
+  d_list_all = alloc_as<int>(neq); d_list_off = alloc_as<int>(nranks + 1); d_pk_cnt = alloc_as<int>(neq); d_pk_off = alloc_as<int64_t>(neq);
+  d_pk_tot = alloc_as<long long>(2 * nranks + 2);
+  if (!d_list_all || !d_list_off || !d_pk_cnt || !d_pk_off || !d_pk_tot) return -10;
+  if (!mem_put(d_list_all, gc_list_all.data(), neq * sizeof(int)) || !mem_put(d_list_off, gc_list_off.data(), (nranks + 1) * sizeof(int))) return -10;
+  return 0;
+}
+// after this rank's columns are in the strided fragment arrays: pack them, exchange the packed segments, unpack the others'
+int exchange_fragments(int cap) {
+  const int N = gc_nranks, me = gc_rank;
+  const size_t neq = (size_t)G.neq;
+  if (!d_pk_row) {
+    d_pk_row = alloc_as<int>(neq * cap); d_pk_val = mem_alloc(neq * cap);
+    if (!d_pk_row || !d_pk_val) return -10;
+    g_allocs.push_back(d_pk_val);
+  }
+  const int a = gc_list_off[me], b = gc_list_off[me + 1];
+  k_gen_segscan<<<1, 1024>>>(d_list_all, d_list_off, me, d_cnt, d_pk_cnt, d_pk_off, d_pk_tot, 1);
+  if (b > a) k_gen_packcopy<<<b - a, 64>>>(d_list_all, d_list_off, N, a, b, cap, d_cnt, d_frow, d_fval, d_pk_cnt, d_pk_off, d_pk_row, d_pk_val, 0, -1);
+  // every rank needs every segment's size on the host (the broadcast counts): all-gather of one number per rank
+  NCK(NCG.AllGather(d_pk_tot + me, d_pk_tot + N + 1, 1, ncclInt64, gc_comm, 0));
+  std::vector<long long> tot(N);
+  if (!ck(cudaMemcpy(tot.data(), d_pk_tot + N + 1, N * sizeof(long long), cudaMemcpyDeviceToHost), "segment sizes")) return -10;
+  NCK(NCG.GroupStart());
+  for (int r = 0; r < N; ++r) {
+    const size_t o = (size_t)gc_list_off[r], n = (size_t)(gc_list_off[r + 1] - gc_list_off[r]);
+    if (n == 0) continue;
+    NCK(NCG.Broadcast(d_pk_cnt + o, d_pk_cnt + o, n, ncclInt32, r, gc_comm, 0));
+    if (tot[r] > 0) {
+      NCK(NCG.Broadcast(d_pk_row + o * cap, d_pk_row + o * cap, (size_t)tot[r], ncclInt32, r, gc_comm, 0));
+      NCK(NCG.Broadcast(d_pk_val + o * cap, d_pk_val + o * cap, (size_t)tot[r], ncclFloat64, r, gc_comm, 0));
+    }
+  }
+  NCK(NCG.GroupEnd());
+  k_gen_segscan<<<N, 1024>>>(d_list_all, d_list_off, 0, d_cnt, d_pk_cnt, d_pk_off, d_pk_tot, 0);
+  k_gen_packcopy<<<(unsigned)neq, 64>>>(d_list_all, d_list_off, N, 0, (int)neq, cap, d_cnt, d_frow, d_fval, d_pk_cnt, d_pk_off, d_pk_row, d_pk_val, 1, me);
+  return 0;
 }
 #endif
 
@@ -514,7 +658,14 @@ int UE_PREFIX(init)(void) {
   if (rc) free_all();
   return rc;
 }
-int UE_PREFIX(finalize)(void) { free_all(); return 0; }
+int UE_PREFIX(finalize)(void) {
+#if !defined(UE_GEN_HOST)
+  if (gc_comm) { cudaDeviceSynchronize(); NCG.CommDestroy(gc_comm); gc_comm = nullptr; }
+  gc_nranks = 1; gc_rank = 0;
+#endif
+  free_all();
+  return 0;
+}
 int UE_PREFIX(step_params)(int64_t n, const double* dt, const double* yo, const double* su, const double* sf) {
   if (!g_ready) { g_err = "init not called"; return -1; }
   if (n != G.neq || !dt || !yo || !su || !sf) { g_err = "step_params: neq mismatch or null pointer"; return -1; }
@@ -545,7 +696,10 @@ int UE_PREFIX(jac_calc)(int64_t n, double t, const double* yl, const double* yld
   if (!mem_put(d_yl, yl, (neq + 2) * 8) || !mem_put(d_y00, yldot00, neq * 8)) return -10;
   const int cap = COLCAP;
   const size_t nslab = (size_t)NPL * G.NC;
-  const int64_t ncols_all = std::max<int64_t>(0, g_ivmax - g_ivmin + 1);
+  int64_t ncols_all = std::max<int64_t>(0, g_ivmax - g_ivmin + 1);
+#if !defined(UE_GEN_HOST)
+  if (gc_nranks > 1) ncols_all = (ncols_all + gc_nranks - 1) / gc_nranks;
+#endif
   // private plane sets: as many unknowns at once as fit in half of the free device memory (host build: 1 GB)
   size_t chunk = g_priv_cols;  // the allocation of the first Jacobian is kept (larger column ranges run in more chunks)
   if (chunk == 0) {
@@ -603,20 +757,31 @@ int UE_PREFIX(jac_calc)(int64_t n, double t, const double* yl, const double* yld
   const int WPB = 4;
   static cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
   if (!e0) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); }
+  static cudaEvent_t ec = nullptr;
+  if (!ec) cudaEventCreate(&ec);
+  int64_t my_lo = g_ivmin, my_hi = g_ivmax;
+  const int* my_list = nullptr;
+  if (gc_nranks > 1) {
+    if (g_ivmin != 1 || g_ivmax != G.neq) { g_err = "a column range and a communicator cannot be combined"; return -1; }
+    my_list = d_list_all + gc_list_off[gc_rank]; my_lo = 1; my_hi = gc_list_off[gc_rank + 1] - gc_list_off[gc_rank];  // positions in the list
+  }
   cudaEventRecord(e0);
-  for (int64_t iv0 = g_ivmin; iv0 <= g_ivmax; iv0 += (int64_t)chunk) {
-    const int ncol = (int)std::min<int64_t>((int64_t)chunk, g_ivmax - iv0 + 1);
+  for (int64_t iv0 = my_lo; iv0 <= my_hi; iv0 += (int64_t)chunk) {
+    const int ncol = (int)std::min<int64_t>((int64_t)chunk, my_hi - iv0 + 1);
+    const int* ivl = my_list ? my_list + (iv0 - 1) : nullptr;
     // few unknowns: every warp is alone on its scheduler, registers are free (158, no spills); many unknowns: 4 blocks per SM
     // (128 registers, a few spills) so that more chains overlap
     if (g_tpu > 32)
-      k_gen_cols<1><<<ncol, g_tpu, sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, iv0, ncol, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, g_tpu, g_band);
+      k_gen_cols<1><<<ncol, g_tpu, sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, iv0, ivl, ncol, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, g_tpu, g_band);
     else if (ncol <= 4096)
-      k_gen_cols<1><<<(ncol + WPB - 1) / WPB, 32 * WPB, WPB * sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, iv0, ncol, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, 32, g_band);
+      k_gen_cols<1><<<(ncol + WPB - 1) / WPB, 32 * WPB, WPB * sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, iv0, ivl, ncol, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, 32, g_band);
     else
-      k_gen_cols<4><<<(ncol + WPB - 1) / WPB, 32 * WPB, WPB * sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, iv0, ncol, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, 32, g_band);
+      k_gen_cols<4><<<(ncol + WPB - 1) / WPB, 32 * WPB, WPB * sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, iv0, ivl, ncol, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, 32, g_band);
     if (!ck(cudaGetLastError(), "k_gen_cols launch")) return -10;
   }
   cudaEventRecord(e1);
+  if (gc_nranks > 1) { const int rc = exchange_fragments(cap); if (rc) return rc; }
+  cudaEventRecord(ec);
   int* rowcnt = d_cnt + neq;
   k_gen_count<<<(unsigned)((neq + 127) / 128), 128>>>((int64_t)neq, cap, d_cnt, d_frow, rowcnt);
   k_gen_scan<<<1, 1024>>>((int64_t)neq, rowcnt, d_ia, rowcnt);
@@ -624,7 +789,7 @@ int UE_PREFIX(jac_calc)(int64_t n, double t, const double* yl, const double* yld
   k_gen_sortrows<<<(unsigned)((neq + 3) / 4), 128>>>((int64_t)neq, d_ia, nnzmx, d_jac2, d_ja2, d_jac, d_ja);
   cudaEventRecord(e2);
   if (!ck(cudaGetLastError(), "CSR kernels launch") || !ck(cudaDeviceSynchronize(), "Jacobian kernels")) return -10;
-  cudaEventElapsedTime(&g_cols_ms, e0, e1); cudaEventElapsedTime(&g_csr_ms, e1, e2);
+  cudaEventElapsedTime(&g_cols_ms, e0, e1); cudaEventElapsedTime(&g_comm_ms, e1, ec); cudaEventElapsedTime(&g_csr_ms, ec, e2);
   int e[4];
   if (!mem_get(e, d_err, sizeof e)) return -10;
   if (e[0]) return report(e[0], e[1]);
@@ -637,6 +802,31 @@ int UE_PREFIX(jac_calc)(int64_t n, double t, const double* yl, const double* yld
   return 0;
 #endif
 }
+// one Jacobian over several GPUs: collective, after ue_gen_init on every rank; id128 from ue_gpu_comm_unique_id on rank 0
+int UE_PREFIX(comm_init)(int64_t nranks, int64_t rank, const char* id128) {
+#if defined(UE_GEN_HOST)
+  (void)nranks; (void)rank; (void)id128; g_err = "host build: no communicator"; return -1;
+#else
+  if (!g_ready) { g_err = "init not called"; return -1; }
+  if (nranks < 1 || rank < 0 || rank >= nranks || !id128) { g_err = "comm_init: bad rank / nranks"; return -1; }
+  int rc = nccl_bind();
+  if (rc) return rc;
+  if (gc_comm) { cudaDeviceSynchronize(); NCG.CommDestroy(gc_comm); gc_comm = nullptr; }
+  ncclUniqueId id;
+  std::memcpy(&id, id128, 128);
+  NCK(NCG.CommInitRank(&gc_comm, (int)nranks, id, (int)rank));
+  gc_nranks = (int)nranks; gc_rank = (int)rank;
+  d_pk_row = nullptr; d_pk_val = nullptr;
+  return nranks > 1 ? build_rank_lists((int)nranks) : 0;
+#endif
+}
+int UE_PREFIX(comm_finalize)(void) {
+#if !defined(UE_GEN_HOST)
+  if (gc_comm) { cudaDeviceSynchronize(); NCG.CommDestroy(gc_comm); gc_comm = nullptr; }
+  gc_nranks = 1; gc_rank = 0;
+#endif
+  return 0;
+}
 // CUDA-event times (ms) of the kernels of the last calls: full-domain residual, Jacobian columns, CSR transpose (0 in the host build)
 int UE_PREFIX(last_kernel_ms)(double* resid_ms, double* cols_ms, double* csr_ms) {
   if (resid_ms) *resid_ms = g_full_ms;
@@ -644,6 +834,7 @@ int UE_PREFIX(last_kernel_ms)(double* resid_ms, double* cols_ms, double* csr_ms)
   if (csr_ms) *csr_ms = g_csr_ms;
   return 0;
 }
+int UE_PREFIX(last_comm_ms)(double* comm_ms) { if (comm_ms) *comm_ms = g_comm_ms; return 0; }
 // copy a named intermediate plane of the base set out ("fnix1", "fnix2", "feex", ...)
 int UE_PREFIX(get_plane)(const char* name, double* out) {
   if (!g_ready || !name || !out) { g_err = "get_plane: not initialised / null pointer"; return -1; }
