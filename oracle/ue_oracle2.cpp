@@ -74,13 +74,16 @@ double ev, qe, me, mp, pi_, cutlo, rt8opi, temin, tgmin, nnorm, ennorm, temp0, v
     delpert, dylconst, jaccliplim, kelhihg, kelhghg, lgvmax, flgamvg, cfvisxn, cfvisyn, flgamtg, cfupcx, cfticx, cfnidh, cfnidh2, cfnidhdis, cfnidhgy,
     cfnidhg2, cftgeqp, flalftxy, flalfgnx, flalfgny, nlimgx, nlimgy, cfloxiplt, cfloygwall, cfjve, rsigpl, rsigplcore, bcen, bceew, bciew, cfqym, cfqydt,
     cfjpy, cfjp2, cfqybf, cfq2bf, cfqybbo, cfqydbo, cfydd_, cfjp2_, cfqyn, cfqyao, cfqya, cfqyae, cfjpy_, fqpsatlb_unused, lnlam_unused, phiwi0, phiwo0,
-    kappamx, kappa0, cfsigm, fqsatlb_u, fupe_cur, dtphi_, cfhcxgc_u, lyphi0, lyphi1, isparmultdt_u, tewallmin_u, cfwjdotelim, cfeexdbo, cfeixdbo, cfkincor;
+    kappamx, kappa0, cfsigm, fqsatlb_u, fupe_cur, dtphi_, cfhcxgc_u, lyphi0, lyphi1, isparmultdt_u, tewallmin_u, cfwjdotelim, cfeexdbo, cfeixdbo, cfkincor,
+    cfyef, cf2ef, cfybf, cf2bf, cfcurv, cfgradb, eycore, icoreelec, cfniybbo, cfeeybbo;
+int ExtendedJacPhi;
+int64_t numvar_;
 V cngfx_, cngfy_, mi, zi, n0, fnorm, n0g_, mg_, ngbackg_, vcony, difpr, difni, difni2, difpr2, difax, travis, parvis, nlimix, nlimiy, dif4order, cpiup, cfvgpx, cfvgpy,
     cfvcsx, cfvcsy, cfvisxy, cngmom, cmwall, cngtgx, cngtgy, cdifg, lgmax, lgtmax, rld2dxg, rld2dyg, cngflox, cngfloy, rtg2ti, tgas, istgcon, keligig,
     ncore, ngcore, upcore, curcore, albedoc, csfaclb, csfacrb, recycp, nwimin, nwomin;
 // geometry planes / lines
 const double *vol, *gx, *gy, *gxf, *gyf, *gxc, *gyc, *sx, *sxnp, *sy, *rr, *rrv, *volv, *syv, *dxnog, *dynog, *btot, *rbfbt, *rbfbt2, *lcone, *lconi, *angfx,
-    *ngfix, *dx_, *dy_;
+    *ngfix, *dx_, *dy_, *curvrby, *gradby, *curvrb2, *gradb2;
 const double *fxm[2], *fx0[2], *fxp[2], *fxmy[2], *fxpy[2], *fym[2], *fy0[2], *fyp[2], *fymx[2], *fypx[2], *fymv[2], *fy0v[2], *fypv[2], *fymxv[2], *fypxv[2];
 const double *ixm1d, *ixp1d, *isxptyd, *isxptxd;
 const double *fgtdx, *fgtdy, *flalfea, *flalfia, *flalfva, *flalfgxa, *flalfgxya, *flalfgya, *flalfvgxa, *flalfvgya, *flalfvgxya, *flalftgxa, *flalftgya, *yyf;
@@ -289,6 +292,7 @@ struct O2 {
   V gprx, gpry, gpex, gtex, gtix, gpey, gtey, gtiy, ex, ey, nity0, nity1, ney0, ney1, tey0, tey1, tiy0, tiy1, phiy0, phiy1;
   V ngy0, ngy1, tgy0, tgy1, pgy0, pgy1, phiv, tiv, tev, prev, prtv, priv[2];
   V loglambda, diffusivwrk, vy[2], vydd[2], vygp[2], v2[2], v2dd[2], v2xgp[2], vytan[2], frice, frici[2], upi[2], uup[2], uu[2], upe, vex, vey;
+  V vyce[2], vycb[2], vycp[2], veycb, v2ce[2], v2cb[2], ve2cb, wjdote;  // cross-field drift velocities (oderhs.m:1167-1420), Joule heating
   V nuiz, nurc, nucx, nuix, psorbgg, psorgc, psorc[2], psordis, psorxrc[2], psorrgc, psorg, psor[2], psorxr[2], psorrg;
   V snic[2], sniv[2], psori[2], smoc[2], smov[2], seec, seev, seic, seiv;
   V conxg, conyg, floxg, floyg, fngx, fngy, fngxy, vygtan, uug, uuxg, vyg, resng;
@@ -297,7 +301,7 @@ struct O2 {
   V floxe, floxi, floye, floyi, conxe, conxi, conye, conyi, feex, feey, feix, feiy, feexy, feixy, resee, resei;
   V erliz, erlrc, eeli, vsoreec, vsoree, pwribkg, pwrebkg, pradhyd;
   V fqp, fqx, fqy, fq2, fqxb, fqyb, fqyn, fqym, fqymi, fqya, fqydt, fqydti, fqyao, fqyae, fqyd, fqygp, fq2d, fqpsatlb_, netap, resphi, dphi_iy1;
-  V fniycbo[2], feeycbo, feiycbo, kappal, kappar, bcel, bcer, bcil, bcir, fqpsatlb, fqpsatrb;
+  V fniycbo[2], feeycbo, feiycbo, kappal, kappar, bcel, bcer, bcil, bcir, fqpsatlb, fqpsatrb, fdiaxlb, fdiaxrb;
   V dtuse, ylodt, suscal, sfscal;
   int64_t ivmin = 1, ivmax = 0;
   std::string err;
@@ -311,6 +315,7 @@ struct O2 {
     P1(gprx) P1(gpry) P1(gpex) P1(gtex) P1(gtix) P1(gpey) P1(gtey) P1(gtiy) P1(ex) P1(ey) P1(nity0) P1(nity1) P1(ney0) P1(ney1) P1(tey0) P1(tey1)
     P1(tiy0) P1(tiy1) P1(phiy0) P1(phiy1) P1(ngy0) P1(ngy1) P1(tgy0) P1(tgy1) P1(pgy0) P1(pgy1) P1(phiv) P1(tiv) P1(tev) P1(prev) P1(prtv) P2(priv)
     P1(loglambda) P1(diffusivwrk) P2(vy) P2(vydd) P2(vygp) P2(v2) P2(v2dd) P2(v2xgp) P2(vytan) P1(frice) P2(frici) P2(upi) P2(uup) P2(uu) P1(upe) P1(vex) P1(vey)
+    P2(vyce) P2(vycb) P2(vycp) P1(veycb) P2(v2ce) P2(v2cb) P1(ve2cb) P1(wjdote)
     P1(nuiz) P1(nurc) P1(nucx) P1(nuix) P1(psorbgg) P1(psorgc) P2(psorc) P1(psordis) P2(psorxrc) P1(psorrgc) P1(psorg) P2(psor) P2(psorxr) P1(psorrg)
     P2(snic) P2(sniv) P2(psori) P2(smoc) P2(smov) P1(seec) P1(seev) P1(seic) P1(seiv)
     P1(conxg) P1(conyg) P1(floxg) P1(floyg) P1(fngx) P1(fngy) P1(fngxy) P1(vygtan) P1(uug) P1(uuxg) P1(vyg) P1(resng)
@@ -789,30 +794,60 @@ struct O2 {
         else if (teev < 50.) A(loglambda, ix, iy) = 23.4 - 1.15 * ue_log10(1.e-6 * nexface) + 3.45 * ue_log10(teev);
         else A(loglambda, ix, iy) = 25.3 - 1.15 * ue_log10(1.e-6 * nexface) + 2.33167537087122e+00 * ue_log10(teev);
       }
-    // radial and "2" velocities of the ion species: diffusive parts only (all drift coefficients are zero) (oderhs.m:1167-1471)
+    // radial and "2" velocities of the ion species: diffusive parts plus the ExB and grad-B / curvature drifts (oderhs.m:1167-1471);
+    // the diamagnetic (cfydd, cf2dd), resistive (cfrd) and classical (cfvycf, cfvycr) parts are refused in init
     for (int f = 0; f < nfsp; ++f) {
       if (!(zi[f] > 1.e-10)) continue;
-      for (int iy = j1; iy <= j5; ++iy)
+      const double qion = zi[f] * qe;
+      for (int iy = j1; iy <= j5; ++iy) {
+        const int iyp1 = std::min(iy + 1, ny + 1);
         for (int ix = i1; ix <= i6; ++ix) {
+          const int ix3 = IXM1(ix, iy), ix4 = IXM1(ix, iy + 1);
+          const double temp1 = (-4.0) * (A(phiv, ix, iy) - A(phiv, ix3, iy)) * A(gxc, ix, iy);
+          const double temp2 = 4.0 * (A(priv[f], ix, iy) - A(priv[f], ix3, iy)) * A(gxc, ix, iy);
+          const double lambd_ci = 1e16 * sq(A(ti, ix, iy) / ev) / A(nit, ix, iy), lambd_ce = 2e16 * sq(A(te, ix, iy) / ev) / A(ne, ix, iy);
+          const double coll_fi = cfnus_i / (cfnus_i + (lambd_ci / (A(lconi, ix, iy)))), coll_fe = cfnus_e / (cfnus_e + (lambd_ce / (A(lcone, ix, iy))));
+          A(vyce[f], ix, iy) = 0.125 * temp1 * (A(rbfbt2, ix, iy) + A(rbfbt2, ix, iy + 1));
+          A(vycb[f], ix, iy) = (cfcurv * (0.5 * (A(ti, ix, iy) + A(ti, ix, iyp1)) + mi[f] * sq(0.25 * (A(up[f], ix, iy) + A(up[f], ix, iyp1) + A(up[f], ix3, iy) + A(up[f], ix4, iyp1)))) * A(curvrby, ix, iy) / qion +
+                                cfgradb * 0.5 * (A(ti, ix, iy) + A(ti, ix, iyp1)) * A(gradby, ix, iy) / qion) * coll_fi;
+          A(veycb, ix, iy) = (-cfcurv * 0.5 * (A(te, ix, iy) + A(te, ix, iyp1)) * A(curvrby, ix, iy) / qe - cfgradb * 0.5 * (A(te, ix, iy) + A(te, ix, iyp1)) * A(gradby, ix, iy) / qe) * coll_fe;
+          A(vycp[f], ix, iy) = -0.25 * temp2 * (A(rbfbt2, ix, iy) + A(rbfbt2, ix, iy + 1)) / (qion * (A(niy0[f], ix, iy) + A(niy1[f], ix, iy)));
+          A(vycp[f], ix, 0) = 0.; A(vycp[f], ix, ny) = 0.;
           A(vydd[f], ix, iy) = vcony[f] + 0. + 0. - (difpr[f] + 0.) * (2 * A(gpry, ix, iy) / (A(pr, ix, iy + 1) + A(pr, ix, iy)) - 3.0 * A(gtey, ix, iy) / (A(tey1, ix, iy) + A(tey0, ix, iy)));
           A(diffusivwrk, ix, iy) = fcdif * difni[f] + 0.;
         }
+      }
       for (int iy = j1; iy <= j5; ++iy)
         for (int ix = i1; ix <= i6; ++ix) {
           double difnimix = A(diffusivwrk, ix, iy);
           A(vydd[f], ix, iy) = A(vydd[f], ix, iy) - 1. * difnimix * (2 * (1 - isvylog) * ((A(niy1[f], ix, iy) - A(niy0[f], ix, iy)) / A(dynog, ix, iy)) / (A(niy1[f], ix, iy) + A(niy0[f], ix, iy)) +
                                                                       isvylog * (ue_log(A(niy1[f], ix, iy)) - ue_log(A(niy0[f], ix, iy))) / A(dynog, ix, iy));
-          A(vy[f], ix, iy) = A(vydd[f], ix, iy);
-          A(vygp[f], ix, iy) = A(vydd[f], ix, iy);
+          A(vy[f], ix, iy) = A(vydd[f], ix, iy) + cfyef * A(vyce[f], ix, iy) + cfybf * A(vycb[f], ix, iy);
+          A(vygp[f], ix, iy) = cfybf * A(vycp[f], ix, iy) + A(vydd[f], ix, iy) + cfyef * A(vyce[f], ix, iy);  // (cfydd + cfybf) bfacyrozh vycp with cfydd = 0, bfacyrozh = 1
         }
       for (int iy = j1; iy <= j6; ++iy)
         for (int ix = i1; ix <= i6; ++ix) {
-          const int ix2 = IXP1(ix, iy);
+          const int ix2 = IXP1(ix, iy), iy1 = std::max(0, iy - 1);
+          const double temp1 = (-4.) * (A(phiv, ix, iy) - A(phiv, ix, iy1)) * A(gyc, ix, iy);
+          const double temp2 = 4. * (A(priv[f], ix, iy) - A(priv[f], ix, iy1)) * A(gyc, ix, iy);
+          A(v2ce[f], ix, iy) = -0.5 * temp1 / (A(btot, ix, iy) + A(btot, ix2, iy));
+          A(v2cb[f], ix, iy) = (cfcurv * (0.5 * (A(tiv, ix, iy) + A(tiv, ix, iy1)) + mi[f] * sq(A(up[f], ix, iy))) * A(curvrb2, ix, iy) + cfgradb * 0.5 * (A(tiv, ix, iy) + A(tiv, ix, iy1)) * A(gradb2, ix, iy)) / qion;
+          A(ve2cb, ix, iy) = -(cfcurv * 0.5 * (A(tev, ix, iy) + A(tev, ix, iy1)) * A(curvrb2, ix, iy) + cfgradb * 0.5 * (A(tev, ix, iy) + A(tev, ix, iy1)) * A(gradb2, ix, iy)) / qe;
+          const double v2cd = temp2 / ((A(btot, ix, iy) + A(btot, ix2, iy)) * qion * (A(ni[f], ix, iy) + A(ni[f], ix2, iy)));
+          // plate electron diamagnetic flux for the sheath potential (oderhs.m:1376-1391)
+          if (ix == ixlb) {
+            const double v2dia = -0.5 * (A(gpey, ixlb + 1, iy) + A(gpey, ixlb + 1, iy1)) / (A(btot, ixlb + 1, iy) * qe * A(ne, ixlb + 1, iy));
+            fdiaxlb[iy] = A(ne, ixlb + 1, iy) * A(sx, ixlb, iy) * v2dia * A(rbfbt, ixlb + 1, iy);
+          }
+          if (ix == ixrb) {
+            const double v2dia = -0.5 * (A(gpey, ixrb, iy) + A(gpey, ixrb, iy1)) / (A(btot, ixrb, iy) * qe * A(ne, ixrb, iy));
+            fdiaxrb[iy] = A(ne, ixrb, iy) * A(sx, ixrb, iy) * v2dia * A(rbfbt, ixrb, iy);
+          }
           A(v2dd[f], ix, iy) = -2. * difpr2[f] * A(gprx, ix, iy) / (A(pr, ix2, iy) / A(rbfbt, ix2, iy) + A(pr, ix, iy) / A(rbfbt, ix, iy)) -
                                2. * (fcdif * difni2[f] + 0.) * (A(ni[f], ix2, iy) - A(ni[f], ix, iy)) /
                                    (A(ni[f], ix2, iy) / (A(rbfbt, ix2, iy) * A(gx, ix2, iy)) + A(ni[f], ix, iy) / (A(rbfbt, ix, iy) * A(gx, ix, iy)));
-          A(v2[f], ix, iy) = A(v2dd[f], ix, iy);
-          A(v2xgp[f], ix, iy) = 0.5 * (A(rbfbt, ix, iy) + A(rbfbt, ix2, iy)) * (A(v2dd[f], ix, iy));
+          A(v2[f], ix, iy) = A(v2dd[f], ix, iy) + cf2ef * A(v2ce[f], ix, iy) + cf2bf * A(v2cb[f], ix, iy);
+          A(v2xgp[f], ix, iy) = 0.5 * (A(rbfbt, ix, iy) + A(rbfbt, ix2, iy)) * (cf2bf * v2cd + A(v2dd[f], ix, iy) + cf2ef * A(v2ce[f], ix, iy));  // (cf2dd + cf2bf) bfacxrozh v2cd
           if (isnonog == 1 && iy <= ny) {  // oderhs.m:1408-1432
             double grdnv = grdnv_y(ni[f], ix, iy, 1) / A(dxnog, ix, iy);
             A(vytan[f], ix, iy) = (fcdif * difni[f] + 0.) * (grdnv / ue_cos(A(angfx, ix, iy)) - (ue_log(A(ni[f], ix2, iy)) - ue_log(A(ni[f], ix, iy))) * A(gxf, ix, iy));
@@ -881,12 +916,15 @@ struct O2 {
         A(upe, ix, iy) = (A(upe, ix, iy) - 1. * A(fqp, ix, iy) / (A(rrv, ix, iy) * A(sx, ix, iy) * qe)) / (0.5 * (A(ne, ix, iy) + A(ne, ix1, iy)));
       }
     for (int iy = j1; iy <= j6; ++iy)
-      for (int ix = i1; ix <= i6; ++ix) A(vex, ix, iy) = A(upe, ix, iy) * A(rrv, ix, iy) + 0. - A(vytan[0], ix, iy);
+      for (int ix = i1; ix <= i6; ++ix)
+        A(vex, ix, iy) = A(upe, ix, iy) * A(rrv, ix, iy) + (cf2ef * A(v2ce[0], ix, iy) + cf2bf * A(ve2cb, ix, iy)) * 0.5 * (A(rbfbt, ix, iy) + A(rbfbt, IXP1(ix, iy), iy)) - A(vytan[0], ix, iy);
     for (int f = 0; f < nfsp; ++f)
       for (int iy = j1; iy <= j5; ++iy)
         for (int ix = i1; ix <= i6; ++ix) A(vey, ix, iy) = A(vey, ix, iy) + A(vy[f], ix, iy) * zi[f] * 0.5 * (A(niy0[f], ix, iy) + A(niy1[f], ix, iy));
     for (int iy = j1; iy <= j5; ++iy)
       for (int ix = i1; ix <= i6; ++ix) A(vey, ix, iy) = (A(vey, ix, iy) - cfjve * A(fqy, ix, iy) / (A(sy, ix, iy) * qe)) / (0.5 * (A(ney0, ix, iy) + A(ney1, ix, iy)));
+    if (isnewpot == 1)  // fqy(,0) = 0 there (oderhs.m:1794-1800)
+      for (int ix = i1; ix <= i6; ++ix) A(vey, ix, 0) = cfybf * A(veycb, ix, 0) + A(vydd[0], ix, 0) + cfyef * A(vyce[0], ix, 0);
 
     // zero the source accumulators (oderhs.m:1818-1835)
     for (int iy = j2; iy <= j5; ++iy)
@@ -1282,7 +1320,8 @@ struct O2 {
             A(fniy[f], ix, iy) = A(fniy[f], ix, iy) + dif4order[f] * d3ndy3 * A(sy, ix, iy) / (A(gyf, ix, iy) * A(gyf, ix, iy));
           }
         }
-      for (int ix = i4; ix <= i8; ++ix) fniycbo[f][ix] = 0.0;  // oderhs.m:3344-3353 with cfybf = 0, cfniydbo = 0
+      for (int ix = i4; ix <= i8; ++ix)  // oderhs.m:3344-3353 (vycp(,0) = 0; isfniycbozero = 0)
+        fniycbo[f][ix] = (A(ni[f], ix, 0) * A(sy, ix, 0)) * ((1 - cfniybbo) * cfybf * A(vycb[f], ix, 0));
     }
     // particle balance (oderhs.m:3407-3456)
     for (int f = 0; f < nfsp; ++f) {
@@ -1464,7 +1503,7 @@ struct O2 {
     for (int iy = j1; iy <= j5; ++iy)
       for (int ix = i4; ix <= i8; ++ix) {  // oderhs.m:4078-4092; vyte_use, vyte_cft, cfybf = 0
         A(floye, ix, iy) = A(floye, ix, iy) + (cfloye / 2.) * (A(ney0, ix, iy) + A(ney1, ix, iy)) * A(vey, ix, iy) * A(sy, ix, iy) + (0. + 0.) * 0.5 * A(sy, ix, iy) * (A(ney0, ix, iy) + A(ney1, ix, iy));
-        if (iy == 0) feeycbo[ix] = 0.;
+        if (iy == 0) feeycbo[ix] = cfloye * (A(ne, ix, 0) * A(te, ix, 0) * A(sy, ix, 0)) * ((1 - cfeeybbo) * cfybf * A(veycb, ix, 0));  // veycp(,0) = 0
       }
     for (int f = 0; f < nfsp; ++f) {  // oderhs.m:4093-4128
       if (isupgon == 1 && f == iigsp) {
@@ -1585,6 +1624,22 @@ struct O2 {
                              cfneut * cfneutsor_ei * ccoldsor * A(ng, ix, iy) * A(nucx, ix, iy) * (1.5 * A(ti, ix, iy) - 0.125 * mi[0] * (us * us) - eion * ev) * A(vol, ix, iy);
         }
       }
+    // Joule heating (oderhs.m:4832-4875)
+    if (jhswitch > 0) {
+      const int iy_min = isnewpot == 1 ? 2 : 1, iy_max = isnewpot == 1 ? ny - 1 : ny;
+      for (int iy = std::max(iy_min, j2); iy <= std::min(iy_max, j5); ++iy)
+        for (int ix = i2; ix <= i5; ++ix) {
+          const int ix1 = IXM1(ix, iy), ix2 = IXP1(ix, iy);
+          if (jhswitch == 1) {
+            A(wjdote, ix, iy) = -0.5 * (A(fqp, ix, iy) + A(fq2, ix, iy)) * (A(phi, ix2, iy) + A(phi, ix, iy)) + 0.5 * (A(fqp, ix1, iy) + A(fq2, ix1, iy)) * (A(phi, ix, iy) + A(phi, ix1, iy)) -
+                                0.5 * A(fqygp, ix, iy) * (A(phi, ix, iy + 1) + A(phi, ix, iy)) + 0.5 * A(fqygp, ix, iy - 1) * (A(phi, ix, iy) + A(phi, ix, iy - 1));
+            A(resee, ix, iy) = A(resee, ix, iy) + A(wjdote, ix, iy) / (1. + cfwjdotelim * powi(A(te, ix, iy) / tebg, iteb));
+          } else {
+            A(wjdote, ix, iy) = 0.5 * (A(ex, ix1, iy) * A(fqx, ix1, iy) + A(ex, ix, iy) * A(fqx, ix, iy)) / A(gx, ix, iy) + 0.5 * (A(ey, ix, iy) * A(fqy, ix, iy) + A(ey, ix, iy - 1) * A(fqy, ix, iy - 1)) / A(gy, ix, iy);
+            A(resee, ix, iy) = A(resee, ix, iy) + A(wjdote, ix, iy);
+          }
+        }
+    }
     // viscous heating (oderhs.m:4879-4930)
     for (int iy = j2; iy <= j5; ++iy)
       for (int ix = i2; ix <= i5; ++ix)
@@ -1639,31 +1694,16 @@ struct O2 {
   int jac_csc(const double* yl_in, const double* yldot00, int64_t ml, int64_t mu, int64_t nnzmx, std::vector<double>& rcsc, std::vector<int64_t>& icsc, std::vector<int64_t>& jcsc);
 };  // struct O2 (the remaining member functions are defined out of line below)
 
-// ---- calc_currents (potencur.m:39-445): fqp, fq2, fqy, fqx without cross-field drift currents ------------------------
-// isfqpave = 0, isimpon = 0, rnewpot and the time-derivative current (cfqydt) as inputs allow; cfqybf = cfq2bf = cfjp2 = cfjpy = 0.
+// ---- calc_currents (potencur.m:39-445): fqp, fq2, fqy, fqx with the grad-B currents (cfqybf, cfq2bf) ------------------------
+// isfqpave = 0, isimpon = 0, rnewpot and the time-derivative current (cfqydt) as inputs allow; cfjp2 = cfjpy = 0 (no diamagnetic current).
 double sigma1_, frfqpn_, cffqpsat_, exjbdry_, rnewpot_, cfqyae_, cfqyai_, cfgpijr_, sigbar0_, r0slab_, dx0_;
 int nfqya0core_, nfqya0pf_, nfqya0ow_;
 V difutm_;
 const double *b_c, *rm_c;
-V g_vyce[2], g_vycp[2];  // ExB and diamagnetic radial drift velocities: enter only the inertia current fqym here
 
 void O2::calc_currents(const Win& w) {
   const int i1 = w.i1, i5 = w.i5, i6 = w.i6;
   const int j1p = w.j1p, j5p = w.j5p, j6p = w.j6p;
-  // drift velocities the inertia current needs (oderhs.m:1178-1226): vyce, vycp on the range of the vy loop
-  for (int f = 0; f < nisp; ++f) {
-    if (!(zi[f] > 1.e-10)) continue;
-    const double qion = zi[f] * qe;
-    for (int iy = w.j1; iy <= w.j5; ++iy)
-      for (int ix = i1; ix <= i6; ++ix) {
-        const int ix3 = IXM1(ix, iy);
-        double temp1 = (-4.0) * (A(phiv, ix, iy) - A(phiv, ix3, iy)) * A(gxc, ix, iy);
-        double temp2 = 4.0 * (A(priv[f], ix, iy) - A(priv[f], ix3, iy)) * A(gxc, ix, iy);
-        A(g_vyce[f], ix, iy) = 0.125 * temp1 * (A(rbfbt2, ix, iy) + A(rbfbt2, ix, iy + 1));
-        A(g_vycp[f], ix, iy) = -0.25 * temp2 * (A(rbfbt2, ix, iy) + A(rbfbt2, ix, iy + 1)) / (qion * (A(niy0[f], ix, iy) + A(niy1[f], ix, iy)));
-        A(g_vycp[f], ix, 0) = 0.; A(g_vycp[f], ix, ny) = 0.;
-      }
-  }
   for (int iy = j1p; iy <= j6p; ++iy)
     for (int ix = i1; ix <= i5; ++ix) {
       const int ix1 = IXP1(ix, iy);
@@ -1685,7 +1725,7 @@ void O2::calc_currents(const Win& w) {
         A(fqp, ix, iy) = (A(rrv, ixlp1, iy) * A(sx, ixlp1, iy) * sigbarx * A(gxf, ixlp1, iy) / qe) *
                          ((A(pre, ixlp2, iy) - A(pre, ixlp1, iy)) / nbarx - qe * (A(phi, ixlp1, iy) - A(phi, ixl, iy)) * A(gxf, ixl, iy) / A(gxf, ixlp1, iy) + cthe * (A(te, ixlp2, iy) - A(te, ixlp1, iy)));
         A(fqp, ix, iy) = (1. - frfqpn_) * fqp_old + frfqpn_ * A(fqp, ix, iy);
-        fqpsatlb[iy] = -qe * isfdiax * (0. + 0.);
+        fqpsatlb[iy] = -qe * isfdiax * (A(ne, ixl, iy) * A(v2ce[0], ixl, iy) * A(rbfbt, ixl, iy) * A(sx, ixl, iy) + fdiaxlb[iy]);
         for (int f = 0; f < nusp; ++f) fqpsatlb[iy] = fqpsatlb[iy] - qe * zi[f] * A(ni[f], ixl, iy) * A(up[f], ixl, iy) * A(sx, ixl, iy) * A(rrv, ixl, iy);
         if (A(fqp, ixl, iy) < 0.) {
           double fp1 = A(fqp, ixl, iy), fp2 = cffqpsat_ * fqpsatlb[iy];
@@ -1698,7 +1738,7 @@ void O2::calc_currents(const Win& w) {
         A(fqp, ix, iy) = (A(rrv, ixrm2, iy) * A(sx, ixrm2, iy) * sigbarx * A(gxf, ixrm2, iy) / qe) *
                          ((A(pre, ixrm1, iy) - A(pre, ixrm2, iy)) / nbarx - qe * (A(phi, ixr, iy) - A(phi, ixrm1, iy)) * A(gxf, ixrm1, iy) / A(gxf, ixrm2, iy) + cthe * (A(te, ixrm1, iy) - A(te, ixrm2, iy)));
         A(fqp, ix, iy) = (1. - frfqpn_) * fqp_old + frfqpn_ * A(fqp, ix, iy);
-        fqpsatrb[iy] = qe * isfdiax * (0. + 0.);
+        fqpsatrb[iy] = qe * isfdiax * (A(ne, ixr, iy) * A(v2ce[0], ixrm1, iy) * A(rbfbt, ixr, iy) * A(sx, ixrm1, iy) + fdiaxrb[iy]);
         for (int f = 0; f < nusp; ++f) fqpsatrb[iy] = fqpsatrb[iy] + qe * zi[f] * A(ni[f], ixr, iy) * A(up[f], ixrm1, iy) * A(sx, ixrm1, iy) * A(rrv, ixrm1, iy);
         if (A(fqp, ixrm1, iy) > 0.) {
           double fp1 = A(fqp, ixrm1, iy), fp2 = cffqpsat_ * fqpsatrb[iy];
@@ -1718,6 +1758,12 @@ void O2::calc_currents(const Win& w) {
       A(fqyae, ix, iy) = (A(sy, ix, iy) * sigbary / (A(dynog, ix, iy) * qe)) * ((A(ney1, ix, iy) * A(tey1, ix, iy) - A(ney0, ix, iy) * A(tey0, ix, iy)) / nbary - qe * (A(phiy1, ix, iy) - A(phiy0, ix, iy)));
       double fqyai = -(A(sy, ix, iy) * sigbary / (A(dynog, ix, iy) * qe * zi[0])) * ((A(niy1[0], ix, iy) * A(tiy1, ix, iy) - A(niy0[0], ix, iy) * A(tiy0, ix, iy)) / nbary + qe * zi[0] * (A(phiy1, ix, iy) - A(phiy0, ix, iy)));
       A(fqyao, ix, iy) = cfqyao * (cfqyae_ * A(fqyae, ix, iy) + cfqyai_ * fqyai);
+      const int ix3 = IXM1(ix, iy);
+      const double temp1 = 4.0 * (A(prtv, ix, iy) - A(prtv, ix3, iy)) * A(gxc, ix, iy);
+      A(fqyd, ix, iy) = -A(sy, ix, iy) * 0.125 * temp1 * (A(rbfbt2, ix, iy) + A(rbfbt2, ix, iy + 1));
+      double nzvibtot = 0.;
+      for (int f = 0; f < nisp; ++f) nzvibtot = nzvibtot + 0.5 * zi[f] * (A(niy0[f], ix, iy) + A(niy1[f], ix, iy)) * A(vycb[f], ix, iy);
+      A(fqyb, ix, iy) = qe * A(sy, ix, iy) * (nzvibtot - 0.5 * (A(ney0, ix, iy) + A(ney1, ix, iy)) * A(veycb, ix, iy));
     }
   // inertia current (potencur.m:291-376); fmity as a local pair of planes per species
   static thread_local V fmity[2], fqymi_[2];
@@ -1736,7 +1782,7 @@ void O2::calc_currents(const Win& w) {
         A(fmity[f], ix, iy + 1) = -0.25 * mi[f] * (difutm_[f] + 0.) * ((A(niy1[f], ix, iy + 1) + A(niy0[f], ix, iy + 1)) * (2 * r0slab_ + A(rm_c, ix, iy + 1) + A(rm_c, ix, iyp2)) * utp -
                                                                         (A(niy1[f], ix, iy) + A(niy0[f], ix, iy)) * (2 * r0slab_ + A(rm_c, ix, iy) + A(rm_c, ix, iy + 1)) * ut0) * A(gy, ix, iy + 1);
         double omgci = qe * zi[f] * A(b_c, ix, iy) / mi[f];
-        A(fqymi_[f], ix, iy) = qe * 0.5 * (A(niy0[f], ix, iy) + A(niy1[f], ix, iy)) * (A(g_vyce[f], ix, iy) + A(g_vycp[f], ix, iy)) *
+        A(fqymi_[f], ix, iy) = qe * 0.5 * (A(niy0[f], ix, iy) + A(niy1[f], ix, iy)) * (A(vyce[f], ix, iy) + A(vycp[f], ix, iy)) *
                                (-0.5 * ((A(btot, ix, iy + 1) + A(btot, ix, iyp2)) * utp - (A(btot, ix, iy - 1) + A(btot, ix, iy)) * utm)) * 0.5 * A(gyf, ix, iy) * A(sy, ix, iy) / omgci;
       }
     }
@@ -1757,13 +1803,17 @@ void O2::calc_currents(const Win& w) {
   }
   for (int iy = j1p; iy <= j5p; ++iy)
     for (int ix = i1; ix <= i6; ++ix) {
-      A(fqy, ix, iy) = (1. - rnewpot_) * A(fqyao, ix, iy) + rnewpot_ * A(fqya, ix, iy) + 0. + cfqym * A(fqym, ix, iy) + 0.;
-      A(fqygp, ix, iy) = (1. - rnewpot_) * A(fqyao, ix, iy) + rnewpot_ * A(fqya, ix, iy) + cfqym * A(fqym, ix, iy) + 0.;
+      A(fqy, ix, iy) = (1. - rnewpot_) * A(fqyao, ix, iy) + rnewpot_ * A(fqya, ix, iy) + cfqybf * A(fqyb, ix, iy) + cfqym * A(fqym, ix, iy) + 0.;
+      A(fqygp, ix, iy) = (1. - rnewpot_) * A(fqyao, ix, iy) + rnewpot_ * A(fqya, ix, iy) + cfqym * A(fqym, ix, iy) + A(fqyd, ix, iy);
       A(fqy, ix, iy) = A(fqy, ix, iy) + cfqydt * A(fqydt, ix, iy);  // nx = nxold, ny = nyold; cfqydt = 0
     }
   for (int iy = j1p; iy <= j6p; ++iy)
     for (int ix = i1; ix <= i5; ++ix) {
-      A(fqx, ix, iy) = A(fqp, ix, iy) + A(fq2, ix, iy) + 0.;
+      const int ix1 = IXP1(ix, iy);
+      double nzvibtot = 0.;
+      for (int f = 0; f < nisp; ++f) nzvibtot = nzvibtot + 0.5 * zi[f] * (A(ni[f], ix, iy) + A(ni[f], ix1, iy)) * A(v2cb[f], ix, iy);
+      A(fqxb, ix, iy) = qe * A(sx, ix, iy) * (nzvibtot - 0.5 * (A(ne, ix, iy) + A(ne, ix1, iy)) * A(ve2cb, ix, iy)) * 0.5 * (A(rbfbt, ix1, iy) + A(rbfbt, ix, iy));
+      A(fqx, ix, iy) = A(fqp, ix, iy) + A(fq2, ix, iy) + cfq2bf * A(fqxb, ix, iy);
       if (ix == ixlb + 1 && isexunif == 1) A(fqx, ixlb, iy) = A(fqx, ixlb + 1, iy);
       if (ix == ixrb && isexunif == 1) A(fqx, ixrb, iy) = A(fqx, ixrb - 1, iy);
     }
@@ -1965,6 +2015,33 @@ int O2::bouncon(const Win& w, const double* yl, double* yldot) {
       if (IDXG(ixrb, 0) >= 0) yldot[IDXG(ixrb + 1, 0)] = nurlxg * (A(ng, ixrb, 0) - A(ng, ixrb + 1, 0)) / n0g_[0];
     }
   }
+  // ===== potential with isnewpot = 1: two equations at iy = 0 and 1 (boundary.m:987-1122) =====
+  if (isnewpot * isphion == 1 && w.j3 <= 3) {
+    const int ixc1 = std::max(0, ixpt1 + 1);
+    for (int ix = std::min(w.i4, ixpt1 + 1); ix <= std::max(w.i8, ixpt2); ++ix) {
+      const int64_t iv = IDXPHI(ix, 0), iv1 = IDXPHI(ix, 1);
+      if (iv < 0 || iv1 < 0) continue;
+      if (isixcore[ix] == 1) {  // core boundary (isphicore0 = 0): phi(,0) poloidally constant, phi(,1) by iphibcc = 1, 2, 3
+        yldot[iv] = -nurlxp * (A(phi, ix, 0) - A(phi, IXP1(ix, 0), 0)) / temp0;
+        if (iphibcc == 1) yldot[iv1] = -nurlxp * ((A(ey, ix, 1) - A(ey, ix, 0)) * A(gy, ix, 1) - (A(ey, ix, 2) - A(ey, ix, 1)) * A(gy, ix, 2)) / (A(gy, ix, 1) * temp0);
+        else if (iphibcc == 2) yldot[iv1] = -nurlxp * (A(te, ix, 1) - A(te, IXP1(ix, 1), 1)) / (ev * temp0);
+        else yldot[iv1] = -nurlxp * (A(phi, ix, 1) - A(phi, IXP1(ix, 1), 1)) / temp0;
+        if (ix == ixmp) {  // midplane column: total radial current through the core boundary = icoreelec (fqyn: cfqyn = 0)
+          int ii = ixc1;
+          double fqytotc = A(fqya, ii, 1) + 0. + cfqym * A(fqym, ii, 1) + cfqybbo * A(fqyb, ii, 1) + cfqydbo * A(fqyd, ii, 1);
+          do { ii = IXP1(ii, 1); fqytotc = fqytotc + A(fqya, ii, 1) + 0. + cfqym * A(fqym, ii, 1) + cfqybbo * A(fqyb, ii, 1) + cfqydbo * A(fqyd, ii, 1); } while (ii != ix_fl_bc);
+          yldot[iv] = -nurlxp * (fqytotc - icoreelec) / (qe * n0[0] * vpnorm * A(sy, ixc1, 0));
+          if (iphibcc == 1) yldot[iv1] = -nurlxp * ((A(ey, ix, 1) - A(ey, ix, 0)) * A(gy, ix, 1) - (A(ey, ix, 2) - A(ey, ix, 1)) * A(gy, ix, 2)) / (A(gy, ix, 1) * temp0);
+          else yldot[iv1] = -nurlxp * (A(ey, ix, 0) - eycore) / (A(gyf, ix, 0) * temp0);
+        }
+      } else {  // private-flux wall
+        const int k = (int)iphibcwiix[ix];
+        if (k == 0) yldot[iv] = nurlxp * (A(phi, ix, 1) - A(phi, ix, 0)) / temp0;
+        else if (k == 1) yldot[iv] = nurlxp * (phintewi_ * A(te, ix, 0) / ev - A(phi, ix, 0)) / temp0;
+        else if (k == 3) yldot[iv] = nurlxp * ((A(phi, ix, 1) - A(phi, ix, 0)) - 0.5 * (A(phi, ix, 1) + A(phi, ix, 0)) / (A(gyf, ix, 0) * lyphiix1[ix])) / temp0;
+      }
+    }
+  }
   // ===== iy = ny+1 boundary (boundary.m:1125-1653) =====
   if (w.j7 >= (ny + 1)) {  // isextrnw = isextrtw = 0
     for (int f = 0; f < nisp; ++f) {
@@ -2132,7 +2209,7 @@ int O2::bouncon(const Win& w, const double* yl, double* yldot) {
                 yldot[iv2] = -nurlxu * (A(fmix[f], ixt1, iy) + vparn * vxn * 0.5 * (A(nm[f], ixt1, iy) + A(nm[f], ixt, iy)) * A(sx, ixt, iy)) / (vpnorm * fnorm[f] * A(sx, ixt, iy));
               }
             } else {
-              double ueb = cfueb * (0. - A(vytan[f], ixt, iy)) / A(rrv, ixt, iy);
+              double ueb = cfueb * (cf2ef * A(v2ce[f], ixt, iy) * A(rbfbt, ixt, iy) - A(vytan[f], ixt, iy)) / A(rrv, ixt, iy);
               yldot[iv2] = nurlxu * (-cs - ueb - A(up[f], ixt, iy)) / vpnorm;  // isbohmms = 0
               if (isupss[f] == 1 && A(up[f], ixt1, iy) + ueb < -cs) yldot[iv2] = nurlxu * (A(up[f], ixt1, iy) - A(up[f], ixt, iy)) / vpnorm;
               if (isupss[f] == -1) yldot[iv2] = nurlxu * (A(up[f], ixt1, iy) - A(up[f], ixt, iy)) / vpnorm;
@@ -2247,7 +2324,7 @@ int O2::bouncon(const Win& w, const double* yl, double* yldot) {
               }
               yldot[iv] = nurlxu * (A(up[f], ixt1, iy) - A(up[f], ixt, iy)) / vpnorm;
             } else {
-              double ueb = cfueb * (0. - A(vytan[f], ixt1, iy)) / A(rrv, ixt1, iy);
+              double ueb = cfueb * (cf2ef * A(v2ce[f], ixt1, iy) * A(rbfbt, ixt, iy) - A(vytan[f], ixt1, iy)) / A(rrv, ixt1, iy);
               yldot[iv2] = nurlxu * (cs - ueb - A(up[f], ixt1, iy)) / vpnorm;  // isbohmms = 0
               if (isupss[f] == 1 && A(up[f], ixt2, iy) + ueb > cs) yldot[iv2] = nurlxu * (A(up[f], ixt2, iy) - A(up[f], ixt1, iy)) / vpnorm;
               if (isupss[f] == -1) yldot[iv2] = nurlxu * (A(up[f], ixt2, iy) - A(up[f], ixt1, iy)) / vpnorm;
@@ -2392,8 +2469,11 @@ int O2::jac_csc(const double* yl_in, const double* yldot00, int64_t ml, int64_t 
     jcsc[iv - 1] = nnz;
     if (iv < ivmin || iv > ivmax) continue;
     int64_t ii1 = std::max(iv - mu, (int64_t)1), ii2 = std::min(iv + ml, neq);
-    for (int64_t ii = ii1; ii <= ii2; ++ii) wk[ii - 1] = yldot00[ii - 1];
     int xc = (int)igyld[iv - 1], yc = (int)igyld[neq + iv - 1];
+    if (ExtendedJacPhi > 0 && isphion * isnewpot == 1 && iv % numvar_ == 0) {  // wider band for a potential perturbation (oderhs.m:8645-8651)
+      ii1 = std::max(iv - 4 * numvar_ * nx, (int64_t)1); ii2 = std::min(iv + 4 * numvar_ * nx, neq);
+    }
+    for (int64_t ii = ii1; ii <= ii2; ++ii) wk[ii - 1] = yldot00[ii - 1];
     double yold = yl[iv - 1];
     double dyl = delpert * (std::fabs(yold) + dylconst / suscal[iv - 1]);
     yl[iv - 1] = yold + dyl;
@@ -2452,7 +2532,7 @@ int init_all() {
   GI(isnonog) GI(isphion) GI(isphiofft) GI(ineudif) GI(isflxvar) GI(isrscalf) GI(isbcwdt) GI(icnuiz) GI(icnucx) GI(isrecmon) GI(ingb) GI(inflbg) GI(isgasdc) GI(isdifxg_aug) GI(isdifyg_aug)
   GI(isvylog) GI(isgxvon) GI(convis) GI(concap) GI(isflxlde) GI(isflxldi) GI(isplflxl) GI(inkxc) GI(isgpye) GI(ishavisy) GI(isvhyha) GI(islnlamcon) GI(isnupdot1sd) GI(iteb) GI(istabon)
   GI(ifxnsgi) GI(iflcore) GI(ifluxni) GI(isrefluxclip) GI(ibctepl) GI(ibctipl) GI(ibctepr) GI(ibctipr) GI(isbohmms) GI(isextrnp) GI(isextrnpf) GI(isextrtpf) GI(isextrngc) GI(isextrnw)
-  GI(isextrtw) GI(isnfmiy) GI(isybdrywd) GI(isnewpot) GI(jhswitch) GI(isfeexpl0) GI(isfeixpl0) GI(isintlog) GI(iskaplex) GI(isexunif) GI(isfdiax) GI(isugfm1side) GI(isvisxn_old) GI(isteon) GI(istion)
+  GI(isextrtw) GI(isnfmiy) GI(isybdrywd) GI(isnewpot) GI(jhswitch) GI(isfeexpl0) GI(isfeixpl0) GI(isintlog) GI(iskaplex) GI(isexunif) GI(isfdiax) GI(isugfm1side) GI(isvisxn_old) GI(isteon) GI(istion) GI(iphibcc)
 #undef GI
   isupgon = I("isupgon", 0); isngon = I("isngon", 0); istgon = I("istgon", 0); isfixlb = I("isfixlb", 0); isfixrb = I("isfixrb", 0); newbcl = I("newbcl", 0); newbcr = I("newbcr", 0);
   isngcore1 = I("isngcore", 0);
@@ -2468,7 +2548,8 @@ int init_all() {
   GR(nurlxn) GR(nurlxu) GR(nurlxe) GR(nurlxi) GR(nurlxg) GR(nurlxp) GR(tcoree) GR(tcorei) GR(pcoree) GR(pcorei) GR(sygytotc) GR(csfacti) GR(cfueb) GR(cgpld) GR(cmneut) GR(eedisspl) GR(eidisspl) GR(cmntgpl)
   GR(ckinfl) GR(isoldalbarea) GR(tbmin) GR(nufak) GR(dtreal) GR(dtphi) GR(dylconst) GR(jaccliplim) GR(kelhihg) GR(kelhghg) GR(lgvmax) GR(flgamvg) GR(cfvisxn) GR(cfvisyn) GR(flgamtg) GR(cfupcx) GR(cfticx)
   GR(cfnidh) GR(cfnidh2) GR(cfnidhdis) GR(cfnidhgy) GR(cfnidhg2) GR(cftgeqp) GR(flalftxy) GR(flalfgnx) GR(flalfgny) GR(nlimgx) GR(nlimgy) GR(cfloxiplt) GR(cfloygwall) GR(cfjve) GR(rsigpl) GR(rsigplcore)
-  GR(bcen) GR(cfqym) GR(cfqydt) GR(cfqyao) GR(cfsigm)
+  GR(bcen) GR(cfqym) GR(cfqydt) GR(cfqyao) GR(cfsigm) GR(cfyef) GR(cf2ef) GR(cfybf) GR(cf2bf) GR(cfcurv) GR(cfgradb) GR(eycore) GR(icoreelec) GR(cfniybbo) GR(cfeeybbo)
+  GR(cfqybf) GR(cfq2bf) GR(cfqybbo) GR(cfqydbo) GR(cfwjdotelim) GR(tebg)
 #undef GR
   erad = SC("erad"); delpert = SC("del");
   sigma1_ = SC("sigma1"); frfqpn_ = SC("frfqpn"); cffqpsat_ = SC("cffqpsat"); exjbdry_ = SC("exjbdry"); rnewpot_ = SC("rnewpot"); cfqyae_ = SC("cfqyae"); cfqyai_ = SC("cfqyai"); cfgpijr_ = SC("cfgpijr");
@@ -2489,8 +2570,9 @@ int init_all() {
   const size_t nc = NC, nxs = NXS, nys = ny + 2;
 #define GP(n) n = ARR(#n, nc);
   GP(vol) GP(gx) GP(gy) GP(gxf) GP(gyf) GP(gxc) GP(gyc) GP(sx) GP(sxnp) GP(sy) GP(rr) GP(rrv) GP(volv) GP(syv) GP(dxnog) GP(dynog) GP(btot) GP(rbfbt) GP(rbfbt2) GP(lcone) GP(lconi) GP(angfx) GP(ngfix)
-#undef GP
   b_c = ARR("b_c", nc); rm_c = ARR("rm_c", nc);
+  GP(curvrby) GP(gradby) GP(curvrb2) GP(gradb2)
+#undef GP
   ixm1d = ARR("ixm1", nc); ixp1d = ARR("ixp1", nc); isxptyd = ARR("isxpty", nc); isxptxd = ARR("isxptx", nc);
   for (int k = 0; k < 2; ++k) {
     auto S2 = [&](const char* n) { return ARR(n, 2 * nc) + (size_t)k * nc; };
@@ -2516,15 +2598,18 @@ int init_all() {
   if (isupgon == 1) { if (nisp != 2 || zi[1] != 0.) { g_err = "oracle2: isupgon=1 needs nisp=2 with zi(2)=0"; return -5; } iigsp = 1; }
   // switches outside this restatement
   struct { const char* n; double want; } must[] = {{"isimpon", 0}, {"ismcnon", 0}, {"ishymol", 0}, {"ifixsrc", 0}, {"ifixpsor", 0}, {"isupdrag", 0}, {"isofric", 0}, {"ishosor", 0}, {"islimon", 0}, {"isudsym", 0},
-                                                   {"nxomit", 0}, {"isbohmcalc", 1}, {"isdifbetap", 0}, {"cfyef", 0}, {"cf2ef", 0}, {"cfybf", 0}, {"cf2bf", 0}, {"cfydd", 0}, {"cf2dd", 0}, {"cfrd", 0}, {"cfbgt", 0},
-                                                   {"cfvycf", 0}, {"cfvycr", 0}, {"cftef", 0}, {"cftdd", 0}, {"cfqybf", 0}, {"cfq2bf", 0}, {"cfjp2", 0}, {"cfjpy", 0}, {"cfqyn", 0}, {"cfeta1", 0}, {"cfrtaue", 0},
+                                                   {"nxomit", 0}, {"isbohmcalc", 1}, {"isdifbetap", 0}, {"cfydd", 0}, {"cf2dd", 0}, {"cfrd", 0}, {"cfbgt", 0},
+                                                   {"cfvycf", 0}, {"cfvycr", 0}, {"cftef", 0}, {"cftdd", 0}, {"cfjp2", 0}, {"cfjpy", 0}, {"cfqyn", 0}, {"cfeta1", 0}, {"cfrtaue", 0},
                                                    {"cfcl_e", 0}, {"cfcl_i", 0}, {"facbni", 0}, {"facbup", 0}, {"facbee", 0}, {"facbei", 0}, {"rtauxfac", 0}, {"ispsorave", 0}, {"iseesorave", 0}, {"cfvisxneov", 0},
-                                                   {"cfvisxneoq", 0}, {"cfvyavis", 0}, {"cfanomvisxg", 0}, {"cfanomvisyg", 0}, {"isnewpot", 0}, {"jhswitch", 0}, {"isnfmiy", 0}, {"isybdrywd", 0}, {"isfeexpl0", 0},
-                                                   {"isfeixpl0", 0}, {"cfeexdbo", 0}, {"cfeixdbo", 0}, {"cfniybbo", 0}, {"cfniydbo", 0}, {"cfeeybbo", 0}, {"cfeeydbo", 0}, {"isextrnp", 0}, {"isextrnpf", 0},
+                                                   {"cfvisxneoq", 0}, {"cfvyavis", 0}, {"cfanomvisxg", 0}, {"cfanomvisyg", 0}, {"isnfmiy", 0}, {"isybdrywd", 0}, {"isfeexpl0", 0},
+                                                   {"isfeixpl0", 0}, {"cfeexdbo", 0}, {"cfeixdbo", 0}, {"cfniydbo", 0}, {"cfeeydbo", 0}, {"isextrnp", 0}, {"isextrnpf", 0},
                                                    {"isextrtpf", 0}, {"isextrngc", 0}, {"isextrnw", 0}, {"isextrtw", 0}, {"isbohmms", 0}, {"ibctepl", 1}, {"ibctipl", 1}, {"ibctepr", 1}, {"ibctipr", 1}, {"isfixrb", 0},
                                                    {"is1D_gbx", 0}, {"isnglf", 0}, {"iszeffcon", 0}, {"isup1up2", 0}, {"isflxvar", 0}, {"istgon", 0}, {"isphilbc", 0}, {"isphirbc", 0}, {"ikapmod", 0},
-                                                   {"isfqpave", 0}, {"isphicore0", 0}, {"iskaprex", 0}};
+                                                   {"isfqpave", 0}, {"isphicore0", 0}, {"iskaprex", 0}, {"isrozhfac", 0}};
   for (auto& m : must) { const V* v = find(m.n); if (!v) { g_err = std::string("oracle2: missing input ") + m.n; return -1; } if ((*v)[0] != m.want) { g_err = std::string("oracle2: switch outside this restatement: ") + m.n; return -5; } }
+  if (isnewpot != 0 && isnewpot != 1) { g_err = "oracle2: isnewpot must be 0 or 1"; return -5; }
+  if (isnewpot * isphion == 1 && (iphibcc < 1 || iphibcc > 3)) { g_err = "oracle2: only iphibcc = 1, 2, 3 available"; return -5; }
+  ExtendedJacPhi = I("ExtendedJacPhi"); numvar_ = I("numvar");
   if (fnnuiz != 1.) { g_err = "oracle2: fnnuiz must be 1"; return -5; }
   if (SC("l_parloss") <= 1e9) { g_err = "oracle2: l_parloss<=1e9 (nuvl) not built"; return -5; }
   if (isfixlb != 0 && isfixlb != 2) { g_err = "oracle2: isfixlb must be 0 or 2"; return -5; }
@@ -2541,9 +2626,9 @@ int init_all() {
   }
   if (!g_missing.empty()) { g_err = "oracle2: missing inputs: " + g_missing; return -1; }
   for (auto& kv : g2.planes()) kv.second->assign(NC, 0.0);
-  for (int f = 0; f < 2; ++f) { g_vyce[f].assign(NC, 0.); g_vycp[f].assign(NC, 0.); g2.fniycbo[f].assign(NXS, 0.); }
+  for (int f = 0; f < 2; ++f) g2.fniycbo[f].assign(NXS, 0.);
   g2.feeycbo.assign(NXS, 0.); g2.feiycbo.assign(NXS, 0.);
-  for (V* v : {&g2.kappal, &g2.kappar, &g2.bcel, &g2.bcer, &g2.bcil, &g2.bcir, &g2.fqpsatlb, &g2.fqpsatrb}) v->assign(ny + 2, 0.);
+  for (V* v : {&g2.kappal, &g2.kappar, &g2.bcel, &g2.bcer, &g2.bcil, &g2.bcir, &g2.fqpsatlb, &g2.fqpsatrb, &g2.fdiaxlb, &g2.fdiaxrb}) v->assign(ny + 2, 0.);
   // fields of equations that are switched off keep the values the host left in them (ueinit copies the restart state)
   auto init_plane = [&](const char* n, V& dst) { const V* v = find(n); if (v && (int)v->size() >= NC) dst.assign(v->begin(), v->begin() + NC); };
   init_plane("ni1_init", g2.ni[0]); init_plane("ni2_init", g2.ni[1]); init_plane("up1_init", g2.up[0]); init_plane("up2_init", g2.up[1]);

@@ -13,7 +13,7 @@ import pytest
 from tests.test_oracle2_golden import twin
 from tests.util import psetnk_inputs
 from uedge_b200.cases import box2_case
-from uedge_b200.cases2 import SUBSETS, Lib2, Oracle2, box2_initial_state, d3d_full_physics_case, inputex_case, switch_variant
+from uedge_b200.cases2 import SUBSETS, Lib2, Oracle2, box2_initial_state, d3d_full_physics_case, inputex_case, jupyter_case, switch_variant
 
 HK = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostcheck")
 
@@ -87,6 +87,25 @@ def test_band_copy_of_the_private_planes_is_sufficient(built, monkeypatch):
     monkeypatch.setenv("UE_GEN_POISON", "1")
     c, yl = d3d_full_physics_case(refine_grid(load_grid_npz(), 2, 2))
     assert c.com.ny + 2 == 18
+    same(Oracle2().bind(c), host(0).bind(c), c, yl)
+
+
+@pytest.mark.parametrize("rev", [0, 1])
+def test_jupyter_drift_case(built, rev):
+    """jupyter/case_setup.py: ExB and grad-B drifts, grad-B currents, isnewpot=1 with its two core conditions (one of them the sum of
+    the radial current over the whole core boundary), Joule heating, the wider Jacobian band of the potential unknowns"""
+    c, yl = jupyter_case()
+    assert c.bbb.numvar == 7 and c.bbb.neq == 1260
+    same(Oracle2().bind(c), host(rev).bind(c), c, yl)
+
+
+def test_jupyter_drift_case_band_copy_is_sufficient(built, monkeypatch):
+    """the same on the 2x-refined mesh with everything outside the copied band poisoned (NaN): the core conditions of the
+    potential read rows 0-2 at every core column whenever the window starts at iy <= 3 - they are inside the band then"""
+    from uedge_b200.cases import load_grid_npz, refine_grid
+    monkeypatch.setenv("UE_GEN_POISON", "1")
+    c, yl = jupyter_case(grid=refine_grid(load_grid_npz(), 2, 2))
+    assert c.com.ny + 2 == 18 and c.bbb.neq == 4284
     same(Oracle2().bind(c), host(0).bind(c), c, yl)
 
 

@@ -10,7 +10,7 @@ from tests.refplanes import check_against_reference
 from tests.test_oracle2_golden import twin
 from tests.util import psetnk_inputs
 from uedge_b200.cases import box2_case
-from uedge_b200.cases2 import SUBSETS, Oracle2, box2_initial_state, d3d_full_physics_case, inputex_case, load_gen, switch_variant
+from uedge_b200.cases2 import SUBSETS, Oracle2, box2_initial_state, d3d_full_physics_case, inputex_case, jupyter_case, load_gen, switch_variant
 
 pytestmark = pytest.mark.gpu
 
@@ -76,6 +76,20 @@ def test_full_physics_on_the_d3d_mesh(built):
     step = (np.full(b.neq, 1e-5), 0.9995 * yl[: b.neq], su, 1.0 / np.maximum(np.abs(yl[: b.neq]), 1e-3))
     y = yl.copy(); y[b.neq] = 1.0
     same(Oracle2().bind(c), load_gen().bind(c), c, y, step)
+
+
+@pytest.mark.parametrize("refine", [1, 2])
+def test_jupyter_drift_case(built, refine):
+    """BASELINE configs[2] (jupyter/case_setup.py): cross-field drifts, grad-B currents, isnewpot=1, iphibcc=3, Joule heating,
+    sheath conditions from the current; 16x8 mesh (1 260 unknowns) and its 2x refinement (4 284): residual, drift planes and the
+    Jacobian with the wider band of the potential unknowns, bit for bit"""
+    from uedge_b200.cases import load_grid_npz, refine_grid
+    c, yl = jupyter_case(grid=refine_grid(load_grid_npz(), refine, refine) if refine > 1 else None)
+    o, g = Oracle2().bind(c), load_gen().bind(c)
+    same(o, g, c, yl)
+    o.pandf1(yl); g.pandf1(yl)
+    for nm in ("vyce1", "vycb1", "v2ce1", "v2cb1", "ve2cb", "veycb", "fqyb", "fqxb", "fqyd", "wjdote", "vex", "vey", "resphi"):
+        assert np.array_equal(o.plane(nm), g.plane(nm)), nm
 
 
 @pytest.mark.parametrize("name", ["d3dHsm", "case2", "case1"])

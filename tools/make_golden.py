@@ -96,3 +96,9 @@ for k, v in d.items():
         out[k.replace("/", "__")] = np.asarray(v)
 np.savez_compressed(os.path.join(OUT, "inputex_solution.npz"), **out)
 print("input_example:", len(out), "arrays")
+
+
+# jupyter/PyUedge.ipynb: the restart state of its drift + potential case (case_setup.py; cell 17 prints fnrm0 = 2.134077960622300)
+d = read_h5(os.path.join(REF, "jupyter/d3d.hdf5"))
+np.savez_compressed(os.path.join(OUT, "jupyter_d3d_state.npz"), **{k.split("@")[0]: np.asarray(v) for k, v in d.items()})
+print("jupyter:", sorted(k.split("@")[0] for k in d))

@@ -9,7 +9,7 @@ from tests.test_oracle2_golden import twin  # noqa: E402
 from tests.util import psetnk_inputs  # noqa: E402
 from uedge_b200.cases import box2_case  # noqa: E402
 from uedge_b200.cases import load_grid_npz, refine_grid  # noqa: E402
-from uedge_b200.cases2 import Oracle2, box2_initial_state, d3d_full_physics_case, inputex_case, load_gen  # noqa: E402
+from uedge_b200.cases2 import Oracle2, box2_initial_state, d3d_full_physics_case, inputex_case, jupyter_case, load_gen  # noqa: E402
 
 
 def cases():
@@ -17,6 +17,8 @@ def cases():
     c = box2_case(isupgon=1); yield "box2 (inertial atoms)", c, box2_initial_state(c)
     c1, c2, yl = twin("d3dHsm"); y, su = psetnk_inputs(c1, yl); yield "d3dHsm via general path", c2, y
     c, yl = d3d_full_physics_case(); yield "d3d mesh, full physics", c, yl
+    c, yl = jupyter_case(); yield "jupyter drift case 16x8", c, yl
+    c, yl = jupyter_case(grid=refine_grid(load_grid_npz(), 4, 4)); yield "jupyter drift case 4x", c, yl
     c, yl = d3d_full_physics_case(refine_grid(load_grid_npz(), 4, 4)); yield "d3d 4x mesh, full physics", c, yl
 
 

@@ -214,6 +214,26 @@ class Case2(Case):
         fl = (self.floor_cons / self.norm_cons)[None, :]
         return (1.0 / np.maximum(y, fl)).reshape(-1)
 
+    def drift_geometry(self):
+        """Geometrical factors of the curvature and grad-B drifts on the y- and x-faces (bbb/geometry.m:1155-1182; b0 = 1, so
+        the s2scal of odesetup.m:1198-1201 is the identity); zero in a slab (mhdgeo < 0)."""
+        b = self.bbb
+        rm, zm, bb, bphi = self.rz["rm"], self.rz["zm"], self.rz["b"], self.rz["bphi"]
+        g = self.geo
+        shp = rm[0].shape
+        if b.mhdgeo < 0:
+            return {k: np.zeros(shp) for k in ("curvrby", "curvrb2", "gradby", "gradb2")}
+        s_bphi = np.sign(bphi[1][0, 0]) if bphi[1][0, 0] != 0 else 1.0
+        with np.errstate(divide="ignore", invalid="ignore"):
+            cossr = -s_bphi * (rm[4] - rm[3]) / ((rm[4] - rm[3]) ** 2 + (zm[4] - zm[3]) ** 2) ** 0.5
+            curvrby = -2 * cossr / (rm[4] * bb[4] + rm[3] * bb[3])
+            cossp = (rm[4] - rm[2]) / ((rm[4] - rm[2]) ** 2 + (zm[4] - zm[2]) ** 2) ** 0.5
+            curvrb2 = -2 * cossp / (rm[4] * bb[4] + rm[2] * bb[2])
+            gradby = -0.5 * (bphi[4] / bb[4] ** 3 + bphi[3] / bb[3] ** 3) * (bb[4] - bb[3]) * g["gxc"]
+            gradb2 = 0.5 * (1 / bb[4] ** 2 + 1 / bb[2] ** 2) * (bb[4] - bb[2]) * g["gyc"] * np.cos(self.angfx)
+        f = lambda a: np.ascontiguousarray(np.nan_to_num(a, nan=0.0, posinf=0.0, neginf=0.0), dtype=np.float64)
+        return dict(curvrby=f(curvrby), curvrb2=f(curvrb2), gradby=f(gradby), gradb2=f(gradb2))
+
     def inputs2(self):
         """name -> float64 array for ue_or2_set: every numeric scalar/array of the namespaces, then the computed data."""
         b, c = self.bbb, self.com
@@ -234,6 +254,7 @@ class Case2(Case):
         for k in ("vol", "gx", "gy", "gxf", "gyf", "gxc", "gyc", "sx", "sxnp", "sy", "rr", "rrv", "volv", "syv", "dxnog", "dynog", "btot", "rbfbt", "rbfbt2", "lcone", "lconi", "isxptx", "isxpty"):
             out[k] = np.asarray(g[k], dtype=float).reshape(-1)
         out["angfx"] = self.angfx.reshape(-1).astype(float)
+        out.update({k: v.reshape(-1) for k, v in self.drift_geometry().items()})
         out["b_c"] = self.rz["b"][0].reshape(-1).astype(float); out["rm_c"] = self.rz["rm"][0].reshape(-1).astype(float)
         out["ixm1"] = self.ixm1.reshape(-1).astype(float); out["ixp1"] = self.ixp1.reshape(-1).astype(float)
         one = np.ones((2,) + shp); zero = np.zeros((2,) + shp)

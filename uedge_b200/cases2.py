@@ -110,6 +110,54 @@ def d3d_full_physics_case(grid=None):
     return c, yl
 
 
+def jupyter_case(mods=None, v8_0_defaults=True, grid=None):
+    """jupyter/case_setup.py (the case of jupyter/PyUedge.ipynb; BASELINE configs[2]): the 16x8 DIII-D mesh, inertial atoms, potential
+    equation with isnewpot=1, ExB and grad-B drifts (cfyef=cf2ef=cfybf=cf2bf=1), grad-B currents, Joule heating, sheath conditions
+    from the current (newbcl=newbcr=1, isfdiax=1), iphibcc=3.  State: jupyter/d3d.hdf5 (tests/golden/jupyter_d3d_state.npz).  The
+    notebook regenerates its mesh from aeqdsk/neqdsk (mesh generation is out of scope); the mesh here is builder/test/facets/gridue, built
+    from the same equilibrium with the same flux-surface and poloidal distribution inputs.  `grid`: a refinement of that mesh (the
+    state is then prolonged piecewise constant - timing and oracle <-> CUDA parity only)."""
+    from .cases import refine_state
+    g = grid or load_grid_npz()
+    fx, fy = g["nxm"] // 16, g["nym"] // 8
+    c = Case2(g)
+    b, com = c.bbb, c.com
+    com.nxleg = np.array([[4 * fx, 4 * fx]]); com.nxcore = np.array([[4 * fx, 4 * fx]]); com.nysol = np.array([6 * fy]); com.nycore = np.array([2 * fy])
+    if v8_0_defaults:
+        b.oldseec = 1.0; b.isoldalbarea = 1.0
+    b.methn = b.methu = b.methe = b.methi = b.methg = 33
+    b.ncore[0] = 2.0e19; b.iflcore = 0; b.tcoree = 100.0; b.tcorei = 100.0; b.tedge = 2.0
+    b.istepfc = 3; b.lyte = np.full_like(np.asarray(b.lyte, dtype=float), 0.03)
+    b.recycp[0] = 0.98; b.recycw[0] = 0.9; b.matwso[0] = 1
+    b.isnwcono = np.ones_like(np.asarray(b.isnwcono)); b.isnwconi = np.ones_like(np.asarray(b.isnwconi))
+    b.nwallo = 1.0e18; b.nwalli = 1.0e18
+    b.difni[0] = 1.0; b.kye = 1.0; b.kyi = 1.0; b.travis[0] = 1.0
+    b.flalfe = 0.21; b.flalfi = 0.21; b.flalfv = 1.0
+    b.flalfgx = np.full(10, 1.0); b.flalfgy = np.full(10, 1.0); b.flalfvgx = 1.0; b.flalfvgy = 1.0; b.flalftgx = 1.0; b.flalftgy = 1.0
+    b.ineudif = 2
+    b.isupgon = np.zeros_like(b.isupgon); b.isupgon[0] = 1; b.isngon = np.zeros_like(b.isngon)
+    com.ngsp = 1; com.nhsp = 2; b.ziin[1] = 0; b.travis[1] = 0.0
+    b.cngmom = np.zeros_like(np.asarray(b.cngmom, dtype=float)); b.cmwall = np.zeros_like(np.asarray(b.cmwall, dtype=float))
+    b.cngtgx = np.zeros_like(np.asarray(b.cngtgx, dtype=float)); b.cngtgy = np.zeros_like(np.asarray(b.cngtgy, dtype=float))
+    b.kxn = 0.0; b.kyn = 0.0
+    b.isnion = np.asarray(b.isnion).copy(); b.isupon = np.asarray(b.isupon).copy(); b.isnion[:2] = 1; b.isupon[:2] = 1
+    b.isphion = 1; b.isphiofft = 0; b.b0 = 1.0; b.rsigpl = 1.0e-8; b.cfjhf = 1.0; b.cfjve = 1.0; b.jhswitch = 1; b.cfjpy = 0.0; b.cfjp2 = 0.0
+    b.newbcl = np.ones_like(np.asarray(b.newbcl)); b.newbcr = np.ones_like(np.asarray(b.newbcr)); b.isfdiax = 1.0
+    b.cfyef = 1.0; b.cf2ef = 1.0; b.cfydd = 0.0; b.cf2dd = 0.0; b.cfrd = 0.0; b.cfbgt = 0.0; b.cfybf = 1.0; b.cf2bf = 1.0; b.cfqybf = 1.0; b.cfq2bf = 1.0
+    b.isnewpot = 1; b.rnewpot = 1.0; b.iphibcc = 3
+    if mods is not None:
+        mods(b, com)
+    c.setup()
+    z = np.load(os.path.join(GOLDEN, "jupyter_d3d_state.npz"))
+    T = lambda a: np.ascontiguousarray(a.T)
+    nis, ups = z["nis"], z["ups"]
+    pl = [T(nis[:, :, 0]), T(nis[:, :, 1]), T(ups[:, :, 0]), T(ups[:, :, 1]), T(z["tes"]), T(z["tis"]), T(z["ngs"][:, :, 0]), T(z["phis"])]
+    if fx > 1 or fy > 1:
+        pl = refine_state(pl, fx, fy)
+    yl = c.set_state2([pl[0], pl[1]], [pl[2], pl[3]], pl[4], pl[5], ng=pl[6], phi=pl[7], tg=pl[5])
+    return c, yl
+
+
 def switch_variant(seed):
     """A random combination of the switches and coefficients the general path implements beyond the input_example deck (differencing
     schemes 0-8, flux limits, viscosity and conductivity options, rate models, boundary options, 4th-order terms): returns a function
@@ -135,6 +183,12 @@ def switch_variant(seed):
         if rng.random() < 0.3:
             idx[(k, i)] = pick(*vals)
     istab = pick(0, 0, 7) if rng.random() < 0.4 else None
+    # cross-field drifts, grad-B currents, the new potential model with its core conditions, Joule heating (jupyter/case_setup.py:87-110)
+    for k, vals in (("cfyef", (1.0, 0.5)), ("cf2ef", (1.0, 0.5)), ("cfybf", (1.0,)), ("cf2bf", (1.0,)), ("cfqybf", (1.0,)), ("cfq2bf", (1.0,)), ("isnewpot", (1,)), ("rnewpot", (1.0, 0.5)),
+                    ("jhswitch", (1, 2)), ("isfdiax", (1.0,)), ("iphibcc", (1, 2, 3)), ("cfcurv", (0.5,)), ("cfgradb", (0.5,)), ("eycore", (10.0,)), ("icoreelec", (5.0,)),
+                    ("cfqybbo", (1.0,)), ("cfqydbo", (1.0,)), ("cfniybbo", (1.0,)), ("cfeeybbo", (1.0,)), ("ExtendedJacPhi", (0,))):
+        if rng.random() < 0.4:
+            ch[k] = pick(*vals)
 
     def mods(b, com):
         for k, v in ch.items():

@@ -142,7 +142,7 @@ template <typename T> T* alloc_as(size_t n) {
 }
 
 // rows copied on each side of the perturbed cell's row, and the number of line arrays at the end of UE_GEN_PLANES
-#define UE_GEN_NLINE 12
+#define UE_GEN_NLINE 14
 #if defined(UE_GEN_HOST)
 bool g_poison = false;  // test aid: fill the private planes with NaN before the band copy
 #endif
@@ -205,7 +205,10 @@ HD int eval_column(Gen& g, const double* base, int npl, int64_t iv, const double
   const int rc = g.pandf1(xc, yc, ylp, wk);
   g.sync();
   if (rc) { if (tid == 0) *cnt = 0; return rc; }
-  const int64_t ii1 = mx(iv - mu, (int64_t)1), ii2 = mn(iv + ml, neq);
+  int64_t ii1 = mx(iv - mu, (int64_t)1), ii2 = mn(iv + ml, neq);
+  if (g.ExtendedJacPhi > 0 && g.isphion * g.isnewpot == 1 && iv % g.numvar_ == 0) {  // wider band for a potential perturbation (oderhs.m:8645-8651)
+    ii1 = mx(iv - 4 * g.numvar_ * g.nx, (int64_t)1); ii2 = mn(iv + 4 * g.numvar_ * g.nx, neq);
+  }
   const bool isphi = g.IDXPHI(xc, yc) == iv - 1;
   // difference, diagonal terms, clip; NaN marks an element that is not kept (a NaN element fails the clip test as well)
   for (int64_t ii = ii1 + tid; ii <= ii2; ii += g.nth) {
@@ -473,7 +476,7 @@ int init_all() {
   GI(isnonog) GI(isphion) GI(isphiofft) GI(ineudif) GI(isflxvar) GI(isrscalf) GI(isbcwdt) GI(icnuiz) GI(icnucx) GI(isrecmon) GI(ingb) GI(inflbg) GI(isgasdc) GI(isdifxg_aug) GI(isdifyg_aug)
   GI(isvylog) GI(isgxvon) GI(convis) GI(concap) GI(isflxlde) GI(isflxldi) GI(isplflxl) GI(inkxc) GI(isgpye) GI(ishavisy) GI(isvhyha) GI(islnlamcon) GI(isnupdot1sd) GI(iteb) GI(istabon)
   GI(ifxnsgi) GI(iflcore) GI(ifluxni) GI(isrefluxclip) GI(ibctepl) GI(ibctipl) GI(ibctepr) GI(ibctipr) GI(isbohmms) GI(isextrnp) GI(isextrnpf) GI(isextrtpf) GI(isextrngc) GI(isextrnw)
-  GI(isextrtw) GI(isnfmiy) GI(isybdrywd) GI(isnewpot) GI(jhswitch) GI(isfeexpl0) GI(isfeixpl0) GI(isintlog) GI(iskaplex) GI(isexunif) GI(isfdiax) GI(isugfm1side) GI(isvisxn_old) GI(isteon) GI(istion)
+  GI(isextrtw) GI(isnfmiy) GI(isybdrywd) GI(isnewpot) GI(jhswitch) GI(isfeexpl0) GI(isfeixpl0) GI(isintlog) GI(iskaplex) GI(isexunif) GI(isfdiax) GI(isugfm1side) GI(isvisxn_old) GI(isteon) GI(istion) GI(iphibcc)
 #undef GI
   g.isupgon = I("isupgon", 0); g.isngon = I("isngon", 0); g.istgon = I("istgon", 0); g.isfixlb = I("isfixlb", 0); g.isfixrb = I("isfixrb", 0); g.newbcl = I("newbcl", 0); g.newbcr = I("newbcr", 0);
   g.isngcore1 = I("isngcore", 0);
@@ -489,7 +492,8 @@ int init_all() {
   GR(nurlxn) GR(nurlxu) GR(nurlxe) GR(nurlxi) GR(nurlxg) GR(nurlxp) GR(tcoree) GR(tcorei) GR(pcoree) GR(pcorei) GR(sygytotc) GR(csfacti) GR(cfueb) GR(cgpld) GR(cmneut) GR(eedisspl) GR(eidisspl) GR(cmntgpl)
   GR(ckinfl) GR(isoldalbarea) GR(tbmin) GR(nufak) GR(dtreal) GR(dtphi) GR(dylconst) GR(jaccliplim) GR(kelhihg) GR(kelhghg) GR(lgvmax) GR(flgamvg) GR(cfvisxn) GR(cfvisyn) GR(flgamtg) GR(cfupcx) GR(cfticx)
   GR(cfnidh) GR(cfnidh2) GR(cfnidhdis) GR(cfnidhgy) GR(cfnidhg2) GR(cftgeqp) GR(flalftxy) GR(flalfgnx) GR(flalfgny) GR(nlimgx) GR(nlimgy) GR(cfloxiplt) GR(cfloygwall) GR(cfjve) GR(rsigpl) GR(rsigplcore)
-  GR(bcen) GR(cfqym) GR(cfqydt) GR(cfqyao) GR(cfsigm)
+  GR(bcen) GR(cfqym) GR(cfqydt) GR(cfqyao) GR(cfsigm) GR(cfyef) GR(cf2ef) GR(cfybf) GR(cf2bf) GR(cfcurv) GR(cfgradb) GR(eycore) GR(icoreelec) GR(cfniybbo) GR(cfeeybbo)
+  GR(cfqybf) GR(cfq2bf) GR(cfqybbo) GR(cfqydbo) GR(cfwjdotelim) GR(tebg)
 #undef GR
   g.erad = SC("erad"); g.delpert = SC("del");
   g.sigma1_ = SC("sigma1"); g.frfqpn_ = SC("frfqpn"); g.cffqpsat_ = SC("cffqpsat"); g.exjbdry_ = SC("exjbdry"); g.rnewpot_ = SC("rnewpot"); g.cfqyae_ = SC("cfqyae"); g.cfqyai_ = SC("cfqyai");
@@ -509,7 +513,7 @@ int init_all() {
   if (g.ineudif == 1 && (g.isnonog != 0 || g.isupgon != 0)) { g_err = "ineudif=1 is built for orthogonal meshes and diffusive atoms only"; return -5; }
   const size_t nc = g.NC, nxs = g.NXS, nys = g.ny + 2;
 #define GP(n) g.n = ARR(#n, nc);
-  GP(vol) GP(gx) GP(gy) GP(gxf) GP(gyf) GP(gxc) GP(gyc) GP(sx) GP(sxnp) GP(sy) GP(rr) GP(rrv) GP(volv) GP(syv) GP(dxnog) GP(dynog) GP(btot) GP(rbfbt) GP(rbfbt2) GP(lcone) GP(lconi) GP(angfx) GP(ngfix)
+  GP(vol) GP(gx) GP(gy) GP(gxf) GP(gyf) GP(gxc) GP(gyc) GP(sx) GP(sxnp) GP(sy) GP(rr) GP(rrv) GP(volv) GP(syv) GP(dxnog) GP(dynog) GP(btot) GP(rbfbt) GP(rbfbt2) GP(lcone) GP(lconi) GP(angfx) GP(ngfix) GP(curvrby) GP(gradby) GP(curvrb2) GP(gradb2)
 #undef GP
   g.b_c = ARR("b_c", nc); g.rm_c = ARR("rm_c", nc);
   g.ixm1d = ARR("ixm1", nc); g.ixp1d = ARR("ixp1", nc); g.isxptyd = ARR("isxpty", nc); g.isxptxd = ARR("isxptx", nc);
@@ -541,19 +545,22 @@ int init_all() {
   if (g.isupgon == 1) { if (g.nisp != 2 || g.zi[1] != 0.) { g_err = "isupgon=1 needs nisp=2 with zi(2)=0"; return -5; } g.iigsp = 1; }
   // switches outside what is built
   struct { const char* n; double want; } must[] = {{"isimpon", 0}, {"ismcnon", 0}, {"ishymol", 0}, {"ifixsrc", 0}, {"ifixpsor", 0}, {"isupdrag", 0}, {"isofric", 0}, {"ishosor", 0}, {"islimon", 0}, {"isudsym", 0},
-                                                   {"nxomit", 0}, {"isbohmcalc", 1}, {"isdifbetap", 0}, {"cfyef", 0}, {"cf2ef", 0}, {"cfybf", 0}, {"cf2bf", 0}, {"cfydd", 0}, {"cf2dd", 0}, {"cfrd", 0}, {"cfbgt", 0},
-                                                   {"cfvycf", 0}, {"cfvycr", 0}, {"cftef", 0}, {"cftdd", 0}, {"cfqybf", 0}, {"cfq2bf", 0}, {"cfjp2", 0}, {"cfjpy", 0}, {"cfqyn", 0}, {"cfeta1", 0}, {"cfrtaue", 0},
+                                                   {"nxomit", 0}, {"isbohmcalc", 1}, {"isdifbetap", 0}, {"cfydd", 0}, {"cf2dd", 0}, {"cfrd", 0}, {"cfbgt", 0},
+                                                   {"cfvycf", 0}, {"cfvycr", 0}, {"cftef", 0}, {"cftdd", 0}, {"cfjp2", 0}, {"cfjpy", 0}, {"cfqyn", 0}, {"cfeta1", 0}, {"cfrtaue", 0},
                                                    {"cfcl_e", 0}, {"cfcl_i", 0}, {"facbni", 0}, {"facbup", 0}, {"facbee", 0}, {"facbei", 0}, {"rtauxfac", 0}, {"ispsorave", 0}, {"iseesorave", 0}, {"cfvisxneov", 0},
-                                                   {"cfvisxneoq", 0}, {"cfvyavis", 0}, {"cfanomvisxg", 0}, {"cfanomvisyg", 0}, {"isnewpot", 0}, {"jhswitch", 0}, {"isnfmiy", 0}, {"isybdrywd", 0}, {"isfeexpl0", 0},
-                                                   {"isfeixpl0", 0}, {"cfeexdbo", 0}, {"cfeixdbo", 0}, {"cfniybbo", 0}, {"cfniydbo", 0}, {"cfeeybbo", 0}, {"cfeeydbo", 0}, {"isextrnp", 0}, {"isextrnpf", 0},
+                                                   {"cfvisxneoq", 0}, {"cfvyavis", 0}, {"cfanomvisxg", 0}, {"cfanomvisyg", 0}, {"isnfmiy", 0}, {"isybdrywd", 0}, {"isfeexpl0", 0},
+                                                   {"isfeixpl0", 0}, {"cfeexdbo", 0}, {"cfeixdbo", 0}, {"cfniydbo", 0}, {"cfeeydbo", 0}, {"isextrnp", 0}, {"isextrnpf", 0},
                                                    {"isextrtpf", 0}, {"isextrngc", 0}, {"isextrnw", 0}, {"isextrtw", 0}, {"isbohmms", 0}, {"ibctepl", 1}, {"ibctipl", 1}, {"ibctepr", 1}, {"ibctipr", 1}, {"isfixrb", 0},
                                                    {"is1D_gbx", 0}, {"isnglf", 0}, {"iszeffcon", 0}, {"isup1up2", 0}, {"isflxvar", 0}, {"istgon", 0}, {"isphilbc", 0}, {"isphirbc", 0}, {"ikapmod", 0},
-                                                   {"isfqpave", 0}, {"isphicore0", 0}, {"iskaprex", 0}};
+                                                   {"isfqpave", 0}, {"isphicore0", 0}, {"iskaprex", 0}, {"isrozhfac", 0}};
   for (auto& m : must) {
     const V* v = find(m.n);
     if (!v) { g_err = std::string("missing input ") + m.n; return -1; }
     if ((*v)[0] != m.want) { g_err = std::string("switch outside the built set: ") + m.n; return -5; }
   }
+  if (g.isnewpot != 0 && g.isnewpot != 1) { g_err = "isnewpot must be 0 or 1"; return -5; }
+  if (g.isnewpot * g.isphion == 1 && (g.iphibcc < 1 || g.iphibcc > 3)) { g_err = "only iphibcc = 1, 2, 3 available"; return -5; }
+  g.ExtendedJacPhi = I("ExtendedJacPhi"); g.numvar_ = I("numvar");
   if (g.fnnuiz != 1.) { g_err = "fnnuiz must be 1"; return -5; }
   if (SC("l_parloss") <= 1e9) { g_err = "l_parloss<=1e9 (nuvl) not built"; return -5; }
   if (g.isfixlb != 0 && g.isfixlb != 2) { g_err = "isfixlb must be 0 or 2"; return -5; }

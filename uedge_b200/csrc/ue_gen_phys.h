@@ -69,8 +69,8 @@ HD int iabs(int a) { return a < 0 ? -a : a; }
   P1(floxe) P1(floxi) P1(floye) P1(floyi) P1(conxe) P1(conxi) P1(conye) P1(conyi) P1(feex) P1(feey) P1(feix) P1(feiy) P1(feexy) P1(feixy) P1(resee) P1(resei) \
   P1(erliz) P1(erlrc) P1(eeli) P1(vsoreec) P1(vsoree) P1(pwribkg) P1(pwrebkg) P1(pradhyd) \
   P1(fqp) P1(fqx) P1(fqy) P1(fq2) P1(fqxb) P1(fqyb) P1(fqyn) P1(fqym) P1(fqymi) P1(fqya) P1(fqydt) P1(fqydti) P1(fqyao) P1(fqyae) P1(fqyd) P1(fqygp) P1(fq2d) P1(netap) P1(resphi) P1(dphi_iy1) \
-  P2(g_vyce) P2(g_vycp) P2(fmity) P2(fqymi_) P2(fniycbo) P1(feeycbo) P1(feiycbo) P1(kappal) P1(kappar) P1(bcel) P1(bcer) P1(bcil) P1(bcir) \
-  P1(fqpsatlb) P1(fqpsatrb)
+  P2(vyce) P2(vycb) P2(vycp) P1(veycb) P2(v2ce) P2(v2cb) P1(ve2cb) P1(wjdote) P2(fmity) P2(fqymi_) P2(fniycbo) P1(feeycbo) P1(feiycbo) P1(kappal) P1(kappar) P1(bcel) P1(bcer) P1(bcil) P1(bcir) \
+  P1(fqpsatlb) P1(fqpsatrb) P1(fdiaxlb) P1(fdiaxrb)
 
 struct Gen {
   // ---- cooperative-thread identity of this context -------------------------------------------------------------------
@@ -110,14 +110,17 @@ double ev, qe, me, mp, pi_, cutlo, rt8opi, temin, tgmin, nnorm, ennorm, temp0, v
     delpert, dylconst, jaccliplim, kelhihg, kelhghg, lgvmax, flgamvg, cfvisxn, cfvisyn, flgamtg, cfupcx, cfticx, cfnidh, cfnidh2, cfnidhdis, cfnidhgy,
     cfnidhg2, cftgeqp, flalftxy, flalfgnx, flalfgny, nlimgx, nlimgy, cfloxiplt, cfloygwall, cfjve, rsigpl, rsigplcore, bcen, bceew, bciew, cfqym, cfqydt,
     cfjpy, cfjp2, cfqybf, cfq2bf, cfqybbo, cfqydbo, cfydd_, cfjp2_, cfqyn, cfqyao, cfqya, cfqyae, cfjpy_, fqpsatlb_unused, lnlam_unused, phiwi0, phiwo0,
-    kappamx, kappa0, cfsigm, fqsatlb_u, fupe_cur, dtphi_, cfhcxgc_u, lyphi0, lyphi1, isparmultdt_u, tewallmin_u, cfwjdotelim, cfeexdbo, cfeixdbo, cfkincor;
+    kappamx, kappa0, cfsigm, fqsatlb_u, fupe_cur, dtphi_, cfhcxgc_u, lyphi0, lyphi1, isparmultdt_u, tewallmin_u, cfwjdotelim, cfeexdbo, cfeixdbo, cfkincor,
+    cfyef, cf2ef, cfybf, cf2bf, cfcurv, cfgradb, eycore, icoreelec, cfniybbo, cfeeybbo;
+int ExtendedJacPhi;
+int64_t numvar_;
 double cngfx_[2], cngfy_[2], mi[2], zi[2], n0[2], fnorm[2], n0g_[2], mg_[2], ngbackg_[2], vcony[2], difpr[2], difni[2], difni2[2], difpr2[2], difax[2], travis[2], parvis[2],
     nlimix[2], nlimiy[2], dif4order[2], cpiup[2], cfvgpx[2], cfvgpy[2], cfvcsx[2], cfvcsy[2], cfvisxy[2], cngmom[2], cmwall[2], cngtgx[2], cngtgy[2], cdifg[2], lgmax[2], lgtmax[2],
     rld2dxg[2], rld2dyg[2], cngflox[2], cngfloy[2], rtg2ti[2], tgas[2], istgcon[2], keligig[2], ncore[2], ngcore[2], upcore[2], curcore[2], albedoc[2], csfaclb[2], csfacrb[2],
     recycp[2], nwimin[2], nwomin[2], difutm_[2];
 // geometry planes / lines
 const double *vol, *gx, *gy, *gxf, *gyf, *gxc, *gyc, *sx, *sxnp, *sy, *rr, *rrv, *volv, *syv, *dxnog, *dynog, *btot, *rbfbt, *rbfbt2, *lcone, *lconi, *angfx,
-    *ngfix, *dx_, *dy_;
+    *ngfix, *dx_, *dy_, *curvrby, *gradby, *curvrb2, *gradb2;
 const double *fxm[2], *fx0[2], *fxp[2], *fxmy[2], *fxpy[2], *fym[2], *fy0[2], *fyp[2], *fymx[2], *fypx[2], *fymv[2], *fy0v[2], *fypv[2], *fymxv[2], *fypxv[2];
 const double *ixm1d, *ixp1d, *isxptyd, *isxptxd;
 const double *fgtdx, *fgtdy, *flalfea, *flalfia, *flalfva, *flalfgxa, *flalfgxya, *flalfgya, *flalfvgxa, *flalfvgya, *flalfvgxya, *flalftgxa, *flalftgya, *yyf;
@@ -335,7 +338,7 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
   double *floxe, *floxi, *floye, *floyi, *conxe, *conxi, *conye, *conyi, *feex, *feey, *feix, *feiy, *feexy, *feixy, *resee, *resei;
   double *erliz, *erlrc, *eeli, *vsoreec, *vsoree, *pwribkg, *pwrebkg, *pradhyd;
   double *fqp, *fqx, *fqy, *fq2, *fqxb, *fqyb, *fqyn, *fqym, *fqymi, *fqya, *fqydt, *fqydti, *fqyao, *fqyae, *fqyd, *fqygp, *fq2d, *fqpsatlb_, *netap, *resphi, *dphi_iy1;
-  double *fniycbo[2], *feeycbo, *feiycbo, *kappal, *kappar, *bcel, *bcer, *bcil, *bcir, *fqpsatlb, *fqpsatrb;
+  double *fniycbo[2], *feeycbo, *feiycbo, *kappal, *kappar, *bcel, *bcer, *bcil, *bcir, *fqpsatlb, *fqpsatrb, *fdiaxlb, *fdiaxrb;
   double *dtuse, *ylodt, *suscal, *sfscal;
   int errc;
 
@@ -781,10 +784,24 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
         else if (teev < 50.) A(loglambda, ix, iy) = 23.4 - 1.15 * ue_log10(1.e-6 * nexface) + 3.45 * ue_log10(teev);
         else A(loglambda, ix, iy) = 25.3 - 1.15 * ue_log10(1.e-6 * nexface) + 2.33167537087122e+00 * ue_log10(teev);
       }
-    // radial and "2" velocities of the ion species: diffusive parts only (all drift coefficients are zero) (oderhs.m:1167-1471)
+    // radial and "2" velocities of the ion species: diffusive parts plus the ExB and grad-B / curvature drifts (oderhs.m:1167-1471);
+    // the diamagnetic (cfydd, cf2dd), resistive (cfrd) and classical (cfvycf, cfvycr) parts are refused in init
     for (int f = 0; f < nfsp; ++f) {
       if (!(zi[f] > 1.e-10)) continue;
+      const double qion = zi[f] * qe;
       FOR2(iy, j1, j5, ix, i1, i6) {
+          const int iyp1 = mn(iy + 1, ny + 1);
+          const int ix3 = IXM1(ix, iy), ix4 = IXM1(ix, iy + 1);
+          const double temp1 = (-4.0) * (A(phiv, ix, iy) - A(phiv, ix3, iy)) * A(gxc, ix, iy);
+          const double temp2 = 4.0 * (A(priv[f], ix, iy) - A(priv[f], ix3, iy)) * A(gxc, ix, iy);
+          const double lambd_ci = 1e16 * sq(A(ti, ix, iy) / ev) / A(nit, ix, iy), lambd_ce = 2e16 * sq(A(te, ix, iy) / ev) / A(ne, ix, iy);
+          const double coll_fi = cfnus_i / (cfnus_i + (lambd_ci / (A(lconi, ix, iy)))), coll_fe = cfnus_e / (cfnus_e + (lambd_ce / (A(lcone, ix, iy))));
+          A(vyce[f], ix, iy) = 0.125 * temp1 * (A(rbfbt2, ix, iy) + A(rbfbt2, ix, iy + 1));
+          A(vycb[f], ix, iy) = (cfcurv * (0.5 * (A(ti, ix, iy) + A(ti, ix, iyp1)) + mi[f] * sq(0.25 * (A(up[f], ix, iy) + A(up[f], ix, iyp1) + A(up[f], ix3, iy) + A(up[f], ix4, iyp1)))) * A(curvrby, ix, iy) / qion +
+                                cfgradb * 0.5 * (A(ti, ix, iy) + A(ti, ix, iyp1)) * A(gradby, ix, iy) / qion) * coll_fi;
+          A(veycb, ix, iy) = (-cfcurv * 0.5 * (A(te, ix, iy) + A(te, ix, iyp1)) * A(curvrby, ix, iy) / qe - cfgradb * 0.5 * (A(te, ix, iy) + A(te, ix, iyp1)) * A(gradby, ix, iy) / qe) * coll_fe;
+          // (the reference zeroes vycp on the faces iy = 0 and ny from every iteration: written here by the iteration that owns the face)
+          A(vycp[f], ix, iy) = (iy == 0 || iy == ny) ? 0. : -0.25 * temp2 * (A(rbfbt2, ix, iy) + A(rbfbt2, ix, iy + 1)) / (qion * (A(niy0[f], ix, iy) + A(niy1[f], ix, iy)));
           A(vydd[f], ix, iy) = vcony[f] + 0. + 0. - (difpr[f] + 0.) * (2 * A(gpry, ix, iy) / (A(pr, ix, iy + 1) + A(pr, ix, iy)) - 3.0 * A(gtey, ix, iy) / (A(tey1, ix, iy) + A(tey0, ix, iy)));
           A(diffusivwrk, ix, iy) = fcdif * difni[f] + 0.;
         }
@@ -792,16 +809,31 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
           double difnimix = A(diffusivwrk, ix, iy);
           A(vydd[f], ix, iy) = A(vydd[f], ix, iy) - 1. * difnimix * (2 * (1 - isvylog) * ((A(niy1[f], ix, iy) - A(niy0[f], ix, iy)) / A(dynog, ix, iy)) / (A(niy1[f], ix, iy) + A(niy0[f], ix, iy)) +
                                                                       isvylog * (ue_log(A(niy1[f], ix, iy)) - ue_log(A(niy0[f], ix, iy))) / A(dynog, ix, iy));
-          A(vy[f], ix, iy) = A(vydd[f], ix, iy);
-          A(vygp[f], ix, iy) = A(vydd[f], ix, iy);
+          A(vy[f], ix, iy) = A(vydd[f], ix, iy) + cfyef * A(vyce[f], ix, iy) + cfybf * A(vycb[f], ix, iy);
+          A(vygp[f], ix, iy) = cfybf * A(vycp[f], ix, iy) + A(vydd[f], ix, iy) + cfyef * A(vyce[f], ix, iy);  // (cfydd + cfybf) bfacyrozh vycp with cfydd = 0, bfacyrozh = 1
         }
       FOR2(iy, j1, j6, ix, i1, i6) {
-          const int ix2 = IXP1(ix, iy);
+          const int ix2 = IXP1(ix, iy), iy1 = mx(0, iy - 1);
+          const double temp1 = (-4.) * (A(phiv, ix, iy) - A(phiv, ix, iy1)) * A(gyc, ix, iy);
+          const double temp2 = 4. * (A(priv[f], ix, iy) - A(priv[f], ix, iy1)) * A(gyc, ix, iy);
+          A(v2ce[f], ix, iy) = -0.5 * temp1 / (A(btot, ix, iy) + A(btot, ix2, iy));
+          A(v2cb[f], ix, iy) = (cfcurv * (0.5 * (A(tiv, ix, iy) + A(tiv, ix, iy1)) + mi[f] * sq(A(up[f], ix, iy))) * A(curvrb2, ix, iy) + cfgradb * 0.5 * (A(tiv, ix, iy) + A(tiv, ix, iy1)) * A(gradb2, ix, iy)) / qion;
+          A(ve2cb, ix, iy) = -(cfcurv * 0.5 * (A(tev, ix, iy) + A(tev, ix, iy1)) * A(curvrb2, ix, iy) + cfgradb * 0.5 * (A(tev, ix, iy) + A(tev, ix, iy1)) * A(gradb2, ix, iy)) / qe;
+          const double v2cd = temp2 / ((A(btot, ix, iy) + A(btot, ix2, iy)) * qion * (A(ni[f], ix, iy) + A(ni[f], ix2, iy)));
+          // plate electron diamagnetic flux for the sheath potential (oderhs.m:1376-1391)
+          if (ix == ixlb) {
+            const double v2dia = -0.5 * (A(gpey, ixlb + 1, iy) + A(gpey, ixlb + 1, iy1)) / (A(btot, ixlb + 1, iy) * qe * A(ne, ixlb + 1, iy));
+            fdiaxlb[iy] = A(ne, ixlb + 1, iy) * A(sx, ixlb, iy) * v2dia * A(rbfbt, ixlb + 1, iy);
+          }
+          if (ix == ixrb) {
+            const double v2dia = -0.5 * (A(gpey, ixrb, iy) + A(gpey, ixrb, iy1)) / (A(btot, ixrb, iy) * qe * A(ne, ixrb, iy));
+            fdiaxrb[iy] = A(ne, ixrb, iy) * A(sx, ixrb, iy) * v2dia * A(rbfbt, ixrb, iy);
+          }
           A(v2dd[f], ix, iy) = -2. * difpr2[f] * A(gprx, ix, iy) / (A(pr, ix2, iy) / A(rbfbt, ix2, iy) + A(pr, ix, iy) / A(rbfbt, ix, iy)) -
                                2. * (fcdif * difni2[f] + 0.) * (A(ni[f], ix2, iy) - A(ni[f], ix, iy)) /
                                    (A(ni[f], ix2, iy) / (A(rbfbt, ix2, iy) * A(gx, ix2, iy)) + A(ni[f], ix, iy) / (A(rbfbt, ix, iy) * A(gx, ix, iy)));
-          A(v2[f], ix, iy) = A(v2dd[f], ix, iy);
-          A(v2xgp[f], ix, iy) = 0.5 * (A(rbfbt, ix, iy) + A(rbfbt, ix2, iy)) * (A(v2dd[f], ix, iy));
+          A(v2[f], ix, iy) = A(v2dd[f], ix, iy) + cf2ef * A(v2ce[f], ix, iy) + cf2bf * A(v2cb[f], ix, iy);
+          A(v2xgp[f], ix, iy) = 0.5 * (A(rbfbt, ix, iy) + A(rbfbt, ix2, iy)) * (cf2bf * v2cd + A(v2dd[f], ix, iy) + cf2ef * A(v2ce[f], ix, iy));  // (cf2dd + cf2bf) bfacxrozh v2cd
           if (isnonog == 1 && iy <= ny) {  // oderhs.m:1408-1432
             double grdnv = grdnv_y(ni[f], ix, iy, 1) / A(dxnog, ix, iy);
             A(vytan[f], ix, iy) = (fcdif * difni[f] + 0.) * (grdnv / ue_cos(A(angfx, ix, iy)) - (ue_log(A(ni[f], ix2, iy)) - ue_log(A(ni[f], ix, iy))) * A(gxf, ix, iy));
@@ -864,10 +896,13 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
         int ix1 = IXP1(ix, iy);
         A(upe, ix, iy) = (A(upe, ix, iy) - 1. * A(fqp, ix, iy) / (A(rrv, ix, iy) * A(sx, ix, iy) * qe)) / (0.5 * (A(ne, ix, iy) + A(ne, ix1, iy)));
       }
-    FOR2(iy, j1, j6, ix, i1, i6) A(vex, ix, iy) = A(upe, ix, iy) * A(rrv, ix, iy) + 0. - A(vytan[0], ix, iy);
+    FOR2(iy, j1, j6, ix, i1, i6)
+        A(vex, ix, iy) = A(upe, ix, iy) * A(rrv, ix, iy) + (cf2ef * A(v2ce[0], ix, iy) + cf2bf * A(ve2cb, ix, iy)) * 0.5 * (A(rbfbt, ix, iy) + A(rbfbt, IXP1(ix, iy), iy)) - A(vytan[0], ix, iy);
     for (int f = 0; f < nfsp; ++f)
       FOR2(iy, j1, j5, ix, i1, i6) A(vey, ix, iy) = A(vey, ix, iy) + A(vy[f], ix, iy) * zi[f] * 0.5 * (A(niy0[f], ix, iy) + A(niy1[f], ix, iy));
     FOR2(iy, j1, j5, ix, i1, i6) A(vey, ix, iy) = (A(vey, ix, iy) - cfjve * A(fqy, ix, iy) / (A(sy, ix, iy) * qe)) / (0.5 * (A(ney0, ix, iy) + A(ney1, ix, iy)));
+    if (isnewpot == 1)  // fqy(,0) = 0 there (oderhs.m:1794-1800)
+      FOR1(ix, i1, i6) A(vey, ix, 0) = cfybf * A(veycb, ix, 0) + A(vydd[0], ix, 0) + cfyef * A(vyce[0], ix, 0);
 
     // zero the source accumulators (oderhs.m:1818-1835)
     FOR2(iy, j2, j5, ix, i2, i5) {
@@ -1239,7 +1274,8 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
             A(fniy[f], ix, iy) = A(fniy[f], ix, iy) + dif4order[f] * d3ndy3 * A(sy, ix, iy) / (A(gyf, ix, iy) * A(gyf, ix, iy));
           }
         }
-      FOR1(ix, i4, i8) fniycbo[f][ix] = 0.0;  // oderhs.m:3344-3353 with cfybf = 0, cfniydbo = 0
+      FOR1(ix, i4, i8)  // oderhs.m:3344-3353 (vycp(,0) = 0; isfniycbozero = 0)
+        fniycbo[f][ix] = (A(ni[f], ix, 0) * A(sy, ix, 0)) * ((1 - cfniybbo) * cfybf * A(vycb[f], ix, 0));
     }
     // particle balance (oderhs.m:3407-3456)
     for (int f = 0; f < nfsp; ++f) {
@@ -1412,7 +1448,7 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
     }
     FOR2(iy, j1, j5, ix, i4, i8) {  // oderhs.m:4078-4092; vyte_use, vyte_cft, cfybf = 0
         A(floye, ix, iy) = A(floye, ix, iy) + (cfloye / 2.) * (A(ney0, ix, iy) + A(ney1, ix, iy)) * A(vey, ix, iy) * A(sy, ix, iy) + (0. + 0.) * 0.5 * A(sy, ix, iy) * (A(ney0, ix, iy) + A(ney1, ix, iy));
-        if (iy == 0) feeycbo[ix] = 0.;
+        if (iy == 0) feeycbo[ix] = cfloye * (A(ne, ix, 0) * A(te, ix, 0) * A(sy, ix, 0)) * ((1 - cfeeybbo) * cfybf * A(veycb, ix, 0));  // veycp(,0) = 0
       }
     for (int f = 0; f < nfsp; ++f) {  // oderhs.m:4093-4128
       if (isupgon == 1 && f == iigsp) {
@@ -1524,6 +1560,21 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
                              cfneut * cfneutsor_ei * ccoldsor * A(ng, ix, iy) * A(nucx, ix, iy) * (1.5 * A(ti, ix, iy) - 0.125 * mi[0] * (us * us) - eion * ev) * A(vol, ix, iy);
         }
       }
+    // Joule heating (oderhs.m:4832-4875)
+    if (jhswitch > 0) {
+      const int iy_min = isnewpot == 1 ? 2 : 1, iy_max = isnewpot == 1 ? ny - 1 : ny;
+      FOR2(iy, mx(iy_min, j2), mn(iy_max, j5), ix, i2, i5) {
+          const int ix1 = IXM1(ix, iy), ix2 = IXP1(ix, iy);
+          if (jhswitch == 1) {
+            A(wjdote, ix, iy) = -0.5 * (A(fqp, ix, iy) + A(fq2, ix, iy)) * (A(phi, ix2, iy) + A(phi, ix, iy)) + 0.5 * (A(fqp, ix1, iy) + A(fq2, ix1, iy)) * (A(phi, ix, iy) + A(phi, ix1, iy)) -
+                                0.5 * A(fqygp, ix, iy) * (A(phi, ix, iy + 1) + A(phi, ix, iy)) + 0.5 * A(fqygp, ix, iy - 1) * (A(phi, ix, iy) + A(phi, ix, iy - 1));
+            A(resee, ix, iy) = A(resee, ix, iy) + A(wjdote, ix, iy) / (1. + cfwjdotelim * powi(A(te, ix, iy) / tebg, iteb));
+          } else {
+            A(wjdote, ix, iy) = 0.5 * (A(ex, ix1, iy) * A(fqx, ix1, iy) + A(ex, ix, iy) * A(fqx, ix, iy)) / A(gx, ix, iy) + 0.5 * (A(ey, ix, iy) * A(fqy, ix, iy) + A(ey, ix, iy - 1) * A(fqy, ix, iy - 1)) / A(gy, ix, iy);
+            A(resee, ix, iy) = A(resee, ix, iy) + A(wjdote, ix, iy);
+          }
+        }
+    }
     // viscous heating (oderhs.m:4879-4930)
     FOR2(iy, j2, j5, ix, i2, i5)
         for (int f = 0; f < nusp; ++f) {
@@ -1579,19 +1630,6 @@ const double *b_c, *rm_c;
 HD void calc_currents(const Win& w) {
   const int i1 = w.i1, i5 = w.i5, i6 = w.i6;
   const int j1p = w.j1p, j5p = w.j5p, j6p = w.j6p;
-  // drift velocities the inertia current needs (oderhs.m:1178-1226): vyce, vycp on the range of the vy loop
-  for (int f = 0; f < nisp; ++f) {
-    if (!(zi[f] > 1.e-10)) continue;
-    const double qion = zi[f] * qe;
-    FOR2(iy, w.j1, w.j5, ix, i1, i6) {
-        const int ix3 = IXM1(ix, iy);
-        double temp1 = (-4.0) * (A(phiv, ix, iy) - A(phiv, ix3, iy)) * A(gxc, ix, iy);
-        double temp2 = 4.0 * (A(priv[f], ix, iy) - A(priv[f], ix3, iy)) * A(gxc, ix, iy);
-        A(g_vyce[f], ix, iy) = 0.125 * temp1 * (A(rbfbt2, ix, iy) + A(rbfbt2, ix, iy + 1));
-        A(g_vycp[f], ix, iy) = -0.25 * temp2 * (A(rbfbt2, ix, iy) + A(rbfbt2, ix, iy + 1)) / (qion * (A(niy0[f], ix, iy) + A(niy1[f], ix, iy)));
-        A(g_vycp[f], ix, 0) = 0.; A(g_vycp[f], ix, ny) = 0.;
-      }
-  }
   FOR2(iy, j1p, j6p, ix, i1, i5) {
       const int ix1 = IXP1(ix, iy);
       double t0 = mx(A(te, ix1, iy), temin * ev), t1 = mx(A(te, ix, iy), temin * ev);
@@ -1612,7 +1650,7 @@ HD void calc_currents(const Win& w) {
         A(fqp, ix, iy) = (A(rrv, ixlp1, iy) * A(sx, ixlp1, iy) * sigbarx * A(gxf, ixlp1, iy) / qe) *
                          ((A(pre, ixlp2, iy) - A(pre, ixlp1, iy)) / nbarx - qe * (A(phi, ixlp1, iy) - A(phi, ixl, iy)) * A(gxf, ixl, iy) / A(gxf, ixlp1, iy) + cthe * (A(te, ixlp2, iy) - A(te, ixlp1, iy)));
         A(fqp, ix, iy) = (1. - frfqpn_) * fqp_old + frfqpn_ * A(fqp, ix, iy);
-        fqpsatlb[iy] = -qe * isfdiax * (0. + 0.);
+        fqpsatlb[iy] = -qe * isfdiax * (A(ne, ixl, iy) * A(v2ce[0], ixl, iy) * A(rbfbt, ixl, iy) * A(sx, ixl, iy) + fdiaxlb[iy]);
         for (int f = 0; f < nusp; ++f) fqpsatlb[iy] = fqpsatlb[iy] - qe * zi[f] * A(ni[f], ixl, iy) * A(up[f], ixl, iy) * A(sx, ixl, iy) * A(rrv, ixl, iy);
         if (A(fqp, ixl, iy) < 0.) {
           double fp1 = A(fqp, ixl, iy), fp2 = cffqpsat_ * fqpsatlb[iy];
@@ -1625,7 +1663,7 @@ HD void calc_currents(const Win& w) {
         A(fqp, ix, iy) = (A(rrv, ixrm2, iy) * A(sx, ixrm2, iy) * sigbarx * A(gxf, ixrm2, iy) / qe) *
                          ((A(pre, ixrm1, iy) - A(pre, ixrm2, iy)) / nbarx - qe * (A(phi, ixr, iy) - A(phi, ixrm1, iy)) * A(gxf, ixrm1, iy) / A(gxf, ixrm2, iy) + cthe * (A(te, ixrm1, iy) - A(te, ixrm2, iy)));
         A(fqp, ix, iy) = (1. - frfqpn_) * fqp_old + frfqpn_ * A(fqp, ix, iy);
-        fqpsatrb[iy] = qe * isfdiax * (0. + 0.);
+        fqpsatrb[iy] = qe * isfdiax * (A(ne, ixr, iy) * A(v2ce[0], ixrm1, iy) * A(rbfbt, ixr, iy) * A(sx, ixrm1, iy) + fdiaxrb[iy]);
         for (int f = 0; f < nusp; ++f) fqpsatrb[iy] = fqpsatrb[iy] + qe * zi[f] * A(ni[f], ixr, iy) * A(up[f], ixrm1, iy) * A(sx, ixrm1, iy) * A(rrv, ixrm1, iy);
         if (A(fqp, ixrm1, iy) > 0.) {
           double fp1 = A(fqp, ixrm1, iy), fp2 = cffqpsat_ * fqpsatrb[iy];
@@ -1643,6 +1681,12 @@ HD void calc_currents(const Win& w) {
       A(fqyae, ix, iy) = (A(sy, ix, iy) * sigbary / (A(dynog, ix, iy) * qe)) * ((A(ney1, ix, iy) * A(tey1, ix, iy) - A(ney0, ix, iy) * A(tey0, ix, iy)) / nbary - qe * (A(phiy1, ix, iy) - A(phiy0, ix, iy)));
       double fqyai = -(A(sy, ix, iy) * sigbary / (A(dynog, ix, iy) * qe * zi[0])) * ((A(niy1[0], ix, iy) * A(tiy1, ix, iy) - A(niy0[0], ix, iy) * A(tiy0, ix, iy)) / nbary + qe * zi[0] * (A(phiy1, ix, iy) - A(phiy0, ix, iy)));
       A(fqyao, ix, iy) = cfqyao * (cfqyae_ * A(fqyae, ix, iy) + cfqyai_ * fqyai);
+      const int ix3 = IXM1(ix, iy);
+      const double temp1 = 4.0 * (A(prtv, ix, iy) - A(prtv, ix3, iy)) * A(gxc, ix, iy);
+      A(fqyd, ix, iy) = -A(sy, ix, iy) * 0.125 * temp1 * (A(rbfbt2, ix, iy) + A(rbfbt2, ix, iy + 1));
+      double nzvibtot = 0.;
+      for (int f = 0; f < nisp; ++f) nzvibtot = nzvibtot + 0.5 * zi[f] * (A(niy0[f], ix, iy) + A(niy1[f], ix, iy)) * A(vycb[f], ix, iy);
+      A(fqyb, ix, iy) = qe * A(sy, ix, iy) * (nzvibtot - 0.5 * (A(ney0, ix, iy) + A(ney1, ix, iy)) * A(veycb, ix, iy));
     }
   // inertia current (potencur.m:291-376); fmity as a local pair of planes per species
   for (int f = 0; f < nisp; ++f) {
@@ -1659,7 +1703,7 @@ HD void calc_currents(const Win& w) {
         A(fmity[f], ix, iy + 1) = -0.25 * mi[f] * (difutm_[f] + 0.) * ((A(niy1[f], ix, iy + 1) + A(niy0[f], ix, iy + 1)) * (2 * r0slab_ + A(rm_c, ix, iy + 1) + A(rm_c, ix, iyp2)) * utp -
                                                                         (A(niy1[f], ix, iy) + A(niy0[f], ix, iy)) * (2 * r0slab_ + A(rm_c, ix, iy) + A(rm_c, ix, iy + 1)) * ut0) * A(gy, ix, iy + 1);
         double omgci = qe * zi[f] * A(b_c, ix, iy) / mi[f];
-        A(fqymi_[f], ix, iy) = qe * 0.5 * (A(niy0[f], ix, iy) + A(niy1[f], ix, iy)) * (A(g_vyce[f], ix, iy) + A(g_vycp[f], ix, iy)) *
+        A(fqymi_[f], ix, iy) = qe * 0.5 * (A(niy0[f], ix, iy) + A(niy1[f], ix, iy)) * (A(vyce[f], ix, iy) + A(vycp[f], ix, iy)) *
                                (-0.5 * ((A(btot, ix, iy + 1) + A(btot, ix, iyp2)) * utp - (A(btot, ix, iy - 1) + A(btot, ix, iy)) * utm)) * 0.5 * A(gyf, ix, iy) * A(sy, ix, iy) / omgci;
       }
     }
@@ -1678,12 +1722,16 @@ HD void calc_currents(const Win& w) {
     for (int iy = ny; iy >= ny + 1 - nfqya0ow_; --iy) A(fqya, ix, iy) = 0.;
   }
   FOR2(iy, j1p, j5p, ix, i1, i6) {
-      A(fqy, ix, iy) = (1. - rnewpot_) * A(fqyao, ix, iy) + rnewpot_ * A(fqya, ix, iy) + 0. + cfqym * A(fqym, ix, iy) + 0.;
-      A(fqygp, ix, iy) = (1. - rnewpot_) * A(fqyao, ix, iy) + rnewpot_ * A(fqya, ix, iy) + cfqym * A(fqym, ix, iy) + 0.;
+      A(fqy, ix, iy) = (1. - rnewpot_) * A(fqyao, ix, iy) + rnewpot_ * A(fqya, ix, iy) + cfqybf * A(fqyb, ix, iy) + cfqym * A(fqym, ix, iy) + 0.;
+      A(fqygp, ix, iy) = (1. - rnewpot_) * A(fqyao, ix, iy) + rnewpot_ * A(fqya, ix, iy) + cfqym * A(fqym, ix, iy) + A(fqyd, ix, iy);
       A(fqy, ix, iy) = A(fqy, ix, iy) + cfqydt * A(fqydt, ix, iy);  // nx = nxold, ny = nyold; cfqydt = 0
     }
   FOR2(iy, j1p, j6p, ix, i1, i5) {
-      A(fqx, ix, iy) = A(fqp, ix, iy) + A(fq2, ix, iy) + 0.;
+      const int ix1 = IXP1(ix, iy);
+      double nzvibtot = 0.;
+      for (int f = 0; f < nisp; ++f) nzvibtot = nzvibtot + 0.5 * zi[f] * (A(ni[f], ix, iy) + A(ni[f], ix1, iy)) * A(v2cb[f], ix, iy);
+      A(fqxb, ix, iy) = qe * A(sx, ix, iy) * (nzvibtot - 0.5 * (A(ne, ix, iy) + A(ne, ix1, iy)) * A(ve2cb, ix, iy)) * 0.5 * (A(rbfbt, ix1, iy) + A(rbfbt, ix, iy));
+      A(fqx, ix, iy) = A(fqp, ix, iy) + A(fq2, ix, iy) + cfq2bf * A(fqxb, ix, iy);
     }
   if (isexunif == 1)
     FOR1(iy, j1p, j6p) {
@@ -1888,6 +1936,33 @@ HD int bouncon(const Win& w, const double* yl, double* yldot) {
       if (IDXG(ixrb, 0) >= 0) yldot[IDXG(ixrb + 1, 0)] = nurlxg * (A(ng, ixrb, 0) - A(ng, ixrb + 1, 0)) / n0g_[0];
     }
   }
+  // ===== potential with isnewpot = 1: two equations at iy = 0 and 1 (boundary.m:987-1122) =====
+  if (isnewpot * isphion == 1 && w.j3 <= 3) {
+    const int ixc1 = mx(0, ixpt1 + 1);
+    FOR1(ix, mn(w.i4, ixpt1 + 1), mx(w.i8, ixpt2)) {
+      const int64_t iv = IDXPHI(ix, 0), iv1 = IDXPHI(ix, 1);
+      if (iv < 0 || iv1 < 0) continue;
+      if (isixcore[ix] == 1) {  // core boundary (isphicore0 = 0): phi(,0) poloidally constant, phi(,1) by iphibcc = 1, 2, 3
+        yldot[iv] = -nurlxp * (A(phi, ix, 0) - A(phi, IXP1(ix, 0), 0)) / temp0;
+        if (iphibcc == 1) yldot[iv1] = -nurlxp * ((A(ey, ix, 1) - A(ey, ix, 0)) * A(gy, ix, 1) - (A(ey, ix, 2) - A(ey, ix, 1)) * A(gy, ix, 2)) / (A(gy, ix, 1) * temp0);
+        else if (iphibcc == 2) yldot[iv1] = -nurlxp * (A(te, ix, 1) - A(te, IXP1(ix, 1), 1)) / (ev * temp0);
+        else yldot[iv1] = -nurlxp * (A(phi, ix, 1) - A(phi, IXP1(ix, 1), 1)) / temp0;
+        if (ix == ixmp) {  // midplane column: total radial current through the core boundary = icoreelec (fqyn: cfqyn = 0)
+          int ii = ixc1;
+          double fqytotc = A(fqya, ii, 1) + 0. + cfqym * A(fqym, ii, 1) + cfqybbo * A(fqyb, ii, 1) + cfqydbo * A(fqyd, ii, 1);
+          do { ii = IXP1(ii, 1); fqytotc = fqytotc + A(fqya, ii, 1) + 0. + cfqym * A(fqym, ii, 1) + cfqybbo * A(fqyb, ii, 1) + cfqydbo * A(fqyd, ii, 1); } while (ii != ix_fl_bc);
+          yldot[iv] = -nurlxp * (fqytotc - icoreelec) / (qe * n0[0] * vpnorm * A(sy, ixc1, 0));
+          if (iphibcc == 1) yldot[iv1] = -nurlxp * ((A(ey, ix, 1) - A(ey, ix, 0)) * A(gy, ix, 1) - (A(ey, ix, 2) - A(ey, ix, 1)) * A(gy, ix, 2)) / (A(gy, ix, 1) * temp0);
+          else yldot[iv1] = -nurlxp * (A(ey, ix, 0) - eycore) / (A(gyf, ix, 0) * temp0);
+        }
+      } else {  // private-flux wall
+        const int k = (int)iphibcwiix[ix];
+        if (k == 0) yldot[iv] = nurlxp * (A(phi, ix, 1) - A(phi, ix, 0)) / temp0;
+        else if (k == 1) yldot[iv] = nurlxp * (phintewi_ * A(te, ix, 0) / ev - A(phi, ix, 0)) / temp0;
+        else if (k == 3) yldot[iv] = nurlxp * ((A(phi, ix, 1) - A(phi, ix, 0)) - 0.5 * (A(phi, ix, 1) + A(phi, ix, 0)) / (A(gyf, ix, 0) * lyphiix1[ix])) / temp0;
+      }
+    }
+  }
   // ===== iy = ny+1 boundary (boundary.m:1125-1653) =====
   if (w.j7 >= (ny + 1)) {  // isextrnw = isextrtw = 0
     for (int f = 0; f < nisp; ++f) {
@@ -2057,7 +2132,7 @@ HD int bouncon(const Win& w, const double* yl, double* yldot) {
                 yldot[iv2] = -nurlxu * (A(fmix[f], ixt1, iy) + vparn * vxn * 0.5 * (A(nm[f], ixt1, iy) + A(nm[f], ixt, iy)) * A(sx, ixt, iy)) / (vpnorm * fnorm[f] * A(sx, ixt, iy));
               }
             } else {
-              double ueb = cfueb * (0. - A(vytan[f], ixt, iy)) / A(rrv, ixt, iy);
+              double ueb = cfueb * (cf2ef * A(v2ce[f], ixt, iy) * A(rbfbt, ixt, iy) - A(vytan[f], ixt, iy)) / A(rrv, ixt, iy);
               yldot[iv2] = nurlxu * (-cs - ueb - A(up[f], ixt, iy)) / vpnorm;  // isbohmms = 0
               if (isupss[f] == 1 && A(up[f], ixt1, iy) + ueb < -cs) yldot[iv2] = nurlxu * (A(up[f], ixt1, iy) - A(up[f], ixt, iy)) / vpnorm;
               if (isupss[f] == -1) yldot[iv2] = nurlxu * (A(up[f], ixt1, iy) - A(up[f], ixt, iy)) / vpnorm;
@@ -2172,7 +2247,7 @@ HD int bouncon(const Win& w, const double* yl, double* yldot) {
               }
               yldot[iv] = nurlxu * (A(up[f], ixt1, iy) - A(up[f], ixt, iy)) / vpnorm;
             } else {
-              double ueb = cfueb * (0. - A(vytan[f], ixt1, iy)) / A(rrv, ixt1, iy);
+              double ueb = cfueb * (cf2ef * A(v2ce[f], ixt1, iy) * A(rbfbt, ixt, iy) - A(vytan[f], ixt1, iy)) / A(rrv, ixt1, iy);
               yldot[iv2] = nurlxu * (cs - ueb - A(up[f], ixt1, iy)) / vpnorm;  // isbohmms = 0
               if (isupss[f] == 1 && A(up[f], ixt2, iy) + ueb > cs) yldot[iv2] = nurlxu * (A(up[f], ixt2, iy) - A(up[f], ixt1, iy)) / vpnorm;
               if (isupss[f] == -1) yldot[iv2] = nurlxu * (A(up[f], ixt2, iy) - A(up[f], ixt1, iy)) / vpnorm;
@@ -2305,7 +2380,7 @@ HD int pandf1(int xc, int yc, const double* yl, double* yldot) {
   return 0;
 }
   // ---- slab layout -----------------------------------------------------------------------------------------------------
-  double *g_vyce[2], *g_vycp[2], *fmity[2], *fqymi_[2];
+  double *vyce[2], *vycb[2], *vycp[2], *veycb, *v2ce[2], *v2cb[2], *ve2cb, *wjdote, *fmity[2], *fqymi_[2];  // drift velocities (oderhs.m:1167-1420), Joule heating, inertia-current work planes
   HD static int nplanes() {
     int n = 0;
 #define P1(x) n += 1;
