@@ -89,16 +89,18 @@ def cpu_baseline(c, ystates, su, budget_s=12.0, nthreads=None):
 
 
 def general_records(steps=10):
-    """The GENERAL path (ue_gen_*, include/ue_gen.h) on the two reference decks it exists for: pyexamples/input_example (8x4
-    non-orthogonal mesh, inertial atoms, potential equation, numvar 7) and pyexamples/box2 as its deck runs it (inertial atoms).
+    """The GENERAL path (ue_gen_*, include/ue_gen.h) on the reference decks it exists for: pyexamples/input_example (8x4
+    non-orthogonal mesh, inertial atoms, potential equation, numvar 7), pyexamples/box2 as its deck runs it (inertial atoms) and
+    jupyter/case_setup.py (BASELINE configs[2]: cross-field drifts + the new potential model on the 16x8 DIII-D mesh, numvar 7).
     Host clock around the C-ABI calls with pageable host buffers (this entry point has no device-buffer variant yet); the CPU
     figure is the general oracle on one host thread, same step."""
     from uedge_b200.cases import box2_case
-    from uedge_b200.cases2 import Oracle2, box2_initial_state, inputex_case, load_gen
+    from uedge_b200.cases2 import Oracle2, box2_initial_state, inputex_case, jupyter_case, load_gen
     out = {}
     c1, y1, _ = inputex_case("default")
     c2 = box2_case(isupgon=1)
-    for name, c, yl in (("input_example", c1, y1), ("box2_inertial_atoms", c2, box2_initial_state(c2))):
+    c3, y3 = jupyter_case()
+    for name, c, yl in (("input_example", c1, y1), ("box2_inertial_atoms", c2, box2_initial_state(c2)), ("jupyter_drifts_potential", c3, y3)):
         b = c.bbb
         g, o = load_gen().bind(c), Oracle2().bind(c)
         f = g.pandf1(yl); fo = o.pandf1(yl)
