@@ -76,7 +76,9 @@ double ev, qe, me, mp, pi_, cutlo, rt8opi, temin, tgmin, nnorm, ennorm, temp0, v
     cfjpy, cfjp2, cfqybf, cfq2bf, cfqybbo, cfqydbo, cfydd_, cfjp2_, cfqyn, cfqyao, cfqya, cfqyae, cfjpy_, fqpsatlb_unused, lnlam_unused, phiwi0, phiwo0,
     kappamx, kappa0, cfsigm, fqsatlb_u, fupe_cur, dtphi_, cfhcxgc_u, lyphi0, lyphi1, isparmultdt_u, tewallmin_u, cfwjdotelim, cfeexdbo, cfeixdbo, cfkincor,
     cfyef, cf2ef, cfybf, cf2bf, cfcurv, cfgradb, eycore, icoreelec, cfniybbo, cfeeybbo;
-int ExtendedJacPhi;
+int ExtendedJacPhi, istgcore, istgpfc, istgwc, istglb, istgrb, isfegxyqflave;
+double tgcore, cftgticore, tgwall, lytg1, lytg2, cftgtipltl, cftgtipltr, cftgtipfc, cftgtiwc, cgengmpl, cgengmw, cfalbedo, recyce, recycwe, cvgpg, cfcvtg, cfegxy, flalftgxy;
+const double* idxtg_;
 int64_t numvar_;
 V cngfx_, cngfy_, mi, zi, n0, fnorm, n0g_, mg_, ngbackg_, vcony, difpr, difni, difni2, difpr2, difax, travis, parvis, nlimix, nlimiy, dif4order, cpiup, cfvgpx, cfvgpy,
     cfvcsx, cfvcsy, cfvisxy, cngmom, cmwall, cngtgx, cngtgy, cdifg, lgmax, lgtmax, rld2dxg, rld2dyg, cngflox, cngfloy, rtg2ti, tgas, istgcon, keligig,
@@ -104,6 +106,7 @@ inline int64_t IDXU(int f, int ix, int iy) { return (int64_t)idxu_[f][ix + NXS *
 inline int64_t IDXTE(int ix, int iy) { return (int64_t)idxte_[ix + NXS * iy] - 1; }
 inline int64_t IDXTI(int ix, int iy) { return (int64_t)idxti_[ix + NXS * iy] - 1; }
 inline int64_t IDXG(int ix, int iy) { return (int64_t)idxg_[ix + NXS * iy] - 1; }
+inline int64_t IDXTG(int ix, int iy) { return (int64_t)idxtg_[ix + NXS * iy] - 1; }
 inline int64_t IDXPHI(int ix, int iy) { return (int64_t)idxphi_[ix + NXS * iy] - 1; }
 inline int ALG(int64_t iv) { return (int)iseqalgd[iv]; }
 
@@ -292,7 +295,8 @@ struct O2 {
   V gprx, gpry, gpex, gtex, gtix, gpey, gtey, gtiy, ex, ey, nity0, nity1, ney0, ney1, tey0, tey1, tiy0, tiy1, phiy0, phiy1;
   V ngy0, ngy1, tgy0, tgy1, pgy0, pgy1, phiv, tiv, tev, prev, prtv, priv[2];
   V loglambda, diffusivwrk, vy[2], vydd[2], vygp[2], v2[2], v2dd[2], v2xgp[2], vytan[2], frice, frici[2], upi[2], uup[2], uu[2], upe, vex, vey;
-  V vyce[2], vycb[2], vycp[2], veycb, v2ce[2], v2cb[2], ve2cb, wjdote;  // cross-field drift velocities (oderhs.m:1167-1420), Joule heating
+  V vyce[2], vycb[2], vycp[2], veycb, v2ce[2], v2cb[2], ve2cb, wjdote;
+  V segc, floxge, floyge, conxge, conyge, fegx, fegy, fegxy, reseg;  // gas energy equation (engbalg, oderhs.m:7508-7878)  // cross-field drift velocities (oderhs.m:1167-1420), Joule heating
   V nuiz, nurc, nucx, nuix, psorbgg, psorgc, psorc[2], psordis, psorxrc[2], psorrgc, psorg, psor[2], psorxr[2], psorrg;
   V snic[2], sniv[2], psori[2], smoc[2], smov[2], seec, seev, seic, seiv;
   V conxg, conyg, floxg, floyg, fngx, fngy, fngxy, vygtan, uug, uuxg, vyg, resng;
@@ -316,6 +320,7 @@ struct O2 {
     P1(tiy0) P1(tiy1) P1(phiy0) P1(phiy1) P1(ngy0) P1(ngy1) P1(tgy0) P1(tgy1) P1(pgy0) P1(pgy1) P1(phiv) P1(tiv) P1(tev) P1(prev) P1(prtv) P2(priv)
     P1(loglambda) P1(diffusivwrk) P2(vy) P2(vydd) P2(vygp) P2(v2) P2(v2dd) P2(v2xgp) P2(vytan) P1(frice) P2(frici) P2(upi) P2(uup) P2(uu) P1(upe) P1(vex) P1(vey)
     P2(vyce) P2(vycb) P2(vycp) P1(veycb) P2(v2ce) P2(v2cb) P1(ve2cb) P1(wjdote)
+    P1(segc) P1(floxge) P1(floyge) P1(conxge) P1(conyge) P1(fegx) P1(fegy) P1(fegxy) P1(reseg)
     P1(nuiz) P1(nurc) P1(nucx) P1(nuix) P1(psorbgg) P1(psorgc) P2(psorc) P1(psordis) P2(psorxrc) P1(psorrgc) P1(psorg) P2(psor) P2(psorxr) P1(psorrg)
     P2(snic) P2(sniv) P2(psori) P2(smoc) P2(smov) P1(seec) P1(seev) P1(seic) P1(seiv)
     P1(conxg) P1(conyg) P1(floxg) P1(floyg) P1(fngx) P1(fngy) P1(fngxy) P1(vygtan) P1(uug) P1(uuxg) P1(vyg) P1(resng)
@@ -366,6 +371,8 @@ struct O2 {
         if (isflxvar == 0) ntemp = nnorm;
         iv = IDXTI(ix, iy);
         if (iv >= 0) { A(ti, ix, iy) = yl[iv] * ennorm / (1.5 * ntemp); A(ti, ix, iy) = std::max(A(ti, ix, iy), temin * ev); }
+        iv = IDXTG(ix, iy);  // convert.m:299-305 (isflxvar = 0: ntemp = n0g)
+        if (iv >= 0) { A(tg, ix, iy) = yl[iv] * ennorm / (1.5 * n0g_[0]); A(tg, ix, iy) = std::max(A(tg, ix, iy), tgmin * ev); }
         iv = IDXPHI(ix, iy);
         if (iv >= 0) A(phi, ix, iy) = yl[iv] * temp0;
       }
@@ -769,6 +776,83 @@ struct O2 {
           A(resng, ix, iy) = cngsor * (A(psorg, ix, iy) + 0. + A(psorrg, ix, iy)) + 0. + 0. * A(vol, ix, iy);
           A(resng, ix, iy) = A(resng, ix, iy) - cfneutdiv * cfneutdiv_fng * ((A(fngx, ix, iy) - A(fngx, ix1, iy)) + fluxfacy * (A(fngy, ix, iy) - A(fngy, ix, iy - 1)));
         }
+  }
+
+  // ---- engbalg (oderhs.m:7508-7878): the gas energy equation, gas species 1 = the inertial atoms (ngsp = 1, nisp = 2) -------------
+  void engbalg(const Win& w) {
+    const int i1 = w.i1, i2 = w.i2, i4 = w.i4, i5 = w.i5, i6 = w.i6, i8 = w.i8;
+    const int j1 = w.j1, j2 = w.j2, j4 = w.j4, j5 = w.j5, j6 = w.j6, j8 = w.j8;
+    for (int iy = j2; iy <= j5; ++iy)
+      for (int ix = i2; ix <= i5; ++ix) A(segc, ix, iy) = 0.0;
+    if (istgon == 1)  // v.grad(pg) work (oderhs.m:7564-7585)
+      for (int iy = j2; iy <= j5; ++iy)
+        for (int ix = i2; ix <= i5; ++ix) {
+          const int ix1 = IXM1(ix, iy), ix2 = IXP1(ix, iy), iy1 = std::max(0, iy - 1);
+          const double tv = (A(pg, ix2, iy) - A(pg, ix, iy)), t1 = (A(pg, ix, iy) - A(pg, ix1, iy));
+          A(segc, ix, iy) = 0.5 * cvgpg * (A(uuxg, ix, iy) * ave(A(gx, ix2, iy), A(gx, ix, iy)) * tv + A(uuxg, ix1, iy) * ave(A(gx, ix, iy), A(gx, ix1, iy)) * t1) * A(vol, ix, iy);
+          const double t2 = cvgpg * 0.5 * (A(vyg, ix, iy) * A(dynog, ix, iy) * (A(pgy1, ix, iy) - A(pgy0, ix, iy)) + A(vyg, ix, iy1) * A(dynog, ix, iy1) * (A(pgy1, ix, iy1) - A(pgy0, ix, iy1)));
+          A(segc, ix, iy) = A(segc, ix, iy) + cvgpg * t2 * A(vol, ix, iy);
+        }
+    for (int iy = j1; iy <= j6; ++iy)
+      for (int ix = i1; ix <= i6; ++ix) { A(floxge, ix, iy) = 0.0; A(floyge, ix, iy) = 0.0; A(conxge, ix, iy) = 0.0; A(conyge, ix, iy) = 0.0; }
+    for (int iy = j4; iy <= j8; ++iy) {  // conduction (oderhs.m:7605-7636); hcxg is flux-limited already
+      for (int ix = i1; ix <= i5; ++ix) A(conxge, ix, iy) = A(sx, ix, iy) * A(hcxg, ix, iy) * A(gxf, ix, iy);
+      A(conxge, nx + 1, iy) = 0;
+    }
+    for (int iy = j1; iy <= j5; ++iy)
+      for (int ix = i4; ix <= i8; ++ix) A(conyge, ix, iy) = A(sy, ix, iy) * A(hcyg, ix, iy) / A(dynog, ix, iy);
+    for (int ix = i1; ix <= i6; ++ix) A(conyge, ix, ny + 1) = 0.0;
+    for (int iy = j4; iy <= j8; ++iy) {  // convection (oderhs.m:7643-7705)
+      for (int ix = i1; ix <= i5; ++ix) A(floxge, ix, iy) = cfcvtg * 2.5 * A(fngx, ix, iy);
+      A(floxge, nx + 1, iy) = 0.;
+    }
+    for (int iy = j4; iy <= j8; ++iy) {  // no inward power from the plates
+      if (A(fngx, ixlb, iy) > 0.) A(floxge, ixlb, iy) = A(floxge, ixlb, iy) - (1. - cfloxiplt) * cfcvti * 2.5 * A(fngx, ixlb, iy);
+      if (A(fngx, ixrb, iy) < 0.) A(floxge, ixrb, iy) = A(floxge, ixrb, iy) - (1. - cfloxiplt) * cfcvti * 2.5 * A(fngx, ixrb, iy);
+      A(floxge, ixrb + 1, iy) = 0.0;
+    }
+    for (int iy = j1; iy <= j5; ++iy)
+      for (int ix = i4; ix <= i8; ++ix) A(floyge, ix, iy) = cfcvtg * 2.5 * A(fngy, ix, iy);
+    for (int ix = i4; ix <= i8; ++ix) {  // ... nor from the walls
+      if (ix <= ixpt1 || ix > ixpt2) { if (A(fngy, ix, 0) > 0.) A(floyge, ix, 0) = A(floyge, ix, 0) - (1. - cfloygwall) * cfcvtg * 2.5 * A(fngy, ix, 0); }
+      if (A(fngy, ix, ny) < 0.) A(floyge, ix, ny) = A(floyge, ix, ny) - (1. - cfloygwall) * cfcvtg * 2.5 * A(fngy, ix, ny);
+      A(floyge, ix, ny + 1) = 0.0;
+    }
+    if (istgon == 1) fd2tra(w, floxge, floyge, conxge, conyge, tg, fegx, fegy, 0, methi);  // oderhs.m:7708-7716
+    if (isnonog == 1 && istgon == 1)  // y-component of the non-orthogonal diffusive flux (oderhs.m:7720-7782)
+      for (int iy = j1; iy <= j6; ++iy) {
+        if (iy > ny) continue;
+        const int iy1 = std::max(iy - 1, 0);
+        for (int ix = i1; ix <= i6; ++ix) {
+          const int ix2 = IXP1(ix, iy), ix4 = IXP1(ix, iy1), ix6 = IXP1(ix, iy + 1);
+          double t0 = std::max(A(tg, ix, iy), tgmin * ev), t1 = std::max(A(tg, ix2, iy), tgmin * ev);
+          const double vtn = std::sqrt(t0 / mg_[0]), vtnp = std::sqrt(t1 / mg_[0]);
+          const double nu1 = A(nuix, ix, iy) + vtn / lgmax[0], nu2 = A(nuix, ix2, iy) + vtnp / lgmax[0];
+          const double grdnv = ((A(fym[1], ix, iy) * ue_log(A(tg, ix2, iy1)) + A(fy0[1], ix, iy) * ue_log(A(tg, ix2, iy)) + A(fyp[1], ix, iy) * ue_log(A(tg, ix2, iy + 1)) +
+                                 A(fymx[1], ix, iy) * ue_log(A(tg, ix, iy1)) + A(fypx[1], ix, iy) * ue_log(A(tg, ix, iy + 1))) -
+                                (A(fym[0], ix, iy) * ue_log(A(tg, ix, iy1)) + A(fy0[0], ix, iy) * ue_log(A(tg, ix, iy)) + A(fyp[0], ix, iy) * ue_log(A(tg, ix, iy + 1)) +
+                                 A(fymx[0], ix, iy) * ue_log(A(tg, ix4, iy1)) + A(fypx[0], ix, iy) * ue_log(A(tg, ix6, iy + 1)))) / A(dxnog, ix, iy);
+          const double difgx2 = ave(A(tg, ix, iy) / nu1, A(tg, ix2, iy) / nu2) / mg_[0] + sq(rld2dxg[0]) * (1 / sq(A(gxf, ix, iy))) * 0.5 * (A(nuiz, ix, iy) + A(nuiz, ix2, iy));
+          A(fegxy, ix, iy) = cfegxy * ue_exp(0.5 * (ue_log(A(tg, ix2, iy)) + ue_log(A(tg, ix, iy)))) * difgx2 * ave(A(ng, ix2, iy), A(ng, ix, iy)) *
+                             (grdnv / ue_cos(A(angfx, ix, iy)) - (ue_log(A(tg, ix2, iy)) - ue_log(A(tg, ix, iy))) * A(gxf, ix, iy)) * A(sx, ix, iy);
+          t0 = std::max(A(tg, ix, iy), tgmin * ev); t1 = std::max(A(tg, ix2, iy), tgmin * ev);
+          const double vttn = t0 * std::sqrt(t0 / mg_[0]), vttp = t1 * std::sqrt(t1 / mg_[0]);
+          double qfl;
+          if (isfegxyqflave == 0) qfl = flalftgxy * 0.25 * A(sx, ix, iy) * (vttn + vttp) * (A(ng, ix, iy) + A(ng, ix2, iy));
+          else qfl = flalftgxy * A(sx, ix, iy) * ave(vttn, vttp) * ave(A(ng, ix, iy), A(ng, ix2, iy));
+          A(fegxy, ix, iy) = A(fegxy, ix, iy) / std::sqrt(1. + sq(A(fegxy, ix, iy) / qfl));
+          A(fegx, ix, iy) = A(fegx, ix, iy) - A(fegxy, ix, iy);
+        }
+      }
+    for (int iy = j2; iy <= j5; ++iy) {  // residual and equipartition with the ions (oderhs.m:7790-7806)
+      const int iy1 = std::max(0, iy - 1);
+      for (int ix = i2; ix <= i5; ++ix) {
+        const int ix1 = IXM1(ix, iy);
+        A(reseg, ix, iy) = -(A(fegx, ix, iy) - A(fegx, ix1, iy) + A(fegy, ix, iy) - A(fegy, ix, iy1)) + A(segc, ix, iy);
+        A(reseg, ix, iy) = A(reseg, ix, iy) + A(vol, ix, iy) * A(eqpg, ix, iy) * (A(ti, ix, iy) - A(tg, ix, iy));
+        A(seic, ix, iy) = A(seic, ix, iy) - A(vol, ix, iy) * (1.0 - cftiexclg) * A(eqpg, ix, iy) * (A(ti, ix, iy) - A(tg, ix, iy));
+      }
+    }
   }
 
   void calc_currents(const Win& w);                       // potencur.m:39-445 (below)
@@ -1260,9 +1344,7 @@ struct O2 {
       if (isupgon == 1) { hcxg = hcxn; hcyg = hcyn; }
       for (int iy = j1; iy <= j6; ++iy)
         for (int ix = i1; ix <= i6; ++ix) A(eqpg, ix, iy) = cftgeqp * A(ng, ix, iy) * (A(ni[0], ix, iy) + cftiexclg * A(ni[1], ix, iy)) * keligig[0];
-      // engbalg (oderhs.m:7508-7882) with istgon = 0: its only effect on the plasma equations (oderhs.m:7803-7806)
-      for (int iy = j2; iy <= j5; ++iy)
-        for (int ix = i2; ix <= i5; ++ix) A(seic, ix, iy) = A(seic, ix, iy) - A(vol, ix, iy) * (1.0 - cftiexclg) * A(eqpg, ix, iy) * (A(ti, ix, iy) - A(tg, ix, iy));
+      engbalg(w);  // oderhs.m:3180
     }
 
     // ---- particle fluxes (oderhs.m:3187-3319) ----
@@ -1617,6 +1699,9 @@ struct O2 {
                              (1.0 - cftiexclg) * t0 +
                              cftiexclg * cfneut * cfneutsor_ei * cnsor * (eion * ev + cfnidhdis * 0.5 * mg_[0] * (t2 * t2 + temp3 + temp4)) * A(psordis, ix, iy) +
                              cfnidh2 * (-mi[0] * t1 * t2 * (A(psor[0], ix, iy) + tv) + 0.5 * mi[0] * t1 * t1 * (A(psor[0], ix, iy) + A(psorrg, ix, iy) + 2 * tv));
+          A(reseg, ix, iy) = A(reseg, ix, iy) - t0 + 0.5 * mg_[0] * ((t1 - t2) * (t1 - t2) + temp3 + temp4) * (A(psorrg, ix, iy) + tv) +
+                             (eion * ev + cfnidh * cfnidhdis * 0.5 * mg_[0] * (t2 * t2 + temp3 + temp4)) * A(psordis, ix, iy) +
+                             cfnidh2 * (-mg_[0] * t1 * t2 * (A(psorrg, ix, iy) + tv) + 0.5 * mg_[0] * (t2 * t2 + temp3 + temp4) * (A(psor[0], ix, iy) + A(psorrg, ix, iy) + 2 * tv));  // oderhs.m:4618-4627
         } else {
           double us = A(upi[0], ix, iy) + A(upi[0], ix1, iy);
           A(resei, ix, iy) = A(resei, ix, iy) + A(w0, ix, iy) + cfneut * cfneutsor_ei * ctsor * 1.25e-1 * mi[0] * (us * us) * fac2sp * A(psor[0], ix, iy) +
@@ -1662,7 +1747,7 @@ struct O2 {
             dupdy = 0.25 * ((A(u, ix, iy + 1) + A(u, ix2, iy + 1) - A(u, ix, iy) - A(u, ix1, iy)) * A(gyf, ix, iy) + (A(u, ix, iy) + A(u, ix1, iy) - A(u, ix, iy - 1) - A(u, ix3, iy - 1)) * A(gyf, ix, iy - 1));
           A(wvh[f], ix, iy) = A(wvh[f], ix, iy) + cfvcsy[f] * cfvisy * A(visy[f], ix, iy) * (dupdy * dupdy);
           A(wvh[f], ix, iy) = A(wvh[f], ix, iy) - ue_ksin(thetacc) * cfvcsy[f] * cfvisy * A(visy[f], ix, iy) * dupdx * dupdy;
-          if (zi[f] == 0.0 && f == iigsp) A(resei, ix, iy) = A(resei, ix, iy) + cftiexclg * A(wvh[f], ix, iy) * A(vol, ix, iy);
+          if (zi[f] == 0.0 && f == iigsp) { A(resei, ix, iy) = A(resei, ix, iy) + cftiexclg * A(wvh[f], ix, iy) * A(vol, ix, iy); A(reseg, ix, iy) = A(reseg, ix, iy) + A(wvh[f], ix, iy) * A(vol, ix, iy); }
           else A(resei, ix, iy) = A(resei, ix, iy) + A(wvh[f], ix, iy) * A(vol, ix, iy);
         }
     for (int iy = w.iys; iy <= w.iyf; ++iy)  // oderhs.m:4936-4947
@@ -1682,6 +1767,7 @@ struct O2 {
         iv = IDXTE(ix, iy); if (iv >= 0) yldot[iv] = (1 - ALG(iv)) * A(resee, ix, iy) / (A(vol, ix, iy) * ennorm);
         iv = IDXTI(ix, iy); if (iv >= 0) yldot[iv] = (1 - ALG(iv)) * A(resei, ix, iy) / (A(vol, ix, iy) * ennorm);
         iv = IDXG(ix, iy); if (iv >= 0) yldot[iv] = (1 - ALG(iv)) * A(resng, ix, iy) / (A(vol, ix, iy) * n0g_[0]);
+        iv = IDXTG(ix, iy); if (iv >= 0) yldot[iv] = (1 - ALG(iv)) * A(reseg, ix, iy) / (A(vol, ix, iy) * ennorm);
       }
     if (isphion == 1) poteneq(w, yl, yldot);  // oderhs.m:5007
     rc = bouncon(w, yl, yldot);               // oderhs.m:5009
@@ -1994,6 +2080,44 @@ int O2::bouncon(const Win& w, const double* yl, double* yldot) {
         }
       }
     }
+    for (int ix = w.i4; ix <= w.i8; ++ix) {  // gas temperature at iy = 0 (boundary.m:769-852)
+      const int64_t iv = IDXTG(ix, 0);
+      if (iv < 0) continue;
+      if (isixcore[ix] == 1) {
+        if (istgcore == 0) yldot[iv] = nurlxg * (A(ti, ix, 0) * cftgticore - A(tg, ix, 0)) / (temp0 * ev);
+        else if (istgcore == 1) yldot[iv] = nurlxg * (tgcore * ev - A(tg, ix, 0)) / (temp0 * ev);
+        else if (istgcore == 2) {
+          double t0 = std::max(A(tg, ix, 0), tgmin * ev);
+          double vyn = std::sqrt(0.5 * t0 / (pi * mg_[0]));
+          double nharmave = 2. * (A(ng, ix, 0) * A(ng, ix, 1)) / (A(ng, ix, 0) + A(ng, ix, 1));
+          double fng_alb = (1 - albedoc[0]) * nharmave * vyn * A(sy, ix, 0);
+          yldot[iv] = -nurlxg * (A(fegy, ix, 0) + cfalbedo * fng_alb * t0) / (vpnorm * ennorm * A(sy, ix, 0));
+        } else yldot[iv] = nurlxg * (A(tg, ix, 1) - A(tg, ix, 0)) / (temp0 * ev);
+      } else {  // private-flux wall
+        if (istgpfc == 0) yldot[iv] = nurlxg * (tgwall * ev - A(tg, ix, 0)) / (temp0 * ev);
+        else if (istgpfc == 1) {
+          double tbound = A(tg, ix, 1) - A(gyf, ix, 1) * (A(tg, ix, 2) - A(tg, ix, 1)) / A(gyf, ix, 0);
+          tbound = std::max(tbound, 0.25 * tbmin * ev);
+          yldot[iv] = nurlxi * (tbound - A(tg, ix, 0)) / (temp0 * ev);
+        } else if (istgpfc == 2) yldot[iv] = nurlxi * ((A(tg, ix, 1) - A(tg, ix, 0)) - 0.5 * (A(tg, ix, 1) + A(tg, ix, 0)) / (A(gyf, ix, 0) * lytg1)) / (temp0 * ev);
+        else if (istgpfc == 3) {  // Maxwellian thermal flux to the wall
+          double t0 = std::max(cdifg[0] * A(tg, ix, 1), temin * ev);
+          double vyn = 0.25 * std::sqrt(8 * t0 / (pi * mg_[0]));
+          yldot[iv] = -nurlxg * (A(fegy, ix, 0) + 2 * cgengmw * A(ng, ix, 1) * vyn * t0 * A(sy, ix, 0)) / (A(sy, ix, 0) * vpnorm * ennorm);
+        } else if (istgpfc == 4) {
+          double t0 = std::max(A(tg, ix, 0), tgmin * ev);
+          double vyn = std::sqrt(0.5 * t0 / (pi * mg_[0]));
+          double nharmave = 2. * (A(ng, ix, 0) * A(ng, ix, 1)) / (A(ng, ix, 0) + A(ng, ix, 1));
+          double fng_alb = (1 - albedoi[ix]) * nharmave * vyn * A(sy, ix, 0), fng_chem = 0.;
+          yldot[iv] = -nurlxg * (A(fegy, ix, 0) + cfalbedo * fng_alb * t0 - 2. * fng_chem * t0) / (vpnorm * ennorm * A(sy, ix, 0));
+          if (matwalli[ix] > 0 && recycwit[ix] > 0) {
+            double fniy_recy = recycwit[ix] * fac2sp * A(fniy[0], ix, 0);
+            if (isrefluxclip == 1) fniy_recy = std::min(fniy_recy, 0.);
+            yldot[iv] = -nurlxg * (A(fegy, ix, 0) + cfalbedo * fng_alb * t0 - 2. * fng_chem * t0 + fniy_recy * (1. - cfdiss) * cfalbedo * recycwe * A(ti, ix, 0)) / (vpnorm * ennorm * A(sy, ix, 0));
+          }
+        } else yldot[iv] = nurlxg * (A(ti, ix, 0) * cftgtipfc - A(tg, ix, 0)) / (temp0 * ev);  // istgpfc = 5
+      }
+    }
     for (int ix = w.i4; ix <= w.i8; ++ix) {  // potential, isnewpot = 0 (boundary.m:856-863)
       const int64_t iv3 = IDXPHI(ix, 0);
       if (iv3 >= 0) yldot[iv3] = nurlxp * ((A(phi, ix, 1) - A(phi, ix, 0)) - 0.5 * (A(phi, ix, 1) + A(phi, ix, 0)) / (A(gyf, ix, 0) * lyphiix1[ix])) / temp0;
@@ -2003,6 +2127,7 @@ int O2::bouncon(const Win& w, const double* yl, double* yldot) {
       if (IDXTE(ixlb, 0) >= 0) yldot[IDXTE(ixlb, 0)] = nurlxe * (0.5 * (A(te, ixlb + 1, 0) + A(te, ixlb, 1)) - A(te, ixlb, 0)) / (temp0 * ev);
       if (IDXTI(ixlb, 0) >= 0) yldot[IDXTI(ixlb, 0)] = nurlxi * (0.5 * (A(ti, ixlb + 1, 0) + A(ti, ixlb, 1)) - A(ti, ixlb, 0)) / (temp0 * ev);
       if (IDXG(ixlb, 0) >= 0) yldot[IDXG(ixlb, 0)] = nurlxg * (A(ng, ixlb + 1, 0) - A(ng, ixlb, 0)) / n0g_[0];
+      if (IDXTG(ixlb, 0) >= 0) yldot[IDXTG(ixlb, 0)] = nurlxg * (A(tg, ixlb + 1, 0) - A(tg, ixlb, 0)) / (temp0 * ev);  // boundary.m:930-937
     }
     if (w.xcnearrb || w.openbox) {  // boundary.m:939-983
       for (int f = 0; f < nusp; ++f)
@@ -2013,6 +2138,7 @@ int O2::bouncon(const Win& w, const double* yl, double* yldot) {
       if (IDXTE(ixrb + 1, 0) >= 0) yldot[IDXTE(ixrb + 1, 0)] = nurlxe * (0.5 * (A(te, ixrb + 1, 1) + A(te, ixrb, 0)) - A(te, ixrb + 1, 0)) / (temp0 * ev);
       if (IDXTI(ixrb + 1, 0) >= 0) yldot[IDXTI(ixrb + 1, 0)] = nurlxi * (0.5 * (A(ti, ixrb + 1, 1) + A(ti, ixrb, 0)) - A(ti, ixrb + 1, 0)) / (temp0 * ev);
       if (IDXG(ixrb, 0) >= 0) yldot[IDXG(ixrb + 1, 0)] = nurlxg * (A(ng, ixrb, 0) - A(ng, ixrb + 1, 0)) / n0g_[0];
+      if (IDXTG(ixrb, 0) >= 0) yldot[IDXTG(ixrb + 1, 0)] = nurlxg * (A(tg, ixrb, 0) - A(tg, ixrb + 1, 0)) / (temp0 * ev);  // boundary.m:975-982
     }
   }
   // ===== potential with isnewpot = 1: two equations at iy = 0 and 1 (boundary.m:987-1122) =====
@@ -2128,6 +2254,32 @@ int O2::bouncon(const Win& w, const double* yl, double* yldot) {
         }
       }
     }
+    for (int ix = w.i4; ix <= w.i8; ++ix) {  // gas temperature at iy = ny+1 (boundary.m:1463-1513)
+      const int64_t iv = IDXTG(ix, ny + 1);
+      if (iv < 0) continue;
+      if (istgwc == 0) yldot[iv] = nurlxg * (tgwall * ev - A(tg, ix, ny + 1)) / (temp0 * ev);
+      else if (istgwc == 1) {
+        double tbound = A(tg, ix, ny) + A(gyf, ix, ny) * (A(tg, ix, ny) - A(tg, ix, ny - 1)) / A(gyf, ix, ny);
+        tbound = std::max(tbound, 0.25 * tbmin * ev);
+        yldot[iv] = nurlxi * (tbound - A(tg, ix, ny + 1)) / (temp0 * ev);
+      } else if (istgwc == 2) yldot[iv] = nurlxi * ((A(tg, ix, ny) - A(tg, ix, ny + 1)) - 0.5 * (A(tg, ix, ny) + A(tg, ix, ny + 1)) / (A(gyf, ix, ny) * lytg2)) / (temp0 * ev);
+      else if (istgwc == 3) {
+        double t0 = std::max(cdifg[0] * A(tg, ix, ny), temin * ev);
+        double vyn = 0.25 * std::sqrt(8 * t0 / (pi * mg_[0]));
+        yldot[iv] = nurlxg * (A(fegy, ix, ny) - 2 * cgengmw * A(ng, ix, ny) * vyn * t0 * A(sy, ix, ny)) / (A(sy, ix, ny) * vpnorm * ennorm);
+      } else if (istgwc == 4) {
+        double t0 = std::max(A(tg, ix, ny + 1), tgmin * ev);
+        double vyn = std::sqrt(0.5 * t0 / (pi * mg_[0]));
+        double nharmave = 2. * (A(ng, ix, ny) * A(ng, ix, ny + 1)) / (A(ng, ix, ny) + A(ng, ix, ny + 1));
+        double fng_alb = (1 - albedoo[ix]) * nharmave * vyn * A(sy, ix, ny), fng_chem = 0.;
+        yldot[iv] = nurlxg * (A(fegy, ix, ny) - cfalbedo * fng_alb * t0 + 2. * fng_chem * t0) / (vpnorm * ennorm * A(sy, ix, ny));
+        if (matwallo[ix] > 0 && recycwot[ix] > 0.) {
+          double fniy_recy = recycwot[ix] * fac2sp * A(fniy[0], ix, ny);
+          if (isrefluxclip == 1) fniy_recy = std::max(fniy_recy, 0.);
+          yldot[iv] = nurlxg * (A(fegy, ix, ny) - cfalbedo * fng_alb * t0 + 2. * fng_chem * t0 + fniy_recy * (1. - cfdiss) * cfalbedo * recycwe * A(ti, ix, ny)) / (vpnorm * ennorm * A(sy, ix, ny));
+        }
+      } else yldot[iv] = nurlxg * (A(ti, ix, ny + 1) * cftgtiwc - A(tg, ix, ny + 1)) / (temp0 * ev);  // istgwc = 5
+    }
     for (int ix = w.i4; ix <= w.i8; ++ix) {  // potential (boundary.m:1522-1540)
       const int64_t iv3 = IDXPHI(ix, ny + 1);
       if (iv3 < 0) continue;
@@ -2141,6 +2293,7 @@ int O2::bouncon(const Win& w, const double* yl, double* yldot) {
       if (IDXTE(ixlb, ny + 1) >= 0) yldot[IDXTE(ixlb, ny + 1)] = nurlxe * (0.5 * (A(te, ixlb + 1, ny + 1) + A(te, ixlb, ny)) - A(te, ixlb, ny + 1)) / (temp0 * ev);
       if (IDXTI(ixlb, ny + 1) >= 0) yldot[IDXTI(ixlb, ny + 1)] = nurlxi * (0.5 * (A(ti, ixlb + 1, ny + 1) + A(ti, ixlb, ny)) - A(ti, ixlb, ny + 1)) / (temp0 * ev);
       if (IDXG(ixlb, ny + 1) >= 0) yldot[IDXG(ixlb, ny + 1)] = nurlxg * (A(ng, ixlb + 1, ny + 1) - A(ng, ixlb, ny + 1)) / n0g_[0];
+      if (IDXTG(ixlb, ny + 1) >= 0) yldot[IDXTG(ixlb, ny + 1)] = nurlxg * (0.5 * (A(tg, ixlb + 1, ny + 1) + A(tg, ixlb, ny)) - A(tg, ixlb, ny + 1)) / (temp0 * ev);
     }
     if (w.xcnearrb || w.openbox) {  // boundary.m:1585-1630
       for (int f = 0; f < nusp; ++f)
@@ -2151,6 +2304,7 @@ int O2::bouncon(const Win& w, const double* yl, double* yldot) {
       if (IDXTE(ixrb + 1, ny + 1) >= 0) yldot[IDXTE(ixrb + 1, ny + 1)] = nurlxe * (0.5 * (A(te, ixrb, ny + 1) + A(te, ixrb + 1, ny)) - A(te, ixrb + 1, ny + 1)) / (temp0 * ev);
       if (IDXTI(ixrb + 1, ny + 1) >= 0) yldot[IDXTI(ixrb + 1, ny + 1)] = nurlxi * (0.5 * (A(ti, ixrb, ny + 1) + A(ti, ixrb + 1, ny)) - A(ti, ixrb + 1, ny + 1)) / (temp0 * ev);
       if (IDXG(ixrb + 1, ny + 1) >= 0) yldot[IDXG(ixrb + 1, ny + 1)] = nurlxg * (A(ng, ixrb, ny + 1) - A(ng, ixrb + 1, ny + 1)) / n0g_[0];
+      if (IDXTG(ixrb + 1, ny + 1) >= 0) yldot[IDXTG(ixrb + 1, ny + 1)] = nurlxg * (0.5 * (A(tg, ixrb, ny + 1) + A(tg, ixrb + 1, ny)) - A(tg, ixrb + 1, ny + 1)) / (temp0 * ev);
     }
   }
   // ===== ix = 0 as a symmetry plane, isfixlb = 2 (boundary.m:1666-1770; rlimiter beyond the mesh) =====
@@ -2161,6 +2315,7 @@ int O2::bouncon(const Win& w, const double* yl, double* yldot) {
       if (IDXTE(0, iy) >= 0) yldot[IDXTE(0, iy)] = nurlxe * A(ne, 0, iy) * (A(te, 1, iy) - A(te, 0, iy)) / ennorm;
       if (IDXTI(0, iy) >= 0) yldot[IDXTI(0, iy)] = nurlxi * A(ne, 0, iy) * (A(ti, 1, iy) - A(ti, 0, iy)) / ennorm;
       if (IDXG(0, iy) >= 0) yldot[IDXG(0, iy)] = nurlxg * (A(ng, 1, iy) - A(ng, 0, iy)) / n0g_[0];
+      if (IDXTG(0, iy) >= 0) yldot[IDXTG(0, iy)] = nurlxg * (A(tg, 1, iy) - A(tg, 0, iy)) / (temp0 * ev);  // boundary.m:1747-1756
       if (IDXPHI(0, iy) >= 0) yldot[IDXPHI(0, iy)] = nurlxp * (A(phi, 1, iy) - A(phi, 0, iy)) / temp0;
     }
   if (isfixlb == 2 && w.i2 <= ixpt2 && w.i5 >= ixpt2 && w.j2 <= iysptrx2)  // boundary.m:1772-1785
@@ -2279,6 +2434,34 @@ int O2::bouncon(const Win& w, const double* yl, double* yldot) {
         }
       }
   }
+  if ((w.xcnearlb || w.openbox) && isfixlb == 0 && w.i3 <= ixlb)  // gas temperature at the left plate (boundary.m:2198-2257)
+    for (int iy = w.j2; iy <= w.j5; ++iy) {
+      const int ixt = ixlb, ixt1 = IXP1(ixt, iy), ixt2 = IXP1(ixt1, iy);
+      const int64_t iv = IDXTG(ixt, iy);
+      if (iv < 0) continue;
+      if (istglb == 0) yldot[iv] = nurlxg * (tgwall * ev - A(tg, ixt, iy)) / (temp0 * ev);
+      else if (istglb == 1) {
+        double tbound = A(tg, ixt1, iy) - A(gyf, ixt1, iy) * (A(tg, ixt2, iy) - A(tg, ixt1, iy)) / A(gxf, ixt, iy);
+        tbound = std::max(tbound, 0.5 * temin * ev);
+        yldot[iv] = nurlxg * (tbound - A(tg, ixt, iy)) / (temp0 * ev);
+      } else if (istglb == 3) {
+        double t0 = std::max(cdifg[0] * A(tg, ixt1, iy), tgmin * ev);
+        double vxn = 0.25 * std::sqrt(8 * t0 / (pi * mg_[0]));
+        yldot[iv] = -nurlxg * (A(fegx, ixt, iy) + 2 * cgengmpl * A(ng, ixt1, iy) * vxn * t0 * A(sx, ixt, iy)) / (A(sx, ixt, iy) * vpnorm * ennorm);
+      } else if (istglb == 4) {
+        const double recy = recylb[iy];
+        double t0 = std::max(A(tg, ixt1, iy), tgmin * ev);
+        if (recy > 0.) {
+          double vxn = 0.25 * std::sqrt(8 * t0 / (pi * mg_[0]));
+          double fng_alb = (1 - alblb[iy]) * A(ng, ixt1, iy) * vxn * A(sx, ixt, iy);
+          yldot[iv] = -nurlxg * (A(fegx, ixt, iy) + cfalbedo * fng_alb * t0 + recy * (1. - cfdiss) * A(fnix[0], ixt, iy) * recyce * cfalbedo * (kappal[iy] * zi[0] * A(te, ixt, iy) + A(ti, ixt, iy))) / (vpnorm * ennorm * A(sx, ixt, iy));
+        } else if (recy >= -1.) {
+          double vyn = std::sqrt(0.5 * t0 / (pi * mg_[0]));
+          double fng_alb = (1 + recy) * A(ng, ixt1, iy) * vyn * A(sx, ixt, iy);
+          yldot[iv] = -nurlxg * (A(fegx, ixt, iy) + cfalbedo * fng_alb * t0) / (vpnorm * ennorm * A(sx, ixt, iy));
+        } else yldot[iv] = -nurlxg * (A(fegx, ixt, iy) + cfalbedo * A(fnix[iigsp], ixt, iy) * t0) / (vpnorm * ennorm * A(sx, ixt, iy));
+      } else yldot[iv] = nurlxg * (A(ti, ixt, iy) * cftgtipltl - A(tg, ixt, iy)) / (temp0 * ev);  // istglb = 5
+    }
   // ===== right plate, ix = ixrb+1 (boundary.m:2320-3002), isfixrb = 0 =====
   if (w.xcnearrb || w.openbox) {
     const int ixt = ixrb + 1;
@@ -2393,6 +2576,34 @@ int O2::bouncon(const Win& w, const double* yl, double* yldot) {
         }
       }
   }
+  if ((w.xcnearrb || w.openbox) && w.i6 >= ixrb + 1)  // gas temperature at the right plate (boundary.m:2880-2937)
+    for (int iy = w.j2; iy <= w.j5; ++iy) {
+      const int ixt = ixrb + 1, ixt1 = IXM1(ixt, iy), ixt2 = IXM1(ixt1, iy);
+      const int64_t iv = IDXTG(ixt, iy);
+      if (iv < 0) continue;
+      if (istgrb == 0) yldot[iv] = nurlxg * (tgwall * ev - A(tg, ixt, iy)) / (temp0 * ev);
+      else if (istgrb == 1) {
+        double tbound = A(tg, ixt1, iy) + A(gxf, ixt2, iy) * (A(tg, ixt1, iy) - A(tg, ixt2, iy)) / A(gxf, ixt1, iy);
+        tbound = std::max(tbound, 0.5 * temin * ev);
+        yldot[iv] = nurlxg * (tbound - A(tg, ixt, iy)) / (temp0 * ev);
+      } else if (istgrb == 3) {
+        double t0 = std::max(cdifg[0] * A(tg, ixt1, iy), temin * ev);
+        double vxn = 0.25 * std::sqrt(8 * t0 / (pi * mg_[0]));
+        yldot[iv] = nurlxg * (A(fegx, ixt1, iy) - 2 * cgengmpl * A(ng, ixt1, iy) * vxn * t0 * A(sx, ixt1, iy)) / (A(sx, ixt1, iy) * vpnorm * ennorm);
+      } else if (istgrb == 4) {
+        const double recy = recyrb[iy];
+        double t0 = std::max(A(tg, ixt1, iy), tgmin * ev);
+        if (recy > 0.) {
+          double vxn = 0.25 * std::sqrt(8 * t0 / (pi * mg_[0]));
+          double fng_alb = (1 - albrb[iy]) * A(ng, ixt1, iy) * vxn * A(sx, ixt1, iy);
+          yldot[iv] = nurlxg * (A(fegx, ixt1, iy) - cfalbedo * fng_alb * t0 + recy * (1. - cfdiss) * A(fnix[0], ixt1, iy) * recyce * cfalbedo * (kappar[iy] * zi[0] * A(te, ixt, iy) + A(ti, ixt, iy))) / (vpnorm * ennorm * A(sx, ixt1, iy));
+        } else if (recy >= -1.) {
+          double vyn = std::sqrt(0.5 * t0 / (pi * mg_[0]));
+          double fng_alb = (1 + recy) * A(ng, ixt1, iy) * vyn * A(sx, ixt1, iy);
+          yldot[iv] = nurlxg * (A(fegx, ixt1, iy) - cfalbedo * fng_alb * t0) / (vpnorm * ennorm * A(sx, ixt1, iy));
+        } else yldot[iv] = nurlxg * (A(fegx, ixt1, iy) - cfalbedo * A(fnix[iigsp], ixt1, iy) * t0) / (vpnorm * ennorm * A(sx, ixt1, iy));
+      } else yldot[iv] = nurlxg * (A(ti, ixt, iy) * cftgtipltr - A(tg, ixt, iy)) / (temp0 * ev);  // istgrb = 5
+    }
   return 0;
 }
 
@@ -2432,6 +2643,8 @@ void O2::rscalf(const Win& w, const double* yl, double* yldot) {
           if (isupgon == 1) yldot[ivi] = (yldot[ivi] * nnorm - yl[ivi] * (nbidot + cftiexclg * nbgdot)) / (A(nit, ix, iy) + cftiexclg * A(ni[1], ix, iy));
           else yldot[ivi] = (yldot[ivi] * nnorm - yl[ivi] * (nbidot + cngtgx[0] * nbg2dot)) / (A(nit, ix, iy) + cngtgx[0] * A(ng, ix, iy));
         }
+        const int64_t ivg = IDXTG(ix, iy);  // oderhs.m:8181-8191 (isupgon = 1)
+        if (ivg >= 0 && ALG(ivg) == 0) yldot[ivg] = (yldot[ivg] * n0g_[0] - yl[ivg] * nbgdot) / A(ni[iigsp], ix, iy);
       }
     }
 }
@@ -2450,7 +2663,7 @@ int O2::pandf1(int xc, int yc, const double* yl, double* yldot) {
       for (int ix = i2l; ix <= i5l; ++ix) {
         for (int f = 0; f < nisp; ++f) step(IDXN(f, ix, iy));
         if (ix != nx + 2 * isbcwdt) for (int f = 0; f < nusp; ++f) step(IDXU(f, ix, iy));
-        step(IDXTE(ix, iy)); step(IDXTI(ix, iy)); step(IDXG(ix, iy));
+        step(IDXTE(ix, iy)); step(IDXTI(ix, iy)); step(IDXG(ix, iy)); step(IDXTG(ix, iy));
         if (isbcwdt == 1) step(IDXPHI(ix, iy));
       }
     if (dtphi < 1e10)
@@ -2604,12 +2817,25 @@ int init_all() {
                                                    {"cfvisxneoq", 0}, {"cfvyavis", 0}, {"cfanomvisxg", 0}, {"cfanomvisyg", 0}, {"isnfmiy", 0}, {"isybdrywd", 0}, {"isfeexpl0", 0},
                                                    {"isfeixpl0", 0}, {"cfeexdbo", 0}, {"cfeixdbo", 0}, {"cfniydbo", 0}, {"cfeeydbo", 0}, {"isextrnp", 0}, {"isextrnpf", 0},
                                                    {"isextrtpf", 0}, {"isextrngc", 0}, {"isextrnw", 0}, {"isextrtw", 0}, {"isbohmms", 0}, {"ibctepl", 1}, {"ibctipl", 1}, {"ibctepr", 1}, {"ibctipr", 1}, {"isfixrb", 0},
-                                                   {"is1D_gbx", 0}, {"isnglf", 0}, {"iszeffcon", 0}, {"isup1up2", 0}, {"isflxvar", 0}, {"istgon", 0}, {"isphilbc", 0}, {"isphirbc", 0}, {"ikapmod", 0},
+                                                   {"is1D_gbx", 0}, {"isnglf", 0}, {"iszeffcon", 0}, {"isup1up2", 0}, {"isflxvar", 0}, {"isphilbc", 0}, {"isphirbc", 0}, {"ikapmod", 0},
                                                    {"isfqpave", 0}, {"isphicore0", 0}, {"iskaprex", 0}, {"isrozhfac", 0}};
   for (auto& m : must) { const V* v = find(m.n); if (!v) { g_err = std::string("oracle2: missing input ") + m.n; return -1; } if ((*v)[0] != m.want) { g_err = std::string("oracle2: switch outside this restatement: ") + m.n; return -5; } }
   if (isnewpot != 0 && isnewpot != 1) { g_err = "oracle2: isnewpot must be 0 or 1"; return -5; }
   if (isnewpot * isphion == 1 && (iphibcc < 1 || iphibcc > 3)) { g_err = "oracle2: only iphibcc = 1, 2, 3 available"; return -5; }
   ExtendedJacPhi = I("ExtendedJacPhi"); numvar_ = I("numvar");
+  // gas energy equation (istgon = 1): the inertial atoms only
+  idxtg_ = ARR("idxtg", nc);
+  istgcore = I("istgcore", 0); istgpfc = I("istgpfc", 0); istgwc = I("istgwc", 0); istglb = I("istglb", 0); istgrb = I("istgrb", 0); isfegxyqflave = I("isfegxyqflave");
+  tgcore = SC("tgcore"); cftgticore = SC("cftgticore"); tgwall = SC("tgwall"); lytg1 = SC("lytg", 0); lytg2 = SC("lytg", 1); cftgtipltl = SC("cftgtipltl"); cftgtipltr = SC("cftgtipltr");
+  cftgtipfc = SC("cftgtipfc"); cftgtiwc = SC("cftgtiwc"); cgengmpl = SC("cgengmpl"); cgengmw = SC("cgengmw"); cfalbedo = SC("cfalbedo"); recyce = SC("recyce"); recycwe = SC("recycwe");
+  cvgpg = SC("cvgpg"); cfcvtg = SC("cfcvtg"); cfegxy = SC("cfegxy"); flalftgxy = SC("flalftgxy");
+  if (istgon != 0 && istgon != 1) { g_err = "oracle2: istgon must be 0 or 1"; return -5; }
+  if (istgon == 1) {
+    if (isupgon != 1 || nisp != 2) { g_err = "oracle2: istgon=1 is restated for inertial atoms (isupgon=1, nisp=2) only"; return -5; }
+    if (istgpfc < 0 || istgpfc > 5 || istgwc < 0 || istgwc > 5) { g_err = "oracle2: invalid istgpfc / istgwc"; return -5; }
+    for (int k : {istglb, istgrb}) if (k < 0 || k > 5 || k == 2) { g_err = "oracle2: istglb / istgrb must be 0, 1, 3, 4 or 5"; return -5; }
+    if (SC("ispfbcvsix") != 0. || SC("iswobcvsix") != 0.) { g_err = "oracle2: poloidally dependent wall options with istgon=1 not built"; return -5; }
+  }
   if (fnnuiz != 1.) { g_err = "oracle2: fnnuiz must be 1"; return -5; }
   if (SC("l_parloss") <= 1e9) { g_err = "oracle2: l_parloss<=1e9 (nuvl) not built"; return -5; }
   if (isfixlb != 0 && isfixlb != 2) { g_err = "oracle2: isfixlb must be 0 or 2"; return -5; }

@@ -13,7 +13,7 @@ import pytest
 from tests.test_oracle2_golden import twin
 from tests.util import psetnk_inputs
 from uedge_b200.cases import box2_case
-from uedge_b200.cases2 import SUBSETS, Lib2, Oracle2, box2_initial_state, d3d_full_physics_case, inputex_case, jupyter_case, switch_variant
+from uedge_b200.cases2 import SUBSETS, Lib2, Oracle2, box2_initial_state, d3d_full_physics_case, gas_energy_case, inputex_case, jupyter_case, switch_variant
 
 HK = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostcheck")
 
@@ -106,6 +106,39 @@ def test_jupyter_drift_case_band_copy_is_sufficient(built, monkeypatch):
     monkeypatch.setenv("UE_GEN_POISON", "1")
     c, yl = jupyter_case(grid=refine_grid(load_grid_npz(), 2, 2))
     assert c.com.ny + 2 == 18 and c.bbb.neq == 4284
+    same(Oracle2().bind(c), host(0).bind(c), c, yl)
+
+
+@pytest.mark.parametrize("rev", [0, 1])
+@pytest.mark.parametrize("deck", ["jupyter", "inputex"])
+def test_gas_energy_equation(built, deck, rev):
+    """istgon = 1 (engbalg, oderhs.m:7508-7878): tg as the eighth unknown per cell on the drift case (orthogonal DIII-D mesh) and on
+    input_example (non-orthogonal: the fegxy term)"""
+    c, yl = gas_energy_case(deck=deck)
+    assert c.bbb.numvar == 8
+    same(Oracle2().bind(c), host(rev).bind(c), c, yl)
+
+
+@pytest.mark.parametrize("k, opts", list(enumerate([(1, 1, 1, 1, 0), (2, 2, 3, 3, 2), (3, 3, 4, 4, 3), (4, 4, 5, 5, 1), (5, 5, 0, 4, 0)])))
+def test_gas_energy_boundary_options(built, k, opts):
+    """every wall / plate / core option of the gas temperature (boundary.m:769-852, 1463-1513, 2198-2257, 2880-2937)"""
+    pfc, wc, lb, rb, core = opts
+
+    def m(b, com):
+        for nm, v in (("istgpfc", pfc), ("istgwc", wc), ("istgcore", core)):
+            a = np.asarray(getattr(b, nm)).copy(); a[0] = v; setattr(b, nm, a)
+        b.istglb = lb; b.istgrb = rb; b.recyce = 0.3; b.recycwe = 0.2; b.lytg = np.full(12, 0.05)
+        b.matwsi = np.asarray(b.matwsi).copy(); b.matwsi[0] = 1
+    for deck in ("jupyter", "inputex"):
+        c, yl = gas_energy_case(m, deck=deck)
+        same(Oracle2().bind(c), host(k & 1).bind(c), c, yl)
+
+
+def test_gas_energy_band_copy_is_sufficient(built, monkeypatch):
+    from uedge_b200.cases import load_grid_npz, refine_grid
+    monkeypatch.setenv("UE_GEN_POISON", "1")
+    c, yl = gas_energy_case(grid=refine_grid(load_grid_npz(), 2, 2))
+    assert c.bbb.neq == 4896
     same(Oracle2().bind(c), host(0).bind(c), c, yl)
 
 

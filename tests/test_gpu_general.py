@@ -10,7 +10,7 @@ from tests.refplanes import check_against_reference
 from tests.test_oracle2_golden import twin
 from tests.util import psetnk_inputs
 from uedge_b200.cases import box2_case
-from uedge_b200.cases2 import SUBSETS, Oracle2, box2_initial_state, d3d_full_physics_case, inputex_case, jupyter_case, load_gen, switch_variant
+from uedge_b200.cases2 import SUBSETS, Oracle2, box2_initial_state, d3d_full_physics_case, gas_energy_case, inputex_case, jupyter_case, load_gen, switch_variant
 
 pytestmark = pytest.mark.gpu
 
@@ -89,6 +89,17 @@ def test_jupyter_drift_case(built, refine):
     same(o, g, c, yl)
     o.pandf1(yl); g.pandf1(yl)
     for nm in ("vyce1", "vycb1", "v2ce1", "v2cb1", "ve2cb", "veycb", "fqyb", "fqxb", "fqyd", "wjdote", "vex", "vey", "resphi"):
+        assert np.array_equal(o.plane(nm), g.plane(nm)), nm
+
+
+@pytest.mark.parametrize("deck", ["jupyter", "inputex"])
+def test_gas_energy_equation(built, deck):
+    """istgon = 1 (engbalg): tg as the eighth unknown per cell on the drift case and on the non-orthogonal input_example mesh"""
+    c, yl = gas_energy_case(deck=deck)
+    o, g = Oracle2().bind(c), load_gen().bind(c)
+    same(o, g, c, yl)
+    o.pandf1(yl); g.pandf1(yl)
+    for nm in ("fegx", "fegy", "segc", "reseg", "conxge", "floyge"):
         assert np.array_equal(o.plane(nm), g.plane(nm)), nm
 
 

@@ -50,6 +50,8 @@ class Case2(Case):
                 nc.append(b.ennorm); isup.append(0)
         if self.hasg:
             nc.append(b.n0g[0]); isup.append(0)
+        if int(b.istgon[0]):
+            nc.append(b.ennorm); isup.append(0)
         isphi = [0] * len(nc)
         if int(b.isphion):
             nc.append(b.temp0); isup.append(0); isphi.append(1)
@@ -137,7 +139,7 @@ class Case2(Case):
         nx, ny = c.nx, c.ny
         shp = (ny + 2, nx + 2)
         idxn = np.zeros((2,) + shp, dtype=np.int64); idxu = np.zeros((2,) + shp, dtype=np.int64)
-        idxte = np.zeros(shp, dtype=np.int64); idxti = np.zeros(shp, dtype=np.int64); idxg = np.zeros(shp, dtype=np.int64); idxphi = np.zeros(shp, dtype=np.int64)
+        idxte = np.zeros(shp, dtype=np.int64); idxti = np.zeros(shp, dtype=np.int64); idxg = np.zeros(shp, dtype=np.int64); idxtg = np.zeros(shp, dtype=np.int64); idxphi = np.zeros(shp, dtype=np.int64)
         igyl = np.zeros((b.neq, 2), dtype=np.int64)
         iv = 0
         for iy in range(ny + 2):
@@ -159,16 +161,18 @@ class Case2(Case):
                     put(idxti)
                 if self.hasg:
                     put(idxg)
+                if int(b.istgon[0]):  # gas temperature follows the gas density (convert.m:120-133)
+                    put(idxtg)
                 if int(b.isphion):
                     put(idxphi)
         assert iv == b.neq
-        self.idx = dict(idxn=idxn, idxu=idxu, idxte=idxte, idxti=idxti, idxg=idxg, idxphi=idxphi)
+        self.idx = dict(idxn=idxn, idxu=idxu, idxte=idxte, idxti=idxti, idxg=idxg, idxtg=idxtg, idxphi=idxphi)
         self.igyl = igyl
         alg = np.zeros(b.neq, dtype=np.int64)
         def mark(a):
             v = a[a > 0]
             alg[v - 1] = 1
-        for arr in [idxn[0], idxn[1], idxu[0], idxu[1], idxte, idxti, idxg, idxphi]:
+        for arr in [idxn[0], idxn[1], idxu[0], idxu[1], idxte, idxti, idxg, idxtg, idxphi]:
             mark(arr[0, :]); mark(arr[ny + 1, :]); mark(arr[1 : ny + 1, 0]); mark(arr[1 : ny + 1, nx + 1])
         for f in range(2):
             mark(idxu[f][1 : ny + 1, nx])  # boundary.m:3812-3815
@@ -201,6 +205,7 @@ class Case2(Case):
         put(ix_["idxte"], 1.5 * b.nnorm * self.st["te"] / b.ennorm)
         put(ix_["idxti"], 1.5 * b.nnorm * self.st["ti"] / b.ennorm)
         put(ix_["idxg"], self.st["ng"] / b.n0g[0])
+        put(ix_["idxtg"], 1.5 * b.n0g[0] * self.st["tg"] / b.ennorm)  # convert.m:123-129 with isflxvar = 0
         put(ix_["idxphi"], self.st["phi"] / b.temp0)
         yl[b.neq] = -1.0
         yl[b.neq + 1] = float(b.nufak) if b.inufaknk == 1 else 0.0

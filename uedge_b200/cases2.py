@@ -158,6 +158,26 @@ def jupyter_case(mods=None, v8_0_defaults=True, grid=None):
     return c, yl
 
 
+def gas_energy_case(mods=None, grid=None, deck="jupyter"):
+    """istgon = 1 (the gas energy equation engbalg, bbb/oderhs.m:7508-7878) on top of a deck with inertial atoms: `jupyter` = the drift
+    case on the DIII-D mesh (numvar 8), `inputex` = pyexamples/input_example on its non-orthogonal mesh (the fegxy term).  As the
+    reference's comments prescribe (bbb.v:345): cftiexclg = 0 (the atoms leave the ion energy equation), istgcon = -1 (tg is an unknown,
+    not a multiple of ti).  State: the deck's restart with tg := 0.8 ti.  No reference vector exists for istgon = 1."""
+    def on(b, com):
+        b.istgon = np.asarray(b.istgon).copy(); b.istgon[0] = 1
+        b.istgcon = np.asarray(b.istgcon, dtype=float).copy(); b.istgcon[0] = -1.0
+        b.cftiexclg = 0.0
+        if mods is not None:
+            mods(b, com)
+    if deck == "jupyter":
+        c, yl = jupyter_case(on, grid=grid)
+    else:
+        c, yl, _ = inputex_case("default", mods=on)
+    st = c.st
+    yl = c.set_state2(st["ni"], st["up"], st["te"], st["ti"], ng=st["ng"], phi=st["phi"], tg=0.8 * st["ti"])
+    return c, yl
+
+
 def switch_variant(seed):
     """A random combination of the switches and coefficients the general path implements beyond the input_example deck (differencing
     schemes 0-8, flux limits, viscosity and conductivity options, rate models, boundary options, 4th-order terms): returns a function
@@ -190,9 +210,22 @@ def switch_variant(seed):
         if rng.random() < 0.4:
             ch[k] = pick(*vals)
 
+    # gas energy equation (engbalg) with its boundary options
+    tgopt = None
+    if rng.random() < 0.35:
+        tgopt = dict(istgpfc=pick(0, 1, 2, 3, 4, 5), istgwc=pick(0, 1, 2, 3, 4, 5), istgcore=pick(0, 1, 2, 3), istglb=pick(0, 1, 3, 4, 5), istgrb=pick(0, 1, 3, 4, 5),
+                     cftiexclg=pick(0.0, 0.0, 1.0), recyce=pick(0.0, 0.3), recycwe=pick(0.0, 0.2), isfegxyqflave=pick(0, 1), lytg=pick(1e20, 0.05))
+
     def mods(b, com):
         for k, v in ch.items():
             setattr(b, k, v)
+        if tgopt is not None:
+            b.istgon = np.asarray(b.istgon).copy(); b.istgon[0] = 1
+            b.istgcon = np.asarray(b.istgcon, dtype=float).copy(); b.istgcon[0] = -1.0
+            for k in ("istgpfc", "istgwc", "istgcore"):
+                a = np.asarray(getattr(b, k)).copy(); a[0] = tgopt[k]; setattr(b, k, a)
+            b.istglb = tgopt["istglb"]; b.istgrb = tgopt["istgrb"]; b.cftiexclg = tgopt["cftiexclg"]; b.recyce = tgopt["recyce"]; b.recycwe = tgopt["recycwe"]
+            b.isfegxyqflave = tgopt["isfegxyqflave"]; b.lytg = np.full(12, tgopt["lytg"])
         for (k, i), v in idx.items():
             a = np.asarray(getattr(b, k)).copy()
             a[i] = v
@@ -200,7 +233,7 @@ def switch_variant(seed):
         if istab is not None:
             com.istabon = istab
 
-    return mods, dict(ch, **{"%s[%d]" % k: v for k, v in idx.items()}, istabon=istab)
+    return mods, dict(ch, **{"%s[%d]" % k: v for k, v in idx.items()}, istabon=istab, **({"istgon": 1, **tgopt} if tgopt else {}))
 
 
 class Lib2:

@@ -551,7 +551,7 @@ int init_all() {
                                                    {"cfvisxneoq", 0}, {"cfvyavis", 0}, {"cfanomvisxg", 0}, {"cfanomvisyg", 0}, {"isnfmiy", 0}, {"isybdrywd", 0}, {"isfeexpl0", 0},
                                                    {"isfeixpl0", 0}, {"cfeexdbo", 0}, {"cfeixdbo", 0}, {"cfniydbo", 0}, {"cfeeydbo", 0}, {"isextrnp", 0}, {"isextrnpf", 0},
                                                    {"isextrtpf", 0}, {"isextrngc", 0}, {"isextrnw", 0}, {"isextrtw", 0}, {"isbohmms", 0}, {"ibctepl", 1}, {"ibctipl", 1}, {"ibctepr", 1}, {"ibctipr", 1}, {"isfixrb", 0},
-                                                   {"is1D_gbx", 0}, {"isnglf", 0}, {"iszeffcon", 0}, {"isup1up2", 0}, {"isflxvar", 0}, {"istgon", 0}, {"isphilbc", 0}, {"isphirbc", 0}, {"ikapmod", 0},
+                                                   {"is1D_gbx", 0}, {"isnglf", 0}, {"iszeffcon", 0}, {"isup1up2", 0}, {"isflxvar", 0}, {"isphilbc", 0}, {"isphirbc", 0}, {"ikapmod", 0},
                                                    {"isfqpave", 0}, {"isphicore0", 0}, {"iskaprex", 0}, {"isrozhfac", 0}};
   for (auto& m : must) {
     const V* v = find(m.n);
@@ -561,6 +561,19 @@ int init_all() {
   if (g.isnewpot != 0 && g.isnewpot != 1) { g_err = "isnewpot must be 0 or 1"; return -5; }
   if (g.isnewpot * g.isphion == 1 && (g.iphibcc < 1 || g.iphibcc > 3)) { g_err = "only iphibcc = 1, 2, 3 available"; return -5; }
   g.ExtendedJacPhi = I("ExtendedJacPhi"); g.numvar_ = I("numvar");
+  // gas energy equation (istgon = 1): the inertial atoms only
+  g.idxtg_ = ARR("idxtg", nc);
+  g.istgcore = I("istgcore", 0); g.istgpfc = I("istgpfc", 0); g.istgwc = I("istgwc", 0); g.istglb = I("istglb", 0); g.istgrb = I("istgrb", 0); g.isfegxyqflave = I("isfegxyqflave");
+  g.tgcore = SC("tgcore"); g.cftgticore = SC("cftgticore"); g.tgwall = SC("tgwall"); g.lytg1 = SC("lytg", 0); g.lytg2 = SC("lytg", 1); g.cftgtipltl = SC("cftgtipltl"); g.cftgtipltr = SC("cftgtipltr");
+  g.cftgtipfc = SC("cftgtipfc"); g.cftgtiwc = SC("cftgtiwc"); g.cgengmpl = SC("cgengmpl"); g.cgengmw = SC("cgengmw"); g.cfalbedo = SC("cfalbedo"); g.recyce = SC("recyce"); g.recycwe = SC("recycwe");
+  g.cvgpg = SC("cvgpg"); g.cfcvtg = SC("cfcvtg"); g.cfegxy = SC("cfegxy"); g.flalftgxy = SC("flalftgxy");
+  if (g.istgon != 0 && g.istgon != 1) { g_err = "istgon must be 0 or 1"; return -5; }
+  if (g.istgon == 1) {
+    if (g.isupgon != 1 || g.nisp != 2) { g_err = "istgon=1 is built for inertial atoms (isupgon=1, nisp=2) only"; return -5; }
+    if (g.istgpfc < 0 || g.istgpfc > 5 || g.istgwc < 0 || g.istgwc > 5) { g_err = "invalid istgpfc / istgwc"; return -5; }
+    for (int k : {g.istglb, g.istgrb}) if (k < 0 || k > 5 || k == 2) { g_err = "istglb / istgrb must be 0, 1, 3, 4 or 5"; return -5; }
+    if (SC("ispfbcvsix") != 0. || SC("iswobcvsix") != 0.) { g_err = "poloidally dependent wall options with istgon=1 not built"; return -5; }
+  }
   if (g.fnnuiz != 1.) { g_err = "fnnuiz must be 1"; return -5; }
   if (SC("l_parloss") <= 1e9) { g_err = "l_parloss<=1e9 (nuvl) not built"; return -5; }
   if (g.isfixlb != 0 && g.isfixlb != 2) { g_err = "isfixlb must be 0 or 2"; return -5; }

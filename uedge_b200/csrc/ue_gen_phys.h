@@ -69,7 +69,7 @@ HD int iabs(int a) { return a < 0 ? -a : a; }
   P1(floxe) P1(floxi) P1(floye) P1(floyi) P1(conxe) P1(conxi) P1(conye) P1(conyi) P1(feex) P1(feey) P1(feix) P1(feiy) P1(feexy) P1(feixy) P1(resee) P1(resei) \
   P1(erliz) P1(erlrc) P1(eeli) P1(vsoreec) P1(vsoree) P1(pwribkg) P1(pwrebkg) P1(pradhyd) \
   P1(fqp) P1(fqx) P1(fqy) P1(fq2) P1(fqxb) P1(fqyb) P1(fqyn) P1(fqym) P1(fqymi) P1(fqya) P1(fqydt) P1(fqydti) P1(fqyao) P1(fqyae) P1(fqyd) P1(fqygp) P1(fq2d) P1(netap) P1(resphi) P1(dphi_iy1) \
-  P2(vyce) P2(vycb) P2(vycp) P1(veycb) P2(v2ce) P2(v2cb) P1(ve2cb) P1(wjdote) P2(fmity) P2(fqymi_) P2(fniycbo) P1(feeycbo) P1(feiycbo) P1(kappal) P1(kappar) P1(bcel) P1(bcer) P1(bcil) P1(bcir) \
+  P2(vyce) P2(vycb) P2(vycp) P1(veycb) P2(v2ce) P2(v2cb) P1(ve2cb) P1(wjdote) P1(segc) P1(floxge) P1(floyge) P1(conxge) P1(conyge) P1(fegx) P1(fegy) P1(fegxy) P1(reseg) P2(fmity) P2(fqymi_) P2(fniycbo) P1(feeycbo) P1(feiycbo) P1(kappal) P1(kappar) P1(bcel) P1(bcer) P1(bcil) P1(bcir) \
   P1(fqpsatlb) P1(fqpsatrb) P1(fdiaxlb) P1(fdiaxrb)
 
 struct Gen {
@@ -112,8 +112,10 @@ double ev, qe, me, mp, pi_, cutlo, rt8opi, temin, tgmin, nnorm, ennorm, temp0, v
     cfjpy, cfjp2, cfqybf, cfq2bf, cfqybbo, cfqydbo, cfydd_, cfjp2_, cfqyn, cfqyao, cfqya, cfqyae, cfjpy_, fqpsatlb_unused, lnlam_unused, phiwi0, phiwo0,
     kappamx, kappa0, cfsigm, fqsatlb_u, fupe_cur, dtphi_, cfhcxgc_u, lyphi0, lyphi1, isparmultdt_u, tewallmin_u, cfwjdotelim, cfeexdbo, cfeixdbo, cfkincor,
     cfyef, cf2ef, cfybf, cf2bf, cfcurv, cfgradb, eycore, icoreelec, cfniybbo, cfeeybbo;
-int ExtendedJacPhi;
+int ExtendedJacPhi, istgcore, istgpfc, istgwc, istglb, istgrb, isfegxyqflave;
 int64_t numvar_;
+double tgcore, cftgticore, tgwall, lytg1, lytg2, cftgtipltl, cftgtipltr, cftgtipfc, cftgtiwc, cgengmpl, cgengmw, cfalbedo, recyce, recycwe, cvgpg, cfcvtg, cfegxy, flalftgxy;
+const double* idxtg_;
 double cngfx_[2], cngfy_[2], mi[2], zi[2], n0[2], fnorm[2], n0g_[2], mg_[2], ngbackg_[2], vcony[2], difpr[2], difni[2], difni2[2], difpr2[2], difax[2], travis[2], parvis[2],
     nlimix[2], nlimiy[2], dif4order[2], cpiup[2], cfvgpx[2], cfvgpy[2], cfvcsx[2], cfvcsy[2], cfvisxy[2], cngmom[2], cmwall[2], cngtgx[2], cngtgy[2], cdifg[2], lgmax[2], lgtmax[2],
     rld2dxg[2], rld2dyg[2], cngflox[2], cngfloy[2], rtg2ti[2], tgas[2], istgcon[2], keligig[2], ncore[2], ngcore[2], upcore[2], curcore[2], albedoc[2], csfaclb[2], csfacrb[2],
@@ -140,6 +142,7 @@ HD int64_t IDXU(int f, int ix, int iy) { return (int64_t)idxu_[f][ix + NXS * iy]
 HD int64_t IDXTE(int ix, int iy) { return (int64_t)idxte_[ix + NXS * iy] - 1; }
 HD int64_t IDXTI(int ix, int iy) { return (int64_t)idxti_[ix + NXS * iy] - 1; }
 HD int64_t IDXG(int ix, int iy) { return (int64_t)idxg_[ix + NXS * iy] - 1; }
+HD int64_t IDXTG(int ix, int iy) { return (int64_t)idxtg_[ix + NXS * iy] - 1; }
 HD int64_t IDXPHI(int ix, int iy) { return (int64_t)idxphi_[ix + NXS * iy] - 1; }
 HD int ALG(int64_t iv) { return (int)iseqalgd[iv]; }
 
@@ -376,6 +379,8 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
         if (isflxvar == 0) ntemp = nnorm;
         iv = IDXTI(ix, iy);
         if (iv >= 0) { A(ti, ix, iy) = yl[iv] * ennorm / (1.5 * ntemp); A(ti, ix, iy) = mx(A(ti, ix, iy), temin * ev); }
+        iv = IDXTG(ix, iy);  // convert.m:299-305 (isflxvar = 0: ntemp = n0g)
+        if (iv >= 0) { A(tg, ix, iy) = yl[iv] * ennorm / (1.5 * n0g_[0]); A(tg, ix, iy) = mx(A(tg, ix, iy), tgmin * ev); }
         iv = IDXPHI(ix, iy);
         if (iv >= 0) A(phi, ix, iy) = yl[iv] * temp0;
       }
@@ -765,6 +770,73 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
         }
   }
 
+
+  // ---- engbalg (oderhs.m:7508-7878): the gas energy equation, gas species 1 = the inertial atoms (ngsp = 1, nisp = 2) -------------
+  HD void engbalg(const Win& w) {
+    const int i1 = w.i1, i2 = w.i2, i4 = w.i4, i5 = w.i5, i6 = w.i6, i8 = w.i8;
+    const int j1 = w.j1, j2 = w.j2, j4 = w.j4, j5 = w.j5, j6 = w.j6, j8 = w.j8;
+    FOR2(iy, j2, j5, ix, i2, i5) A(segc, ix, iy) = 0.0;
+    if (istgon == 1)  // v.grad(pg) work (oderhs.m:7564-7585)
+      FOR2(iy, j2, j5, ix, i2, i5) {
+          const int ix1 = IXM1(ix, iy), ix2 = IXP1(ix, iy), iy1 = mx(0, iy - 1);
+          const double tv = (A(pg, ix2, iy) - A(pg, ix, iy)), t1 = (A(pg, ix, iy) - A(pg, ix1, iy));
+          A(segc, ix, iy) = 0.5 * cvgpg * (A(uuxg, ix, iy) * ave(A(gx, ix2, iy), A(gx, ix, iy)) * tv + A(uuxg, ix1, iy) * ave(A(gx, ix, iy), A(gx, ix1, iy)) * t1) * A(vol, ix, iy);
+          const double t2 = cvgpg * 0.5 * (A(vyg, ix, iy) * A(dynog, ix, iy) * (A(pgy1, ix, iy) - A(pgy0, ix, iy)) + A(vyg, ix, iy1) * A(dynog, ix, iy1) * (A(pgy1, ix, iy1) - A(pgy0, ix, iy1)));
+          A(segc, ix, iy) = A(segc, ix, iy) + cvgpg * t2 * A(vol, ix, iy);
+        }
+    FOR2(iy, j1, j6, ix, i1, i6) { A(floxge, ix, iy) = 0.0; A(floyge, ix, iy) = 0.0; A(conxge, ix, iy) = 0.0; A(conyge, ix, iy) = 0.0; }
+    FOR1(iy, j4, j8) {  // conduction (oderhs.m:7605-7636); hcxg is flux-limited already
+      for (int ix = i1; ix <= i5; ++ix) A(conxge, ix, iy) = A(sx, ix, iy) * A(hcxg, ix, iy) * A(gxf, ix, iy);
+      A(conxge, nx + 1, iy) = 0;
+    }
+    FOR2(iy, j1, j5, ix, i4, i8) A(conyge, ix, iy) = A(sy, ix, iy) * A(hcyg, ix, iy) / A(dynog, ix, iy);
+    FOR1(ix, i1, i6) A(conyge, ix, ny + 1) = 0.0;
+    FOR1(iy, j4, j8) {  // convection (oderhs.m:7643-7705)
+      for (int ix = i1; ix <= i5; ++ix) A(floxge, ix, iy) = cfcvtg * 2.5 * A(fngx, ix, iy);
+      A(floxge, nx + 1, iy) = 0.;
+    }
+    FOR1(iy, j4, j8) {  // no inward power from the plates
+      if (A(fngx, ixlb, iy) > 0.) A(floxge, ixlb, iy) = A(floxge, ixlb, iy) - (1. - cfloxiplt) * cfcvti * 2.5 * A(fngx, ixlb, iy);
+      if (A(fngx, ixrb, iy) < 0.) A(floxge, ixrb, iy) = A(floxge, ixrb, iy) - (1. - cfloxiplt) * cfcvti * 2.5 * A(fngx, ixrb, iy);
+      A(floxge, ixrb + 1, iy) = 0.0;
+    }
+    FOR2(iy, j1, j5, ix, i4, i8) A(floyge, ix, iy) = cfcvtg * 2.5 * A(fngy, ix, iy);
+    FOR1(ix, i4, i8) {  // ... nor from the walls
+      if (ix <= ixpt1 || ix > ixpt2) { if (A(fngy, ix, 0) > 0.) A(floyge, ix, 0) = A(floyge, ix, 0) - (1. - cfloygwall) * cfcvtg * 2.5 * A(fngy, ix, 0); }
+      if (A(fngy, ix, ny) < 0.) A(floyge, ix, ny) = A(floyge, ix, ny) - (1. - cfloygwall) * cfcvtg * 2.5 * A(fngy, ix, ny);
+      A(floyge, ix, ny + 1) = 0.0;
+    }
+    if (istgon == 1) fd2tra(w, floxge, floyge, conxge, conyge, tg, fegx, fegy, 0, methi);  // oderhs.m:7708-7716
+    if (isnonog == 1 && istgon == 1)  // y-component of the non-orthogonal diffusive flux (oderhs.m:7720-7782)
+      FOR2(iy, j1, mn(j6, ny), ix, i1, i6) {
+          const int iy1 = mx(iy - 1, 0);
+          const int ix2 = IXP1(ix, iy), ix4 = IXP1(ix, iy1), ix6 = IXP1(ix, iy + 1);
+          double t0 = mx(A(tg, ix, iy), tgmin * ev), t1 = mx(A(tg, ix2, iy), tgmin * ev);
+          const double vtn = sqrt(t0 / mg_[0]), vtnp = sqrt(t1 / mg_[0]);
+          const double nu1 = A(nuix, ix, iy) + vtn / lgmax[0], nu2 = A(nuix, ix2, iy) + vtnp / lgmax[0];
+          const double grdnv = ((A(fym[1], ix, iy) * ue_log(A(tg, ix2, iy1)) + A(fy0[1], ix, iy) * ue_log(A(tg, ix2, iy)) + A(fyp[1], ix, iy) * ue_log(A(tg, ix2, iy + 1)) +
+                                 A(fymx[1], ix, iy) * ue_log(A(tg, ix, iy1)) + A(fypx[1], ix, iy) * ue_log(A(tg, ix, iy + 1))) -
+                                (A(fym[0], ix, iy) * ue_log(A(tg, ix, iy1)) + A(fy0[0], ix, iy) * ue_log(A(tg, ix, iy)) + A(fyp[0], ix, iy) * ue_log(A(tg, ix, iy + 1)) +
+                                 A(fymx[0], ix, iy) * ue_log(A(tg, ix4, iy1)) + A(fypx[0], ix, iy) * ue_log(A(tg, ix6, iy + 1)))) / A(dxnog, ix, iy);
+          const double difgx2 = ave(A(tg, ix, iy) / nu1, A(tg, ix2, iy) / nu2) / mg_[0] + sq(rld2dxg[0]) * (1 / sq(A(gxf, ix, iy))) * 0.5 * (A(nuiz, ix, iy) + A(nuiz, ix2, iy));
+          A(fegxy, ix, iy) = cfegxy * ue_exp(0.5 * (ue_log(A(tg, ix2, iy)) + ue_log(A(tg, ix, iy)))) * difgx2 * ave(A(ng, ix2, iy), A(ng, ix, iy)) *
+                             (grdnv / ue_cos(A(angfx, ix, iy)) - (ue_log(A(tg, ix2, iy)) - ue_log(A(tg, ix, iy))) * A(gxf, ix, iy)) * A(sx, ix, iy);
+          t0 = mx(A(tg, ix, iy), tgmin * ev); t1 = mx(A(tg, ix2, iy), tgmin * ev);
+          const double vttn = t0 * sqrt(t0 / mg_[0]), vttp = t1 * sqrt(t1 / mg_[0]);
+          double qfl;
+          if (isfegxyqflave == 0) qfl = flalftgxy * 0.25 * A(sx, ix, iy) * (vttn + vttp) * (A(ng, ix, iy) + A(ng, ix2, iy));
+          else qfl = flalftgxy * A(sx, ix, iy) * ave(vttn, vttp) * ave(A(ng, ix, iy), A(ng, ix2, iy));
+          A(fegxy, ix, iy) = A(fegxy, ix, iy) / sqrt(1. + sq(A(fegxy, ix, iy) / qfl));
+          A(fegx, ix, iy) = A(fegx, ix, iy) - A(fegxy, ix, iy);
+        }
+    FOR2(iy, j2, j5, ix, i2, i5) {  // residual and equipartition with the ions (oderhs.m:7790-7806)
+        const int iy1 = mx(0, iy - 1);
+        const int ix1 = IXM1(ix, iy);
+        A(reseg, ix, iy) = -(A(fegx, ix, iy) - A(fegx, ix1, iy) + A(fegy, ix, iy) - A(fegy, ix, iy1)) + A(segc, ix, iy);
+        A(reseg, ix, iy) = A(reseg, ix, iy) + A(vol, ix, iy) * A(eqpg, ix, iy) * (A(ti, ix, iy) - A(tg, ix, iy));
+        A(seic, ix, iy) = A(seic, ix, iy) - A(vol, ix, iy) * (1.0 - cftiexclg) * A(eqpg, ix, iy) * (A(ti, ix, iy) - A(tg, ix, iy));
+      }
+  }
 
   // ---- pandf (oderhs.m:537-5070) -------------------------------------------------------------------------------------
   HD int pandf(int xc, int yc, const double* yl, double* yldot) {
@@ -1217,8 +1289,7 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
     if (nisp >= 2) {  // gas conductivities as stored (oderhs.m:3156-3160) and atom/ion equipartition (oderhs.m:3163-3176)
       if (isupgon == 1) FOR1(c_, 0, NC - 1) { hcxg[c_] = hcxn[c_]; hcyg[c_] = hcyn[c_]; }
       FOR2(iy, j1, j6, ix, i1, i6) A(eqpg, ix, iy) = cftgeqp * A(ng, ix, iy) * (A(ni[0], ix, iy) + cftiexclg * A(ni[1], ix, iy)) * keligig[0];
-      // engbalg (oderhs.m:7508-7882) with istgon = 0: its only effect on the plasma equations (oderhs.m:7803-7806)
-      FOR2(iy, j2, j5, ix, i2, i5) A(seic, ix, iy) = A(seic, ix, iy) - A(vol, ix, iy) * (1.0 - cftiexclg) * A(eqpg, ix, iy) * (A(ti, ix, iy) - A(tg, ix, iy));
+      engbalg(w);  // oderhs.m:3180
     }
 
     // ---- particle fluxes (oderhs.m:3187-3319) ----
@@ -1553,6 +1624,9 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
                              (1.0 - cftiexclg) * t0 +
                              cftiexclg * cfneut * cfneutsor_ei * cnsor * (eion * ev + cfnidhdis * 0.5 * mg_[0] * (t2 * t2 + temp3 + temp4)) * A(psordis, ix, iy) +
                              cfnidh2 * (-mi[0] * t1 * t2 * (A(psor[0], ix, iy) + tv) + 0.5 * mi[0] * t1 * t1 * (A(psor[0], ix, iy) + A(psorrg, ix, iy) + 2 * tv));
+          A(reseg, ix, iy) = A(reseg, ix, iy) - t0 + 0.5 * mg_[0] * ((t1 - t2) * (t1 - t2) + temp3 + temp4) * (A(psorrg, ix, iy) + tv) +
+                             (eion * ev + cfnidh * cfnidhdis * 0.5 * mg_[0] * (t2 * t2 + temp3 + temp4)) * A(psordis, ix, iy) +
+                             cfnidh2 * (-mg_[0] * t1 * t2 * (A(psorrg, ix, iy) + tv) + 0.5 * mg_[0] * (t2 * t2 + temp3 + temp4) * (A(psor[0], ix, iy) + A(psorrg, ix, iy) + 2 * tv));  // oderhs.m:4618-4627
         } else {
           double us = A(upi[0], ix, iy) + A(upi[0], ix1, iy);
           A(resei, ix, iy) = A(resei, ix, iy) + A(w0, ix, iy) + cfneut * cfneutsor_ei * ctsor * 1.25e-1 * mi[0] * (us * us) * fac2sp * A(psor[0], ix, iy) +
@@ -1596,7 +1670,7 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
             dupdy = 0.25 * ((A(u, ix, iy + 1) + A(u, ix2, iy + 1) - A(u, ix, iy) - A(u, ix1, iy)) * A(gyf, ix, iy) + (A(u, ix, iy) + A(u, ix1, iy) - A(u, ix, iy - 1) - A(u, ix3, iy - 1)) * A(gyf, ix, iy - 1));
           A(wvh[f], ix, iy) = A(wvh[f], ix, iy) + cfvcsy[f] * cfvisy * A(visy[f], ix, iy) * (dupdy * dupdy);
           A(wvh[f], ix, iy) = A(wvh[f], ix, iy) - ue_ksin(thetacc) * cfvcsy[f] * cfvisy * A(visy[f], ix, iy) * dupdx * dupdy;
-          if (zi[f] == 0.0 && f == iigsp) A(resei, ix, iy) = A(resei, ix, iy) + cftiexclg * A(wvh[f], ix, iy) * A(vol, ix, iy);
+          if (zi[f] == 0.0 && f == iigsp) { A(resei, ix, iy) = A(resei, ix, iy) + cftiexclg * A(wvh[f], ix, iy) * A(vol, ix, iy); A(reseg, ix, iy) = A(reseg, ix, iy) + A(wvh[f], ix, iy) * A(vol, ix, iy); }
           else A(resei, ix, iy) = A(resei, ix, iy) + A(wvh[f], ix, iy) * A(vol, ix, iy);
         }
     FOR2(iy, w.iys, w.iyf, ix, w.ixs, w.ixf) A(pwribkg, ix, iy) = powi(tibg * ev / A(ti, ix, iy), iteb) * pwribkg_c;  // oderhs.m:4936-4947
@@ -1613,6 +1687,7 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
         iv = IDXTE(ix, iy); if (iv >= 0) yldot[iv] = (1 - ALG(iv)) * A(resee, ix, iy) / (A(vol, ix, iy) * ennorm);
         iv = IDXTI(ix, iy); if (iv >= 0) yldot[iv] = (1 - ALG(iv)) * A(resei, ix, iy) / (A(vol, ix, iy) * ennorm);
         iv = IDXG(ix, iy); if (iv >= 0) yldot[iv] = (1 - ALG(iv)) * A(resng, ix, iy) / (A(vol, ix, iy) * n0g_[0]);
+        iv = IDXTG(ix, iy); if (iv >= 0) yldot[iv] = (1 - ALG(iv)) * A(reseg, ix, iy) / (A(vol, ix, iy) * ennorm);
       }
     if (isphion == 1) poteneq(w, yl, yldot);  // oderhs.m:5007
     rc = bouncon(w, yl, yldot);               // oderhs.m:5009
@@ -1915,6 +1990,44 @@ HD int bouncon(const Win& w, const double* yl, double* yldot) {
         }
       }
     }
+    FOR1(ix, w.i4, w.i8) {  // gas temperature at iy = 0 (boundary.m:769-852)
+      const int64_t iv = IDXTG(ix, 0);
+      if (iv < 0) continue;
+      if (isixcore[ix] == 1) {
+        if (istgcore == 0) yldot[iv] = nurlxg * (A(ti, ix, 0) * cftgticore - A(tg, ix, 0)) / (temp0 * ev);
+        else if (istgcore == 1) yldot[iv] = nurlxg * (tgcore * ev - A(tg, ix, 0)) / (temp0 * ev);
+        else if (istgcore == 2) {
+          double t0 = mx(A(tg, ix, 0), tgmin * ev);
+          double vyn = sqrt(0.5 * t0 / (pi * mg_[0]));
+          double nharmave = 2. * (A(ng, ix, 0) * A(ng, ix, 1)) / (A(ng, ix, 0) + A(ng, ix, 1));
+          double fng_alb = (1 - albedoc[0]) * nharmave * vyn * A(sy, ix, 0);
+          yldot[iv] = -nurlxg * (A(fegy, ix, 0) + cfalbedo * fng_alb * t0) / (vpnorm * ennorm * A(sy, ix, 0));
+        } else yldot[iv] = nurlxg * (A(tg, ix, 1) - A(tg, ix, 0)) / (temp0 * ev);
+      } else {  // private-flux wall
+        if (istgpfc == 0) yldot[iv] = nurlxg * (tgwall * ev - A(tg, ix, 0)) / (temp0 * ev);
+        else if (istgpfc == 1) {
+          double tbound = A(tg, ix, 1) - A(gyf, ix, 1) * (A(tg, ix, 2) - A(tg, ix, 1)) / A(gyf, ix, 0);
+          tbound = mx(tbound, 0.25 * tbmin * ev);
+          yldot[iv] = nurlxi * (tbound - A(tg, ix, 0)) / (temp0 * ev);
+        } else if (istgpfc == 2) yldot[iv] = nurlxi * ((A(tg, ix, 1) - A(tg, ix, 0)) - 0.5 * (A(tg, ix, 1) + A(tg, ix, 0)) / (A(gyf, ix, 0) * lytg1)) / (temp0 * ev);
+        else if (istgpfc == 3) {  // Maxwellian thermal flux to the wall
+          double t0 = mx(cdifg[0] * A(tg, ix, 1), temin * ev);
+          double vyn = 0.25 * sqrt(8 * t0 / (pi * mg_[0]));
+          yldot[iv] = -nurlxg * (A(fegy, ix, 0) + 2 * cgengmw * A(ng, ix, 1) * vyn * t0 * A(sy, ix, 0)) / (A(sy, ix, 0) * vpnorm * ennorm);
+        } else if (istgpfc == 4) {
+          double t0 = mx(A(tg, ix, 0), tgmin * ev);
+          double vyn = sqrt(0.5 * t0 / (pi * mg_[0]));
+          double nharmave = 2. * (A(ng, ix, 0) * A(ng, ix, 1)) / (A(ng, ix, 0) + A(ng, ix, 1));
+          double fng_alb = (1 - albedoi[ix]) * nharmave * vyn * A(sy, ix, 0), fng_chem = 0.;
+          yldot[iv] = -nurlxg * (A(fegy, ix, 0) + cfalbedo * fng_alb * t0 - 2. * fng_chem * t0) / (vpnorm * ennorm * A(sy, ix, 0));
+          if (matwalli[ix] > 0 && recycwit[ix] > 0) {
+            double fniy_recy = recycwit[ix] * fac2sp * A(fniy[0], ix, 0);
+            if (isrefluxclip == 1) fniy_recy = mn(fniy_recy, 0.);
+            yldot[iv] = -nurlxg * (A(fegy, ix, 0) + cfalbedo * fng_alb * t0 - 2. * fng_chem * t0 + fniy_recy * (1. - cfdiss) * cfalbedo * recycwe * A(ti, ix, 0)) / (vpnorm * ennorm * A(sy, ix, 0));
+          }
+        } else yldot[iv] = nurlxg * (A(ti, ix, 0) * cftgtipfc - A(tg, ix, 0)) / (temp0 * ev);  // istgpfc = 5
+      }
+    }
     FOR1(ix, w.i4, w.i8) {  // potential, isnewpot = 0 (boundary.m:856-863)
       const int64_t iv3 = IDXPHI(ix, 0);
       if (iv3 >= 0) yldot[iv3] = nurlxp * ((A(phi, ix, 1) - A(phi, ix, 0)) - 0.5 * (A(phi, ix, 1) + A(phi, ix, 0)) / (A(gyf, ix, 0) * lyphiix1[ix])) / temp0;
@@ -1924,6 +2037,7 @@ HD int bouncon(const Win& w, const double* yl, double* yldot) {
       if (IDXTE(ixlb, 0) >= 0) yldot[IDXTE(ixlb, 0)] = nurlxe * (0.5 * (A(te, ixlb + 1, 0) + A(te, ixlb, 1)) - A(te, ixlb, 0)) / (temp0 * ev);
       if (IDXTI(ixlb, 0) >= 0) yldot[IDXTI(ixlb, 0)] = nurlxi * (0.5 * (A(ti, ixlb + 1, 0) + A(ti, ixlb, 1)) - A(ti, ixlb, 0)) / (temp0 * ev);
       if (IDXG(ixlb, 0) >= 0) yldot[IDXG(ixlb, 0)] = nurlxg * (A(ng, ixlb + 1, 0) - A(ng, ixlb, 0)) / n0g_[0];
+      if (IDXTG(ixlb, 0) >= 0) yldot[IDXTG(ixlb, 0)] = nurlxg * (A(tg, ixlb + 1, 0) - A(tg, ixlb, 0)) / (temp0 * ev);  // boundary.m:930-937
     }
     if (w.xcnearrb || w.openbox) SER {  // boundary.m:939-983
       for (int f = 0; f < nusp; ++f)
@@ -1934,6 +2048,7 @@ HD int bouncon(const Win& w, const double* yl, double* yldot) {
       if (IDXTE(ixrb + 1, 0) >= 0) yldot[IDXTE(ixrb + 1, 0)] = nurlxe * (0.5 * (A(te, ixrb + 1, 1) + A(te, ixrb, 0)) - A(te, ixrb + 1, 0)) / (temp0 * ev);
       if (IDXTI(ixrb + 1, 0) >= 0) yldot[IDXTI(ixrb + 1, 0)] = nurlxi * (0.5 * (A(ti, ixrb + 1, 1) + A(ti, ixrb, 0)) - A(ti, ixrb + 1, 0)) / (temp0 * ev);
       if (IDXG(ixrb, 0) >= 0) yldot[IDXG(ixrb + 1, 0)] = nurlxg * (A(ng, ixrb, 0) - A(ng, ixrb + 1, 0)) / n0g_[0];
+      if (IDXTG(ixrb, 0) >= 0) yldot[IDXTG(ixrb + 1, 0)] = nurlxg * (A(tg, ixrb, 0) - A(tg, ixrb + 1, 0)) / (temp0 * ev);  // boundary.m:975-982
     }
   }
   // ===== potential with isnewpot = 1: two equations at iy = 0 and 1 (boundary.m:987-1122) =====
@@ -2051,6 +2166,32 @@ HD int bouncon(const Win& w, const double* yl, double* yldot) {
         }
       }
     }
+    FOR1(ix, w.i4, w.i8) {  // gas temperature at iy = ny+1 (boundary.m:1463-1513)
+      const int64_t iv = IDXTG(ix, ny + 1);
+      if (iv < 0) continue;
+      if (istgwc == 0) yldot[iv] = nurlxg * (tgwall * ev - A(tg, ix, ny + 1)) / (temp0 * ev);
+      else if (istgwc == 1) {
+        double tbound = A(tg, ix, ny) + A(gyf, ix, ny) * (A(tg, ix, ny) - A(tg, ix, ny - 1)) / A(gyf, ix, ny);
+        tbound = mx(tbound, 0.25 * tbmin * ev);
+        yldot[iv] = nurlxi * (tbound - A(tg, ix, ny + 1)) / (temp0 * ev);
+      } else if (istgwc == 2) yldot[iv] = nurlxi * ((A(tg, ix, ny) - A(tg, ix, ny + 1)) - 0.5 * (A(tg, ix, ny) + A(tg, ix, ny + 1)) / (A(gyf, ix, ny) * lytg2)) / (temp0 * ev);
+      else if (istgwc == 3) {
+        double t0 = mx(cdifg[0] * A(tg, ix, ny), temin * ev);
+        double vyn = 0.25 * sqrt(8 * t0 / (pi * mg_[0]));
+        yldot[iv] = nurlxg * (A(fegy, ix, ny) - 2 * cgengmw * A(ng, ix, ny) * vyn * t0 * A(sy, ix, ny)) / (A(sy, ix, ny) * vpnorm * ennorm);
+      } else if (istgwc == 4) {
+        double t0 = mx(A(tg, ix, ny + 1), tgmin * ev);
+        double vyn = sqrt(0.5 * t0 / (pi * mg_[0]));
+        double nharmave = 2. * (A(ng, ix, ny) * A(ng, ix, ny + 1)) / (A(ng, ix, ny) + A(ng, ix, ny + 1));
+        double fng_alb = (1 - albedoo[ix]) * nharmave * vyn * A(sy, ix, ny), fng_chem = 0.;
+        yldot[iv] = nurlxg * (A(fegy, ix, ny) - cfalbedo * fng_alb * t0 + 2. * fng_chem * t0) / (vpnorm * ennorm * A(sy, ix, ny));
+        if (matwallo[ix] > 0 && recycwot[ix] > 0.) {
+          double fniy_recy = recycwot[ix] * fac2sp * A(fniy[0], ix, ny);
+          if (isrefluxclip == 1) fniy_recy = mx(fniy_recy, 0.);
+          yldot[iv] = nurlxg * (A(fegy, ix, ny) - cfalbedo * fng_alb * t0 + 2. * fng_chem * t0 + fniy_recy * (1. - cfdiss) * cfalbedo * recycwe * A(ti, ix, ny)) / (vpnorm * ennorm * A(sy, ix, ny));
+        }
+      } else yldot[iv] = nurlxg * (A(ti, ix, ny + 1) * cftgtiwc - A(tg, ix, ny + 1)) / (temp0 * ev);  // istgwc = 5
+    }
     FOR1(ix, w.i4, w.i8) {  // potential (boundary.m:1522-1540)
       const int64_t iv3 = IDXPHI(ix, ny + 1);
       if (iv3 < 0) continue;
@@ -2064,6 +2205,7 @@ HD int bouncon(const Win& w, const double* yl, double* yldot) {
       if (IDXTE(ixlb, ny + 1) >= 0) yldot[IDXTE(ixlb, ny + 1)] = nurlxe * (0.5 * (A(te, ixlb + 1, ny + 1) + A(te, ixlb, ny)) - A(te, ixlb, ny + 1)) / (temp0 * ev);
       if (IDXTI(ixlb, ny + 1) >= 0) yldot[IDXTI(ixlb, ny + 1)] = nurlxi * (0.5 * (A(ti, ixlb + 1, ny + 1) + A(ti, ixlb, ny)) - A(ti, ixlb, ny + 1)) / (temp0 * ev);
       if (IDXG(ixlb, ny + 1) >= 0) yldot[IDXG(ixlb, ny + 1)] = nurlxg * (A(ng, ixlb + 1, ny + 1) - A(ng, ixlb, ny + 1)) / n0g_[0];
+      if (IDXTG(ixlb, ny + 1) >= 0) yldot[IDXTG(ixlb, ny + 1)] = nurlxg * (0.5 * (A(tg, ixlb + 1, ny + 1) + A(tg, ixlb, ny)) - A(tg, ixlb, ny + 1)) / (temp0 * ev);
     }
     if (w.xcnearrb || w.openbox) SER {  // boundary.m:1585-1630
       for (int f = 0; f < nusp; ++f)
@@ -2074,6 +2216,7 @@ HD int bouncon(const Win& w, const double* yl, double* yldot) {
       if (IDXTE(ixrb + 1, ny + 1) >= 0) yldot[IDXTE(ixrb + 1, ny + 1)] = nurlxe * (0.5 * (A(te, ixrb, ny + 1) + A(te, ixrb + 1, ny)) - A(te, ixrb + 1, ny + 1)) / (temp0 * ev);
       if (IDXTI(ixrb + 1, ny + 1) >= 0) yldot[IDXTI(ixrb + 1, ny + 1)] = nurlxi * (0.5 * (A(ti, ixrb, ny + 1) + A(ti, ixrb + 1, ny)) - A(ti, ixrb + 1, ny + 1)) / (temp0 * ev);
       if (IDXG(ixrb + 1, ny + 1) >= 0) yldot[IDXG(ixrb + 1, ny + 1)] = nurlxg * (A(ng, ixrb, ny + 1) - A(ng, ixrb + 1, ny + 1)) / n0g_[0];
+      if (IDXTG(ixrb + 1, ny + 1) >= 0) yldot[IDXTG(ixrb + 1, ny + 1)] = nurlxg * (0.5 * (A(tg, ixrb, ny + 1) + A(tg, ixrb + 1, ny)) - A(tg, ixrb + 1, ny + 1)) / (temp0 * ev);
     }
   }
   // ===== ix = 0 as a symmetry plane, isfixlb = 2 (boundary.m:1666-1770; rlimiter beyond the mesh) =====
@@ -2084,6 +2227,7 @@ HD int bouncon(const Win& w, const double* yl, double* yldot) {
       if (IDXTE(0, iy) >= 0) yldot[IDXTE(0, iy)] = nurlxe * A(ne, 0, iy) * (A(te, 1, iy) - A(te, 0, iy)) / ennorm;
       if (IDXTI(0, iy) >= 0) yldot[IDXTI(0, iy)] = nurlxi * A(ne, 0, iy) * (A(ti, 1, iy) - A(ti, 0, iy)) / ennorm;
       if (IDXG(0, iy) >= 0) yldot[IDXG(0, iy)] = nurlxg * (A(ng, 1, iy) - A(ng, 0, iy)) / n0g_[0];
+      if (IDXTG(0, iy) >= 0) yldot[IDXTG(0, iy)] = nurlxg * (A(tg, 1, iy) - A(tg, 0, iy)) / (temp0 * ev);  // boundary.m:1747-1756
       if (IDXPHI(0, iy) >= 0) yldot[IDXPHI(0, iy)] = nurlxp * (A(phi, 1, iy) - A(phi, 0, iy)) / temp0;
     }
   if (isfixlb == 2 && w.i2 <= ixpt2 && w.i5 >= ixpt2 && w.j2 <= iysptrx2)  // boundary.m:1772-1785
@@ -2202,6 +2346,34 @@ HD int bouncon(const Win& w, const double* yl, double* yldot) {
         }
       }
   }
+  if ((w.xcnearlb || w.openbox) && isfixlb == 0 && w.i3 <= ixlb)  // gas temperature at the left plate (boundary.m:2198-2257)
+    FOR1(iy, w.j2, w.j5) {
+      const int ixt = ixlb, ixt1 = IXP1(ixt, iy), ixt2 = IXP1(ixt1, iy);
+      const int64_t iv = IDXTG(ixt, iy);
+      if (iv < 0) continue;
+      if (istglb == 0) yldot[iv] = nurlxg * (tgwall * ev - A(tg, ixt, iy)) / (temp0 * ev);
+      else if (istglb == 1) {
+        double tbound = A(tg, ixt1, iy) - A(gyf, ixt1, iy) * (A(tg, ixt2, iy) - A(tg, ixt1, iy)) / A(gxf, ixt, iy);
+        tbound = mx(tbound, 0.5 * temin * ev);
+        yldot[iv] = nurlxg * (tbound - A(tg, ixt, iy)) / (temp0 * ev);
+      } else if (istglb == 3) {
+        double t0 = mx(cdifg[0] * A(tg, ixt1, iy), tgmin * ev);
+        double vxn = 0.25 * sqrt(8 * t0 / (pi * mg_[0]));
+        yldot[iv] = -nurlxg * (A(fegx, ixt, iy) + 2 * cgengmpl * A(ng, ixt1, iy) * vxn * t0 * A(sx, ixt, iy)) / (A(sx, ixt, iy) * vpnorm * ennorm);
+      } else if (istglb == 4) {
+        const double recy = recylb[iy];
+        double t0 = mx(A(tg, ixt1, iy), tgmin * ev);
+        if (recy > 0.) {
+          double vxn = 0.25 * sqrt(8 * t0 / (pi * mg_[0]));
+          double fng_alb = (1 - alblb[iy]) * A(ng, ixt1, iy) * vxn * A(sx, ixt, iy);
+          yldot[iv] = -nurlxg * (A(fegx, ixt, iy) + cfalbedo * fng_alb * t0 + recy * (1. - cfdiss) * A(fnix[0], ixt, iy) * recyce * cfalbedo * (kappal[iy] * zi[0] * A(te, ixt, iy) + A(ti, ixt, iy))) / (vpnorm * ennorm * A(sx, ixt, iy));
+        } else if (recy >= -1.) {
+          double vyn = sqrt(0.5 * t0 / (pi * mg_[0]));
+          double fng_alb = (1 + recy) * A(ng, ixt1, iy) * vyn * A(sx, ixt, iy);
+          yldot[iv] = -nurlxg * (A(fegx, ixt, iy) + cfalbedo * fng_alb * t0) / (vpnorm * ennorm * A(sx, ixt, iy));
+        } else yldot[iv] = -nurlxg * (A(fegx, ixt, iy) + cfalbedo * A(fnix[iigsp], ixt, iy) * t0) / (vpnorm * ennorm * A(sx, ixt, iy));
+      } else yldot[iv] = nurlxg * (A(ti, ixt, iy) * cftgtipltl - A(tg, ixt, iy)) / (temp0 * ev);  // istglb = 5
+    }
   // ===== right plate, ix = ixrb+1 (boundary.m:2320-3002), isfixrb = 0 =====
   if (w.xcnearrb || w.openbox) {
     const int ixt = ixrb + 1;
@@ -2316,6 +2488,34 @@ HD int bouncon(const Win& w, const double* yl, double* yldot) {
         }
       }
   }
+  if ((w.xcnearrb || w.openbox) && w.i6 >= ixrb + 1)  // gas temperature at the right plate (boundary.m:2880-2937)
+    FOR1(iy, w.j2, w.j5) {
+      const int ixt = ixrb + 1, ixt1 = IXM1(ixt, iy), ixt2 = IXM1(ixt1, iy);
+      const int64_t iv = IDXTG(ixt, iy);
+      if (iv < 0) continue;
+      if (istgrb == 0) yldot[iv] = nurlxg * (tgwall * ev - A(tg, ixt, iy)) / (temp0 * ev);
+      else if (istgrb == 1) {
+        double tbound = A(tg, ixt1, iy) + A(gxf, ixt2, iy) * (A(tg, ixt1, iy) - A(tg, ixt2, iy)) / A(gxf, ixt1, iy);
+        tbound = mx(tbound, 0.5 * temin * ev);
+        yldot[iv] = nurlxg * (tbound - A(tg, ixt, iy)) / (temp0 * ev);
+      } else if (istgrb == 3) {
+        double t0 = mx(cdifg[0] * A(tg, ixt1, iy), temin * ev);
+        double vxn = 0.25 * sqrt(8 * t0 / (pi * mg_[0]));
+        yldot[iv] = nurlxg * (A(fegx, ixt1, iy) - 2 * cgengmpl * A(ng, ixt1, iy) * vxn * t0 * A(sx, ixt1, iy)) / (A(sx, ixt1, iy) * vpnorm * ennorm);
+      } else if (istgrb == 4) {
+        const double recy = recyrb[iy];
+        double t0 = mx(A(tg, ixt1, iy), tgmin * ev);
+        if (recy > 0.) {
+          double vxn = 0.25 * sqrt(8 * t0 / (pi * mg_[0]));
+          double fng_alb = (1 - albrb[iy]) * A(ng, ixt1, iy) * vxn * A(sx, ixt1, iy);
+          yldot[iv] = nurlxg * (A(fegx, ixt1, iy) - cfalbedo * fng_alb * t0 + recy * (1. - cfdiss) * A(fnix[0], ixt1, iy) * recyce * cfalbedo * (kappar[iy] * zi[0] * A(te, ixt, iy) + A(ti, ixt, iy))) / (vpnorm * ennorm * A(sx, ixt1, iy));
+        } else if (recy >= -1.) {
+          double vyn = sqrt(0.5 * t0 / (pi * mg_[0]));
+          double fng_alb = (1 + recy) * A(ng, ixt1, iy) * vyn * A(sx, ixt1, iy);
+          yldot[iv] = nurlxg * (A(fegx, ixt1, iy) - cfalbedo * fng_alb * t0) / (vpnorm * ennorm * A(sx, ixt1, iy));
+        } else yldot[iv] = nurlxg * (A(fegx, ixt1, iy) - cfalbedo * A(fnix[iigsp], ixt1, iy) * t0) / (vpnorm * ennorm * A(sx, ixt1, iy));
+      } else yldot[iv] = nurlxg * (A(ti, ixt, iy) * cftgtipltr - A(tg, ixt, iy)) / (temp0 * ev);  // istgrb = 5
+    }
   return 0;
 }
 
@@ -2354,6 +2554,8 @@ HD void rscalf(const Win& w, const double* yl, double* yldot) {
           if (isupgon == 1) yldot[ivi] = (yldot[ivi] * nnorm - yl[ivi] * (nbidot + cftiexclg * nbgdot)) / (A(nit, ix, iy) + cftiexclg * A(ni[1], ix, iy));
           else yldot[ivi] = (yldot[ivi] * nnorm - yl[ivi] * (nbidot + cngtgx[0] * nbg2dot)) / (A(nit, ix, iy) + cngtgx[0] * A(ng, ix, iy));
         }
+        const int64_t ivg = IDXTG(ix, iy);  // oderhs.m:8181-8191 (isupgon = 1)
+        if (ivg >= 0 && ALG(ivg) == 0) yldot[ivg] = (yldot[ivg] * n0g_[0] - yl[ivg] * nbgdot) / A(ni[iigsp], ix, iy);
       }
     }
 }
@@ -2371,7 +2573,7 @@ HD int pandf1(int xc, int yc, const double* yl, double* yldot) {
     FOR2(iy, j2l, j5l, ix, i2l, i5l) {
         for (int f = 0; f < nisp; ++f) step(IDXN(f, ix, iy));
         if (ix != nx + 2 * isbcwdt) for (int f = 0; f < nusp; ++f) step(IDXU(f, ix, iy));
-        step(IDXTE(ix, iy)); step(IDXTI(ix, iy)); step(IDXG(ix, iy));
+        step(IDXTE(ix, iy)); step(IDXTI(ix, iy)); step(IDXG(ix, iy)); step(IDXTG(ix, iy));
         if (isbcwdt == 1) step(IDXPHI(ix, iy));
       }
     if (dtphi < 1e10)
@@ -2380,7 +2582,8 @@ HD int pandf1(int xc, int yc, const double* yl, double* yldot) {
   return 0;
 }
   // ---- slab layout -----------------------------------------------------------------------------------------------------
-  double *vyce[2], *vycb[2], *vycp[2], *veycb, *v2ce[2], *v2cb[2], *ve2cb, *wjdote, *fmity[2], *fqymi_[2];  // drift velocities (oderhs.m:1167-1420), Joule heating, inertia-current work planes
+  double *vyce[2], *vycb[2], *vycp[2], *veycb, *v2ce[2], *v2cb[2], *ve2cb, *wjdote, *fmity[2], *fqymi_[2];
+  double *segc, *floxge, *floyge, *conxge, *conyge, *fegx, *fegy, *fegxy, *reseg;  // gas energy equation (engbalg, oderhs.m:7508-7878)  // drift velocities (oderhs.m:1167-1420), Joule heating, inertia-current work planes
   HD static int nplanes() {
     int n = 0;
 #define P1(x) n += 1;
