@@ -20,6 +20,8 @@ def cases():
     c, yl = jupyter_case(); yield "jupyter drift case 16x8", c, yl
     c, yl = jupyter_case(grid=refine_grid(load_grid_npz(), 4, 4)); yield "jupyter drift case 4x", c, yl
     c, yl = d3d_full_physics_case(refine_grid(load_grid_npz(), 4, 4)); yield "d3d 4x mesh, full physics", c, yl
+    if "--8x" in sys.argv:
+        c, yl = jupyter_case(grid=refine_grid(load_grid_npz(), 8, 8)); yield "jupyter drift case 8x", c, yl
 
 
 for name, c, yl in (cases() if __name__ == "__main__" else ()):

@@ -85,6 +85,9 @@ float g_full_ms = 0.f, g_cols_ms = 0.f, g_csr_ms = 0.f;  // CUDA-event times of 
 #define UE_GEN_BAND_DEFAULT 5
 int g_band = UE_GEN_BAND_DEFAULT;  // rows of the private copy on each side of the perturbed cell (env UE_GEN_BAND; large = all rows)
 int g_tpu = 32;  // threads per unknown in the Jacobian kernel: 32 (a warp) or 64 (a two-warp block)
+int g_sms = 0, g_full_grid = -1;  // SM count; blocks of the grid-mode residual (-1: by mesh size; env UE_GEN_FULL_GRID)
+bool g_grid_ok = false;           // cooperative launch available and no thread can leave the evaluation on its own (see init)
+int* d_gbar = nullptr;            // grid barrier ticket counter + error flags
 V g_last_yl;  // the state the base planes were last evaluated at
 int64_t g_ivmin = 1, g_ivmax = 0;
 
@@ -128,7 +131,7 @@ void free_all() {
   for (void* p : g_allocs) mem_free(p);
   g_allocs.clear(); g_dev.clear();
   d_G = nullptr; d_base = d_priv = d_yl = d_yldot = d_y00 = d_ylp = d_wk = d_step = d_fval = d_jac = nullptr;
-  d_cnt = d_frow = d_err = nullptr; d_ia = d_ja = d_ja2 = nullptr; d_jac2 = nullptr;
+  d_cnt = d_frow = d_err = d_gbar = nullptr; d_ia = d_ja = d_ja2 = nullptr; d_jac2 = nullptr;
   g_priv_cols = 0; g_nnzmx = 0; g_ready = false; g_last_yl.clear();
 #if !defined(UE_GEN_HOST)
   gc_nranks = 1; gc_rank = 0;  // (the lists belonged to the case that was just freed; the communicator itself lives until comm_finalize)
@@ -243,10 +246,20 @@ __global__ void k_gen_full(const Gen* gsrc, double* base, const double* yl, doub
   Gen* g = (Gen*)g_smem;
   load_ctx(g, gsrc, threadIdx.x, blockDim.x);
   __syncthreads();
-  if (threadIdx.x == 0) { g->nth = blockDim.x; g->errc = 0; g->assign_planes(base); }
+  if (threadIdx.x == 0) { g->nth = blockDim.x; g->gridmode = 0; g->errc = 0; g->assign_planes(base); }
   __syncthreads();
   const int rc = eval_full(*g, yl, yldot);
   if (rc && threadIdx.x == 0) { err[0] = rc; err[1] = g->errc; }
+}
+// the same over a co-resident grid (cooperative launch): one context = all threads, barriers between the nests are grid barriers
+__global__ void __launch_bounds__(128) k_gen_full_grid(const Gen* gsrc, double* base, const double* yl, double* yldot, int* err, unsigned* gbar, int* gflag) {
+  Gen* g = (Gen*)g_smem;
+  load_ctx(g, gsrc, threadIdx.x, blockDim.x);
+  __syncthreads();
+  if (threadIdx.x == 0) { g->nth = (int)(gridDim.x * blockDim.x); g->gridmode = 1; g->gbar = gbar; g->gflag = gflag; g->errc = 0; g->assign_planes(base); }
+  __syncthreads();
+  const int rc = eval_full(*g, yl, yldot);
+  if (rc && blockIdx.x == 0 && threadIdx.x == 0) { err[0] = rc; err[1] = g->errc; }
 }
 // one warp per unknown of the chunk [iv0, iv0 + ncol): every warp has its own context (shared memory) and its own planes
 template <int MINB>
@@ -260,7 +273,7 @@ __global__ void __launch_bounds__(128, MINB) k_gen_cols(const Gen* gsrc, const d
   const int c = tpu > 32 ? (int)blockIdx.x : (int)(blockIdx.x * (blockDim.x >> 5) + unit);
   if (c >= ncol) return;
   const size_t nslab = (size_t)npl * g->NC;
-  if (lane == 0) { g->nth = tpu; g->errc = 0; g->assign_planes(priv + (size_t)c * nslab); }
+  if (lane == 0) { g->nth = tpu; g->gridmode = 0; g->errc = 0; g->assign_planes(priv + (size_t)c * nslab); }
   if (tpu > 32) __syncthreads(); else __syncwarp();
   const int64_t iv = ivlist ? (int64_t)ivlist[c] : iv0 + c;  // (multi-GPU: this rank's unknowns are a list of mesh rows)
   const int64_t neq = g->neq;
@@ -561,6 +574,7 @@ int init_all() {
   if (g.isnewpot != 0 && g.isnewpot != 1) { g_err = "isnewpot must be 0 or 1"; return -5; }
   if (g.isnewpot * g.isphion == 1 && (g.iphibcc < 1 || g.iphibcc > 3)) { g_err = "only iphibcc = 1, 2, 3 available"; return -5; }
   g.ExtendedJacPhi = I("ExtendedJacPhi"); g.numvar_ = I("numvar");
+  g.gridmode = 0; g.gbar = nullptr; g.gflag = nullptr;
   // gas energy equation (istgon = 1): the inertial atoms only
   g.idxtg_ = ARR("idxtg", nc);
   g.istgcore = I("istgcore", 0); g.istgpfc = I("istgpfc", 0); g.istgwc = I("istgwc", 0); g.istglb = I("istglb", 0); g.istgrb = I("istgrb", 0); g.isfegxyqflave = I("isfegxyqflave");
@@ -615,13 +629,29 @@ int init_all() {
   d_yl = mem_alloc(neq + 2); d_yldot = mem_alloc(neq); d_y00 = mem_alloc(neq);
   if (!d_yl || !d_yldot || !d_y00) return -10;
   g_allocs.push_back(d_yl); g_allocs.push_back(d_yldot); g_allocs.push_back(d_y00);
-  d_err = alloc_as<int>(4);
+  d_err = alloc_as<int>(4); d_gbar = alloc_as<int>(2);
   d_G = alloc_as<Gen>(1);
   if (!d_err || !d_G) return -10;
   g.nth = 1; g.errc = 0;
   if (!mem_put(d_G, &g, sizeof(Gen))) return -10;
   if (const char* e = getenv("UE_GEN_COLCAP")) COLCAP = std::max(16, atoi(e));
   if (const char* e = getenv("UE_GEN_TPU")) g_tpu = atoi(e) > 32 ? 64 : 32;
+  g_full_grid = -1;
+  if (const char* e = getenv("UE_GEN_FULL_GRID")) g_full_grid = atoi(e);
+#if !defined(UE_GEN_HOST)
+  {  // grid-mode residual: needs cooperative launch, one resident block per SM, and switch sets whose only early exit is the
+     // negative-density test (which is made uniform over the grid); the configuration errors of bouncon leave per thread
+    int dev = 0, coop = 0, occ = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gen_full_grid, 128, sizeof(Gen));
+    bool cfg_ok = true;
+    for (int f = 0; f < G.nisp; ++f) if (G.isnicore[f] != 0 && G.isnicore[f] != 1) cfg_ok = false;
+    for (const char* nm : {"recylb", "recyrb"}) { const V* v = find(nm); if (v) for (double x : *v) if (x < -1.) cfg_ok = false; }
+    g_grid_ok = coop != 0 && occ >= 1 && cfg_ok && d_gbar != nullptr;
+  }
+#endif
   if (const char* e = getenv("UE_GEN_BAND")) g_band = std::max(UE_GEN_BAND_DEFAULT, atoi(e));
 #if defined(UE_GEN_HOST)
   g_poison = getenv("UE_GEN_POISON") != nullptr;
@@ -645,7 +675,18 @@ int run_full(const double* yl_host, double* yldot_host) {
   static cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (!e0) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
   cudaEventRecord(e0);
-  k_gen_full<<<1, nthr, sizeof(Gen)>>>(d_G, d_base, d_yl, d_yldot, d_err);
+  // meshes beyond one block's reach: all cells at once on a co-resident grid (one cell per thread, at most one block per SM)
+  const int gthr = 128;
+  int nblk = std::min(g_sms, (G.NC + gthr - 1) / gthr);
+  if (g_full_grid >= 0) nblk = std::min(g_sms, g_full_grid);  // (env UE_GEN_FULL_GRID: 0 = one block, n = n blocks)
+  if (!g_grid_ok || (g_full_grid < 0 && G.NC <= 1024)) nblk = 0;
+  if (nblk > 1) {
+    if (!ck(cudaMemsetAsync(d_gbar, 0, 2 * sizeof(int)), "grid barrier reset")) return -10;
+    const Gen* a0 = d_G; double* a1 = d_base; const double* a2 = d_yl; double* a3 = d_yldot; int* a4 = d_err; unsigned* a5 = (unsigned*)d_gbar; int* a6 = d_gbar + 1;
+    void* args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6};
+    if (!ck(cudaLaunchCooperativeKernel((const void*)k_gen_full_grid, dim3(nblk), dim3(gthr), args, sizeof(Gen), 0), "k_gen_full_grid launch")) return -10;
+  } else
+    k_gen_full<<<1, nthr, sizeof(Gen)>>>(d_G, d_base, d_yl, d_yldot, d_err);
   cudaEventRecord(e1);
   if (!ck(cudaGetLastError(), "k_gen_full launch") || !ck(cudaDeviceSynchronize(), "k_gen_full")) return -10;
   cudaEventElapsedTime(&g_full_ms, e0, e1);

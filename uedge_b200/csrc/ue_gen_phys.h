@@ -74,9 +74,16 @@ HD int iabs(int a) { return a < 0 ? -a : a; }
 
 struct Gen {
   // ---- cooperative-thread identity of this context -------------------------------------------------------------------
-  int nth;  // threads of the context: 1 (host), 32 (a warp) or the block size
+  int nth;  // threads of the context: 1 (host), 32 (a warp), the block size, or - grid mode - all threads of a co-resident grid
+  // Grid mode (full-domain residual on large meshes): the context is the whole grid of a cooperative launch.  Every block holds its
+  // own copy of this struct in shared memory, all working on the same planes; the barrier between two loop nests is a grid barrier
+  // (one atomic ticket per block on gbar, a spin on its acquire load, fences on both sides: what cooperative_groups' grid sync does).
+  int gridmode;
+  unsigned* gbar;  // monotonic ticket counter (zeroed before the launch)
+  int* gflag;      // error flags raised by any thread, read by all after a barrier (uniform returns)
   HD int TID() const {
 #if defined(__CUDA_ARCH__)
+    if (gridmode) return (int)(blockIdx.x * blockDim.x + threadIdx.x);
     return nth > 32 ? (int)threadIdx.x : (int)(threadIdx.x & 31);
 #else
     return 0;
@@ -84,8 +91,32 @@ struct Gen {
   }
   HD void sync() const {
 #if defined(__CUDA_ARCH__)
-    if (nth > 32) __syncthreads(); else __syncwarp();
+    if (gridmode) {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned nb = gridDim.x, ticket = atomicAdd(gbar, 1u);
+        const unsigned target = (ticket / nb + 1u) * nb;
+        unsigned seen;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(gbar) : "memory"); } while ((int)(seen - target) < 0);
+        __threadfence();
+      }
+      __syncthreads();
+    } else if (nth > 32) __syncthreads(); else __syncwarp();
 #endif
+  }
+  // a thread-local error seen inside a nest becomes the same answer for every thread of the context (grid mode: no thread may leave
+  // the evaluation on its own; the other modes keep the plain test)
+  HD int any_flag(int mine, int bit) const {
+#if defined(__CUDA_ARCH__)
+    if (gridmode) {
+      if (mine) atomicOr(gflag, bit);
+      sync();
+      return (*(volatile int*)gflag) & bit;
+    }
+#endif
+    (void)bit;
+    return mine;
   }
 // ---- dimensions and switches ---------------------------------------------------------------------------------------
 int nx, ny, NXS, NC, nisp, nusp, ngsp, nhsp, nfsp, iigsp;  // iigsp: 0-based species index of the inertial atoms (or -1)
@@ -294,6 +325,15 @@ HD XR xrange(int is, int ie, int jinc, int jstart) {
   return r;
 }
 
+// element q of the sequence FORXS walks (regular elements, then the extra one); false beyond its end.  XRQ opens the body of a
+// FOR2 nest over (row, q): the rows' sequences are walked by different threads, q < xw bounds every row's length
+HD bool xr_at(const XR& r, int q, int& ix) const {
+  if (q < r.n) { ix = r.first + q * r.inc; return true; }
+  if (q == r.n && r.extra >= 0) { ix = r.extra; return true; }
+  return false;
+}
+#define XRQ(ix, xs, q) int ix = 0; if (!xr_at(xs, q, ix)) continue;
+
 // 5-point stencil of the non-orthogonal mesh at the y-face above cell (ix,iy), side k (convert.m:422-482)
 struct St5 { int c[5]; double f[5]; };
 HD St5 stx(int ix, int iy, int k) {
@@ -384,8 +424,8 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
         iv = IDXPHI(ix, iy);
         if (iv >= 0) A(phi, ix, iy) = yl[iv] * temp0;
       }
-    if (inegni) { errc = 1; return -3; }
-    if (inegng) { errc = 2; return -3; }
+    if (any_flag(inegni, 1)) { errc = 1; return -3; }
+    if (any_flag(inegng, 2)) { errc = 2; return -3; }
     for (int f = 0; f < nusp; ++f)
       FOR2(iy, js, je, ix, is, ie)
           if (IDXU(f, ix, iy) >= 0) {
@@ -423,17 +463,18 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
         if (istgcon[0] > -1.e-20) A(tg, ix, iy) = (1 - istgcon[0]) * rtg2ti[0] * A(ti, ix, iy) + istgcon[0] * tgas[0] * ev;
         A(pg, ix, iy) = A(ng, ix, iy) * A(tg, ix, iy);
       }
-    FOR1(iy, js, je) { XR xs = xrange(is, ie, iy, iy); FORXS(ix, xs) A(gprx, ix, iy) = 0.0; }
+    const int xw = (is == ie) ? 3 : ie - is + 3;  // upper bound of the length of a row's x-sequence (two neighbours + the extra one, or the whole row)
+    FOR2(iy, js, je, q_, 0, xw - 1) { XR xs = xrange(is, ie, iy, iy); XRQ(ix, xs, q_) A(gprx, ix, iy) = 0.0; }
     const int jlo = mx(js - 1, 0), jhi = mn(ny, je);
-    FOR1(iy, jlo, jhi) {
+    FOR2(iy, jlo, jhi, q_, 0, xw - 1) {
       XR xs = xrange(is, ie, js, js);
       xs.extra = IXP1(ie, iy);
-      FORXS(ix, xs) { A(ney0, ix, iy) = 0.; A(ney1, ix, iy) = 0.; A(nity0, ix, iy) = 0.; A(nity1, ix, iy) = 0.; A(gpry, ix, iy) = 0.; }
+      XRQ(ix, xs, q_) { A(ney0, ix, iy) = 0.; A(ney1, ix, iy) = 0.; A(nity0, ix, iy) = 0.; A(nity1, ix, iy) = 0.; A(gpry, ix, iy) = 0.; }
     }
     for (int f = 0; f < nisp; ++f)
-      FOR1(iy, js, je) {
+      FOR2(iy, js, je, q_, 0, xw - 1) {
         XR xs = xrange(is, ie, iy, iy);
-        FORXS(ix, xs) {
+        XRQ(ix, xs, q_) {
           int ix1 = IXP1(ix, iy);
           A(gpix[f], ix, iy) = (A(pri[f], ix1, iy) - A(pri[f], ix, iy)) * A(gxf, ix, iy);
           if (zi[f] != 0.) A(gprx, ix, iy) = A(gprx, ix, iy) + A(gpix[f], ix, iy);
@@ -453,32 +494,32 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
       if (zi[f] != 0.) A(gpry, ix, iy) = A(gpry, ix, iy) + A(gpiy[f], ix, iy);
     };
     for (int f = 0; f < nisp; ++f)
-      FOR1(iy, jlo, jhi) { XR xs = xrange(is, ie, js, js); xs.extra = IXP1(ie, iy); FORXS(ix, xs) yface_ion(f, ix, iy); }
-    FOR1(iy, jlo, jhi) {  // convert.m:669-700
+      FOR2(iy, jlo, jhi, q_, 0, xw - 1) { XR xs = xrange(is, ie, js, js); xs.extra = IXP1(ie, iy); XRQ(ix, xs, q_) yface_ion(f, ix, iy); }
+    FOR2(iy, jlo, jhi, q_, 0, xw - 1) {  // convert.m:669-700
       XR xs = xrange(is, ie, js, js); xs.extra = IXP1(ie, iy);
-      FORXS(ix, xs) {
+      XRQ(ix, xs, q_) {
         const St5 s0 = stx(ix, iy, 0), s1 = stx(ix, iy, 1);
         A(tey0, ix, iy) = st_lin(s0, te); A(tey1, ix, iy) = st_lin(s1, te);
         A(tiy0, ix, iy) = st_lin(s0, ti); A(tiy1, ix, iy) = st_lin(s1, ti);
         A(phiy0, ix, iy) = st_lin(s0, phi); A(phiy1, ix, iy) = st_lin(s1, phi);
       }
     }
-    FOR1(iy, jlo, jhi) {  // convert.m:703-717
+    FOR2(iy, jlo, jhi, q_, 0, xw - 1) {  // convert.m:703-717
       XR xs = xrange(is, ie, js, js); xs.extra = IXP1(ie, iy);
-      FORXS(ix, xs) {
+      XRQ(ix, xs, q_) {
         const St5 s0 = stx(ix, iy, 0), s1 = stx(ix, iy, 1);
         A(ngy0, ix, iy) = st_log(s0, ng); A(ngy1, ix, iy) = st_log(s1, ng);
         A(tgy0, ix, iy) = st_lin(s0, tg); A(tgy1, ix, iy) = st_lin(s1, tg);
       }
     }
     if (ineudif == 2)
-      FOR1(iy, jlo, jhi) {
+      FOR2(iy, jlo, jhi, q_, 0, xw - 1) {
         XR xs = xrange(is, ie, js, js); xs.extra = IXP1(ie, iy);
-        FORXS(ix, xs) { A(pgy0, ix, iy) = st_log(stx(ix, iy, 0), pg); A(pgy1, ix, iy) = st_log(stx(ix, iy, 1), pg); }
+        XRQ(ix, xs, q_) { A(pgy0, ix, iy) = st_log(stx(ix, iy, 0), pg); A(pgy1, ix, iy) = st_log(stx(ix, iy, 1), pg); }
       }
-    FOR1(iy, js, je) {  // convert.m:736-765
+    FOR2(iy, js, je, q_, 0, xw - 1) {  // convert.m:736-765
       XR xs = xrange(is, ie, iy, iy);
-      FORXS(ix, xs) {
+      XRQ(ix, xs, q_) {
         int ix1 = IXP1(ix, iy);
         A(gpex, ix, iy) = (A(pre, ix1, iy) - A(pre, ix, iy)) * A(gxf, ix, iy);
         A(gtex, ix, iy) = (A(te, ix1, iy) - A(te, ix, iy)) * A(gxf, ix, iy);
@@ -486,11 +527,11 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
         A(gprx, ix, iy) = A(gprx, ix, iy) + A(gpex, ix, iy);
         if (isphion + isphiofft == 1) A(ex, ix, iy) = (A(phi, ix, iy) - A(phi, ix1, iy)) * A(gxf, ix, iy);
       }
-      if (iysptrx < ny) { A(ex, ixlb, iy) = A(ex, ixlb + 1, iy); A(ex, ixrb, iy) = A(ex, ixrb - 1, iy); }
     }
-    FOR1(iy, jlo, jhi) {  // convert.m:768-786 (eymask1d = 1)
+    if (iysptrx < ny) FOR1(iy, js, je) { A(ex, ixlb, iy) = A(ex, ixlb + 1, iy); A(ex, ixrb, iy) = A(ex, ixrb - 1, iy); }
+    FOR2(iy, jlo, jhi, q_, 0, xw - 1) {  // convert.m:768-786 (eymask1d = 1)
       XR xs = xrange(is, ie, js, js); xs.extra = IXP1(ie, iy);
-      FORXS(ix, xs) {
+      XRQ(ix, xs, q_) {
         A(gpey, ix, iy) = (A(ney1, ix, iy) * A(tey1, ix, iy) - A(ney0, ix, iy) * A(tey0, ix, iy)) / A(dynog, ix, iy);
         A(gtey, ix, iy) = (A(tey1, ix, iy) - A(tey0, ix, iy)) / A(dynog, ix, iy);
         A(gtiy, ix, iy) = (A(tiy1, ix, iy) - A(tiy0, ix, iy)) / A(dynog, ix, iy);
@@ -499,9 +540,9 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
       }
     }
     // vertex values (convert.m:791-868)
-    FOR1(iy, jlo, jhi) {
+    FOR2(iy, jlo, jhi, q_, 0, xw - 1) {
       XR xs = xrange(is, ie, iy, iy);
-      FORXS(ix, xs) {
+      XRQ(ix, xs, q_) {
         int ix1 = IXP1(ix, iy), ix2 = IXP1(ix, iy + 1);
         A(phiv, ix, iy) = 0.25 * (A(phi, ix, iy) + A(phi, ix1, iy) + A(phi, ix, iy + 1) + A(phi, ix2, iy + 1));
         A(tiv, ix, iy) = 0.25 * (A(ti, ix, iy) + A(ti, ix1, iy) + A(ti, ix, iy + 1) + A(ti, ix2, iy + 1));
@@ -511,9 +552,9 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
       }
     }
     for (int f = 0; f < nisp; ++f)
-      FOR1(iy, jlo, jhi) {
+      FOR2(iy, jlo, jhi, q_, 0, xw - 1) {
         XR xs = xrange(is, ie, iy, iy);
-        FORXS(ix, xs) {
+        XRQ(ix, xs, q_) {
           int ix1 = IXP1(ix, iy), ix2 = IXP1(ix, iy + 1);
           A(priv[f], ix, iy) = 0.25 * (A(pri[f], ix, iy) + A(pri[f], ix1, iy) + A(pri[f], ix, iy + 1) + A(pri[f], ix2, iy + 1));
           if (zi[f] != 0.) A(prtv, ix, iy) = A(prtv, ix, iy) + A(priv[f], ix, iy);
@@ -585,8 +626,7 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
   HD void neudif(const Win& w) {
     const int methgx = methg % 10, methgy = methg / 10;
     const double mg = mg_[0];
-    FOR1(iy, w.j4, w.j8) {
-      for (int ix = w.i1; ix <= w.i5; ++ix) {
+    FOR2(iy, w.j4, w.j8, ix, w.i1, w.i5) {
         const int ix2 = IXP1(ix, iy);
         double t0 = mx(A(tg, ix, iy), temin * ev), t1 = mx(A(tg, ix2, iy), temin * ev);
         double vtn = sqrt(t0 / mg), vtnp = sqrt(t1 / mg);
@@ -607,8 +647,7 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
         A(floxg, ix, iy) = qtgf / ue_pow(1 + ue_pow(qr, flgamg), 1 / flgamg);
         A(floxg, ix, iy) = A(floxg, ix, iy) + cngflox[0] * A(sx, ix, iy) * A(uu[0], ix, iy);
       }
-      A(conxg, nx + 1, iy) = 0;
-    }
+    FOR1(iy, w.j4, w.j8) { A(conxg, nx + 1, iy) = 0; }
     FOR2(iy, w.j1, w.j5, ix, w.i4, w.i8) {
         double t0 = mx(A(tg, ix, iy), temin * ev), t1 = mx(A(tg, ix, iy + 1), temin * ev);
         double vtn = sqrt(t0 / mg), vtnp = sqrt(t1 / mg);
@@ -644,8 +683,7 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
   HD void neudifpg(const Win& w) {
     const int methgx = methg % 10, methgy = methg / 10;
     const double mg = mg_[0], ngb = ngbackg_[0];
-    FOR1(iy, w.j4, w.j8) {
-      for (int ix = w.i1; ix <= w.i5; ++ix) {
+    FOR2(iy, w.j4, w.j8, ix, w.i1, w.i5) {
         const int ix2 = IXP1(ix, iy);
         double ngxface = 0.5 * (A(ng, ix, iy) + A(ng, ix2, iy));
         double t0 = mx(A(tg, ix, iy), temin * ev), t1 = mx(A(tg, ix2, iy), temin * ev);
@@ -676,8 +714,7 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
         A(floxg, ix, iy) = (qtgf / tgf) / ue_pow(1 + ue_pow(qr, flgamg), 1 / flgamg);
         A(floxg, ix, iy) = A(floxg, ix, iy) + cngflox[0] * A(sx, ix, iy) * A(uu[0], ix, iy) / tgf;
       }
-      A(conxg, nx + 1, iy) = 0;
-    }
+    FOR1(iy, w.j4, w.j8) { A(conxg, nx + 1, iy) = 0; }
     FOR2(iy, w.j1, w.j5, ix, w.i4, w.i8) {
         double ngyface = 0.5 * (A(ng, ix, iy) + A(ng, ix, iy + 1));
         double t0 = mx(A(tg, ix, iy), tgmin * ev), t1 = mx(A(tg, ix, iy + 1), tgmin * ev);
@@ -745,8 +782,7 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
         }
     }
     // neutral flow velocities (oderhs.m:6512-6554)
-    FOR1(iy, w.j1, w.j5) {
-      for (int ix = w.i1; ix <= w.i5; ++ix) {
+    FOR2(iy, w.j1, w.j5, ix, w.i1, w.i5) {
         const int ix1 = IXP1(ix, iy);
         if (1. - A(rrv, ix, iy) > 1.e-4 || isupgon == 0) {
           A(uug, ix, iy) = A(fngx, ix, iy) / (0.5 * (A(ng, ix, iy) + A(ng, ix1, iy)) * A(sx, ix, iy));
@@ -755,8 +791,7 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
         A(vyg, ix, iy) = A(fngy, ix, iy) / (0.5 * (A(ng, ix, iy) + A(ng, ix, iy + 1)) * A(sy, ix, iy));
         if (isupgon == 1) A(vy[iigsp], ix, iy) = A(vyg, ix, iy);
       }
-      if (iy <= iysptrx2 && isfixlb == 2) A(uug, ixpt2, iy) = 0;
-    }
+    FOR1(iy, w.j1, w.j5) { if (iy <= iysptrx2 && isfixlb == 2) A(uug, ixpt2, iy) = 0; }
     if (isupgon == 1)
       FOR2(iy, w.j4, w.j6, ix, w.i1, w.i6) {
           A(uu[iigsp], ix, iy) = A(uug, ix, iy);
@@ -785,16 +820,12 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
           A(segc, ix, iy) = A(segc, ix, iy) + cvgpg * t2 * A(vol, ix, iy);
         }
     FOR2(iy, j1, j6, ix, i1, i6) { A(floxge, ix, iy) = 0.0; A(floyge, ix, iy) = 0.0; A(conxge, ix, iy) = 0.0; A(conyge, ix, iy) = 0.0; }
-    FOR1(iy, j4, j8) {  // conduction (oderhs.m:7605-7636); hcxg is flux-limited already
-      for (int ix = i1; ix <= i5; ++ix) A(conxge, ix, iy) = A(sx, ix, iy) * A(hcxg, ix, iy) * A(gxf, ix, iy);
-      A(conxge, nx + 1, iy) = 0;
-    }
+    FOR2(iy, j4, j8, ix, i1, i5) A(conxge, ix, iy) = A(sx, ix, iy) * A(hcxg, ix, iy) * A(gxf, ix, iy);  // conduction (oderhs.m:7605-7636); hcxg is flux-limited already
+    FOR1(iy, j4, j8) { A(conxge, nx + 1, iy) = 0; }
     FOR2(iy, j1, j5, ix, i4, i8) A(conyge, ix, iy) = A(sy, ix, iy) * A(hcyg, ix, iy) / A(dynog, ix, iy);
     FOR1(ix, i1, i6) A(conyge, ix, ny + 1) = 0.0;
-    FOR1(iy, j4, j8) {  // convection (oderhs.m:7643-7705)
-      for (int ix = i1; ix <= i5; ++ix) A(floxge, ix, iy) = cfcvtg * 2.5 * A(fngx, ix, iy);
-      A(floxge, nx + 1, iy) = 0.;
-    }
+    FOR2(iy, j4, j8, ix, i1, i5) A(floxge, ix, iy) = cfcvtg * 2.5 * A(fngx, ix, iy);  // convection (oderhs.m:7643-7705)
+    FOR1(iy, j4, j8) { A(floxge, nx + 1, iy) = 0.; }
     FOR1(iy, j4, j8) {  // no inward power from the plates
       if (A(fngx, ixlb, iy) > 0.) A(floxge, ixlb, iy) = A(floxge, ixlb, iy) - (1. - cfloxiplt) * cfcvti * 2.5 * A(fngx, ixlb, iy);
       if (A(fngx, ixrb, iy) < 0.) A(floxge, ixrb, iy) = A(floxge, ixrb, iy) - (1. - cfloxiplt) * cfcvti * 2.5 * A(fngx, ixrb, iy);
@@ -938,25 +969,23 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
                           isphiofft * ((A(phi, ix1, iy) - A(phi, ix2, iy)) * A(gxf, ix1, iy));
         }
     // upi, uup (oderhs.m:1577-1643): every species with a momentum equation takes its own up
-    FOR1(iy, w.iys1, w.iyf6) {
-      if (xc > 0) {
+    if (xc > 0)
+      FOR1(iy, w.iys1, w.iyf6) {
         int ix1 = IXM1(xc, iy);
         for (int f = 0; f < nfsp; ++f) { if (f < nusp) A(upi[f], ix1, iy) = A(up[f], ix1, iy); A(uup[f], ix1, iy) = A(rrv, ix1, iy) * A(upi[f], ix1, iy); }
       }
-      for (int ix = w.ixs1; ix <= mn(w.ixf6, nx); ++ix)
+    FOR2(iy, w.iys1, w.iyf6, ix, w.ixs1, mn(w.ixf6, nx))
         for (int f = 0; f < nfsp; ++f) { if (f < nusp) A(upi[f], ix, iy) = A(up[f], ix, iy); A(uup[f], ix, iy) = A(rrv, ix, iy) * A(upi[f], ix, iy); }
-    }
     // poloidal velocities uu (oderhs.m:1648-1682)
-    for (int f = 0; f < nfsp; ++f)
-      FOR1(iy, j1, j6) {
-        auto uuf = [&](int ix, int ixe) {  // face ix, its eastern cell ixe
-          return A(uup[f], ix, iy) + 0.5 * (A(rbfbt, ixe, iy) + A(rbfbt, ix, iy)) * A(v2[f], ix, iy) - A(vytan[f], ix, iy) -
-                 difax[f] * 0.5 * (sq(0.5 * (A(ni[f], ix, iy) / A(ni[f], ixe, iy) + A(ni[f], ixe, iy) / A(ni[f], ix, iy)) - 1)) * (A(ni[f], ixe, iy) - A(ni[f], ix, iy)) * A(gxf, ix, iy) /
-                     (A(ni[f], ixe, iy) + A(ni[f], ix, iy));
-        };
-        if (i1 > 0) { int ix1 = IXM1(i1, iy); A(uu[f], ix1, iy) = uuf(ix1, i1); }
-        for (int ix = i1; ix <= i6; ++ix) A(uu[f], ix, iy) = uuf(ix, IXP1(ix, iy));
-      }
+    for (int f = 0; f < nfsp; ++f) {
+      auto uuf = [&](int ix, int ixe, int iy) {  // face ix, its eastern cell ixe
+        return A(uup[f], ix, iy) + 0.5 * (A(rbfbt, ixe, iy) + A(rbfbt, ix, iy)) * A(v2[f], ix, iy) - A(vytan[f], ix, iy) -
+               difax[f] * 0.5 * (sq(0.5 * (A(ni[f], ix, iy) / A(ni[f], ixe, iy) + A(ni[f], ixe, iy) / A(ni[f], ix, iy)) - 1)) * (A(ni[f], ixe, iy) - A(ni[f], ix, iy)) * A(gxf, ix, iy) /
+                   (A(ni[f], ixe, iy) + A(ni[f], ix, iy));
+      };
+      if (i1 > 0) FOR1(iy, j1, j6) { int ix1 = IXM1(i1, iy); A(uu[f], ix1, iy) = uuf(ix1, i1, iy); }
+      FOR2(iy, j1, j6, ix, i1, i6) A(uu[f], ix, iy) = uuf(ix, IXP1(ix, iy), iy);
+    }
     // electron velocities (oderhs.m:1729-1808)
     FOR2(iy, j1, j6, ix, i1, i6) { A(vex, ix, iy) = 0.; A(vey, ix, iy) = 0.; A(upe, ix, iy) = 0.; }
     for (int f = 0; f < nfsp; ++f)
@@ -1095,9 +1124,8 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
     // viscosities (oderhs.m:2624-2799)
     for (int f = 0; f < nfsp; ++f) {
       if (isupgon == 1 && zi[f] == 0) {  // inertial atoms
-        FOR1(iy, j1, j6) {
-          const int iyp1 = mn(iy + 1, ny + 1);
-          for (int ix = i1; ix <= i6; ++ix) {
+        FOR2(iy, j1, j6, ix, i1, i6) {
+            const int iyp1 = mn(iy + 1, ny + 1);
             const int ix1 = IXM1(ix, iy);
             double vtn = sqrt(mx(A(tg, ix, iy), tgmin * ev) / mi[f]);
             double qfl = flalfvgxa[ix] * A(nm[f], ix, iy) * vtn * vtn;
@@ -1124,7 +1152,6 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
             qsh = csh * (A(up[f], ix, iy) - A(up[f], ix, iyp1)) * A(gyf, ix, iy);
             A(visy[f], ix, iy) = cfvisyn * csh / ue_pow(1 + ue_pow(fabs(qsh / (qfl + cutlo)), flgamvg), 1. / flgamvg) + 0. * travis[f] * nmxface;
           }
-        }
       }
       if (zi[f] > 1.e-20) {
         FOR2(iy, j1, j6, ix, i1, i6) A(this->w, ix, iy) = 0.0;
@@ -1247,9 +1274,8 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
         }
       }
     if (isupgon == 1)  // oderhs.m:3019-3063
-      FOR1(iy, j1, j6) {
-        const int iy1 = mn(iy, ny);
-        for (int ix = i1; ix <= i6; ++ix) {
+      FOR2(iy, j1, j6, ix, i1, i6) {
+          const int iy1 = mn(iy, ny);
           const int ix1 = IXP1(ix, iy), g = iigsp;
           double tgavex = mx(0.5 * (A(tg, ix, iy) + A(tg, ix1, iy)), temin * ev);
           double tgavey = mx(0.5 * (A(tgy0, ix, iy) + A(tgy1, ix, iy)), temin * ev);
@@ -1270,7 +1296,6 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
           A(hcyn, ix, iy) = cshy / ue_pow(1 + ue_pow(fabs(qshy / qfly), flgamtg), 1. / flgamtg);
           A(hcyi, ix, iy) = A(hcyi, ix, iy) + cftiexclg * cfneut * cfneutsor_ei * A(hcyn, ix, iy);
         }
-      }
     // equipartition (oderhs.m:3074-3102)
     FOR2(iy, j1, j6, ix, i1, i6) A(w3, ix, iy) = 0.0;
     for (int f = 0; f < nisp; ++f) {
@@ -1334,9 +1359,8 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
     }
     for (int f = 0; f < nfsp; ++f) {  // oderhs.m:3321-3339 (4th-order radial diffusion)
       if (fabs(dif4order[f]) > 1.e-50)
-        FOR1(iy, w.j2p, w.j5m) {
-          int iym1 = mx(iy - 1, 0), iyp1 = mn(iy + 1, ny + 1), iyp2 = mn(iy + 2, ny + 1);
-          for (int ix = i4; ix <= i8; ++ix) {
+        FOR2(iy, w.j2p, w.j5m, ix, i4, i8) {
+            int iym1 = mx(iy - 1, 0), iyp1 = mn(iy + 1, ny + 1), iyp2 = mn(iy + 2, ny + 1);
             double dndym1 = (A(ni[f], ix, iy) - A(ni[f], ix, iym1)) * A(gyf, ix, iym1);
             double dndy0 = (A(ni[f], ix, iyp1) - A(ni[f], ix, iy)) * A(gyf, ix, iy);
             double dndyp1 = (A(ni[f], ix, iyp2) - A(ni[f], ix, iyp1)) * A(gyf, ix, iyp1);
@@ -1344,7 +1368,6 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
             double d3ndy3 = (d2ndy2p1 - d2ndy20) * A(gyf, ix, iy);
             A(fniy[f], ix, iy) = A(fniy[f], ix, iy) + dif4order[f] * d3ndy3 * A(sy, ix, iy) / (A(gyf, ix, iy) * A(gyf, ix, iy));
           }
-        }
       FOR1(ix, i4, i8)  // oderhs.m:3344-3353 (vycp(,0) = 0; isfniycbozero = 0)
         fniycbo[f][ix] = (A(ni[f], ix, 0) * A(sy, ix, 0)) * ((1 - cfniybbo) * cfybf * A(vycb[f], ix, 0));
     }
@@ -1364,16 +1387,14 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
     // ---- parallel momentum (oderhs.m:3463-3911), every species with a momentum equation ----
     for (int f = 0; f < nusp; ++f) {
       if (isupon[f] == 0) continue;
-      FOR1(iy, j4, j8) {
-        A(flox, 0, iy) = 0.0; A(conx, 0, iy) = 0.0;
-        for (int ix = i2; ix <= i6; ++ix) {
+      FOR1(iy, j4, j8) { A(flox, 0, iy) = 0.0; A(conx, 0, iy) = 0.0; }
+      FOR2(iy, j4, j8, ix, i2, i6) {
           int ix1 = IXM1(ix, iy);
           double uuv = 0.5 * (A(uu[f], ix1, iy) + A(uu[f], ix, iy));
           A(flox, ix, iy) = cmfx * A(nm[f], ix, iy) * uuv * A(vol, ix, iy) * A(gx, ix, iy);
           if (isgxvon == 0) A(conx, ix, iy) = A(visx[f], ix, iy) * A(vol, ix, iy) * A(gx, ix, iy) * A(gx, ix, iy);
           else A(conx, ix, iy) = A(visx[f], ix, iy) * A(vol, ix, iy) * A(gx, ix, iy) * 2 * A(gxf, ix, iy) * A(gxf, ix1, iy) / (A(gxf, ix, iy) + A(gxf, ix1, iy));
         }
-      }
       FOR2(iy, j1, j5, ix, i4, i8) {  // oderhs.m:3506-3575
           int ix2 = IXP1(ix, iy), ix4 = IXP1(ix, iy + 1);
           if (iy == iysptrx1 && (ix == ixpt1 || ix == ixpt2)) {
@@ -1394,9 +1415,8 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
         }
       fd2tra(w, flox, floy, conx, cony, up[f], fmix[f], fmiy[f], 1, methu);  // oderhs.m:3579
       if (isnonog == 1)  // y-part of the non-orthogonal diffusive momentum flux (oderhs.m:3583-3633)
-        FOR1(iy, j2, j5) {
-          const int iy1 = mx(iy - 1, 0);
-          for (int ix = i2; ix <= i5 + 1; ++ix) {
+        FOR2(iy, j2, j5, ix, i2, i5 + 1) {
+            const int iy1 = mx(iy - 1, 0);
             const int c = ix + NXS * iy;
             const int ix1 = IXM1(ix, iy), ix3 = IXM1(ix, iy1), ix5 = IXM1(ix, iy + 1);
             const double* u = up[f];
@@ -1412,7 +1432,6 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
               A(fmixy[f], ix, iy) = A(fmixy[f], ix, iy) / sqrt(1 + sq(A(fmixy[f], ix, iy) / qfl));
             }
           }
-        }
       FOR2(iy, j2, j5, ix, i2, i5) {  // sources and pressure gradient (oderhs.m:3746-3836)
           const int ix2 = IXP1(ix, iy);
           if (zi[f] != 0) {
@@ -1458,8 +1477,7 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
         feiycbo[ix] = 0.; feeycbo[ix] = 0.; A(w0, ix, iy) = 0.; A(w1, ix, iy) = 0.;
       }
     for (int f = 0; f < nusp; ++f) FOR1(c_, 0, NC - 1) wvh[f][c_] = 0.;
-    FOR1(iy, j4, j8) {
-      for (int ix = i1; ix <= i5; ++ix) {
+    FOR2(iy, j4, j8, ix, i1, i5) {
         int ix2 = IXP1(ix, iy);
         double t0 = mx(A(te, ix, iy), temin * ev), t1 = mx(A(te, ix2, iy), temin * ev);
         double vt0 = sqrt(t0 / me), vt1 = sqrt(t1 / me);
@@ -1486,36 +1504,28 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
           A(floxi, ix, iy) = A(floxi, ix, iy) + (sgn(qr * qr, qsh) / ((1 + qr) * (1 + qr))) * flalfia[ix] * A(sx, ix, iy) * (A(ne, ix, iy) * A(rr, ix, iy) * vt0 + A(ne, ix2, iy) * A(rr, ix2, iy) * vt1) / 2;
         } else A(conxi, ix, iy) = A(sx, ix, iy) * A(hcxi, ix, iy) * A(gxf, ix, iy);
       }
-      A(conxe, nx + 1, iy) = 0; A(conxi, nx + 1, iy) = 0;
-    }
+    FOR1(iy, j4, j8) { A(conxe, nx + 1, iy) = 0; A(conxi, nx + 1, iy) = 0; }
     FOR2(iy, j1, j5, ix, i4, i8) {
         A(conye, ix, iy) = A(sy, ix, iy) * A(hcye, ix, iy) / A(dynog, ix, iy);
         A(conyi, ix, iy) = A(sy, ix, iy) * A(hcyi, ix, iy) / A(dynog, ix, iy);
       }
     FOR1(ix, i1, i6) { A(conye, ix, ny + 1) = 0.0; A(conyi, ix, ny + 1) = 0.0; }
-    FOR1(iy, j4, j8) {  // oderhs.m:4024-4036
-      for (int ix = i1; ix <= i5; ++ix) {
+    FOR2(iy, j4, j8, ix, i1, i5) {  // oderhs.m:4024-4036
         int ix1 = IXP1(ix, iy);
         double ltmax = mn(fabs(A(te, ix, iy) / (A(rrv, ix, iy) * A(gtex, ix, iy) + cutlo)), A(lcone, ix, iy));
         double lmfpe = 2e16 * ((A(te, ix, iy) / ev) * (A(te, ix, iy) / ev)) / A(ne, ix, iy);
         double flxlimf = flalftf * ltmax / (flalftf * ltmax + lmfpe);
         A(floxe, ix, iy) = A(floxe, ix, iy) + cfcvte * 1.25 * (A(ne, ix, iy) + A(ne, ix1, iy)) * A(vex, ix, iy) * A(sx, ix, iy) - cthe * flxlimf * cfjhf * A(fqp, ix, iy) / ev;
       }
-      A(floxe, nx + 1, iy) = 0.0;
-    }
+    FOR1(iy, j4, j8) { A(floxe, nx + 1, iy) = 0.0; }
     for (int f = 0; f < nfsp; ++f) {  // oderhs.m:4038-4072
       if (isupgon == 1 && f == iigsp) {
-        FOR1(iy, j4, j8) {
-          for (int ix = i1; ix <= i5; ++ix) A(floxi, ix, iy) = A(floxi, ix, iy) + cftiexclg * cfcvti * 2.5 * cfneut * cfneutsor_ei * A(fnix[f], ix, iy);
-          if (A(fnix[f], ixlb, iy) > 0.) A(floxi, ixlb, iy) = A(floxi, ixlb, iy) - (1. - cfloxiplt) * cftiexclg * cfcvti * 2.5 * cfneut * cfneutsor_ei * A(fnix[f], ixlb, iy);
-          if (A(fnix[f], ixrb, iy) < 0.) A(floxi, ixrb, iy) = A(floxi, ixrb, iy) - (1. - cfloxiplt) * cftiexclg * cfcvti * 2.5 * cfneut * cfneutsor_ei * A(fnix[f], ixrb, iy);
-          A(floxi, ixrb + 1, iy) = 0.0;
-        }
-      } else
-        FOR1(iy, j4, j8) {
-          for (int ix = i1; ix <= i5; ++ix) A(floxi, ix, iy) = A(floxi, ix, iy) + cfcvti * 2.5 * A(fnix[f], ix, iy);
-          A(floxi, nx + 1, iy) = 0.0;
-        }
+        FOR2(iy, j4, j8, ix, i1, i5) A(floxi, ix, iy) = A(floxi, ix, iy) + cftiexclg * cfcvti * 2.5 * cfneut * cfneutsor_ei * A(fnix[f], ix, iy);
+        FOR1(iy, j4, j8) { if (A(fnix[f], ixlb, iy) > 0.) A(floxi, ixlb, iy) = A(floxi, ixlb, iy) - (1. - cfloxiplt) * cftiexclg * cfcvti * 2.5 * cfneut * cfneutsor_ei * A(fnix[f], ixlb, iy); if (A(fnix[f], ixrb, iy) < 0.) A(floxi, ixrb, iy) = A(floxi, ixrb, iy) - (1. - cfloxiplt) * cftiexclg * cfcvti * 2.5 * cfneut * cfneutsor_ei * A(fnix[f], ixrb, iy); A(floxi, ixrb + 1, iy) = 0.0; }
+      } else {
+        FOR2(iy, j4, j8, ix, i1, i5) A(floxi, ix, iy) = A(floxi, ix, iy) + cfcvti * 2.5 * A(fnix[f], ix, iy);
+        FOR1(iy, j4, j8) { A(floxi, nx + 1, iy) = 0.0; }
+      }
     }
     FOR2(iy, j1, j5, ix, i4, i8) {  // oderhs.m:4078-4092; vyte_use, vyte_cft, cfybf = 0
         A(floye, ix, iy) = A(floye, ix, iy) + (cfloye / 2.) * (A(ney0, ix, iy) + A(ney1, ix, iy)) * A(vey, ix, iy) * A(sy, ix, iy) + (0. + 0.) * 0.5 * A(sy, ix, iy) * (A(ney0, ix, iy) + A(ney1, ix, iy));
@@ -1540,17 +1550,14 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
             if (iy == 0) feiycbo[ix] = feiycbo[ix] + cfloyi * fniycbo[f][ix] * A(ti, ix, 0);
           }
     }
-    FOR1(iy, j4, j8) {  // oderhs.m:4234-4240
-      for (int ix = i1; ix <= i5; ++ix) A(floxi, ix, iy) = A(floxi, ix, iy) + cftiexclg * cfneut * cfneutsor_ei * cngtgx[0] * cfcvti * 2.5 * A(fngx, ix, iy);
-      A(floxi, nx + 1, iy) = 0.0;
-    }
+    FOR2(iy, j4, j8, ix, i1, i5) A(floxi, ix, iy) = A(floxi, ix, iy) + cftiexclg * cfneut * cfneutsor_ei * cngtgx[0] * cfcvti * 2.5 * A(fngx, ix, iy);  // oderhs.m:4234-4240
+    FOR1(iy, j4, j8) { A(floxi, nx + 1, iy) = 0.0; }
     FOR2(iy, j1, j5, ix, i4, i8) A(floyi, ix, iy) = A(floyi, ix, iy) + cftiexclg * cfneut * cfneutsor_ei * cngtgy[0] * 2.5 * A(fngy, ix, iy);
     if (isteon == 1) fd2tra(w, floxe, floye, conxe, conye, te, feex, feey, 0, methe);  // oderhs.m:4256
     if (istion == 1) fd2tra(w, floxi, floyi, conxi, conyi, ti, feix, feiy, 0, methi);  // oderhs.m:4260
     if (fabs(kye4order) > 1.e-50 || fabs(kyi4order) > 1.e-50)  // oderhs.m:4263-4291
-      FOR1(iy, w.j2p, w.j5m) {
-        int iym1 = mx(iy - 1, 0), iyp1 = mn(iy + 1, ny + 1), iyp2 = mn(iy + 2, ny + 1);
-        for (int ix = i4; ix <= i8; ++ix) {
+      FOR2(iy, w.j2p, w.j5m, ix, i4, i8) {
+          int iym1 = mx(iy - 1, 0), iyp1 = mn(iy + 1, ny + 1), iyp2 = mn(iy + 2, ny + 1);
           auto d3 = [&](const double* t) {
             double dm1 = (A(t, ix, iy) - A(t, ix, iym1)) * A(gyf, ix, iym1), d0 = (A(t, ix, iyp1) - A(t, ix, iy)) * A(gyf, ix, iy), dp1 = (A(t, ix, iyp2) - A(t, ix, iyp1)) * A(gyf, ix, iyp1);
             double d20 = (d0 - dm1) * A(gy, ix, iy), d2p1 = (dp1 - d0) * A(gy, ix, iyp1);
@@ -1559,16 +1566,14 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
           A(feey, ix, iy) = A(feey, ix, iy) + kye4order * d3(te) * A(ney1, ix, iy) * A(sy, ix, iy) / (A(gyf, ix, iy) * A(gyf, ix, iy));
           A(feiy, ix, iy) = A(feiy, ix, iy) + kyi4order * d3(ti) * A(niy1[0], ix, iy) * A(sy, ix, iy) / (A(gyf, ix, iy) * A(gyf, ix, iy));
         }
-      }
     FOR2(iy, j2, j5, ix, i2, i5) {  // oderhs.m:4300-4313 (pwrsore/pwrsori/nuvl zero)
         A(resee, ix, iy) = A(seec, ix, iy) + A(seev, ix, iy) * A(te, ix, iy) + 0. + 0. - 0.;
         A(resei, ix, iy) = A(seic, ix, iy) + A(seiv, ix, iy) * A(ti, ix, iy) + 0. + 0. - 0.;
       }
     if (isnonog == 1) {  // y-part of the non-orthogonal diffusive heat fluxes (oderhs.m:4318-4393)
-      FOR1(iy, j1, j6) {
-        if (iy > ny) continue;
-        const int iy1 = mx(iy - 1, 0);
-        for (int ix = i1; ix <= i6; ++ix) {
+      FOR2(iy, j1, j6, ix, i1, i6) {
+          if (iy > ny) continue;
+          const int iy1 = mx(iy - 1, 0);
           const int ix2 = IXP1(ix, iy), ix4 = IXP1(ix, iy1);
           double grdnv = grdnv_y(te, ix, iy, 1) / A(dxnog, ix, iy);
           A(feexy, ix, iy) = ue_exp(0.5 * (ue_log(A(te, ix2, iy)) + ue_log(A(te, ix, iy)))) * (fcdif * kye + 0.) * 0.5 * (A(ne, ix2, iy) + A(ne, ix, iy)) *
@@ -1584,7 +1589,6 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
                        (A(ni[0], ix, iy) + cftiexclg * A(ng, ix, iy) + A(ni[0], ix2, iy) + cftiexclg * A(ng, ix2, iy));
           A(feixy, ix, iy) = A(feixy, ix, iy) / sqrt(1. + sq(A(feixy, ix, iy) / qfl));
         }
-      }
       FOR2(iy, j4, j8, ix, i1, i5) { A(feex, ix, iy) = A(feex, ix, iy) - A(feexy, ix, iy); A(feix, ix, iy) = A(feix, ix, iy) - A(feixy, ix, iy); }
     }
     FOR2(iy, j2, j5, ix, i2, i5) {  // oderhs.m:4439-4478
@@ -1766,9 +1770,8 @@ HD void calc_currents(const Win& w) {
   // inertia current (potencur.m:291-376); fmity as a local pair of planes per species
   for (int f = 0; f < nisp; ++f) {
     if (!(zi[f] > 1.e-10)) continue;
-    FOR1(iy, mx(j1p, 1), mn(j5p, ny)) {
-      const int iyp2 = mn(iy + 2, ny + 1);
-      for (int ix = i1; ix <= i6; ++ix) {
+    FOR2(iy, mx(j1p, 1), mn(j5p, ny), ix, i1, i6) {
+        const int iyp2 = mn(iy + 2, ny + 1);
         auto ut = [&](int jy, int jy1) {  // faces jy (between rows jy and jy1)
           return (4 / sq(A(btot, ix, jy) + A(btot, ix, jy1))) * (A(ey, ix, jy) - 2 * cfgpijr_ * A(gpiy[f], ix, jy) / (qe * zi[f] * (A(niy1[f], ix, jy) + A(niy0[f], ix, jy))));
         };
@@ -1781,7 +1784,6 @@ HD void calc_currents(const Win& w) {
         A(fqymi_[f], ix, iy) = qe * 0.5 * (A(niy0[f], ix, iy) + A(niy1[f], ix, iy)) * (A(vyce[f], ix, iy) + A(vycp[f], ix, iy)) *
                                (-0.5 * ((A(btot, ix, iy + 1) + A(btot, ix, iyp2)) * utp - (A(btot, ix, iy - 1) + A(btot, ix, iy)) * utm)) * 0.5 * A(gyf, ix, iy) * A(sy, ix, iy) / omgci;
       }
-    }
   }
   FOR2(iy, mx(j1p, 1), mn(j5p, ny), ix, i1, i6) {
       A(fqya, ix, iy) = 0.; A(fqym, ix, iy) = 0.; A(fqydt, ix, iy) = 0.;
