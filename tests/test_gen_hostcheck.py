@@ -90,6 +90,16 @@ def test_band_copy_of_the_private_planes_is_sufficient(built, monkeypatch):
     same(Oracle2().bind(c), host(0).bind(c), c, yl)
 
 
+@pytest.mark.parametrize("subset", ["ni-0", "up-0", "te", "phi", "default"])
+def test_window_copy_with_few_unknowns_per_cell(built, monkeypatch, subset):
+    """the private copy of a column holds the band rows x the window columns (+2), whole rows at the core and wall boundaries and at
+    the X-point, and the line arrays; with one unknown per cell the Jacobian band spans the whole 8x4 mesh, so a stale far cell
+    (e.g. the corner cells every wall window sets) would show up as an extra entry - everything else is poisoned with NaN here"""
+    monkeypatch.setenv("UE_GEN_POISON", "1")
+    c, yl, _ = inputex_case(subset)
+    same(Oracle2().bind(c), host(0).bind(c), c, yl)
+
+
 @pytest.mark.parametrize("rev", [0, 1])
 def test_jupyter_drift_case(built, rev):
     """jupyter/case_setup.py: ExB and grad-B drifts, grad-B currents, isnewpot=1 with its two core conditions (one of them the sum of

@@ -84,6 +84,7 @@ float g_comm_ms = 0.f;
 float g_full_ms = 0.f, g_cols_ms = 0.f, g_csr_ms = 0.f;  // CUDA-event times of the last residual / column / CSR kernels
 #define UE_GEN_BAND_DEFAULT 5
 int g_band = UE_GEN_BAND_DEFAULT;  // rows of the private copy on each side of the perturbed cell (env UE_GEN_BAND; large = all rows)
+int g_colpad = 2;  // columns of the private copy on each side of the window i1..i6 (env UE_GEN_COLPAD; negative = whole rows)
 int g_tpu = 32;  // threads per unknown in the Jacobian kernel: 32 (a warp) or 64 (a two-warp block)
 int g_sms = 0, g_full_grid = -1;  // SM count; blocks of the grid-mode residual (-1: by mesh size; env UE_GEN_FULL_GRID)
 bool g_grid_ok = false;           // cooperative launch available and no thread can leave the evaluation on its own (see init)
@@ -156,16 +157,22 @@ HD int eval_full(Gen& g, const double* yl, double* yldot) { return g.pandf1(-1, 
 // one Jacobian column (oderhs.m:8600-8720).  g: private context (planes = private copy of the base set).
 // ylp: private copy of yl (neq+2); wk: private residual (neq); frow/fval: the column's fragment, capacity cap.
 HD int eval_column(Gen& g, const double* base, int npl, int64_t iv, const double* yl, double* ylp, double* wk, const double* yldot00, int64_t ml, int64_t mu,
-                   int cap, int* frow, double* fval, int* cnt, int band) {
+                   int cap, int* frow, double* fval, int* cnt, int band, int colpad) {
   const int64_t neq = g.neq;
   const int tid = g.TID();
   double* priv = g.ne;  // first plane of the slab
   const int xc = (int)g.igyld[iv - 1], yc = (int)g.igyld[neq + iv - 1];
   g.sync();
-  // Private copy of the base planes: only the band of rows the windowed evaluation can touch (ranges j1p-1 .. j6p+2 of
-  // oderhs.m:868-964 around yc, all ix so that the X-point cuts stay connected), the two rows of the X-point vertex average
-  // (convert.m:831-868, evaluated by every window) and the line arrays in full.  Rows outside the band keep whatever an earlier
-  // unknown left there: nothing in the band's result reads them (tests/test_gen_hostcheck.py poisons them with NaN to show it).
+  // Private copy of the base planes: only what the windowed evaluation can touch -
+  //  * the band of rows yc +- band (ranges j1p-1 .. j6p+2 of oderhs.m:868-964), and in them the columns of the window
+  //    i1-2 .. i6+2; windows that reach an X-point cut span all ix in the reference (xccuts, oderhs.m:960-1019) and take whole rows;
+  //  * whole rows 0-2 when the band holds them: the core conditions sum fluxes and currents over the entire core boundary and, with
+  //    isnewpot = 1, set the potential rows at every core column (boundary.m:229-240, 492-502, 987-1122); whole rows ny, ny+1 likewise
+  //    (every window at a wall sets the density rows of the four corner cells, boundary.m:246-262);
+  //  * the two rows of the X-point vertex average (convert.m:831-868, evaluated by every window), whole;
+  //  * the line arrays in full.
+  // Everything else keeps whatever an earlier unknown left there: nothing in the band's result reads it
+  // (tests/test_gen_hostcheck.py poisons it with NaN to show that).
   {
     const int NXS = g.NXS, NC = g.NC, nrow = g.ny + 2;
     const int r0 = mx(0, yc - band), r1 = mn(nrow - 1, yc + band);
@@ -173,23 +180,39 @@ HD int eval_column(Gen& g, const double* base, int npl, int64_t iv, const double
 #if defined(UE_GEN_HOST)
     if (g_poison) for (size_t k = 0; k < (size_t)npl * NC; ++k) priv[k] = (double)NAN;
 #endif
-    const int w = (r1 - r0 + 1) * NXS;
-    {  // one flat loop over (plane, element of the band): independent loads, so that several are in flight per thread
-      const int tot = nfield * w;
-      const size_t o0 = (size_t)r0 * NXS;
+    const auto w = g.make_win(xc, yc);
+    const bool fullx = w.xccuts || colpad < 0 || (w.i1 <= colpad && w.i6 >= g.nx + 1 - colpad);
+    const int cx0 = fullx ? 0 : mx(0, w.i1 - colpad), cx1 = fullx ? NXS - 1 : mn(NXS - 1, w.i6 + colpad);
+    {  // one flat loop over (plane, row of the band, column of the window): independent loads, several in flight per thread
+      const int wc = cx1 - cx0 + 1, rw = (r1 - r0 + 1) * wc;
+      const int tot = nfield * rw;
+      const bool small = tot < (1 << 22);  // (the float quotients are exact below 2^22)
 #pragma unroll 4
       for (int k = tid; k < tot; k += g.nth) {
-        const int p = tot < (1 << 22) ? UE_ROW_(k, w) : k / w;  // (the float quotient is exact below 2^22)
-        const size_t o = (size_t)p * NC + o0 + (size_t)(k - p * w);
+        const int p = small ? UE_ROW_(k, rw) : k / rw;
+        const int q = k - p * rw;
+        const int r = small ? UE_ROW_(q, wc) : q / wc;
+        const size_t o = (size_t)p * NC + (size_t)(r0 + r) * NXS + (size_t)(cx0 + q - r * wc);
         priv[o] = base[o];
       }
     }
-    if (g.iysptrx1 >= 0 && (g.iysptrx1 < r0 || g.iysptrx1 + 1 > r1)) {  // X-point rows jsx, jsx+1 when they lie outside the band
-      const int x0 = mx(0, g.iysptrx1), x1 = mn(nrow - 1, g.iysptrx1 + 1);
-      const int wx = (x1 - x0 + 1) * NXS;
-      for (int p = 0; p < nfield; ++p) {
-        const size_t o = (size_t)p * NC + (size_t)x0 * NXS;
-        for (int k = tid; k < wx; k += g.nth) priv[o + k] = base[o + k];
+    int frows[7], nf = 0;  // rows taken whole
+    if (!fullx) for (int r = r0; r <= mn(2, r1); ++r) frows[nf++] = r;
+    if (!fullx) for (int r = mx(r0, mx(3, nrow - 2)); r <= r1; ++r) frows[nf++] = r;  // outer-wall rows: its corner cells are set by every window at the wall
+    if (g.iysptrx1 >= 0)
+      for (int r = mx(0, g.iysptrx1); r <= mn(nrow - 1, g.iysptrx1 + 1); ++r) {
+        const bool inband = r >= r0 && r <= r1;
+        bool have = inband && fullx;
+        for (int k = 0; k < nf; ++k) have = have || frows[k] == r;
+        if (!have) frows[nf++] = r;
+      }
+    for (int f = 0; f < nf; ++f) {
+      const int tot = nfield * NXS;
+      const size_t o0 = (size_t)frows[f] * NXS;
+      for (int k = tid; k < tot; k += g.nth) {
+        const int p = UE_ROW_(k, NXS);
+        const size_t o = (size_t)p * NC + o0 + (size_t)(k - p * NXS);
+        priv[o] = base[o];
       }
     }
     const int nl = mx(NXS, nrow);
@@ -264,7 +287,7 @@ __global__ void __launch_bounds__(128) k_gen_full_grid(const Gen* gsrc, double* 
 // one warp per unknown of the chunk [iv0, iv0 + ncol): every warp has its own context (shared memory) and its own planes
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_gen_cols(const Gen* gsrc, const double* base, double* priv, int npl, int64_t iv0, const int* ivlist, int ncol, const double* yl, double* ylp, double* wk,
-                           const double* yldot00, int64_t ml, int64_t mu, int cap, int* frow, double* fval, int* cnt, int* err, int tpu, int band) {
+                           const double* yldot00, int64_t ml, int64_t mu, int cap, int* frow, double* fval, int* cnt, int* err, int tpu, int band, int colpad) {
   // a unit = the threads that evaluate one unknown: a warp (4 units per block) or, with tpu > 32, the whole block
   const int unit = tpu > 32 ? 0 : (int)(threadIdx.x >> 5), lane = tpu > 32 ? (int)threadIdx.x : (int)(threadIdx.x & 31);
   Gen* g = (Gen*)g_smem + unit;
@@ -278,7 +301,7 @@ __global__ void __launch_bounds__(128, MINB) k_gen_cols(const Gen* gsrc, const d
   const int64_t iv = ivlist ? (int64_t)ivlist[c] : iv0 + c;  // (multi-GPU: this rank's unknowns are a list of mesh rows)
   const int64_t neq = g->neq;
   const int rc = eval_column(*g, base, npl, iv, yl, ylp + (size_t)c * (neq + 2), wk + (size_t)c * neq, yldot00, ml, mu, cap, frow + (size_t)(iv - 1) * cap,
-                             fval + (size_t)(iv - 1) * cap, cnt + (iv - 1), band);
+                             fval + (size_t)(iv - 1) * cap, cnt + (iv - 1), band, colpad);
   if (tpu > 32) __syncthreads(); else __syncwarp();
   if (rc && lane == 0) { err[0] = rc; err[1] = g->errc; }
   if (lane == 0 && cnt[iv - 1] > cap) err[2] = cnt[iv - 1];
@@ -653,6 +676,8 @@ int init_all() {
   }
 #endif
   if (const char* e = getenv("UE_GEN_BAND")) g_band = std::max(UE_GEN_BAND_DEFAULT, atoi(e));
+  g_colpad = 2;
+  if (const char* e = getenv("UE_GEN_COLPAD")) g_colpad = atoi(e);
 #if defined(UE_GEN_HOST)
   g_poison = getenv("UE_GEN_POISON") != nullptr;
 #endif
@@ -679,7 +704,7 @@ int run_full(const double* yl_host, double* yldot_host) {
   const int gthr = 128;
   int nblk = std::min(g_sms, (G.NC + gthr - 1) / gthr);
   if (g_full_grid >= 0) nblk = std::min(g_sms, g_full_grid);  // (env UE_GEN_FULL_GRID: 0 = one block, n = n blocks)
-  if (!g_grid_ok || (g_full_grid < 0 && G.NC <= 1024)) nblk = 0;
+  if (!g_grid_ok || (g_full_grid < 0 && G.NC <= 640)) nblk = 0;
   if (nblk > 1) {
     if (!ck(cudaMemsetAsync(d_gbar, 0, 2 * sizeof(int)), "grid barrier reset")) return -10;
     const Gen* a0 = d_G; double* a1 = d_base; const double* a2 = d_yl; double* a3 = d_yldot; int* a4 = d_err; unsigned* a5 = (unsigned*)d_gbar; int* a6 = d_gbar + 1;
@@ -794,7 +819,7 @@ int UE_PREFIX(jac_calc)(int64_t n, double t, const double* yl, const double* yld
   for (int64_t iv = g_ivmin; iv <= g_ivmax; ++iv) {
     Gen me = G; me.nth = 1; me.errc = 0;
     me.assign_planes(d_priv);
-    const int rc = eval_column(me, d_base, NPL, iv, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow + (size_t)(iv - 1) * cap, d_fval + (size_t)(iv - 1) * cap, d_cnt + (iv - 1), g_band);
+    const int rc = eval_column(me, d_base, NPL, iv, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow + (size_t)(iv - 1) * cap, d_fval + (size_t)(iv - 1) * cap, d_cnt + (iv - 1), g_band, g_colpad);
     if (rc) return report(rc, me.errc);
     if (d_cnt[iv - 1] > cap) { g_err = "column fragment capacity exceeded: set UE_GEN_COLCAP"; return -2; }
   }
@@ -833,11 +858,11 @@ int UE_PREFIX(jac_calc)(int64_t n, double t, const double* yl, const double* yld
     // few unknowns: every warp is alone on its scheduler, registers are free (158, no spills); many unknowns: 4 blocks per SM
     // (128 registers, a few spills) so that more chains overlap
     if (g_tpu > 32)
-      k_gen_cols<1><<<ncol, g_tpu, sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, iv0, ivl, ncol, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, g_tpu, g_band);
+      k_gen_cols<1><<<ncol, g_tpu, sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, iv0, ivl, ncol, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, g_tpu, g_band, g_colpad);
     else if (ncol <= 4096)
-      k_gen_cols<1><<<(ncol + WPB - 1) / WPB, 32 * WPB, WPB * sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, iv0, ivl, ncol, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, 32, g_band);
+      k_gen_cols<1><<<(ncol + WPB - 1) / WPB, 32 * WPB, WPB * sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, iv0, ivl, ncol, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, 32, g_band, g_colpad);
     else
-      k_gen_cols<4><<<(ncol + WPB - 1) / WPB, 32 * WPB, WPB * sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, iv0, ivl, ncol, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, 32, g_band);
+      k_gen_cols<4><<<(ncol + WPB - 1) / WPB, 32 * WPB, WPB * sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, iv0, ivl, ncol, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, 32, g_band, g_colpad);
     if (!ck(cudaGetLastError(), "k_gen_cols launch")) return -10;
   }
   cudaEventRecord(e1);
