@@ -221,8 +221,25 @@ HD int eval_column(Gen& g, const double* base, int npl, int64_t iv, const double
       for (int k = tid; k < nl; k += g.nth) priv[o + k] = base[o + k];
     }
   }
-  for (int64_t k = tid; k < neq + 2; k += g.nth) ylp[k] = yl[k];
-  for (int64_t k = tid; k < neq; k += g.nth) wk[k] = yldot00[k];
+  // private state vector and residual: the unknowns of the band's rows (the windowed evaluation converts the perturbed cell, rescales
+  // and writes inside its window and at the boundary rows of the band) and whatever the differencing range ii1..ii2 reaches; the whole
+  // vectors when the time-step term of pandf1 is active (it runs over every cell) or the window is the whole mesh
+  int64_t ii1 = mx(iv - mu, (int64_t)1), ii2 = mn(iv + ml, neq);
+  if (g.ExtendedJacPhi > 0 && g.isphion * g.isnewpot == 1 && iv % g.numvar_ == 0) {  // wider band for a potential perturbation (oderhs.m:8645-8651)
+    ii1 = mx(iv - 4 * g.numvar_ * g.nx, (int64_t)1); ii2 = mn(iv + 4 * g.numvar_ * g.nx, neq);
+  }
+  {
+    const int nrow = g.ny + 2;
+    const int r0 = mx(0, yc - band), r1 = mn(nrow - 1, yc + band);
+    int64_t lo = 0, hi = neq;
+    const bool whole = (g.dtreal < 1.e15 && yl[neq] < 0) || g.yinc >= 6 || colpad < 0;
+    if (!whole) { lo = mn((int64_t)g.rowiv_[r0], ii1 - 1); hi = mx((int64_t)g.rowiv_[r1 + 1], ii2); }
+#if defined(UE_GEN_HOST)
+    if (g_poison) for (int64_t k = 0; k < neq; ++k) { ylp[k] = (double)NAN; wk[k] = (double)NAN; }
+#endif
+    for (int64_t k = lo + tid; k < hi; k += g.nth) { ylp[k] = yl[k]; wk[k] = yldot00[k]; }
+    if (tid == 0) { ylp[neq] = yl[neq]; ylp[neq + 1] = yl[neq + 1]; }
+  }
   g.sync();
   const double yold = yl[iv - 1];
   const double dyl = g.delpert * (fabs(yold) + g.dylconst / g.suscal[iv - 1]);
@@ -231,10 +248,6 @@ HD int eval_column(Gen& g, const double* base, int npl, int64_t iv, const double
   const int rc = g.pandf1(xc, yc, ylp, wk);
   g.sync();
   if (rc) { if (tid == 0) *cnt = 0; return rc; }
-  int64_t ii1 = mx(iv - mu, (int64_t)1), ii2 = mn(iv + ml, neq);
-  if (g.ExtendedJacPhi > 0 && g.isphion * g.isnewpot == 1 && iv % g.numvar_ == 0) {  // wider band for a potential perturbation (oderhs.m:8645-8651)
-    ii1 = mx(iv - 4 * g.numvar_ * g.nx, (int64_t)1); ii2 = mn(iv + 4 * g.numvar_ * g.nx, neq);
-  }
   const bool isphi = g.IDXPHI(xc, yc) == iv - 1;
   // difference, diagonal terms, clip; NaN marks an element that is not kept (a NaN element fails the clip test as well)
   for (int64_t ii = ii1 + tid; ii <= ii2; ii += g.nth) {
@@ -570,6 +583,22 @@ int init_all() {
   g.lyup_ = ARR("lyup", 2);
   g.isnwconiix = ARR("isnwconiix", 2 * nxs); g.isnwconoix = ARR("isnwconoix", 2 * nxs); g.isupwiix = ARR("isupwiix", 2 * nxs); g.isupwoix = ARR("isupwoix", 2 * nxs);
   g.iseqalgd = ARR("iseqalg", (size_t)g.neq); g.igyld = ARR("igyl", (size_t)(2 * g.neq));
+  {  // first unknown (0-based) of every mesh row; the unknowns are numbered row by row (convert.m:25-155)
+    const V* ig = find("igyl");
+    if (!ig || ig->size() < (size_t)(2 * g.neq)) { g_err = "missing input igyl"; return -1; }
+    std::vector<int> rowiv(g.ny + 3, (int)g.neq);
+    int prev = -1;
+    for (int64_t k = 0; k < g.neq; ++k) {
+      const int r = (int)(*ig)[(size_t)g.neq + k];
+      if (r < prev || r < 0 || r > g.ny + 1) { g_err = "igyl: the unknowns are not numbered row by row"; return -1; }
+      prev = r;
+      if (rowiv[r] == (int)g.neq) rowiv[r] = (int)k;
+    }
+    for (int r = g.ny + 1; r >= 0; --r) if (rowiv[r] == (int)g.neq) rowiv[r] = rowiv[r + 1];
+    int* d = alloc_as<int>(rowiv.size());
+    if (!d || !mem_put(d, rowiv.data(), rowiv.size() * sizeof(int))) return -10;
+    g.rowiv_ = d;
+  }
   for (int f = 0; f < 2; ++f) {
     const double *pn = ARR("idxn", 2 * nc), *pu = ARR("idxu", 2 * nc);
     g.idxn_[f] = pn ? pn + (size_t)f * nc : nullptr; g.idxu_[f] = pu ? pu + (size_t)f * nc : nullptr;
