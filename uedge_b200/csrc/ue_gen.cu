@@ -86,9 +86,11 @@ float g_full_ms = 0.f, g_cols_ms = 0.f, g_csr_ms = 0.f;  // CUDA-event times of 
 int g_band = UE_GEN_BAND_DEFAULT;  // rows of the private copy on each side of the perturbed cell (env UE_GEN_BAND; large = all rows)
 int g_colpad = 2;  // columns of the private copy on each side of the window i1..i6 (env UE_GEN_COLPAD; negative = whole rows)
 int g_tpu = 32;  // threads per unknown in the Jacobian kernel: 32 (a warp) or 64 (a two-warp block)
+int g_occ1 = 0, g_occ4 = 0;  // resident blocks per SM of the two builds of the column kernel (0: not asked yet)
 int g_sms = 0, g_full_grid = -1;  // SM count; blocks of the grid-mode residual (-1: by mesh size; env UE_GEN_FULL_GRID)
 bool g_grid_ok = false;           // cooperative launch available and no thread can leave the evaluation on its own (see init)
 int* d_gbar = nullptr;            // grid barrier ticket counter + error flags
+int* d_order = nullptr;           // work list of the persistent column kernel (neq entries) + its queue counter
 V g_last_yl;  // the state the base planes were last evaluated at
 int64_t g_ivmin = 1, g_ivmax = 0;
 
@@ -132,7 +134,7 @@ void free_all() {
   for (void* p : g_allocs) mem_free(p);
   g_allocs.clear(); g_dev.clear();
   d_G = nullptr; d_base = d_priv = d_yl = d_yldot = d_y00 = d_ylp = d_wk = d_step = d_fval = d_jac = nullptr;
-  d_cnt = d_frow = d_err = d_gbar = nullptr; d_ia = d_ja = d_ja2 = nullptr; d_jac2 = nullptr;
+  d_cnt = d_frow = d_err = d_gbar = d_order = nullptr; d_ia = d_ja = d_ja2 = nullptr; d_jac2 = nullptr;
   g_priv_cols = 0; g_nnzmx = 0; g_ready = false; g_last_yl.clear();
 #if !defined(UE_GEN_HOST)
   gc_nranks = 1; gc_rank = 0;  // (the lists belonged to the case that was just freed; the communicator itself lives until comm_finalize)
@@ -375,6 +377,36 @@ __global__ void k_gen_sortrows(int64_t neq, const int64_t* ia, int64_t nnzmx, co
 #endif
 
 #if !defined(UE_GEN_HOST)
+// Persistent form of the column kernel: as many warps as are resident on the device (or unknowns, if fewer), each with ONE private
+// plane set that it reuses; the warps draw unknowns from a work queue (atomic counter) in the order of `order` - the host puts the
+// unknowns whose window spans all ix (windows at an X-point cut, oderhs.m:960-1019: 10-30 x the work of the others) first, so that
+// they start at once and the short ones fill in behind them.  No chunking by memory, no tail of long windows at the end of a launch.
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_gen_cols_q(const Gen* gsrc, const double* base, double* priv, int npl, const int* order, int ncol, int* queue, const double* yl, double* ylp,
+                             double* wk, const double* yldot00, int64_t ml, int64_t mu, int cap, int* frow, double* fval, int* cnt, int* err, int band, int colpad) {
+  const int unit = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
+  Gen* g = (Gen*)g_smem + unit;
+  load_ctx(g, gsrc, lane, 32);
+  __syncwarp();
+  const int slot = (int)(blockIdx.x * (blockDim.x >> 5) + unit);
+  const size_t nslab = (size_t)npl * g->NC;
+  if (lane == 0) { g->nth = 32; g->gridmode = 0; g->errc = 0; g->assign_planes(priv + (size_t)slot * nslab); }
+  __syncwarp();
+  const int64_t neq = g->neq;
+  for (;;) {
+    int c = 0;
+    if (lane == 0) c = atomicAdd(queue, 1);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    if (c >= ncol) break;
+    const int64_t iv = (int64_t)order[c];
+    const int rc = eval_column(*g, base, npl, iv, yl, ylp + (size_t)slot * (neq + 2), wk + (size_t)slot * neq, yldot00, ml, mu, cap, frow + (size_t)(iv - 1) * cap,
+                               fval + (size_t)(iv - 1) * cap, cnt + (iv - 1), band, colpad);
+    __syncwarp();
+    if (rc && lane == 0) { err[0] = rc; err[1] = g->errc; }
+    if (lane == 0 && cnt[iv - 1] > cap) err[2] = cnt[iv - 1];
+    if (rc) break;
+  }
+}
 // ---- packing of the column fragments for the exchange (multi-GPU) ---------------------------------------------------------
 // segment = the unknowns of one rank in list order.  k_gen_segscan: block s scans the counts of segment s (exclusive) and leaves
 // the segment total; own = 1: the counts are first gathered from cnt[iv-1] (this rank's fresh results) into pk_cnt.
@@ -815,16 +847,29 @@ int UE_PREFIX(jac_calc)(int64_t n, double t, const double* yl, const double* yld
 #if !defined(UE_GEN_HOST)
   if (gc_nranks > 1) ncols_all = (ncols_all + gc_nranks - 1) / gc_nranks;
 #endif
-  // private plane sets: as many unknowns at once as fit in half of the free device memory (host build: 1 GB)
-  size_t chunk = g_priv_cols;  // the allocation of the first Jacobian is kept (larger column ranges run in more chunks)
-  if (chunk == 0) {
+  // private plane sets: one per resident warp of the persistent column kernel (or per unknown, if fewer), within half of the free device
+  // memory (host build: one set).  The allocation of the first Jacobian is kept.
+  size_t chunk = 1;
+  {
     size_t budget = 1ull << 30;
 #if !defined(UE_GEN_HOST)
     { size_t fr = 0, tot = 0; if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) budget = fr / 2; }
+    if (g_occ1 == 0) {
+      int occ1 = 1, occ4 = 1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_gen_cols_q<1>, 128, 4 * sizeof(Gen));
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4, k_gen_cols_q<4>, 128, 4 * sizeof(Gen));
+      g_occ1 = std::max(1, occ1); g_occ4 = std::max(1, occ4);
+    }
+    const int64_t resident = (int64_t)g_sms * 4 * std::max(g_occ1, g_occ4);
+    const int64_t want = std::max<int64_t>(4, std::min<int64_t>(ncols_all, g_tpu > 32 ? ncols_all : resident));
+    chunk = (size_t)want;
+    if (g_priv_cols < chunk) chunk = (size_t)std::max<int64_t>(4, std::min<int64_t>(want, (int64_t)(budget / (nslab * 8))));  // (a new allocation: within the budget)
+    if (g_priv_cols >= chunk) chunk = g_priv_cols;
 #endif
-    chunk = (size_t)std::max<int64_t>(1, std::min<int64_t>(ncols_all, (int64_t)(budget / (nslab * 8))));
   }
   if (g_priv_cols < chunk) {
+    for (double* q : {d_priv, d_ylp, d_wk})  // a larger set replaces the one a narrower column range allocated
+      if (q) { g_allocs.erase(std::remove(g_allocs.begin(), g_allocs.end(), (void*)q), g_allocs.end()); mem_free(q); }
     d_priv = mem_alloc(chunk * nslab); d_ylp = mem_alloc(chunk * (neq + 2)); d_wk = mem_alloc(chunk * neq);
     if (!d_priv || !d_ylp || !d_wk) return -10;
     g_allocs.push_back(d_priv); g_allocs.push_back(d_ylp); g_allocs.push_back(d_wk);
@@ -881,6 +926,37 @@ int UE_PREFIX(jac_calc)(int64_t n, double t, const double* yl, const double* yld
     my_list = d_list_all + gc_list_off[gc_rank]; my_lo = 1; my_hi = gc_list_off[gc_rank + 1] - gc_list_off[gc_rank];  // positions in the list
   }
   cudaEventRecord(e0);
+  if (g_tpu <= 32) {
+    // work list: this call's unknowns, those with a window over all ix first (same test as make_win's xccuts, oderhs.m:960-1019)
+    const V* ig = find("igyl");
+    std::vector<int> slow, fast;
+    auto add = [&](int64_t iv) {
+      const int xc = (int)(*ig)[(size_t)iv - 1], yc = (int)(*ig)[neq + (size_t)iv - 1];
+      const bool cut = ((xc - G.xlinc <= G.ixpt1 + 1) && (xc + G.xrinc + 1 >= G.ixpt1) && (yc - G.yinc <= G.iysptrx1) && (G.iysptrx1 > 0)) ||
+                       ((xc - G.xlinc <= G.ixpt2 + 1) && (xc + G.xrinc + 1 >= G.ixpt2) && (yc - G.yinc <= G.iysptrx2) && (G.iysptrx2 > 0));
+      (cut ? slow : fast).push_back((int)iv);
+    };
+    if (gc_nranks > 1) for (int k = gc_list_off[gc_rank]; k < gc_list_off[gc_rank + 1]; ++k) add(gc_list_all[k]);
+    else for (int64_t iv = g_ivmin; iv <= g_ivmax; ++iv) add(iv);
+    slow.insert(slow.end(), fast.begin(), fast.end());
+    const int ncol = (int)slow.size();
+    if (!d_order) { d_order = alloc_as<int>(neq + 1); if (!d_order) return -10; }
+    if (ncol > 0 && !mem_put(d_order, slow.data(), (size_t)ncol * sizeof(int))) return -10;
+    int* d_queue = d_order + neq;
+    if (!ck(cudaMemsetAsync(d_queue, 0, sizeof(int)), "work queue reset")) return -10;
+    // few unknowns: every warp is alone on its scheduler, registers are free (no spills); many unknowns: 4 blocks per SM (128 registers, a
+    // few spills) so that more chains overlap
+    const bool many = ncol > 4096;
+    const int64_t resident = (int64_t)g_sms * WPB * (many ? g_occ4 : g_occ1);
+    const int nslots = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>((int64_t)chunk, resident), ncol));
+    const int nblk = (nslots + WPB - 1) / WPB;  // (a last block with idle warps never exceeds the allocation: chunk >= 4 and slots are clipped below)
+    const int nblk_ok = std::min<int>(nblk, (int)(chunk / WPB));
+    if (ncol > 0) {
+      if (many) k_gen_cols_q<4><<<std::max(1, nblk_ok), 32 * WPB, WPB * sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, d_order, ncol, d_queue, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, g_band, g_colpad);
+      else k_gen_cols_q<1><<<std::max(1, nblk_ok), 32 * WPB, WPB * sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, d_order, ncol, d_queue, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, g_band, g_colpad);
+      if (!ck(cudaGetLastError(), "k_gen_cols_q launch")) return -10;
+    }
+  } else
   for (int64_t iv0 = my_lo; iv0 <= my_hi; iv0 += (int64_t)chunk) {
     const int ncol = (int)std::min<int64_t>((int64_t)chunk, my_hi - iv0 + 1);
     const int* ivl = my_list ? my_list + (iv0 - 1) : nullptr;
