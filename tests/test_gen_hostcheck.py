@@ -100,6 +100,24 @@ def test_window_copy_with_few_unknowns_per_cell(built, monkeypatch, subset):
     same(Oracle2().bind(c), host(0).bind(c), c, yl)
 
 
+@pytest.mark.parametrize("name, kw", [("iflcore=1", dict(iflcore=1, pcoree=2e5, pcorei=2e5)), ("isnicore=0", dict(isnicore=(0, 0), curcore=(0, 10.0))),
+                                      ("iphibcc=1", dict(iphibcc=1)), ("isnewpot=0", dict(isnewpot=0, rnewpot=0.0))])
+def test_window_copy_with_core_boundary_sums(built, monkeypatch, name, kw):
+    """core conditions that sum over the whole core boundary (power, current) or set the potential rows at every core column: rows 0-2
+    of the private copy hold all core columns; 2x-refined drift case, everything else poisoned"""
+    from uedge_b200.cases import load_grid_npz, refine_grid
+    monkeypatch.setenv("UE_GEN_POISON", "1")
+
+    def m(b, com):
+        for k, v in kw.items():
+            if isinstance(v, tuple):
+                a = np.asarray(getattr(b, k)).copy(); a[v[0]] = v[1]; setattr(b, k, a)
+            else:
+                setattr(b, k, v)
+    c, yl = jupyter_case(m, grid=refine_grid(load_grid_npz(), 2, 2))
+    same(Oracle2().bind(c), host(0).bind(c), c, yl)
+
+
 @pytest.mark.parametrize("rev", [0, 1])
 def test_jupyter_drift_case(built, rev):
     """jupyter/case_setup.py: ExB and grad-B drifts, grad-B currents, isnewpot=1 with its two core conditions (one of them the sum of

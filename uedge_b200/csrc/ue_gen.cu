@@ -86,6 +86,7 @@ float g_full_ms = 0.f, g_cols_ms = 0.f, g_csr_ms = 0.f;  // CUDA-event times of 
 int g_band = UE_GEN_BAND_DEFAULT;  // rows of the private copy on each side of the perturbed cell (env UE_GEN_BAND; large = all rows)
 int g_colpad = 2;  // columns of the private copy on each side of the window i1..i6 (env UE_GEN_COLPAD; negative = whole rows)
 int g_tpu = 32;  // threads per unknown in the Jacobian kernel: 32 (a warp) or 64 (a two-warp block)
+int g_nslow = 0;
 int g_occ1 = 0, g_occ4 = 0;  // resident blocks per SM of the two builds of the column kernel (0: not asked yet)
 int g_sms = 0, g_full_grid = -1;  // SM count; blocks of the grid-mode residual (-1: by mesh size; env UE_GEN_FULL_GRID)
 bool g_grid_ok = false;           // cooperative launch available and no thread can leave the evaluation on its own (see init)
@@ -168,10 +169,10 @@ HD int eval_column(Gen& g, const double* base, int npl, int64_t iv, const double
   // Private copy of the base planes: only what the windowed evaluation can touch -
   //  * the band of rows yc +- band (ranges j1p-1 .. j6p+2 of oderhs.m:868-964), and in them the columns of the window
   //    i1-2 .. i6+2; windows that reach an X-point cut span all ix in the reference (xccuts, oderhs.m:960-1019) and take whole rows;
-  //  * whole rows 0-2 when the band holds them: the core conditions sum fluxes and currents over the entire core boundary and, with
-  //    isnewpot = 1, set the potential rows at every core column (boundary.m:229-240, 492-502, 987-1122); whole rows ny, ny+1 likewise
-  //    (every window at a wall sets the density rows of the four corner cells, boundary.m:246-262);
-  //  * the two rows of the X-point vertex average (convert.m:831-868, evaluated by every window), whole;
+  //  * in rows 0-2, when the band holds them, all core columns: the core conditions sum fluxes and currents over the entire core
+  //    boundary and, with isnewpot = 1, set the potential rows at every core column (boundary.m:229-240, 492-502, 987-1122); the
+  //    corner cells of both walls (every window at a wall sets their density rows, boundary.m:246-262);
+  //  * the eight cells of the X-point vertex average (convert.m:831-868, evaluated by every window);
   //  * the line arrays in full.
   // Everything else keeps whatever an earlier unknown left there: nothing in the band's result reads it
   // (tests/test_gen_hostcheck.py poisons it with NaN to show that).
@@ -184,36 +185,35 @@ HD int eval_column(Gen& g, const double* base, int npl, int64_t iv, const double
 #endif
     const auto w = g.make_win(xc, yc);
     const bool fullx = w.xccuts || colpad < 0 || (w.i1 <= colpad && w.i6 >= g.nx + 1 - colpad);
-    const int cx0 = fullx ? 0 : mx(0, w.i1 - colpad), cx1 = fullx ? NXS - 1 : mn(NXS - 1, w.i6 + colpad);
-    {  // one flat loop over (plane, row of the band, column of the window): independent loads, several in flight per thread
-      const int wc = cx1 - cx0 + 1, rw = (r1 - r0 + 1) * wc;
+    // the copy is a union of rectangles (rows a..b) x (columns c..d); overlaps are copied twice (same values)
+    int ra[9], rb[9], ca[9], cb[9], nr = 0;
+    auto rect = [&](int a, int b_, int c, int d) {
+      a = mx(a, 0); b_ = mn(b_, nrow - 1); c = mx(c, 0); d = mn(d, NXS - 1);
+      if (a <= b_ && c <= d) { ra[nr] = a; rb[nr] = b_; ca[nr] = c; cb[nr] = d; ++nr; }
+    };
+    if (fullx) rect(r0, r1, 0, NXS - 1);
+    else {
+      rect(r0, r1, w.i1 - colpad, w.i6 + colpad);                            // the window
+      if (r0 <= 2) {
+        rect(r0, mn(2, r1), g.ixpt1, g.ixpt2 + 1);                             // core boundary: sums over all core columns
+        rect(r0, mn(2, r1), 0, 1); rect(r0, mn(2, r1), g.nx, g.nx + 1);       // corner cells of the inner wall
+      }
+      if (r1 >= nrow - 2) { rect(mx(r0, nrow - 2), r1, 0, 1); rect(mx(r0, nrow - 2), r1, g.nx, g.nx + 1); }  // ... and of the outer wall
+    }
+    if (g.iysptrx1 >= 0 && g.ixpt1 >= 0 && g.ixpt2 >= 0 && !(fullx && g.iysptrx1 >= r0 && g.iysptrx1 + 1 <= r1)) {  // X-point vertex: 8 cells
+      rect(g.iysptrx1, g.iysptrx1 + 1, g.ixpt1 - 1, g.ixpt1 + 2);
+      rect(g.iysptrx1, g.iysptrx1 + 1, g.ixpt2 - 1, g.ixpt2 + 2);
+    }
+    for (int q = 0; q < nr; ++q) {  // one flat loop over (plane, row, column) of a rectangle: independent loads, several in flight per thread
+      const int wc = cb[q] - ca[q] + 1, rw = (rb[q] - ra[q] + 1) * wc;
       const int tot = nfield * rw;
       const bool small = tot < (1 << 22);  // (the float quotients are exact below 2^22)
 #pragma unroll 4
       for (int k = tid; k < tot; k += g.nth) {
         const int p = small ? UE_ROW_(k, rw) : k / rw;
-        const int q = k - p * rw;
-        const int r = small ? UE_ROW_(q, wc) : q / wc;
-        const size_t o = (size_t)p * NC + (size_t)(r0 + r) * NXS + (size_t)(cx0 + q - r * wc);
-        priv[o] = base[o];
-      }
-    }
-    int frows[7], nf = 0;  // rows taken whole
-    if (!fullx) for (int r = r0; r <= mn(2, r1); ++r) frows[nf++] = r;
-    if (!fullx) for (int r = mx(r0, mx(3, nrow - 2)); r <= r1; ++r) frows[nf++] = r;  // outer-wall rows: its corner cells are set by every window at the wall
-    if (g.iysptrx1 >= 0)
-      for (int r = mx(0, g.iysptrx1); r <= mn(nrow - 1, g.iysptrx1 + 1); ++r) {
-        const bool inband = r >= r0 && r <= r1;
-        bool have = inband && fullx;
-        for (int k = 0; k < nf; ++k) have = have || frows[k] == r;
-        if (!have) frows[nf++] = r;
-      }
-    for (int f = 0; f < nf; ++f) {
-      const int tot = nfield * NXS;
-      const size_t o0 = (size_t)frows[f] * NXS;
-      for (int k = tid; k < tot; k += g.nth) {
-        const int p = UE_ROW_(k, NXS);
-        const size_t o = (size_t)p * NC + o0 + (size_t)(k - p * NXS);
+        const int e = k - p * rw;
+        const int r = small ? UE_ROW_(e, wc) : e / wc;
+        const size_t o = (size_t)p * NC + (size_t)(ra[q] + r) * NXS + (size_t)(ca[q] + e - r * wc);
         priv[o] = base[o];
       }
     }
@@ -393,18 +393,23 @@ __global__ void __launch_bounds__(128, MINB) k_gen_cols_q(const Gen* gsrc, const
   if (lane == 0) { g->nth = 32; g->gridmode = 0; g->errc = 0; g->assign_planes(priv + (size_t)slot * nslab); }
   __syncwarp();
   const int64_t neq = g->neq;
+  // a block draws its warps' unknowns together: neighbours in the list are the unknowns of one cell - the same window, so the warps
+  // read the same part of the base planes (L1 hits) and take equally long
+  __shared__ int s_first;
   for (;;) {
-    int c = 0;
-    if (lane == 0) c = atomicAdd(queue, 1);
-    c = __shfl_sync(0xffffffffu, c, 0);
-    if (c >= ncol) break;
+    __syncthreads();
+    if (threadIdx.x == 0) s_first = (*(volatile int*)err) ? ncol : atomicAdd(queue, (int)(blockDim.x >> 5));
+    __syncthreads();
+    const int first = s_first;
+    if (first >= ncol) break;
+    const int c = first + unit;
+    if (c >= ncol) continue;
     const int64_t iv = (int64_t)order[c];
     const int rc = eval_column(*g, base, npl, iv, yl, ylp + (size_t)slot * (neq + 2), wk + (size_t)slot * neq, yldot00, ml, mu, cap, frow + (size_t)(iv - 1) * cap,
                                fval + (size_t)(iv - 1) * cap, cnt + (iv - 1), band, colpad);
     __syncwarp();
     if (rc && lane == 0) { err[0] = rc; err[1] = g->errc; }
     if (lane == 0 && cnt[iv - 1] > cap) err[2] = cnt[iv - 1];
-    if (rc) break;
   }
 }
 // ---- packing of the column fragments for the exchange (multi-GPU) ---------------------------------------------------------
@@ -853,7 +858,6 @@ int UE_PREFIX(jac_calc)(int64_t n, double t, const double* yl, const double* yld
   {
     size_t budget = 1ull << 30;
 #if !defined(UE_GEN_HOST)
-    { size_t fr = 0, tot = 0; if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) budget = fr / 2; }
     if (g_occ1 == 0) {
       int occ1 = 1, occ4 = 1;
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_gen_cols_q<1>, 128, 4 * sizeof(Gen));
@@ -863,7 +867,11 @@ int UE_PREFIX(jac_calc)(int64_t n, double t, const double* yl, const double* yld
     const int64_t resident = (int64_t)g_sms * 4 * std::max(g_occ1, g_occ4);
     const int64_t want = std::max<int64_t>(4, std::min<int64_t>(ncols_all, g_tpu > 32 ? ncols_all : resident));
     chunk = (size_t)want;
-    if (g_priv_cols < chunk) chunk = (size_t)std::max<int64_t>(4, std::min<int64_t>(want, (int64_t)(budget / (nslab * 8))));  // (a new allocation: within the budget)
+    if (g_priv_cols < chunk) {  // a new allocation: within half of the free memory
+      size_t fr = 0, tot = 0;
+      if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) budget = fr / 2;
+      chunk = (size_t)std::max<int64_t>(4, std::min<int64_t>(want, (int64_t)(budget / (nslab * 8))));
+    }
     if (g_priv_cols >= chunk) chunk = g_priv_cols;
 #endif
   }
@@ -938,6 +946,10 @@ int UE_PREFIX(jac_calc)(int64_t n, double t, const double* yl, const double* yld
     };
     if (gc_nranks > 1) for (int k = gc_list_off[gc_rank]; k < gc_list_off[gc_rank + 1]; ++k) add(gc_list_all[k]);
     else for (int64_t iv = g_ivmin; iv <= g_ivmax; ++iv) add(iv);
+    if (const char* e = getenv("UE_GEN_DEBUG_LIST")) {  // developer switch: time the two classes separately (the Jacobian is then incomplete)
+      if (e[0] == 's') fast.clear(); else if (e[0] == 'f') slow.clear();
+    }
+    g_nslow = (int)slow.size();
     slow.insert(slow.end(), fast.begin(), fast.end());
     const int ncol = (int)slow.size();
     if (!d_order) { d_order = alloc_as<int>(neq + 1); if (!d_order) return -10; }
