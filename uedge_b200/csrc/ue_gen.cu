@@ -233,13 +233,26 @@ HD int eval_column(Gen& g, const double* base, int npl, int64_t iv, const double
   {
     const int nrow = g.ny + 2;
     const int r0 = mx(0, yc - band), r1 = mn(nrow - 1, yc + band);
-    int64_t lo = 0, hi = neq;
     const bool whole = (g.dtreal < 1.e15 && yl[neq] < 0) || g.yinc >= 6 || colpad < 0;
-    if (!whole) { lo = mn((int64_t)g.rowiv_[r0], ii1 - 1); hi = mx((int64_t)g.rowiv_[r1 + 1], ii2); }
 #if defined(UE_GEN_HOST)
     if (g_poison) for (int64_t k = 0; k < neq; ++k) { ylp[k] = (double)NAN; wk[k] = (double)NAN; }
 #endif
-    for (int64_t k = lo + tid; k < hi; k += g.nth) { ylp[k] = yl[k]; wk[k] = yldot00[k]; }
+    const auto w = g.make_win(xc, yc);
+    const bool fullx = w.xccuts || g.rowuniform_ == 0 || (w.i1 <= colpad && w.i6 >= g.nx + 1 - colpad);
+    if (whole || fullx) {
+      int64_t lo = 0, hi = neq;
+      if (!whole) { lo = mn((int64_t)g.rowiv_[r0], ii1 - 1); hi = mx((int64_t)g.rowiv_[r1 + 1], ii2); }
+      for (int64_t k = lo + tid; k < hi; k += g.nth) { ylp[k] = yl[k]; wk[k] = yldot00[k]; }
+    } else {  // the differencing range, and in the band's rows the unknowns of the window's columns (every cell holds numvar unknowns)
+      for (int64_t k = ii1 - 1 + tid; k < ii2; k += g.nth) { ylp[k] = yl[k]; wk[k] = yldot00[k]; }
+      const int c0 = mx(0, w.i1 - colpad), c1 = mn(g.NXS - 1, w.i6 + colpad);
+      const int per = (int)g.numvar_ * (c1 - c0 + 1), tot = per * (r1 - r0 + 1);
+      for (int e = tid; e < tot; e += g.nth) {
+        const int r = e / per;
+        const int64_t k = (int64_t)g.rowiv_[r0 + r] + g.numvar_ * c0 + (e - r * per);
+        ylp[k] = yl[k]; wk[k] = yldot00[k];
+      }
+    }
     if (tid == 0) { ylp[neq] = yl[neq]; ylp[neq + 1] = yl[neq + 1]; }
   }
   g.sync();
@@ -632,6 +645,12 @@ int init_all() {
       if (rowiv[r] == (int)g.neq) rowiv[r] = (int)k;
     }
     for (int r = g.ny + 1; r >= 0; --r) if (rowiv[r] == (int)g.neq) rowiv[r] = rowiv[r + 1];
+    g.rowuniform_ = 1;  // every cell holds numvar unknowns, numbered along the row: unknown k of row r belongs to column (k - rowiv[r]) / numvar
+    const int64_t nv = (int64_t)I("numvar");
+    for (int64_t k = 0; k < g.neq && g.rowuniform_; ++k) {
+      const int r = (int)(*ig)[(size_t)g.neq + k], x = (int)(*ig)[(size_t)k];
+      if (nv < 1 || (k - rowiv[r]) / nv != x) g.rowuniform_ = 0;
+    }
     int* d = alloc_as<int>(rowiv.size());
     if (!d || !mem_put(d, rowiv.data(), rowiv.size() * sizeof(int))) return -10;
     g.rowiv_ = d;

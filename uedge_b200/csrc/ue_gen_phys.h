@@ -147,6 +147,7 @@ int ExtendedJacPhi, istgcore, istgpfc, istgwc, istglb, istgrb, isfegxyqflave;
 int64_t numvar_;
 double tgcore, cftgticore, tgwall, lytg1, lytg2, cftgtipltl, cftgtipltr, cftgtipfc, cftgtiwc, cgengmpl, cgengmw, cfalbedo, recyce, recycwe, cvgpg, cfcvtg, cfegxy, flalftgxy;
 const double* idxtg_;
+int rowuniform_;    // 1: every cell holds numvar unknowns in column order (the private state copies may then be cut to the window's columns)
 const int* rowiv_;  // first unknown (0-based) of every mesh row, ny+3 entries (private copies of the state vector, ue_gen.cu)
 double cngfx_[2], cngfy_[2], mi[2], zi[2], n0[2], fnorm[2], n0g_[2], mg_[2], ngbackg_[2], vcony[2], difpr[2], difni[2], difni2[2], difpr2[2], difax[2], travis[2], parvis[2],
     nlimix[2], nlimiy[2], dif4order[2], cpiup[2], cfvgpx[2], cfvgpy[2], cfvcsx[2], cfvcsy[2], cfvisxy[2], cngmom[2], cmwall[2], cngtgx[2], cngtgy[2], cdifg[2], lgmax[2], lgtmax[2],
