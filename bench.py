@@ -119,7 +119,7 @@ def general_records(steps=10):
         t = time.perf_counter(); fo = o.pandf1(y2); tro = time.perf_counter() - t
         t = time.perf_counter(); o.jac_calc(y2, fo, b.lbw, b.ubw, b.nnzmx); tjo = time.perf_counter() - t
         out[name] = dict(neq=int(b.neq), numvar=int(b.numvar), nnz=len(j[0]), bit_identical_to_oracle=same, e2e_ms_per_step=tg * 1e3, e2e_value=len(j[0]) / tg, unit="nnz/s",
-                         resid_e2e_ms=tr * 1e3, cpu_1thread_ms_per_step=(tro + tjo) * 1e3, cpu_1thread_value=len(j[0]) / (tro + tjo), kernels="k_gen_full, k_gen_cols (one warp per unknown), k_gen_count/scan/fill/sortrows")
+                         resid_e2e_ms=tr * 1e3, cpu_1thread_ms_per_step=(tro + tjo) * 1e3, cpu_1thread_value=len(j[0]) / (tro + tjo), kernels="k_gen_full | k_gen_full_grid (residual), k_gen_cols_q (persistent, one warp per unknown, work queue), k_gen_count/scan/fill/sortrows")
         g._f("finalize")()
     return out
 
