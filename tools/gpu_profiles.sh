@@ -21,7 +21,13 @@ done
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${R}_launches_general_input_example.csv python tools/one_gen.py input_example 2 > /dev/null 2>&1
 ncu --set full --clock-control none --cache-control none -c 12 -o /tmp/gen -f python tools/one_gen.py input_example 2 > /dev/null 2>&1
 python tools/ncu_summary.py /tmp/gen.ncu-rep gpurun_out/${R}_ncu_warm_general_input_example.json
-python tools/time_general.py > gpurun_out/${R}_general_times.txt 2>&1
+# ... and of the drift case (BASELINE configs[2]) on the 16x8 and the 4x mesh (grid-mode residual, persistent column kernel)
+ncu --set full --clock-control none --cache-control none -c 12 -o /tmp/gen_j -f python tools/one_gen.py "jupyter drift case 16x8" 2 > /dev/null 2>&1
+python tools/ncu_summary.py /tmp/gen_j.ncu-rep gpurun_out/${R}_ncu_warm_general_jupyter.json
+ncu --set full --clock-control none --cache-control none -c 12 -o /tmp/gen_j4 -f python tools/one_gen.py "jupyter drift case 4x" 2 > /dev/null 2>&1
+python tools/ncu_summary.py /tmp/gen_j4.ncu-rep gpurun_out/${R}_ncu_warm_general_jupyter4x.json
+python tools/time_general.py --8x > gpurun_out/${R}_general_times.txt 2>&1
+python tools/slowfast.py 4 >> gpurun_out/${R}_general_times.txt 2>&1
 # memory checker on both paths (one residual + Jacobian each)
 ( compute-sanitizer --tool memcheck python tools/one_jac.py d3dHsm 1 2>&1 | tail -3; compute-sanitizer --tool memcheck python tools/one_gen.py input_example 1 2>&1 | tail -3; \
   compute-sanitizer --tool racecheck python tools/one_gen.py input_example 1 2>&1 | tail -3 ) > gpurun_out/${R}_sanitizer.txt

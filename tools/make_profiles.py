@@ -63,5 +63,15 @@ json.dump(it, open(os.path.join(P, "%s_ncu_warm_general_input_example.json" % R)
 traffic["general_input_example"] = {"kernel_us_warm": [[r["kernel"], round(r["duration_us"], 2)] for r in it],
                                     "fp64_flops_per_jacobian": sum(r.get("fp64_flop", 0) for r in it if r["kernel"].startswith("k_gen_cols")),
                                     "dram_bytes_per_jacobian_warm": sum(r.get("dram_read_bytes", 0) + r.get("dram_write_bytes", 0) for r in it if not r["kernel"].startswith("k_gen_full"))}
+# ... and of the drift case (jupyter/case_setup.py) on the 16x8 and the 4x mesh
+for tag in ("jupyter", "jupyter4x"):
+    src = os.path.join(G, "%s_ncu_warm_general_%s.json" % (R, tag))
+    if not os.path.exists(src):
+        continue
+    it = one_iteration(json.load(open(src)), last="k_gen_sortrows")
+    json.dump(it, open(os.path.join(P, "%s_ncu_warm_general_%s.json" % (R, tag)), "w"), indent=1)
+    traffic["general_" + tag] = {"kernel_us_warm": [[r["kernel"], round(r["duration_us"], 2)] for r in it],
+                                 "fp64_flops_per_jacobian": sum(r.get("fp64_flop", 0) for r in it if r["kernel"].startswith("k_gen_cols")),
+                                 "dram_bytes_per_jacobian_warm": sum(r.get("dram_read_bytes", 0) + r.get("dram_write_bytes", 0) for r in it if not r["kernel"].startswith("k_gen_full"))}
 json.dump(traffic, open(os.path.join(P, "%s_traffic.json" % R), "w"), indent=1)
 print(json.dumps(traffic, indent=1))
