@@ -261,6 +261,21 @@ HD int eval_column(Gen& g, const double* base, int npl, int64_t iv, const double
   if (tid == 0) ylp[iv - 1] = yold + dyl;
   g.sync();
   const int rc = g.pandf1(xc, yc, ylp, wk);
+#if defined(UE_GEN_HOST)
+  if (g_poison && getenv("UE_GEN_OOB")) {  // developer aid: which planes does a windowed evaluation write outside the band's rows?
+    static std::map<std::pair<int, int>, int> seen;  // (plane, row offset class) -> count
+    const int NXS = g.NXS, NC = g.NC, nrow = g.ny + 2;
+    const int r0 = mx(0, yc - band), r1 = mn(nrow - 1, yc + band);
+    for (int p = 0; p < npl - UE_GEN_NLINE; ++p)
+      for (int r = 0; r < nrow; ++r) {
+        if (r >= r0 && r <= r1) continue;
+        if (g.iysptrx1 >= 0 && (r == g.iysptrx1 || r == g.iysptrx1 + 1)) continue;
+        bool w = false;
+        for (int c = 0; c < NXS; ++c) { const double v = priv[(size_t)p * NC + (size_t)r * NXS + c]; if (v == v) w = true; }
+        if (w) { const int cls = r <= 2 ? r : (r >= nrow - 2 ? 100 + (r - (nrow - 2)) : 50); if (seen[{p, cls}]++ == 0) fprintf(stderr, "OOB write: plane %d row class %d (row %d, band %d..%d)\n", p, cls, r, r0, r1); }
+      }
+  }
+#endif
   g.sync();
   if (rc) { if (tid == 0) *cnt = 0; return rc; }
   const bool isphi = g.IDXPHI(xc, yc) == iv - 1;
@@ -979,7 +994,8 @@ int UE_PREFIX(jac_calc)(int64_t n, double t, const double* yl, const double* yld
     // few spills) so that more chains overlap
     const bool many = ncol > 4096;
     const int64_t resident = (int64_t)g_sms * WPB * (many ? g_occ4 : g_occ1);
-    const int nslots = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>((int64_t)chunk, resident), ncol));
+    int nslots = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>((int64_t)chunk, resident), ncol));
+    if (const char* e = getenv("UE_GEN_SLOTS")) nslots = std::max(4, std::min(nslots, atoi(e)));  // developer switch: fewer resident warps
     const int nblk = (nslots + WPB - 1) / WPB;  // (a last block with idle warps never exceeds the allocation: chunk >= 4 and slots are clipped below)
     const int nblk_ok = std::min<int>(nblk, (int)(chunk / WPB));
     if (ncol > 0) {
