@@ -75,7 +75,7 @@ double ev, qe, me, mp, pi_, cutlo, rt8opi, temin, tgmin, nnorm, ennorm, temp0, v
     cfnidhg2, cftgeqp, flalftxy, flalfgnx, flalfgny, nlimgx, nlimgy, cfloxiplt, cfloygwall, cfjve, rsigpl, rsigplcore, bcen, bceew, bciew, cfqym, cfqydt,
     cfjpy, cfjp2, cfqybf, cfq2bf, cfqybbo, cfqydbo, cfydd_, cfjp2_, cfqyn, cfqyao, cfqya, cfqyae, cfjpy_, fqpsatlb_unused, lnlam_unused, phiwi0, phiwo0,
     kappamx, kappa0, cfsigm, fqsatlb_u, fupe_cur, dtphi_, cfhcxgc_u, lyphi0, lyphi1, isparmultdt_u, tewallmin_u, cfwjdotelim, cfeexdbo, cfeixdbo, cfkincor,
-    cfyef, cf2ef, cfybf, cf2bf, cfcurv, cfgradb, eycore, icoreelec, cfniybbo, cfeeybbo;
+    cfyef, cf2ef, cfybf, cf2bf, cfcurv, cfgradb, eycore, icoreelec, cfniybbo, cfeeybbo, cfydd, cf2dd, cfrd, cfbgt;
 int ExtendedJacPhi, istgcore, istgpfc, istgwc, istglb, istgrb, isfegxyqflave;
 double tgcore, cftgticore, tgwall, lytg1, lytg2, cftgtipltl, cftgtipltr, cftgtipfc, cftgtiwc, cgengmpl, cgengmw, cfalbedo, recyce, recycwe, cvgpg, cfcvtg, cfegxy, flalftgxy;
 const double* idxtg_;
@@ -295,7 +295,7 @@ struct O2 {
   V gprx, gpry, gpex, gtex, gtix, gpey, gtey, gtiy, ex, ey, nity0, nity1, ney0, ney1, tey0, tey1, tiy0, tiy1, phiy0, phiy1;
   V ngy0, ngy1, tgy0, tgy1, pgy0, pgy1, phiv, tiv, tev, prev, prtv, priv[2];
   V loglambda, diffusivwrk, vy[2], vydd[2], vygp[2], v2[2], v2dd[2], v2xgp[2], vytan[2], frice, frici[2], upi[2], uup[2], uu[2], upe, vex, vey;
-  V vyce[2], vycb[2], vycp[2], veycb, v2ce[2], v2cb[2], ve2cb, wjdote;
+  V vyce[2], vycb[2], vycp[2], veycb, v2ce[2], v2cb[2], ve2cb, ve2cd, wjdote;
   V segc, floxge, floyge, conxge, conyge, fegx, fegy, fegxy, reseg;  // gas energy equation (engbalg, oderhs.m:7508-7878)  // cross-field drift velocities (oderhs.m:1167-1420), Joule heating
   V nuiz, nurc, nucx, nuix, psorbgg, psorgc, psorc[2], psordis, psorxrc[2], psorrgc, psorg, psor[2], psorxr[2], psorrg;
   V snic[2], sniv[2], psori[2], smoc[2], smov[2], seec, seev, seic, seiv;
@@ -319,7 +319,7 @@ struct O2 {
     P1(gprx) P1(gpry) P1(gpex) P1(gtex) P1(gtix) P1(gpey) P1(gtey) P1(gtiy) P1(ex) P1(ey) P1(nity0) P1(nity1) P1(ney0) P1(ney1) P1(tey0) P1(tey1)
     P1(tiy0) P1(tiy1) P1(phiy0) P1(phiy1) P1(ngy0) P1(ngy1) P1(tgy0) P1(tgy1) P1(pgy0) P1(pgy1) P1(phiv) P1(tiv) P1(tev) P1(prev) P1(prtv) P2(priv)
     P1(loglambda) P1(diffusivwrk) P2(vy) P2(vydd) P2(vygp) P2(v2) P2(v2dd) P2(v2xgp) P2(vytan) P1(frice) P2(frici) P2(upi) P2(uup) P2(uu) P1(upe) P1(vex) P1(vey)
-    P2(vyce) P2(vycb) P2(vycp) P1(veycb) P2(v2ce) P2(v2cb) P1(ve2cb) P1(wjdote)
+    P2(vyce) P2(vycb) P2(vycp) P1(veycb) P2(v2ce) P2(v2cb) P1(ve2cb) P1(ve2cd) P1(wjdote)
     P1(segc) P1(floxge) P1(floyge) P1(conxge) P1(conyge) P1(fegx) P1(fegy) P1(fegxy) P1(reseg)
     P1(nuiz) P1(nurc) P1(nucx) P1(nuix) P1(psorbgg) P1(psorgc) P2(psorc) P1(psordis) P2(psorxrc) P1(psorrgc) P1(psorg) P2(psor) P2(psorxr) P1(psorrg)
     P2(snic) P2(sniv) P2(psori) P2(smoc) P2(smov) P1(seec) P1(seev) P1(seic) P1(seiv)
@@ -333,6 +333,9 @@ struct O2 {
 #undef P2
     return p;
   }
+
+  // perpendicular resistivity (statement function of pandf, oderhs.m:698)
+  double etaper(int ix, int iy) const { return 3.234e-9 * A(loglambda, ix, iy) / ue_pow(std::max(A(te, ix, iy), temin * ev) / (1000. * ev), 1.5); }
 
   // ---- convsr_vo (convert.m:158-375) ------------------------------------------------------------------------------
   int convsr_vo(int ixl, int iyl, const double* yl) {
@@ -879,7 +882,7 @@ struct O2 {
         else A(loglambda, ix, iy) = 25.3 - 1.15 * ue_log10(1.e-6 * nexface) + 2.33167537087122e+00 * ue_log10(teev);
       }
     // radial and "2" velocities of the ion species: diffusive parts plus the ExB and grad-B / curvature drifts (oderhs.m:1167-1471);
-    // the diamagnetic (cfydd, cf2dd), resistive (cfrd) and classical (cfvycf, cfvycr) parts are refused in init
+    // with the diamagnetic (cfydd, cf2dd) and resistive (cfrd) parts; the classical ones (cfvycf, cfvycr) are refused in init; bfacx/yrozh = 1
     for (int f = 0; f < nfsp; ++f) {
       if (!(zi[f] > 1.e-10)) continue;
       const double qion = zi[f] * qe;
@@ -906,8 +909,9 @@ struct O2 {
           double difnimix = A(diffusivwrk, ix, iy);
           A(vydd[f], ix, iy) = A(vydd[f], ix, iy) - 1. * difnimix * (2 * (1 - isvylog) * ((A(niy1[f], ix, iy) - A(niy0[f], ix, iy)) / A(dynog, ix, iy)) / (A(niy1[f], ix, iy) + A(niy0[f], ix, iy)) +
                                                                       isvylog * (ue_log(A(niy1[f], ix, iy)) - ue_log(A(niy0[f], ix, iy))) / A(dynog, ix, iy));
-          A(vy[f], ix, iy) = A(vydd[f], ix, iy) + cfyef * A(vyce[f], ix, iy) + cfybf * A(vycb[f], ix, iy);
-          A(vygp[f], ix, iy) = cfybf * A(vycp[f], ix, iy) + A(vydd[f], ix, iy) + cfyef * A(vyce[f], ix, iy);  // (cfydd + cfybf) bfacyrozh vycp with cfydd = 0, bfacyrozh = 1
+          const double vyrd = -2. * A(gpry, ix, iy) / (sq(A(btot, ix, iy)) / etaper(ix, iy) + sq(A(btot, ix, iy + 1)) / etaper(ix, iy + 1));
+          A(vy[f], ix, iy) = cfydd * A(vycp[f], ix, iy) + cfrd * vyrd + A(vydd[f], ix, iy) + cfyef * A(vyce[f], ix, iy) + cfybf * A(vycb[f], ix, iy);
+          A(vygp[f], ix, iy) = (cfydd + cfybf) * A(vycp[f], ix, iy) + cfrd * vyrd + A(vydd[f], ix, iy) + cfyef * A(vyce[f], ix, iy);
         }
       for (int iy = j1; iy <= j6; ++iy)
         for (int ix = i1; ix <= i6; ++ix) {
@@ -930,8 +934,11 @@ struct O2 {
           A(v2dd[f], ix, iy) = -2. * difpr2[f] * A(gprx, ix, iy) / (A(pr, ix2, iy) / A(rbfbt, ix2, iy) + A(pr, ix, iy) / A(rbfbt, ix, iy)) -
                                2. * (fcdif * difni2[f] + 0.) * (A(ni[f], ix2, iy) - A(ni[f], ix, iy)) /
                                    (A(ni[f], ix2, iy) / (A(rbfbt, ix2, iy) * A(gx, ix2, iy)) + A(ni[f], ix, iy) / (A(rbfbt, ix, iy) * A(gx, ix, iy)));
-          A(v2[f], ix, iy) = A(v2dd[f], ix, iy) + cf2ef * A(v2ce[f], ix, iy) + cf2bf * A(v2cb[f], ix, iy);
-          A(v2xgp[f], ix, iy) = 0.5 * (A(rbfbt, ix, iy) + A(rbfbt, ix2, iy)) * (cf2bf * v2cd + A(v2dd[f], ix, iy) + cf2ef * A(v2ce[f], ix, iy));  // (cf2dd + cf2bf) bfacxrozh v2cd
+          const double temp3 = 4. * (A(prev, ix, iy) - A(prev, ix, iy1)) * A(gyc, ix, iy);
+          A(ve2cd, ix, iy) = -temp3 / ((A(btot, ix, iy) + A(btot, ix2, iy)) * qe * (A(ni[f], ix, iy) + A(ni[f], ix2, iy)));
+          const double v2rd = -2. * A(gprx, ix, iy) / (A(btot, ix, iy) / (etaper(ix, iy) * A(rbfbt2, ix, iy)) + A(btot, ix2, iy) / (etaper(ix2, iy) * A(rbfbt2, ix2, iy)));
+          A(v2[f], ix, iy) = cf2dd * v2cd + cfrd * v2rd + A(v2dd[f], ix, iy) + cf2ef * A(v2ce[f], ix, iy) + cf2bf * A(v2cb[f], ix, iy);
+          A(v2xgp[f], ix, iy) = 0.5 * (A(rbfbt, ix, iy) + A(rbfbt, ix2, iy)) * ((cf2dd + cf2bf) * v2cd + cfrd * v2rd + A(v2dd[f], ix, iy) + cf2ef * A(v2ce[f], ix, iy));
           if (isnonog == 1 && iy <= ny) {  // oderhs.m:1408-1432
             double grdnv = grdnv_y(ni[f], ix, iy, 1) / A(dxnog, ix, iy);
             A(vytan[f], ix, iy) = (fcdif * difni[f] + 0.) * (grdnv / ue_cos(A(angfx, ix, iy)) - (ue_log(A(ni[f], ix2, iy)) - ue_log(A(ni[f], ix, iy))) * A(gxf, ix, iy));
@@ -1001,7 +1008,7 @@ struct O2 {
       }
     for (int iy = j1; iy <= j6; ++iy)
       for (int ix = i1; ix <= i6; ++ix)
-        A(vex, ix, iy) = A(upe, ix, iy) * A(rrv, ix, iy) + (cf2ef * A(v2ce[0], ix, iy) + cf2bf * A(ve2cb, ix, iy)) * 0.5 * (A(rbfbt, ix, iy) + A(rbfbt, IXP1(ix, iy), iy)) - A(vytan[0], ix, iy);
+        A(vex, ix, iy) = A(upe, ix, iy) * A(rrv, ix, iy) + (cf2ef * A(v2ce[0], ix, iy) + cf2bf * A(ve2cb, ix, iy) + cf2dd * A(ve2cd, ix, iy)) * 0.5 * (A(rbfbt, ix, iy) + A(rbfbt, IXP1(ix, iy), iy)) - A(vytan[0], ix, iy);
     for (int f = 0; f < nfsp; ++f)
       for (int iy = j1; iy <= j5; ++iy)
         for (int ix = i1; ix <= i6; ++ix) A(vey, ix, iy) = A(vey, ix, iy) + A(vy[f], ix, iy) * zi[f] * 0.5 * (A(niy0[f], ix, iy) + A(niy1[f], ix, iy));
@@ -1608,6 +1615,38 @@ struct O2 {
             if (iy == 0) feiycbo[ix] = feiycbo[ix] + cfloyi * fniycbo[f][ix] * A(ti, ix, 0);
           }
     }
+    if (std::fabs(cfbgt) > 0) {  // B x grad(T) heat flows (oderhs.m:4131-4229); the plate terms of cfeexdbo / cfeixdbo are refused in init
+      for (int f = 0; f < nfsp; ++f) {
+      for (int iy = j4; iy <= j8; ++iy)
+        for (int ix = i1; ix <= i5; ++ix) {
+          const int iy1 = std::max(0, iy - 1), ix1 = IXP1(ix, iy);
+          if (iy == 0 || iy == ny + 1) continue;
+          const double temp1 = 4.0 * (A(tiv, ix, iy) - A(tiv, ix, iy1)) * A(gyc, ix, iy);
+          if (zi[f] > 1.e-10) A(floxi, ix, iy) = A(floxi, ix, iy) + cfbgt * ((5 * A(sx, ix, iy) / (32 * qe * zi[f])) * (A(ni[f], ix, iy) + A(ni[f], ix1, iy)) * (A(rbfbt2, ix, iy) + A(rbfbt2, ix1, iy)) * temp1);
+        }
+      for (int iy = j1; iy <= j5; ++iy)
+        for (int ix = i4; ix <= i8; ++ix) {
+          const int ix3 = IXM1(ix, iy);
+          if (ix == ixlb || ix == ixrb + 1) continue;
+          const double temp1 = 4.0 * (A(tiv, ix, iy) - A(tiv, ix3, iy)) * A(gxc, ix, iy);
+          if (zi[f] > 1.e-10) A(floyi, ix, iy) = A(floyi, ix, iy) - cfbgt * (5 * A(sy, ix, iy) / (32 * qe * zi[f])) * (A(ni[f], ix, iy) + A(ni[f], ix, iy + 1)) * (A(rbfbt2, ix, iy) + A(rbfbt2, ix, iy + 1)) * temp1;
+        }
+      }
+      for (int iy = j4; iy <= j8; ++iy)
+        for (int ix = i1; ix <= i5; ++ix) {
+          const int iy1 = std::max(0, iy - 1), ix1 = IXP1(ix, iy);
+          if (iy == 0 || iy == ny + 1) continue;
+          const double temp1 = 4.0 * (A(tev, ix, iy) - A(tev, ix, iy1)) * A(gyc, ix, iy);
+          A(floxe, ix, iy) = A(floxe, ix, iy) - cfbgt * ((5 * A(sx, ix, iy) / (32 * qe)) * (A(ne, ix, iy) + A(ne, ix1, iy)) * (A(rbfbt2, ix, iy) + A(rbfbt2, ix1, iy)) * temp1);
+        }
+      for (int iy = j1; iy <= j5; ++iy)
+        for (int ix = i4; ix <= i8; ++ix) {
+          const int ix3 = IXM1(ix, iy);
+          if (ix == ixlb || ix == ixrb + 1) continue;
+          const double temp1 = 4.0 * (A(tev, ix, iy) - A(tev, ix3, iy)) * A(gxc, ix, iy);
+          A(floye, ix, iy) = A(floye, ix, iy) + cfbgt * (5 * A(sy, ix, iy) / (32 * qe)) * (A(ne, ix, iy) + A(ne, ix, iy + 1)) * (A(rbfbt2, ix, iy) + A(rbfbt2, ix, iy + 1)) * temp1;
+        }
+    }
     for (int iy = j4; iy <= j8; ++iy) {  // oderhs.m:4234-4240
       for (int ix = i1; ix <= i5; ++ix) A(floxi, ix, iy) = A(floxi, ix, iy) + cftiexclg * cfneut * cfneutsor_ei * cngtgx[0] * cfcvti * 2.5 * A(fngx, ix, iy);
       A(floxi, nx + 1, iy) = 0.0;
@@ -1833,7 +1872,12 @@ void O2::calc_currents(const Win& w) {
       }
     }
   for (int iy = j1p; iy <= j6p; ++iy)
-    for (int ix = i1; ix <= i5; ++ix) A(fq2, ix, iy) = 0.;  // cfjp2 = 0 (potencur.m:206-230)
+    for (int ix = i1; ix <= i5; ++ix) {  // potencur.m:206-221
+      const int iy1 = std::max(0, iy - 1), ix1 = IXP1(ix, iy);
+      const double temp1 = 4.0 * (A(prtv, ix, iy) - A(prtv, ix, iy1)) * A(gyc, ix, iy);
+      A(fq2d, ix, iy) = A(sx, ix, iy) * 0.25 * temp1 * (A(rbfbt, ix1, iy) + A(rbfbt, ix, iy)) / (A(btot, ix, iy) + A(btot, ix1, iy));
+      A(fq2, ix, iy) = cfjp2 * A(fq2d, ix, iy);
+    }
   for (int iy = j1p; iy <= j5p; ++iy)
     for (int ix = i1; ix <= i6; ++ix) {  // potencur.m:235-290
       double nbary = (A(ne, ix, iy + 1) * A(gy, ix, iy + 1) + A(ne, ix, iy) * A(gy, ix, iy)) / (A(gy, ix, iy + 1) + A(gy, ix, iy));
@@ -1889,7 +1933,7 @@ void O2::calc_currents(const Win& w) {
   }
   for (int iy = j1p; iy <= j5p; ++iy)
     for (int ix = i1; ix <= i6; ++ix) {
-      A(fqy, ix, iy) = (1. - rnewpot_) * A(fqyao, ix, iy) + rnewpot_ * A(fqya, ix, iy) + cfqybf * A(fqyb, ix, iy) + cfqym * A(fqym, ix, iy) + 0.;
+      A(fqy, ix, iy) = (1. - rnewpot_) * A(fqyao, ix, iy) + rnewpot_ * A(fqya, ix, iy) + cfqybf * A(fqyb, ix, iy) + cfqym * A(fqym, ix, iy) + cfjpy * A(fqyd, ix, iy);
       A(fqygp, ix, iy) = (1. - rnewpot_) * A(fqyao, ix, iy) + rnewpot_ * A(fqya, ix, iy) + cfqym * A(fqym, ix, iy) + A(fqyd, ix, iy);
       A(fqy, ix, iy) = A(fqy, ix, iy) + cfqydt * A(fqydt, ix, iy);  // nx = nxold, ny = nyold; cfqydt = 0
     }
@@ -2762,7 +2806,7 @@ int init_all() {
   GR(ckinfl) GR(isoldalbarea) GR(tbmin) GR(nufak) GR(dtreal) GR(dtphi) GR(dylconst) GR(jaccliplim) GR(kelhihg) GR(kelhghg) GR(lgvmax) GR(flgamvg) GR(cfvisxn) GR(cfvisyn) GR(flgamtg) GR(cfupcx) GR(cfticx)
   GR(cfnidh) GR(cfnidh2) GR(cfnidhdis) GR(cfnidhgy) GR(cfnidhg2) GR(cftgeqp) GR(flalftxy) GR(flalfgnx) GR(flalfgny) GR(nlimgx) GR(nlimgy) GR(cfloxiplt) GR(cfloygwall) GR(cfjve) GR(rsigpl) GR(rsigplcore)
   GR(bcen) GR(cfqym) GR(cfqydt) GR(cfqyao) GR(cfsigm) GR(cfyef) GR(cf2ef) GR(cfybf) GR(cf2bf) GR(cfcurv) GR(cfgradb) GR(eycore) GR(icoreelec) GR(cfniybbo) GR(cfeeybbo)
-  GR(cfqybf) GR(cfq2bf) GR(cfqybbo) GR(cfqydbo) GR(cfwjdotelim) GR(tebg)
+  GR(cfqybf) GR(cfq2bf) GR(cfqybbo) GR(cfqydbo) GR(cfwjdotelim) GR(tebg) GR(cfydd) GR(cf2dd) GR(cfrd) GR(cfbgt) GR(cfjpy) GR(cfjp2)
 #undef GR
   erad = SC("erad"); delpert = SC("del");
   sigma1_ = SC("sigma1"); frfqpn_ = SC("frfqpn"); cffqpsat_ = SC("cffqpsat"); exjbdry_ = SC("exjbdry"); rnewpot_ = SC("rnewpot"); cfqyae_ = SC("cfqyae"); cfqyai_ = SC("cfqyai"); cfgpijr_ = SC("cfgpijr");
@@ -2811,8 +2855,8 @@ int init_all() {
   if (isupgon == 1) { if (nisp != 2 || zi[1] != 0.) { g_err = "oracle2: isupgon=1 needs nisp=2 with zi(2)=0"; return -5; } iigsp = 1; }
   // switches outside this restatement
   struct { const char* n; double want; } must[] = {{"isimpon", 0}, {"ismcnon", 0}, {"ishymol", 0}, {"ifixsrc", 0}, {"ifixpsor", 0}, {"isupdrag", 0}, {"isofric", 0}, {"ishosor", 0}, {"islimon", 0}, {"isudsym", 0},
-                                                   {"nxomit", 0}, {"isbohmcalc", 1}, {"isdifbetap", 0}, {"cfydd", 0}, {"cf2dd", 0}, {"cfrd", 0}, {"cfbgt", 0},
-                                                   {"cfvycf", 0}, {"cfvycr", 0}, {"cftef", 0}, {"cftdd", 0}, {"cfjp2", 0}, {"cfjpy", 0}, {"cfqyn", 0}, {"cfeta1", 0}, {"cfrtaue", 0},
+                                                   {"nxomit", 0}, {"isbohmcalc", 1}, {"isdifbetap", 0}, 
+                                                   {"cfvycf", 0}, {"cfvycr", 0}, {"cftef", 0}, {"cftdd", 0}, {"cfqyn", 0}, {"cfeta1", 0}, {"cfrtaue", 0},
                                                    {"cfcl_e", 0}, {"cfcl_i", 0}, {"facbni", 0}, {"facbup", 0}, {"facbee", 0}, {"facbei", 0}, {"rtauxfac", 0}, {"ispsorave", 0}, {"iseesorave", 0}, {"cfvisxneov", 0},
                                                    {"cfvisxneoq", 0}, {"cfvyavis", 0}, {"cfanomvisxg", 0}, {"cfanomvisyg", 0}, {"isnfmiy", 0}, {"isybdrywd", 0}, {"isfeexpl0", 0},
                                                    {"isfeixpl0", 0}, {"cfeexdbo", 0}, {"cfeixdbo", 0}, {"cfniydbo", 0}, {"cfeeydbo", 0}, {"isextrnp", 0}, {"isextrnpf", 0},

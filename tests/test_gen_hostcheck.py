@@ -13,7 +13,7 @@ import pytest
 from tests.test_oracle2_golden import twin
 from tests.util import psetnk_inputs
 from uedge_b200.cases import box2_case
-from uedge_b200.cases2 import SUBSETS, Lib2, Oracle2, box2_initial_state, d3d_full_physics_case, gas_energy_case, inputex_case, jupyter_case, switch_variant
+from uedge_b200.cases2 import SUBSETS, Lib2, Oracle2, all_drifts, box2_initial_state, d3d_full_physics_case, gas_energy_case, inputex_case, jupyter_case, switch_variant
 
 HK = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostcheck")
 
@@ -124,6 +124,17 @@ def test_jupyter_drift_case(built, rev):
     the radial current over the whole core boundary), Joule heating, the wider Jacobian band of the potential unknowns"""
     c, yl = jupyter_case()
     assert c.bbb.numvar == 7 and c.bbb.neq == 1260
+    same(Oracle2().bind(c), host(rev).bind(c), c, yl)
+
+
+@pytest.mark.parametrize("rev", [0, 1])
+def test_every_drift_part(built, rev, monkeypatch):
+    """diamagnetic (cfydd, cf2dd), resistive (cfrd) and B x grad(T) (cfbgt) parts and the diamagnetic currents (cfjpy, cfjp2) on top of
+    the deck's ExB / grad-B set; 2x-refined mesh with the private copies poisoned in the forward order"""
+    from uedge_b200.cases import load_grid_npz, refine_grid
+    if rev == 0:
+        monkeypatch.setenv("UE_GEN_POISON", "1")
+    c, yl = jupyter_case(all_drifts, grid=refine_grid(load_grid_npz(), 2, 2) if rev == 0 else None)
     same(Oracle2().bind(c), host(rev).bind(c), c, yl)
 
 

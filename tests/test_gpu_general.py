@@ -10,7 +10,7 @@ from tests.refplanes import check_against_reference
 from tests.test_oracle2_golden import twin
 from tests.util import psetnk_inputs
 from uedge_b200.cases import box2_case
-from uedge_b200.cases2 import SUBSETS, Oracle2, box2_initial_state, d3d_full_physics_case, gas_energy_case, inputex_case, jupyter_case, load_gen, switch_variant
+from uedge_b200.cases2 import SUBSETS, Oracle2, all_drifts, box2_initial_state, d3d_full_physics_case, gas_energy_case, inputex_case, jupyter_case, load_gen, switch_variant
 
 pytestmark = pytest.mark.gpu
 
@@ -90,6 +90,12 @@ def test_jupyter_drift_case(built, refine):
     o.pandf1(yl); g.pandf1(yl)
     for nm in ("vyce1", "vycb1", "v2ce1", "v2cb1", "ve2cb", "veycb", "fqyb", "fqxb", "fqyd", "wjdote", "vex", "vey", "resphi"):
         assert np.array_equal(o.plane(nm), g.plane(nm)), nm
+
+
+def test_every_drift_part(built):
+    """the diamagnetic, resistive and B x grad(T) parts and the diamagnetic currents switched on as well"""
+    c, yl = jupyter_case(all_drifts)
+    same(Oracle2().bind(c), load_gen().bind(c), c, yl)
 
 
 @pytest.mark.parametrize("deck", ["jupyter", "inputex"])

@@ -158,6 +158,12 @@ def jupyter_case(mods=None, v8_0_defaults=True, grid=None):
     return c, yl
 
 
+def all_drifts(b, com):
+    """mods for jupyter_case: the diamagnetic and resistive parts of the drifts and currents on top of the deck's ExB / grad-B set
+    (the decks keep them at zero: `cfydd`, `cf2dd` 'always = 0' in jupyter/case_setup.py:99-103)"""
+    b.cfydd = 1.0; b.cf2dd = 1.0; b.cfrd = 1.0; b.cfbgt = 1.0; b.cfjpy = 1.0; b.cfjp2 = 1.0
+
+
 def gas_energy_case(mods=None, grid=None, deck="jupyter"):
     """istgon = 1 (the gas energy equation engbalg, bbb/oderhs.m:7508-7878) on top of a deck with inertial atoms: `jupyter` = the drift
     case on the DIII-D mesh (numvar 8), `inputex` = pyexamples/input_example on its non-orthogonal mesh (the fegxy term).  As the
@@ -206,7 +212,8 @@ def switch_variant(seed):
     # cross-field drifts, grad-B currents, the new potential model with its core conditions, Joule heating (jupyter/case_setup.py:87-110)
     for k, vals in (("cfyef", (1.0, 0.5)), ("cf2ef", (1.0, 0.5)), ("cfybf", (1.0,)), ("cf2bf", (1.0,)), ("cfqybf", (1.0,)), ("cfq2bf", (1.0,)), ("isnewpot", (1,)), ("rnewpot", (1.0, 0.5)),
                     ("jhswitch", (1, 2)), ("isfdiax", (1.0,)), ("iphibcc", (1, 2, 3)), ("cfcurv", (0.5,)), ("cfgradb", (0.5,)), ("eycore", (10.0,)), ("icoreelec", (5.0,)),
-                    ("cfqybbo", (1.0,)), ("cfqydbo", (1.0,)), ("cfniybbo", (1.0,)), ("cfeeybbo", (1.0,)), ("ExtendedJacPhi", (0,))):
+                    ("cfqybbo", (1.0,)), ("cfqydbo", (1.0,)), ("cfniybbo", (1.0,)), ("cfeeybbo", (1.0,)), ("ExtendedJacPhi", (0,)),
+                    ("cfydd", (1.0,)), ("cf2dd", (1.0,)), ("cfrd", (1.0, 0.5)), ("cfbgt", (1.0,)), ("cfjpy", (1.0,)), ("cfjp2", (1.0,))):
         if rng.random() < 0.4:
             ch[k] = pick(*vals)
 

@@ -69,7 +69,7 @@ HD int iabs(int a) { return a < 0 ? -a : a; }
   P1(floxe) P1(floxi) P1(floye) P1(floyi) P1(conxe) P1(conxi) P1(conye) P1(conyi) P1(feex) P1(feey) P1(feix) P1(feiy) P1(feexy) P1(feixy) P1(resee) P1(resei) \
   P1(erliz) P1(erlrc) P1(eeli) P1(vsoreec) P1(vsoree) P1(pwribkg) P1(pwrebkg) P1(pradhyd) \
   P1(fqp) P1(fqx) P1(fqy) P1(fq2) P1(fqxb) P1(fqyb) P1(fqyn) P1(fqym) P1(fqymi) P1(fqya) P1(fqydt) P1(fqydti) P1(fqyao) P1(fqyae) P1(fqyd) P1(fqygp) P1(fq2d) P1(netap) P1(resphi) P1(dphi_iy1) \
-  P2(vyce) P2(vycb) P2(vycp) P1(veycb) P2(v2ce) P2(v2cb) P1(ve2cb) P1(wjdote) P1(segc) P1(floxge) P1(floyge) P1(conxge) P1(conyge) P1(fegx) P1(fegy) P1(fegxy) P1(reseg) P2(fmity) P2(fqymi_) P2(fniycbo) P1(feeycbo) P1(feiycbo) P1(kappal) P1(kappar) P1(bcel) P1(bcer) P1(bcil) P1(bcir) \
+  P2(vyce) P2(vycb) P2(vycp) P1(veycb) P2(v2ce) P2(v2cb) P1(ve2cb) P1(ve2cd) P1(wjdote) P1(segc) P1(floxge) P1(floyge) P1(conxge) P1(conyge) P1(fegx) P1(fegy) P1(fegxy) P1(reseg) P2(fmity) P2(fqymi_) P2(fniycbo) P1(feeycbo) P1(feiycbo) P1(kappal) P1(kappar) P1(bcel) P1(bcer) P1(bcil) P1(bcir) \
   P1(fqpsatlb) P1(fqpsatrb) P1(fdiaxlb) P1(fdiaxrb)
 
 struct Gen {
@@ -142,7 +142,7 @@ double ev, qe, me, mp, pi_, cutlo, rt8opi, temin, tgmin, nnorm, ennorm, temp0, v
     cfnidhg2, cftgeqp, flalftxy, flalfgnx, flalfgny, nlimgx, nlimgy, cfloxiplt, cfloygwall, cfjve, rsigpl, rsigplcore, bcen, bceew, bciew, cfqym, cfqydt,
     cfjpy, cfjp2, cfqybf, cfq2bf, cfqybbo, cfqydbo, cfydd_, cfjp2_, cfqyn, cfqyao, cfqya, cfqyae, cfjpy_, fqpsatlb_unused, lnlam_unused, phiwi0, phiwo0,
     kappamx, kappa0, cfsigm, fqsatlb_u, fupe_cur, dtphi_, cfhcxgc_u, lyphi0, lyphi1, isparmultdt_u, tewallmin_u, cfwjdotelim, cfeexdbo, cfeixdbo, cfkincor,
-    cfyef, cf2ef, cfybf, cf2bf, cfcurv, cfgradb, eycore, icoreelec, cfniybbo, cfeeybbo;
+    cfyef, cf2ef, cfybf, cf2bf, cfcurv, cfgradb, eycore, icoreelec, cfniybbo, cfeeybbo, cfydd, cf2dd, cfrd, cfbgt;
 int ExtendedJacPhi, istgcore, istgpfc, istgwc, istglb, istgrb, isfegxyqflave;
 int64_t numvar_;
 double tgcore, cftgticore, tgwall, lytg1, lytg2, cftgtipltl, cftgtipltr, cftgtipfc, cftgtiwc, cgengmpl, cgengmw, cfalbedo, recyce, recycwe, cvgpg, cfcvtg, cfegxy, flalftgxy;
@@ -182,6 +182,8 @@ HD int ALG(int64_t iv) { return (int)iseqalgd[iv]; }
 HD double ave(double t0, double t1) { return 2 * t0 * t1 / (cutlo + t0 + t1); }  // oderhs.m:697
 HD double sgn(double a, double b) { return copysign(fabs(a), b); }     // Fortran sign(a,b)
 HD double sq(double x) { return x * x; }
+// perpendicular resistivity (statement function of pandf, oderhs.m:698)
+HD double etaper(int ix, int iy) const { return 3.234e-9 * A(loglambda, ix, iy) / ue_pow(mx(A(te, ix, iy), temin * ev) / (1000. * ev), 1.5); }
 HD double powi(double x, int64_t n) { double r = 1.0; while (n > 0) { if (n & 1) r *= x; x *= x; n >>= 1; } return r; }
 
 // ---- hydrogen rates (aph/aphrates.m), istabon 0 / 7 / 10: same restatement as ue_oracle.cpp ----------------------
@@ -890,7 +892,7 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
         else A(loglambda, ix, iy) = 25.3 - 1.15 * ue_log10(1.e-6 * nexface) + 2.33167537087122e+00 * ue_log10(teev);
       }
     // radial and "2" velocities of the ion species: diffusive parts plus the ExB and grad-B / curvature drifts (oderhs.m:1167-1471);
-    // the diamagnetic (cfydd, cf2dd), resistive (cfrd) and classical (cfvycf, cfvycr) parts are refused in init
+    // with the diamagnetic (cfydd, cf2dd) and resistive (cfrd) parts; the classical ones (cfvycf, cfvycr) are refused in init; bfacx/yrozh = 1
     for (int f = 0; f < nfsp; ++f) {
       if (!(zi[f] > 1.e-10)) continue;
       const double qion = zi[f] * qe;
@@ -914,8 +916,9 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
           double difnimix = A(diffusivwrk, ix, iy);
           A(vydd[f], ix, iy) = A(vydd[f], ix, iy) - 1. * difnimix * (2 * (1 - isvylog) * ((A(niy1[f], ix, iy) - A(niy0[f], ix, iy)) / A(dynog, ix, iy)) / (A(niy1[f], ix, iy) + A(niy0[f], ix, iy)) +
                                                                       isvylog * (ue_log(A(niy1[f], ix, iy)) - ue_log(A(niy0[f], ix, iy))) / A(dynog, ix, iy));
-          A(vy[f], ix, iy) = A(vydd[f], ix, iy) + cfyef * A(vyce[f], ix, iy) + cfybf * A(vycb[f], ix, iy);
-          A(vygp[f], ix, iy) = cfybf * A(vycp[f], ix, iy) + A(vydd[f], ix, iy) + cfyef * A(vyce[f], ix, iy);  // (cfydd + cfybf) bfacyrozh vycp with cfydd = 0, bfacyrozh = 1
+          const double vyrd = -2. * A(gpry, ix, iy) / (sq(A(btot, ix, iy)) / etaper(ix, iy) + sq(A(btot, ix, iy + 1)) / etaper(ix, iy + 1));
+          A(vy[f], ix, iy) = cfydd * A(vycp[f], ix, iy) + cfrd * vyrd + A(vydd[f], ix, iy) + cfyef * A(vyce[f], ix, iy) + cfybf * A(vycb[f], ix, iy);
+          A(vygp[f], ix, iy) = (cfydd + cfybf) * A(vycp[f], ix, iy) + cfrd * vyrd + A(vydd[f], ix, iy) + cfyef * A(vyce[f], ix, iy);
         }
       FOR2(iy, j1, j6, ix, i1, i6) {
           const int ix2 = IXP1(ix, iy), iy1 = mx(0, iy - 1);
@@ -937,8 +940,11 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
           A(v2dd[f], ix, iy) = -2. * difpr2[f] * A(gprx, ix, iy) / (A(pr, ix2, iy) / A(rbfbt, ix2, iy) + A(pr, ix, iy) / A(rbfbt, ix, iy)) -
                                2. * (fcdif * difni2[f] + 0.) * (A(ni[f], ix2, iy) - A(ni[f], ix, iy)) /
                                    (A(ni[f], ix2, iy) / (A(rbfbt, ix2, iy) * A(gx, ix2, iy)) + A(ni[f], ix, iy) / (A(rbfbt, ix, iy) * A(gx, ix, iy)));
-          A(v2[f], ix, iy) = A(v2dd[f], ix, iy) + cf2ef * A(v2ce[f], ix, iy) + cf2bf * A(v2cb[f], ix, iy);
-          A(v2xgp[f], ix, iy) = 0.5 * (A(rbfbt, ix, iy) + A(rbfbt, ix2, iy)) * (cf2bf * v2cd + A(v2dd[f], ix, iy) + cf2ef * A(v2ce[f], ix, iy));  // (cf2dd + cf2bf) bfacxrozh v2cd
+          const double temp3 = 4. * (A(prev, ix, iy) - A(prev, ix, iy1)) * A(gyc, ix, iy);
+          A(ve2cd, ix, iy) = -temp3 / ((A(btot, ix, iy) + A(btot, ix2, iy)) * qe * (A(ni[f], ix, iy) + A(ni[f], ix2, iy)));
+          const double v2rd = -2. * A(gprx, ix, iy) / (A(btot, ix, iy) / (etaper(ix, iy) * A(rbfbt2, ix, iy)) + A(btot, ix2, iy) / (etaper(ix2, iy) * A(rbfbt2, ix2, iy)));
+          A(v2[f], ix, iy) = cf2dd * v2cd + cfrd * v2rd + A(v2dd[f], ix, iy) + cf2ef * A(v2ce[f], ix, iy) + cf2bf * A(v2cb[f], ix, iy);
+          A(v2xgp[f], ix, iy) = 0.5 * (A(rbfbt, ix, iy) + A(rbfbt, ix2, iy)) * ((cf2dd + cf2bf) * v2cd + cfrd * v2rd + A(v2dd[f], ix, iy) + cf2ef * A(v2ce[f], ix, iy));
           if (isnonog == 1 && iy <= ny) {  // oderhs.m:1408-1432
             double grdnv = grdnv_y(ni[f], ix, iy, 1) / A(dxnog, ix, iy);
             A(vytan[f], ix, iy) = (fcdif * difni[f] + 0.) * (grdnv / ue_cos(A(angfx, ix, iy)) - (ue_log(A(ni[f], ix2, iy)) - ue_log(A(ni[f], ix, iy))) * A(gxf, ix, iy));
@@ -1000,7 +1006,7 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
         A(upe, ix, iy) = (A(upe, ix, iy) - 1. * A(fqp, ix, iy) / (A(rrv, ix, iy) * A(sx, ix, iy) * qe)) / (0.5 * (A(ne, ix, iy) + A(ne, ix1, iy)));
       }
     FOR2(iy, j1, j6, ix, i1, i6)
-        A(vex, ix, iy) = A(upe, ix, iy) * A(rrv, ix, iy) + (cf2ef * A(v2ce[0], ix, iy) + cf2bf * A(ve2cb, ix, iy)) * 0.5 * (A(rbfbt, ix, iy) + A(rbfbt, IXP1(ix, iy), iy)) - A(vytan[0], ix, iy);
+        A(vex, ix, iy) = A(upe, ix, iy) * A(rrv, ix, iy) + (cf2ef * A(v2ce[0], ix, iy) + cf2bf * A(ve2cb, ix, iy) + cf2dd * A(ve2cd, ix, iy)) * 0.5 * (A(rbfbt, ix, iy) + A(rbfbt, IXP1(ix, iy), iy)) - A(vytan[0], ix, iy);
     for (int f = 0; f < nfsp; ++f)
       FOR2(iy, j1, j5, ix, i1, i6) A(vey, ix, iy) = A(vey, ix, iy) + A(vy[f], ix, iy) * zi[f] * 0.5 * (A(niy0[f], ix, iy) + A(niy1[f], ix, iy));
     FOR2(iy, j1, j5, ix, i1, i6) A(vey, ix, iy) = (A(vey, ix, iy) - cfjve * A(fqy, ix, iy) / (A(sy, ix, iy) * qe)) / (0.5 * (A(ney0, ix, iy) + A(ney1, ix, iy)));
@@ -1552,6 +1558,34 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
             if (iy == 0) feiycbo[ix] = feiycbo[ix] + cfloyi * fniycbo[f][ix] * A(ti, ix, 0);
           }
     }
+    if (fabs(cfbgt) > 0) {  // B x grad(T) heat flows (oderhs.m:4131-4229); the plate terms of cfeexdbo / cfeixdbo are refused in init
+      for (int f = 0; f < nfsp; ++f) {
+      FOR2(iy, j4, j8, ix, i1, i5) {
+          const int iy1 = mx(0, iy - 1), ix1 = IXP1(ix, iy);
+          if (iy == 0 || iy == ny + 1) continue;
+          const double temp1 = 4.0 * (A(tiv, ix, iy) - A(tiv, ix, iy1)) * A(gyc, ix, iy);
+          if (zi[f] > 1.e-10) A(floxi, ix, iy) = A(floxi, ix, iy) + cfbgt * ((5 * A(sx, ix, iy) / (32 * qe * zi[f])) * (A(ni[f], ix, iy) + A(ni[f], ix1, iy)) * (A(rbfbt2, ix, iy) + A(rbfbt2, ix1, iy)) * temp1);
+        }
+      FOR2(iy, j1, j5, ix, i4, i8) {
+          const int ix3 = IXM1(ix, iy);
+          if (ix == ixlb || ix == ixrb + 1) continue;
+          const double temp1 = 4.0 * (A(tiv, ix, iy) - A(tiv, ix3, iy)) * A(gxc, ix, iy);
+          if (zi[f] > 1.e-10) A(floyi, ix, iy) = A(floyi, ix, iy) - cfbgt * (5 * A(sy, ix, iy) / (32 * qe * zi[f])) * (A(ni[f], ix, iy) + A(ni[f], ix, iy + 1)) * (A(rbfbt2, ix, iy) + A(rbfbt2, ix, iy + 1)) * temp1;
+        }
+      }
+      FOR2(iy, j4, j8, ix, i1, i5) {
+          const int iy1 = mx(0, iy - 1), ix1 = IXP1(ix, iy);
+          if (iy == 0 || iy == ny + 1) continue;
+          const double temp1 = 4.0 * (A(tev, ix, iy) - A(tev, ix, iy1)) * A(gyc, ix, iy);
+          A(floxe, ix, iy) = A(floxe, ix, iy) - cfbgt * ((5 * A(sx, ix, iy) / (32 * qe)) * (A(ne, ix, iy) + A(ne, ix1, iy)) * (A(rbfbt2, ix, iy) + A(rbfbt2, ix1, iy)) * temp1);
+        }
+      FOR2(iy, j1, j5, ix, i4, i8) {
+          const int ix3 = IXM1(ix, iy);
+          if (ix == ixlb || ix == ixrb + 1) continue;
+          const double temp1 = 4.0 * (A(tev, ix, iy) - A(tev, ix3, iy)) * A(gxc, ix, iy);
+          A(floye, ix, iy) = A(floye, ix, iy) + cfbgt * (5 * A(sy, ix, iy) / (32 * qe)) * (A(ne, ix, iy) + A(ne, ix, iy + 1)) * (A(rbfbt2, ix, iy) + A(rbfbt2, ix, iy + 1)) * temp1;
+        }
+    }
     FOR2(iy, j4, j8, ix, i1, i5) A(floxi, ix, iy) = A(floxi, ix, iy) + cftiexclg * cfneut * cfneutsor_ei * cngtgx[0] * cfcvti * 2.5 * A(fngx, ix, iy);  // oderhs.m:4234-4240
     FOR1(iy, j4, j8) { A(floxi, nx + 1, iy) = 0.0; }
     FOR2(iy, j1, j5, ix, i4, i8) A(floyi, ix, iy) = A(floyi, ix, iy) + cftiexclg * cfneut * cfneutsor_ei * cngtgy[0] * 2.5 * A(fngy, ix, iy);
@@ -1752,7 +1786,12 @@ HD void calc_currents(const Win& w) {
         }
       }
     }
-  FOR2(iy, j1p, j6p, ix, i1, i5) A(fq2, ix, iy) = 0.;  // cfjp2 = 0 (potencur.m:206-230)
+  FOR2(iy, j1p, j6p, ix, i1, i5) {  // potencur.m:206-221
+      const int iy1 = mx(0, iy - 1), ix1 = IXP1(ix, iy);
+      const double temp1 = 4.0 * (A(prtv, ix, iy) - A(prtv, ix, iy1)) * A(gyc, ix, iy);
+      A(fq2d, ix, iy) = A(sx, ix, iy) * 0.25 * temp1 * (A(rbfbt, ix1, iy) + A(rbfbt, ix, iy)) / (A(btot, ix, iy) + A(btot, ix1, iy));
+      A(fq2, ix, iy) = cfjp2 * A(fq2d, ix, iy);
+    }
   FOR2(iy, j1p, j5p, ix, i1, i6) {  // potencur.m:235-290
       double nbary = (A(ne, ix, iy + 1) * A(gy, ix, iy + 1) + A(ne, ix, iy) * A(gy, ix, iy)) / (A(gy, ix, iy + 1) + A(gy, ix, iy));
       double zfac = 1. / (A(zeff, ix, iy) * (1.193 - 0.2205 * A(zeff, ix, iy) + 0.0275 * sq(A(zeff, ix, iy))));
@@ -1801,7 +1840,7 @@ HD void calc_currents(const Win& w) {
     for (int iy = ny; iy >= ny + 1 - nfqya0ow_; --iy) A(fqya, ix, iy) = 0.;
   }
   FOR2(iy, j1p, j5p, ix, i1, i6) {
-      A(fqy, ix, iy) = (1. - rnewpot_) * A(fqyao, ix, iy) + rnewpot_ * A(fqya, ix, iy) + cfqybf * A(fqyb, ix, iy) + cfqym * A(fqym, ix, iy) + 0.;
+      A(fqy, ix, iy) = (1. - rnewpot_) * A(fqyao, ix, iy) + rnewpot_ * A(fqya, ix, iy) + cfqybf * A(fqyb, ix, iy) + cfqym * A(fqym, ix, iy) + cfjpy * A(fqyd, ix, iy);
       A(fqygp, ix, iy) = (1. - rnewpot_) * A(fqyao, ix, iy) + rnewpot_ * A(fqya, ix, iy) + cfqym * A(fqym, ix, iy) + A(fqyd, ix, iy);
       A(fqy, ix, iy) = A(fqy, ix, iy) + cfqydt * A(fqydt, ix, iy);  // nx = nxold, ny = nyold; cfqydt = 0
     }
@@ -2586,7 +2625,7 @@ HD int pandf1(int xc, int yc, const double* yl, double* yldot) {
   return 0;
 }
   // ---- slab layout -----------------------------------------------------------------------------------------------------
-  double *vyce[2], *vycb[2], *vycp[2], *veycb, *v2ce[2], *v2cb[2], *ve2cb, *wjdote, *fmity[2], *fqymi_[2];
+  double *vyce[2], *vycb[2], *vycp[2], *veycb, *v2ce[2], *v2cb[2], *ve2cb, *ve2cd, *wjdote, *fmity[2], *fqymi_[2];
   double *segc, *floxge, *floyge, *conxge, *conyge, *fegx, *fegy, *fegxy, *reseg;  // gas energy equation (engbalg, oderhs.m:7508-7878)  // drift velocities (oderhs.m:1167-1420), Joule heating, inertia-current work planes
   HD static int nplanes() {
     int n = 0;
