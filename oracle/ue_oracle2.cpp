@@ -909,7 +909,7 @@ struct O2 {
           double difnimix = A(diffusivwrk, ix, iy);
           A(vydd[f], ix, iy) = A(vydd[f], ix, iy) - 1. * difnimix * (2 * (1 - isvylog) * ((A(niy1[f], ix, iy) - A(niy0[f], ix, iy)) / A(dynog, ix, iy)) / (A(niy1[f], ix, iy) + A(niy0[f], ix, iy)) +
                                                                       isvylog * (ue_log(A(niy1[f], ix, iy)) - ue_log(A(niy0[f], ix, iy))) / A(dynog, ix, iy));
-          const double vyrd = -2. * A(gpry, ix, iy) / (sq(A(btot, ix, iy)) / etaper(ix, iy) + sq(A(btot, ix, iy + 1)) / etaper(ix, iy + 1));
+          const double vyrd = cfrd == 0. ? 0. : -2. * A(gpry, ix, iy) / (sq(A(btot, ix, iy)) / etaper(ix, iy) + sq(A(btot, ix, iy + 1)) / etaper(ix, iy + 1));  // (not evaluated when switched off)
           A(vy[f], ix, iy) = cfydd * A(vycp[f], ix, iy) + cfrd * vyrd + A(vydd[f], ix, iy) + cfyef * A(vyce[f], ix, iy) + cfybf * A(vycb[f], ix, iy);
           A(vygp[f], ix, iy) = (cfydd + cfybf) * A(vycp[f], ix, iy) + cfrd * vyrd + A(vydd[f], ix, iy) + cfyef * A(vyce[f], ix, iy);
         }
@@ -936,7 +936,7 @@ struct O2 {
                                    (A(ni[f], ix2, iy) / (A(rbfbt, ix2, iy) * A(gx, ix2, iy)) + A(ni[f], ix, iy) / (A(rbfbt, ix, iy) * A(gx, ix, iy)));
           const double temp3 = 4. * (A(prev, ix, iy) - A(prev, ix, iy1)) * A(gyc, ix, iy);
           A(ve2cd, ix, iy) = -temp3 / ((A(btot, ix, iy) + A(btot, ix2, iy)) * qe * (A(ni[f], ix, iy) + A(ni[f], ix2, iy)));
-          const double v2rd = -2. * A(gprx, ix, iy) / (A(btot, ix, iy) / (etaper(ix, iy) * A(rbfbt2, ix, iy)) + A(btot, ix2, iy) / (etaper(ix2, iy) * A(rbfbt2, ix2, iy)));
+          const double v2rd = cfrd == 0. ? 0. : -2. * A(gprx, ix, iy) / (A(btot, ix, iy) / (etaper(ix, iy) * A(rbfbt2, ix, iy)) + A(btot, ix2, iy) / (etaper(ix2, iy) * A(rbfbt2, ix2, iy)));
           A(v2[f], ix, iy) = cf2dd * v2cd + cfrd * v2rd + A(v2dd[f], ix, iy) + cf2ef * A(v2ce[f], ix, iy) + cf2bf * A(v2cb[f], ix, iy);
           A(v2xgp[f], ix, iy) = 0.5 * (A(rbfbt, ix, iy) + A(rbfbt, ix2, iy)) * ((cf2dd + cf2bf) * v2cd + cfrd * v2rd + A(v2dd[f], ix, iy) + cf2ef * A(v2ce[f], ix, iy));
           if (isnonog == 1 && iy <= ny) {  // oderhs.m:1408-1432

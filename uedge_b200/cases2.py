@@ -297,6 +297,17 @@ class Lib2:
         n = nnz.value
         return jac[:n].copy(), ja[:n].copy(), ia
 
+    def jac_calc_raw(self, yl, y0, ml, mu, nnzmx, bufs=None):
+        """The same C-ABI call into caller-owned arrays (what a host code does): returns nnz and the buffers (jac, ja, ia)."""
+        if bufs is None:
+            bufs = (np.zeros(nnzmx), np.zeros(nnzmx, dtype=np.int64), np.zeros(self.neq + 1, dtype=np.int64))
+        jac, ja, ia = bufs
+        nnz = C.c_int64(0)
+        self._f("jac_calc").argtypes = [C.c_int64, C.c_double] + [C.c_void_p] * 2 + [C.c_int64] * 3 + [C.c_void_p] * 3 + [C.POINTER(C.c_int64)]
+        P = lambda a: a.ctypes.data_as(C.c_void_p)
+        self._ck(self._f("jac_calc")(self.neq, 0.0, P(yl), P(y0), int(ml), int(mu), int(nnzmx), P(jac), P(ja), P(ia), C.byref(nnz)), "jac_calc")
+        return nnz.value, bufs
+
     def plane(self, name):
         out = np.zeros(self.NC)
         self._f("get_plane").argtypes = [C.c_char_p, C.c_void_p]
