@@ -75,7 +75,7 @@ double ev, qe, me, mp, pi_, cutlo, rt8opi, temin, tgmin, nnorm, ennorm, temp0, v
     cfnidhg2, cftgeqp, flalftxy, flalfgnx, flalfgny, nlimgx, nlimgy, cfloxiplt, cfloygwall, cfjve, rsigpl, rsigplcore, bcen, bceew, bciew, cfqym, cfqydt,
     cfjpy, cfjp2, cfqybf, cfq2bf, cfqybbo, cfqydbo, cfydd_, cfjp2_, cfqyn, cfqyao, cfqya, cfqyae, cfjpy_, fqpsatlb_unused, lnlam_unused, phiwi0, phiwo0,
     kappamx, kappa0, cfsigm, fqsatlb_u, fupe_cur, dtphi_, cfhcxgc_u, lyphi0, lyphi1, isparmultdt_u, tewallmin_u, cfwjdotelim, cfeexdbo, cfeixdbo, cfkincor,
-    cfyef, cf2ef, cfybf, cf2bf, cfcurv, cfgradb, eycore, icoreelec, cfniybbo, cfeeybbo, cfydd, cf2dd, cfrd, cfbgt;
+    cfyef, cf2ef, cfybf, cf2bf, cfcurv, cfgradb, eycore, icoreelec, cfniybbo, cfeeybbo, cfydd, cf2dd, cfrd, cfbgt, cfvycf, cfvycr, cfeta1, cfrtaue, cfcl_e, cfcl_i, omgci_taui, omgce_taue, nuneo;
 int ExtendedJacPhi, istgcore, istgpfc, istgwc, istglb, istgrb, isfegxyqflave;
 double tgcore, cftgticore, tgwall, lytg1, lytg2, cftgtipltl, cftgtipltr, cftgtipfc, cftgtiwc, cgengmpl, cgengmw, cfalbedo, recyce, recycwe, cvgpg, cfcvtg, cfegxy, flalftgxy;
 const double* idxtg_;
@@ -86,6 +86,7 @@ V cngfx_, cngfy_, mi, zi, n0, fnorm, n0g_, mg_, ngbackg_, vcony, difpr, difni, d
 // geometry planes / lines
 const double *vol, *gx, *gy, *gxf, *gyf, *gxc, *gyc, *sx, *sxnp, *sy, *rr, *rrv, *volv, *syv, *dxnog, *dynog, *btot, *rbfbt, *rbfbt2, *lcone, *lconi, *angfx,
     *ngfix, *dx_, *dy_, *curvrby, *gradby, *curvrb2, *gradb2;
+const double *b_c, *rm_c;  // b(,,0), rm(,,0): cell-centre field and major radius
 const double *fxm[2], *fx0[2], *fxp[2], *fxmy[2], *fxpy[2], *fym[2], *fy0[2], *fyp[2], *fymx[2], *fypx[2], *fymv[2], *fy0v[2], *fypv[2], *fymxv[2], *fypxv[2];
 const double *ixm1d, *ixp1d, *isxptyd, *isxptxd;
 const double *fgtdx, *fgtdy, *flalfea, *flalfia, *flalfva, *flalfgxa, *flalfgxya, *flalfgya, *flalfvgxa, *flalfvgya, *flalfvgxya, *flalftgxa, *flalftgya, *yyf;
@@ -295,7 +296,7 @@ struct O2 {
   V gprx, gpry, gpex, gtex, gtix, gpey, gtey, gtiy, ex, ey, nity0, nity1, ney0, ney1, tey0, tey1, tiy0, tiy1, phiy0, phiy1;
   V ngy0, ngy1, tgy0, tgy1, pgy0, pgy1, phiv, tiv, tev, prev, prtv, priv[2];
   V loglambda, diffusivwrk, vy[2], vydd[2], vygp[2], v2[2], v2dd[2], v2xgp[2], vytan[2], frice, frici[2], upi[2], uup[2], uu[2], upe, vex, vey;
-  V vyce[2], vycb[2], vycp[2], veycb, v2ce[2], v2cb[2], ve2cb, ve2cd, wjdote;
+  V vyce[2], vycb[2], vycp[2], veycb, v2ce[2], v2cb[2], ve2cb, ve2cd, v2cd[2], vycf, vycr, wjdote;
   V segc, floxge, floyge, conxge, conyge, fegx, fegy, fegxy, reseg;  // gas energy equation (engbalg, oderhs.m:7508-7878)  // cross-field drift velocities (oderhs.m:1167-1420), Joule heating
   V nuiz, nurc, nucx, nuix, psorbgg, psorgc, psorc[2], psordis, psorxrc[2], psorrgc, psorg, psor[2], psorxr[2], psorrg;
   V snic[2], sniv[2], psori[2], smoc[2], smov[2], seec, seev, seic, seiv;
@@ -319,7 +320,7 @@ struct O2 {
     P1(gprx) P1(gpry) P1(gpex) P1(gtex) P1(gtix) P1(gpey) P1(gtey) P1(gtiy) P1(ex) P1(ey) P1(nity0) P1(nity1) P1(ney0) P1(ney1) P1(tey0) P1(tey1)
     P1(tiy0) P1(tiy1) P1(phiy0) P1(phiy1) P1(ngy0) P1(ngy1) P1(tgy0) P1(tgy1) P1(pgy0) P1(pgy1) P1(phiv) P1(tiv) P1(tev) P1(prev) P1(prtv) P2(priv)
     P1(loglambda) P1(diffusivwrk) P2(vy) P2(vydd) P2(vygp) P2(v2) P2(v2dd) P2(v2xgp) P2(vytan) P1(frice) P2(frici) P2(upi) P2(uup) P2(uu) P1(upe) P1(vex) P1(vey)
-    P2(vyce) P2(vycb) P2(vycp) P1(veycb) P2(v2ce) P2(v2cb) P1(ve2cb) P1(ve2cd) P1(wjdote)
+    P2(vyce) P2(vycb) P2(vycp) P1(veycb) P2(v2ce) P2(v2cb) P1(ve2cb) P1(ve2cd) P2(v2cd) P1(vycf) P1(vycr) P1(wjdote)
     P1(segc) P1(floxge) P1(floyge) P1(conxge) P1(conyge) P1(fegx) P1(fegy) P1(fegxy) P1(reseg)
     P1(nuiz) P1(nurc) P1(nucx) P1(nuix) P1(psorbgg) P1(psorgc) P2(psorc) P1(psordis) P2(psorxrc) P1(psorrgc) P1(psorg) P2(psor) P2(psorxr) P1(psorrg)
     P2(snic) P2(sniv) P2(psori) P2(smoc) P2(smov) P1(seec) P1(seev) P1(seic) P1(seiv)
@@ -334,6 +335,11 @@ struct O2 {
     return p;
   }
 
+// classical (Braginskii) collisional factors of pandf's simple model (oderhs.m:1157-1166), evaluated where they are used
+   double eta1_(int ix, int iy) const { return cfeta1 * 0.3 * A(nm[0], ix, iy) * A(ti, ix, iy) * (1 / (qe * A(btot, ix, iy))) / omgci_taui; }
+   double rtaue_(int ix, int iy) const { return cfrtaue * (1 / (qe * A(btot, ix, iy))) / omgce_taue; }
+   double dclass_i_(int ix, int iy) const { return cfcl_i == 0. ? 0. : cfcl_i * eta1_(ix, iy) / (0.3 * A(nm[0], ix, iy)); }
+   double dclass_e_(int ix, int iy) const { return cfcl_e == 0. ? 0. : cfcl_e * A(te, ix, iy) * rtaue_(ix, iy); }
   // perpendicular resistivity (statement function of pandf, oderhs.m:698)
   double etaper(int ix, int iy) const { return 3.234e-9 * A(loglambda, ix, iy) / ue_pow(std::max(A(te, ix, iy), temin * ev) / (1000. * ev), 1.5); }
 
@@ -902,6 +908,16 @@ struct O2 {
           A(vycp[f], ix, 0) = 0.; A(vycp[f], ix, ny) = 0.;
           A(vydd[f], ix, iy) = vcony[f] + 0. + 0. - (difpr[f] + 0.) * (2 * A(gpry, ix, iy) / (A(pr, ix, iy + 1) + A(pr, ix, iy)) - 3.0 * A(gtey, ix, iy) / (A(tey1, ix, iy) + A(tey0, ix, iy)));
           A(diffusivwrk, ix, iy) = fcdif * difni[f] + 0.;
+          if (cfrtaue != 0.)  // classical momentum-transfer and viscosity velocities (oderhs.m:1240-1262)
+            A(vycr, ix, iy) = -0.5 * (rtaue_(ix, iy) + rtaue_(ix, iyp1)) * ((A(gpiy[0], ix, iy) + A(gpey, ix, iy)) / (0.5 * (A(niy1[0], ix, iy) + A(niy0[0], ix, iy))) - 1.5 * A(gtey, ix, iy));
+          if (cfeta1 != 0. && iy <= ny - 1 && iy > 0) {
+            const int iym1 = std::max(iy - 1, 0);
+            const double geyym = 2 * A(gpiy[0], ix, iym1) / (A(ney1, ix, iym1) + A(ney0, ix, iym1)) - qe * A(ey, ix, iym1);
+            const double geyy0 = 2 * A(gpiy[0], ix, iy) / (A(ney1, ix, iy) + A(ney0, ix, iy)) - qe * A(ey, ix, iy);
+            const double geyyp = 2 * A(gpiy[0], ix, iyp1) / (A(ney1, ix, iyp1) + A(ney0, ix, iyp1)) - qe * A(ey, ix, iyp1);
+            const double dgeyy0 = (geyy0 - geyym) * eta1_(ix, iy) * A(gy, ix, iy), dgeyy1 = (geyyp - geyy0) * eta1_(ix, iyp1) * A(gy, ix, iyp1);
+            A(vycf, ix, iy) = 2 * (dgeyy1 - dgeyy0) * A(gy, ix, iy) / ((A(ney1, ix, iy) + A(ney0, ix, iy)) * sq(qe * 0.5 * (A(btot, ix, iy) + A(btot, ix, iym1))));
+          }
         }
       }
       for (int iy = j1; iy <= j5; ++iy)
@@ -910,8 +926,8 @@ struct O2 {
           A(vydd[f], ix, iy) = A(vydd[f], ix, iy) - 1. * difnimix * (2 * (1 - isvylog) * ((A(niy1[f], ix, iy) - A(niy0[f], ix, iy)) / A(dynog, ix, iy)) / (A(niy1[f], ix, iy) + A(niy0[f], ix, iy)) +
                                                                       isvylog * (ue_log(A(niy1[f], ix, iy)) - ue_log(A(niy0[f], ix, iy))) / A(dynog, ix, iy));
           const double vyrd = cfrd == 0. ? 0. : -2. * A(gpry, ix, iy) / (sq(A(btot, ix, iy)) / etaper(ix, iy) + sq(A(btot, ix, iy + 1)) / etaper(ix, iy + 1));  // (not evaluated when switched off)
-          A(vy[f], ix, iy) = cfydd * A(vycp[f], ix, iy) + cfrd * vyrd + A(vydd[f], ix, iy) + cfyef * A(vyce[f], ix, iy) + cfybf * A(vycb[f], ix, iy);
-          A(vygp[f], ix, iy) = (cfydd + cfybf) * A(vycp[f], ix, iy) + cfrd * vyrd + A(vydd[f], ix, iy) + cfyef * A(vyce[f], ix, iy);
+          A(vy[f], ix, iy) = cfydd * A(vycp[f], ix, iy) + cfrd * vyrd + A(vydd[f], ix, iy) + cfyef * A(vyce[f], ix, iy) + cfybf * A(vycb[f], ix, iy) + cfvycf * A(vycf, ix, iy) + cfvycr * A(vycr, ix, iy);
+          A(vygp[f], ix, iy) = (cfydd + cfybf) * A(vycp[f], ix, iy) + cfrd * vyrd + A(vydd[f], ix, iy) + cfyef * A(vyce[f], ix, iy) + cfvycf * A(vycf, ix, iy) + cfvycr * A(vycr, ix, iy);
         }
       for (int iy = j1; iy <= j6; ++iy)
         for (int ix = i1; ix <= i6; ++ix) {
@@ -922,6 +938,7 @@ struct O2 {
           A(v2cb[f], ix, iy) = (cfcurv * (0.5 * (A(tiv, ix, iy) + A(tiv, ix, iy1)) + mi[f] * sq(A(up[f], ix, iy))) * A(curvrb2, ix, iy) + cfgradb * 0.5 * (A(tiv, ix, iy) + A(tiv, ix, iy1)) * A(gradb2, ix, iy)) / qion;
           A(ve2cb, ix, iy) = -(cfcurv * 0.5 * (A(tev, ix, iy) + A(tev, ix, iy1)) * A(curvrb2, ix, iy) + cfgradb * 0.5 * (A(tev, ix, iy) + A(tev, ix, iy1)) * A(gradb2, ix, iy)) / qe;
           const double v2cd = temp2 / ((A(btot, ix, iy) + A(btot, ix2, iy)) * qion * (A(ni[f], ix, iy) + A(ni[f], ix2, iy)));
+          A(this->v2cd[f], ix, iy) = v2cd;
           // plate electron diamagnetic flux for the sheath potential (oderhs.m:1376-1391)
           if (ix == ixlb) {
             const double v2dia = -0.5 * (A(gpey, ixlb + 1, iy) + A(gpey, ixlb + 1, iy1)) / (A(btot, ixlb + 1, iy) * qe * A(ne, ixlb + 1, iy));
@@ -1064,6 +1081,17 @@ struct O2 {
         if (isupgon == 1) { A(psor[1], ix, iy) = -A(psor[0], ix, iy); A(psorxr[1], ix, iy) = -A(psorxr[0], ix, iy); }
       }
 
+    if (cfqyn > 0.) {  // calc_curr_cx (potencur.m:446-495): current from charge exchange and neoclassical damping, now that nucx is known
+      for (int iy = std::max(w.j1p, 1); iy <= std::min(w.j5p, ny - 1); ++iy)
+        for (int ix = i1; ix <= i6; ++ix) {
+          const double omgci = qe * A(b_c, ix, iy) / mi[0];
+          const int ix3 = IXM1(ix, iy + 1), ix4 = IXM1(ix, iy);
+          A(fqyn, ix, iy) = qe * 0.125 * ((A(ngy0, ix, iy) + A(ngy1, ix, iy)) * A(nucx, ix, iy) + (A(niy0[0], ix, iy) + A(niy1[0], ix, iy)) * nuneo) * A(sy, ix, iy) *
+                            (A(v2ce[0], ix, iy) + A(v2cd[0], ix, iy) + A(v2ce[0], ix, iy + 1) + A(v2cd[0], ix, iy + 1) + A(v2ce[0], ix4, iy) + A(v2cd[0], ix4, iy) + A(v2ce[0], ix3, iy + 1) + A(v2cd[0], ix3, iy + 1)) / omgci;
+        }
+      for (int iy = w.j1p; iy <= w.j5p; ++iy)
+        for (int ix = i1; ix <= i6; ++ix) A(fqy, ix, iy) = A(fqy, ix, iy) + cfqyn * A(fqyn, ix, iy);
+    }
     if (ineudif == 1) neudif(w); else neudifpg(w);  // oderhs.m:2423-2435
 
     // half-space problem: no flux and no gradients through the cut (oderhs.m:2447-2466)
@@ -1239,11 +1267,11 @@ struct O2 {
           A(hcxe, ix, iy) = A(hcxe, ix, iy) + fxet * niavex / A(w1, ix, iy);
           double kyemix = fcdif * kye + 0.;
           if (kyet > 1.e-20 && iy > iysptrx) kyemix = (1. - ckyet) * kyemix + ckyet * kyet * A(diffusivwrk, ix, iy);
-          A(hcye, ix, iy) = A(hcye, ix, iy) + (kyemix + 2.33 * (0. + 0.)) * zi[f] * niavey;
+          A(hcye, ix, iy) = A(hcye, ix, iy) + (kyemix + 2.33 * (dclass_e_(ix, iy) + dclass_e_(ix, iyp1))) * zi[f] * niavey;
           A(hcxij[f], ix, iy) = fxit * niavex / A(w2, ix, iy);
           double kyimix = fcdif * kyi + 0.;
           if (kyit > 1.e-20 && iy > iysptrx) kyimix = (1. - ckyit) * kyimix + ckyit * kyit * A(diffusivwrk, ix, iy);
-          A(hcyij[f], ix, iy) = A(hcyij[f], ix, iy) + (kyimix + (0. + 0.)) * niavey;
+          A(hcyij[f], ix, iy) = A(hcyij[f], ix, iy) + (kyimix + (dclass_i_(ix, iy) + dclass_i_(ix, iyp1))) * niavey;
         }
     }
     for (int f = 0; f < nisp; ++f) {  // oderhs.m:2906-2965
@@ -1824,7 +1852,6 @@ struct O2 {
 double sigma1_, frfqpn_, cffqpsat_, exjbdry_, rnewpot_, cfqyae_, cfqyai_, cfgpijr_, sigbar0_, r0slab_, dx0_;
 int nfqya0core_, nfqya0pf_, nfqya0ow_;
 V difutm_;
-const double *b_c, *rm_c;
 
 void O2::calc_currents(const Win& w) {
   const int i1 = w.i1, i5 = w.i5, i6 = w.i6;
@@ -1936,6 +1963,7 @@ void O2::calc_currents(const Win& w) {
       A(fqy, ix, iy) = (1. - rnewpot_) * A(fqyao, ix, iy) + rnewpot_ * A(fqya, ix, iy) + cfqybf * A(fqyb, ix, iy) + cfqym * A(fqym, ix, iy) + cfjpy * A(fqyd, ix, iy);
       A(fqygp, ix, iy) = (1. - rnewpot_) * A(fqyao, ix, iy) + rnewpot_ * A(fqya, ix, iy) + cfqym * A(fqym, ix, iy) + A(fqyd, ix, iy);
       A(fqy, ix, iy) = A(fqy, ix, iy) + cfqydt * A(fqydt, ix, iy);  // nx = nxold, ny = nyold; cfqydt = 0
+      if (cfvycf != 0.) A(fqy, ix, iy) = qe * 0.5 * (A(niy1[0], ix, iy) + A(niy0[0], ix, iy)) * A(vycf, ix, iy);  // classical Braginskii model (potencur.m:405-408)
     }
   for (int iy = j1p; iy <= j6p; ++iy)
     for (int ix = i1; ix <= i5; ++ix) {
@@ -2198,11 +2226,16 @@ int O2::bouncon(const Win& w, const double* yl, double* yldot) {
         else yldot[iv1] = -nurlxp * (A(phi, ix, 1) - A(phi, IXP1(ix, 1), 1)) / temp0;
         if (ix == ixmp) {  // midplane column: total radial current through the core boundary = icoreelec (fqyn: cfqyn = 0)
           int ii = ixc1;
-          double fqytotc = A(fqya, ii, 1) + 0. + cfqym * A(fqym, ii, 1) + cfqybbo * A(fqyb, ii, 1) + cfqydbo * A(fqyd, ii, 1);
-          do { ii = IXP1(ii, 1); fqytotc = fqytotc + A(fqya, ii, 1) + 0. + cfqym * A(fqym, ii, 1) + cfqybbo * A(fqyb, ii, 1) + cfqydbo * A(fqyd, ii, 1); } while (ii != ix_fl_bc);
+          double fqytotc = A(fqya, ii, 1) + cfqyn * A(fqyn, ii, 1) + cfqym * A(fqym, ii, 1) + cfqybbo * A(fqyb, ii, 1) + cfqydbo * A(fqyd, ii, 1);
+          do { ii = IXP1(ii, 1); fqytotc = fqytotc + A(fqya, ii, 1) + cfqyn * A(fqyn, ii, 1) + cfqym * A(fqym, ii, 1) + cfqybbo * A(fqyb, ii, 1) + cfqydbo * A(fqyd, ii, 1); } while (ii != ix_fl_bc);
           yldot[iv] = -nurlxp * (fqytotc - icoreelec) / (qe * n0[0] * vpnorm * A(sy, ixc1, 0));
           if (iphibcc == 1) yldot[iv1] = -nurlxp * ((A(ey, ix, 1) - A(ey, ix, 0)) * A(gy, ix, 1) - (A(ey, ix, 2) - A(ey, ix, 1)) * A(gy, ix, 2)) / (A(gy, ix, 1) * temp0);
           else yldot[iv1] = -nurlxp * (A(ey, ix, 0) - eycore) / (A(gyf, ix, 0) * temp0);
+        }
+        if (cfvycf > 1e-20) {  // boundary.m:1095-1100 (classical Braginskii model)
+          const int ix3 = IXM1(ix, 1);
+          yldot[iv] = -nurlxp * (A(ey, ix, 0) - A(gpiy[0], ix, 0) / (qe * zi[0] * A(niy0[0], ix, 0))) / (A(btot, ix, 0) * vpnorm);
+          yldot[iv1] = nurlxp * (A(fqy, ix, 1) - (A(fqx, ix, 1) - A(fqx, ix3, 1))) / (A(rrv, ix, 0) * A(sy, ix, 0) * vpnorm * ev * n0[0]);
         }
       } else {  // private-flux wall
         const int k = (int)iphibcwiix[ix];
@@ -2806,7 +2839,7 @@ int init_all() {
   GR(ckinfl) GR(isoldalbarea) GR(tbmin) GR(nufak) GR(dtreal) GR(dtphi) GR(dylconst) GR(jaccliplim) GR(kelhihg) GR(kelhghg) GR(lgvmax) GR(flgamvg) GR(cfvisxn) GR(cfvisyn) GR(flgamtg) GR(cfupcx) GR(cfticx)
   GR(cfnidh) GR(cfnidh2) GR(cfnidhdis) GR(cfnidhgy) GR(cfnidhg2) GR(cftgeqp) GR(flalftxy) GR(flalfgnx) GR(flalfgny) GR(nlimgx) GR(nlimgy) GR(cfloxiplt) GR(cfloygwall) GR(cfjve) GR(rsigpl) GR(rsigplcore)
   GR(bcen) GR(cfqym) GR(cfqydt) GR(cfqyao) GR(cfsigm) GR(cfyef) GR(cf2ef) GR(cfybf) GR(cf2bf) GR(cfcurv) GR(cfgradb) GR(eycore) GR(icoreelec) GR(cfniybbo) GR(cfeeybbo)
-  GR(cfqybf) GR(cfq2bf) GR(cfqybbo) GR(cfqydbo) GR(cfwjdotelim) GR(tebg) GR(cfydd) GR(cf2dd) GR(cfrd) GR(cfbgt) GR(cfjpy) GR(cfjp2)
+  GR(cfqybf) GR(cfq2bf) GR(cfqybbo) GR(cfqydbo) GR(cfwjdotelim) GR(tebg) GR(cfydd) GR(cf2dd) GR(cfrd) GR(cfbgt) GR(cfjpy) GR(cfjp2) GR(cfvycf) GR(cfvycr) GR(cfeta1) GR(cfrtaue) GR(cfcl_e) GR(cfcl_i) GR(omgci_taui) GR(omgce_taue) GR(nuneo) GR(cfqyn)
 #undef GR
   erad = SC("erad"); delpert = SC("del");
   sigma1_ = SC("sigma1"); frfqpn_ = SC("frfqpn"); cffqpsat_ = SC("cffqpsat"); exjbdry_ = SC("exjbdry"); rnewpot_ = SC("rnewpot"); cfqyae_ = SC("cfqyae"); cfqyai_ = SC("cfqyai"); cfgpijr_ = SC("cfgpijr");
@@ -2856,8 +2889,8 @@ int init_all() {
   // switches outside this restatement
   struct { const char* n; double want; } must[] = {{"isimpon", 0}, {"ismcnon", 0}, {"ishymol", 0}, {"ifixsrc", 0}, {"ifixpsor", 0}, {"isupdrag", 0}, {"isofric", 0}, {"ishosor", 0}, {"islimon", 0}, {"isudsym", 0},
                                                    {"nxomit", 0}, {"isbohmcalc", 1}, {"isdifbetap", 0}, 
-                                                   {"cfvycf", 0}, {"cfvycr", 0}, {"cftef", 0}, {"cftdd", 0}, {"cfqyn", 0}, {"cfeta1", 0}, {"cfrtaue", 0},
-                                                   {"cfcl_e", 0}, {"cfcl_i", 0}, {"facbni", 0}, {"facbup", 0}, {"facbee", 0}, {"facbei", 0}, {"rtauxfac", 0}, {"ispsorave", 0}, {"iseesorave", 0}, {"cfvisxneov", 0},
+                                                   {"cftef", 0}, {"cftdd", 0}, 
+                                                   {"facbni", 0}, {"facbup", 0}, {"facbee", 0}, {"facbei", 0}, {"rtauxfac", 0}, {"ispsorave", 0}, {"iseesorave", 0}, {"cfvisxneov", 0},
                                                    {"cfvisxneoq", 0}, {"cfvyavis", 0}, {"cfanomvisxg", 0}, {"cfanomvisyg", 0}, {"isnfmiy", 0}, {"isybdrywd", 0}, {"isfeexpl0", 0},
                                                    {"isfeixpl0", 0}, {"cfeexdbo", 0}, {"cfeixdbo", 0}, {"cfniydbo", 0}, {"cfeeydbo", 0}, {"isextrnp", 0}, {"isextrnpf", 0},
                                                    {"isextrtpf", 0}, {"isextrngc", 0}, {"isextrnw", 0}, {"isextrtw", 0}, {"isbohmms", 0}, {"ibctepl", 1}, {"ibctipl", 1}, {"ibctepr", 1}, {"ibctipr", 1}, {"isfixrb", 0},

@@ -13,7 +13,7 @@ import pytest
 from tests.test_oracle2_golden import twin
 from tests.util import psetnk_inputs
 from uedge_b200.cases import box2_case
-from uedge_b200.cases2 import SUBSETS, Lib2, Oracle2, all_drifts, box2_initial_state, d3d_full_physics_case, gas_energy_case, inputex_case, jupyter_case, switch_variant
+from uedge_b200.cases2 import SUBSETS, Lib2, Oracle2, all_drifts, braginskii_current, box2_initial_state, d3d_full_physics_case, gas_energy_case, inputex_case, jupyter_case, switch_variant
 
 HK = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostcheck")
 
@@ -129,12 +129,21 @@ def test_jupyter_drift_case(built, rev):
 
 @pytest.mark.parametrize("rev", [0, 1])
 def test_every_drift_part(built, rev, monkeypatch):
-    """diamagnetic (cfydd, cf2dd), resistive (cfrd) and B x grad(T) (cfbgt) parts and the diamagnetic currents (cfjpy, cfjp2) on top of
-    the deck's ExB / grad-B set; 2x-refined mesh with the private copies poisoned in the forward order"""
+    """diamagnetic (cfydd, cf2dd), resistive (cfrd) and B x grad(T) (cfbgt) parts, the diamagnetic currents (cfjpy, cfjp2), the classical
+    momentum-transfer velocity and conductivities (cfvycr, cfrtaue, cfeta1, cfcl_e, cfcl_i) and the charge-exchange current (cfqyn) on top
+    of the deck's ExB / grad-B set; 2x-refined mesh with the private copies poisoned in the forward order"""
     from uedge_b200.cases import load_grid_npz, refine_grid
     if rev == 0:
         monkeypatch.setenv("UE_GEN_POISON", "1")
     c, yl = jupyter_case(all_drifts, grid=refine_grid(load_grid_npz(), 2, 2) if rev == 0 else None)
+    same(Oracle2().bind(c), host(rev).bind(c), c, yl)
+
+
+@pytest.mark.parametrize("rev", [0, 1])
+def test_braginskii_radial_current(built, rev, monkeypatch):
+    """cfvycf: the radial current from the classical viscosity velocity and its core potential conditions"""
+    monkeypatch.setenv("UE_GEN_POISON", "1")
+    c, yl = jupyter_case(braginskii_current)
     same(Oracle2().bind(c), host(rev).bind(c), c, yl)
 
 

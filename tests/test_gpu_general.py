@@ -10,7 +10,7 @@ from tests.refplanes import check_against_reference
 from tests.test_oracle2_golden import twin
 from tests.util import psetnk_inputs
 from uedge_b200.cases import box2_case
-from uedge_b200.cases2 import SUBSETS, Oracle2, all_drifts, box2_initial_state, d3d_full_physics_case, gas_energy_case, inputex_case, jupyter_case, load_gen, switch_variant
+from uedge_b200.cases2 import SUBSETS, Oracle2, all_drifts, braginskii_current, box2_initial_state, d3d_full_physics_case, gas_energy_case, inputex_case, jupyter_case, load_gen, switch_variant
 
 pytestmark = pytest.mark.gpu
 
@@ -92,9 +92,11 @@ def test_jupyter_drift_case(built, refine):
         assert np.array_equal(o.plane(nm), g.plane(nm)), nm
 
 
-def test_every_drift_part(built):
-    """the diamagnetic, resistive and B x grad(T) parts and the diamagnetic currents switched on as well"""
-    c, yl = jupyter_case(all_drifts)
+@pytest.mark.parametrize("mods", [all_drifts, braginskii_current])
+def test_every_drift_part(built, mods):
+    """the diamagnetic, resistive, B x grad(T) and classical parts, the diamagnetic and charge-exchange currents switched on as well; the
+    radial current of the classical viscosity model"""
+    c, yl = jupyter_case(mods)
     same(Oracle2().bind(c), load_gen().bind(c), c, yl)
 
 

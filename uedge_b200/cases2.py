@@ -162,6 +162,14 @@ def all_drifts(b, com):
     """mods for jupyter_case: the diamagnetic and resistive parts of the drifts and currents on top of the deck's ExB / grad-B set
     (the decks keep them at zero: `cfydd`, `cf2dd` 'always = 0' in jupyter/case_setup.py:99-103)"""
     b.cfydd = 1.0; b.cf2dd = 1.0; b.cfrd = 1.0; b.cfbgt = 1.0; b.cfjpy = 1.0; b.cfjp2 = 1.0
+    # the classical (Braginskii) momentum-transfer velocity and conductivities, the charge-exchange / neoclassical current
+    b.cfvycr = 1.0; b.cfrtaue = 1.0; b.cfeta1 = 1.0; b.cfcl_e = 1.0; b.cfcl_i = 1.0; b.cfqyn = 1.0; b.nuneo = 1.0e3
+
+
+def braginskii_current(b, com):
+    """mods for jupyter_case: the radial current from the classical viscosity alone (cfvycf: fqy := e n vycf, potencur.m:405-408, and
+    the core potential conditions of boundary.m:1095-1100)"""
+    b.cfvycf = 1.0; b.cfeta1 = 1.0
 
 
 def gas_energy_case(mods=None, grid=None, deck="jupyter"):
@@ -213,7 +221,8 @@ def switch_variant(seed):
     for k, vals in (("cfyef", (1.0, 0.5)), ("cf2ef", (1.0, 0.5)), ("cfybf", (1.0,)), ("cf2bf", (1.0,)), ("cfqybf", (1.0,)), ("cfq2bf", (1.0,)), ("isnewpot", (1,)), ("rnewpot", (1.0, 0.5)),
                     ("jhswitch", (1, 2)), ("isfdiax", (1.0,)), ("iphibcc", (1, 2, 3)), ("cfcurv", (0.5,)), ("cfgradb", (0.5,)), ("eycore", (10.0,)), ("icoreelec", (5.0,)),
                     ("cfqybbo", (1.0,)), ("cfqydbo", (1.0,)), ("cfniybbo", (1.0,)), ("cfeeybbo", (1.0,)), ("ExtendedJacPhi", (0,)),
-                    ("cfydd", (1.0,)), ("cf2dd", (1.0,)), ("cfrd", (1.0, 0.5)), ("cfbgt", (1.0,)), ("cfjpy", (1.0,)), ("cfjp2", (1.0,))):
+                    ("cfydd", (1.0,)), ("cf2dd", (1.0,)), ("cfrd", (1.0, 0.5)), ("cfbgt", (1.0,)), ("cfjpy", (1.0,)), ("cfjp2", (1.0,)),
+                    ("cfvycr", (1.0,)), ("cfrtaue", (1.0,)), ("cfvycf", (1.0,)), ("cfeta1", (1.0,)), ("cfcl_e", (1.0,)), ("cfcl_i", (1.0,)), ("cfqyn", (1.0,)), ("nuneo", (1e3,))):
         if rng.random() < 0.4:
             ch[k] = pick(*vals)
 

@@ -607,7 +607,7 @@ int init_all() {
   GR(ckinfl) GR(isoldalbarea) GR(tbmin) GR(nufak) GR(dtreal) GR(dtphi) GR(dylconst) GR(jaccliplim) GR(kelhihg) GR(kelhghg) GR(lgvmax) GR(flgamvg) GR(cfvisxn) GR(cfvisyn) GR(flgamtg) GR(cfupcx) GR(cfticx)
   GR(cfnidh) GR(cfnidh2) GR(cfnidhdis) GR(cfnidhgy) GR(cfnidhg2) GR(cftgeqp) GR(flalftxy) GR(flalfgnx) GR(flalfgny) GR(nlimgx) GR(nlimgy) GR(cfloxiplt) GR(cfloygwall) GR(cfjve) GR(rsigpl) GR(rsigplcore)
   GR(bcen) GR(cfqym) GR(cfqydt) GR(cfqyao) GR(cfsigm) GR(cfyef) GR(cf2ef) GR(cfybf) GR(cf2bf) GR(cfcurv) GR(cfgradb) GR(eycore) GR(icoreelec) GR(cfniybbo) GR(cfeeybbo)
-  GR(cfqybf) GR(cfq2bf) GR(cfqybbo) GR(cfqydbo) GR(cfwjdotelim) GR(tebg) GR(cfydd) GR(cf2dd) GR(cfrd) GR(cfbgt) GR(cfjpy) GR(cfjp2)
+  GR(cfqybf) GR(cfq2bf) GR(cfqybbo) GR(cfqydbo) GR(cfwjdotelim) GR(tebg) GR(cfydd) GR(cf2dd) GR(cfrd) GR(cfbgt) GR(cfjpy) GR(cfjp2) GR(cfvycf) GR(cfvycr) GR(cfeta1) GR(cfrtaue) GR(cfcl_e) GR(cfcl_i) GR(omgci_taui) GR(omgce_taue) GR(nuneo) GR(cfqyn)
 #undef GR
   g.erad = SC("erad"); g.delpert = SC("del");
   g.sigma1_ = SC("sigma1"); g.frfqpn_ = SC("frfqpn"); g.cffqpsat_ = SC("cffqpsat"); g.exjbdry_ = SC("exjbdry"); g.rnewpot_ = SC("rnewpot"); g.cfqyae_ = SC("cfqyae"); g.cfqyai_ = SC("cfqyai");
@@ -682,8 +682,8 @@ int init_all() {
   // switches outside what is built
   struct { const char* n; double want; } must[] = {{"isimpon", 0}, {"ismcnon", 0}, {"ishymol", 0}, {"ifixsrc", 0}, {"ifixpsor", 0}, {"isupdrag", 0}, {"isofric", 0}, {"ishosor", 0}, {"islimon", 0}, {"isudsym", 0},
                                                    {"nxomit", 0}, {"isbohmcalc", 1}, {"isdifbetap", 0}, 
-                                                   {"cfvycf", 0}, {"cfvycr", 0}, {"cftef", 0}, {"cftdd", 0}, {"cfqyn", 0}, {"cfeta1", 0}, {"cfrtaue", 0},
-                                                   {"cfcl_e", 0}, {"cfcl_i", 0}, {"facbni", 0}, {"facbup", 0}, {"facbee", 0}, {"facbei", 0}, {"rtauxfac", 0}, {"ispsorave", 0}, {"iseesorave", 0}, {"cfvisxneov", 0},
+                                                   {"cftef", 0}, {"cftdd", 0}, 
+                                                   {"facbni", 0}, {"facbup", 0}, {"facbee", 0}, {"facbei", 0}, {"rtauxfac", 0}, {"ispsorave", 0}, {"iseesorave", 0}, {"cfvisxneov", 0},
                                                    {"cfvisxneoq", 0}, {"cfvyavis", 0}, {"cfanomvisxg", 0}, {"cfanomvisyg", 0}, {"isnfmiy", 0}, {"isybdrywd", 0}, {"isfeexpl0", 0},
                                                    {"isfeixpl0", 0}, {"cfeexdbo", 0}, {"cfeixdbo", 0}, {"cfniydbo", 0}, {"cfeeydbo", 0}, {"isextrnp", 0}, {"isextrnpf", 0},
                                                    {"isextrtpf", 0}, {"isextrngc", 0}, {"isextrnw", 0}, {"isextrtw", 0}, {"isbohmms", 0}, {"ibctepl", 1}, {"ibctipl", 1}, {"ibctepr", 1}, {"ibctipr", 1}, {"isfixrb", 0},

@@ -69,7 +69,7 @@ HD int iabs(int a) { return a < 0 ? -a : a; }
   P1(floxe) P1(floxi) P1(floye) P1(floyi) P1(conxe) P1(conxi) P1(conye) P1(conyi) P1(feex) P1(feey) P1(feix) P1(feiy) P1(feexy) P1(feixy) P1(resee) P1(resei) \
   P1(erliz) P1(erlrc) P1(eeli) P1(vsoreec) P1(vsoree) P1(pwribkg) P1(pwrebkg) P1(pradhyd) \
   P1(fqp) P1(fqx) P1(fqy) P1(fq2) P1(fqxb) P1(fqyb) P1(fqyn) P1(fqym) P1(fqymi) P1(fqya) P1(fqydt) P1(fqydti) P1(fqyao) P1(fqyae) P1(fqyd) P1(fqygp) P1(fq2d) P1(netap) P1(resphi) P1(dphi_iy1) \
-  P2(vyce) P2(vycb) P2(vycp) P1(veycb) P2(v2ce) P2(v2cb) P1(ve2cb) P1(ve2cd) P1(wjdote) P1(segc) P1(floxge) P1(floyge) P1(conxge) P1(conyge) P1(fegx) P1(fegy) P1(fegxy) P1(reseg) P2(fmity) P2(fqymi_) P2(fniycbo) P1(feeycbo) P1(feiycbo) P1(kappal) P1(kappar) P1(bcel) P1(bcer) P1(bcil) P1(bcir) \
+  P2(vyce) P2(vycb) P2(vycp) P1(veycb) P2(v2ce) P2(v2cb) P1(ve2cb) P1(ve2cd) P2(v2cd) P1(vycf) P1(vycr) P1(wjdote) P1(segc) P1(floxge) P1(floyge) P1(conxge) P1(conyge) P1(fegx) P1(fegy) P1(fegxy) P1(reseg) P2(fmity) P2(fqymi_) P2(fniycbo) P1(feeycbo) P1(feiycbo) P1(kappal) P1(kappar) P1(bcel) P1(bcer) P1(bcil) P1(bcir) \
   P1(fqpsatlb) P1(fqpsatrb) P1(fdiaxlb) P1(fdiaxrb)
 
 struct Gen {
@@ -142,7 +142,7 @@ double ev, qe, me, mp, pi_, cutlo, rt8opi, temin, tgmin, nnorm, ennorm, temp0, v
     cfnidhg2, cftgeqp, flalftxy, flalfgnx, flalfgny, nlimgx, nlimgy, cfloxiplt, cfloygwall, cfjve, rsigpl, rsigplcore, bcen, bceew, bciew, cfqym, cfqydt,
     cfjpy, cfjp2, cfqybf, cfq2bf, cfqybbo, cfqydbo, cfydd_, cfjp2_, cfqyn, cfqyao, cfqya, cfqyae, cfjpy_, fqpsatlb_unused, lnlam_unused, phiwi0, phiwo0,
     kappamx, kappa0, cfsigm, fqsatlb_u, fupe_cur, dtphi_, cfhcxgc_u, lyphi0, lyphi1, isparmultdt_u, tewallmin_u, cfwjdotelim, cfeexdbo, cfeixdbo, cfkincor,
-    cfyef, cf2ef, cfybf, cf2bf, cfcurv, cfgradb, eycore, icoreelec, cfniybbo, cfeeybbo, cfydd, cf2dd, cfrd, cfbgt;
+    cfyef, cf2ef, cfybf, cf2bf, cfcurv, cfgradb, eycore, icoreelec, cfniybbo, cfeeybbo, cfydd, cf2dd, cfrd, cfbgt, cfvycf, cfvycr, cfeta1, cfrtaue, cfcl_e, cfcl_i, omgci_taui, omgce_taue, nuneo;
 int ExtendedJacPhi, istgcore, istgpfc, istgwc, istglb, istgrb, isfegxyqflave;
 int64_t numvar_;
 double tgcore, cftgticore, tgwall, lytg1, lytg2, cftgtipltl, cftgtipltr, cftgtipfc, cftgtiwc, cgengmpl, cgengmw, cfalbedo, recyce, recycwe, cvgpg, cfcvtg, cfegxy, flalftgxy;
@@ -182,6 +182,11 @@ HD int ALG(int64_t iv) { return (int)iseqalgd[iv]; }
 HD double ave(double t0, double t1) { return 2 * t0 * t1 / (cutlo + t0 + t1); }  // oderhs.m:697
 HD double sgn(double a, double b) { return copysign(fabs(a), b); }     // Fortran sign(a,b)
 HD double sq(double x) { return x * x; }
+// classical (Braginskii) collisional factors of pandf's simple model (oderhs.m:1157-1166), evaluated where they are used
+HD double eta1_(int ix, int iy) const { return cfeta1 * 0.3 * A(nm[0], ix, iy) * A(ti, ix, iy) * (1 / (qe * A(btot, ix, iy))) / omgci_taui; }
+HD double rtaue_(int ix, int iy) const { return cfrtaue * (1 / (qe * A(btot, ix, iy))) / omgce_taue; }
+HD double dclass_i_(int ix, int iy) const { return cfcl_i == 0. ? 0. : cfcl_i * eta1_(ix, iy) / (0.3 * A(nm[0], ix, iy)); }
+HD double dclass_e_(int ix, int iy) const { return cfcl_e == 0. ? 0. : cfcl_e * A(te, ix, iy) * rtaue_(ix, iy); }
 // perpendicular resistivity (statement function of pandf, oderhs.m:698)
 HD double etaper(int ix, int iy) const { return 3.234e-9 * A(loglambda, ix, iy) / ue_pow(mx(A(te, ix, iy), temin * ev) / (1000. * ev), 1.5); }
 HD double powi(double x, int64_t n) { double r = 1.0; while (n > 0) { if (n & 1) r *= x; x *= x; n >>= 1; } return r; }
@@ -911,14 +916,24 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
           A(vycp[f], ix, iy) = (iy == 0 || iy == ny) ? 0. : -0.25 * temp2 * (A(rbfbt2, ix, iy) + A(rbfbt2, ix, iy + 1)) / (qion * (A(niy0[f], ix, iy) + A(niy1[f], ix, iy)));
           A(vydd[f], ix, iy) = vcony[f] + 0. + 0. - (difpr[f] + 0.) * (2 * A(gpry, ix, iy) / (A(pr, ix, iy + 1) + A(pr, ix, iy)) - 3.0 * A(gtey, ix, iy) / (A(tey1, ix, iy) + A(tey0, ix, iy)));
           A(diffusivwrk, ix, iy) = fcdif * difni[f] + 0.;
+          if (cfrtaue != 0.)  // classical momentum-transfer and viscosity velocities (oderhs.m:1240-1262)
+            A(vycr, ix, iy) = -0.5 * (rtaue_(ix, iy) + rtaue_(ix, iyp1)) * ((A(gpiy[0], ix, iy) + A(gpey, ix, iy)) / (0.5 * (A(niy1[0], ix, iy) + A(niy0[0], ix, iy))) - 1.5 * A(gtey, ix, iy));
+          if (cfeta1 != 0. && iy <= ny - 1 && iy > 0) {
+            const int iym1 = mx(iy - 1, 0);
+            const double geyym = 2 * A(gpiy[0], ix, iym1) / (A(ney1, ix, iym1) + A(ney0, ix, iym1)) - qe * A(ey, ix, iym1);
+            const double geyy0 = 2 * A(gpiy[0], ix, iy) / (A(ney1, ix, iy) + A(ney0, ix, iy)) - qe * A(ey, ix, iy);
+            const double geyyp = 2 * A(gpiy[0], ix, iyp1) / (A(ney1, ix, iyp1) + A(ney0, ix, iyp1)) - qe * A(ey, ix, iyp1);
+            const double dgeyy0 = (geyy0 - geyym) * eta1_(ix, iy) * A(gy, ix, iy), dgeyy1 = (geyyp - geyy0) * eta1_(ix, iyp1) * A(gy, ix, iyp1);
+            A(vycf, ix, iy) = 2 * (dgeyy1 - dgeyy0) * A(gy, ix, iy) / ((A(ney1, ix, iy) + A(ney0, ix, iy)) * sq(qe * 0.5 * (A(btot, ix, iy) + A(btot, ix, iym1))));
+          }
         }
       FOR2(iy, j1, j5, ix, i1, i6) {
           double difnimix = A(diffusivwrk, ix, iy);
           A(vydd[f], ix, iy) = A(vydd[f], ix, iy) - 1. * difnimix * (2 * (1 - isvylog) * ((A(niy1[f], ix, iy) - A(niy0[f], ix, iy)) / A(dynog, ix, iy)) / (A(niy1[f], ix, iy) + A(niy0[f], ix, iy)) +
                                                                       isvylog * (ue_log(A(niy1[f], ix, iy)) - ue_log(A(niy0[f], ix, iy))) / A(dynog, ix, iy));
           const double vyrd = cfrd == 0. ? 0. : -2. * A(gpry, ix, iy) / (sq(A(btot, ix, iy)) / etaper(ix, iy) + sq(A(btot, ix, iy + 1)) / etaper(ix, iy + 1));  // (not evaluated when switched off)
-          A(vy[f], ix, iy) = cfydd * A(vycp[f], ix, iy) + cfrd * vyrd + A(vydd[f], ix, iy) + cfyef * A(vyce[f], ix, iy) + cfybf * A(vycb[f], ix, iy);
-          A(vygp[f], ix, iy) = (cfydd + cfybf) * A(vycp[f], ix, iy) + cfrd * vyrd + A(vydd[f], ix, iy) + cfyef * A(vyce[f], ix, iy);
+          A(vy[f], ix, iy) = cfydd * A(vycp[f], ix, iy) + cfrd * vyrd + A(vydd[f], ix, iy) + cfyef * A(vyce[f], ix, iy) + cfybf * A(vycb[f], ix, iy) + cfvycf * A(vycf, ix, iy) + cfvycr * A(vycr, ix, iy);
+          A(vygp[f], ix, iy) = (cfydd + cfybf) * A(vycp[f], ix, iy) + cfrd * vyrd + A(vydd[f], ix, iy) + cfyef * A(vyce[f], ix, iy) + cfvycf * A(vycf, ix, iy) + cfvycr * A(vycr, ix, iy);
         }
       FOR2(iy, j1, j6, ix, i1, i6) {
           const int ix2 = IXP1(ix, iy), iy1 = mx(0, iy - 1);
@@ -928,6 +943,7 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
           A(v2cb[f], ix, iy) = (cfcurv * (0.5 * (A(tiv, ix, iy) + A(tiv, ix, iy1)) + mi[f] * sq(A(up[f], ix, iy))) * A(curvrb2, ix, iy) + cfgradb * 0.5 * (A(tiv, ix, iy) + A(tiv, ix, iy1)) * A(gradb2, ix, iy)) / qion;
           A(ve2cb, ix, iy) = -(cfcurv * 0.5 * (A(tev, ix, iy) + A(tev, ix, iy1)) * A(curvrb2, ix, iy) + cfgradb * 0.5 * (A(tev, ix, iy) + A(tev, ix, iy1)) * A(gradb2, ix, iy)) / qe;
           const double v2cd = temp2 / ((A(btot, ix, iy) + A(btot, ix2, iy)) * qion * (A(ni[f], ix, iy) + A(ni[f], ix2, iy)));
+          A(this->v2cd[f], ix, iy) = v2cd;
           // plate electron diamagnetic flux for the sheath potential (oderhs.m:1376-1391)
           if (ix == ixlb) {
             const double v2dia = -0.5 * (A(gpey, ixlb + 1, iy) + A(gpey, ixlb + 1, iy1)) / (A(btot, ixlb + 1, iy) * qe * A(ne, ixlb + 1, iy));
@@ -1057,6 +1073,15 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
         if (isupgon == 1) { A(psor[1], ix, iy) = -A(psor[0], ix, iy); A(psorxr[1], ix, iy) = -A(psorxr[0], ix, iy); }
       }
 
+    if (cfqyn > 0.) {  // calc_curr_cx (potencur.m:446-495): current from charge exchange and neoclassical damping, now that nucx is known
+      FOR2(iy, mx(w.j1p, 1), mn(w.j5p, ny - 1), ix, i1, i6) {
+          const double omgci = qe * A(b_c, ix, iy) / mi[0];
+          const int ix3 = IXM1(ix, iy + 1), ix4 = IXM1(ix, iy);
+          A(fqyn, ix, iy) = qe * 0.125 * ((A(ngy0, ix, iy) + A(ngy1, ix, iy)) * A(nucx, ix, iy) + (A(niy0[0], ix, iy) + A(niy1[0], ix, iy)) * nuneo) * A(sy, ix, iy) *
+                            (A(v2ce[0], ix, iy) + A(v2cd[0], ix, iy) + A(v2ce[0], ix, iy + 1) + A(v2cd[0], ix, iy + 1) + A(v2ce[0], ix4, iy) + A(v2cd[0], ix4, iy) + A(v2ce[0], ix3, iy + 1) + A(v2cd[0], ix3, iy + 1)) / omgci;
+        }
+      FOR2(iy, w.j1p, w.j5p, ix, i1, i6) A(fqy, ix, iy) = A(fqy, ix, iy) + cfqyn * A(fqyn, ix, iy);
+    }
     if (ineudif == 1) neudif(w); else neudifpg(w);  // oderhs.m:2423-2435
 
     // half-space problem: no flux and no gradients through the cut (oderhs.m:2447-2466)
@@ -1218,11 +1243,11 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
           A(hcxe, ix, iy) = A(hcxe, ix, iy) + fxet * niavex / A(w1, ix, iy);
           double kyemix = fcdif * kye + 0.;
           if (kyet > 1.e-20 && iy > iysptrx) kyemix = (1. - ckyet) * kyemix + ckyet * kyet * A(diffusivwrk, ix, iy);
-          A(hcye, ix, iy) = A(hcye, ix, iy) + (kyemix + 2.33 * (0. + 0.)) * zi[f] * niavey;
+          A(hcye, ix, iy) = A(hcye, ix, iy) + (kyemix + 2.33 * (dclass_e_(ix, iy) + dclass_e_(ix, iyp1))) * zi[f] * niavey;
           A(hcxij[f], ix, iy) = fxit * niavex / A(w2, ix, iy);
           double kyimix = fcdif * kyi + 0.;
           if (kyit > 1.e-20 && iy > iysptrx) kyimix = (1. - ckyit) * kyimix + ckyit * kyit * A(diffusivwrk, ix, iy);
-          A(hcyij[f], ix, iy) = A(hcyij[f], ix, iy) + (kyimix + (0. + 0.)) * niavey;
+          A(hcyij[f], ix, iy) = A(hcyij[f], ix, iy) + (kyimix + (dclass_i_(ix, iy) + dclass_i_(ix, iyp1))) * niavey;
         }
     }
     for (int f = 0; f < nisp; ++f) {  // oderhs.m:2906-2965
@@ -1843,6 +1868,7 @@ HD void calc_currents(const Win& w) {
       A(fqy, ix, iy) = (1. - rnewpot_) * A(fqyao, ix, iy) + rnewpot_ * A(fqya, ix, iy) + cfqybf * A(fqyb, ix, iy) + cfqym * A(fqym, ix, iy) + cfjpy * A(fqyd, ix, iy);
       A(fqygp, ix, iy) = (1. - rnewpot_) * A(fqyao, ix, iy) + rnewpot_ * A(fqya, ix, iy) + cfqym * A(fqym, ix, iy) + A(fqyd, ix, iy);
       A(fqy, ix, iy) = A(fqy, ix, iy) + cfqydt * A(fqydt, ix, iy);  // nx = nxold, ny = nyold; cfqydt = 0
+      if (cfvycf != 0.) A(fqy, ix, iy) = qe * 0.5 * (A(niy1[0], ix, iy) + A(niy0[0], ix, iy)) * A(vycf, ix, iy);  // classical Braginskii model (potencur.m:405-408)
     }
   FOR2(iy, j1p, j6p, ix, i1, i5) {
       const int ix1 = IXP1(ix, iy);
@@ -2107,11 +2133,16 @@ HD int bouncon(const Win& w, const double* yl, double* yldot) {
         else yldot[iv1] = -nurlxp * (A(phi, ix, 1) - A(phi, IXP1(ix, 1), 1)) / temp0;
         if (ix == ixmp) {  // midplane column: total radial current through the core boundary = icoreelec (fqyn: cfqyn = 0)
           int ii = ixc1;
-          double fqytotc = A(fqya, ii, 1) + 0. + cfqym * A(fqym, ii, 1) + cfqybbo * A(fqyb, ii, 1) + cfqydbo * A(fqyd, ii, 1);
-          do { ii = IXP1(ii, 1); fqytotc = fqytotc + A(fqya, ii, 1) + 0. + cfqym * A(fqym, ii, 1) + cfqybbo * A(fqyb, ii, 1) + cfqydbo * A(fqyd, ii, 1); } while (ii != ix_fl_bc);
+          double fqytotc = A(fqya, ii, 1) + cfqyn * A(fqyn, ii, 1) + cfqym * A(fqym, ii, 1) + cfqybbo * A(fqyb, ii, 1) + cfqydbo * A(fqyd, ii, 1);
+          do { ii = IXP1(ii, 1); fqytotc = fqytotc + A(fqya, ii, 1) + cfqyn * A(fqyn, ii, 1) + cfqym * A(fqym, ii, 1) + cfqybbo * A(fqyb, ii, 1) + cfqydbo * A(fqyd, ii, 1); } while (ii != ix_fl_bc);
           yldot[iv] = -nurlxp * (fqytotc - icoreelec) / (qe * n0[0] * vpnorm * A(sy, ixc1, 0));
           if (iphibcc == 1) yldot[iv1] = -nurlxp * ((A(ey, ix, 1) - A(ey, ix, 0)) * A(gy, ix, 1) - (A(ey, ix, 2) - A(ey, ix, 1)) * A(gy, ix, 2)) / (A(gy, ix, 1) * temp0);
           else yldot[iv1] = -nurlxp * (A(ey, ix, 0) - eycore) / (A(gyf, ix, 0) * temp0);
+        }
+        if (cfvycf > 1e-20) {  // boundary.m:1095-1100 (classical Braginskii model)
+          const int ix3 = IXM1(ix, 1);
+          yldot[iv] = -nurlxp * (A(ey, ix, 0) - A(gpiy[0], ix, 0) / (qe * zi[0] * A(niy0[0], ix, 0))) / (A(btot, ix, 0) * vpnorm);
+          yldot[iv1] = nurlxp * (A(fqy, ix, 1) - (A(fqx, ix, 1) - A(fqx, ix3, 1))) / (A(rrv, ix, 0) * A(sy, ix, 0) * vpnorm * ev * n0[0]);
         }
       } else {  // private-flux wall
         const int k = (int)iphibcwiix[ix];
@@ -2625,7 +2656,7 @@ HD int pandf1(int xc, int yc, const double* yl, double* yldot) {
   return 0;
 }
   // ---- slab layout -----------------------------------------------------------------------------------------------------
-  double *vyce[2], *vycb[2], *vycp[2], *veycb, *v2ce[2], *v2cb[2], *ve2cb, *ve2cd, *wjdote, *fmity[2], *fqymi_[2];
+  double *vyce[2], *vycb[2], *vycp[2], *veycb, *v2ce[2], *v2cb[2], *ve2cb, *ve2cd, *v2cd[2], *vycf, *vycr, *wjdote, *fmity[2], *fqymi_[2];
   double *segc, *floxge, *floyge, *conxge, *conyge, *fegx, *fegy, *fegxy, *reseg;  // gas energy equation (engbalg, oderhs.m:7508-7878)  // drift velocities (oderhs.m:1167-1420), Joule heating, inertia-current work planes
   HD static int nplanes() {
     int n = 0;
