@@ -12,6 +12,7 @@
 // run in the reference's order, or reversed with -DUE_GEN_REVERSE.  The host build exists for tests only; the product is
 // the CUDA build and it fails loudly without a device.
 #include <algorithm>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -84,6 +85,8 @@ float g_comm_ms = 0.f;
 float g_full_ms = 0.f, g_cols_ms = 0.f, g_csr_ms = 0.f;  // CUDA-event times of the last residual / column / CSR kernels
 #define UE_GEN_BAND_DEFAULT 5
 int g_band = UE_GEN_BAND_DEFAULT;  // rows of the private copy on each side of the perturbed cell (env UE_GEN_BAND; large = all rows)
+int g_compact = 1;    // private planes hold the band's rows only (env UE_GEN_COMPACT=0: full-size planes)
+size_t g_pad = 0;     // padding (doubles) in front of the first private slab
 int g_colpad = 2;  // columns of the private copy on each side of the window i1..i6 (env UE_GEN_COLPAD; negative = whole rows)
 int g_tpu = 32;  // threads per unknown in the Jacobian kernel: 32 (a warp) or 64 (a two-warp block)
 int g_nslow = 0;
@@ -160,10 +163,11 @@ HD int eval_full(Gen& g, const double* yl, double* yldot) { return g.pandf1(-1, 
 // one Jacobian column (oderhs.m:8600-8720).  g: private context (planes = private copy of the base set).
 // ylp: private copy of yl (neq+2); wk: private residual (neq); frow/fval: the column's fragment, capacity cap.
 HD int eval_column(Gen& g, const double* base, int npl, int64_t iv, const double* yl, double* ylp, double* wk, const double* yldot00, int64_t ml, int64_t mu,
-                   int cap, int* frow, double* fval, int* cnt, int band, int colpad) {
+                   int cap, int* frow, double* fval, int* cnt, int band, int colpad, double* priv, int compact) {
+  // priv: this context's private slab - full-size planes (compact = 0: NPL x NC doubles, plane pointers already assigned) or band-rows-only
+  // planes (compact = 1: (NPL - NLINE) x (2 band + 1) rows x NXS + NLINE line arrays; the plane pointers are set here for every unknown)
   const int64_t neq = g.neq;
   const int tid = g.TID();
-  double* priv = g.ne;  // first plane of the slab
   const int xc = (int)g.igyld[iv - 1], yc = (int)g.igyld[neq + iv - 1];
   g.sync();
   // Private copy of the base planes: only what the windowed evaluation can touch -
@@ -180,8 +184,22 @@ HD int eval_column(Gen& g, const double* base, int npl, int64_t iv, const double
     const int NXS = g.NXS, NC = g.NC, nrow = g.ny + 2;
     const int r0 = mx(0, yc - band), r1 = mn(nrow - 1, yc + band);
     const int nfield = npl - UE_GEN_NLINE;
+    const int brows = 2 * band + 1, nline = mx(NXS, nrow);
+    const size_t bpl = (size_t)brows * NXS;  // a band plane
+    g.sync();
+    if (tid == 0) {
+      if (compact) { g.assign_planes_band(priv, r0, brows, UE_GEN_NLINE, nline); g.rowlo = r0; g.rowhi = r1; }
+      else { g.rowlo = 0; g.rowhi = nrow - 1; }
+    }
+    g.sync();
 #if defined(UE_GEN_HOST)
-    if (g_poison) for (size_t k = 0; k < (size_t)npl * NC; ++k) priv[k] = (double)NAN;
+    if (g_poison && compact) { for (size_t k = 0; k < (size_t)nfield * bpl + (size_t)UE_GEN_NLINE * nline; ++k) priv[k] = (double)NAN; }
+    else
+    if (g_poison) {
+      if (getenv("UE_GEN_OOB")) {  // every cell its own NaN payload: a later bit-compare finds any write, copies of poison included
+        for (size_t k = 0; k < (size_t)npl * NC; ++k) { const uint64_t bits = 0x7ff8000000000000ull | (uint64_t)(k + 1); std::memcpy(&priv[k], &bits, 8); }
+      } else for (size_t k = 0; k < (size_t)npl * NC; ++k) priv[k] = (double)NAN;
+    }
 #endif
     const auto w = g.make_win(xc, yc);
     const bool fullx = w.xccuts || colpad < 0 || (w.i1 <= colpad && w.i6 >= g.nx + 1 - colpad);
@@ -200,7 +218,8 @@ HD int eval_column(Gen& g, const double* base, int npl, int64_t iv, const double
       }
       if (r1 >= nrow - 2) { rect(mx(r0, nrow - 2), r1, 0, 1); rect(mx(r0, nrow - 2), r1, g.nx, g.nx + 1); }  // ... and of the outer wall
     }
-    if (g.iysptrx1 >= 0 && g.ixpt1 >= 0 && g.ixpt2 >= 0 && !(fullx && g.iysptrx1 >= r0 && g.iysptrx1 + 1 <= r1)) {  // X-point vertex: 8 cells
+    if (g.iysptrx1 >= 0 && g.ixpt1 >= 0 && g.ixpt2 >= 0 && !(fullx && g.iysptrx1 >= r0 && g.iysptrx1 + 1 <= r1) &&
+        (!compact || (g.iysptrx1 >= r0 && g.iysptrx1 + 1 <= r1))) {  // X-point vertex: 8 cells (band-rows-only planes: evaluated only inside the band)
       rect(g.iysptrx1, g.iysptrx1 + 1, g.ixpt1 - 1, g.ixpt1 + 2);
       rect(g.iysptrx1, g.iysptrx1 + 1, g.ixpt2 - 1, g.ixpt2 + 2);
     }
@@ -214,13 +233,13 @@ HD int eval_column(Gen& g, const double* base, int npl, int64_t iv, const double
         const int e = k - p * rw;
         const int r = small ? UE_ROW_(e, wc) : e / wc;
         const size_t o = (size_t)p * NC + (size_t)(ra[q] + r) * NXS + (size_t)(ca[q] + e - r * wc);
-        priv[o] = base[o];
+        if (compact) priv[(size_t)p * bpl + (size_t)(ra[q] + r - r0) * NXS + (size_t)(ca[q] + e - r * wc)] = base[o];
+        else priv[o] = base[o];
       }
     }
-    const int nl = mx(NXS, nrow);
     for (int p = nfield; p < npl; ++p) {
-      const size_t o = (size_t)p * NC;
-      for (int k = tid; k < nl; k += g.nth) priv[o + k] = base[o + k];
+      const size_t o = (size_t)p * NC, oc = (size_t)nfield * bpl + (size_t)(p - nfield) * nline;
+      for (int k = tid; k < nline; k += g.nth) priv[compact ? oc + k : o + k] = base[o + k];
     }
   }
   // private state vector and residual: the unknowns of the band's rows (the windowed evaluation converts the perturbed cell, rescales
@@ -262,7 +281,7 @@ HD int eval_column(Gen& g, const double* base, int npl, int64_t iv, const double
   g.sync();
   const int rc = g.pandf1(xc, yc, ylp, wk);
 #if defined(UE_GEN_HOST)
-  if (g_poison && getenv("UE_GEN_OOB")) {  // developer aid: which planes does a windowed evaluation write outside the band's rows?
+  if (g_poison && !compact && getenv("UE_GEN_OOB")) {  // developer aid: which planes does a windowed evaluation write outside the band's rows?
     static std::map<std::pair<int, int>, int> seen;  // (plane, row offset class) -> count
     const int NXS = g.NXS, NC = g.NC, nrow = g.ny + 2;
     const int r0 = mx(0, yc - band), r1 = mn(nrow - 1, yc + band);
@@ -271,7 +290,14 @@ HD int eval_column(Gen& g, const double* base, int npl, int64_t iv, const double
         if (r >= r0 && r <= r1) continue;
         if (g.iysptrx1 >= 0 && (r == g.iysptrx1 || r == g.iysptrx1 + 1)) continue;
         bool w = false;
-        for (int c = 0; c < NXS; ++c) { const double v = priv[(size_t)p * NC + (size_t)r * NXS + c]; if (v == v) w = true; }
+        for (int c = 0; c < NXS; ++c) {
+          const size_t k = (size_t)p * NC + (size_t)r * NXS + c;
+          uint64_t bits; std::memcpy(&bits, &priv[k], 8);
+          if (bits != (0x7ff8000000000000ull | (uint64_t)(k + 1))) {
+            // cells the copy itself filled (rectangles outside the band's rows: none, by construction of this scan) are excluded above
+            w = true;
+          }
+        }
         if (w) { const int cls = r <= 2 ? r : (r >= nrow - 2 ? 100 + (r - (nrow - 2)) : 50); if (seen[{p, cls}]++ == 0) fprintf(stderr, "OOB write: plane %d row class %d (row %d, band %d..%d)\n", p, cls, r, r0, r1); }
       }
   }
@@ -344,7 +370,7 @@ __global__ void __launch_bounds__(128, MINB) k_gen_cols(const Gen* gsrc, const d
   const int64_t iv = ivlist ? (int64_t)ivlist[c] : iv0 + c;  // (multi-GPU: this rank's unknowns are a list of mesh rows)
   const int64_t neq = g->neq;
   const int rc = eval_column(*g, base, npl, iv, yl, ylp + (size_t)c * (neq + 2), wk + (size_t)c * neq, yldot00, ml, mu, cap, frow + (size_t)(iv - 1) * cap,
-                             fval + (size_t)(iv - 1) * cap, cnt + (iv - 1), band, colpad);
+                             fval + (size_t)(iv - 1) * cap, cnt + (iv - 1), band, colpad, priv + (size_t)c * nslab, 0);
   if (tpu > 32) __syncthreads(); else __syncwarp();
   if (rc && lane == 0) { err[0] = rc; err[1] = g->errc; }
   if (lane == 0 && cnt[iv - 1] > cap) err[2] = cnt[iv - 1];
@@ -411,14 +437,13 @@ __global__ void k_gen_sortrows(int64_t neq, const int64_t* ia, int64_t nnzmx, co
 // they start at once and the short ones fill in behind them.  No chunking by memory, no tail of long windows at the end of a launch.
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_gen_cols_q(const Gen* gsrc, const double* base, double* priv, int npl, const int* order, int ncol, int* queue, const double* yl, double* ylp,
-                             double* wk, const double* yldot00, int64_t ml, int64_t mu, int cap, int* frow, double* fval, int* cnt, int* err, int band, int colpad) {
+                             double* wk, const double* yldot00, int64_t ml, int64_t mu, int cap, int* frow, double* fval, int* cnt, int* err, int band, int colpad, size_t slab, int compact) {
   const int unit = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
   Gen* g = (Gen*)g_smem + unit;
   load_ctx(g, gsrc, lane, 32);
   __syncwarp();
   const int slot = (int)(blockIdx.x * (blockDim.x >> 5) + unit);
-  const size_t nslab = (size_t)npl * g->NC;
-  if (lane == 0) { g->nth = 32; g->gridmode = 0; g->errc = 0; g->assign_planes(priv + (size_t)slot * nslab); }
+  if (lane == 0) { g->nth = 32; g->gridmode = 0; g->errc = 0; if (!compact) g->assign_planes(priv + (size_t)slot * slab); }
   __syncwarp();
   const int64_t neq = g->neq;
   // a block draws its warps' unknowns together: neighbours in the list are the unknowns of one cell - the same window, so the warps
@@ -434,7 +459,7 @@ __global__ void __launch_bounds__(128, MINB) k_gen_cols_q(const Gen* gsrc, const
     if (c >= ncol) continue;
     const int64_t iv = (int64_t)order[c];
     const int rc = eval_column(*g, base, npl, iv, yl, ylp + (size_t)slot * (neq + 2), wk + (size_t)slot * neq, yldot00, ml, mu, cap, frow + (size_t)(iv - 1) * cap,
-                               fval + (size_t)(iv - 1) * cap, cnt + (iv - 1), band, colpad);
+                               fval + (size_t)(iv - 1) * cap, cnt + (iv - 1), band, colpad, priv + (size_t)slot * slab, compact);
     __syncwarp();
     if (rc && lane == 0) { err[0] = rc; err[1] = g->errc; }
     if (lane == 0 && cnt[iv - 1] > cap) err[2] = cnt[iv - 1];
@@ -698,6 +723,7 @@ int init_all() {
   if (g.isnewpot * g.isphion == 1 && (g.iphibcc < 1 || g.iphibcc > 3)) { g_err = "only iphibcc = 1, 2, 3 available"; return -5; }
   g.ExtendedJacPhi = I("ExtendedJacPhi"); g.numvar_ = I("numvar");
   g.gridmode = 0; g.gbar = nullptr; g.gflag = nullptr;
+  g.rowlo = 0; g.rowhi = g.ny + 1;
   // gas energy equation (istgon = 1): the inertial atoms only
   g.idxtg_ = ARR("idxtg", nc);
   g.istgcore = I("istgcore", 0); g.istgpfc = I("istgpfc", 0); g.istgwc = I("istgwc", 0); g.istglb = I("istglb", 0); g.istgrb = I("istgrb", 0); g.isfegxyqflave = I("isfegxyqflave");
@@ -778,6 +804,10 @@ int init_all() {
   if (const char* e = getenv("UE_GEN_BAND")) g_band = std::max(UE_GEN_BAND_DEFAULT, atoi(e));
   g_colpad = 2;
   if (const char* e = getenv("UE_GEN_COLPAD")) g_colpad = atoi(e);
+  g_compact = 1;
+  if (const char* e = getenv("UE_GEN_COMPACT")) g_compact = atoi(e) != 0;
+  if (g_tpu > 32 || g_band > 2 * (G.ny + 2)) g_compact = 0;  // (the block-per-unknown kernel and all-rows bands keep full-size planes)
+
 #if defined(UE_GEN_HOST)
   g_poison = getenv("UE_GEN_POISON") != nullptr;
 #endif
@@ -881,7 +911,10 @@ int UE_PREFIX(jac_calc)(int64_t n, double t, const double* yl, const double* yld
   }
   if (!mem_put(d_yl, yl, (neq + 2) * 8) || !mem_put(d_y00, yldot00, neq * 8)) return -10;
   const int cap = COLCAP;
-  const size_t nslab = (size_t)NPL * G.NC;
+  // a private plane set: full-size planes, or band rows only (UE_GEN_COMPACT, the default) - then with one mesh of padding on both sides of
+  // the whole allocation, because reads outside the band (harmless: see eval_column) land in neighbouring planes or slabs
+  g_pad = g_compact ? (size_t)G.NC : 0;
+  const size_t nslab = g_compact ? (size_t)(NPL - UE_GEN_NLINE) * (2 * g_band + 1) * G.NXS + (size_t)UE_GEN_NLINE * std::max(G.NXS, G.ny + 2) : (size_t)NPL * G.NC;
   int64_t ncols_all = std::max<int64_t>(0, g_ivmax - g_ivmin + 1);
 #if !defined(UE_GEN_HOST)
   if (gc_nranks > 1) ncols_all = (ncols_all + gc_nranks - 1) / gc_nranks;
@@ -894,7 +927,7 @@ int UE_PREFIX(jac_calc)(int64_t n, double t, const double* yl, const double* yld
 #if !defined(UE_GEN_HOST)
     if (g_occ1 == 0) {
       int occ1 = 1, occ4 = 1;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_gen_cols_q<1>, 128, 4 * sizeof(Gen));
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_gen_cols_q<3>, 128, 4 * sizeof(Gen));
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4, k_gen_cols_q<4>, 128, 4 * sizeof(Gen));
       g_occ1 = std::max(1, occ1); g_occ4 = std::max(1, occ4);
     }
@@ -912,7 +945,7 @@ int UE_PREFIX(jac_calc)(int64_t n, double t, const double* yl, const double* yld
   if (g_priv_cols < chunk) {
     for (double* q : {d_priv, d_ylp, d_wk})  // a larger set replaces the one a narrower column range allocated
       if (q) { g_allocs.erase(std::remove(g_allocs.begin(), g_allocs.end(), (void*)q), g_allocs.end()); mem_free(q); }
-    d_priv = mem_alloc(chunk * nslab); d_ylp = mem_alloc(chunk * (neq + 2)); d_wk = mem_alloc(chunk * neq);
+    d_priv = mem_alloc(chunk * nslab + 2 * g_pad); d_ylp = mem_alloc(chunk * (neq + 2)); d_wk = mem_alloc(chunk * neq);
     if (!d_priv || !d_ylp || !d_wk) return -10;
     g_allocs.push_back(d_priv); g_allocs.push_back(d_ylp); g_allocs.push_back(d_wk);
     g_priv_cols = chunk;
@@ -934,8 +967,8 @@ int UE_PREFIX(jac_calc)(int64_t n, double t, const double* yl, const double* yld
   std::memset(d_cnt, 0, (2 * neq + 2) * sizeof(int));
   for (int64_t iv = g_ivmin; iv <= g_ivmax; ++iv) {
     Gen me = G; me.nth = 1; me.errc = 0;
-    me.assign_planes(d_priv);
-    const int rc = eval_column(me, d_base, NPL, iv, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow + (size_t)(iv - 1) * cap, d_fval + (size_t)(iv - 1) * cap, d_cnt + (iv - 1), g_band, g_colpad);
+    me.assign_planes(d_priv + g_pad);
+    const int rc = eval_column(me, d_base, NPL, iv, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow + (size_t)(iv - 1) * cap, d_fval + (size_t)(iv - 1) * cap, d_cnt + (iv - 1), g_band, g_colpad, d_priv + g_pad, g_compact);
     if (rc) return report(rc, me.errc);
     if (d_cnt[iv - 1] > cap) { g_err = "column fragment capacity exceeded: set UE_GEN_COLCAP"; return -2; }
   }
@@ -999,8 +1032,8 @@ int UE_PREFIX(jac_calc)(int64_t n, double t, const double* yl, const double* yld
     const int nblk = (nslots + WPB - 1) / WPB;  // (a last block with idle warps never exceeds the allocation: chunk >= 4 and slots are clipped below)
     const int nblk_ok = std::min<int>(nblk, (int)(chunk / WPB));
     if (ncol > 0) {
-      if (many) k_gen_cols_q<4><<<std::max(1, nblk_ok), 32 * WPB, WPB * sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, d_order, ncol, d_queue, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, g_band, g_colpad);
-      else k_gen_cols_q<1><<<std::max(1, nblk_ok), 32 * WPB, WPB * sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, d_order, ncol, d_queue, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, g_band, g_colpad);
+      if (many) k_gen_cols_q<4><<<std::max(1, nblk_ok), 32 * WPB, WPB * sizeof(Gen)>>>(d_G, d_base, d_priv + g_pad, NPL, d_order, ncol, d_queue, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, g_band, g_colpad, nslab, g_compact);
+      else k_gen_cols_q<3><<<std::max(1, nblk_ok), 32 * WPB, WPB * sizeof(Gen)>>>(d_G, d_base, d_priv + g_pad, NPL, d_order, ncol, d_queue, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, g_band, g_colpad, nslab, g_compact);
       if (!ck(cudaGetLastError(), "k_gen_cols_q launch")) return -10;
     }
   } else

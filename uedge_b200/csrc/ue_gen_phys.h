@@ -79,6 +79,11 @@ struct Gen {
   // own copy of this struct in shared memory, all working on the same planes; the barrier between two loop nests is a grid barrier
   // (one atomic ticket per block on gbar, a spin on its acquire load, fences on both sides: what cooperative_groups' grid sync does).
   int gridmode;
+  // rows the planes of this context hold: all of them (full evaluation, full-size private slabs) or the band of a Jacobian column whose
+  // planes are stored band-rows-only (assign_planes_band).  Statements of the reference that touch FIXED rows or whole planes regardless
+  // of the window (cosmetic zeroing of row ny+1, guard rows of fqya, ...) are skipped outside: nothing in the band reads them.
+  int rowlo, rowhi;
+  HD bool inrow(int iy) const { return iy >= rowlo && iy <= rowhi; }
   unsigned* gbar;  // monotonic ticket counter (zeroed before the launch)
   int* gflag;      // error flags raised by any thread, read by all after a barrier (uniform returns)
   HD int TID() const {
@@ -571,7 +576,7 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
       }
     SER {  // X-point vertex: 8-cell average (convert.m:831-868); nyomitmx = 0
       const int isx = ixpt1, jsx = iysptrx1, iex = ixpt2;
-      if (!(isx < 0 || iex < 0 || iex > nx)) {
+      if (!(isx < 0 || iex < 0 || iex > nx) && inrow(jsx) && inrow(jsx + 1)) {
         auto av8 = [&](const double* a) {
           return 0.125 * (A(a, isx, jsx) + A(a, isx + 1, jsx) + A(a, isx, jsx + 1) + A(a, isx + 1, jsx + 1) + A(a, iex, jsx) + A(a, iex + 1, jsx) + A(a, iex, jsx + 1) + A(a, iex + 1, jsx + 1));
         };
@@ -832,7 +837,7 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
     FOR2(iy, j4, j8, ix, i1, i5) A(conxge, ix, iy) = A(sx, ix, iy) * A(hcxg, ix, iy) * A(gxf, ix, iy);  // conduction (oderhs.m:7605-7636); hcxg is flux-limited already
     FOR1(iy, j4, j8) { A(conxge, nx + 1, iy) = 0; }
     FOR2(iy, j1, j5, ix, i4, i8) A(conyge, ix, iy) = A(sy, ix, iy) * A(hcyg, ix, iy) / A(dynog, ix, iy);
-    FOR1(ix, i1, i6) A(conyge, ix, ny + 1) = 0.0;
+    if (inrow(ny + 1)) FOR1(ix, i1, i6) A(conyge, ix, ny + 1) = 0.0;
     FOR2(iy, j4, j8, ix, i1, i5) A(floxge, ix, iy) = cfcvtg * 2.5 * A(fngx, ix, iy);  // convection (oderhs.m:7643-7705)
     FOR1(iy, j4, j8) { A(floxge, nx + 1, iy) = 0.; }
     FOR1(iy, j4, j8) {  // no inward power from the plates
@@ -842,9 +847,9 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
     }
     FOR2(iy, j1, j5, ix, i4, i8) A(floyge, ix, iy) = cfcvtg * 2.5 * A(fngy, ix, iy);
     FOR1(ix, i4, i8) {  // ... nor from the walls
-      if (ix <= ixpt1 || ix > ixpt2) { if (A(fngy, ix, 0) > 0.) A(floyge, ix, 0) = A(floyge, ix, 0) - (1. - cfloygwall) * cfcvtg * 2.5 * A(fngy, ix, 0); }
-      if (A(fngy, ix, ny) < 0.) A(floyge, ix, ny) = A(floyge, ix, ny) - (1. - cfloygwall) * cfcvtg * 2.5 * A(fngy, ix, ny);
-      A(floyge, ix, ny + 1) = 0.0;
+      if (inrow(0) && (ix <= ixpt1 || ix > ixpt2)) { if (A(fngy, ix, 0) > 0.) A(floyge, ix, 0) = A(floyge, ix, 0) - (1. - cfloygwall) * cfcvtg * 2.5 * A(fngy, ix, 0); }
+      if (inrow(ny) && A(fngy, ix, ny) < 0.) A(floyge, ix, ny) = A(floyge, ix, ny) - (1. - cfloygwall) * cfcvtg * 2.5 * A(fngy, ix, ny);
+      if (inrow(ny + 1)) A(floyge, ix, ny + 1) = 0.0;
     }
     if (istgon == 1) fd2tra(w, floxge, floyge, conxge, conyge, tg, fegx, fegy, 0, methi);  // oderhs.m:7708-7716
     if (isnonog == 1 && istgon == 1)  // y-component of the non-orthogonal diffusive flux (oderhs.m:7720-7782)
@@ -966,7 +971,7 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
             A(vytan[f], ix, iy) = (fcdif * difni[f] + 0.) * (grdnv / ue_cos(A(angfx, ix, iy)) - (ue_log(A(ni[f], ix2, iy)) - ue_log(A(ni[f], ix, iy))) * A(gxf, ix, iy));
           }
         }
-      FOR1(ix, i1, i6) A(vy[f], ix, ny + 1) = 0.0;
+      if (inrow(ny + 1)) FOR1(ix, i1, i6) A(vy[f], ix, ny + 1) = 0.0;
     }
     if (isphion + isphiofft == 1) calc_currents(w);  // oderhs.m:1499
     // thermal force / friction (oderhs.m:1516-1534)
@@ -1026,7 +1031,7 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
     for (int f = 0; f < nfsp; ++f)
       FOR2(iy, j1, j5, ix, i1, i6) A(vey, ix, iy) = A(vey, ix, iy) + A(vy[f], ix, iy) * zi[f] * 0.5 * (A(niy0[f], ix, iy) + A(niy1[f], ix, iy));
     FOR2(iy, j1, j5, ix, i1, i6) A(vey, ix, iy) = (A(vey, ix, iy) - cfjve * A(fqy, ix, iy) / (A(sy, ix, iy) * qe)) / (0.5 * (A(ney0, ix, iy) + A(ney1, ix, iy)));
-    if (isnewpot == 1)  // fqy(,0) = 0 there (oderhs.m:1794-1800)
+    if (isnewpot == 1 && inrow(0))  // fqy(,0) = 0 there (oderhs.m:1794-1800)
       FOR1(ix, i1, i6) A(vey, ix, 0) = cfybf * A(veycb, ix, 0) + A(vydd[0], ix, 0) + cfyef * A(vyce[0], ix, 0);
 
     // zero the source accumulators (oderhs.m:1818-1835)
@@ -1088,7 +1093,7 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
     if (isfixlb == 2) {
       const int ix = ixpt2;
       if (ix >= i2 && ix <= i5 + 1 && iysptrx1 > 0)
-        FOR1(iy, 0, iysptrx1) {
+        FOR1(iy, mx(0, rowlo), mn(iysptrx1, rowhi)) {
           A(gpex, ix, iy) = 0.; A(frice, ix, iy) = 0.; A(ex, ix, iy) = 0.; A(upe, ix, iy) = 0.;
           for (int f = 0; f < nfsp; ++f) { A(gpix[f], ix, iy) = 0.; A(frici[f], ix, iy) = 0.; A(uu[f], ix, iy) = 0.; A(upi[f], ix, iy) = 0.; }
         }
@@ -1345,7 +1350,7 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
         A(eqp, ix, iy) = A(eqp, ix, iy) * (d * d) / (cutlo + d * d + s * s);
       }
     if (nisp >= 2) {  // gas conductivities as stored (oderhs.m:3156-3160) and atom/ion equipartition (oderhs.m:3163-3176)
-      if (isupgon == 1) FOR1(c_, 0, NC - 1) { hcxg[c_] = hcxn[c_]; hcyg[c_] = hcyn[c_]; }
+      if (isupgon == 1) FOR1(c_, rowlo * NXS, (rowhi + 1) * NXS - 1) { hcxg[c_] = hcxn[c_]; hcyg[c_] = hcyn[c_]; }
       FOR2(iy, j1, j6, ix, i1, i6) A(eqpg, ix, iy) = cftgeqp * A(ng, ix, iy) * (A(ni[0], ix, iy) + cftiexclg * A(ni[1], ix, iy)) * keligig[0];
       engbalg(w);  // oderhs.m:3180
     }
@@ -1387,7 +1392,7 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
               A(fniy[f], ix, iy) = A(fniy[f], ix, iy) / (1 + r1 * r1 + r2 * r2);
             }
           }
-        FOR1(ix, i4, i8) A(fniy[f], ix, ny + 1) = 0.0;
+        if (inrow(ny + 1)) FOR1(ix, i4, i8) A(fniy[f], ix, ny + 1) = 0.0;
       }
     }
     for (int f = 0; f < nfsp; ++f) {  // oderhs.m:3321-3339 (4th-order radial diffusion)
@@ -1509,7 +1514,7 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
         A(floxe, ix, iy) = 0.; A(floxi, ix, iy) = 0.; A(floye, ix, iy) = 0.; A(floyi, ix, iy) = 0.;
         feiycbo[ix] = 0.; feeycbo[ix] = 0.; A(w0, ix, iy) = 0.; A(w1, ix, iy) = 0.;
       }
-    for (int f = 0; f < nusp; ++f) FOR1(c_, 0, NC - 1) wvh[f][c_] = 0.;
+    for (int f = 0; f < nusp; ++f) FOR1(c_, rowlo * NXS, (rowhi + 1) * NXS - 1) wvh[f][c_] = 0.;
     FOR2(iy, j4, j8, ix, i1, i5) {
         int ix2 = IXP1(ix, iy);
         double t0 = mx(A(te, ix, iy), temin * ev), t1 = mx(A(te, ix2, iy), temin * ev);
@@ -1542,7 +1547,7 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
         A(conye, ix, iy) = A(sy, ix, iy) * A(hcye, ix, iy) / A(dynog, ix, iy);
         A(conyi, ix, iy) = A(sy, ix, iy) * A(hcyi, ix, iy) / A(dynog, ix, iy);
       }
-    FOR1(ix, i1, i6) { A(conye, ix, ny + 1) = 0.0; A(conyi, ix, ny + 1) = 0.0; }
+    if (inrow(ny + 1)) FOR1(ix, i1, i6) { A(conye, ix, ny + 1) = 0.0; A(conyi, ix, ny + 1) = 0.0; }
     FOR2(iy, j4, j8, ix, i1, i5) {  // oderhs.m:4024-4036
         int ix1 = IXP1(ix, iy);
         double ltmax = mn(fabs(A(te, ix, iy) / (A(rrv, ix, iy) * A(gtex, ix, iy) + cutlo)), A(lcone, ix, iy));
@@ -1568,11 +1573,11 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
       if (isupgon == 1 && f == iigsp) {
         FOR2(iy, j1, j5, ix, i4, i8) A(floyi, ix, iy) = A(floyi, ix, iy) + cftiexclg * cfneut * cfneutsor_ei * 2.5 * A(fniy[f], ix, iy);
         FOR1(ix, i4, i8) {
-          if (matwallo[ix] > 0 && recycwot[ix] > 0.) {
+          if (inrow(ny) && matwallo[ix] > 0 && recycwot[ix] > 0.) {
             double fniy_recy = mx(recycwot[ix] * fac2sp * A(fniy[0], ix, ny), 0.);
             A(floyi, ix, ny) = A(floyi, ix, ny) + cftiexclg * cfneut * cfneutsor_ei * 2.5 * (1. - cfloygwall) * fniy_recy;
           }
-          if (matwalli[ix] > 0 && recycwit[ix] > 0.) {
+          if (inrow(0) && matwalli[ix] > 0 && recycwit[ix] > 0.) {
             double fniy_recy = mn(recycwit[ix] * fac2sp * A(fniy[0], ix, 0), 0.);
             A(floyi, ix, 0) = A(floyi, ix, 0) + cftiexclg * cfneut * cfneutsor_ei * 2.5 * (1. - cfloygwall) * fniy_recy;
           }
@@ -1860,9 +1865,9 @@ HD void calc_currents(const Win& w) {
         }
     }
   FOR1(ix, i1, i6) {
-    if (isixcore[ix] == 1) { for (int iy = 0; iy <= nfqya0core_; ++iy) A(fqya, ix, iy) = 0.; }
-    else { for (int iy = 0; iy <= nfqya0pf_; ++iy) A(fqya, ix, iy) = 0.; }
-    for (int iy = ny; iy >= ny + 1 - nfqya0ow_; --iy) A(fqya, ix, iy) = 0.;
+    if (isixcore[ix] == 1) { for (int iy = 0; iy <= nfqya0core_; ++iy) if (inrow(iy)) A(fqya, ix, iy) = 0.; }
+    else { for (int iy = 0; iy <= nfqya0pf_; ++iy) if (inrow(iy)) A(fqya, ix, iy) = 0.; }
+    for (int iy = ny; iy >= ny + 1 - nfqya0ow_; --iy) if (inrow(iy)) A(fqya, ix, iy) = 0.;
   }
   FOR2(iy, j1p, j5p, ix, i1, i6) {
       A(fqy, ix, iy) = (1. - rnewpot_) * A(fqyao, ix, iy) + rnewpot_ * A(fqya, ix, iy) + cfqybf * A(fqyb, ix, iy) + cfqym * A(fqym, ix, iy) + cfjpy * A(fqyd, ix, iy);
@@ -2666,6 +2671,19 @@ HD int pandf1(int xc, int yc, const double* yl, double* yldot) {
 #undef P1
 #undef P2
     return n;
+  }
+  // band-rows-only storage: every field plane holds `nrows` rows starting at mesh row r0 (plane pointer offset by -r0 rows, so that the
+  // A(a,ix,iy) indexing is unchanged inside the band), the line arrays follow with `line` doubles each
+  HD void assign_planes_band(double* slab, int r0, int nrows, int nline_planes, int line) {
+    const size_t pl = (size_t)nrows * NXS;
+    const int nfield = nplanes() - nline_planes;
+    int k = 0;
+    const ptrdiff_t off = -(ptrdiff_t)r0 * NXS;
+#define P1(x) { x = (k < nfield) ? slab + (size_t)k * pl + off : slab + (size_t)nfield * pl + (size_t)(k - nfield) * line; ++k; }
+#define P2(x) { x[0] = (k < nfield) ? slab + (size_t)k * pl + off : slab + (size_t)nfield * pl + (size_t)(k - nfield) * line; ++k; x[1] = (k < nfield) ? slab + (size_t)k * pl + off : slab + (size_t)nfield * pl + (size_t)(k - nfield) * line; ++k; }
+    UE_GEN_PLANES(P1, P2)
+#undef P1
+#undef P2
   }
   HD void assign_planes(double* slab) {  // slab: nplanes() x NC doubles
     size_t k = 0;
