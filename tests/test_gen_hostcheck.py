@@ -78,35 +78,40 @@ def test_switch_combinations(built, seed):
     assert all(np.array_equal(p, q, equal_nan=True) for p, q in zip(jo, jh)), desc
 
 
-def test_band_copy_of_the_private_planes_is_sufficient(built, monkeypatch):
-    """Every Jacobian column works on a private copy of the field planes; only a band of rows around the perturbed cell (plus the
+@pytest.mark.parametrize("poison", ["1", "2"])
+def test_band_copy_of_the_private_planes_is_sufficient(built, monkeypatch, poison):
+    """(poison 1: everything outside the copy is NaN - a cell the evaluation needs but the copy lacks loses an entry; poison 2: finite
+    garbage that differs from unknown to unknown - a stale cell that reaches a kept row adds a spurious entry, which NaN cannot show
+    because a NaN element fails the clip test and is dropped.)  Every Jacobian column works on a private copy of the field planes; only a band of rows around the perturbed cell (plus the
     X-point rows and the line arrays) is copied from the base set.  With UE_GEN_POISON the host build fills everything else with NaN
     first: on a refined mesh (32x16, 18 rows; band 11 rows) the Jacobian stays bit-identical to the oracle, so nothing outside the
     band is read by what the band produces."""
     from uedge_b200.cases import load_grid_npz, refine_grid
-    monkeypatch.setenv("UE_GEN_POISON", "1")
+    monkeypatch.setenv("UE_GEN_POISON", poison)
     c, yl = d3d_full_physics_case(refine_grid(load_grid_npz(), 2, 2))
     assert c.com.ny + 2 == 18
     same(Oracle2().bind(c), host(0).bind(c), c, yl)
 
 
+@pytest.mark.parametrize("poison", ["1", "2"])
 @pytest.mark.parametrize("subset", ["ni-0", "up-0", "te", "phi", "default"])
-def test_window_copy_with_few_unknowns_per_cell(built, monkeypatch, subset):
+def test_window_copy_with_few_unknowns_per_cell(built, monkeypatch, subset, poison):
     """the private copy of a column holds the band rows x the window columns (+2), whole rows at the core and wall boundaries and at
     the X-point, and the line arrays; with one unknown per cell the Jacobian band spans the whole 8x4 mesh, so a stale far cell
     (e.g. the corner cells every wall window sets) would show up as an extra entry - everything else is poisoned with NaN here"""
-    monkeypatch.setenv("UE_GEN_POISON", "1")
+    monkeypatch.setenv("UE_GEN_POISON", poison)
     c, yl, _ = inputex_case(subset)
     same(Oracle2().bind(c), host(0).bind(c), c, yl)
 
 
 @pytest.mark.parametrize("name, kw", [("iflcore=1", dict(iflcore=1, pcoree=2e5, pcorei=2e5)), ("isnicore=0", dict(isnicore=(0, 0), curcore=(0, 10.0))),
                                       ("iphibcc=1", dict(iphibcc=1)), ("isnewpot=0", dict(isnewpot=0, rnewpot=0.0))])
-def test_window_copy_with_core_boundary_sums(built, monkeypatch, name, kw):
+@pytest.mark.parametrize("poison", ["1", "2"])
+def test_window_copy_with_core_boundary_sums(built, monkeypatch, name, kw, poison):
     """core conditions that sum over the whole core boundary (power, current) or set the potential rows at every core column: rows 0-2
     of the private copy hold all core columns; 2x-refined drift case, everything else poisoned"""
     from uedge_b200.cases import load_grid_npz, refine_grid
-    monkeypatch.setenv("UE_GEN_POISON", "1")
+    monkeypatch.setenv("UE_GEN_POISON", poison)
 
     def m(b, com):
         for k, v in kw.items():
@@ -147,11 +152,12 @@ def test_braginskii_radial_current(built, rev, monkeypatch):
     same(Oracle2().bind(c), host(rev).bind(c), c, yl)
 
 
-def test_jupyter_drift_case_band_copy_is_sufficient(built, monkeypatch):
+@pytest.mark.parametrize("poison", ["1", "2"])
+def test_jupyter_drift_case_band_copy_is_sufficient(built, monkeypatch, poison):
     """the same on the 2x-refined mesh with everything outside the copied band poisoned (NaN): the core conditions of the
     potential read rows 0-2 at every core column whenever the window starts at iy <= 3 - they are inside the band then"""
     from uedge_b200.cases import load_grid_npz, refine_grid
-    monkeypatch.setenv("UE_GEN_POISON", "1")
+    monkeypatch.setenv("UE_GEN_POISON", poison)
     c, yl = jupyter_case(grid=refine_grid(load_grid_npz(), 2, 2))
     assert c.com.ny + 2 == 18 and c.bbb.neq == 4284
     same(Oracle2().bind(c), host(0).bind(c), c, yl)
@@ -182,9 +188,10 @@ def test_gas_energy_boundary_options(built, k, opts):
         same(Oracle2().bind(c), host(k & 1).bind(c), c, yl)
 
 
-def test_gas_energy_band_copy_is_sufficient(built, monkeypatch):
+@pytest.mark.parametrize("poison", ["1", "2"])
+def test_gas_energy_band_copy_is_sufficient(built, monkeypatch, poison):
     from uedge_b200.cases import load_grid_npz, refine_grid
-    monkeypatch.setenv("UE_GEN_POISON", "1")
+    monkeypatch.setenv("UE_GEN_POISON", poison)
     c, yl = gas_energy_case(grid=refine_grid(load_grid_npz(), 2, 2))
     assert c.bbb.neq == 4896
     same(Oracle2().bind(c), host(0).bind(c), c, yl)

@@ -168,6 +168,27 @@ def test_grid_mode_residual_on_the_4x_mesh(built, case):
     assert np.array_equal(o.pandf1(y2), g.pandf1(y2))
 
 
+def test_repeated_jacobians_on_the_4x_mesh(built):
+    """the persistent column kernel reuses its private planes from unknown to unknown and from call to call: what an earlier
+    evaluation left there (here also: another state) must not reach a kept row.  Drift case on the 4x mesh (15 708 unknowns): three
+    Jacobians at two states, each bit-identical to the oracle"""
+    from uedge_b200.cases import load_grid_npz, refine_grid
+    c, yl = jupyter_case(grid=refine_grid(load_grid_npz(), 4, 4))
+    b = c.bbb
+    o, g = Oracle2().bind(c), load_gen().bind(c)
+    y2 = yl.copy(); y2[: b.neq] *= 1.0 + 3e-4
+    ref = {}
+    for k, y in enumerate((yl, y2, yl)):
+        fg = g.pandf1(y)
+        jg = g.jac_calc(y, fg, b.lbw, b.ubw, b.nnzmx)
+        if id(y) not in ref:
+            fo = o.pandf1(y)
+            ref[id(y)] = (fo, o.jac_calc(y, fo, b.lbw, b.ubw, b.nnzmx))
+        fo, jo = ref[id(y)]
+        assert np.array_equal(fo, fg), k
+        assert all(np.array_equal(p, q) for p, q in zip(jo, jg)), (k, len(jo[0]), len(jg[0]))
+
+
 def test_errors_are_reported(built):
     c, yl, _ = inputex_case("default")
     g = load_gen().bind(c)

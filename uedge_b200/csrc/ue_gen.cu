@@ -154,7 +154,8 @@ template <typename T> T* alloc_as(size_t n) {
 // rows copied on each side of the perturbed cell's row, and the number of line arrays at the end of UE_GEN_PLANES
 #define UE_GEN_NLINE 14
 #if defined(UE_GEN_HOST)
-bool g_poison = false;  // test aid: fill the private planes with NaN before the band copy
+int g_poison = 0;  // test aid: before the copy, fill the private planes with NaN (1: a missing cell shows up as a lost entry) or with finite
+                   // garbage that changes from unknown to unknown (2: a stale cell that reaches a kept row shows up as a spurious entry)
 #endif
 // ---- the two evaluation bodies (shared by the kernels and the host build) ----------------------------------------------
 // full-domain residual in place on the context's planes
@@ -193,7 +194,10 @@ HD int eval_column(Gen& g, const double* base, int npl, int64_t iv, const double
     }
     g.sync();
 #if defined(UE_GEN_HOST)
-    if (g_poison && compact) { for (size_t k = 0; k < (size_t)nfield * bpl + (size_t)UE_GEN_NLINE * nline; ++k) priv[k] = (double)NAN; }
+    if (g_poison == 2) {  // positive, finite, different for every cell and every unknown
+      const size_t n = compact ? (size_t)nfield * bpl + (size_t)UE_GEN_NLINE * nline : (size_t)npl * NC;
+      for (size_t k = 0; k < n; ++k) priv[k] = 1.0e3 * (1.0 + 0.37 * (double)((k * 2654435761ull + (size_t)iv * 40503ull) % 1000003ull) / 1000003.0);
+    } else if (g_poison && compact) { for (size_t k = 0; k < (size_t)nfield * bpl + (size_t)UE_GEN_NLINE * nline; ++k) priv[k] = (double)NAN; }
     else
     if (g_poison) {
       if (getenv("UE_GEN_OOB")) {  // every cell its own NaN payload: a later bit-compare finds any write, copies of poison included
@@ -213,7 +217,8 @@ HD int eval_column(Gen& g, const double* base, int npl, int64_t iv, const double
     else {
       rect(r0, r1, w.i1 - colpad, w.i6 + colpad);                            // the window
       if (r0 <= 2) {
-        rect(r0, mn(2, r1), g.ixpt1, g.ixpt2 + 1);                             // core boundary: sums over all core columns
+        rect(r0, mn(2, r1), mn(w.i1 - colpad, g.ixpt1), mx(w.i6 + colpad, g.ixpt2 + 1));  // core boundary: sums over all core columns; with
+                                                                                   // isnewpot = 1 the potential rows are set from the window to the far end of the core
         rect(r0, mn(2, r1), 0, 1); rect(r0, mn(2, r1), g.nx, g.nx + 1);       // corner cells of the inner wall
       }
       if (r1 >= nrow - 2) { rect(mx(r0, nrow - 2), r1, 0, 1); rect(mx(r0, nrow - 2), r1, g.nx, g.nx + 1); }  // ... and of the outer wall
@@ -254,7 +259,7 @@ HD int eval_column(Gen& g, const double* base, int npl, int64_t iv, const double
     const int r0 = mx(0, yc - band), r1 = mn(nrow - 1, yc + band);
     const bool whole = (g.dtreal < 1.e15 && yl[neq] < 0) || g.yinc >= 6 || colpad < 0;
 #if defined(UE_GEN_HOST)
-    if (g_poison) for (int64_t k = 0; k < neq; ++k) { ylp[k] = (double)NAN; wk[k] = (double)NAN; }
+    if (g_poison) for (int64_t k = 0; k < neq; ++k) { ylp[k] = g_poison == 2 ? 0.731 + 1e-3 * (double)(k % 977) : (double)NAN; wk[k] = g_poison == 2 ? 1.0e5 + (double)(k % 991) : (double)NAN; }
 #endif
     const auto w = g.make_win(xc, yc);
     const bool fullx = w.xccuts || g.rowuniform_ == 0 || (w.i1 <= colpad && w.i6 >= g.nx + 1 - colpad);
@@ -809,7 +814,7 @@ int init_all() {
   if (g_tpu > 32 || g_band > 2 * (G.ny + 2)) g_compact = 0;  // (the block-per-unknown kernel and all-rows bands keep full-size planes)
 
 #if defined(UE_GEN_HOST)
-  g_poison = getenv("UE_GEN_POISON") != nullptr;
+  g_poison = getenv("UE_GEN_POISON") ? std::max(1, atoi(getenv("UE_GEN_POISON"))) : 0;
 #endif
   g_ivmin = 1; g_ivmax = g.neq;
   g_ready = true;
