@@ -1045,14 +1045,8 @@ int UE_PREFIX(jac_calc)(int64_t n, double t, const double* yl, const double* yld
   for (int64_t iv0 = my_lo; iv0 <= my_hi; iv0 += (int64_t)chunk) {
     const int ncol = (int)std::min<int64_t>((int64_t)chunk, my_hi - iv0 + 1);
     const int* ivl = my_list ? my_list + (iv0 - 1) : nullptr;
-    // few unknowns: every warp is alone on its scheduler, registers are free (158, no spills); many unknowns: 4 blocks per SM
-    // (128 registers, a few spills) so that more chains overlap
-    if (g_tpu > 32)
-      k_gen_cols<1><<<ncol, g_tpu, sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, iv0, ivl, ncol, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, g_tpu, g_band, g_colpad);
-    else if (ncol <= 4096)
-      k_gen_cols<1><<<(ncol + WPB - 1) / WPB, 32 * WPB, WPB * sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, iv0, ivl, ncol, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, 32, g_band, g_colpad);
-    else
-      k_gen_cols<4><<<(ncol + WPB - 1) / WPB, 32 * WPB, WPB * sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, iv0, ivl, ncol, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, 32, g_band, g_colpad);
+    // (the block-per-unknown variant, UE_GEN_TPU=64: one launch per memory-sized chunk, full-size private planes)
+    k_gen_cols<1><<<ncol, g_tpu, sizeof(Gen)>>>(d_G, d_base, d_priv, NPL, iv0, ivl, ncol, d_yl, d_ylp, d_wk, d_y00, ml, mu, cap, d_frow, d_fval, d_cnt, d_err, g_tpu, g_band, g_colpad);
     if (!ck(cudaGetLastError(), "k_gen_cols launch")) return -10;
   }
   cudaEventRecord(e1);
