@@ -6,9 +6,13 @@
 //     (isupgon(1)=1, nhsp=2, zi(2)=0: pyexamples/box2, pyexamples/input_example, jupyter/case_setup.py);
 //   * orthogonal AND non-orthogonal meshes (isnonog 0/1: 5-point stencils fxm..fypx, vytan, fngxy, fmixy, feexy, feixy);
 //   * every fd2tra scheme (methX 0..8 in x, 0..8 in y);
-//   * the potential equation (isphion=1: calc_currents, poteneq, phi boundary rows) without cross-field drifts;
-//   * any subset of equations switched on (isnion/isupon/isteon/istion/isngon/isphion per species), general idx* maps.
-// Cross-field drift coefficients, impurities, molecules, MC neutrals, Bohm-like transport must be off (refused in init).
+//   * the potential equation (isphion=1: calc_currents, calc_curr_cx, poteneq, phi boundary rows; isnewpot 0/1 with the
+//     core conditions iphibcc 1-3, the ExtendedJacPhi band of jac_calc);
+//   * every cross-field drift part of bbb/oderhs.m:1137-1471 (ExB, grad-B / curvature, diamagnetic, resistive, classical),
+//     the B x grad(T) heat flows, Joule heating, the drift and diamagnetic currents (jupyter/case_setup.py);
+//   * the gas energy equation engbalg (istgon=1 for the inertial atoms) with every wall / plate / core option of tg;
+//   * any subset of equations switched on (isnion/isupon/isteon/istion/isngon/istgon/isphion per species), general idx* maps.
+// Impurities, molecules, MC neutrals, Bohm-like transport, dnull / limiter must be off (refused in init).
 //
 // It keeps the reference's stateful, windowed semantics (persistent field arrays = the Fortran module state; loop ranges
 // i1..i8 x j1..j8 of bbb/oderhs.m:868-964), so jac_calc can be the reference's one-unknown-at-a-time loop.
@@ -18,6 +22,9 @@
 // resei, resphi ...) for eleven equation subsets, held in pyexamples/input_example/solution.h5 under pytests/<subset>
 // (8x4 single-null non-orthogonal mesh, inertial atoms, potential).  The d3dHsm-family oracle (ue_oracle.cpp), whose
 // arithmetic the CUDA kernels reproduce bit for bit, is in turn pinned to this one on its own switch set.
+// PARITY UNPINNED: the drift terms (the only reference-held number for a case with drifts is fnrm0 = 2.134077960622300 of
+// jupyter/PyUedge.ipynb, reproduced to 7.6 %: test_jupyter_drift_case_fnrm0 holds the breakdown) and the gas energy equation
+// (no file of the tree was computed with istgon=1).  Both are restated line by line from the cited ranges.
 //
 // Inputs: ONE generic setter, ue_or2_set(name, data, n): every scalar and array crosses as doubles under the reference's
 // own variable name (species arrays as arrays).  Citations "oderhs.m:N" are file:line under bbb/ of the reference tree.

@@ -1,19 +1,23 @@
 // uedge_b200/csrc/ue_gen_phys.h — the GENERAL residual of the hot path: pandf1 for the hydrogen family of switch sets
 //   * one or two "ion" species (hydrogen ions + INERTIAL atoms, isupgon=1, nhsp=2) or diffusive atoms (isngon),
 //   * orthogonal and NON-ORTHOGONAL meshes (isnonog=1: 5-point stencils fxm..fypx, vytan, fngxy, fmixy, feexy, feixy),
-//   * every fd2tra scheme, the potential equation (isphion=1: calc_currents, poteneq, phi boundary rows),
-//   * any subset of equations (isnion/isupon/isteon/istion/isngon/isphion), general idx* maps.
+//   * every fd2tra scheme, the potential equation (isphion=1: calc_currents, calc_curr_cx, poteneq, phi boundary rows, isnewpot 0/1),
+//   * every cross-field drift part (ExB, grad-B / curvature, diamagnetic, resistive, classical), B x grad(T) heat flows, Joule heating,
+//   * the gas energy equation engbalg (istgon=1 for the inertial atoms),
+//   * any subset of equations (isnion/isupon/isteon/istion/isngon/istgon/isphion), general idx* maps.
 // Reference: bbb/convert.m:158-875 (convsr_vo, convsr_aux), bbb/oderhs.m:7-534 (fd2tra), :537-5070 (pandf), :5584-6648
-// (neudif, neudifpg), :7883-8213 (pandf1, rscalf), bbb/potencur.m:39-597 (calc_currents, poteneq), bbb/boundary.m:4-3002
-// (bouncon), aph/aphrates.m (hydrogen rates).  Cross-field drifts, impurities, molecules are refused at init.
+// (neudif, neudifpg), :7508-7878 (engbalg), :7883-8213 (pandf1, rscalf), bbb/potencur.m:39-597 (calc_currents, calc_curr_cx, poteneq),
+// bbb/boundary.m:4-3002 (bouncon), aph/aphrates.m (hydrogen rates).  Impurities, molecules, dnull / limiter are refused at init.
 //
-// EXECUTION MODEL.  One evaluation context = one `Gen` object: the constants and input-array pointers of the case plus
-// pointers to ONE private set of field planes (HBM slab of NPL x NC doubles) and the number of cooperating threads nth.  The reference's loop nests become cooperative loops: FOR2 / FOR1 distribute the iterations of a nest over
-// the nth threads of the context and begin with a barrier, so that everything an earlier nest wrote is visible; code
-// between nests that writes fields runs on the context's first thread (SER).  On the GPU a context is a warp (Jacobian:
-// one perturbed unknown per warp, window ranges i1..i8 x j1..j8 of oderhs.m:868-1019) or a thread block (full-domain
-// residual); compiled for the host (tests/hostcheck) a context is one thread and the loops run in the reference's order
-// - or reversed (UE_GEN_REVERSE), which exposes any dependence between iterations of one nest.
+// EXECUTION MODEL.  One evaluation context = one `Gen` object: the constants and input-array pointers of the case plus pointers to
+// ONE set of field planes in HBM and the identity of the cooperating threads.  The reference's loop nests become cooperative loops
+// (FOR2 / FOR1: every nest two-dimensional, the row walks of convsr_aux flattened with XRQ) whose iterations are dealt out to the
+// threads of the context and which begin with a barrier, so that everything an earlier nest wrote is visible; code between nests
+// that writes fields runs on the context's first thread (SER).  On the GPU a context is a warp (Jacobian: one perturbed unknown,
+// window ranges i1..i8 x j1..j8 of oderhs.m:868-1019, private planes that hold the band's rows only: rowlo..rowhi, inrow()), a
+// thread block (full-domain residual on small meshes) or a co-resident grid with grid barriers (gridmode: large meshes);
+// compiled for the host (tests/hostcheck) a context is one thread and the loops run in the reference's order - or reversed
+// (UE_GEN_REVERSE), which exposes any dependence between iterations of one nest.
 //
 // Arithmetic: no FMA contraction, ue_math.h transcendental functions - the same bits on host and device.
 #pragma once
