@@ -853,6 +853,11 @@ int run_full(const double* yl_host, double* yldot_host) {
   int e[4];
   if (!mem_get(e, d_err, sizeof e)) return -10;
   if (e[0]) return report(e[0], e[1]);
+  if (nblk > 1) {
+    int fl[2] = {0, 0};
+    if (!mem_get(fl, d_gbar, sizeof fl)) return -10;
+    if (fl[1] & 0x100) { g_err = "grid barrier of the residual kernel timed out (blocks not co-resident?): set UE_GEN_FULL_GRID=0"; return -10; }
+  }
 #endif
   if (yldot_host && !mem_get(yldot_host, d_yldot, neq * sizeof(double))) return -10;
   g_last_yl.assign(yl_host, yl_host + neq + 2);

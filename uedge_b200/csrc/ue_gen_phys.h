@@ -106,8 +106,13 @@ struct Gen {
         __threadfence();
         const unsigned nb = gridDim.x, ticket = atomicAdd(gbar, 1u);
         const unsigned target = (ticket / nb + 1u) * nb;
-        unsigned seen;
-        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(gbar) : "memory"); } while ((int)(seen - target) < 0);
+        unsigned seen, spins = 0;
+        // (a block that never arrives would hang the device: after ~2^22 polls - seconds - the barrier gives up, raises flag 0x100 and
+        //  every later barrier falls through; the host reports the evaluation as failed)
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(gbar) : "memory");
+          if (++spins > (1u << 22) || ((*(volatile int*)gflag) & 0x100)) { atomicOr(gflag, 0x100); break; }
+        } while ((int)(seen - target) < 0);
         __threadfence();
       }
       __syncthreads();
