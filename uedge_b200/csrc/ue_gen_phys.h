@@ -111,7 +111,7 @@ struct Gen {
         //  every later barrier falls through; the host reports the evaluation as failed)
         do {
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(gbar) : "memory");
-          if (++spins > (1u << 22) || ((*(volatile int*)gflag) & 0x100)) { atomicOr(gflag, 0x100); break; }
+          if ((++spins & 1023u) == 0 && (spins > (1u << 22) || ((*(volatile int*)gflag) & 0x100))) { atomicOr(gflag, 0x100); break; }
         } while ((int)(seen - target) < 0);
         __threadfence();
       }
