@@ -83,6 +83,7 @@ double ev, qe, me, mp, pi_, cutlo, rt8opi, temin, tgmin, nnorm, ennorm, temp0, v
     cfjpy, cfjp2, cfqybf, cfq2bf, cfqybbo, cfqydbo, cfydd_, cfjp2_, cfqyn, cfqyao, cfqya, cfqyae, cfjpy_, fqpsatlb_unused, lnlam_unused, phiwi0, phiwo0,
     kappamx, kappa0, cfsigm, fqsatlb_u, fupe_cur, dtphi_, cfhcxgc_u, lyphi0, lyphi1, isparmultdt_u, tewallmin_u, cfwjdotelim, cfeexdbo, cfeixdbo, cfkincor,
     cfyef, cf2ef, cfybf, cf2bf, cfcurv, cfgradb, eycore, icoreelec, cfniybbo, cfeeybbo, cfydd, cf2dd, cfrd, cfbgt, cfvycf, cfvycr, cfeta1, cfrtaue, cfcl_e, cfcl_i, omgci_taui, omgce_taue, nuneo;
+int isphilbc, isphirbc, isphicore0, isfqpave;
 int ExtendedJacPhi, istgcore, istgpfc, istgwc, istglb, istgrb, isfegxyqflave;
 double tgcore, cftgticore, tgwall, lytg1, lytg2, cftgtipltl, cftgtipltr, cftgtipfc, cftgtiwc, cgengmpl, cgengmw, cfalbedo, recyce, recycwe, cvgpg, cfcvtg, cfegxy, flalftgxy;
 const double* idxtg_;
@@ -935,6 +936,7 @@ struct O2 {
           const double vyrd = cfrd == 0. ? 0. : -2. * A(gpry, ix, iy) / (sq(A(btot, ix, iy)) / etaper(ix, iy) + sq(A(btot, ix, iy + 1)) / etaper(ix, iy + 1));  // (not evaluated when switched off)
           A(vy[f], ix, iy) = cfydd * A(vycp[f], ix, iy) + cfrd * vyrd + A(vydd[f], ix, iy) + cfyef * A(vyce[f], ix, iy) + cfybf * A(vycb[f], ix, iy) + cfvycf * A(vycf, ix, iy) + cfvycr * A(vycr, ix, iy);
           A(vygp[f], ix, iy) = (cfydd + cfybf) * A(vycp[f], ix, iy) + cfrd * vyrd + A(vydd[f], ix, iy) + cfyef * A(vyce[f], ix, iy) + cfvycf * A(vycf, ix, iy) + cfvycr * A(vycr, ix, iy);
+          if (isybdrywd == 1 && ((iy == 0 && matwalli[ix] > 0) || (iy == ny && matwallo[ix] > 0))) A(vy[f], ix, iy) = A(vydd[f], ix, iy);  // diffusive in wall cells (oderhs.m:1312-1318)
         }
       for (int iy = j1; iy <= j6; ++iy)
         for (int ix = i1; ix <= i6; ++ix) {
@@ -1040,6 +1042,11 @@ struct O2 {
       for (int ix = i1; ix <= i6; ++ix) A(vey, ix, iy) = (A(vey, ix, iy) - cfjve * A(fqy, ix, iy) / (A(sy, ix, iy) * qe)) / (0.5 * (A(ney0, ix, iy) + A(ney1, ix, iy)));
     if (isnewpot == 1)  // fqy(,0) = 0 there (oderhs.m:1794-1800)
       for (int ix = i1; ix <= i6; ++ix) A(vey, ix, 0) = cfybf * A(veycb, ix, 0) + A(vydd[0], ix, 0) + cfyef * A(vyce[0], ix, 0);
+    if (isybdrywd == 1)  // vey diffusive in wall cells, like vy (oderhs.m:1803-1808)
+      for (int ix = i1; ix <= i6; ++ix) {
+        if (matwalli[ix] > 0) A(vey, ix, 0) = A(vydd[0], ix, 0);
+        if (matwallo[ix] > 0) A(vey, ix, ny) = A(vydd[0], ix, ny);
+      }
 
     // zero the source accumulators (oderhs.m:1818-1835)
     for (int iy = j2; iy <= j5; ++iy)
@@ -1873,6 +1880,11 @@ void O2::calc_currents(const Win& w) {
       double nbarx = (A(ne, ix1, iy) * A(gx, ix1, iy) + A(ne, ix, iy) * A(gx, ix, iy)) / (A(gx, ix1, iy) + A(gx, ix, iy));
       double sigbarx = zfac * cfsigm * sigma1_ * (A(rr, ix1, iy) * ue_pow(t0, 1.5) * A(gx, ix1, iy) + A(rr, ix, iy) * ue_pow(t1, 1.5) * A(gx, ix, iy)) /
                        ((A(gx, ix1, iy) + A(gx, ix, iy)) * ue_pow(ev, 1.5));
+      if (isfqpave != 0) {  // simple averages (potencur.m:106-111)
+        zfac = 0.5 * (zfac0 + zfac1);
+        nbarx = 0.5 * (A(ne, ix1, iy) + A(ne, ix, iy));
+        sigbarx = zfac * cfsigm * sigma1_ * A(rrv, ix, iy) * ue_pow(0.5 * (t0 + t1) / ev, 1.5);
+      }
       A(netap, ix, iy) = nbarx / sigbarx;
       A(fqp, ix, iy) = (A(rrv, ix, iy) * A(sx, ix, iy) * sigbarx * A(gxf, ix, iy) / qe) *
                        ((A(pre, ix1, iy) - A(pre, ix, iy)) / nbarx - qe * (A(phi, ix1, iy) - A(phi, ix, iy)) + qe * (0. - 0.) + 0. / (A(rrv, ix, iy) * nbarx) + cthe * (A(te, ix1, iy) - A(te, ix, iy)));
@@ -2469,6 +2481,7 @@ int O2::bouncon(const Win& w, const double* yl, double* yldot) {
           if (newbcl == 0 && iskaplex == 0) kappal[iy] = 3.0;
           const int64_t iv = IDXPHI(ixt, iy);
           if (iv >= 0) yldot[iv] = -nurlxp * (1. - bctype[iy]) * (A(phi, ixt, iy) - kappal[iy] * A(te, ixt, iy) / ev - phi0l[iy]) / temp0 - nurlxp * bctype[iy] * (1. - gamsec_) * A(fqp, ixt, iy) / (fqpsatlb[iy] + cutlo);
+          if (iv >= 0 && isphilbc == 1) yldot[iv] = -nurlxp * (A(phi, ixt, iy) - phi0l[iy]) / temp0;  // boundary.m:1962-1963
         } else { fqpsate = 0.; kappal[iy] = 3.; }
         const int isphion2 = isphion + isphiofft;
         bcel[iy] = (1 - newbcl * isphion2) * bcee + newbcl * isphion2 * (2. + kappal[iy]);
@@ -2612,6 +2625,7 @@ int O2::bouncon(const Win& w, const double* yl, double* yldot) {
           kappar[iy] = -ue_log(arglgphi);  // iskaprex = 0 (note: NOT reset to 3 when newbcr = 0, unlike the left plate)
           const int64_t iv = IDXPHI(ixt, iy);
           if (iv >= 0) yldot[iv] = -nurlxp * (1. - bctype[iy]) * (A(phi, ixt, iy) - kappar[iy] * A(te, ixt, iy) / ev - phi0r[iy]) / temp0 - nurlxp * bctype[iy] * (1. - gamsec_) * A(fqp, ixt1, iy) / (fqpsatrb[iy] + cutlo);
+          if (iv >= 0 && isphirbc == 1) yldot[iv] = -nurlxp * (A(phi, ixt, iy) - phi0r[iy]) / temp0;  // boundary.m:2638-2639
         } else { fqpsate = 0.; kappar[iy] = 3.; }
         const int isphion2 = isphion + isphiofft;
         bcer[iy] = (1 - newbcr * isphion2) * bcee + newbcr * isphion2 * (2. + kappar[iy]);
@@ -2898,15 +2912,15 @@ int init_all() {
                                                    {"nxomit", 0}, {"isbohmcalc", 1}, {"isdifbetap", 0}, 
                                                    {"cftef", 0}, {"cftdd", 0}, 
                                                    {"facbni", 0}, {"facbup", 0}, {"facbee", 0}, {"facbei", 0}, {"rtauxfac", 0}, {"ispsorave", 0}, {"iseesorave", 0}, {"cfvisxneov", 0},
-                                                   {"cfvisxneoq", 0}, {"cfvyavis", 0}, {"cfanomvisxg", 0}, {"cfanomvisyg", 0}, {"isnfmiy", 0}, {"isybdrywd", 0}, {"isfeexpl0", 0},
-                                                   {"isfeixpl0", 0}, {"cfeexdbo", 0}, {"cfeixdbo", 0}, {"cfniydbo", 0}, {"cfeeydbo", 0}, {"isextrnp", 0}, {"isextrnpf", 0},
+                                                   {"cfvisxneoq", 0}, {"cfvyavis", 0}, {"cfanomvisxg", 0}, {"cfanomvisyg", 0}, {"isnfmiy", 0}, {"isfeexpl0", 0},
+                                                   {"isfeixpl0", 0}, {"cfeexdbo", 0}, {"cfeixdbo", 0}, {"isextrnp", 0}, {"isextrnpf", 0},
                                                    {"isextrtpf", 0}, {"isextrngc", 0}, {"isextrnw", 0}, {"isextrtw", 0}, {"isbohmms", 0}, {"ibctepl", 1}, {"ibctipl", 1}, {"ibctepr", 1}, {"ibctipr", 1}, {"isfixrb", 0},
-                                                   {"is1D_gbx", 0}, {"isnglf", 0}, {"iszeffcon", 0}, {"isup1up2", 0}, {"isflxvar", 0}, {"isphilbc", 0}, {"isphirbc", 0}, {"ikapmod", 0},
-                                                   {"isfqpave", 0}, {"isphicore0", 0}, {"iskaprex", 0}, {"isrozhfac", 0}};
+                                                   {"is1D_gbx", 0}, {"isnglf", 0}, {"iszeffcon", 0}, {"isup1up2", 0}, {"isflxvar", 0}, {"ikapmod", 0},
+                                                   {"isphicore0", 0}, {"iskaprex", 0}, {"isrozhfac", 0}};
   for (auto& m : must) { const V* v = find(m.n); if (!v) { g_err = std::string("oracle2: missing input ") + m.n; return -1; } if ((*v)[0] != m.want) { g_err = std::string("oracle2: switch outside this restatement: ") + m.n; return -5; } }
   if (isnewpot != 0 && isnewpot != 1) { g_err = "oracle2: isnewpot must be 0 or 1"; return -5; }
   if (isnewpot * isphion == 1 && (iphibcc < 1 || iphibcc > 3)) { g_err = "oracle2: only iphibcc = 1, 2, 3 available"; return -5; }
-  ExtendedJacPhi = I("ExtendedJacPhi"); numvar_ = I("numvar");
+  ExtendedJacPhi = I("ExtendedJacPhi"); isphilbc = I("isphilbc"); isphirbc = I("isphirbc"); isfqpave = I("isfqpave"); numvar_ = I("numvar");
   // gas energy equation (istgon = 1): the inertial atoms only
   idxtg_ = ARR("idxtg", nc);
   istgcore = I("istgcore", 0); istgpfc = I("istgpfc", 0); istgwc = I("istgwc", 0); istglb = I("istglb", 0); istgrb = I("istgrb", 0); isfegxyqflave = I("isfegxyqflave");

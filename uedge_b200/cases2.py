@@ -222,6 +222,7 @@ def switch_variant(seed):
                     ("jhswitch", (1, 2)), ("isfdiax", (1.0,)), ("iphibcc", (1, 2, 3)), ("cfcurv", (0.5,)), ("cfgradb", (0.5,)), ("eycore", (10.0,)), ("icoreelec", (5.0,)),
                     ("cfqybbo", (1.0,)), ("cfqydbo", (1.0,)), ("cfniybbo", (1.0,)), ("cfeeybbo", (1.0,)), ("ExtendedJacPhi", (0,)),
                     ("cfydd", (1.0,)), ("cf2dd", (1.0,)), ("cfrd", (1.0, 0.5)), ("cfbgt", (1.0,)), ("cfjpy", (1.0,)), ("cfjp2", (1.0,)),
+                    ("isybdrywd", (1,)), ("isphilbc", (1,)), ("isphirbc", (1,)), ("isfqpave", (1,)), ("cfniydbo", (1.0,)), ("cfeeydbo", (1.0,)),
                     ("cfvycr", (1.0,)), ("cfrtaue", (1.0,)), ("cfvycf", (1.0,)), ("cfeta1", (1.0,)), ("cfcl_e", (1.0,)), ("cfcl_i", (1.0,)), ("cfqyn", (1.0,)), ("nuneo", (1e3,))):
         if rng.random() < 0.4:
             ch[k] = pick(*vals)

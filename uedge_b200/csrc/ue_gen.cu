@@ -714,11 +714,11 @@ int init_all() {
                                                    {"nxomit", 0}, {"isbohmcalc", 1}, {"isdifbetap", 0}, 
                                                    {"cftef", 0}, {"cftdd", 0}, 
                                                    {"facbni", 0}, {"facbup", 0}, {"facbee", 0}, {"facbei", 0}, {"rtauxfac", 0}, {"ispsorave", 0}, {"iseesorave", 0}, {"cfvisxneov", 0},
-                                                   {"cfvisxneoq", 0}, {"cfvyavis", 0}, {"cfanomvisxg", 0}, {"cfanomvisyg", 0}, {"isnfmiy", 0}, {"isybdrywd", 0}, {"isfeexpl0", 0},
-                                                   {"isfeixpl0", 0}, {"cfeexdbo", 0}, {"cfeixdbo", 0}, {"cfniydbo", 0}, {"cfeeydbo", 0}, {"isextrnp", 0}, {"isextrnpf", 0},
+                                                   {"cfvisxneoq", 0}, {"cfvyavis", 0}, {"cfanomvisxg", 0}, {"cfanomvisyg", 0}, {"isnfmiy", 0}, {"isfeexpl0", 0},
+                                                   {"isfeixpl0", 0}, {"cfeexdbo", 0}, {"cfeixdbo", 0}, {"isextrnp", 0}, {"isextrnpf", 0},
                                                    {"isextrtpf", 0}, {"isextrngc", 0}, {"isextrnw", 0}, {"isextrtw", 0}, {"isbohmms", 0}, {"ibctepl", 1}, {"ibctipl", 1}, {"ibctepr", 1}, {"ibctipr", 1}, {"isfixrb", 0},
-                                                   {"is1D_gbx", 0}, {"isnglf", 0}, {"iszeffcon", 0}, {"isup1up2", 0}, {"isflxvar", 0}, {"isphilbc", 0}, {"isphirbc", 0}, {"ikapmod", 0},
-                                                   {"isfqpave", 0}, {"isphicore0", 0}, {"iskaprex", 0}, {"isrozhfac", 0}};
+                                                   {"is1D_gbx", 0}, {"isnglf", 0}, {"iszeffcon", 0}, {"isup1up2", 0}, {"isflxvar", 0}, {"ikapmod", 0},
+                                                   {"isphicore0", 0}, {"iskaprex", 0}, {"isrozhfac", 0}};
   for (auto& m : must) {
     const V* v = find(m.n);
     if (!v) { g_err = std::string("missing input ") + m.n; return -1; }
@@ -726,7 +726,7 @@ int init_all() {
   }
   if (g.isnewpot != 0 && g.isnewpot != 1) { g_err = "isnewpot must be 0 or 1"; return -5; }
   if (g.isnewpot * g.isphion == 1 && (g.iphibcc < 1 || g.iphibcc > 3)) { g_err = "only iphibcc = 1, 2, 3 available"; return -5; }
-  g.ExtendedJacPhi = I("ExtendedJacPhi"); g.numvar_ = I("numvar");
+  g.ExtendedJacPhi = I("ExtendedJacPhi"); g.isphilbc = I("isphilbc"); g.isphirbc = I("isphirbc"); g.isfqpave = I("isfqpave"); g.numvar_ = I("numvar");
   g.gridmode = 0; g.gbar = nullptr; g.gflag = nullptr;
   g.rowlo = 0; g.rowhi = g.ny + 1;
   // gas energy equation (istgon = 1): the inertial atoms only

@@ -157,6 +157,7 @@ double ev, qe, me, mp, pi_, cutlo, rt8opi, temin, tgmin, nnorm, ennorm, temp0, v
     cfjpy, cfjp2, cfqybf, cfq2bf, cfqybbo, cfqydbo, cfydd_, cfjp2_, cfqyn, cfqyao, cfqya, cfqyae, cfjpy_, fqpsatlb_unused, lnlam_unused, phiwi0, phiwo0,
     kappamx, kappa0, cfsigm, fqsatlb_u, fupe_cur, dtphi_, cfhcxgc_u, lyphi0, lyphi1, isparmultdt_u, tewallmin_u, cfwjdotelim, cfeexdbo, cfeixdbo, cfkincor,
     cfyef, cf2ef, cfybf, cf2bf, cfcurv, cfgradb, eycore, icoreelec, cfniybbo, cfeeybbo, cfydd, cf2dd, cfrd, cfbgt, cfvycf, cfvycr, cfeta1, cfrtaue, cfcl_e, cfcl_i, omgci_taui, omgce_taue, nuneo;
+int isphilbc, isphirbc, isphicore0, isfqpave;
 int ExtendedJacPhi, istgcore, istgpfc, istgwc, istglb, istgrb, isfegxyqflave;
 int64_t numvar_;
 double tgcore, cftgticore, tgwall, lytg1, lytg2, cftgtipltl, cftgtipltr, cftgtipfc, cftgtiwc, cgengmpl, cgengmw, cfalbedo, recyce, recycwe, cvgpg, cfcvtg, cfegxy, flalftgxy;
@@ -948,6 +949,7 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
           const double vyrd = cfrd == 0. ? 0. : -2. * A(gpry, ix, iy) / (sq(A(btot, ix, iy)) / etaper(ix, iy) + sq(A(btot, ix, iy + 1)) / etaper(ix, iy + 1));  // (not evaluated when switched off)
           A(vy[f], ix, iy) = cfydd * A(vycp[f], ix, iy) + cfrd * vyrd + A(vydd[f], ix, iy) + cfyef * A(vyce[f], ix, iy) + cfybf * A(vycb[f], ix, iy) + cfvycf * A(vycf, ix, iy) + cfvycr * A(vycr, ix, iy);
           A(vygp[f], ix, iy) = (cfydd + cfybf) * A(vycp[f], ix, iy) + cfrd * vyrd + A(vydd[f], ix, iy) + cfyef * A(vyce[f], ix, iy) + cfvycf * A(vycf, ix, iy) + cfvycr * A(vycr, ix, iy);
+          if (isybdrywd == 1 && ((iy == 0 && matwalli[ix] > 0) || (iy == ny && matwallo[ix] > 0))) A(vy[f], ix, iy) = A(vydd[f], ix, iy);  // diffusive in wall cells (oderhs.m:1312-1318)
         }
       FOR2(iy, j1, j6, ix, i1, i6) {
           const int ix2 = IXP1(ix, iy), iy1 = mx(0, iy - 1);
@@ -1042,6 +1044,11 @@ HD double upwind(double f, double p1, double p2) { return mx(f, 0.0) * p1 + mn(f
     FOR2(iy, j1, j5, ix, i1, i6) A(vey, ix, iy) = (A(vey, ix, iy) - cfjve * A(fqy, ix, iy) / (A(sy, ix, iy) * qe)) / (0.5 * (A(ney0, ix, iy) + A(ney1, ix, iy)));
     if (isnewpot == 1 && inrow(0))  // fqy(,0) = 0 there (oderhs.m:1794-1800)
       FOR1(ix, i1, i6) A(vey, ix, 0) = cfybf * A(veycb, ix, 0) + A(vydd[0], ix, 0) + cfyef * A(vyce[0], ix, 0);
+    if (isybdrywd == 1)  // vey diffusive in wall cells, like vy (oderhs.m:1803-1808)
+      FOR1(ix, i1, i6) {
+        if (inrow(0) && matwalli[ix] > 0) A(vey, ix, 0) = A(vydd[0], ix, 0);
+        if (inrow(ny) && matwallo[ix] > 0) A(vey, ix, ny) = A(vydd[0], ix, ny);
+      }
 
     // zero the source accumulators (oderhs.m:1818-1835)
     FOR2(iy, j2, j5, ix, i2, i5) {
@@ -1793,6 +1800,11 @@ HD void calc_currents(const Win& w) {
       double nbarx = (A(ne, ix1, iy) * A(gx, ix1, iy) + A(ne, ix, iy) * A(gx, ix, iy)) / (A(gx, ix1, iy) + A(gx, ix, iy));
       double sigbarx = zfac * cfsigm * sigma1_ * (A(rr, ix1, iy) * ue_pow(t0, 1.5) * A(gx, ix1, iy) + A(rr, ix, iy) * ue_pow(t1, 1.5) * A(gx, ix, iy)) /
                        ((A(gx, ix1, iy) + A(gx, ix, iy)) * ue_pow(ev, 1.5));
+      if (isfqpave != 0) {  // simple averages (potencur.m:106-111)
+        zfac = 0.5 * (zfac0 + zfac1);
+        nbarx = 0.5 * (A(ne, ix1, iy) + A(ne, ix, iy));
+        sigbarx = zfac * cfsigm * sigma1_ * A(rrv, ix, iy) * ue_pow(0.5 * (t0 + t1) / ev, 1.5);
+      }
       A(netap, ix, iy) = nbarx / sigbarx;
       A(fqp, ix, iy) = (A(rrv, ix, iy) * A(sx, ix, iy) * sigbarx * A(gxf, ix, iy) / qe) *
                        ((A(pre, ix1, iy) - A(pre, ix, iy)) / nbarx - qe * (A(phi, ix1, iy) - A(phi, ix, iy)) + qe * (0. - 0.) + 0. / (A(rrv, ix, iy) * nbarx) + cthe * (A(te, ix1, iy) - A(te, ix, iy)));
@@ -2385,6 +2397,7 @@ HD int bouncon(const Win& w, const double* yl, double* yldot) {
           if (newbcl == 0 && iskaplex == 0) kappal[iy] = 3.0;
           const int64_t iv = IDXPHI(ixt, iy);
           if (iv >= 0) yldot[iv] = -nurlxp * (1. - bctype[iy]) * (A(phi, ixt, iy) - kappal[iy] * A(te, ixt, iy) / ev - phi0l[iy]) / temp0 - nurlxp * bctype[iy] * (1. - gamsec_) * A(fqp, ixt, iy) / (fqpsatlb[iy] + cutlo);
+          if (iv >= 0 && isphilbc == 1) yldot[iv] = -nurlxp * (A(phi, ixt, iy) - phi0l[iy]) / temp0;  // boundary.m:1962-1963
         } else { fqpsate = 0.; kappal[iy] = 3.; }
         const int isphion2 = isphion + isphiofft;
         bcel[iy] = (1 - newbcl * isphion2) * bcee + newbcl * isphion2 * (2. + kappal[iy]);
@@ -2528,6 +2541,7 @@ HD int bouncon(const Win& w, const double* yl, double* yldot) {
           kappar[iy] = -ue_log(arglgphi);  // iskaprex = 0 (note: NOT reset to 3 when newbcr = 0, unlike the left plate)
           const int64_t iv = IDXPHI(ixt, iy);
           if (iv >= 0) yldot[iv] = -nurlxp * (1. - bctype[iy]) * (A(phi, ixt, iy) - kappar[iy] * A(te, ixt, iy) / ev - phi0r[iy]) / temp0 - nurlxp * bctype[iy] * (1. - gamsec_) * A(fqp, ixt1, iy) / (fqpsatrb[iy] + cutlo);
+          if (iv >= 0 && isphirbc == 1) yldot[iv] = -nurlxp * (A(phi, ixt, iy) - phi0r[iy]) / temp0;  // boundary.m:2638-2639
         } else { fqpsate = 0.; kappar[iy] = 3.; }
         const int isphion2 = isphion + isphiofft;
         bcer[iy] = (1 - newbcr * isphion2) * bcee + newbcr * isphion2 * (2. + kappar[iy]);
